@@ -1,0 +1,157 @@
+/* jxl_b200 -- C ABI of the B200-native JPEG XL hot path.
+ *
+ * Drop-in boundary: the symbols below are what jpegxl-sys would bind for the
+ * decode/encode path (jpegxl-sys/src/decode.rs:363-1532 declares libjxl's
+ * JxlDecoder* functions as `extern "C-unwind"`; jpegxl-rs drives them from
+ * jpegxl-rs/src/decode.rs:207-325). Two groups of entry points:
+ *
+ *  1. JxlB200* batch API (new): one call decodes a batch of independent
+ *     codestreams on the GPU. A single 256x256 group is a serial entropy-coded
+ *     chain, so a B200 is filled by #groups x #frames, not by one image.
+ *  2. Jxl* libjxl-compatible subset (same names, argument meaning, status codes and
+ *     event order as libjxl 0.11.2, lib/include/jxl/decode.h) so that jpegxl-rs's
+ *     event loop runs unchanged; internally a batch of one.
+ *
+ * Plain pointers and sizes only. All functions return 0 (JXL_DEC_SUCCESS) on
+ * success unless stated otherwise. The library needs a CUDA device: without one
+ * every compute entry point fails (there is no CPU fallback).
+ */
+#ifndef JXL_B200_H_
+#define JXL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- types shared with libjxl (jpegxl-sys/src/common/types.rs:25-148) ---- */
+typedef int JXL_BOOL;
+typedef enum { JXL_TYPE_FLOAT = 0, JXL_TYPE_UINT8 = 2, JXL_TYPE_UINT16 = 3, JXL_TYPE_FLOAT16 = 5 } JxlDataType;
+typedef enum { JXL_NATIVE_ENDIAN = 0, JXL_LITTLE_ENDIAN = 1, JXL_BIG_ENDIAN = 2 } JxlEndianness;
+typedef struct {
+  uint32_t num_channels;
+  JxlDataType data_type;
+  JxlEndianness endianness;
+  size_t align;
+} JxlPixelFormat;
+
+/* JxlBasicInfo, byte-identical to libjxl 0.11.2 (lib/include/jxl/codestream_header.h;
+ * jpegxl-sys/src/metadata/codestream_header.rs:108-238; 204 bytes, lib/jxl/decode.cc:2061). */
+typedef struct { uint32_t xsize, ysize; } JxlPreviewHeader;
+typedef struct { uint32_t tps_numerator, tps_denominator, num_loops; JXL_BOOL have_timecodes; } JxlAnimationHeader;
+typedef struct {
+  JXL_BOOL have_container;
+  uint32_t xsize;
+  uint32_t ysize;
+  uint32_t bits_per_sample;
+  uint32_t exponent_bits_per_sample;
+  float intensity_target;
+  float min_nits;
+  JXL_BOOL relative_to_max_display;
+  float linear_below;
+  JXL_BOOL uses_original_profile;
+  JXL_BOOL have_preview;
+  JXL_BOOL have_animation;
+  uint32_t orientation; /* JxlOrientation */
+  uint32_t num_color_channels;
+  uint32_t num_extra_channels;
+  uint32_t alpha_bits;
+  uint32_t alpha_exponent_bits;
+  JXL_BOOL alpha_premultiplied;
+  JxlPreviewHeader preview;
+  JxlAnimationHeader animation;
+  uint32_t intrinsic_xsize;
+  uint32_t intrinsic_ysize;
+  uint8_t padding[100];
+} JxlBasicInfo;
+
+/* ---- 1. batch API ---- */
+typedef struct JxlB200Decoder JxlB200Decoder;
+
+/* Creates a batch decoder bound to CUDA device `device`. NULL if no usable GPU. */
+JxlB200Decoder* JxlB200DecoderCreate(int device);
+void JxlB200DecoderDestroy(JxlB200Decoder* dec);
+/* Message of the last failure on this handle (never NULL). */
+const char* JxlB200DecoderGetError(const JxlB200Decoder* dec);
+
+/* Host parse of `n` files (headers, TOC, histograms, MA trees, group headers) on
+ * `num_threads` host threads, then upload of bitstreams and tables to HBM.
+ * The files are only read during the call. Replaces libjxl's
+ * JxlDecoderSetInput + the header part of JxlDecoderProcessInput
+ * (jpegxl-rs/src/decode.rs:231-252). */
+int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files, const size_t* sizes, size_t n,
+                                const JxlPixelFormat* format, int num_threads);
+size_t JxlB200DecoderNumFrames(const JxlB200Decoder* dec);
+int JxlB200DecoderGetBasicInfo(const JxlB200Decoder* dec, size_t i, JxlBasicInfo* info);
+/* Bytes of frame i in the requested pixel format (JxlDecoderImageOutBufferSize). */
+size_t JxlB200DecoderImageOutBufferSize(const JxlB200Decoder* dec, size_t i);
+
+/* Runs the decode kernels for the whole batch on `cuda_stream` (a cudaStream_t
+ * passed as void*, NULL = the decoder's own stream). Asynchronous: returns after
+ * the launches. The pixels stay in HBM. */
+int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream);
+/* Waits for the last Run and reports per-stream decode errors. */
+int JxlB200DecoderWait(JxlB200Decoder* dec, void* cuda_stream);
+/* Device pointer (HBM) of frame i's pixels after Run. */
+void* JxlB200DecoderDeviceOutput(const JxlB200Decoder* dec, size_t i);
+/* Device -> host copy of frame i into `dst` (JxlDecoderSetImageOutBuffer semantics:
+ * rows of align_up(xsize * channels * bytes, align) bytes). Synchronous. */
+int JxlB200DecoderReadOutput(JxlB200Decoder* dec, size_t i, void* dst, size_t size);
+/* Device -> host copy of all frames; dsts[i] receives frame i. */
+int JxlB200DecoderReadOutputs(JxlB200Decoder* dec, void* const* dsts, const size_t* sizes, size_t n);
+
+/* Workload figures for benchmarks. */
+typedef struct {
+  uint64_t compressed_bytes; /* bitstream bytes resident in HBM */
+  uint64_t output_bytes;     /* pixels written per Run */
+  uint64_t pixels;           /* sum of xsize * ysize */
+  uint64_t num_streams;      /* entropy-coded streams = decode-kernel threads */
+  uint64_t arena_bytes;      /* intermediate int32 planes */
+  uint32_t kernel_launches;  /* launches per Run */
+} JxlB200Stats;
+int JxlB200DecoderGetStats(const JxlB200Decoder* dec, JxlB200Stats* stats);
+/* Per-kernel device time: when enabled, Run brackets each kernel with CUDA events on the
+ * launching stream (the timed region of a benchmark). ms4 = accumulated milliseconds of
+ * {entropy decode, group transforms, global transforms, output write}; runs = number of Runs. */
+int JxlB200DecoderSetProfiling(JxlB200Decoder* dec, int enabled);
+int JxlB200DecoderGetKernelTimes(JxlB200Decoder* dec, double* ms4, uint32_t* runs);
+
+/* ---- 2. libjxl-compatible subset (decode) ---- */
+typedef struct JxlDecoderStruct JxlDecoder;
+typedef enum {
+  JXL_DEC_SUCCESS = 0, JXL_DEC_ERROR = 1, JXL_DEC_NEED_MORE_INPUT = 2, JXL_DEC_NEED_PREVIEW_OUT_BUFFER = 3,
+  JXL_DEC_NEED_IMAGE_OUT_BUFFER = 5, JXL_DEC_JPEG_NEED_MORE_OUTPUT = 6, JXL_DEC_BOX_NEED_MORE_OUTPUT = 7,
+  JXL_DEC_BASIC_INFO = 0x40, JXL_DEC_COLOR_ENCODING = 0x100, JXL_DEC_PREVIEW_IMAGE = 0x200, JXL_DEC_FRAME = 0x400,
+  JXL_DEC_FULL_IMAGE = 0x1000, JXL_DEC_JPEG_RECONSTRUCTION = 0x2000, JXL_DEC_BOX = 0x4000,
+  JXL_DEC_FRAME_PROGRESSION = 0x8000, JXL_DEC_BOX_COMPLETE = 0x10000
+} JxlDecoderStatus;
+typedef enum { JXL_SIG_NOT_ENOUGH_BYTES = 0, JXL_SIG_INVALID = 1, JXL_SIG_CODESTREAM = 2, JXL_SIG_CONTAINER = 3 } JxlSignature;
+
+uint32_t JxlDecoderVersion(void);
+JxlSignature JxlSignatureCheck(const uint8_t* buf, size_t len);
+/* memory_manager must be NULL (custom allocators are not routed to the GPU path). */
+JxlDecoder* JxlDecoderCreate(const void* memory_manager);
+void JxlDecoderReset(JxlDecoder* dec);
+void JxlDecoderDestroy(JxlDecoder* dec);
+/* Accepted and ignored: the GPU path does not use host thread pools for pixels. */
+JxlDecoderStatus JxlDecoderSetParallelRunner(JxlDecoder* dec, void* parallel_runner, void* parallel_runner_opaque);
+JxlDecoderStatus JxlDecoderSubscribeEvents(JxlDecoder* dec, int events_wanted);
+JxlDecoderStatus JxlDecoderSetKeepOrientation(JxlDecoder* dec, JXL_BOOL skip_reorientation);
+JxlDecoderStatus JxlDecoderSetUnpremultiplyAlpha(JxlDecoder* dec, JXL_BOOL unpremul_alpha);
+JxlDecoderStatus JxlDecoderSetRenderSpotcolors(JxlDecoder* dec, JXL_BOOL render_spotcolors);
+JxlDecoderStatus JxlDecoderSetCoalescing(JxlDecoder* dec, JXL_BOOL coalescing);
+JxlDecoderStatus JxlDecoderSetDesiredIntensityTarget(JxlDecoder* dec, float desired_intensity_target);
+JxlDecoderStatus JxlDecoderSetInput(JxlDecoder* dec, const uint8_t* data, size_t size);
+void JxlDecoderCloseInput(JxlDecoder* dec);
+JxlDecoderStatus JxlDecoderProcessInput(JxlDecoder* dec);
+JxlDecoderStatus JxlDecoderGetBasicInfo(const JxlDecoder* dec, JxlBasicInfo* info);
+JxlDecoderStatus JxlDecoderImageOutBufferSize(const JxlDecoder* dec, const JxlPixelFormat* format, size_t* size);
+JxlDecoderStatus JxlDecoderSetImageOutBuffer(JxlDecoder* dec, const JxlPixelFormat* format, void* buffer, size_t size);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* JXL_B200_H_ */

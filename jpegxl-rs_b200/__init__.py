@@ -1,0 +1,442 @@
+"""jxl_b200: host-side mirror of the jpegxl-rs decode API over the B200 C ABI.
+
+The reference's safe wrapper is Rust (jpegxl-rs/src/decode.rs); there is no Rust
+toolchain in this image, so the same surface is mirrored here in Python on top of
+``libjxl_b200.so`` (include/jxl_b200.h) through ctypes:
+
+* ``decoder_builder()`` / ``JxlDecoder``   -> jpegxl-rs/src/decode.rs:85-204 (builder fields)
+* ``JxlDecoder.decode`` / ``decode_with``  -> jpegxl-rs/src/decode.rs:440-491
+* ``Metadata`` / ``Pixels``                -> jpegxl-rs/src/decode/result.rs:25-75
+* ``DecodeError`` variants                 -> jpegxl-rs/src/errors.rs:27-60
+* ``decode_batch``                         -> new: the batch extension (JxlB200Decoder*)
+
+All pixel work happens in the CUDA kernels; importing this module without the built
+library or without a GPU raises (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjxl_b200.so")
+
+# ---- enums (jpegxl-sys/src/common/types.rs:45-103, jpegxl-sys/src/decode.rs:84-247) ----
+JXL_TYPE_FLOAT, JXL_TYPE_UINT8, JXL_TYPE_UINT16, JXL_TYPE_FLOAT16 = 0, 2, 3, 5
+JXL_NATIVE_ENDIAN, JXL_LITTLE_ENDIAN, JXL_BIG_ENDIAN = 0, 1, 2
+JXL_DEC_SUCCESS, JXL_DEC_ERROR, JXL_DEC_NEED_MORE_INPUT = 0, 1, 2
+JXL_DEC_NEED_IMAGE_OUT_BUFFER = 5
+JXL_DEC_BASIC_INFO, JXL_DEC_FULL_IMAGE = 0x40, 0x1000
+
+_NP_DTYPE = {JXL_TYPE_FLOAT: np.float32, JXL_TYPE_UINT8: np.uint8, JXL_TYPE_UINT16: np.uint16,
+             JXL_TYPE_FLOAT16: np.float16}
+
+
+class JxlPixelFormat(ctypes.Structure):
+    _fields_ = [("num_channels", ctypes.c_uint32), ("data_type", ctypes.c_int), ("endianness", ctypes.c_int),
+                ("align", ctypes.c_size_t)]
+
+
+class JxlBasicInfo(ctypes.Structure):
+    _fields_ = [("have_container", ctypes.c_int), ("xsize", ctypes.c_uint32), ("ysize", ctypes.c_uint32),
+                ("bits_per_sample", ctypes.c_uint32), ("exponent_bits_per_sample", ctypes.c_uint32),
+                ("intensity_target", ctypes.c_float), ("min_nits", ctypes.c_float),
+                ("relative_to_max_display", ctypes.c_int), ("linear_below", ctypes.c_float),
+                ("uses_original_profile", ctypes.c_int), ("have_preview", ctypes.c_int),
+                ("have_animation", ctypes.c_int), ("orientation", ctypes.c_uint32),
+                ("num_color_channels", ctypes.c_uint32), ("num_extra_channels", ctypes.c_uint32),
+                ("alpha_bits", ctypes.c_uint32), ("alpha_exponent_bits", ctypes.c_uint32),
+                ("alpha_premultiplied", ctypes.c_int), ("preview_xsize", ctypes.c_uint32),
+                ("preview_ysize", ctypes.c_uint32), ("tps_numerator", ctypes.c_uint32),
+                ("tps_denominator", ctypes.c_uint32), ("num_loops", ctypes.c_uint32),
+                ("have_timecodes", ctypes.c_int), ("intrinsic_xsize", ctypes.c_uint32),
+                ("intrinsic_ysize", ctypes.c_uint32), ("padding", ctypes.c_uint8 * 100)]
+
+
+assert ctypes.sizeof(JxlBasicInfo) == 204  # lib/jxl/decode.cc:2061
+
+
+class JxlB200Stats(ctypes.Structure):
+    _fields_ = [("compressed_bytes", ctypes.c_uint64), ("output_bytes", ctypes.c_uint64), ("pixels", ctypes.c_uint64),
+                ("num_streams", ctypes.c_uint64), ("arena_bytes", ctypes.c_uint64),
+                ("kernel_launches", ctypes.c_uint32)]
+
+
+class DecodeError(Exception):
+    """Mirrors jpegxl-rs/src/errors.rs:27-60."""
+
+
+class CannotCreateDecoder(DecodeError):
+    pass
+
+
+class GenericError(DecodeError):
+    pass
+
+
+class InvalidInput(DecodeError):
+    pass
+
+
+class UnsupportedBitWidth(DecodeError):
+    pass
+
+
+class NotImplementedFeature(DecodeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads libjxl_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a) first")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    lib.JxlB200DecoderCreate.restype = vp
+    lib.JxlB200DecoderCreate.argtypes = [ctypes.c_int]
+    lib.JxlB200DecoderDestroy.argtypes = [vp]
+    lib.JxlB200DecoderGetError.restype = ctypes.c_char_p
+    lib.JxlB200DecoderGetError.argtypes = [vp]
+    lib.JxlB200DecoderSetInputBatch.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), sz,
+                                                ctypes.POINTER(JxlPixelFormat), ctypes.c_int]
+    lib.JxlB200DecoderNumFrames.restype = sz
+    lib.JxlB200DecoderNumFrames.argtypes = [vp]
+    lib.JxlB200DecoderGetBasicInfo.argtypes = [vp, sz, ctypes.POINTER(JxlBasicInfo)]
+    lib.JxlB200DecoderImageOutBufferSize.restype = sz
+    lib.JxlB200DecoderImageOutBufferSize.argtypes = [vp, sz]
+    lib.JxlB200DecoderRun.argtypes = [vp, vp]
+    lib.JxlB200DecoderWait.argtypes = [vp, vp]
+    lib.JxlB200DecoderDeviceOutput.restype = vp
+    lib.JxlB200DecoderDeviceOutput.argtypes = [vp, sz]
+    lib.JxlB200DecoderReadOutput.argtypes = [vp, sz, vp, sz]
+    lib.JxlB200DecoderReadOutputs.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), sz]
+    lib.JxlB200DecoderGetStats.argtypes = [vp, ctypes.POINTER(JxlB200Stats)]
+    lib.JxlB200DecoderSetProfiling.argtypes = [vp, ctypes.c_int]
+    lib.JxlB200DecoderGetKernelTimes.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
+    lib.JxlDecoderVersion.restype = ctypes.c_uint32
+    lib.JxlSignatureCheck.argtypes = [ctypes.c_char_p, sz]
+    lib.JxlDecoderCreate.restype = vp
+    lib.JxlDecoderCreate.argtypes = [vp]
+    lib.JxlDecoderReset.argtypes = [vp]
+    lib.JxlDecoderDestroy.argtypes = [vp]
+    lib.JxlDecoderSetParallelRunner.argtypes = [vp, vp, vp]
+    lib.JxlDecoderSubscribeEvents.argtypes = [vp, ctypes.c_int]
+    lib.JxlDecoderSetKeepOrientation.argtypes = [vp, ctypes.c_int]
+    lib.JxlDecoderSetUnpremultiplyAlpha.argtypes = [vp, ctypes.c_int]
+    lib.JxlDecoderSetRenderSpotcolors.argtypes = [vp, ctypes.c_int]
+    lib.JxlDecoderSetCoalescing.argtypes = [vp, ctypes.c_int]
+    lib.JxlDecoderSetDesiredIntensityTarget.argtypes = [vp, ctypes.c_float]
+    lib.JxlDecoderSetInput.argtypes = [vp, ctypes.c_char_p, sz]
+    lib.JxlDecoderCloseInput.argtypes = [vp]
+    lib.JxlDecoderProcessInput.argtypes = [vp]
+    lib.JxlDecoderGetBasicInfo.argtypes = [vp, ctypes.POINTER(JxlBasicInfo)]
+    lib.JxlDecoderImageOutBufferSize.argtypes = [vp, ctypes.POINTER(JxlPixelFormat), ctypes.POINTER(sz)]
+    lib.JxlDecoderSetImageOutBuffer.argtypes = [vp, ctypes.POINTER(JxlPixelFormat), vp, sz]
+    _lib = lib
+    return lib
+
+
+# Every symbol include/jxl_b200.h declares (checked by the CPU test-suite).
+EXPORTED_SYMBOLS = [
+    "JxlB200DecoderCreate", "JxlB200DecoderDestroy", "JxlB200DecoderGetError", "JxlB200DecoderSetInputBatch",
+    "JxlB200DecoderNumFrames", "JxlB200DecoderGetBasicInfo", "JxlB200DecoderImageOutBufferSize", "JxlB200DecoderRun",
+    "JxlB200DecoderWait", "JxlB200DecoderDeviceOutput", "JxlB200DecoderReadOutput", "JxlB200DecoderReadOutputs",
+    "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderGetKernelTimes",
+    "JxlDecoderVersion", "JxlSignatureCheck", "JxlDecoderCreate", "JxlDecoderReset",
+    "JxlDecoderDestroy", "JxlDecoderSetParallelRunner", "JxlDecoderSubscribeEvents", "JxlDecoderSetKeepOrientation",
+    "JxlDecoderSetUnpremultiplyAlpha", "JxlDecoderSetRenderSpotcolors", "JxlDecoderSetCoalescing",
+    "JxlDecoderSetDesiredIntensityTarget", "JxlDecoderSetInput", "JxlDecoderCloseInput", "JxlDecoderProcessInput",
+    "JxlDecoderGetBasicInfo", "JxlDecoderImageOutBufferSize", "JxlDecoderSetImageOutBuffer",
+]
+
+
+@dataclass
+class PixelFormat:
+    """jpegxl-rs/src/decode.rs:52-83. num_channels == 0 means colour (+ alpha if present)."""
+    num_channels: int = 0
+    endianness: int = JXL_NATIVE_ENDIAN
+    align: int = 0
+
+
+@dataclass
+class Metadata:
+    """jpegxl-rs/src/decode/result.rs:25-49."""
+    width: int
+    height: int
+    intensity_target: float
+    min_nits: float
+    orientation: int
+    num_color_channels: int
+    has_alpha_channel: bool
+    intrinsic_width: int
+    intrinsic_height: int
+    icc_profile: Optional[bytes] = None
+
+
+@dataclass
+class Pixels:
+    """jpegxl-rs/src/decode/result.rs:51-75: the variant is the numpy dtype."""
+    data: np.ndarray
+    data_type: int
+
+    @property
+    def variant(self) -> str:
+        return {JXL_TYPE_FLOAT: "Float", JXL_TYPE_UINT8: "Uint8", JXL_TYPE_UINT16: "Uint16",
+                JXL_TYPE_FLOAT16: "Float16"}[self.data_type]
+
+    def __len__(self) -> int:
+        return int(self.data.size)
+
+
+def _metadata(info: JxlBasicInfo) -> Metadata:
+    return Metadata(info.xsize, info.ysize, info.intensity_target, info.min_nits, info.orientation,
+                    info.num_color_channels, info.alpha_bits > 0, info.intrinsic_xsize, info.intrinsic_ysize)
+
+
+def check_valid_signature(data: bytes) -> Optional[bool]:
+    """jpegxl-rs/src/utils.rs:24-33."""
+    sig = load_library().JxlSignatureCheck(bytes(data), len(data))
+    if sig == 0:
+        return None
+    return sig in (2, 3)
+
+
+def _default_data_type(info: JxlBasicInfo) -> int:
+    """jpegxl-rs/src/decode.rs:394-404."""
+    bits, exp = info.bits_per_sample, info.exponent_bits_per_sample
+    if exp == 0 and bits <= 8:
+        return JXL_TYPE_UINT8
+    if exp == 0 and bits <= 16:
+        return JXL_TYPE_UINT16
+    if bits == 16:
+        return JXL_TYPE_FLOAT16
+    if bits == 32:
+        return JXL_TYPE_FLOAT
+    raise UnsupportedBitWidth(bits)
+
+
+class JxlDecoder:
+    """Event-loop decoder over the libjxl-compatible subset (one image per call)."""
+
+    def __init__(self, pixel_format: Optional[PixelFormat] = None, skip_reorientation: Optional[bool] = None,
+                 unpremul_alpha: Optional[bool] = None, render_spotcolors: Optional[bool] = None,
+                 coalescing: Optional[bool] = None, desired_intensity_target: Optional[float] = None,
+                 decompress: Optional[bool] = None, icc_profile: bool = False, parallel_runner=None):
+        self._lib = load_library()
+        self._dec = self._lib.JxlDecoderCreate(None)
+        if not self._dec:
+            raise CannotCreateDecoder()
+        self.pixel_format = pixel_format
+        self.skip_reorientation = skip_reorientation
+        self.unpremul_alpha = unpremul_alpha
+        self.render_spotcolors = render_spotcolors
+        self.coalescing = coalescing
+        self.desired_intensity_target = desired_intensity_target
+        self.decompress = decompress
+        self.icc_profile = icc_profile
+        self.parallel_runner = parallel_runner
+
+    def __del__(self):
+        if getattr(self, "_dec", None):
+            self._lib.JxlDecoderDestroy(self._dec)
+            self._dec = None
+
+    def _check(self, status: int) -> None:
+        if status != JXL_DEC_SUCCESS:
+            raise GenericError(f"decoder status {status}")
+
+    def _setup(self) -> None:  # jpegxl-rs/src/decode.rs:327-366
+        lib, dec = self._lib, self._dec
+        self._check(lib.JxlDecoderSetParallelRunner(dec, None, None))
+        self._check(lib.JxlDecoderSubscribeEvents(dec, JXL_DEC_BASIC_INFO | JXL_DEC_FULL_IMAGE))
+        if self.skip_reorientation is not None:
+            self._check(lib.JxlDecoderSetKeepOrientation(dec, int(self.skip_reorientation)))
+        if self.unpremul_alpha is not None:
+            self._check(lib.JxlDecoderSetUnpremultiplyAlpha(dec, int(self.unpremul_alpha)))
+        if self.render_spotcolors is not None:
+            self._check(lib.JxlDecoderSetRenderSpotcolors(dec, int(self.render_spotcolors)))
+        if self.coalescing is not None:
+            self._check(lib.JxlDecoderSetCoalescing(dec, int(self.coalescing)))
+        if self.desired_intensity_target is not None:
+            self._check(lib.JxlDecoderSetDesiredIntensityTarget(dec, float(self.desired_intensity_target)))
+
+    def _decode_internal(self, data: bytes, data_type: Optional[int]) -> Tuple[Metadata, Pixels]:
+        valid = check_valid_signature(data)
+        if not valid:
+            raise InvalidInput()
+        lib, dec = self._lib, self._dec
+        self._setup()
+        data = bytes(data)
+        self._check(lib.JxlDecoderSetInput(dec, data, len(data)))
+        lib.JxlDecoderCloseInput(dec)
+        info = JxlBasicInfo()
+        fmt = JxlPixelFormat()
+        buf = None
+        try:
+            while True:
+                status = lib.JxlDecoderProcessInput(dec)
+                if status in (JXL_DEC_NEED_MORE_INPUT, JXL_DEC_ERROR):
+                    raise GenericError()
+                if status == JXL_DEC_BASIC_INFO:
+                    self._check(lib.JxlDecoderGetBasicInfo(dec, ctypes.byref(info)))
+                elif status == JXL_DEC_NEED_IMAGE_OUT_BUFFER:
+                    dt = data_type if data_type is not None else _default_data_type(info)
+                    f = self.pixel_format or PixelFormat()
+                    fmt.num_channels = f.num_channels or (info.num_color_channels + (1 if info.alpha_bits > 0 else 0))
+                    fmt.data_type, fmt.endianness, fmt.align = dt, f.endianness, f.align
+                    size = ctypes.c_size_t(0)
+                    self._check(lib.JxlDecoderImageOutBufferSize(dec, ctypes.byref(fmt), ctypes.byref(size)))
+                    buf = np.zeros(size.value, dtype=np.uint8)
+                    self._check(lib.JxlDecoderSetImageOutBuffer(dec, ctypes.byref(fmt), buf.ctypes.data, size.value))
+                elif status == JXL_DEC_FULL_IMAGE:
+                    pass
+                elif status == JXL_DEC_SUCCESS:
+                    break
+                else:
+                    raise NotImplementedFeature(f"event {status:#x}")
+        finally:
+            lib.JxlDecoderReset(dec)
+        pixels = buf.view(_NP_DTYPE[fmt.data_type])
+        if fmt.endianness == JXL_BIG_ENDIAN and pixels.dtype.itemsize > 1:
+            pixels = pixels.byteswap()  # jpegxl-rs/src/common.rs:37-125 converts to native values
+        return _metadata(info), Pixels(pixels, fmt.data_type)
+
+    def decode(self, data: bytes) -> Tuple[Metadata, Pixels]:
+        """jpegxl-rs/src/decode.rs:440-455."""
+        return self._decode_internal(data, None)
+
+    def decode_with(self, data: bytes, dtype) -> Tuple[Metadata, np.ndarray]:
+        """jpegxl-rs/src/decode.rs:457-491; dtype in {u8, u16, f16, f32} as a numpy dtype."""
+        dt = {np.dtype(np.uint8): JXL_TYPE_UINT8, np.dtype(np.uint16): JXL_TYPE_UINT16,
+              np.dtype(np.float16): JXL_TYPE_FLOAT16, np.dtype(np.float32): JXL_TYPE_FLOAT}[np.dtype(dtype)]
+        meta, px = self._decode_internal(data, dt)
+        return meta, px.data
+
+
+def decoder_builder(**kwargs):
+    """jpegxl-rs/src/lib.rs:36-42: `decoder_builder().…build()`."""
+
+    class _Builder:
+        def __init__(self, kw):
+            self._kw = dict(kw)
+
+        def __getattr__(self, name):
+            def setter(value):
+                self._kw[name] = value
+                return self
+            return setter
+
+        def build(self) -> JxlDecoder:
+            return JxlDecoder(**self._kw)
+
+    return _Builder(kwargs)
+
+
+class BatchDecoder:
+    """The batch extension: n independent codestreams -> one set of kernel launches."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._dec = self._lib.JxlB200DecoderCreate(device)
+        if not self._dec:
+            raise CannotCreateDecoder("no usable CUDA device (jxl_b200 has no CPU fallback)")
+        self._keep = None
+
+    def __del__(self):
+        if getattr(self, "_dec", None):
+            self._lib.JxlB200DecoderDestroy(self._dec)
+            self._dec = None
+
+    def _err(self) -> str:
+        return self._lib.JxlB200DecoderGetError(self._dec).decode()
+
+    def set_input(self, files: Sequence[bytes], num_channels: int = 4, data_type: int = JXL_TYPE_UINT8,
+                  endianness: int = JXL_NATIVE_ENDIAN, align: int = 0, threads: int = 0) -> None:
+        n = len(files)
+        bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
+        ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (ctypes.c_size_t * n)(*[b.size for b in bufs])
+        fmt = JxlPixelFormat(num_channels, data_type, endianness, align)
+        if threads <= 0:
+            threads = min(os.cpu_count() or 1, 32)
+        rc = self._lib.JxlB200DecoderSetInputBatch(self._dec, ptrs, sizes, n, ctypes.byref(fmt), threads)
+        if rc != 0:
+            raise GenericError(self._err())
+        self.format = fmt
+        self.num_frames = n
+
+    def run(self, cuda_stream: int = 0) -> None:
+        if self._lib.JxlB200DecoderRun(self._dec, ctypes.c_void_p(cuda_stream)) != 0:
+            raise GenericError(self._err())
+
+    def wait(self, cuda_stream: int = 0) -> None:
+        if self._lib.JxlB200DecoderWait(self._dec, ctypes.c_void_p(cuda_stream)) != 0:
+            raise GenericError(self._err())
+
+    def basic_info(self, i: int) -> JxlBasicInfo:
+        info = JxlBasicInfo()
+        if self._lib.JxlB200DecoderGetBasicInfo(self._dec, i, ctypes.byref(info)) != 0:
+            raise GenericError("bad frame index")
+        return info
+
+    def out_size(self, i: int) -> int:
+        return self._lib.JxlB200DecoderImageOutBufferSize(self._dec, i)
+
+    def device_output(self, i: int) -> int:
+        return self._lib.JxlB200DecoderDeviceOutput(self._dec, i)
+
+    def read_output(self, i: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n = self.out_size(i)
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        if self._lib.JxlB200DecoderReadOutput(self._dec, i, out.ctypes.data, out.nbytes) != 0:
+            raise GenericError(self._err())
+        return out
+
+    def read_outputs(self, outs: Sequence[np.ndarray]) -> None:
+        n = len(outs)
+        ptrs = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+        sizes = (ctypes.c_size_t * n)(*[o.nbytes for o in outs])
+        if self._lib.JxlB200DecoderReadOutputs(self._dec, ptrs, sizes, n) != 0:
+            raise GenericError(self._err())
+
+    def set_profiling(self, enabled: bool) -> None:
+        self._lib.JxlB200DecoderSetProfiling(self._dec, int(enabled))
+
+    def kernel_times(self):
+        """(ms per kernel accumulated [decode, group transforms, global transforms, output], runs)."""
+        ms = (ctypes.c_double * 4)()
+        runs = ctypes.c_uint32(0)
+        self._lib.JxlB200DecoderGetKernelTimes(self._dec, ms, ctypes.byref(runs))
+        return list(ms), runs.value
+
+    def stats(self) -> JxlB200Stats:
+        st = JxlB200Stats()
+        self._lib.JxlB200DecoderGetStats(self._dec, ctypes.byref(st))
+        return st
+
+
+def decode_batch(files: Sequence[bytes], num_channels: int = 4, dtype=np.uint8, device: int = 0) -> List[np.ndarray]:
+    """Decodes n files on the GPU and returns one (H, W, C) array per file."""
+    dt = {np.dtype(np.uint8): JXL_TYPE_UINT8, np.dtype(np.uint16): JXL_TYPE_UINT16,
+          np.dtype(np.float16): JXL_TYPE_FLOAT16, np.dtype(np.float32): JXL_TYPE_FLOAT}[np.dtype(dtype)]
+    dec = BatchDecoder(device)
+    dec.set_input(files, num_channels, dt)
+    dec.run()
+    dec.wait()
+    out = []
+    for i in range(len(files)):
+        info = dec.basic_info(i)
+        raw = dec.read_output(i)
+        out.append(raw.view(dtype).reshape(info.ysize, info.xsize, num_channels))
+    return out

@@ -1,0 +1,132 @@
+// jxl_b200: plain-old-data descriptors shared by the host planner and the CUDA
+// kernels. Everything the device needs is expressed as offsets into a handful
+// of flat pools that are uploaded once per batch:
+//   bitstream bytes | alias entries | prefix tables | uint configs | tree nodes |
+//   channel descriptors | stream descriptors | plane descriptors | transform ops.
+#ifndef JXLB_DEV_H_
+#define JXLB_DEV_H_
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define JXLB_HD __host__ __device__ __forceinline__
+#define JXLB_ALIGN(n) __align__(n)
+#else
+#define JXLB_HD inline
+#define JXLB_ALIGN(n) alignas(n)
+#endif
+
+namespace jxlb {
+
+// 8-byte alias-table entry, same field meaning as libjxl's AliasTable::Entry
+// (lib/jxl/ans_common.h:67-76) so one 64-bit load fetches everything.
+struct JXLB_ALIGN(8) DevAlias {
+  uint8_t cutoff;
+  uint8_t right_value;
+  uint16_t freq0;
+  uint16_t offsets1;
+  uint16_t freq1_xor_freq0;
+};
+
+// One entropy code (histogram set). Offsets index the pools.
+struct DevCode {
+  uint32_t alias_off;    // DevAlias index of cluster 0
+  uint32_t cfg_off;      // uint32 index: per-cluster packed HybridUintConfig
+  uint32_t prefix_off;   // uint32 index: per-cluster table offsets (relative to prefix pool), then tables
+  uint32_t ctx_map_off;  // byte index into ctx pool (context -> cluster); unused when leaves are pre-mapped
+  uint32_t num_clusters;
+  uint32_t log_alpha_size;
+  uint32_t use_prefix;
+  uint32_t lz77_enabled;
+  uint32_t lz77_min_symbol;
+  uint32_t lz77_min_length;
+  uint32_t lz77_length_cfg;    // packed config
+  uint32_t lz77_dist_cluster;  // cluster of the distance context
+};
+
+// Packed HybridUintConfig: split_exponent | msb << 8 | lsb << 16.
+JXLB_HD uint32_t PackCfg(uint32_t split_exp, uint32_t msb, uint32_t lsb) {
+  return split_exp | (msb << 8) | (lsb << 16);
+}
+
+// MA-tree node, 16 bytes. Inner node: prop >= 0, a = splitval, b = left child
+// (property > splitval), c = right child. Leaf: prop = -1,
+// a = cluster | predictor << 16, b = offset (int32), c = multiplier.
+struct JXLB_ALIGN(16) DevTreeNode {
+  int32_t prop;
+  int32_t a;
+  uint32_t b;
+  uint32_t c;
+};
+
+struct DevPlane {
+  uint64_t off;  // int32 index into the sample arena
+  uint32_t w, h;
+};
+
+// One channel of one Modular stream, in decode order.
+struct DevChannel {
+  uint32_t plane;     // DevPlane index receiving the samples
+  uint32_t prop0;     // value of property 0 (channel index inside the stream's image)
+  uint32_t ref_off;   // index into the ref pool: plane ids of reference channels
+  uint32_t ref_count;
+};
+
+// One Modular entropy-coded stream = one thread of the decode kernel.
+struct DevStream {
+  uint64_t bit_pos;      // absolute bit offset of the first symbol's ANS state in the byte pool
+  uint64_t bit_end;      // absolute bit offset of the end of the section
+  uint32_t code;         // DevCode index
+  uint32_t tree_off;     // DevTreeNode index of the root
+  uint32_t stream_id;    // property 1
+  uint32_t chan_begin, chan_end;  // DevChannel range
+  uint32_t dist_multiplier;       // LZ77 special distances
+  uint32_t wp_params[3];          // p1C | p2C<<8 | p3Ca<<16 | p3Cb<<24 ; p3Cc | p3Cd<<8 | p3Ce<<16 ; w0|w1<<8|w2<<16|w3<<24
+  uint32_t uses_wp;               // tree needs the weighted predictor
+  uint32_t num_props;             // number of properties the tree reads (>= 16)
+  uint32_t max_w;                 // widest channel (sizes the WP scratch)
+  uint32_t scratch_slot;          // WP scratch slot
+  uint32_t lz77_slot;             // LZ77 window slot or 0xFFFFFFFF
+};
+
+enum DevOpKind : uint32_t {
+  kOpRCT = 0,        // a,b,c = planes; p0 = rct_type
+  kOpPalette = 1,    // a = index plane (= first output), b = palette plane, c = first extra output plane (nb-1 consecutive);
+                     // p0 = nb, p1 = bit_depth, p2 = nb_deltas, p3 = predictor
+  kOpCopy = 2,       // a = src plane, b = dst plane; p0 = dst x, p1 = dst y
+  kOpHSqueeze = 3,   // a = avg plane, b = residual plane, c = out plane
+  kOpVSqueeze = 4,
+};
+
+struct DevOp {
+  uint32_t kind;
+  uint32_t a, b, c;
+  uint32_t p0, p1, p2, p3;
+  uint32_t wp_params[3];
+  uint32_t pad;
+};
+
+// One group's (or one frame's global) inverse-transform program.
+struct DevProgram {
+  uint32_t op_begin, op_end;
+};
+
+// Output conversion of one frame (lib/jxl/dec_modular.cc:534-708 int->float, then
+// lib/jxl/render_pipeline/stage_write.cc:98-113 float->sample).
+struct DevFrameOut {
+  uint32_t xsize, ysize;
+  uint32_t num_channels;   // of the caller's pixel format (1..4)
+  uint32_t data_type;      // JxlDataType: 0 float, 2 u8, 3 u16, 5 f16
+  uint32_t big_endian;
+  uint32_t plane[4];       // source planes per output channel; 0xFFFFFFFF = constant 1.0 (opaque alpha)
+  float factor[4];         // int -> float multiplier per output channel
+  uint32_t is_float[4];    // source samples are custom floats: bits | exp_bits << 8 (0 = integer)
+  uint64_t out_off;        // byte offset of this frame in the output buffer
+  uint64_t stride;         // bytes per output row
+};
+
+constexpr uint32_t kNoPlane = 0xFFFFFFFFu;
+
+}  // namespace jxlb
+
+#endif  // JXLB_DEV_H_

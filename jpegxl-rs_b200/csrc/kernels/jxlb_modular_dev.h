@@ -1,0 +1,470 @@
+// jxl_b200 device code: one Modular entropy-coded stream decoded by one thread.
+//
+// The per-sample loop of libjxl's DecodeModularChannelMAANS
+// (lib/jxl/modular/encoding/encoding.cc:143-483, generic WP path) re-expressed for
+// SIMT: every lane owns one (frame, group, pass) stream, walks the flat MA tree,
+// pulls one rANS / prefix symbol (lib/jxl/dec_ans.h:168-195, :223-255, :286-343)
+// and applies the predictor (lib/jxl/modular/encoding/context_predict.h:355-488,
+// weighted predictor :134-214). A 256x256 group is a strictly serial chain, so the
+// parallelism is #groups x #frames of the batch.
+//
+// The functions are __host__ __device__ so that tests/ can run the very same
+// statements on the CPU when no GPU is present (logic check only; the product
+// never executes them on the host).
+#ifndef JXLB_MODULAR_DEV_H_
+#define JXLB_MODULAR_DEV_H_
+
+#include "jxlb_dev.h"
+
+namespace jxlb {
+
+struct DevPools {
+  const uint32_t* words;  // bitstream pool viewed as little-endian 32-bit words
+  const DevAlias* alias;
+  const uint32_t* prefix;
+  const uint32_t* cfg;
+  const DevTreeNode* tree;
+  const DevChannel* chans;
+  const DevStream* streams;
+  const DevPlane* planes;
+  const uint32_t* refs;
+  const DevCode* codes;
+  int32_t* arena;
+  int32_t* wp_scratch;   // per slot: 5 arrays x 2 rows x (wp_width + 2)
+  uint32_t wp_width;
+  uint32_t* lz77;        // per slot: 1 << 20 entries
+  uint32_t* status;      // per stream: 0 ok, else error bits
+  uint32_t num_streams;
+};
+
+enum DevStatus : uint32_t { kStatusOk = 0, kStatusOverread = 1, kStatusBadFinalState = 2, kStatusNotRun = 0x80000000u };
+
+#if defined(__CUDA_ARCH__)
+#define JXLB_LDG(p) __ldg(p)
+#else
+#define JXLB_LDG(p) (*(p))
+#endif
+
+struct DevBits {
+  const uint32_t* words;
+  uint64_t next_word;
+  uint64_t buf;
+  uint32_t n;
+
+  JXLB_HD void Init(const uint32_t* w, uint64_t bit_pos) {
+    words = w;
+    next_word = bit_pos >> 5;
+    uint32_t sh = static_cast<uint32_t>(bit_pos & 31);
+    buf = static_cast<uint64_t>(JXLB_LDG(words + next_word)) >> sh;
+    next_word++;
+    n = 32 - sh;
+  }
+  JXLB_HD void Fill() {
+    if (n < 32) {
+      buf |= static_cast<uint64_t>(JXLB_LDG(words + next_word)) << n;
+      next_word++;
+      n += 32;
+    }
+  }
+  // k <= 32
+  JXLB_HD uint32_t Read(uint32_t k) {
+    Fill();
+    uint32_t v = static_cast<uint32_t>(buf & ((uint64_t{1} << k) - 1));
+    buf >>= k;
+    n -= k;
+    return v;
+  }
+  JXLB_HD uint32_t Peek(uint32_t k) {
+    Fill();
+    return static_cast<uint32_t>(buf & ((uint64_t{1} << k) - 1));
+  }
+  JXLB_HD void Skip(uint32_t k) {
+    buf >>= k;
+    n -= k;
+  }
+  JXLB_HD uint64_t Pos() const { return next_word * 32 - n; }
+};
+
+JXLB_HD uint32_t DevReadHybrid(uint32_t cfg, uint32_t token, DevBits& br) {
+  const uint32_t split_exp = cfg & 0xFF, msb = (cfg >> 8) & 0xFF, lsb = (cfg >> 16) & 0xFF;
+  const uint32_t split_token = 1u << split_exp;
+  if (token < split_token) return token;
+  const uint32_t in_token = msb + lsb;
+  const uint32_t nbits = (split_exp - in_token + ((token - split_token) >> in_token)) & 31;
+  const uint32_t low = token & ((1u << lsb) - 1);
+  token >>= lsb;
+  const uint32_t bits = br.Read(nbits);
+  const uint32_t hi = (1u << msb) | (token & ((1u << msb) - 1));
+  return (((hi << nbits) | bits) << lsb) | low;
+}
+
+constexpr uint32_t kDevLZ77Mask = (1u << 20) - 1;
+
+struct DevSymbolReader {
+  const DevAlias* alias;
+  const uint32_t* cfg;
+  const uint32_t* prefix;  // per-cluster offsets followed by tables
+  uint32_t state;
+  uint32_t log_alpha;
+  uint32_t use_prefix;
+  // LZ77
+  uint32_t lz77_enabled, lz77_min_symbol, lz77_min_length, lz77_length_cfg, lz77_dist_cluster;
+  uint32_t num_special, dist_mult;
+  uint32_t num_to_copy;
+  uint64_t copy_pos, num_decoded;
+  uint32_t* window;
+
+  JXLB_HD void Init(const DevPools& P, const DevCode& c, DevBits& br, uint32_t dist_multiplier, uint32_t* win) {
+    alias = P.alias + c.alias_off;
+    cfg = P.cfg + c.cfg_off;
+    prefix = P.prefix + c.prefix_off;
+    log_alpha = c.log_alpha_size;
+    use_prefix = c.use_prefix;
+    state = use_prefix ? (0x13u << 16) : br.Read(32);
+    lz77_enabled = c.lz77_enabled;
+    lz77_min_symbol = c.lz77_min_symbol;
+    lz77_min_length = c.lz77_min_length;
+    lz77_length_cfg = c.lz77_length_cfg;
+    lz77_dist_cluster = c.lz77_dist_cluster;
+    num_special = dist_multiplier == 0 ? 0 : 120;
+    dist_mult = dist_multiplier;
+    num_to_copy = 0;
+    copy_pos = 0;
+    num_decoded = 0;
+    window = win;
+  }
+
+  JXLB_HD uint32_t ReadSymbol(uint32_t cluster, DevBits& br) {
+    if (use_prefix) {
+      const uint32_t* t = prefix + JXLB_LDG(prefix + cluster);
+      br.Fill();
+      uint32_t w = static_cast<uint32_t>(br.buf);
+      uint32_t e = JXLB_LDG(t + (w & 0xFF));
+      if (e & 0x80000000u) {
+        uint32_t bits = (e >> 16) & 0xFF;
+        e = JXLB_LDG(t + (e & 0xFFFF) + ((w >> 8) & ((1u << bits) - 1)));
+      }
+      br.Skip((e >> 16) & 0xFF);
+      return e & 0xFFFF;
+    }
+    const uint32_t log_entry = 12 - log_alpha;
+    const uint32_t res = state & 0xFFF;
+    const uint32_t i = res >> log_entry;
+    const uint32_t pos = res & ((1u << log_entry) - 1);
+#if defined(__CUDA_ARCH__)
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(alias + (cluster << log_alpha) + i));
+    const uint32_t cutoff = raw.x & 0xFF, right_value = (raw.x >> 8) & 0xFF, freq0 = raw.x >> 16;
+    const uint32_t offsets1 = raw.y & 0xFFFF, fx = raw.y >> 16;
+#else
+    const DevAlias& e = alias[(cluster << log_alpha) + i];
+    const uint32_t cutoff = e.cutoff, right_value = e.right_value, freq0 = e.freq0;
+    const uint32_t offsets1 = e.offsets1, fx = e.freq1_xor_freq0;
+#endif
+    const bool right = pos >= cutoff;
+    const uint32_t sym = right ? right_value : i;
+    const uint32_t offset = (right ? offsets1 : 0u) + pos;
+    const uint32_t freq = right ? (freq0 ^ fx) : freq0;
+    state = freq * (state >> 12) + offset;
+    if (state < (1u << 16)) state = (state << 16) | br.Read(16);
+    return sym;
+  }
+
+  JXLB_HD uint32_t SpecialDistance(uint32_t i) const {
+    // lib/jxl/dec_ans.h:121-143 kSpecialDistances, packed as (first + 8) | second << 5.
+    const uint8_t k[120] = {
+        0x28, 0x09, 0x29, 0x27, 0x48, 0x0A, 0x49, 0x47, 0x2A, 0x26, 0x4A, 0x46, 0x68, 0x0B, 0x69, 0x67, 0x2B, 0x25, 0x6A, 0x66,
+        0x4B, 0x45, 0x88, 0x0C, 0x89, 0x87, 0x2C, 0x24, 0x6B, 0x65, 0x8A, 0x86, 0x4C, 0x44, 0xA8, 0x8B, 0x85, 0x6C, 0x64, 0x0D,
+        0xA9, 0xA7, 0x2D, 0x23, 0xAA, 0xA6, 0x4D, 0x43, 0x8C, 0x84, 0xAB, 0xA5, 0x6D, 0x63, 0xC8, 0x0E, 0xC9, 0xC7, 0x2E, 0x22,
+        0xCA, 0xC6, 0x4E, 0x42, 0xAC, 0xA4, 0x8D, 0x83, 0xCB, 0xC5, 0x6E, 0x62, 0xE8, 0x0F, 0xE9, 0xE7, 0xAD, 0xA3, 0x2F, 0x21,
+        0xCC, 0xC4, 0x8E, 0x82, 0xEA, 0xE6, 0x4F, 0x41, 0xEB, 0xE5, 0x6F, 0x61, 0xCD, 0xC3, 0xAE, 0xA2, 0x10, 0xEC, 0xE4, 0x8F,
+        0x81, 0x30, 0x50, 0xCE, 0xC2, 0x70, 0xED, 0xE3, 0xAF, 0xA1, 0x90, 0xEE, 0xE2, 0xCF, 0xC1, 0xB0, 0xEF, 0xE1, 0xD0, 0xF0};
+    const int first = static_cast<int>(k[i] & 0x1F) - 8;
+    const int second = static_cast<int>(k[i] >> 5);
+    const int d = first + static_cast<int>(dist_mult) * second;
+    return d > 1 ? static_cast<uint32_t>(d) : 1u;
+  }
+
+  JXLB_HD uint32_t CopyOne() {
+    uint32_t v = window[(copy_pos++) & kDevLZ77Mask];
+    num_to_copy--;
+    window[(num_decoded++) & kDevLZ77Mask] = v;
+    return v;
+  }
+
+  JXLB_HD uint32_t ReadUint(uint32_t cluster, DevBits& br) {
+    if (!lz77_enabled) return DevReadHybrid(JXLB_LDG(cfg + cluster), ReadSymbol(cluster, br), br);
+    if (num_to_copy > 0) return CopyOne();
+    uint32_t token = ReadSymbol(cluster, br);
+    if (token >= lz77_min_symbol) {
+      num_to_copy = DevReadHybrid(lz77_length_cfg, token - lz77_min_symbol, br) + lz77_min_length;
+      uint32_t dtok = ReadSymbol(lz77_dist_cluster, br);
+      uint64_t distance = DevReadHybrid(JXLB_LDG(cfg + lz77_dist_cluster), dtok, br);
+      if (distance < num_special) {
+        distance = SpecialDistance(static_cast<uint32_t>(distance));
+      } else {
+        distance = distance + 1 - num_special;
+      }
+      if (distance > num_decoded) distance = num_decoded;
+      if (distance > (1u << 20)) distance = 1u << 20;
+      copy_pos = num_decoded - distance;
+      if (distance == 0) {
+        uint32_t fill = num_to_copy < (1u << 20) ? num_to_copy : (1u << 20);
+        for (uint32_t k = 0; k < fill; k++) window[k] = 0;
+      }
+      if (num_to_copy < lz77_min_length) return 0;
+      return CopyOne();
+    }
+    uint32_t v = DevReadHybrid(JXLB_LDG(cfg + cluster), token, br);
+    window[(num_decoded++) & kDevLZ77Mask] = v;
+    return v;
+  }
+};
+
+JXLB_HD DevTreeNode DevLoadNode(const DevTreeNode* p) {
+#if defined(__CUDA_ARCH__)
+  const int4 raw = __ldg(reinterpret_cast<const int4*>(p));
+  DevTreeNode n;
+  n.prop = raw.x;
+  n.a = raw.y;
+  n.b = static_cast<uint32_t>(raw.z);
+  n.c = static_cast<uint32_t>(raw.w);
+  return n;
+#else
+  return *p;
+#endif
+}
+
+JXLB_HD int32_t DevUnpackSigned(uint32_t u) { return static_cast<int32_t>((u >> 1) ^ (~(u & 1) + 1)); }
+
+JXLB_HD int32_t DevClampedGradient(int32_t n, int32_t w, int32_t l) {
+  const int32_t m = n < w ? n : w, M = n < w ? w : n;
+  const int32_t grad = static_cast<int32_t>(static_cast<uint32_t>(n) + static_cast<uint32_t>(w) - static_cast<uint32_t>(l));
+  const int32_t g = l < m ? M : grad;
+  return l > M ? m : g;
+}
+
+JXLB_HD int64_t DevAbs64(int64_t v) { return v < 0 ? -v : v; }
+
+struct DevNeighbors {
+  int64_t left, top, topleft, topright, leftleft, toptop, toprightright;
+};
+
+JXLB_HD DevNeighbors DevLoadNeighbors(const int32_t* row, const int32_t* prev, const int32_t* prevprev, int x, int y, int w) {
+  DevNeighbors n;
+  n.left = x ? row[x - 1] : (y ? prev[x] : 0);
+  n.top = y ? prev[x] : n.left;
+  n.topleft = (x && y) ? prev[x - 1] : n.left;
+  n.topright = (x + 1 < w && y) ? prev[x + 1] : n.top;
+  n.leftleft = x > 1 ? row[x - 2] : n.left;
+  n.toptop = y > 1 ? prevprev[x] : n.top;
+  n.toprightright = (x + 2 < w && y) ? prev[x + 2] : n.topright;
+  return n;
+}
+
+JXLB_HD int64_t DevPredictOne(uint32_t p, const DevNeighbors& n, int64_t wp_pred) {
+  switch (p) {
+    case 0: return 0;
+    case 1: return n.left;
+    case 2: return n.top;
+    case 3: return (n.left + n.top) / 2;
+    case 4: {
+      const int64_t pp = n.left + n.top - n.topleft;
+      return DevAbs64(pp - n.left) < DevAbs64(pp - n.top) ? n.left : n.top;
+    }
+    case 5: return DevClampedGradient(static_cast<int32_t>(n.left), static_cast<int32_t>(n.top), static_cast<int32_t>(n.topleft));
+    case 6: return wp_pred;
+    case 7: return n.topright;
+    case 8: return n.topleft;
+    case 9: return n.leftleft;
+    case 10: return (n.left + n.topleft) / 2;
+    case 11: return (n.topleft + n.top) / 2;
+    case 12: return (n.top + n.topright) / 2;
+    case 13: return (6 * n.top - 2 * n.toptop + 7 * n.left + n.leftleft + n.toprightright + 3 * n.topright + 8) / 16;
+    default: return 0;
+  }
+}
+
+JXLB_HD uint32_t DevFloorLog2(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return 63 - __clzll(static_cast<long long>(v));
+#else
+  return 63 - __builtin_clzll(v);
+#endif
+}
+
+// Weighted predictor state: prediction errors of the current and previous row,
+// kept in a per-stream scratch (5 arrays x 2 rows x (width + 2)).
+struct DevWP {
+  int32_t p1C, p2C, p3Ca, p3Cb, p3Cc, p3Cd, p3Ce;
+  uint32_t w[4];
+  int64_t prediction[4];
+  int64_t pred;
+  uint32_t* pred_errors[4];
+  int32_t* error;
+
+  JXLB_HD void Init(const uint32_t params[3], int32_t* scratch, uint32_t stride) {
+    p1C = params[0] & 0xFF; p2C = (params[0] >> 8) & 0xFF; p3Ca = (params[0] >> 16) & 0xFF; p3Cb = params[0] >> 24;
+    p3Cc = params[1] & 0xFF; p3Cd = (params[1] >> 8) & 0xFF; p3Ce = (params[1] >> 16) & 0xFF;
+    for (int i = 0; i < 4; i++) w[i] = (params[2] >> (8 * i)) & 0xFF;
+    for (int i = 0; i < 4; i++) pred_errors[i] = reinterpret_cast<uint32_t*>(scratch) + static_cast<size_t>(i) * 2 * stride;
+    error = scratch + static_cast<size_t>(4) * 2 * stride;
+    pred = 0;
+    for (int i = 0; i < 4; i++) prediction[i] = 0;
+  }
+  JXLB_HD void Reset(uint32_t xsize) {
+    const uint32_t n = (xsize + 2) * 2;
+    for (int i = 0; i < 4; i++)
+      for (uint32_t k = 0; k < n; k++) pred_errors[i][k] = 0;
+    for (uint32_t k = 0; k < n; k++) error[k] = 0;
+  }
+  static JXLB_HD uint32_t DivLookup(uint32_t i) { return (1u << 24) / (i + 1); }
+  static JXLB_HD uint32_t ErrorWeight(uint64_t x, uint32_t maxweight) {
+    int shift = static_cast<int>(DevFloorLog2(x + 1)) - 5;
+    if (shift < 0) shift = 0;
+    return 4 + static_cast<uint32_t>((static_cast<uint64_t>(maxweight) * DivLookup(static_cast<uint32_t>(x >> shift))) >> shift);
+  }
+  JXLB_HD int64_t Predict(uint32_t x, uint32_t y, uint32_t xsize, int64_t N, int64_t W, int64_t NE, int64_t NW, int64_t NN,
+                          int32_t* max_error) {
+    const uint32_t cur_row = (y & 1) ? 0 : (xsize + 2);
+    const uint32_t prev_row = (y & 1) ? (xsize + 2) : 0;
+    const uint32_t pos_N = prev_row + x;
+    const uint32_t pos_NE = x < xsize - 1 ? pos_N + 1 : pos_N;
+    const uint32_t pos_NW = x > 0 ? pos_N - 1 : pos_N;
+    uint32_t weights[4];
+    for (int i = 0; i < 4; i++) {
+      const uint32_t e = pred_errors[i][pos_N] + pred_errors[i][pos_NE] + pred_errors[i][pos_NW];
+      weights[i] = ErrorWeight(e, w[i]);
+    }
+    N *= 8; W *= 8; NE *= 8; NW *= 8; NN *= 8;
+    const int64_t teW = x == 0 ? 0 : error[cur_row + x - 1];
+    const int64_t teN = error[pos_N], teNW = error[pos_NW], teNE = error[pos_NE];
+    const int64_t sumWN = teN + teW;
+    if (max_error) {
+      int64_t p = teW;
+      if (DevAbs64(teN) > DevAbs64(p)) p = teN;
+      if (DevAbs64(teNW) > DevAbs64(p)) p = teNW;
+      if (DevAbs64(teNE) > DevAbs64(p)) p = teNE;
+      *max_error = static_cast<int32_t>(p);
+    }
+    prediction[0] = W + NE - N;
+    prediction[1] = N - (((sumWN + teNE) * p1C) >> 5);
+    prediction[2] = W - (((sumWN + teNW) * p2C) >> 5);
+    prediction[3] = N - ((teNW * p3Ca + teN * p3Cb + teNE * p3Cc + (NN - N) * p3Cd + (NW - W) * p3Ce) >> 5);
+    uint32_t wsum = weights[0] + weights[1] + weights[2] + weights[3];
+    const uint32_t log_weight = DevFloorLog2(wsum);
+    wsum = 0;
+    for (int i = 0; i < 4; i++) {
+      weights[i] >>= log_weight - 4;
+      wsum += weights[i];
+    }
+    int64_t sum = (wsum >> 1) - 1;
+    for (int i = 0; i < 4; i++) sum += prediction[i] * weights[i];
+    pred = (sum * DivLookup(wsum - 1)) >> 24;
+    if (((teN ^ teW) | (teN ^ teNW)) > 0) return (pred + 3) >> 3;
+    int64_t mx = W > NE ? W : NE;
+    if (N > mx) mx = N;
+    int64_t mn = W < NE ? W : NE;
+    if (N < mn) mn = N;
+    if (pred > mx) pred = mx;
+    if (pred < mn) pred = mn;
+    return (pred + 3) >> 3;
+  }
+  JXLB_HD void Update(int64_t val, uint32_t x, uint32_t y, uint32_t xsize) {
+    const uint32_t cur_row = (y & 1) ? 0 : (xsize + 2);
+    const uint32_t prev_row = (y & 1) ? (xsize + 2) : 0;
+    val *= 8;
+    error[cur_row + x] = static_cast<int32_t>(pred - val);
+    for (int i = 0; i < 4; i++) {
+      const uint32_t err = static_cast<uint32_t>((DevAbs64(prediction[i] - val) + 3) >> 3);
+      pred_errors[i][cur_row + x] = err;
+      pred_errors[i][prev_row + x + 1] += err;
+    }
+  }
+};
+
+constexpr int kDevMaxProps = 16 + 4 * 8;  // static 2 + 13 + WP + up to 8 reference channels
+
+// Decodes every channel of stream `s`. Returns the status word.
+JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s) {
+  const DevStream st = P.streams[s];
+  const DevCode code = P.codes[st.code];
+  DevBits br;
+  br.Init(P.words, st.bit_pos);
+  DevSymbolReader reader;
+  uint32_t* window = (st.lz77_slot != 0xFFFFFFFFu) ? P.lz77 + (static_cast<size_t>(st.lz77_slot) << 20) : nullptr;
+  reader.Init(P, code, br, st.dist_multiplier, window);
+  const DevTreeNode* tree = P.tree + st.tree_off;
+  const uint32_t wp_stride = P.wp_width + 2;
+  DevWP wp;
+  if (st.uses_wp) wp.Init(st.wp_params, P.wp_scratch + static_cast<size_t>(st.scratch_slot) * 10 * wp_stride, wp_stride);
+  int32_t props[kDevMaxProps];
+  for (int i = 0; i < kDevMaxProps; i++) props[i] = 0;
+  props[1] = static_cast<int32_t>(st.stream_id);
+  for (uint32_t ci = st.chan_begin; ci < st.chan_end; ci++) {
+    const DevChannel ch = P.chans[ci];
+    const DevPlane pl = P.planes[ch.plane];
+    const int w = static_cast<int>(pl.w), h = static_cast<int>(pl.h);
+    if (w == 0 || h == 0) continue;
+    int32_t* base = P.arena + pl.off;
+    props[0] = static_cast<int32_t>(ch.prop0);
+    if (st.uses_wp) wp.Reset(w);
+    for (int y = 0; y < h; y++) {
+      int32_t* row = base + static_cast<size_t>(y) * w;
+      const int32_t* prev = y ? row - w : nullptr;
+      const int32_t* prevprev = y > 1 ? row - 2 * w : nullptr;
+      props[2] = y;
+      props[9] = 0;
+      for (int x = 0; x < w; x++) {
+        const DevNeighbors n = DevLoadNeighbors(row, prev, prevprev, x, y, w);
+        props[3] = x;
+        props[4] = static_cast<int32_t>(n.top > 0 ? n.top : -n.top);
+        props[5] = static_cast<int32_t>(n.left > 0 ? n.left : -n.left);
+        props[6] = static_cast<int32_t>(n.top);
+        props[7] = static_cast<int32_t>(n.left);
+        props[8] = static_cast<int32_t>(n.left - props[9]);
+        props[9] = static_cast<int32_t>(n.left + n.top - n.topleft);
+        props[10] = static_cast<int32_t>(n.left - n.topleft);
+        props[11] = static_cast<int32_t>(n.topleft - n.top);
+        props[12] = static_cast<int32_t>(n.top - n.topright);
+        props[13] = static_cast<int32_t>(n.top - n.toptop);
+        props[14] = static_cast<int32_t>(n.left - n.leftleft);
+        int64_t wp_pred = 0;
+        if (st.uses_wp) wp_pred = wp.Predict(x, y, w, n.top, n.left, n.topright, n.topleft, n.toptop, &props[15]);
+        for (uint32_t r = 0; r < ch.ref_count; r++) {
+          const DevPlane rp = P.planes[P.refs[ch.ref_off + r]];
+          const int32_t* rrow = P.arena + rp.off + static_cast<size_t>(y) * w;
+          const int32_t* rprev = y ? rrow - w : rrow;
+          const int64_t v = rrow[x];
+          const int64_t vleft = x ? rrow[x - 1] : 0;
+          const int64_t vtop = y ? rprev[x] : vleft;
+          const int64_t vtopleft = (x && y) ? rprev[x - 1] : vleft;
+          const int64_t vpred = DevClampedGradient(static_cast<int32_t>(vleft), static_cast<int32_t>(vtop), static_cast<int32_t>(vtopleft));
+          props[16 + 4 * r + 0] = static_cast<int32_t>(DevAbs64(v));
+          props[16 + 4 * r + 1] = static_cast<int32_t>(v);
+          props[16 + 4 * r + 2] = static_cast<int32_t>(DevAbs64(v - vpred));
+          props[16 + 4 * r + 3] = static_cast<int32_t>(v - vpred);
+        }
+        DevTreeNode node = DevLoadNode(tree);
+        while (node.prop >= 0) {
+          const uint32_t pos = props[node.prop] > node.a ? node.b : node.c;
+          node = DevLoadNode(tree + pos);
+        }
+        const uint32_t cluster = static_cast<uint32_t>(node.a) & 0xFFFF;
+        const uint32_t predictor = static_cast<uint32_t>(node.a) >> 16;
+        const uint32_t u = reader.ReadUint(cluster, br);
+        const int64_t guess = static_cast<int64_t>(static_cast<int32_t>(node.b)) + DevPredictOne(predictor, n, wp_pred);
+        const int64_t val = static_cast<int64_t>(DevUnpackSigned(u)) * static_cast<int64_t>(node.c) + guess;
+        row[x] = static_cast<int32_t>(val);
+        if (st.uses_wp) wp.Update(row[x], x, y, w);
+      }
+    }
+  }
+  uint32_t status = kStatusOk;
+  if (!code.use_prefix && reader.state != (0x13u << 16)) status |= kStatusBadFinalState;
+  if (br.Pos() > st.bit_end) status |= kStatusOverread;
+  return status;
+}
+
+}  // namespace jxlb
+
+#endif  // JXLB_MODULAR_DEV_H_

@@ -1,0 +1,46 @@
+"""ctypes wrapper of tests/emul/libjxlb_emul.so: the kernels' __host__ __device__ bodies run on the CPU.
+Test infrastructure only (logic check without a GPU)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+_NP = {0: np.float32, 2: np.uint8, 3: np.uint16, 5: np.float16}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        d = os.path.join(HERE, "emul")
+        subprocess.check_call(["make", "-s"], cwd=d)
+        _lib = ctypes.CDLL(os.path.join(d, "libjxlb_emul.so"))
+    return _lib
+
+
+class EmulError(Exception):
+    pass
+
+
+def decode(files, num_channels, data_type, shapes, endianness=0, align=0):
+    """shapes: list of (h, w). Returns one array per file."""
+    n = len(files)
+    arr = (ctypes.c_char_p * n)(*files)
+    sizes = (ctypes.c_size_t * n)(*[len(f) for f in files])
+    bps = np.dtype(_NP[data_type]).itemsize
+    cap = sum(((h * w * num_channels * bps + 255) // 256 + 1) * 256 for h, w in shapes) + 4096
+    out = np.zeros(cap, np.uint8)
+    offs = (ctypes.c_uint64 * n)()
+    err = ctypes.create_string_buffer(512)
+    rc = lib().jxlb_emul_decode(arr, sizes, ctypes.c_size_t(n), num_channels, data_type, endianness,
+                                ctypes.c_size_t(align), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(cap),
+                                offs, err, ctypes.c_size_t(512))
+    if rc != 0:
+        raise EmulError(err.value.decode())
+    res = []
+    for i, (h, w) in enumerate(shapes):
+        nb = h * w * num_channels * bps
+        res.append(out[offs[i]:offs[i] + nb].view(_NP[data_type]).reshape(h, w, num_channels))
+    return res

@@ -1,0 +1,76 @@
+"""ctypes wrapper of the oracle (oracle/libjxlo.so). Checker only: tests, smoke(), bench cpu_baseline."""
+import ctypes
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FLOAT, UINT8, UINT16, FLOAT16 = 0, 2, 3, 5
+_NP = {FLOAT: np.float32, UINT8: np.uint8, UINT16: np.uint16, FLOAT16: np.float16}
+
+
+class Info(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in
+                "xsize ysize bits exp num_color num_extra alpha_bits xyb orientation num_frames".split()]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ROOT, "oracle", "libjxlo.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-s"], cwd=os.path.join(ROOT, "oracle"))
+        L = ctypes.CDLL(path)
+        L.jxlo_decode.restype = ctypes.c_void_p
+        L.jxlo_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+        L.jxlo_output_size.restype = ctypes.c_size_t
+        L.jxlo_output_size.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t]
+        L.jxlo_write_pixels.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                        ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        L.jxlo_frame_info.restype = ctypes.c_char_p
+        L.jxlo_frame_info.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+        L.jxlo_get_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(Info)]
+        L.jxlo_free.argtypes = [ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+class OracleError(Exception):
+    pass
+
+
+class Decoded:
+    def __init__(self, data: bytes):
+        L = lib()
+        err = ctypes.create_string_buffer(512)
+        self.h = L.jxlo_decode(data, len(data), err, 512)
+        if not self.h:
+            raise OracleError(err.value.decode())
+        self.info = Info()
+        L.jxlo_get_info(self.h, ctypes.byref(self.info))
+
+    def frame_info(self):
+        return [lib().jxlo_frame_info(self.h, i).decode() for i in range(self.info.num_frames)]
+
+    def pixels(self, num_channels, data_type, endianness=0, align=0, raw=False):
+        L = lib()
+        n = L.jxlo_output_size(self.h, num_channels, data_type, align)
+        buf = np.zeros(n, np.uint8)
+        rc = L.jxlo_write_pixels(self.h, num_channels, data_type, endianness, align, buf.ctypes.data, n)
+        assert rc == 0
+        if raw or align > 1:
+            return buf
+        return buf.view(_NP[data_type]).reshape(self.info.ysize, self.info.xsize, num_channels)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().jxlo_free(self.h)
+            self.h = None
+
+
+def decode(data: bytes, num_channels: int, data_type: int, endianness: int = 0) -> np.ndarray:
+    return Decoded(data).pixels(num_channels, data_type, endianness)

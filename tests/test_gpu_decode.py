@@ -1,0 +1,101 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the oracle and the reference's goldens."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import jxlo
+from conftest import GOLDEN, read_golden
+
+pytestmark = pytest.mark.gpu
+G = json.load(open(os.path.join(GOLDEN, "golden.json")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_simple_sample_uint16(pkg):
+    # jpegxl-rs/src/tests/decode.rs:44-67 + image.rs:158-174
+    dec = pkg.decoder_builder().build()
+    meta, px = dec.decode(read_golden("sample.jxl"))
+    assert px.variant == "Uint16"
+    assert len(px) == meta.width * meta.height * 4
+    assert (meta.width, meta.height, meta.num_color_channels, meta.has_alpha_channel) == (40, 50, 3, True)
+    assert sha(px.data) == G["sample.jxl"]["sha256"]
+
+
+def test_bench_jxl_rgba8_golden(pkg):
+    # the reference's criterion bench input (jpegxl-rs/benches/decode.rs:10-40): decode_with::<u8>
+    dec = pkg.decoder_builder().build()
+    meta, px = dec.decode_with(read_golden("bench.jxl"), np.uint8)
+    assert px.size == 2122 * 1433 * 4
+    assert sha(px) == G["bench.jxl"]["sha256"]
+
+
+@pytest.mark.parametrize("nch", [1, 2, 3, 4])
+@pytest.mark.parametrize("dt,npdt", [(jxlo.UINT8, np.uint8), (jxlo.UINT16, np.uint16), (jxlo.FLOAT16, np.float16),
+                                     (jxlo.FLOAT, np.float32)])
+def test_pixel_types_match_oracle(pkg, nch, dt, npdt):
+    # jpegxl-rs/src/tests/decode.rs:95-120
+    data = read_golden("sample.jxl")
+    dec = pkg.decoder_builder().pixel_format(pkg.PixelFormat(num_channels=nch)).build()
+    meta, px = dec.decode_with(data, npdt)
+    want = jxlo.decode(data, nch, dt)
+    assert px.size == 40 * 50 * nch
+    assert np.array_equal(px.view(np.uint8), want.reshape(-1).view(np.uint8))
+
+
+def test_big_endian_and_alignment(pkg):
+    data = read_golden("sample.jxl")
+    dec = pkg.decoder_builder().pixel_format(pkg.PixelFormat(num_channels=3, endianness=pkg.JXL_BIG_ENDIAN)).build()
+    _, be = dec.decode_with(data, np.uint16)
+    want = jxlo.decode(data, 3, jxlo.UINT16)
+    assert np.array_equal(be.reshape(want.shape), want)  # wrapper converts to native values like jpegxl-rs
+    bd = pkg.BatchDecoder(0)
+    bd.set_input([data], 3, pkg.JXL_TYPE_UINT8, align=64)
+    bd.run()
+    bd.wait()
+    raw = bd.read_output(0)
+    ref = jxlo.Decoded(data).pixels(3, jxlo.UINT8, align=64)
+    stride = 128
+    assert raw.size == stride * 50
+    assert np.array_equal(raw.reshape(50, stride)[:, :120], ref.reshape(50, stride)[:, :120])
+
+
+def test_batch_of_mixed_frames_matches_oracle(pkg):
+    a, b = read_golden("bench.jxl"), read_golden("sample.jxl")
+    files = [a, b, a, b, a]
+    outs = pkg.decode_batch(files, 4, np.uint8)
+    wa, wb = jxlo.decode(a, 4, jxlo.UINT8), jxlo.decode(b, 4, jxlo.UINT8)
+    for f, o in zip(files, outs):
+        assert np.array_equal(o, wa if f is a else wb)
+
+
+def test_full_size_batch_property(pkg):
+    # size-independent property at bench size: every replica of the same codestream decodes to the same
+    # checksum, equal to the golden one
+    a = read_golden("bench.jxl")
+    outs = pkg.decode_batch([a] * 16, 4, np.uint8)
+    assert {sha(o) for o in outs} == {G["bench.jxl"]["sha256"]}
+
+
+def test_errors(pkg):
+    dec = pkg.decoder_builder().build()
+    with pytest.raises(pkg.InvalidInput):
+        dec.decode(b"")
+    with pytest.raises(pkg.InvalidInput):
+        dec.decode(b"\0" * 64)
+    with pytest.raises(pkg.DecodeError):
+        dec.decode(read_golden("sample.jxl")[:300])
+    # corrupted payload: flipped bytes inside a group section must be reported, not silently decoded
+    bad = bytearray(read_golden("bench.jxl"))
+    for i in range(600000, 600064):
+        bad[i] ^= 0x5A
+    bd = pkg.BatchDecoder(0)
+    bd.set_input([bytes(bad)], 4, pkg.JXL_TYPE_UINT8)
+    bd.run()
+    with pytest.raises(pkg.GenericError):
+        bd.wait()

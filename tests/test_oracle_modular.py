@@ -1,0 +1,75 @@
+"""CPU: the oracle against the reference's golden vectors."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import jxlo
+from conftest import GOLDEN, read_golden
+
+G = json.load(open(os.path.join(GOLDEN, "golden.json")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_fixture_files_are_the_reference_samples():
+    for name, g in G.items():
+        assert hashlib.sha256(read_golden(name)).hexdigest() == g["file_sha256"]
+
+
+def test_g1_sample_jxl_equals_sample_png_rgba16():
+    # jpegxl-rs/src/image.rs:158-174: decode(sample.jxl).to_rgba16() == sample.png.to_rgba16()
+    import cv2
+    png = cv2.cvtColor(cv2.imread(os.path.join(GOLDEN, "sample.png"), cv2.IMREAD_UNCHANGED), cv2.COLOR_BGRA2RGBA)
+    got = jxlo.decode(read_golden("sample.jxl"), 4, jxlo.UINT16)
+    assert got.dtype == np.uint16 and got.shape == (50, 40, 4)
+    assert np.array_equal(got, png)
+    assert sha(got) == G["sample.jxl"]["sha256"]
+
+
+def test_g2_bench_jxl_equals_bench_png_rgba8():
+    got = jxlo.decode(read_golden("bench.jxl"), 4, jxlo.UINT8)
+    assert got.shape == (1433, 2122, 4)
+    assert sha(got[0]) == G["bench.jxl"]["row_sha256_first"]
+    assert sha(got[-1]) == G["bench.jxl"]["row_sha256_last"]
+    assert sha(got) == G["bench.jxl"]["sha256"]
+
+
+def test_decode_tests_of_the_reference_shapes():
+    # jpegxl-rs/src/tests/decode.rs:44-67: sample.jxl -> Uint16, len = w*h*4
+    d = jxlo.Decoded(read_golden("sample.jxl"))
+    assert (d.info.xsize, d.info.ysize, d.info.bits, d.info.num_color, d.info.alpha_bits) == (40, 50, 16, 3, 16)
+    assert d.pixels(4, jxlo.UINT16).size == 40 * 50 * 4
+
+
+@pytest.mark.parametrize("nch", [1, 2, 3, 4])
+@pytest.mark.parametrize("dt", [jxlo.UINT8, jxlo.UINT16, jxlo.FLOAT16, jxlo.FLOAT])
+def test_pixel_types_lengths(nch, dt):
+    # jpegxl-rs/src/tests/decode.rs:95-120 (every data type / channel count decodes, lengths)
+    px = jxlo.decode(read_golden("sample.jxl"), nch, dt)
+    assert px.shape == (50, 40, nch)
+
+
+def test_u16_to_u8_is_scaled_and_dithered_not_truncated():
+    d = jxlo.Decoded(read_golden("sample.jxl"))
+    p16 = d.pixels(4, jxlo.UINT16).astype(np.float64)
+    p8 = d.pixels(4, jxlo.UINT8).astype(np.float64)
+    assert np.abs(p16 / 65535 * 255 - p8).max() < 1.0  # dither < 0.5 + rounding 0.5
+
+
+def test_big_endian_u16():
+    d = jxlo.Decoded(read_golden("sample.jxl"))
+    le = d.pixels(4, jxlo.UINT16, endianness=1)
+    be = d.pixels(4, jxlo.UINT16, endianness=2)
+    assert np.array_equal(le, be.byteswap())
+
+
+def test_errors():
+    # jpegxl-rs/src/errors.rs:109-161: empty / zeros invalid, truncated fails
+    for bad in [b"", b"\0" * 64, read_golden("sample.jxl")[:200]]:
+        with pytest.raises(jxlo.OracleError):
+            jxlo.Decoded(bad)
