@@ -44,7 +44,7 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
   b->prefix.insert(b->prefix.end(), f.prefix.begin(), f.prefix.end());
   b->cfg.insert(b->cfg.end(), f.cfg.begin(), f.cfg.end());
   for (uint32_t r : f.refs) b->refs.push_back(r + planes0);
-  // tree children are relative to the tree root, no relocation needed
+  // tree children are relative to each pruned tree's root, no relocation needed
   b->tree.insert(b->tree.end(), f.tree.begin(), f.tree.end());
   for (DevCode c : f.codes) {
     c.alias_off += alias0;
@@ -55,16 +55,15 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
   for (DevChannel c : f.chans) {
     c.plane += planes0;
     c.ref_off += refs0;
+    c.tree_off += tree0;
     b->chans.push_back(c);
   }
   for (DevStream s : f.streams) {
     s.bit_pos += byte_base * 8;
     s.bit_end += byte_base * 8;
     s.code += codes0;
-    s.tree_off += tree0;
     s.chan_begin += chans0;
     s.chan_end += chans0;
-    if (s.uses_wp) s.scratch_slot += b->wp_slots;
     if (s.lz77_slot != 0xFFFFFFFFu) s.lz77_slot += b->lz77_slots;
     b->streams.push_back(s);
   }

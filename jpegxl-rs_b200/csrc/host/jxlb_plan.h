@@ -11,6 +11,7 @@
 #ifndef JXLB_PLAN_H_
 #define JXLB_PLAN_H_
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -141,7 +142,7 @@ struct HImage {
 };
 
 struct HostTree {
-  uint32_t tree_off = 0;
+  std::shared_ptr<std::vector<DevTreeNode>> nodes;  // full tree, leaves already mapped to clusters
   uint32_t code = 0;
   bool uses_wp = false;
   uint32_t num_props = 16;
@@ -249,7 +250,7 @@ class FramePlanner {
     EntropyCode code;
     ReadEntropyCode(br, (nodes.size() + 1) / 2, &code);
     ht.code = AddCode(code);
-    ht.tree_off = p_->tree.size();
+    ht.nodes = std::make_shared<std::vector<DevTreeNode>>();
     ht.num_props = std::max(max_prop, 16);
     if (ht.num_props > 16) ht.num_props = 16 + ((ht.num_props - 16 + 3) / 4) * 4;
     JXLB_CHECK(ht.num_props <= static_cast<uint32_t>(kHostMaxProps), "MA tree references too many earlier channels");
@@ -266,11 +267,43 @@ class FramePlanner {
         d.b = n.l;
         d.c = n.r;
       }
-      p_->tree.push_back(d);
+      ht.nodes->push_back(d);
     }
     ht.valid = true;
     ht.lz77 = code.lz77_enabled;
     return ht;
+  }
+
+  // Resolves the static properties (0 = channel, 1 = stream id) the way FilterTree does
+  // (lib/jxl/modular/encoding/encoding.cc:36-138) and appends the remaining tree in
+  // breadth-first order (children adjacent) to the tree pool. Returns its offset.
+  uint32_t PruneTree(const std::vector<DevTreeNode>& t, int32_t chan, int32_t stream_id, bool* uses_wp) {
+    const uint32_t off = p_->tree.size();
+    auto resolve = [&](uint32_t i) {
+      while (t[i].prop >= 0 && t[i].prop < 2) {
+        const int32_t v = t[i].prop == 0 ? chan : stream_id;
+        i = v > t[i].a ? t[i].b : t[i].c;
+      }
+      return i;
+    };
+    *uses_wp = false;
+    std::vector<uint32_t> queue;  // source node of output node k
+    queue.push_back(resolve(0));
+    for (size_t k = 0; k < queue.size(); k++) {
+      DevTreeNode n = t[queue[k]];
+      if (n.prop < 0) {
+        if ((static_cast<uint32_t>(n.a) >> 16) == 6) *uses_wp = true;
+      } else {
+        if (n.prop == 15) *uses_wp = true;
+        const uint32_t l = resolve(n.b), r = resolve(n.c);
+        n.b = queue.size();
+        n.c = queue.size() + 1;
+        queue.push_back(l);
+        queue.push_back(r);
+      }
+      p_->tree.push_back(n);
+    }
+    return off;
   }
 
   // lib/jxl/modular/encoding/dec_ma.cc:23-67: property ranges must stay non-empty
@@ -564,12 +597,12 @@ class FramePlanner {
     st.bit_pos = file_bit_base + br.BitPos();
     st.bit_end = file_bit_base + br.Size() * 8;
     st.code = tree.code;
-    st.tree_off = tree.tree_off;
+    st.tree_off = 0;
     st.stream_id = stream_id;
     st.chan_begin = p_->chans.size();
     st.dist_multiplier = distance_multiplier;
     header.wp.Pack(st.wp_params);
-    st.uses_wp = tree.uses_wp;
+    st.uses_wp = 0;
     st.num_props = tree.num_props;
     st.lz77_slot = 0xFFFFFFFFu;
     uint32_t max_w = 0;
@@ -588,15 +621,16 @@ class FramePlanner {
         p_->refs.push_back(r.plane);
         dc.ref_count++;
       }
+      bool ch_wp = false;
+      dc.tree_off = PruneTree(*tree.nodes, static_cast<int32_t>(i), static_cast<int32_t>(stream_id), &ch_wp);
+      dc.uses_wp = ch_wp;
+      if (ch_wp) st.uses_wp = 1;
       p_->chans.push_back(dc);
       max_w = std::max<uint32_t>(max_w, c.w);
     }
     st.chan_end = p_->chans.size();
     st.max_w = max_w;
-    if (st.uses_wp) {
-      st.scratch_slot = p_->wp_slots++;
-      p_->wp_width = std::max(p_->wp_width, max_w);
-    }
+    p_->wp_width = std::max(p_->wp_width, max_w);
     if (tree.lz77) st.lz77_slot = p_->lz77_slots++;
     p_->streams.push_back(st);
     return header;

@@ -20,10 +20,25 @@
 namespace jxlb {
 
 // ------------------------------------------------------------------ kernels
+// One warp per CTA: 32 streams in lock step. Properties live in shared memory as
+// [property][lane] (bank = lane, conflict free for any per-lane property index).
 __global__ void __launch_bounds__(32) k_modular_decode(DevPools P) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int32_t props_s[kDevMaxProps * 32];
+  __shared__ uint32_t div_s[64];
+  const uint32_t lane = threadIdx.x;
+  for (uint32_t i = lane; i < 64; i += 32) div_s[i] = (1u << 24) / (i + 1);
+  __syncwarp();
+  const uint32_t s = blockIdx.x * 32 + lane;
   if (s >= P.num_streams) return;
-  P.status[s] = DevDecodeModularStream(P, s);
+  DevLaneMem m;
+  m.props = props_s + lane;
+  m.props_stride = 32;
+  m.divlut = div_s;
+  m.ring_w = P.wp_width;
+  m.lane_stride = 32;
+  m.ring = P.ring + static_cast<size_t>(blockIdx.x) * 3 * P.wp_width * 32 + lane;
+  m.wp = P.wp_scratch + static_cast<size_t>(blockIdx.x) * 10 * (P.wp_width + 2) * 32 + lane;
+  P.status[s] = DevDecodeModularStream(P, s, m);
 }
 
 __global__ void __launch_bounds__(256) k_group_programs(DevPools P, const DevOp* ops, const DevProgram* programs) {
@@ -130,7 +145,7 @@ struct JxlB200Decoder {
   DevBuf<DevOp> d_ops;
   DevBuf<DevProgram> d_group_programs, d_levels;
   DevBuf<DevFrameOut> d_frames;
-  DevBuf<int32_t> d_arena, d_wp;
+  DevBuf<int32_t> d_arena, d_wp, d_ring;
   std::vector<size_t> level_off;  // offset of each level inside d_levels
   std::vector<uint32_t> h_status;
   bool uniform_rgba8 = false;
@@ -138,12 +153,26 @@ struct JxlB200Decoder {
   DevPools pools{};
   // optional per-kernel timing (CUDA events on the launching stream)
   bool profiling = false;
-  cudaEvent_t ev[8] = {};
-  int num_ev = 0;
-  double kernel_ms[4] = {0, 0, 0, 0};  // decode, group programs, frame levels, output (accumulated)
+  static constexpr int kEvRuns = 64;          // event sets kept before folding
+  cudaEvent_t ev[kEvRuns][5] = {};
+  bool ev_created = false;
+  int ev_used = 0;                            // recorded, not yet folded
+  double kernel_ms[4] = {0, 0, 0, 0};         // decode, group programs, frame levels, output (accumulated)
   uint32_t profiled_runs = 0;
-  bool pending = false;
 };
+
+static void FoldEvents(JxlB200Decoder* dec) {
+  for (int r = 0; r < dec->ev_used; r++) {
+    if (cudaEventSynchronize(dec->ev[r][4]) != cudaSuccess) continue;
+    for (int k = 0; k < 4; k++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, dec->ev[r][k], dec->ev[r][k + 1]);
+      dec->kernel_ms[k] += ms;
+    }
+    dec->profiled_runs++;
+  }
+  dec->ev_used = 0;
+}
 
 extern "C" {
 
@@ -214,7 +243,9 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   CUDA_OK(dec->d_levels.Upload(all_levels, s));
   CUDA_OK(dec->d_frames.Upload(b.frames, s));
   CUDA_OK(dec->d_arena.Alloc(b.arena_size + 16));
-  CUDA_OK(dec->d_wp.Alloc(static_cast<size_t>(b.wp_slots) * 10 * (b.wp_width + 2) + 16));
+  const size_t num_warps = (b.streams.size() + 31) / 32;
+  CUDA_OK(dec->d_wp.Alloc(num_warps * 10 * (b.wp_width + 2) * 32 + 16));
+  CUDA_OK(dec->d_ring.Alloc(num_warps * 3 * b.wp_width * 32 + 16));
   CUDA_OK(dec->d_lz77.Alloc(static_cast<size_t>(b.lz77_slots) << 20));
   CUDA_OK(dec->d_status.Alloc(b.streams.size()));
   CUDA_OK(dec->d_out.Alloc(b.out_size));
@@ -232,6 +263,7 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   P.codes = dec->d_codes.p;
   P.arena = dec->d_arena.p;
   P.wp_scratch = dec->d_wp.p;
+  P.ring = dec->d_ring.p;
   P.wp_width = b.wp_width;
   P.lz77 = dec->d_lz77.p;
   P.status = dec->d_status.p;
@@ -299,41 +331,32 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   const DevPools& P = dec->pools;
   uint32_t launches = 0;
   const bool prof = dec->profiling;
-  if (prof && dec->pending) {
-    // fold the previous run's events before re-recording them
-    if (cudaEventSynchronize(dec->ev[4]) == cudaSuccess) {
-      for (int k = 0; k < 4; k++) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, dec->ev[k], dec->ev[k + 1]);
-        dec->kernel_ms[k] += ms;
-      }
-      dec->profiled_runs++;
-    }
-    dec->pending = false;
+  if (prof && !dec->ev_created) {
+    for (auto& set : dec->ev)
+      for (auto& e : set) CUDA_OK(cudaEventCreate(&e));
+    dec->ev_created = true;
   }
-  if (prof && !dec->num_ev) {
-    for (int k = 0; k < 5; k++) CUDA_OK(cudaEventCreate(&dec->ev[k]));
-    dec->num_ev = 5;
-  }
-  if (prof) cudaEventRecord(dec->ev[0], s);
+  if (prof && dec->ev_used == JxlB200Decoder::kEvRuns) FoldEvents(dec);  // blocks only every 64 runs
+  cudaEvent_t* ev = prof ? dec->ev[dec->ev_used] : nullptr;
+  if (prof) cudaEventRecord(ev[0], s);
   if (!b.streams.empty()) {
     const uint32_t block = 32;
     k_modular_decode<<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
     launches++;
   }
-  if (prof) cudaEventRecord(dec->ev[1], s);
+  if (prof) cudaEventRecord(ev[1], s);
   if (!b.group_programs.empty()) {
     k_group_programs<<<b.group_programs.size(), 256, 0, s>>>(P, dec->d_ops.p, dec->d_group_programs.p);
     launches++;
   }
-  if (prof) cudaEventRecord(dec->ev[2], s);
+  if (prof) cudaEventRecord(ev[2], s);
   for (size_t k = 0; k < b.levels.size(); k++) {
     const uint32_t tiles = std::max<uint32_t>(1, std::min<uint32_t>(1024, (b.max_frame_pixels + 1023) / 1024));
     dim3 grid(tiles, b.levels[k].size());
     k_frame_level<<<grid, 256, 0, s>>>(P, dec->d_ops.p, dec->d_levels.p + dec->level_off[k]);
     launches++;
   }
-  if (prof) cudaEventRecord(dec->ev[3], s);
+  if (prof) cudaEventRecord(ev[3], s);
   {
     const uint32_t tiles = std::max<uint32_t>(1, std::min<uint32_t>(4096, (b.max_frame_pixels + 255) / 256));
     dim3 grid(tiles, b.frames.size());
@@ -345,8 +368,8 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     launches++;
   }
   if (prof) {
-    cudaEventRecord(dec->ev[4], s);
-    dec->pending = true;
+    cudaEventRecord(ev[4], s);
+    dec->ev_used++;
   }
   dec->launches = launches;
   CUDA_OK(cudaGetLastError());
@@ -358,21 +381,13 @@ int JxlB200DecoderSetProfiling(JxlB200Decoder* dec, int enabled) {
   dec->profiling = enabled != 0;
   for (double& m : dec->kernel_ms) m = 0;
   dec->profiled_runs = 0;
-  dec->pending = false;
+  dec->ev_used = 0;
   return 0;
 }
 
 int JxlB200DecoderGetKernelTimes(JxlB200Decoder* dec, double* ms4, uint32_t* runs) {
   if (!dec || !ms4 || !runs) return 1;
-  if (dec->pending && cudaEventSynchronize(dec->ev[4]) == cudaSuccess) {
-    for (int k = 0; k < 4; k++) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, dec->ev[k], dec->ev[k + 1]);
-      dec->kernel_ms[k] += ms;
-    }
-    dec->profiled_runs++;
-    dec->pending = false;
-  }
+  FoldEvents(dec);
   for (int k = 0; k < 4; k++) ms4[k] = dec->kernel_ms[k];
   *runs = dec->profiled_runs;
   return 0;

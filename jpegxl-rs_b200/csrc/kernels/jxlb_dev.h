@@ -70,6 +70,9 @@ struct DevChannel {
   uint32_t prop0;     // value of property 0 (channel index inside the stream's image)
   uint32_t ref_off;   // index into the ref pool: plane ids of reference channels
   uint32_t ref_count;
+  uint32_t tree_off;  // DevTreeNode index of this channel's tree: the stream's MA tree with the
+                      // static properties 0 (channel) and 1 (stream id) already resolved
+  uint32_t uses_wp;   // that pruned tree needs the weighted predictor
 };
 
 // One Modular entropy-coded stream = one thread of the decode kernel.

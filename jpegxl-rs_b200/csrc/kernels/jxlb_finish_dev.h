@@ -133,12 +133,14 @@ JXLB_HD void DevRunOp(const DevPools& P, const DevOp& op, uint32_t tid, uint32_t
           const int c = static_cast<int>(tid);
           int32_t* chan = c == 0 ? out0 : P.arena + P.planes[op.c + c - 1].off;
           const int w = static_cast<int>(idx.w), h = static_cast<int>(idx.h);
-          DevWP wp;
+          DevWPPlain wp;
           const bool use_wp = predictor == 6;
           // WP scratch for this op lives behind the index copy.
           int32_t* scratch = indices + n + static_cast<size_t>(c) * 10 * (w + 2);
+          uint32_t lut[64];
           if (use_wp) {
-            wp.Init(op.wp_params, scratch, w + 2);
+            for (uint32_t k = 0; k < 64; k++) lut[k] = (1u << 24) / (k + 1);
+            wp.InitPlain(op.wp_params, scratch, w, lut);
             wp.Reset(w);
           }
           for (int y = 0; y < h; y++) {
@@ -153,7 +155,7 @@ JXLB_HD void DevRunOp(const DevPools& P, const DevOp& op, uint32_t tid, uint32_t
               if (use_wp) wp_pred = wp.Predict(x, y, w, nbh.top, nbh.left, nbh.topright, nbh.topleft, nbh.toptop, nullptr);
               if (index < static_cast<int32_t>(nb_deltas)) val += DevPredictOne(predictor, nbh, wp_pred);
               row[x] = static_cast<int32_t>(val);
-              if (use_wp) wp.Update(row[x], x, y, w);
+              if (use_wp) wp.Update(row[x], x, y);
             }
           }
         }

@@ -30,8 +30,9 @@ struct DevPools {
   const uint32_t* refs;
   const DevCode* codes;
   int32_t* arena;
-  int32_t* wp_scratch;   // per slot: 5 arrays x 2 rows x (wp_width + 2)
-  uint32_t wp_width;
+  int32_t* wp_scratch;   // per warp: 5 arrays x 2 rows x (wp_width + 2) x 32 lanes, [pos][lane]
+  int32_t* ring;         // per warp: 3 rows x wp_width x 32 lanes, [x][lane]
+  uint32_t wp_width;     // widest channel of the batch
   uint32_t* lz77;        // per slot: 1 << 20 entries
   uint32_t* status;      // per stream: 0 ok, else error bits
   uint32_t num_streams;
@@ -292,52 +293,72 @@ JXLB_HD uint32_t DevFloorLog2(uint64_t v) {
 #endif
 }
 
-// Weighted predictor state: prediction errors of the current and previous row,
-// kept in a per-stream scratch (5 arrays x 2 rows x (width + 2)).
+// Per-lane working memory of the decode kernel. One warp decodes 32 streams in lock
+// step, so every array that is indexed by the position inside the row is laid out
+// [position][lane]: the 32 lanes of a load/store instruction then touch 32 consecutive
+// words (one 128-byte line) instead of 32 different lines.
+struct DevLaneMem {
+  int32_t* props;          // properties: props[p * props_stride]
+  uint32_t props_stride;   // 32 (shared memory, bank = lane) on the device
+  const uint32_t* divlut;  // 64-entry (1 << 24) / (i + 1)
+  int32_t* ring;           // 3 rows x ring_w samples: ring[(r * ring_w + x) * lane_stride]
+  int32_t* wp;             // 5 arrays x 2 rows x (ring_w + 2): wp[((a * 2 + r) * (ring_w + 2) + pos) * lane_stride]
+  uint32_t ring_w;
+  uint32_t lane_stride;
+};
+
+// Weighted predictor (lib/jxl/modular/encoding/context_predict.h:134-214) on the
+// interleaved scratch.
 struct DevWP {
   int32_t p1C, p2C, p3Ca, p3Cb, p3Cc, p3Cd, p3Ce;
   uint32_t w[4];
   int64_t prediction[4];
   int64_t pred;
-  uint32_t* pred_errors[4];
-  int32_t* error;
+  int32_t* base;
+  uint32_t row_len;      // ring_w + 2
+  uint32_t lane_stride;
+  const uint32_t* divlut;
 
-  JXLB_HD void Init(const uint32_t params[3], int32_t* scratch, uint32_t stride) {
+  JXLB_HD void Init(const uint32_t params[3], const DevLaneMem& m) {
     p1C = params[0] & 0xFF; p2C = (params[0] >> 8) & 0xFF; p3Ca = (params[0] >> 16) & 0xFF; p3Cb = params[0] >> 24;
     p3Cc = params[1] & 0xFF; p3Cd = (params[1] >> 8) & 0xFF; p3Ce = (params[1] >> 16) & 0xFF;
     for (int i = 0; i < 4; i++) w[i] = (params[2] >> (8 * i)) & 0xFF;
-    for (int i = 0; i < 4; i++) pred_errors[i] = reinterpret_cast<uint32_t*>(scratch) + static_cast<size_t>(i) * 2 * stride;
-    error = scratch + static_cast<size_t>(4) * 2 * stride;
+    base = m.wp;
+    row_len = m.ring_w + 2;
+    lane_stride = m.lane_stride;
+    divlut = m.divlut;
     pred = 0;
     for (int i = 0; i < 4; i++) prediction[i] = 0;
   }
-  JXLB_HD void Reset(uint32_t xsize) {
-    const uint32_t n = (xsize + 2) * 2;
-    for (int i = 0; i < 4; i++)
-      for (uint32_t k = 0; k < n; k++) pred_errors[i][k] = 0;
-    for (uint32_t k = 0; k < n; k++) error[k] = 0;
+  // element `pos` of row `r` (0/1) of array `a` (0..3 pred_errors, 4 error)
+  JXLB_HD int32_t& At(uint32_t a, uint32_t r, uint32_t pos) const {
+    return base[static_cast<size_t>((a * 2 + r) * row_len + pos) * lane_stride];
   }
-  static JXLB_HD uint32_t DivLookup(uint32_t i) { return (1u << 24) / (i + 1); }
-  static JXLB_HD uint32_t ErrorWeight(uint64_t x, uint32_t maxweight) {
-    int shift = static_cast<int>(DevFloorLog2(x + 1)) - 5;
+  JXLB_HD void Reset(uint32_t xsize) {
+    for (uint32_t a = 0; a < 5; a++)
+      for (uint32_t r = 0; r < 2; r++)
+        for (uint32_t k = 0; k < xsize + 2; k++) At(a, r, k) = 0;
+  }
+  JXLB_HD uint32_t ErrorWeight(uint32_t x, uint32_t maxweight) const {
+    int shift = static_cast<int>(DevFloorLog2(static_cast<uint64_t>(x) + 1)) - 5;
     if (shift < 0) shift = 0;
-    return 4 + static_cast<uint32_t>((static_cast<uint64_t>(maxweight) * DivLookup(static_cast<uint32_t>(x >> shift))) >> shift);
+    return 4 + ((maxweight * divlut[x >> shift]) >> shift);
   }
   JXLB_HD int64_t Predict(uint32_t x, uint32_t y, uint32_t xsize, int64_t N, int64_t W, int64_t NE, int64_t NW, int64_t NN,
                           int32_t* max_error) {
-    const uint32_t cur_row = (y & 1) ? 0 : (xsize + 2);
-    const uint32_t prev_row = (y & 1) ? (xsize + 2) : 0;
-    const uint32_t pos_N = prev_row + x;
-    const uint32_t pos_NE = x < xsize - 1 ? pos_N + 1 : pos_N;
-    const uint32_t pos_NW = x > 0 ? pos_N - 1 : pos_N;
+    const uint32_t cur = (y & 1) ? 0 : 1, prev = cur ^ 1;
+    const uint32_t pos_N = x;
+    const uint32_t pos_NE = x < xsize - 1 ? x + 1 : x;
+    const uint32_t pos_NW = x > 0 ? x - 1 : x;
     uint32_t weights[4];
-    for (int i = 0; i < 4; i++) {
-      const uint32_t e = pred_errors[i][pos_N] + pred_errors[i][pos_NE] + pred_errors[i][pos_NW];
+    for (uint32_t i = 0; i < 4; i++) {
+      const uint32_t e = static_cast<uint32_t>(At(i, prev, pos_N)) + static_cast<uint32_t>(At(i, prev, pos_NE)) +
+                         static_cast<uint32_t>(At(i, prev, pos_NW));
       weights[i] = ErrorWeight(e, w[i]);
     }
     N *= 8; W *= 8; NE *= 8; NW *= 8; NN *= 8;
-    const int64_t teW = x == 0 ? 0 : error[cur_row + x - 1];
-    const int64_t teN = error[pos_N], teNW = error[pos_NW], teNE = error[pos_NE];
+    const int64_t teW = x == 0 ? 0 : At(4, cur, x - 1);
+    const int64_t teN = At(4, prev, pos_N), teNW = At(4, prev, pos_NW), teNE = At(4, prev, pos_NE);
     const int64_t sumWN = teN + teW;
     if (max_error) {
       int64_t p = teW;
@@ -359,7 +380,7 @@ struct DevWP {
     }
     int64_t sum = (wsum >> 1) - 1;
     for (int i = 0; i < 4; i++) sum += prediction[i] * weights[i];
-    pred = (sum * DivLookup(wsum - 1)) >> 24;
+    pred = (sum * divlut[wsum - 1]) >> 24;
     if (((teN ^ teW) | (teN ^ teNW)) > 0) return (pred + 3) >> 3;
     int64_t mx = W > NE ? W : NE;
     if (N > mx) mx = N;
@@ -369,23 +390,34 @@ struct DevWP {
     if (pred < mn) pred = mn;
     return (pred + 3) >> 3;
   }
-  JXLB_HD void Update(int64_t val, uint32_t x, uint32_t y, uint32_t xsize) {
-    const uint32_t cur_row = (y & 1) ? 0 : (xsize + 2);
-    const uint32_t prev_row = (y & 1) ? (xsize + 2) : 0;
+  JXLB_HD void Update(int64_t val, uint32_t x, uint32_t y) {
+    const uint32_t cur = (y & 1) ? 0 : 1, prev = cur ^ 1;
     val *= 8;
-    error[cur_row + x] = static_cast<int32_t>(pred - val);
-    for (int i = 0; i < 4; i++) {
+    At(4, cur, x) = static_cast<int32_t>(pred - val);
+    for (uint32_t i = 0; i < 4; i++) {
       const uint32_t err = static_cast<uint32_t>((DevAbs64(prediction[i] - val) + 3) >> 3);
-      pred_errors[i][cur_row + x] = err;
-      pred_errors[i][prev_row + x + 1] += err;
+      At(i, cur, x) = static_cast<int32_t>(err);
+      At(i, prev, x + 1) = static_cast<int32_t>(static_cast<uint32_t>(At(i, prev, x + 1)) + err);
     }
+  }
+};
+
+// A plain-memory WP for the (rare) delta-palette inverse, same arithmetic.
+struct DevWPPlain : public DevWP {
+  JXLB_HD void InitPlain(const uint32_t params[3], int32_t* scratch, uint32_t xsize, const uint32_t* lut) {
+    DevLaneMem m{};
+    m.wp = scratch;
+    m.ring_w = xsize;
+    m.lane_stride = 1;
+    m.divlut = lut;
+    Init(params, m);
   }
 };
 
 constexpr int kDevMaxProps = 16 + 4 * 8;  // static 2 + 13 + WP + up to 8 reference channels
 
-// Decodes every channel of stream `s`. Returns the status word.
-JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s) {
+// Decodes every channel of stream `s` with the lane memory `m`. Returns the status word.
+JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const DevLaneMem& m) {
   const DevStream st = P.streams[s];
   const DevCode code = P.codes[st.code];
   DevBits br;
@@ -393,43 +425,59 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s) {
   DevSymbolReader reader;
   uint32_t* window = (st.lz77_slot != 0xFFFFFFFFu) ? P.lz77 + (static_cast<size_t>(st.lz77_slot) << 20) : nullptr;
   reader.Init(P, code, br, st.dist_multiplier, window);
-  const DevTreeNode* tree = P.tree + st.tree_off;
-  const uint32_t wp_stride = P.wp_width + 2;
+  const uint32_t PS = m.props_stride, LS = m.lane_stride, RW = m.ring_w;
+  int32_t* props = m.props;
+  for (int i = 0; i < kDevMaxProps; i++) props[i * PS] = 0;
+  props[1 * PS] = static_cast<int32_t>(st.stream_id);
   DevWP wp;
-  if (st.uses_wp) wp.Init(st.wp_params, P.wp_scratch + static_cast<size_t>(st.scratch_slot) * 10 * wp_stride, wp_stride);
-  int32_t props[kDevMaxProps];
-  for (int i = 0; i < kDevMaxProps; i++) props[i] = 0;
-  props[1] = static_cast<int32_t>(st.stream_id);
+  wp.Init(st.wp_params, m);
   for (uint32_t ci = st.chan_begin; ci < st.chan_end; ci++) {
     const DevChannel ch = P.chans[ci];
     const DevPlane pl = P.planes[ch.plane];
     const int w = static_cast<int>(pl.w), h = static_cast<int>(pl.h);
     if (w == 0 || h == 0) continue;
-    int32_t* base = P.arena + pl.off;
+    int32_t* out = P.arena + pl.off;
+    const DevTreeNode* tree = P.tree + ch.tree_off;
+    const bool uses_wp = ch.uses_wp != 0;
     props[0] = static_cast<int32_t>(ch.prop0);
-    if (st.uses_wp) wp.Reset(w);
+    props[15 * PS] = 0;
+    if (uses_wp) wp.Reset(w);
     for (int y = 0; y < h; y++) {
-      int32_t* row = base + static_cast<size_t>(y) * w;
-      const int32_t* prev = y ? row - w : nullptr;
-      const int32_t* prevprev = y > 1 ? row - 2 * w : nullptr;
-      props[2] = y;
-      props[9] = 0;
+      int32_t* row = m.ring + static_cast<size_t>((y % 3) * RW) * LS;
+      const int32_t* prev = m.ring + static_cast<size_t>(((y + 2) % 3) * RW) * LS;
+      const int32_t* prevprev = m.ring + static_cast<size_t>(((y + 1) % 3) * RW) * LS;
+      int32_t* out_row = out + static_cast<size_t>(y) * w;
+      props[2 * PS] = y;
+      int32_t prev_grad = 0;  // property 9 of the previous pixel
+      int64_t left = 0, leftleft = 0;
       for (int x = 0; x < w; x++) {
-        const DevNeighbors n = DevLoadNeighbors(row, prev, prevprev, x, y, w);
-        props[3] = x;
-        props[4] = static_cast<int32_t>(n.top > 0 ? n.top : -n.top);
-        props[5] = static_cast<int32_t>(n.left > 0 ? n.left : -n.left);
-        props[6] = static_cast<int32_t>(n.top);
-        props[7] = static_cast<int32_t>(n.left);
-        props[8] = static_cast<int32_t>(n.left - props[9]);
-        props[9] = static_cast<int32_t>(n.left + n.top - n.topleft);
-        props[10] = static_cast<int32_t>(n.left - n.topleft);
-        props[11] = static_cast<int32_t>(n.topleft - n.top);
-        props[12] = static_cast<int32_t>(n.top - n.topright);
-        props[13] = static_cast<int32_t>(n.top - n.toptop);
-        props[14] = static_cast<int32_t>(n.left - n.leftleft);
+        DevNeighbors n;
+        n.left = x ? left : (y ? prev[0] : 0);
+        n.top = y ? prev[static_cast<size_t>(x) * LS] : n.left;
+        n.topleft = (x && y) ? prev[static_cast<size_t>(x - 1) * LS] : n.left;
+        n.topright = (x + 1 < w && y) ? prev[static_cast<size_t>(x + 1) * LS] : n.top;
+        n.leftleft = x > 1 ? leftleft : n.left;
+        n.toptop = y > 1 ? prevprev[static_cast<size_t>(x) * LS] : n.top;
+        n.toprightright = (x + 2 < w && y) ? prev[static_cast<size_t>(x + 2) * LS] : n.topright;
+        props[3 * PS] = x;
+        props[4 * PS] = static_cast<int32_t>(n.top > 0 ? n.top : -n.top);
+        props[5 * PS] = static_cast<int32_t>(n.left > 0 ? n.left : -n.left);
+        props[6 * PS] = static_cast<int32_t>(n.top);
+        props[7 * PS] = static_cast<int32_t>(n.left);
+        props[8 * PS] = static_cast<int32_t>(n.left - prev_grad);
+        prev_grad = static_cast<int32_t>(n.left + n.top - n.topleft);
+        props[9 * PS] = prev_grad;
+        props[10 * PS] = static_cast<int32_t>(n.left - n.topleft);
+        props[11 * PS] = static_cast<int32_t>(n.topleft - n.top);
+        props[12 * PS] = static_cast<int32_t>(n.top - n.topright);
+        props[13 * PS] = static_cast<int32_t>(n.top - n.toptop);
+        props[14 * PS] = static_cast<int32_t>(n.left - n.leftleft);
         int64_t wp_pred = 0;
-        if (st.uses_wp) wp_pred = wp.Predict(x, y, w, n.top, n.left, n.topright, n.topleft, n.toptop, &props[15]);
+        if (uses_wp) {
+          int32_t max_error;
+          wp_pred = wp.Predict(x, y, w, n.top, n.left, n.topright, n.topleft, n.toptop, &max_error);
+          props[15 * PS] = max_error;
+        }
         for (uint32_t r = 0; r < ch.ref_count; r++) {
           const DevPlane rp = P.planes[P.refs[ch.ref_off + r]];
           const int32_t* rrow = P.arena + rp.off + static_cast<size_t>(y) * w;
@@ -439,23 +487,27 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s) {
           const int64_t vtop = y ? rprev[x] : vleft;
           const int64_t vtopleft = (x && y) ? rprev[x - 1] : vleft;
           const int64_t vpred = DevClampedGradient(static_cast<int32_t>(vleft), static_cast<int32_t>(vtop), static_cast<int32_t>(vtopleft));
-          props[16 + 4 * r + 0] = static_cast<int32_t>(DevAbs64(v));
-          props[16 + 4 * r + 1] = static_cast<int32_t>(v);
-          props[16 + 4 * r + 2] = static_cast<int32_t>(DevAbs64(v - vpred));
-          props[16 + 4 * r + 3] = static_cast<int32_t>(v - vpred);
+          props[(16 + 4 * r + 0) * PS] = static_cast<int32_t>(DevAbs64(v));
+          props[(16 + 4 * r + 1) * PS] = static_cast<int32_t>(v);
+          props[(16 + 4 * r + 2) * PS] = static_cast<int32_t>(DevAbs64(v - vpred));
+          props[(16 + 4 * r + 3) * PS] = static_cast<int32_t>(v - vpred);
         }
         DevTreeNode node = DevLoadNode(tree);
         while (node.prop >= 0) {
-          const uint32_t pos = props[node.prop] > node.a ? node.b : node.c;
+          const uint32_t pos = props[node.prop * PS] > node.a ? node.b : node.c;
           node = DevLoadNode(tree + pos);
         }
         const uint32_t cluster = static_cast<uint32_t>(node.a) & 0xFFFF;
         const uint32_t predictor = static_cast<uint32_t>(node.a) >> 16;
         const uint32_t u = reader.ReadUint(cluster, br);
         const int64_t guess = static_cast<int64_t>(static_cast<int32_t>(node.b)) + DevPredictOne(predictor, n, wp_pred);
-        const int64_t val = static_cast<int64_t>(DevUnpackSigned(u)) * static_cast<int64_t>(node.c) + guess;
-        row[x] = static_cast<int32_t>(val);
-        if (st.uses_wp) wp.Update(row[x], x, y, w);
+        const int64_t val64 = static_cast<int64_t>(DevUnpackSigned(u)) * static_cast<int64_t>(node.c) + guess;
+        const int32_t val = static_cast<int32_t>(val64);
+        row[static_cast<size_t>(x) * LS] = val;
+        out_row[x] = val;
+        leftleft = left;
+        left = val;
+        if (uses_wp) wp.Update(val, x, y);
       }
     }
   }

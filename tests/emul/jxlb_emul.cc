@@ -27,8 +27,12 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     PlanBatch(files, sizes, n, fmt, 2, &b);
     if (b.out_size > out_cap) throw Error("output buffer too small");
     std::vector<int32_t> arena(b.arena_size + 16, 0);
-    const uint32_t wp_stride = b.wp_width + 2;
-    std::vector<int32_t> wp(static_cast<size_t>(b.wp_slots) * 10 * wp_stride + 16, 0);
+    const size_t num_warps = (b.streams.size() + 31) / 32;
+    std::vector<int32_t> wp(num_warps * 10 * (b.wp_width + 2) * 32 + 16, 0);
+    std::vector<int32_t> ring(num_warps * 3 * b.wp_width * 32 + 16, 0);
+    std::vector<int32_t> props(kDevMaxProps * 32, 0);
+    uint32_t divlut[64];
+    for (uint32_t i = 0; i < 64; i++) divlut[i] = (1u << 24) / (i + 1);
     std::vector<uint32_t> lz(static_cast<size_t>(b.lz77_slots) << 20, 0);
     DevPools P{};
     P.words = reinterpret_cast<const uint32_t*>(b.bytes.data());
@@ -43,11 +47,22 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     P.codes = b.codes.data();
     P.arena = arena.data();
     P.wp_scratch = wp.data();
+    P.ring = ring.data();
     P.wp_width = b.wp_width;
     P.lz77 = lz.data();
     P.num_streams = b.streams.size();
     for (uint32_t s = 0; s < b.streams.size(); s++) {
-      uint32_t st = DevDecodeModularStream(P, s);
+      // same addressing as the kernel: warp = s / 32, lane = s % 32
+      const uint32_t warp = s / 32, lane = s % 32;
+      DevLaneMem m;
+      m.props = props.data() + lane;
+      m.props_stride = 32;
+      m.divlut = divlut;
+      m.ring_w = b.wp_width;
+      m.lane_stride = 32;
+      m.ring = ring.data() + static_cast<size_t>(warp) * 3 * b.wp_width * 32 + lane;
+      m.wp = wp.data() + static_cast<size_t>(warp) * 10 * (b.wp_width + 2) * 32 + lane;
+      uint32_t st = DevDecodeModularStream(P, s, m);
       if (st != 0) throw Error("stream " + std::to_string(s) + " failed with status " + std::to_string(st));
     }
     const uint32_t nt = 4;  // emulate a few cooperating workers
