@@ -174,7 +174,10 @@ def main():
     dec = pkg.BatchDecoder(local_rank)
     dec.set_input(files, 4, pkg.JXL_TYPE_UINT8)
     st = dec.stats()
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def barrier():
         torch.cuda.synchronize()

@@ -2,8 +2,10 @@
 #ifndef JXLB_BATCH_H_
 #define JXLB_BATCH_H_
 
+#include <algorithm>
 #include <atomic>
 #include <thread>
+#include <tuple>
 
 #include "jxlb_frame_plan.h"
 
@@ -29,7 +31,50 @@ struct BatchPlan {
   uint64_t total_pixels = 0;
   uint64_t compressed_bytes = 0;
   std::vector<BasicInfo> info;
+  std::vector<uint32_t> warp_chans, warp_dims_off, warp_dims;
+  bool narrow = true;  // every frame promises that 16-bit buffers suffice -> 32-bit predictor math
 };
+
+// Orders the streams so that the 32 lanes of a warp decode planes of the same shape
+// (they run one loop nest in lock step) and derives the warp-uniform loop bounds.
+inline void BundleStreams(BatchPlan* b) {
+  auto key = [&](const DevStream& s) {
+    const uint32_t n = s.chan_end - s.chan_begin;
+    uint32_t w = 0, h = 0;
+    if (n) {
+      const DevPlane& p = b->planes[b->chans[s.chan_end - 1].plane];
+      w = p.w;
+      h = p.h;
+    }
+    return std::make_tuple(n, w, h);
+  };
+  std::stable_sort(b->streams.begin(), b->streams.end(),
+                   [&](const DevStream& x, const DevStream& y) { return key(x) > key(y); });
+  const size_t num_warps = (b->streams.size() + 31) / 32;
+  b->warp_chans.assign(num_warps, 0);
+  b->warp_dims_off.assign(num_warps, 0);
+  b->warp_dims.clear();
+  for (size_t wi = 0; wi < num_warps; wi++) {
+    uint32_t nmax = 0;
+    const size_t s0 = wi * 32, s1 = std::min(b->streams.size(), s0 + 32);
+    for (size_t s = s0; s < s1; s++) nmax = std::max(nmax, b->streams[s].chan_end - b->streams[s].chan_begin);
+    b->warp_chans[wi] = nmax;
+    b->warp_dims_off[wi] = b->warp_dims.size();
+    for (uint32_t k = 0; k < nmax; k++) {
+      uint32_t mw = 0, mh = 0;
+      for (size_t s = s0; s < s1; s++) {
+        const DevStream& st = b->streams[s];
+        if (k >= st.chan_end - st.chan_begin) continue;
+        const DevPlane& p = b->planes[b->chans[st.chan_begin + k].plane];
+        if (p.w == 0 || p.h == 0) continue;
+        mw = std::max(mw, p.w);
+        mh = std::max(mh, p.h);
+      }
+      b->warp_dims.push_back(mw);
+      b->warp_dims.push_back(mh);
+    }
+  }
+}
 
 inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, BatchPlan* b) {
   const uint64_t byte_base = b->bytes.size();
@@ -104,6 +149,10 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
   b->lz77_slots += f.lz77_slots;
   b->max_frame_pixels = std::max<uint32_t>(b->max_frame_pixels, f.pixels);
   b->total_pixels += f.pixels;
+  if (!(f.meta.modular_16_bit_buffer_sufficient && f.meta.bit_depth.bits <= 16 && !f.meta.bit_depth.floating_point))
+    b->narrow = false;
+  for (const auto& e : f.meta.extra)
+    if (e.bit_depth.bits > 16 || e.bit_depth.floating_point) b->narrow = false;
   BasicInfo bi;
   bi.xsize = f.xsize;
   bi.ysize = f.ysize;
@@ -144,6 +193,7 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
   }
   for (size_t i = 0; i < n; i++) MergeFrame(plans[i], views[i].data, views[i].size, batch);
   batch->bytes.resize(batch->bytes.size() + 64, 0);  // read-ahead padding for the device bit reader
+  BundleStreams(batch);
 }
 
 }  // namespace jxlb

@@ -22,6 +22,7 @@ namespace jxlb {
 // ------------------------------------------------------------------ kernels
 // One warp per CTA: 32 streams in lock step. Properties live in shared memory as
 // [property][lane] (bank = lane, conflict free for any per-lane property index).
+template <typename WT>
 __global__ void __launch_bounds__(32) k_modular_decode(DevPools P) {
   __shared__ int32_t props_s[kDevMaxProps * 32];
   __shared__ uint32_t div_s[64];
@@ -29,7 +30,6 @@ __global__ void __launch_bounds__(32) k_modular_decode(DevPools P) {
   for (uint32_t i = lane; i < 64; i += 32) div_s[i] = (1u << 24) / (i + 1);
   __syncwarp();
   const uint32_t s = blockIdx.x * 32 + lane;
-  if (s >= P.num_streams) return;
   DevLaneMem m;
   m.props = props_s + lane;
   m.props_stride = 32;
@@ -38,7 +38,10 @@ __global__ void __launch_bounds__(32) k_modular_decode(DevPools P) {
   m.lane_stride = 32;
   m.ring = P.ring + static_cast<size_t>(blockIdx.x) * 3 * P.wp_width * 32 + lane;
   m.wp = P.wp_scratch + static_cast<size_t>(blockIdx.x) * 10 * (P.wp_width + 2) * 32 + lane;
-  P.status[s] = DevDecodeModularStream(P, s, m);
+  const bool valid = s < P.num_streams;
+  const uint32_t status = DevDecodeModularStream<WT>(P, s, m, P.warp_dims + P.warp_dims_off[blockIdx.x],
+                                                     P.warp_chans[blockIdx.x], valid);
+  if (valid) P.status[s] = status;
 }
 
 __global__ void __launch_bounds__(256) k_group_programs(DevPools P, const DevOp* ops, const DevProgram* programs) {
@@ -136,7 +139,7 @@ struct JxlB200Decoder {
   std::unique_ptr<BatchPlan> plan;
   DevBuf<uint8_t> d_bytes, d_out;
   DevBuf<DevAlias> d_alias;
-  DevBuf<uint32_t> d_prefix, d_cfg, d_refs, d_lz77, d_status;
+  DevBuf<uint32_t> d_prefix, d_cfg, d_refs, d_lz77, d_status, d_warp_chans, d_warp_dims_off, d_warp_dims;
   DevBuf<DevTreeNode> d_tree;
   DevBuf<DevCode> d_codes;
   DevBuf<DevChannel> d_chans;
@@ -242,6 +245,9 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   }
   CUDA_OK(dec->d_levels.Upload(all_levels, s));
   CUDA_OK(dec->d_frames.Upload(b.frames, s));
+  CUDA_OK(dec->d_warp_chans.Upload(b.warp_chans, s));
+  CUDA_OK(dec->d_warp_dims_off.Upload(b.warp_dims_off, s));
+  CUDA_OK(dec->d_warp_dims.Upload(b.warp_dims, s));
   CUDA_OK(dec->d_arena.Alloc(b.arena_size + 16));
   const size_t num_warps = (b.streams.size() + 31) / 32;
   CUDA_OK(dec->d_wp.Alloc(num_warps * 10 * (b.wp_width + 2) * 32 + 16));
@@ -268,6 +274,9 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   P.lz77 = dec->d_lz77.p;
   P.status = dec->d_status.p;
   P.num_streams = b.streams.size();
+  P.warp_chans = dec->d_warp_chans.p;
+  P.warp_dims_off = dec->d_warp_dims_off.p;
+  P.warp_dims = dec->d_warp_dims.p;
   dec->uniform_rgba8 = fmt.num_channels == 4 && fmt.data_type == 2;
   for (const DevFrameOut& fo : b.frames)
     for (int c = 0; c < 4; c++)
@@ -341,7 +350,11 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   if (prof) cudaEventRecord(ev[0], s);
   if (!b.streams.empty()) {
     const uint32_t block = 32;
-    k_modular_decode<<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
+    if (b.narrow) {
+      k_modular_decode<int32_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
+    } else {
+      k_modular_decode<int64_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
+    }
     launches++;
   }
   if (prof) cudaEventRecord(ev[1], s);

@@ -133,7 +133,7 @@ JXLB_HD void DevRunOp(const DevPools& P, const DevOp& op, uint32_t tid, uint32_t
           const int c = static_cast<int>(tid);
           int32_t* chan = c == 0 ? out0 : P.arena + P.planes[op.c + c - 1].off;
           const int w = static_cast<int>(idx.w), h = static_cast<int>(idx.h);
-          DevWPPlain wp;
+          DevWPPlain wp{};
           const bool use_wp = predictor == 6;
           // WP scratch for this op lives behind the index copy.
           int32_t* scratch = indices + n + static_cast<size_t>(c) * 10 * (w + 2);

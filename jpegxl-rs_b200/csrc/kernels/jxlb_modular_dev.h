@@ -36,6 +36,11 @@ struct DevPools {
   uint32_t* lz77;        // per slot: 1 << 20 entries
   uint32_t* status;      // per stream: 0 ok, else error bits
   uint32_t num_streams;
+  // per warp of 32 consecutive streams: number of channel slots and, per slot, the
+  // largest (width, height) among its lanes -- the warp-uniform loop bounds
+  const uint32_t* warp_chans;
+  const uint32_t* warp_dims_off;
+  const uint32_t* warp_dims;
 };
 
 enum DevStatus : uint32_t { kStatusOk = 0, kStatusOverread = 1, kStatusBadFinalState = 2, kStatusNotRun = 0x80000000u };
@@ -307,33 +312,29 @@ struct DevLaneMem {
   uint32_t lane_stride;
 };
 
-// Weighted predictor (lib/jxl/modular/encoding/context_predict.h:134-214) on the
-// interleaved scratch.
-struct DevWP {
+// Plain weighted predictor (lib/jxl/modular/encoding/context_predict.h:134-214) with
+// the error arrays in memory; only the rare delta-palette inverse uses it. The decode
+// kernel keeps the same state in registers (see DevDecodeModularStream).
+struct DevWPPlain {
   int32_t p1C, p2C, p3Ca, p3Cb, p3Cc, p3Cd, p3Ce;
   uint32_t w[4];
   int64_t prediction[4];
   int64_t pred;
   int32_t* base;
-  uint32_t row_len;      // ring_w + 2
-  uint32_t lane_stride;
+  uint32_t row_len;
   const uint32_t* divlut;
 
-  JXLB_HD void Init(const uint32_t params[3], const DevLaneMem& m) {
+  JXLB_HD void InitPlain(const uint32_t params[3], int32_t* scratch, uint32_t xsize, const uint32_t* lut) {
     p1C = params[0] & 0xFF; p2C = (params[0] >> 8) & 0xFF; p3Ca = (params[0] >> 16) & 0xFF; p3Cb = params[0] >> 24;
     p3Cc = params[1] & 0xFF; p3Cd = (params[1] >> 8) & 0xFF; p3Ce = (params[1] >> 16) & 0xFF;
     for (int i = 0; i < 4; i++) w[i] = (params[2] >> (8 * i)) & 0xFF;
-    base = m.wp;
-    row_len = m.ring_w + 2;
-    lane_stride = m.lane_stride;
-    divlut = m.divlut;
+    base = scratch;
+    row_len = xsize + 2;
+    divlut = lut;
     pred = 0;
     for (int i = 0; i < 4; i++) prediction[i] = 0;
   }
-  // element `pos` of row `r` (0/1) of array `a` (0..3 pred_errors, 4 error)
-  JXLB_HD int32_t& At(uint32_t a, uint32_t r, uint32_t pos) const {
-    return base[static_cast<size_t>((a * 2 + r) * row_len + pos) * lane_stride];
-  }
+  JXLB_HD int32_t& At(uint32_t a, uint32_t r, uint32_t pos) const { return base[(a * 2 + r) * row_len + pos]; }
   JXLB_HD void Reset(uint32_t xsize) {
     for (uint32_t a = 0; a < 5; a++)
       for (uint32_t r = 0; r < 2; r++)
@@ -402,118 +403,272 @@ struct DevWP {
   }
 };
 
-// A plain-memory WP for the (rare) delta-palette inverse, same arithmetic.
-struct DevWPPlain : public DevWP {
-  JXLB_HD void InitPlain(const uint32_t params[3], int32_t* scratch, uint32_t xsize, const uint32_t* lut) {
-    DevLaneMem m{};
-    m.wp = scratch;
-    m.ring_w = xsize;
-    m.lane_stride = 1;
-    m.divlut = lut;
-    Init(params, m);
-  }
-};
-
 constexpr int kDevMaxProps = 16 + 4 * 8;  // static 2 + 13 + WP + up to 8 reference channels
 
-// Decodes every channel of stream `s` with the lane memory `m`. Returns the status word.
-JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const DevLaneMem& m) {
-  const DevStream st = P.streams[s];
-  const DevCode code = P.codes[st.code];
-  DevBits br;
-  br.Init(P.words, st.bit_pos);
-  DevSymbolReader reader;
-  uint32_t* window = (st.lz77_slot != 0xFFFFFFFFu) ? P.lz77 + (static_cast<size_t>(st.lz77_slot) << 20) : nullptr;
-  reader.Init(P, code, br, st.dist_multiplier, window);
-  const uint32_t PS = m.props_stride, LS = m.lane_stride, RW = m.ring_w;
+template <typename WT>
+JXLB_HD WT DevAbsW(WT v) { return v < 0 ? -v : v; }
+
+template <typename WT>
+JXLB_HD WT DevPredictW(uint32_t p, WT left, WT top, WT topleft, WT topright, WT leftleft, WT toptop, WT toprightright,
+                       WT wp_pred) {
+  switch (p) {
+    case 0: return 0;
+    case 1: return left;
+    case 2: return top;
+    case 3: return (left + top) / 2;
+    case 4: {
+      const WT pp = left + top - topleft;
+      return DevAbsW<WT>(pp - left) < DevAbsW<WT>(pp - top) ? left : top;
+    }
+    case 5: return DevClampedGradient(static_cast<int32_t>(left), static_cast<int32_t>(top), static_cast<int32_t>(topleft));
+    case 6: return wp_pred;
+    case 7: return topright;
+    case 8: return topleft;
+    case 9: return leftleft;
+    case 10: return (left + topleft) / 2;
+    case 11: return (topleft + top) / 2;
+    case 12: return (top + topright) / 2;
+    case 13: return (6 * top - 2 * toptop + 7 * left + leftleft + toprightright + 3 * topright + 8) / 16;
+    default: return 0;
+  }
+}
+
+// Decodes every channel of stream `s` (lane `s % 32` of warp `s / 32`).
+//
+// WT is the arithmetic width of predictor math: int32_t when the codestream promises
+// that 16-bit buffers suffice (ImageMetadata::modular_16_bit_buffer_sufficient,
+// lib/jxl/image_metadata.cc:322) -- every intermediate of the reference's int64
+// formulas then fits 32 bits except the final 28 x 24 bit product of the weighted
+// average, which stays 64-bit -- and int64_t otherwise.
+//
+// All 32 lanes run the same (channel, y, x) loop nest with warp-uniform bounds
+// (warp_dims: per channel slot the largest width / height of the warp) and mask
+// themselves off outside their own plane: the warp never splits.
+//
+// The weighted predictor's error rows are kept as sliding NW/N/NE registers; the
+// reference's `pred_errors[prev_row + x + 1] += err` (context_predict.h:209) only
+// ever influences the next two pixels of the same row, so it is applied to the
+// registers and never stored.
+template <typename WT>
+JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const DevLaneMem& m, const uint32_t* warp_dims,
+                                        uint32_t warp_chans, bool lane_valid) {
+  DevStream st{};
+  DevCode code{};
+  DevBits br{};
+  DevSymbolReader reader{};
+  uint32_t my_chans = 0;
+  if (lane_valid) {
+    st = P.streams[s];
+    code = P.codes[st.code];
+    br.Init(P.words, st.bit_pos);
+    uint32_t* window = (st.lz77_slot != 0xFFFFFFFFu) ? P.lz77 + (static_cast<size_t>(st.lz77_slot) << 20) : nullptr;
+    reader.Init(P, code, br, st.dist_multiplier, window);
+    my_chans = st.chan_end - st.chan_begin;
+  }
+  const uint32_t PS = m.props_stride, LS = m.lane_stride, RW = m.ring_w, WL = m.ring_w + 2;
   int32_t* props = m.props;
   for (int i = 0; i < kDevMaxProps; i++) props[i * PS] = 0;
   props[1 * PS] = static_cast<int32_t>(st.stream_id);
-  DevWP wp;
-  wp.Init(st.wp_params, m);
-  for (uint32_t ci = st.chan_begin; ci < st.chan_end; ci++) {
-    const DevChannel ch = P.chans[ci];
-    const DevPlane pl = P.planes[ch.plane];
-    const int w = static_cast<int>(pl.w), h = static_cast<int>(pl.h);
-    if (w == 0 || h == 0) continue;
-    int32_t* out = P.arena + pl.off;
+  // weighted predictor parameters
+  const int32_t p1C = st.wp_params[0] & 0xFF, p2C = (st.wp_params[0] >> 8) & 0xFF, p3Ca = (st.wp_params[0] >> 16) & 0xFF,
+                p3Cb = st.wp_params[0] >> 24, p3Cc = st.wp_params[1] & 0xFF, p3Cd = (st.wp_params[1] >> 8) & 0xFF,
+                p3Ce = (st.wp_params[1] >> 16) & 0xFF;
+  uint32_t wpw[4];
+  for (int i = 0; i < 4; i++) wpw[i] = (st.wp_params[2] >> (8 * i)) & 0xFF;
+  const uint32_t* divlut = m.divlut;
+
+  for (uint32_t k = 0; k < warp_chans; k++) {
+    const int max_w = static_cast<int>(warp_dims[2 * k]), max_h = static_cast<int>(warp_dims[2 * k + 1]);
+    DevChannel ch{};
+    int w = 0, h = 0;
+    int32_t* out = nullptr;
+    if (k < my_chans) {
+      ch = P.chans[st.chan_begin + k];
+      const DevPlane pl = P.planes[ch.plane];
+      w = static_cast<int>(pl.w);
+      h = static_cast<int>(pl.h);
+      out = P.arena + pl.off;
+    }
     const DevTreeNode* tree = P.tree + ch.tree_off;
     const bool uses_wp = ch.uses_wp != 0;
     props[0] = static_cast<int32_t>(ch.prop0);
     props[15 * PS] = 0;
-    if (uses_wp) wp.Reset(w);
-    for (int y = 0; y < h; y++) {
+    if (uses_wp) {
+      // row "prev" of y = 0 must read as zero (rows alternate: y = 0 uses row 0 as prev)
+      for (uint32_t a = 0; a < 5; a++)
+        for (int q = 0; q < w + 2; q++) m.wp[static_cast<size_t>((a * 2 + 0) * WL + q) * LS] = 0;
+    }
+    for (int y = 0; y < max_h; y++) {
+      const bool row_on = y < h;
       int32_t* row = m.ring + static_cast<size_t>((y % 3) * RW) * LS;
       const int32_t* prev = m.ring + static_cast<size_t>(((y + 2) % 3) * RW) * LS;
       const int32_t* prevprev = m.ring + static_cast<size_t>(((y + 1) % 3) * RW) * LS;
       int32_t* out_row = out + static_cast<size_t>(y) * w;
+      const uint32_t cur = (y & 1) ? 0 : 1, prv = cur ^ 1;
+      int32_t* pe_cur[4];
+      const int32_t* pe_prv[4];
+      for (uint32_t i = 0; i < 4; i++) {
+        pe_cur[i] = m.wp + static_cast<size_t>((i * 2 + cur) * WL) * LS;
+        pe_prv[i] = m.wp + static_cast<size_t>((i * 2 + prv) * WL) * LS;
+      }
+      int32_t* er_cur = m.wp + static_cast<size_t>((4 * 2 + cur) * WL) * LS;
+      const int32_t* er_prv = m.wp + static_cast<size_t>((4 * 2 + prv) * WL) * LS;
       props[2 * PS] = y;
       int32_t prev_grad = 0;  // property 9 of the previous pixel
-      int64_t left = 0, leftleft = 0;
-      for (int x = 0; x < w; x++) {
-        DevNeighbors n;
-        n.left = x ? left : (y ? prev[0] : 0);
-        n.top = y ? prev[static_cast<size_t>(x) * LS] : n.left;
-        n.topleft = (x && y) ? prev[static_cast<size_t>(x - 1) * LS] : n.left;
-        n.topright = (x + 1 < w && y) ? prev[static_cast<size_t>(x + 1) * LS] : n.top;
-        n.leftleft = x > 1 ? leftleft : n.left;
-        n.toptop = y > 1 ? prevprev[static_cast<size_t>(x) * LS] : n.top;
-        n.toprightright = (x + 2 < w && y) ? prev[static_cast<size_t>(x + 2) * LS] : n.topright;
-        props[3 * PS] = x;
-        props[4 * PS] = static_cast<int32_t>(n.top > 0 ? n.top : -n.top);
-        props[5 * PS] = static_cast<int32_t>(n.left > 0 ? n.left : -n.left);
-        props[6 * PS] = static_cast<int32_t>(n.top);
-        props[7 * PS] = static_cast<int32_t>(n.left);
-        props[8 * PS] = static_cast<int32_t>(n.left - prev_grad);
-        prev_grad = static_cast<int32_t>(n.left + n.top - n.topleft);
-        props[9 * PS] = prev_grad;
-        props[10 * PS] = static_cast<int32_t>(n.left - n.topleft);
-        props[11 * PS] = static_cast<int32_t>(n.topleft - n.top);
-        props[12 * PS] = static_cast<int32_t>(n.top - n.topright);
-        props[13 * PS] = static_cast<int32_t>(n.top - n.toptop);
-        props[14 * PS] = static_cast<int32_t>(n.left - n.leftleft);
-        int64_t wp_pred = 0;
+      // sliding neighbourhood (valid when y > 0): t = prev[x], tl = prev[x-1], tr = prev[x+1], trr = prev[x+2]
+      int32_t left = 0, leftleft = 0, t = 0, tl = 0, tr = 0, trr = 0;
+      uint32_t eNW[4] = {0, 0, 0, 0}, eN[4] = {0, 0, 0, 0}, eNE[4] = {0, 0, 0, 0};
+      int32_t teW = 0, teNW = 0, teN = 0, teNE = 0;
+      if (row_on && w > 0) {
+        if (y > 0) {
+          t = prev[0];
+          tr = w > 1 ? prev[static_cast<size_t>(1) * LS] : t;
+          trr = w > 2 ? prev[static_cast<size_t>(2) * LS] : tr;
+        }
         if (uses_wp) {
-          int32_t max_error;
-          wp_pred = wp.Predict(x, y, w, n.top, n.left, n.topright, n.topleft, n.toptop, &max_error);
-          props[15 * PS] = max_error;
+          for (uint32_t i = 0; i < 4; i++) {
+            eN[i] = static_cast<uint32_t>(pe_prv[i][0]);
+            eNW[i] = eN[i];
+            eNE[i] = w > 1 ? static_cast<uint32_t>(pe_prv[i][static_cast<size_t>(1) * LS]) : eN[i];
+          }
+          teN = er_prv[0];
+          teNW = teN;
+          teNE = w > 1 ? er_prv[static_cast<size_t>(1) * LS] : teN;
         }
-        for (uint32_t r = 0; r < ch.ref_count; r++) {
-          const DevPlane rp = P.planes[P.refs[ch.ref_off + r]];
-          const int32_t* rrow = P.arena + rp.off + static_cast<size_t>(y) * w;
-          const int32_t* rprev = y ? rrow - w : rrow;
-          const int64_t v = rrow[x];
-          const int64_t vleft = x ? rrow[x - 1] : 0;
-          const int64_t vtop = y ? rprev[x] : vleft;
-          const int64_t vtopleft = (x && y) ? rprev[x - 1] : vleft;
-          const int64_t vpred = DevClampedGradient(static_cast<int32_t>(vleft), static_cast<int32_t>(vtop), static_cast<int32_t>(vtopleft));
-          props[(16 + 4 * r + 0) * PS] = static_cast<int32_t>(DevAbs64(v));
-          props[(16 + 4 * r + 1) * PS] = static_cast<int32_t>(v);
-          props[(16 + 4 * r + 2) * PS] = static_cast<int32_t>(DevAbs64(v - vpred));
-          props[(16 + 4 * r + 3) * PS] = static_cast<int32_t>(v - vpred);
+      }
+      for (int x = 0; x < max_w; x++) {
+        if (row_on && x < w) {
+          // neighbours with the edge rules of context_predict.h:496-504
+          const WT n_left = x ? left : (y ? t : 0);
+          const WT n_top = y ? t : n_left;
+          const WT n_topleft = (x && y) ? tl : n_left;
+          const WT n_topright = (x + 1 < w && y) ? tr : n_top;
+          const WT n_leftleft = x > 1 ? leftleft : n_left;
+          const WT n_toptop = y > 1 ? prevprev[static_cast<size_t>(x) * LS] : n_top;
+          const WT n_toprightright = (x + 2 < w && y) ? trr : n_topright;
+          props[3 * PS] = x;
+          props[4 * PS] = static_cast<int32_t>(n_top > 0 ? n_top : -n_top);
+          props[5 * PS] = static_cast<int32_t>(n_left > 0 ? n_left : -n_left);
+          props[6 * PS] = static_cast<int32_t>(n_top);
+          props[7 * PS] = static_cast<int32_t>(n_left);
+          props[8 * PS] = static_cast<int32_t>(n_left - prev_grad);
+          prev_grad = static_cast<int32_t>(n_left + n_top - n_topleft);
+          props[9 * PS] = prev_grad;
+          props[10 * PS] = static_cast<int32_t>(n_left - n_topleft);
+          props[11 * PS] = static_cast<int32_t>(n_topleft - n_top);
+          props[12 * PS] = static_cast<int32_t>(n_top - n_topright);
+          props[13 * PS] = static_cast<int32_t>(n_top - n_toptop);
+          props[14 * PS] = static_cast<int32_t>(n_left - n_leftleft);
+          WT wp_pred = 0, wp_raw = 0;
+          WT prediction[4] = {0, 0, 0, 0};
+          if (uses_wp) {
+            uint32_t weights[4];
+            for (uint32_t i = 0; i < 4; i++) {
+              const uint32_t e = eN[i] + eNE[i] + eNW[i];
+              int shift = static_cast<int>(DevFloorLog2(static_cast<uint64_t>(e) + 1)) - 5;
+              if (shift < 0) shift = 0;
+              weights[i] = 4 + ((wpw[i] * divlut[e >> shift]) >> shift);
+            }
+            const WT N8 = n_top * 8, W8 = n_left * 8, NE8 = n_topright * 8, NW8 = n_topleft * 8, NN8 = n_toptop * 8;
+            const WT eW = x == 0 ? 0 : teW;
+            const WT sumWN = static_cast<WT>(teN) + eW;
+            {
+              WT pm = eW;
+              if (DevAbsW<WT>(teN) > DevAbsW<WT>(pm)) pm = teN;
+              if (DevAbsW<WT>(teNW) > DevAbsW<WT>(pm)) pm = teNW;
+              if (DevAbsW<WT>(teNE) > DevAbsW<WT>(pm)) pm = teNE;
+              props[15 * PS] = static_cast<int32_t>(pm);
+            }
+            prediction[0] = W8 + NE8 - N8;
+            prediction[1] = N8 - (((sumWN + teNE) * p1C) >> 5);
+            prediction[2] = W8 - (((sumWN + teNW) * p2C) >> 5);
+            prediction[3] = N8 - ((static_cast<WT>(teNW) * p3Ca + static_cast<WT>(teN) * p3Cb +
+                                   static_cast<WT>(teNE) * p3Cc + (NN8 - N8) * p3Cd + (NW8 - W8) * p3Ce) >> 5);
+            uint32_t wsum = weights[0] + weights[1] + weights[2] + weights[3];
+            const uint32_t log_weight = DevFloorLog2(wsum);
+            wsum = 0;
+            for (int i = 0; i < 4; i++) {
+              weights[i] >>= log_weight - 4;
+              wsum += weights[i];
+            }
+            WT sum = static_cast<WT>((wsum >> 1) - 1);
+            for (int i = 0; i < 4; i++) sum += prediction[i] * static_cast<WT>(weights[i]);
+            wp_raw = static_cast<WT>((static_cast<int64_t>(sum) * static_cast<int64_t>(divlut[wsum - 1])) >> 24);
+            if (!(((static_cast<WT>(teN) ^ eW) | (static_cast<WT>(teN) ^ static_cast<WT>(teNW))) > 0)) {
+              WT mx = W8 > NE8 ? W8 : NE8;
+              if (N8 > mx) mx = N8;
+              WT mn = W8 < NE8 ? W8 : NE8;
+              if (N8 < mn) mn = N8;
+              if (wp_raw > mx) wp_raw = mx;
+              if (wp_raw < mn) wp_raw = mn;
+            }
+            wp_pred = (wp_raw + 3) >> 3;
+          }
+          for (uint32_t r = 0; r < ch.ref_count; r++) {
+            const DevPlane rp = P.planes[P.refs[ch.ref_off + r]];
+            const int32_t* rrow = P.arena + rp.off + static_cast<size_t>(y) * w;
+            const int32_t* rprev = y ? rrow - w : rrow;
+            const int64_t v = rrow[x];
+            const int64_t vleft = x ? rrow[x - 1] : 0;
+            const int64_t vtop = y ? rprev[x] : vleft;
+            const int64_t vtopleft = (x && y) ? rprev[x - 1] : vleft;
+            const int64_t vpred = DevClampedGradient(static_cast<int32_t>(vleft), static_cast<int32_t>(vtop), static_cast<int32_t>(vtopleft));
+            props[(16 + 4 * r + 0) * PS] = static_cast<int32_t>(DevAbs64(v));
+            props[(16 + 4 * r + 1) * PS] = static_cast<int32_t>(v);
+            props[(16 + 4 * r + 2) * PS] = static_cast<int32_t>(DevAbs64(v - vpred));
+            props[(16 + 4 * r + 3) * PS] = static_cast<int32_t>(v - vpred);
+          }
+          DevTreeNode node = DevLoadNode(tree);
+          while (node.prop >= 0) {
+            const uint32_t pos = props[node.prop * PS] > node.a ? node.b : node.c;
+            node = DevLoadNode(tree + pos);
+          }
+          const uint32_t cluster = static_cast<uint32_t>(node.a) & 0xFFFF;
+          const uint32_t predictor = static_cast<uint32_t>(node.a) >> 16;
+          const uint32_t u = reader.ReadUint(cluster, br);
+          const WT guess = static_cast<WT>(static_cast<int32_t>(node.b)) +
+                           DevPredictW<WT>(predictor, n_left, n_top, n_topleft, n_topright, n_leftleft, n_toptop,
+                                           n_toprightright, wp_pred);
+          // low 32 bits of (unpacked * multiplier + guess), as in make_pixel (encoding.cc:168-173)
+          const int32_t val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) * node.c +
+                                                   static_cast<uint32_t>(guess));
+          row[static_cast<size_t>(x) * LS] = val;
+          out_row[x] = val;
+          leftleft = left;
+          left = val;
+          // slide the previous-row window
+          tl = t;
+          t = tr;
+          tr = trr;
+          if (y > 0 && x + 3 < w) trr = prev[static_cast<size_t>(x + 3) * LS];
+          if (uses_wp) {
+            const WT val8 = static_cast<WT>(val) * 8;
+            const int32_t te = static_cast<int32_t>(wp_raw - val8);
+            er_cur[static_cast<size_t>(x) * LS] = te;
+            const bool more = x + 2 < w;  // position x + 2 exists in the previous row
+            for (uint32_t i = 0; i < 4; i++) {
+              const uint32_t err = static_cast<uint32_t>((DevAbsW<WT>(prediction[i] - val8) + 3) >> 3);
+              pe_cur[i][static_cast<size_t>(x) * LS] = static_cast<int32_t>(err);
+              // next pixel: NW <- N, N <- (entry x + 1) + err, NE <- entry x + 2 (or N at the row end)
+              const uint32_t n_next = eNE[i] + err;
+              eNW[i] = eN[i];
+              eN[i] = n_next;
+              eNE[i] = more ? static_cast<uint32_t>(pe_prv[i][static_cast<size_t>(x + 2) * LS]) : n_next;
+            }
+            teW = te;
+            teNW = teN;
+            teN = teNE;
+            teNE = more ? er_prv[static_cast<size_t>(x + 2) * LS] : teN;
+          }
         }
-        DevTreeNode node = DevLoadNode(tree);
-        while (node.prop >= 0) {
-          const uint32_t pos = props[node.prop * PS] > node.a ? node.b : node.c;
-          node = DevLoadNode(tree + pos);
-        }
-        const uint32_t cluster = static_cast<uint32_t>(node.a) & 0xFFFF;
-        const uint32_t predictor = static_cast<uint32_t>(node.a) >> 16;
-        const uint32_t u = reader.ReadUint(cluster, br);
-        const int64_t guess = static_cast<int64_t>(static_cast<int32_t>(node.b)) + DevPredictOne(predictor, n, wp_pred);
-        const int64_t val64 = static_cast<int64_t>(DevUnpackSigned(u)) * static_cast<int64_t>(node.c) + guess;
-        const int32_t val = static_cast<int32_t>(val64);
-        row[static_cast<size_t>(x) * LS] = val;
-        out_row[x] = val;
-        leftleft = left;
-        left = val;
-        if (uses_wp) wp.Update(val, x, y);
       }
     }
   }
   uint32_t status = kStatusOk;
-  if (!code.use_prefix && reader.state != (0x13u << 16)) status |= kStatusBadFinalState;
-  if (br.Pos() > st.bit_end) status |= kStatusOverread;
+  if (lane_valid) {
+    if (!code.use_prefix && reader.state != (0x13u << 16)) status |= kStatusBadFinalState;
+    if (br.Pos() > st.bit_end) status |= kStatusOverread;
+  }
   return status;
 }
 

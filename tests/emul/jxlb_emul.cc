@@ -18,6 +18,8 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
                      uint32_t data_type, uint32_t endianness, size_t align, uint8_t* out, size_t out_cap,
                      uint64_t* frame_offsets, char* err, size_t errlen) {
   try {
+    const bool force_wide = (endianness & 0x100) != 0;  // test hook: run the 64-bit predictor path
+    endianness &= 0xFF;
     PixelFormat fmt;
     fmt.num_channels = num_channels;
     fmt.data_type = data_type;
@@ -51,6 +53,9 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     P.wp_width = b.wp_width;
     P.lz77 = lz.data();
     P.num_streams = b.streams.size();
+    P.warp_chans = b.warp_chans.data();
+    P.warp_dims_off = b.warp_dims_off.data();
+    P.warp_dims = b.warp_dims.data();
     for (uint32_t s = 0; s < b.streams.size(); s++) {
       // same addressing as the kernel: warp = s / 32, lane = s % 32
       const uint32_t warp = s / 32, lane = s % 32;
@@ -62,7 +67,9 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       m.lane_stride = 32;
       m.ring = ring.data() + static_cast<size_t>(warp) * 3 * b.wp_width * 32 + lane;
       m.wp = wp.data() + static_cast<size_t>(warp) * 10 * (b.wp_width + 2) * 32 + lane;
-      uint32_t st = DevDecodeModularStream(P, s, m);
+      const uint32_t* dims = b.warp_dims.data() + b.warp_dims_off[warp];
+      uint32_t st = force_wide || !b.narrow ? DevDecodeModularStream<int64_t>(P, s, m, dims, b.warp_chans[warp], true)
+                                            : DevDecodeModularStream<int32_t>(P, s, m, dims, b.warp_chans[warp], true);
       if (st != 0) throw Error("stream " + std::to_string(s) + " failed with status " + std::to_string(st));
     }
     const uint32_t nt = 4;  // emulate a few cooperating workers

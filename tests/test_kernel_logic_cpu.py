@@ -30,3 +30,11 @@ def test_unsupported_files_fail_loudly():
     for name in ["sample_jpg.jxl", "2bit.jxl"]:
         with pytest.raises(emul_lib.EmulError):
             emul_lib.decode([read_golden(name)], 3, jxlo.UINT8, [(600, 800)])
+
+
+def test_wide_predictor_path_matches_oracle():
+    # 0x100 in the endianness argument is the emulation's hook for the 64-bit predictor arithmetic
+    a, b = read_golden("bench.jxl"), read_golden("sample.jxl")
+    got = emul_lib.decode([a, b], 4, jxlo.UINT8, [(1433, 2122), (50, 40)], endianness=0x100)
+    assert np.array_equal(got[0], jxlo.decode(a, 4, jxlo.UINT8))
+    assert np.array_equal(got[1], jxlo.decode(b, 4, jxlo.UINT8))
