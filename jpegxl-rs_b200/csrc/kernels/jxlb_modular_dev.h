@@ -490,6 +490,16 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
       out = P.arena + pl.off;
     }
     const DevTreeNode* tree = P.tree + ch.tree_off;
+    // The first two levels of the tree are walked for every sample: keep them in registers.
+    DevTreeNode root{}, root_l{}, root_r{};
+    root.prop = -1;
+    if (k < my_chans) {
+      root = DevLoadNode(tree);
+      if (root.prop >= 0) {
+        root_l = DevLoadNode(tree + root.b);
+        root_r = DevLoadNode(tree + root.c);
+      }
+    }
     const bool uses_wp = ch.uses_wp != 0;
     props[0] = static_cast<int32_t>(ch.prop0);
     props[15 * PS] = 0;
@@ -618,7 +628,8 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
             props[(16 + 4 * r + 2) * PS] = static_cast<int32_t>(DevAbs64(v - vpred));
             props[(16 + 4 * r + 3) * PS] = static_cast<int32_t>(v - vpred);
           }
-          DevTreeNode node = DevLoadNode(tree);
+          DevTreeNode node = root;
+          if (node.prop >= 0) node = props[node.prop * PS] > node.a ? root_l : root_r;
           while (node.prop >= 0) {
             const uint32_t pos = props[node.prop * PS] > node.a ? node.b : node.c;
             node = DevLoadNode(tree + pos);
