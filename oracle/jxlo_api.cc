@@ -65,4 +65,34 @@ int jxlo_write_pixels(void* h, uint32_t num_channels, uint32_t data_type, uint32
 
 void jxlo_free(void* h) { delete static_cast<DecodedImage*>(h); }
 
+// ---- known-answer hooks for the transform restatement (tests/test_oracle_vardct.py) ----
+// rows x cols pixels -> coefficients in the min x max layout (ComputeScaledDCT).
+void jxlo_scaled_dct(int rows, int cols, const float* pixels, float* coeffs) {
+  std::vector<float> scratch(static_cast<size_t>(rows) * cols + 3 * std::max(rows, cols) + 16);
+  ScaledDCT(rows, cols, pixels, cols, coeffs, scratch.data());
+}
+void jxlo_scaled_idct(int rows, int cols, const float* coeffs, float* pixels) {
+  std::vector<float> from(coeffs, coeffs + static_cast<size_t>(rows) * cols);
+  std::vector<float> scratch(static_cast<size_t>(rows) * cols + 2 * std::max(rows, cols) + 16);
+  ScaledIDCT(rows, cols, from.data(), pixels, cols, scratch.data());
+}
+// TransformToPixels for any AcStrategy; pixels is (8 * covered_y) x (8 * covered_x), dense.
+void jxlo_transform_to_pixels(int strategy, const float* coeffs, float* pixels) {
+  const size_t n = 64u * kCoveredX[strategy] * kCoveredY[strategy];
+  std::vector<float> c(coeffs, coeffs + n), scratch(3 * n + 64);
+  TransformToPixels(strategy, c.data(), pixels, 8 * kCoveredX[strategy], scratch.data());
+}
+void jxlo_llf_from_dc(int strategy, const float* dc, size_t dc_stride, float* llf) {
+  LowestFrequenciesFromDC(strategy, dc, dc_stride, llf);
+}
+void jxlo_natural_coeff_order(int strategy, uint32_t* order) { NaturalCoeffOrder(strategy, order); }
+// Library dequantisation table of quant table `table` (3 * 64 * rx * ry floats); returns the count.
+size_t jxlo_library_quant_table(int table, float* out, size_t cap) {
+  std::vector<float> t = ComputeQuantTable(LibraryEncoding(table), table);
+  if (out && cap >= t.size()) std::memcpy(out, t.data(), t.size() * sizeof(float));
+  return t.size();
+}
+float jxlo_fast_powf(float b, float e) { return FastPowf(b, e); }
+float jxlo_srgb_from_linear(float v) { return SrgbFromLinear(v); }
+
 }  // extern "C"

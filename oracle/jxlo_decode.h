@@ -84,7 +84,7 @@ inline FrameHeader DecodeFrame(BitReader& br, CodestreamState* cs, bool is_previ
 
   auto section = [&](size_t i) { return BitReader(data + base + toc.offsets[i], toc.logical_size[i]); };
   auto dc_global = [&](BitReader& r) {
-    if (fh.flags & kFlagPatches) ReadPatches(r, dim, cs->meta, &feat);
+    if (fh.flags & kFlagPatches) ReadPatches(r, dim, cs->meta, *cs, &feat);
     JXLO_CHECK(!(fh.flags & kFlagSplines), "splines are not supported by the oracle");
     JXLO_CHECK(!(fh.flags & kFlagNoise), "noise is not supported by the oracle");
     if (!r.ReadBool()) {  // DequantMatrices::DecodeDC, lib/jxl/quant_weights.cc:507-520
