@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "jxlo_decode.h"
+#include "jxlo_encode.h"
 
 using namespace jxlo;
 
@@ -92,6 +93,31 @@ size_t jxlo_library_quant_table(int table, float* out, size_t cap) {
   if (out && cap >= t.size()) std::memcpy(out, t.data(), t.size() * sizeof(float));
   return t.size();
 }
+// VarDCT stream generator (oracle/jxlo_encode.h). Returns the codestream size, or 0 on error;
+// call with out == NULL to get the size... the stream is kept until the next call on this thread.
+static thread_local std::vector<uint8_t> g_encoded;
+size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float distance, int strategy_mode,
+                          uint32_t seed, int gab, uint32_t epf_iters, int dc_smoothing, int random_side_info,
+                          uint32_t num_passes, char* err, size_t errlen) {
+  try {
+    EncodeParams p;
+    p.distance = distance;
+    p.strategy_mode = strategy_mode;
+    p.seed = seed;
+    p.gab = gab != 0;
+    p.epf_iters = epf_iters;
+    p.dc_smoothing = dc_smoothing != 0;
+    p.random_side_info = random_side_info != 0;
+    p.num_passes = num_passes;
+    g_encoded = EncodeVarDCT(rgb, xsize, ysize, p);
+    return g_encoded.size();
+  } catch (const std::exception& e) {
+    SetErr(err, errlen, e.what());
+    return 0;
+  }
+}
+void jxlo_encoded_copy(uint8_t* out) { std::memcpy(out, g_encoded.data(), g_encoded.size()); }
+
 float jxlo_fast_powf(float b, float e) { return FastPowf(b, e); }
 float jxlo_srgb_from_linear(float v) { return SrgbFromLinear(v); }
 

@@ -1,0 +1,898 @@
+// ORACLE (test infrastructure, not the product). See jxlo_bits.h.
+//
+// A plain CPU VarDCT *encoder*: the stream generator behind the decoder parity tests and
+// the 4K bench frames (the reference ships no VarDCT fixture larger than 40x50 and libjxl
+// cannot be built here), and the CPU statement of the encode rows of SURVEY.md 8a (E1, E2,
+// E8, E10-E14) that the CUDA encoder will be checked against. It writes conforming
+// codestreams the way libjxl does, without libjxl's rate-distortion heuristics:
+//   headers            lib/jxl/enc_fields.cc, lib/jxl/frame_header.cc:206-440, lib/jxl/enc_toc.cc
+//   RGB -> XYB         lib/jxl/enc_xyb.cc:41-104, lib/jxl/cms/opsin_params.h
+//   forward transforms lib/jxl/enc_transforms-inl.h (ComputeScaledDCT; the 8x8 special
+//                      transforms by inverting the decoder's basis numerically)
+//   quantisation       lib/jxl/enc_group.cc:46-90, :370-524 (no adaptive dead zone)
+//   tokenisation       lib/jxl/enc_entropy_coder.cc:148-244 (mirror of DecodeACVarBlock)
+//   histograms + rANS  lib/jxl/enc_ans.cc:253-364 (EncodeCounts), :1731-1816 (WriteTokens)
+//   DC / AC metadata   lib/jxl/enc_modular.cc (single-leaf gradient trees)
+#ifndef JXLO_ENCODE_H_
+#define JXLO_ENCODE_H_
+
+#include <algorithm>
+#include <map>
+#include <random>
+
+#include "jxlo_render.h"
+#include "jxlo_vardct.h"
+
+namespace jxlo {
+
+class BitWriter {
+ public:
+  void Write(unsigned n, uint64_t v) {  // n <= 56, LSB first
+    for (unsigned i = 0; i < n; i++) {
+      if ((bits_ & 7) == 0) bytes_.push_back(0);
+      if ((v >> i) & 1) bytes_.back() |= static_cast<uint8_t>(1u << (bits_ & 7));
+      bits_++;
+    }
+  }
+  void ZeroPadToByte() { bits_ = (bits_ + 7) & ~size_t{7}; }
+  size_t BitsWritten() const { return bits_; }
+  std::vector<uint8_t>& Bytes() { return bytes_; }
+  void Append(const std::vector<uint8_t>& other) {
+    ZeroPadToByte();
+    bytes_.insert(bytes_.end(), other.begin(), other.end());
+    bits_ = bytes_.size() * 8;
+  }
+
+ private:
+  std::vector<uint8_t> bytes_;
+  size_t bits_ = 0;
+};
+
+inline void WriteU32(BitWriter& w, uint32_t v, U32Dist d0, U32Dist d1, U32Dist d2, U32Dist d3) {
+  const U32Dist d[4] = {d0, d1, d2, d3};
+  for (uint32_t s = 0; s < 4; s++) {
+    if (d[s].bits == 0xFF) {
+      if (d[s].offset == v) {
+        w.Write(2, s);
+        return;
+      }
+    } else if (v >= d[s].offset && (d[s].bits >= 32 || v - d[s].offset < (1ull << d[s].bits))) {
+      w.Write(2, s);
+      w.Write(d[s].bits, v - d[s].offset);
+      return;
+    }
+  }
+  throw Error("jxlo: value not representable in U32 field");
+}
+
+inline void WriteU64(BitWriter& w, uint64_t v) {
+  if (v == 0) {
+    w.Write(2, 0);
+  } else if (v <= 16) {
+    w.Write(2, 1);
+    w.Write(4, v - 1);
+  } else if (v <= 272) {
+    w.Write(2, 2);
+    w.Write(8, v - 17);
+  } else {
+    w.Write(2, 3);
+    w.Write(12, v & 4095);
+    v >>= 12;
+    unsigned shift = 12;
+    while (v > 0 && shift < 60) {
+      w.Write(1, 1);
+      w.Write(8, v & 255);
+      v >>= 8;
+      shift += 8;
+    }
+    if (shift == 60) {
+      if (v > 0) {
+        w.Write(1, 1);
+        w.Write(4, v & 15);
+      } else {
+        w.Write(1, 0);
+      }
+    } else {
+      w.Write(1, 0);
+    }
+  }
+}
+
+inline void WriteF16(BitWriter& w, float f) {
+  w.Write(16, FloatToHalf(f));
+}
+
+inline void WriteVarLenUint8(BitWriter& w, uint32_t v) {
+  if (v == 0) {
+    w.Write(1, 0);
+    return;
+  }
+  w.Write(1, 1);
+  const unsigned n = FloorLog2(v);
+  w.Write(3, n);
+  w.Write(n, v - (1u << n));
+}
+
+inline uint32_t PackSigned(int32_t v) { return (static_cast<uint32_t>(v) << 1) ^ (v < 0 ? 0xFFFFFFFFu : 0u); }
+
+// ---------------------------------------------------------------- entropy coding
+struct Token {
+  uint32_t ctx, value;
+};
+
+struct EncodedUint {
+  uint32_t token, nbits, bits;
+};
+
+inline EncodedUint EncodeHybrid(const HybridUintConfig& c, uint32_t v) {  // HybridUintConfig::Encode, dec_ans.h:73-90
+  if (v < c.split_token) return {v, 0, 0};
+  const uint32_t n = FloorLog2(v);
+  const uint32_t m = v - (1u << n);
+  EncodedUint e;
+  e.token = c.split_token + ((n - c.split_exponent) << (c.msb_in_token + c.lsb_in_token)) +
+            ((m >> (n - c.msb_in_token)) << c.lsb_in_token) + (m & ((1u << c.lsb_in_token) - 1));
+  e.nbits = n - c.msb_in_token - c.lsb_in_token;
+  e.bits = (m >> c.lsb_in_token) & ((1ull << e.nbits) - 1);
+  return e;
+}
+
+// Normalises counts to a sum of 4096 keeping every used symbol (enc_ans.cc:119-219, simplified).
+inline std::vector<int32_t> NormalizeCounts(const std::vector<uint64_t>& counts) {
+  uint64_t total = 0;
+  size_t used = 0;
+  for (uint64_t c : counts) {
+    total += c;
+    used += c != 0;
+  }
+  std::vector<int32_t> out(counts.size(), 0);
+  if (total == 0) {
+    out.assign(1, kAnsTabSize);
+    return out;
+  }
+  JXLO_CHECK(used <= kAnsTabSize, "too many symbols");
+  int64_t sum = 0;
+  size_t largest = 0;
+  for (size_t i = 0; i < counts.size(); i++) {
+    if (!counts[i]) continue;
+    int32_t v = static_cast<int32_t>((counts[i] * kAnsTabSize + total / 2) / total);
+    if (v < 1) v = 1;
+    out[i] = v;
+    sum += v;
+    if (counts[i] > counts[largest] || !counts[largest]) largest = i;
+  }
+  int64_t diff = static_cast<int64_t>(kAnsTabSize) - sum;
+  // spread the correction over the largest entries
+  while (diff != 0) {
+    size_t best = 0;
+    for (size_t i = 0; i < out.size(); i++)
+      if (out[i] > out[best]) best = i;
+    const int64_t step = diff > 0 ? diff : std::max<int64_t>(diff, -(out[best] - 1));
+    JXLO_CHECK(step != 0, "cannot normalise histogram");
+    out[best] += static_cast<int32_t>(step);
+    diff -= step;
+  }
+  return out;
+}
+
+// EncodeCounts-compatible writer (reads back through ReadAnsHistogram).
+inline void WriteAnsHistogram(BitWriter& w, const std::vector<int32_t>& counts) {
+  size_t used = 0, last = 0, first = 0;
+  for (size_t i = 0; i < counts.size(); i++)
+    if (counts[i]) {
+      if (!used) first = i;
+      used++;
+      last = i;
+    }
+  if (used == 1) {
+    w.Write(1, 1);  // simple
+    w.Write(1, 0);  // one symbol
+    WriteVarLenUint8(w, first);
+    return;
+  }
+  w.Write(1, 0);  // not simple
+  w.Write(1, 0);  // not flat
+  // shift = 13: full precision for every count. log = 3 -> three 1 bits, then (shift + 1) - 8 in 3 bits.
+  w.Write(3, 7);
+  w.Write(3, 14 - 8);
+  const size_t length = std::max<size_t>(3, last + 1);
+  WriteVarLenUint8(w, length - 3);
+  static const uint8_t kLen[14] = {5, 4, 4, 4, 4, 4, 3, 3, 3, 3, 3, 6, 7, 7};
+  static const uint8_t kCode[14] = {17, 11, 15, 3, 9, 7, 4, 2, 5, 6, 0, 33, 1, 65};
+  std::vector<int> logcounts(length, 0);
+  int omit_log = -1;
+  size_t omit_pos = 0;
+  for (size_t i = 0; i < length; i++) {
+    const int32_t c = i < counts.size() ? counts[i] : 0;
+    logcounts[i] = c == 0 ? 0 : static_cast<int>(FloorLog2(c)) + 1;
+    if (logcounts[i] > omit_log) {
+      omit_log = logcounts[i];
+      omit_pos = i;
+    }
+    w.Write(kLen[logcounts[i]], kCode[logcounts[i]]);
+  }
+  for (size_t i = 0; i < length; i++) {
+    const int code = logcounts[i];
+    if (i == omit_pos || code <= 1) continue;
+    const int bitcount = PopulationCountPrecision(code - 1, 13);
+    const int32_t c = counts[i];
+    w.Write(bitcount, (c - (1 << (code - 1))) >> (code - 1 - bitcount));
+  }
+}
+
+// A complete entropy-coded stream over `num_ctx` contexts: header (no LZ77, context map,
+// ANS histograms) + symbols. `cluster_of[ctx]` must use ids 0..n-1 without gaps.
+class EntropyEncoder {
+ public:
+  EntropyEncoder(size_t num_ctx, std::vector<uint8_t> cluster_of) : num_ctx_(num_ctx), cluster_of_(std::move(cluster_of)) {
+    JXLO_CHECK(cluster_of_.size() == num_ctx_, "bad cluster map");
+    num_clusters_ = 1;
+    for (uint8_t c : cluster_of_) num_clusters_ = std::max<uint32_t>(num_clusters_, c + 1);
+    cfg_ = HybridUintConfig(4, 2, 0);
+  }
+
+  // Pass 1: statistics over every token that will be written with this code.
+  void Count(const std::vector<Token>& tokens) {
+    if (hist_.empty()) hist_.assign(num_clusters_, std::vector<uint64_t>());
+    for (const Token& t : tokens) {
+      const EncodedUint e = EncodeHybrid(cfg_, t.value);
+      std::vector<uint64_t>& h = hist_[cluster_of_[t.ctx]];
+      if (h.size() <= e.token) h.resize(e.token + 1, 0);
+      h[e.token]++;
+    }
+  }
+
+  void WriteHeader(BitWriter& w) {
+    if (hist_.empty()) hist_.assign(num_clusters_, std::vector<uint64_t>());
+    w.Write(1, 0);  // no LZ77
+    if (num_ctx_ > 1) WriteContextMap(w);
+    w.Write(1, 0);  // ANS, not prefix codes
+    size_t max_alphabet = 1;
+    for (auto& h : hist_) max_alphabet = std::max(max_alphabet, h.size());
+    log_alpha_ = 5;
+    while ((size_t{1} << log_alpha_) < max_alphabet) log_alpha_++;
+    JXLO_CHECK(log_alpha_ <= 8, "alphabet too large");
+    w.Write(2, log_alpha_ - 5);
+    for (uint32_t c = 0; c < num_clusters_; c++) {  // uint configs
+      w.Write(CeilLog2(log_alpha_ + 1), cfg_.split_exponent);
+      w.Write(CeilLog2(cfg_.split_exponent + 1), cfg_.msb_in_token);
+      w.Write(CeilLog2(cfg_.split_exponent - cfg_.msb_in_token + 1), cfg_.lsb_in_token);
+    }
+    const uint32_t ts = 1u << log_alpha_;
+    alias_.assign(static_cast<size_t>(num_clusters_) * ts, AliasEntry{});
+    freq_.assign(num_clusters_, std::vector<int32_t>());
+    reverse_.assign(num_clusters_, std::vector<std::vector<uint16_t>>());
+    for (uint32_t c = 0; c < num_clusters_; c++) {
+      std::vector<int32_t> counts = NormalizeCounts(hist_[c]);
+      WriteAnsHistogram(w, counts);
+      freq_[c] = counts;
+      BuildAliasTable(counts, log_alpha_, &alias_[static_cast<size_t>(c) * ts]);
+      // reverse map from the decoder's own lookup (ANSBuildInfoTable, enc_ans.cc:44-68)
+      reverse_[c].assign(counts.size(), std::vector<uint16_t>());
+      for (size_t s = 0; s < counts.size(); s++) reverse_[c][s].assign(counts[s], 0);
+      const uint32_t log_entry = kAnsLogTabSize - log_alpha_;
+      for (uint32_t res = 0; res < kAnsTabSize; res++) {
+        const AliasEntry& e = alias_[static_cast<size_t>(c) * ts + (res >> log_entry)];
+        const uint32_t pos = res & ((1u << log_entry) - 1);
+        const bool right = pos >= e.cutoff;
+        const uint32_t sym = right ? e.right_value : (res >> log_entry);
+        const uint32_t offset = (right ? e.offsets1 : 0) + pos;
+        if (sym < reverse_[c].size() && offset < reverse_[c][sym].size()) reverse_[c][sym][offset] = res;
+      }
+    }
+  }
+
+  // Pass 2: one ANS stream (32-bit state + interleaved refills and raw bits).
+  void WriteTokens(BitWriter& w, const std::vector<Token>& tokens) const {
+    struct Out { uint32_t nbits, bits; };
+    std::vector<Out> out;
+    out.reserve(tokens.size() * 2);
+    uint32_t state = kAnsSignature << 16;
+    for (size_t i = tokens.size(); i-- > 0;) {
+      const Token& t = tokens[i];
+      const uint32_t c = cluster_of_[t.ctx];
+      const EncodedUint e = EncodeHybrid(cfg_, t.value);
+      if (e.nbits) out.push_back({e.nbits, e.bits});
+      JXLO_CHECK(e.token < freq_[c].size() && freq_[c][e.token] > 0, "token outside the histogram");
+      const uint32_t f = freq_[c][e.token];
+      if ((state >> (32 - kAnsLogTabSize)) >= f) {
+        out.push_back({16, state & 0xFFFF});
+        state >>= 16;
+      }
+      state = ((state / f) << kAnsLogTabSize) | reverse_[c][e.token][state % f];
+    }
+    w.Write(32, state);
+    for (size_t i = out.size(); i-- > 0;) w.Write(out[i].nbits, out[i].bits);
+  }
+
+ private:
+  void WriteContextMap(BitWriter& w) {
+    if (num_clusters_ == 1) {
+      w.Write(1, 1);  // simple
+      w.Write(2, 0);  // zero bits per entry
+      return;
+    }
+    if (num_clusters_ <= 8 && num_ctx_ < 64) {
+      const unsigned bits = CeilLog2(num_clusters_);
+      w.Write(1, 1);
+      w.Write(2, bits);
+      for (uint8_t c : cluster_of_) w.Write(bits, c);
+      return;
+    }
+    w.Write(1, 0);  // not simple
+    w.Write(1, 0);  // no move-to-front
+    std::vector<Token> toks;
+    toks.reserve(num_ctx_);
+    for (uint8_t c : cluster_of_) toks.push_back({0, c});
+    EntropyEncoder nested(1, std::vector<uint8_t>(1, 0));
+    nested.Count(toks);
+    nested.WriteHeader(w);
+    nested.WriteTokens(w, toks);
+  }
+
+  size_t num_ctx_;
+  std::vector<uint8_t> cluster_of_;
+  uint32_t num_clusters_ = 1;
+  HybridUintConfig cfg_;
+  uint32_t log_alpha_ = 5;
+  std::vector<std::vector<uint64_t>> hist_;
+  std::vector<AliasEntry> alias_;
+  std::vector<std::vector<int32_t>> freq_;
+  std::vector<std::vector<std::vector<uint16_t>>> reverse_;
+};
+
+// One self-contained Modular sub-stream (GroupHeader + local single-leaf tree + samples,
+// Gradient predictor). Channels with an empty dimension are skipped, as the decoder does.
+inline void WriteModularStream(BitWriter& w, const std::vector<Channel>& channels) {
+  bool any = false;
+  for (const Channel& c : channels) any |= c.w > 0 && c.h > 0;
+  if (channels.empty()) return;
+  w.Write(1, 0);  // use_global_tree = false
+  w.Write(1, 1);  // default weighted-predictor header
+  w.Write(2, 0);  // no transforms
+  if (!any) return;
+  {  // tree: one leaf, predictor Gradient, offset 0, multiplier 1
+    std::vector<Token> t = {{1, 0}, {2, kPredGradient}, {3, 0}, {4, 0}, {5, 0}};
+    EntropyEncoder enc(6, {0, 0, 0, 0, 0, 0});
+    enc.Count(t);
+    enc.WriteHeader(w);
+    enc.WriteTokens(w, t);
+  }
+  std::vector<Token> toks;
+  for (const Channel& c : channels) {
+    if (c.w == 0 || c.h == 0) continue;
+    for (int y = 0; y < c.h; y++) {
+      const int32_t* row = c.Row(y);
+      const int32_t* prev = y ? c.Row(y - 1) : nullptr;
+      for (int x = 0; x < c.w; x++) {
+        const int32_t left = x ? row[x - 1] : (y ? prev[x] : 0);
+        const int32_t top = y ? prev[x] : left;
+        const int32_t topleft = (x && y) ? prev[x - 1] : left;
+        const int32_t pred = ClampedGradient(top, left, topleft);
+        toks.push_back({0, PackSigned(row[x] - pred)});
+      }
+    }
+  }
+  EntropyEncoder enc(1, {0});
+  enc.Count(toks);
+  enc.WriteHeader(w);
+  enc.WriteTokens(w, toks);
+}
+
+// ---------------------------------------------------------------- forward transforms
+// The 8x8 special transforms (IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, AFV0-3) are
+// inverted numerically from the decoder's basis: pixels = A * coeffs, coeffs = A^-1 * pixels.
+inline const std::vector<double>& SpecialForwardMatrix(int strategy) {
+  static std::map<int, std::vector<double>> cache;
+  auto it = cache.find(strategy);
+  if (it != cache.end()) return it->second;
+  std::vector<double> a(64 * 64), inv(64 * 64, 0.0);
+  float scratch[256];
+  for (int k = 0; k < 64; k++) {
+    float coeffs[64] = {0}, px[64];
+    coeffs[k] = 1.0f;
+    TransformToPixels(strategy, coeffs, px, 8, scratch);
+    for (int p = 0; p < 64; p++) a[p * 64 + k] = px[p];
+  }
+  for (int i = 0; i < 64; i++) inv[i * 64 + i] = 1.0;
+  for (int col = 0; col < 64; col++) {  // Gauss-Jordan with partial pivoting
+    int piv = col;
+    for (int r = col + 1; r < 64; r++)
+      if (std::fabs(a[r * 64 + col]) > std::fabs(a[piv * 64 + col])) piv = r;
+    JXLO_CHECK(std::fabs(a[piv * 64 + col]) > 1e-12, "singular transform basis");
+    if (piv != col)
+      for (int k = 0; k < 64; k++) {
+        std::swap(a[piv * 64 + k], a[col * 64 + k]);
+        std::swap(inv[piv * 64 + k], inv[col * 64 + k]);
+      }
+    const double d = 1.0 / a[col * 64 + col];
+    for (int k = 0; k < 64; k++) {
+      a[col * 64 + k] *= d;
+      inv[col * 64 + k] *= d;
+    }
+    for (int r = 0; r < 64; r++) {
+      if (r == col) continue;
+      const double f = a[r * 64 + col];
+      if (f == 0.0) continue;
+      for (int k = 0; k < 64; k++) {
+        a[r * 64 + k] -= f * a[col * 64 + k];
+        inv[r * 64 + k] -= f * inv[col * 64 + k];
+      }
+    }
+  }
+  return cache[strategy] = inv;
+}
+
+// TransformFromPixels: pixels (stride) -> coefficients in the decoder's layout.
+inline void TransformFromPixels(int strategy, const float* pixels, size_t stride, float* coeffs, float* scratch) {
+  if (IsPlainDCT(strategy)) {
+    ScaledDCT(kCoveredY[strategy] * 8, kCoveredX[strategy] * 8, pixels, stride, coeffs, scratch);
+    return;
+  }
+  const std::vector<double>& m = SpecialForwardMatrix(strategy);
+  for (int k = 0; k < 64; k++) {
+    double s = 0;
+    for (int p = 0; p < 64; p++) s += m[k * 64 + p] * pixels[(p / 8) * stride + (p % 8)];
+    coeffs[k] = static_cast<float>(s);
+  }
+}
+
+// ---------------------------------------------------------------- colour
+inline float SrgbToLinear(float v) {
+  return v <= 0.04045f ? v / 12.92f : std::pow((v + 0.055f) / 1.055f, 2.4f);
+}
+
+// lib/jxl/enc_xyb.cc:41-104 with the default opsin matrix (intensity target 255).
+inline void LinearRgbToXyb(float r, float g, float b, float* x, float* y, float* bb) {
+  const float bias = 0.0037930732552754493f;
+  const float kM[9] = {0.30f, 1.0f - 0.078f - 0.30f, 0.078f, 0.23f, 1.0f - 0.078f - 0.23f, 0.078f,
+                       0.24342268924547819f, 0.20476744424496821f, 1.0f - 0.24342268924547819f - 0.20476744424496821f};
+  float mixed[3];
+  for (int i = 0; i < 3; i++) {
+    mixed[i] = kM[3 * i] * r + kM[3 * i + 1] * g + kM[3 * i + 2] * b + bias;
+    if (mixed[i] < 0) mixed[i] = 0;
+    mixed[i] = std::cbrt(mixed[i]) - std::cbrt(bias);
+  }
+  *x = 0.5f * (mixed[0] - mixed[1]);
+  *y = 0.5f * (mixed[0] + mixed[1]);
+  *bb = mixed[2];
+}
+
+// ---------------------------------------------------------------- the encoder
+struct EncodeParams {
+  float distance = 1.0f;
+  // 0: DCT8 only; 1: seeded random mix of all 27 strategies (decoder coverage);
+  // 2: variance heuristic over {8x8, 16x16, 32x32, 16x8, 8x16, 64x64}
+  int strategy_mode = 2;
+  uint32_t seed = 1;
+  bool gab = true;
+  uint32_t epf_iters = 2;
+  bool dc_smoothing = true;
+  bool random_side_info = false;  // random CfL factors, quant field and EPF sharpness (decoder coverage)
+  uint32_t x_qm_scale = 3, b_qm_scale = 2;
+  uint32_t num_passes = 1;        // > 1: coefficients split by magnitude shift (passes.shift)
+};
+
+struct EncoderStats {
+  size_t num_groups = 0, num_varblocks = 0, bytes = 0;
+  size_t strategy_count[27] = {0};
+};
+
+inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize) {
+  w.Write(16, 0x0AFF);
+  // SizeHeader
+  w.Write(1, 0);  // not "small"
+  WriteU32(w, ysize, BitsOffset(9, 1), BitsOffset(13, 1), BitsOffset(18, 1), BitsOffset(30, 1));
+  w.Write(3, 0);  // no fixed aspect ratio
+  WriteU32(w, xsize, BitsOffset(9, 1), BitsOffset(13, 1), BitsOffset(18, 1), BitsOffset(30, 1));
+  w.Write(1, 1);  // ImageMetadata all_default: 8-bit sRGB, XYB encoded, no extra channels
+  w.Write(1, 1);  // CustomTransformData all_default
+  w.ZeroPadToByte();
+}
+
+inline void WriteFrameHeader(BitWriter& w, const EncodeParams& p) {
+  w.Write(1, 0);  // not all_default
+  w.Write(2, kRegularFrame);
+  w.Write(1, 0);  // VarDCT
+  WriteU64(w, p.dc_smoothing ? uint64_t{0} : uint64_t{kFlagSkipAdaptiveDCSmoothing});
+  WriteU32(w, 1, Val(1), Val(2), Val(4), Val(8));  // upsampling
+  w.Write(3, p.x_qm_scale);
+  w.Write(3, p.b_qm_scale);
+  WriteU32(w, p.num_passes, Val(1), Val(2), Val(3), BitsOffset(3, 4));
+  if (p.num_passes != 1) {
+    WriteU32(w, 0, Val(0), Val(1), Val(2), BitsOffset(1, 3));  // num_downsample
+    for (uint32_t i = 0; i + 1 < p.num_passes; i++) w.Write(2, p.num_passes - 1 - i);  // shift
+  }
+  w.Write(1, 0);  // no custom size or origin
+  WriteU32(w, 0, Val(0), Val(1), Val(2), BitsOffset(2, 3));  // blend mode kReplace
+  w.Write(1, 1);  // is_last
+  WriteU32(w, 0, Val(0), Bits(4), BitsOffset(5, 16), BitsOffset(10, 48));  // name
+  // LoopFilter
+  if (p.gab && p.epf_iters == 2) {
+    w.Write(1, 1);  // all_default
+  } else {
+    w.Write(1, 0);
+    w.Write(1, p.gab ? 1 : 0);
+    if (p.gab) w.Write(1, 0);  // default weights
+    w.Write(2, p.epf_iters);
+    if (p.epf_iters > 0) {
+      w.Write(1, 0);  // epf_sharp_custom
+      w.Write(1, 0);  // epf_weight_custom
+      w.Write(1, 0);  // epf_sigma_custom
+    }
+    WriteU64(w, 0);  // loop-filter extensions
+  }
+  WriteU64(w, 0);  // frame-header extensions
+}
+
+inline void WriteToc(BitWriter& w, const std::vector<std::vector<uint8_t>>& sections) {
+  w.Write(1, 0);  // not permuted
+  w.ZeroPadToByte();
+  for (const auto& s : sections)
+    WriteU32(w, s.size(), Bits(10), BitsOffset(14, 1024), BitsOffset(22, 17408), BitsOffset(30, 4211712));
+  w.ZeroPadToByte();
+}
+
+// Static clustering of the 495 * 15 AC contexts of the default block context map.
+inline std::vector<uint8_t> ACContextClusters(const BlockCtxMap& bctx) {
+  const uint32_t n = bctx.NumACContexts();
+  std::vector<uint8_t> cl(n, 0);
+  const uint32_t nz_end = bctx.num_ctxs * kNonZeroBuckets;
+  for (uint32_t ctx = 0; ctx < n; ctx++) {
+    if (ctx < nz_end) {
+      const uint32_t bucket = ctx / bctx.num_ctxs, block_ctx = ctx % bctx.num_ctxs;
+      cl[ctx] = static_cast<uint8_t>((block_ctx < 7 ? 0 : 10) + std::min<uint32_t>(9, bucket / 4));
+    } else {
+      const uint32_t rel = ctx - nz_end;
+      const uint32_t block_ctx = rel / kZeroDensityContextCount, zdc = rel % kZeroDensityContextCount;
+      const uint32_t idx = zdc >> 1, prev = zdc & 1;
+      cl[ctx] = static_cast<uint8_t>(20 + (block_ctx < 7 ? 0 : 60) + std::min<uint32_t>(29, idx / 8) * 2 + prev);
+    }
+  }
+  // compact ids so that every cluster id is in use
+  std::vector<int> remap(256, -1);
+  int next = 0;
+  for (uint8_t& c : cl) {
+    if (remap[c] < 0) remap[c] = next++;
+    c = static_cast<uint8_t>(remap[c]);
+  }
+  return cl;
+}
+
+inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, const EncodeParams& p,
+                                         EncoderStats* stats = nullptr) {
+  JXLO_CHECK(xsize > 0 && ysize > 0, "empty image");
+  // ---- frame geometry
+  FrameHeader fh;
+  fh.is_modular = false;
+  fh.xsize = xsize;
+  fh.ysize = ysize;
+  fh.x_qm_scale = p.x_qm_scale;
+  fh.b_qm_scale = p.b_qm_scale;
+  fh.flags = p.dc_smoothing ? uint64_t{0} : uint64_t{kFlagSkipAdaptiveDCSmoothing};
+  fh.lf = DefaultLoopFilter();
+  fh.lf.gab = p.gab;
+  fh.lf.epf_iters = p.epf_iters;
+  fh.passes.num_passes = p.num_passes;
+  for (uint32_t i = 0; i + 1 < p.num_passes; i++) fh.passes.shift[i] = p.num_passes - 1 - i;
+  const FrameDimensions dim = ToFrameDimensions(fh);
+  const size_t W = dim.xsize_blocks, H = dim.ysize_blocks;
+  const size_t PW = W * 8, PH = H * 8;
+  std::mt19937 rng(p.seed);
+
+  // ---- RGB8 -> XYB planes, edge-replicated to whole blocks
+  Plane xyb[3] = {Plane(PW, PH), Plane(PW, PH), Plane(PW, PH)};
+  {
+    float lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = SrgbToLinear(i / 255.0f);
+    for (size_t y = 0; y < PH; y++) {
+      const size_t sy = std::min<size_t>(y, ysize - 1);
+      for (size_t x = 0; x < PW; x++) {
+        const size_t sx = std::min<size_t>(x, xsize - 1);
+        const uint8_t* px = rgb + (sy * xsize + sx) * 3;
+        LinearRgbToXyb(lut[px[0]], lut[px[1]], lut[px[2]], &xyb[0].Row(y)[x], &xyb[1].Row(y)[x], &xyb[2].Row(y)[x]);
+      }
+    }
+  }
+
+  // ---- global quantiser: dequant step = table * inv_global_scale / raw_quant
+  // quant value ~ 0.79 / distance as in libjxl's InitialQuantField target
+  const float quant_ac = 0.79f / std::max(0.1f, p.distance);
+  const int base_raw = 16;  // typical raw quant field value
+  const int global_scale = std::max(1, std::min(65535 + 8192, static_cast<int>(quant_ac * 65536 / base_raw + 0.5f)));
+  const int quant_dc = std::max(1, std::min(65536, static_cast<int>(0.9f / std::max(0.1f, p.distance) * 65536 / global_scale + 0.5f)));
+  const float inv_global_scale = 1.0 * 65536 / global_scale;
+  const float dc_quant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256};
+  float mul_dc[3];
+  for (int c = 0; c < 3; c++) mul_dc[c] = (inv_global_scale / quant_dc) * dc_quant[c];
+  const float x_dm = std::pow(1 / (1.25f), p.x_qm_scale - 2.0f), b_dm = std::pow(1 / (1.25f), p.b_qm_scale - 2.0f);
+
+  // ---- side information per block
+  std::vector<uint8_t> acs(W * H, 0xFF), sharp(W * H, 4);
+  std::vector<int32_t> raw_quant(W * H, 0);
+  const size_t cmw = DivCeil(W, size_t{8}), cmh = DivCeil(H, size_t{8});
+  std::vector<int8_t> ytox(cmw * cmh, 0), ytob(cmw * cmh, 0);
+  if (p.random_side_info) {
+    for (auto& v : ytox) v = static_cast<int8_t>(static_cast<int>(rng() % 21) - 10);
+    for (auto& v : ytob) v = static_cast<int8_t>(static_cast<int>(rng() % 21) - 10);
+    for (auto& v : sharp) v = rng() % 8;
+  }
+  auto block_variance = [&](size_t bx, size_t by, size_t nx, size_t ny) {
+    double s = 0, s2 = 0;
+    const size_t n = nx * ny * 64;
+    for (size_t y = by * 8; y < (by + ny) * 8; y++)
+      for (size_t x = bx * 8; x < (bx + nx) * 8; x++) {
+        const double v = xyb[1].Row(y)[x];
+        s += v;
+        s2 += v * v;
+      }
+    return s2 / n - (s / n) * (s / n);
+  };
+  auto fits = [&](size_t bx, size_t by, int s) {
+    const size_t cx = kCoveredX[s], cy = kCoveredY[s];
+    if (bx + cx > W || by + cy > H) return false;
+    if (bx / 32 != (bx + cx - 1) / 32 || by / 32 != (by + cy - 1) / 32) return false;  // stay inside one group
+    for (size_t y = by; y < by + cy; y++)
+      for (size_t x = bx; x < bx + cx; x++)
+        if (acs[y * W + x] != 0xFF) return false;
+    return true;
+  };
+  size_t num_varblocks = 0;
+  for (size_t by = 0; by < H; by++) {
+    for (size_t bx = 0; bx < W; bx++) {
+      if (acs[by * W + bx] != 0xFF) continue;
+      int s = kDCT;
+      if (p.strategy_mode == 1) {
+        // all 27 strategies; the larger ones only where they are aligned to their own size
+        for (int attempt = 0; attempt < 4; attempt++) {
+          const int cand = rng() % 27;
+          const size_t cx = kCoveredX[cand], cy = kCoveredY[cand];
+          if (cx * cy > 16 && (rng() % 4) != 0) continue;  // keep huge blocks rare
+          if (bx % std::min<size_t>(cx, 8) == 0 && by % std::min<size_t>(cy, 8) == 0 && fits(bx, by, cand)) {
+            s = cand;
+            break;
+          }
+        }
+      } else if (p.strategy_mode == 2) {
+        static const int kCands[] = {kDCT64X64, kDCT32X32, kDCT16X16, kDCT16X8, kDCT8X16};
+        static const double kThresh[] = {2e-6, 1e-5, 6e-5, 1.5e-4, 1.5e-4};
+        for (int i = 0; i < 5; i++) {
+          const int cand = kCands[i];
+          const size_t cx = kCoveredX[cand], cy = kCoveredY[cand];
+          if (bx % cx || by % cy || !fits(bx, by, cand)) continue;
+          if (block_variance(bx, by, cx, cy) < kThresh[i] * p.distance) {
+            s = cand;
+            break;
+          }
+        }
+      }
+      for (size_t y = 0; y < kCoveredY[s]; y++)
+        for (size_t x = 0; x < kCoveredX[s]; x++)
+          acs[(by + y) * W + bx + x] = static_cast<uint8_t>((s << 1) | ((x | y) == 0 ? 1 : 0));
+      int rq = base_raw;
+      if (p.random_side_info) rq = 8 + rng() % 24;
+      raw_quant[by * W + bx] = rq;
+      num_varblocks++;
+      if (stats) stats->strategy_count[s]++;
+    }
+  }
+
+  // ---- DC: block means, quantised with chroma-from-luma on DC (default factors: X 0, B 1)
+  std::vector<Channel> dcq = {Channel(W, H), Channel(W, H), Channel(W, H)};  // [0] = Y, [1] = X, [2] = B
+  Plane dc_rec[3] = {Plane(W, H), Plane(W, H), Plane(W, H)};
+  for (size_t by = 0; by < H; by++)
+    for (size_t bx = 0; bx < W; bx++) {
+      float mean[3];
+      for (int c = 0; c < 3; c++) {
+        double s = 0;
+        for (int y = 0; y < 8; y++)
+          for (int x = 0; x < 8; x++) s += xyb[c].Row(by * 8 + y)[bx * 8 + x];
+        mean[c] = static_cast<float>(s / 64);
+      }
+      const int32_t qy = static_cast<int32_t>(std::lrintf(mean[1] / mul_dc[1]));
+      const float ry = qy * mul_dc[1];
+      const int32_t qx = static_cast<int32_t>(std::lrintf((mean[0] - 0.0f * ry) / mul_dc[0]));
+      const int32_t qb = static_cast<int32_t>(std::lrintf((mean[2] - 1.0f * ry) / mul_dc[2]));
+      dcq[0].Row(by)[bx] = qy;
+      dcq[1].Row(by)[bx] = qx;
+      dcq[2].Row(by)[bx] = qb;
+      dc_rec[1].Row(by)[bx] = ry;
+      dc_rec[0].Row(by)[bx] = std::fmaf(ry, 0.0f, qx * mul_dc[0]);
+      dc_rec[2].Row(by)[bx] = std::fmaf(ry, 1.0f, qb * mul_dc[2]);
+    }
+
+  // ---- AC: transform, quantise, tokenise per group and pass
+  const BlockCtxMap bctx;
+  const std::vector<uint8_t> clusters = ACContextClusters(bctx);
+  std::vector<float> tables[17];
+  auto table_for = [&](int strategy) -> const std::vector<float>& {
+    const int t = kStrategyToQuantTable[strategy];
+    if (tables[t].empty()) tables[t] = ComputeQuantTable(LibraryEncoding(t), t);
+    return tables[t];
+  };
+  std::vector<uint32_t> natural[13];
+  auto order_for = [&](int strategy) -> const std::vector<uint32_t>& {
+    const int ord = kStrategyOrder[strategy];
+    if (natural[ord].empty()) {
+      natural[ord].resize(64u * kCoveredX[strategy] * kCoveredY[strategy]);
+      NaturalCoeffOrder(strategy, natural[ord].data());
+    }
+    return natural[ord];
+  };
+  const size_t num_groups = dim.num_groups, num_passes = p.num_passes;
+  std::vector<std::vector<Token>> group_tokens(num_groups * num_passes);
+  const float* biases = kDefaultQuantBias;
+  std::vector<float> coeff(3 * 65536), scratch(3 * 65536 + 1024);
+  std::vector<int32_t> quantized(3 * 65536);
+  for (size_t g = 0; g < num_groups; g++) {
+    const BlockRect r = BlockGroupRect(dim, g);
+    std::vector<std::vector<int32_t>> nzeros(num_passes, std::vector<int32_t>(3 * 32 * 32, 0));
+    for (size_t by = 0; by < r.ys; by++) {
+      for (size_t bx = 0; bx < r.xs; bx++) {
+        const size_t pos = (r.y0 + by) * W + r.x0 + bx;
+        const uint8_t a = acs[pos];
+        if (!(a & 1)) continue;
+        const int s = a >> 1;
+        const size_t cx = kCoveredX[s], cy = kCoveredY[s];
+        const size_t covered = cx * cy, size = covered * 64, log2c = kLog2Covered[s];
+        const std::vector<float>& dm = table_for(s);
+        const std::vector<uint32_t>& order = order_for(s);
+        const float sd_base = inv_global_scale / raw_quant[pos];
+        const float sd[3] = {sd_base * x_dm, sd_base, sd_base * b_dm};
+        const size_t tile = ((r.y0 + by) / 8) * cmw + (r.x0 + bx) / 8;
+        const float x_cc = 0.0f + ytox[tile] * (1.0f / 84), b_cc = 1.0f + ytob[tile] * (1.0f / 84);
+        for (int c = 0; c < 3; c++)
+          TransformFromPixels(s, xyb[c].Row((r.y0 + by) * 8) + (r.x0 + bx) * 8, PW, coeff.data() + c * size, scratch.data());
+        // Y first (the decoder adds ratio * dequantised Y to X and B)
+        for (size_t k = 0; k < size; k++) {
+          const int32_t q = static_cast<int32_t>(std::lrintf(coeff[size + k] / (dm[size + k] * sd[1])));
+          quantized[size + k] = q;
+          const float dq_y = AdjustQuantBias(1, q, biases) * (dm[size + k] * sd[1]);
+          quantized[k] = static_cast<int32_t>(std::lrintf((coeff[k] - x_cc * dq_y) / (dm[k] * sd[0])));
+          quantized[2 * size + k] =
+              static_cast<int32_t>(std::lrintf((coeff[2 * size + k] - b_cc * dq_y) / (dm[2 * size + k] * sd[2])));
+        }
+        // the lowest frequencies come from the DC image
+        const size_t lcx = std::max(cx, cy), lcy = std::min(cx, cy);
+        for (int c = 0; c < 3; c++)
+          for (size_t y = 0; y < lcy; y++)
+            for (size_t x = 0; x < lcx; x++) quantized[c * size + y * lcx * 8 + x] = 0;
+        // tokens, channel order Y, X, B; pass i carries (value >> shift_i) - (what earlier passes carried)
+        for (int c : {1, 0, 2}) {
+          for (size_t pass = 0; pass < num_passes; pass++) {
+            const uint32_t shift = fh.passes.shift[pass];
+            const uint32_t prev_shift = pass == 0 ? 32 : fh.passes.shift[pass - 1];
+            auto pass_value = [&](int32_t v) -> int32_t {
+              // sum over passes of (part << shift) must equal v: part_i = (v >> s_i) - ((v >> s_{i-1}) << (s_{i-1} - s_i))
+              const int64_t hi = prev_shift >= 32 ? 0 : (static_cast<int64_t>(v) >> prev_shift);
+              const int64_t cur = static_cast<int64_t>(v) >> shift;
+              return static_cast<int32_t>(cur - (prev_shift >= 32 ? 0 : (hi << (prev_shift - shift))));
+            };
+            std::vector<Token>& toks = group_tokens[pass * num_groups + g];
+            int32_t* row_nz = &nzeros[pass][(c * 32 + by) * 32];
+            const int32_t* row_top = by == 0 ? nullptr : row_nz - 32;
+            const int32_t predicted = PredictFromTopAndLeft(row_top, row_nz, bx, 32);
+            const size_t ord = kStrategyOrder[s];
+            const size_t block_ctx = bctx.Context(0, raw_quant[(r.y0 + by) * W + r.x0 + bx], ord, c);
+            size_t nz = 0;
+            for (size_t k = covered; k < size; k++) nz += pass_value(quantized[c * size + order[k]]) != 0;
+            toks.push_back({bctx.NonZeroContext(predicted, block_ctx), static_cast<uint32_t>(nz)});
+            for (size_t y = 0; y < cy; y++)
+              for (size_t x = 0; x < cx; x++) row_nz[bx + x + y * 32] = (nz + covered - 1) >> log2c;
+            const size_t histo_offset = bctx.ZeroDensityContextsOffset(block_ctx);
+            size_t prev = (nz > size / 16 ? 0 : 1);
+            for (size_t k = covered; k < size && nz != 0; ++k) {
+              const size_t nzl = (nz + covered - 1) >> log2c;
+              const size_t ctx = histo_offset + (kCoeffNumNonzeroContext[nzl] + kCoeffFreqContext[k >> log2c]) * 2 + prev;
+              const int32_t v = pass_value(quantized[c * size + order[k]]);
+              const uint32_t u = PackSigned(v);
+              toks.push_back({static_cast<uint32_t>(ctx), u});
+              prev = u != 0;
+              nz -= prev;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- sections
+  std::vector<std::vector<uint8_t>> sections;
+  auto finish = [&](BitWriter& w) {
+    w.ZeroPadToByte();
+    sections.push_back(w.Bytes());
+  };
+  BitWriter dc_global;
+  {
+    dc_global.Write(1, 1);  // default DC quantisation
+    WriteU32(dc_global, global_scale, BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193));
+    WriteU32(dc_global, quant_dc, Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1));
+    dc_global.Write(1, 1);  // default block context map
+    dc_global.Write(1, 1);  // default colour correlation
+    dc_global.Write(1, 0);  // no global MA tree
+  }
+  std::vector<BitWriter> dc_groups(dim.num_dc_groups);
+  for (size_t g = 0; g < dim.num_dc_groups; g++) {
+    BitWriter& w = dc_groups[g];
+    const BlockRect r = DCGroupRect(dim, g);
+    w.Write(2, 0);  // extra_precision
+    std::vector<Channel> ch = {Channel(r.xs, r.ys), Channel(r.xs, r.ys), Channel(r.xs, r.ys)};
+    for (int c = 0; c < 3; c++)
+      for (size_t y = 0; y < r.ys; y++)
+        for (size_t x = 0; x < r.xs; x++) ch[c].Row(y)[x] = dcq[c].Row(r.y0 + y)[r.x0 + x];
+    WriteModularStream(w, ch);
+    // (no Modular DC-group channels)
+    // AC metadata
+    size_t count = 0;
+    for (size_t y = 0; y < r.ys; y++)
+      for (size_t x = 0; x < r.xs; x++) count += acs[(r.y0 + y) * W + r.x0 + x] & 1;
+    w.Write(CeilLog2(r.xs * r.ys), count - 1);
+    const size_t cx0 = r.x0 >> 3, cy0 = r.y0 >> 3, cw = (r.xs + 7) >> 3, chh = (r.ys + 7) >> 3;
+    std::vector<Channel> meta = {Channel(cw, chh, 3, 3), Channel(cw, chh, 3, 3), Channel(count, 2), Channel(r.xs, r.ys)};
+    for (size_t y = 0; y < chh; y++)
+      for (size_t x = 0; x < cw; x++) {
+        meta[0].Row(y)[x] = ytox[(cy0 + y) * cmw + cx0 + x];
+        meta[1].Row(y)[x] = ytob[(cy0 + y) * cmw + cx0 + x];
+      }
+    size_t num = 0;
+    for (size_t y = 0; y < r.ys; y++)
+      for (size_t x = 0; x < r.xs; x++) {
+        const size_t pos = (r.y0 + y) * W + r.x0 + x;
+        meta[3].Row(y)[x] = sharp[pos];
+        if (!(acs[pos] & 1)) continue;
+        meta[2].Row(0)[num] = acs[pos] >> 1;
+        meta[2].Row(1)[num] = raw_quant[pos] - 1;
+        num++;
+      }
+    WriteModularStream(w, meta);
+  }
+  BitWriter ac_global;
+  std::vector<EntropyEncoder> pass_codes;
+  {
+    ac_global.Write(1, 1);  // default quantisation matrices
+    ac_global.Write(CeilLog2(num_groups), 0);  // one set of histograms
+    for (size_t pass = 0; pass < num_passes; pass++) {
+      WriteU32(ac_global, 0, Val(0x5F), Val(0x13), Val(0), Bits(13));  // natural coefficient orders
+      pass_codes.emplace_back(bctx.NumACContexts(), clusters);
+      for (size_t g = 0; g < num_groups; g++) pass_codes.back().Count(group_tokens[pass * num_groups + g]);
+      pass_codes.back().WriteHeader(ac_global);
+    }
+  }
+  std::vector<BitWriter> ac_groups(num_groups * num_passes);
+  for (size_t pass = 0; pass < num_passes; pass++)
+    for (size_t g = 0; g < num_groups; g++)
+      pass_codes[pass].WriteTokens(ac_groups[pass * num_groups + g], group_tokens[pass * num_groups + g]);
+
+  if (num_groups == 1 && num_passes == 1) {
+    BitWriter all = dc_global;
+    auto append_bits = [&](BitWriter& src) {
+      const size_t n = src.BitsWritten();
+      const std::vector<uint8_t>& b = src.Bytes();
+      for (size_t i = 0; i < n; i++) all.Write(1, (b[i >> 3] >> (i & 7)) & 1);
+    };
+    append_bits(dc_groups[0]);
+    append_bits(ac_global);
+    append_bits(ac_groups[0]);
+    finish(all);
+  } else {
+    finish(dc_global);
+    for (auto& w : dc_groups) finish(w);
+    finish(ac_global);
+    for (auto& w : ac_groups) finish(w);
+  }
+
+  BitWriter out;
+  WriteImageHeaders(out, xsize, ysize);
+  WriteFrameHeader(out, p);
+  WriteToc(out, sections);
+  for (const auto& s : sections) out.Append(s);
+  if (stats) {
+    stats->num_groups = num_groups;
+    stats->num_varblocks = num_varblocks;
+    stats->bytes = out.Bytes().size();
+  }
+  return out.Bytes();
+}
+
+}  // namespace jxlo
+
+#endif  // JXLO_ENCODE_H_
