@@ -12,7 +12,7 @@
 //   quantisation       lib/jxl/enc_group.cc:46-90, :370-524 (no adaptive dead zone)
 //   tokenisation       lib/jxl/enc_entropy_coder.cc:148-244 (mirror of DecodeACVarBlock)
 //   histograms + rANS  lib/jxl/enc_ans.cc:253-364 (EncodeCounts), :1731-1816 (WriteTokens)
-//   DC / AC metadata   lib/jxl/enc_modular.cc (single-leaf gradient trees)
+//   DC / AC metadata   lib/jxl/enc_modular.cc (global tree: fixed weighted-predictor DC tree + AC-metadata tree)
 #ifndef JXLO_ENCODE_H_
 #define JXLO_ENCODE_H_
 
@@ -340,42 +340,162 @@ class EntropyEncoder {
   std::vector<std::vector<std::vector<uint16_t>>> reverse_;
 };
 
-// One self-contained Modular sub-stream (GroupHeader + local single-leaf tree + samples,
-// Gradient predictor). Channels with an empty dimension are skipped, as the decoder does.
-inline void WriteModularStream(BitWriter& w, const std::vector<Channel>& channels) {
-  bool any = false;
-  for (const Channel& c : channels) any |= c.w > 0 && c.h > 0;
-  if (channels.empty()) return;
-  w.Write(1, 0);  // use_global_tree = false
-  w.Write(1, 1);  // default weighted-predictor header
-  w.Write(2, 0);  // no transforms
-  if (!any) return;
-  {  // tree: one leaf, predictor Gradient, offset 0, multiplier 1
-    std::vector<Token> t = {{1, 0}, {2, kPredGradient}, {3, 0}, {4, 0}, {5, 0}};
-    EntropyEncoder enc(6, {0, 0, 0, 0, 0, 0});
-    enc.Count(t);
-    enc.WriteHeader(w);
-    enc.WriteTokens(w, t);
+// ---------------------------------------------------------------- Modular sub-streams (global tree)
+// The DC and AC-metadata streams of a VarDCT frame share one global MA tree, like libjxl's
+// encoder builds it at its default effort (lib/jxl/enc_modular.cc:1185-1215 and MergeTrees): the
+// root splits on the stream id (static property 1); DC streams use the fixed weighted-predictor tree
+// (PredefinedTree kWPFixedDC, lib/jxl/modular/encoding/enc_encoding.cc:66-97, :266-273) and AC-metadata
+// streams the kACMeta tree (:218-265).
+struct EncTreeNode {
+  int property = -1;  // -1: leaf
+  int32_t splitval = 0;
+  int left = -1, right = -1;  // indices into the builder's node list (property > splitval ? left : right)
+  uint32_t predictor = 0;
+};
+
+struct GlobalTree {
+  Tree tree;                  // in decoder (breadth-first) order, leaves numbered in that order
+  std::vector<Token> tokens;  // the tree itself, contexts of lib/jxl/modular/encoding/ma_common.h:13-22
+  size_t num_leaves = 0;
+};
+
+inline int EncTreeFixed(std::vector<EncTreeNode>* n, int property, const std::vector<int32_t>& cutoffs, size_t begin,
+                        size_t end, uint32_t predictor) {
+  const int id = static_cast<int>(n->size());
+  n->push_back(EncTreeNode());
+  if (begin >= end) {
+    (*n)[id].predictor = predictor;
+    return id;
   }
-  std::vector<Token> toks;
-  for (const Channel& c : channels) {
-    if (c.w == 0 || c.h == 0) continue;
-    for (int y = 0; y < c.h; y++) {
-      const int32_t* row = c.Row(y);
-      const int32_t* prev = y ? c.Row(y - 1) : nullptr;
-      for (int x = 0; x < c.w; x++) {
-        const int32_t left = x ? row[x - 1] : (y ? prev[x] : 0);
-        const int32_t top = y ? prev[x] : left;
-        const int32_t topleft = (x && y) ? prev[x - 1] : left;
-        const int32_t pred = ClampedGradient(top, left, topleft);
-        toks.push_back({0, PackSigned(row[x] - pred)});
+  const size_t split = (begin + end) / 2;
+  (*n)[id].property = property;
+  (*n)[id].splitval = cutoffs[split];
+  const int l = EncTreeFixed(n, property, cutoffs, split + 1, end, predictor);
+  const int r = EncTreeFixed(n, property, cutoffs, begin, split, predictor);
+  (*n)[id].left = l;
+  (*n)[id].right = r;
+  return id;
+}
+
+inline GlobalTree BuildGlobalTree(uint32_t num_dc_groups) {
+  std::vector<EncTreeNode> n;
+  auto leaf = [&](uint32_t pred) {
+    n.push_back(EncTreeNode());
+    n.back().predictor = pred;
+    return static_cast<int>(n.size() - 1);
+  };
+  auto split = [&](int prop, int32_t val, int l, int r) {
+    EncTreeNode e;
+    e.property = prop;
+    e.splitval = val;
+    e.left = l;
+    e.right = r;
+    n.push_back(e);
+    return static_cast<int>(n.size() - 1);
+  };
+  static const std::vector<int32_t> kCutoffs = {-500, -392, -255, -191, -127, -95, -63, -47, -31, -23, -15, -11, -7, -4, -3, -1, 0,
+                                                1, 3, 5, 7, 11, 15, 23, 31, 47, 63, 95, 127, 191, 255, 392, 500};
+  const int dc = EncTreeFixed(&n, kWPProp, kCutoffs, 0, kCutoffs.size(), kPredWeighted);
+  // AC metadata: channel 0 / 1 = chroma-from-luma maps, 2 = (strategy row, quant row), 3 = EPF sharpness
+  auto four = [&](int prop, uint32_t pred) {  // splits at 11, 5, 3 on `prop`
+    const int hi = split(prop, 11, leaf(pred), leaf(pred));
+    const int lo = split(prop, 3, leaf(pred), leaf(pred));
+    return split(prop, 5, hi, lo);
+  };
+  const int qf = four(7, kPredLeft), acs = four(7, kPredZero);
+  const int acs_qf = split(2, 0, qf, acs);  // y > 0: quant field row
+  const int epf_hi = split(7, 3, leaf(kPredZero), leaf(kPredZero)), epf_lo = split(7, 3, leaf(kPredZero), leaf(kPredZero));
+  const int epf = split(6, 3, epf_hi, epf_lo);
+  const int c23 = split(0, 2, epf, acs_qf);
+  const int c01 = split(0, 0, leaf(kPredGradient), leaf(kPredGradient));
+  const int meta = split(0, 1, c23, c01);
+  const int root = split(1, static_cast<int32_t>(num_dc_groups), meta, dc);
+  // breadth-first serialisation = the order ReadTree assigns child positions in
+  GlobalTree g;
+  std::vector<int> queue = {root};
+  for (size_t k = 0; k < queue.size(); k++) {
+    const EncTreeNode& e = n[queue[k]];
+    TreeNode t{};
+    if (e.property < 0) {
+      t.property = -1;
+      t.predictor = e.predictor;
+      t.multiplier = 1;
+      t.lchild = g.num_leaves++;
+      g.tokens.push_back({1, 0});
+      g.tokens.push_back({2, e.predictor});
+      g.tokens.push_back({3, 0});
+      g.tokens.push_back({4, 0});
+      g.tokens.push_back({5, 0});
+    } else {
+      t.property = e.property;
+      t.splitval = e.splitval;
+      t.lchild = queue.size();
+      t.rchild = queue.size() + 1;
+      t.multiplier = 1;
+      queue.push_back(e.left);
+      queue.push_back(e.right);
+      g.tokens.push_back({1, static_cast<uint32_t>(e.property + 1)});
+      g.tokens.push_back({0, PackSigned(e.splitval)});
+    }
+    g.tree.push_back(t);
+  }
+  return g;
+}
+
+// Tokens of one Modular sub-stream under the global tree: the mirror of DecodeChannel (jxlo_modular.h).
+inline void TokenizeModularStream(const Tree& tree, uint32_t stream_id, const std::vector<Channel>& channels,
+                                  std::vector<Token>* toks) {
+  const WPHeader wp_header;
+  for (size_t chan = 0; chan < channels.size(); chan++) {
+    const Channel& ch = channels[chan];
+    if (ch.w == 0 || ch.h == 0) continue;
+    std::vector<int32_t> props(kNumNonrefProps, 0);
+    WPState wp(wp_header, ch.w);
+    const int w = ch.w;
+    for (int y = 0; y < ch.h; y++) {
+      const int32_t* row = ch.Row(y);
+      const int32_t* prev = y ? ch.Row(y - 1) : nullptr;
+      const int32_t* prevprev = y > 1 ? ch.Row(y - 2) : nullptr;
+      props[0] = static_cast<int32_t>(chan);
+      props[1] = static_cast<int32_t>(stream_id);
+      props[2] = y;
+      props[9] = 0;
+      for (int x = 0; x < w; x++) {
+        const Neighbors n = LoadNeighbors(row, prev, prevprev, x, y, w);
+        props[3] = x;
+        props[4] = static_cast<int32_t>(n.top > 0 ? n.top : -n.top);
+        props[5] = static_cast<int32_t>(n.left > 0 ? n.left : -n.left);
+        props[6] = static_cast<int32_t>(n.top);
+        props[7] = static_cast<int32_t>(n.left);
+        props[8] = static_cast<int32_t>(n.left - props[9]);
+        props[9] = static_cast<int32_t>(n.left + n.top - n.topleft);
+        props[10] = static_cast<int32_t>(n.left - n.topleft);
+        props[11] = static_cast<int32_t>(n.topleft - n.top);
+        props[12] = static_cast<int32_t>(n.top - n.topright);
+        props[13] = static_cast<int32_t>(n.top - n.toptop);
+        props[14] = static_cast<int32_t>(n.left - n.leftleft);
+        const int64_t wp_pred = wp.Predict(x, y, w, n.top, n.left, n.topright, n.topleft, n.toptop, &props[kWPProp]);
+        size_t pos = 0;
+        while (tree[pos].property >= 0) pos = props[tree[pos].property] > tree[pos].splitval ? tree[pos].lchild : tree[pos].rchild;
+        const int64_t guess = PredictOne(tree[pos].predictor, n, wp_pred);
+        toks->push_back({tree[pos].lchild, PackSigned(static_cast<int32_t>(row[x] - guess))});
+        wp.Update(row[x], x, y, w);
       }
     }
   }
-  EntropyEncoder enc(1, {0});
-  enc.Count(toks);
-  enc.WriteHeader(w);
-  enc.WriteTokens(w, toks);
+}
+
+// GroupHeader of a sub-stream that uses the global tree, followed by its symbols.
+inline void WriteModularStream(BitWriter& w, const EntropyEncoder& code, const std::vector<Channel>& channels,
+                               const std::vector<Token>& toks) {
+  bool any = false;
+  for (const Channel& c : channels) any |= c.w > 0 && c.h > 0;
+  if (channels.empty()) return;
+  w.Write(1, 1);  // use_global_tree
+  w.Write(1, 1);  // default weighted-predictor header
+  w.Write(2, 0);  // no transforms
+  if (!any) return;
+  code.WriteTokens(w, toks);
 }
 
 // ---------------------------------------------------------------- forward transforms
@@ -801,31 +921,20 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
     w.ZeroPadToByte();
     sections.push_back(w.Bytes());
   };
-  BitWriter dc_global;
-  {
-    dc_global.Write(1, 1);  // default DC quantisation
-    WriteU32(dc_global, global_scale, BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193));
-    WriteU32(dc_global, quant_dc, Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1));
-    dc_global.Write(1, 1);  // default block context map
-    dc_global.Write(1, 1);  // default colour correlation
-    dc_global.Write(1, 0);  // no global MA tree
-  }
-  std::vector<BitWriter> dc_groups(dim.num_dc_groups);
+  // Modular sub-streams (DC, AC metadata) under one global tree and one entropy code
+  const GlobalTree gtree = BuildGlobalTree(dim.num_dc_groups);
+  std::vector<std::vector<Channel>> dc_chans(dim.num_dc_groups), meta_chans(dim.num_dc_groups);
+  std::vector<std::vector<Token>> dc_toks(dim.num_dc_groups), meta_toks(dim.num_dc_groups);
+  std::vector<size_t> meta_count(dim.num_dc_groups, 0);
   for (size_t g = 0; g < dim.num_dc_groups; g++) {
-    BitWriter& w = dc_groups[g];
     const BlockRect r = DCGroupRect(dim, g);
-    w.Write(2, 0);  // extra_precision
     std::vector<Channel> ch = {Channel(r.xs, r.ys), Channel(r.xs, r.ys), Channel(r.xs, r.ys)};
     for (int c = 0; c < 3; c++)
       for (size_t y = 0; y < r.ys; y++)
         for (size_t x = 0; x < r.xs; x++) ch[c].Row(y)[x] = dcq[c].Row(r.y0 + y)[r.x0 + x];
-    WriteModularStream(w, ch);
-    // (no Modular DC-group channels)
-    // AC metadata
     size_t count = 0;
     for (size_t y = 0; y < r.ys; y++)
       for (size_t x = 0; x < r.xs; x++) count += acs[(r.y0 + y) * W + r.x0 + x] & 1;
-    w.Write(CeilLog2(r.xs * r.ys), count - 1);
     const size_t cx0 = r.x0 >> 3, cy0 = r.y0 >> 3, cw = (r.xs + 7) >> 3, chh = (r.ys + 7) >> 3;
     std::vector<Channel> meta = {Channel(cw, chh, 3, 3), Channel(cw, chh, 3, 3), Channel(count, 2), Channel(r.xs, r.ys)};
     for (size_t y = 0; y < chh; y++)
@@ -843,7 +952,42 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
         meta[2].Row(1)[num] = raw_quant[pos] - 1;
         num++;
       }
-    WriteModularStream(w, meta);
+    TokenizeModularStream(gtree.tree, StreamVarDCTDC(dim, g), ch, &dc_toks[g]);
+    TokenizeModularStream(gtree.tree, StreamACMetadata(dim, g), meta, &meta_toks[g]);
+    dc_chans[g] = std::move(ch);
+    meta_chans[g] = std::move(meta);
+    meta_count[g] = count;
+  }
+  EntropyEncoder tree_code(6, {0, 1, 2, 3, 4, 5});
+  tree_code.Count(gtree.tokens);
+  std::vector<uint8_t> leaf_clusters(gtree.num_leaves);
+  for (size_t i = 0; i < gtree.num_leaves; i++) leaf_clusters[i] = static_cast<uint8_t>(i);
+  EntropyEncoder modular_code(gtree.num_leaves, leaf_clusters);
+  for (size_t g = 0; g < dim.num_dc_groups; g++) {
+    modular_code.Count(dc_toks[g]);
+    modular_code.Count(meta_toks[g]);
+  }
+  BitWriter dc_global;
+  {
+    dc_global.Write(1, 1);  // default DC quantisation
+    WriteU32(dc_global, global_scale, BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193));
+    WriteU32(dc_global, quant_dc, Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1));
+    dc_global.Write(1, 1);  // default block context map
+    dc_global.Write(1, 1);  // default colour correlation
+    dc_global.Write(1, 1);  // global MA tree
+    tree_code.WriteHeader(dc_global);
+    tree_code.WriteTokens(dc_global, gtree.tokens);
+    modular_code.WriteHeader(dc_global);
+  }
+  std::vector<BitWriter> dc_groups(dim.num_dc_groups);
+  for (size_t g = 0; g < dim.num_dc_groups; g++) {
+    BitWriter& w = dc_groups[g];
+    const BlockRect r = DCGroupRect(dim, g);
+    w.Write(2, 0);  // extra_precision
+    WriteModularStream(w, modular_code, dc_chans[g], dc_toks[g]);
+    // (no Modular DC-group channels)
+    w.Write(CeilLog2(r.xs * r.ys), meta_count[g] - 1);
+    WriteModularStream(w, modular_code, meta_chans[g], meta_toks[g]);
   }
   BitWriter ac_global;
   std::vector<EntropyEncoder> pass_codes;
