@@ -33,7 +33,22 @@ struct BatchPlan {
   std::vector<BasicInfo> info;
   std::vector<uint32_t> warp_chans, warp_dims_off, warp_dims;
   bool narrow = true;  // every frame promises that 16-bit buffers suffice -> 32-bit predictor math
+  // VarDCT frames
+  std::vector<DevVFrame> vframes;
+  std::vector<DevAcStream> ac_streams;
+  std::vector<float> fpool;
+  std::vector<uint16_t> opool;
+  std::vector<uint8_t> cpool;
+  std::vector<uint32_t> upool;
+  uint64_t farena_size = 0, barena_size = 0, uarena_size = 0, tok_size = 0;
+  uint64_t pix_plane_max = 0;  // floats per pixel plane slot
+  uint32_t wave_frames = 1;    // VarDCT frames whose pixel planes are live at the same time
 };
+
+// Pixel planes are the largest intermediate (24 bytes per pixel for two sets of three float
+// planes), so they are allocated for a wave of frames and reused: the entropy kernels run over
+// the whole batch, the dequant / IDCT / filter / colour kernels wave by wave.
+constexpr uint64_t kWavePixelBytes = uint64_t{4} << 30;
 
 // Orders the streams so that the 32 lanes of a warp decode planes of the same shape
 // (they run one loop nest in lock step) and derives the warp-uniform loop bounds.
@@ -135,6 +150,65 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
     p.op_end += ops0;
     b->levels[k].push_back(p);
   }
+  if (f.is_vardct) {
+    const VarDCTPlan& v = f.v;
+    if (b->vframes.empty()) {  // shared tables sit at offset 0 of the pools
+      const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
+      JXLB_CHECK(b->fpool.empty() && b->opool.empty(), "internal: pools not empty");
+      JXLB_CHECK(b->upool.empty(), "internal: pools not empty");
+      b->fpool = sh.fpool;
+      b->opool = sh.opool;
+      b->upool = sh.upool;
+    }
+    const uint32_t fpool0 = b->fpool.size(), opool0 = b->opool.size(), cpool0 = b->cpool.size(), upool0 = b->upool.size();
+    b->fpool.insert(b->fpool.end(), v.fpool.begin(), v.fpool.end());
+    b->opool.insert(b->opool.end(), v.opool.begin(), v.opool.end());
+    b->cpool.insert(b->cpool.end(), v.cpool.begin(), v.cpool.end());
+    b->upool.insert(b->upool.end(), v.upool.begin(), v.upool.end());
+    DevVFrame vf = v.vf;
+    for (int c = 0; c < 3; c++) {
+      vf.dc[c] += b->farena_size;
+      vf.dc_final[c] += b->farena_size;
+    }
+    vf.inv_sigma += b->farena_size;
+    vf.acs += b->barena_size;
+    vf.qdc += b->barena_size;
+    vf.sharp += b->barena_size;
+    vf.rawq += b->barena_size;
+    vf.ytox += b->barena_size;
+    vf.ytob += b->barena_size;
+    vf.tok_start += b->uarena_size;
+    vf.tok_count += b->uarena_size;
+    vf.bctx_off += upool0;
+    vf.order_index += upool0;
+    vf.dcg_index += upool0;
+    for (uint32_t i = 0; i < vf.num_passes * 39; i++) {
+      uint32_t& e = b->upool[vf.order_index + i];
+      e = (e & kSharedFlag) ? (e & ~kSharedFlag) : e + opool0;
+    }
+    for (uint32_t g = 0; g < vf.xdcgroups * vf.ydcgroups; g++)
+      for (uint32_t i = 0; i < 7; i++) b->upool[vf.dcg_index + 8 * g + i] += planes0;
+    for (uint32_t k = 0; k < 17; k++)
+      vf.table_off[k] = (vf.table_off[k] & kSharedFlag) ? (vf.table_off[k] & ~kSharedFlag) : vf.table_off[k] + fpool0;
+    for (uint32_t p = 0; p < vf.num_passes; p++) {
+      vf.ac_code[p] += codes0;
+      vf.ctx_map_off[p] += cpool0;
+    }
+    vf.out_off = b->out_size;
+    for (DevAcStream s : v.ac_streams) {
+      s.bit_pos += byte_base * 8;
+      s.bit_end += byte_base * 8;
+      s.frame = b->vframes.size();
+      s.tok_off += b->tok_size;
+      b->ac_streams.push_back(s);
+    }
+    b->farena_size += v.farena_size;
+    b->barena_size += v.barena_size;
+    b->uarena_size += v.uarena_size;
+    b->tok_size += v.tok_size;
+    b->pix_plane_max = std::max(b->pix_plane_max, v.pix_plane);
+    b->vframes.push_back(vf);
+  }
   DevFrameOut fo = f.out;
   for (uint32_t c = 0; c < 4; c++)
     if (c < fo.num_channels && fo.plane[c] != kNoPlane) fo.plane[c] += planes0;
@@ -158,6 +232,27 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
   bi.ysize = f.ysize;
   bi.meta = f.meta;
   b->info.push_back(bi);
+}
+
+// After a run in which some AC streams produced more tokens than their capacity: gives every
+// stream at least what it used (`used[s]`, reported by the decode kernel) and lays the token
+// arena out again. Returns false if nothing overflowed.
+inline bool GrowTokenCapacity(BatchPlan* b, const uint32_t* used) {
+  bool grew = false;
+  for (size_t s = 0; s < b->ac_streams.size(); s++) {
+    if (used[s] > b->ac_streams[s].tok_cap) {
+      b->ac_streams[s].tok_cap = used[s] + 64;
+      grew = true;
+    }
+  }
+  if (!grew) return false;
+  uint64_t off = 0;
+  for (DevAcStream& s : b->ac_streams) {
+    s.tok_off = off;
+    off += s.tok_cap;
+  }
+  b->tok_size = off;
+  return true;
 }
 
 // Plans `n` files on `threads` host threads and merges them in input order.
@@ -194,6 +289,24 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
   for (size_t i = 0; i < n; i++) MergeFrame(plans[i], views[i].data, views[i].size, batch);
   batch->bytes.resize(batch->bytes.size() + 64, 0);  // read-ahead padding for the device bit reader
   BundleStreams(batch);
+  if (!batch->vframes.empty()) {
+    // pixel-plane slots for one wave of frames, after the per-frame planes of the float arena
+    const uint64_t per_frame = 6 * batch->pix_plane_max;
+    batch->wave_frames = static_cast<uint32_t>(
+        std::max<uint64_t>(1, std::min<uint64_t>(batch->vframes.size(), kWavePixelBytes / (per_frame * 4))));
+    const uint64_t pix_base = batch->farena_size;
+    batch->farena_size += per_frame * batch->wave_frames;
+    for (size_t i = 0; i < batch->vframes.size(); i++) {
+      const uint64_t slot = pix_base + (i % batch->wave_frames) * per_frame;
+      for (int set = 0; set < 2; set++)
+        for (int c = 0; c < 3; c++) batch->vframes[i].pix[set][c] = slot + (set * 3 + c) * batch->pix_plane_max;
+    }
+    JXLB_CHECK(batch->tok_size < (uint64_t{1} << 32), "batch too large: token arena exceeds 2^32 entries");
+    // lanes of a warp run until their longest stream ends: put streams of similar length together
+    std::stable_sort(batch->ac_streams.begin(), batch->ac_streams.end(), [](const DevAcStream& x, const DevAcStream& y) {
+      return x.bit_end - x.bit_pos > y.bit_end - y.bit_pos;
+    });
+  }
 }
 
 }  // namespace jxlb

@@ -6,22 +6,9 @@
 #define JXLB_FRAME_PLAN_H_
 
 #include "jxlb_plan.h"
+#include "jxlb_vardct_frame.h"
 
 namespace jxlb {
-
-struct PixelFormat {
-  uint32_t num_channels = 4;
-  uint32_t data_type = 2;   // JxlDataType
-  uint32_t endianness = 0;  // JxlEndianness
-  size_t align = 0;
-};
-
-inline size_t BytesPerSample(uint32_t data_type) { return data_type == 2 ? 1 : (data_type == 0 ? 4 : 2); }
-inline size_t OutputStride(uint32_t xsize, const PixelFormat& f) {
-  size_t row = static_cast<size_t>(xsize) * f.num_channels * BytesPerSample(f.data_type);
-  if (f.align > 1) row = DivCeil(row, f.align) * f.align;
-  return row;
-}
 
 // Locates the codestream inside `data` without copying when possible.
 struct CodestreamView {
@@ -117,14 +104,13 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   size.ysize = bi.ysize;
   FrameHeader fh;
   ReadFrameHeader(br, size, meta, false, &fh);
-  JXLB_CHECK(fh.is_modular, "unsupported: VarDCT frame (Modular only in this build)");
   JXLB_CHECK(fh.frame_type == kRegularFrame && fh.is_last, "unsupported: multi-frame codestream");
-  JXLB_CHECK(fh.color_transform == kCTNone, "unsupported: XYB / YCbCr Modular frame");
+  JXLB_CHECK(!fh.is_modular || fh.color_transform == kCTNone, "unsupported: XYB / YCbCr Modular frame");
   JXLB_CHECK(!fh.custom_size_or_origin, "unsupported: cropped frame");
   JXLB_CHECK(fh.upsampling == 1, "unsupported: upsampling");
   for (uint32_t u : fh.ec_upsampling) JXLB_CHECK(u == 1, "unsupported: extra-channel upsampling");
   JXLB_CHECK(!(fh.flags & (kFlagPatches | kFlagSplines | kFlagNoise | kFlagUseDcFrame)), "unsupported: patches / splines / noise / DC frame");
-  JXLB_CHECK(!fh.lf.gab && fh.lf.epf_iters == 0, "unsupported: loop filter on a Modular frame");
+  JXLB_CHECK(!fh.is_modular || (!fh.lf.gab && fh.lf.epf_iters == 0), "unsupported: loop filter on a Modular frame");
   JXLB_CHECK(fh.blending.mode == kReplace, "unsupported: blending");
   FrameDimensions dim = ToFrameDimensions(fh);
   const size_t num_passes = fh.passes.num_passes;
@@ -133,6 +119,19 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   const size_t base = br.BitPos() / 8;
   JXLB_CHECK(base + toc.total <= cs_size, "truncated frame");
 
+  if (!fh.is_modular) {
+    PlanVarDCTFrame(cs, cs_size, fh, dim, meta, toc, base, fmt, plan);
+    DevFrameOut& fo = plan->out;
+    fo = DevFrameOut{};
+    fo.xsize = bi.xsize;
+    fo.ysize = bi.ysize;
+    fo.num_channels = fmt.num_channels;
+    fo.data_type = fmt.data_type;
+    fo.stride = OutputStride(bi.xsize, fmt);
+    fo.vardct = 1;
+    for (uint32_t c = 0; c < 4; c++) fo.plane[c] = kNoPlane;
+    return;
+  }
   FramePlanner planner(plan);
   const bool is_gray = meta.color.IsGray();
   const size_t nb_chans = is_gray ? 1 : 3;

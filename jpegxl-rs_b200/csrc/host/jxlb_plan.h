@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../kernels/jxlb_dev.h"
+#include "../kernels/jxlb_vardct_desc.h"
 #include "jxlb_headers.h"
 
 namespace jxlb {
@@ -109,7 +110,21 @@ inline GroupHeader ReadGroupHeader(BitReader& br) {
 // ---------------------------------------------------------------- the plan
 // Everything one frame contributes to the batch; indices are frame-local and are
 // relocated when the frame is merged into the batch.
+// What a VarDCT frame adds to its FramePlan (offsets frame-local, relocated by MergeFrame).
+struct VarDCTPlan {
+  DevVFrame vf;
+  std::vector<DevAcStream> ac_streams;
+  std::vector<float> fpool;     // frame-specific dequantisation tables
+  std::vector<uint16_t> opool;  // frame-specific coefficient orders
+  std::vector<uint8_t> cpool;   // AC context maps
+  std::vector<uint32_t> upool;  // block context map, order index, DC-group plane lists
+  uint64_t farena_size = 0, barena_size = 0, uarena_size = 0, tok_size = 0;
+  uint64_t pix_plane = 0;       // floats per padded pixel plane
+};
+
 struct FramePlan {
+  bool is_vardct = false;
+  VarDCTPlan v;
   std::vector<DevAlias> alias;
   std::vector<uint32_t> prefix, cfg, refs;
   std::vector<DevTreeNode> tree;

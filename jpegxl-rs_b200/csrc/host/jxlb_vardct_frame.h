@@ -1,0 +1,323 @@
+// jxl_b200 host planner: section walk of one VarDCT frame (lib/jxl/dec_frame.cc:568-731,
+// :266-339, :367-476) producing the device descriptors of jxlb_vardct_desc.h.
+#ifndef JXLB_VARDCT_FRAME_H_
+#define JXLB_VARDCT_FRAME_H_
+
+#include "jxlb_vardct_plan.h"
+
+namespace jxlb {
+
+struct PixelFormat {
+  uint32_t num_channels = 4;
+  uint32_t data_type = 2;   // JxlDataType
+  uint32_t endianness = 0;  // JxlEndianness
+  size_t align = 0;
+};
+
+inline size_t BytesPerSample(uint32_t data_type) { return data_type == 2 ? 1 : (data_type == 0 ? 4 : 2); }
+inline size_t OutputStride(uint32_t xsize, const PixelFormat& f) {
+  size_t row = static_cast<size_t>(xsize) * f.num_channels * BytesPerSample(f.data_type);
+  if (f.align > 1) row = DivCeil(row, f.align) * f.align;
+  return row;
+}
+
+// Plans the sections of a VarDCT frame. `br` is positioned after the TOC, `base` is the byte
+// offset of the first section inside `cs`.
+inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader& fh, const FrameDimensions& dim,
+                            const ImageMetadata& meta, const Toc& toc, size_t base, const PixelFormat& fmt, FramePlan* plan) {
+  JXLB_CHECK(fh.Is444(), "unsupported: chroma-subsampled VarDCT frame");
+  JXLB_CHECK(meta.extra.empty(), "unsupported: VarDCT frame with extra channels");
+  JXLB_CHECK(fh.passes.num_passes <= kMaxPasses, "too many passes");
+  const size_t num_passes = fh.passes.num_passes;
+  JXLB_CHECK(toc.offsets.size() > 1, "unsupported: single-section VarDCT frame (sub-streams chained across host-parsed headers)");
+  plan->is_vardct = true;
+  VarDCTPlan& v = plan->v;
+  DevVFrame& vf = v.vf;
+  vf = DevVFrame{};
+  FramePlanner planner(plan);
+  const size_t W = dim.xsize_blocks, H = dim.ysize_blocks, nb = W * H;
+
+  auto section = [&](size_t i, uint64_t* bit_base) {
+    *bit_base = (base + toc.offsets[i]) * 8;
+    return BitReader(cs + base + toc.offsets[i], toc.logical_size[i]);
+  };
+  uint64_t bb = 0;
+
+  // ---- DC global (lib/jxl/dec_frame.cc:266-313, :61-77)
+  float dc_quant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256};
+  HostBlockCtx bctx;
+  HostTree global_tree;
+  {
+    BitReader r = section(0, &bb);
+    if (!r.ReadBool()) {
+      for (int c = 0; c < 3; c++) {
+        dc_quant[c] = ReadF16(r) * (1.0f / 128.0f);
+        JXLB_CHECK(dc_quant[c] >= 1e-8f, "bad DC quantisation step");
+      }
+    }
+    const uint32_t global_scale = ReadU32(r, BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193));
+    const uint32_t quant_dc = ReadU32(r, Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1));
+    vf.global_scale_f = global_scale * (1.0 / 65536);
+    vf.inv_global_scale = 1.0 * 65536 / global_scale;
+    const float inv_quant_dc = vf.inv_global_scale / quant_dc;
+    for (int c = 0; c < 3; c++) {
+      vf.mul_dc[c] = inv_quant_dc * dc_quant[c];
+      vf.inv_mul_dc[c] = 1.0f / vf.mul_dc[c];
+    }
+    ReadBlockCtx(r, &bctx);
+    uint32_t color_factor = 84;
+    vf.base_x = 0.0f;
+    vf.base_b = 1.0f;
+    int ytox_dc = 0, ytob_dc = 0;
+    if (!r.ReadBool()) {  // ColorCorrelation::DecodeDC, lib/jxl/chroma_from_luma.cc:20-41
+      color_factor = ReadU32(r, Val(84), Val(256), BitsOffset(8, 2), BitsOffset(16, 258));
+      vf.base_x = ReadF16(r);
+      JXLB_CHECK(std::fabs(vf.base_x) <= 4.0f, "base X correlation out of range");
+      vf.base_b = ReadF16(r);
+      JXLB_CHECK(std::fabs(vf.base_b) <= 4.0f, "base B correlation out of range");
+      ytox_dc = static_cast<int>(r.Read(8)) - 128;
+      ytob_dc = static_cast<int>(r.Read(8)) - 128;
+    }
+    vf.color_scale = 1.0f / color_factor;
+    vf.cfl_dc_x = vf.base_x + ytox_dc * vf.color_scale;
+    vf.cfl_dc_b = vf.base_b + ytob_dc * vf.color_scale;
+    if (r.ReadBool()) {
+      const size_t limit = std::min<size_t>(size_t{1} << 22, 1024 + dim.xsize * dim.ysize * 3 / 16);
+      global_tree = planner.ReadTreeAndCode(r, limit);
+    }
+    r.CheckInBounds();
+  }
+
+  // ---- DC groups: quantised DC + AC metadata, two chained Modular streams decoded by one thread
+  vf.dcg_index = v.upool.size();
+  for (size_t g = 0; g < dim.num_dc_groups; g++) {
+    BitReader r = section(1 + g, &bb);
+    const size_t gx = g % dim.xsize_dc_groups, gy = g / dim.xsize_dc_groups;
+    const size_t x0 = gx * dim.group_dim, y0 = gy * dim.group_dim;  // in blocks (2048 px / 8 = group_dim)
+    const size_t xs = std::min(dim.group_dim, W - x0), ys = std::min(dim.group_dim, H - y0);
+    const uint32_t extra_precision = r.Read(2);
+    GroupHeader hdr = ReadGroupHeader(r);
+    r.CheckInBounds();
+    JXLB_CHECK(hdr.use_global_tree && global_tree.valid, "unsupported: VarDCT DC stream with a local MA tree");
+    JXLB_CHECK(hdr.transforms.empty(), "unsupported: transforms in a VarDCT DC stream");
+    JXLB_CHECK(!global_tree.lz77, "unsupported: LZ77 in VarDCT DC / AC-metadata streams");
+    DevStream st{};
+    st.bit_pos = bb + r.BitPos();
+    st.bit_end = bb + r.Size() * 8;
+    st.code = global_tree.code;
+    st.stream_id = 1 + g;
+    st.chan_begin = plan->chans.size();
+    st.dist_multiplier = xs;
+    hdr.wp.Pack(st.wp_params);
+    st.num_props = global_tree.num_props;
+    st.lz77_slot = 0xFFFFFFFFu;
+    const int want_refs = (static_cast<int>(global_tree.num_props) - 16) / 4;
+    struct Ch { uint32_t w, h, plane; bool dyn; };
+    std::vector<Ch> image;
+    auto add_channels = [&](const std::vector<Ch>& chs, uint32_t stream_id, uint32_t count_bits) {
+      const size_t first = image.size();
+      for (size_t i = 0; i < chs.size(); i++) {
+        DevChannel dc{};
+        dc.plane = chs[i].plane;
+        dc.prop0 = i;
+        dc.ref_off = plan->refs.size();
+        for (int j = static_cast<int>(i) - 1; j >= 0 && static_cast<int>(dc.ref_count) < want_refs; j--) {
+          if (chs[j].dyn || chs[i].dyn || chs[j].w != chs[i].w || chs[j].h != chs[i].h) continue;
+          plan->refs.push_back(chs[j].plane);
+          dc.ref_count++;
+        }
+        bool ch_wp = false;
+        dc.tree_off = planner.PruneTree(*global_tree.nodes, static_cast<int32_t>(i), static_cast<int32_t>(stream_id), &ch_wp);
+        dc.uses_wp = ch_wp;
+        if (ch_wp) st.uses_wp = 1;
+        dc.dyn = chs[i].dyn;
+        if (i == 0 && first != 0) {
+          dc.preamble = 1;
+          dc.count_bits = count_bits;
+        }
+        plan->chans.push_back(dc);
+        image.push_back(chs[i]);
+      }
+    };
+    std::vector<Ch> dcs, metas;
+    for (int c = 0; c < 3; c++) dcs.push_back(Ch{static_cast<uint32_t>(xs), static_cast<uint32_t>(ys), planner.NewPlane(xs, ys), false});
+    add_channels(dcs, 1 + g, 0);
+    const uint32_t cw = (xs + 7) >> 3, chh = (ys + 7) >> 3, cap = xs * ys;
+    metas.push_back(Ch{cw, chh, planner.NewPlane(cw, chh), false});
+    metas.push_back(Ch{cw, chh, planner.NewPlane(cw, chh), false});
+    metas.push_back(Ch{cap, 2, planner.NewPlane(cap, 2, 4), true});
+    metas.push_back(Ch{static_cast<uint32_t>(xs), static_cast<uint32_t>(ys), planner.NewPlane(xs, ys), false});
+    add_channels(metas, 1 + 2 * dim.num_dc_groups + g, CeilLog2(cap));
+    st.chan_end = plan->chans.size();
+    st.max_w = xs;
+    plan->wp_width = std::max<uint32_t>(plan->wp_width, xs);
+    plan->streams.push_back(st);
+    for (int i = 0; i < 7; i++) v.upool.push_back(image[i].plane);
+    v.upool.push_back(extra_precision);
+  }
+
+  // ---- AC global (lib/jxl/dec_frame.cc:367-476)
+  const SharedVarDCTTables& shared = SharedVarDCTTables::Get();
+  {
+    BitReader r = section(1 + dim.num_dc_groups, &bb);
+    const bool all_default = r.ReadBool();
+    for (int k = 0; k < kNumQuantKinds; k++) vf.table_off[k] = kSharedFlag | shared.table_off[k];
+    if (!all_default) {
+      for (int k = 0; k < kNumQuantKinds; k++) {
+        QuantTableSpec spec;
+        ReadQuantTableSpec(r, k, &spec);
+        if (spec.mode == kQLib) continue;
+        vf.table_off[k] = v.fpool.size();
+        std::vector<float> tab = BuildDequantTable(spec, k);
+        v.fpool.insert(v.fpool.end(), tab.begin(), tab.end());
+      }
+    }
+    vf.num_histograms = 1 + r.Read(CeilLog2(dim.num_groups));
+    vf.order_index = v.upool.size();
+    v.upool.resize(v.upool.size() + num_passes * 39, 0);
+    const uint32_t num_ac_ctx = bctx.NumACContexts();
+    for (size_t p = 0; p < num_passes; p++) {
+      const uint32_t used_orders = ReadU32(r, Val(0x5F), Val(0x13), Val(0), Bits(13));
+      EntropyCode perm_code;
+      std::unique_ptr<SymbolReader> reader;
+      if (used_orders != 0) {
+        ReadEntropyCode(r, 8, &perm_code);
+        reader.reset(new SymbolReader(&perm_code, r));
+      }
+      std::vector<uint32_t> perm;
+      for (uint32_t ord = 0; ord < kNumOrders; ord++) {
+        const StrategyInfo si = GetStrategyInfo(kOrderFirstStrategy[ord]);
+        const size_t llf = static_cast<size_t>(si.cx) * si.cy, size = 64 * llf;
+        uint32_t* index = &v.upool[vf.order_index + p * 39 + 3 * ord];
+        if (!(used_orders & (1u << ord))) {
+          for (int c = 0; c < 3; c++) index[c] = kSharedFlag | shared.order_off[ord];
+          continue;
+        }
+        const uint16_t* natural = shared.opool.data() + shared.order_off[ord];
+        for (int c = 0; c < 3; c++) {
+          perm.resize(size);
+          ReadPermutation(r, *reader, llf, size, perm.data());
+          v.upool[vf.order_index + p * 39 + 3 * ord + c] = v.opool.size();
+          for (size_t k = 0; k < size; k++) v.opool.push_back(natural[perm[k]]);
+        }
+      }
+      if (used_orders) JXLB_CHECK(reader->FinalStateOk(), "coefficient orders: bad ANS final state");
+      EntropyCode code;
+      ReadEntropyCode(r, static_cast<size_t>(vf.num_histograms) * num_ac_ctx, &code);
+      JXLB_CHECK(!code.lz77_enabled, "unsupported: LZ77 in AC coefficient streams");
+      vf.ac_code[p] = planner.AddCode(code);
+      vf.ctx_map_off[p] = v.cpool.size();
+      v.cpool.insert(v.cpool.end(), code.ctx_map.begin(), code.ctx_map.end());
+      v.cpool.resize(v.cpool.size() + 16 + 3, 0);  // lib/jxl/dec_frame.cc:406-408 padding
+      v.cpool.resize(v.cpool.size() & ~size_t{3});
+    }
+    r.CheckInBounds();
+  }
+
+  // ---- AC groups: one stream per (pass, group)
+  for (size_t p = 0; p < num_passes; p++) {
+    for (size_t g = 0; g < dim.num_groups; g++) {
+      const size_t idx = 2 + dim.num_dc_groups + p * dim.num_groups + g;
+      DevAcStream s{};
+      s.bit_pos = (base + toc.offsets[idx]) * 8;
+      s.bit_end = s.bit_pos + static_cast<uint64_t>(toc.logical_size[idx]) * 8;
+      s.frame = 0;
+      s.group = g;
+      s.pass = p;
+      s.tok_cap = std::min<uint64_t>(3 * 65536 * 2, 2 * static_cast<uint64_t>(toc.logical_size[idx]) + 512);
+      s.tok_off = v.tok_size;
+      v.tok_size += s.tok_cap;
+      v.ac_streams.push_back(s);
+    }
+  }
+
+  // ---- frame descriptor
+  vf.xsize = dim.xsize;
+  vf.ysize = dim.ysize;
+  vf.xblocks = W;
+  vf.yblocks = H;
+  vf.xgroups = dim.xsize_groups;
+  vf.ygroups = dim.ysize_groups;
+  vf.xdcgroups = dim.xsize_dc_groups;
+  vf.ydcgroups = dim.ysize_dc_groups;
+  vf.cmw = DivCeil(W, size_t{8});
+  vf.cmh = DivCeil(H, size_t{8});
+  vf.num_passes = num_passes;
+  for (size_t p = 0; p < num_passes; p++) vf.pass_shift[p] = fh.passes.shift[p];
+  vf.skip_dc_smoothing = ((fh.flags & kFlagSkipAdaptiveDCSmoothing) != 0 || W <= 2 || H <= 2) ? 1 : 0;
+  vf.gab = fh.lf.gab;
+  vf.epf_iters = fh.lf.epf_iters;
+  uint64_t f = 0;
+  for (int c = 0; c < 3; c++) {
+    vf.dc[c] = f;
+    f += nb;
+  }
+  for (int c = 0; c < 3; c++) {
+    vf.dc_final[c] = vf.skip_dc_smoothing ? vf.dc[c] : f;
+    if (!vf.skip_dc_smoothing) f += nb;
+  }
+  vf.inv_sigma = f;
+  f += nb;
+  v.farena_size = (f + 3) & ~uint64_t{3};
+  v.pix_plane = static_cast<uint64_t>(W * 8) * (H * 8);
+  uint64_t b = 0;
+  vf.acs = b; b += nb;
+  vf.qdc = b; b += nb;
+  vf.sharp = b; b += nb;
+  b = (b + 1) & ~uint64_t{1};
+  vf.rawq = b; b += 2 * nb;
+  vf.ytox = b; b += vf.cmw * vf.cmh;
+  vf.ytob = b; b += vf.cmw * vf.cmh;
+  v.barena_size = (b + 15) & ~uint64_t{15};
+  vf.tok_start = 0;
+  vf.tok_count = num_passes * 3 * nb;
+  v.uarena_size = 2 * num_passes * 3 * nb;
+  // quantiser
+  vf.x_dm = std::pow(1 / (1.25f), fh.x_qm_scale - 2.0f);  // lib/jxl/dec_cache.h:161-162
+  vf.b_dm = std::pow(1 / (1.25f), fh.b_qm_scale - 2.0f);
+  for (int i = 0; i < 4; i++) vf.biases[i] = meta.quant_biases[i];
+  // block context map -> upool: dc thresholds (3 lists), qf thresholds, then the map bytes packed 4 per word
+  vf.bctx_off = v.upool.size();
+  vf.num_ctxs = bctx.num_ctxs;
+  vf.num_dc_ctxs = bctx.num_dc_ctxs;
+  vf.num_qf_thr = bctx.qf_thr.size();
+  for (int j = 0; j < 3; j++) {
+    vf.num_dc_thr[j] = bctx.dc_thr[j].size();
+    for (int32_t t : bctx.dc_thr[j]) v.upool.push_back(static_cast<uint32_t>(t));
+  }
+  for (uint32_t t : bctx.qf_thr) v.upool.push_back(t);
+  for (size_t i = 0; i < bctx.ctx_map.size(); i += 4) {
+    uint32_t wv = 0;
+    for (size_t k = 0; k < 4 && i + k < bctx.ctx_map.size(); k++) wv |= static_cast<uint32_t>(bctx.ctx_map[i + k]) << (8 * k);
+    v.upool.push_back(wv);
+  }
+  // loop filter (lib/jxl/render_pipeline/stage_gaborish.cc:22-48, stage_epf.cc, lib/jxl/epf.cc)
+  const LoopFilter& lf = fh.lf;
+  const float gw[3][2] = {{lf.gab_x_weight1, lf.gab_x_weight2}, {lf.gab_y_weight1, lf.gab_y_weight2},
+                          {lf.gab_b_weight1, lf.gab_b_weight2}};
+  for (int c = 0; c < 3; c++) {
+    float w[3] = {1.0f, gw[c][0], gw[c][1]};
+    const float div = w[0] + 4 * (w[1] + w[2]);
+    const float mul = 1.0f / div;
+    for (int i = 0; i < 3; i++) vf.gab_w[c][i] = w[i] * mul;
+  }
+  vf.epf_sigma_scale[0] = lf.epf_pass0_sigma_scale * 1.65;
+  vf.epf_sigma_scale[1] = 1.65f;
+  vf.epf_sigma_scale[2] = lf.epf_pass2_sigma_scale * 1.65;
+  vf.epf_border_sad_mul = lf.epf_border_sad_mul;
+  for (int c = 0; c < 3; c++) vf.epf_channel_scale[c] = lf.epf_channel_scale[c];
+  vf.epf_quant_mul = lf.epf_quant_mul;
+  for (int i = 0; i < 8; i++) vf.epf_sharp_lut[i] = lf.epf_sharp_lut[i];
+  // colour + output
+  vf.color_transform = fh.color_transform;
+  if (fh.color_transform == kCTXYB) FillOutputColor(meta, &vf);
+  vf.out_channels = fmt.num_channels;
+  vf.out_type = fmt.data_type;
+  vf.out_big_endian = fmt.endianness == 2;
+  vf.out_stride = OutputStride(dim.xsize, fmt);
+  if (fmt.num_channels < 3) JXLB_CHECK(meta.color.IsGray(), "grey output requested for a colour image");
+}
+
+}  // namespace jxlb
+
+#endif  // JXLB_VARDCT_FRAME_H_

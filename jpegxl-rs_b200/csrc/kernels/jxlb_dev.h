@@ -73,6 +73,15 @@ struct DevChannel {
   uint32_t tree_off;  // DevTreeNode index of this channel's tree: the stream's MA tree with the
                       // static properties 0 (channel) and 1 (stream id) already resolved
   uint32_t uses_wp;   // that pruned tree needs the weighted predictor
+  // Chained sub-streams (a VarDCT DC group section holds the DC stream and the AC-metadata
+  // stream back to back, lib/jxl/dec_frame.cc:315-339): when `preamble` is set the previous
+  // entropy-coded stream ends before this channel and a new one begins: `count_bits` bits
+  // (a value whose + 1 is the width of the `dyn` channel), a GroupHeader that must select the
+  // global tree without transforms, and a fresh ANS state.
+  uint32_t preamble;
+  uint32_t count_bits;
+  uint32_t dyn;       // 1: the width of this channel is the count read in the preamble; the plane is
+                      // allocated at its upper bound and the count is stored after the plane's samples
 };
 
 // One Modular entropy-coded stream = one thread of the decode kernel.
@@ -126,6 +135,8 @@ struct DevFrameOut {
   uint32_t is_float[4];    // source samples are custom floats: bits | exp_bits << 8 (0 = integer)
   uint64_t out_off;        // byte offset of this frame in the output buffer
   uint64_t stride;         // bytes per output row
+  uint32_t vardct;         // 1: the frame is written by the VarDCT colour kernel, not by k_write_output
+  uint32_t pad_;
 };
 
 constexpr uint32_t kNoPlane = 0xFFFFFFFFu;

@@ -43,7 +43,8 @@ struct DevPools {
   const uint32_t* warp_dims;
 };
 
-enum DevStatus : uint32_t { kStatusOk = 0, kStatusOverread = 1, kStatusBadFinalState = 2, kStatusNotRun = 0x80000000u };
+enum DevStatus : uint32_t { kStatusOk = 0, kStatusOverread = 1, kStatusBadFinalState = 2, kStatusUnsupported = 4,
+                            kStatusNotRun = 0x80000000u };
 
 #if defined(__CUDA_ARCH__)
 #define JXLB_LDG(p) __ldg(p)
@@ -470,9 +471,11 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
   for (int i = 0; i < kDevMaxProps; i++) props[i * PS] = 0;
   props[1 * PS] = static_cast<int32_t>(st.stream_id);
   // weighted predictor parameters
-  const int32_t p1C = st.wp_params[0] & 0xFF, p2C = (st.wp_params[0] >> 8) & 0xFF, p3Ca = (st.wp_params[0] >> 16) & 0xFF,
-                p3Cb = st.wp_params[0] >> 24, p3Cc = st.wp_params[1] & 0xFF, p3Cd = (st.wp_params[1] >> 8) & 0xFF,
-                p3Ce = (st.wp_params[1] >> 16) & 0xFF;
+  int32_t p1C = st.wp_params[0] & 0xFF, p2C = (st.wp_params[0] >> 8) & 0xFF, p3Ca = (st.wp_params[0] >> 16) & 0xFF,
+          p3Cb = st.wp_params[0] >> 24, p3Cc = st.wp_params[1] & 0xFF, p3Cd = (st.wp_params[1] >> 8) & 0xFF,
+          p3Ce = (st.wp_params[1] >> 16) & 0xFF;
+  uint32_t status = kStatusOk;
+  uint32_t dyn_count = 0;
   uint32_t wpw[4];
   for (int i = 0; i < 4; i++) wpw[i] = (st.wp_params[2] >> (8 * i)) & 0xFF;
   const uint32_t* divlut = m.divlut;
@@ -481,13 +484,43 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
     const int max_w = static_cast<int>(warp_dims[2 * k]), max_h = static_cast<int>(warp_dims[2 * k + 1]);
     DevChannel ch{};
     int w = 0, h = 0;
+    uint32_t stride = 0;
+    bool direct = false;  // neighbours are read from the output plane instead of the lane's row ring
     int32_t* out = nullptr;
     if (k < my_chans) {
       ch = P.chans[st.chan_begin + k];
+      if (ch.preamble) {
+        // the previous entropy-coded stream ends here; the next one follows bit by bit
+        if (!code.use_prefix && reader.state != (0x13u << 16)) status |= kStatusBadFinalState;
+        dyn_count = br.Read(ch.count_bits) + 1;
+        const uint32_t use_global_tree = br.Read(1);
+        if (br.Read(1)) {  // default weighted-predictor header (context_predict.h:37-61)
+          p1C = 16; p2C = 10; p3Ca = 7; p3Cb = 7; p3Cc = 7; p3Cd = 0; p3Ce = 0;
+          wpw[0] = 0xd; wpw[1] = 0xc; wpw[2] = 0xc; wpw[3] = 0xc;
+        } else {
+          p1C = br.Read(5); p2C = br.Read(5); p3Ca = br.Read(5); p3Cb = br.Read(5); p3Cc = br.Read(5);
+          p3Cd = br.Read(5); p3Ce = br.Read(5);
+          for (int i = 0; i < 4; i++) wpw[i] = br.Read(4);
+        }
+        const uint32_t transforms_selector = br.Read(2);
+        if (!use_global_tree || transforms_selector != 0) status |= kStatusUnsupported;
+        reader.state = code.use_prefix ? (0x13u << 16) : br.Read(32);
+      }
       const DevPlane pl = P.planes[ch.plane];
       w = static_cast<int>(pl.w);
       h = static_cast<int>(pl.h);
+      stride = pl.w;
       out = P.arena + pl.off;
+      if (ch.dyn) {
+        if (dyn_count > pl.w) {
+          status |= kStatusUnsupported;
+          dyn_count = pl.w;
+        }
+        w = static_cast<int>(dyn_count);
+        out[static_cast<size_t>(pl.w) * pl.h] = static_cast<int32_t>(dyn_count);
+        direct = true;
+        if (ch.uses_wp) status |= kStatusUnsupported;
+      }
     }
     const DevTreeNode* tree = P.tree + ch.tree_off;
     // The first two levels of the tree are walked for every sample: keep them in registers.
@@ -500,7 +533,8 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
         root_r = DevLoadNode(tree + root.c);
       }
     }
-    const bool uses_wp = ch.uses_wp != 0;
+    const bool uses_wp = ch.uses_wp != 0 && !direct;
+    const size_t RS = direct ? 1 : LS;
     props[0] = static_cast<int32_t>(ch.prop0);
     props[15 * PS] = 0;
     if (uses_wp) {
@@ -510,10 +544,11 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
     }
     for (int y = 0; y < max_h; y++) {
       const bool row_on = y < h;
-      int32_t* row = m.ring + static_cast<size_t>((y % 3) * RW) * LS;
-      const int32_t* prev = m.ring + static_cast<size_t>(((y + 2) % 3) * RW) * LS;
-      const int32_t* prevprev = m.ring + static_cast<size_t>(((y + 1) % 3) * RW) * LS;
-      int32_t* out_row = out + static_cast<size_t>(y) * w;
+      int32_t* out_row = out + static_cast<size_t>(y) * stride;
+      int32_t* row = direct ? out_row : m.ring + static_cast<size_t>((y % 3) * RW) * LS;
+      const int32_t* prev = direct ? out_row - stride : m.ring + static_cast<size_t>(((y + 2) % 3) * RW) * LS;
+      const int32_t* prevprev = direct ? out_row - 2 * static_cast<size_t>(stride)
+                                       : m.ring + static_cast<size_t>(((y + 1) % 3) * RW) * LS;
       const uint32_t cur = (y & 1) ? 0 : 1, prv = cur ^ 1;
       int32_t* pe_cur[4];
       const int32_t* pe_prv[4];
@@ -532,8 +567,8 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
       if (row_on && w > 0) {
         if (y > 0) {
           t = prev[0];
-          tr = w > 1 ? prev[static_cast<size_t>(1) * LS] : t;
-          trr = w > 2 ? prev[static_cast<size_t>(2) * LS] : tr;
+          tr = w > 1 ? prev[static_cast<size_t>(1) * RS] : t;
+          trr = w > 2 ? prev[static_cast<size_t>(2) * RS] : tr;
         }
         if (uses_wp) {
           for (uint32_t i = 0; i < 4; i++) {
@@ -554,7 +589,7 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
           const WT n_topleft = (x && y) ? tl : n_left;
           const WT n_topright = (x + 1 < w && y) ? tr : n_top;
           const WT n_leftleft = x > 1 ? leftleft : n_left;
-          const WT n_toptop = y > 1 ? prevprev[static_cast<size_t>(x) * LS] : n_top;
+          const WT n_toptop = y > 1 ? prevprev[static_cast<size_t>(x) * RS] : n_top;
           const WT n_toprightright = (x + 2 < w && y) ? trr : n_topright;
           props[3 * PS] = x;
           props[4 * PS] = static_cast<int32_t>(n_top > 0 ? n_top : -n_top);
@@ -643,7 +678,7 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
           // low 32 bits of (unpacked * multiplier + guess), as in make_pixel (encoding.cc:168-173)
           const int32_t val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) * node.c +
                                                    static_cast<uint32_t>(guess));
-          row[static_cast<size_t>(x) * LS] = val;
+          row[static_cast<size_t>(x) * RS] = val;
           out_row[x] = val;
           leftleft = left;
           left = val;
@@ -651,7 +686,7 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
           tl = t;
           t = tr;
           tr = trr;
-          if (y > 0 && x + 3 < w) trr = prev[static_cast<size_t>(x + 3) * LS];
+          if (y > 0 && x + 3 < w) trr = prev[static_cast<size_t>(x + 3) * RS];
           if (uses_wp) {
             const WT val8 = static_cast<WT>(val) * 8;
             const int32_t te = static_cast<int32_t>(wp_raw - val8);
@@ -675,7 +710,6 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
       }
     }
   }
-  uint32_t status = kStatusOk;
   if (lane_valid) {
     if (!code.use_prefix && reader.state != (0x13u << 16)) status |= kStatusBadFinalState;
     if (br.Pos() > st.bit_end) status |= kStatusOverread;

@@ -1,0 +1,1197 @@
+// jxl_b200 device code of the VarDCT path (lossy frames).
+//
+// Kernel map (wrappers in jxl_b200.cu; the bodies below are __host__ __device__ so that
+// tests/ can run the same statements on the CPU, the product never does):
+//   DevDcGroupFinish   one CTA per DC group: quantised DC -> float DC (+ chroma-from-luma on DC),
+//                      quant-DC bucket, AC-metadata rows -> strategy / quant / sharpness / sigma maps
+//                        lib/jxl/compressed_dc.cc:197-290, lib/jxl/dec_modular.cc:437-532, lib/jxl/epf.cc:39-147
+//   DevDcSmoothPixel   adaptive DC smoothing, lib/jxl/compressed_dc.cc:124-195
+//   DevDecodeAcStream  one thread per (frame, group, pass): block contexts, non-zero counts, the
+//                      coefficient symbol loop; emits sparse tokens
+//                        lib/jxl/dec_group.cc:454-527, :534-645, lib/jxl/ac_context.h, lib/jxl/dec_ans.h:168-255
+//   DevVarblock        one warp / CTA per varblock: token scatter, dequantisation + quant bias + chroma
+//                      from luma, lowest frequencies from DC, the 27 inverse transforms
+//                        lib/jxl/dec_group.cc:98-166, lib/jxl/quantizer-inl.h:34-71,
+//                        lib/jxl/dec_transforms-inl.h:30-813, lib/jxl/dct-inl.h:50-335
+//   DevGaborishPixel / DevEpfPixel / DevColorPixel   per-pixel render stages
+//                        lib/jxl/render_pipeline/stage_{gaborish,epf,xyb,ycbcr,from_linear,write}.cc
+//
+// Floating point: every multiply-add that libjxl writes as MulAdd / NegMulAdd is an explicit fmaf;
+// everything else is a separately rounded IEEE operation (the library is built with --fmad=false),
+// so the results do not depend on how the work is spread over threads.
+#ifndef JXLB_VARDCT_DEV_H_
+#define JXLB_VARDCT_DEV_H_
+
+#include <math.h>
+
+#include "jxlb_finish_dev.h"
+#include "jxlb_vardct_desc.h"
+
+namespace jxlb {
+
+struct DevVPools {
+  const DevVFrame* frames;
+  const DevAcStream* streams;
+  uint32_t num_streams;
+  const float* fpool;
+  const uint16_t* opool;
+  const uint8_t* cpool;
+  const uint32_t* upool;
+  float* farena;
+  uint8_t* barena;
+  uint32_t* uarena;
+  uint32_t* tokens;
+  uint32_t* ac_status;  // per AC stream
+  uint32_t* ac_used;    // per AC stream: tokens produced (may exceed the capacity -> retry with more)
+  uint32_t* dc_status;  // per (frame, DC group)
+  uint32_t wc_off, llf_off, afv_off;  // fpool: WcMultipliers, DC -> LLF resample scales, AFV basis
+  uint32_t sinfo_off;                 // upool: packed StrategyInfo x 27
+  uint32_t ctxtab_off;                // upool: kCoeffFreqContext[64] then kCoeffNumNonzeroContext[64]
+  uint8_t* out;
+};
+
+template <int SCOPE>
+JXLB_HD void CoopSync() {
+#if defined(__CUDA_ARCH__)
+  if (SCOPE == 1) __syncwarp();
+  if (SCOPE == 2) __syncthreads();
+#endif
+}
+
+#if defined(__CUDA_ARCH__)
+#define JXLB_WARP_ALL(p) __all_sync(0xFFFFFFFFu, (p))
+#else
+#define JXLB_WARP_ALL(p) (p)
+#endif
+
+constexpr float kDevSqrt2 = 1.41421356237f;
+
+// ---------------------------------------------------------------- DC groups
+template <int SCOPE>
+JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t frame, uint32_t g, uint32_t tid, uint32_t nt,
+                              uint32_t status_index) {
+  const DevVFrame& vf = V.frames[frame];
+  const uint32_t W = vf.xblocks, H = vf.yblocks;
+  const uint32_t gx = g % vf.xdcgroups, gy = g / vf.xdcgroups;
+  const uint32_t x0 = gx * 256, y0 = gy * 256;
+  const uint32_t xs = W - x0 < 256 ? W - x0 : 256, ys = H - y0 < 256 ? H - y0 : 256;
+  const uint32_t* dcg = V.upool + vf.dcg_index + 8 * g;
+  const int32_t* qy = P.arena + P.planes[dcg[0]].off;
+  const int32_t* qx = P.arena + P.planes[dcg[1]].off;
+  const int32_t* qb = P.arena + P.planes[dcg[2]].off;
+  const int32_t* m_ytox = P.arena + P.planes[dcg[3]].off;
+  const int32_t* m_ytob = P.arena + P.planes[dcg[4]].off;
+  const DevPlane pl_rows = P.planes[dcg[5]];
+  const int32_t* m_rows = P.arena + pl_rows.off;
+  const int32_t* m_sharp = P.arena + P.planes[dcg[6]].off;
+  const uint32_t extra_precision = dcg[7];
+  const float mul = 1.0f / static_cast<float>(1u << extra_precision);
+  const float fac_x = vf.mul_dc[0] * mul, fac_y = vf.mul_dc[1] * mul, fac_b = vf.mul_dc[2] * mul;
+  float* dcx = V.farena + vf.dc[0];
+  float* dcy = V.farena + vf.dc[1];
+  float* dcb = V.farena + vf.dc[2];
+  uint8_t* acs = V.barena + vf.acs;
+  uint8_t* qdc = V.barena + vf.qdc;
+  uint8_t* sharp = V.barena + vf.sharp;
+  uint16_t* rawq = reinterpret_cast<uint16_t*>(V.barena + vf.rawq);
+  const uint32_t* thr = V.upool + vf.bctx_off;
+  uint32_t status = 0;
+  // (a) per block: dequantised DC, quant-DC bucket, sharpness; strategy map cleared
+  for (uint32_t i = tid; i < xs * ys; i += nt) {
+    const uint32_t x = i % xs, y = i / xs;
+    const size_t pos = static_cast<size_t>(y0 + y) * W + x0 + x;
+    const int32_t vx = qx[i], vy = qy[i], vb = qb[i];
+    const float in_x = static_cast<float>(vx) * fac_x;
+    const float in_y = static_cast<float>(vy) * fac_y;
+    const float in_b = static_cast<float>(vb) * fac_b;
+    dcy[pos] = in_y;
+    dcx[pos] = fmaf(in_y, vf.cfl_dc_x, in_x);
+    dcb[pos] = fmaf(in_y, vf.cfl_dc_b, in_b);
+    uint32_t bucket = 0;
+    if (vf.num_dc_ctxs > 1) {
+      const uint32_t n0 = vf.num_dc_thr[0], n1 = vf.num_dc_thr[1], n2 = vf.num_dc_thr[2];
+      uint32_t bx = 0, by = 0, bb = 0;
+      for (uint32_t t = 0; t < n0; t++) bx += vx > static_cast<int32_t>(thr[t]);
+      for (uint32_t t = 0; t < n1; t++) by += vy > static_cast<int32_t>(thr[n0 + t]);
+      for (uint32_t t = 0; t < n2; t++) bb += vb > static_cast<int32_t>(thr[n0 + n1 + t]);
+      bucket = (bx * (n2 + 1) + bb) * (n1 + 1) + by;
+    }
+    qdc[pos] = static_cast<uint8_t>(bucket);
+    const int32_t sh = m_sharp[i];
+    if (sh < 0 || sh >= 8) status |= kVBadStream;
+    sharp[pos] = static_cast<uint8_t>(sh & 7);
+    acs[pos] = 0xFF;
+  }
+  // colour correlation maps (one entry per 64x64 tile)
+  const uint32_t cw = (xs + 7) >> 3, chh = (ys + 7) >> 3, cx0 = x0 >> 3, cy0 = y0 >> 3;
+  int8_t* ytox = reinterpret_cast<int8_t*>(V.barena + vf.ytox);
+  int8_t* ytob = reinterpret_cast<int8_t*>(V.barena + vf.ytob);
+  for (uint32_t i = tid; i < cw * chh; i += nt) {
+    const uint32_t x = i % cw, y = i / cw;
+    int32_t a = m_ytox[i], b = m_ytob[i];
+    a = a < -128 ? -128 : (a > 127 ? 127 : a);
+    b = b < -128 ? -128 : (b > 127 ? 127 : b);
+    ytox[(cy0 + y) * vf.cmw + cx0 + x] = static_cast<int8_t>(a);
+    ytob[(cy0 + y) * vf.cmw + cx0 + x] = static_cast<int8_t>(b);
+  }
+  CoopSync<SCOPE>();
+  // (b) the strategy / quant rows list one entry per varblock in raster order of their top-left
+  // blocks; where the next varblock starts depends on the extents of all earlier ones: serial.
+  if (tid == 0) {
+    const uint32_t cap = pl_rows.w;
+    const uint32_t count = static_cast<uint32_t>(m_rows[static_cast<size_t>(cap) * 2]);
+    const int32_t* row_strategy = m_rows;
+    const int32_t* row_quant = m_rows + cap;
+    uint32_t num = 0;
+    for (uint32_t iy = 0; iy < ys && !(status & kVBadStream); iy++) {
+      const uint32_t y = y0 + iy;
+      for (uint32_t ix = 0; ix < xs; ix++) {
+        const uint32_t x = x0 + ix;
+        const size_t pos = static_cast<size_t>(y) * W + x;
+        if (acs[pos] != 0xFF) continue;
+        if (num >= count) {
+          status |= kVBadStream;
+          break;
+        }
+        const int32_t raw = row_strategy[num];
+        if (raw < 0 || raw >= static_cast<int32_t>(kNumStrategies)) {
+          status |= kVBadStream;
+          break;
+        }
+        const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + raw]);
+        const uint32_t next_x = (x / 32 + 1) * 32, next_y = (y / 32 + 1) * 32;  // varblocks stay inside their 256x256 group
+        const uint32_t xlim = x0 + xs, ylim = y0 + ys;
+        if (x + si.cx > next_x || x + si.cx > xlim || y + si.cy > next_y || y + si.cy > ylim) {
+          status |= kVBadStream;
+          break;
+        }
+        bool overlap = false;
+        for (uint32_t jy = 0; jy < si.cy; jy++)
+          for (uint32_t jx = 0; jx < si.cx; jx++) {
+            uint8_t& e = acs[pos + static_cast<size_t>(jy) * W + jx];
+            overlap |= e != 0xFF;
+            e = static_cast<uint8_t>((raw << 1) | ((jy | jx) == 0 ? 1 : 0));
+          }
+        if (overlap) {
+          status |= kVBadStream;
+          break;
+        }
+        int32_t q = row_quant[num];
+        q = q < 0 ? 0 : (q > 255 ? 255 : q);
+        rawq[pos] = static_cast<uint16_t>(1 + q);
+        num++;
+      }
+    }
+  }
+  CoopSync<SCOPE>();
+  // (c) EPF sigma per block (ComputeSigma): every varblock fills the blocks it covers
+  if (vf.epf_iters > 0) {
+    float* inv_sigma = V.farena + vf.inv_sigma;
+    const float kInvSigmaNum = -1.1715728752538099024f;
+    for (uint32_t i = tid; i < xs * ys; i += nt) {
+      const uint32_t x = i % xs, y = i / xs;
+      const size_t pos = static_cast<size_t>(y0 + y) * W + x0 + x;
+      const uint8_t a = acs[pos];
+      if (a == 0xFF || !(a & 1)) continue;
+      const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
+      const float sigma_quant = vf.epf_quant_mul / (vf.global_scale_f * static_cast<float>(rawq[pos]) * kInvSigmaNum);
+      for (uint32_t iy = 0; iy < si.cy; iy++)
+        for (uint32_t ix = 0; ix < si.cx; ix++) {
+          const size_t q = pos + static_cast<size_t>(iy) * W + ix;
+          float sigma = sigma_quant * vf.epf_sharp_lut[sharp[q]];
+          sigma = sigma < -1e-4f ? sigma : -1e-4f;
+          inv_sigma[q] = 1.0f / sigma;
+        }
+    }
+  }
+  if (status && V.dc_status) V.dc_status[status_index] = status;  // pre-zeroed by the host
+}
+
+// One block of AdaptiveDCSmoothing: dc -> dc_final (only called when smoothing is on).
+JXLB_HD void DevDcSmoothBlock(const DevVPools& V, const DevVFrame& vf, uint32_t x, uint32_t y) {
+  const uint32_t W = vf.xblocks, H = vf.yblocks;
+  const size_t pos = static_cast<size_t>(y) * W + x;
+  if (x == 0 || y == 0 || x + 1 >= W || y + 1 >= H) {
+    for (int c = 0; c < 3; c++) V.farena[vf.dc_final[c] + pos] = V.farena[vf.dc[c] + pos];
+    return;
+  }
+  const float w1 = 0.20345139757231578f, w2 = 0.0334829185968739f;
+  const float w0 = 1.0f - 4.0f * (w1 + w2);
+  float mc[3], sm[3];
+  float gap = 0.5f;
+  for (int c = 0; c < 3; c++) {
+    const float* rm = V.farena + vf.dc[c] + pos;
+    const float* rt = rm - W;
+    const float* rb = rm + W;
+    mc[c] = rm[0];
+    const float corner = (rt[-1] + rt[1]) + (rb[-1] + rb[1]);
+    const float side = (rm[-1] + rm[1]) + (rt[0] + rb[0]);
+    sm[c] = fmaf(corner, w2, fmaf(side, w1, mc[c] * w0));
+    const float d = fabsf((mc[c] - sm[c]) / vf.mul_dc[c]);
+    gap = gap > d ? gap : d;
+  }
+  float factor = fmaf(-4.0f, gap, 3.0f);
+  if (factor < 0.0f) factor = 0.0f;
+  for (int c = 0; c < 3; c++) V.farena[vf.dc_final[c] + pos] = fmaf(sm[c] - mc[c], factor, mc[c]);
+}
+
+// ---------------------------------------------------------------- AC coefficient streams
+struct DevAcLaneMem {
+  uint8_t* colnz;          // [3 * 32] entries, element stride `stride`: last non-zero bucket per column
+  uint32_t stride;
+  const uint16_t* freq_ctx;  // kCoeffFreqContext[64]
+  const uint16_t* nnz_ctx;   // kCoeffNumNonzeroContext[64]
+};
+
+JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32_t s, const DevAcLaneMem& m, bool valid) {
+  enum { kNeedBlock = 0, kReadNz = 1, kCoeff = 2, kDone = 3 };
+  uint32_t mode = kDone, status = 0;
+  DevAcStream st{};
+  DevBits br{};
+  DevSymbolReader reader{};
+  DevCode code{};
+  const DevVFrame* vf = nullptr;
+  uint32_t W = 0, x0 = 0, y0 = 0, xs = 0, ys = 0, shift_unused = 0;
+  uint32_t ctx_offset = 0, num_ctxs = 0;
+  const uint8_t* ctx_map = nullptr;
+  const uint8_t* acs = nullptr;
+  const uint8_t* qdc = nullptr;
+  const uint16_t* rawq = nullptr;
+  uint32_t* tok = nullptr;
+  uint32_t* ts = nullptr;
+  uint32_t* tc = nullptr;
+  size_t nb = 0;
+  if (valid) {
+    st = V.streams[s];
+    vf = V.frames + st.frame;
+    W = vf->xblocks;
+    nb = static_cast<size_t>(W) * vf->yblocks;
+    const uint32_t gx = st.group % vf->xgroups, gy = st.group / vf->xgroups;
+    x0 = gx * 32;
+    y0 = gy * 32;
+    xs = W - x0 < 32 ? W - x0 : 32;
+    ys = vf->yblocks - y0 < 32 ? vf->yblocks - y0 : 32;
+    br.Init(P.words, st.bit_pos);
+    num_ctxs = vf->num_ctxs;
+    uint32_t selector_bits = 0;
+    while ((1u << selector_bits) < vf->num_histograms) selector_bits++;
+    const uint32_t cur = selector_bits ? br.Read(selector_bits) : 0;
+    if (cur >= vf->num_histograms) status |= kVBadStream;
+    ctx_offset = cur * num_ctxs * 495;
+    code = P.codes[vf->ac_code[st.pass]];
+    reader.Init(P, code, br, 0, nullptr);
+    ctx_map = V.cpool + vf->ctx_map_off[st.pass];
+    acs = V.barena + vf->acs;
+    qdc = V.barena + vf->qdc;
+    rawq = reinterpret_cast<const uint16_t*>(V.barena + vf->rawq);
+    tok = V.tokens + st.tok_off;
+    ts = V.uarena + vf->tok_start + static_cast<size_t>(st.pass) * 3 * nb;
+    tc = V.uarena + vf->tok_count + static_cast<size_t>(st.pass) * 3 * nb;
+    mode = (status == 0) ? kNeedBlock : kDone;
+  }
+  (void)shift_unused;
+  const uint32_t* bthr = vf ? V.upool + vf->bctx_off : nullptr;
+  uint32_t nqf = 0, bmap_off = 0;
+  if (vf) {
+    nqf = vf->num_qf_thr;
+    bmap_off = vf->num_dc_thr[0] + vf->num_dc_thr[1] + vf->num_dc_thr[2] + nqf;
+  }
+  const uint32_t LS = m.stride;
+  uint32_t bx = 0, by = 0, ci = 3;                 // position inside the group, channel step (Y, X, B)
+  uint32_t cx = 1, log2c = 0, covered = 1, size = 64, ord = 0;
+  uint32_t c = 0, k = 0, nz = 0, prev = 0, histo_offset = 0, ctx = 0, ntok = 0, chan_start = 0;
+  size_t pos = 0;
+  const uint16_t* order = nullptr;
+  for (;;) {
+    if (mode == kNeedBlock) {
+      if (ci >= 3) {  // next varblock in raster order of the top-left blocks
+        for (;;) {
+          if (bx >= xs) {
+            bx = 0;
+            by++;
+          }
+          if (by >= ys) break;
+          pos = static_cast<size_t>(y0 + by) * W + x0 + bx;
+          const uint8_t a = acs[pos];
+          if (a == 0xFF) {
+            status |= kVBadStream;
+            by = ys;
+            break;
+          }
+          const StrategyInfo si = UnpackStrategyInfo(JXLB_LDG(V.upool + V.sinfo_off + (a >> 1)));
+          cx = si.cx;
+          if (a & 1) {
+            log2c = si.log2_covered;
+            covered = 1u << log2c;
+            size = covered * 64;
+            ord = si.order;
+            break;
+          }
+          bx += cx;
+        }
+        ci = 0;
+      }
+      if (by >= ys) {
+        mode = kDone;
+      } else {
+        c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);
+        // block context (lib/jxl/ac_context.h:99-109)
+        const uint32_t qf = rawq[pos];
+        uint32_t qf_idx = 0;
+        for (uint32_t t = 0; t < nqf; t++) qf_idx += qf > bthr[bmap_off - nqf + t];
+        uint32_t idx = (c < 2 ? c ^ 1 : 2) * kNumOrders + ord;
+        idx = idx * (nqf + 1) + qf_idx;
+        idx = idx * vf->num_dc_ctxs + qdc[pos];
+        const uint32_t block_ctx = (bthr[bmap_off + (idx >> 2)] >> (8 * (idx & 3))) & 0xFF;
+        // predicted number of non-zeros from the top and left neighbours
+        uint32_t predicted;
+        const uint8_t* col = m.colnz + static_cast<size_t>(c * 32 + bx) * LS;
+        if (bx == 0) {
+          predicted = by == 0 ? 32 : col[0];
+        } else if (by == 0) {
+          predicted = col[-static_cast<ptrdiff_t>(LS)];
+        } else {
+          predicted = (static_cast<uint32_t>(col[0]) + col[-static_cast<ptrdiff_t>(LS)] + 1) / 2;
+        }
+        uint32_t bucket = predicted >= 64 ? 64 : predicted;
+        bucket = bucket < 8 ? bucket : 4 + bucket / 2;
+        ctx = ctx_offset + bucket * num_ctxs + block_ctx;
+        histo_offset = ctx_offset + num_ctxs * 37 + 458 * block_ctx;
+        order = V.opool + JXLB_LDG(V.upool + vf->order_index + st.pass * 39 + 3 * ord + c);
+        mode = kReadNz;
+      }
+    }
+    if (JXLB_WARP_ALL(mode == kDone)) break;
+    if (mode == kDone) continue;
+    if (mode == kCoeff) {
+      const uint32_t nzl = (nz + covered - 1) >> log2c;
+      ctx = histo_offset + (m.nnz_ctx[nzl] + m.freq_ctx[k >> log2c]) * 2 + prev;
+    }
+    const uint32_t u = reader.ReadUint(JXLB_LDG(ctx_map + ctx), br);
+    bool chan_done = false;
+    if (mode == kReadNz) {
+      nz = u;
+      if (nz > size - covered) {
+        status |= kVBadStream;
+        mode = kDone;
+        continue;
+      }
+      const uint8_t v = static_cast<uint8_t>((nz + covered - 1) >> log2c);
+      uint8_t* col = m.colnz + static_cast<size_t>(c * 32 + bx) * LS;
+      for (uint32_t i = 0; i < cx; i++) col[static_cast<size_t>(i) * LS] = v;
+      chan_start = ntok;
+      ts[c * nb + pos] = static_cast<uint32_t>(st.tok_off) + (ntok < st.tok_cap ? ntok : st.tok_cap);
+      k = covered;
+      prev = nz > size / 16 ? 0 : 1;
+      if (nz == 0) {
+        chan_done = true;
+      } else {
+        mode = kCoeff;
+      }
+    } else {
+      if (u != 0) {
+        const uint32_t magnitude = u >> 1, neg_sign = (~u) & 1;
+        const int32_t coeff = static_cast<int32_t>(magnitude ^ (neg_sign - 1));
+        if (coeff > 32767 || coeff < -32767) status |= kVUnsupported;  // the token format holds 16-bit values
+        if (ntok < st.tok_cap) tok[ntok] = static_cast<uint32_t>(JXLB_LDG(order + k)) | (static_cast<uint32_t>(coeff) << 16);
+        ntok++;
+        nz--;
+        prev = 1;
+      } else {
+        prev = 0;
+      }
+      k++;
+      if (nz == 0) {
+        chan_done = true;
+      } else if (k >= size) {
+        status |= kVBadStream;  // non-zeros left at the end of the block
+        chan_done = true;
+      }
+    }
+    if (chan_done) {
+      tc[c * nb + pos] = (ntok < st.tok_cap ? ntok : st.tok_cap) - (chan_start < st.tok_cap ? chan_start : st.tok_cap);
+      ci++;
+      if (ci >= 3) bx += cx;
+      mode = kNeedBlock;
+    }
+  }
+  if (valid) {
+    if (!code.use_prefix && reader.state != (0x13u << 16)) status |= kVBadFinalState;
+    if (br.Pos() > st.bit_end) status |= kVOverread;
+    if (ntok > st.tok_cap) status |= kVTokenOverflow;
+    V.ac_used[s] = ntok;
+  }
+  return status;
+}
+
+// ---------------------------------------------------------------- 1-D transforms, staged
+// An N-point transform of libjxl's recursive DCT (lib/jxl/dct-inl.h:167-222) unrolled into
+// 2 * log2(N) - 1 stages in which every element is computed independently: any number of
+// threads can share a stage, and the arithmetic per element is exactly the recursion's.
+// A "line" is the 1-D signal; element e of line l lives at buf[l * ls + e * es].
+
+// Inverse. Returns the buffer that holds the result (src or dst).
+template <int SCOPE>
+JXLB_HD float* CoopIDCT(uint32_t n, uint32_t lines, uint32_t ls, uint32_t es, float* src, float* dst, const float* wc,
+                        uint32_t tid, uint32_t nt) {
+  if (n < 2) return src;
+  uint32_t log2n = 0;
+  while ((1u << log2n) < n) log2n++;
+  const uint32_t total = lines * n;
+  // downward: even/odd split of every sub-problem of size m, B-transpose on the odd half
+  for (uint32_t m = n; m > 2; m >>= 1) {
+    const uint32_t h = m >> 1;
+    for (uint32_t i = tid; i < total; i += nt) {
+      const uint32_t l = i >> log2n, e = i & (n - 1);
+      const uint32_t sub = e & ~(m - 1), r = e & (m - 1);
+      const float* line = src + static_cast<size_t>(l) * ls;
+      float v;
+      if (r < h) {
+        v = line[static_cast<size_t>(sub + 2 * r) * es];
+      } else {
+        const uint32_t j = r - h;
+        const float t = line[static_cast<size_t>(sub + 2 * j + 1) * es];
+        v = j == 0 ? t * kDevSqrt2 : t + line[static_cast<size_t>(sub + 2 * j - 1) * es];
+      }
+      dst[static_cast<size_t>(l) * ls + static_cast<size_t>(e) * es] = v;
+    }
+    CoopSync<SCOPE>();
+    float* t = src;
+    src = dst;
+    dst = t;
+  }
+  // 2-point butterflies
+  for (uint32_t i = tid; i < total; i += nt) {
+    const uint32_t l = i >> log2n, e = i & (n - 1);
+    const float* line = src + static_cast<size_t>(l) * ls;
+    const float a = line[static_cast<size_t>(e & ~1u) * es], b = line[static_cast<size_t>(e | 1u) * es];
+    dst[static_cast<size_t>(l) * ls + static_cast<size_t>(e) * es] = (e & 1) ? a - b : a + b;
+  }
+  CoopSync<SCOPE>();
+  {
+    float* t = src;
+    src = dst;
+    dst = t;
+  }
+  // upward: out[i] = in1 + mul[i] * in2, out[m - 1 - i] = in1 - mul[i] * in2
+  for (uint32_t m = 4; m <= n; m <<= 1) {
+    const uint32_t h = m >> 1;
+    const float* mul = wc + (m / 2 - 2);
+    for (uint32_t i = tid; i < total; i += nt) {
+      const uint32_t l = i >> log2n, e = i & (n - 1);
+      const uint32_t sub = e & ~(m - 1), r = e & (m - 1);
+      const float* line = src + static_cast<size_t>(l) * ls;
+      const uint32_t j = r < h ? r : m - 1 - r;
+      const float in1 = line[static_cast<size_t>(sub + j) * es], in2 = line[static_cast<size_t>(sub + h + j) * es];
+      const float w = mul[j];
+      dst[static_cast<size_t>(l) * ls + static_cast<size_t>(e) * es] = fmaf(r < h ? w : -w, in2, in1);
+    }
+    CoopSync<SCOPE>();
+    float* t = src;
+    src = dst;
+    dst = t;
+  }
+  return src;
+}
+
+// Forward (DCT1DImpl), scaled by 1 / n. Returns the buffer that holds the result.
+template <int SCOPE>
+JXLB_HD float* CoopDCT(uint32_t n, uint32_t lines, uint32_t ls, uint32_t es, float* src, float* dst, const float* wc,
+                       uint32_t tid, uint32_t nt) {
+  uint32_t log2n = 0;
+  while ((1u << log2n) < n) log2n++;
+  const uint32_t total = lines * n;
+  if (n >= 2) {
+    for (uint32_t m = n; m > 2; m >>= 1) {  // AddReverse / SubReverse + Multiply
+      const uint32_t h = m >> 1;
+      const float* mul = wc + (m / 2 - 2);
+      for (uint32_t i = tid; i < total; i += nt) {
+        const uint32_t l = i >> log2n, e = i & (n - 1);
+        const uint32_t sub = e & ~(m - 1), r = e & (m - 1);
+        const float* line = src + static_cast<size_t>(l) * ls;
+        const uint32_t j = r < h ? r : r - h;
+        const float a = line[static_cast<size_t>(sub + j) * es], b = line[static_cast<size_t>(sub + m - 1 - j) * es];
+        dst[static_cast<size_t>(l) * ls + static_cast<size_t>(e) * es] = r < h ? a + b : (a - b) * mul[j];
+      }
+      CoopSync<SCOPE>();
+      float* t = src;
+      src = dst;
+      dst = t;
+    }
+    for (uint32_t i = tid; i < total; i += nt) {
+      const uint32_t l = i >> log2n, e = i & (n - 1);
+      const float* line = src + static_cast<size_t>(l) * ls;
+      const float a = line[static_cast<size_t>(e & ~1u) * es], b = line[static_cast<size_t>(e | 1u) * es];
+      dst[static_cast<size_t>(l) * ls + static_cast<size_t>(e) * es] = (e & 1) ? a - b : a + b;
+    }
+    CoopSync<SCOPE>();
+    {
+      float* t = src;
+      src = dst;
+      dst = t;
+    }
+    for (uint32_t m = 4; m <= n; m <<= 1) {  // B + InverseEvenOdd
+      const uint32_t h = m >> 1;
+      for (uint32_t i = tid; i < total; i += nt) {
+        const uint32_t l = i >> log2n, e = i & (n - 1);
+        const uint32_t sub = e & ~(m - 1), r = e & (m - 1);
+        const float* line = src + static_cast<size_t>(l) * ls;
+        float v;
+        if ((r & 1) == 0) {
+          v = line[static_cast<size_t>(sub + (r >> 1)) * es];
+        } else {
+          const uint32_t j = r >> 1;
+          const float t0 = line[static_cast<size_t>(sub + h + j) * es];
+          if (j == 0) {
+            v = fmaf(t0, kDevSqrt2, line[static_cast<size_t>(sub + h + 1) * es]);
+          } else if (j + 1 < h) {
+            v = t0 + line[static_cast<size_t>(sub + h + j + 1) * es];
+          } else {
+            v = t0;
+          }
+        }
+        dst[static_cast<size_t>(l) * ls + static_cast<size_t>(e) * es] = v;
+      }
+      CoopSync<SCOPE>();
+      float* t = src;
+      src = dst;
+      dst = t;
+    }
+  }
+  const float scale = 1.0f / static_cast<float>(n);
+  for (uint32_t i = tid; i < total; i += nt) {
+    const uint32_t l = i >> log2n, e = i & (n - 1);
+    const size_t at = static_cast<size_t>(l) * ls + static_cast<size_t>(e) * es;
+    src[at] = scale * src[at];
+  }
+  CoopSync<SCOPE>();
+  return src;
+}
+
+// ---------------------------------------------------------------- scalar 8x8 special transforms
+// IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4 and AFV0-3 cover one 8x8 block; one thread per channel
+// runs libjxl's statements (lib/jxl/dec_transforms-inl.h:61-88, :380-449, :458-576).
+template <int N>
+JXLB_HD void ScalarIDCT1D(const float* from, int fs, float* to, int ts, const float* wc) {
+  if (N == 1) {
+    to[0] = from[0];
+    return;
+  }
+  if (N == 2) {
+    const float a = from[0], b = from[fs];
+    to[0] = a + b;
+    to[ts] = a - b;
+    return;
+  }
+  constexpr int H = N / 2 > 0 ? N / 2 : 1;
+  float tmp[N];
+  for (int i = 0; i < H; i++) tmp[i] = from[2 * i * fs];
+  for (int i = H; i < N; i++) tmp[i] = from[(2 * (i - H) + 1) * fs];
+  ScalarIDCT1D<H>(tmp, 1, tmp, 1, wc);
+  for (int i = H - 1; i > 0; i--) tmp[H + i] = tmp[H + i] + tmp[H + i - 1];
+  tmp[H] = tmp[H] * kDevSqrt2;
+  ScalarIDCT1D<H>(tmp + H, 1, tmp + H, 1, wc);
+  const float* mul = wc + (N / 2 - 2);
+  for (int i = 0; i < H; i++) {
+    const float in1 = tmp[i], in2 = tmp[H + i];
+    to[i * ts] = fmaf(mul[i], in2, in1);
+    to[(N - i - 1) * ts] = fmaf(-mul[i], in2, in1);
+  }
+}
+template <>
+JXLB_HD void ScalarIDCT1D<0>(const float*, int, float*, int, const float*) {}
+
+// ComputeScaledIDCT<R, C> for R, C in {4, 8}; `from` is in the min x max layout.
+template <int R, int C>
+JXLB_HD void ScalarScaledIDCT(const float* from, float* to, int to_stride, const float* wc) {
+  float a[R * C], b[R * C];
+  // x direction (C-point) first, then y (R-point); the layout rules follow ComputeScaledIDCT
+  if (R < C) {
+    // from: R rows x C cols, [yfreq][xfreq]
+    for (int i = 0; i < R; i++) ScalarIDCT1D<C>(from + i * C, 1, a + i * C, 1, wc);      // a[yfreq][x]
+    for (int x = 0; x < C; x++) ScalarIDCT1D<R>(a + x, C, b + x, C, wc);                  // b[y][x]
+    for (int y = 0; y < R; y++)
+      for (int x = 0; x < C; x++) to[y * to_stride + x] = b[y * C + x];
+  } else {
+    // from: C rows x R cols, [xfreq][yfreq]
+    for (int j = 0; j < R; j++) ScalarIDCT1D<C>(from + j, R, a + j, R, wc);               // a[x][yfreq]
+    for (int x = 0; x < C; x++) ScalarIDCT1D<R>(a + x * R, 1, b + x * R, 1, wc);          // b[x][y]
+    for (int y = 0; y < R; y++)
+      for (int x = 0; x < C; x++) to[y * to_stride + x] = b[x * R + y];
+  }
+}
+
+JXLB_HD void ScalarIDCT2TopBlock(int S, float* block) {  // in place on an 8x8 row-major block
+  float temp[64];
+  const int num = S / 2;
+  for (int y = 0; y < num; y++)
+    for (int x = 0; x < num; x++) {
+      const float c00 = block[y * 8 + x], c01 = block[y * 8 + num + x];
+      const float c10 = block[(y + num) * 8 + x], c11 = block[(y + num) * 8 + num + x];
+      temp[y * 2 * 8 + x * 2] = c00 + c01 + c10 + c11;
+      temp[y * 2 * 8 + x * 2 + 1] = c00 + c01 - c10 - c11;
+      temp[(y * 2 + 1) * 8 + x * 2] = c00 - c01 + c10 - c11;
+      temp[(y * 2 + 1) * 8 + x * 2 + 1] = c00 - c01 - c10 + c11;
+    }
+  for (int y = 0; y < S; y++)
+    for (int x = 0; x < S; x++) block[y * 8 + x] = temp[y * 8 + x];
+}
+
+// coefficients: 64 floats (8x8 row-major); pixels: 8 rows of `stride`.
+JXLB_HD void DevSpecialToPixels(uint32_t strategy, const float* coefficients, float* pixels, int stride, const float* wc,
+                                const float* afv_basis) {
+  switch (strategy) {
+    case 1: {  // IDENTITY
+      const float b00 = coefficients[0], b01 = coefficients[1], b10 = coefficients[8], b11 = coefficients[9];
+      const float dcs[4] = {b00 + b01 + b10 + b11, b00 + b01 - b10 - b11, b00 - b01 + b10 - b11, b00 - b01 - b10 + b11};
+      for (int y = 0; y < 2; y++)
+        for (int x = 0; x < 2; x++) {
+          const float block_dc = dcs[y * 2 + x];
+          float residual_sum = 0;
+          for (int iy = 0; iy < 4; iy++)
+            for (int ix = 0; ix < 4; ix++) {
+              if (ix == 0 && iy == 0) continue;
+              residual_sum += coefficients[(y + iy * 2) * 8 + x + ix * 2];
+            }
+          const float centre = block_dc - residual_sum * (1.0f / 16);
+          pixels[(4 * y + 1) * stride + 4 * x + 1] = centre;
+          for (int iy = 0; iy < 4; iy++)
+            for (int ix = 0; ix < 4; ix++) {
+              if (ix == 1 && iy == 1) continue;
+              pixels[(y * 4 + iy) * stride + x * 4 + ix] = coefficients[(y + iy * 2) * 8 + x + ix * 2] + centre;
+            }
+          pixels[y * 4 * stride + x * 4] = coefficients[(y + 2) * 8 + x + 2] + centre;
+        }
+      return;
+    }
+    case 13:    // DCT8X4
+    case 12: {  // DCT4X8
+      const float block0 = coefficients[0], block1 = coefficients[8];
+      const float dcs[2] = {block0 + block1, block0 - block1};
+      for (int h = 0; h < 2; h++) {
+        float block[32];
+        block[0] = dcs[h];
+        for (int iy = 0; iy < 4; iy++)
+          for (int ix = 0; ix < 8; ix++) {
+            if (ix == 0 && iy == 0) continue;
+            block[iy * 8 + ix] = coefficients[(h + iy * 2) * 8 + ix];
+          }
+        if (strategy == 13) {
+          ScalarScaledIDCT<8, 4>(block, pixels + h * 4, stride, wc);
+        } else {
+          ScalarScaledIDCT<4, 8>(block, pixels + h * 4 * stride, stride, wc);
+        }
+      }
+      return;
+    }
+    case 3: {  // DCT4X4
+      const float b00 = coefficients[0], b01 = coefficients[1], b10 = coefficients[8], b11 = coefficients[9];
+      const float dcs[4] = {b00 + b01 + b10 + b11, b00 + b01 - b10 - b11, b00 - b01 + b10 - b11, b00 - b01 - b10 + b11};
+      for (int y = 0; y < 2; y++)
+        for (int x = 0; x < 2; x++) {
+          float block[16];
+          block[0] = dcs[y * 2 + x];
+          for (int iy = 0; iy < 4; iy++)
+            for (int ix = 0; ix < 4; ix++) {
+              if (ix == 0 && iy == 0) continue;
+              block[iy * 4 + ix] = coefficients[(y + iy * 2) * 8 + x + ix * 2];
+            }
+          ScalarScaledIDCT<4, 4>(block, pixels + y * 4 * stride + x * 4, stride, wc);
+        }
+      return;
+    }
+    case 2: {  // DCT2X2
+      float coeffs[64];
+      for (int i = 0; i < 64; i++) coeffs[i] = coefficients[i];
+      ScalarIDCT2TopBlock(2, coeffs);
+      ScalarIDCT2TopBlock(4, coeffs);
+      ScalarIDCT2TopBlock(8, coeffs);
+      for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) pixels[y * stride + x] = coeffs[y * 8 + x];
+      return;
+    }
+    default: {  // AFV0..3
+      const int afv_kind = static_cast<int>(strategy) - 14;
+      const int afv_x = afv_kind & 1, afv_y = afv_kind / 2;
+      const float block00 = coefficients[0], block01 = coefficients[1], block10 = coefficients[8];
+      const float dcs[3] = {(block00 + block10 + block01) * 4.0f, (block00 + block10 - block01), block00 - block10};
+      float coeff[16];
+      coeff[0] = dcs[0];
+      for (int iy = 0; iy < 4; iy++)
+        for (int ix = 0; ix < 4; ix++) {
+          if (ix == 0 && iy == 0) continue;
+          coeff[iy * 4 + ix] = coefficients[iy * 2 * 8 + ix * 2];
+        }
+      float block[32];
+      for (int i = 0; i < 16; i++) {
+        float pixel = 0.0f;
+        for (int j = 0; j < 16; j++) pixel = fmaf(coeff[j], afv_basis[j * 16 + i], pixel);
+        block[i] = pixel;
+      }
+      for (int iy = 0; iy < 4; iy++)
+        for (int ix = 0; ix < 4; ix++)
+          pixels[(iy + afv_y * 4) * stride + afv_x * 4 + ix] = block[(afv_y == 1 ? 3 - iy : iy) * 4 + (afv_x == 1 ? 3 - ix : ix)];
+      block[0] = dcs[1];
+      for (int iy = 0; iy < 4; iy++)
+        for (int ix = 0; ix < 4; ix++) {
+          if (ix == 0 && iy == 0) continue;
+          block[iy * 4 + ix] = coefficients[iy * 2 * 8 + ix * 2 + 1];
+        }
+      ScalarScaledIDCT<4, 4>(block, pixels + afv_y * 4 * stride + (afv_x == 1 ? 0 : 4), stride, wc);
+      block[0] = dcs[2];
+      for (int iy = 0; iy < 4; iy++)
+        for (int ix = 0; ix < 8; ix++) {
+          if (ix == 0 && iy == 0) continue;
+          block[iy * 8 + ix] = coefficients[(1 + iy * 2) * 8 + ix];
+        }
+      ScalarScaledIDCT<4, 8>(block, pixels + (afv_y == 1 ? 0 : 4) * stride, stride, wc);
+      return;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- one varblock
+// AdjustQuantBias with an exact reciprocal (lib/jxl/quantizer-inl.h:34-71; the reference's x86
+// builds use the 12-bit rcpps approximation there, see DESIGN.md "numerics").
+JXLB_HD float DevAdjustQuantBias(int c, int32_t quant_i, const float* biases) {
+  const float quant = static_cast<float>(quant_i);
+  const float abs_quant = fabsf(quant);
+  if (abs_quant < 1.125f) {
+    if (!(abs_quant > 0.0f)) return 0.0f;
+    return quant_i < 0 ? -biases[c] : biases[c];
+  }
+  return fmaf(-biases[3], 1.0f / quant, quant);
+}
+
+// Decodes varblock (bx, by) [absolute block coordinates, strategy `s`] of frame `vf` into the
+// pixel planes pix[0]. `buf` provides 4 * 64 * covered floats of scratch visible to the `nt`
+// cooperating threads (shared memory for <= 64x64 pixels, global memory above).
+template <int SCOPE>
+JXLB_HD void DevVarblock(const DevVPools& V, const DevVFrame& vf, uint32_t bx, uint32_t by, uint32_t s, float* buf,
+                         uint32_t tid, uint32_t nt) {
+  const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + s]);
+  const uint32_t covered = static_cast<uint32_t>(si.cx) * si.cy;
+  const uint32_t N = covered * 64;
+  const uint32_t W = vf.xblocks;
+  const size_t nb = static_cast<size_t>(W) * vf.yblocks;
+  const size_t pos = static_cast<size_t>(by) * W + bx;
+  float* ch[3] = {buf, buf + N, buf + 2 * static_cast<size_t>(N)};
+  float* scratch = buf + 3 * static_cast<size_t>(N);
+  int32_t* qi = reinterpret_cast<int32_t*>(buf);
+  const float* wc = V.fpool + V.wc_off;
+  // 1. quantised coefficients: zero, then add every pass's tokens (positions are unique within a pass)
+  for (uint32_t i = tid; i < 3 * N; i += nt) qi[i] = 0;
+  CoopSync<SCOPE>();
+  for (uint32_t p = 0; p < vf.num_passes; p++) {
+    const uint32_t shift = vf.pass_shift[p];
+    for (uint32_t c = 0; c < 3; c++) {
+      const size_t e = (static_cast<size_t>(p) * 3 + c) * nb + pos;
+      const uint32_t start = V.uarena[vf.tok_start + e], count = V.uarena[vf.tok_count + e];
+      const uint32_t* tok = V.tokens + start;
+      int32_t* q = qi + static_cast<size_t>(c) * N;
+      for (uint32_t i = tid; i < count; i += nt) {
+        const uint32_t t = JXLB_LDG(tok + i);
+        const int32_t val = static_cast<int16_t>(t >> 16);
+        const uint32_t k = t & 0xFFFF;
+        if (k < N) q[k] = static_cast<int32_t>(static_cast<uint32_t>(q[k]) + (static_cast<uint32_t>(val) << shift));
+      }
+    }
+    CoopSync<SCOPE>();
+  }
+  // 2. dequantisation, quantisation-bias adjustment, chroma from luma (DequantBlock)
+  {
+    const uint16_t* rawq = reinterpret_cast<const uint16_t*>(V.barena + vf.rawq);
+    const float scaled = vf.inv_global_scale / static_cast<float>(rawq[pos]);
+    const float sd0 = scaled * vf.x_dm, sd1 = scaled, sd2 = scaled * vf.b_dm;
+    const size_t tile = static_cast<size_t>(by / 8) * vf.cmw + bx / 8;
+    const int8_t fx = reinterpret_cast<const int8_t*>(V.barena + vf.ytox)[tile];
+    const int8_t fb = reinterpret_cast<const int8_t*>(V.barena + vf.ytob)[tile];
+    const float x_cc = vf.base_x + static_cast<float>(fx) * vf.color_scale;
+    const float b_cc = vf.base_b + static_cast<float>(fb) * vf.color_scale;
+    const float* dm = V.fpool + vf.table_off[si.table];
+    for (uint32_t k = tid; k < N; k += nt) {
+      const float x_mul = JXLB_LDG(dm + k) * sd0, y_mul = JXLB_LDG(dm + N + k) * sd1, b_mul = JXLB_LDG(dm + 2 * N + k) * sd2;
+      const int32_t qx = qi[k], qy = qi[N + k], qb = qi[2 * N + k];
+      const float dq_x = DevAdjustQuantBias(0, qx, vf.biases) * x_mul;
+      const float dq_y = DevAdjustQuantBias(1, qy, vf.biases) * y_mul;
+      const float dq_b = DevAdjustQuantBias(2, qb, vf.biases) * b_mul;
+      ch[0][k] = fmaf(x_cc, dq_y, dq_x);
+      ch[1][k] = dq_y;
+      ch[2][k] = fmaf(b_cc, dq_y, dq_b);
+    }
+  }
+  CoopSync<SCOPE>();
+  // 3. lowest frequencies from the DC image (LowestFrequenciesFromDC)
+  const uint32_t Rb = si.cy, Cb = si.cx;
+  for (uint32_t c = 0; c < 3; c++) {
+    const float* dcp = V.farena + vf.dc_final[c] + pos;
+    if (!si.plain_dct || s == 0) {
+      if (tid == 0) ch[c][0] = dcp[0];
+      continue;
+    }
+    float* a = scratch;
+    float* b = scratch + covered;
+    for (uint32_t i = tid; i < covered; i += nt) a[i] = dcp[static_cast<size_t>(i / Cb) * W + i % Cb];
+    CoopSync<SCOPE>();
+    float* r1 = CoopDCT<SCOPE>(Rb, Cb, 1, Cb, a, b, wc, tid, nt);            // along y for every x
+    float* r2 = CoopDCT<SCOPE>(Cb, Rb, Cb, 1, r1, r1 == a ? b : a, wc, tid, nt);  // along x for every y
+    const float* ks = V.fpool + V.llf_off;
+    if (Rb < Cb) {
+      const uint32_t out_stride = 8 * Cb;
+      for (uint32_t i = tid; i < covered; i += nt) {
+        const uint32_t y = i / Cb, x = i % Cb;
+        ch[c][y * out_stride + x] = r2[y * Cb + x] * ks[Rb - 1 + y] * ks[Cb - 1 + x];
+      }
+    } else {
+      const uint32_t out_stride = 8 * Rb;
+      for (uint32_t i = tid; i < covered; i += nt) {
+        const uint32_t y = i / Rb, x = i % Rb;  // y < Cb (x frequency), x < Rb (y frequency)
+        ch[c][y * out_stride + x] = r2[x * Cb + y] * ks[Cb - 1 + y] * ks[Rb - 1 + x];
+      }
+    }
+    CoopSync<SCOPE>();
+  }
+  CoopSync<SCOPE>();
+  // 4. inverse transform into the pixel planes
+  const uint32_t PW = W * 8;
+  if (!si.plain_dct) {
+    for (uint32_t c = tid; c < 3; c += nt) {
+      float* out = V.farena + vf.pix[0][c] + static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+      DevSpecialToPixels(s, ch[c], out, static_cast<int>(PW), wc, V.fpool + V.afv_off);
+    }
+    CoopSync<SCOPE>();
+    return;
+  }
+  const uint32_t R = 8 * Rb, C = 8 * Cb;
+  for (uint32_t c = 0; c < 3; c++) {
+    float* out = V.farena + vf.pix[0][c] + static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+    const float* res;
+    if (R >= C) {
+      // coef[i * R + j]: i = horizontal frequency, j = vertical frequency
+      float* r1 = CoopIDCT<SCOPE>(C, R, 1, R, ch[c], scratch, wc, tid, nt);
+      res = CoopIDCT<SCOPE>(R, C, R, 1, r1, r1 == ch[c] ? scratch : ch[c], wc, tid, nt);  // res[x * R + y]
+      for (uint32_t i = tid; i < R * C; i += nt) {
+        const uint32_t y = i / C, x = i % C;
+        out[static_cast<size_t>(y) * PW + x] = res[x * R + y];
+      }
+    } else {
+      // coef[i * C + j]: i = vertical frequency, j = horizontal frequency
+      float* r1 = CoopIDCT<SCOPE>(C, R, C, 1, ch[c], scratch, wc, tid, nt);
+      res = CoopIDCT<SCOPE>(R, C, 1, C, r1, r1 == ch[c] ? scratch : ch[c], wc, tid, nt);  // res[y * C + x]
+      for (uint32_t i = tid; i < R * C; i += nt) {
+        const uint32_t y = i / C, x = i % C;
+        out[static_cast<size_t>(y) * PW + x] = res[y * C + x];
+      }
+    }
+    CoopSync<SCOPE>();
+  }
+}
+
+// ---------------------------------------------------------------- render stages (per pixel)
+JXLB_HD int DevMirror(int x, int size) {  // lib/jxl/image_ops.h:184-195
+  while (x < 0 || x >= size) x = x < 0 ? -x - 1 : 2 * size - 1 - x;
+  return x;
+}
+
+struct DevPlaneView {
+  const float* p;
+  uint32_t stride;
+  int xsize, ysize;
+  JXLB_HD float At(int x, int y) const {
+    return p[static_cast<size_t>(DevMirror(y, ysize)) * stride + DevMirror(x, xsize)];
+  }
+};
+
+JXLB_HD DevPlaneView DevView(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t c) {
+  DevPlaneView v;
+  v.p = V.farena + vf.pix[set][c];
+  v.stride = vf.xblocks * 8;
+  v.xsize = static_cast<int>(vf.xsize);
+  v.ysize = static_cast<int>(vf.ysize);
+  return v;
+}
+
+// Gaborish, one sample of channel c (lib/jxl/render_pipeline/stage_gaborish.cc:22-100).
+JXLB_HD void DevGaborishPixel(const DevVPools& V, const DevVFrame& vf, uint32_t in_set, uint32_t out_set, uint32_t c, int x,
+                              int y) {
+  const DevPlaneView m = DevView(V, vf, in_set, c);
+  const float sum0 = m.At(x, y);
+  const float sum1 = (m.At(x - 1, y) + m.At(x + 1, y)) + (m.At(x, y - 1) + m.At(x, y + 1));
+  const float sum2 = (m.At(x - 1, y - 1) + m.At(x + 1, y - 1)) + (m.At(x - 1, y + 1) + m.At(x + 1, y + 1));
+  V.farena[vf.pix[out_set][c] + static_cast<size_t>(y) * m.stride + x] =
+      fmaf(sum2, vf.gab_w[c][2], fmaf(sum1, vf.gab_w[c][1], sum0 * vf.gab_w[c][0]));
+}
+
+// One pixel of EPF stage 0 / 1 / 2 (lib/jxl/render_pipeline/stage_epf.cc:43-500).
+JXLB_HD void DevEpfPixel(const DevVPools& V, const DevVFrame& vf, uint32_t stage, uint32_t in_set, uint32_t out_set, int x,
+                         int y) {
+  const DevPlaneView m[3] = {DevView(V, vf, in_set, 0), DevView(V, vf, in_set, 1), DevView(V, vf, in_set, 2)};
+  const size_t at = static_cast<size_t>(y) * m[0].stride + x;
+  float X = m[0].p[at], Y = m[1].p[at], B = m[2].p[at];
+  const uint32_t sbx = static_cast<uint32_t>(x) / 8 < vf.xblocks - 1 ? static_cast<uint32_t>(x) / 8 : vf.xblocks - 1;
+  const uint32_t sby = static_cast<uint32_t>(y) / 8 < vf.yblocks - 1 ? static_cast<uint32_t>(y) / 8 : vf.yblocks - 1;
+  const float row_sigma = V.farena[vf.inv_sigma + static_cast<size_t>(sby) * vf.xblocks + sbx];
+  const float kMinSigma = -3.90524291751269967465540850526868f;
+  if (!(row_sigma < kMinSigma)) {
+    const float sm = vf.epf_sigma_scale[stage];
+    const float bsm = sm * vf.epf_border_sad_mul;
+    const int iy = y % 8, ix = x % 8;
+    const float sad_mul = (iy == 0 || iy == 7 || ix == 0 || ix == 7) ? bsm : sm;
+    const float inv_sigma = row_sigma * sad_mul;
+    float w = 1.0f;
+#define JXLB_EPF_ADD(dx, dy, sad)                                \
+  {                                                              \
+    float weight = fmaf((sad), inv_sigma, 1.0f);                 \
+    if (weight < 0.0f) weight = 0.0f;                            \
+    w = w + weight;                                              \
+    X = fmaf(weight, m[0].At(x + (dx), y + (dy)), X);            \
+    Y = fmaf(weight, m[1].At(x + (dx), y + (dy)), Y);            \
+    B = fmaf(weight, m[2].At(x + (dx), y + (dy)), B);            \
+  }
+    if (stage == 0) {
+      const int sads_off[12][2] = {{-2, 0}, {-1, -1}, {-1, 0}, {-1, 1}, {0, -2}, {0, -1},
+                                   {0, 1},  {0, 2},   {1, -1}, {1, 0},  {1, 1},  {2, 0}};  // {row, col}
+      const int plus_off[5][2] = {{0, 0}, {-1, 0}, {0, -1}, {1, 0}, {0, 1}};
+      float sads[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < 3; c++) {
+        const float scale = vf.epf_channel_scale[c];
+        for (int i = 0; i < 12; i++) {
+          float sad = 0.0f;
+          for (int k = 0; k < 5; k++) {
+            const float r11 = m[c].At(x + plus_off[k][1], y + plus_off[k][0]);
+            const float c11 = m[c].At(x + sads_off[i][1] + plus_off[k][1], y + sads_off[i][0] + plus_off[k][0]);
+            sad = sad + fabsf(r11 - c11);
+          }
+          sads[i] = fmaf(sad, scale, sads[i]);
+        }
+      }
+      for (int i = 0; i < 12; i++) JXLB_EPF_ADD(sads_off[i][1], sads_off[i][0], sads[i]);
+    } else if (stage == 1) {
+      float sad0 = 0, sad1 = 0, sad2 = 0, sad3 = 0;
+      for (int c = 0; c < 3; c++) {
+#define JXLB_P(col, row) m[c].At(x + (col) - 2, y + (row) - 2)
+        const float p20 = JXLB_P(2, 0), p21 = JXLB_P(2, 1);
+        float sad0c = fabsf(p20 - p21);
+        const float p11 = JXLB_P(1, 1);
+        float sad1c = fabsf(p11 - p21);
+        const float p31 = JXLB_P(3, 1);
+        float sad2c = fabsf(p31 - p21);
+        const float p02 = JXLB_P(0, 2), p12 = JXLB_P(1, 2);
+        sad1c = sad1c + fabsf(p02 - p12);
+        sad0c = sad0c + fabsf(p11 - p12);
+        const float p22 = JXLB_P(2, 2);
+        float t = fabsf(p12 - p22);
+        sad1c = sad1c + t;
+        sad2c = sad2c + t;
+        t = fabsf(p22 - p21);
+        float sad3c = t;
+        sad0c = sad0c + t;
+        const float p32 = JXLB_P(3, 2);
+        sad0c = sad0c + fabsf(p31 - p32);
+        t = fabsf(p22 - p32);
+        sad1c = sad1c + t;
+        sad2c = sad2c + t;
+        const float p42 = JXLB_P(4, 2);
+        sad2c = sad2c + fabsf(p42 - p32);
+        const float p13 = JXLB_P(1, 3);
+        sad3c = sad3c + fabsf(p13 - p12);
+        const float p23 = JXLB_P(2, 3);
+        t = fabsf(p22 - p23);
+        sad0c = sad0c + t;
+        sad3c = sad3c + t;
+        sad1c = sad1c + fabsf(p13 - p23);
+        const float p33 = JXLB_P(3, 3);
+        sad2c = sad2c + fabsf(p33 - p23);
+        sad3c = sad3c + fabsf(p33 - p32);
+        const float p24 = JXLB_P(2, 4);
+        sad3c = sad3c + fabsf(p24 - p23);
+#undef JXLB_P
+        const float scale = vf.epf_channel_scale[c];
+        sad0 = fmaf(sad0c, scale, sad0);
+        sad1 = fmaf(sad1c, scale, sad1);
+        sad2 = fmaf(sad2c, scale, sad2);
+        sad3 = fmaf(sad3c, scale, sad3);
+      }
+      JXLB_EPF_ADD(0, -1, sad0);
+      JXLB_EPF_ADD(-1, 0, sad1);
+      JXLB_EPF_ADD(1, 0, sad2);
+      JXLB_EPF_ADD(0, 1, sad3);
+    } else {
+      const float rx = X, ry = Y, rb = B;
+      const int offs[4][2] = {{0, -1}, {-1, 0}, {1, 0}, {0, 1}};
+      for (int i = 0; i < 4; i++) {
+        const int dx = offs[i][0], dy = offs[i][1];
+        const float cx = m[0].At(x + dx, y + dy), cy = m[1].At(x + dx, y + dy), cb = m[2].At(x + dx, y + dy);
+        float sad = fabsf(cx - rx) * vf.epf_channel_scale[0];
+        sad = fmaf(fabsf(cy - ry), vf.epf_channel_scale[1], sad);
+        sad = fmaf(fabsf(cb - rb), vf.epf_channel_scale[2], sad);
+        JXLB_EPF_ADD(dx, dy, sad);
+      }
+    }
+#undef JXLB_EPF_ADD
+    const float inv_w = 1.0f / w;
+    X = X * inv_w;
+    Y = Y * inv_w;
+    B = B * inv_w;
+  }
+  V.farena[vf.pix[out_set][0] + at] = X;
+  V.farena[vf.pix[out_set][1] + at] = Y;
+  V.farena[vf.pix[out_set][2] + at] = B;
+}
+
+// ---- colour: XYB -> linear RGB -> transfer function (lib/jxl/dec_xyb-inl.h:37-83,
+// lib/jxl/cms/transfer_functions-inl.h:219-242, lib/jxl/base/fast_math-inl.h:46-90)
+JXLB_HD float DevRational2(float x, const float p[3], const float q[3]) {
+  float yp = p[2], yq = q[2];
+  yp = fmaf(yp, x, p[1]);
+  yq = fmaf(yq, x, q[1]);
+  yp = fmaf(yp, x, p[0]);
+  yq = fmaf(yq, x, q[0]);
+  return yp / yq;
+}
+
+JXLB_HD float DevBitsToFloat(int32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+JXLB_HD int32_t DevFloatToBits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  int32_t b;
+  memcpy(&b, &f, 4);
+  return b;
+#endif
+}
+
+JXLB_HD float DevFastPowf(float base, float exponent) {
+  const float lp[3] = {-1.8503833400518310E-06f, 1.4287160470083755E+00f, 7.4245873327820566E-01f};
+  const float lq[3] = {9.9032814277590719E-01f, 1.0096718572241148E+00f, 1.7409343003366853E-01f};
+  const int32_t x_bits = DevFloatToBits(base);
+  const int32_t exp_bits = x_bits - 0x3f2aaaab;
+  const int32_t exp_shifted = exp_bits >> 23;
+  const float mantissa = DevBitsToFloat(x_bits - static_cast<int32_t>(static_cast<uint32_t>(exp_shifted) << 23));
+  const float log2 = DevRational2(mantissa - 1.0f, lp, lq) + static_cast<float>(exp_shifted);
+  const float x = log2 * exponent;
+  const float floorx = floorf(x);
+  const float exp = DevBitsToFloat(static_cast<int32_t>(static_cast<uint32_t>(static_cast<int32_t>(floorx) + 127) << 23));
+  const float frac = x - floorx;
+  float num = frac + 1.01749063e+01f;
+  num = fmaf(num, frac, 4.88687798e+01f);
+  num = fmaf(num, frac, 9.85506591e+01f);
+  num = num * exp;
+  float den = fmaf(frac, 2.10242958e-01f, -2.22328856e-02f);
+  den = fmaf(den, frac, -1.94414990e+01f);
+  den = fmaf(den, frac, 9.85506633e+01f);
+  return num / den;
+}
+
+JXLB_HD float DevSrgbFromLinear(float v) {
+  const float p[5] = {-5.135152395e-04f, 5.287254571e-03f, 3.903842876e-01f, 1.474205315e+00f, 7.352629620e-01f};
+  const float q[5] = {1.004519624e-02f, 3.036675394e-01f, 1.340816930e+00f, 9.258482155e-01f, 2.424867759e-02f};
+  const float x = fabsf(v);
+  const float linear = x * 12.92f;
+  const float s = sqrtf(x);
+  float yp = p[4], yq = q[4];
+  for (int i = 3; i >= 0; i--) {
+    yp = fmaf(yp, s, p[i]);
+    yq = fmaf(yq, s, q[i]);
+  }
+  const float poly = yp / yq;
+  const float magnitude = x > 0.0031308f ? poly : linear;
+  return copysignf(magnitude, v);
+}
+
+JXLB_HD float DevFromLinear(const DevVFrame& vf, float v) {
+  if (vf.tf == 2) return v <= 1e-5f ? 0.0f : DevFastPowf(v, vf.inv_gamma);
+  if (vf.tf == 1) return DevSrgbFromLinear(v);
+  return v;
+}
+
+// float sample -> output sample at (x, y), channel slot `idx` of the row (stage_write.cc:98-113)
+JXLB_HD void DevStoreSample(uint8_t* row, size_t idx, float v, uint32_t data_type, uint32_t big_endian, uint32_t x,
+                            uint32_t y) {
+  if (data_type == 2 || data_type == 3) {
+    const float mul = data_type == 2 ? 255.0f : 65535.0f;
+    v = v * mul;
+    if (data_type == 2) v = v + DevDither(x, y);
+    if (!(v >= 0.0f)) v = 0.0f;
+    if (v > mul) v = mul;
+#if defined(__CUDA_ARCH__)
+    const int r = __float2int_rn(v);
+#else
+    const int r = static_cast<int>(lrintf(v));
+#endif
+    if (data_type == 2) {
+      row[idx] = static_cast<uint8_t>(r);
+    } else {
+      uint16_t u = static_cast<uint16_t>(r);
+      if (big_endian) u = static_cast<uint16_t>((u >> 8) | (u << 8));
+      reinterpret_cast<uint16_t*>(row)[idx] = u;
+    }
+  } else if (data_type == 5) {
+    uint16_t u = DevFloatToHalf(v);
+    if (big_endian) u = static_cast<uint16_t>((u >> 8) | (u << 8));
+    reinterpret_cast<uint16_t*>(row)[idx] = u;
+  } else {
+    uint32_t u = static_cast<uint32_t>(DevFloatToBits(v));
+    if (big_endian) u = ((u & 0xFF) << 24) | ((u & 0xFF00) << 8) | ((u >> 8) & 0xFF00) | (u >> 24);
+    reinterpret_cast<uint32_t*>(row)[idx] = u;
+  }
+}
+
+// One output pixel: colour transform of the filtered planes + sample conversion + interleaved store.
+JXLB_HD void DevColorPixel(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t x, uint32_t y) {
+  const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
+  const float p0 = V.farena[vf.pix[set][0] + at], p1 = V.farena[vf.pix[set][1] + at], p2 = V.farena[vf.pix[set][2] + at];
+  float r, g, b;
+  if (vf.color_transform == 0) {
+    float gamma_r = p1 + p0, gamma_g = p1 - p0, gamma_b = p2;
+    gamma_r = gamma_r - vf.opsin_bias_cbrt[0];
+    gamma_g = gamma_g - vf.opsin_bias_cbrt[1];
+    gamma_b = gamma_b - vf.opsin_bias_cbrt[2];
+    const float r2 = gamma_r * gamma_r, g2 = gamma_g * gamma_g, b2 = gamma_b * gamma_b;
+    const float mixed_r = fmaf(r2, gamma_r, vf.opsin_bias[0]);
+    const float mixed_g = fmaf(g2, gamma_g, vf.opsin_bias[1]);
+    const float mixed_b = fmaf(b2, gamma_b, vf.opsin_bias[2]);
+    const float* mt = vf.inv_mat;
+    float lr = mt[0] * mixed_r, lg = mt[3] * mixed_r, lb = mt[6] * mixed_r;
+    lr = fmaf(mt[1], mixed_g, lr);
+    lg = fmaf(mt[4], mixed_g, lg);
+    lb = fmaf(mt[7], mixed_g, lb);
+    lr = fmaf(mt[2], mixed_b, lr);
+    lg = fmaf(mt[5], mixed_b, lg);
+    lb = fmaf(mt[8], mixed_b, lb);
+    r = DevFromLinear(vf, lr);
+    g = DevFromLinear(vf, lg);
+    b = DevFromLinear(vf, lb);
+  } else if (vf.color_transform == 2) {
+    const float c128 = 128.0f / 255, crcr = 1.402f, cgcb = -0.114f * 1.772f / 0.587f, cgcr = -0.299f * 1.402f / 0.587f,
+                cbcb = 1.772f;
+    const float yv = p1 + c128, cb = p0, cr = p2;
+    r = fmaf(crcr, cr, yv);
+    g = fmaf(cgcr, cr, fmaf(cgcb, cb, yv));
+    b = fmaf(cbcb, cb, yv);
+  } else {
+    r = p0;
+    g = p1;
+    b = p2;
+  }
+  uint8_t* row = V.out + vf.out_off + vf.out_stride * y;
+  const uint32_t nc = vf.out_channels;
+  const uint32_t num_color = nc < 3 ? 1 : 3;
+  const float col[3] = {r, g, b};
+  for (uint32_t c = 0; c < nc; c++) {
+    const float v = c < num_color ? col[c] : 1.0f;
+    DevStoreSample(row, static_cast<size_t>(x) * nc + c, v, vf.out_type, vf.out_big_endian, x, y);
+  }
+}
+
+}  // namespace jxlb
+
+#endif  // JXLB_VARDCT_DEV_H_

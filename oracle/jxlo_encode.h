@@ -581,7 +581,7 @@ inline void LinearRgbToXyb(float r, float g, float b, float* x, float* y, float*
 struct EncodeParams {
   float distance = 1.0f;
   // 0: DCT8 only; 1: seeded random mix of all 27 strategies (decoder coverage);
-  // 2: variance heuristic over {8x8, 16x16, 32x32, 16x8, 8x16, 64x64}
+  // 2: variance heuristic over {8x8, 16x16, 32x32, 16x8, 8x16, 64x64}; 100 + s: strategy s wherever it fits
   int strategy_mode = 2;
   uint32_t seed = 1;
   bool gab = true;
@@ -772,6 +772,10 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
             break;
           }
         }
+      } else if (p.strategy_mode >= 100) {  // one forced strategy wherever it fits (decoder coverage per transform)
+        const int cand = p.strategy_mode - 100;
+        JXLO_CHECK(cand < kNumStrategies, "bad forced strategy");
+        if (bx % kCoveredX[cand] == 0 && by % kCoveredY[cand] == 0 && fits(bx, by, cand)) s = cand;
       } else if (p.strategy_mode == 2) {
         static const int kCands[] = {kDCT64X64, kDCT32X32, kDCT16X16, kDCT16X8, kDCT8X16};
         static const double kThresh[] = {2e-6, 1e-5, 6e-5, 1.5e-4, 1.5e-4};

@@ -7,6 +7,7 @@
 
 #include "../../jpegxl-rs_b200/csrc/host/jxlb_batch.h"
 #include "../../jpegxl-rs_b200/csrc/kernels/jxlb_finish_dev.h"
+#include "../../jpegxl-rs_b200/csrc/kernels/jxlb_vardct_dev.h"
 
 using namespace jxlb;
 
@@ -83,8 +84,112 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     for (size_t f = 0; f < b.frames.size(); f++) {
       const DevFrameOut& fo = b.frames[f];
       frame_offsets[f] = fo.out_off;
+      if (fo.vardct) continue;
       for (uint32_t y = 0; y < fo.ysize; y++)
         for (uint32_t x = 0; x < fo.xsize; x++) DevWritePixel(P, fo, out, x, y);
+    }
+    if (!b.vframes.empty()) {
+      // ---- VarDCT frames: the same device functions, one "thread" at a time
+      const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
+      std::vector<float> farena(b.farena_size + 16, 0.0f);
+      std::vector<uint8_t> barena(b.barena_size + 16, 0);
+      std::vector<uint32_t> uarena(b.uarena_size + 16, 0);
+      std::vector<uint32_t> tokens(b.tok_size + 16, 0);
+      std::vector<uint32_t> ac_status(b.ac_streams.size() + 1, 0), ac_used(b.ac_streams.size() + 1, 0);
+      size_t num_dcg = 0;
+      for (const DevVFrame& vf : b.vframes) num_dcg += vf.xdcgroups * vf.ydcgroups;
+      std::vector<uint32_t> dc_status(num_dcg + 1, 0);
+      DevVPools V{};
+      V.frames = b.vframes.data();
+      V.streams = b.ac_streams.data();
+      V.num_streams = b.ac_streams.size();
+      V.fpool = b.fpool.data();
+      V.opool = b.opool.data();
+      V.cpool = b.cpool.data();
+      V.upool = b.upool.data();
+      V.farena = farena.data();
+      V.barena = barena.data();
+      V.uarena = uarena.data();
+      V.tokens = tokens.data();
+      V.ac_status = ac_status.data();
+      V.ac_used = ac_used.data();
+      V.dc_status = dc_status.data();
+      V.wc_off = sh.wc_off;
+      V.llf_off = sh.llf_off;
+      V.afv_off = sh.afv_off;
+      V.sinfo_off = sh.sinfo_off;
+      V.ctxtab_off = sh.ctxtab_off;
+      V.out = out;
+      uint32_t dcg = 0;
+      for (uint32_t f = 0; f < b.vframes.size(); f++) {
+        const DevVFrame& vf = b.vframes[f];
+        for (uint32_t g = 0; g < vf.xdcgroups * vf.ydcgroups; g++, dcg++) DevDcGroupFinish<0>(P, V, f, g, 0, 1, dcg);
+        if (!vf.skip_dc_smoothing)
+          for (uint32_t y = 0; y < vf.yblocks; y++)
+            for (uint32_t x = 0; x < vf.xblocks; x++) DevDcSmoothBlock(V, vf, x, y);
+      }
+      for (uint32_t i = 0; i < dcg; i++)
+        if (dc_status[i]) throw Error("DC group " + std::to_string(i) + " failed with status " + std::to_string(dc_status[i]));
+      uint16_t ctxtab[128];
+      for (int i = 0; i < 128; i++) ctxtab[i] = static_cast<uint16_t>(b.upool[sh.ctxtab_off + i]);
+      for (int attempt = 0; attempt < 2; attempt++) {
+        bool overflow = false;
+        V.streams = b.ac_streams.data();
+        for (uint32_t s = 0; s < b.ac_streams.size(); s++) {
+          uint8_t colnz[96] = {0};
+          DevAcLaneMem m;
+          m.colnz = colnz;
+          m.stride = 1;
+          m.freq_ctx = ctxtab;
+          m.nnz_ctx = ctxtab + 64;
+          const uint32_t st = DevDecodeAcStream(P, V, s, m, true);
+          if (st == kVTokenOverflow && attempt == 0) {
+            overflow = true;
+          } else if (st != 0) {
+            throw Error("AC stream " + std::to_string(s) + " failed with status " + std::to_string(st));
+          }
+        }
+        if (!overflow) break;
+        // the product does the same in JxlB200DecoderWait: grow the token arena and decode again
+        if (!GrowTokenCapacity(&b, ac_used.data())) throw Error("token overflow without growth");
+        tokens.assign(b.tok_size + 16, 0);
+        V.tokens = tokens.data();
+      }
+      for (uint32_t s = 0; s < 0 * b.ac_streams.size(); s++) {
+        uint8_t colnz[96] = {0};
+        DevAcLaneMem m;
+        m.colnz = colnz;
+        m.stride = 1;
+        m.freq_ctx = ctxtab;
+        m.nnz_ctx = ctxtab + 64;
+        const uint32_t st = DevDecodeAcStream(P, V, s, m, true);
+        if (st != 0) throw Error("AC stream " + std::to_string(s) + " failed with status " + std::to_string(st) + " (used " +
+                                 std::to_string(ac_used[s]) + " of " + std::to_string(b.ac_streams[s].tok_cap) + " tokens)");
+      }
+      std::vector<float> buf(4 * 65536 + 64);
+      for (uint32_t f = 0; f < b.vframes.size(); f++) {
+        const DevVFrame& vf = b.vframes[f];
+        for (uint32_t by = 0; by < vf.yblocks; by++)
+          for (uint32_t bx = 0; bx < vf.xblocks; bx++) {
+            const uint8_t a = barena[vf.acs + static_cast<size_t>(by) * vf.xblocks + bx];
+            if (a & 1) DevVarblock<0>(V, vf, bx, by, a >> 1, buf.data(), 0, 1);
+          }
+        uint32_t set = 0;
+        if (vf.gab) {
+          for (uint32_t c = 0; c < 3; c++)
+            for (uint32_t y = 0; y < vf.ysize; y++)
+              for (uint32_t x = 0; x < vf.xsize; x++) DevGaborishPixel(V, vf, set, set ^ 1, c, x, y);
+          set ^= 1;
+        }
+        for (uint32_t stage = 0; stage < 3; stage++) {
+          if (vf.epf_iters == 0 || (stage == 0 && vf.epf_iters < 3) || (stage == 2 && vf.epf_iters < 2)) continue;
+          for (uint32_t y = 0; y < vf.ysize; y++)
+            for (uint32_t x = 0; x < vf.xsize; x++) DevEpfPixel(V, vf, stage, set, set ^ 1, x, y);
+          set ^= 1;
+        }
+        for (uint32_t y = 0; y < vf.ysize; y++)
+          for (uint32_t x = 0; x < vf.xsize; x++) DevColorPixel(V, vf, set, x, y);
+      }
     }
     return 0;
   } catch (const std::exception& e) {
