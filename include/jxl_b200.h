@@ -110,6 +110,9 @@ typedef struct {
   uint64_t num_streams;      /* entropy-coded streams = decode-kernel threads */
   uint64_t arena_bytes;      /* intermediate int32 planes */
   uint32_t kernel_launches;  /* launches per Run */
+  uint32_t num_ac_streams;   /* VarDCT (frame, group, pass) coefficient streams among num_streams */
+  uint32_t vardct_frames;    /* lossy frames in the batch */
+  uint32_t wave_frames;      /* lossy frames whose pixel planes are live at once */
 } JxlB200Stats;
 int JxlB200DecoderGetStats(const JxlB200Decoder* dec, JxlB200Stats* stats);
 /* Per-kernel device time: when enabled, Run brackets each kernel with CUDA events on the
@@ -117,6 +120,11 @@ int JxlB200DecoderGetStats(const JxlB200Decoder* dec, JxlB200Stats* stats);
  * {entropy decode, group transforms, global transforms, output write}; runs = number of Runs. */
 int JxlB200DecoderSetProfiling(JxlB200Decoder* dec, int enabled);
 int JxlB200DecoderGetKernelTimes(JxlB200Decoder* dec, double* ms4, uint32_t* runs);
+/* All kernel classes: ms[0..n) = {Modular entropy decode, group transforms, global transforms,
+ * Modular output write, VarDCT DC finish, AC entropy decode, dequant + inverse transforms,
+ * Gaborish + EPF, colour + output write}; n <= 9. */
+#define JXL_B200_NUM_KERNEL_CLASSES 9
+int JxlB200DecoderGetKernelTimesEx(JxlB200Decoder* dec, double* ms, uint32_t n, uint32_t* runs);
 
 /* ---- 2. libjxl-compatible subset (decode) ---- */
 typedef struct JxlDecoderStruct JxlDecoder;

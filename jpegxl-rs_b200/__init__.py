@@ -63,7 +63,8 @@ assert ctypes.sizeof(JxlBasicInfo) == 204  # lib/jxl/decode.cc:2061
 class JxlB200Stats(ctypes.Structure):
     _fields_ = [("compressed_bytes", ctypes.c_uint64), ("output_bytes", ctypes.c_uint64), ("pixels", ctypes.c_uint64),
                 ("num_streams", ctypes.c_uint64), ("arena_bytes", ctypes.c_uint64),
-                ("kernel_launches", ctypes.c_uint32)]
+                ("kernel_launches", ctypes.c_uint32), ("num_ac_streams", ctypes.c_uint32),
+                ("vardct_frames", ctypes.c_uint32), ("wave_frames", ctypes.c_uint32)]
 
 
 class DecodeError(Exception):
@@ -123,6 +124,8 @@ def load_library() -> ctypes.CDLL:
     lib.JxlB200DecoderGetStats.argtypes = [vp, ctypes.POINTER(JxlB200Stats)]
     lib.JxlB200DecoderSetProfiling.argtypes = [vp, ctypes.c_int]
     lib.JxlB200DecoderGetKernelTimes.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
+    lib.JxlB200DecoderGetKernelTimesEx.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_uint32,
+                                                   ctypes.POINTER(ctypes.c_uint32)]
     lib.JxlDecoderVersion.restype = ctypes.c_uint32
     lib.JxlSignatureCheck.argtypes = [ctypes.c_char_p, sz]
     lib.JxlDecoderCreate.restype = vp
@@ -152,7 +155,7 @@ EXPORTED_SYMBOLS = [
     "JxlB200DecoderNumFrames", "JxlB200DecoderGetBasicInfo", "JxlB200DecoderImageOutBufferSize", "JxlB200DecoderRun",
     "JxlB200DecoderWait", "JxlB200DecoderDeviceOutput", "JxlB200DecoderReadOutput", "JxlB200DecoderReadOutputs",
     "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderGetKernelTimes",
-    "JxlDecoderVersion", "JxlSignatureCheck", "JxlDecoderCreate", "JxlDecoderReset",
+    "JxlB200DecoderGetKernelTimesEx", "JxlDecoderVersion", "JxlSignatureCheck", "JxlDecoderCreate", "JxlDecoderReset",
     "JxlDecoderDestroy", "JxlDecoderSetParallelRunner", "JxlDecoderSubscribeEvents", "JxlDecoderSetKeepOrientation",
     "JxlDecoderSetUnpremultiplyAlpha", "JxlDecoderSetRenderSpotcolors", "JxlDecoderSetCoalescing",
     "JxlDecoderSetDesiredIntensityTarget", "JxlDecoderSetInput", "JxlDecoderCloseInput", "JxlDecoderProcessInput",
@@ -419,6 +422,17 @@ class BatchDecoder:
         runs = ctypes.c_uint32(0)
         self._lib.JxlB200DecoderGetKernelTimes(self._dec, ms, ctypes.byref(runs))
         return list(ms), runs.value
+
+    KERNEL_CLASSES = ["modular_decode", "group_programs", "frame_levels", "write_output", "dc_finish", "ac_decode",
+                      "dequant_idct", "filters", "color_write"]
+
+    def kernel_times_ex(self):
+        """({kernel class: accumulated ms}, runs) over all kernel classes (include/jxl_b200.h)."""
+        n = len(self.KERNEL_CLASSES)
+        ms = (ctypes.c_double * n)()
+        runs = ctypes.c_uint32(0)
+        self._lib.JxlB200DecoderGetKernelTimesEx(self._dec, ms, n, ctypes.byref(runs))
+        return dict(zip(self.KERNEL_CLASSES, list(ms))), runs.value
 
     def stats(self) -> JxlB200Stats:
         st = JxlB200Stats()

@@ -5,6 +5,14 @@
 //   k_group_programs  one CTA = one group's inverse transforms + scatter into the frame planes
 //   k_frame_level     grid-wide: the k-th global inverse transform of every frame
 //   k_write_output    int32 planes -> interleaved u8/u16/f16/f32 pixels, coalesced stores
+// VarDCT frames (kernels/jxlb_vardct_dev.h):
+//   k_dc_finish       one CTA = one DC group: DC dequantisation, block side information, EPF sigma
+//   k_dc_smooth       adaptive DC smoothing
+//   k_ac_decode       one thread = one (frame, group, pass) AC stream -> sparse coefficient tokens
+//   k_dequant_idct    one CTA = one 256x256 group: token scatter, dequant + CfL, inverse transforms
+//                     (warp per varblock up to 32x32, CTA per varblock up to 64x64)
+//   k_idct_big        varblocks of 128x128 and larger, scratch in global memory
+//   k_gaborish / k_epf / k_color_write   render stages, one thread per pixel
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -16,6 +24,7 @@
 #include "../../include/jxl_b200.h"
 #include "host/jxlb_batch.h"
 #include "kernels/jxlb_finish_dev.h"
+#include "kernels/jxlb_vardct_dev.h"
 
 namespace jxlb {
 
@@ -64,6 +73,7 @@ __global__ void __launch_bounds__(256) k_frame_level(DevPools P, const DevOp* op
 // One thread per pixel; blockIdx.y = frame.
 __global__ void __launch_bounds__(256) k_write_output(DevPools P, const DevFrameOut* frames, uint8_t* out) {
   const DevFrameOut& fo = frames[blockIdx.y];
+  if (fo.vardct) return;
   const uint64_t n = static_cast<uint64_t>(fo.xsize) * fo.ysize;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
@@ -75,6 +85,7 @@ __global__ void __launch_bounds__(256) k_write_output(DevPools P, const DevFrame
 // RGBA8 fast path: 4 integer planes -> one 32-bit store per pixel.
 __global__ void __launch_bounds__(256) k_write_output_rgba8(DevPools P, const DevFrameOut* frames, uint8_t* out) {
   const DevFrameOut& fo = frames[blockIdx.y];
+  if (fo.vardct) return;
   const uint64_t n = static_cast<uint64_t>(fo.xsize) * fo.ysize;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
@@ -91,6 +102,156 @@ __global__ void __launch_bounds__(256) k_write_output_rgba8(DevPools P, const De
     }
     *reinterpret_cast<uint32_t*>(out + fo.out_off + fo.stride * y + 4ull * x) = px;
   }
+}
+
+// ------------------------------------------------------------------ VarDCT kernels
+// blockIdx.x indexes a flat list of (frame, DC group) pairs.
+__global__ void __launch_bounds__(256) k_dc_finish(DevPools P, DevVPools V, const uint2* dcg_list) {
+  const uint2 e = dcg_list[blockIdx.x];
+  DevDcGroupFinish<2>(P, V, e.x, e.y, threadIdx.x, blockDim.x, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) k_dc_smooth(DevVPools V) {
+  const DevVFrame& vf = V.frames[blockIdx.y];
+  if (vf.skip_dc_smoothing) return;
+  const uint32_t n = vf.xblocks * vf.yblocks;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    DevDcSmoothBlock(V, vf, i % vf.xblocks, i / vf.xblocks);
+}
+
+// One warp per CTA, 32 AC streams in lock step.
+__global__ void __launch_bounds__(32) k_ac_decode(DevPools P, DevVPools V) {
+  __shared__ uint8_t colnz_s[96 * 32];
+  __shared__ uint16_t ctxtab_s[128];
+  const uint32_t lane = threadIdx.x;
+  for (uint32_t i = lane; i < 128; i += 32) ctxtab_s[i] = static_cast<uint16_t>(V.upool[V.ctxtab_off + i]);
+  for (uint32_t i = lane; i < 96 * 32; i += 32) colnz_s[i] = 0;
+  __syncwarp();
+  const uint32_t s = blockIdx.x * 32 + lane;
+  DevAcLaneMem m;
+  m.colnz = colnz_s + lane;
+  m.stride = 32;
+  m.freq_ctx = ctxtab_s;
+  m.nnz_ctx = ctxtab_s + 64;
+  const bool valid = s < V.num_streams;
+  const uint32_t status = DevDecodeAcStream(P, V, s, m, valid);
+  if (valid) V.ac_status[s] = status;
+}
+
+constexpr uint32_t kIdctThreads = 128;
+constexpr uint32_t kIdctSmemFloats = 4 * 4096;  // 64 KiB: four buffers of a 64x64 varblock
+
+// blockIdx.x = group, blockIdx.y = frame - frame0.
+__global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint32_t frame0) {
+  extern __shared__ float idct_smem[];
+  __shared__ uint32_t next_s, has_big_s;
+  const DevVFrame& vf = V.frames[frame0 + blockIdx.y];
+  const uint32_t g = blockIdx.x;
+  if (g >= vf.xgroups * vf.ygroups) return;
+  const uint32_t x0 = (g % vf.xgroups) * 32, y0 = (g / vf.xgroups) * 32;
+  const uint32_t xs = min(32u, vf.xblocks - x0), ys = min(32u, vf.yblocks - y0);
+  const uint8_t* acs = V.barena + vf.acs;
+  if (threadIdx.x == 0) {
+    next_s = 0;
+    has_big_s = 0;
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* wbuf = idct_smem + warp * 4096;
+  const uint32_t total = xs * ys;
+  for (;;) {  // varblocks of up to 32x32 pixels: one warp each
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&next_s, 1u);
+    i = __shfl_sync(0xFFFFFFFFu, i, 0);
+    if (i >= total) break;
+    const uint32_t bx = i % xs, by = i / xs;
+    const uint8_t a = acs[static_cast<size_t>(y0 + by) * vf.xblocks + x0 + bx];
+    if (!(a & 1) || a == 0xFF) continue;
+    const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
+    if (static_cast<uint32_t>(si.cx) * si.cy > 16) {
+      if (lane == 0) has_big_s = 1;
+      continue;
+    }
+    DevVarblock<1>(V, vf, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
+  }
+  __syncthreads();
+  if (!has_big_s) return;
+  for (uint32_t i = 0; i < total; i++) {  // 64x32, 32x64, 64x64: the whole CTA per varblock
+    const uint32_t bx = i % xs, by = i / xs;
+    const uint8_t a = acs[static_cast<size_t>(y0 + by) * vf.xblocks + x0 + bx];
+    if (!(a & 1) || a == 0xFF) continue;
+    const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
+    const uint32_t covered = static_cast<uint32_t>(si.cx) * si.cy;
+    if (covered <= 16 || covered > 64) continue;
+    DevVarblock<2>(V, vf, x0 + bx, y0 + by, a >> 1, idct_smem, threadIdx.x, kIdctThreads);
+  }
+}
+
+// Persistent CTAs with 4 * 65536 floats of global scratch each: varblocks above 64x64 pixels.
+__global__ void __launch_bounds__(256) k_idct_big(DevVPools V, uint32_t frame0, uint32_t num_frames, float* scratch) {
+  __shared__ uint32_t list_s[64], count_s;
+  float* buf = scratch + static_cast<size_t>(blockIdx.x) * 4 * 65536;
+  for (uint32_t f = 0; f < num_frames; f++) {
+    const DevVFrame& vf = V.frames[frame0 + f];
+    const uint8_t* acs = V.barena + vf.acs;
+    for (uint32_t g = blockIdx.x; g < vf.xgroups * vf.ygroups; g += gridDim.x) {
+      const uint32_t x0 = (g % vf.xgroups) * 32, y0 = (g / vf.xgroups) * 32;
+      const uint32_t xs = min(32u, vf.xblocks - x0), ys = min(32u, vf.yblocks - y0);
+      __syncthreads();
+      if (threadIdx.x == 0) count_s = 0;
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < xs * ys; i += blockDim.x) {
+        const uint8_t a = acs[static_cast<size_t>(y0 + i / xs) * vf.xblocks + x0 + i % xs];
+        if (!(a & 1) || a == 0xFF) continue;
+        const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
+        if (static_cast<uint32_t>(si.cx) * si.cy <= 64) continue;
+        const uint32_t k = atomicAdd(&count_s, 1u);
+        if (k < 64) list_s[k] = i | (static_cast<uint32_t>(a >> 1) << 16);  // at most 4 such varblocks fit a group
+      }
+      __syncthreads();
+      const uint32_t n = min(count_s, 64u);
+      for (uint32_t k = 0; k < n; k++) {
+        const uint32_t i = list_s[k] & 0xFFFF, strategy = list_s[k] >> 16;
+        DevVarblock<2>(V, vf, x0 + i % xs, y0 + i / xs, strategy, buf, threadIdx.x, blockDim.x);
+        __threadfence_block();
+      }
+    }
+  }
+}
+
+// Render stages: blockDim (32, 8), grid (x tiles, y tiles, frames of the wave).
+__global__ void __launch_bounds__(256) k_gaborish(DevVPools V, uint32_t frame0, uint32_t in_set, uint32_t out_set) {
+  const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
+  const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (!vf.gab || x >= vf.xsize || y >= vf.ysize) return;
+  for (uint32_t c = 0; c < 3; c++) DevGaborishPixel(V, vf, in_set, out_set, c, static_cast<int>(x), static_cast<int>(y));
+}
+
+// `sets` packs, per frame class, which plane set holds the input: frames with / without
+// Gaborish (and different EPF iteration counts) take different numbers of ping-pong steps, so the
+// current set is derived per frame from its own flags.
+__device__ __forceinline__ uint32_t SetBeforeStage(const DevVFrame& vf, uint32_t stage) {
+  uint32_t set = vf.gab ? 1u : 0u;
+  if (stage > 0 && vf.epf_iters >= 3) set ^= 1;  // stage 0 ran
+  if (stage > 1 && vf.epf_iters >= 1) set ^= 1;  // stage 1 ran
+  if (stage > 2 && vf.epf_iters >= 2) set ^= 1;  // stage 2 ran
+  return set;
+}
+
+__global__ void __launch_bounds__(256) k_epf(DevVPools V, uint32_t frame0, uint32_t stage) {
+  const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
+  const bool runs = vf.epf_iters > 0 && !(stage == 0 && vf.epf_iters < 3) && !(stage == 2 && vf.epf_iters < 2);
+  const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (!runs || x >= vf.xsize || y >= vf.ysize) return;
+  const uint32_t set = SetBeforeStage(vf, stage);
+  DevEpfPixel(V, vf, stage, set, set ^ 1, static_cast<int>(x), static_cast<int>(y));
+}
+
+__global__ void __launch_bounds__(256) k_color_write(DevVPools V, uint32_t frame0) {
+  const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
+  const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= vf.xsize || y >= vf.ysize) return;
+  DevColorPixel(V, vf, SetBeforeStage(vf, 3), x, y);
 }
 
 // ------------------------------------------------------------------ runtime
@@ -132,6 +293,11 @@ using namespace jxlb;
     }                                                                                        \
   } while (0)
 
+enum KernelClass {
+  kKModular = 0, kKGroupPrograms, kKFrameLevels, kKWriteOutput, kKDcFinish, kKAcDecode, kKDequantIdct, kKFilters,
+  kKColorWrite, kNumKernelClasses
+};
+
 struct JxlB200Decoder {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -149,33 +315,75 @@ struct JxlB200Decoder {
   DevBuf<DevProgram> d_group_programs, d_levels;
   DevBuf<DevFrameOut> d_frames;
   DevBuf<int32_t> d_arena, d_wp, d_ring;
+  // VarDCT
+  DevBuf<DevVFrame> d_vframes;
+  DevBuf<DevAcStream> d_ac_streams;
+  DevBuf<float> d_fpool, d_farena, d_big_scratch;
+  DevBuf<uint16_t> d_opool;
+  DevBuf<uint8_t> d_cpool, d_barena;
+  DevBuf<uint32_t> d_upool, d_uarena, d_tokens, d_ac_status, d_ac_used, d_dc_status;
+  DevBuf<uint2> d_dcg_list;
+  std::vector<uint2> dcg_list;
+  std::vector<uint32_t> h_ac_status, h_ac_used, h_dc_status;
+  DevVPools vpools{};
+  uint32_t max_groups = 0, max_xsize = 0, max_ysize = 0, max_blocks = 0;
+  bool any_gab = false;
+  uint32_t max_epf = 0;
   std::vector<size_t> level_off;  // offset of each level inside d_levels
   std::vector<uint32_t> h_status;
   bool uniform_rgba8 = false;
+  bool any_modular_frame = false;
   uint32_t launches = 0;
   DevPools pools{};
   // optional per-kernel timing (CUDA events on the launching stream)
   bool profiling = false;
-  static constexpr int kEvRuns = 64;          // event sets kept before folding
-  cudaEvent_t ev[kEvRuns][5] = {};
-  bool ev_created = false;
-  int ev_used = 0;                            // recorded, not yet folded
-  double kernel_ms[4] = {0, 0, 0, 0};         // decode, group programs, frame levels, output (accumulated)
+  struct Timed { cudaEvent_t a, b; int cls; };
+  std::vector<Timed> timed;            // recorded, not yet folded
+  std::vector<cudaEvent_t> free_events;
+  double kernel_ms[kNumKernelClasses] = {};
   uint32_t profiled_runs = 0;
+  static constexpr uint32_t kBigCtas = 148;
 };
 
-static void FoldEvents(JxlB200Decoder* dec) {
-  for (int r = 0; r < dec->ev_used; r++) {
-    if (cudaEventSynchronize(dec->ev[r][4]) != cudaSuccess) continue;
-    for (int k = 0; k < 4; k++) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, dec->ev[r][k], dec->ev[r][k + 1]);
-      dec->kernel_ms[k] += ms;
-    }
-    dec->profiled_runs++;
+static cudaEvent_t GetEvent(JxlB200Decoder* dec) {
+  if (!dec->free_events.empty()) {
+    cudaEvent_t e = dec->free_events.back();
+    dec->free_events.pop_back();
+    return e;
   }
-  dec->ev_used = 0;
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
 }
+
+static void FoldEvents(JxlB200Decoder* dec) {
+  for (auto& t : dec->timed) {
+    float ms = 0;
+    if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess)
+      dec->kernel_ms[t.cls] += ms;
+    dec->free_events.push_back(t.a);
+    dec->free_events.push_back(t.b);
+  }
+  dec->timed.clear();
+}
+
+// Brackets the launches of one kernel class with events when profiling is on.
+struct ScopedTimer {
+  JxlB200Decoder* dec;
+  cudaStream_t s;
+  cudaEvent_t b = nullptr;
+  int cls;
+  ScopedTimer(JxlB200Decoder* d, cudaStream_t st, int c) : dec(d), s(st), cls(c) {
+    if (!dec->profiling) return;
+    cudaEvent_t a = GetEvent(dec);
+    b = GetEvent(dec);
+    cudaEventRecord(a, s);
+    dec->timed.push_back({a, b, cls});
+  }
+  ~ScopedTimer() {
+    if (b) cudaEventRecord(b, s);
+  }
+};
 
 extern "C" {
 
@@ -189,17 +397,29 @@ JxlB200Decoder* JxlB200DecoderCreate(int device) {
     delete dec;
     return nullptr;
   }
+  cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, kIdctSmemFloats * sizeof(float));
   return dec;
 }
 
 void JxlB200DecoderDestroy(JxlB200Decoder* dec) {
   if (!dec) return;
   cudaSetDevice(dec->device);
+  FoldEvents(dec);
+  for (cudaEvent_t e : dec->free_events) cudaEventDestroy(e);
   if (dec->stream) cudaStreamDestroy(dec->stream);
   delete dec;
 }
 
 const char* JxlB200DecoderGetError(const JxlB200Decoder* dec) { return dec ? dec->error.c_str() : "null decoder"; }
+
+static int UploadTokensLayout(JxlB200Decoder* dec) {
+  BatchPlan& b = *dec->plan;
+  CUDA_OK(dec->d_ac_streams.Upload(b.ac_streams, dec->stream));
+  CUDA_OK(dec->d_tokens.Alloc(b.tok_size + 16));
+  dec->vpools.streams = dec->d_ac_streams.p;
+  dec->vpools.tokens = dec->d_tokens.p;
+  return 0;
+}
 
 int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files, const size_t* sizes, size_t n,
                                 const JxlPixelFormat* format, int num_threads) {
@@ -255,7 +475,6 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   CUDA_OK(dec->d_lz77.Alloc(static_cast<size_t>(b.lz77_slots) << 20));
   CUDA_OK(dec->d_status.Alloc(b.streams.size()));
   CUDA_OK(dec->d_out.Alloc(b.out_size));
-  CUDA_OK(cudaStreamSynchronize(s));
   DevPools& P = dec->pools;
   P.words = reinterpret_cast<const uint32_t*>(dec->d_bytes.p);
   P.alias = dec->d_alias.p;
@@ -278,10 +497,66 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   P.warp_dims_off = dec->d_warp_dims_off.p;
   P.warp_dims = dec->d_warp_dims.p;
   dec->uniform_rgba8 = fmt.num_channels == 4 && fmt.data_type == 2;
-  for (const DevFrameOut& fo : b.frames)
+  dec->any_modular_frame = false;
+  for (const DevFrameOut& fo : b.frames) {
+    if (fo.vardct) continue;
+    dec->any_modular_frame = true;
     for (int c = 0; c < 4; c++)
       if (fo.is_float[c] || fo.stride % 4) dec->uniform_rgba8 = false;
+  }
   dec->plan = std::move(plan);
+  // ---- VarDCT
+  dec->dcg_list.clear();
+  dec->max_groups = dec->max_xsize = dec->max_ysize = dec->max_blocks = dec->max_epf = 0;
+  dec->any_gab = false;
+  if (!b.vframes.empty()) {
+    const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
+    for (uint32_t f = 0; f < b.vframes.size(); f++) {
+      const DevVFrame& vf = b.vframes[f];
+      for (uint32_t g = 0; g < vf.xdcgroups * vf.ydcgroups; g++) dec->dcg_list.push_back(make_uint2(f, g));
+      dec->max_groups = std::max(dec->max_groups, vf.xgroups * vf.ygroups);
+      dec->max_xsize = std::max(dec->max_xsize, vf.xsize);
+      dec->max_ysize = std::max(dec->max_ysize, vf.ysize);
+      dec->max_blocks = std::max(dec->max_blocks, vf.xblocks * vf.yblocks);
+      dec->max_epf = std::max(dec->max_epf, vf.epf_iters);
+      dec->any_gab |= vf.gab != 0;
+    }
+    CUDA_OK(dec->d_vframes.Upload(b.vframes, s));
+    CUDA_OK(dec->d_fpool.Upload(b.fpool, s));
+    CUDA_OK(dec->d_opool.Upload(b.opool, s));
+    CUDA_OK(dec->d_cpool.Upload(b.cpool, s));
+    CUDA_OK(dec->d_upool.Upload(b.upool, s));
+    CUDA_OK(dec->d_dcg_list.Upload(dec->dcg_list, s));
+    CUDA_OK(dec->d_farena.Alloc(b.farena_size + 16));
+    CUDA_OK(dec->d_barena.Alloc(b.barena_size + 16));
+    CUDA_OK(dec->d_uarena.Alloc(b.uarena_size + 16));
+    CUDA_OK(dec->d_ac_status.Alloc(b.ac_streams.size() + 1));
+    CUDA_OK(dec->d_ac_used.Alloc(b.ac_streams.size() + 1));
+    CUDA_OK(dec->d_dc_status.Alloc(dec->dcg_list.size() + 1));
+    CUDA_OK(dec->d_big_scratch.Alloc(static_cast<size_t>(JxlB200Decoder::kBigCtas) * 4 * 65536));
+    DevVPools& V = dec->vpools;
+    V = DevVPools{};
+    V.frames = dec->d_vframes.p;
+    V.num_streams = b.ac_streams.size();
+    V.fpool = dec->d_fpool.p;
+    V.opool = dec->d_opool.p;
+    V.cpool = dec->d_cpool.p;
+    V.upool = dec->d_upool.p;
+    V.farena = dec->d_farena.p;
+    V.barena = dec->d_barena.p;
+    V.uarena = dec->d_uarena.p;
+    V.ac_status = dec->d_ac_status.p;
+    V.ac_used = dec->d_ac_used.p;
+    V.dc_status = dec->d_dc_status.p;
+    V.wc_off = sh.wc_off;
+    V.llf_off = sh.llf_off;
+    V.afv_off = sh.afv_off;
+    V.sinfo_off = sh.sinfo_off;
+    V.ctxtab_off = sh.ctxtab_off;
+    V.out = dec->d_out.p;
+    if (UploadTokensLayout(dec) != 0) return 1;
+  }
+  CUDA_OK(cudaStreamSynchronize(s));
   return 0;
 }
 
@@ -339,16 +614,8 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   const BatchPlan& b = *dec->plan;
   const DevPools& P = dec->pools;
   uint32_t launches = 0;
-  const bool prof = dec->profiling;
-  if (prof && !dec->ev_created) {
-    for (auto& set : dec->ev)
-      for (auto& e : set) CUDA_OK(cudaEventCreate(&e));
-    dec->ev_created = true;
-  }
-  if (prof && dec->ev_used == JxlB200Decoder::kEvRuns) FoldEvents(dec);  // blocks only every 64 runs
-  cudaEvent_t* ev = prof ? dec->ev[dec->ev_used] : nullptr;
-  if (prof) cudaEventRecord(ev[0], s);
   if (!b.streams.empty()) {
+    ScopedTimer t(dec, s, kKModular);
     const uint32_t block = 32;
     if (b.narrow) {
       k_modular_decode<int32_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
@@ -357,20 +624,22 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     }
     launches++;
   }
-  if (prof) cudaEventRecord(ev[1], s);
   if (!b.group_programs.empty()) {
+    ScopedTimer t(dec, s, kKGroupPrograms);
     k_group_programs<<<b.group_programs.size(), 256, 0, s>>>(P, dec->d_ops.p, dec->d_group_programs.p);
     launches++;
   }
-  if (prof) cudaEventRecord(ev[2], s);
-  for (size_t k = 0; k < b.levels.size(); k++) {
-    const uint32_t tiles = std::max<uint32_t>(1, std::min<uint32_t>(1024, (b.max_frame_pixels + 1023) / 1024));
-    dim3 grid(tiles, b.levels[k].size());
-    k_frame_level<<<grid, 256, 0, s>>>(P, dec->d_ops.p, dec->d_levels.p + dec->level_off[k]);
-    launches++;
-  }
-  if (prof) cudaEventRecord(ev[3], s);
   {
+    ScopedTimer t(dec, s, kKFrameLevels);
+    for (size_t k = 0; k < b.levels.size(); k++) {
+      const uint32_t tiles = std::max<uint32_t>(1, std::min<uint32_t>(1024, (b.max_frame_pixels + 1023) / 1024));
+      dim3 grid(tiles, b.levels[k].size());
+      k_frame_level<<<grid, 256, 0, s>>>(P, dec->d_ops.p, dec->d_levels.p + dec->level_off[k]);
+      launches++;
+    }
+  }
+  if (dec->any_modular_frame) {
+    ScopedTimer t(dec, s, kKWriteOutput);
     const uint32_t tiles = std::max<uint32_t>(1, std::min<uint32_t>(4096, (b.max_frame_pixels + 255) / 256));
     dim3 grid(tiles, b.frames.size());
     if (dec->uniform_rgba8) {
@@ -380,10 +649,52 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     }
     launches++;
   }
-  if (prof) {
-    cudaEventRecord(ev[4], s);
-    dec->ev_used++;
+  if (!b.vframes.empty()) {
+    const DevVPools& V = dec->vpools;
+    const uint32_t nvf = b.vframes.size();
+    {
+      ScopedTimer t(dec, s, kKDcFinish);
+      CUDA_OK(cudaMemsetAsync(dec->d_dc_status.p, 0, (dec->dcg_list.size() + 1) * 4, s));
+      k_dc_finish<<<dec->dcg_list.size(), 256, 0, s>>>(P, V, dec->d_dcg_list.p);
+      dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(256, (dec->max_blocks + 255) / 256)), nvf);
+      k_dc_smooth<<<grid, 256, 0, s>>>(V);
+      launches += 2;
+    }
+    {
+      ScopedTimer t(dec, s, kKAcDecode);
+      k_ac_decode<<<(b.ac_streams.size() + 31) / 32, 32, 0, s>>>(P, V);
+      launches++;
+    }
+    const dim3 px_block(32, 8);
+    for (uint32_t f0 = 0; f0 < nvf; f0 += b.wave_frames) {
+      const uint32_t nf = std::min<uint32_t>(b.wave_frames, nvf - f0);
+      {
+        ScopedTimer t(dec, s, kKDequantIdct);
+        k_dequant_idct<<<dim3(dec->max_groups, nf), kIdctThreads, kIdctSmemFloats * sizeof(float), s>>>(V, f0);
+        k_idct_big<<<JxlB200Decoder::kBigCtas, 256, 0, s>>>(V, f0, nf, dec->d_big_scratch.p);
+        launches += 2;
+      }
+      const dim3 px_grid((dec->max_xsize + 31) / 32, (dec->max_ysize + 7) / 8, nf);
+      {
+        ScopedTimer t(dec, s, kKFilters);
+        if (dec->any_gab) {
+          k_gaborish<<<px_grid, px_block, 0, s>>>(V, f0, 0, 1);
+          launches++;
+        }
+        for (uint32_t stage = 0; stage < 3; stage++) {
+          if (dec->max_epf == 0 || (stage == 0 && dec->max_epf < 3) || (stage == 2 && dec->max_epf < 2)) continue;
+          k_epf<<<px_grid, px_block, 0, s>>>(V, f0, stage);
+          launches++;
+        }
+      }
+      {
+        ScopedTimer t(dec, s, kKColorWrite);
+        k_color_write<<<px_grid, px_block, 0, s>>>(V, f0);
+        launches++;
+      }
+    }
   }
+  if (dec->profiling) dec->profiled_runs++;
   dec->launches = launches;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -391,10 +702,10 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
 
 int JxlB200DecoderSetProfiling(JxlB200Decoder* dec, int enabled) {
   if (!dec) return 1;
+  FoldEvents(dec);
   dec->profiling = enabled != 0;
   for (double& m : dec->kernel_ms) m = 0;
   dec->profiled_runs = 0;
-  dec->ev_used = 0;
   return 0;
 }
 
@@ -406,20 +717,76 @@ int JxlB200DecoderGetKernelTimes(JxlB200Decoder* dec, double* ms4, uint32_t* run
   return 0;
 }
 
-int JxlB200DecoderWait(JxlB200Decoder* dec, void* cuda_stream) {
-  if (!dec || !dec->plan) return 1;
-  CUDA_OK(cudaSetDevice(dec->device));
-  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : dec->stream;
-  dec->h_status.resize(dec->plan->streams.size());
+int JxlB200DecoderGetKernelTimesEx(JxlB200Decoder* dec, double* ms, uint32_t n, uint32_t* runs) {
+  if (!dec || !ms || !runs) return 1;
+  FoldEvents(dec);
+  for (uint32_t k = 0; k < n; k++) ms[k] = k < kNumKernelClasses ? dec->kernel_ms[k] : 0.0;
+  *runs = dec->profiled_runs;
+  return 0;
+}
+
+static int CheckOnce(JxlB200Decoder* dec, cudaStream_t s, bool* overflow) {
+  BatchPlan& b = *dec->plan;
+  *overflow = false;
+  dec->h_status.resize(b.streams.size());
   if (!dec->h_status.empty())
     CUDA_OK(cudaMemcpyAsync(dec->h_status.data(), dec->d_status.p, dec->h_status.size() * 4, cudaMemcpyDeviceToHost, s));
+  if (!b.vframes.empty()) {
+    dec->h_ac_status.resize(b.ac_streams.size());
+    dec->h_ac_used.resize(b.ac_streams.size());
+    dec->h_dc_status.resize(dec->dcg_list.size());
+    CUDA_OK(cudaMemcpyAsync(dec->h_ac_status.data(), dec->d_ac_status.p, dec->h_ac_status.size() * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(dec->h_ac_used.data(), dec->d_ac_used.p, dec->h_ac_used.size() * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(dec->h_dc_status.data(), dec->d_dc_status.p, dec->h_dc_status.size() * 4, cudaMemcpyDeviceToHost, s));
+  }
   CUDA_OK(cudaStreamSynchronize(s));
   for (size_t i = 0; i < dec->h_status.size(); i++) {
     if (dec->h_status[i] != 0) {
       dec->error = "entropy-coded stream " + std::to_string(i) + " failed (status " + std::to_string(dec->h_status[i]) +
-                   ": 1 = read past section end, 2 = bad ANS final state)";
+                   ": 1 = read past section end, 2 = bad ANS final state, 4 = unsupported chained stream header)";
       return 1;
     }
+  }
+  if (!b.vframes.empty()) {
+    for (size_t i = 0; i < dec->h_dc_status.size(); i++) {
+      if (dec->h_dc_status[i] != 0) {
+        dec->error = "DC group " + std::to_string(i) + ": corrupted AC metadata (status " + std::to_string(dec->h_dc_status[i]) + ")";
+        return 1;
+      }
+    }
+    for (size_t i = 0; i < dec->h_ac_status.size(); i++) {
+      const uint32_t st = dec->h_ac_status[i];
+      if (st == kVTokenOverflow) {
+        *overflow = true;
+      } else if (st != 0) {
+        dec->error = "AC stream " + std::to_string(i) + " failed (status " + std::to_string(st) +
+                     ": 1 = read past section end, 2 = bad ANS final state, 8 = corrupted, 16 = coefficient outside 16 bits)";
+        return 1;
+      }
+    }
+  }
+  return 0;
+}
+
+int JxlB200DecoderWait(JxlB200Decoder* dec, void* cuda_stream) {
+  if (!dec || !dec->plan) return 1;
+  CUDA_OK(cudaSetDevice(dec->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : dec->stream;
+  bool overflow = false;
+  if (CheckOnce(dec, s, &overflow) != 0) return 1;
+  if (!overflow) return 0;
+  // Some AC stream held more non-zero coefficients than its token budget (sized from the
+  // section's byte count): lay the token arena out again with what was needed and decode again.
+  if (!GrowTokenCapacity(dec->plan.get(), dec->h_ac_used.data())) {
+    dec->error = "internal: token overflow without growth";
+    return 1;
+  }
+  if (UploadTokensLayout(dec) != 0) return 1;
+  if (JxlB200DecoderRun(dec, cuda_stream) != 0) return 1;
+  if (CheckOnce(dec, s, &overflow) != 0) return 1;
+  if (overflow) {
+    dec->error = "internal: token overflow after growth";
+    return 1;
   }
   return 0;
 }
@@ -464,9 +831,13 @@ int JxlB200DecoderGetStats(const JxlB200Decoder* dec, JxlB200Stats* st) {
   st->output_bytes = 0;
   for (uint64_t s : b.frame_out_size) st->output_bytes += s;
   st->pixels = b.total_pixels;
-  st->num_streams = b.streams.size();
-  st->arena_bytes = b.arena_size * 4;
-  st->kernel_launches = (b.streams.empty() ? 0 : 1) + (b.group_programs.empty() ? 0 : 1) + b.levels.size() + 1;
+  st->num_streams = b.streams.size() + b.ac_streams.size();
+  st->arena_bytes = b.arena_size * 4 + b.farena_size * 4 + b.barena_size + b.uarena_size * 4 + b.tok_size * 4;
+  st->kernel_launches = dec->launches ? dec->launches
+                                      : (b.streams.empty() ? 0 : 1) + (b.group_programs.empty() ? 0 : 1) + b.levels.size() + 1;
+  st->num_ac_streams = b.ac_streams.size();
+  st->vardct_frames = b.vframes.size();
+  st->wave_frames = b.vframes.empty() ? 0 : b.wave_frames;
   return 0;
 }
 

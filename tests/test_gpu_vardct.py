@@ -1,0 +1,63 @@
+"""GPU: VarDCT decode through the C ABI against the oracle (lossy parity is pinned on the oracle,
+the oracle on the reference's goldens and known-answer tests). The bar is bit-exact output samples."""
+import numpy as np
+import pytest
+
+import jxlo
+import vardct_cases as vc
+from conftest import read_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_all_cases_in_one_batch(pkg):
+    names = [c[0] for c in vc.SMALL_CASES + vc.STRATEGY_CASES]
+    files = [vc.encoded(n)[0] for n in names]
+    outs = pkg.decode_batch(files, 3, np.uint8)
+    bad = [n for n, f, o in zip(names, files, outs) if not np.array_equal(o, jxlo.decode(f, 3, jxlo.UINT8))]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("dt,npdt", [(jxlo.UINT16, np.uint16), (jxlo.FLOAT16, np.float16), (jxlo.FLOAT, np.float32)])
+def test_pixel_types(pkg, dt, npdt):
+    names = ["all_strategies", "three_passes", "strategy_24"]
+    files = [vc.encoded(n)[0] for n in names]
+    outs = pkg.decode_batch(files, 4, npdt)
+    for f, o in zip(files, outs):
+        want = jxlo.decode(f, 4, dt)
+        assert np.array_equal(o.view(np.uint8), want.view(np.uint8))
+
+
+def test_event_api_decodes_a_lossy_file(pkg):
+    data, shape = vc.encoded("heuristic")
+    dec = pkg.decoder_builder().build()
+    meta, px = dec.decode(data)
+    assert px.variant == "Uint8" and (meta.height, meta.width) == shape and not meta.has_alpha_channel
+    assert np.array_equal(px.data.reshape(shape + (3,)), jxlo.decode(data, 3, jxlo.UINT8))
+
+
+def test_mixed_modular_and_vardct_batch(pkg):
+    a, _ = vc.encoded("heuristic")
+    m = read_golden("bench.jxl")
+    outs = pkg.decode_batch([a, m, a], 4, np.uint8)
+    assert np.array_equal(outs[0], jxlo.decode(a, 4, jxlo.UINT8))
+    assert np.array_equal(outs[1], jxlo.decode(m, 4, jxlo.UINT8))
+    assert np.array_equal(outs[2], outs[0])
+
+
+def test_4k_frame_full_size(pkg):
+    # BASELINE.json configs[1]: a 3840x2160 lossy frame, compared sample by sample
+    img = vc.frame_4k()
+    data = jxlo.encode_vardct(img, distance=1.0, strategy_mode=2)
+    got = pkg.decode_batch([data, data], 3, np.uint8)
+    want = jxlo.decode(data, 3, jxlo.UINT8)
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
+    err = got[0].astype(np.float64) - img
+    assert 10 * np.log10(255 ** 2 / (err ** 2).mean()) > 30  # and it is the picture that was encoded
+
+
+def test_token_budget_retry(pkg):
+    # three passes over noisy content produce more tokens than the byte-count heuristic allows: Wait() regrows
+    data, shape = vc.encoded("three_passes")
+    out = pkg.decode_batch([data], 3, np.uint8)[0]
+    assert np.array_equal(out, jxlo.decode(data, 3, jxlo.UINT8))
