@@ -4,13 +4,19 @@
   python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on the host cores
 
-A "step" = one pass of the hot path over one batch of synthetic input: BATCH independent
-bench.jxl-shaped frames (2122x1433 lossless Modular RGBA8, 54 groups each), i.e. the workload the
-reference's own criterion bench decodes (jpegxl-rs/benches/decode.rs:10-40), replicated so that the
-#groups x #frames parallelism fills the GPU. Every rank works on its own batch (weak scaling, no
-data-path collective; the final gather of pixels is left to the caller).
+A "step" = one pass of the hot path over one batch of synthetic input. Workloads:
+
+  vardct4k (default)  BATCH lossy 3840x2160 VarDCT frames per GPU (BASELINE.json configs[1]; 64 per GPU is
+                      configs[3]'s 512 frames on 8 GPUs), alternating two committed fixtures
+                      (tests/golden/vardct_4k_{natural,synthetic}.jxl, written by tests/golden/make_vardct_fixtures.py),
+                      decoded to RGB8.
+  modular             BATCH bench.jxl-shaped frames (2122x1433 lossless Modular RGBA8, 54 groups each): the input of
+                      the reference's own criterion bench (jpegxl-rs/benches/decode.rs:10-40).
+
+Every rank works on its own batch (weak scaling, no data-path collective: frames are independent).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -24,8 +30,41 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "Mpixels/s decode (lossless Modular RGBA8, bench.jxl shape)"
 UNIT = "Mpx/s"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+class Workload:
+    def __init__(self, name, batch):
+        g = json.load(open(os.path.join(GOLDEN, "golden.json")))
+        self.name = name
+        if name == "vardct4k":
+            names = ["vardct_4k_natural.jxl", "vardct_4k_synthetic.jxl"]
+            self.batch = batch or 64
+            self.channels = 3
+            self.metric = "Mpixels/s decode (lossy VarDCT 3840x2160 -> RGB8)"
+            self.dtype = "f32"
+            self.sha = [g[n]["sha256_rgb8"] for n in names]
+            self.desc = ("decode %d lossy VarDCT 4K frames per GPU (3840x2160, d=1.0, 135 groups/frame; two fixtures "
+                         "alternating: bench image tiled to 4K at %.2f bpp, procedural frame at %.2f bpp) to RGB8"
+                         % (self.batch, g[names[0]]["bpp"], g[names[1]]["bpp"]))
+            self.data = "synthetic (oracle-encoded 4K fixtures; the reference ships no VarDCT file larger than 40x50)"
+        else:
+            names = ["bench.jxl"]
+            self.batch = batch or 256
+            self.channels = 4
+            self.metric = "Mpixels/s decode (lossless Modular RGBA8, bench.jxl shape)"
+            self.dtype = "int32"
+            self.sha = [g["bench.jxl"]["sha256"]]
+            self.desc = ("decode %d bench.jxl-shaped frames per GPU (2122x1433 lossless Modular RGBA8, 54 groups/frame)"
+                         % self.batch)
+            self.data = "synthetic (replicas of the reference's bench.jxl)"
+        self.blobs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names]
+        self.files = [self.blobs[i % len(self.blobs)] for i in range(self.batch)]
+
+    def check(self, outs):
+        idx = sorted({0, 1 % self.batch, self.batch // 2, self.batch - 1})
+        return all(hashlib.sha256(outs[i].tobytes()).hexdigest() == self.sha[i % len(self.sha)] for i in idx)
 
 
 def measured_peak_hbm():
@@ -85,23 +124,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(data, seconds=15.0, threads=None):
-    """The oracle (CPU restatement of libjxl's algorithm; libjxl itself cannot be built here) decoding the same
-    frame on the host cores: `threads` Python threads (ctypes releases the GIL), one frame each, for ~`seconds`."""
+def cpu_baseline(wl, seconds=15.0, threads=None):
+    """The oracle (CPU restatement of libjxl's algorithm; libjxl itself cannot be built here) decoding the workload's
+    frames on the host cores: `threads` Python threads (ctypes releases the GIL), one frame at a time each, for about
+    `seconds` (every thread finishes the frame it started)."""
     import jxlo
     threads = threads or (os.cpu_count() or 1)
     jxlo.lib()
-    w = h = 0
-    d = jxlo.Decoded(data)
+    d = jxlo.Decoded(wl.blobs[0])
     w, h = d.info.xsize, d.info.ysize
     del d
     count = [0] * threads
     stop = time.time() + seconds
 
     def work(i):
+        k = i
         while time.time() < stop:
-            jxlo.Decoded(data).pixels(4, jxlo.UINT8, raw=True)
+            jxlo.Decoded(wl.blobs[k % len(wl.blobs)]).pixels(wl.channels, jxlo.UINT8, raw=True)
             count[i] += 1
+            k += 1
 
     t0 = time.time()
     ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
@@ -112,30 +153,32 @@ def cpu_baseline(data, seconds=15.0, threads=None):
     dt = time.time() - t0
     frames = sum(count)
     return {"value": frames * w * h / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{frames} bench.jxl frames (2122x1433 RGBA8) in {dt:.1f} s, oracle-CPU (not libjxl)"}, dt / max(frames, 1)
+            "sample": f"{frames} {wl.name} frames ({w}x{h}) in {dt:.1f} s on {threads} threads, oracle-CPU (not libjxl)"}, dt
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    data = open(os.path.join(ROOT, "tests", "golden", "bench.jxl"), "rb").read()
-    # bounded: steps x ~ (15 s / steps) so that the whole run stays within a couple of minutes
-    per_step = max(2.0, min(15.0, 60.0 / max(args.steps + args.warmup, 1)))
+    wl = Workload(args.workload, args.batch)
+    # bounded: the whole --steps K --warmup W run stays within a few minutes
+    per_step = max(6.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
     vals, ms = [], []
+    cb = None
     for i in range(args.warmup + args.steps):
-        cb, per_frame = cpu_baseline(data, seconds=per_step)
+        cb, dt = cpu_baseline(wl, seconds=per_step)
         if i >= args.warmup:
             vals.append(cb["value"])
-            ms.append(per_step * 1e3)
+            ms.append(dt * 1e3)
     v = float(np.mean(vals))
     cb["value"] = v
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": wl.metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic (replicas of the reference's bench.jxl)",
-            "config": {"workload": "decode bench.jxl-shaped frames (2122x1433 lossless Modular RGBA8) on host cores",
-                       "note": "libjxl cannot be built in this image (Highway/brotli submodules empty); "
-                               "the CPU arm is the scalar oracle restating libjxl 0.11.2"},
+            "vs_baseline": None, "dtype": wl.dtype, "data": wl.data,
+            "config": {"workload": wl.desc + " -- CPU arm: each step decodes as many of these frames as the host cores "
+                                             "finish in %.0f s" % per_step,
+                       "note": "libjxl cannot be built in this image (Highway / brotli submodules are empty, no Rust "
+                               "toolchain); the CPU arm is the scalar oracle restating libjxl 0.11.2, all host threads"},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -146,9 +189,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--workload", default="vardct4k", choices=["vardct4k", "modular"])
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 64 vardct4k, 256 modular)")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -169,11 +213,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    data = open(os.path.join(ROOT, "tests", "golden", "bench.jxl"), "rb").read()
-    files = [data] * args.batch
+    wl = Workload(args.workload, args.batch)
+    files = wl.files
     dec = pkg.BatchDecoder(local_rank)
-    dec.set_input(files, 4, pkg.JXL_TYPE_UINT8)
-    st = dec.stats()
+    dec.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8)
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
@@ -185,10 +228,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput: inputs and tables already in HBM ----
+    # ---- device-resident throughput: bitstreams and tables already in HBM ----
     for _ in range(args.warmup):
         dec.run(stream)
-    dec.wait(stream)
+        dec.wait(stream)  # (the first wait may regrow the token arena and decode again)
+    st = dec.stats()
     dec.set_profiling(True)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -202,7 +246,7 @@ def main():
     clocks = sampler.stop()
     dec.wait(stream)
     ms_total = e0.elapsed_time(e1)
-    kernel_ms, runs = dec.kernel_times()
+    kernel_ms, runs = dec.kernel_times_ex()
     dec.set_profiling(False)
     t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -213,16 +257,16 @@ def main():
     value = pixels_per_step / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end through the public API with host buffers ----
-    outs = [torch.empty(dec.out_size(i), dtype=torch.uint8).pin_memory().numpy() for i in range(args.batch)]
+    outs = [torch.empty(dec.out_size(i), dtype=torch.uint8).pin_memory().numpy() for i in range(wl.batch)]
     e2e_steps = max(2, min(args.steps, 5))
     for i in range(1 + e2e_steps):
         if i == 1:
             barrier()
             t0 = time.perf_counter()
-        dec.set_input(files, 4, pkg.JXL_TYPE_UINT8)  # host parse + H2D of bitstreams and tables
+        dec.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8)  # host parse + H2D of bitstreams and tables
         dec.run(stream)
         dec.wait(stream)
-        dec.read_outputs(outs)                        # D2H into pinned host memory
+        dec.read_outputs(outs)                                  # D2H into pinned host memory
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -231,48 +275,49 @@ def main():
     e2e_s = float(t.item())
     e2e_value = pixels_per_step / e2e_s / 1e6
 
-    # checksum gate: the batch decodes to the golden pixels
-    import hashlib
-    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["bench.jxl"]["sha256"]
-    ok = all(hashlib.sha256(outs[i].tobytes()).hexdigest() == g for i in (0, args.batch // 2, args.batch - 1))
+    ok = wl.check(outs)  # checksum gate: the batch decodes to the golden pixels
+    okt = torch.tensor([1 if ok else 0], device="cuda")
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    ok = bool(okt.item())
 
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
-        # algorithmic bytes of the dominant kernel per launch: bitstream read + pixels written
+        per_run = {k: v / max(runs, 1) for k, v in kernel_ms.items()}
+        top = max(per_run, key=per_run.get)
+        # algorithmic bytes per launch: one read of the bitstream + one write of the output pixels
         alg_bytes = st.compressed_bytes + st.output_bytes
-        dec_ms = kernel_ms[0] / max(runs, 1)
-        achieved = alg_bytes / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
+        top_ms = per_run[top]
+        achieved = alg_bytes / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("batch") == args.batch:
-                traffic = tj.get("k_modular_decode_dram_bytes")
+            e = tj.get(wl.name, {})
+            if e.get("batch") == wl.batch and e.get("kernel") == top:
+                traffic = e.get("dram_bytes_per_launch")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic (replicas of the reference's bench.jxl)",
-            "config": {"workload": f"decode {args.batch} bench.jxl-shaped frames per GPU (2122x1433 lossless Modular "
-                                   f"RGBA8, 54 groups/frame, {st.num_streams} entropy streams)",
-                       "batch_per_gpu": args.batch, "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)"
+            "vs_baseline": None, "dtype": wl.dtype, "data": wl.data,
+            "config": {"workload": wl.desc, "batch_per_gpu": wl.batch, "entropy_streams": int(st.num_streams),
+                       "wave_frames": int(st.wave_frames),
+                       "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)"
                        % ((st.arena_bytes + st.output_bytes + st.compressed_bytes) / 1e9),
-                       "golden_checksum_ok": bool(ok)},
+                       "golden_checksum_ok": ok},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(st.compressed_bytes), "d2h_bytes_per_step": int(st.output_bytes),
                     "includes": "host parse (threads) + H2D bitstreams/tables + kernels + D2H to pinned host"},
             "gpu_launches": int(st.kernel_launches) * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_modular_decode", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": dec_ms,
-                         "kernel_share_of_step": dec_ms / ms_per_step if ms_per_step else None,
-                         "all_kernels_ms": {"modular_decode": kernel_ms[0] / max(runs, 1),
-                                            "group_programs": kernel_ms[1] / max(runs, 1),
-                                            "frame_levels": kernel_ms[2] / max(runs, 1),
-                                            "write_output": kernel_ms[3] / max(runs, 1)}},
+                         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": top_ms,
+                         "kernel_share_of_step": top_ms / ms_per_step if ms_per_step else None,
+                         "all_kernels_ms": per_run},
         }
         if not args.no_cpu_baseline and world == 1:
-            cb, _ = cpu_baseline(data, seconds=args.cpu_seconds)
+            cb, _ = cpu_baseline(wl, seconds=args.cpu_seconds)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:

@@ -11,7 +11,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 name = sys.argv[2] if len(sys.argv) > 2 else "bench.jxl"
 data = open(os.path.join(ROOT, "tests", "golden", name), "rb").read()
 dec = pkg.BatchDecoder(0)
-dec.set_input([data] * n, 4, pkg.JXL_TYPE_UINT8)
+nch = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+dec.set_input([data] * n, nch, pkg.JXL_TYPE_UINT8)
 for _ in range(2):
     dec.run()
     dec.wait()
