@@ -26,7 +26,7 @@ def main():
         open(os.path.join(HERE, name), "wb").write(data)
         px = jxlo.decode(data, 3, jxlo.UINT8)
         err = px.astype(float) - img
-        g[name] = {"sha256_rgb8": hashlib.sha256(px.tobytes()).hexdigest(), "width": 3840, "height": 2160,
+        g[name] = {"file_sha256": hashlib.sha256(data).hexdigest(), "sha256_rgb8": hashlib.sha256(px.tobytes()).hexdigest(), "width": 3840, "height": 2160,
                    "bytes": len(data), "bpp": round(8 * len(data) / (3840 * 2160), 4),
                    "psnr_vs_source": round(float(10 * __import__("numpy").log10(255 ** 2 / (err ** 2).mean())), 2),
                    "encoder": "oracle/jxlo_encode.h " + json.dumps(kw, sort_keys=True)}
