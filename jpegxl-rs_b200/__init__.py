@@ -454,3 +454,55 @@ def decode_batch(files: Sequence[bytes], num_channels: int = 4, dtype=np.uint8, 
         raw = dec.read_output(i)
         out.append(raw.view(dtype).reshape(info.ysize, info.xsize, num_channels))
     return out
+
+
+# ---- multi-GPU: frames are independent, frame i -> rank i mod R ----
+def shard_indices(n: int, rank: int, world: int) -> List[int]:
+    """Indices of the frames rank `rank` of `world` decodes: round-robin, so every rank gets a similar mix."""
+    return list(range(rank, n, world))
+
+
+def gather_frames(local: Sequence[np.ndarray], n_total: int, rank: int, world: int, dst: int = 0, device=None):
+    """The one collective of the path: gathers the decoded frames of every rank on rank `dst` (returns the list in
+    the original order there, None elsewhere). Works on any torch.distributed backend (NCCL with `device` a CUDA
+    device, gloo on the CPU): sizes are exchanged first, then one padded gather of bytes."""
+    import torch
+    import torch.distributed as dist
+    dev = device if device is not None else torch.device("cpu")
+    meta = [(a.shape, a.dtype.str) for a in local]
+    metas = [None] * world
+    dist.all_gather_object(metas, meta)
+    sizes = [sum(int(np.prod(sh)) * np.dtype(dt).itemsize for sh, dt in m) for m in metas]
+    cap = max(max(sizes), 1)
+    flat = np.zeros(cap, np.uint8)
+    off = 0
+    for a in local:
+        b = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        flat[off:off + b.size] = b
+        off += b.size
+    mine = torch.from_numpy(flat).to(dev)
+    bufs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == dst else None
+    dist.gather(mine, bufs, dst=dst)
+    if rank != dst:
+        return None
+    out = [None] * n_total
+    for r in range(world):
+        raw = bufs[r].cpu().numpy()
+        off = 0
+        for i, (sh, dt) in zip(shard_indices(n_total, r, world), metas[r]):
+            nbytes = int(np.prod(sh)) * np.dtype(dt).itemsize
+            out[i] = raw[off:off + nbytes].view(np.dtype(dt)).reshape(sh).copy()
+            off += nbytes
+    return out
+
+
+def decode_batch_distributed(files: Sequence[bytes], num_channels: int = 4, dtype=np.uint8, dst: int = 0, decode_fn=None,
+                             device=None):
+    """Every rank decodes its shard of `files` (all ranks pass the same list); rank `dst` gets all frames.
+    `decode_fn(files, num_channels, dtype)` defaults to decode_batch on this rank's GPU."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    idx = shard_indices(len(files), rank, world)
+    fn = decode_fn or decode_batch
+    local = fn([files[i] for i in idx], num_channels, dtype) if idx else []
+    return gather_frames(local, len(files), rank, world, dst, device)
