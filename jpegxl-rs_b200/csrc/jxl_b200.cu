@@ -9,8 +9,9 @@
 //   k_dc_finish       one CTA = one DC group: DC dequantisation, block side information, EPF sigma
 //   k_dc_smooth       adaptive DC smoothing
 //   k_ac_decode       one thread = one (frame, group, pass) AC stream -> sparse coefficient tokens
-//   k_dequant_idct    one CTA = one 256x256 group: token scatter, dequant + CfL, inverse transforms
-//                     (warp per varblock up to 32x32, CTA per varblock up to 64x64)
+//   k_dequant_idct    one CTA = one 256x256 group: token scatter, dequant + CfL, inverse transforms;
+//                     warp per varblock up to 32x32 (register-resident IDCTs)
+//   k_idct_mid        64x32 / 32x64 / 64x64 varblocks, one CTA per varblock, staged transforms in shared memory
 //   k_idct_big        varblocks of 128x128 and larger, scratch in global memory
 //   k_gaborish / k_epf / k_color_write   render stages, one thread per pixel
 #include <cuda_runtime.h>
@@ -138,28 +139,29 @@ __global__ void __launch_bounds__(32) k_ac_decode(DevPools P, DevVPools V) {
   if (valid) V.ac_status[s] = status;
 }
 
-constexpr uint32_t kIdctThreads = 128;
-constexpr uint32_t kIdctSmemFloats = 4 * 4096;  // 64 KiB: four buffers of a 64x64 varblock
+constexpr uint32_t kIdctThreads = 128;                                  // 4 warps, one small varblock each at a time
+constexpr uint32_t kIdctSmemFloats = (kIdctThreads / 32) * kFastBufFloats;  // 51.7 KB: four CTAs per SM
+constexpr uint32_t kMidThreads = 256;
+constexpr uint32_t kMidSmemFloats = kFastBufFloats64;                   // 49 KB: three padded 64x64 channels
 
-// blockIdx.x = group, blockIdx.y = frame - frame0.
-__global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint32_t frame0) {
+// blockIdx.x = group, blockIdx.y = frame - frame0. Varblocks of up to 32x32 pixels: one warp each, handed out
+// dynamically. Plain DCTs take the register-IDCT fast path, the 8x8 special transforms the generic one.
+__global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint32_t frame0, uint32_t* has_mid) {
   extern __shared__ float idct_smem[];
-  __shared__ uint32_t next_s, has_big_s;
+  __shared__ uint32_t next_s;
   const DevVFrame& vf = V.frames[frame0 + blockIdx.y];
   const uint32_t g = blockIdx.x;
   if (g >= vf.xgroups * vf.ygroups) return;
   const uint32_t x0 = (g % vf.xgroups) * 32, y0 = (g / vf.xgroups) * 32;
   const uint32_t xs = min(32u, vf.xblocks - x0), ys = min(32u, vf.yblocks - y0);
   const uint8_t* acs = V.barena + vf.acs;
-  if (threadIdx.x == 0) {
-    next_s = 0;
-    has_big_s = 0;
-  }
+  if (threadIdx.x == 0) next_s = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* wbuf = idct_smem + warp * 4096;
+  float* wbuf = idct_smem + warp * kFastBufFloats;
   const uint32_t total = xs * ys;
-  for (;;) {  // varblocks of up to 32x32 pixels: one warp each
+  bool mid = false;
+  for (;;) {
     uint32_t i = 0;
     if (lane == 0) i = atomicAdd(&next_s, 1u);
     i = __shfl_sync(0xFFFFFFFFu, i, 0);
@@ -169,27 +171,44 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
     if (!(a & 1) || a == 0xFF) continue;
     const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
     if (static_cast<uint32_t>(si.cx) * si.cy > 16) {
-      if (lane == 0) has_big_s = 1;
+      mid = true;
       continue;
     }
-    DevVarblock<1>(V, vf, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
+    if (si.plain_dct) {
+      DevVarblockFast<1, 32>(V, vf, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
+    } else {
+      DevVarblock<1>(V, vf, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
+    }
   }
-  __syncthreads();
-  if (!has_big_s) return;
-  for (uint32_t i = 0; i < total; i++) {  // 64x32, 32x64, 64x64: the whole CTA per varblock
+  if (mid && lane == 0) *has_mid = 1;  // some frame of the batch needs k_idct_mid / k_idct_big
+}
+
+// 64x32, 32x64 and 64x64 varblocks: the whole CTA per varblock, one 64-point register IDCT per thread and line.
+__global__ void __launch_bounds__(kMidThreads) k_idct_mid(DevVPools V, uint32_t frame0, const uint32_t* has_mid) {
+  extern __shared__ float idct_smem[];
+  if (*has_mid == 0) return;
+  const DevVFrame& vf = V.frames[frame0 + blockIdx.y];
+  const uint32_t g = blockIdx.x;
+  if (g >= vf.xgroups * vf.ygroups) return;
+  const uint32_t x0 = (g % vf.xgroups) * 32, y0 = (g / vf.xgroups) * 32;
+  const uint32_t xs = min(32u, vf.xblocks - x0), ys = min(32u, vf.yblocks - y0);
+  const uint8_t* acs = V.barena + vf.acs;
+  for (uint32_t i = 0; i < xs * ys; i++) {
     const uint32_t bx = i % xs, by = i / xs;
     const uint8_t a = acs[static_cast<size_t>(y0 + by) * vf.xblocks + x0 + bx];
     if (!(a & 1) || a == 0xFF) continue;
     const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
     const uint32_t covered = static_cast<uint32_t>(si.cx) * si.cy;
     if (covered <= 16 || covered > 64) continue;
-    DevVarblock<2>(V, vf, x0 + bx, y0 + by, a >> 1, idct_smem, threadIdx.x, kIdctThreads);
+    DevVarblockFast<2, 64>(V, vf, x0 + bx, y0 + by, a >> 1, idct_smem, threadIdx.x, kMidThreads);
   }
 }
 
 // Persistent CTAs with 4 * 65536 floats of global scratch each: varblocks above 64x64 pixels.
-__global__ void __launch_bounds__(256) k_idct_big(DevVPools V, uint32_t frame0, uint32_t num_frames, float* scratch) {
+__global__ void __launch_bounds__(256) k_idct_big(DevVPools V, uint32_t frame0, uint32_t num_frames, float* scratch,
+                                                  const uint32_t* has_mid) {
   __shared__ uint32_t list_s[64], count_s;
+  if (*has_mid == 0) return;
   float* buf = scratch + static_cast<size_t>(blockIdx.x) * 4 * 65536;
   for (uint32_t f = 0; f < num_frames; f++) {
     const DevVFrame& vf = V.frames[frame0 + f];
@@ -224,7 +243,14 @@ __global__ void __launch_bounds__(256) k_gaborish(DevVPools V, uint32_t frame0, 
   const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
   const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if (!vf.gab || x >= vf.xsize || y >= vf.ysize) return;
-  for (uint32_t c = 0; c < 3; c++) DevGaborishPixel(V, vf, in_set, out_set, c, static_cast<int>(x), static_cast<int>(y));
+  const bool interior = x >= 1 && y >= 1 && x + 1 < vf.xsize && y + 1 < vf.ysize;
+  for (uint32_t c = 0; c < 3; c++) {
+    if (interior) {
+      DevGaborishPixel<true>(V, vf, in_set, out_set, c, static_cast<int>(x), static_cast<int>(y));
+    } else {
+      DevGaborishPixel<false>(V, vf, in_set, out_set, c, static_cast<int>(x), static_cast<int>(y));
+    }
+  }
 }
 
 // `sets` packs, per frame class, which plane set holds the input: frames with / without
@@ -244,14 +270,32 @@ __global__ void __launch_bounds__(256) k_epf(DevVPools V, uint32_t frame0, uint3
   const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if (!runs || x >= vf.xsize || y >= vf.ysize) return;
   const uint32_t set = SetBeforeStage(vf, stage);
-  DevEpfPixel(V, vf, stage, set, set ^ 1, static_cast<int>(x), static_cast<int>(y));
+  if (x >= 3 && y >= 3 && x + 3 < vf.xsize && y + 3 < vf.ysize) {
+    DevEpfPixel<true>(V, vf, stage, set, set ^ 1, static_cast<int>(x), static_cast<int>(y));
+  } else {
+    DevEpfPixel<false>(V, vf, stage, set, set ^ 1, static_cast<int>(x), static_cast<int>(y));
+  }
 }
 
 __global__ void __launch_bounds__(256) k_color_write(DevVPools V, uint32_t frame0) {
   const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
-  const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if (x >= vf.xsize || y >= vf.ysize) return;
-  DevColorPixel(V, vf, SetBeforeStage(vf, 3), x, y);
+  const uint32_t y = blockIdx.y * 8 + threadIdx.y;
+  if (y >= vf.ysize) return;
+  const uint32_t set = SetBeforeStage(vf, 3);
+  if (vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0) {
+    // RGB8: each thread converts 4 consecutive pixels and writes 12 bytes as three words
+    const uint32_t x = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (x + 4 <= vf.xsize) {
+      DevColorPixelsRgb8x4(V, vf, set, x, y);
+    } else {
+      for (uint32_t i = x; i < vf.xsize; i++) DevColorPixel(V, vf, set, i, y);
+    }
+    return;
+  }
+  for (uint32_t k = 0; k < 4; k++) {  // grid.x covers 128 pixels per CTA row
+    const uint32_t x = (blockIdx.x * 4 + k) * 32 + threadIdx.x;
+    if (x < vf.xsize) DevColorPixel(V, vf, set, x, y);
+  }
 }
 
 // ------------------------------------------------------------------ runtime
@@ -398,6 +442,7 @@ JxlB200Decoder* JxlB200DecoderCreate(int device) {
     return nullptr;
   }
   cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, kIdctSmemFloats * sizeof(float));
+  cudaFuncSetAttribute(k_idct_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kMidSmemFloats * sizeof(float));
   return dec;
 }
 
@@ -670,9 +715,11 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
       const uint32_t nf = std::min<uint32_t>(b.wave_frames, nvf - f0);
       {
         ScopedTimer t(dec, s, kKDequantIdct);
-        k_dequant_idct<<<dim3(dec->max_groups, nf), kIdctThreads, kIdctSmemFloats * sizeof(float), s>>>(V, f0);
-        k_idct_big<<<JxlB200Decoder::kBigCtas, 256, 0, s>>>(V, f0, nf, dec->d_big_scratch.p);
-        launches += 2;
+        uint32_t* has_mid = dec->d_dc_status.p + dec->dcg_list.size();  // spare word after the DC status words
+        k_dequant_idct<<<dim3(dec->max_groups, nf), kIdctThreads, kIdctSmemFloats * sizeof(float), s>>>(V, f0, has_mid);
+        k_idct_mid<<<dim3(dec->max_groups, nf), kMidThreads, kMidSmemFloats * sizeof(float), s>>>(V, f0, has_mid);
+        k_idct_big<<<JxlB200Decoder::kBigCtas, 256, 0, s>>>(V, f0, nf, dec->d_big_scratch.p, has_mid);
+        launches += 3;
       }
       const dim3 px_grid((dec->max_xsize + 31) / 32, (dec->max_ysize + 7) / 8, nf);
       {
@@ -689,7 +736,8 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
       }
       {
         ScopedTimer t(dec, s, kKColorWrite);
-        k_color_write<<<px_grid, px_block, 0, s>>>(V, f0);
+        const dim3 cw_grid((dec->max_xsize + 127) / 128, (dec->max_ysize + 7) / 8, nf);
+        k_color_write<<<cw_grid, px_block, 0, s>>>(V, f0);
         launches++;
       }
     }

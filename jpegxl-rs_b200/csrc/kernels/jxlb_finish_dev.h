@@ -212,11 +212,11 @@ JXLB_HD void DevRunOp(const DevPools& P, const DevOp& op, uint32_t tid, uint32_t
 
 // ---------------------------------------------------------------- output
 JXLB_HD float DevDither(uint32_t x, uint32_t y) {
-  // lib/jxl/render_pipeline/stage_write.cc:51-84: kDither[i] = ((bayer8x8 + 0.5) / 64) - 0.5.
-  const uint8_t kBayer[64] = {0,  32, 8,  40, 2,  34, 10, 42, 48, 16, 56, 24, 50, 18, 58, 26, 12, 44, 4,  36, 14, 46,
-                              6,  38, 60, 28, 52, 20, 62, 30, 54, 22, 3,  35, 11, 43, 1,  33, 9,  41, 51, 19, 59, 27,
-                              49, 17, 57, 25, 15, 47, 7,  39, 13, 45, 5,  37, 63, 31, 55, 23, 61, 29, 53, 21};
-  return (static_cast<float>(kBayer[(y & 7) * 8 + (x & 7)]) + 0.5f) * (1.0f / 64.0f) - 0.5f;
+  // lib/jxl/render_pipeline/stage_write.cc:51-84: kDither[i] = ((bayer8x8 + 0.5) / 64) - 0.5. The 8x8 Bayer
+  // index is 16 * f(x0, y0) + 4 * f(x1, y1) + f(x2, y2) with f(a, b) = 2 * (a ^ b) + b over the bits of x, y.
+  const uint32_t b = y & 7, t = (x ^ y) & 7;
+  const uint32_t bayer = ((t & 1) << 5) | ((b & 1) << 4) | ((t & 2) << 2) | ((b & 2) << 1) | ((t & 4) >> 1) | ((b & 4) >> 2);
+  return (static_cast<float>(bayer) + 0.5f) * (1.0f / 64.0f) - 0.5f;
 }
 
 JXLB_HD float DevIntToFloat(int32_t in, int bits, int exp_bits) {

@@ -26,6 +26,7 @@
 
 #include "jxlb_finish_dev.h"
 #include "jxlb_vardct_desc.h"
+#include "jxlb_wc.h"
 
 namespace jxlb {
 
@@ -49,6 +50,12 @@ struct DevVPools {
   uint32_t ctxtab_off;                // upool: kCoeffFreqContext[64] then kCoeffNumNonzeroContext[64]
   uint8_t* out;
 };
+
+#if defined(__CUDACC__)
+#define JXLB_UNROLL _Pragma("unroll")
+#else
+#define JXLB_UNROLL
+#endif
 
 template <int SCOPE>
 JXLB_HD void CoopSync() {
@@ -887,23 +894,253 @@ JXLB_HD void DevVarblock(const DevVPools& V, const DevVFrame& vf, uint32_t bx, u
   }
 }
 
+// ---------------------------------------------------------------- fast path: varblocks up to 32x32
+// Same arithmetic as DevVarblock, organised for the common block sizes:
+//  * coefficients live in a padded layout (row stride max(R, C) + 1 floats) so that both the row-wise and the
+//    column-wise pass touch 32 different shared-memory banks;
+//  * single-pass frames dequantise straight from the tokens (cost ~ non-zeros, not block size): Y first, then
+//    X / B with their chroma-from-luma term read back from Y;
+//  * every 1-D IDCT is one thread's register-resident, fully unrolled recursion (RegIDCT), in place; the second
+//    pass stores its result directly into the pixel planes.
+template <int N>
+struct RegIDCT {
+  static JXLB_HD void Run(float* v) {
+    constexpr int H = N / 2;
+    float t[N];
+JXLB_UNROLL
+    for (int i = 0; i < H; i++) {
+      t[i] = v[2 * i];
+      t[H + i] = v[2 * i + 1];
+    }
+    RegIDCT<H>::Run(t);
+JXLB_UNROLL
+    for (int i = H - 1; i > 0; i--) t[H + i] = t[H + i] + t[H + i - 1];
+    t[H] = t[H] * kDevSqrt2;
+    RegIDCT<H>::Run(t + H);
+JXLB_UNROLL
+    for (int i = 0; i < H; i++) {
+      const float w = WcMul(N, i);
+      v[i] = fmaf(w, t[H + i], t[i]);
+      v[N - 1 - i] = fmaf(-w, t[H + i], t[i]);
+    }
+  }
+};
+template <>
+struct RegIDCT<2> {
+  static JXLB_HD void Run(float* v) {
+    const float a = v[0], b = v[1];
+    v[0] = a + b;
+    v[1] = a - b;
+  }
+};
+
+// In-place N-point IDCT of `lines` lines per channel (3 channels of P floats each): element e of line l at
+// base[c * P + l * lstride + e * estride].
+template <int N>
+JXLB_HD void IdctLinesInPlace(float* buf, uint32_t P, uint32_t lines, uint32_t lstride, uint32_t estride, uint32_t tid,
+                              uint32_t nt) {
+  for (uint32_t l = tid; l < 3 * lines; l += nt) {
+    const uint32_t c = l / lines, li = l - c * lines;
+    float* p = buf + c * P + li * lstride;
+    float v[N];
+JXLB_UNROLL
+    for (int e = 0; e < N; e++) v[e] = p[e * estride];
+    RegIDCT<N>::Run(v);
+JXLB_UNROLL
+    for (int e = 0; e < N; e++) p[e * estride] = v[e];
+  }
+}
+
+// Second pass: line x of channel c holds the column x of the block; results go to out[c][y * PW + x].
+template <int N>
+JXLB_HD void IdctLinesToPixels(const float* buf, uint32_t P, uint32_t lines, uint32_t lstride, uint32_t estride,
+                               float* const out[3], uint32_t PW, uint32_t tid, uint32_t nt) {
+  for (uint32_t l = tid; l < 3 * lines; l += nt) {
+    const uint32_t c = l / lines, x = l - c * lines;
+    const float* p = buf + c * P + x * lstride;
+    float v[N];
+JXLB_UNROLL
+    for (int e = 0; e < N; e++) v[e] = p[e * estride];
+    RegIDCT<N>::Run(v);
+    float* o = out[c] + x;
+JXLB_UNROLL
+    for (int e = 0; e < N; e++) o[static_cast<size_t>(e) * PW] = v[e];
+  }
+}
+
+constexpr uint32_t kFastBufFloats = 3 * 32 * 33 + 64;    // three padded 32x32 channels + LLF scratch
+constexpr uint32_t kFastBufFloats64 = 3 * 64 * 65 + 128;  // the same for blocks up to 64x64
+
+// Varblock with a plain DCT of at most MAXN x MAXN pixels (MAXN = 32: strategies 0, 4..11; MAXN = 64: also
+// 18..20). `buf`: kFastBufFloats (kFastBufFloats64) floats shared by the cooperating threads.
+template <int SCOPE, int MAXN>
+JXLB_HD void DevVarblockFast(const DevVPools& V, const DevVFrame& vf, uint32_t bx, uint32_t by, uint32_t s, float* buf,
+                             uint32_t tid, uint32_t nt) {
+  const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + s]);
+  const uint32_t Rb = si.cy, Cb = si.cx, covered = Rb * Cb;
+  const uint32_t R = 8 * Rb, C = 8 * Cb, N = R * C;
+  const uint32_t mx = R > C ? R : C, mn = R > C ? C : R;
+  uint32_t log2mx = 3;
+  while ((1u << log2mx) < mx) log2mx++;
+  const uint32_t S = mx + 1, P = mn * S;
+  const uint32_t W = vf.xblocks;
+  const size_t nb = static_cast<size_t>(W) * vf.yblocks;
+  const size_t pos = static_cast<size_t>(by) * W + bx;
+  float* ch[3] = {buf, buf + P, buf + 2 * P};
+  float* scratch = buf + 3 * P;
+  const float* wc = V.fpool + V.wc_off;
+  // dequantisation constants (DequantBlock)
+  const uint16_t* rawq = reinterpret_cast<const uint16_t*>(V.barena + vf.rawq);
+  const float scaled = vf.inv_global_scale / static_cast<float>(rawq[pos]);
+  const float sd[3] = {scaled * vf.x_dm, scaled, scaled * vf.b_dm};
+  const size_t tile = static_cast<size_t>(by / 8) * vf.cmw + bx / 8;
+  const float x_cc = vf.base_x + static_cast<float>(reinterpret_cast<const int8_t*>(V.barena + vf.ytox)[tile]) * vf.color_scale;
+  const float b_cc = vf.base_b + static_cast<float>(reinterpret_cast<const int8_t*>(V.barena + vf.ytob)[tile]) * vf.color_scale;
+  const float* dm = V.fpool + vf.table_off[si.table];
+  for (uint32_t i = tid; i < 3 * P; i += nt) buf[i] = 0.0f;
+  CoopSync<SCOPE>();
+  if (vf.num_passes == 1) {
+    // Y tokens: Y = dq_y; X = x_cc * dq_y (+ 0), B = b_cc * dq_y (+ 0)
+    {
+      const uint32_t start = V.uarena[vf.tok_start + 1 * nb + pos], count = V.uarena[vf.tok_count + 1 * nb + pos];
+      const uint32_t* tok = V.tokens + start;
+      for (uint32_t i = tid; i < count; i += nt) {
+        const uint32_t t = JXLB_LDG(tok + i);
+        const uint32_t k = t & 0xFFFF;
+        if (k >= N) continue;
+        const int32_t q = static_cast<int16_t>(t >> 16);
+        const float dq_y = DevAdjustQuantBias(1, q, vf.biases) * (JXLB_LDG(dm + N + k) * sd[1]);
+        const uint32_t kp = k + (k >> log2mx);
+        ch[1][kp] = dq_y;
+        ch[0][kp] = fmaf(x_cc, dq_y, 0.0f);
+        ch[2][kp] = fmaf(b_cc, dq_y, 0.0f);
+      }
+    }
+    CoopSync<SCOPE>();
+    for (uint32_t c = 0; c < 3; c += 2) {
+      const uint32_t start = V.uarena[vf.tok_start + c * nb + pos], count = V.uarena[vf.tok_count + c * nb + pos];
+      const uint32_t* tok = V.tokens + start;
+      const float cc = c == 0 ? x_cc : b_cc;
+      for (uint32_t i = tid; i < count; i += nt) {
+        const uint32_t t = JXLB_LDG(tok + i);
+        const uint32_t k = t & 0xFFFF;
+        if (k >= N) continue;
+        const int32_t q = static_cast<int16_t>(t >> 16);
+        const float dq = DevAdjustQuantBias(static_cast<int>(c), q, vf.biases) * (JXLB_LDG(dm + c * N + k) * sd[c]);
+        const uint32_t kp = k + (k >> log2mx);
+        ch[c][kp] = fmaf(cc, ch[1][kp], dq);
+      }
+    }
+  } else {
+    // several passes: sum the integer contributions first, then dequantise every position
+    int32_t* qi = reinterpret_cast<int32_t*>(buf);
+    for (uint32_t p = 0; p < vf.num_passes; p++) {
+      const uint32_t shift = vf.pass_shift[p];
+      for (uint32_t c = 0; c < 3; c++) {
+        const size_t e = (static_cast<size_t>(p) * 3 + c) * nb + pos;
+        const uint32_t start = V.uarena[vf.tok_start + e], count = V.uarena[vf.tok_count + e];
+        const uint32_t* tok = V.tokens + start;
+        int32_t* q = qi + c * P;
+        for (uint32_t i = tid; i < count; i += nt) {
+          const uint32_t t = JXLB_LDG(tok + i);
+          const int32_t val = static_cast<int16_t>(t >> 16);
+          const uint32_t k = t & 0xFFFF;
+          if (k >= N) continue;
+          const uint32_t kp = k + (k >> log2mx);
+          q[kp] = static_cast<int32_t>(static_cast<uint32_t>(q[kp]) + (static_cast<uint32_t>(val) << shift));
+        }
+      }
+      CoopSync<SCOPE>();
+    }
+    for (uint32_t k = tid; k < N; k += nt) {
+      const uint32_t kp = k + (k >> log2mx);
+      const int32_t qx = qi[kp], qy = qi[P + kp], qb = qi[2 * P + kp];
+      if ((qx | qy | qb) == 0) continue;  // stays +0.0f: the bit pattern of integer 0
+      const float dq_x = DevAdjustQuantBias(0, qx, vf.biases) * (JXLB_LDG(dm + k) * sd[0]);
+      const float dq_y = DevAdjustQuantBias(1, qy, vf.biases) * (JXLB_LDG(dm + N + k) * sd[1]);
+      const float dq_b = DevAdjustQuantBias(2, qb, vf.biases) * (JXLB_LDG(dm + 2 * N + k) * sd[2]);
+      ch[0][kp] = fmaf(x_cc, dq_y, dq_x);
+      ch[1][kp] = dq_y;
+      ch[2][kp] = fmaf(b_cc, dq_y, dq_b);
+    }
+  }
+  CoopSync<SCOPE>();
+  // lowest frequencies from the DC image
+  if (s == 0) {
+    for (uint32_t c = tid; c < 3; c += nt) ch[c][0] = V.farena[vf.dc_final[c] + pos];
+  } else {
+    const float* ks = V.fpool + V.llf_off;
+    for (uint32_t c = 0; c < 3; c++) {
+      const float* dcp = V.farena + vf.dc_final[c] + pos;
+      float* a = scratch;
+      float* b = scratch + covered;
+      for (uint32_t i = tid; i < covered; i += nt) a[i] = dcp[static_cast<size_t>(i / Cb) * W + i % Cb];
+      CoopSync<SCOPE>();
+      float* r1 = CoopDCT<SCOPE>(Rb, Cb, 1, Cb, a, b, wc, tid, nt);
+      float* r2 = CoopDCT<SCOPE>(Cb, Rb, Cb, 1, r1, r1 == a ? b : a, wc, tid, nt);
+      if (Rb < Cb) {
+        for (uint32_t i = tid; i < covered; i += nt) {
+          const uint32_t y = i / Cb, x = i % Cb;
+          ch[c][y * S + x] = r2[y * Cb + x] * ks[Rb - 1 + y] * ks[Cb - 1 + x];
+        }
+      } else {
+        for (uint32_t i = tid; i < covered; i += nt) {
+          const uint32_t y = i / Rb, x = i % Rb;
+          ch[c][y * S + x] = r2[x * Cb + y] * ks[Cb - 1 + y] * ks[Rb - 1 + x];
+        }
+      }
+      CoopSync<SCOPE>();
+    }
+  }
+  CoopSync<SCOPE>();
+  // pass 1: C-point IDCT along x for each of the R lines
+  const uint32_t l1 = R >= C ? 1 : S, e1 = R >= C ? S : 1;
+  switch (C) {
+    case 8: IdctLinesInPlace<8>(buf, P, R, l1, e1, tid, nt); break;
+    case 16: IdctLinesInPlace<16>(buf, P, R, l1, e1, tid, nt); break;
+    case 32: IdctLinesInPlace<32>(buf, P, R, l1, e1, tid, nt); break;
+    default:
+      if (MAXN >= 64) IdctLinesInPlace<(MAXN >= 64 ? 64 : 32)>(buf, P, R, l1, e1, tid, nt);
+      break;
+  }
+  CoopSync<SCOPE>();
+  // pass 2: R-point IDCT along y for each of the C columns, straight into the pixel planes
+  const uint32_t PW = W * 8;
+  const size_t origin = static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+  float* const out[3] = {V.farena + vf.pix[0][0] + origin, V.farena + vf.pix[0][1] + origin, V.farena + vf.pix[0][2] + origin};
+  const uint32_t l2 = R >= C ? S : 1, e2 = R >= C ? 1 : S;
+  switch (R) {
+    case 8: IdctLinesToPixels<8>(buf, P, C, l2, e2, out, PW, tid, nt); break;
+    case 16: IdctLinesToPixels<16>(buf, P, C, l2, e2, out, PW, tid, nt); break;
+    case 32: IdctLinesToPixels<32>(buf, P, C, l2, e2, out, PW, tid, nt); break;
+    default:
+      if (MAXN >= 64) IdctLinesToPixels<(MAXN >= 64 ? 64 : 32)>(buf, P, C, l2, e2, out, PW, tid, nt);
+      break;
+  }
+  CoopSync<SCOPE>();
+}
+
 // ---------------------------------------------------------------- render stages (per pixel)
 JXLB_HD int DevMirror(int x, int size) {  // lib/jxl/image_ops.h:184-195
   while (x < 0 || x >= size) x = x < 0 ? -x - 1 : 2 * size - 1 - x;
   return x;
 }
 
+// INTERIOR: the caller guarantees that every access stays inside the frame (no mirroring needed).
+template <bool INTERIOR>
 struct DevPlaneView {
   const float* p;
   uint32_t stride;
   int xsize, ysize;
   JXLB_HD float At(int x, int y) const {
+    if (INTERIOR) return p[static_cast<uint32_t>(y) * stride + static_cast<uint32_t>(x)];
     return p[static_cast<size_t>(DevMirror(y, ysize)) * stride + DevMirror(x, xsize)];
   }
 };
 
-JXLB_HD DevPlaneView DevView(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t c) {
-  DevPlaneView v;
+template <bool INTERIOR>
+JXLB_HD DevPlaneView<INTERIOR> DevView(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t c) {
+  DevPlaneView<INTERIOR> v;
   v.p = V.farena + vf.pix[set][c];
   v.stride = vf.xblocks * 8;
   v.xsize = static_cast<int>(vf.xsize);
@@ -912,9 +1149,10 @@ JXLB_HD DevPlaneView DevView(const DevVPools& V, const DevVFrame& vf, uint32_t s
 }
 
 // Gaborish, one sample of channel c (lib/jxl/render_pipeline/stage_gaborish.cc:22-100).
+template <bool INTERIOR>
 JXLB_HD void DevGaborishPixel(const DevVPools& V, const DevVFrame& vf, uint32_t in_set, uint32_t out_set, uint32_t c, int x,
                               int y) {
-  const DevPlaneView m = DevView(V, vf, in_set, c);
+  const DevPlaneView<INTERIOR> m = DevView<INTERIOR>(V, vf, in_set, c);
   const float sum0 = m.At(x, y);
   const float sum1 = (m.At(x - 1, y) + m.At(x + 1, y)) + (m.At(x, y - 1) + m.At(x, y + 1));
   const float sum2 = (m.At(x - 1, y - 1) + m.At(x + 1, y - 1)) + (m.At(x - 1, y + 1) + m.At(x + 1, y + 1));
@@ -923,9 +1161,11 @@ JXLB_HD void DevGaborishPixel(const DevVPools& V, const DevVFrame& vf, uint32_t 
 }
 
 // One pixel of EPF stage 0 / 1 / 2 (lib/jxl/render_pipeline/stage_epf.cc:43-500).
+template <bool INTERIOR>
 JXLB_HD void DevEpfPixel(const DevVPools& V, const DevVFrame& vf, uint32_t stage, uint32_t in_set, uint32_t out_set, int x,
                          int y) {
-  const DevPlaneView m[3] = {DevView(V, vf, in_set, 0), DevView(V, vf, in_set, 1), DevView(V, vf, in_set, 2)};
+  const DevPlaneView<INTERIOR> m[3] = {DevView<INTERIOR>(V, vf, in_set, 0), DevView<INTERIOR>(V, vf, in_set, 1),
+                                       DevView<INTERIOR>(V, vf, in_set, 2)};
   const size_t at = static_cast<size_t>(y) * m[0].stride + x;
   float X = m[0].p[at], Y = m[1].p[at], B = m[2].p[at];
   const uint32_t sbx = static_cast<uint32_t>(x) / 8 < vf.xblocks - 1 ? static_cast<uint32_t>(x) / 8 : vf.xblocks - 1;
@@ -1145,10 +1385,8 @@ JXLB_HD void DevStoreSample(uint8_t* row, size_t idx, float v, uint32_t data_typ
   }
 }
 
-// One output pixel: colour transform of the filtered planes + sample conversion + interleaved store.
-JXLB_HD void DevColorPixel(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t x, uint32_t y) {
-  const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
-  const float p0 = V.farena[vf.pix[set][0] + at], p1 = V.farena[vf.pix[set][1] + at], p2 = V.farena[vf.pix[set][2] + at];
+// Colour transform of one pixel of the filtered planes -> non-linear output samples in [0, 1].
+JXLB_HD void DevColorTransform(const DevVFrame& vf, float p0, float p1, float p2, float* out_r, float* out_g, float* out_b) {
   float r, g, b;
   if (vf.color_transform == 0) {
     float gamma_r = p1 + p0, gamma_g = p1 - p0, gamma_b = p2;
@@ -1182,14 +1420,76 @@ JXLB_HD void DevColorPixel(const DevVPools& V, const DevVFrame& vf, uint32_t set
     g = p1;
     b = p2;
   }
+  *out_r = r;
+  *out_g = g;
+  *out_b = b;
+}
+
+// float -> 8-bit sample with the ordered dither of stage_write.cc:98-113
+JXLB_HD uint32_t DevToU8(float v, uint32_t x, uint32_t y) {
+  v = v * 255.0f;
+  v = v + DevDither(x, y);
+  if (!(v >= 0.0f)) v = 0.0f;
+  if (v > 255.0f) v = 255.0f;
+#if defined(__CUDA_ARCH__)
+  return static_cast<uint32_t>(__float2int_rn(v));
+#else
+  return static_cast<uint32_t>(lrintf(v));
+#endif
+}
+
+// One output pixel: colour transform + sample conversion + interleaved store.
+JXLB_HD void DevColorPixel(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t x, uint32_t y) {
+  const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
+  float r, g, b;
+  DevColorTransform(vf, V.farena[vf.pix[set][0] + at], V.farena[vf.pix[set][1] + at], V.farena[vf.pix[set][2] + at], &r, &g, &b);
   uint8_t* row = V.out + vf.out_off + vf.out_stride * y;
   const uint32_t nc = vf.out_channels;
+  if (nc == 4 && vf.out_type == 2) {  // RGBA8: one aligned 32-bit store
+    reinterpret_cast<uint32_t*>(row)[x] = DevToU8(r, x, y) | (DevToU8(g, x, y) << 8) | (DevToU8(b, x, y) << 16) | 0xFF000000u;
+    return;
+  }
   const uint32_t num_color = nc < 3 ? 1 : 3;
   const float col[3] = {r, g, b};
   for (uint32_t c = 0; c < nc; c++) {
     const float v = c < num_color ? col[c] : 1.0f;
     DevStoreSample(row, static_cast<size_t>(x) * nc + c, v, vf.out_type, vf.out_big_endian, x, y);
   }
+}
+
+// Four consecutive RGB8 pixels (x multiple of 4, row 4-byte aligned): 12 bytes as three 32-bit stores.
+JXLB_HD void DevColorPixelsRgb8x4(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t x, uint32_t y) {
+  const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
+  float p0[4], p1[4], p2[4];
+#if defined(__CUDA_ARCH__)
+  {  // planes and rows are 16-byte aligned and x is a multiple of 4
+    const float4 a0 = *reinterpret_cast<const float4*>(V.farena + vf.pix[set][0] + at);
+    const float4 a1 = *reinterpret_cast<const float4*>(V.farena + vf.pix[set][1] + at);
+    const float4 a2 = *reinterpret_cast<const float4*>(V.farena + vf.pix[set][2] + at);
+    p0[0] = a0.x; p0[1] = a0.y; p0[2] = a0.z; p0[3] = a0.w;
+    p1[0] = a1.x; p1[1] = a1.y; p1[2] = a1.z; p1[3] = a1.w;
+    p2[0] = a2.x; p2[1] = a2.y; p2[2] = a2.z; p2[3] = a2.w;
+  }
+#else
+  for (uint32_t i = 0; i < 4; i++) {
+    p0[i] = V.farena[vf.pix[set][0] + at + i];
+    p1[i] = V.farena[vf.pix[set][1] + at + i];
+    p2[i] = V.farena[vf.pix[set][2] + at + i];
+  }
+#endif
+  uint32_t b[12];
+JXLB_UNROLL
+  for (uint32_t i = 0; i < 4; i++) {
+    float r, g, bl;
+    DevColorTransform(vf, p0[i], p1[i], p2[i], &r, &g, &bl);
+    b[3 * i] = DevToU8(r, x + i, y);
+    b[3 * i + 1] = DevToU8(g, x + i, y);
+    b[3 * i + 2] = DevToU8(bl, x + i, y);
+  }
+  uint32_t* o = reinterpret_cast<uint32_t*>(V.out + vf.out_off + vf.out_stride * y + 3 * static_cast<size_t>(x));
+  o[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+  o[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+  o[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
 }
 
 }  // namespace jxlb

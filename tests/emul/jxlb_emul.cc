@@ -20,7 +20,9 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
                      uint64_t* frame_offsets, char* err, size_t errlen) {
   try {
     const bool force_wide = (endianness & 0x100) != 0;  // test hook: run the 64-bit predictor path
+    const bool generic_only = (endianness & 0x200) != 0;  // test hook: generic varblock path for every block
     endianness &= 0xFF;
+    (void)generic_only;
     PixelFormat fmt;
     fmt.num_channels = num_channels;
     fmt.data_type = data_type;
@@ -172,23 +174,47 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
         for (uint32_t by = 0; by < vf.yblocks; by++)
           for (uint32_t bx = 0; bx < vf.xblocks; bx++) {
             const uint8_t a = barena[vf.acs + static_cast<size_t>(by) * vf.xblocks + bx];
-            if (a & 1) DevVarblock<0>(V, vf, bx, by, a >> 1, buf.data(), 0, 1);
+            if (!(a & 1)) continue;
+            const StrategyInfo si = GetStrategyInfo(a >> 1);
+            if (si.plain_dct && si.cx * si.cy <= 16 && !generic_only) {
+              DevVarblockFast<0, 32>(V, vf, bx, by, a >> 1, buf.data(), 0, 1);  // what k_dequant_idct runs for these
+            } else if (si.plain_dct && si.cx * si.cy <= 64 && !generic_only) {
+              DevVarblockFast<0, 64>(V, vf, bx, by, a >> 1, buf.data(), 0, 1);  // k_idct_mid
+            } else {
+              DevVarblock<0>(V, vf, bx, by, a >> 1, buf.data(), 0, 1);
+            }
           }
         uint32_t set = 0;
         if (vf.gab) {
           for (uint32_t c = 0; c < 3; c++)
             for (uint32_t y = 0; y < vf.ysize; y++)
-              for (uint32_t x = 0; x < vf.xsize; x++) DevGaborishPixel(V, vf, set, set ^ 1, c, x, y);
+              for (uint32_t x = 0; x < vf.xsize; x++) {
+                const bool in = x >= 1 && y >= 1 && x + 1 < vf.xsize && y + 1 < vf.ysize;
+                if (in) DevGaborishPixel<true>(V, vf, set, set ^ 1, c, x, y);
+                else DevGaborishPixel<false>(V, vf, set, set ^ 1, c, x, y);
+              }
           set ^= 1;
         }
         for (uint32_t stage = 0; stage < 3; stage++) {
           if (vf.epf_iters == 0 || (stage == 0 && vf.epf_iters < 3) || (stage == 2 && vf.epf_iters < 2)) continue;
           for (uint32_t y = 0; y < vf.ysize; y++)
-            for (uint32_t x = 0; x < vf.xsize; x++) DevEpfPixel(V, vf, stage, set, set ^ 1, x, y);
+            for (uint32_t x = 0; x < vf.xsize; x++) {
+              const bool in = x >= 3 && y >= 3 && x + 3 < vf.xsize && y + 3 < vf.ysize;
+              if (in) DevEpfPixel<true>(V, vf, stage, set, set ^ 1, x, y);
+              else DevEpfPixel<false>(V, vf, stage, set, set ^ 1, x, y);
+            }
           set ^= 1;
         }
+        const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0;
         for (uint32_t y = 0; y < vf.ysize; y++)
-          for (uint32_t x = 0; x < vf.xsize; x++) DevColorPixel(V, vf, set, x, y);
+          for (uint32_t x = 0; x < vf.xsize; x++) {
+            if (x4 && x % 4 == 0 && x + 4 <= vf.xsize) {  // the kernel's vector path
+              DevColorPixelsRgb8x4(V, vf, set, x, y);
+              x += 3;
+            } else {
+              DevColorPixel(V, vf, set, x, y);
+            }
+          }
       }
     }
     return 0;

@@ -1,7 +1,5 @@
 set -x
-nvidia-smi --query-gpu=name,memory.total --format=csv
-nproc; free -g | head -2
-python bench.py --steps 5 --warmup 3 --cpu-seconds 20 > gpurun_out/bench_vardct4k_b64.json 2> gpurun_out/bench_vardct4k_b64.err; tail -c 4000 gpurun_out/bench_vardct4k_b64.json; tail -5 gpurun_out/bench_vardct4k_b64.err
-python bench.py --workload modular --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_modular_b256.json 2> gpurun_out/bench_modular_b256.err; tail -c 3000 gpurun_out/bench_modular_b256.json; tail -5 gpurun_out/bench_modular_b256.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_vardct4k.csv python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-tail -3 gpurun_out/ncu_launch.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 6 --warmup 3 --no-cpu-baseline --inflight 1 > gpurun_out/bench_v3_b64_if1.json 2> gpurun_out/bench_v3.err; python tools/show_bench.py gpurun_out/bench_v3_b64_if1.json; tail -3 gpurun_out/bench_v3.err
+python bench.py --steps 6 --warmup 2 --no-cpu-baseline --inflight 2 --batch 256 > gpurun_out/bench_v3_b256_if2.json 2> gpurun_out/bench_v3.err; python tools/show_bench.py gpurun_out/bench_v3_b256_if2.json; tail -3 gpurun_out/bench_v3.err
+python bench.py --workload modular --steps 3 --warmup 2 --no-cpu-baseline --inflight 1 > gpurun_out/bench_v3_mod.json 2> gpurun_out/bench_v3.err; python tools/show_bench.py gpurun_out/bench_v3_mod.json; tail -3 gpurun_out/bench_v3.err
