@@ -15,6 +15,7 @@ struct BatchPlan {
   std::vector<uint8_t> bytes;  // all codestreams, each starting on a 4-byte boundary, zero padded
   std::vector<DevAlias> alias;
   std::vector<uint32_t> prefix, cfg, refs;
+  std::vector<uint16_t> lut;
   std::vector<DevTreeNode> tree;
   std::vector<DevCode> codes;
   std::vector<DevChannel> chans;
@@ -97,7 +98,8 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
   b->bytes.resize((b->bytes.size() + 3) & ~size_t{3}, 0);
   b->compressed_bytes += cs_size;
   const uint32_t alias0 = b->alias.size(), prefix0 = b->prefix.size(), cfg0 = b->cfg.size(), refs0 = b->refs.size();
-  const uint32_t tree0 = b->tree.size(), codes0 = b->codes.size(), chans0 = b->chans.size();
+  const uint32_t tree0 = b->tree.size(), codes0 = b->codes.size(), chans0 = b->chans.size(), lut0 = b->lut.size();
+  b->lut.insert(b->lut.end(), f.lut.begin(), f.lut.end());
   const uint32_t planes0 = b->planes.size(), ops0 = b->ops.size();
   const uint64_t arena0 = b->arena_size;
   b->alias.insert(b->alias.end(), f.alias.begin(), f.alias.end());
@@ -116,6 +118,7 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
     c.plane += planes0;
     c.ref_off += refs0;
     c.tree_off += tree0;
+    c.lut_off += lut0;
     b->chans.push_back(c);
   }
   for (DevStream s : f.streams) {
@@ -302,7 +305,8 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
         for (int c = 0; c < 3; c++) batch->vframes[i].pix[set][c] = slot + (set * 3 + c) * batch->pix_plane_max;
     }
     JXLB_CHECK(batch->tok_size < (uint64_t{1} << 32), "batch too large: token arena exceeds 2^32 entries");
-    // lanes of a warp run until their longest stream ends: put streams of similar length together
+    // Lanes of a warp run until their longest stream ends: put streams of similar length together, longest first
+    // (measured: bundling by frame instead, for L1 locality of the alias tables, is 1.6x slower).
     std::stable_sort(batch->ac_streams.begin(), batch->ac_streams.end(), [](const DevAcStream& x, const DevAcStream& y) {
       return x.bit_end - x.bit_pos > y.bit_end - y.bit_pos;
     });

@@ -127,6 +127,7 @@ struct FramePlan {
   VarDCTPlan v;
   std::vector<DevAlias> alias;
   std::vector<uint32_t> prefix, cfg, refs;
+  std::vector<uint16_t> lut;       // weighted-predictor LUTs of the channels that qualify
   std::vector<DevTreeNode> tree;
   std::vector<DevCode> codes;
   std::vector<DevChannel> chans;
@@ -319,6 +320,40 @@ class FramePlanner {
       p_->tree.push_back(n);
     }
     return off;
+  }
+
+  // If the pruned tree at `tree_off` only tests property 15 (weighted predictor max error) and all its leaves are
+  // (Weighted, offset 0, multiplier 1), builds the property -> cluster table and marks the channel.
+  void TryWpLut(DevChannel* dc, bool has_refs) {
+    const DevTreeNode* t = p_->tree.data() + dc->tree_off;
+    const size_t n = p_->tree.size() - dc->tree_off;
+    int64_t lo = INT32_MAX, hi = INT32_MIN;
+    for (size_t i = 0; i < n; i++) {
+      if (t[i].prop >= 0) {
+        if (t[i].prop != 15) return;
+        lo = std::min<int64_t>(lo, t[i].a);
+        hi = std::max<int64_t>(hi, t[i].a);
+      } else if ((static_cast<uint32_t>(t[i].a) >> 16) != 6 || t[i].b != 0 || t[i].c != 1 ||
+                 (static_cast<uint32_t>(t[i].a) & 0xFFFF) > 0xFFFF) {
+        return;
+      }
+    }
+    (void)has_refs;
+    if (lo > hi) {  // a single leaf
+      lo = 0;
+      hi = -1;
+    }
+    const int64_t size = hi - lo + 2;  // values lo .. hi + 1; anything outside behaves like the nearest end
+    if (size > 8192) return;
+    dc->wp_lut = 1;
+    dc->lut_off = p_->lut.size();
+    dc->lut_lo = static_cast<int32_t>(lo);
+    dc->lut_size = static_cast<uint32_t>(size);
+    for (int64_t v = lo; v <= hi + 1; v++) {
+      size_t pos = 0;
+      while (t[pos].prop >= 0) pos = v > t[pos].a ? t[pos].b : t[pos].c;
+      p_->lut.push_back(static_cast<uint16_t>(static_cast<uint32_t>(t[pos].a) & 0xFFFF));
+    }
   }
 
   // lib/jxl/modular/encoding/dec_ma.cc:23-67: property ranges must stay non-empty
@@ -640,6 +675,7 @@ class FramePlanner {
       dc.tree_off = PruneTree(*tree.nodes, static_cast<int32_t>(i), static_cast<int32_t>(stream_id), &ch_wp);
       dc.uses_wp = ch_wp;
       if (ch_wp) st.uses_wp = 1;
+      if (ch_wp) TryWpLut(&dc, dc.ref_count != 0);
       p_->chans.push_back(dc);
       max_w = std::max<uint32_t>(max_w, c.w);
     }

@@ -54,6 +54,35 @@ __global__ void __launch_bounds__(32) k_modular_decode(DevPools P) {
   if (valid) P.status[s] = status;
 }
 
+// Few streams (a batch of lossy frames has only four DC-group chains per 4K frame): the chip is empty and each
+// stream is a latency-bound serial chain, so spread them out -- kSparseLanes streams per warp -- and keep each
+// stream's row ring and weighted-predictor rows in shared memory instead of global memory.
+constexpr uint32_t kSparseLanes = 8;
+template <typename WT>
+__global__ void __launch_bounds__(32) k_modular_decode_sparse(DevPools P) {
+  extern __shared__ int32_t sparse_smem[];
+  __shared__ int32_t props_s[kDevMaxProps * 32];
+  __shared__ uint32_t div_s[64];
+  const uint32_t lane = threadIdx.x;
+  for (uint32_t i = lane; i < 64; i += 32) div_s[i] = (1u << 24) / (i + 1);
+  __syncwarp();
+  const uint32_t s = blockIdx.x * kSparseLanes + lane;
+  DevLaneMem m;
+  m.props = props_s + lane;
+  m.props_stride = 32;
+  m.divlut = div_s;
+  m.ring_w = P.wp_width;
+  m.lane_stride = kSparseLanes;
+  m.ring = sparse_smem + (lane < kSparseLanes ? lane : 0);
+  m.wp = sparse_smem + 3 * P.wp_width * kSparseLanes + (lane < kSparseLanes ? lane : 0);
+  const bool valid = lane < kSparseLanes && s < P.num_streams;
+  const uint32_t bundle = s / 32;  // loop bounds of the 32-stream bundle this stream belongs to (a superset)
+  const uint32_t b0 = (blockIdx.x * kSparseLanes) / 32;
+  (void)bundle;
+  const uint32_t status = DevDecodeModularStream<WT>(P, s, m, P.warp_dims + P.warp_dims_off[b0], P.warp_chans[b0], valid);
+  if (valid) P.status[s] = status;
+}
+
 __global__ void __launch_bounds__(256) k_group_programs(DevPools P, const DevOp* ops, const DevProgram* programs) {
   const DevProgram pr = programs[blockIdx.x];
   for (uint32_t o = pr.op_begin; o < pr.op_end; o++) {
@@ -108,8 +137,9 @@ __global__ void __launch_bounds__(256) k_write_output_rgba8(DevPools P, const De
 // ------------------------------------------------------------------ VarDCT kernels
 // blockIdx.x indexes a flat list of (frame, DC group) pairs.
 __global__ void __launch_bounds__(256) k_dc_finish(DevPools P, DevVPools V, const uint2* dcg_list) {
+  extern __shared__ uint8_t acs_smem[];  // 64 KiB: the strategy map of one DC group (256 x 256 blocks)
   const uint2 e = dcg_list[blockIdx.x];
-  DevDcGroupFinish<2>(P, V, e.x, e.y, threadIdx.x, blockDim.x, blockIdx.x);
+  DevDcGroupFinish<2>(P, V, e.x, e.y, threadIdx.x, blockDim.x, blockIdx.x, acs_smem);
 }
 
 __global__ void __launch_bounds__(256) k_dc_smooth(DevVPools V) {
@@ -363,7 +393,7 @@ struct JxlB200Decoder {
   DevBuf<DevVFrame> d_vframes;
   DevBuf<DevAcStream> d_ac_streams;
   DevBuf<float> d_fpool, d_farena, d_big_scratch;
-  DevBuf<uint16_t> d_opool;
+  DevBuf<uint16_t> d_opool, d_lut;
   DevBuf<uint8_t> d_cpool, d_barena;
   DevBuf<uint32_t> d_upool, d_uarena, d_tokens, d_ac_status, d_ac_used, d_dc_status;
   DevBuf<uint2> d_dcg_list;
@@ -443,6 +473,9 @@ JxlB200Decoder* JxlB200DecoderCreate(int device) {
   }
   cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, kIdctSmemFloats * sizeof(float));
   cudaFuncSetAttribute(k_idct_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kMidSmemFloats * sizeof(float));
+  cudaFuncSetAttribute(k_dc_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  cudaFuncSetAttribute(k_modular_decode_sparse<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_modular_decode_sparse<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   return dec;
 }
 
@@ -495,6 +528,7 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   CUDA_OK(dec->d_prefix.Upload(b.prefix, s));
   CUDA_OK(dec->d_cfg.Upload(b.cfg, s));
   CUDA_OK(dec->d_refs.Upload(b.refs, s));
+  CUDA_OK(dec->d_lut.Upload(b.lut, s));
   CUDA_OK(dec->d_tree.Upload(b.tree, s));
   CUDA_OK(dec->d_codes.Upload(b.codes, s));
   CUDA_OK(dec->d_chans.Upload(b.chans, s));
@@ -530,6 +564,7 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   P.streams = dec->d_streams.p;
   P.planes = dec->d_planes.p;
   P.refs = dec->d_refs.p;
+  P.lut = dec->d_lut.p;
   P.codes = dec->d_codes.p;
   P.arena = dec->d_arena.p;
   P.wp_scratch = dec->d_wp.p;
@@ -662,7 +697,15 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   if (!b.streams.empty()) {
     ScopedTimer t(dec, s, kKModular);
     const uint32_t block = 32;
-    if (b.narrow) {
+    const size_t sparse_smem = static_cast<size_t>(13 * b.wp_width + 20) * kSparseLanes * sizeof(int32_t);
+    if (b.streams.size() <= 2 * 148 * kSparseLanes && sparse_smem <= 160 * 1024) {
+      const uint32_t grid = (b.streams.size() + kSparseLanes - 1) / kSparseLanes;
+      if (b.narrow) {
+        k_modular_decode_sparse<int32_t><<<grid, block, sparse_smem, s>>>(P);
+      } else {
+        k_modular_decode_sparse<int64_t><<<grid, block, sparse_smem, s>>>(P);
+      }
+    } else if (b.narrow) {
       k_modular_decode<int32_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
     } else {
       k_modular_decode<int64_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
@@ -700,7 +743,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     {
       ScopedTimer t(dec, s, kKDcFinish);
       CUDA_OK(cudaMemsetAsync(dec->d_dc_status.p, 0, (dec->dcg_list.size() + 1) * 4, s));
-      k_dc_finish<<<dec->dcg_list.size(), 256, 0, s>>>(P, V, dec->d_dcg_list.p);
+      k_dc_finish<<<dec->dcg_list.size(), 256, 65536, s>>>(P, V, dec->d_dcg_list.p);
       dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(256, (dec->max_blocks + 255) / 256)), nvf);
       k_dc_smooth<<<grid, 256, 0, s>>>(V);
       launches += 2;

@@ -82,6 +82,14 @@ struct DevChannel {
   uint32_t count_bits;
   uint32_t dyn;       // 1: the width of this channel is the count read in the preamble; the plane is
                       // allocated at its upper bound and the count is stored after the plane's samples
+  // Fast path (libjxl's fixed weighted-predictor trees, lib/jxl/modular/encoding/enc_encoding.cc:266-273, and
+  // its own LUT fast path, lib/jxl/modular/encoding/encoding.h:70-131): when every inner node of the pruned
+  // tree tests the weighted predictor's max-error property and every leaf is (Weighted, offset 0, multiplier 1),
+  // lut[clamp(property, lut_lo, lut_lo + lut_size - 1) - lut_lo] is the leaf's cluster.
+  uint32_t wp_lut;    // 1: use the LUT
+  uint32_t lut_off;   // index into the lut pool (uint16)
+  int32_t lut_lo;
+  uint32_t lut_size;
 };
 
 // One Modular entropy-coded stream = one thread of the decode kernel.

@@ -28,6 +28,7 @@ struct DevPools {
   const DevStream* streams;
   const DevPlane* planes;
   const uint32_t* refs;
+  const uint16_t* lut;
   const DevCode* codes;
   int32_t* arena;
   int32_t* wp_scratch;   // per warp: 5 arrays x 2 rows x (wp_width + 2) x 32 lanes, [pos][lane]
@@ -48,8 +49,10 @@ enum DevStatus : uint32_t { kStatusOk = 0, kStatusOverread = 1, kStatusBadFinalS
 
 #if defined(__CUDA_ARCH__)
 #define JXLB_LDG(p) __ldg(p)
+#define JXLB_WARP_ALL_M(p) __all_sync(0xFFFFFFFFu, (p))
 #else
 #define JXLB_LDG(p) (*(p))
+#define JXLB_WARP_ALL_M(p) (p)
 #endif
 
 struct DevBits {
@@ -535,6 +538,10 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
     }
     const bool uses_wp = ch.uses_wp != 0 && !direct;
     const size_t RS = direct ? 1 : LS;
+    // every lane of the warp that has this channel slot qualifies for the weighted-predictor LUT path
+    const bool fast = JXLB_WARP_ALL_M(k >= my_chans || (ch.wp_lut != 0 && uses_wp && ch.ref_count == 0));
+    const uint16_t* lut = P.lut + ch.lut_off;
+    const int32_t lut_lo = ch.lut_lo, lut_hi = ch.lut_lo + static_cast<int32_t>(ch.lut_size) - 1;
     props[0] = static_cast<int32_t>(ch.prop0);
     props[15 * PS] = 0;
     if (uses_wp) {
@@ -591,19 +598,22 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
           const WT n_leftleft = x > 1 ? leftleft : n_left;
           const WT n_toptop = y > 1 ? prevprev[static_cast<size_t>(x) * RS] : n_top;
           const WT n_toprightright = (x + 2 < w && y) ? trr : n_topright;
-          props[3 * PS] = x;
-          props[4 * PS] = static_cast<int32_t>(n_top > 0 ? n_top : -n_top);
-          props[5 * PS] = static_cast<int32_t>(n_left > 0 ? n_left : -n_left);
-          props[6 * PS] = static_cast<int32_t>(n_top);
-          props[7 * PS] = static_cast<int32_t>(n_left);
-          props[8 * PS] = static_cast<int32_t>(n_left - prev_grad);
-          prev_grad = static_cast<int32_t>(n_left + n_top - n_topleft);
-          props[9 * PS] = prev_grad;
-          props[10 * PS] = static_cast<int32_t>(n_left - n_topleft);
-          props[11 * PS] = static_cast<int32_t>(n_topleft - n_top);
-          props[12 * PS] = static_cast<int32_t>(n_top - n_topright);
-          props[13 * PS] = static_cast<int32_t>(n_top - n_toptop);
-          props[14 * PS] = static_cast<int32_t>(n_left - n_leftleft);
+          if (!fast) {
+            props[3 * PS] = x;
+            props[4 * PS] = static_cast<int32_t>(n_top > 0 ? n_top : -n_top);
+            props[5 * PS] = static_cast<int32_t>(n_left > 0 ? n_left : -n_left);
+            props[6 * PS] = static_cast<int32_t>(n_top);
+            props[7 * PS] = static_cast<int32_t>(n_left);
+            props[8 * PS] = static_cast<int32_t>(n_left - prev_grad);
+            prev_grad = static_cast<int32_t>(n_left + n_top - n_topleft);
+            props[9 * PS] = prev_grad;
+            props[10 * PS] = static_cast<int32_t>(n_left - n_topleft);
+            props[11 * PS] = static_cast<int32_t>(n_topleft - n_top);
+            props[12 * PS] = static_cast<int32_t>(n_top - n_topright);
+            props[13 * PS] = static_cast<int32_t>(n_top - n_toptop);
+            props[14 * PS] = static_cast<int32_t>(n_left - n_leftleft);
+          }
+          int32_t wp_max_error = 0;
           WT wp_pred = 0, wp_raw = 0;
           WT prediction[4] = {0, 0, 0, 0};
           if (uses_wp) {
@@ -622,7 +632,8 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
               if (DevAbsW<WT>(teN) > DevAbsW<WT>(pm)) pm = teN;
               if (DevAbsW<WT>(teNW) > DevAbsW<WT>(pm)) pm = teNW;
               if (DevAbsW<WT>(teNE) > DevAbsW<WT>(pm)) pm = teNE;
-              props[15 * PS] = static_cast<int32_t>(pm);
+              wp_max_error = static_cast<int32_t>(pm);
+              if (!fast) props[15 * PS] = wp_max_error;
             }
             prediction[0] = W8 + NE8 - N8;
             prediction[1] = N8 - (((sumWN + teNE) * p1C) >> 5);
@@ -649,7 +660,7 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
             }
             wp_pred = (wp_raw + 3) >> 3;
           }
-          for (uint32_t r = 0; r < ch.ref_count; r++) {
+          for (uint32_t r = 0; !fast && r < ch.ref_count; r++) {
             const DevPlane rp = P.planes[P.refs[ch.ref_off + r]];
             const int32_t* rrow = P.arena + rp.off + static_cast<size_t>(y) * w;
             const int32_t* rprev = y ? rrow - w : rrow;
@@ -663,21 +674,29 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
             props[(16 + 4 * r + 2) * PS] = static_cast<int32_t>(DevAbs64(v - vpred));
             props[(16 + 4 * r + 3) * PS] = static_cast<int32_t>(v - vpred);
           }
-          DevTreeNode node = root;
-          if (node.prop >= 0) node = props[node.prop * PS] > node.a ? root_l : root_r;
-          while (node.prop >= 0) {
-            const uint32_t pos = props[node.prop * PS] > node.a ? node.b : node.c;
-            node = DevLoadNode(tree + pos);
+          int32_t val;
+          if (fast) {
+            // single-property tree on the max-error property, leaves (Weighted, 0, 1): one table lookup
+            const int32_t pv = wp_max_error < lut_lo ? lut_lo : (wp_max_error > lut_hi ? lut_hi : wp_max_error);
+            const uint32_t cluster = JXLB_LDG(lut + (pv - lut_lo));
+            const uint32_t u = reader.ReadUint(cluster, br);
+            val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) + static_cast<uint32_t>(wp_pred));
+          } else {
+            DevTreeNode node = root;
+            if (node.prop >= 0) node = props[node.prop * PS] > node.a ? root_l : root_r;
+            while (node.prop >= 0) {
+              const uint32_t pos = props[node.prop * PS] > node.a ? node.b : node.c;
+              node = DevLoadNode(tree + pos);
+            }
+            const uint32_t cluster = static_cast<uint32_t>(node.a) & 0xFFFF;
+            const uint32_t predictor = static_cast<uint32_t>(node.a) >> 16;
+            const uint32_t u = reader.ReadUint(cluster, br);
+            const WT guess = static_cast<WT>(static_cast<int32_t>(node.b)) +
+                             DevPredictW<WT>(predictor, n_left, n_top, n_topleft, n_topright, n_leftleft, n_toptop,
+                                             n_toprightright, wp_pred);
+            // low 32 bits of (unpacked * multiplier + guess), as in make_pixel (encoding.cc:168-173)
+            val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) * node.c + static_cast<uint32_t>(guess));
           }
-          const uint32_t cluster = static_cast<uint32_t>(node.a) & 0xFFFF;
-          const uint32_t predictor = static_cast<uint32_t>(node.a) >> 16;
-          const uint32_t u = reader.ReadUint(cluster, br);
-          const WT guess = static_cast<WT>(static_cast<int32_t>(node.b)) +
-                           DevPredictW<WT>(predictor, n_left, n_top, n_topleft, n_topright, n_leftleft, n_toptop,
-                                           n_toprightright, wp_pred);
-          // low 32 bits of (unpacked * multiplier + guess), as in make_pixel (encoding.cc:168-173)
-          const int32_t val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) * node.c +
-                                                   static_cast<uint32_t>(guess));
           row[static_cast<size_t>(x) * RS] = val;
           out_row[x] = val;
           leftleft = left;

@@ -74,9 +74,11 @@ JXLB_HD void CoopSync() {
 constexpr float kDevSqrt2 = 1.41421356237f;
 
 // ---------------------------------------------------------------- DC groups
+// `acs_local`: xs * ys bytes of scratch for the group's strategy map (shared memory on the device: the serial scan
+// below then runs on shared-memory latency), or nullptr to work in the frame's map directly.
 template <int SCOPE>
 JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t frame, uint32_t g, uint32_t tid, uint32_t nt,
-                              uint32_t status_index) {
+                              uint32_t status_index, uint8_t* acs_local) {
   const DevVFrame& vf = V.frames[frame];
   const uint32_t W = vf.xblocks, H = vf.yblocks;
   const uint32_t gx = g % vf.xdcgroups, gy = g / vf.xdcgroups;
@@ -97,7 +99,10 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
   float* dcx = V.farena + vf.dc[0];
   float* dcy = V.farena + vf.dc[1];
   float* dcb = V.farena + vf.dc[2];
-  uint8_t* acs = V.barena + vf.acs;
+  uint8_t* acs_frame = V.barena + vf.acs;
+  // the map the scan works on: element (x, y) of the group at acs[y * astride + x]
+  uint8_t* acs = acs_local ? acs_local : acs_frame + static_cast<size_t>(y0) * W + x0;
+  const uint32_t astride = acs_local ? xs : W;
   uint8_t* qdc = V.barena + vf.qdc;
   uint8_t* sharp = V.barena + vf.sharp;
   uint16_t* rawq = reinterpret_cast<uint16_t*>(V.barena + vf.rawq);
@@ -127,7 +132,7 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
     const int32_t sh = m_sharp[i];
     if (sh < 0 || sh >= 8) status |= kVBadStream;
     sharp[pos] = static_cast<uint8_t>(sh & 7);
-    acs[pos] = 0xFF;
+    acs[static_cast<size_t>(y) * astride + x] = 0xFF;
   }
   // colour correlation maps (one entry per 64x64 tile)
   const uint32_t cw = (xs + 7) >> 3, chh = (ys + 7) >> 3, cx0 = x0 >> 3, cy0 = y0 >> 3;
@@ -150,22 +155,31 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
     const int32_t* row_strategy = m_rows;
     const int32_t* row_quant = m_rows + cap;
     uint32_t num = 0;
+    // the list entries are consumed strictly in order: keep the next one (and its geometry) loaded ahead of use
+    int32_t next_raw = count > 0 ? row_strategy[0] : 0, next_q = count > 0 ? row_quant[0] : 0;
+    uint32_t next_info = V.upool[V.sinfo_off + (static_cast<uint32_t>(next_raw) < kNumStrategies ? next_raw : 0)];
     for (uint32_t iy = 0; iy < ys && !(status & kVBadStream); iy++) {
       const uint32_t y = y0 + iy;
       for (uint32_t ix = 0; ix < xs; ix++) {
         const uint32_t x = x0 + ix;
         const size_t pos = static_cast<size_t>(y) * W + x;
-        if (acs[pos] != 0xFF) continue;
+        uint8_t* cell = acs + static_cast<size_t>(iy) * astride + ix;
+        if (*cell != 0xFF) continue;
         if (num >= count) {
           status |= kVBadStream;
           break;
         }
-        const int32_t raw = row_strategy[num];
+        const int32_t raw = next_raw, cur_q = next_q;
+        const StrategyInfo si = UnpackStrategyInfo(next_info);
+        if (num + 1 < count) {
+          next_raw = row_strategy[num + 1];
+          next_q = row_quant[num + 1];
+          next_info = V.upool[V.sinfo_off + (static_cast<uint32_t>(next_raw) < kNumStrategies ? next_raw : 0)];
+        }
         if (raw < 0 || raw >= static_cast<int32_t>(kNumStrategies)) {
           status |= kVBadStream;
           break;
         }
-        const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + raw]);
         const uint32_t next_x = (x / 32 + 1) * 32, next_y = (y / 32 + 1) * 32;  // varblocks stay inside their 256x256 group
         const uint32_t xlim = x0 + xs, ylim = y0 + ys;
         if (x + si.cx > next_x || x + si.cx > xlim || y + si.cy > next_y || y + si.cy > ylim) {
@@ -175,7 +189,7 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
         bool overlap = false;
         for (uint32_t jy = 0; jy < si.cy; jy++)
           for (uint32_t jx = 0; jx < si.cx; jx++) {
-            uint8_t& e = acs[pos + static_cast<size_t>(jy) * W + jx];
+            uint8_t& e = cell[static_cast<size_t>(jy) * astride + jx];
             overlap |= e != 0xFF;
             e = static_cast<uint8_t>((raw << 1) | ((jy | jx) == 0 ? 1 : 0));
           }
@@ -183,7 +197,7 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
           status |= kVBadStream;
           break;
         }
-        int32_t q = row_quant[num];
+        int32_t q = cur_q;
         q = q < 0 ? 0 : (q > 255 ? 255 : q);
         rawq[pos] = static_cast<uint16_t>(1 + q);
         num++;
@@ -191,6 +205,10 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
     }
   }
   CoopSync<SCOPE>();
+  if (acs_local) {
+    for (uint32_t i = tid; i < xs * ys; i += nt)
+      acs_frame[static_cast<size_t>(y0 + i / xs) * W + x0 + i % xs] = acs_local[i];
+  }
   // (c) EPF sigma per block (ComputeSigma): every varblock fills the blocks it covers
   if (vf.epf_iters > 0) {
     float* inv_sigma = V.farena + vf.inv_sigma;
@@ -198,7 +216,7 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
     for (uint32_t i = tid; i < xs * ys; i += nt) {
       const uint32_t x = i % xs, y = i / xs;
       const size_t pos = static_cast<size_t>(y0 + y) * W + x0 + x;
-      const uint8_t a = acs[pos];
+      const uint8_t a = acs[static_cast<size_t>(y) * astride + x];
       if (a == 0xFF || !(a & 1)) continue;
       const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
       const float sigma_quant = vf.epf_quant_mul / (vf.global_scale_f * static_cast<float>(rawq[pos]) * kInvSigmaNum);
@@ -307,6 +325,8 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
   uint32_t bx = 0, by = 0, ci = 3;                 // position inside the group, channel step (Y, X, B)
   uint32_t cx = 1, log2c = 0, covered = 1, size = 64, ord = 0;
   uint32_t c = 0, k = 0, nz = 0, prev = 0, histo_offset = 0, ctx = 0, ntok = 0, chan_start = 0;
+  uint32_t pre_zero = 0, pre_nonzero = 0;
+  bool pre_valid = false;
   size_t pos = 0;
   const uint16_t* order = nullptr;
   for (;;) {
@@ -370,11 +390,26 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
     }
     if (JXLB_WARP_ALL(mode == kDone)) break;
     if (mode == kDone) continue;
-    if (mode == kCoeff) {
-      const uint32_t nzl = (nz + covered - 1) >> log2c;
-      ctx = histo_offset + (m.nnz_ctx[nzl] + m.freq_ctx[k >> log2c]) * 2 + prev;
+    uint32_t cluster;
+    if (mode == kCoeff && pre_valid) {
+      cluster = prev ? pre_nonzero : pre_zero;  // looked up while the previous symbol was being decoded
+    } else {
+      if (mode == kCoeff) {
+        const uint32_t nzl = (nz + covered - 1) >> log2c;
+        ctx = histo_offset + (m.nnz_ctx[nzl] + m.freq_ctx[k >> log2c]) * 2 + prev;
+      }
+      cluster = JXLB_LDG(ctx_map + ctx);
     }
-    const uint32_t u = reader.ReadUint(JXLB_LDG(ctx_map + ctx), br);
+    pre_valid = false;
+    if (mode == kCoeff && k + 1 < size) {
+      // The context of the next coefficient depends on this one only through (is it zero?): fetch the cluster
+      // of both outcomes now, off the critical path of the serial rANS chain.
+      const uint32_t f = m.freq_ctx[(k + 1) >> log2c];
+      pre_zero = JXLB_LDG(ctx_map + histo_offset + (m.nnz_ctx[(nz + covered - 1) >> log2c] + f) * 2);
+      pre_nonzero = nz > 1 ? JXLB_LDG(ctx_map + histo_offset + (m.nnz_ctx[(nz - 1 + covered - 1) >> log2c] + f) * 2 + 1) : 0;
+      pre_valid = true;
+    }
+    const uint32_t u = reader.ReadUint(cluster, br);
     bool chan_done = false;
     if (mode == kReadNz) {
       nz = u;
@@ -416,6 +451,7 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
       }
     }
     if (chan_done) {
+      pre_valid = false;
       tc[c * nb + pos] = (ntok < st.tok_cap ? ntok : st.tok_cap) - (chan_start < st.tok_cap ? chan_start : st.tok_cap);
       ci++;
       if (ci >= 3) bx += cx;

@@ -49,6 +49,7 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     P.streams = b.streams.data();
     P.planes = b.planes.data();
     P.refs = b.refs.data();
+    P.lut = b.lut.data();
     P.codes = b.codes.data();
     P.arena = arena.data();
     P.wp_scratch = wp.data();
@@ -123,9 +124,10 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       V.ctxtab_off = sh.ctxtab_off;
       V.out = out;
       uint32_t dcg = 0;
+      std::vector<uint8_t> acs_local(65536);  // stands in for the kernel's shared memory
       for (uint32_t f = 0; f < b.vframes.size(); f++) {
         const DevVFrame& vf = b.vframes[f];
-        for (uint32_t g = 0; g < vf.xdcgroups * vf.ydcgroups; g++, dcg++) DevDcGroupFinish<0>(P, V, f, g, 0, 1, dcg);
+        for (uint32_t g = 0; g < vf.xdcgroups * vf.ydcgroups; g++, dcg++) DevDcGroupFinish<0>(P, V, f, g, 0, 1, dcg, acs_local.data());
         if (!vf.skip_dc_smoothing)
           for (uint32_t y = 0; y < vf.yblocks; y++)
             for (uint32_t x = 0; x < vf.xblocks; x++) DevDcSmoothBlock(V, vf, x, y);
