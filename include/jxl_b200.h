@@ -158,6 +158,28 @@ JxlDecoderStatus JxlDecoderGetBasicInfo(const JxlDecoder* dec, JxlBasicInfo* inf
 JxlDecoderStatus JxlDecoderImageOutBufferSize(const JxlDecoder* dec, const JxlPixelFormat* format, size_t* size);
 JxlDecoderStatus JxlDecoderSetImageOutBuffer(JxlDecoder* dec, const JxlPixelFormat* format, void* buffer, size_t size);
 
+/* ---- 3. batch encoder (lossy VarDCT) ----
+ * Replaces what jpegxl-rs reaches through JxlEncoderAddImageFrame + JxlEncoderProcessOutput
+ * (jpegxl-rs/src/encode.rs:323-378) for RGB8 input: one call encodes a batch of independent images. */
+typedef struct JxlB200Encoder JxlB200Encoder;
+typedef struct {
+  float distance;      /* JxlEncoderSetFrameDistance: 1.0 = visually lossless target */
+  int strategy_mode;   /* 0: 8x8 DCT only; 2: variance heuristic over 8x8 ... 64x64 */
+  int gaborish;        /* loop-filter flags written to the frame header (decoder side filters) */
+  uint32_t epf_iters;
+  int dc_smoothing;
+} JxlB200EncodeOptions;
+JxlB200Encoder* JxlB200EncoderCreate(int device);
+void JxlB200EncoderDestroy(JxlB200Encoder* enc);
+const char* JxlB200EncoderGetError(const JxlB200Encoder* enc);
+/* rgb[i]: xsizes[i] * ysizes[i] interleaved RGB8 samples (sRGB). Synchronous. */
+int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, const uint32_t* xsizes, const uint32_t* ysizes,
+                              size_t n, const JxlB200EncodeOptions* options);
+size_t JxlB200EncoderOutputSize(const JxlB200Encoder* enc, size_t i);
+int JxlB200EncoderReadOutput(const JxlB200Encoder* enc, size_t i, uint8_t* dst, size_t size);
+/* Device time of the last EncodeBatch: {pixels -> tokens + histograms, host tables (incl. D2H), rANS emission} in ms. */
+int JxlB200EncoderGetPhaseTimes(const JxlB200Encoder* enc, double* ms3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,15 @@ class JxlB200Stats(ctypes.Structure):
                 ("vardct_frames", ctypes.c_uint32), ("wave_frames", ctypes.c_uint32)]
 
 
+class JxlB200EncodeOptions(ctypes.Structure):
+    _fields_ = [("distance", ctypes.c_float), ("strategy_mode", ctypes.c_int), ("gaborish", ctypes.c_int),
+                ("epf_iters", ctypes.c_uint32), ("dc_smoothing", ctypes.c_int)]
+
+
+class EncodeError(Exception):
+    """Mirrors jpegxl-rs/src/errors.rs:62-98."""
+
+
 class DecodeError(Exception):
     """Mirrors jpegxl-rs/src/errors.rs:27-60."""
 
@@ -126,6 +135,17 @@ def load_library() -> ctypes.CDLL:
     lib.JxlB200DecoderGetKernelTimes.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
     lib.JxlB200DecoderGetKernelTimesEx.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_uint32,
                                                    ctypes.POINTER(ctypes.c_uint32)]
+    lib.JxlB200EncoderCreate.restype = vp
+    lib.JxlB200EncoderCreate.argtypes = [ctypes.c_int]
+    lib.JxlB200EncoderDestroy.argtypes = [vp]
+    lib.JxlB200EncoderGetError.restype = ctypes.c_char_p
+    lib.JxlB200EncoderGetError.argtypes = [vp]
+    lib.JxlB200EncoderEncodeBatch.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32),
+                                              ctypes.POINTER(ctypes.c_uint32), sz, ctypes.POINTER(JxlB200EncodeOptions)]
+    lib.JxlB200EncoderOutputSize.restype = sz
+    lib.JxlB200EncoderOutputSize.argtypes = [vp, sz]
+    lib.JxlB200EncoderReadOutput.argtypes = [vp, sz, vp, sz]
+    lib.JxlB200EncoderGetPhaseTimes.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.JxlDecoderVersion.restype = ctypes.c_uint32
     lib.JxlSignatureCheck.argtypes = [ctypes.c_char_p, sz]
     lib.JxlDecoderCreate.restype = vp
@@ -155,7 +175,9 @@ EXPORTED_SYMBOLS = [
     "JxlB200DecoderNumFrames", "JxlB200DecoderGetBasicInfo", "JxlB200DecoderImageOutBufferSize", "JxlB200DecoderRun",
     "JxlB200DecoderWait", "JxlB200DecoderDeviceOutput", "JxlB200DecoderReadOutput", "JxlB200DecoderReadOutputs",
     "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderGetKernelTimes",
-    "JxlB200DecoderGetKernelTimesEx", "JxlDecoderVersion", "JxlSignatureCheck", "JxlDecoderCreate", "JxlDecoderReset",
+    "JxlB200DecoderGetKernelTimesEx", "JxlB200EncoderCreate", "JxlB200EncoderDestroy", "JxlB200EncoderGetError",
+    "JxlB200EncoderEncodeBatch", "JxlB200EncoderOutputSize", "JxlB200EncoderReadOutput", "JxlB200EncoderGetPhaseTimes",
+    "JxlDecoderVersion", "JxlSignatureCheck", "JxlDecoderCreate", "JxlDecoderReset",
     "JxlDecoderDestroy", "JxlDecoderSetParallelRunner", "JxlDecoderSubscribeEvents", "JxlDecoderSetKeepOrientation",
     "JxlDecoderSetUnpremultiplyAlpha", "JxlDecoderSetRenderSpotcolors", "JxlDecoderSetCoalescing",
     "JxlDecoderSetDesiredIntensityTarget", "JxlDecoderSetInput", "JxlDecoderCloseInput", "JxlDecoderProcessInput",
@@ -506,3 +528,92 @@ def decode_batch_distributed(files: Sequence[bytes], num_channels: int = 4, dtyp
     fn = decode_fn or decode_batch
     local = fn([files[i] for i in idx], num_channels, dtype) if idx else []
     return gather_frames(local, len(files), rank, world, dst, device)
+
+
+# ---- encoder: mirror of jpegxl-rs's JxlEncoder builder for the lossy RGB8 path ----
+@dataclass
+class EncoderResult:
+    """jpegxl-rs/src/encode.rs:505-509."""
+    data: bytes
+
+
+class JxlEncoder:
+    """jpegxl-rs/src/encode.rs:60-187 (builder fields) and :477-486 (`encode::<u8, u8>`): lossy VarDCT of RGB8 input on
+    the GPU. `quality` is the Butteraugli distance as in jpegxl-rs (default 1.0); `speed` selects the AcStrategy
+    search: the fastest tiers use 8x8 DCTs only, the others the variance heuristic over 8x8 ... 64x64."""
+
+    def __init__(self, has_alpha: bool = False, lossless: bool = False, speed: int = 7, quality: float = 1.0,
+                 use_container: bool = False, decoding_speed: int = 0, device: int = 0):
+        if lossless:
+            raise EncodeError("NotSupported: lossless encoding is not part of the GPU path")
+        if has_alpha:
+            raise EncodeError("NotSupported: alpha")
+        if use_container:
+            raise EncodeError("NotSupported: container output")
+        self._lib = load_library()
+        self._enc = self._lib.JxlB200EncoderCreate(device)
+        if not self._enc:
+            raise EncodeError("CannotCreateEncoder: no usable CUDA device (jxl_b200 has no CPU fallback)")
+        self.speed, self.quality, self.decoding_speed = speed, quality, decoding_speed
+
+    def __del__(self):
+        if getattr(self, "_enc", None):
+            self._lib.JxlB200EncoderDestroy(self._enc)
+            self._enc = None
+
+    def _options(self) -> JxlB200EncodeOptions:
+        return JxlB200EncodeOptions(float(self.quality), 0 if self.speed <= 2 else 2, 1, 2, 1)
+
+    def encode_batch(self, images: Sequence[np.ndarray]) -> List[EncoderResult]:
+        imgs = [np.ascontiguousarray(a, np.uint8) for a in images]
+        for a in imgs:
+            if a.ndim != 3 or a.shape[2] != 3:
+                raise EncodeError("ApiUsage: expected (height, width, 3) uint8 arrays")
+        n = len(imgs)
+        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in imgs])
+        xs = (ctypes.c_uint32 * n)(*[a.shape[1] for a in imgs])
+        ys = (ctypes.c_uint32 * n)(*[a.shape[0] for a in imgs])
+        opt = self._options()
+        if self._lib.JxlB200EncoderEncodeBatch(self._enc, ptrs, xs, ys, n, ctypes.byref(opt)) != 0:
+            raise EncodeError(self._lib.JxlB200EncoderGetError(self._enc).decode())
+        out = []
+        for i in range(n):
+            size = self._lib.JxlB200EncoderOutputSize(self._enc, i)
+            buf = np.empty(size, np.uint8)
+            if self._lib.JxlB200EncoderReadOutput(self._enc, i, buf.ctypes.data, size) != 0:
+                raise EncodeError("internal: output read failed")
+            out.append(EncoderResult(buf.tobytes()))
+        return out
+
+    def encode(self, data: np.ndarray, width: Optional[int] = None, height: Optional[int] = None) -> EncoderResult:
+        """jpegxl-rs/src/encode.rs:477-486: `data` is height * width * 3 bytes (or an (H, W, 3) array)."""
+        a = np.asarray(data, np.uint8)
+        if a.ndim == 1:
+            if not width or not height or a.size != width * height * 3:
+                raise EncodeError("ApiUsage: buffer size does not match width * height * 3")
+            a = a.reshape(height, width, 3)
+        return self.encode_batch([a])[0]
+
+    def phase_times(self):
+        ms = (ctypes.c_double * 3)()
+        self._lib.JxlB200EncoderGetPhaseTimes(self._enc, ms)
+        return {"tokens_ms": ms[0], "host_tables_ms": ms[1], "emit_ms": ms[2]}
+
+
+def encoder_builder(**kwargs):
+    """jpegxl-rs/src/lib.rs:36-42: `encoder_builder().quality(1.0).build()`."""
+
+    class _Builder:
+        def __init__(self, kw):
+            self._kw = dict(kw)
+
+        def __getattr__(self, name):
+            def setter(value):
+                self._kw[name] = value
+                return self
+            return setter
+
+        def build(self) -> JxlEncoder:
+            return JxlEncoder(**self._kw)
+
+    return _Builder(kwargs)

@@ -26,6 +26,8 @@
 #include "host/jxlb_batch.h"
 #include "kernels/jxlb_finish_dev.h"
 #include "kernels/jxlb_vardct_dev.h"
+#include "kernels/jxlb_enc_dev.h"
+#include "host/jxlb_enc_host.h"
 
 namespace jxlb {
 
@@ -1086,6 +1088,399 @@ JxlDecoderStatus JxlDecoderSetImageOutBuffer(JxlDecoder* dec, const JxlPixelForm
   dec->out_buffer = buffer;
   dec->out_size = size;
   return JXL_DEC_SUCCESS;
+}
+
+}  // extern "C"
+
+// ================================================================== encoder
+namespace jxlb {
+
+__global__ void __launch_bounds__(256) k_enc_xyb(DevEPools E, DevEFrame ef) {
+  const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x < ef.xblocks * 8 && y < ef.yblocks * 8) DevEncXybPixel(E, ef, x, y);
+}
+
+// one thread per 256x256 group (the greedy choice is serial inside a group)
+__global__ void __launch_bounds__(32) k_enc_strategy(DevEPools E, DevEFrame ef) {
+  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
+  if (g < ef.xgroups * ef.ygroups) DevEncStrategyGroup(E, ef, g);
+}
+
+__global__ void k_enc_number(DevEPools E, DevEFrame ef) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ef.xdcgroups * ef.ydcgroups) DevEncNumberBlocks(E, ef, g);
+}
+
+__global__ void __launch_bounds__(256) k_enc_dc(DevEPools E, DevEFrame ef) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ef.xblocks * ef.yblocks) DevEncDcBlock(E, ef, i % ef.xblocks, i / ef.xblocks);
+}
+
+constexpr uint32_t kEncThreads = 128;
+constexpr uint32_t kEncSmemFloats = 4 * 4096;  // four buffers of a 64x64 varblock, or one 32x32 set per warp
+
+// blockIdx.x = group: forward transform + quantisation; warp per varblock up to 32x32, CTA per 64x64 class.
+__global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, DevEFrame ef) {
+  extern __shared__ float enc_smem[];
+  __shared__ uint32_t next_s, has_big_s;
+  const uint32_t g = blockIdx.x;
+  const uint32_t x0 = (g % ef.xgroups) * 32, y0 = (g / ef.xgroups) * 32;
+  const uint32_t xs = min(32u, ef.xblocks - x0), ys = min(32u, ef.yblocks - y0);
+  const uint8_t* acs = E.barena + ef.acs;
+  if (threadIdx.x == 0) {
+    next_s = 0;
+    has_big_s = 0;
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* wbuf = enc_smem + warp * 4096;
+  const uint32_t total = xs * ys;
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&next_s, 1u);
+    i = __shfl_sync(0xFFFFFFFFu, i, 0);
+    if (i >= total) break;
+    const uint32_t bx = i % xs, by = i / xs;
+    const uint8_t a = acs[static_cast<size_t>(y0 + by) * ef.xblocks + x0 + bx];
+    if (!(a & 1)) continue;
+    const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
+    if (static_cast<uint32_t>(si.cx) * si.cy > 16) {
+      if (lane == 0) has_big_s = 1;
+      continue;
+    }
+    DevEncVarblock<1>(E, ef, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
+  }
+  __syncthreads();
+  if (!has_big_s) return;
+  for (uint32_t i = 0; i < total; i++) {
+    const uint32_t bx = i % xs, by = i / xs;
+    const uint8_t a = acs[static_cast<size_t>(y0 + by) * ef.xblocks + x0 + bx];
+    if (!(a & 1)) continue;
+    const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
+    if (static_cast<uint32_t>(si.cx) * si.cy <= 16) continue;
+    DevEncVarblock<2>(E, ef, x0 + bx, y0 + by, a >> 1, enc_smem, threadIdx.x, kEncThreads);
+  }
+}
+
+__global__ void __launch_bounds__(32) k_enc_tokenize(DevEPools E, DevEFrame ef) {
+  __shared__ uint16_t ctxtab_s[128];
+  for (uint32_t i = threadIdx.x; i < 128; i += 32) ctxtab_s[i] = static_cast<uint16_t>(E.upool[E.ctxtab_off + i]);
+  __syncwarp();
+  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
+  if (g < ef.xgroups * ef.ygroups) DevEncTokenizeGroup(E, ef, g, ctxtab_s, ctxtab_s + 64);
+}
+
+// blockIdx.y = DC group; one thread per sample of its DC + AC-metadata streams
+__global__ void __launch_bounds__(256) k_enc_modular(DevEPools E, DevEFrame ef) {
+  const uint32_t g = blockIdx.y;
+  const DevDcGroupLayout L = DevDcGroupGeometry(E, ef, g);
+  const uint32_t total = L.dc_tokens + L.meta_tokens;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    DevEncModularSample(E, ef, g, L, i);
+}
+
+// rANS emission: one thread per section. `off` = word offset of every section, `bits` receives its bit length.
+__global__ void __launch_bounds__(32) k_enc_emit_ac(DevEPools E, DevEFrame ef, DevEncCode code, uint32_t* words, const uint64_t* off,
+                                                    uint64_t* bits) {
+  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
+  if (g >= ef.xgroups * ef.ygroups) return;
+  const uint32_t n = static_cast<uint32_t>(E.iarena[ef.group_tokens + g]);
+  bits[g] = DevRansEmit(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words + off[g], 0);
+}
+
+__global__ void k_enc_emit_dc(DevEPools E, DevEFrame ef, DevEncCode code, uint32_t* words, const uint64_t* off, uint64_t* bits) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ef.xdcgroups * ef.ydcgroups) return;
+  bits[g] = DevEncEmitDcGroup(E, ef, g, code, words + off[g]);
+}
+
+}  // namespace jxlb
+
+struct JxlB200Encoder {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  std::vector<std::vector<uint8_t>> outputs;
+  double phase_ms[3] = {0, 0, 0};  // kernels before the histogram sync, host table building, emit kernels
+};
+
+#undef CUDA_OK
+#define CUDA_OK(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      enc->error = std::string(#expr) + ": " + cudaGetErrorString(e_);                       \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+extern "C" {
+
+JxlB200Encoder* JxlB200EncoderCreate(int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= device || device < 0) return nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  JxlB200Encoder* enc = new JxlB200Encoder();
+  enc->device = device;
+  if (cudaStreamCreateWithFlags(&enc->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete enc;
+    return nullptr;
+  }
+  cudaFuncSetAttribute(k_enc_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemFloats * sizeof(float));
+  return enc;
+}
+
+void JxlB200EncoderDestroy(JxlB200Encoder* enc) {
+  if (!enc) return;
+  cudaSetDevice(enc->device);
+  if (enc->stream) cudaStreamDestroy(enc->stream);
+  delete enc;
+}
+
+const char* JxlB200EncoderGetError(const JxlB200Encoder* enc) { return enc ? enc->error.c_str() : "null encoder"; }
+
+int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, const uint32_t* xsizes, const uint32_t* ysizes,
+                              size_t n, const JxlB200EncodeOptions* opt) {
+  if (!enc || !rgb || !xsizes || !ysizes || !opt || n == 0) return 1;
+  enc->error.clear();
+  enc->outputs.clear();
+  EncParams p;
+  p.distance = opt->distance;
+  p.strategy_mode = opt->strategy_mode;
+  p.gab = opt->gaborish != 0;
+  p.epf_iters = opt->epf_iters;
+  p.dc_smoothing = opt->dc_smoothing != 0;
+  if (!(p.strategy_mode == 0 || p.strategy_mode == 2) || p.epf_iters > 3 || !(p.distance > 0.0f)) {
+    enc->error = "invalid encode options";
+    return 1;
+  }
+  CUDA_OK(cudaSetDevice(enc->device));
+  cudaStream_t s = enc->stream;
+  try {
+    const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
+    uint32_t num_ac_clusters = 0;
+    const std::vector<uint8_t> ac_cluster_of = AcContextClusters(&num_ac_clusters);
+    // ---- layout of every frame in the arenas
+    struct Frame {
+      DevEFrame ef;
+      EncLayout L;
+      EncTree tree;
+      uint32_t global_scale, quant_dc;
+      uint64_t tree_off;
+      EncGlobals G;
+      std::vector<uint64_t> ac_off, dc_off;  // word offsets of the sections
+      uint64_t bits_off;                     // index of this frame's first entry in d_bits
+    };
+    std::vector<Frame> fr(n);
+    uint64_t fbase = 0, ibase = 0, bbase = 0, tbase = 0, inbase = 0, treebase = 0;
+    std::vector<DevEncTreeNode> all_trees;
+    for (size_t i = 0; i < n; i++) {
+      Frame& f = fr[i];
+      JXLB_CHECK(xsizes[i] > 0 && ysizes[i] > 0 && xsizes[i] <= (1u << 16) && ysizes[i] <= (1u << 16), "bad image size");
+      f.ef = DevEFrame{};
+      FillQuantizer(p, &f.ef, &f.global_scale, &f.quant_dc);
+      FrameHeader fh0;
+      fh0.xsize = xsizes[i];
+      fh0.ysize = ysizes[i];
+      f.tree = BuildEncTree(ToFrameDimensions(fh0).num_dc_groups);
+      f.L = LayoutEncFrame(xsizes[i], ysizes[i], num_ac_clusters, f.tree.num_leaves, &f.ef);
+      DevEFrame& e = f.ef;
+      for (int c = 0; c < 3; c++) {
+        e.xyb[c] += fbase;
+        e.coef[c] += ibase;
+        e.dcq[c] += ibase;
+      }
+      e.first_index += ibase;
+      e.block_of_num += ibase;
+      e.dcg_count += ibase;
+      e.group_tokens += ibase;
+      e.ac_hist += ibase;
+      e.mod_hist += ibase;
+      e.acs += bbase;
+      e.ac_tokens += tbase;
+      e.mod_tokens += tbase;
+      e.rgb = inbase;
+      f.tree_off = treebase;
+      all_trees.insert(all_trees.end(), f.tree.nodes.begin(), f.tree.nodes.end());
+      treebase += f.tree.nodes.size();
+      fbase += f.L.fsize;
+      ibase += f.L.isize;
+      bbase += f.L.bsize;
+      tbase += f.L.tsize;
+      inbase += (static_cast<uint64_t>(xsizes[i]) * ysizes[i] * 3 + 15) & ~uint64_t{15};
+    }
+    DevBuf<uint8_t> d_in, d_barena, d_cluster;
+    DevBuf<float> d_farena, d_fpool, d_lut;
+    DevBuf<int32_t> d_iarena;
+    DevBuf<uint2> d_tokens;
+    DevBuf<uint16_t> d_opool;
+    DevBuf<uint32_t> d_upool;
+    DevBuf<DevEncTreeNode> d_trees;
+    CUDA_OK(d_in.Alloc(inbase + 16));
+    CUDA_OK(d_farena.Alloc(fbase + 16));
+    CUDA_OK(d_iarena.Alloc(ibase + 16));
+    CUDA_OK(d_barena.Alloc(bbase + 16));
+    CUDA_OK(d_tokens.Alloc(tbase + 16));
+    CUDA_OK(d_fpool.Upload(sh.fpool, s));
+    CUDA_OK(d_opool.Upload(sh.opool, s));
+    CUDA_OK(d_upool.Upload(sh.upool, s));
+    CUDA_OK(d_cluster.Upload(ac_cluster_of, s));
+    CUDA_OK(d_trees.Upload(all_trees, s));
+    std::vector<float> lut(256);
+    for (int i = 0; i < 256; i++) lut[i] = SrgbToLinearHost(i / 255.0f);
+    CUDA_OK(d_lut.Upload(lut, s));
+    for (size_t i = 0; i < n; i++)
+      CUDA_OK(cudaMemcpyAsync(d_in.p + fr[i].ef.rgb, rgb[i], static_cast<size_t>(xsizes[i]) * ysizes[i] * 3, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(d_iarena.p, 0, (ibase + 16) * sizeof(int32_t), s));
+    CUDA_OK(cudaMemsetAsync(d_barena.p, 0xFF, bbase + 16, s));
+    DevEPools E{};
+    E.bytes_in = d_in.p;
+    E.farena = d_farena.p;
+    E.iarena = d_iarena.p;
+    E.barena = d_barena.p;
+    E.tokens = d_tokens.p;
+    E.srgb_lut = d_lut.p;
+    E.fpool = d_fpool.p;
+    E.opool = d_opool.p;
+    E.upool = d_upool.p;
+    for (int i = 0; i < 17; i++) E.table_off[i] = sh.table_off[i];
+    for (int i = 0; i < 13; i++) E.order_off[i] = sh.order_off[i];
+    E.wc_off = sh.wc_off;
+    E.sinfo_off = sh.sinfo_off;
+    E.ctxtab_off = sh.ctxtab_off;
+    E.ac_cluster_of = d_cluster.p;
+    cudaEvent_t ev[4];
+    for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+    CUDA_OK(cudaEventRecord(ev[0], s));
+    // ---- phase 1: pixels -> tokens + histograms
+    for (size_t i = 0; i < n; i++) {
+      const DevEFrame& ef = fr[i].ef;
+      const FrameDimensions& d = fr[i].L.dim;
+      DevEPools Ef = E;
+      Ef.tree = d_trees.p + fr[i].tree_off;
+      const uint32_t W = d.xsize_blocks, H = d.ysize_blocks;
+      k_enc_xyb<<<dim3((W * 8 + 31) / 32, H), dim3(32, 8), 0, s>>>(Ef, ef);
+      k_enc_strategy<<<(d.num_groups + 31) / 32, 32, 0, s>>>(Ef, ef);
+      k_enc_number<<<1, 32 * ((d.num_dc_groups + 31) / 32), 0, s>>>(Ef, ef);
+      k_enc_dc<<<(W * H + 255) / 256, 256, 0, s>>>(Ef, ef);
+      k_enc_coeffs<<<d.num_groups, kEncThreads, kEncSmemFloats * sizeof(float), s>>>(Ef, ef);
+      k_enc_tokenize<<<(d.num_groups + 31) / 32, 32, 0, s>>>(Ef, ef);
+      k_enc_modular<<<dim3(256, d.num_dc_groups), 256, 0, s>>>(Ef, ef);
+    }
+    CUDA_OK(cudaEventRecord(ev[1], s));
+    // ---- host: histograms -> codes, global sections, section layout
+    std::vector<int32_t> h_small;
+    uint64_t words_total = 0, nsec = 0;
+    std::vector<uint16_t> h_tables;
+    struct CodeOff { uint64_t mod_f, mod_s, mod_r, ac_f, ac_s, ac_r; };
+    std::vector<CodeOff> code_off(n);
+    for (size_t i = 0; i < n; i++) {
+      Frame& f = fr[i];
+      const FrameDimensions& d = f.L.dim;
+      const uint64_t first = f.ef.dcg_count, count = f.ef.mod_hist + static_cast<uint64_t>(f.L.num_leaves) * 256 - first;
+      h_small.resize(count);
+      CUDA_OK(cudaMemcpyAsync(h_small.data(), d_iarena.p + first, count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      const int32_t* dcg_count = h_small.data();
+      const int32_t* group_tokens = h_small.data() + (f.ef.group_tokens - first);
+      const uint32_t* ac_hist = reinterpret_cast<const uint32_t*>(h_small.data() + (f.ef.ac_hist - first));
+      const uint32_t* mod_hist = reinterpret_cast<const uint32_t*>(h_small.data() + (f.ef.mod_hist - first));
+      BuildEncGlobals(p, f.L, f.tree, ac_cluster_of, f.global_scale, f.quant_dc, mod_hist, ac_hist, &f.G);
+      f.bits_off = nsec;
+      for (uint32_t g = 0; g < d.num_dc_groups; g++) {
+        const uint32_t gx = g % d.xsize_dc_groups, gy = g / d.xsize_dc_groups;
+        const uint64_t xs = std::min<uint64_t>(256, d.xsize_blocks - gx * 256), ys = std::min<uint64_t>(256, d.ysize_blocks - gy * 256);
+        const uint64_t toks = 3 * xs * ys + 2 * ((xs + 7) / 8) * ((ys + 7) / 8) + 2 * static_cast<uint64_t>(dcg_count[g]) + xs * ys;
+        f.dc_off.push_back(words_total);
+        words_total += (toks * 6 + 64) / 4 + 4;
+      }
+      for (uint32_t g = 0; g < d.num_groups; g++) {
+        f.ac_off.push_back(words_total);
+        words_total += (static_cast<uint64_t>(group_tokens[g]) * 6 + 64) / 4 + 4;
+      }
+      nsec += d.num_dc_groups + d.num_groups;
+      auto push = [&](const std::vector<uint16_t>& v) {
+        const uint64_t off = h_tables.size();
+        h_tables.insert(h_tables.end(), v.begin(), v.end());
+        return off;
+      };
+      code_off[i] = CodeOff{push(f.G.mod_code.freq), push(f.G.mod_code.start), push(f.G.mod_code.reverse),
+                            push(f.G.ac_code.freq), push(f.G.ac_code.start), push(f.G.ac_code.reverse)};
+    }
+    DevBuf<uint16_t> d_tables;
+    DevBuf<uint32_t> d_words;
+    DevBuf<uint64_t> d_off, d_bits;
+    std::vector<uint64_t> h_off;
+    for (size_t i = 0; i < n; i++) {
+      h_off.insert(h_off.end(), fr[i].dc_off.begin(), fr[i].dc_off.end());
+      h_off.insert(h_off.end(), fr[i].ac_off.begin(), fr[i].ac_off.end());
+    }
+    CUDA_OK(d_tables.Upload(h_tables, s));
+    CUDA_OK(d_off.Upload(h_off, s));
+    CUDA_OK(d_bits.Alloc(nsec + 1));
+    CUDA_OK(d_words.Alloc(words_total + 16));
+    CUDA_OK(cudaMemsetAsync(d_words.p, 0, (words_total + 16) * sizeof(uint32_t), s));
+    CUDA_OK(cudaEventRecord(ev[2], s));
+    // ---- phase 2: rANS emission of every section
+    for (size_t i = 0; i < n; i++) {
+      const Frame& f = fr[i];
+      const FrameDimensions& d = f.L.dim;
+      DevEPools Ef = E;
+      Ef.tree = d_trees.p + f.tree_off;
+      const CodeOff& co = code_off[i];
+      DevEncCode mod{d_tables.p + co.mod_f, d_tables.p + co.mod_s, d_tables.p + co.mod_r, nullptr};
+      DevEncCode ac{d_tables.p + co.ac_f, d_tables.p + co.ac_s, d_tables.p + co.ac_r, d_cluster.p};
+      k_enc_emit_dc<<<1, 32 * ((d.num_dc_groups + 31) / 32), 0, s>>>(Ef, f.ef, mod, d_words.p, d_off.p + f.bits_off, d_bits.p + f.bits_off);
+      k_enc_emit_ac<<<(d.num_groups + 31) / 32, 32, 0, s>>>(Ef, f.ef, ac, d_words.p, d_off.p + f.bits_off + d.num_dc_groups,
+                                                           d_bits.p + f.bits_off + d.num_dc_groups);
+    }
+    CUDA_OK(cudaEventRecord(ev[3], s));
+    std::vector<uint64_t> h_bits(nsec);
+    std::vector<uint32_t> h_words(words_total + 16);
+    CUDA_OK(cudaMemcpyAsync(h_bits.data(), d_bits.p, nsec * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(h_words.data(), d_words.p, (words_total + 16) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    enc->phase_ms[0] = ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]);
+    enc->phase_ms[1] = ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]);
+    enc->phase_ms[2] = ms;
+    for (auto& e : ev) cudaEventDestroy(e);
+    // ---- assemble
+    for (size_t i = 0; i < n; i++) {
+      const Frame& f = fr[i];
+      const FrameDimensions& d = f.L.dim;
+      std::vector<std::pair<const uint8_t*, uint64_t>> dcg, acg;
+      for (uint32_t g = 0; g < d.num_dc_groups; g++)
+        dcg.push_back({reinterpret_cast<const uint8_t*>(h_words.data() + f.dc_off[g]), h_bits[f.bits_off + g]});
+      for (uint32_t g = 0; g < d.num_groups; g++)
+        acg.push_back({reinterpret_cast<const uint8_t*>(h_words.data() + f.ac_off[g]), h_bits[f.bits_off + d.num_dc_groups + g]});
+      enc->outputs.push_back(AssembleCodestream(p, f.L, f.G, dcg, acg));
+    }
+  } catch (const std::exception& e) {
+    enc->error = e.what();
+    return 1;
+  }
+  return 0;
+}
+
+size_t JxlB200EncoderOutputSize(const JxlB200Encoder* enc, size_t i) {
+  return enc && i < enc->outputs.size() ? enc->outputs[i].size() : 0;
+}
+
+int JxlB200EncoderReadOutput(const JxlB200Encoder* enc, size_t i, uint8_t* dst, size_t size) {
+  if (!enc || i >= enc->outputs.size() || !dst || size < enc->outputs[i].size()) return 1;
+  std::memcpy(dst, enc->outputs[i].data(), enc->outputs[i].size());
+  return 0;
+}
+
+int JxlB200EncoderGetPhaseTimes(const JxlB200Encoder* enc, double* ms3) {
+  if (!enc || !ms3) return 1;
+  for (int k = 0; k < 3; k++) ms3[k] = enc->phase_ms[k];
+  return 0;
 }
 
 }  // extern "C"

@@ -1,0 +1,62 @@
+// jxl_b200 encoder: descriptors shared by the host side and the kernels.
+#ifndef JXLB_ENC_DESC_H_
+#define JXLB_ENC_DESC_H_
+
+#include "jxlb_vardct_desc.h"
+
+#if !defined(__CUDACC__)
+// host build of the device functions (tests only): the CUDA vector type used for tokens
+struct uint2 {
+  unsigned int x, y;
+};
+inline uint2 make_uint2(unsigned int x, unsigned int y) {
+  uint2 r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+#endif
+
+namespace jxlb {
+
+// Node of the global Modular tree in the encoder's form: inner node: prop >= 0, a = split value,
+// l / r = child indices (property > split ? l : r); leaf: prop = -1, a = predictor, l = context (leaf id).
+struct DevEncTreeNode {
+  int32_t prop;
+  int32_t a;
+  uint32_t l, r;
+};
+
+// One frame being encoded. Offsets index the encoder's arenas (element units of the arena's type).
+struct DevEFrame {
+  uint32_t xsize, ysize;
+  uint32_t xblocks, yblocks;  // 8x8 blocks; planes are xblocks * 8 wide (edge-replicated padding)
+  uint32_t xgroups, ygroups, xdcgroups, ydcgroups;
+  uint32_t strategy_mode;
+  float distance;
+  float inv_global_scale, mul_dc[3], x_dm, b_dm;
+  float biases[4];
+  // input
+  uint64_t rgb;        // byte arena: interleaved RGB8
+  // float arena
+  uint64_t xyb[3];
+  // int arena
+  uint64_t coef[3];    // quantised coefficients, stored in each varblock's pixel footprint (row-major)
+  uint64_t dcq[3];     // quantised DC: [0] = Y, [1] = X, [2] = B, xblocks * yblocks
+  uint64_t first_index;  // per block: index of the varblock in its DC group's list (first blocks only)
+  uint64_t block_of_num; // per DC group region: list position -> block position (y * xblocks + x)
+  uint64_t dcg_count;    // per DC group: number of varblocks
+  uint64_t group_tokens; // per AC group: number of tokens written
+  uint64_t ac_hist;      // [num_ac_clusters][256]
+  uint64_t mod_hist;     // [num_leaves][256]
+  // byte arena
+  uint64_t acs;        // strategy << 1 | is_first per block
+  // token arena (uint2: context, value)
+  uint64_t ac_tokens;  // group g at ac_tokens + 3 * 65536 * g
+  uint64_t mod_tokens; // DC group g at mod_tokens + mod_tokens_stride * g
+  uint64_t mod_tokens_stride;
+};
+
+}  // namespace jxlb
+
+#endif  // JXLB_ENC_DESC_H_

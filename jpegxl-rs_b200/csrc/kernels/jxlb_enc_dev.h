@@ -1,0 +1,520 @@
+// jxl_b200 device code of the VarDCT encode path (the mirror of jxlb_vardct_dev.h).
+//
+//   DevEncXybPixel        RGB8 -> XYB (sRGB table, opsin mix, cube root)      lib/jxl/enc_xyb.cc:41-104, :226-275
+//   DevEncStrategyGroup   AcStrategy per 256x256 group (variance heuristic)     lib/jxl/enc_ac_strategy.cc (role of)
+//   DevEncNumberBlocks    raster numbering of the varblocks of a DC group       lib/jxl/enc_modular.cc AddACMetadata
+//   DevEncDcBlock         DC = block mean, quantised with CfL on DC             lib/jxl/enc_cache.cc:207-228, compressed_dc.cc
+//   DevEncVarblock        forward transform + quantisation (Y round trip, CfL)  lib/jxl/enc_group.cc:46-90, :370-524
+//   DevEncTokenizeGroup   coefficient tokens + histogram counts                 lib/jxl/enc_entropy_coder.cc:148-244
+//   DevEncModularToken    DC / AC-metadata tokens under the fixed global tree   lib/jxl/modular/encoding/enc_encoding.cc
+//   DevRansEmit           rANS writer (reverse pass)                            lib/jxl/enc_ans.cc:1731-1816, enc_ans.h:53-70
+//
+// The heuristics are those of the oracle's plain encoder (oracle/jxlo_encode.h), not libjxl's rate-distortion
+// search; every statement is arranged so that the bytes produced equal the oracle's.
+#ifndef JXLB_ENC_DEV_H_
+#define JXLB_ENC_DEV_H_
+
+#include "jxlb_enc_desc.h"
+#include "jxlb_vardct_dev.h"
+
+namespace jxlb {
+
+struct DevEPools {
+  const uint8_t* bytes_in;   // RGB8 inputs
+  float* farena;
+  int32_t* iarena;
+  uint8_t* barena;
+  uint2* tokens;
+  const float* srgb_lut;     // 256 entries: sRGB byte -> linear
+  const float* fpool;        // shared VarDCT tables (dequantisation tables, WcMultipliers)
+  const uint16_t* opool;     // natural coefficient orders
+  const uint32_t* upool;     // packed StrategyInfo, coefficient context tables
+  uint32_t table_off[17], order_off[13];
+  uint32_t wc_off, sinfo_off, ctxtab_off;
+  const uint8_t* ac_cluster_of;  // 15 * 495 contexts -> cluster
+  const DevEncTreeNode* tree;
+  uint32_t num_dc_groups_for_tree;
+};
+
+JXLB_HD int32_t DevRoundToInt(float v) {
+#if defined(__CUDA_ARCH__)
+  return __float2int_rn(v);
+#else
+  return static_cast<int32_t>(lrintf(v));
+#endif
+}
+
+JXLB_HD float DevCubeRootAndAdd(float x, float add) {  // lib/jxl/base/fast_math-inl.h:177-224
+  const float k1_3 = 1.0f / 3, k4_3 = 4.0f / 3;
+  const float xa_3 = k1_3 * x;
+  const int32_t m1 = DevFloatToBits(x);
+  const int32_t m2 = m1 == 0 ? 0 : 0x54800000 - (m1 >> 23) * 0x002AAAAA;
+  float r = DevBitsToFloat(m2);
+  for (int i = 0; i < 3; i++) {
+    const float r2 = r * r;
+    r = fmaf(-xa_3, r2 * r2, k4_3 * r);
+  }
+  float r2 = r * r;
+  r = fmaf(k1_3, fmaf(-x, r2 * r2, r), r);
+  r2 = r * r;
+  return fmaf(r2, x, add);
+}
+
+// One sample position of the padded planes.
+JXLB_HD void DevEncXybPixel(const DevEPools& E, const DevEFrame& ef, uint32_t x, uint32_t y) {
+  const uint32_t PW = ef.xblocks * 8;
+  const uint32_t sx = x < ef.xsize ? x : ef.xsize - 1, sy = y < ef.ysize ? y : ef.ysize - 1;
+  const uint8_t* px = E.bytes_in + ef.rgb + (static_cast<size_t>(sy) * ef.xsize + sx) * 3;
+  const float r = E.srgb_lut[px[0]], g = E.srgb_lut[px[1]], b = E.srgb_lut[px[2]];
+  const float bias = 0.0037930732552754493f;
+  const float kNegBiasCbrt = -0.15595420054924863f;
+  const float m00 = 0.30f, m01 = 1.0f - 0.078f - 0.30f, m02 = 0.078f;
+  const float m10 = 0.23f, m11 = 1.0f - 0.078f - 0.23f, m12 = 0.078f;
+  const float m20 = 0.24342268924547819f, m21 = 0.20476744424496821f, m22 = 1.0f - 0.24342268924547819f - 0.20476744424496821f;
+  float mixed0 = m00 * r + m01 * g + m02 * b + bias;
+  float mixed1 = m10 * r + m11 * g + m12 * b + bias;
+  float mixed2 = m20 * r + m21 * g + m22 * b + bias;
+  if (mixed0 < 0) mixed0 = 0;
+  if (mixed1 < 0) mixed1 = 0;
+  if (mixed2 < 0) mixed2 = 0;
+  mixed0 = DevCubeRootAndAdd(mixed0, kNegBiasCbrt);
+  mixed1 = DevCubeRootAndAdd(mixed1, kNegBiasCbrt);
+  mixed2 = DevCubeRootAndAdd(mixed2, kNegBiasCbrt);
+  const size_t at = static_cast<size_t>(y) * PW + x;
+  E.farena[ef.xyb[0] + at] = 0.5f * (mixed0 - mixed1);
+  E.farena[ef.xyb[1] + at] = 0.5f * (mixed0 + mixed1);
+  E.farena[ef.xyb[2] + at] = mixed2;
+}
+
+// AcStrategy of one 256x256 group: greedy raster scan, large smooth blocks first (serial: a choice depends on
+// which blocks are still free). acs must be 0xFF on entry.
+JXLB_HD void DevEncStrategyGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g) {
+  const uint32_t W = ef.xblocks, H = ef.yblocks, PW = W * 8;
+  const uint32_t x0 = (g % ef.xgroups) * 32, y0 = (g / ef.xgroups) * 32;
+  const uint32_t xs = W - x0 < 32 ? W - x0 : 32, ys = H - y0 < 32 ? H - y0 : 32;
+  uint8_t* acs = E.barena + ef.acs;
+  const float* yplane = E.farena + ef.xyb[1];
+  const int kCands[5] = {18, 5, 4, 6, 7};  // 64x64, 32x32, 16x16, 16x8, 8x16
+  const double kThresh[5] = {2e-6, 1e-5, 6e-5, 1.5e-4, 1.5e-4};
+  for (uint32_t iy = 0; iy < ys; iy++) {
+    for (uint32_t ix = 0; ix < xs; ix++) {
+      const uint32_t bx = x0 + ix, by = y0 + iy;
+      const size_t pos = static_cast<size_t>(by) * W + bx;
+      if (acs[pos] != 0xFF) continue;
+      uint32_t s = 0, scx = 1, scy = 1;
+      if (ef.strategy_mode == 2) {
+        for (int i = 0; i < 5; i++) {
+          const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + kCands[i]]);
+          const uint32_t cx = si.cx, cy = si.cy;
+          if (bx % cx || by % cy) continue;
+          if (bx + cx > W || by + cy > H) continue;
+          if (bx / 32 != (bx + cx - 1) / 32 || by / 32 != (by + cy - 1) / 32) continue;
+          bool free_cells = true;
+          for (uint32_t y = 0; y < cy && free_cells; y++)
+            for (uint32_t x = 0; x < cx; x++)
+              if (acs[pos + static_cast<size_t>(y) * W + x] != 0xFF) {
+                free_cells = false;
+                break;
+              }
+          if (!free_cells) continue;
+          double sum = 0, sum2 = 0;
+          const uint32_t n = cx * cy * 64;
+          for (uint32_t y = by * 8; y < (by + cy) * 8; y++)
+            for (uint32_t x = bx * 8; x < (bx + cx) * 8; x++) {
+              const double v = yplane[static_cast<size_t>(y) * PW + x];
+              sum += v;
+              sum2 += v * v;
+            }
+          const double var = sum2 / n - (sum / n) * (sum / n);
+          if (var < kThresh[i] * ef.distance) {
+            s = kCands[i];
+            scx = cx;
+            scy = cy;
+            break;
+          }
+        }
+      }
+      for (uint32_t y = 0; y < scy; y++)
+        for (uint32_t x = 0; x < scx; x++)
+          acs[pos + static_cast<size_t>(y) * W + x] = static_cast<uint8_t>((s << 1) | ((x | y) == 0 ? 1 : 0));
+    }
+  }
+}
+
+// Numbers the varblocks of DC group g in raster order of their top-left blocks.
+JXLB_HD void DevEncNumberBlocks(const DevEPools& E, const DevEFrame& ef, uint32_t g) {
+  const uint32_t W = ef.xblocks, H = ef.yblocks;
+  const uint32_t x0 = (g % ef.xdcgroups) * 256, y0 = (g / ef.xdcgroups) * 256;
+  const uint32_t xs = W - x0 < 256 ? W - x0 : 256, ys = H - y0 < 256 ? H - y0 : 256;
+  const uint8_t* acs = E.barena + ef.acs;
+  int32_t* first_index = E.iarena + ef.first_index;
+  int32_t* block_of_num = E.iarena + ef.block_of_num + static_cast<size_t>(g) * 65536;
+  uint32_t num = 0;
+  for (uint32_t y = 0; y < ys; y++)
+    for (uint32_t x = 0; x < xs; x++) {
+      const size_t pos = static_cast<size_t>(y0 + y) * W + x0 + x;
+      if (!(acs[pos] & 1)) continue;
+      first_index[pos] = static_cast<int32_t>(num);
+      block_of_num[num] = static_cast<int32_t>(pos);
+      num++;
+    }
+  E.iarena[ef.dcg_count + g] = static_cast<int32_t>(num);
+}
+
+JXLB_HD void DevEncDcBlock(const DevEPools& E, const DevEFrame& ef, uint32_t bx, uint32_t by) {
+  const uint32_t W = ef.xblocks, PW = W * 8;
+  float mean[3];
+  for (int c = 0; c < 3; c++) {
+    const float* p = E.farena + ef.xyb[c] + static_cast<size_t>(by) * 8 * PW + bx * 8;
+    double s = 0;
+    for (int y = 0; y < 8; y++)
+      for (int x = 0; x < 8; x++) s += p[static_cast<size_t>(y) * PW + x];
+    mean[c] = static_cast<float>(s / 64);
+  }
+  const int32_t qy = DevRoundToInt(mean[1] / ef.mul_dc[1]);
+  const float ry = static_cast<float>(qy) * ef.mul_dc[1];
+  const int32_t qx = DevRoundToInt((mean[0] - 0.0f * ry) / ef.mul_dc[0]);
+  const int32_t qb = DevRoundToInt((mean[2] - 1.0f * ry) / ef.mul_dc[2]);
+  const size_t pos = static_cast<size_t>(by) * W + bx;
+  E.iarena[ef.dcq[0] + pos] = qy;
+  E.iarena[ef.dcq[1] + pos] = qx;
+  E.iarena[ef.dcq[2] + pos] = qb;
+}
+
+// Forward transform + quantisation of one varblock (plain DCT strategies). `buf`: 4 * 64 * covered floats.
+template <int SCOPE>
+JXLB_HD void DevEncVarblock(const DevEPools& E, const DevEFrame& ef, uint32_t bx, uint32_t by, uint32_t s, float* buf,
+                            uint32_t tid, uint32_t nt) {
+  const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + s]);
+  const uint32_t Rb = si.cy, Cb = si.cx, R = 8 * Rb, C = 8 * Cb, N = R * C;
+  const uint32_t W = ef.xblocks, PW = W * 8;
+  const float* wc = E.fpool + E.wc_off;
+  float* ch[3] = {buf, buf + N, buf + 2 * static_cast<size_t>(N)};
+  float* scratch = buf + 3 * static_cast<size_t>(N);
+  const float* F[3];
+  const size_t origin = static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+  for (uint32_t c = 0; c < 3; c++) {
+    const float* px = E.farena + ef.xyb[c] + origin;
+    for (uint32_t i = tid; i < N; i += nt) ch[c][i] = px[static_cast<size_t>(i / C) * PW + i % C];
+    CoopSync<SCOPE>();
+    float* r1 = CoopDCT<SCOPE>(R, C, 1, C, ch[c], scratch, wc, tid, nt);            // along y for every column
+    float* r2 = CoopDCT<SCOPE>(C, R, C, 1, r1, r1 == ch[c] ? scratch : ch[c], wc, tid, nt);  // along x for every row
+    if (r2 != ch[c]) {
+      for (uint32_t i = tid; i < N; i += nt) ch[c][i] = r2[i];
+      CoopSync<SCOPE>();
+    }
+    F[c] = ch[c];  // F[yfreq * C + xfreq]
+  }
+  const float sd_base = ef.inv_global_scale / 16.0f;  // raw quant field value 16 everywhere
+  const float sd0 = sd_base * ef.x_dm, sd1 = sd_base, sd2 = sd_base * ef.b_dm;
+  const float x_cc = 0.0f, b_cc = 1.0f;
+  const float* dm = E.fpool + E.table_off[si.table];
+  const uint32_t lcx = Cb > Rb ? Cb : Rb, lcy = Cb > Rb ? Rb : Cb;
+  int32_t* out[3] = {E.iarena + ef.coef[0] + origin, E.iarena + ef.coef[1] + origin, E.iarena + ef.coef[2] + origin};
+  for (uint32_t k = tid; k < N; k += nt) {
+    const uint32_t fi = R < C ? k : (k % R) * C + k / R;  // coefficient layout: min(R, C) rows x max(R, C) columns
+    const float y_mul = dm[N + k] * sd1;
+    int32_t qy = DevRoundToInt(F[1][fi] / y_mul);
+    const float dq_y = DevAdjustQuantBias(1, qy, ef.biases) * y_mul;
+    int32_t qx = DevRoundToInt((F[0][fi] - x_cc * dq_y) / (dm[k] * sd0));
+    int32_t qb = DevRoundToInt((F[2][fi] - b_cc * dq_y) / (dm[2 * N + k] * sd2));
+    const uint32_t ly = k / (lcx * 8), lx = k % (lcx * 8);
+    if (ly < lcy && lx < lcx) qx = qy = qb = 0;  // the lowest frequencies come from the DC image
+    const size_t at = static_cast<size_t>(k / C) * PW + k % C;
+    out[0][at] = qx;
+    out[1][at] = qy;
+    out[2][at] = qb;
+  }
+  CoopSync<SCOPE>();
+}
+
+JXLB_HD uint32_t DevPackSigned(int32_t v) { return (static_cast<uint32_t>(v) << 1) ^ (v < 0 ? 0xFFFFFFFFu : 0u); }
+
+// HybridUintConfig(4, 2, 0)
+JXLB_HD void DevHybrid420(uint32_t v, uint32_t* token, uint32_t* nbits, uint32_t* bits) {
+  if (v < 16) {
+    *token = v;
+    *nbits = 0;
+    *bits = 0;
+    return;
+  }
+  const uint32_t n = DevFloorLog2(v), m = v - (1u << n);
+  *token = 16 + ((n - 4) << 2) + (m >> (n - 2));
+  *nbits = n - 2;
+  *bits = m & ((1u << (n - 2)) - 1);
+}
+
+JXLB_HD void DevCountToken(uint32_t* hist, uint32_t cluster, uint32_t value) {
+  uint32_t token, nbits, bits;
+  DevHybrid420(value, &token, &nbits, &bits);
+#if defined(__CUDA_ARCH__)
+  atomicAdd(hist + cluster * 256 + token, 1u);
+#else
+  hist[cluster * 256 + token]++;
+#endif
+}
+
+// Tokens of AC group g (one thread: the contexts chain through the non-zero counts).
+JXLB_HD void DevEncTokenizeGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g, const uint16_t* freq_ctx,
+                                 const uint16_t* nnz_ctx) {
+  const uint8_t kBlockCtx[39] = {0, 1, 2, 2, 3, 3, 4, 5, 6, 6, 6, 6, 6, 7, 8, 9, 9, 10, 11, 12,
+                                 13, 14, 14, 14, 14, 14, 7, 8, 9, 9, 10, 11, 12, 13, 14, 14, 14, 14, 14};
+  const uint32_t W = ef.xblocks, H = ef.yblocks, PW = W * 8;
+  const uint32_t x0 = (g % ef.xgroups) * 32, y0 = (g / ef.xgroups) * 32;
+  const uint32_t xs = W - x0 < 32 ? W - x0 : 32, ys = H - y0 < 32 ? H - y0 : 32;
+  const uint8_t* acs = E.barena + ef.acs;
+  uint2* tok = E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(E.iarena + ef.ac_hist);
+  uint32_t ntok = 0;
+  uint8_t colnz[3 * 32];
+  for (int i = 0; i < 96; i++) colnz[i] = 0;
+  const uint32_t num_ctxs = 15;
+  for (uint32_t by = 0; by < ys; by++) {
+    for (uint32_t bx = 0; bx < xs; bx++) {
+      const size_t pos = static_cast<size_t>(y0 + by) * W + x0 + bx;
+      const uint8_t a = acs[pos];
+      if (!(a & 1)) continue;
+      const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
+      const uint32_t cx = si.cx, log2c = si.log2_covered, covered = 1u << log2c, size = covered * 64, ord = si.order;
+      const uint32_t C = cx * 8;
+      const uint16_t* order = E.opool + E.order_off[ord];
+      const size_t origin = static_cast<size_t>(y0 + by) * 8 * PW + static_cast<size_t>(x0 + bx) * 8;
+      for (uint32_t ci = 0; ci < 3; ci++) {
+        const uint32_t c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);
+        const int32_t* coef = E.iarena + ef.coef[c] + origin;
+        uint32_t predicted;
+        uint8_t* col = colnz + c * 32 + bx;
+        if (bx == 0) {
+          predicted = by == 0 ? 32 : col[0];
+        } else if (by == 0) {
+          predicted = col[-1];
+        } else {
+          predicted = (static_cast<uint32_t>(col[0]) + col[-1] + 1) / 2;
+        }
+        const uint32_t block_ctx = kBlockCtx[(c < 2 ? c ^ 1 : 2) * kNumOrders + ord];
+        uint32_t nz = 0;
+        for (uint32_t k = covered; k < size; k++) {
+          const uint32_t p = order[k];
+          nz += coef[static_cast<size_t>(p / C) * PW + p % C] != 0;
+        }
+        uint32_t bucket = predicted >= 64 ? 64 : predicted;
+        bucket = bucket < 8 ? bucket : 4 + bucket / 2;
+        const uint32_t nz_ctx = bucket * num_ctxs + block_ctx;
+        tok[ntok++] = make_uint2(nz_ctx, nz);
+        DevCountToken(hist, E.ac_cluster_of[nz_ctx], nz);
+        const uint8_t v8 = static_cast<uint8_t>((nz + covered - 1) >> log2c);
+        for (uint32_t i = 0; i < cx; i++) col[i] = v8;
+        const uint32_t histo_offset = num_ctxs * 37 + 458 * block_ctx;
+        uint32_t prev = nz > size / 16 ? 0 : 1;
+        for (uint32_t k = covered; k < size && nz != 0; k++) {
+          const uint32_t nzl = (nz + covered - 1) >> log2c;
+          const uint32_t ctx = histo_offset + (nnz_ctx[nzl] + freq_ctx[k >> log2c]) * 2 + prev;
+          const uint32_t p = order[k];
+          const uint32_t u = DevPackSigned(coef[static_cast<size_t>(p / C) * PW + p % C]);
+          tok[ntok++] = make_uint2(ctx, u);
+          DevCountToken(hist, E.ac_cluster_of[ctx], u);
+          prev = u != 0;
+          nz -= prev;
+        }
+      }
+    }
+  }
+  E.iarena[ef.group_tokens + g] = static_cast<int32_t>(ntok);
+}
+
+// ---- Modular sub-streams (DC, AC metadata) under the fixed global tree: every sample's context and prediction
+// depend only on already-known neighbours, so the tokens are produced in parallel, sample i at slot i.
+struct DevModChan {
+  // value of sample (x, y): kind 0 = quantised DC plane `plane` at (x0 + x, y0 + y); 1 = constant `konst`;
+  // 2 = the (strategy, quant - 1) rows of the DC group's varblock list
+  uint32_t kind, w, h;
+  int32_t konst;
+  uint64_t plane;
+};
+
+JXLB_HD int32_t DevModValue(const DevEPools& E, const DevEFrame& ef, const DevModChan& ch, uint32_t g, uint32_t x0,
+                            uint32_t y0, uint32_t x, uint32_t y) {
+  if (ch.kind == 0) return E.iarena[ch.plane + static_cast<size_t>(y0 + y) * ef.xblocks + x0 + x];
+  if (ch.kind == 1) return ch.konst;
+  if (y == 1) return 15;  // raw quant - 1
+  const int32_t pos = E.iarena[ef.block_of_num + static_cast<size_t>(g) * 65536 + x];
+  return E.barena[ef.acs + pos] >> 1;
+}
+
+// Token of sample (x, y) of channel `chan` (index inside its stream's image) of stream `stream_id`.
+JXLB_HD uint2 DevEncModularToken(const DevEPools& E, const DevEFrame& ef, const DevModChan& ch, uint32_t chan,
+                                 uint32_t stream_id, uint32_t g, uint32_t x0, uint32_t y0, uint32_t x, uint32_t y) {
+  const int32_t v = DevModValue(E, ef, ch, g, x0, y0, x, y);
+  const int32_t left = x ? DevModValue(E, ef, ch, g, x0, y0, x - 1, y) : (y ? DevModValue(E, ef, ch, g, x0, y0, x, y - 1) : 0);
+  const int32_t top = y ? DevModValue(E, ef, ch, g, x0, y0, x, y - 1) : left;
+  const int32_t topleft = (x && y) ? DevModValue(E, ef, ch, g, x0, y0, x - 1, y - 1) : left;
+  int32_t props[12];
+  props[0] = static_cast<int32_t>(chan);
+  props[1] = static_cast<int32_t>(stream_id);
+  props[2] = static_cast<int32_t>(y);
+  props[3] = static_cast<int32_t>(x);
+  props[4] = top > 0 ? top : -top;
+  props[5] = left > 0 ? left : -left;
+  props[6] = top;
+  props[7] = left;
+  props[8] = 0;  // (the fixed tree never tests property 8)
+  props[9] = left + top - topleft;
+  props[10] = left - topleft;
+  props[11] = topleft - top;
+  uint32_t pos = 0;
+  DevEncTreeNode n = E.tree[0];
+  while (n.prop >= 0) {
+    pos = props[n.prop] > n.a ? n.l : n.r;
+    n = E.tree[pos];
+  }
+  int32_t guess = 0;
+  if (n.a == 1) guess = left;
+  else if (n.a == 2) guess = top;
+  else if (n.a == 5) guess = DevClampedGradient(left, top, topleft);
+  return make_uint2(n.l, DevPackSigned(v - guess));
+}
+
+// ---- rANS writer. Tables of one code: freq / start [cluster][256], reverse [cluster][4096].
+struct DevEncCode {
+  const uint16_t* freq;
+  const uint16_t* start;
+  const uint16_t* reverse;
+  const uint8_t* cluster_of;  // context -> cluster, or nullptr for identity
+};
+
+JXLB_HD void DevWriteBitsAt(uint32_t* words, uint64_t pos, uint32_t nbits, uint32_t value) {
+  if (nbits == 0) return;
+  const uint32_t sh = static_cast<uint32_t>(pos & 31);
+  words[pos >> 5] |= value << sh;
+  if (sh + nbits > 32) words[(pos >> 5) + 1] |= value >> (32 - sh);
+}
+
+// Writes the rANS stream of `n` tokens at bit position `bit_pos` of `words` (zero-initialised, owned by the calling
+// thread) and returns the position after it. Symbols are pushed in reverse order (the decoder pops them forwards);
+// the stream is laid out back to front, so a first pass only measures its length.
+JXLB_HD uint64_t DevRansEmit(const uint2* tok, uint32_t n, const DevEncCode& code, uint32_t* words, uint64_t bit_pos) {
+  uint64_t total = 32;
+  for (int pass = 0; pass < 2; pass++) {
+    uint32_t state = 0x13u << 16;
+    uint64_t cursor = bit_pos + total;
+    for (uint32_t i = n; i-- > 0;) {
+      const uint2 t = tok[i];
+      const uint32_t c = code.cluster_of ? code.cluster_of[t.x] : t.x;
+      uint32_t token, nbits, bits;
+      DevHybrid420(t.y, &token, &nbits, &bits);
+      if (nbits) {
+        if (pass == 0) {
+          total += nbits;
+        } else {
+          cursor -= nbits;
+          DevWriteBitsAt(words, cursor, nbits, bits);
+        }
+      }
+      const uint32_t f = code.freq[c * 256 + token];
+      if ((state >> 20) >= f) {
+        if (pass == 0) {
+          total += 16;
+        } else {
+          cursor -= 16;
+          DevWriteBitsAt(words, cursor, 16, state & 0xFFFF);
+        }
+        state >>= 16;
+      }
+      state = ((state / f) << 12) | code.reverse[c * 4096 + code.start[c * 256 + token] + state % f];
+    }
+    if (pass == 1) DevWriteBitsAt(words, bit_pos, 32, state);
+  }
+  return bit_pos + total;
+}
+
+// Token slots of DC group g's Modular streams: [DC Y | DC X | DC B | ytox | ytob | strategy row, quant row | sharpness].
+struct DevDcGroupLayout {
+  uint32_t x0, y0, xs, ys, cw, chh, count;
+  uint32_t dc_tokens, meta_tokens;  // counts
+};
+
+JXLB_HD DevDcGroupLayout DevDcGroupGeometry(const DevEPools& E, const DevEFrame& ef, uint32_t g) {
+  DevDcGroupLayout L;
+  L.x0 = (g % ef.xdcgroups) * 256;
+  L.y0 = (g / ef.xdcgroups) * 256;
+  L.xs = ef.xblocks - L.x0 < 256 ? ef.xblocks - L.x0 : 256;
+  L.ys = ef.yblocks - L.y0 < 256 ? ef.yblocks - L.y0 : 256;
+  L.cw = (L.xs + 7) >> 3;
+  L.chh = (L.ys + 7) >> 3;
+  L.count = static_cast<uint32_t>(E.iarena[ef.dcg_count + g]);
+  L.dc_tokens = 3 * L.xs * L.ys;
+  L.meta_tokens = 2 * L.cw * L.chh + 2 * L.count + L.xs * L.ys;
+  return L;
+}
+
+// Token `i` of DC group g (0 <= i < dc_tokens + meta_tokens), written to its slot and counted.
+JXLB_HD void DevEncModularSample(const DevEPools& E, const DevEFrame& ef, uint32_t g, const DevDcGroupLayout& L, uint32_t i) {
+  const uint32_t ndc = ef.xdcgroups * ef.ydcgroups;
+  DevModChan ch;
+  uint32_t chan, stream_id, local;
+  if (i < L.dc_tokens) {
+    chan = i / (L.xs * L.ys);
+    local = i - chan * L.xs * L.ys;
+    ch.kind = 0;
+    ch.w = L.xs;
+    ch.h = L.ys;
+    ch.konst = 0;
+    ch.plane = ef.dcq[chan];
+    stream_id = 1 + g;
+  } else {
+    uint32_t j = i - L.dc_tokens;
+    stream_id = 1 + 2 * ndc + g;
+    const uint32_t n01 = L.cw * L.chh;
+    ch.plane = 0;
+    if (j < 2 * n01) {
+      chan = j / n01;
+      local = j - chan * n01;
+      ch.kind = 1;
+      ch.konst = 0;
+      ch.w = L.cw;
+      ch.h = L.chh;
+    } else if (j < 2 * n01 + 2 * L.count) {
+      chan = 2;
+      local = j - 2 * n01;
+      ch.kind = 2;
+      ch.konst = 0;
+      ch.w = L.count;
+      ch.h = 2;
+    } else {
+      chan = 3;
+      local = j - 2 * n01 - 2 * L.count;
+      ch.kind = 1;
+      ch.konst = 4;  // EPF sharpness
+      ch.w = L.xs;
+      ch.h = L.ys;
+    }
+  }
+  const uint32_t x = local % ch.w, y = local / ch.w;
+  const uint2 t = DevEncModularToken(E, ef, ch, chan, stream_id, g, L.x0, L.y0, x, y);
+  E.tokens[ef.mod_tokens + ef.mod_tokens_stride * g + i] = t;
+  DevCountToken(reinterpret_cast<uint32_t*>(E.iarena + ef.mod_hist), t.x, t.y);
+}
+
+// The DC group section: extra_precision, DC stream, varblock count, AC-metadata stream. Returns its length in bits.
+JXLB_HD uint64_t DevEncEmitDcGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g, const DevEncCode& code, uint32_t* words) {
+  const DevDcGroupLayout L = DevDcGroupGeometry(E, ef, g);
+  const uint2* tok = E.tokens + ef.mod_tokens + ef.mod_tokens_stride * g;
+  uint64_t pos = 0;
+  DevWriteBitsAt(words, pos, 2, 0);  // extra_precision
+  pos += 2;
+  DevWriteBitsAt(words, pos, 4, 0x3);  // use_global_tree = 1, default WP header = 1, no transforms
+  pos += 4;
+  pos = DevRansEmit(tok, L.dc_tokens, code, words, pos);
+  uint32_t count_bits = 0;
+  while ((1u << count_bits) < L.xs * L.ys) count_bits++;
+  DevWriteBitsAt(words, pos, count_bits, L.count - 1);
+  pos += count_bits;
+  DevWriteBitsAt(words, pos, 4, 0x3);
+  pos += 4;
+  pos = DevRansEmit(tok + L.dc_tokens, L.meta_tokens, code, words, pos);
+  return pos;
+}
+
+}  // namespace jxlb
+
+#endif  // JXLB_ENC_DEV_H_

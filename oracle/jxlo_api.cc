@@ -98,7 +98,7 @@ size_t jxlo_library_quant_table(int table, float* out, size_t cap) {
 static thread_local std::vector<uint8_t> g_encoded;
 size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float distance, int strategy_mode,
                           uint32_t seed, int gab, uint32_t epf_iters, int dc_smoothing, int random_side_info,
-                          uint32_t num_passes, char* err, size_t errlen) {
+                          uint32_t num_passes, int dc_tree, char* err, size_t errlen) {
   try {
     EncodeParams p;
     p.distance = distance;
@@ -109,6 +109,7 @@ size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, fl
     p.dc_smoothing = dc_smoothing != 0;
     p.random_side_info = random_side_info != 0;
     p.num_passes = num_passes;
+    p.dc_tree = dc_tree;
     g_encoded = EncodeVarDCT(rgb, xsize, ysize, p);
     return g_encoded.size();
   } catch (const std::exception& e) {

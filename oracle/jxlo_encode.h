@@ -377,7 +377,7 @@ inline int EncTreeFixed(std::vector<EncTreeNode>* n, int property, const std::ve
   return id;
 }
 
-inline GlobalTree BuildGlobalTree(uint32_t num_dc_groups) {
+inline GlobalTree BuildGlobalTree(uint32_t num_dc_groups, int dc_tree = 0) {
   std::vector<EncTreeNode> n;
   auto leaf = [&](uint32_t pred) {
     n.push_back(EncTreeNode());
@@ -395,7 +395,8 @@ inline GlobalTree BuildGlobalTree(uint32_t num_dc_groups) {
   };
   static const std::vector<int32_t> kCutoffs = {-500, -392, -255, -191, -127, -95, -63, -47, -31, -23, -15, -11, -7, -4, -3, -1, 0,
                                                 1, 3, 5, 7, 11, 15, 23, 31, 47, 63, 95, 127, 191, 255, 392, 500};
-  const int dc = EncTreeFixed(&n, kWPProp, kCutoffs, 0, kCutoffs.size(), kPredWeighted);
+  const int dc = dc_tree == 0 ? EncTreeFixed(&n, kWPProp, kCutoffs, 0, kCutoffs.size(), kPredWeighted)
+                              : EncTreeFixed(&n, 9, kCutoffs, 0, kCutoffs.size(), kPredGradient);
   // AC metadata: channel 0 / 1 = chroma-from-luma maps, 2 = (strategy row, quant row), 3 = EPF sharpness
   auto four = [&](int prop, uint32_t pred) {  // splits at 11, 5, 3 on `prop`
     const int hi = split(prop, 11, leaf(pred), leaf(pred));
@@ -561,6 +562,27 @@ inline float SrgbToLinear(float v) {
   return v <= 0.04045f ? v / 12.92f : std::pow((v + 0.055f) / 1.055f, 2.4f);
 }
 
+// CubeRootAndAdd, lib/jxl/base/fast_math-inl.h:177-224: cbrt(x) + add by Newton-Raphson on 1 / cbrt.
+inline float CubeRootAndAdd(float x, float add) {
+  const float k1_3 = 1.0f / 3, k4_3 = 4.0f / 3;
+  const float xa_3 = k1_3 * x;
+  int32_t m1;
+  std::memcpy(&m1, &x, 4);
+  const int32_t m2 = m1 == 0 ? 0 : 0x54800000 - (m1 >> 23) * 0x002AAAAA;
+  float r;
+  std::memcpy(&r, &m2, 4);
+  for (int i = 0; i < 3; i++) {
+    const float r2 = r * r;
+    r = std::fmaf(-xa_3, r2 * r2, k4_3 * r);
+  }
+  float r2 = r * r;
+  r = std::fmaf(k1_3, std::fmaf(-x, r2 * r2, r), r);
+  r2 = r * r;
+  return std::fmaf(r2, x, add);
+}
+
+constexpr float kNegOpsinBiasCbrt = -0.15595420054924863f;  // -cbrt(0.0037930732552754493)
+
 // lib/jxl/enc_xyb.cc:41-104 with the default opsin matrix (intensity target 255).
 inline void LinearRgbToXyb(float r, float g, float b, float* x, float* y, float* bb) {
   const float bias = 0.0037930732552754493f;
@@ -570,7 +592,7 @@ inline void LinearRgbToXyb(float r, float g, float b, float* x, float* y, float*
   for (int i = 0; i < 3; i++) {
     mixed[i] = kM[3 * i] * r + kM[3 * i + 1] * g + kM[3 * i + 2] * b + bias;
     if (mixed[i] < 0) mixed[i] = 0;
-    mixed[i] = std::cbrt(mixed[i]) - std::cbrt(bias);
+    mixed[i] = CubeRootAndAdd(mixed[i], kNegOpsinBiasCbrt);
   }
   *x = 0.5f * (mixed[0] - mixed[1]);
   *y = 0.5f * (mixed[0] + mixed[1]);
@@ -590,6 +612,9 @@ struct EncodeParams {
   bool random_side_info = false;  // random CfL factors, quant field and EPF sharpness (decoder coverage)
   uint32_t x_qm_scale = 3, b_qm_scale = 2;
   uint32_t num_passes = 1;        // > 1: coefficients split by magnitude shift (passes.shift)
+  // DC streams: 0 = fixed weighted-predictor tree (libjxl's default effort, kWPFixedDC), 1 = fixed gradient tree
+  // (kGradientFixedDC, what libjxl writes for decoding_speed_tier >= 1): contexts from property 9, no WP state.
+  int dc_tree = 0;
 };
 
 struct EncoderStats {
@@ -926,7 +951,7 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
     sections.push_back(w.Bytes());
   };
   // Modular sub-streams (DC, AC metadata) under one global tree and one entropy code
-  const GlobalTree gtree = BuildGlobalTree(dim.num_dc_groups);
+  const GlobalTree gtree = BuildGlobalTree(dim.num_dc_groups, p.dc_tree);
   std::vector<std::vector<Channel>> dc_chans(dim.num_dc_groups), meta_chans(dim.num_dc_groups);
   std::vector<std::vector<Token>> dc_toks(dim.num_dc_groups), meta_toks(dim.num_dc_groups);
   std::vector<size_t> meta_count(dim.num_dc_groups, 0);

@@ -226,3 +226,106 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
   }
 }
 }
+
+// ---------------------------------------------------------------- encoder
+#include "../../jpegxl-rs_b200/csrc/host/jxlb_enc_host.h"
+#include "../../jpegxl-rs_b200/csrc/kernels/jxlb_enc_dev.h"
+
+extern "C" {
+
+// Encodes one RGB8 image with the kernels' device functions run on the CPU; returns the size or -1.
+long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float distance, int strategy_mode, int gab,
+                      uint32_t epf_iters, int dc_smoothing, uint8_t* out, size_t out_cap, char* err, size_t errlen) {
+  try {
+    EncParams p;
+    p.distance = distance;
+    p.strategy_mode = strategy_mode;
+    p.gab = gab != 0;
+    p.epf_iters = epf_iters;
+    p.dc_smoothing = dc_smoothing != 0;
+    JXLB_CHECK(strategy_mode == 0 || strategy_mode == 2, "unsupported strategy mode");
+    const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
+    uint32_t num_ac_clusters = 0;
+    const std::vector<uint8_t> ac_cluster_of = AcContextClusters(&num_ac_clusters);
+    DevEFrame ef{};
+    uint32_t global_scale = 0, quant_dc = 0;
+    FillQuantizer(p, &ef, &global_scale, &quant_dc);
+    FrameHeader fh0;
+    fh0.xsize = xsize;
+    fh0.ysize = ysize;
+    const EncTree tree = BuildEncTree(ToFrameDimensions(fh0).num_dc_groups);
+    const EncLayout L = LayoutEncFrame(xsize, ysize, num_ac_clusters, tree.num_leaves, &ef);
+    std::vector<float> farena(L.fsize + 16, 0.0f);
+    std::vector<int32_t> iarena(L.isize + 16, 0);
+    std::vector<uint8_t> barena(L.bsize + 16, 0xFF);
+    std::vector<uint2> tokens(L.tsize + 16);
+    float lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = SrgbToLinearHost(i / 255.0f);
+    DevEPools E{};
+    E.bytes_in = rgb;
+    E.farena = farena.data();
+    E.iarena = iarena.data();
+    E.barena = barena.data();
+    E.tokens = tokens.data();
+    E.srgb_lut = lut;
+    E.fpool = sh.fpool.data();
+    E.opool = sh.opool.data();
+    E.upool = sh.upool.data();
+    for (int i = 0; i < 17; i++) E.table_off[i] = sh.table_off[i];
+    for (int i = 0; i < 13; i++) E.order_off[i] = sh.order_off[i];
+    E.wc_off = sh.wc_off;
+    E.sinfo_off = sh.sinfo_off;
+    E.ctxtab_off = sh.ctxtab_off;
+    E.ac_cluster_of = ac_cluster_of.data();
+    E.tree = tree.nodes.data();
+    ef.rgb = 0;
+    const FrameDimensions& d = L.dim;
+    const uint32_t W = d.xsize_blocks, H = d.ysize_blocks;
+    for (uint32_t y = 0; y < H * 8; y++)
+      for (uint32_t x = 0; x < W * 8; x++) DevEncXybPixel(E, ef, x, y);
+    for (uint32_t g = 0; g < d.num_groups; g++) DevEncStrategyGroup(E, ef, g);
+    for (uint32_t g = 0; g < d.num_dc_groups; g++) DevEncNumberBlocks(E, ef, g);
+    for (uint32_t by = 0; by < H; by++)
+      for (uint32_t bx = 0; bx < W; bx++) DevEncDcBlock(E, ef, bx, by);
+    std::vector<float> buf(4 * 4096 + 64);
+    for (uint32_t by = 0; by < H; by++)
+      for (uint32_t bx = 0; bx < W; bx++) {
+        const uint8_t a = barena[static_cast<size_t>(by) * W + bx];
+        if (a & 1) DevEncVarblock<0>(E, ef, bx, by, a >> 1, buf.data(), 0, 1);
+      }
+    uint16_t ctxtab[128];
+    for (int i = 0; i < 128; i++) ctxtab[i] = static_cast<uint16_t>(sh.upool[sh.ctxtab_off + i]);
+    for (uint32_t g = 0; g < d.num_groups; g++) DevEncTokenizeGroup(E, ef, g, ctxtab, ctxtab + 64);
+    for (uint32_t g = 0; g < d.num_dc_groups; g++) {
+      const DevDcGroupLayout gl = DevDcGroupGeometry(E, ef, g);
+      for (uint32_t i = 0; i < gl.dc_tokens + gl.meta_tokens; i++) DevEncModularSample(E, ef, g, gl, i);
+    }
+    EncGlobals G;
+    BuildEncGlobals(p, L, tree, ac_cluster_of, global_scale, quant_dc, reinterpret_cast<uint32_t*>(iarena.data() + ef.mod_hist),
+                    reinterpret_cast<uint32_t*>(iarena.data() + ef.ac_hist), &G);
+    DevEncCode mod{G.mod_code.freq.data(), G.mod_code.start.data(), G.mod_code.reverse.data(), nullptr};
+    DevEncCode ac{G.ac_code.freq.data(), G.ac_code.start.data(), G.ac_code.reverse.data(), ac_cluster_of.data()};
+    std::vector<std::vector<uint32_t>> dc_words(d.num_dc_groups), ac_words(d.num_groups);
+    std::vector<std::pair<const uint8_t*, uint64_t>> dcg, acg;
+    for (uint32_t g = 0; g < d.num_dc_groups; g++) {
+      const DevDcGroupLayout gl = DevDcGroupGeometry(E, ef, g);
+      dc_words[g].assign((static_cast<size_t>(gl.dc_tokens + gl.meta_tokens) * 6 + 64) / 4 + 4, 0);
+      const uint64_t bits = DevEncEmitDcGroup(E, ef, g, mod, dc_words[g].data());
+      dcg.push_back({reinterpret_cast<const uint8_t*>(dc_words[g].data()), bits});
+    }
+    for (uint32_t g = 0; g < d.num_groups; g++) {
+      const uint32_t n = static_cast<uint32_t>(iarena[ef.group_tokens + g]);
+      ac_words[g].assign((static_cast<size_t>(n) * 6 + 64) / 4 + 4, 0);
+      const uint64_t bits = DevRansEmit(tokens.data() + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, ac, ac_words[g].data(), 0);
+      acg.push_back({reinterpret_cast<const uint8_t*>(ac_words[g].data()), bits});
+    }
+    const std::vector<uint8_t> cs = AssembleCodestream(p, L, G, dcg, acg);
+    if (cs.size() > out_cap) throw Error("output buffer too small");
+    std::memcpy(out, cs.data(), cs.size());
+    return static_cast<long>(cs.size());
+  } catch (const std::exception& e) {
+    std::snprintf(err, errlen, "%s", e.what());
+    return -1;
+  }
+}
+}

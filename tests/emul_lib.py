@@ -44,3 +44,21 @@ def decode(files, num_channels, data_type, shapes, endianness=0, align=0):
         nb = h * w * num_channels * bps
         res.append(out[offs[i]:offs[i] + nb].view(_NP[data_type]).reshape(h, w, num_channels))
     return res
+
+
+def encode(rgb, distance=1.0, strategy_mode=2, gab=True, epf_iters=2, dc_smoothing=True) -> bytes:
+    """RGB8 (H, W, 3) -> codestream, the encoder kernels' device functions run on the CPU."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    h, w, _ = rgb.shape
+    cap = h * w * 6 + (1 << 20)
+    out = np.zeros(cap, np.uint8)
+    err = ctypes.create_string_buffer(512)
+    L = lib()
+    L.jxlb_emul_encode.restype = ctypes.c_long
+    n = L.jxlb_emul_encode(rgb.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(w), ctypes.c_uint32(h),
+                           ctypes.c_float(distance), ctypes.c_int(strategy_mode), ctypes.c_int(int(gab)),
+                           ctypes.c_uint32(epf_iters), ctypes.c_int(int(dc_smoothing)),
+                           out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(cap), err, ctypes.c_size_t(512))
+    if n < 0:
+        raise EmulError(err.value.decode())
+    return out[:n].tobytes()

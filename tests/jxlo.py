@@ -38,7 +38,7 @@ def lib():
         L.jxlo_encode_vardct.restype = ctypes.c_size_t
         L.jxlo_encode_vardct.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_int,
                                          ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
-                                         ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t]
+                                         ctypes.c_uint32, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
         L.jxlo_encoded_copy.argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
@@ -82,7 +82,7 @@ def decode(data: bytes, num_channels: int, data_type: int, endianness: int = 0) 
 
 
 def encode_vardct(rgb: np.ndarray, distance=1.0, strategy_mode=2, seed=1, gab=True, epf_iters=2, dc_smoothing=True,
-                  random_side_info=False, num_passes=1) -> bytes:
+                  random_side_info=False, num_passes=1, dc_tree=0) -> bytes:
     """RGB8 (H, W, 3) -> a VarDCT codestream written by the oracle's plain encoder (stream generator)."""
     L = lib()
     rgb = np.ascontiguousarray(rgb, np.uint8)
@@ -90,7 +90,7 @@ def encode_vardct(rgb: np.ndarray, distance=1.0, strategy_mode=2, seed=1, gab=Tr
     assert c == 3
     err = ctypes.create_string_buffer(512)
     n = L.jxlo_encode_vardct(rgb.ctypes.data, w, h, distance, strategy_mode, seed, int(gab), epf_iters,
-                             int(dc_smoothing), int(random_side_info), num_passes, err, 512)
+                             int(dc_smoothing), int(random_side_info), num_passes, dc_tree, err, 512)
     if n == 0:
         raise OracleError(err.value.decode())
     out = np.zeros(n, np.uint8)
