@@ -49,6 +49,17 @@ class Workload:
                          "alternating: bench image tiled to 4K at %.2f bpp, procedural frame at %.2f bpp) to RGB8"
                          % (self.batch, g[names[0]]["bpp"], g[names[1]]["bpp"]))
             self.data = "synthetic (oracle-encoded 4K fixtures; the reference ships no VarDCT file larger than 40x50)"
+        elif name == "encode4k":
+            names = ["vardct_4k_natural.jxl", "vardct_4k_synthetic.jxl"]
+            self.batch = batch or 8
+            self.channels = 3
+            self.metric = "Mpixels/s encode (RGB8 3840x2160 -> lossy VarDCT, d = 1.0)"
+            self.dtype = "f32"
+            self.sha = [g[n]["reencoded_sha256"] for n in names]
+            self.decoded_sha = [g[n]["sha256_rgb8"] for n in names]
+            self.desc = ("encode %d RGB8 4K frames per GPU (3840x2160; the two decoded 4K fixtures alternating) to lossy "
+                         "VarDCT at distance 1.0, variance-heuristic block sizes 8x8 ... 64x64" % self.batch)
+            self.data = "synthetic (the decoded 4K fixtures)"
         else:
             names = ["bench.jxl"]
             self.batch = batch or 256
@@ -156,11 +167,115 @@ def cpu_baseline(wl, seconds=15.0, threads=None):
             "sample": f"{frames} {wl.name} frames ({w}x{h}) in {dt:.1f} s on {threads} threads, oracle-CPU (not libjxl)"}, dt
 
 
+def cpu_encode_baseline(wl, images, seconds=15.0, threads=None):
+    """The oracle's plain encoder on the host cores, one frame at a time per thread."""
+    import jxlo
+    threads = threads or (os.cpu_count() or 1)
+    jxlo.lib()
+    count = [0] * threads
+    stop = time.time() + seconds
+
+    def work(i):
+        k = i
+        while time.time() < stop:
+            jxlo.encode_vardct(images[k % len(images)], distance=1.0, strategy_mode=2, dc_tree=1)
+            count[i] += 1
+            k += 1
+
+    t0 = time.time()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.time() - t0
+    frames = sum(count)
+    h, w = images[0].shape[:2]
+    return {"value": frames * w * h / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{frames} 4K frames encoded in {dt:.1f} s on {threads} threads, oracle-CPU encoder (not libjxl)"}, dt
+
+
+def run_encode(args, wl):
+    """Encode workload: `value` from the encoder's device events (kernels + host table build between them), `e2e` the
+    wall time of the public call with host buffers (H2D of the pixels, kernels, D2H of the sections, assembly)."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    base = pkg.decode_batch(wl.blobs, 3, np.uint8, device=local_rank)  # the inputs: our own decode of the fixtures
+    ok = all(hashlib.sha256(b.tobytes()).hexdigest() == s for b, s in zip(base, wl.decoded_sha))
+    images = [base[i % len(base)] for i in range(wl.batch)]
+    enc = pkg.JxlEncoder(quality=1.0, device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(1, args.warmup)):
+        outs = enc.encode_batch(images)
+    ok = ok and all(hashlib.sha256(outs[i].data).hexdigest() == wl.sha[i % len(wl.sha)] for i in range(wl.batch))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, phases = 0.0, {"tokens_ms": 0.0, "host_tables_ms": 0.0, "emit_ms": 0.0}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        enc.encode_batch(images)
+        pt = enc.phase_times()
+        for k in phases:
+            phases[k] += pt[k] / args.steps
+        dev_ms += sum(pt.values())
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms / args.steps, wall / args.steps * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_wall = float(t[0].item()), float(t[1].item())
+    pixels = sum(a.shape[0] * a.shape[1] for a in images) * world
+    in_bytes = sum(a.nbytes for a in images)
+    out_bytes = sum(len(o.data) for o in outs)
+    if rank == 0:
+        peak, peak_kind = measured_peak_hbm()
+        top = max(phases, key=phases.get)
+        alg = in_bytes + out_bytes  # SURVEY.md 8d: pixels read once + compressed bytes written once
+        line = {"metric": wl.metric, "value": pixels / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": wl.data,
+                "config": {"workload": wl.desc, "batch_per_gpu": wl.batch,
+                           "l2": "working set %.1f GB per step >> 126 MB L2" % (wl.batch * 0.45),
+                           "golden_checksum_ok": bool(ok)},
+                "clocks": clocks,
+                "e2e": {"value": pixels / (ms_wall * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes),
+                        "d2h_bytes_per_step": int(out_bytes),
+                        "includes": "H2D of the RGB8 frames + kernels + host histogram / table build + D2H of the sections + "
+                                    "codestream assembly"},
+                "gpu_launches": args.steps * wl.batch * 9,
+                "roofline": {"bound": "hbm", "kernel": top, "achieved": alg / (phases[top] * 1e-3) / 1e9, "peak": peak,
+                             "peak_kind": peak_kind, "unit": "GB/s", "frac": alg / (phases[top] * 1e-3) / 1e9 / peak,
+                             "traffic": None, "algorithmic_bytes_per_launch": int(alg), "kernel_ms": phases[top],
+                             "kernel_share_of_step": phases[top] / ms_dev, "all_kernels_ms": phases}}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"], _ = cpu_encode_baseline(wl, base, seconds=args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = Workload(args.workload, args.batch)
+    if wl.name == "encode4k":
+        raise SystemExit("--impl reference covers the decode workloads; the CPU encoder is timed as cpu_baseline")
     # bounded: the whole --steps K --warmup W run stays within a few minutes
     per_step = max(6.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
     vals, ms = [], []
@@ -189,7 +304,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="vardct4k", choices=["vardct4k", "modular"])
+    ap.add_argument("--workload", default="vardct4k", choices=["vardct4k", "modular", "encode4k"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 64 vardct4k, 256 modular)")
     ap.add_argument("--inflight", type=int, default=2,
                     help="decoder handles in flight, each with its own buffers and CUDA stream: the latency-bound "
@@ -200,6 +315,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+
+    if args.workload == "encode4k":
+        run_encode(args, Workload(args.workload, args.batch))
         return
 
     import torch

@@ -34,6 +34,27 @@ class BitWriter {
   void AppendBits(const uint8_t* data, size_t nbits) {
     for (size_t i = 0; i < nbits; i++) Write(1, (data[i >> 3] >> (i & 7)) & 1);
   }
+  // Appends `nbits` bits that start at bit `first` of the 32-bit word array `words` (word-wise, any alignment).
+  void AppendWordBits(const uint32_t* words, uint64_t first, uint64_t nbits) {
+    while (nbits > 0) {
+      const uint32_t sh = static_cast<uint32_t>(first & 31);
+      uint64_t v = words[first >> 5] >> sh;
+      uint32_t have = 32 - sh;
+      if (have < 32 && nbits > have) {
+        v |= static_cast<uint64_t>(words[(first >> 5) + 1]) << have;
+        have = 32;  // (only `take` of them are used)
+      }
+      const uint32_t take = static_cast<uint32_t>(std::min<uint64_t>(nbits, std::min<uint32_t>(have, 32)));
+      if ((bits_ & 7) == 0 && take == 32) {  // fast path: byte-aligned output
+        for (int k = 0; k < 4; k++) bytes_.push_back(static_cast<uint8_t>(v >> (8 * k)));
+        bits_ += 32;
+      } else {
+        Write(take, v & ((uint64_t{1} << take) - 1));
+      }
+      first += take;
+      nbits -= take;
+    }
+  }
   void AppendBytes(const uint8_t* data, size_t n) {
     ZeroPadToByte();
     bytes_.insert(bytes_.end(), data, data + n);
@@ -176,6 +197,12 @@ struct EncCode {
   std::vector<uint16_t> freq;   // [cluster][256]
   std::vector<uint16_t> start;  // [cluster][256]: first slot of the symbol in `reverse`
   std::vector<uint16_t> reverse;  // [cluster][4096]: (symbol, offset) -> rANS residue
+  // device form of freq / start: [cluster][256] = freq | start << 16
+  std::vector<uint32_t> Fs() const {
+    std::vector<uint32_t> v(freq.size());
+    for (size_t i = 0; i < freq.size(); i++) v[i] = freq[i] | (static_cast<uint32_t>(start[i]) << 16);
+    return v;
+  }
 };
 
 inline void WriteSimpleCode(BitWriter& w, const std::vector<uint32_t>& values, uint32_t num_values_alphabet);
@@ -579,24 +606,34 @@ inline void BuildEncGlobals(const EncParams& p, const EncLayout& L, const EncTre
   WriteCodeHeader(a, ac_cluster_of, L.num_ac_clusters, ac_hist, &g->ac_code);
 }
 
-// Final codestream from the sections: `dcg` / `acg` = (pointer, bit length) of the device-written sections.
+// A device-written section: `nbits` bits starting at bit `first` of `words`.
+struct EncSection {
+  const uint32_t* words;
+  uint64_t first, nbits;
+};
+
+// Final codestream from the sections.
 inline std::vector<uint8_t> AssembleCodestream(const EncParams& p, const EncLayout& L, const EncGlobals& g,
-                                               const std::vector<std::pair<const uint8_t*, uint64_t>>& dcg,
-                                               const std::vector<std::pair<const uint8_t*, uint64_t>>& acg) {
+                                               const std::vector<EncSection>& dcg, const std::vector<EncSection>& acg) {
   std::vector<std::vector<uint8_t>> sections;
-  auto bytes_of = [](const uint8_t* ptr, uint64_t bits) { return std::vector<uint8_t>(ptr, ptr + (bits + 7) / 8); };
+  auto bytes_of = [](const EncSection& s) {
+    BitWriter w;
+    w.AppendWordBits(s.words, s.first, s.nbits);
+    w.ZeroPadToByte();
+    return w.Bytes();
+  };
   if (L.dim.num_groups == 1) {
     BitWriter all;
     all.AppendBits(g.dc_global.Bytes().data(), g.dc_global.BitsWritten());
-    all.AppendBits(dcg[0].first, dcg[0].second);
+    all.AppendWordBits(dcg[0].words, dcg[0].first, dcg[0].nbits);
     all.AppendBits(g.ac_global.Bytes().data(), g.ac_global.BitsWritten());
-    all.AppendBits(acg[0].first, acg[0].second);
+    all.AppendWordBits(acg[0].words, acg[0].first, acg[0].nbits);
     sections.push_back(all.Bytes());
   } else {
     sections.push_back(g.dc_global.Bytes());
-    for (const auto& s : dcg) sections.push_back(bytes_of(s.first, s.second));
+    for (const auto& s : dcg) sections.push_back(bytes_of(s));
     sections.push_back(g.ac_global.Bytes());
-    for (const auto& s : acg) sections.push_back(bytes_of(s.first, s.second));
+    for (const auto& s : acg) sections.push_back(bytes_of(s));
   }
   BitWriter out;
   WriteImageHeaders(out, L.dim.xsize, L.dim.ysize);

@@ -1095,23 +1095,34 @@ JxlDecoderStatus JxlDecoderSetImageOutBuffer(JxlDecoder* dec, const JxlPixelForm
 // ================================================================== encoder
 namespace jxlb {
 
-__global__ void __launch_bounds__(256) k_enc_xyb(DevEPools E, DevEFrame ef) {
+// Every encoder kernel covers the whole batch: the last grid dimension is the frame.
+__device__ __forceinline__ DevEPools FramePools(const DevEPools& E, const DevEFrame& ef) {
+  DevEPools El = E;
+  El.tree = E.tree + ef.tree_off;
+  return El;
+}
+
+__global__ void __launch_bounds__(256) k_enc_xyb(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.z];
   const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if (x < ef.xblocks * 8 && y < ef.yblocks * 8) DevEncXybPixel(E, ef, x, y);
 }
 
 // one thread per 256x256 group (the greedy choice is serial inside a group)
-__global__ void __launch_bounds__(32) k_enc_strategy(DevEPools E, DevEFrame ef) {
+__global__ void __launch_bounds__(32) k_enc_strategy(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.y];
   const uint32_t g = blockIdx.x * 32 + threadIdx.x;
   if (g < ef.xgroups * ef.ygroups) DevEncStrategyGroup(E, ef, g);
 }
 
-__global__ void k_enc_number(DevEPools E, DevEFrame ef) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32) k_enc_number(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.y];
+  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
   if (g < ef.xdcgroups * ef.ydcgroups) DevEncNumberBlocks(E, ef, g);
 }
 
-__global__ void __launch_bounds__(256) k_enc_dc(DevEPools E, DevEFrame ef) {
+__global__ void __launch_bounds__(256) k_enc_dc(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.y];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < ef.xblocks * ef.yblocks) DevEncDcBlock(E, ef, i % ef.xblocks, i / ef.xblocks);
 }
@@ -1120,10 +1131,12 @@ constexpr uint32_t kEncThreads = 128;
 constexpr uint32_t kEncSmemFloats = 4 * 4096;  // four buffers of a 64x64 varblock, or one 32x32 set per warp
 
 // blockIdx.x = group: forward transform + quantisation; warp per varblock up to 32x32, CTA per 64x64 class.
-__global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, DevEFrame ef) {
+__global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, const DevEFrame* frames) {
   extern __shared__ float enc_smem[];
   __shared__ uint32_t next_s, has_big_s;
+  const DevEFrame& ef = frames[blockIdx.y];
   const uint32_t g = blockIdx.x;
+  if (g >= ef.xgroups * ef.ygroups) return;
   const uint32_t x0 = (g % ef.xgroups) * 32, y0 = (g / ef.xgroups) * 32;
   const uint32_t xs = min(32u, ef.xblocks - x0), ys = min(32u, ef.yblocks - y0);
   const uint8_t* acs = E.barena + ef.acs;
@@ -1162,36 +1175,48 @@ __global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, DevEFra
   }
 }
 
-__global__ void __launch_bounds__(32) k_enc_tokenize(DevEPools E, DevEFrame ef) {
+__global__ void __launch_bounds__(32) k_enc_tokenize(DevEPools E, const DevEFrame* frames) {
   __shared__ uint16_t ctxtab_s[128];
   for (uint32_t i = threadIdx.x; i < 128; i += 32) ctxtab_s[i] = static_cast<uint16_t>(E.upool[E.ctxtab_off + i]);
   __syncwarp();
+  const DevEFrame& ef = frames[blockIdx.y];
   const uint32_t g = blockIdx.x * 32 + threadIdx.x;
   if (g < ef.xgroups * ef.ygroups) DevEncTokenizeGroup(E, ef, g, ctxtab_s, ctxtab_s + 64);
 }
 
-// blockIdx.y = DC group; one thread per sample of its DC + AC-metadata streams
-__global__ void __launch_bounds__(256) k_enc_modular(DevEPools E, DevEFrame ef) {
+// blockIdx.y = DC group, blockIdx.z = frame; one thread per sample of the DC + AC-metadata streams
+__global__ void __launch_bounds__(256) k_enc_modular(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.z];
   const uint32_t g = blockIdx.y;
-  const DevDcGroupLayout L = DevDcGroupGeometry(E, ef, g);
+  if (g >= ef.xdcgroups * ef.ydcgroups) return;
+  const DevEPools El = FramePools(E, ef);
+  const DevDcGroupLayout L = DevDcGroupGeometry(El, ef, g);
   const uint32_t total = L.dc_tokens + L.meta_tokens;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
-    DevEncModularSample(E, ef, g, L, i);
+    DevEncModularSample(El, ef, g, L, i);
 }
 
-// rANS emission: one thread per section. `off` = word offset of every section, `bits` receives its bit length.
-__global__ void __launch_bounds__(32) k_enc_emit_ac(DevEPools E, DevEFrame ef, DevEncCode code, uint32_t* words, const uint64_t* off,
-                                                    uint64_t* bits) {
+// rANS emission: one thread per section, written back to front so that it ends at the end of its region
+// (`off[sec]` .. `off[sec + 1]`, in words); `first[sec]` receives the bit position of its first bit.
+__global__ void __launch_bounds__(32) k_enc_emit_ac(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
+                                                    const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first) {
+  const DevEFrame& ef = frames[blockIdx.y];
   const uint32_t g = blockIdx.x * 32 + threadIdx.x;
   if (g >= ef.xgroups * ef.ygroups) return;
+  const DevEncCode code{fs_tables + ef.code_off[2], rev_tables + ef.code_off[3]};
   const uint32_t n = static_cast<uint32_t>(E.iarena[ef.group_tokens + g]);
-  bits[g] = DevRansEmit(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words + off[g], 0);
+  const uint32_t sec = ef.sec_base + ef.xdcgroups * ef.ydcgroups + g;
+  first[sec] = DevEncEmitAcGroup(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words, off[sec + 1] * 32);
 }
 
-__global__ void k_enc_emit_dc(DevEPools E, DevEFrame ef, DevEncCode code, uint32_t* words, const uint64_t* off, uint64_t* bits) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32) k_enc_emit_dc(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
+                                                    const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first) {
+  const DevEFrame& ef = frames[blockIdx.y];
+  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
   if (g >= ef.xdcgroups * ef.ydcgroups) return;
-  bits[g] = DevEncEmitDcGroup(E, ef, g, code, words + off[g]);
+  const DevEncCode code{fs_tables + ef.code_off[0], rev_tables + ef.code_off[1]};
+  const uint32_t sec = ef.sec_base + g;
+  first[sec] = DevEncEmitDcGroup(E, ef, g, code, words, off[sec + 1] * 32);
 }
 
 }  // namespace jxlb
@@ -1352,27 +1377,36 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     cudaEvent_t ev[4];
     for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
     CUDA_OK(cudaEventRecord(ev[0], s));
-    // ---- phase 1: pixels -> tokens + histograms
+    // ---- phase 1: pixels -> tokens + histograms, all frames of the batch in every launch
+    uint32_t maxW = 0, maxH = 0, max_groups = 0, max_dcg = 0;
+    std::vector<DevEFrame> efs(n);
     for (size_t i = 0; i < n; i++) {
-      const DevEFrame& ef = fr[i].ef;
+      fr[i].ef.tree_off = static_cast<uint32_t>(fr[i].tree_off);
+      efs[i] = fr[i].ef;
       const FrameDimensions& d = fr[i].L.dim;
-      DevEPools Ef = E;
-      Ef.tree = d_trees.p + fr[i].tree_off;
-      const uint32_t W = d.xsize_blocks, H = d.ysize_blocks;
-      k_enc_xyb<<<dim3((W * 8 + 31) / 32, H), dim3(32, 8), 0, s>>>(Ef, ef);
-      k_enc_strategy<<<(d.num_groups + 31) / 32, 32, 0, s>>>(Ef, ef);
-      k_enc_number<<<1, 32 * ((d.num_dc_groups + 31) / 32), 0, s>>>(Ef, ef);
-      k_enc_dc<<<(W * H + 255) / 256, 256, 0, s>>>(Ef, ef);
-      k_enc_coeffs<<<d.num_groups, kEncThreads, kEncSmemFloats * sizeof(float), s>>>(Ef, ef);
-      k_enc_tokenize<<<(d.num_groups + 31) / 32, 32, 0, s>>>(Ef, ef);
-      k_enc_modular<<<dim3(256, d.num_dc_groups), 256, 0, s>>>(Ef, ef);
+      maxW = std::max<uint32_t>(maxW, d.xsize_blocks);
+      maxH = std::max<uint32_t>(maxH, d.ysize_blocks);
+      max_groups = std::max<uint32_t>(max_groups, d.num_groups);
+      max_dcg = std::max<uint32_t>(max_dcg, d.num_dc_groups);
     }
+    DevBuf<DevEFrame> d_efs;
+    CUDA_OK(d_efs.Upload(efs, s));
+    E.tree = d_trees.p;
+    const uint32_t nf = static_cast<uint32_t>(n);
+    k_enc_xyb<<<dim3((maxW * 8 + 31) / 32, maxH, nf), dim3(32, 8), 0, s>>>(E, d_efs.p);
+    k_enc_strategy<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
+    k_enc_number<<<dim3((max_dcg + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
+    k_enc_dc<<<dim3((maxW * maxH + 255) / 256, nf), 256, 0, s>>>(E, d_efs.p);
+    k_enc_coeffs<<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
+    k_enc_tokenize<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
+    k_enc_modular<<<dim3(256, max_dcg, nf), 256, 0, s>>>(E, d_efs.p);
     CUDA_OK(cudaEventRecord(ev[1], s));
     // ---- host: histograms -> codes, global sections, section layout
     std::vector<int32_t> h_small;
     uint64_t words_total = 0, nsec = 0;
-    std::vector<uint16_t> h_tables;
-    struct CodeOff { uint64_t mod_f, mod_s, mod_r, ac_f, ac_s, ac_r; };
+    std::vector<uint16_t> h_rev;
+    std::vector<uint32_t> h_fs;
+    struct CodeOff { uint64_t mod_fs, mod_r, ac_fs, ac_r; };
     std::vector<CodeOff> code_off(n);
     for (size_t i = 0; i < n; i++) {
       Frame& f = fr[i];
@@ -1399,41 +1433,45 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
         words_total += (static_cast<uint64_t>(group_tokens[g]) * 6 + 64) / 4 + 4;
       }
       nsec += d.num_dc_groups + d.num_groups;
-      auto push = [&](const std::vector<uint16_t>& v) {
-        const uint64_t off = h_tables.size();
-        h_tables.insert(h_tables.end(), v.begin(), v.end());
+      auto push_rev = [&](const std::vector<uint16_t>& v) {
+        const uint64_t off = h_rev.size();
+        h_rev.insert(h_rev.end(), v.begin(), v.end());
         return off;
       };
-      code_off[i] = CodeOff{push(f.G.mod_code.freq), push(f.G.mod_code.start), push(f.G.mod_code.reverse),
-                            push(f.G.ac_code.freq), push(f.G.ac_code.start), push(f.G.ac_code.reverse)};
+      auto push_fs = [&](const std::vector<uint32_t>& v) {
+        const uint64_t off = h_fs.size();
+        h_fs.insert(h_fs.end(), v.begin(), v.end());
+        return off;
+      };
+      code_off[i] = CodeOff{push_fs(f.G.mod_code.Fs()), push_rev(f.G.mod_code.reverse), push_fs(f.G.ac_code.Fs()),
+                            push_rev(f.G.ac_code.reverse)};
     }
-    DevBuf<uint16_t> d_tables;
-    DevBuf<uint32_t> d_words;
+    DevBuf<uint16_t> d_rev;
+    DevBuf<uint32_t> d_words, d_fs;
     DevBuf<uint64_t> d_off, d_bits;
     std::vector<uint64_t> h_off;
     for (size_t i = 0; i < n; i++) {
       h_off.insert(h_off.end(), fr[i].dc_off.begin(), fr[i].dc_off.end());
       h_off.insert(h_off.end(), fr[i].ac_off.begin(), fr[i].ac_off.end());
     }
-    CUDA_OK(d_tables.Upload(h_tables, s));
+    h_off.push_back(words_total);  // region of section k: words [h_off[k], h_off[k + 1])
+    CUDA_OK(d_rev.Upload(h_rev, s));
+    CUDA_OK(d_fs.Upload(h_fs, s));
     CUDA_OK(d_off.Upload(h_off, s));
     CUDA_OK(d_bits.Alloc(nsec + 1));
     CUDA_OK(d_words.Alloc(words_total + 16));
     CUDA_OK(cudaMemsetAsync(d_words.p, 0, (words_total + 16) * sizeof(uint32_t), s));
     CUDA_OK(cudaEventRecord(ev[2], s));
-    // ---- phase 2: rANS emission of every section
+    // ---- phase 2: rANS emission of every section of every frame
     for (size_t i = 0; i < n; i++) {
-      const Frame& f = fr[i];
-      const FrameDimensions& d = f.L.dim;
-      DevEPools Ef = E;
-      Ef.tree = d_trees.p + f.tree_off;
       const CodeOff& co = code_off[i];
-      DevEncCode mod{d_tables.p + co.mod_f, d_tables.p + co.mod_s, d_tables.p + co.mod_r, nullptr};
-      DevEncCode ac{d_tables.p + co.ac_f, d_tables.p + co.ac_s, d_tables.p + co.ac_r, d_cluster.p};
-      k_enc_emit_dc<<<1, 32 * ((d.num_dc_groups + 31) / 32), 0, s>>>(Ef, f.ef, mod, d_words.p, d_off.p + f.bits_off, d_bits.p + f.bits_off);
-      k_enc_emit_ac<<<(d.num_groups + 31) / 32, 32, 0, s>>>(Ef, f.ef, ac, d_words.p, d_off.p + f.bits_off + d.num_dc_groups,
-                                                           d_bits.p + f.bits_off + d.num_dc_groups);
+      const uint64_t offs[4] = {co.mod_fs, co.mod_r, co.ac_fs, co.ac_r};
+      for (int k = 0; k < 4; k++) efs[i].code_off[k] = offs[k];
+      efs[i].sec_base = static_cast<uint32_t>(fr[i].bits_off);
     }
+    CUDA_OK(d_efs.Upload(efs, s));
+    k_enc_emit_dc<<<dim3((max_dcg + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p);
+    k_enc_emit_ac<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p);
     CUDA_OK(cudaEventRecord(ev[3], s));
     std::vector<uint64_t> h_bits(nsec);
     std::vector<uint32_t> h_words(words_total + 16);
@@ -1453,11 +1491,15 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     for (size_t i = 0; i < n; i++) {
       const Frame& f = fr[i];
       const FrameDimensions& d = f.L.dim;
-      std::vector<std::pair<const uint8_t*, uint64_t>> dcg, acg;
-      for (uint32_t g = 0; g < d.num_dc_groups; g++)
-        dcg.push_back({reinterpret_cast<const uint8_t*>(h_words.data() + f.dc_off[g]), h_bits[f.bits_off + g]});
-      for (uint32_t g = 0; g < d.num_groups; g++)
-        acg.push_back({reinterpret_cast<const uint8_t*>(h_words.data() + f.ac_off[g]), h_bits[f.bits_off + d.num_dc_groups + g]});
+      std::vector<EncSection> dcg, acg;  // h_bits[sec] = first bit of the section, its end = end of its region
+      for (uint32_t g = 0; g < d.num_dc_groups; g++) {
+        const uint64_t sec = f.bits_off + g, end = h_off[sec + 1] * 32;
+        dcg.push_back({h_words.data(), h_bits[sec], end - h_bits[sec]});
+      }
+      for (uint32_t g = 0; g < d.num_groups; g++) {
+        const uint64_t sec = f.bits_off + d.num_dc_groups + g, end = h_off[sec + 1] * 32;
+        acg.push_back({h_words.data(), h_bits[sec], end - h_bits[sec]});
+      }
       enc->outputs.push_back(AssembleCodestream(p, f.L, f.G, dcg, acg));
     }
   } catch (const std::exception& e) {

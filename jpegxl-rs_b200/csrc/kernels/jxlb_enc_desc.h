@@ -55,6 +55,10 @@ struct DevEFrame {
   uint64_t ac_tokens;  // group g at ac_tokens + 3 * 65536 * g
   uint64_t mod_tokens; // DC group g at mod_tokens + mod_tokens_stride * g
   uint64_t mod_tokens_stride;
+  // batch bookkeeping
+  uint32_t tree_off;   // first node of this frame's tree in the tree pool
+  uint32_t sec_base;   // index of this frame's first section (DC groups, then AC groups) in the offset / length arrays
+  uint64_t code_off[6];  // uint16 table pool: Modular code freq, start, reverse; AC code freq, start, reverse
 };
 
 }  // namespace jxlb

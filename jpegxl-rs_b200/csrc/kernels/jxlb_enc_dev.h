@@ -300,8 +300,9 @@ JXLB_HD void DevEncTokenizeGroup(const DevEPools& E, const DevEFrame& ef, uint32
         uint32_t bucket = predicted >= 64 ? 64 : predicted;
         bucket = bucket < 8 ? bucket : 4 + bucket / 2;
         const uint32_t nz_ctx = bucket * num_ctxs + block_ctx;
-        tok[ntok++] = make_uint2(nz_ctx, nz);
-        DevCountToken(hist, E.ac_cluster_of[nz_ctx], nz);
+        const uint32_t nz_cluster = E.ac_cluster_of[nz_ctx];
+        tok[ntok++] = make_uint2(nz_cluster, nz);  // tokens carry the cluster of their context
+        DevCountToken(hist, nz_cluster, nz);
         const uint8_t v8 = static_cast<uint8_t>((nz + covered - 1) >> log2c);
         for (uint32_t i = 0; i < cx; i++) col[i] = v8;
         const uint32_t histo_offset = num_ctxs * 37 + 458 * block_ctx;
@@ -311,8 +312,9 @@ JXLB_HD void DevEncTokenizeGroup(const DevEPools& E, const DevEFrame& ef, uint32
           const uint32_t ctx = histo_offset + (nnz_ctx[nzl] + freq_ctx[k >> log2c]) * 2 + prev;
           const uint32_t p = order[k];
           const uint32_t u = DevPackSigned(coef[static_cast<size_t>(p / C) * PW + p % C]);
-          tok[ntok++] = make_uint2(ctx, u);
-          DevCountToken(hist, E.ac_cluster_of[ctx], u);
+          const uint32_t cluster = E.ac_cluster_of[ctx];
+          tok[ntok++] = make_uint2(cluster, u);
+          DevCountToken(hist, cluster, u);
           prev = u != 0;
           nz -= prev;
         }
@@ -374,12 +376,10 @@ JXLB_HD uint2 DevEncModularToken(const DevEPools& E, const DevEFrame& ef, const 
   return make_uint2(n.l, DevPackSigned(v - guess));
 }
 
-// ---- rANS writer. Tables of one code: freq / start [cluster][256], reverse [cluster][4096].
+// ---- rANS writer. Tables of one code: fs[cluster][256] = freq | first reverse slot << 16, reverse[cluster][4096].
 struct DevEncCode {
-  const uint16_t* freq;
-  const uint16_t* start;
+  const uint32_t* fs;
   const uint16_t* reverse;
-  const uint8_t* cluster_of;  // context -> cluster, or nullptr for identity
 };
 
 JXLB_HD void DevWriteBitsAt(uint32_t* words, uint64_t pos, uint32_t nbits, uint32_t value) {
@@ -389,42 +389,79 @@ JXLB_HD void DevWriteBitsAt(uint32_t* words, uint64_t pos, uint32_t nbits, uint3
   if (sh + nbits > 32) words[(pos >> 5) + 1] |= value >> (32 - sh);
 }
 
-// Writes the rANS stream of `n` tokens at bit position `bit_pos` of `words` (zero-initialised, owned by the calling
-// thread) and returns the position after it. Symbols are pushed in reverse order (the decoder pops them forwards);
-// the stream is laid out back to front, so a first pass only measures its length.
-JXLB_HD uint64_t DevRansEmit(const uint2* tok, uint32_t n, const DevEncCode& code, uint32_t* words, uint64_t bit_pos) {
-  uint64_t total = 32;
-  for (int pass = 0; pass < 2; pass++) {
-    uint32_t state = 0x13u << 16;
-    uint64_t cursor = bit_pos + total;
-    for (uint32_t i = n; i-- > 0;) {
-      const uint2 t = tok[i];
-      const uint32_t c = code.cluster_of ? code.cluster_of[t.x] : t.x;
-      uint32_t token, nbits, bits;
-      DevHybrid420(t.y, &token, &nbits, &bits);
-      if (nbits) {
-        if (pass == 0) {
-          total += nbits;
-        } else {
-          cursor -= nbits;
-          DevWriteBitsAt(words, cursor, nbits, bits);
-        }
-      }
-      const uint32_t f = code.freq[c * 256 + token];
-      if ((state >> 20) >= f) {
-        if (pass == 0) {
-          total += 16;
-        } else {
-          cursor -= 16;
-          DevWriteBitsAt(words, cursor, 16, state & 0xFFFF);
-        }
-        state >>= 16;
-      }
-      state = ((state / f) << 12) | code.reverse[c * 4096 + code.start[c * 256 + token] + state % f];
-    }
-    if (pass == 1) DevWriteBitsAt(words, bit_pos, 32, state);
+// Bits written back to front: `acc` holds the bits of [cursor, cursor + nacc); whole aligned words leave with a plain
+// store, only the two ends of the range are merged into words that hold other data.
+struct DevBackWriter {
+  uint32_t* words;
+  uint64_t cursor;
+  uint64_t acc;
+  uint32_t nacc;
+  JXLB_HD void Init(uint32_t* w, uint64_t end_pos) {
+    words = w;
+    cursor = end_pos;
+    acc = 0;
+    nacc = 0;
   }
-  return bit_pos + total;
+  JXLB_HD void Put(uint32_t nbits, uint32_t value) {  // nbits <= 32
+    acc = (acc << nbits) | value;
+    nacc += nbits;
+    cursor -= nbits;
+    uint64_t hi = cursor + nacc;
+    const uint32_t r = static_cast<uint32_t>(hi & 31);
+    if (r != 0 && nacc >= r) {  // (only until the top end reaches a word boundary)
+      words[hi >> 5] |= static_cast<uint32_t>(acc >> (nacc - r)) & ((1u << r) - 1);
+      nacc -= r;
+      acc &= (uint64_t{1} << nacc) - 1;
+      hi -= r;
+    }
+    if ((hi & 31) == 0 && nacc >= 32) {
+      words[(hi >> 5) - 1] = static_cast<uint32_t>(acc >> (nacc - 32));
+      nacc -= 32;
+      acc &= (uint64_t{1} << nacc) - 1;
+    }
+  }
+  JXLB_HD void Finish() {  // the remaining low bits share their word with whatever precedes the range
+    if (nacc == 0) return;
+    const uint64_t hi = cursor + nacc;
+    const uint32_t r = static_cast<uint32_t>(hi & 31);
+    if (r != 0 && nacc > r) {  // spans the boundary below an unaligned top: split
+      words[hi >> 5] |= static_cast<uint32_t>(acc >> (nacc - r)) & ((1u << r) - 1);
+      nacc -= r;
+      acc &= (uint64_t{1} << nacc) - 1;
+    }
+    words[cursor >> 5] |= static_cast<uint32_t>(acc) << (cursor & 31);
+    nacc = 0;
+  }
+};
+
+// Pushes the `n` tokens (cluster, value) onto the rANS stream in reverse order (the decoder pops them forwards),
+// writing back to front through `w`; ends with the 32-bit state. Everything that does not depend on the coder
+// state (the next token, its hybrid split, its frequency entry) is fetched one token ahead.
+JXLB_HD void DevRansPush(const uint2* tok, uint32_t n, const DevEncCode& code, DevBackWriter& w) {
+  uint32_t state = 0x13u << 16;
+  uint2 t = n ? tok[n - 1] : make_uint2(0, 0);
+  uint32_t token = 0, nbits = 0, bits = 0, fs = 0;
+  if (n) {
+    DevHybrid420(t.y, &token, &nbits, &bits);
+    fs = JXLB_LDG(code.fs + t.x * 256 + token);
+  }
+  for (uint32_t i = n; i-- > 0;) {
+    const uint32_t cluster = t.x, cur_nbits = nbits, cur_bits = bits, cur_fs = fs;
+    if (i > 0) {
+      t = tok[i - 1];
+      DevHybrid420(t.y, &token, &nbits, &bits);
+      fs = JXLB_LDG(code.fs + t.x * 256 + token);
+    }
+    if (cur_nbits) w.Put(cur_nbits, cur_bits);
+    const uint32_t f = cur_fs & 0xFFFF;
+    if ((state >> 20) >= f) {
+      w.Put(16, state & 0xFFFF);
+      state >>= 16;
+    }
+    const uint32_t q = state / f, r = state - q * f;
+    state = (q << 12) | JXLB_LDG(code.reverse + cluster * 4096 + (cur_fs >> 16) + r);
+  }
+  w.Put(32, state);
 }
 
 // Token slots of DC group g's Modular streams: [DC Y | DC X | DC B | ytox | ytob | strategy row, quant row | sharpness].
@@ -495,24 +532,33 @@ JXLB_HD void DevEncModularSample(const DevEPools& E, const DevEFrame& ef, uint32
   DevCountToken(reinterpret_cast<uint32_t*>(E.iarena + ef.mod_hist), t.x, t.y);
 }
 
-// The DC group section: extra_precision, DC stream, varblock count, AC-metadata stream. Returns its length in bits.
-JXLB_HD uint64_t DevEncEmitDcGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g, const DevEncCode& code, uint32_t* words) {
+// The DC group section -- extra_precision, DC stream, varblock count, AC-metadata stream -- written back to front
+// so that it ends at bit `end_pos` of `words`. Returns the position of its first bit.
+JXLB_HD uint64_t DevEncEmitDcGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g, const DevEncCode& code, uint32_t* words,
+                                   uint64_t end_pos) {
   const DevDcGroupLayout L = DevDcGroupGeometry(E, ef, g);
   const uint2* tok = E.tokens + ef.mod_tokens + ef.mod_tokens_stride * g;
-  uint64_t pos = 0;
-  DevWriteBitsAt(words, pos, 2, 0);  // extra_precision
-  pos += 2;
-  DevWriteBitsAt(words, pos, 4, 0x3);  // use_global_tree = 1, default WP header = 1, no transforms
-  pos += 4;
-  pos = DevRansEmit(tok, L.dc_tokens, code, words, pos);
+  DevBackWriter w;
+  w.Init(words, end_pos);
+  DevRansPush(tok + L.dc_tokens, L.meta_tokens, code, w);
+  w.Put(4, 0x3);  // use_global_tree = 1, default WP header = 1, no transforms
   uint32_t count_bits = 0;
   while ((1u << count_bits) < L.xs * L.ys) count_bits++;
-  DevWriteBitsAt(words, pos, count_bits, L.count - 1);
-  pos += count_bits;
-  DevWriteBitsAt(words, pos, 4, 0x3);
-  pos += 4;
-  pos = DevRansEmit(tok + L.dc_tokens, L.meta_tokens, code, words, pos);
-  return pos;
+  if (count_bits) w.Put(count_bits, L.count - 1);
+  DevRansPush(tok, L.dc_tokens, code, w);
+  w.Put(4, 0x3);
+  w.Put(2, 0);  // extra_precision
+  w.Finish();
+  return w.cursor;
+}
+
+// An AC group section ending at bit `end_pos`; returns the position of its first bit.
+JXLB_HD uint64_t DevEncEmitAcGroup(const uint2* tok, uint32_t n, const DevEncCode& code, uint32_t* words, uint64_t end_pos) {
+  DevBackWriter w;
+  w.Init(words, end_pos);
+  DevRansPush(tok, n, code, w);
+  w.Finish();
+  return w.cursor;
 }
 
 }  // namespace jxlb

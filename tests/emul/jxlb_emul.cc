@@ -303,21 +303,26 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
     EncGlobals G;
     BuildEncGlobals(p, L, tree, ac_cluster_of, global_scale, quant_dc, reinterpret_cast<uint32_t*>(iarena.data() + ef.mod_hist),
                     reinterpret_cast<uint32_t*>(iarena.data() + ef.ac_hist), &G);
-    DevEncCode mod{G.mod_code.freq.data(), G.mod_code.start.data(), G.mod_code.reverse.data(), nullptr};
-    DevEncCode ac{G.ac_code.freq.data(), G.ac_code.start.data(), G.ac_code.reverse.data(), ac_cluster_of.data()};
+    const std::vector<uint32_t> mod_fs = G.mod_code.Fs(), ac_fs = G.ac_code.Fs();
+    DevEncCode mod{mod_fs.data(), G.mod_code.reverse.data()};
+    DevEncCode ac{ac_fs.data(), G.ac_code.reverse.data()};
     std::vector<std::vector<uint32_t>> dc_words(d.num_dc_groups), ac_words(d.num_groups);
-    std::vector<std::pair<const uint8_t*, uint64_t>> dcg, acg;
+    std::vector<EncSection> dcg, acg;
     for (uint32_t g = 0; g < d.num_dc_groups; g++) {
       const DevDcGroupLayout gl = DevDcGroupGeometry(E, ef, g);
-      dc_words[g].assign((static_cast<size_t>(gl.dc_tokens + gl.meta_tokens) * 6 + 64) / 4 + 4, 0);
-      const uint64_t bits = DevEncEmitDcGroup(E, ef, g, mod, dc_words[g].data());
-      dcg.push_back({reinterpret_cast<const uint8_t*>(dc_words[g].data()), bits});
+      const size_t cap = (static_cast<size_t>(gl.dc_tokens + gl.meta_tokens) * 6 + 64) / 4 + 4;
+      dc_words[g].assign(cap, 0);
+      const uint64_t end = (cap - 1) * 32 - 5;  // an unaligned end, like a shared region could have
+      const uint64_t first = DevEncEmitDcGroup(E, ef, g, mod, dc_words[g].data(), end);
+      dcg.push_back({dc_words[g].data(), first, end - first});
     }
     for (uint32_t g = 0; g < d.num_groups; g++) {
       const uint32_t n = static_cast<uint32_t>(iarena[ef.group_tokens + g]);
-      ac_words[g].assign((static_cast<size_t>(n) * 6 + 64) / 4 + 4, 0);
-      const uint64_t bits = DevRansEmit(tokens.data() + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, ac, ac_words[g].data(), 0);
-      acg.push_back({reinterpret_cast<const uint8_t*>(ac_words[g].data()), bits});
+      const size_t cap = (static_cast<size_t>(n) * 6 + 64) / 4 + 4;
+      ac_words[g].assign(cap, 0);
+      const uint64_t end = cap * 32;
+      const uint64_t first = DevEncEmitAcGroup(tokens.data() + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, ac, ac_words[g].data(), end);
+      acg.push_back({ac_words[g].data(), first, end - first});
     }
     const std::vector<uint8_t> cs = AssembleCodestream(p, L, G, dcg, acg);
     if (cs.size() > out_cap) throw Error("output buffer too small");

@@ -30,6 +30,10 @@ def main():
                    "bytes": len(data), "bpp": round(8 * len(data) / (3840 * 2160), 4),
                    "psnr_vs_source": round(float(10 * __import__("numpy").log10(255 ** 2 / (err ** 2).mean())), 2),
                    "encoder": "oracle/jxlo_encode.h " + json.dumps(kw, sort_keys=True)}
+        # what the encoder bench feeds back in: the decoded frame, encoded again (gradient DC tree, as the GPU encoder)
+        again = jxlo.encode_vardct(px, distance=1.0, strategy_mode=2, dc_tree=1)
+        g[name]["reencoded_sha256"] = hashlib.sha256(again).hexdigest()
+        g[name]["reencoded_bytes"] = len(again)
         print(name, g[name])
     json.dump(g, open(gpath, "w"), indent=1, sort_keys=True)
 

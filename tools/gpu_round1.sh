@@ -1,6 +1,5 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline > gpurun_out/bench_v6_b64_if1.json 2> gpurun_out/bench_v6.err; python tools/show_bench.py gpurun_out/bench_v6_b64_if1.json; tail -3 gpurun_out/bench_v6.err
-python bench.py --steps 8 --warmup 3 --inflight 2 --no-cpu-baseline > gpurun_out/bench_v6_b64_if2.json 2> gpurun_out/bench_v6.err; python tools/show_bench.py gpurun_out/bench_v6_b64_if2.json; tail -3 gpurun_out/bench_v6.err
-python bench.py --steps 9 --warmup 3 --inflight 3 --no-cpu-baseline > gpurun_out/bench_v6_b64_if3.json 2> gpurun_out/bench_v6.err; python tools/show_bench.py gpurun_out/bench_v6_b64_if3.json; tail -3 gpurun_out/bench_v6.err
-python bench.py --steps 6 --warmup 2 --inflight 2 --batch 256 --no-cpu-baseline > gpurun_out/bench_v6_b256_if2.json 2> gpurun_out/bench_v6.err; python tools/show_bench.py gpurun_out/bench_v6_b256_if2.json; tail -3 gpurun_out/bench_v6.err
+python -m pytest tests/test_encoder.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --workload encode4k --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/bench_enc_v2.json 2> gpurun_out/bench_enc.err; python tools/show_bench.py gpurun_out/bench_enc_v2.json; tail -5 gpurun_out/bench_enc.err
+python bench.py --workload encode4k --batch 32 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_enc_v2_b32.json 2> gpurun_out/bench_enc.err; python tools/show_bench.py gpurun_out/bench_enc_v2_b32.json; tail -5 gpurun_out/bench_enc.err
+ncu --metrics gpu__time_duration.sum --clock-control none -s 9 -c 9 --csv --log-file gpurun_out/launches_enc.csv python bench.py --workload encode4k --batch 8 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_enc.log 2>&1; tail -2 gpurun_out/ncu_enc.log
