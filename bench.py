@@ -6,10 +6,11 @@
 
 A "step" = one pass of the hot path over one batch of synthetic input. Workloads:
 
-  vardct4k (default)  BATCH lossy 3840x2160 VarDCT frames per GPU (BASELINE.json configs[1]; 64 per GPU is
-                      configs[3]'s 512 frames on 8 GPUs), alternating two committed fixtures
+  vardct4k (default)  BATCH (256) lossy 3840x2160 VarDCT frames per GPU (BASELINE.json configs[1]; configs[3]'s 512
+                      frames are two GPUs' worth), alternating two committed fixtures
                       (tests/golden/vardct_4k_{natural,synthetic}.jxl, written by tests/golden/make_vardct_fixtures.py),
                       decoded to RGB8.
+  encode4k            BATCH (8) RGB8 3840x2160 frames per GPU encoded to lossy VarDCT at distance 1.0 (configs[2]).
   modular             BATCH bench.jxl-shaped frames (2122x1433 lossless Modular RGBA8, 54 groups each): the input of
                       the reference's own criterion bench (jpegxl-rs/benches/decode.rs:10-40).
 
@@ -40,7 +41,7 @@ class Workload:
         self.name = name
         if name == "vardct4k":
             names = ["vardct_4k_natural.jxl", "vardct_4k_synthetic.jxl"]
-            self.batch = batch or 64
+            self.batch = batch or 256
             self.channels = 3
             self.metric = "Mpixels/s decode (lossy VarDCT 3840x2160 -> RGB8)"
             self.dtype = "f32"
@@ -305,7 +306,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="vardct4k", choices=["vardct4k", "modular", "encode4k"])
-    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 64 vardct4k, 256 modular)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 256 vardct4k, 256 modular, 8 encode4k)")
     ap.add_argument("--inflight", type=int, default=2,
                     help="decoder handles in flight, each with its own buffers and CUDA stream: the latency-bound "
                          "entropy kernels of one batch overlap the per-pixel kernels of the previous one")
