@@ -560,6 +560,12 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
   }
   ef->first_index = i; i += nb;
   ef->block_of_num = i; i += d.num_dc_groups * 65536;
+  for (int c = 0; c < 3; c++) {
+    ef->blk_nz[c] = i; i += nb;
+    ef->blk_ntok[c] = i; i += nb;
+    ef->blk_bucket[c] = i; i += nb;
+  }
+  // (the host reads everything from here to the end of the frame's region back after the tokenisation kernels)
   ef->dcg_count = i; i += d.num_dc_groups;
   ef->group_tokens = i; i += d.num_groups;
   ef->ac_hist = i; i += static_cast<uint64_t>(num_ac_clusters) * 256;

@@ -1175,13 +1175,27 @@ __global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, const D
   }
 }
 
-__global__ void __launch_bounds__(32) k_enc_tokenize(DevEPools E, const DevEFrame* frames) {
-  __shared__ uint16_t ctxtab_s[128];
-  for (uint32_t i = threadIdx.x; i < 128; i += 32) ctxtab_s[i] = static_cast<uint16_t>(E.upool[E.ctxtab_off + i]);
-  __syncwarp();
+// Tokenisation, data-parallel: thread per (block, channel) for the statistics and for the tokens, thread per group
+// for the offsets in between. blockIdx.y = channel, blockIdx.z = frame.
+__global__ void __launch_bounds__(128) k_enc_block_stats(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.z];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ef.xblocks * ef.yblocks) DevEncBlockStats(E, ef, i % ef.xblocks, i / ef.xblocks, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(32) k_enc_token_offsets(DevEPools E, const DevEFrame* frames) {
   const DevEFrame& ef = frames[blockIdx.y];
   const uint32_t g = blockIdx.x * 32 + threadIdx.x;
-  if (g < ef.xgroups * ef.ygroups) DevEncTokenizeGroup(E, ef, g, ctxtab_s, ctxtab_s + 64);
+  if (g < ef.xgroups * ef.ygroups) DevEncTokenOffsets(E, ef, g);
+}
+
+__global__ void __launch_bounds__(128) k_enc_block_tokens(DevEPools E, const DevEFrame* frames) {
+  __shared__ uint16_t ctxtab_s[128];
+  for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) ctxtab_s[i] = static_cast<uint16_t>(E.upool[E.ctxtab_off + i]);
+  __syncthreads();
+  const DevEFrame& ef = frames[blockIdx.z];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ef.xblocks * ef.yblocks) DevEncBlockTokens(E, ef, i % ef.xblocks, i / ef.xblocks, blockIdx.y, ctxtab_s, ctxtab_s + 64);
 }
 
 // blockIdx.y = DC group, blockIdx.z = frame; one thread per sample of the DC + AC-metadata streams
@@ -1197,26 +1211,26 @@ __global__ void __launch_bounds__(256) k_enc_modular(DevEPools E, const DevEFram
 }
 
 // rANS emission: one thread per section, written back to front so that it ends at the end of its region
-// (`off[sec]` .. `off[sec + 1]`, in words); `first[sec]` receives the bit position of its first bit.
-__global__ void __launch_bounds__(32) k_enc_emit_ac(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
-                                                    const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first) {
+// (`off[sec]` .. `off[sec + 1]`, in words); `first[sec]` receives the bit position of its first bit. blockIdx.x
+// below `dc_blocks` handles DC-group sections (the long ones, scheduled first), the rest AC-group sections.
+__global__ void __launch_bounds__(32) k_enc_emit(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
+                                                 const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first,
+                                                 uint32_t dc_blocks) {
   const DevEFrame& ef = frames[blockIdx.y];
-  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x < dc_blocks) {
+    const uint32_t g = blockIdx.x * 32 + threadIdx.x;
+    if (g >= ef.xdcgroups * ef.ydcgroups) return;
+    const DevEncCode code{fs_tables + ef.code_off[0], rev_tables + ef.code_off[1]};
+    const uint32_t sec = ef.sec_base + g;
+    first[sec] = DevEncEmitDcGroup(E, ef, g, code, words, off[sec + 1] * 32);
+    return;
+  }
+  const uint32_t g = (blockIdx.x - dc_blocks) * 32 + threadIdx.x;
   if (g >= ef.xgroups * ef.ygroups) return;
   const DevEncCode code{fs_tables + ef.code_off[2], rev_tables + ef.code_off[3]};
   const uint32_t n = static_cast<uint32_t>(E.iarena[ef.group_tokens + g]);
   const uint32_t sec = ef.sec_base + ef.xdcgroups * ef.ydcgroups + g;
   first[sec] = DevEncEmitAcGroup(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words, off[sec + 1] * 32);
-}
-
-__global__ void __launch_bounds__(32) k_enc_emit_dc(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
-                                                    const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first) {
-  const DevEFrame& ef = frames[blockIdx.y];
-  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
-  if (g >= ef.xdcgroups * ef.ydcgroups) return;
-  const DevEncCode code{fs_tables + ef.code_off[0], rev_tables + ef.code_off[1]};
-  const uint32_t sec = ef.sec_base + g;
-  first[sec] = DevEncEmitDcGroup(E, ef, g, code, words, off[sec + 1] * 32);
 }
 
 }  // namespace jxlb
@@ -1314,6 +1328,9 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
         e.xyb[c] += fbase;
         e.coef[c] += ibase;
         e.dcq[c] += ibase;
+        e.blk_nz[c] += ibase;
+        e.blk_ntok[c] += ibase;
+        e.blk_bucket[c] += ibase;
       }
       e.first_index += ibase;
       e.block_of_num += ibase;
@@ -1398,28 +1415,56 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     k_enc_number<<<dim3((max_dcg + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_dc<<<dim3((maxW * maxH + 255) / 256, nf), 256, 0, s>>>(E, d_efs.p);
     k_enc_coeffs<<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
-    k_enc_tokenize<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
+    k_enc_block_stats<<<dim3((maxW * maxH + 127) / 128, 3, nf), 128, 0, s>>>(E, d_efs.p);
+    k_enc_token_offsets<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
+    k_enc_block_tokens<<<dim3((maxW * maxH + 127) / 128, 3, nf), 128, 0, s>>>(E, d_efs.p);
     k_enc_modular<<<dim3(256, max_dcg, nf), 256, 0, s>>>(E, d_efs.p);
     CUDA_OK(cudaEventRecord(ev[1], s));
     // ---- host: histograms -> codes, global sections, section layout
-    std::vector<int32_t> h_small;
     uint64_t words_total = 0, nsec = 0;
     std::vector<uint16_t> h_rev;
     std::vector<uint32_t> h_fs;
     struct CodeOff { uint64_t mod_fs, mod_r, ac_fs, ac_r; };
     std::vector<CodeOff> code_off(n);
+    std::vector<std::vector<int32_t>> h_small(n);
+    for (size_t i = 0; i < n; i++) {  // counts + histograms of every frame: one copy each, one synchronisation
+      const Frame& f = fr[i];
+      const uint64_t first = f.ef.dcg_count, count = f.ef.mod_hist + static_cast<uint64_t>(f.L.num_leaves) * 256 - first;
+      h_small[i].resize(count);
+      CUDA_OK(cudaMemcpyAsync(h_small[i].data(), d_iarena.p + first, count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_OK(cudaStreamSynchronize(s));
+    {  // histogram normalisation, header coding and table building per frame, on host threads
+      std::atomic<size_t> next{0};
+      std::vector<std::string> errors(n);
+      auto work = [&]() {
+        for (;;) {
+          const size_t i = next.fetch_add(1);
+          if (i >= n) break;
+          try {
+            Frame& f = fr[i];
+            const uint64_t first = f.ef.dcg_count;
+            const uint32_t* ac_hist = reinterpret_cast<const uint32_t*>(h_small[i].data() + (f.ef.ac_hist - first));
+            const uint32_t* mod_hist = reinterpret_cast<const uint32_t*>(h_small[i].data() + (f.ef.mod_hist - first));
+            BuildEncGlobals(p, f.L, f.tree, ac_cluster_of, f.global_scale, f.quant_dc, mod_hist, ac_hist, &f.G);
+          } catch (const std::exception& e) {
+            errors[i] = e.what();
+          }
+        }
+      };
+      const size_t nthreads = std::max<size_t>(1, std::min<size_t>(n, std::min<unsigned>(16, std::thread::hardware_concurrency())));
+      std::vector<std::thread> pool;
+      for (size_t t = 0; t < nthreads; t++) pool.emplace_back(work);
+      for (auto& t : pool) t.join();
+      for (const std::string& e : errors)
+        if (!e.empty()) throw Error(e);
+    }
     for (size_t i = 0; i < n; i++) {
       Frame& f = fr[i];
       const FrameDimensions& d = f.L.dim;
-      const uint64_t first = f.ef.dcg_count, count = f.ef.mod_hist + static_cast<uint64_t>(f.L.num_leaves) * 256 - first;
-      h_small.resize(count);
-      CUDA_OK(cudaMemcpyAsync(h_small.data(), d_iarena.p + first, count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      CUDA_OK(cudaStreamSynchronize(s));
-      const int32_t* dcg_count = h_small.data();
-      const int32_t* group_tokens = h_small.data() + (f.ef.group_tokens - first);
-      const uint32_t* ac_hist = reinterpret_cast<const uint32_t*>(h_small.data() + (f.ef.ac_hist - first));
-      const uint32_t* mod_hist = reinterpret_cast<const uint32_t*>(h_small.data() + (f.ef.mod_hist - first));
-      BuildEncGlobals(p, f.L, f.tree, ac_cluster_of, f.global_scale, f.quant_dc, mod_hist, ac_hist, &f.G);
+      const uint64_t first = f.ef.dcg_count;
+      const int32_t* dcg_count = h_small[i].data();
+      const int32_t* group_tokens = h_small[i].data() + (f.ef.group_tokens - first);
       f.bits_off = nsec;
       for (uint32_t g = 0; g < d.num_dc_groups; g++) {
         const uint32_t gx = g % d.xsize_dc_groups, gy = g / d.xsize_dc_groups;
@@ -1470,8 +1515,9 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       efs[i].sec_base = static_cast<uint32_t>(fr[i].bits_off);
     }
     CUDA_OK(d_efs.Upload(efs, s));
-    k_enc_emit_dc<<<dim3((max_dcg + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p);
-    k_enc_emit_ac<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p);
+    const uint32_t dc_blocks = (max_dcg + 31) / 32;
+    k_enc_emit<<<dim3(dc_blocks + (max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p,
+                                                                            dc_blocks);
     CUDA_OK(cudaEventRecord(ev[3], s));
     std::vector<uint64_t> h_bits(nsec);
     std::vector<uint32_t> h_words(words_total + 16);
@@ -1487,20 +1533,32 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     cudaEventElapsedTime(&ms, ev[2], ev[3]);
     enc->phase_ms[2] = ms;
     for (auto& e : ev) cudaEventDestroy(e);
-    // ---- assemble
-    for (size_t i = 0; i < n; i++) {
-      const Frame& f = fr[i];
-      const FrameDimensions& d = f.L.dim;
-      std::vector<EncSection> dcg, acg;  // h_bits[sec] = first bit of the section, its end = end of its region
-      for (uint32_t g = 0; g < d.num_dc_groups; g++) {
-        const uint64_t sec = f.bits_off + g, end = h_off[sec + 1] * 32;
-        dcg.push_back({h_words.data(), h_bits[sec], end - h_bits[sec]});
-      }
-      for (uint32_t g = 0; g < d.num_groups; g++) {
-        const uint64_t sec = f.bits_off + d.num_dc_groups + g, end = h_off[sec + 1] * 32;
-        acg.push_back({h_words.data(), h_bits[sec], end - h_bits[sec]});
-      }
-      enc->outputs.push_back(AssembleCodestream(p, f.L, f.G, dcg, acg));
+    // ---- assemble (host threads)
+    enc->outputs.assign(n, std::vector<uint8_t>());
+    {
+      std::atomic<size_t> next{0};
+      auto work = [&]() {
+        for (;;) {
+          const size_t i = next.fetch_add(1);
+          if (i >= n) break;
+          const Frame& f = fr[i];
+          const FrameDimensions& d = f.L.dim;
+          std::vector<EncSection> dcg, acg;  // h_bits[sec] = first bit of the section, its end = end of its region
+          for (uint32_t g = 0; g < d.num_dc_groups; g++) {
+            const uint64_t sec = f.bits_off + g, end = h_off[sec + 1] * 32;
+            dcg.push_back({h_words.data(), h_bits[sec], end - h_bits[sec]});
+          }
+          for (uint32_t g = 0; g < d.num_groups; g++) {
+            const uint64_t sec = f.bits_off + d.num_dc_groups + g, end = h_off[sec + 1] * 32;
+            acg.push_back({h_words.data(), h_bits[sec], end - h_bits[sec]});
+          }
+          enc->outputs[i] = AssembleCodestream(p, f.L, f.G, dcg, acg);
+        }
+      };
+      const size_t nthreads = std::max<size_t>(1, std::min<size_t>(n, std::min<unsigned>(16, std::thread::hardware_concurrency())));
+      std::vector<std::thread> pool;
+      for (size_t t = 0; t < nthreads; t++) pool.emplace_back(work);
+      for (auto& t : pool) t.join();
     }
   } catch (const std::exception& e) {
     enc->error = e.what();

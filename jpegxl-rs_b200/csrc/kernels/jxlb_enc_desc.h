@@ -47,6 +47,7 @@ struct DevEFrame {
   uint64_t block_of_num; // per DC group region: list position -> block position (y * xblocks + x)
   uint64_t dcg_count;    // per DC group: number of varblocks
   uint64_t group_tokens; // per AC group: number of tokens written
+  uint64_t blk_nz[3], blk_ntok[3], blk_bucket[3];  // per block and channel: see DevEncBlockStats
   uint64_t ac_hist;      // [num_ac_clusters][256]
   uint64_t mod_hist;     // [num_leaves][256]
   // byte arena

@@ -254,74 +254,106 @@ JXLB_HD void DevCountToken(uint32_t* hist, uint32_t cluster, uint32_t value) {
 #endif
 }
 
-// Tokens of AC group g (one thread: the contexts chain through the non-zero counts).
-JXLB_HD void DevEncTokenizeGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g, const uint16_t* freq_ctx,
-                                 const uint16_t* nnz_ctx) {
-  const uint8_t kBlockCtx[39] = {0, 1, 2, 2, 3, 3, 4, 5, 6, 6, 6, 6, 6, 7, 8, 9, 9, 10, 11, 12,
-                                 13, 14, 14, 14, 14, 14, 7, 8, 9, 9, 10, 11, 12, 13, 14, 14, 14, 14, 14};
-  const uint32_t W = ef.xblocks, H = ef.yblocks, PW = W * 8;
+// ---- AC tokenisation in three data-parallel steps. The context of a coefficient depends on the number of
+// non-zeros still to come and on whether the previous coefficient (in scan order) was zero: both follow from a
+// scan of the block alone, so every (varblock, channel) is tokenised independently once the token offsets are known.
+//   1. DevEncBlockStats     per (varblock, channel): non-zero count, token count, non-zero bucket of its cells
+//   2. DevEncTokenOffsets   per group: prefix sum of the token counts in stream order (raster varblocks, Y X B)
+//   3. DevEncBlockTokens    per (varblock, channel): the tokens at their final slots + histogram counts
+// iarena planes used (xblocks * yblocks each, per channel c): blk_nz[c] (non-zero count, first blocks),
+// blk_ntok[c] (token count, then token offset), blk_bucket[c] (per cell: non-zero bucket of the covering varblock).
+JXLB_HD void DevEncBlockStats(const DevEPools& E, const DevEFrame& ef, uint32_t bx, uint32_t by, uint32_t c) {
+  const uint32_t W = ef.xblocks, PW = W * 8;
+  const size_t pos = static_cast<size_t>(by) * W + bx;
+  const uint8_t a = E.barena[ef.acs + pos];
+  if (!(a & 1)) return;
+  const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
+  const uint32_t log2c = si.log2_covered, covered = 1u << log2c, size = covered * 64, C = si.cx * 8u;
+  const uint16_t* order = E.opool + E.order_off[si.order];
+  const int32_t* coef = E.iarena + ef.coef[c] + static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+  uint32_t nz = 0, last = 0;
+  for (uint32_t k = covered; k < size; k++) {
+    const uint32_t p = JXLB_LDG(order + k);
+    if (coef[static_cast<size_t>(p / C) * PW + p % C] != 0) {
+      nz++;
+      last = k;
+    }
+  }
+  E.iarena[ef.blk_nz[c] + pos] = static_cast<int32_t>(nz);
+  E.iarena[ef.blk_ntok[c] + pos] = static_cast<int32_t>(nz == 0 ? 1 : 2 + last - covered);
+  const int32_t bucket = static_cast<int32_t>((nz + covered - 1) >> log2c);
+  for (uint32_t y = 0; y < si.cy; y++)
+    for (uint32_t x = 0; x < si.cx; x++) E.iarena[ef.blk_bucket[c] + pos + static_cast<size_t>(y) * W + x] = bucket;
+}
+
+// blk_ntok: counts -> offsets inside the group's token region; group_tokens[g] = total.
+JXLB_HD void DevEncTokenOffsets(const DevEPools& E, const DevEFrame& ef, uint32_t g) {
+  const uint32_t W = ef.xblocks, H = ef.yblocks;
   const uint32_t x0 = (g % ef.xgroups) * 32, y0 = (g / ef.xgroups) * 32;
   const uint32_t xs = W - x0 < 32 ? W - x0 : 32, ys = H - y0 < 32 ? H - y0 : 32;
   const uint8_t* acs = E.barena + ef.acs;
-  uint2* tok = E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536;
-  uint32_t* hist = reinterpret_cast<uint32_t*>(E.iarena + ef.ac_hist);
-  uint32_t ntok = 0;
-  uint8_t colnz[3 * 32];
-  for (int i = 0; i < 96; i++) colnz[i] = 0;
-  const uint32_t num_ctxs = 15;
-  for (uint32_t by = 0; by < ys; by++) {
+  uint32_t acc = 0;
+  for (uint32_t by = 0; by < ys; by++)
     for (uint32_t bx = 0; bx < xs; bx++) {
       const size_t pos = static_cast<size_t>(y0 + by) * W + x0 + bx;
-      const uint8_t a = acs[pos];
-      if (!(a & 1)) continue;
-      const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
-      const uint32_t cx = si.cx, log2c = si.log2_covered, covered = 1u << log2c, size = covered * 64, ord = si.order;
-      const uint32_t C = cx * 8;
-      const uint16_t* order = E.opool + E.order_off[ord];
-      const size_t origin = static_cast<size_t>(y0 + by) * 8 * PW + static_cast<size_t>(x0 + bx) * 8;
+      if (!(acs[pos] & 1)) continue;
       for (uint32_t ci = 0; ci < 3; ci++) {
         const uint32_t c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);
-        const int32_t* coef = E.iarena + ef.coef[c] + origin;
-        uint32_t predicted;
-        uint8_t* col = colnz + c * 32 + bx;
-        if (bx == 0) {
-          predicted = by == 0 ? 32 : col[0];
-        } else if (by == 0) {
-          predicted = col[-1];
-        } else {
-          predicted = (static_cast<uint32_t>(col[0]) + col[-1] + 1) / 2;
-        }
-        const uint32_t block_ctx = kBlockCtx[(c < 2 ? c ^ 1 : 2) * kNumOrders + ord];
-        uint32_t nz = 0;
-        for (uint32_t k = covered; k < size; k++) {
-          const uint32_t p = order[k];
-          nz += coef[static_cast<size_t>(p / C) * PW + p % C] != 0;
-        }
-        uint32_t bucket = predicted >= 64 ? 64 : predicted;
-        bucket = bucket < 8 ? bucket : 4 + bucket / 2;
-        const uint32_t nz_ctx = bucket * num_ctxs + block_ctx;
-        const uint32_t nz_cluster = E.ac_cluster_of[nz_ctx];
-        tok[ntok++] = make_uint2(nz_cluster, nz);  // tokens carry the cluster of their context
-        DevCountToken(hist, nz_cluster, nz);
-        const uint8_t v8 = static_cast<uint8_t>((nz + covered - 1) >> log2c);
-        for (uint32_t i = 0; i < cx; i++) col[i] = v8;
-        const uint32_t histo_offset = num_ctxs * 37 + 458 * block_ctx;
-        uint32_t prev = nz > size / 16 ? 0 : 1;
-        for (uint32_t k = covered; k < size && nz != 0; k++) {
-          const uint32_t nzl = (nz + covered - 1) >> log2c;
-          const uint32_t ctx = histo_offset + (nnz_ctx[nzl] + freq_ctx[k >> log2c]) * 2 + prev;
-          const uint32_t p = order[k];
-          const uint32_t u = DevPackSigned(coef[static_cast<size_t>(p / C) * PW + p % C]);
-          const uint32_t cluster = E.ac_cluster_of[ctx];
-          tok[ntok++] = make_uint2(cluster, u);
-          DevCountToken(hist, cluster, u);
-          prev = u != 0;
-          nz -= prev;
-        }
+        const uint32_t n = static_cast<uint32_t>(E.iarena[ef.blk_ntok[c] + pos]);
+        E.iarena[ef.blk_ntok[c] + pos] = static_cast<int32_t>(acc);
+        acc += n;
       }
     }
+  E.iarena[ef.group_tokens + g] = static_cast<int32_t>(acc);
+}
+
+JXLB_HD void DevEncBlockTokens(const DevEPools& E, const DevEFrame& ef, uint32_t bx, uint32_t by, uint32_t c,
+                               const uint16_t* freq_ctx, const uint16_t* nnz_ctx) {
+  const uint8_t kBlockCtx[39] = {0, 1, 2, 2, 3, 3, 4, 5, 6, 6, 6, 6, 6, 7, 8, 9, 9, 10, 11, 12,
+                                 13, 14, 14, 14, 14, 14, 7, 8, 9, 9, 10, 11, 12, 13, 14, 14, 14, 14, 14};
+  const uint32_t W = ef.xblocks, PW = W * 8;
+  const size_t pos = static_cast<size_t>(by) * W + bx;
+  const uint8_t a = E.barena[ef.acs + pos];
+  if (!(a & 1)) return;
+  const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
+  const uint32_t log2c = si.log2_covered, covered = 1u << log2c, size = covered * 64, C = si.cx * 8u, ord = si.order;
+  const uint16_t* order = E.opool + E.order_off[ord];
+  const int32_t* coef = E.iarena + ef.coef[c] + static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+  const uint32_t g = (by / 32) * ef.xgroups + bx / 32;
+  uint2* tok = E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536 + static_cast<uint32_t>(E.iarena[ef.blk_ntok[c] + pos]);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(E.iarena + ef.ac_hist);
+  const uint32_t num_ctxs = 15;
+  const uint32_t gbx = bx % 32, gby = by % 32;  // position inside the group: prediction does not cross groups
+  const int32_t* bucket_plane = E.iarena + ef.blk_bucket[c] + pos;
+  uint32_t predicted;
+  if (gbx == 0) {
+    predicted = gby == 0 ? 32 : static_cast<uint32_t>(bucket_plane[-static_cast<ptrdiff_t>(W)]);
+  } else if (gby == 0) {
+    predicted = static_cast<uint32_t>(bucket_plane[-1]);
+  } else {
+    predicted = (static_cast<uint32_t>(bucket_plane[-static_cast<ptrdiff_t>(W)]) + static_cast<uint32_t>(bucket_plane[-1]) + 1) / 2;
   }
-  E.iarena[ef.group_tokens + g] = static_cast<int32_t>(ntok);
+  const uint32_t block_ctx = kBlockCtx[(c < 2 ? c ^ 1 : 2) * kNumOrders + ord];
+  uint32_t nz = static_cast<uint32_t>(E.iarena[ef.blk_nz[c] + pos]);
+  uint32_t bucket = predicted >= 64 ? 64 : predicted;
+  bucket = bucket < 8 ? bucket : 4 + bucket / 2;
+  const uint32_t nz_cluster = E.ac_cluster_of[bucket * num_ctxs + block_ctx];
+  uint32_t ntok = 0;
+  tok[ntok++] = make_uint2(nz_cluster, nz);  // tokens carry the cluster of their context
+  DevCountToken(hist, nz_cluster, nz);
+  const uint32_t histo_offset = num_ctxs * 37 + 458 * block_ctx;
+  uint32_t prev = nz > size / 16 ? 0 : 1;
+  for (uint32_t k = covered; k < size && nz != 0; k++) {
+    const uint32_t nzl = (nz + covered - 1) >> log2c;
+    const uint32_t ctx = histo_offset + (nnz_ctx[nzl] + freq_ctx[k >> log2c]) * 2 + prev;
+    const uint32_t p = JXLB_LDG(order + k);
+    const uint32_t u = DevPackSigned(coef[static_cast<size_t>(p / C) * PW + p % C]);
+    const uint32_t cluster = E.ac_cluster_of[ctx];
+    tok[ntok++] = make_uint2(cluster, u);
+    DevCountToken(hist, cluster, u);
+    prev = u != 0;
+    nz -= prev;
+  }
 }
 
 // ---- Modular sub-streams (DC, AC metadata) under the fixed global tree: every sample's context and prediction

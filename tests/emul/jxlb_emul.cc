@@ -295,7 +295,13 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
       }
     uint16_t ctxtab[128];
     for (int i = 0; i < 128; i++) ctxtab[i] = static_cast<uint16_t>(sh.upool[sh.ctxtab_off + i]);
-    for (uint32_t g = 0; g < d.num_groups; g++) DevEncTokenizeGroup(E, ef, g, ctxtab, ctxtab + 64);
+    for (uint32_t c = 0; c < 3; c++)
+      for (uint32_t by = 0; by < H; by++)
+        for (uint32_t bx = 0; bx < W; bx++) DevEncBlockStats(E, ef, bx, by, c);
+    for (uint32_t g = 0; g < d.num_groups; g++) DevEncTokenOffsets(E, ef, g);
+    for (uint32_t c = 0; c < 3; c++)
+      for (uint32_t by = 0; by < H; by++)
+        for (uint32_t bx = 0; bx < W; bx++) DevEncBlockTokens(E, ef, bx, by, c, ctxtab, ctxtab + 64);
     for (uint32_t g = 0; g < d.num_dc_groups; g++) {
       const DevDcGroupLayout gl = DevDcGroupGeometry(E, ef, g);
       for (uint32_t i = 0; i < gl.dc_tokens + gl.meta_tokens; i++) DevEncModularSample(E, ef, g, gl, i);

@@ -1,5 +1,5 @@
 set -x
-python bench.py --steps 6 --warmup 2 --inflight 2 --batch 256 --no-cpu-baseline > gpurun_out/bench_v8_b256_if2.json 2> gpurun_out/bench_v8.err; python tools/show_bench.py gpurun_out/bench_v8_b256_if2.json; tail -3 gpurun_out/bench_v8.err
-python bench.py --steps 6 --warmup 2 --inflight 3 --batch 128 --no-cpu-baseline > gpurun_out/bench_v8_b128_if3.json 2> gpurun_out/bench_v8.err; python tools/show_bench.py gpurun_out/bench_v8_b128_if3.json; tail -3 gpurun_out/bench_v8.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_v8_ref.json 2> gpurun_out/bench_v8.err; cat gpurun_out/bench_v8_ref.json | cut -c1-600; tail -3 gpurun_out/bench_v8.err
-python -c "import __graft_entry__ as g; g.smoke()"
+python -m pytest tests/test_encoder.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --workload encode4k --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/bench_enc_v3.json 2> gpurun_out/bench_enc.err; python tools/show_bench.py gpurun_out/bench_enc_v3.json; tail -5 gpurun_out/bench_enc.err
+python bench.py --workload encode4k --batch 32 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_enc_v3_b32.json 2> gpurun_out/bench_enc.err; python tools/show_bench.py gpurun_out/bench_enc_v3_b32.json; tail -5 gpurun_out/bench_enc.err
+ncu --metrics gpu__time_duration.sum --clock-control none -s 11 -c 11 --csv --log-file gpurun_out/launches_enc.csv python bench.py --workload encode4k --batch 8 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_enc.log 2>&1; tail -1 gpurun_out/ncu_enc.log | cut -c1-100
