@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <thread>
 #include <tuple>
 
@@ -258,36 +259,86 @@ inline bool GrowTokenCapacity(BatchPlan* b, const uint32_t* used) {
   return true;
 }
 
-// Plans `n` files on `threads` host threads and merges them in input order.
+// Runs the Modular streams of a probe batch on the device: `end_bits[s]` = first bit after stream s (absolute, in
+// `probe.bytes`), `arena` = the sample arena afterwards. Throws on a failed stream.
+using ProbeFn = std::function<void(const BatchPlan& probe, std::vector<uint64_t>* end_bits, std::vector<int32_t>* arena)>;
+
+constexpr int kMaxProbeRounds = 24;  // one DC chain + at most 17 raw quantisation tables, with slack
+
+// Plans `n` files on `threads` host threads and merges them in input order. Files whose plan depends on where the
+// device stops reading a stream (ProbeCtx) are planned in rounds, one launch of `probe` per round for all of them.
 inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n, const PixelFormat& fmt,
-                      int threads, BatchPlan* batch) {
+                      int threads, BatchPlan* batch, const ProbeFn& probe = ProbeFn()) {
   std::vector<FramePlan> plans(n);
   std::vector<CodestreamView> views(n);
   std::vector<std::string> errors(n);
-  std::atomic<size_t> next{0};
-  auto work = [&]() {
-    for (;;) {
-      size_t i = next.fetch_add(1);
-      if (i >= n) break;
-      try {
-        views[i] = FindCodestream(files[i], sizes[i]);
-        PlanCodestream(views[i].data, views[i].size, fmt, &plans[i]);
-      } catch (const std::exception& e) {
-        errors[i] = e.what();
-        if (errors[i].empty()) errors[i] = "unknown error";
-      }
-    }
-  };
+  std::vector<ProbeCtx> ctx(n);
+  std::vector<size_t> todo(n);
+  for (size_t i = 0; i < n; i++) todo[i] = i;
   threads = std::max(1, std::min<int>(threads, static_cast<int>(n)));
-  if (threads == 1) {
-    work();
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; t++) pool.emplace_back(work);
-    for (auto& t : pool) t.join();
-  }
-  for (size_t i = 0; i < n; i++) {
-    if (!errors[i].empty()) throw Error("frame " + std::to_string(i) + ": " + errors[i]);
+  for (int round = 0; !todo.empty(); round++) {
+    JXLB_CHECK(round < kMaxProbeRounds, "too many chained sub-streams");
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+      for (;;) {
+        const size_t k = next.fetch_add(1);
+        if (k >= todo.size()) break;
+        const size_t i = todo[k];
+        try {
+          if (round == 0) views[i] = FindCodestream(files[i], sizes[i]);
+          plans[i] = FramePlan();
+          ctx[i].next = 0;
+          ctx[i].pending = false;
+          PlanCodestream(views[i].data, views[i].size, fmt, &plans[i], probe ? &ctx[i] : nullptr);
+        } catch (const ProbePending&) {
+        } catch (const std::exception& e) {
+          errors[i] = e.what();
+          if (errors[i].empty()) errors[i] = "unknown error";
+        }
+      }
+    };
+    if (threads == 1 || todo.size() == 1) {
+      work();
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < std::min<int>(threads, todo.size()); t++) pool.emplace_back(work);
+      for (auto& t : pool) t.join();
+    }
+    for (size_t i = 0; i < n; i++) {
+      if (!errors[i].empty()) throw Error("frame " + std::to_string(i) + ": " + errors[i]);
+    }
+    std::vector<size_t> pending;
+    for (size_t i : todo)
+      if (ctx[i].pending) pending.push_back(i);
+    todo = pending;
+    if (todo.empty()) break;
+    // one probe batch for every file that waits for the device
+    BatchPlan pb;
+    std::vector<uint64_t> byte_base, plane_base;
+    for (size_t i : todo) {
+      JXLB_CHECK(plans[i].streams.size() == 1, "internal: a probe is exactly one stream");
+      byte_base.push_back(pb.bytes.size());
+      plane_base.push_back(pb.planes.size());
+      MergeFrame(plans[i], views[i].data, views[i].size, &pb);
+    }
+    pb.bytes.resize(pb.bytes.size() + 64, 0);
+    BundleStreams(&pb);
+    std::vector<uint64_t> end_bits;
+    std::vector<int32_t> arena;
+    probe(pb, &end_bits, &arena);
+    JXLB_CHECK(end_bits.size() == pb.streams.size() && arena.size() >= pb.arena_size, "internal: bad probe result");
+    for (size_t s = 0; s < pb.streams.size(); s++) {
+      const uint64_t byte = pb.streams[s].bit_pos / 8;
+      const size_t k = std::upper_bound(byte_base.begin(), byte_base.end(), byte) - byte_base.begin() - 1;
+      ProbeCtx& c = ctx[todo[k]];
+      ProbeResult res;
+      res.end_bit = end_bits[s] - byte_base[k] * 8;
+      for (uint32_t pl : c.want_planes) {
+        const DevPlane& dp = pb.planes[plane_base[k] + pl];
+        res.samples.insert(res.samples.end(), arena.begin() + dp.off, arena.begin() + dp.off + static_cast<size_t>(dp.w) * dp.h);
+      }
+      c.done.push_back(std::move(res));
+    }
   }
   for (size_t i = 0; i < n; i++) MergeFrame(plans[i], views[i].data, views[i].size, batch);
   batch->bytes.resize(batch->bytes.size() + 64, 0);  // read-ahead padding for the device bit reader

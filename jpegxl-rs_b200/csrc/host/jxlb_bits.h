@@ -44,6 +44,7 @@ class BitReader {
     return static_cast<uint32_t>(Window() & ((uint64_t{1} << n) - 1));
   }
   void Skip(size_t n) { pos_ += n; }
+  void SeekTo(size_t bit) { pos_ = bit; }
   uint32_t Read(unsigned n) {
     uint32_t v = Peek(n);
     pos_ += n;

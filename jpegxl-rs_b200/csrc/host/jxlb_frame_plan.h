@@ -87,7 +87,7 @@ constexpr uint32_t kNumQuantTables = 17;
 // Plans the (single) frame of a lossless / non-XYB Modular codestream.
 // `cs` must stay alive until the batch has been uploaded; DevStream::bit_pos is
 // relative to cs.
-inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat& fmt, FramePlan* plan) {
+inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat& fmt, FramePlan* plan, ProbeCtx* pc = nullptr) {
   BitReader br;
   BasicInfo bi = ReadBasicInfo(cs, cs_size, &br);
   const ImageMetadata& meta = bi.meta;
@@ -120,7 +120,7 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   JXLB_CHECK(base + toc.total <= cs_size, "truncated frame");
 
   if (!fh.is_modular) {
-    PlanVarDCTFrame(cs, cs_size, fh, dim, meta, toc, base, fmt, plan);
+    PlanVarDCTFrame(cs, cs_size, fh, dim, meta, toc, base, fmt, plan, pc);
     DevFrameOut& fo = plan->out;
     fo = DevFrameOut{};
     fo.xsize = bi.xsize;

@@ -122,6 +122,23 @@ struct VarDCTPlan {
   uint64_t pix_plane = 0;       // floats per padded pixel plane
 };
 
+// A sub-stream that starts where an entropy-coded Modular stream ends (single-section frames, lib/jxl/dec_frame.cc:
+// 597-677; raw quantisation tables inside the AC global section, lib/jxl/dec_modular.cc:765-812) can only be planned
+// once the device has decoded that stream. The planner then stops with a *probe*: a plan that holds just that stream.
+// The batch layer runs the probes of all such files in one launch of the Modular decode kernel, hands the end
+// positions (and, for tables, the decoded samples) back through ProbeCtx::done and plans the file again.
+struct ProbeResult {
+  uint64_t end_bit = 0;            // first bit after the stream, relative to the codestream
+  std::vector<int32_t> samples;    // the planes the planner asked for, back to back
+};
+struct ProbeCtx {
+  std::vector<ProbeResult> done;   // answers of earlier rounds, in the order the planner asks
+  size_t next = 0;
+  bool pending = false;
+  std::vector<uint32_t> want_planes;  // planes of the pending probe whose samples the planner needs
+};
+struct ProbePending {};  // thrown by the planner after it turned the plan into a probe
+
 struct FramePlan {
   bool is_vardct = false;
   VarDCTPlan v;
@@ -611,6 +628,24 @@ class FramePlanner {
 
   // Header part of ModularDecode + emission of the device stream. `file_bit_base`
   // is the bit offset of br's first byte inside the file.
+  // What the device found when it decoded the stream planned last (`first_stream` = its index): the answer of an
+  // earlier probe round, or -- after turning the plan into a probe for exactly that stream -- ProbePending.
+  const ProbeResult& DeviceResult(ProbeCtx* pc, size_t first_stream, const std::vector<uint32_t>& planes) {
+    JXLB_CHECK(pc != nullptr, "unsupported: sub-streams chained across host-parsed headers (no device probe available)");
+    if (pc->next < pc->done.size()) return pc->done[pc->next++];
+    JXLB_CHECK(p_->streams.size() == first_stream + 1, "internal: a probe is exactly one stream");
+    p_->streams.erase(p_->streams.begin(), p_->streams.begin() + first_stream);
+    p_->is_vardct = false;
+    p_->group_programs.clear();
+    p_->frame_levels.clear();
+    p_->ops.clear();
+    p_->out = DevFrameOut{};
+    p_->out.vardct = 1;  // nothing to write
+    pc->pending = true;
+    pc->want_planes = planes;
+    throw ProbePending{};
+  }
+
   GroupHeader PlanStream(BitReader& br, uint64_t file_bit_base, HImage& image, uint32_t stream_id,
                          size_t max_chan_size, const HostTree& global) {
     GroupHeader header;

@@ -24,12 +24,17 @@ inline size_t OutputStride(uint32_t xsize, const PixelFormat& f) {
 // Plans the sections of a VarDCT frame. `br` is positioned after the TOC, `base` is the byte
 // offset of the first section inside `cs`.
 inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader& fh, const FrameDimensions& dim,
-                            const ImageMetadata& meta, const Toc& toc, size_t base, const PixelFormat& fmt, FramePlan* plan) {
+                            const ImageMetadata& meta, const Toc& toc, size_t base, const PixelFormat& fmt, FramePlan* plan,
+                            ProbeCtx* pc = nullptr) {
   JXLB_CHECK(fh.Is444(), "unsupported: chroma-subsampled VarDCT frame");
   JXLB_CHECK(meta.extra.empty(), "unsupported: VarDCT frame with extra channels");
   JXLB_CHECK(fh.passes.num_passes <= kMaxPasses, "too many passes");
   const size_t num_passes = fh.passes.num_passes;
-  JXLB_CHECK(toc.offsets.size() > 1, "unsupported: single-section VarDCT frame (sub-streams chained across host-parsed headers)");
+  // A frame with one group and one pass has a single section in which DC global, the DC group, AC global and the AC
+  // group follow each other bit by bit (lib/jxl/dec_frame.cc:597-677): `whole` walks it, and the positions that only
+  // the device can know (the end of the DC / AC-metadata chain) come from the probe rounds.
+  const bool single = toc.offsets.size() == 1;
+  BitReader whole(cs + base + toc.offsets[0], toc.logical_size[0]);
   plan->is_vardct = true;
   VarDCTPlan& v = plan->v;
   DevVFrame& vf = v.vf;
@@ -38,8 +43,9 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   const size_t W = dim.xsize_blocks, H = dim.ysize_blocks, nb = W * H;
 
   auto section = [&](size_t i, uint64_t* bit_base) {
+    if (single) i = 0;
     *bit_base = (base + toc.offsets[i]) * 8;
-    return BitReader(cs + base + toc.offsets[i], toc.logical_size[i]);
+    return single ? whole : BitReader(cs + base + toc.offsets[i], toc.logical_size[i]);
   };
   uint64_t bb = 0;
 
@@ -86,6 +92,7 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
       global_tree = planner.ReadTreeAndCode(r, limit);
     }
     r.CheckInBounds();
+    whole = r;
   }
 
   // ---- DC groups: quantised DC + AC metadata, two chained Modular streams decoded by one thread
@@ -155,6 +162,11 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
     plan->streams.push_back(st);
     for (int i = 0; i < 7; i++) v.upool.push_back(image[i].plane);
     v.upool.push_back(extra_precision);
+    if (single) {  // AC global starts where the device stops reading this chain
+      const ProbeResult& res = planner.DeviceResult(pc, plan->streams.size() - 1, {});
+      JXLB_CHECK(res.end_bit >= bb && res.end_bit <= bb + whole.Size() * 8, "DC group: read past end of section");
+      whole.SeekTo(res.end_bit - bb);
+    }
   }
 
   // ---- AC global (lib/jxl/dec_frame.cc:367-476)
@@ -163,10 +175,37 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
     BitReader r = section(1 + dim.num_dc_groups, &bb);
     const bool all_default = r.ReadBool();
     for (int k = 0; k < kNumQuantKinds; k++) vf.table_off[k] = kSharedFlag | shared.table_off[k];
+    // Raw tables (what a transcoded JPEG carries) are Modular-coded images: decoded by the device in a probe round.
+    auto read_raw = [&](BitReader& rr, int kind, QuantTableSpec* q) {
+      q->qtable_den = ReadF16(rr);
+      JXLB_CHECK(q->qtable_den >= 1e-8f, "invalid qtable_den");
+      HImage image;
+      image.bitdepth = 8;
+      const int tw = 8 * kQuantSizeX[kind], th = 8 * kQuantSizeY[kind];
+      std::vector<uint32_t> planes;
+      for (int c = 0; c < 3; c++) {
+        HChan ch;
+        ch.w = tw;
+        ch.h = th;
+        ch.plane = planner.NewPlane(tw, th);
+        planes.push_back(ch.plane);
+        image.ch.push_back(ch);
+      }
+      const size_t first = plan->streams.size();
+      const GroupHeader hdr = planner.PlanStream(rr, bb, image, 1 + 3 * dim.num_dc_groups + kind, 0xFFFFFF, global_tree);
+      JXLB_CHECK(hdr.transforms.empty(), "unsupported: transforms in a raw quantisation table");
+      JXLB_CHECK(plan->streams.size() == first + 1, "raw quantisation table without samples");
+      const ProbeResult& res = planner.DeviceResult(pc, first, planes);
+      JXLB_CHECK(res.end_bit >= bb && res.end_bit <= bb + rr.Size() * 8, "raw quantisation table: read past end of section");
+      rr.SeekTo(res.end_bit - bb);
+      JXLB_CHECK(res.samples.size() == static_cast<size_t>(3) * tw * th, "internal: probe returned the wrong planes");
+      q->qtable = res.samples;
+      for (int32_t t : q->qtable) JXLB_CHECK(t > 0, "invalid raw quantisation table");
+    };
     if (!all_default) {
       for (int k = 0; k < kNumQuantKinds; k++) {
         QuantTableSpec spec;
-        ReadQuantTableSpec(r, k, &spec);
+        ReadQuantTableSpec(r, k, &spec, read_raw);
         if (spec.mode == kQLib) continue;
         vf.table_off[k] = v.fpool.size();
         std::vector<float> tab = BuildDequantTable(spec, k);
@@ -213,15 +252,20 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
       v.cpool.resize(v.cpool.size() & ~size_t{3});
     }
     r.CheckInBounds();
+    whole = r;
   }
 
   // ---- AC groups: one stream per (pass, group)
   for (size_t p = 0; p < num_passes; p++) {
     for (size_t g = 0; g < dim.num_groups; g++) {
-      const size_t idx = 2 + dim.num_dc_groups + p * dim.num_groups + g;
+      const size_t idx = single ? 0 : 2 + dim.num_dc_groups + p * dim.num_groups + g;
       DevAcStream s{};
       s.bit_pos = (base + toc.offsets[idx]) * 8;
       s.bit_end = s.bit_pos + static_cast<uint64_t>(toc.logical_size[idx]) * 8;
+      if (single) {
+        s.bit_end = (base + toc.offsets[0]) * 8 + static_cast<uint64_t>(toc.logical_size[0]) * 8;
+        s.bit_pos = (base + toc.offsets[0]) * 8 + whole.BitPos();
+      }
       s.frame = 0;
       s.group = g;
       s.pass = p;

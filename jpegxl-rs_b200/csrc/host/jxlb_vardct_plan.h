@@ -80,6 +80,8 @@ struct QuantTableSpec {
   int mode = kQLib;
   BandParams dct, dct4x4;
   float idweights[3][3] = {}, dct2weights[3][6] = {}, dct4mul[3][2] = {}, dct4x8mul[3] = {}, afv[3][9] = {};
+  float qtable_den = 0;       // raw mode (lib/jxl/quant_weights.cc:339-346): weight = 1 / (qtable_den * qtable[i])
+  std::vector<int32_t> qtable;
 };
 
 inline QuantTableSpec LibrarySpec(int kind) {
@@ -242,8 +244,12 @@ inline std::vector<float> BuildDequantTable(const QuantTableSpec& q, int kind) {
       }
       break;
     }
+    case kQRAW:
+      JXLB_CHECK(q.qtable.size() == 3 * num, "invalid raw quantisation table");
+      for (size_t i = 0; i < 3 * num; i++) w[i] = 1.0f / (q.qtable_den * q.qtable[i]);
+      break;
     default:
-      throw Error("unsupported: raw quantisation tables");
+      throw Error("invalid quantisation table mode");
   }
   std::vector<float> out(3 * num);
   for (size_t i = 0; i < 3 * num; i++) {
@@ -253,7 +259,10 @@ inline std::vector<float> BuildDequantTable(const QuantTableSpec& q, int kind) {
   return out;
 }
 
-inline void ReadQuantTableSpec(BitReader& br, int kind, QuantTableSpec* q) {
+// `read_raw(br, kind, q)` fills q->qtable_den / q->qtable for the raw mode: the table is a Modular-coded image
+// (lib/jxl/dec_modular.cc:765-812) whose samples come back from the device (ProbeCtx).
+template <typename ReadRaw>
+inline void ReadQuantTableSpec(BitReader& br, int kind, QuantTableSpec* q, const ReadRaw& read_raw) {
   const int blocks = kQuantSizeX[kind] * kQuantSizeY[kind];
   const int mode = br.Read(3);
   auto small_only = [&]() { JXLB_CHECK(blocks == 1, "invalid quant mode"); };
@@ -309,9 +318,8 @@ inline void ReadQuantTableSpec(BitReader& br, int kind, QuantTableSpec* q) {
       ReadBandParams(br, &q->dct);
       break;
     default:
-      // The raw mode carries a Modular-coded table (lib/jxl/dec_modular.cc:765-812) inside the AC global
-      // section; its samples would have to come back from the device before the section can be parsed on.
-      throw Error("unsupported: raw quantisation tables");
+      read_raw(br, kind, q);
+      break;
   }
   q->mode = mode;
 }

@@ -51,9 +51,13 @@ __global__ void __launch_bounds__(32) k_modular_decode(DevPools P) {
   m.ring = P.ring + static_cast<size_t>(blockIdx.x) * 3 * P.wp_width * 32 + lane;
   m.wp = P.wp_scratch + static_cast<size_t>(blockIdx.x) * 10 * (P.wp_width + 2) * 32 + lane;
   const bool valid = s < P.num_streams;
+  uint64_t end_pos = 0;
   const uint32_t status = DevDecodeModularStream<WT>(P, s, m, P.warp_dims + P.warp_dims_off[blockIdx.x],
-                                                     P.warp_chans[blockIdx.x], valid);
-  if (valid) P.status[s] = status;
+                                                     P.warp_chans[blockIdx.x], valid, &end_pos);
+  if (valid) {
+    P.status[s] = status;
+    if (P.end_bits) P.end_bits[s] = end_pos;
+  }
 }
 
 // Few streams (a batch of lossy frames has only four DC-group chains per 4K frame): the chip is empty and each
@@ -81,8 +85,12 @@ __global__ void __launch_bounds__(32) k_modular_decode_sparse(DevPools P) {
   const uint32_t bundle = s / 32;  // loop bounds of the 32-stream bundle this stream belongs to (a superset)
   const uint32_t b0 = (blockIdx.x * kSparseLanes) / 32;
   (void)bundle;
-  const uint32_t status = DevDecodeModularStream<WT>(P, s, m, P.warp_dims + P.warp_dims_off[b0], P.warp_chans[b0], valid);
-  if (valid) P.status[s] = status;
+  uint64_t end_pos = 0;
+  const uint32_t status = DevDecodeModularStream<WT>(P, s, m, P.warp_dims + P.warp_dims_off[b0], P.warp_chans[b0], valid, &end_pos);
+  if (valid) {
+    P.status[s] = status;
+    if (P.end_bits) P.end_bits[s] = end_pos;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_group_programs(DevPools P, const DevOp* ops, const DevProgram* programs) {
@@ -391,6 +399,8 @@ struct JxlB200Decoder {
   DevBuf<DevProgram> d_group_programs, d_levels;
   DevBuf<DevFrameOut> d_frames;
   DevBuf<int32_t> d_arena, d_wp, d_ring;
+  DevBuf<uint64_t> d_end_bits;    // probe launches only
+  uint32_t probe_launches = 0;    // Modular decode launches made while planning (probe rounds)
   // VarDCT
   DevBuf<DevVFrame> d_vframes;
   DevBuf<DevAcStream> d_ac_streams;
@@ -501,30 +511,12 @@ static int UploadTokensLayout(JxlB200Decoder* dec) {
   return 0;
 }
 
-int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files, const size_t* sizes, size_t n,
-                                const JxlPixelFormat* format, int num_threads) {
-  if (!dec || !files || !sizes || !format || n == 0) return 1;
-  dec->error.clear();
-  PixelFormat fmt;
-  fmt.num_channels = format->num_channels;
-  fmt.data_type = format->data_type;
-  fmt.endianness = format->endianness;
-  fmt.align = format->align;
-  if (fmt.num_channels < 1 || fmt.num_channels > 4 ||
-      !(fmt.data_type == 0 || fmt.data_type == 2 || fmt.data_type == 3 || fmt.data_type == 5)) {
-    dec->error = "invalid pixel format";
-    return 1;
-  }
-  std::unique_ptr<BatchPlan> plan(new BatchPlan());
-  try {
-    PlanBatch(files, sizes, n, fmt, num_threads, plan.get());
-  } catch (const std::exception& e) {
-    dec->error = e.what();
-    return 1;
-  }
+static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s);
+
+// Uploads the pools of `b` and allocates the arenas; `dec->pools` / `dec->vpools` describe them afterwards.
+static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat& fmt, bool want_end_bits) {
   CUDA_OK(cudaSetDevice(dec->device));
   cudaStream_t s = dec->stream;
-  BatchPlan& b = *plan;
   CUDA_OK(dec->d_bytes.Upload(b.bytes, s));
   CUDA_OK(dec->d_alias.Upload(b.alias, s));
   CUDA_OK(dec->d_prefix.Upload(b.prefix, s));
@@ -555,6 +547,7 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   CUDA_OK(dec->d_ring.Alloc(num_warps * 3 * b.wp_width * 32 + 16));
   CUDA_OK(dec->d_lz77.Alloc(static_cast<size_t>(b.lz77_slots) << 20));
   CUDA_OK(dec->d_status.Alloc(b.streams.size()));
+  if (want_end_bits) CUDA_OK(dec->d_end_bits.Alloc(b.streams.size()));
   CUDA_OK(dec->d_out.Alloc(b.out_size));
   DevPools& P = dec->pools;
   P.words = reinterpret_cast<const uint32_t*>(dec->d_bytes.p);
@@ -574,6 +567,7 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   P.wp_width = b.wp_width;
   P.lz77 = dec->d_lz77.p;
   P.status = dec->d_status.p;
+  P.end_bits = want_end_bits ? dec->d_end_bits.p : nullptr;
   P.num_streams = b.streams.size();
   P.warp_chans = dec->d_warp_chans.p;
   P.warp_dims_off = dec->d_warp_dims_off.p;
@@ -586,7 +580,6 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
     for (int c = 0; c < 4; c++)
       if (fo.is_float[c] || fo.stride % 4) dec->uniform_rgba8 = false;
   }
-  dec->plan = std::move(plan);
   // ---- VarDCT
   dec->dcg_list.clear();
   dec->max_groups = dec->max_xsize = dec->max_ysize = dec->max_blocks = dec->max_epf = 0;
@@ -636,9 +629,65 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
     V.sinfo_off = sh.sinfo_off;
     V.ctxtab_off = sh.ctxtab_off;
     V.out = dec->d_out.p;
-    if (UploadTokensLayout(dec) != 0) return 1;
+    CUDA_OK(dec->d_ac_streams.Upload(b.ac_streams, s));
+    CUDA_OK(dec->d_tokens.Alloc(b.tok_size + 16));
+    V.streams = dec->d_ac_streams.p;
+    V.tokens = dec->d_tokens.p;
   }
   CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files, const size_t* sizes, size_t n,
+                                const JxlPixelFormat* format, int num_threads) {
+  if (!dec || !files || !sizes || !format || n == 0) return 1;
+  dec->error.clear();
+  PixelFormat fmt;
+  fmt.num_channels = format->num_channels;
+  fmt.data_type = format->data_type;
+  fmt.endianness = format->endianness;
+  fmt.align = format->align;
+  if (fmt.num_channels < 1 || fmt.num_channels > 4 ||
+      !(fmt.data_type == 0 || fmt.data_type == 2 || fmt.data_type == 3 || fmt.data_type == 5)) {
+    dec->error = "invalid pixel format";
+    return 1;
+  }
+  // Probe rounds (single-section frames, raw quantisation tables): the Modular decode kernel runs over the probe
+  // streams alone and the host reads back where each one ended and the samples it asked for.
+  const ProbeFn probe = [dec](const BatchPlan& pb, std::vector<uint64_t>* end_bits, std::vector<int32_t>* arena) {
+    JxlB200Decoder tmp;
+    tmp.device = dec->device;
+    tmp.stream = dec->stream;  // borrowed
+    PixelFormat pf;
+    std::vector<uint32_t> status(pb.streams.size());
+    end_bits->assign(pb.streams.size(), 0);
+    arena->assign(pb.arena_size, 0);
+    auto ok = [&](cudaError_t e) {
+      if (e != cudaSuccess) throw Error(std::string("probe launch: ") + cudaGetErrorString(e));
+    };
+    if (UploadPlan(&tmp, pb, pf, true) != 0) throw Error("probe launch: " + tmp.error);
+    ok(cudaMemsetAsync(tmp.d_arena.p, 0, pb.arena_size * sizeof(int32_t), tmp.stream));
+    if (LaunchModular(&tmp, pb, tmp.stream) != 0) throw Error("probe launch: " + tmp.error);
+    ok(cudaGetLastError());
+    ok(cudaMemcpyAsync(status.data(), tmp.d_status.p, status.size() * 4, cudaMemcpyDeviceToHost, tmp.stream));
+    ok(cudaMemcpyAsync(end_bits->data(), tmp.d_end_bits.p, end_bits->size() * 8, cudaMemcpyDeviceToHost, tmp.stream));
+    if (pb.arena_size)
+      ok(cudaMemcpyAsync(arena->data(), tmp.d_arena.p, pb.arena_size * sizeof(int32_t), cudaMemcpyDeviceToHost, tmp.stream));
+    ok(cudaStreamSynchronize(tmp.stream));
+    dec->probe_launches++;
+    for (size_t i = 0; i < status.size(); i++)
+      if (status[i] != 0) throw Error("chained sub-stream " + std::to_string(i) + " failed (status " + std::to_string(status[i]) + ")");
+  };
+  std::unique_ptr<BatchPlan> plan(new BatchPlan());
+  try {
+    if (cudaSetDevice(dec->device) != cudaSuccess) throw Error("cudaSetDevice failed");
+    PlanBatch(files, sizes, n, fmt, num_threads, plan.get(), probe);
+  } catch (const std::exception& e) {
+    dec->error = e.what();
+    return 1;
+  }
+  if (UploadPlan(dec, *plan, fmt, false) != 0) return 1;
+  dec->plan = std::move(plan);
   return 0;
 }
 
@@ -689,6 +738,26 @@ size_t JxlB200DecoderImageOutBufferSize(const JxlB200Decoder* dec, size_t i) {
   return dec->plan->frame_out_size[i];
 }
 
+static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s) {
+  const DevPools& P = dec->pools;
+  const uint32_t block = 32;
+  const size_t sparse_smem = static_cast<size_t>(13 * b.wp_width + 20) * kSparseLanes * sizeof(int32_t);
+  if (b.streams.size() <= 2 * 148 * kSparseLanes && sparse_smem <= 160 * 1024) {
+    const uint32_t grid = (b.streams.size() + kSparseLanes - 1) / kSparseLanes;
+    if (b.narrow) {
+      k_modular_decode_sparse<int32_t><<<grid, block, sparse_smem, s>>>(P);
+    } else {
+      k_modular_decode_sparse<int64_t><<<grid, block, sparse_smem, s>>>(P);
+    }
+  } else if (b.narrow) {
+    k_modular_decode<int32_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
+  } else {
+    k_modular_decode<int64_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   if (!dec || !dec->plan) return 1;
   CUDA_OK(cudaSetDevice(dec->device));
@@ -698,20 +767,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   uint32_t launches = 0;
   if (!b.streams.empty()) {
     ScopedTimer t(dec, s, kKModular);
-    const uint32_t block = 32;
-    const size_t sparse_smem = static_cast<size_t>(13 * b.wp_width + 20) * kSparseLanes * sizeof(int32_t);
-    if (b.streams.size() <= 2 * 148 * kSparseLanes && sparse_smem <= 160 * 1024) {
-      const uint32_t grid = (b.streams.size() + kSparseLanes - 1) / kSparseLanes;
-      if (b.narrow) {
-        k_modular_decode_sparse<int32_t><<<grid, block, sparse_smem, s>>>(P);
-      } else {
-        k_modular_decode_sparse<int64_t><<<grid, block, sparse_smem, s>>>(P);
-      }
-    } else if (b.narrow) {
-      k_modular_decode<int32_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
-    } else {
-      k_modular_decode<int64_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
-    }
+    if (LaunchModular(dec, b, s) != 0) return 1;
     launches++;
   }
   if (!b.group_programs.empty()) {

@@ -36,6 +36,7 @@ struct DevPools {
   uint32_t wp_width;     // widest channel of the batch
   uint32_t* lz77;        // per slot: 1 << 20 entries
   uint32_t* status;      // per stream: 0 ok, else error bits
+  uint64_t* end_bits;    // per stream: first bit after the stream (probe launches only, else null)
   uint32_t num_streams;
   // per warp of 32 consecutive streams: number of channel slots and, per slot, the
   // largest (width, height) among its lanes -- the warp-uniform loop bounds
@@ -455,7 +456,7 @@ JXLB_HD WT DevPredictW(uint32_t p, WT left, WT top, WT topleft, WT topright, WT 
 // registers and never stored.
 template <typename WT>
 JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const DevLaneMem& m, const uint32_t* warp_dims,
-                                        uint32_t warp_chans, bool lane_valid) {
+                                        uint32_t warp_chans, bool lane_valid, uint64_t* end_pos = nullptr) {
   DevStream st{};
   DevCode code{};
   DevBits br{};
@@ -732,6 +733,7 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
   if (lane_valid) {
     if (!code.use_prefix && reader.state != (0x13u << 16)) status |= kStatusBadFinalState;
     if (br.Pos() > st.bit_end) status |= kStatusOverread;
+    if (end_pos) *end_pos = br.Pos();
   }
   return status;
 }

@@ -28,54 +28,71 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     fmt.data_type = data_type;
     fmt.endianness = endianness;
     fmt.align = align;
+    // the Modular decode "kernel": every stream of `b`, one lane at a time
+    auto run_modular = [&](const BatchPlan& b, std::vector<int32_t>& arena, DevPools* pools_out, std::vector<uint64_t>* end_bits) {
+      const size_t num_warps = (b.streams.size() + 31) / 32;
+      std::vector<int32_t> wp(num_warps * 10 * (b.wp_width + 2) * 32 + 16, 0);
+      std::vector<int32_t> ring(num_warps * 3 * b.wp_width * 32 + 16, 0);
+      std::vector<int32_t> props(kDevMaxProps * 32, 0);
+      uint32_t divlut[64];
+      for (uint32_t i = 0; i < 64; i++) divlut[i] = (1u << 24) / (i + 1);
+      std::vector<uint32_t> lz(static_cast<size_t>(b.lz77_slots) << 20, 0);
+      DevPools P{};
+      P.words = reinterpret_cast<const uint32_t*>(b.bytes.data());
+      P.alias = b.alias.data();
+      P.prefix = b.prefix.data();
+      P.cfg = b.cfg.data();
+      P.tree = b.tree.data();
+      P.chans = b.chans.data();
+      P.streams = b.streams.data();
+      P.planes = b.planes.data();
+      P.refs = b.refs.data();
+      P.lut = b.lut.data();
+      P.codes = b.codes.data();
+      P.arena = arena.data();
+      P.wp_scratch = wp.data();
+      P.ring = ring.data();
+      P.wp_width = b.wp_width;
+      P.lz77 = lz.data();
+      P.num_streams = b.streams.size();
+      P.warp_chans = b.warp_chans.data();
+      P.warp_dims_off = b.warp_dims_off.data();
+      P.warp_dims = b.warp_dims.data();
+      if (end_bits) end_bits->assign(b.streams.size(), 0);
+      for (uint32_t s = 0; s < b.streams.size(); s++) {
+        // same addressing as the kernel: warp = s / 32, lane = s % 32
+        const uint32_t warp = s / 32, lane = s % 32;
+        DevLaneMem m;
+        m.props = props.data() + lane;
+        m.props_stride = 32;
+        m.divlut = divlut;
+        m.ring_w = b.wp_width;
+        m.lane_stride = 32;
+        m.ring = ring.data() + static_cast<size_t>(warp) * 3 * b.wp_width * 32 + lane;
+        m.wp = wp.data() + static_cast<size_t>(warp) * 10 * (b.wp_width + 2) * 32 + lane;
+        const uint32_t* dims = b.warp_dims.data() + b.warp_dims_off[warp];
+        uint64_t end = 0;
+        uint32_t st = force_wide || !b.narrow ? DevDecodeModularStream<int64_t>(P, s, m, dims, b.warp_chans[warp], true, &end)
+                                              : DevDecodeModularStream<int32_t>(P, s, m, dims, b.warp_chans[warp], true, &end);
+        if (st != 0) throw Error("stream " + std::to_string(s) + " failed with status " + std::to_string(st));
+        if (end_bits) (*end_bits)[s] = end;
+      }
+      P.wp_scratch = nullptr;  // scratch dies with this call
+      P.ring = nullptr;
+      P.lz77 = nullptr;
+      if (pools_out) *pools_out = P;
+    };
+    // probe rounds, as JxlB200DecoderSetInputBatch runs them on the device
+    const ProbeFn probe = [&](const BatchPlan& pb, std::vector<uint64_t>* end_bits, std::vector<int32_t>* arena) {
+      arena->assign(pb.arena_size + 16, 0);
+      run_modular(pb, *arena, nullptr, end_bits);
+    };
     BatchPlan b;
-    PlanBatch(files, sizes, n, fmt, 2, &b);
+    PlanBatch(files, sizes, n, fmt, 2, &b, probe);
     if (b.out_size > out_cap) throw Error("output buffer too small");
     std::vector<int32_t> arena(b.arena_size + 16, 0);
-    const size_t num_warps = (b.streams.size() + 31) / 32;
-    std::vector<int32_t> wp(num_warps * 10 * (b.wp_width + 2) * 32 + 16, 0);
-    std::vector<int32_t> ring(num_warps * 3 * b.wp_width * 32 + 16, 0);
-    std::vector<int32_t> props(kDevMaxProps * 32, 0);
-    uint32_t divlut[64];
-    for (uint32_t i = 0; i < 64; i++) divlut[i] = (1u << 24) / (i + 1);
-    std::vector<uint32_t> lz(static_cast<size_t>(b.lz77_slots) << 20, 0);
     DevPools P{};
-    P.words = reinterpret_cast<const uint32_t*>(b.bytes.data());
-    P.alias = b.alias.data();
-    P.prefix = b.prefix.data();
-    P.cfg = b.cfg.data();
-    P.tree = b.tree.data();
-    P.chans = b.chans.data();
-    P.streams = b.streams.data();
-    P.planes = b.planes.data();
-    P.refs = b.refs.data();
-    P.lut = b.lut.data();
-    P.codes = b.codes.data();
-    P.arena = arena.data();
-    P.wp_scratch = wp.data();
-    P.ring = ring.data();
-    P.wp_width = b.wp_width;
-    P.lz77 = lz.data();
-    P.num_streams = b.streams.size();
-    P.warp_chans = b.warp_chans.data();
-    P.warp_dims_off = b.warp_dims_off.data();
-    P.warp_dims = b.warp_dims.data();
-    for (uint32_t s = 0; s < b.streams.size(); s++) {
-      // same addressing as the kernel: warp = s / 32, lane = s % 32
-      const uint32_t warp = s / 32, lane = s % 32;
-      DevLaneMem m;
-      m.props = props.data() + lane;
-      m.props_stride = 32;
-      m.divlut = divlut;
-      m.ring_w = b.wp_width;
-      m.lane_stride = 32;
-      m.ring = ring.data() + static_cast<size_t>(warp) * 3 * b.wp_width * 32 + lane;
-      m.wp = wp.data() + static_cast<size_t>(warp) * 10 * (b.wp_width + 2) * 32 + lane;
-      const uint32_t* dims = b.warp_dims.data() + b.warp_dims_off[warp];
-      uint32_t st = force_wide || !b.narrow ? DevDecodeModularStream<int64_t>(P, s, m, dims, b.warp_chans[warp], true)
-                                            : DevDecodeModularStream<int32_t>(P, s, m, dims, b.warp_chans[warp], true);
-      if (st != 0) throw Error("stream " + std::to_string(s) + " failed with status " + std::to_string(st));
-    }
+    run_modular(b, arena, &P, nullptr);
     const uint32_t nt = 4;  // emulate a few cooperating workers
     for (const DevProgram& pr : b.group_programs)
       for (uint32_t o = pr.op_begin; o < pr.op_end; o++)

@@ -61,3 +61,36 @@ def test_token_budget_retry(pkg):
     data, shape = vc.encoded("three_passes")
     out = pkg.decode_batch([data], 3, np.uint8)[0]
     assert np.array_equal(out, jxlo.decode(data, 3, jxlo.UINT8))
+
+
+def test_single_section_frames(pkg):
+    # frames of one group: the sub-streams are chained inside one section, positions come from probe launches
+    files, shapes = [], []
+    for h, w, mode, seed in [(80, 100, 1, 3), (256, 256, 2, 4), (17, 9, 1, 5), (200, 256, 0, 6)]:
+        files.append(jxlo.encode_vardct(vc.crop(h, w, 300, 500), strategy_mode=mode, random_side_info=True, epf_iters=3, seed=seed))
+    big, _ = vc.encoded("heuristic")
+    outs = pkg.decode_batch(files + [big], 3, np.uint8)
+    for f, o in zip(files + [big], outs):
+        assert np.array_equal(o, jxlo.decode(f, 3, jxlo.UINT8))
+
+
+def test_g3_sample_jpg_jxl(pkg):
+    """The reference's own VarDCT fixture, written by libjxl (lossless transcode of samples/sample.jpg: container,
+    YCbCr, DCT8, raw quantisation tables, single section): the GPU path equals the oracle bit for bit, and the pixels
+    follow from the JPEG's coefficients (jpegxl-rs/src/tests/encode.rs:54-72 asserts the coefficient identity)."""
+    import jpeg_coeffs
+    from test_oracle_vardct import _float_cfl_reconstruction
+    jpg = read_golden("sample_jpg.jxl")
+    got8 = pkg.decode_batch([jpg, jpg], 3, np.uint8)
+    want8 = jxlo.decode(jpg, 3, jxlo.UINT8)
+    assert np.array_equal(got8[0], want8) and np.array_equal(got8[1], want8)
+    gotf = pkg.decode_batch([jpg], 3, np.float32)[0]
+    assert np.array_equal(gotf.view(np.uint32), jxlo.decode(jpg, 3, jxlo.FLOAT).view(np.uint32))
+    frame = jpeg_coeffs.parse(read_golden("sample.jpg"))
+    want = _float_cfl_reconstruction(frame, -15, 47)  # dequantised JPEG coefficients -> IDCT -> YCbCr -> RGB, in double
+    # the decoder's quantisation-bias adjustment (lib/jxl/quantizer-inl.h:34-71) moves samples by a few levels
+    assert np.abs(got8[0].astype(float) - np.clip(np.round(want), 0, 255)).max() <= 6
+    dec = pkg.decoder_builder().build()
+    meta, px = dec.decode(jpg)
+    assert (meta.width, meta.height) == (40, 50) and px.variant == "Uint8"
+    assert np.array_equal(np.asarray(px.data).reshape(50, 40, 3), want8)

@@ -33,8 +33,27 @@ def test_mixed_batch_and_formats():
         assert np.array_equal(g, jxlo.decode(d, 4, jxlo.UINT16))
 
 
-def test_single_section_vardct_fails_loudly():
-    img = vc.crop(200, 200)
-    data = jxlo.encode_vardct(img)
-    with pytest.raises(emul_lib.EmulError, match="single-section"):
-        emul_lib.decode([data], 3, jxlo.UINT8, [(200, 200)])
+SINGLE_SECTION = [(80, 100, 1, 3), (256, 256, 2, 4), (17, 9, 1, 5), (200, 256, 0, 6)]
+
+
+@pytest.mark.parametrize("h,w,mode,seed", SINGLE_SECTION)
+def test_single_section_frames_match_oracle(h, w, mode, seed):
+    # one group, one pass: DC global, DC group, AC global and AC group share a section; the planner learns where
+    # the DC / AC-metadata chain ends from a probe launch of the Modular decode kernel (ProbeCtx)
+    img = vc.crop(h, w, 300, 500)
+    data = jxlo.encode_vardct(img, strategy_mode=mode, random_side_info=True, epf_iters=3, seed=seed)
+    got = emul_lib.decode([data], 3, jxlo.UINT8, [(h, w)])[0]
+    assert np.array_equal(got, jxlo.decode(data, 3, jxlo.UINT8))
+
+
+def test_g3_sample_jpg_jxl_matches_oracle():
+    # the reference's own VarDCT fixture (libjxl-written: container, YCbCr, raw quantisation tables decoded in a
+    # second probe round, single section), in a batch with other files
+    jpg = read_golden("sample_jpg.jxl")
+    a, sa = vc.encoded("odd_size")
+    got = emul_lib.decode([jpg, a, jpg], 3, jxlo.UINT8, [(50, 40), sa, (50, 40)])
+    want = jxlo.decode(jpg, 3, jxlo.UINT8)
+    assert np.array_equal(got[0], want) and np.array_equal(got[2], want)
+    assert np.array_equal(got[1], jxlo.decode(a, 3, jxlo.UINT8))
+    gotf = emul_lib.decode([jpg], 3, jxlo.FLOAT, [(50, 40)])[0]
+    assert np.array_equal(gotf.view(np.uint32), jxlo.decode(jpg, 3, jxlo.FLOAT).view(np.uint32))
