@@ -157,6 +157,12 @@ JxlDecoderStatus JxlDecoderProcessInput(JxlDecoder* dec);
 JxlDecoderStatus JxlDecoderGetBasicInfo(const JxlDecoder* dec, JxlBasicInfo* info);
 JxlDecoderStatus JxlDecoderImageOutBufferSize(const JxlDecoder* dec, const JxlPixelFormat* format, size_t* size);
 JxlDecoderStatus JxlDecoderSetImageOutBuffer(JxlDecoder* dec, const JxlPixelFormat* format, void* buffer, size_t size);
+/* Declared because jpegxl-rs binds them (jpegxl-rs/src/decode.rs:260-283, :329-357); ICC synthesis and JPEG
+ * reconstruction are not built: these return JXL_DEC_ERROR / 0. `target` is JxlColorProfileTarget. */
+JxlDecoderStatus JxlDecoderGetICCProfileSize(const JxlDecoder* dec, int target, size_t* size);
+JxlDecoderStatus JxlDecoderGetColorAsICCProfile(const JxlDecoder* dec, int target, uint8_t* icc_profile, size_t size);
+JxlDecoderStatus JxlDecoderSetJPEGBuffer(JxlDecoder* dec, uint8_t* data, size_t size);
+size_t JxlDecoderReleaseJPEGBuffer(JxlDecoder* dec);
 
 /* ---- 3. batch encoder (lossy VarDCT) ----
  * Replaces what jpegxl-rs reaches through JxlEncoderAddImageFrame + JxlEncoderProcessOutput
@@ -179,6 +185,99 @@ size_t JxlB200EncoderOutputSize(const JxlB200Encoder* enc, size_t i);
 int JxlB200EncoderReadOutput(const JxlB200Encoder* enc, size_t i, uint8_t* dst, size_t size);
 /* Device time of the last EncodeBatch: {pixels -> tokens + histograms, host tables (incl. D2H), rANS emission} in ms. */
 int JxlB200EncoderGetPhaseTimes(const JxlB200Encoder* enc, double* ms3);
+
+/* ---- 4. libjxl-compatible subset (encode) ----
+ * The 23 encoder symbols jpegxl-rs calls (jpegxl-rs/src/encode.rs:156-467, jpegxl-rs/src/encode/options.rs:46-70;
+ * declared in jpegxl-sys/src/encoder/encode.rs), same names, argument meaning, status and error codes as libjxl
+ * 0.11.2 (lib/include/jxl/encode.h, lib/jxl/encode.cc); internally a batch of one on the CUDA encoder. What the CUDA
+ * encoder does not cover returns JXL_ENC_ERROR with JxlEncoderGetError() == JXL_ENC_ERR_NOT_SUPPORTED: lossless
+ * (Modular) encoding, alpha / extra channels, samples other than 8-bit sRGB, JPEG transcoding, metadata boxes. */
+typedef struct JxlEncoderStruct JxlEncoder;
+typedef struct JxlEncoderFrameSettingsStruct JxlEncoderFrameSettings;
+typedef enum { JXL_ENC_SUCCESS = 0, JXL_ENC_ERROR = 1, JXL_ENC_NEED_MORE_OUTPUT = 2 } JxlEncoderStatus;
+typedef enum {
+  JXL_ENC_ERR_OK = 0, JXL_ENC_ERR_GENERIC = 1, JXL_ENC_ERR_OOM = 2, JXL_ENC_ERR_JBRD = 3, JXL_ENC_ERR_BAD_INPUT = 4,
+  JXL_ENC_ERR_NOT_SUPPORTED = 0x80, JXL_ENC_ERR_API_USAGE = 0x81
+} JxlEncoderError;
+/* jpegxl-sys/src/encoder/encode.rs:110-341; the ids between DECODING_SPEED and LAST are accepted without effect. */
+typedef enum {
+  JXL_ENC_FRAME_SETTING_EFFORT = 0, JXL_ENC_FRAME_SETTING_DECODING_SPEED = 1, JXL_ENC_FRAME_SETTING_LAST = 39,
+  JXL_ENC_FRAME_SETTING_FILL_ENUM = 65535
+} JxlEncoderFrameSettingId;
+/* JxlColorEncoding, byte-identical to libjxl (jpegxl-sys/src/color/color_encoding.rs:30-159). */
+typedef enum { JXL_COLOR_SPACE_RGB = 0, JXL_COLOR_SPACE_GRAY, JXL_COLOR_SPACE_XYB, JXL_COLOR_SPACE_UNKNOWN } JxlColorSpace;
+typedef enum { JXL_WHITE_POINT_D65 = 1, JXL_WHITE_POINT_CUSTOM = 2, JXL_WHITE_POINT_E = 10, JXL_WHITE_POINT_DCI = 11 } JxlWhitePoint;
+typedef enum { JXL_PRIMARIES_SRGB = 1, JXL_PRIMARIES_CUSTOM = 2, JXL_PRIMARIES_2100 = 9, JXL_PRIMARIES_P3 = 11 } JxlPrimaries;
+typedef enum {
+  JXL_TRANSFER_FUNCTION_709 = 1, JXL_TRANSFER_FUNCTION_UNKNOWN = 2, JXL_TRANSFER_FUNCTION_LINEAR = 8,
+  JXL_TRANSFER_FUNCTION_SRGB = 13, JXL_TRANSFER_FUNCTION_PQ = 16, JXL_TRANSFER_FUNCTION_DCI = 17,
+  JXL_TRANSFER_FUNCTION_HLG = 18, JXL_TRANSFER_FUNCTION_GAMMA = 65535
+} JxlTransferFunction;
+typedef enum {
+  JXL_RENDERING_INTENT_PERCEPTUAL = 0, JXL_RENDERING_INTENT_RELATIVE, JXL_RENDERING_INTENT_SATURATION,
+  JXL_RENDERING_INTENT_ABSOLUTE
+} JxlRenderingIntent;
+typedef struct {
+  JxlColorSpace color_space;
+  JxlWhitePoint white_point;
+  double white_point_xy[2];
+  JxlPrimaries primaries;
+  double primaries_red_xy[2];
+  double primaries_green_xy[2];
+  double primaries_blue_xy[2];
+  JxlTransferFunction transfer_function;
+  double gamma;
+  JxlRenderingIntent rendering_intent;
+} JxlColorEncoding;
+
+uint32_t JxlEncoderVersion(void);
+/* memory_manager: accepted, not used (the codestream is the only host allocation; pixels live in device memory). */
+JxlEncoder* JxlEncoderCreate(const void* memory_manager);
+void JxlEncoderReset(JxlEncoder* enc);
+void JxlEncoderDestroy(JxlEncoder* enc);
+JxlEncoderError JxlEncoderGetError(JxlEncoder* enc);
+/* Accepted and ignored, as on the decoder. */
+JxlEncoderStatus JxlEncoderSetParallelRunner(JxlEncoder* enc, void* parallel_runner, void* parallel_runner_opaque);
+JxlEncoderFrameSettings* JxlEncoderFrameSettingsCreate(JxlEncoder* enc, const JxlEncoderFrameSettings* source);
+JxlEncoderStatus JxlEncoderUseContainer(JxlEncoder* enc, JXL_BOOL use_container);
+JxlEncoderStatus JxlEncoderUseBoxes(JxlEncoder* enc);
+JxlEncoderStatus JxlEncoderAddBox(JxlEncoder* enc, const char* type, const uint8_t* contents, size_t size, JXL_BOOL compress_box);
+JxlEncoderStatus JxlEncoderStoreJPEGMetadata(JxlEncoder* enc, JXL_BOOL store_jpeg_metadata);
+JxlEncoderStatus JxlEncoderSetFrameLossless(JxlEncoderFrameSettings* frame_settings, JXL_BOOL lossless);
+JxlEncoderStatus JxlEncoderSetFrameDistance(JxlEncoderFrameSettings* frame_settings, float distance);
+float JxlEncoderDistanceFromQuality(float quality);
+JxlEncoderStatus JxlEncoderFrameSettingsSetOption(JxlEncoderFrameSettings* frame_settings, JxlEncoderFrameSettingId option, int64_t value);
+void JxlEncoderInitBasicInfo(JxlBasicInfo* info);
+JxlEncoderStatus JxlEncoderSetBasicInfo(JxlEncoder* enc, const JxlBasicInfo* info);
+JxlEncoderStatus JxlEncoderSetColorEncoding(JxlEncoder* enc, const JxlColorEncoding* color);
+void JxlColorEncodingSetToSRGB(JxlColorEncoding* color_encoding, JXL_BOOL is_gray);
+void JxlColorEncodingSetToLinearSRGB(JxlColorEncoding* color_encoding, JXL_BOOL is_gray);
+JxlEncoderStatus JxlEncoderAddImageFrame(const JxlEncoderFrameSettings* frame_settings, const JxlPixelFormat* pixel_format,
+                                         const void* buffer, size_t size);
+JxlEncoderStatus JxlEncoderAddJPEGFrame(const JxlEncoderFrameSettings* frame_settings, const uint8_t* buffer, size_t size);
+void JxlEncoderCloseInput(JxlEncoder* enc);
+/* Runs the CUDA encoder on the first call after a frame was added; NEED_MORE_OUTPUT until everything is written. */
+JxlEncoderStatus JxlEncoderProcessOutput(JxlEncoder* enc, uint8_t** next_out, size_t* avail_out);
+/* Text of the last error (extension; libjxl only prints it in debug builds). */
+const char* JxlB200EncoderApiMessage(const JxlEncoder* enc);
+
+/* ---- 5. libjxl_threads symbols (jpegxl-sys/src/threads/{thread,resizable}_parallel_runner.rs) ----
+ * jpegxl-rs hands the two runner functions to SetParallelRunner by value (jpegxl-rs/src/parallel/). The GPU path
+ * never calls a runner; the symbols exist so that the crate links, and they behave like libjxl's runner with zero
+ * worker threads (the range runs on the calling thread). */
+typedef int (*JxlParallelRunInit)(void* jpegxl_opaque, size_t num_threads);
+typedef void (*JxlParallelRunFunction)(void* jpegxl_opaque, uint32_t value, size_t thread_id);
+int JxlThreadParallelRunner(void* runner_opaque, void* jpegxl_opaque, JxlParallelRunInit init, JxlParallelRunFunction func,
+                            uint32_t start_range, uint32_t end_range);
+void* JxlThreadParallelRunnerCreate(const void* memory_manager, size_t num_worker_threads);
+void JxlThreadParallelRunnerDestroy(void* runner_opaque);
+size_t JxlThreadParallelRunnerDefaultNumWorkerThreads(void);
+int JxlResizableParallelRunner(void* runner_opaque, void* jpegxl_opaque, JxlParallelRunInit init, JxlParallelRunFunction func,
+                               uint32_t start_range, uint32_t end_range);
+void* JxlResizableParallelRunnerCreate(const void* memory_manager);
+void JxlResizableParallelRunnerSetThreads(void* runner_opaque, size_t num_threads);
+uint32_t JxlResizableParallelRunnerSuggestThreads(uint64_t xsize, uint64_t ysize);
+void JxlResizableParallelRunnerDestroy(void* runner_opaque);
 
 #ifdef __cplusplus
 }

@@ -72,8 +72,22 @@ class JxlB200EncodeOptions(ctypes.Structure):
                 ("epf_iters", ctypes.c_uint32), ("dc_smoothing", ctypes.c_int)]
 
 
+class JxlColorEncoding(ctypes.Structure):
+    """jpegxl-sys/src/color/color_encoding.rs:125-159."""
+    _fields_ = [("color_space", ctypes.c_int), ("white_point", ctypes.c_int), ("white_point_xy", ctypes.c_double * 2),
+                ("primaries", ctypes.c_int), ("primaries_red_xy", ctypes.c_double * 2),
+                ("primaries_green_xy", ctypes.c_double * 2), ("primaries_blue_xy", ctypes.c_double * 2),
+                ("transfer_function", ctypes.c_int), ("gamma", ctypes.c_double), ("rendering_intent", ctypes.c_int)]
+
+
 class EncodeError(Exception):
     """Mirrors jpegxl-rs/src/errors.rs:62-98."""
+
+
+# JxlEncoderError -> the EncodeError variant names of jpegxl-rs/src/errors.rs:62-98 (check_enc_status, encode.rs:205-221)
+_ENC_ERROR_NAMES = {1: "GenericError", 2: "OutOfMemory", 3: "Jbrd", 4: "BadInput", 0x80: "NotSupported", 0x81: "ApiUsage"}
+JXL_ENC_SUCCESS, JXL_ENC_ERROR, JXL_ENC_NEED_MORE_OUTPUT = 0, 1, 2
+JXL_ENC_FRAME_SETTING_EFFORT, JXL_ENC_FRAME_SETTING_DECODING_SPEED = 0, 1
 
 
 class DecodeError(Exception):
@@ -146,6 +160,45 @@ def load_library() -> ctypes.CDLL:
     lib.JxlB200EncoderOutputSize.argtypes = [vp, sz]
     lib.JxlB200EncoderReadOutput.argtypes = [vp, sz, vp, sz]
     lib.JxlB200EncoderGetPhaseTimes.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    lib.JxlEncoderVersion.restype = ctypes.c_uint32
+    lib.JxlEncoderCreate.restype = vp
+    lib.JxlEncoderCreate.argtypes = [vp]
+    lib.JxlEncoderReset.argtypes = [vp]
+    lib.JxlEncoderDestroy.argtypes = [vp]
+    lib.JxlEncoderGetError.argtypes = [vp]
+    lib.JxlB200EncoderApiMessage.restype = ctypes.c_char_p
+    lib.JxlB200EncoderApiMessage.argtypes = [vp]
+    lib.JxlEncoderSetParallelRunner.argtypes = [vp, vp, vp]
+    lib.JxlEncoderFrameSettingsCreate.restype = vp
+    lib.JxlEncoderFrameSettingsCreate.argtypes = [vp, vp]
+    lib.JxlEncoderUseContainer.argtypes = [vp, ctypes.c_int]
+    lib.JxlEncoderUseBoxes.argtypes = [vp]
+    lib.JxlEncoderAddBox.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, sz, ctypes.c_int]
+    lib.JxlEncoderStoreJPEGMetadata.argtypes = [vp, ctypes.c_int]
+    lib.JxlEncoderSetFrameLossless.argtypes = [vp, ctypes.c_int]
+    lib.JxlEncoderSetFrameDistance.argtypes = [vp, ctypes.c_float]
+    lib.JxlEncoderDistanceFromQuality.restype = ctypes.c_float
+    lib.JxlEncoderDistanceFromQuality.argtypes = [ctypes.c_float]
+    lib.JxlEncoderFrameSettingsSetOption.argtypes = [vp, ctypes.c_int, ctypes.c_int64]
+    lib.JxlEncoderInitBasicInfo.argtypes = [ctypes.POINTER(JxlBasicInfo)]
+    lib.JxlEncoderSetBasicInfo.argtypes = [vp, ctypes.POINTER(JxlBasicInfo)]
+    lib.JxlEncoderSetColorEncoding.argtypes = [vp, ctypes.POINTER(JxlColorEncoding)]
+    lib.JxlColorEncodingSetToSRGB.argtypes = [ctypes.POINTER(JxlColorEncoding), ctypes.c_int]
+    lib.JxlColorEncodingSetToLinearSRGB.argtypes = [ctypes.POINTER(JxlColorEncoding), ctypes.c_int]
+    lib.JxlEncoderAddImageFrame.argtypes = [vp, ctypes.POINTER(JxlPixelFormat), vp, sz]
+    lib.JxlEncoderAddJPEGFrame.argtypes = [vp, ctypes.c_char_p, sz]
+    lib.JxlEncoderCloseInput.argtypes = [vp]
+    lib.JxlEncoderProcessOutput.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz)]
+    lib.JxlThreadParallelRunnerCreate.restype = vp
+    lib.JxlThreadParallelRunnerCreate.argtypes = [vp, sz]
+    lib.JxlThreadParallelRunnerDestroy.argtypes = [vp]
+    lib.JxlThreadParallelRunnerDefaultNumWorkerThreads.restype = sz
+    lib.JxlResizableParallelRunnerCreate.restype = vp
+    lib.JxlResizableParallelRunnerCreate.argtypes = [vp]
+    lib.JxlResizableParallelRunnerSetThreads.argtypes = [vp, sz]
+    lib.JxlResizableParallelRunnerSuggestThreads.restype = ctypes.c_uint32
+    lib.JxlResizableParallelRunnerSuggestThreads.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
+    lib.JxlResizableParallelRunnerDestroy.argtypes = [vp]
     lib.JxlDecoderVersion.restype = ctypes.c_uint32
     lib.JxlSignatureCheck.argtypes = [ctypes.c_char_p, sz]
     lib.JxlDecoderCreate.restype = vp
@@ -182,6 +235,19 @@ EXPORTED_SYMBOLS = [
     "JxlDecoderSetUnpremultiplyAlpha", "JxlDecoderSetRenderSpotcolors", "JxlDecoderSetCoalescing",
     "JxlDecoderSetDesiredIntensityTarget", "JxlDecoderSetInput", "JxlDecoderCloseInput", "JxlDecoderProcessInput",
     "JxlDecoderGetBasicInfo", "JxlDecoderImageOutBufferSize", "JxlDecoderSetImageOutBuffer",
+    "JxlDecoderGetICCProfileSize", "JxlDecoderGetColorAsICCProfile", "JxlDecoderSetJPEGBuffer", "JxlDecoderReleaseJPEGBuffer",
+    # the encoder symbols jpegxl-rs calls (jpegxl-rs/src/encode.rs:156-467)
+    "JxlEncoderVersion", "JxlEncoderCreate", "JxlEncoderReset", "JxlEncoderDestroy", "JxlEncoderGetError",
+    "JxlEncoderSetParallelRunner", "JxlEncoderFrameSettingsCreate", "JxlEncoderUseContainer", "JxlEncoderUseBoxes",
+    "JxlEncoderAddBox", "JxlEncoderStoreJPEGMetadata", "JxlEncoderSetFrameLossless", "JxlEncoderSetFrameDistance",
+    "JxlEncoderDistanceFromQuality", "JxlEncoderFrameSettingsSetOption", "JxlEncoderInitBasicInfo",
+    "JxlEncoderSetBasicInfo", "JxlEncoderSetColorEncoding", "JxlColorEncodingSetToSRGB", "JxlColorEncodingSetToLinearSRGB",
+    "JxlEncoderAddImageFrame", "JxlEncoderAddJPEGFrame", "JxlEncoderCloseInput", "JxlEncoderProcessOutput",
+    "JxlB200EncoderApiMessage",
+    # libjxl_threads (jpegxl-sys/src/threads)
+    "JxlThreadParallelRunner", "JxlThreadParallelRunnerCreate", "JxlThreadParallelRunnerDestroy",
+    "JxlThreadParallelRunnerDefaultNumWorkerThreads", "JxlResizableParallelRunner", "JxlResizableParallelRunnerCreate",
+    "JxlResizableParallelRunnerSetThreads", "JxlResizableParallelRunnerSuggestThreads", "JxlResizableParallelRunnerDestroy",
 ]
 
 
@@ -540,31 +606,107 @@ class EncoderResult:
 class JxlEncoder:
     """jpegxl-rs/src/encode.rs:60-187 (builder fields) and :477-486 (`encode::<u8, u8>`): lossy VarDCT of RGB8 input on
     the GPU. `quality` is the Butteraugli distance as in jpegxl-rs (default 1.0); `speed` selects the AcStrategy
-    search: the fastest tiers use 8x8 DCTs only, the others the variance heuristic over 8x8 ... 64x64."""
+    search: the fastest tiers use 8x8 DCTs only, the others the variance heuristic over 8x8 ... 64x64.
+
+    `encode()` drives the libjxl-compatible JxlEncoder* entry points in the order jpegxl-rs does
+    (setup_encoder -> add_frame -> CloseInput -> ProcessOutput with a doubling buffer, encode.rs:225-378);
+    `encode_batch()` is the batch extension (one call, many images). What the CUDA encoder does not cover
+    (lossless, alpha, non-8-bit samples, JPEG transcoding, boxes) fails with the reference's error variants."""
 
     def __init__(self, has_alpha: bool = False, lossless: bool = False, speed: int = 7, quality: float = 1.0,
-                 use_container: bool = False, decoding_speed: int = 0, device: int = 0):
-        if lossless:
-            raise EncodeError("NotSupported: lossless encoding is not part of the GPU path")
-        if has_alpha:
-            raise EncodeError("NotSupported: alpha")
-        if use_container:
-            raise EncodeError("NotSupported: container output")
+                 use_container: bool = False, uses_original_profile: bool = False, decoding_speed: int = 0,
+                 init_buffer_size: int = 512 * 1024, device: int = 0):
         self._lib = load_library()
-        self._enc = self._lib.JxlB200EncoderCreate(device)
-        if not self._enc:
-            raise EncodeError("CannotCreateEncoder: no usable CUDA device (jxl_b200 has no CPU fallback)")
-        self.speed, self.quality, self.decoding_speed = speed, quality, decoding_speed
+        self._handle = self._lib.JxlEncoderCreate(None)
+        if not self._handle:
+            raise EncodeError("CannotCreateEncoder")
+        self._options = self._lib.JxlEncoderFrameSettingsCreate(self._handle, None)
+        self._enc = None  # batch encoder, created on first use
+        self.device = device
+        self.has_alpha, self.lossless, self.speed, self.quality = has_alpha, lossless, speed, quality
+        self.use_container, self.uses_original_profile = use_container, uses_original_profile
+        self.decoding_speed, self.init_buffer_size = decoding_speed, max(32, init_buffer_size)
 
     def __del__(self):
         if getattr(self, "_enc", None):
             self._lib.JxlB200EncoderDestroy(self._enc)
             self._enc = None
+        if getattr(self, "_handle", None):
+            self._lib.JxlEncoderDestroy(self._handle)
+            self._handle = None
 
-    def _options(self) -> JxlB200EncodeOptions:
+    # -- jpegxl-rs/src/encode.rs:205-221
+    def _check(self, status: int):
+        if status == JXL_ENC_SUCCESS:
+            return
+        if status == JXL_ENC_NEED_MORE_OUTPUT:
+            raise EncodeError("NeedMoreOutput")
+        code = self._lib.JxlEncoderGetError(self._handle)
+        raise EncodeError("%s: %s" % (_ENC_ERROR_NAMES.get(code, "GenericError"),
+                                      self._lib.JxlB200EncoderApiMessage(self._handle).decode()))
+
+    # -- jpegxl-rs/src/encode.rs:225-254
+    def _set_options(self):
+        L = self._lib
+        self._check(L.JxlEncoderUseContainer(self._handle, int(self.use_container)))
+        if self.lossless is not None:
+            self._check(L.JxlEncoderSetFrameLossless(self._options, int(self.lossless)))
+        self._check(L.JxlEncoderFrameSettingsSetOption(self._options, JXL_ENC_FRAME_SETTING_EFFORT, int(self.speed)))
+        self._check(L.JxlEncoderSetFrameDistance(self._options, float(self.quality)))
+        self._check(L.JxlEncoderFrameSettingsSetOption(self._options, JXL_ENC_FRAME_SETTING_DECODING_SPEED,
+                                                       int(self.decoding_speed)))
+
+    # -- jpegxl-rs/src/encode.rs:257-319
+    def _setup_encoder(self, width: int, height: int, bits: int, exp: int, has_alpha: bool):
+        L = self._lib
+        self._set_options()
+        info = JxlBasicInfo()
+        L.JxlEncoderInitBasicInfo(ctypes.byref(info))
+        info.xsize, info.ysize = width, height
+        info.have_container = int(self.use_container)
+        info.uses_original_profile = int(self.uses_original_profile)
+        info.bits_per_sample, info.exponent_bits_per_sample = bits, exp
+        if has_alpha:
+            info.num_extra_channels, info.alpha_bits, info.alpha_exponent_bits = 1, bits, exp
+        self._check(L.JxlEncoderSetBasicInfo(self._handle, ctypes.byref(info)))
+
+    # -- jpegxl-rs/src/encode.rs:345-378
+    def _internal(self) -> bytes:
+        L = self._lib
+        L.JxlEncoderCloseInput(self._handle)
+        buf = (ctypes.c_uint8 * self.init_buffer_size)()
+        written = 0
+        while True:
+            next_out = ctypes.c_void_p(ctypes.addressof(buf) + written)
+            avail = ctypes.c_size_t(len(buf) - written)
+            status = L.JxlEncoderProcessOutput(self._handle, ctypes.byref(next_out), ctypes.byref(avail))
+            written = next_out.value - ctypes.addressof(buf)
+            if status != JXL_ENC_NEED_MORE_OUTPUT:
+                break
+            bigger = (ctypes.c_uint8 * (len(buf) * 2))()
+            ctypes.memmove(bigger, buf, written)
+            buf = bigger
+        try:
+            self._check(status)
+        finally:
+            L.JxlEncoderReset(self._handle)
+            self._options = L.JxlEncoderFrameSettingsCreate(self._handle, None)
+        return bytes(buf[:written])
+
+    def _batch_options(self) -> JxlB200EncodeOptions:
         return JxlB200EncodeOptions(float(self.quality), 0 if self.speed <= 2 else 2, 1, 2, 1)
 
     def encode_batch(self, images: Sequence[np.ndarray]) -> List[EncoderResult]:
+        if self.lossless:
+            raise EncodeError("NotSupported: lossless encoding is not part of the GPU path")
+        if self.has_alpha:
+            raise EncodeError("NotSupported: alpha")
+        if self.use_container:
+            raise EncodeError("NotSupported: container output in batch mode")
+        if self._enc is None:
+            self._enc = self._lib.JxlB200EncoderCreate(self.device)
+            if not self._enc:
+                raise EncodeError("CannotCreateEncoder: no usable CUDA device (jxl_b200 has no CPU fallback)")
         imgs = [np.ascontiguousarray(a, np.uint8) for a in images]
         for a in imgs:
             if a.ndim != 3 or a.shape[2] != 3:
@@ -573,7 +715,7 @@ class JxlEncoder:
         ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in imgs])
         xs = (ctypes.c_uint32 * n)(*[a.shape[1] for a in imgs])
         ys = (ctypes.c_uint32 * n)(*[a.shape[0] for a in imgs])
-        opt = self._options()
+        opt = self._batch_options()
         if self._lib.JxlB200EncoderEncodeBatch(self._enc, ptrs, xs, ys, n, ctypes.byref(opt)) != 0:
             raise EncodeError(self._lib.JxlB200EncoderGetError(self._enc).decode())
         out = []
@@ -586,16 +728,41 @@ class JxlEncoder:
         return out
 
     def encode(self, data: np.ndarray, width: Optional[int] = None, height: Optional[int] = None) -> EncoderResult:
-        """jpegxl-rs/src/encode.rs:477-486: `data` is height * width * 3 bytes (or an (H, W, 3) array)."""
-        a = np.asarray(data, np.uint8)
+        """jpegxl-rs/src/encode.rs:477-486: `data` is height * width * channels samples (or an (H, W, C) array) of
+        u8 / u16 / f32; channels = 3, + 1 with `has_alpha`."""
+        a = np.asarray(data)
+        if a.dtype not in (np.uint8, np.uint16, np.float32, np.float16):
+            a = a.astype(np.uint8)
+        channels = 4 if self.has_alpha else 3
         if a.ndim == 1:
-            if not width or not height or a.size != width * height * 3:
-                raise EncodeError("ApiUsage: buffer size does not match width * height * 3")
-            a = a.reshape(height, width, 3)
-        return self.encode_batch([a])[0]
+            if not width or not height or a.size != width * height * channels:
+                raise EncodeError("ApiUsage: buffer size does not match width * height * channels")
+            a = a.reshape(height, width, channels)
+        a = np.ascontiguousarray(a)
+        height, width = a.shape[:2]
+        bits, exp, dt = {np.dtype(np.uint8): (8, 0, JXL_TYPE_UINT8), np.dtype(np.uint16): (16, 0, JXL_TYPE_UINT16),
+                         np.dtype(np.float16): (16, 5, JXL_TYPE_FLOAT16), np.dtype(np.float32): (32, 8, JXL_TYPE_FLOAT)}[a.dtype]
+        self._setup_encoder(width, height, bits, exp, self.has_alpha)
+        fmt = JxlPixelFormat(a.shape[2], dt, JXL_NATIVE_ENDIAN, 0)
+        try:
+            self._check(self._lib.JxlEncoderAddImageFrame(self._options, ctypes.byref(fmt), a.ctypes.data, a.nbytes))
+        except EncodeError:
+            self._lib.JxlEncoderReset(self._handle)
+            self._options = self._lib.JxlEncoderFrameSettingsCreate(self._handle, None)
+            raise
+        return EncoderResult(self._internal())
+
+    def encode_jpeg(self, data: bytes) -> EncoderResult:
+        """jpegxl-rs/src/encode.rs:444-466. JPEG transcoding is not built: NotSupported, as the C API reports."""
+        self._set_options()
+        self._check(self._lib.JxlEncoderStoreJPEGMetadata(self._handle, 1))
+        self._check(self._lib.JxlEncoderAddJPEGFrame(self._options, data, len(data)))
+        return EncoderResult(self._internal())
 
     def phase_times(self):
         ms = (ctypes.c_double * 3)()
+        if self._enc is None:
+            return {"tokens_ms": 0.0, "host_tables_ms": 0.0, "emit_ms": 0.0}
         self._lib.JxlB200EncoderGetPhaseTimes(self._enc, ms)
         return {"tokens_ms": ms[0], "host_tables_ms": ms[1], "emit_ms": ms[2]}
 

@@ -1146,6 +1146,39 @@ JxlDecoderStatus JxlDecoderSetImageOutBuffer(JxlDecoder* dec, const JxlPixelForm
   return JXL_DEC_SUCCESS;
 }
 
+// jpegxl-rs asks for the ICC profile only when the `icc_profile` option is set (jpegxl-rs/src/decode.rs:329-357).
+// libjxl synthesises one from the enumerated colour encoding (lib/jxl/cms/jxl_cms_internal.h); that generator and the
+// ICC codec are container / metadata work, not built: the calls fail, as libjxl's do when it cannot
+// produce a profile.
+JxlDecoderStatus JxlDecoderGetICCProfileSize(const JxlDecoder* dec, int target, size_t* size) {
+  (void)dec;
+  (void)target;
+  if (size) *size = 0;
+  return JXL_DEC_ERROR;
+}
+
+JxlDecoderStatus JxlDecoderGetColorAsICCProfile(const JxlDecoder* dec, int target, uint8_t* icc_profile, size_t size) {
+  (void)dec;
+  (void)target;
+  (void)icc_profile;
+  (void)size;
+  return JXL_DEC_ERROR;
+}
+
+// JPEG reconstruction is not built: JXL_DEC_JPEG_RECONSTRUCTION is never emitted, so jpegxl-rs
+// never reaches these (jpegxl-rs/src/decode.rs:260-283); they refuse, like libjxl outside that event.
+JxlDecoderStatus JxlDecoderSetJPEGBuffer(JxlDecoder* dec, uint8_t* data, size_t size) {
+  (void)dec;
+  (void)data;
+  (void)size;
+  return JXL_DEC_ERROR;
+}
+
+size_t JxlDecoderReleaseJPEGBuffer(JxlDecoder* dec) {
+  (void)dec;
+  return 0;
+}
+
 }  // extern "C"
 
 // ================================================================== encoder
@@ -1640,3 +1673,5 @@ int JxlB200EncoderGetPhaseTimes(const JxlB200Encoder* enc, double* ms3) {
 }
 
 }  // extern "C"
+
+#include "jxl_encode_api.inc"

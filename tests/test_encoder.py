@@ -59,3 +59,16 @@ def test_gpu_round_trip_4k(pkg):
     err = out.astype(np.float64) - img
     assert 10 * np.log10(255 ** 2 / (err ** 2).mean()) > 33
     assert np.array_equal(out, jxlo.decode(data, 3, jxlo.UINT8))
+
+
+@pytest.mark.gpu
+def test_event_api_container_output_round_trips(pkg):
+    # JxlEncoderUseContainer: signature box + ftyp + jxlc around the same codestream (lib/jxl/encode.cc:376-560)
+    img = vc.crop(300, 400, 500, 700)
+    plain = pkg.encoder_builder().build().encode(img).data
+    boxed = pkg.encoder_builder().use_container(True).init_buffer_size(64).build().encode(img).data
+    assert pkg.check_valid_signature(boxed) and boxed[:12] == b"\0\0\0\x0cJXL \r\n\x87\n" and boxed.endswith(plain)
+    assert plain == jxlo.encode_vardct(img, dc_tree=1, strategy_mode=2)
+    meta, px = pkg.decoder_builder().build().decode(boxed)
+    assert (meta.width, meta.height) == (400, 300)
+    assert np.array_equal(np.asarray(px.data).reshape(300, 400, 3), jxlo.decode(plain, 3, jxlo.UINT8))
