@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(32) k_modular_decode(DevPools P) {
   m.wp = P.wp_scratch + static_cast<size_t>(blockIdx.x) * 10 * (P.wp_width + 2) * 32 + lane;
   const bool valid = s < P.num_streams;
   uint64_t end_pos = 0;
-  const uint32_t status = DevDecodeModularStream<WT>(P, s, m, P.warp_dims + P.warp_dims_off[blockIdx.x],
-                                                     P.warp_chans[blockIdx.x], valid, &end_pos);
+  const uint32_t status = DevDecodeModularStream<WT, 32>(P, s, m, P.warp_dims + P.warp_dims_off[blockIdx.x],
+                                                         P.warp_chans[blockIdx.x], valid, &end_pos);
   if (valid) {
     P.status[s] = status;
     if (P.end_bits) P.end_bits[s] = end_pos;
@@ -80,13 +80,13 @@ __global__ void __launch_bounds__(32) k_modular_decode_sparse(DevPools P) {
   m.ring_w = P.wp_width;
   m.lane_stride = kSparseLanes;
   m.ring = sparse_smem + (lane < kSparseLanes ? lane : 0);
-  m.wp = sparse_smem + 3 * P.wp_width * kSparseLanes + (lane < kSparseLanes ? lane : 0);
+  m.wp = sparse_smem + 2 * P.wp_width * kSparseLanes + (lane < kSparseLanes ? lane : 0);
   const bool valid = lane < kSparseLanes && s < P.num_streams;
   const uint32_t bundle = s / 32;  // loop bounds of the 32-stream bundle this stream belongs to (a superset)
   const uint32_t b0 = (blockIdx.x * kSparseLanes) / 32;
   (void)bundle;
   uint64_t end_pos = 0;
-  const uint32_t status = DevDecodeModularStream<WT>(P, s, m, P.warp_dims + P.warp_dims_off[b0], P.warp_chans[b0], valid, &end_pos);
+  const uint32_t status = DevDecodeModularStream<WT, kSparseLanes>(P, s, m, P.warp_dims + P.warp_dims_off[b0], P.warp_chans[b0], valid, &end_pos);
   if (valid) {
     P.status[s] = status;
     if (P.end_bits) P.end_bits[s] = end_pos;
@@ -741,7 +741,7 @@ size_t JxlB200DecoderImageOutBufferSize(const JxlB200Decoder* dec, size_t i) {
 static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s) {
   const DevPools& P = dec->pools;
   const uint32_t block = 32;
-  const size_t sparse_smem = static_cast<size_t>(13 * b.wp_width + 20) * kSparseLanes * sizeof(int32_t);
+  const size_t sparse_smem = static_cast<size_t>(7 * b.wp_width + 10) * kSparseLanes * sizeof(int32_t);
   if (b.streams.size() <= 2 * 148 * kSparseLanes && sparse_smem <= 160 * 1024) {
     const uint32_t grid = (b.streams.size() + kSparseLanes - 1) / kSparseLanes;
     if (b.narrow) {

@@ -202,6 +202,31 @@ struct DevSymbolReader {
     return v;
   }
 
+  // The code is ANS without LZ77 (checked for the whole warp by the caller): no mode tests per symbol.
+  JXLB_HD uint32_t ReadUintPlainAns(uint32_t cluster, DevBits& br) {
+    const uint32_t log_entry = 12 - log_alpha;
+    const uint32_t res = state & 0xFFF;
+    const uint32_t i = res >> log_entry;
+    const uint32_t pos = res & ((1u << log_entry) - 1);
+    const uint32_t cfg_word = JXLB_LDG(cfg + cluster);
+#if defined(__CUDA_ARCH__)
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(alias + (cluster << log_alpha) + i));
+    const uint32_t cutoff = raw.x & 0xFF, right_value = (raw.x >> 8) & 0xFF, freq0 = raw.x >> 16;
+    const uint32_t offsets1 = raw.y & 0xFFFF, fx = raw.y >> 16;
+#else
+    const DevAlias& e = alias[(cluster << log_alpha) + i];
+    const uint32_t cutoff = e.cutoff, right_value = e.right_value, freq0 = e.freq0;
+    const uint32_t offsets1 = e.offsets1, fx = e.freq1_xor_freq0;
+#endif
+    const bool right = pos >= cutoff;
+    const uint32_t sym = right ? right_value : i;
+    const uint32_t offset = (right ? offsets1 : 0u) + pos;
+    const uint32_t freq = right ? (freq0 ^ fx) : freq0;
+    state = freq * (state >> 12) + offset;
+    if (state < (1u << 16)) state = (state << 16) | br.Read(16);
+    return DevReadHybrid(cfg_word, sym, br);
+  }
+
   JXLB_HD uint32_t ReadUint(uint32_t cluster, DevBits& br) {
     if (!lz77_enabled) return DevReadHybrid(JXLB_LDG(cfg + cluster), ReadSymbol(cluster, br), br);
     if (num_to_copy > 0) return CopyOne();
@@ -300,6 +325,14 @@ JXLB_HD uint32_t DevFloorLog2(uint64_t v) {
   return 63 - __clzll(static_cast<long long>(v));
 #else
   return 63 - __builtin_clzll(v);
+#endif
+}
+
+JXLB_HD uint32_t DevFloorLog2_32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(static_cast<int>(v));
+#else
+  return 31 - __builtin_clz(v);
 #endif
 }
 
@@ -438,6 +471,227 @@ JXLB_HD WT DevPredictW(uint32_t p, WT left, WT top, WT topleft, WT topright, WT 
   }
 }
 
+struct DevWpParams {
+  int32_t p1C, p2C, p3Ca, p3Cb, p3Cc, p3Cd, p3Ce;
+  uint32_t w[4];
+};
+
+// The sample loops of one channel slot of the warp (see DevDecodeModularStream). kFast: every lane that has this
+// slot decodes it through the weighted-predictor LUT -- no properties, no tree walk, no reference channels; the
+// generic code is compiled out of that instance.
+//
+// Row storage (per lane, `[position][lane]`): the lane's row ring is two rows, A and B. A holds the previous row and
+// is overwritten in place by the current one (the previous row's samples around x live in the sliding registers
+// tl / t / tr / trr, loaded three positions ahead of the write), B receives the previous row's sample just before A
+// loses it and so holds the row above the previous one when the next row reads it. The weighted predictor's five
+// error rows are updated in place the same way (entries x - 1 .. x + 1 of the previous row are in registers).
+template <typename WT, bool kFast, uint32_t kLS, bool kPlainAns>
+JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const DevChannel& ch, const DevWpParams& wpp,
+                                  const int w, const int h, const int max_w, const int max_h, const uint32_t stride,
+                                  int32_t* out, const bool lane_direct, const bool lane_uses_wp, const DevTreeNode* tree,
+                                  DevSymbolReader& reader, DevBits& br) {
+  const bool direct = kFast ? false : lane_direct;  // (the fast path never reads neighbours from the output plane)
+  // kLS: the lane stride when the kernel fixes it at compile time (index arithmetic becomes shifts), 0 = m.lane_stride
+  const uint32_t PS = m.props_stride, LS = kLS ? kLS : m.lane_stride, RW = m.ring_w, WL = m.ring_w + 2;
+  int32_t* props = m.props;
+  const uint32_t* divlut = m.divlut;
+  const bool uses_wp = kFast ? true : lane_uses_wp;
+  // The first two levels of the tree are walked for every sample: keep them in registers.
+  DevTreeNode root{}, root_l{}, root_r{};
+  root.prop = -1;
+  if (!kFast && h > 0) {
+    root = DevLoadNode(tree);
+    if (root.prop >= 0) {
+      root_l = DevLoadNode(tree + root.b);
+      root_r = DevLoadNode(tree + root.c);
+    }
+  }
+  const uint32_t RS = direct ? 1 : LS;
+  const uint16_t* lut = P.lut + ch.lut_off;
+  const int32_t lut_lo = ch.lut_lo, lut_hi = ch.lut_lo + static_cast<int32_t>(ch.lut_size) - 1;
+  int32_t* pe[4];
+  for (uint32_t i = 0; i < 4; i++) pe[i] = m.wp + static_cast<uint32_t>(i * WL) * LS;
+  int32_t* er = m.wp + static_cast<uint32_t>(4 * WL) * LS;
+  int32_t* rowA = m.ring;
+  int32_t* rowB = m.ring + static_cast<uint32_t>(RW) * LS;
+  if (uses_wp) {  // the rows above y = 0 read as zero
+    for (uint32_t a = 0; a < 5; a++)
+      for (int q = 0; q < w + 2; q++) m.wp[static_cast<uint32_t>(a * WL + q) * LS] = 0;
+  }
+  for (int y = 0; y < max_h; y++) {
+    const bool row_on = y < h;
+    int32_t* out_row = out + static_cast<size_t>(y) * stride;
+    int32_t* row = direct ? out_row : rowA;
+    const int32_t* prev = direct ? out_row - stride : rowA;
+    const int32_t* prevprev = direct ? out_row - 2 * static_cast<size_t>(stride) : rowB;
+    if (!kFast) props[2 * PS] = y;
+    int32_t prev_grad = 0;  // property 9 of the previous pixel
+    // sliding neighbourhood (valid when y > 0): t = prev[x], tl = prev[x-1], tr = prev[x+1], trr = prev[x+2]
+    int32_t left = 0, leftleft = 0, t = 0, tl = 0, tr = 0, trr = 0;
+    uint32_t eNW[4] = {0, 0, 0, 0}, eN[4] = {0, 0, 0, 0}, eNE[4] = {0, 0, 0, 0};
+    int32_t teW = 0, teNW = 0, teN = 0, teNE = 0;
+    if (row_on && w > 0) {
+      if (y > 0) {
+        t = prev[0];
+        tr = w > 1 ? prev[static_cast<uint32_t>(1) * RS] : t;
+        trr = w > 2 ? prev[static_cast<uint32_t>(2) * RS] : tr;
+      }
+      if (uses_wp) {
+        for (uint32_t i = 0; i < 4; i++) {
+          eN[i] = static_cast<uint32_t>(pe[i][0]);
+          eNW[i] = eN[i];
+          eNE[i] = w > 1 ? static_cast<uint32_t>(pe[i][static_cast<uint32_t>(1) * LS]) : eN[i];
+        }
+        teN = er[0];
+        teNW = teN;
+        teNE = w > 1 ? er[static_cast<uint32_t>(1) * LS] : teN;
+      }
+    }
+    for (int x = 0; x < max_w; x++) {
+      if (row_on && x < w) {
+        // neighbours with the edge rules of context_predict.h:496-504
+        const WT n_left = x ? left : (y ? t : 0);
+        const WT n_top = y ? t : n_left;
+        const WT n_topleft = (x && y) ? tl : n_left;
+        const WT n_topright = (x + 1 < w && y) ? tr : n_top;
+        const WT n_leftleft = x > 1 ? leftleft : n_left;
+        const WT n_toptop = y > 1 ? prevprev[static_cast<uint32_t>(x) * RS] : n_top;
+        const WT n_toprightright = (x + 2 < w && y) ? trr : n_topright;
+        if (!kFast) {
+          props[3 * PS] = x;
+          props[4 * PS] = static_cast<int32_t>(n_top > 0 ? n_top : -n_top);
+          props[5 * PS] = static_cast<int32_t>(n_left > 0 ? n_left : -n_left);
+          props[6 * PS] = static_cast<int32_t>(n_top);
+          props[7 * PS] = static_cast<int32_t>(n_left);
+          props[8 * PS] = static_cast<int32_t>(n_left - prev_grad);
+          prev_grad = static_cast<int32_t>(n_left + n_top - n_topleft);
+          props[9 * PS] = prev_grad;
+          props[10 * PS] = static_cast<int32_t>(n_left - n_topleft);
+          props[11 * PS] = static_cast<int32_t>(n_topleft - n_top);
+          props[12 * PS] = static_cast<int32_t>(n_top - n_topright);
+          props[13 * PS] = static_cast<int32_t>(n_top - n_toptop);
+          props[14 * PS] = static_cast<int32_t>(n_left - n_leftleft);
+        }
+        int32_t wp_max_error = 0;
+        WT wp_pred = 0, wp_raw = 0;
+        WT prediction[4] = {0, 0, 0, 0};
+        if (uses_wp) {
+          uint32_t weights[4];
+          for (uint32_t i = 0; i < 4; i++) {
+            const uint32_t e = eN[i] + eNE[i] + eNW[i];
+            // (32-bit sums cannot wrap when 16-bit buffers suffice: every error term is below 2^20)
+            int shift = static_cast<int>(sizeof(WT) == 4 ? DevFloorLog2_32(e + 1) : DevFloorLog2(static_cast<uint64_t>(e) + 1)) - 5;
+            if (shift < 0) shift = 0;
+            weights[i] = 4 + ((wpp.w[i] * divlut[e >> shift]) >> shift);
+          }
+          const WT N8 = n_top * 8, W8 = n_left * 8, NE8 = n_topright * 8, NW8 = n_topleft * 8, NN8 = n_toptop * 8;
+          const WT eW = x == 0 ? 0 : teW;
+          const WT sumWN = static_cast<WT>(teN) + eW;
+          {
+            WT pm = eW;
+            if (DevAbsW<WT>(teN) > DevAbsW<WT>(pm)) pm = teN;
+            if (DevAbsW<WT>(teNW) > DevAbsW<WT>(pm)) pm = teNW;
+            if (DevAbsW<WT>(teNE) > DevAbsW<WT>(pm)) pm = teNE;
+            wp_max_error = static_cast<int32_t>(pm);
+            if (!kFast) props[15 * PS] = wp_max_error;
+          }
+          prediction[0] = W8 + NE8 - N8;
+          prediction[1] = N8 - (((sumWN + teNE) * wpp.p1C) >> 5);
+          prediction[2] = W8 - (((sumWN + teNW) * wpp.p2C) >> 5);
+          prediction[3] = N8 - ((static_cast<WT>(teNW) * wpp.p3Ca + static_cast<WT>(teN) * wpp.p3Cb +
+                                 static_cast<WT>(teNE) * wpp.p3Cc + (NN8 - N8) * wpp.p3Cd + (NW8 - W8) * wpp.p3Ce) >> 5);
+          uint32_t wsum = weights[0] + weights[1] + weights[2] + weights[3];
+          const uint32_t log_weight = DevFloorLog2_32(wsum);
+          wsum = 0;
+          for (int i = 0; i < 4; i++) {
+            weights[i] >>= log_weight - 4;
+            wsum += weights[i];
+          }
+          WT sum = static_cast<WT>((wsum >> 1) - 1);
+          for (int i = 0; i < 4; i++) sum += prediction[i] * static_cast<WT>(weights[i]);
+          wp_raw = static_cast<WT>((static_cast<int64_t>(sum) * static_cast<int64_t>(divlut[wsum - 1])) >> 24);
+          if (!(((static_cast<WT>(teN) ^ eW) | (static_cast<WT>(teN) ^ static_cast<WT>(teNW))) > 0)) {
+            WT mx = W8 > NE8 ? W8 : NE8;
+            if (N8 > mx) mx = N8;
+            WT mn = W8 < NE8 ? W8 : NE8;
+            if (N8 < mn) mn = N8;
+            if (wp_raw > mx) wp_raw = mx;
+            if (wp_raw < mn) wp_raw = mn;
+          }
+          wp_pred = (wp_raw + 3) >> 3;
+        }
+        for (uint32_t r = 0; !kFast && r < ch.ref_count; r++) {
+          const DevPlane rp = P.planes[P.refs[ch.ref_off + r]];
+          const int32_t* rrow = P.arena + rp.off + static_cast<size_t>(y) * w;
+          const int32_t* rprev = y ? rrow - w : rrow;
+          const int64_t v = rrow[x];
+          const int64_t vleft = x ? rrow[x - 1] : 0;
+          const int64_t vtop = y ? rprev[x] : vleft;
+          const int64_t vtopleft = (x && y) ? rprev[x - 1] : vleft;
+          const int64_t vpred = DevClampedGradient(static_cast<int32_t>(vleft), static_cast<int32_t>(vtop), static_cast<int32_t>(vtopleft));
+          props[(16 + 4 * r + 0) * PS] = static_cast<int32_t>(DevAbs64(v));
+          props[(16 + 4 * r + 1) * PS] = static_cast<int32_t>(v);
+          props[(16 + 4 * r + 2) * PS] = static_cast<int32_t>(DevAbs64(v - vpred));
+          props[(16 + 4 * r + 3) * PS] = static_cast<int32_t>(v - vpred);
+        }
+        int32_t val;
+        if (kFast) {
+          // single-property tree on the max-error property, leaves (Weighted, 0, 1): one table lookup
+          const int32_t pv = wp_max_error < lut_lo ? lut_lo : (wp_max_error > lut_hi ? lut_hi : wp_max_error);
+          const uint32_t cluster = JXLB_LDG(lut + (pv - lut_lo));
+          const uint32_t u = kPlainAns ? reader.ReadUintPlainAns(cluster, br) : reader.ReadUint(cluster, br);
+          val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) + static_cast<uint32_t>(wp_pred));
+        } else {
+          DevTreeNode node = root;
+          if (node.prop >= 0) node = props[node.prop * PS] > node.a ? root_l : root_r;
+          while (node.prop >= 0) {
+            const uint32_t pos = props[node.prop * PS] > node.a ? node.b : node.c;
+            node = DevLoadNode(tree + pos);
+          }
+          const uint32_t cluster = static_cast<uint32_t>(node.a) & 0xFFFF;
+          const uint32_t predictor = static_cast<uint32_t>(node.a) >> 16;
+          const uint32_t u = kPlainAns ? reader.ReadUintPlainAns(cluster, br) : reader.ReadUint(cluster, br);
+          const WT guess = static_cast<WT>(static_cast<int32_t>(node.b)) +
+                           DevPredictW<WT>(predictor, n_left, n_top, n_topleft, n_topright, n_leftleft, n_toptop,
+                                           n_toprightright, wp_pred);
+          // low 32 bits of (unpacked * multiplier + guess), as in make_pixel (encoding.cc:168-173)
+          val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) * node.c + static_cast<uint32_t>(guess));
+        }
+        if (!direct) rowB[static_cast<uint32_t>(x) * LS] = t;  // the sample A loses below: next row's N-N
+        row[static_cast<uint32_t>(x) * RS] = val;
+        out_row[x] = val;
+        leftleft = left;
+        left = val;
+        // slide the previous-row window
+        tl = t;
+        t = tr;
+        tr = trr;
+        if (y > 0 && x + 3 < w) trr = prev[static_cast<uint32_t>(x + 3) * RS];
+        if (uses_wp) {
+          const WT val8 = static_cast<WT>(val) * 8;
+          const int32_t te = static_cast<int32_t>(wp_raw - val8);
+          const bool more = x + 2 < w;  // position x + 2 exists in the previous row
+          const int32_t er_ahead = more ? er[static_cast<uint32_t>(x + 2) * LS] : 0;
+          er[static_cast<uint32_t>(x) * LS] = te;
+          for (uint32_t i = 0; i < 4; i++) {
+            const uint32_t err = static_cast<uint32_t>((DevAbsW<WT>(prediction[i] - val8) + 3) >> 3);
+            // next pixel: NW <- N, N <- (entry x + 1) + err, NE <- entry x + 2 (or N at the row end)
+            const uint32_t n_next = eNE[i] + err;
+            eNW[i] = eN[i];
+            eN[i] = n_next;
+            eNE[i] = more ? static_cast<uint32_t>(pe[i][static_cast<uint32_t>(x + 2) * LS]) : n_next;
+            pe[i][static_cast<uint32_t>(x) * LS] = static_cast<int32_t>(err);
+          }
+          teW = te;
+          teNW = teN;
+          teN = teNE;
+          teNE = more ? er_ahead : teN;
+        }
+      }
+    }
+  }
+}
+
 // Decodes every channel of stream `s` (lane `s % 32` of warp `s / 32`).
 //
 // WT is the arithmetic width of predictor math: int32_t when the codestream promises
@@ -454,7 +708,7 @@ JXLB_HD WT DevPredictW(uint32_t p, WT left, WT top, WT topleft, WT topright, WT 
 // reference's `pred_errors[prev_row + x + 1] += err` (context_predict.h:209) only
 // ever influences the next two pixels of the same row, so it is applied to the
 // registers and never stored.
-template <typename WT>
+template <typename WT, uint32_t kLS = 0>
 JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const DevLaneMem& m, const uint32_t* warp_dims,
                                         uint32_t warp_chans, bool lane_valid, uint64_t* end_pos = nullptr) {
   DevStream st{};
@@ -470,19 +724,20 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
     reader.Init(P, code, br, st.dist_multiplier, window);
     my_chans = st.chan_end - st.chan_begin;
   }
-  const uint32_t PS = m.props_stride, LS = m.lane_stride, RW = m.ring_w, WL = m.ring_w + 2;
+  // every lane of the warp reads plain ANS (no prefix codes, no LZ77): the per-symbol mode tests are compiled out
+  const bool plain_ans = JXLB_WARP_ALL_M(!lane_valid || (!code.use_prefix && !code.lz77_enabled));
+  const uint32_t PS = m.props_stride;
   int32_t* props = m.props;
   for (int i = 0; i < kDevMaxProps; i++) props[i * PS] = 0;
   props[1 * PS] = static_cast<int32_t>(st.stream_id);
   // weighted predictor parameters
-  int32_t p1C = st.wp_params[0] & 0xFF, p2C = (st.wp_params[0] >> 8) & 0xFF, p3Ca = (st.wp_params[0] >> 16) & 0xFF,
-          p3Cb = st.wp_params[0] >> 24, p3Cc = st.wp_params[1] & 0xFF, p3Cd = (st.wp_params[1] >> 8) & 0xFF,
-          p3Ce = (st.wp_params[1] >> 16) & 0xFF;
+  DevWpParams wpp;
+  wpp.p1C = st.wp_params[0] & 0xFF; wpp.p2C = (st.wp_params[0] >> 8) & 0xFF; wpp.p3Ca = (st.wp_params[0] >> 16) & 0xFF;
+  wpp.p3Cb = st.wp_params[0] >> 24; wpp.p3Cc = st.wp_params[1] & 0xFF; wpp.p3Cd = (st.wp_params[1] >> 8) & 0xFF;
+  wpp.p3Ce = (st.wp_params[1] >> 16) & 0xFF;
   uint32_t status = kStatusOk;
   uint32_t dyn_count = 0;
-  uint32_t wpw[4];
-  for (int i = 0; i < 4; i++) wpw[i] = (st.wp_params[2] >> (8 * i)) & 0xFF;
-  const uint32_t* divlut = m.divlut;
+  for (int i = 0; i < 4; i++) wpp.w[i] = (st.wp_params[2] >> (8 * i)) & 0xFF;
 
   for (uint32_t k = 0; k < warp_chans; k++) {
     const int max_w = static_cast<int>(warp_dims[2 * k]), max_h = static_cast<int>(warp_dims[2 * k + 1]);
@@ -499,12 +754,12 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
         dyn_count = br.Read(ch.count_bits) + 1;
         const uint32_t use_global_tree = br.Read(1);
         if (br.Read(1)) {  // default weighted-predictor header (context_predict.h:37-61)
-          p1C = 16; p2C = 10; p3Ca = 7; p3Cb = 7; p3Cc = 7; p3Cd = 0; p3Ce = 0;
-          wpw[0] = 0xd; wpw[1] = 0xc; wpw[2] = 0xc; wpw[3] = 0xc;
+          wpp.p1C = 16; wpp.p2C = 10; wpp.p3Ca = 7; wpp.p3Cb = 7; wpp.p3Cc = 7; wpp.p3Cd = 0; wpp.p3Ce = 0;
+          wpp.w[0] = 0xd; wpp.w[1] = 0xc; wpp.w[2] = 0xc; wpp.w[3] = 0xc;
         } else {
-          p1C = br.Read(5); p2C = br.Read(5); p3Ca = br.Read(5); p3Cb = br.Read(5); p3Cc = br.Read(5);
-          p3Cd = br.Read(5); p3Ce = br.Read(5);
-          for (int i = 0; i < 4; i++) wpw[i] = br.Read(4);
+          wpp.p1C = br.Read(5); wpp.p2C = br.Read(5); wpp.p3Ca = br.Read(5); wpp.p3Cb = br.Read(5); wpp.p3Cc = br.Read(5);
+          wpp.p3Cd = br.Read(5); wpp.p3Ce = br.Read(5);
+          for (int i = 0; i < 4; i++) wpp.w[i] = br.Read(4);
         }
         const uint32_t transforms_selector = br.Read(2);
         if (!use_global_tree || transforms_selector != 0) status |= kStatusUnsupported;
@@ -527,207 +782,19 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
       }
     }
     const DevTreeNode* tree = P.tree + ch.tree_off;
-    // The first two levels of the tree are walked for every sample: keep them in registers.
-    DevTreeNode root{}, root_l{}, root_r{};
-    root.prop = -1;
-    if (k < my_chans) {
-      root = DevLoadNode(tree);
-      if (root.prop >= 0) {
-        root_l = DevLoadNode(tree + root.b);
-        root_r = DevLoadNode(tree + root.c);
-      }
-    }
     const bool uses_wp = ch.uses_wp != 0 && !direct;
-    const size_t RS = direct ? 1 : LS;
     // every lane of the warp that has this channel slot qualifies for the weighted-predictor LUT path
     const bool fast = JXLB_WARP_ALL_M(k >= my_chans || (ch.wp_lut != 0 && uses_wp && ch.ref_count == 0));
-    const uint16_t* lut = P.lut + ch.lut_off;
-    const int32_t lut_lo = ch.lut_lo, lut_hi = ch.lut_lo + static_cast<int32_t>(ch.lut_size) - 1;
     props[0] = static_cast<int32_t>(ch.prop0);
     props[15 * PS] = 0;
-    if (uses_wp) {
-      // row "prev" of y = 0 must read as zero (rows alternate: y = 0 uses row 0 as prev)
-      for (uint32_t a = 0; a < 5; a++)
-        for (int q = 0; q < w + 2; q++) m.wp[static_cast<size_t>((a * 2 + 0) * WL + q) * LS] = 0;
-    }
-    for (int y = 0; y < max_h; y++) {
-      const bool row_on = y < h;
-      int32_t* out_row = out + static_cast<size_t>(y) * stride;
-      int32_t* row = direct ? out_row : m.ring + static_cast<size_t>((y % 3) * RW) * LS;
-      const int32_t* prev = direct ? out_row - stride : m.ring + static_cast<size_t>(((y + 2) % 3) * RW) * LS;
-      const int32_t* prevprev = direct ? out_row - 2 * static_cast<size_t>(stride)
-                                       : m.ring + static_cast<size_t>(((y + 1) % 3) * RW) * LS;
-      const uint32_t cur = (y & 1) ? 0 : 1, prv = cur ^ 1;
-      int32_t* pe_cur[4];
-      const int32_t* pe_prv[4];
-      for (uint32_t i = 0; i < 4; i++) {
-        pe_cur[i] = m.wp + static_cast<size_t>((i * 2 + cur) * WL) * LS;
-        pe_prv[i] = m.wp + static_cast<size_t>((i * 2 + prv) * WL) * LS;
-      }
-      int32_t* er_cur = m.wp + static_cast<size_t>((4 * 2 + cur) * WL) * LS;
-      const int32_t* er_prv = m.wp + static_cast<size_t>((4 * 2 + prv) * WL) * LS;
-      props[2 * PS] = y;
-      int32_t prev_grad = 0;  // property 9 of the previous pixel
-      // sliding neighbourhood (valid when y > 0): t = prev[x], tl = prev[x-1], tr = prev[x+1], trr = prev[x+2]
-      int32_t left = 0, leftleft = 0, t = 0, tl = 0, tr = 0, trr = 0;
-      uint32_t eNW[4] = {0, 0, 0, 0}, eN[4] = {0, 0, 0, 0}, eNE[4] = {0, 0, 0, 0};
-      int32_t teW = 0, teNW = 0, teN = 0, teNE = 0;
-      if (row_on && w > 0) {
-        if (y > 0) {
-          t = prev[0];
-          tr = w > 1 ? prev[static_cast<size_t>(1) * RS] : t;
-          trr = w > 2 ? prev[static_cast<size_t>(2) * RS] : tr;
-        }
-        if (uses_wp) {
-          for (uint32_t i = 0; i < 4; i++) {
-            eN[i] = static_cast<uint32_t>(pe_prv[i][0]);
-            eNW[i] = eN[i];
-            eNE[i] = w > 1 ? static_cast<uint32_t>(pe_prv[i][static_cast<size_t>(1) * LS]) : eN[i];
-          }
-          teN = er_prv[0];
-          teNW = teN;
-          teNE = w > 1 ? er_prv[static_cast<size_t>(1) * LS] : teN;
-        }
-      }
-      for (int x = 0; x < max_w; x++) {
-        if (row_on && x < w) {
-          // neighbours with the edge rules of context_predict.h:496-504
-          const WT n_left = x ? left : (y ? t : 0);
-          const WT n_top = y ? t : n_left;
-          const WT n_topleft = (x && y) ? tl : n_left;
-          const WT n_topright = (x + 1 < w && y) ? tr : n_top;
-          const WT n_leftleft = x > 1 ? leftleft : n_left;
-          const WT n_toptop = y > 1 ? prevprev[static_cast<size_t>(x) * RS] : n_top;
-          const WT n_toprightright = (x + 2 < w && y) ? trr : n_topright;
-          if (!fast) {
-            props[3 * PS] = x;
-            props[4 * PS] = static_cast<int32_t>(n_top > 0 ? n_top : -n_top);
-            props[5 * PS] = static_cast<int32_t>(n_left > 0 ? n_left : -n_left);
-            props[6 * PS] = static_cast<int32_t>(n_top);
-            props[7 * PS] = static_cast<int32_t>(n_left);
-            props[8 * PS] = static_cast<int32_t>(n_left - prev_grad);
-            prev_grad = static_cast<int32_t>(n_left + n_top - n_topleft);
-            props[9 * PS] = prev_grad;
-            props[10 * PS] = static_cast<int32_t>(n_left - n_topleft);
-            props[11 * PS] = static_cast<int32_t>(n_topleft - n_top);
-            props[12 * PS] = static_cast<int32_t>(n_top - n_topright);
-            props[13 * PS] = static_cast<int32_t>(n_top - n_toptop);
-            props[14 * PS] = static_cast<int32_t>(n_left - n_leftleft);
-          }
-          int32_t wp_max_error = 0;
-          WT wp_pred = 0, wp_raw = 0;
-          WT prediction[4] = {0, 0, 0, 0};
-          if (uses_wp) {
-            uint32_t weights[4];
-            for (uint32_t i = 0; i < 4; i++) {
-              const uint32_t e = eN[i] + eNE[i] + eNW[i];
-              int shift = static_cast<int>(DevFloorLog2(static_cast<uint64_t>(e) + 1)) - 5;
-              if (shift < 0) shift = 0;
-              weights[i] = 4 + ((wpw[i] * divlut[e >> shift]) >> shift);
-            }
-            const WT N8 = n_top * 8, W8 = n_left * 8, NE8 = n_topright * 8, NW8 = n_topleft * 8, NN8 = n_toptop * 8;
-            const WT eW = x == 0 ? 0 : teW;
-            const WT sumWN = static_cast<WT>(teN) + eW;
-            {
-              WT pm = eW;
-              if (DevAbsW<WT>(teN) > DevAbsW<WT>(pm)) pm = teN;
-              if (DevAbsW<WT>(teNW) > DevAbsW<WT>(pm)) pm = teNW;
-              if (DevAbsW<WT>(teNE) > DevAbsW<WT>(pm)) pm = teNE;
-              wp_max_error = static_cast<int32_t>(pm);
-              if (!fast) props[15 * PS] = wp_max_error;
-            }
-            prediction[0] = W8 + NE8 - N8;
-            prediction[1] = N8 - (((sumWN + teNE) * p1C) >> 5);
-            prediction[2] = W8 - (((sumWN + teNW) * p2C) >> 5);
-            prediction[3] = N8 - ((static_cast<WT>(teNW) * p3Ca + static_cast<WT>(teN) * p3Cb +
-                                   static_cast<WT>(teNE) * p3Cc + (NN8 - N8) * p3Cd + (NW8 - W8) * p3Ce) >> 5);
-            uint32_t wsum = weights[0] + weights[1] + weights[2] + weights[3];
-            const uint32_t log_weight = DevFloorLog2(wsum);
-            wsum = 0;
-            for (int i = 0; i < 4; i++) {
-              weights[i] >>= log_weight - 4;
-              wsum += weights[i];
-            }
-            WT sum = static_cast<WT>((wsum >> 1) - 1);
-            for (int i = 0; i < 4; i++) sum += prediction[i] * static_cast<WT>(weights[i]);
-            wp_raw = static_cast<WT>((static_cast<int64_t>(sum) * static_cast<int64_t>(divlut[wsum - 1])) >> 24);
-            if (!(((static_cast<WT>(teN) ^ eW) | (static_cast<WT>(teN) ^ static_cast<WT>(teNW))) > 0)) {
-              WT mx = W8 > NE8 ? W8 : NE8;
-              if (N8 > mx) mx = N8;
-              WT mn = W8 < NE8 ? W8 : NE8;
-              if (N8 < mn) mn = N8;
-              if (wp_raw > mx) wp_raw = mx;
-              if (wp_raw < mn) wp_raw = mn;
-            }
-            wp_pred = (wp_raw + 3) >> 3;
-          }
-          for (uint32_t r = 0; !fast && r < ch.ref_count; r++) {
-            const DevPlane rp = P.planes[P.refs[ch.ref_off + r]];
-            const int32_t* rrow = P.arena + rp.off + static_cast<size_t>(y) * w;
-            const int32_t* rprev = y ? rrow - w : rrow;
-            const int64_t v = rrow[x];
-            const int64_t vleft = x ? rrow[x - 1] : 0;
-            const int64_t vtop = y ? rprev[x] : vleft;
-            const int64_t vtopleft = (x && y) ? rprev[x - 1] : vleft;
-            const int64_t vpred = DevClampedGradient(static_cast<int32_t>(vleft), static_cast<int32_t>(vtop), static_cast<int32_t>(vtopleft));
-            props[(16 + 4 * r + 0) * PS] = static_cast<int32_t>(DevAbs64(v));
-            props[(16 + 4 * r + 1) * PS] = static_cast<int32_t>(v);
-            props[(16 + 4 * r + 2) * PS] = static_cast<int32_t>(DevAbs64(v - vpred));
-            props[(16 + 4 * r + 3) * PS] = static_cast<int32_t>(v - vpred);
-          }
-          int32_t val;
-          if (fast) {
-            // single-property tree on the max-error property, leaves (Weighted, 0, 1): one table lookup
-            const int32_t pv = wp_max_error < lut_lo ? lut_lo : (wp_max_error > lut_hi ? lut_hi : wp_max_error);
-            const uint32_t cluster = JXLB_LDG(lut + (pv - lut_lo));
-            const uint32_t u = reader.ReadUint(cluster, br);
-            val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) + static_cast<uint32_t>(wp_pred));
-          } else {
-            DevTreeNode node = root;
-            if (node.prop >= 0) node = props[node.prop * PS] > node.a ? root_l : root_r;
-            while (node.prop >= 0) {
-              const uint32_t pos = props[node.prop * PS] > node.a ? node.b : node.c;
-              node = DevLoadNode(tree + pos);
-            }
-            const uint32_t cluster = static_cast<uint32_t>(node.a) & 0xFFFF;
-            const uint32_t predictor = static_cast<uint32_t>(node.a) >> 16;
-            const uint32_t u = reader.ReadUint(cluster, br);
-            const WT guess = static_cast<WT>(static_cast<int32_t>(node.b)) +
-                             DevPredictW<WT>(predictor, n_left, n_top, n_topleft, n_topright, n_leftleft, n_toptop,
-                                             n_toprightright, wp_pred);
-            // low 32 bits of (unpacked * multiplier + guess), as in make_pixel (encoding.cc:168-173)
-            val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) * node.c + static_cast<uint32_t>(guess));
-          }
-          row[static_cast<size_t>(x) * RS] = val;
-          out_row[x] = val;
-          leftleft = left;
-          left = val;
-          // slide the previous-row window
-          tl = t;
-          t = tr;
-          tr = trr;
-          if (y > 0 && x + 3 < w) trr = prev[static_cast<size_t>(x + 3) * RS];
-          if (uses_wp) {
-            const WT val8 = static_cast<WT>(val) * 8;
-            const int32_t te = static_cast<int32_t>(wp_raw - val8);
-            er_cur[static_cast<size_t>(x) * LS] = te;
-            const bool more = x + 2 < w;  // position x + 2 exists in the previous row
-            for (uint32_t i = 0; i < 4; i++) {
-              const uint32_t err = static_cast<uint32_t>((DevAbsW<WT>(prediction[i] - val8) + 3) >> 3);
-              pe_cur[i][static_cast<size_t>(x) * LS] = static_cast<int32_t>(err);
-              // next pixel: NW <- N, N <- (entry x + 1) + err, NE <- entry x + 2 (or N at the row end)
-              const uint32_t n_next = eNE[i] + err;
-              eNW[i] = eN[i];
-              eN[i] = n_next;
-              eNE[i] = more ? static_cast<uint32_t>(pe_prv[i][static_cast<size_t>(x + 2) * LS]) : n_next;
-            }
-            teW = te;
-            teNW = teN;
-            teN = teNE;
-            teNE = more ? er_prv[static_cast<size_t>(x + 2) * LS] : teN;
-          }
-        }
-      }
+    if (fast && plain_ans) {
+      DevDecodeChannelRows<WT, true, kLS, true>(P, m, ch, wpp, w, h, max_w, max_h, stride, out, direct, uses_wp, tree, reader, br);
+    } else if (fast) {
+      DevDecodeChannelRows<WT, true, kLS, false>(P, m, ch, wpp, w, h, max_w, max_h, stride, out, direct, uses_wp, tree, reader, br);
+    } else if (plain_ans) {
+      DevDecodeChannelRows<WT, false, kLS, true>(P, m, ch, wpp, w, h, max_w, max_h, stride, out, direct, uses_wp, tree, reader, br);
+    } else {
+      DevDecodeChannelRows<WT, false, kLS, false>(P, m, ch, wpp, w, h, max_w, max_h, stride, out, direct, uses_wp, tree, reader, br);
     }
   }
   if (lane_valid) {
