@@ -43,6 +43,9 @@ struct BatchPlan {
   std::vector<uint8_t> cpool;
   std::vector<uint32_t> upool;
   uint64_t farena_size = 0, barena_size = 0, uarena_size = 0, tok_size = 0;
+  std::vector<DevPatch> patches;
+  std::vector<DevRefFrame> ref_frames;
+  uint32_t max_patch_pixels = 0;
   uint64_t pix_plane_max = 0;  // floats per pixel plane slot
   uint32_t wave_frames = 1;    // VarDCT frames whose pixel planes are live at the same time
 };
@@ -199,6 +202,19 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
       vf.ctx_map_off[p] += cpool0;
     }
     vf.out_off = b->out_size;
+    vf.patch_begin = b->patches.size();
+    for (DevPatch p : v.patches) {
+      for (int c = 0; c < 3; c++) p.src[c] += b->farena_size;
+      b->max_patch_pixels = std::max(b->max_patch_pixels, p.xsize * p.ysize);
+      b->patches.push_back(p);
+    }
+    for (DevRefFrame r : v.ref_frames) {
+      r.plane_y += planes0;
+      r.plane_x += planes0;
+      r.plane_b += planes0;
+      for (int c = 0; c < 3; c++) r.dst[c] += b->farena_size;
+      b->ref_frames.push_back(r);
+    }
     for (DevAcStream s : v.ac_streams) {
       s.bit_pos += byte_base * 8;
       s.bit_end += byte_base * 8;

@@ -98,20 +98,33 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   JXLB_CHECK(!meta.color.want_icc, "unsupported: embedded ICC profile");
   JXLB_CHECK(!meta.have_preview, "unsupported: preview frame");
   JXLB_CHECK(meta.orientation == 1, "unsupported: orientation != 1");
-  br.AlignToByte();
   SizeHeader size;
   size.xsize = bi.xsize;
   size.ysize = bi.ysize;
+  RefSlot refs[4];
+  // Frames: any number of reference-only frames (kReferenceOnly: Modular, saved before the colour transform; what
+  // libjxl's encoder writes for patches, lib/jxl/enc_patch_dictionary.cc), then the one regular frame.
+  for (int frame_index = 0;; frame_index++) {
+  JXLB_CHECK(frame_index < 16, "unsupported: more than 16 frames");
+  br.AlignToByte();
   FrameHeader fh;
   ReadFrameHeader(br, size, meta, false, &fh);
-  JXLB_CHECK(fh.frame_type == kRegularFrame && fh.is_last, "unsupported: multi-frame codestream");
-  JXLB_CHECK(!fh.is_modular || fh.color_transform == kCTNone, "unsupported: XYB / YCbCr Modular frame");
-  JXLB_CHECK(!fh.custom_size_or_origin, "unsupported: cropped frame");
+  const bool is_ref = fh.frame_type == kReferenceOnly;
+  if (is_ref) {
+    JXLB_CHECK(fh.is_modular && fh.save_before_color_transform && fh.color_transform == kCTXYB && meta.extra.empty(),
+               "unsupported: reference frame that is not an XYB Modular frame");
+    JXLB_CHECK(fh.flags == 0, "unsupported: image features inside a reference frame");
+  } else {
+    JXLB_CHECK(fh.frame_type == kRegularFrame && fh.is_last, "unsupported: multi-frame codestream (animation / layers)");
+    JXLB_CHECK(!fh.is_modular || fh.color_transform == kCTNone, "unsupported: XYB / YCbCr Modular frame");
+    JXLB_CHECK(!fh.custom_size_or_origin, "unsupported: cropped frame");
+    JXLB_CHECK(!fh.is_modular || !(fh.flags & (kFlagPatches | kFlagSplines | kFlagNoise | kFlagUseDcFrame)),
+               "unsupported: patches / splines / noise / DC frame on a Modular frame");
+    JXLB_CHECK(fh.blending.mode == kReplace, "unsupported: blending");
+  }
   JXLB_CHECK(fh.upsampling == 1, "unsupported: upsampling");
   for (uint32_t u : fh.ec_upsampling) JXLB_CHECK(u == 1, "unsupported: extra-channel upsampling");
-  JXLB_CHECK(!(fh.flags & (kFlagPatches | kFlagSplines | kFlagNoise | kFlagUseDcFrame)), "unsupported: patches / splines / noise / DC frame");
   JXLB_CHECK(!fh.is_modular || (!fh.lf.gab && fh.lf.epf_iters == 0), "unsupported: loop filter on a Modular frame");
-  JXLB_CHECK(fh.blending.mode == kReplace, "unsupported: blending");
   FrameDimensions dim = ToFrameDimensions(fh);
   const size_t num_passes = fh.passes.num_passes;
   const size_t entries = NumTocEntries(dim.num_groups, dim.num_dc_groups, num_passes);
@@ -120,7 +133,7 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   JXLB_CHECK(base + toc.total <= cs_size, "truncated frame");
 
   if (!fh.is_modular) {
-    PlanVarDCTFrame(cs, cs_size, fh, dim, meta, toc, base, fmt, plan, pc);
+    PlanVarDCTFrame(cs, cs_size, fh, dim, meta, toc, base, fmt, plan, pc, refs);
     DevFrameOut& fo = plan->out;
     fo = DevFrameOut{};
     fo.xsize = bi.xsize;
@@ -133,7 +146,7 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
     return;
   }
   FramePlanner planner(plan);
-  const bool is_gray = meta.color.IsGray();
+  const bool is_gray = meta.color.IsGray() && fh.color_transform == kCTNone;
   const size_t nb_chans = is_gray ? 1 : 3;
   const size_t nb_extra = meta.extra.size();
 
@@ -147,9 +160,13 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   HostTree global_tree;
   GroupHeader global_header;
 
+  float dc_quant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256};
   auto dc_global = [&](BitReader& r, uint64_t bit_base) {
-    if (!r.ReadBool()) {  // DequantMatrices::DecodeDC; irrelevant for non-XYB Modular
-      for (int c = 0; c < 3; c++) ReadF16(r);
+    if (!r.ReadBool()) {  // DequantMatrices::DecodeDC (lib/jxl/quant_weights.cc:507-520): the XYB scale of Modular frames
+      for (int c = 0; c < 3; c++) {
+        dc_quant[c] = ReadF16(r) * (1.0f / 128.0f);
+        JXLB_CHECK(dc_quant[c] >= 1e-8f, "bad DC quantisation step");
+      }
     }
     bool has_tree = r.ReadBool();
     if (has_tree) {
@@ -169,7 +186,7 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
     global_header = planner.PlanStream(r, bit_base, full, 0, dim.group_dim, global_tree);
   };
 
-  std::vector<DevOp> ops;  // group programs first, then global levels
+  std::vector<DevOp> ops = plan->ops;  // (continues after earlier frames) group programs first, then global levels
   auto group = [&](BitReader& r, uint64_t bit_base, size_t x0, size_t y0, size_t xs, size_t ys, int min_shift,
                    int max_shift, uint32_t stream_id) {
     HImage gi;
@@ -237,14 +254,15 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
     // a later one starts where the device decode of the earlier one ends. With a
     // single group every channel fits the global stream (or none does), hence at
     // most one of them carries samples; anything else cannot be planned on the host.
+    const size_t before = plan->streams.size();
     BitReader r = section(0, &bb);
     dc_global(r, bb);
     const size_t after_global = plan->streams.size();
     dc_group(r, bb, 0);
     ac_group(r, bb, 0, 0);
-    JXLB_CHECK(after_global == 0 || plan->streams.size() == after_global,
+    JXLB_CHECK(after_global == before || plan->streams.size() == after_global,
                "unsupported: single-section frame with chained Modular streams");
-    JXLB_CHECK(plan->streams.size() <= 1, "unsupported: single-section frame with chained Modular streams");
+    JXLB_CHECK(plan->streams.size() - before <= 1, "unsupported: single-section frame with chained Modular streams");
   } else {
     {
       BitReader r = section(0, &bb);
@@ -272,9 +290,35 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
     plan->frame_levels.push_back(lvl);
   }
   plan->ops = ops;
+  JXLB_CHECK(full.ch.size() == nb_chans + nb_extra, "modular: unexpected channel count after transforms");
+
+  if (is_ref) {
+    // ModularImageToDecodedRect for an XYB frame (lib/jxl/dec_modular.cc:534-708): three float planes in the
+    // codestream's part of farena, kept for the patches of the frame that follows.
+    DevRefFrame rf{};
+    rf.plane_y = full.ch[0].plane;
+    rf.plane_x = full.ch[1].plane;
+    rf.plane_b = full.ch[2].plane;
+    rf.w = dim.xsize;
+    rf.h = dim.ysize;
+    for (int c = 0; c < 3; c++) {
+      JXLB_CHECK(full.ch[c].w == static_cast<int>(dim.xsize) && full.ch[c].h == static_cast<int>(dim.ysize),
+                 "unsupported: subsampled channel in a reference frame");
+      rf.factor[c] = dc_quant[c];
+      rf.dst[c] = plan->v.farena_size;
+      plan->v.farena_size += (static_cast<uint64_t>(rf.w) * rf.h + 3) & ~uint64_t{3};
+    }
+    plan->v.ref_frames.push_back(rf);
+    RefSlot& slot = refs[fh.save_as_reference & 3];
+    slot.valid = true;
+    slot.w = rf.w;
+    slot.h = rf.h;
+    for (int c = 0; c < 3; c++) slot.off[c] = rf.dst[c];
+    br.SeekTo((base + toc.total) * 8);
+    continue;
+  }
 
   // output mapping (lib/jxl/dec_modular.cc:534-708 + stage_write)
-  JXLB_CHECK(full.ch.size() == nb_chans + nb_extra, "modular: unexpected channel count after transforms");
   DevFrameOut& fo = plan->out;
   fo = DevFrameOut{};
   fo.xsize = bi.xsize;
@@ -308,6 +352,8 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
       fo.factor[c] = static_cast<float>(1.0 / ((1u << bd->bits) - 1));
     }
   }
+  return;
+  }  // frames
 }
 
 }  // namespace jxlb

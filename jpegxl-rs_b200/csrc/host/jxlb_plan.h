@@ -120,6 +120,16 @@ struct VarDCTPlan {
   std::vector<uint32_t> upool;  // block context map, order index, DC-group plane lists
   uint64_t farena_size = 0, barena_size = 0, uarena_size = 0, tok_size = 0;
   uint64_t pix_plane = 0;       // floats per padded pixel plane
+  std::vector<DevPatch> patches;        // src offsets frame-local (farena)
+  std::vector<DevRefFrame> ref_frames;  // reference-only frames decoded before this frame (dst frame-local)
+};
+
+// Reference slots of one codestream (lib/jxl/dec_cache.h reference_frames[4]) as far as patches need them:
+// frames saved before the colour transform, as three float XYB planes in the frame's part of farena.
+struct RefSlot {
+  bool valid = false;
+  uint32_t w = 0, h = 0;
+  uint64_t off[3] = {0, 0, 0};
 };
 
 // A sub-stream that starts where an entropy-coded Modular stream ends (single-section frames, lib/jxl/dec_frame.cc:

@@ -25,7 +25,7 @@ inline size_t OutputStride(uint32_t xsize, const PixelFormat& f) {
 // offset of the first section inside `cs`.
 inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader& fh, const FrameDimensions& dim,
                             const ImageMetadata& meta, const Toc& toc, size_t base, const PixelFormat& fmt, FramePlan* plan,
-                            ProbeCtx* pc = nullptr) {
+                            ProbeCtx* pc = nullptr, const RefSlot* refs = nullptr) {
   JXLB_CHECK(fh.Is444(), "unsupported: chroma-subsampled VarDCT frame");
   JXLB_CHECK(meta.extra.empty(), "unsupported: VarDCT frame with extra channels");
   JXLB_CHECK(fh.passes.num_passes <= kMaxPasses, "too many passes");
@@ -39,6 +39,7 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   VarDCTPlan& v = plan->v;
   DevVFrame& vf = v.vf;
   vf = DevVFrame{};
+  JXLB_CHECK(!(fh.flags & (kFlagSplines | kFlagNoise | kFlagUseDcFrame)), "unsupported: splines / noise / DC frame");
   FramePlanner planner(plan);
   const size_t W = dim.xsize_blocks, H = dim.ysize_blocks, nb = W * H;
 
@@ -55,6 +56,62 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   HostTree global_tree;
   {
     BitReader r = section(0, &bb);
+    if (fh.flags & kFlagPatches) {
+      // PatchDictionary::Decode, lib/jxl/dec_patch_dictionary.cc:28-200 (contexts: :21-32 of the header)
+      JXLB_CHECK(refs != nullptr, "patches without reference frames");
+      EntropyCode code;
+      ReadEntropyCode(r, 10, &code);
+      SymbolReader reader(&code, r);
+      auto read_num = [&](uint32_t ctx) { return reader.ReadUint(ctx, r); };
+      const size_t num_ref_patch = read_num(0);
+      const size_t max_ref_patches = 1024 + dim.xsize_padded * dim.ysize_padded / 4, max_patches = max_ref_patches * 4;
+      JXLB_CHECK(num_ref_patch <= max_ref_patches, "too many patches");
+      size_t total = 0;
+      uint32_t last_x = 0, last_y = 0;
+      for (size_t id = 0; id < num_ref_patch; id++) {
+        const uint32_t ref = read_num(1);
+        JXLB_CHECK(ref < 4 && refs[ref].valid, "invalid patch reference frame");
+        const RefSlot& slot = refs[ref];
+        DevPatch p{};
+        for (int c = 0; c < 3; c++) p.src[c] = slot.off[c];
+        p.src_w = slot.w;
+        p.x0 = read_num(3);
+        p.y0 = read_num(3);
+        p.xsize = read_num(2) + 1;
+        p.ysize = read_num(2) + 1;
+        JXLB_CHECK(static_cast<uint64_t>(p.x0) + p.xsize <= slot.w && static_cast<uint64_t>(p.y0) + p.ysize <= slot.h,
+                   "invalid patch position in reference frame");
+        size_t id_count = read_num(7);
+        JXLB_CHECK(id_count <= max_patches, "too many patches");
+        id_count++;
+        total += id_count;
+        JXLB_CHECK(total <= max_patches, "too many patches");
+        for (size_t i = 0; i < id_count; i++) {
+          if (i == 0) {
+            p.x = read_num(4);
+            p.y = read_num(4);
+          } else {
+            const int64_t dx = UnpackSigned(read_num(6));
+            JXLB_CHECK(!(dx < 0 && static_cast<uint64_t>(-dx) > last_x), "negative patch x");
+            p.x = static_cast<uint32_t>(last_x + dx);
+            const int64_t dy = UnpackSigned(read_num(6));
+            JXLB_CHECK(!(dy < 0 && static_cast<uint64_t>(-dy) > last_y), "negative patch y");
+            p.y = static_cast<uint32_t>(last_y + dy);
+          }
+          last_x = p.x;
+          last_y = p.y;
+          JXLB_CHECK(static_cast<uint64_t>(p.x) + p.xsize <= dim.xsize_padded && static_cast<uint64_t>(p.y) + p.ysize <= dim.ysize_padded,
+                     "patch outside the frame");
+          // one blending per colour + one per extra channel; VarDCT frames with extra channels are refused above
+          p.mode = read_num(5);
+          JXLB_CHECK(p.mode < 8, "invalid patch blend mode");
+          JXLB_CHECK(p.mode <= 3, "unsupported: alpha patch blending");
+          p.clamp = p.mode == 3 ? (read_num(9) != 0) : 0;
+          v.patches.push_back(p);
+        }
+      }
+      JXLB_CHECK(reader.FinalStateOk(), "patches: bad ANS final state");
+    }
     if (!r.ReadBool()) {
       for (int c = 0; c < 3; c++) {
         dc_quant[c] = ReadF16(r) * (1.0f / 128.0f);
@@ -292,7 +349,9 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   vf.skip_dc_smoothing = ((fh.flags & kFlagSkipAdaptiveDCSmoothing) != 0 || W <= 2 || H <= 2) ? 1 : 0;
   vf.gab = fh.lf.gab;
   vf.epf_iters = fh.lf.epf_iters;
-  uint64_t f = 0;
+  vf.patch_begin = 0;
+  vf.patch_count = v.patches.size();
+  uint64_t f = v.farena_size;  // (reference frames of this codestream come first)
   for (int c = 0; c < 3; c++) {
     vf.dc[c] = f;
     f += nb;

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(32) k_ac_decode(DevPools P, DevVPools V) {
   m.freq_ctx = ctxtab_s;
   m.nnz_ctx = ctxtab_s + 64;
   const bool valid = s < V.num_streams;
-  const uint32_t status = DevDecodeAcStream(P, V, s, m, valid);
+  const uint32_t status = V.ac_plain_ans ? DevDecodeAcStream<true>(P, V, s, m, valid) : DevDecodeAcStream<false>(P, V, s, m, valid);
   if (valid) V.ac_status[s] = status;
 }
 
@@ -317,6 +317,24 @@ __global__ void __launch_bounds__(256) k_epf(DevVPools V, uint32_t frame0, uint3
   }
 }
 
+// Reference-only frames: Modular samples -> float XYB planes. blockIdx.y = reference frame.
+__global__ void __launch_bounds__(256) k_ref_frames(DevPools P, DevVPools V) {
+  const DevRefFrame& rf = V.ref_frames[blockIdx.y];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rf.w * rf.h; i += gridDim.x * blockDim.x)
+    DevRefFrameSample(P, V, rf, i);
+}
+
+// Patches of one frame per CTA, one after the other (a later patch may cover an earlier one).
+__global__ void __launch_bounds__(256) k_patches(DevVPools V, uint32_t frame0) {
+  const DevVFrame& vf = V.frames[frame0 + blockIdx.x];
+  const uint32_t set = SetBeforeStage(vf, 3);
+  for (uint32_t k = 0; k < vf.patch_count; k++) {
+    const DevPatch& p = V.patches[vf.patch_begin + k];
+    for (uint32_t i = threadIdx.x; i < p.xsize * p.ysize; i += blockDim.x) DevPatchPixel(V, vf, p, set, i % p.xsize, i / p.xsize);
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256) k_color_write(DevVPools V, uint32_t frame0) {
   const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
   const uint32_t y = blockIdx.y * 8 + threadIdx.y;
@@ -409,6 +427,8 @@ struct JxlB200Decoder {
   DevBuf<uint8_t> d_cpool, d_barena;
   DevBuf<uint32_t> d_upool, d_uarena, d_tokens, d_ac_status, d_ac_used, d_dc_status;
   DevBuf<uint2> d_dcg_list;
+  DevBuf<DevPatch> d_patches;
+  DevBuf<DevRefFrame> d_ref_frames;
   std::vector<uint2> dcg_list;
   std::vector<uint32_t> h_ac_status, h_ac_used, h_dc_status;
   DevVPools vpools{};
@@ -602,6 +622,8 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     CUDA_OK(dec->d_cpool.Upload(b.cpool, s));
     CUDA_OK(dec->d_upool.Upload(b.upool, s));
     CUDA_OK(dec->d_dcg_list.Upload(dec->dcg_list, s));
+    CUDA_OK(dec->d_patches.Upload(b.patches, s));
+    CUDA_OK(dec->d_ref_frames.Upload(b.ref_frames, s));
     CUDA_OK(dec->d_farena.Alloc(b.farena_size + 16));
     CUDA_OK(dec->d_barena.Alloc(b.barena_size + 16));
     CUDA_OK(dec->d_uarena.Alloc(b.uarena_size + 16));
@@ -629,6 +651,13 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     V.sinfo_off = sh.sinfo_off;
     V.ctxtab_off = sh.ctxtab_off;
     V.out = dec->d_out.p;
+    V.ref_frames = dec->d_ref_frames.p;
+    V.num_ref_frames = b.ref_frames.size();
+    V.patches = dec->d_patches.p;
+    V.ac_plain_ans = 1;
+    for (const DevVFrame& vf : b.vframes)
+      for (uint32_t p = 0; p < vf.num_passes; p++)
+        if (b.codes[vf.ac_code[p]].use_prefix || b.codes[vf.ac_code[p]].lz77_enabled) V.ac_plain_ans = 0;
     CUDA_OK(dec->d_ac_streams.Upload(b.ac_streams, s));
     CUDA_OK(dec->d_tokens.Alloc(b.tok_size + 16));
     V.streams = dec->d_ac_streams.p;
@@ -798,6 +827,11 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   if (!b.vframes.empty()) {
     const DevVPools& V = dec->vpools;
     const uint32_t nvf = b.vframes.size();
+    if (!b.ref_frames.empty()) {
+      ScopedTimer t(dec, s, kKFrameLevels);
+      k_ref_frames<<<dim3(16, b.ref_frames.size()), 256, 0, s>>>(P, V);
+      launches++;
+    }
     {
       ScopedTimer t(dec, s, kKDcFinish);
       CUDA_OK(cudaMemsetAsync(dec->d_dc_status.p, 0, (dec->dcg_list.size() + 1) * 4, s));
@@ -834,6 +868,11 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
           k_epf<<<px_grid, px_block, 0, s>>>(V, f0, stage);
           launches++;
         }
+      }
+      if (!b.patches.empty()) {
+        ScopedTimer t(dec, s, kKFilters);
+        k_patches<<<nf, 256, 0, s>>>(V, f0);
+        launches++;
       }
       {
         ScopedTimer t(dec, s, kKColorWrite);

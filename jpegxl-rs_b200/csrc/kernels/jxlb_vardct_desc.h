@@ -73,6 +73,30 @@ struct DevVFrame {
   // output
   uint32_t out_channels, out_type, out_big_endian;
   uint64_t out_off, out_stride;
+  // patches (lib/jxl/dec_patch_dictionary.cc): DevPatch range, applied in order after the loop filters
+  uint32_t patch_begin, patch_count;
+};
+
+// A reference-only frame (lib/jxl/frame_header.h kReferenceOnly, saved before the colour transform): its Modular
+// sample planes become three float XYB planes in farena (ModularImageToDecodedRect, lib/jxl/dec_modular.cc:534-708:
+// modular channel 0 is Y, 1 is X, 2 is B - Y; factor = DC quantisation step per channel).
+struct DevRefFrame {
+  uint32_t plane_y, plane_x, plane_b;  // DevPlane ids
+  uint32_t w, h;
+  float factor[3];                     // for X, Y, B
+  uint64_t dst[3];                     // farena index of the X, Y, B planes (w * h each)
+};
+
+// One patch position (lib/jxl/dec_patch_dictionary.cc:28-200, blending of lib/jxl/blending.cc:42-160 for the three
+// colour channels): the rectangle (x0, y0, xsize, ysize) of a reference frame goes to (x, y) of the frame.
+struct DevPatch {
+  uint64_t src[3];   // farena index of the reference planes
+  uint32_t src_w;    // their row stride
+  uint32_t x0, y0, xsize, ysize;
+  uint32_t x, y;
+  uint32_t mode;     // 0 none, 1 replace, 2 add, 3 multiply
+  uint32_t clamp;
+  uint32_t pad_;
 };
 
 // One AC entropy-coded stream = (frame, group, pass) = one thread of the AC decode kernel.

@@ -49,6 +49,10 @@ struct DevVPools {
   uint32_t sinfo_off;                 // upool: packed StrategyInfo x 27
   uint32_t ctxtab_off;                // upool: kCoeffFreqContext[64] then kCoeffNumNonzeroContext[64]
   uint8_t* out;
+  const DevRefFrame* ref_frames;  // reference-only frames of the batch
+  uint32_t num_ref_frames;
+  const DevPatch* patches;
+  uint32_t ac_plain_ans;  // every AC coefficient code of the batch is ANS without LZ77
 };
 
 #if defined(__CUDACC__)
@@ -268,6 +272,8 @@ struct DevAcLaneMem {
   const uint16_t* nnz_ctx;   // kCoeffNumNonzeroContext[64]
 };
 
+// kPlainAns: every AC code of the batch is ANS without LZ77 (the host checked): no mode tests per symbol.
+template <bool kPlainAns = false>
 JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32_t s, const DevAcLaneMem& m, bool valid) {
   enum { kNeedBlock = 0, kReadNz = 1, kCoeff = 2, kDone = 3 };
   uint32_t mode = kDone, status = 0;
@@ -409,7 +415,7 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
       pre_nonzero = nz > 1 ? JXLB_LDG(ctx_map + histo_offset + (m.nnz_ctx[(nz - 1 + covered - 1) >> log2c] + f) * 2 + 1) : 0;
       pre_valid = true;
     }
-    const uint32_t u = reader.ReadUint(cluster, br);
+    const uint32_t u = kPlainAns ? reader.ReadUintPlainAns(cluster, br) : reader.ReadUint(cluster, br);
     bool chan_done = false;
     if (mode == kReadNz) {
       nz = u;
@@ -1475,6 +1481,35 @@ JXLB_HD uint32_t DevToU8(float v, uint32_t x, uint32_t y) {
 }
 
 // One output pixel: colour transform + sample conversion + interleaved store.
+// Sample i of a reference-only frame: int -> float XYB (see DevRefFrame).
+JXLB_HD void DevRefFrameSample(const DevPools& P, const DevVPools& V, const DevRefFrame& rf, uint32_t i) {
+  const int32_t vy = P.arena[P.planes[rf.plane_y].off + i];
+  const int32_t vx = P.arena[P.planes[rf.plane_x].off + i];
+  const int32_t vb = P.arena[P.planes[rf.plane_b].off + i];
+  V.farena[rf.dst[0] + i] = static_cast<float>(vx) * rf.factor[0];
+  V.farena[rf.dst[1] + i] = static_cast<float>(vy) * rf.factor[1];
+  V.farena[rf.dst[2] + i] = static_cast<float>(vb + vy) * rf.factor[2];
+}
+
+// Pixel (ix, iy) of one patch, all three channels, onto plane set `set` of the frame.
+JXLB_HD void DevPatchPixel(const DevVPools& V, const DevVFrame& vf, const DevPatch& p, uint32_t set, uint32_t ix, uint32_t iy) {
+  const uint32_t x = p.x + ix, y = p.y + iy;
+  if (x >= vf.xsize || y >= vf.ysize || p.mode == 0) return;
+  const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
+  const size_t from = static_cast<size_t>(p.y0 + iy) * p.src_w + p.x0 + ix;
+  for (uint32_t c = 0; c < 3; c++) {
+    const float v = V.farena[p.src[c] + from];
+    float& o = V.farena[vf.pix[set][c] + at];
+    if (p.mode == 1) {
+      o = v;
+    } else if (p.mode == 2) {
+      o = o + v;
+    } else {
+      o = o * (p.clamp ? fminf(1.0f, fmaxf(0.0f, v)) : v);
+    }
+  }
+}
+
 JXLB_HD void DevColorPixel(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t x, uint32_t y) {
   const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
   float r, g, b;

@@ -140,6 +140,11 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       V.sinfo_off = sh.sinfo_off;
       V.ctxtab_off = sh.ctxtab_off;
       V.out = out;
+      V.ref_frames = b.ref_frames.data();
+      V.num_ref_frames = b.ref_frames.size();
+      V.patches = b.patches.data();
+      for (const DevRefFrame& rf : b.ref_frames)  // k_ref_frames
+        for (uint32_t i = 0; i < rf.w * rf.h; i++) DevRefFrameSample(P, V, rf, i);
       uint32_t dcg = 0;
       std::vector<uint8_t> acs_local(65536);  // stands in for the kernel's shared memory
       for (uint32_t f = 0; f < b.vframes.size(); f++) {
@@ -153,6 +158,10 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
         if (dc_status[i]) throw Error("DC group " + std::to_string(i) + " failed with status " + std::to_string(dc_status[i]));
       uint16_t ctxtab[128];
       for (int i = 0; i < 128; i++) ctxtab[i] = static_cast<uint16_t>(b.upool[sh.ctxtab_off + i]);
+      bool ac_plain = true;  // as JxlB200DecoderSetInputBatch decides
+      for (const DevVFrame& vf : b.vframes)
+        for (uint32_t p = 0; p < vf.num_passes; p++)
+          if (b.codes[vf.ac_code[p]].use_prefix || b.codes[vf.ac_code[p]].lz77_enabled) ac_plain = false;
       for (int attempt = 0; attempt < 2; attempt++) {
         bool overflow = false;
         V.streams = b.ac_streams.data();
@@ -163,7 +172,7 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
           m.stride = 1;
           m.freq_ctx = ctxtab;
           m.nnz_ctx = ctxtab + 64;
-          const uint32_t st = DevDecodeAcStream(P, V, s, m, true);
+          const uint32_t st = ac_plain ? DevDecodeAcStream<true>(P, V, s, m, true) : DevDecodeAcStream<false>(P, V, s, m, true);
           if (st == kVTokenOverflow && attempt == 0) {
             overflow = true;
           } else if (st != 0) {
@@ -223,6 +232,11 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
               else DevEpfPixel<false>(V, vf, stage, set, set ^ 1, x, y);
             }
           set ^= 1;
+        }
+        for (uint32_t k = 0; k < vf.patch_count; k++) {  // k_patches: in order, one patch after the other
+          const DevPatch& pt = b.patches[vf.patch_begin + k];
+          for (uint32_t iy = 0; iy < pt.ysize; iy++)
+            for (uint32_t ix = 0; ix < pt.xsize; ix++) DevPatchPixel(V, vf, pt, set, ix, iy);
         }
         const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0;
         for (uint32_t y = 0; y < vf.ysize; y++)

@@ -94,3 +94,18 @@ def test_g3_sample_jpg_jxl(pkg):
     meta, px = dec.decode(jpg)
     assert (meta.width, meta.height) == (40, 50) and px.variant == "Uint8"
     assert np.array_equal(np.asarray(px.data).reshape(50, 40, 3), want8)
+
+
+def test_g4_sample_grey_jxl(pkg):
+    """The reference's grey fixture (libjxl-written): reference-only XYB Modular frame + single-section VarDCT frame with
+    patches, Gaborish, EPF. jpegxl-rs/src/tests/decode.rs:82-93 asserts Pixels::Uint16 and len == width * height; here
+    additionally bit-exact against the oracle, alone and inside a mixed batch."""
+    grey = read_golden("sample_grey.jxl")
+    dec = pkg.decoder_builder().build()
+    meta, px = dec.decode(grey)
+    assert px.variant == "Uint16" and len(px.data) == meta.width * meta.height == 2000
+    assert np.array_equal(np.asarray(px.data).reshape(50, 40, 1), jxlo.decode(grey, 1, jxlo.UINT16))
+    a, _ = vc.encoded("heuristic")
+    outs = pkg.decode_batch([a, grey, read_golden("sample_jpg.jxl"), grey], 3, np.uint8)
+    assert np.array_equal(outs[1], jxlo.decode(grey, 3, jxlo.UINT8)) and np.array_equal(outs[3], outs[1])
+    assert np.array_equal(outs[0], jxlo.decode(a, 3, jxlo.UINT8))

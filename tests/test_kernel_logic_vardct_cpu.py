@@ -57,3 +57,17 @@ def test_g3_sample_jpg_jxl_matches_oracle():
     assert np.array_equal(got[1], jxlo.decode(a, 3, jxlo.UINT8))
     gotf = emul_lib.decode([jpg], 3, jxlo.FLOAT, [(50, 40)])[0]
     assert np.array_equal(gotf.view(np.uint32), jxlo.decode(jpg, 3, jxlo.FLOAT).view(np.uint32))
+
+
+def test_g4_sample_grey_jxl_matches_oracle():
+    # the reference's grey fixture (libjxl-written): a reference-only XYB Modular frame, then a single-section VarDCT
+    # frame with patches from it, Gaborish and one EPF iteration; 16-bit grey output as jpegxl-rs asks for
+    # (jpegxl-rs/src/tests/decode.rs:82-93), RGB8 and float
+    grey = read_golden("sample_grey.jxl")
+    for nc, dt in [(1, jxlo.UINT16), (3, jxlo.UINT8), (1, jxlo.FLOAT), (2, jxlo.UINT16)]:
+        got = emul_lib.decode([grey], nc, dt, [(50, 40)])[0]
+        assert np.array_equal(got.view(np.uint8), jxlo.decode(grey, nc, dt).view(np.uint8))
+    a, sa = vc.encoded("odd_size")
+    got = emul_lib.decode([a, grey, read_golden("sample_jpg.jxl")], 3, jxlo.UINT8, [sa, (50, 40), (50, 40)])
+    assert np.array_equal(got[1], jxlo.decode(grey, 3, jxlo.UINT8))
+    assert np.array_equal(got[0], jxlo.decode(a, 3, jxlo.UINT8))
