@@ -518,6 +518,19 @@ inline void FillQuantizer(const EncParams& p, DevEFrame* ef, uint32_t* global_sc
   ef->distance = p.distance;
   ef->strategy_mode = p.strategy_mode;
   for (int i = 0; i < 4; i++) ef->biases[i] = kDefaultQuantBias[i];
+  // inverse Gaborish weights (lib/jxl/enc_gaborish.cc:21-48 with mul = 1, as lib/jxl/enc_heuristics.cc:1121-1131 passes)
+  ef->gab = p.gab ? 1 : 0;
+  {
+    static const float kGaborish[5] = {-0.09495815671340026, -0.041031725066768575, 0.013710004822696948,
+                                       0.006510206083837737, -0.0014789063378272242};
+    const float mul = 1.0f;
+    double sum = 1.0 + mul * 4 * (kGaborish[0] + kGaborish[1] + kGaborish[2] + kGaborish[4] + 2 * kGaborish[3]);
+    if (sum < 1e-5) sum = 1e-5;
+    const float normalize = static_cast<float>(1.0 / sum);
+    const float nm = mul * normalize;
+    const float w[6] = {normalize, nm * kGaborish[0], nm * kGaborish[2], nm * kGaborish[1], nm * kGaborish[4], nm * kGaborish[3]};
+    for (int i = 0; i < 6; i++) ef->gabinv_w[i] = w[i];
+  }
   *global_scale_out = global_scale;
   *quant_dc_out = quant_dc;
 }
@@ -548,6 +561,10 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
   uint64_t f = 0, i = 0;
   for (int c = 0; c < 3; c++) {
     ef->xyb[c] = f;
+    f += px;
+  }
+  for (int c = 0; c < 3; c++) {  // (only used when the frame signals Gaborish)
+    ef->xyb_raw[c] = f;
     f += px;
   }
   for (int c = 0; c < 3; c++) {

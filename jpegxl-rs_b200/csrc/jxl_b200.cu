@@ -1236,6 +1236,20 @@ __global__ void __launch_bounds__(256) k_enc_xyb(DevEPools E, const DevEFrame* f
   if (x < ef.xblocks * 8 && y < ef.yblocks * 8) DevEncXybPixel(E, ef, x, y);
 }
 
+// blockIdx.z = frame * 3 + channel
+__global__ void __launch_bounds__(256) k_enc_gaborish_inv(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.z / 3];
+  const uint32_t c = blockIdx.z % 3;
+  const int32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const int32_t PW = ef.xblocks * 8, PH = ef.yblocks * 8;
+  if (!ef.gab || x >= PW || y >= PH) return;
+  if (x >= 2 && y >= 2 && x + 2 < PW && y + 2 < PH) {
+    DevEncGaborishInvPixel<true>(E, ef, c, x, y);
+  } else {
+    DevEncGaborishInvPixel<false>(E, ef, c, x, y);
+  }
+}
+
 // one thread per 256x256 group (the greedy choice is serial inside a group)
 __global__ void __launch_bounds__(32) k_enc_strategy(DevEPools E, const DevEFrame* frames) {
   const DevEFrame& ef = frames[blockIdx.y];
@@ -1454,6 +1468,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       DevEFrame& e = f.ef;
       for (int c = 0; c < 3; c++) {
         e.xyb[c] += fbase;
+        e.xyb_raw[c] += fbase;
         e.coef[c] += ibase;
         e.dcq[c] += ibase;
         e.blk_nz[c] += ibase;
@@ -1539,6 +1554,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     E.tree = d_trees.p;
     const uint32_t nf = static_cast<uint32_t>(n);
     k_enc_xyb<<<dim3((maxW * 8 + 31) / 32, maxH, nf), dim3(32, 8), 0, s>>>(E, d_efs.p);
+    if (p.gab) k_enc_gaborish_inv<<<dim3((maxW * 8 + 31) / 32, maxH, nf * 3), dim3(32, 8), 0, s>>>(E, d_efs.p);
     k_enc_strategy<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_number<<<dim3((max_dcg + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_dc<<<dim3((maxW * maxH + 255) / 256, nf), 256, 0, s>>>(E, d_efs.p);

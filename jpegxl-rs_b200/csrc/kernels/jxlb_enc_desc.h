@@ -39,7 +39,10 @@ struct DevEFrame {
   // input
   uint64_t rgb;        // byte arena: interleaved RGB8
   // float arena
-  uint64_t xyb[3];
+  uint64_t xyb[3];      // the planes the transforms read
+  uint64_t xyb_raw[3];  // gab != 0: XYB before the inverse Gaborish (k_enc_xyb writes here, k_enc_gaborish_inv reads)
+  uint32_t gab;
+  float gabinv_w[6];    // c, r, R, d, D, L of lib/jxl/convolve.h WeightsSymmetric5
   // int arena
   uint64_t coef[3];    // quantised coefficients, stored in each varblock's pixel footprint (row-major)
   uint64_t dcq[3];     // quantised DC: [0] = Y, [1] = X, [2] = B, xblocks * yblocks

@@ -81,9 +81,39 @@ JXLB_HD void DevEncXybPixel(const DevEPools& E, const DevEFrame& ef, uint32_t x,
   mixed1 = DevCubeRootAndAdd(mixed1, kNegBiasCbrt);
   mixed2 = DevCubeRootAndAdd(mixed2, kNegBiasCbrt);
   const size_t at = static_cast<size_t>(y) * PW + x;
-  E.farena[ef.xyb[0] + at] = 0.5f * (mixed0 - mixed1);
-  E.farena[ef.xyb[1] + at] = 0.5f * (mixed0 + mixed1);
-  E.farena[ef.xyb[2] + at] = mixed2;
+  const uint64_t* dst = ef.gab ? ef.xyb_raw : ef.xyb;
+  E.farena[dst[0] + at] = 0.5f * (mixed0 - mixed1);
+  E.farena[dst[1] + at] = 0.5f * (mixed0 + mixed1);
+  E.farena[dst[2] + at] = mixed2;
+}
+
+// GaborishInverse (lib/jxl/enc_gaborish.cc:21-70): the symmetric 5x5 sharpening of lib/jxl/convolve_symmetric5.cc:28-118
+// with its summation order and mirrored borders at the size of the padded planes. One sample of channel c.
+JXLB_HD int32_t DevEncMirror(int32_t v, int32_t size) {
+  while (v < 0 || v >= size) v = v < 0 ? -v - 1 : 2 * size - 1 - v;
+  return v;
+}
+template <bool INTERIOR>
+JXLB_HD void DevEncGaborishInvPixel(const DevEPools& E, const DevEFrame& ef, uint32_t c, int32_t x, int32_t y) {
+  const int32_t PW = static_cast<int32_t>(ef.xblocks * 8), PH = static_cast<int32_t>(ef.yblocks * 8);
+  const float* in = E.farena + ef.xyb_raw[c];
+  const float wc = ef.gabinv_w[0], wr = ef.gabinv_w[1], wR = ef.gabinv_w[2], wd = ef.gabinv_w[3], wD = ef.gabinv_w[4],
+              wL = ef.gabinv_w[5];
+  const int32_t xm2 = INTERIOR ? x - 2 : DevEncMirror(x - 2, PW), xm1 = INTERIOR ? x - 1 : DevEncMirror(x - 1, PW);
+  const int32_t xp1 = INTERIOR ? x + 1 : DevEncMirror(x + 1, PW), xp2 = INTERIOR ? x + 2 : DevEncMirror(x + 2, PW);
+  auto row_sum = [&](int32_t yy, float wx0, float wx1, float wx2) {
+    const float* row = in + static_cast<size_t>(INTERIOR ? yy : DevEncMirror(yy, PH)) * PW;
+    const float sum_2 = wx2 * (row[xm2] + row[xp2]);
+    const float sum_1 = wx1 * (row[xm1] + row[xp1]);
+    const float sum_0 = wx0 * row[x];
+    return sum_2 + (sum_1 + sum_0);
+  };
+  float sum0 = row_sum(y, wc, wr, wR);
+  sum0 += row_sum(y - 2, wR, wL, wD);
+  float sum1 = row_sum(y + 2, wR, wL, wD);
+  sum0 += row_sum(y - 1, wr, wd, wL);
+  sum1 += row_sum(y + 1, wr, wd, wL);
+  E.farena[ef.xyb[c] + static_cast<size_t>(y) * PW + x] = sum0 + sum1;
 }
 
 // AcStrategy of one 256x256 group: greedy raster scan, large smooth blocks first (serial: a choice depends on

@@ -703,6 +703,50 @@ inline std::vector<uint8_t> ACContextClusters(const BlockCtxMap& bctx) {
   return cl;
 }
 
+// GaborishInverse, lib/jxl/enc_gaborish.cc:21-70 (weights) + Symmetric5, lib/jxl/convolve_symmetric5.cc:28-118
+// (summation order; mirrored borders at the size of the padded image), with mul = {1, 1, 1} as
+// lib/jxl/enc_heuristics.cc:1121-1131 calls it.
+struct GaborishInverseWeights {
+  float c, r, R, d, D, L;  // lower-right quadrant:  c r R / r d L / R L D
+};
+inline GaborishInverseWeights MakeGaborishInverseWeights(float mul) {
+  static const float kGaborish[5] = {-0.09495815671340026, -0.041031725066768575, 0.013710004822696948,
+                                     0.006510206083837737, -0.0014789063378272242};
+  double sum = 1.0 + mul * 4 * (kGaborish[0] + kGaborish[1] + kGaborish[2] + kGaborish[4] + 2 * kGaborish[3]);
+  if (sum < 1e-5) sum = 1e-5;
+  const float normalize = static_cast<float>(1.0 / sum);
+  const float normalize_mul = mul * normalize;
+  return GaborishInverseWeights{normalize, normalize_mul * kGaborish[0], normalize_mul * kGaborish[2],
+                                normalize_mul * kGaborish[1], normalize_mul * kGaborish[4], normalize_mul * kGaborish[3]};
+}
+inline int64_t EncMirror(int64_t x, int64_t size) {
+  while (x < 0 || x >= size) x = x < 0 ? -x - 1 : 2 * size - 1 - x;
+  return x;
+}
+inline void GaborishInverse(Plane xyb[3]) {
+  const GaborishInverseWeights k = MakeGaborishInverseWeights(1.0f);
+  for (int c = 0; c < 3; c++) {
+    const Plane in = xyb[c];
+    const int64_t w = in.w, h = in.h;
+    auto row_sum = [&](int64_t x, int64_t y, float wx0, float wx1, float wx2) {
+      const float* row = in.Row(EncMirror(y, h));
+      const float sum_2 = wx2 * (row[EncMirror(x - 2, w)] + row[EncMirror(x + 2, w)]);
+      const float sum_1 = wx1 * (row[EncMirror(x - 1, w)] + row[EncMirror(x + 1, w)]);
+      const float sum_0 = wx0 * row[x];
+      return sum_2 + (sum_1 + sum_0);
+    };
+    for (int64_t y = 0; y < h; y++)
+      for (int64_t x = 0; x < w; x++) {
+        float sum0 = row_sum(x, y, k.c, k.r, k.R);
+        sum0 += row_sum(x, y - 2, k.R, k.L, k.D);
+        float sum1 = row_sum(x, y + 2, k.R, k.L, k.D);
+        sum0 += row_sum(x, y - 1, k.r, k.d, k.L);
+        sum1 += row_sum(x, y + 1, k.r, k.d, k.L);
+        xyb[c].Row(y)[x] = sum0 + sum1;
+      }
+  }
+}
+
 inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, const EncodeParams& p,
                                          EncoderStats* stats = nullptr) {
   JXLO_CHECK(xsize > 0 && ysize > 0, "empty image");
@@ -738,6 +782,9 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
       }
     }
   }
+
+  // ---- inverse Gaborish: the 5x5 sharpening that the decoder's Gaborish smoothing undoes
+  if (p.gab) GaborishInverse(xyb);
 
   // ---- global quantiser: dequant step = table * inv_global_scale / raw_quant
   // quant value ~ 0.79 / distance as in libjxl's InitialQuantField target

@@ -314,6 +314,15 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
     const uint32_t W = d.xsize_blocks, H = d.ysize_blocks;
     for (uint32_t y = 0; y < H * 8; y++)
       for (uint32_t x = 0; x < W * 8; x++) DevEncXybPixel(E, ef, x, y);
+    if (ef.gab) {
+      for (uint32_t c = 0; c < 3; c++)
+        for (uint32_t y = 0; y < H * 8; y++)
+          for (uint32_t x = 0; x < W * 8; x++) {
+            const bool in = x >= 2 && y >= 2 && x + 2 < W * 8 && y + 2 < H * 8;
+            if (in) DevEncGaborishInvPixel<true>(E, ef, c, x, y);
+            else DevEncGaborishInvPixel<false>(E, ef, c, x, y);
+          }
+    }
     for (uint32_t g = 0; g < d.num_groups; g++) DevEncStrategyGroup(E, ef, g);
     for (uint32_t g = 0; g < d.num_dc_groups; g++) DevEncNumberBlocks(E, ef, g);
     for (uint32_t by = 0; by < H; by++)
