@@ -453,6 +453,7 @@ struct EncParams {
   uint32_t epf_iters = 2;
   bool dc_smoothing = true;
   uint32_t x_qm_scale = 3, b_qm_scale = 2;
+  bool coeff_orders = true;  // coefficient orders from zero counts (lib/jxl/enc_coeff_order.cc); false: natural orders
 };
 
 inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize) {
@@ -583,6 +584,10 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
     ef->blk_bucket[c] = i; i += nb;
   }
   // (the host reads everything from here to the end of the frame's region back after the tokenisation kernels)
+  ef->order_mask = i; i += 1;
+  ef->group_first = i; i += d.num_groups;
+  ef->zero_counts = i; i += kCustomOrderCounters;
+  for (uint32_t& o : ef->custom_order) o = 0xFFFFFFFFu;
   ef->dcg_count = i; i += d.num_dc_groups;
   ef->group_tokens = i; i += d.num_groups;
   ef->ac_hist = i; i += static_cast<uint64_t>(num_ac_clusters) * 256;
@@ -600,6 +605,109 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
   return L;
 }
 
+// ---- coefficient orders (lib/jxl/enc_coeff_order.cc)
+// Which varblocks enter the statistics when only every other one does (:92-111): xorshift128+ with libjxl's seed,
+// one draw per varblock in group order.
+inline std::vector<uint8_t> MakeOrderSampleBits(size_t n) {
+  std::vector<uint8_t> bits(n);
+  const uint64_t threshold = static_cast<uint64_t>((std::numeric_limits<uint64_t>::max() >> 32) * 0.5);
+  uint64_t s[2] = {0x94D049BB133111EBull, 0xBF58476D1CE4E5B9ull};
+  for (size_t i = 0; i < n; i++) {
+    uint64_t s1 = s[0];
+    const uint64_t s0 = s[1];
+    const uint64_t b = s1 + s0;
+    s[0] = s0;
+    s1 ^= s1 << 23;
+    s1 ^= s0 ^ (s1 >> 18) ^ (s0 >> 5);
+    s[1] = s1;
+    bits[i] = (b >> 32) <= threshold ? 1 : 0;
+  }
+  return bits;
+}
+
+struct CustomOrders {
+  uint32_t used = 0;                                // bit ord: the order is transmitted
+  std::vector<uint16_t> order[kNumCustomOrders][3];  // coefficient positions in scan order
+};
+
+// The sort of ComputeCoeffOrder (:160-238): positions in natural order, stably sorted by their quantised zero count.
+// `mask` = orders that occur in the frame, `zero_counts` = the device's counters.
+inline CustomOrders ComputeCustomOrders(uint32_t mask, const int32_t* zero_counts, uint32_t xblocks, uint32_t yblocks) {
+  CustomOrders co;
+  uint32_t customize = mask & ((1u << kNumCustomOrders) - 1);
+  if (xblocks < 5 && yblocks < 5) customize = 0;  // default orders for small images (:72-74)
+  const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
+  for (uint32_t ord = 0; ord < kNumCustomOrders; ord++) {
+    if (!(customize & (1u << ord))) continue;
+    const StrategyInfo si = GetStrategyInfo(kOrderFirstStrategy[ord]);
+    const uint32_t sz = CustomOrderSize(ord);
+    uint32_t lcx = si.cx, lcy = si.cy;
+    if (lcy > lcx) std::swap(lcx, lcy);
+    const uint16_t* natural = sh.opool.data() + sh.order_off[ord];
+    bool is_nondefault = false;
+    for (uint32_t c = 0; c < 3; c++) {
+      struct PosAndCount { uint32_t pos, count; };
+      std::vector<PosAndCount> pv(sz);
+      const float inv_sqrt_sz = 1.0f / std::sqrt(static_cast<float>(sz));
+      for (uint32_t i = 0; i < sz; i++) {
+        const uint32_t pos = natural[i];
+        const bool llf = pos % (8 * lcx) < lcx && pos / (8 * lcx) < lcy;
+        const int32_t nz = llf ? -1 : zero_counts[CustomOrderBase(ord) + c * sz + pos];
+        const float q = nz * inv_sqrt_sz + 0.1f;
+        pv[i].pos = pos;
+        pv[i].count = q <= 0.0f ? 0u : static_cast<uint32_t>(q);
+      }
+      std::stable_sort(pv.begin(), pv.end(), [](const PosAndCount& a, const PosAndCount& b) { return a.count < b.count; });
+      co.order[ord][c].resize(sz);
+      for (uint32_t i = 0; i < sz; i++) {
+        co.order[ord][c][i] = static_cast<uint16_t>(pv[i].pos);
+        is_nondefault |= natural[i] != pv[i].pos;
+      }
+    }
+    if (is_nondefault) {
+      co.used |= 1u << ord;
+    } else {
+      for (uint32_t c = 0; c < 3; c++) co.order[ord][c].clear();
+    }
+  }
+  return co;
+}
+
+// EncodeCoeffOrders (:293-337): the permutations relative to the natural orders as Lehmer codes, one ANS stream.
+inline void WriteCoeffOrders(BitWriter& w, const CustomOrders& co) {
+  WriteU32(w, co.used, Val(0x5F), Val(0x13), Val(0), Bits(13));
+  if (co.used == 0) return;
+  const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
+  std::vector<std::pair<uint32_t, uint32_t>> tokens;
+  for (uint32_t ord = 0; ord < kNumCustomOrders; ord++) {
+    if (!(co.used & (1u << ord))) continue;
+    const StrategyInfo si = GetStrategyInfo(kOrderFirstStrategy[ord]);
+    const uint32_t llf = static_cast<uint32_t>(si.cx) * si.cy, sz = 64 * llf;
+    const uint16_t* natural = sh.opool.data() + sh.order_off[ord];
+    std::vector<uint32_t> lut(sz);
+    for (uint32_t i = 0; i < sz; i++) lut[natural[i]] = i;
+    for (uint32_t c = 0; c < 3; c++) {
+      std::vector<uint32_t> lehmer(sz), avail(sz);
+      for (uint32_t i = 0; i < sz; i++) avail[i] = i;
+      for (uint32_t i = 0; i < sz; i++) {
+        const auto it = std::lower_bound(avail.begin(), avail.end(), lut[co.order[ord][c][i]]);
+        lehmer[i] = static_cast<uint32_t>(it - avail.begin());
+        avail.erase(it);
+      }
+      uint32_t end = sz;
+      while (end > llf && lehmer[end - 1] == 0) end--;
+      tokens.push_back({CoeffOrderContext(sz), end - llf});
+      uint32_t last = 0;
+      for (uint32_t i = llf; i < end; i++) {
+        tokens.push_back({CoeffOrderContext(last), lehmer[i]});
+        last = lehmer[i];
+      }
+    }
+  }
+  const std::vector<uint8_t> eight = {0, 1, 2, 3, 4, 5, 6, 7};
+  WriteHostStream(w, 8, eight, 8, tokens);
+}
+
 // After the tokenisation kernels: the two host-written sections and the code tables for the emit kernels.
 struct EncGlobals {
   BitWriter dc_global, ac_global;
@@ -608,7 +716,7 @@ struct EncGlobals {
 
 inline void BuildEncGlobals(const EncParams& p, const EncLayout& L, const EncTree& tree, const std::vector<uint8_t>& ac_cluster_of,
                             uint32_t global_scale, uint32_t quant_dc, const uint32_t* mod_hist, const uint32_t* ac_hist,
-                            EncGlobals* g) {
+                            const CustomOrders& orders, EncGlobals* g) {
   (void)p;
   BitWriter& d = g->dc_global;
   d.Write(1, 1);  // default DC quantisation
@@ -625,7 +733,7 @@ inline void BuildEncGlobals(const EncParams& p, const EncLayout& L, const EncTre
   BitWriter& a = g->ac_global;
   a.Write(1, 1);  // default quantisation matrices
   a.Write(CeilLog2(L.dim.num_groups), 0);  // one set of histograms
-  WriteU32(a, 0, Val(0x5F), Val(0x13), Val(0), Bits(13));  // natural coefficient orders
+  WriteCoeffOrders(a, orders);
   WriteCodeHeader(a, ac_cluster_of, L.num_ac_clusters, ac_hist, &g->ac_code);
 }
 

@@ -1317,6 +1317,20 @@ __global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, const D
   }
 }
 
+// Coefficient-order statistics: thread per group, then CTA per group (see DevEncOrderStatsGroup).
+__global__ void __launch_bounds__(32) k_enc_group_orders(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.y];
+  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
+  if (g < ef.xgroups * ef.ygroups) DevEncGroupOrders(E, ef, g);
+}
+
+__global__ void __launch_bounds__(256) k_enc_order_stats(DevEPools E, const DevEFrame* frames) {
+  __shared__ uint32_t local[kCustomOrderCounters + 1024];
+  const DevEFrame& ef = frames[blockIdx.y];
+  if (blockIdx.x >= ef.xgroups * ef.ygroups) return;
+  DevEncOrderStatsGroup<2>(E, ef, blockIdx.x, threadIdx.x, blockDim.x, local);
+}
+
 // Tokenisation, data-parallel: thread per (block, channel) for the statistics and for the tokens, thread per group
 // for the offsets in between. blockIdx.y = channel, blockIdx.z = frame.
 __global__ void __launch_bounds__(128) k_enc_block_stats(DevEPools E, const DevEFrame* frames) {
@@ -1559,6 +1573,54 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     k_enc_number<<<dim3((max_dcg + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_dc<<<dim3((maxW * maxH + 255) / 256, nf), 256, 0, s>>>(E, d_efs.p);
     k_enc_coeffs<<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
+    // ---- coefficient orders: zero counts on the device, sort + permutation coding on the host, orders back
+    std::vector<CustomOrders> orders(n);
+    DevBuf<uint16_t> d_custom;
+    DevBuf<uint8_t> d_sample;
+    std::vector<uint16_t> custom_pool;
+    std::vector<uint8_t> sample_bits;
+    if (p.coeff_orders) {
+      sample_bits = MakeOrderSampleBits(static_cast<size_t>(maxW) * maxH);
+      CUDA_OK(d_sample.Upload(sample_bits, s));
+      E.sample_bits = d_sample.p;
+      k_enc_group_orders<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
+      k_enc_order_stats<<<dim3(max_groups, nf), 256, 0, s>>>(E, d_efs.p);
+      std::vector<std::vector<int32_t>> h_stats(n);
+      for (size_t i = 0; i < n; i++) {
+        const uint64_t first = fr[i].ef.order_mask, count = fr[i].ef.zero_counts + kCustomOrderCounters - first;
+        h_stats[i].resize(count);
+        CUDA_OK(cudaMemcpyAsync(h_stats[i].data(), d_iarena.p + first, count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      }
+      CUDA_OK(cudaStreamSynchronize(s));
+      {
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+          for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            const DevEFrame& e = fr[i].ef;
+            orders[i] = ComputeCustomOrders(static_cast<uint32_t>(h_stats[i][0]), h_stats[i].data() + (e.zero_counts - e.order_mask),
+                                            e.xblocks, e.yblocks);
+          }
+        };
+        const size_t nthreads = std::max<size_t>(1, std::min<size_t>(n, std::min<unsigned>(16, std::thread::hardware_concurrency())));
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < nthreads; t++) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+      }
+      for (size_t i = 0; i < n; i++)
+        for (uint32_t ord = 0; ord < kNumCustomOrders; ord++) {
+          if (!(orders[i].used & (1u << ord))) continue;
+          for (uint32_t c = 0; c < 3; c++) {
+            JXLB_CHECK(custom_pool.size() < 0xFFFFFFFFu, "custom order pool too large");
+            efs[i].custom_order[3 * ord + c] = fr[i].ef.custom_order[3 * ord + c] = static_cast<uint32_t>(custom_pool.size());
+            custom_pool.insert(custom_pool.end(), orders[i].order[ord][c].begin(), orders[i].order[ord][c].end());
+          }
+        }
+      CUDA_OK(d_custom.Upload(custom_pool, s));
+      E.opool_custom = d_custom.p;
+      CUDA_OK(d_efs.Upload(efs, s));
+    }
     k_enc_block_stats<<<dim3((maxW * maxH + 127) / 128, 3, nf), 128, 0, s>>>(E, d_efs.p);
     k_enc_token_offsets<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_block_tokens<<<dim3((maxW * maxH + 127) / 128, 3, nf), 128, 0, s>>>(E, d_efs.p);
@@ -1590,7 +1652,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
             const uint64_t first = f.ef.dcg_count;
             const uint32_t* ac_hist = reinterpret_cast<const uint32_t*>(h_small[i].data() + (f.ef.ac_hist - first));
             const uint32_t* mod_hist = reinterpret_cast<const uint32_t*>(h_small[i].data() + (f.ef.mod_hist - first));
-            BuildEncGlobals(p, f.L, f.tree, ac_cluster_of, f.global_scale, f.quant_dc, mod_hist, ac_hist, &f.G);
+            BuildEncGlobals(p, f.L, f.tree, ac_cluster_of, f.global_scale, f.quant_dc, mod_hist, ac_hist, orders[i], &f.G);
           } catch (const std::exception& e) {
             errors[i] = e.what();
           }

@@ -27,6 +27,19 @@ struct DevEncTreeNode {
   uint32_t l, r;
 };
 
+// Coefficient orders that may be customised (lib/jxl/enc_coeff_order.cc:47-76: orders 0..6, blocks up to 32x32):
+// coefficients per order and where the zero counters of (order, channel) start: kCustomOrderBase[ord] + c * size.
+constexpr uint32_t kNumCustomOrders = 7;
+constexpr uint32_t kCustomOrderCounters = 6912;
+JXLB_HD uint32_t CustomOrderSize(uint32_t ord) {
+  const uint16_t k[7] = {64, 64, 256, 1024, 128, 256, 512};
+  return k[ord];
+}
+JXLB_HD uint32_t CustomOrderBase(uint32_t ord) {
+  const uint16_t k[7] = {0, 192, 384, 1152, 4224, 4608, 5376};
+  return k[ord];
+}
+
 // One frame being encoded. Offsets index the encoder's arenas (element units of the arena's type).
 struct DevEFrame {
   uint32_t xsize, ysize;
@@ -51,6 +64,11 @@ struct DevEFrame {
   uint64_t dcg_count;    // per DC group: number of varblocks
   uint64_t group_tokens; // per AC group: number of tokens written
   uint64_t blk_nz[3], blk_ntok[3], blk_bucket[3];  // per block and channel: see DevEncBlockStats
+  // coefficient-order statistics (read back by the host before the tokenisation kernels)
+  uint64_t order_mask;   // one word: bit ord set when a varblock with that coefficient order exists
+  uint64_t group_first;  // per AC group: number of varblocks
+  uint64_t zero_counts;  // kCustomOrderCounters words: zero coefficients per (order, channel, position) over the sampled varblocks
+  uint32_t custom_order[3 * kNumCustomOrders];  // [3 * ord + c]: offset into the custom order pool, 0xFFFFFFFF = natural
   uint64_t ac_hist;      // [num_ac_clusters][256]
   uint64_t mod_hist;     // [num_leaves][256]
   // byte arena

@@ -28,6 +28,8 @@ struct DevEPools {
   const float* srgb_lut;     // 256 entries: sRGB byte -> linear
   const float* fpool;        // shared VarDCT tables (dequantisation tables, WcMultipliers)
   const uint16_t* opool;     // natural coefficient orders
+  const uint16_t* opool_custom;  // per-frame custom orders (DevEFrame::custom_order), uploaded after the statistics
+  const uint8_t* sample_bits;    // sample_bits[n]: the n-th varblock (group order) enters the statistics when only half do
   const uint32_t* upool;     // packed StrategyInfo, coefficient context tables
   uint32_t table_off[17], order_off[13];
   uint32_t wc_off, sinfo_off, ctxtab_off;
@@ -284,6 +286,98 @@ JXLB_HD void DevCountToken(uint32_t* hist, uint32_t cluster, uint32_t value) {
 #endif
 }
 
+// ---- coefficient-order statistics (ComputeUsedOrders + the counting loop of ComputeCoeffOrder,
+// lib/jxl/enc_coeff_order.cc:47-160). Step 1, one thread per group: varblocks of the group and the orders they use.
+JXLB_HD void DevEncGroupOrders(const DevEPools& E, const DevEFrame& ef, uint32_t g) {
+  const uint32_t W = ef.xblocks, H = ef.yblocks;
+  const uint32_t x0 = (g % ef.xgroups) * 32, y0 = (g / ef.xgroups) * 32;
+  const uint32_t xs = W - x0 < 32 ? W - x0 : 32, ys = H - y0 < 32 ? H - y0 : 32;
+  const uint8_t* acs = E.barena + ef.acs;
+  uint32_t count = 0, mask = 0;
+  for (uint32_t by = 0; by < ys; by++)
+    for (uint32_t bx = 0; bx < xs; bx++) {
+      const uint8_t a = acs[static_cast<size_t>(y0 + by) * W + x0 + bx];
+      if (!(a & 1)) continue;
+      count++;
+      mask |= 1u << UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]).order;
+    }
+  E.iarena[ef.group_first + g] = static_cast<int32_t>(count);
+#if defined(__CUDA_ARCH__)
+  atomicOr(reinterpret_cast<uint32_t*>(E.iarena + ef.order_mask), mask);
+#else
+  E.iarena[ef.order_mask] |= static_cast<int32_t>(mask);
+#endif
+}
+
+// Step 2, one CTA per group (`nt` cooperating threads, `local`: kCustomOrderCounters + 1024 words of shared memory):
+// zero coefficients per (order, channel, position). libjxl walks the varblocks in group order and, when only 8x8
+// DCT orders can be customised, takes every other one by a fixed xorshift128+ sequence: sample_bits[rank].
+template <int SCOPE>
+JXLB_HD void DevEncOrderStatsGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g, uint32_t tid, uint32_t nt, uint32_t* local) {
+  const uint32_t W = ef.xblocks, H = ef.yblocks, PW = W * 8;
+  const uint32_t x0 = (g % ef.xgroups) * 32, y0 = (g / ef.xgroups) * 32;
+  const uint32_t xs = W - x0 < 32 ? W - x0 : 32, ys = H - y0 < 32 ? H - y0 : 32;
+  const uint8_t* acs = E.barena + ef.acs;
+  uint32_t* counts = local;
+  uint32_t* rank = local + kCustomOrderCounters;  // per cell of the group: rank of its varblock, or 0xFFFFFFFF
+  for (uint32_t i = tid; i < kCustomOrderCounters; i += nt) counts[i] = 0;
+  const bool half = (static_cast<uint32_t>(E.iarena[ef.order_mask]) & 0x7Fu) == 1u;
+  if (tid == 0) {
+    uint32_t r = 0;
+    for (uint32_t q = 0; q < g; q++) r += static_cast<uint32_t>(E.iarena[ef.group_first + q]);
+    for (uint32_t by = 0; by < ys; by++)
+      for (uint32_t bx = 0; bx < xs; bx++) {
+        const bool first = (acs[static_cast<size_t>(y0 + by) * W + x0 + bx] & 1) != 0;
+        rank[by * 32 + bx] = first ? r : 0xFFFFFFFFu;
+        r += first ? 1 : 0;
+      }
+  }
+  CoopSync<SCOPE>();
+  for (uint32_t cell = 0; cell < xs * ys; cell++) {  // (uniform loop: the threads split each varblock's coefficients)
+    const uint32_t bx = cell % xs, by = cell / xs;
+    const uint32_t r = rank[by * 32 + bx];
+    if (r == 0xFFFFFFFFu) continue;
+    if (half && !E.sample_bits[r]) continue;
+    const size_t pos = static_cast<size_t>(y0 + by) * W + x0 + bx;
+    const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (acs[pos] >> 1)]);
+    if (si.order >= kNumCustomOrders) continue;
+    const uint32_t size = 64u << si.log2_covered, C = si.cx * 8u;
+    uint32_t lcx = si.cx, lcy = si.cy;  // the lowest frequencies: lcy rows of lcx in the (cx >= cy) coefficient layout
+    if (lcy > lcx) {
+      const uint32_t t = lcx;
+      lcx = lcy;
+      lcy = t;
+    }
+    for (uint32_t i = tid; i < 3 * size; i += nt) {
+      const uint32_t c = i / size, p = i % size;
+      if (p % (8 * lcx) < lcx && p / (8 * lcx) < lcy) continue;  // LLF: pinned to the front by the host
+      const int32_t* coef = E.iarena + ef.coef[c] + static_cast<size_t>(y0 + by) * 8 * PW + static_cast<size_t>(x0 + bx) * 8;
+      if (coef[static_cast<size_t>(p / C) * PW + p % C] == 0) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(counts + CustomOrderBase(si.order) + c * size + p, 1u);
+#else
+        counts[CustomOrderBase(si.order) + c * size + p]++;
+#endif
+      }
+    }
+  }
+  CoopSync<SCOPE>();
+  for (uint32_t i = tid; i < kCustomOrderCounters; i += nt) {
+    if (counts[i] == 0) continue;
+#if defined(__CUDA_ARCH__)
+    atomicAdd(reinterpret_cast<uint32_t*>(E.iarena + ef.zero_counts) + i, counts[i]);
+#else
+    E.iarena[ef.zero_counts + i] += static_cast<int32_t>(counts[i]);
+#endif
+  }
+}
+
+// The coefficient order of (order class, channel): the frame's custom one if the host made one, else the natural one.
+JXLB_HD const uint16_t* DevEncOrder(const DevEPools& E, const DevEFrame& ef, uint32_t ord, uint32_t c) {
+  if (ord < kNumCustomOrders && ef.custom_order[3 * ord + c] != 0xFFFFFFFFu) return E.opool_custom + ef.custom_order[3 * ord + c];
+  return E.opool + E.order_off[ord];
+}
+
 // ---- AC tokenisation in three data-parallel steps. The context of a coefficient depends on the number of
 // non-zeros still to come and on whether the previous coefficient (in scan order) was zero: both follow from a
 // scan of the block alone, so every (varblock, channel) is tokenised independently once the token offsets are known.
@@ -299,7 +393,7 @@ JXLB_HD void DevEncBlockStats(const DevEPools& E, const DevEFrame& ef, uint32_t 
   if (!(a & 1)) return;
   const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
   const uint32_t log2c = si.log2_covered, covered = 1u << log2c, size = covered * 64, C = si.cx * 8u;
-  const uint16_t* order = E.opool + E.order_off[si.order];
+  const uint16_t* order = DevEncOrder(E, ef, si.order, c);
   const int32_t* coef = E.iarena + ef.coef[c] + static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
   uint32_t nz = 0, last = 0;
   for (uint32_t k = covered; k < size; k++) {
@@ -347,7 +441,7 @@ JXLB_HD void DevEncBlockTokens(const DevEPools& E, const DevEFrame& ef, uint32_t
   if (!(a & 1)) return;
   const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
   const uint32_t log2c = si.log2_covered, covered = 1u << log2c, size = covered * 64, C = si.cx * 8u, ord = si.order;
-  const uint16_t* order = E.opool + E.order_off[ord];
+  const uint16_t* order = DevEncOrder(E, ef, ord, c);
   const int32_t* coef = E.iarena + ef.coef[c] + static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
   const uint32_t g = (by / 32) * ef.xgroups + bx / 32;
   uint2* tok = E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536 + static_cast<uint32_t>(E.iarena[ef.blk_ntok[c] + pos]);

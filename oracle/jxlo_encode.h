@@ -615,6 +615,10 @@ struct EncodeParams {
   // DC streams: 0 = fixed weighted-predictor tree (libjxl's default effort, kWPFixedDC), 1 = fixed gradient tree
   // (kGradientFixedDC, what libjxl writes for decoding_speed_tier >= 1): contexts from property 9, no WP state.
   int dc_tree = 0;
+  // Encoder-side heuristics that change which (valid) stream is written, not how a decoder reads it; the committed
+  // 4K decode fixtures predate them and are regenerated with both off.
+  bool gab_inverse = true;    // inverse Gaborish before the transforms when the frame signals Gaborish (E4)
+  bool coeff_orders = true;   // coefficient orders from zero counts (E9); false: natural orders
 };
 
 struct EncoderStats {
@@ -703,6 +707,12 @@ inline std::vector<uint8_t> ACContextClusters(const BlockCtxMap& bctx) {
   return cl;
 }
 
+inline int kOrderFirstStrategyOf(uint32_t ord) {
+  for (int o = 0; o < kNumStrategies; o++)
+    if (kStrategyOrder[o] == static_cast<int>(ord)) return o;
+  return -1;
+}
+
 // GaborishInverse, lib/jxl/enc_gaborish.cc:21-70 (weights) + Symmetric5, lib/jxl/convolve_symmetric5.cc:28-118
 // (summation order; mirrored borders at the size of the padded image), with mul = {1, 1, 1} as
 // lib/jxl/enc_heuristics.cc:1121-1131 calls it.
@@ -784,7 +794,7 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   }
 
   // ---- inverse Gaborish: the 5x5 sharpening that the decoder's Gaborish smoothing undoes
-  if (p.gab) GaborishInverse(xyb);
+  if (p.gab && p.gab_inverse) GaborishInverse(xyb);
 
   // ---- global quantiser: dequant step = table * inv_global_scale / raw_quant
   // quant value ~ 0.79 / distance as in libjxl's InitialQuantField target
@@ -918,10 +928,10 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   std::vector<std::vector<Token>> group_tokens(num_groups * num_passes);
   const float* biases = kDefaultQuantBias;
   std::vector<float> coeff(3 * 65536), scratch(3 * 65536 + 1024);
-  std::vector<int32_t> quantized(3 * 65536);
+  // quantised coefficients of every varblock (3 * size values at its first block), kept for the order statistics
+  std::vector<std::vector<int32_t>> qblocks(W * H);
   for (size_t g = 0; g < num_groups; g++) {
     const BlockRect r = BlockGroupRect(dim, g);
-    std::vector<std::vector<int32_t>> nzeros(num_passes, std::vector<int32_t>(3 * 32 * 32, 0));
     for (size_t by = 0; by < r.ys; by++) {
       for (size_t bx = 0; bx < r.xs; bx++) {
         const size_t pos = (r.y0 + by) * W + r.x0 + bx;
@@ -929,9 +939,10 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
         if (!(a & 1)) continue;
         const int s = a >> 1;
         const size_t cx = kCoveredX[s], cy = kCoveredY[s];
-        const size_t covered = cx * cy, size = covered * 64, log2c = kLog2Covered[s];
+        const size_t covered = cx * cy, size = covered * 64;
         const std::vector<float>& dm = table_for(s);
-        const std::vector<uint32_t>& order = order_for(s);
+        qblocks[pos].assign(3 * size, 0);
+        int32_t* quantized = qblocks[pos].data();
         const float sd_base = inv_global_scale / raw_quant[pos];
         const float sd[3] = {sd_base * x_dm, sd_base, sd_base * b_dm};
         const size_t tile = ((r.y0 + by) / 8) * cmw + (r.x0 + bx) / 8;
@@ -952,6 +963,110 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
         for (int c = 0; c < 3; c++)
           for (size_t y = 0; y < lcy; y++)
             for (size_t x = 0; x < lcx; x++) quantized[c * size + y * lcx * 8 + x] = 0;
+      }
+    }
+  }
+
+  // ---- coefficient orders (E9): ComputeUsedOrders + ComputeCoeffOrder, lib/jxl/enc_coeff_order.cc:47-238, as libjxl's
+  // effort 7 (kSquirrel) runs them; single-pass frames only (with more passes the natural orders stay)
+  std::vector<uint32_t> custom[13][3];
+  uint32_t used_orders = 0;
+  if (p.coeff_orders && num_passes == 1) {
+    uint32_t used_acs = 0, customize = 0;
+    for (size_t i = 0; i < W * H; i++) {
+      if (acs[i] == 0xFF) continue;
+      const uint32_t ord = kStrategyOrder[acs[i] >> 1];
+      used_acs |= 1u << ord;
+      if (ord <= 6) customize |= 1u << ord;  // no custom orders for blocks larger than 32x32
+    }
+    if (W < 5 && H < 5) customize = 0;  // default orders for small images
+    if (customize != 0) {
+      std::vector<int32_t> num_zeros[13][3];
+      const double block_fraction = customize == 1 ? 0.5 : 1.0;  // only 8x8 DCTs: every other block is enough
+      const uint64_t threshold = static_cast<uint64_t>((std::numeric_limits<uint64_t>::max() >> 32) * block_fraction);
+      uint64_t rs[2] = {0x94D049BB133111EBull, 0xBF58476D1CE4E5B9ull};
+      auto use_sample = [&]() {  // xorshift128+
+        uint64_t s1 = rs[0];
+        const uint64_t s0 = rs[1];
+        const uint64_t bits = s1 + s0;
+        rs[0] = s0;
+        s1 ^= s1 << 23;
+        s1 ^= s0 ^ (s1 >> 18) ^ (s0 >> 5);
+        rs[1] = s1;
+        return (bits >> 32) <= threshold;
+      };
+      for (size_t g = 0; g < num_groups; g++) {
+        const BlockRect r = BlockGroupRect(dim, g);
+        for (size_t by = 0; by < r.ys; by++)
+          for (size_t bx = 0; bx < r.xs; bx++) {
+            const size_t pos = (r.y0 + by) * W + r.x0 + bx;
+            if (!(acs[pos] & 1)) continue;
+            if (!use_sample()) continue;
+            const int s = acs[pos] >> 1;
+            const uint32_t ord = kStrategyOrder[s];
+            size_t cx = kCoveredX[s], cy = kCoveredY[s];
+            const size_t size = cx * cy * 64;
+            if (cy > cx) std::swap(cx, cy);
+            for (int c = 0; c < 3; c++) {
+              std::vector<int32_t>& nzv = num_zeros[ord][c];
+              if (nzv.empty()) nzv.assign(size, 0);
+              const int32_t* q = qblocks[pos].data() + c * size;
+              for (size_t k = 0; k < size; k++) nzv[k] += q[k] == 0 ? 1 : 0;
+              for (size_t iy = 0; iy < cy; iy++)  // the lowest frequencies stay first
+                for (size_t ix = 0; ix < cx; ix++) nzv[iy * 8 * cx + ix] = -1;
+            }
+          }
+      }
+      used_orders = customize;
+      for (int o = 0; o < kNumStrategies; o++) {
+        const uint32_t ord = kStrategyOrder[o];
+        if (!(used_orders & (1u << ord)) || !custom[ord][0].empty()) continue;
+        if (!(used_acs & (1u << ord))) continue;
+        const size_t sz = 64u * kCoveredX[o] * kCoveredY[o];
+        const std::vector<uint32_t>& natural_order = order_for(o);
+        bool is_nondefault = false;
+        for (int c = 0; c < 3; c++) {
+          struct PosAndCount { uint32_t pos, count; };
+          std::vector<PosAndCount> pv(sz);
+          const float inv_sqrt_sz = 1.0f / std::sqrt(static_cast<float>(sz));
+          for (size_t i = 0; i < sz; i++) {
+            const uint32_t pos = natural_order[i];
+            pv[i].pos = pos;
+            const int32_t nzc = num_zeros[ord][c].empty() ? 0 : num_zeros[ord][c][pos];
+            const float q = nzc * inv_sqrt_sz + 0.1f;  // quantised counts: a less permuted order
+            pv[i].count = q <= 0.0f ? 0u : static_cast<uint32_t>(q);
+          }
+          std::stable_sort(pv.begin(), pv.end(), [](const PosAndCount& a, const PosAndCount& b) { return a.count < b.count; });
+          custom[ord][c].resize(sz);
+          for (size_t i = 0; i < sz; i++) {
+            custom[ord][c][i] = pv[i].pos;
+            is_nondefault |= natural_order[i] != pv[i].pos;
+          }
+        }
+        if (!is_nondefault) {
+          used_orders &= ~(1u << ord);
+          for (int c = 0; c < 3; c++) custom[ord][c].clear();
+        }
+      }
+      // (an order bit whose strategies do not occur keeps no custom order)
+      for (uint32_t ord = 0; ord < 13; ord++)
+        if ((used_orders & (1u << ord)) && custom[ord][0].empty()) used_orders &= ~(1u << ord);
+    }
+  }
+
+  // ---- tokens per group and pass
+  for (size_t g = 0; g < num_groups; g++) {
+    const BlockRect r = BlockGroupRect(dim, g);
+    std::vector<std::vector<int32_t>> nzeros(num_passes, std::vector<int32_t>(3 * 32 * 32, 0));
+    for (size_t by = 0; by < r.ys; by++) {
+      for (size_t bx = 0; bx < r.xs; bx++) {
+        const size_t pos = (r.y0 + by) * W + r.x0 + bx;
+        const uint8_t a = acs[pos];
+        if (!(a & 1)) continue;
+        const int s = a >> 1;
+        const size_t cx = kCoveredX[s], cy = kCoveredY[s];
+        const size_t covered = cx * cy, size = covered * 64, log2c = kLog2Covered[s];
+        const int32_t* quantized = qblocks[pos].data();
         // tokens, channel order Y, X, B; pass i carries (value >> shift_i) - (what earlier passes carried)
         for (int c : {1, 0, 2}) {
           for (size_t pass = 0; pass < num_passes; pass++) {
@@ -968,6 +1083,7 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
             const int32_t* row_top = by == 0 ? nullptr : row_nz - 32;
             const int32_t predicted = PredictFromTopAndLeft(row_top, row_nz, bx, 32);
             const size_t ord = kStrategyOrder[s];
+            const std::vector<uint32_t>& order = custom[ord][c].empty() ? order_for(s) : custom[ord][c];
             const size_t block_ctx = bctx.Context(0, raw_quant[(r.y0 + by) * W + r.x0 + bx], ord, c);
             size_t nz = 0;
             for (size_t k = covered; k < size; k++) nz += pass_value(quantized[c * size + order[k]]) != 0;
@@ -1071,7 +1187,44 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
     ac_global.Write(1, 1);  // default quantisation matrices
     ac_global.Write(CeilLog2(num_groups), 0);  // one set of histograms
     for (size_t pass = 0; pass < num_passes; pass++) {
-      WriteU32(ac_global, 0, Val(0x5F), Val(0x13), Val(0), Bits(13));  // natural coefficient orders
+      WriteU32(ac_global, used_orders, Val(0x5F), Val(0x13), Val(0), Bits(13));
+      if (used_orders != 0) {
+        // EncodeCoeffOrders, lib/jxl/enc_coeff_order.cc:293-337: per order and channel the permutation relative to the
+        // natural order as a Lehmer code (trailing zeros dropped), one ANS stream over the 8 permutation contexts
+        std::vector<Token> ptoks;
+        for (int o = 0; o < kNumStrategies; o++) {
+          const uint32_t ord = kStrategyOrder[o];
+          if (!(used_orders & (1u << ord)) || kOrderFirstStrategyOf(ord) != o) continue;
+          const size_t llf = kCoveredX[o] * kCoveredY[o], sz = 64 * llf;
+          const std::vector<uint32_t>& nat = order_for(o);
+          std::vector<uint32_t> lut(sz);
+          for (size_t i = 0; i < sz; i++) lut[nat[i]] = i;
+          for (int c = 0; c < 3; c++) {
+            std::vector<uint32_t> zz(sz), lehmer(sz, 0);
+            for (size_t i = 0; i < sz; i++) zz[i] = lut[custom[ord][c][i]];
+            // Lehmer code: how many later elements are smaller (lib/jxl/lehmer_code.h)
+            std::vector<uint32_t> avail(sz);
+            for (size_t i = 0; i < sz; i++) avail[i] = i;
+            for (size_t i = 0; i < sz; i++) {
+              const auto it = std::lower_bound(avail.begin(), avail.end(), zz[i]);
+              lehmer[i] = static_cast<uint32_t>(it - avail.begin());
+              avail.erase(it);
+            }
+            size_t end = sz;
+            while (end > llf && lehmer[end - 1] == 0) end--;
+            ptoks.push_back({CoeffOrderContext(sz), static_cast<uint32_t>(end - llf)});
+            uint32_t last = 0;
+            for (size_t i = llf; i < end; i++) {
+              ptoks.push_back({CoeffOrderContext(last), lehmer[i]});
+              last = lehmer[i];
+            }
+          }
+        }
+        EntropyEncoder perm_code(8, {0, 1, 2, 3, 4, 5, 6, 7});
+        perm_code.Count(ptoks);
+        perm_code.WriteHeader(ac_global);
+        perm_code.WriteTokens(ac_global, ptoks);
+      }
       pass_codes.emplace_back(bctx.NumACContexts(), clusters);
       for (size_t g = 0; g < num_groups; g++) pass_codes.back().Count(group_tokens[pass * num_groups + g]);
       pass_codes.back().WriteHeader(ac_global);

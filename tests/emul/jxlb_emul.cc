@@ -333,6 +333,24 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
         const uint8_t a = barena[static_cast<size_t>(by) * W + bx];
         if (a & 1) DevEncVarblock<0>(E, ef, bx, by, a >> 1, buf.data(), 0, 1);
       }
+    // coefficient orders: statistics kernels, then the host's sort, then the custom orders go back to the "device"
+    CustomOrders orders;
+    std::vector<uint16_t> custom_pool;
+    const std::vector<uint8_t> sample_bits = MakeOrderSampleBits(static_cast<size_t>(W) * H);
+    E.sample_bits = sample_bits.data();
+    if (p.coeff_orders) {
+      for (uint32_t g = 0; g < d.num_groups; g++) DevEncGroupOrders(E, ef, g);
+      std::vector<uint32_t> local(kCustomOrderCounters + 1024);
+      for (uint32_t g = 0; g < d.num_groups; g++) DevEncOrderStatsGroup<0>(E, ef, g, 0, 1, local.data());
+      orders = ComputeCustomOrders(static_cast<uint32_t>(iarena[ef.order_mask]), iarena.data() + ef.zero_counts, W, H);
+      for (uint32_t ord = 0; ord < kNumCustomOrders; ord++)
+        for (uint32_t c = 0; c < 3; c++) {
+          if (!(orders.used & (1u << ord))) continue;
+          ef.custom_order[3 * ord + c] = custom_pool.size();
+          custom_pool.insert(custom_pool.end(), orders.order[ord][c].begin(), orders.order[ord][c].end());
+        }
+    }
+    E.opool_custom = custom_pool.data();
     uint16_t ctxtab[128];
     for (int i = 0; i < 128; i++) ctxtab[i] = static_cast<uint16_t>(sh.upool[sh.ctxtab_off + i]);
     for (uint32_t c = 0; c < 3; c++)
@@ -348,7 +366,7 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
     }
     EncGlobals G;
     BuildEncGlobals(p, L, tree, ac_cluster_of, global_scale, quant_dc, reinterpret_cast<uint32_t*>(iarena.data() + ef.mod_hist),
-                    reinterpret_cast<uint32_t*>(iarena.data() + ef.ac_hist), &G);
+                    reinterpret_cast<uint32_t*>(iarena.data() + ef.ac_hist), orders, &G);
     const std::vector<uint32_t> mod_fs = G.mod_code.Fs(), ac_fs = G.ac_code.Fs();
     DevEncCode mod{mod_fs.data(), G.mod_code.reverse.data()};
     DevEncCode ac{ac_fs.data(), G.ac_code.reverse.data()};
