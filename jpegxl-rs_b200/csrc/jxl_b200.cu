@@ -1491,6 +1491,9 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       }
       e.first_index += ibase;
       e.block_of_num += ibase;
+      e.order_mask += ibase;
+      e.group_first += ibase;
+      e.zero_counts += ibase;
       e.dcg_count += ibase;
       e.group_tokens += ibase;
       e.ac_hist += ibase;

@@ -38,3 +38,29 @@ def test_wide_predictor_path_matches_oracle():
     got = emul_lib.decode([a, b], 4, jxlo.UINT8, [(1433, 2122), (50, 40)], endianness=0x100)
     assert np.array_equal(got[0], jxlo.decode(a, 4, jxlo.UINT8))
     assert np.array_equal(got[1], jxlo.decode(b, 4, jxlo.UINT8))
+
+
+def test_corrupted_and_truncated_inputs_fail_with_an_error():
+    """Seeded bit flips and truncations of every fixture: the planner or the stream status words report an error
+    (or, rarely, the damage is harmless) -- never a crash, a hang or an out-of-bounds write (the arenas of the
+    emulation are plain vectors, so a wild index shows up as a crash of this process)."""
+    import numpy as np
+    import vardct_cases as vc
+    files = {"sample.jxl": (read_golden("sample.jxl"), (50, 40)), "sample_jpg.jxl": (read_golden("sample_jpg.jxl"), (50, 40)),
+             "sample_grey.jxl": (read_golden("sample_grey.jxl"), (50, 40)), "lossy": vc.encoded("heuristic"),
+             "passes": vc.encoded("three_passes")}
+    rng = np.random.default_rng(7)
+    errors = 0
+    for name, (data, shape) in files.items():
+        for trial in range(24):
+            b = bytearray(data)
+            if trial % 4 == 0:
+                b = b[:int(len(b) * (0.2 + 0.03 * trial))]
+            else:
+                for _ in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(2, len(b)))] ^= 1 << int(rng.integers(8))
+            try:
+                emul_lib.decode([bytes(b)], 3, jxlo.UINT8, [shape])
+            except emul_lib.EmulError:
+                errors += 1
+    assert errors > 90  # almost every damaged file is detected (ANS final state, bounds, header checks)

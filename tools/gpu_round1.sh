@@ -1,4 +1,4 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --workload encode4k --batch 32 --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/bench_enc_v4_b32.json 2> gpurun_out/bench_enc.err; python tools/show_bench.py gpurun_out/bench_enc_v4_b32.json; tail -3 gpurun_out/bench_enc.err
-python bench.py --steps 8 --warmup 2 --inflight 1 --batch 64 --no-cpu-baseline > gpurun_out/bench_v13_b64_if1.json 2> gpurun_out/bench_v13.err; python tools/show_bench.py gpurun_out/bench_v13_b64_if1.json; tail -3 gpurun_out/bench_v13.err
+python -m pytest tests/test_encoder.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --workload encode4k --batch 32 --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/bench_enc_v5_b32.json 2> gpurun_out/bench_enc.err; python tools/show_bench.py gpurun_out/bench_enc_v5_b32.json; tail -3 gpurun_out/bench_enc.err
+ncu --metrics gpu__time_duration.sum --clock-control none -s 13 -c 13 --csv --log-file gpurun_out/launches_enc_v5.csv python bench.py --workload encode4k --batch 8 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_enc.log 2>&1; tail -1 gpurun_out/ncu_enc.log | cut -c1-100
