@@ -687,12 +687,15 @@ inline void WriteCoeffOrders(BitWriter& w, const CustomOrders& co) {
     std::vector<uint32_t> lut(sz);
     for (uint32_t i = 0; i < sz; i++) lut[natural[i]] = i;
     for (uint32_t c = 0; c < 3; c++) {
-      std::vector<uint32_t> lehmer(sz), avail(sz);
-      for (uint32_t i = 0; i < sz; i++) avail[i] = i;
+      // Lehmer code (lib/jxl/lehmer_code.h): lehmer[i] = how many not yet used values are below value i,
+      // = value - (used values below it), counted with a Fenwick tree
+      std::vector<uint32_t> lehmer(sz), fen(sz + 1, 0);
       for (uint32_t i = 0; i < sz; i++) {
-        const auto it = std::lower_bound(avail.begin(), avail.end(), lut[co.order[ord][c][i]]);
-        lehmer[i] = static_cast<uint32_t>(it - avail.begin());
-        avail.erase(it);
+        const uint32_t v = lut[co.order[ord][c][i]];
+        uint32_t below = 0;
+        for (uint32_t k = v; k > 0; k -= k & (~k + 1)) below += fen[k];
+        lehmer[i] = v - below;
+        for (uint32_t k = v + 1; k <= sz; k += k & (~k + 1)) fen[k]++;
       }
       uint32_t end = sz;
       while (end > llf && lehmer[end - 1] == 0) end--;

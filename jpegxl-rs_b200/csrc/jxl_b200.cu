@@ -148,8 +148,10 @@ __global__ void __launch_bounds__(256) k_write_output_rgba8(DevPools P, const De
 // blockIdx.x indexes a flat list of (frame, DC group) pairs.
 __global__ void __launch_bounds__(256) k_dc_finish(DevPools P, DevVPools V, const uint2* dcg_list) {
   extern __shared__ uint8_t acs_smem[];  // 64 KiB: the strategy map of one DC group (256 x 256 blocks)
+  __shared__ uint16_t stage_s[kDcStageEntries];
+  __shared__ uint32_t sinfo_s[kNumStrategies];
   const uint2 e = dcg_list[blockIdx.x];
-  DevDcGroupFinish<2>(P, V, e.x, e.y, threadIdx.x, blockDim.x, blockIdx.x, acs_smem);
+  DevDcGroupFinish<2>(P, V, e.x, e.y, threadIdx.x, blockDim.x, blockIdx.x, acs_smem, stage_s, sinfo_s);
 }
 
 __global__ void __launch_bounds__(256) k_dc_smooth(DevVPools V) {

@@ -80,9 +80,13 @@ constexpr float kDevSqrt2 = 1.41421356237f;
 // ---------------------------------------------------------------- DC groups
 // `acs_local`: xs * ys bytes of scratch for the group's strategy map (shared memory on the device: the serial scan
 // below then runs on shared-memory latency), or nullptr to work in the frame's map directly.
+constexpr uint32_t kDcStageEntries = 2048;  // list entries staged per chunk (uint16 each) by DevDcGroupFinish
+
+// `stage` / `sinfo_stage`: kDcStageEntries uint16 + kNumStrategies uint32 of shared memory for the serial scan, or nullptr.
 template <int SCOPE>
 JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t frame, uint32_t g, uint32_t tid, uint32_t nt,
-                              uint32_t status_index, uint8_t* acs_local) {
+                              uint32_t status_index, uint8_t* acs_local, uint16_t* stage = nullptr,
+                              uint32_t* sinfo_stage = nullptr) {
   const DevVFrame& vf = V.frames[frame];
   const uint32_t W = vf.xblocks, H = vf.yblocks;
   const uint32_t gx = g % vf.xdcgroups, gy = g / vf.xdcgroups;
@@ -152,60 +156,82 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
   }
   CoopSync<SCOPE>();
   // (b) the strategy / quant rows list one entry per varblock in raster order of their top-left
-  // blocks; where the next varblock starts depends on the extents of all earlier ones: serial.
-  if (tid == 0) {
+  // blocks; where the next varblock starts depends on the extents of all earlier ones: serial. The list is
+  // staged chunk by chunk (all threads load, thread 0 consumes), so that the serial scan only ever waits for
+  // shared memory (`stage` != nullptr) instead of for a dependent global load per varblock.
+  {
     const uint32_t cap = pl_rows.w;
     const uint32_t count = static_cast<uint32_t>(m_rows[static_cast<size_t>(cap) * 2]);
     const int32_t* row_strategy = m_rows;
     const int32_t* row_quant = m_rows + cap;
-    uint32_t num = 0;
-    // the list entries are consumed strictly in order: keep the next one (and its geometry) loaded ahead of use
-    int32_t next_raw = count > 0 ? row_strategy[0] : 0, next_q = count > 0 ? row_quant[0] : 0;
-    uint32_t next_info = V.upool[V.sinfo_off + (static_cast<uint32_t>(next_raw) < kNumStrategies ? next_raw : 0)];
-    for (uint32_t iy = 0; iy < ys && !(status & kVBadStream); iy++) {
-      const uint32_t y = y0 + iy;
-      for (uint32_t ix = 0; ix < xs; ix++) {
-        const uint32_t x = x0 + ix;
-        const size_t pos = static_cast<size_t>(y) * W + x;
-        uint8_t* cell = acs + static_cast<size_t>(iy) * astride + ix;
-        if (*cell != 0xFF) continue;
-        if (num >= count) {
-          status |= kVBadStream;
-          break;
+    uint32_t num = 0, iy = 0, ix = 0;  // (thread 0's scan position, kept across chunks)
+    for (uint32_t chunk = 0; chunk == 0 || chunk < count; chunk += kDcStageEntries) {
+      const uint32_t chunk_end = chunk + kDcStageEntries < count ? chunk + kDcStageEntries : count;
+      if (stage) {
+        for (uint32_t i = chunk + tid; i < chunk_end; i += nt) {
+          const int32_t raw = row_strategy[i];
+          int32_t q = row_quant[i];
+          q = q < 0 ? 0 : (q > 255 ? 255 : q);
+          stage[i - chunk] = static_cast<uint16_t>((static_cast<uint32_t>(raw) < kNumStrategies ? raw : 0xFF) | (q << 8));
         }
-        const int32_t raw = next_raw, cur_q = next_q;
-        const StrategyInfo si = UnpackStrategyInfo(next_info);
-        if (num + 1 < count) {
-          next_raw = row_strategy[num + 1];
-          next_q = row_quant[num + 1];
-          next_info = V.upool[V.sinfo_off + (static_cast<uint32_t>(next_raw) < kNumStrategies ? next_raw : 0)];
-        }
-        if (raw < 0 || raw >= static_cast<int32_t>(kNumStrategies)) {
-          status |= kVBadStream;
-          break;
-        }
-        const uint32_t next_x = (x / 32 + 1) * 32, next_y = (y / 32 + 1) * 32;  // varblocks stay inside their 256x256 group
-        const uint32_t xlim = x0 + xs, ylim = y0 + ys;
-        if (x + si.cx > next_x || x + si.cx > xlim || y + si.cy > next_y || y + si.cy > ylim) {
-          status |= kVBadStream;
-          break;
-        }
-        bool overlap = false;
-        for (uint32_t jy = 0; jy < si.cy; jy++)
-          for (uint32_t jx = 0; jx < si.cx; jx++) {
-            uint8_t& e = cell[static_cast<size_t>(jy) * astride + jx];
-            overlap |= e != 0xFF;
-            e = static_cast<uint8_t>((raw << 1) | ((jy | jx) == 0 ? 1 : 0));
-          }
-        if (overlap) {
-          status |= kVBadStream;
-          break;
-        }
-        int32_t q = cur_q;
-        q = q < 0 ? 0 : (q > 255 ? 255 : q);
-        rawq[pos] = static_cast<uint16_t>(1 + q);
-        num++;
+        for (uint32_t i = tid; chunk == 0 && i < kNumStrategies; i += nt) sinfo_stage[i] = V.upool[V.sinfo_off + i];
+        CoopSync<SCOPE>();
       }
+      if (tid == 0) {
+        const bool last_chunk = chunk_end == count;
+        for (; iy < ys && !(status & kVBadStream); iy++, ix = 0) {
+          const uint32_t y = y0 + iy;
+          bool paused = false;
+          for (; ix < xs; ix++) {
+            const uint32_t x = x0 + ix;
+            const size_t pos = static_cast<size_t>(y) * W + x;
+            uint8_t* cell = acs + static_cast<size_t>(iy) * astride + ix;
+            if (*cell != 0xFF) continue;
+            if (num >= chunk_end) {
+              if (last_chunk) status |= kVBadStream;  // more varblocks than list entries
+              paused = true;
+              break;
+            }
+            int32_t raw, cur_q;
+            if (stage) {
+              const uint32_t e = stage[num - chunk];
+              raw = (e & 0xFF) == 0xFF ? -1 : static_cast<int32_t>(e & 0xFF);
+              cur_q = static_cast<int32_t>(e >> 8);
+            } else {
+              raw = row_strategy[num];
+              cur_q = row_quant[num];
+            }
+            if (raw < 0 || raw >= static_cast<int32_t>(kNumStrategies)) {
+              status |= kVBadStream;
+              break;
+            }
+            const StrategyInfo si = UnpackStrategyInfo(stage ? sinfo_stage[raw] : V.upool[V.sinfo_off + raw]);
+            const uint32_t next_x = (x / 32 + 1) * 32, next_y = (y / 32 + 1) * 32;  // varblocks stay inside their 256x256 group
+            const uint32_t xlim = x0 + xs, ylim = y0 + ys;
+            if (x + si.cx > next_x || x + si.cx > xlim || y + si.cy > next_y || y + si.cy > ylim) {
+              status |= kVBadStream;
+              break;
+            }
+            bool overlap = false;
+            for (uint32_t jy = 0; jy < si.cy; jy++)
+              for (uint32_t jx = 0; jx < si.cx; jx++) {
+                uint8_t& e = cell[static_cast<size_t>(jy) * astride + jx];
+                overlap |= e != 0xFF;
+                e = static_cast<uint8_t>((raw << 1) | ((jy | jx) == 0 ? 1 : 0));
+              }
+            if (overlap) {
+              status |= kVBadStream;
+              break;
+            }
+            int32_t q = cur_q;
+            q = q < 0 ? 0 : (q > 255 ? 255 : q);
+            rawq[pos] = static_cast<uint16_t>(1 + q);
+            num++;
+          }
+          if (paused || (status & kVBadStream)) break;
+        }
+      }
+      if (stage) CoopSync<SCOPE>();
     }
   }
   CoopSync<SCOPE>();

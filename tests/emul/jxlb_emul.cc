@@ -149,7 +149,10 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       std::vector<uint8_t> acs_local(65536);  // stands in for the kernel's shared memory
       for (uint32_t f = 0; f < b.vframes.size(); f++) {
         const DevVFrame& vf = b.vframes[f];
-        for (uint32_t g = 0; g < vf.xdcgroups * vf.ydcgroups; g++, dcg++) DevDcGroupFinish<0>(P, V, f, g, 0, 1, dcg, acs_local.data());
+        std::vector<uint16_t> stage(kDcStageEntries);
+        uint32_t sinfo_stage[kNumStrategies];
+        for (uint32_t g = 0; g < vf.xdcgroups * vf.ydcgroups; g++, dcg++)
+          DevDcGroupFinish<0>(P, V, f, g, 0, 1, dcg, acs_local.data(), stage.data(), sinfo_stage);
         if (!vf.skip_dc_smoothing)
           for (uint32_t y = 0; y < vf.yblocks; y++)
             for (uint32_t x = 0; x < vf.xblocks; x++) DevDcSmoothBlock(V, vf, x, y);
