@@ -107,6 +107,7 @@ size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, fl
     p.gab = (gab & 1) != 0;          // bit 0: Gaborish signalled; bit 1: no inverse Gaborish; bit 2: natural orders
     p.gab_inverse = (gab & 2) == 0;
     p.coeff_orders = (gab & 4) == 0;
+    p.cfl = (gab & 8) == 0;          // bit 3: no chroma-from-luma fit
     p.epf_iters = epf_iters;
     p.dc_smoothing = dc_smoothing != 0;
     p.random_side_info = random_side_info != 0;

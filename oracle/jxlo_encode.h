@@ -619,6 +619,7 @@ struct EncodeParams {
   // 4K decode fixtures predate them and are regenerated with both off.
   bool gab_inverse = true;    // inverse Gaborish before the transforms when the frame signals Gaborish (E4)
   bool coeff_orders = true;   // coefficient orders from zero counts (E9); false: natural orders
+  bool cfl = true;            // chroma-from-luma factors per 64x64 tile fitted to the AC coefficients (E6); false: 0
 };
 
 struct EncoderStats {
@@ -705,6 +706,57 @@ inline std::vector<uint8_t> ACContextClusters(const BlockCtxMap& bctx) {
     c = static_cast<uint8_t>(remap[c]);
   }
   return cl;
+}
+
+// FindBestMultiplier, lib/jxl/enc_chroma_from_luma.cc:118-175 with `fast == false` (what libjxl's effort 7 passes,
+// lib/jxl/enc_heuristics.cc:1176-1182): Newton iterations on f'(x), f = 1/3 sum((|colour residual| + 1)^2 - 1) +
+// distance_mul * x^2 * num, derivatives by central differences (CFLFunction::Compute, :41-112). The sums run over
+// 8 SIMD lanes (element i in lane i % 8) that are added in Highway's AVX2 SumOfLanes order.
+inline float CflSumOfLanes(const float l[8]) { return ((l[0] + l[4]) + (l[2] + l[6])) + ((l[1] + l[5]) + (l[3] + l[7])); }
+inline int32_t FindBestMultiplier(const float* values_m, const float* values_s, size_t num, float base, float distance_mul) {
+  if (num == 0) return 0;
+  const float kInvColorFactor = 1.0f / 84, kCoeff = 1.0f / 3, kThres = 100.0f, eps = 100, kClamp = 20.0f;
+  const float coeffx2 = kCoeff * 2.0f;
+  float x = 0;
+  for (size_t iter = 0; iter < 20; iter++) {
+    const float first_derivative = 2 * distance_mul * num * x;
+    const float first_derivative_peps = 2 * distance_mul * num * (x + eps);
+    const float first_derivative_meps = 2 * distance_mul * num * (x - eps);
+    float fd[8] = {0}, fdpe[8] = {0}, fdme[8] = {0};
+    const float xpe = x + eps, xme = x - eps;
+    for (size_t i = 0; i < num; i++) {
+      const float a = kInvColorFactor * values_m[i];
+      const float b = base * values_m[i] - values_s[i];
+      const float v = std::fmaf(a, x, b), vpe = std::fmaf(a, xpe, b), vme = std::fmaf(a, xme, b);
+      const float av = std::fabs(v), avpe = std::fabs(vpe), avme = std::fabs(vme);
+      const float acoeffx2 = coeffx2 * a;
+      float d = acoeffx2 * (av + 1.0f), dpe = acoeffx2 * (avpe + 1.0f), dme = acoeffx2 * (avme + 1.0f);
+      d = v < 0.0f ? 0.0f - d : d;
+      dpe = vpe < 0.0f ? 0.0f - dpe : dpe;
+      dme = vme < 0.0f ? 0.0f - dme : dme;
+      const bool above = av >= kThres;  // (one mask for all three, as in the reference)
+      fd[i % 8] = fd[i % 8] + (above ? 0.0f : d);
+      fdpe[i % 8] = fdpe[i % 8] + (above ? 0.0f : dpe);
+      fdme[i % 8] = fdme[i % 8] + (above ? 0.0f : dme);
+    }
+    const float dfpeps = first_derivative_peps + CflSumOfLanes(fdpe);
+    const float dfmeps = first_derivative_meps + CflSumOfLanes(fdme);
+    const float df = first_derivative + CflSumOfLanes(fd);
+    const float ddf = (dfpeps - dfmeps) / (2 * eps);
+    const float kExperimentalInsignificantStabilizer = 0.85f;
+    const float step = df / (ddf + kExperimentalInsignificantStabilizer);
+    x -= std::min(kClamp, std::max(-kClamp, step));
+    if (std::fabs(step) < 3e-3f) break;
+  }
+  const float towards_zero = 2.6f;
+  if (x >= towards_zero) {
+    x -= towards_zero;
+  } else if (x <= -towards_zero) {
+    x += towards_zero;
+  } else {
+    x = 0;
+  }
+  return static_cast<int32_t>(std::max(-128.0f, std::min(127.0f, std::roundf(x))));
 }
 
 inline int kOrderFirstStrategyOf(uint32_t ord) {
@@ -808,6 +860,12 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   for (int c = 0; c < 3; c++) mul_dc[c] = (inv_global_scale / quant_dc) * dc_quant[c];
   const float x_dm = std::pow(1 / (1.25f), p.x_qm_scale - 2.0f), b_dm = std::pow(1 / (1.25f), p.b_qm_scale - 2.0f);
 
+  std::vector<float> cfl_tables[17];
+  auto table_for_cfl = [&](int strategy) -> const std::vector<float>& {
+    const int t = kStrategyToQuantTable[strategy];
+    if (cfl_tables[t].empty()) cfl_tables[t] = ComputeQuantTable(LibraryEncoding(t), t);
+    return cfl_tables[t];
+  };
   // ---- side information per block
   std::vector<uint8_t> acs(W * H, 0xFF), sharp(W * H, 4);
   std::vector<int32_t> raw_quant(W * H, 0);
@@ -880,6 +938,47 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
       num_varblocks++;
       if (stats) stats->strategy_count[s]++;
     }
+  }
+
+  // ---- chroma-from-luma map (E6): CfLHeuristics::ComputeTile, lib/jxl/enc_chroma_from_luma.cc:196-342, as libjxl runs it
+  // after the block sizes are known (lib/jxl/enc_heuristics.cc:1176-1182): per 64x64 tile the AC coefficients of the
+  // varblocks that lie inside the tile, weighted by the quantisation step, and one robust fit per chroma channel.
+  // (InvMatrix is taken as 1 / Matrix; the DC-level factors stay at their defaults.)
+  if (p.cfl && !p.random_side_info) {
+    const float scale = global_scale * (1.0f / 65536);
+    std::vector<float> byx(4096), bxx(4096), byb(4096), bbb(4096), blk(3 * 4096), scr(3 * 4096 + 1024);
+    for (size_t ty = 0; ty < cmh; ty++)
+      for (size_t tx = 0; tx < cmw; tx++) {
+        const size_t x0 = tx * 8, y0 = ty * 8, x1 = std::min(W, x0 + 8), y1 = std::min(H, y0 + 8);
+        size_t num_ac = 0;
+        for (size_t by = y0; by < y1; by++)
+          for (size_t bx = x0; bx < x1; bx++) {
+            const uint8_t a = acs[by * W + bx];
+            if (!(a & 1)) continue;
+            const int st = a >> 1;
+            size_t cx = kCoveredX[st], cy = kCoveredY[st];
+            if (cx + x0 > x1 || cy + y0 > y1) continue;  // (the reference's test: blocks larger than the tile)
+            const size_t size = cx * cy * 64;
+            for (int c = 0; c < 3; c++)
+              TransformFromPixels(st, xyb[c].Row(by * 8) + bx * 8, PW, blk.data() + c * size, scr.data());
+            if (cy > cx) std::swap(cx, cy);
+            for (size_t iy = 0; iy < cy; iy++)
+              for (size_t ix = 0; ix < cx; ix++)
+                for (int c = 0; c < 3; c++) blk[c * size + cx * 8 * iy + ix] = 0;
+            const std::vector<float>& dm = table_for_cfl(st);
+            const float q = scale * 128.0f * raw_quant[by * W + bx];
+            for (size_t i = 0; i < size; i++) {
+              const float qqm_x = q * (1.0f / dm[i]), qqm_b = q * (1.0f / dm[2 * size + i]);
+              byx[num_ac] = blk[size + i] * qqm_x;
+              bxx[num_ac] = blk[i] * qqm_x;
+              byb[num_ac] = blk[size + i] * qqm_b;
+              bbb[num_ac] = blk[2 * size + i] * qqm_b;
+              num_ac++;
+            }
+          }
+        ytox[ty * cmw + tx] = static_cast<int8_t>(FindBestMultiplier(byx.data(), bxx.data(), num_ac, 0.0f, 1e-9f));
+        ytob[ty * cmw + tx] = static_cast<int8_t>(FindBestMultiplier(byb.data(), bbb.data(), num_ac, 1.0f, 1e-9f));
+      }
   }
 
   // ---- DC: block means, quantised with chroma-from-luma on DC (default factors: X 0, B 1)

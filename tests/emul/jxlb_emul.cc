@@ -2,7 +2,9 @@
 // the CPU so that the planner and the per-stream logic can be checked on a box
 // without a GPU. The product library never does this (it fails without CUDA);
 // nothing outside tests/ builds or loads this file.
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../jpegxl-rs_b200/csrc/host/jxlb_batch.h"
@@ -368,8 +370,12 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
       for (uint32_t i = 0; i < gl.dc_tokens + gl.meta_tokens; i++) DevEncModularSample(E, ef, g, gl, i);
     }
     EncGlobals G;
+    const auto t_globals = std::chrono::steady_clock::now();
     BuildEncGlobals(p, L, tree, ac_cluster_of, global_scale, quant_dc, reinterpret_cast<uint32_t*>(iarena.data() + ef.mod_hist),
                     reinterpret_cast<uint32_t*>(iarena.data() + ef.ac_hist), orders, &G);
+    if (std::getenv("JXLB_EMUL_TIMING"))
+      std::fprintf(stderr, "BuildEncGlobals: %.2f ms\n",
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_globals).count());
     const std::vector<uint32_t> mod_fs = G.mod_code.Fs(), ac_fs = G.ac_code.Fs();
     DevEncCode mod{mod_fs.data(), G.mod_code.reverse.data()};
     DevEncCode ac{ac_fs.data(), G.ac_code.reverse.data()};
