@@ -454,6 +454,7 @@ struct EncParams {
   bool dc_smoothing = true;
   uint32_t x_qm_scale = 3, b_qm_scale = 2;
   bool coeff_orders = true;  // coefficient orders from zero counts (lib/jxl/enc_coeff_order.cc); false: natural orders
+  bool cfl = true;           // chroma-from-luma factors per tile (lib/jxl/enc_chroma_from_luma.cc); false: zero
 };
 
 inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize) {
@@ -519,6 +520,9 @@ inline void FillQuantizer(const EncParams& p, DevEFrame* ef, uint32_t* global_sc
   ef->distance = p.distance;
   ef->strategy_mode = p.strategy_mode;
   for (int i = 0; i < 4; i++) ef->biases[i] = kDefaultQuantBias[i];
+  // chroma-from-luma fit: Quantizer::Scale() * kStrangeMultiplier * raw quant (lib/jxl/enc_chroma_from_luma.cc:311-316)
+  ef->cfl = p.cfl ? 1 : 0;
+  ef->cfl_q = (global_scale * (1.0f / 65536)) * 128.0f * static_cast<float>(base_raw);
   // inverse Gaborish weights (lib/jxl/enc_gaborish.cc:21-48 with mul = 1, as lib/jxl/enc_heuristics.cc:1121-1131 passes)
   ef->gab = p.gab ? 1 : 0;
   {
@@ -598,7 +602,11 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
   ef->mod_tokens_stride = 6 * 65536 + 2048;
   L.fsize = f;
   L.isize = (i + 3) & ~uint64_t{3};
-  L.bsize = (nb + 15) & ~uint64_t{15};
+  ef->cmw = static_cast<uint32_t>((W + 7) / 8);
+  ef->cmh = static_cast<uint32_t>((H + 7) / 8);
+  ef->ytox = (nb + 15) & ~uint64_t{15};
+  ef->ytob = ef->ytox + ((static_cast<uint64_t>(ef->cmw) * ef->cmh + 15) & ~uint64_t{15});
+  L.bsize = ef->ytob + ((static_cast<uint64_t>(ef->cmw) * ef->cmh + 15) & ~uint64_t{15});
   L.tsize = ef->mod_tokens + ef->mod_tokens_stride * d.num_dc_groups;
   L.num_ac_clusters = num_ac_clusters;
   L.num_leaves = num_leaves;

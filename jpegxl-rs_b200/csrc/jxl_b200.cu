@@ -1274,7 +1274,17 @@ __global__ void __launch_bounds__(256) k_enc_dc(DevEPools E, const DevEFrame* fr
 constexpr uint32_t kEncThreads = 128;
 constexpr uint32_t kEncSmemFloats = 4 * 4096;  // four buffers of a 64x64 varblock, or one 32x32 set per warp
 
-// blockIdx.x = group: forward transform + quantisation; warp per varblock up to 32x32, CTA per 64x64 class.
+// blockIdx.x = tile (64x64 pixels), blockIdx.y = frame: chroma-from-luma fit over the float coefficients.
+__global__ void __launch_bounds__(128) k_enc_cfl(DevEPools E, const DevEFrame* frames) {
+  extern __shared__ float cfl_vals[];  // 4 * 4096 floats
+  __shared__ float red[64];
+  const DevEFrame& ef = frames[blockIdx.y];
+  if (blockIdx.x >= ef.cmw * ef.cmh) return;
+  DevEncCflTile<2>(E, ef, blockIdx.x % ef.cmw, blockIdx.x / ef.cmw, threadIdx.x, blockDim.x, cfl_vals, red);
+}
+
+// blockIdx.x = group: MODE 0 forward transforms, MODE 1 quantisation; warp per varblock up to 32x32, CTA per 64x64 class.
+template <int MODE>
 __global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, const DevEFrame* frames) {
   extern __shared__ float enc_smem[];
   __shared__ uint32_t next_s, has_big_s;
@@ -1305,7 +1315,7 @@ __global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, const D
       if (lane == 0) has_big_s = 1;
       continue;
     }
-    DevEncVarblock<1>(E, ef, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
+    DevEncVarblock<1, MODE>(E, ef, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
   }
   __syncthreads();
   if (!has_big_s) return;
@@ -1315,7 +1325,7 @@ __global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, const D
     if (!(a & 1)) continue;
     const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
     if (static_cast<uint32_t>(si.cx) * si.cy <= 16) continue;
-    DevEncVarblock<2>(E, ef, x0 + bx, y0 + by, a >> 1, enc_smem, threadIdx.x, kEncThreads);
+    DevEncVarblock<2, MODE>(E, ef, x0 + bx, y0 + by, a >> 1, enc_smem, threadIdx.x, kEncThreads);
   }
 }
 
@@ -1423,7 +1433,9 @@ JxlB200Encoder* JxlB200EncoderCreate(int device) {
     delete enc;
     return nullptr;
   }
-  cudaFuncSetAttribute(k_enc_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemFloats * sizeof(float));
+  cudaFuncSetAttribute(k_enc_coeffs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemFloats * sizeof(float));
+  cudaFuncSetAttribute(k_enc_coeffs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemFloats * sizeof(float));
+  cudaFuncSetAttribute(k_enc_cfl, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * sizeof(float));
   return enc;
 }
 
@@ -1501,6 +1513,8 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       e.ac_hist += ibase;
       e.mod_hist += ibase;
       e.acs += bbase;
+      e.ytox += bbase;
+      e.ytob += bbase;
       e.ac_tokens += tbase;
       e.mod_tokens += tbase;
       e.rgb = inbase;
@@ -1577,7 +1591,9 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     k_enc_strategy<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_number<<<dim3((max_dcg + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_dc<<<dim3((maxW * maxH + 255) / 256, nf), 256, 0, s>>>(E, d_efs.p);
-    k_enc_coeffs<<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
+    k_enc_coeffs<0><<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
+    k_enc_cfl<<<dim3(((maxW + 7) / 8) * ((maxH + 7) / 8), nf), 128, 4 * 4096 * sizeof(float), s>>>(E, d_efs.p);
+    k_enc_coeffs<1><<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
     // ---- coefficient orders: zero counts on the device, sort + permutation coding on the host, orders back
     std::vector<CustomOrders> orders(n);
     DevBuf<uint16_t> d_custom;

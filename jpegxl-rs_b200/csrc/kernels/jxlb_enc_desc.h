@@ -56,6 +56,12 @@ struct DevEFrame {
   uint64_t xyb_raw[3];  // gab != 0: XYB before the inverse Gaborish (k_enc_xyb writes here, k_enc_gaborish_inv reads)
   uint32_t gab;
   float gabinv_w[6];    // c, r, R, d, D, L of lib/jxl/convolve.h WeightsSymmetric5
+  // chroma from luma: the forward transforms leave the float coefficients in the xyb_raw planes (free by then, each
+  // varblock's coefficients in layout order inside its pixel footprint), the fit reads them, the quantisation reads both
+  uint32_t cfl;         // 1: fit the factors per 64x64 tile (lib/jxl/enc_chroma_from_luma.cc), 0: all zero
+  uint32_t cmw, cmh;    // tiles
+  float cfl_q;          // quantizer scale * 128 * raw quant (the reference's weighting of the coefficients)
+  uint64_t ytox, ytob;  // byte arena: int8 per tile
   // int arena
   uint64_t coef[3];    // quantised coefficients, stored in each varblock's pixel footprint (row-major)
   uint64_t dcq[3];     // quantised DC: [0] = Y, [1] = X, [2] = B, xblocks * yblocks

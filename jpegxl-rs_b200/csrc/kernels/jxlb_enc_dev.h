@@ -213,18 +213,22 @@ JXLB_HD void DevEncDcBlock(const DevEPools& E, const DevEFrame& ef, uint32_t bx,
   E.iarena[ef.dcq[2] + pos] = qb;
 }
 
-// Forward transform + quantisation of one varblock (plain DCT strategies). `buf`: 4 * 64 * covered floats.
-template <int SCOPE>
+// One varblock (plain DCT strategies), in two steps around the chroma-from-luma fit. MODE 0: forward transform, the
+// float coefficients go to the xyb_raw planes (layout order inside the varblock's footprint); `buf`: 4 * 64 * covered
+// floats. MODE 1: quantisation of those coefficients (Y round trip, chroma relative to decoded Y with the tile's factors).
+template <int SCOPE, int MODE>
 JXLB_HD void DevEncVarblock(const DevEPools& E, const DevEFrame& ef, uint32_t bx, uint32_t by, uint32_t s, float* buf,
                             uint32_t tid, uint32_t nt) {
   const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + s]);
   const uint32_t Rb = si.cy, Cb = si.cx, R = 8 * Rb, C = 8 * Cb, N = R * C;
   const uint32_t W = ef.xblocks, PW = W * 8;
   const float* wc = E.fpool + E.wc_off;
+  const size_t origin = static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+  float* dct[3] = {E.farena + ef.xyb_raw[0] + origin, E.farena + ef.xyb_raw[1] + origin, E.farena + ef.xyb_raw[2] + origin};
+  if (MODE == 0) {
   float* ch[3] = {buf, buf + N, buf + 2 * static_cast<size_t>(N)};
   float* scratch = buf + 3 * static_cast<size_t>(N);
   const float* F[3];
-  const size_t origin = static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
   for (uint32_t c = 0; c < 3; c++) {
     const float* px = E.farena + ef.xyb[c] + origin;
     for (uint32_t i = tid; i < N; i += nt) ch[c][i] = px[static_cast<size_t>(i / C) * PW + i % C];
@@ -237,19 +241,31 @@ JXLB_HD void DevEncVarblock(const DevEPools& E, const DevEFrame& ef, uint32_t bx
     }
     F[c] = ch[c];  // F[yfreq * C + xfreq]
   }
+  for (uint32_t k = tid; k < N; k += nt) {
+    const uint32_t fi = R < C ? k : (k % R) * C + k / R;  // coefficient layout: min(R, C) rows x max(R, C) columns
+    const size_t at = static_cast<size_t>(k / C) * PW + k % C;
+    dct[0][at] = F[0][fi];
+    dct[1][at] = F[1][fi];
+    dct[2][at] = F[2][fi];
+  }
+  CoopSync<SCOPE>();
+  return;
+  }
   const float sd_base = ef.inv_global_scale / 16.0f;  // raw quant field value 16 everywhere
   const float sd0 = sd_base * ef.x_dm, sd1 = sd_base, sd2 = sd_base * ef.b_dm;
-  const float x_cc = 0.0f, b_cc = 1.0f;
+  const size_t tile = static_cast<size_t>(by / 8) * ef.cmw + bx / 8;
+  const float x_cc = 0.0f + static_cast<float>(reinterpret_cast<const int8_t*>(E.barena + ef.ytox)[tile]) * (1.0f / 84);
+  const float b_cc = 1.0f + static_cast<float>(reinterpret_cast<const int8_t*>(E.barena + ef.ytob)[tile]) * (1.0f / 84);
   const float* dm = E.fpool + E.table_off[si.table];
   const uint32_t lcx = Cb > Rb ? Cb : Rb, lcy = Cb > Rb ? Rb : Cb;
   int32_t* out[3] = {E.iarena + ef.coef[0] + origin, E.iarena + ef.coef[1] + origin, E.iarena + ef.coef[2] + origin};
   for (uint32_t k = tid; k < N; k += nt) {
-    const uint32_t fi = R < C ? k : (k % R) * C + k / R;  // coefficient layout: min(R, C) rows x max(R, C) columns
+    const size_t from = static_cast<size_t>(k / C) * PW + k % C;
     const float y_mul = dm[N + k] * sd1;
-    int32_t qy = DevRoundToInt(F[1][fi] / y_mul);
+    int32_t qy = DevRoundToInt(dct[1][from] / y_mul);
     const float dq_y = DevAdjustQuantBias(1, qy, ef.biases) * y_mul;
-    int32_t qx = DevRoundToInt((F[0][fi] - x_cc * dq_y) / (dm[k] * sd0));
-    int32_t qb = DevRoundToInt((F[2][fi] - b_cc * dq_y) / (dm[2 * N + k] * sd2));
+    int32_t qx = DevRoundToInt((dct[0][from] - x_cc * dq_y) / (dm[k] * sd0));
+    int32_t qb = DevRoundToInt((dct[2][from] - b_cc * dq_y) / (dm[2 * N + k] * sd2));
     const uint32_t ly = k / (lcx * 8), lx = k % (lcx * 8);
     if (ly < lcy && lx < lcx) qx = qy = qb = 0;  // the lowest frequencies come from the DC image
     const size_t at = static_cast<size_t>(k / C) * PW + k % C;
@@ -258,6 +274,112 @@ JXLB_HD void DevEncVarblock(const DevEPools& E, const DevEFrame& ef, uint32_t bx
     out[2][at] = qb;
   }
   CoopSync<SCOPE>();
+}
+
+// Chroma-from-luma factors of one 64x64 tile: CfLHeuristics::ComputeTile + FindBestMultiplier (fast == false),
+// lib/jxl/enc_chroma_from_luma.cc:41-175, :196-342, over the float coefficients MODE 0 left behind. `vals`: 4 * 4096
+// floats (luma and chroma coefficients weighted for X and for B), `red`: 64 floats. The three sums of a Newton step
+// run as 8 lanes each (element i in lane i % 8, added in increasing i), combined in Highway's AVX2 SumOfLanes order --
+// 2 channels x 3 sums x 8 lanes = 48 independent chains for the threads of the CTA.
+template <int SCOPE>
+JXLB_HD void DevEncCflTile(const DevEPools& E, const DevEFrame& ef, uint32_t tx, uint32_t ty, uint32_t tid, uint32_t nt,
+                           float* vals, float* red) {
+  int8_t* ytox = reinterpret_cast<int8_t*>(E.barena + ef.ytox);
+  int8_t* ytob = reinterpret_cast<int8_t*>(E.barena + ef.ytob);
+  const size_t tile = static_cast<size_t>(ty) * ef.cmw + tx;
+  if (!ef.cfl) {
+    if (tid == 0) ytox[tile] = ytob[tile] = 0;
+    return;
+  }
+  const uint32_t W = ef.xblocks, H = ef.yblocks, PW = W * 8;
+  const uint32_t x0 = tx * 8, y0 = ty * 8, x1 = x0 + 8 < W ? x0 + 8 : W, y1 = y0 + 8 < H ? y0 + 8 : H;
+  const uint8_t* acs = E.barena + ef.acs;
+  float* v_m[2] = {vals, vals + 8192};          // luma weighted for X, for B
+  float* v_s[2] = {vals + 4096, vals + 12288};  // X, B
+  uint32_t num_ac = 0;
+  for (uint32_t by = y0; by < y1; by++)
+    for (uint32_t bx = x0; bx < x1; bx++) {
+      const uint8_t a = acs[static_cast<size_t>(by) * W + bx];
+      if (!(a & 1)) continue;
+      const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + (a >> 1)]);
+      if (si.cx + x0 > x1 || si.cy + y0 > y1) continue;  // (the reference's test: blocks larger than the tile)
+      const uint32_t N = 64u * si.cx * si.cy, C = si.cx * 8u;
+      const uint32_t lcx = si.cx > si.cy ? si.cx : si.cy, lcy = si.cx > si.cy ? si.cy : si.cx;
+      const float* dm = E.fpool + E.table_off[si.table];
+      const size_t origin = static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+      for (uint32_t k = tid; k < N; k += nt) {
+        const size_t at = origin + static_cast<size_t>(k / C) * PW + k % C;
+        const bool llf = k / (lcx * 8) < lcy && k % (lcx * 8) < lcx;
+        const float cy = llf ? 0.0f : E.farena[ef.xyb_raw[1] + at];
+        const float cxv = llf ? 0.0f : E.farena[ef.xyb_raw[0] + at];
+        const float cb = llf ? 0.0f : E.farena[ef.xyb_raw[2] + at];
+        const float qqm_x = ef.cfl_q * (1.0f / dm[k]), qqm_b = ef.cfl_q * (1.0f / dm[2 * N + k]);
+        v_m[0][num_ac + k] = cy * qqm_x;
+        v_s[0][num_ac + k] = cxv * qqm_x;
+        v_m[1][num_ac + k] = cy * qqm_b;
+        v_s[1][num_ac + k] = cb * qqm_b;
+      }
+      num_ac += N;
+    }
+  // red[0..1]: x per channel, red[2..3]: done flags, red[8 + 24 * ch + 8 * which + lane]: lane sums
+  for (uint32_t i = tid; i < 4; i += nt) red[i] = 0.0f;
+  CoopSync<SCOPE>();
+  const float kInvColorFactor = 1.0f / 84, kThres = 100.0f, eps = 100, kClamp = 20.0f, distance_mul = 1e-9f;
+  const float coeffx2 = (1.0f / 3) * 2.0f;
+  for (uint32_t iter = 0; iter < 20 && num_ac != 0; iter++) {
+    for (uint32_t chain = tid; chain < 48; chain += nt) {
+      const uint32_t ch = chain / 24, which = (chain / 8) % 3, lane = chain % 8;
+      if (red[2 + ch] != 0.0f) continue;
+      const float base = ch == 0 ? 0.0f : 1.0f;
+      const float x = red[ch];
+      const float xw = which == 0 ? x : (which == 1 ? x + eps : x - eps);
+      const float* vm = v_m[ch];
+      const float* vs = v_s[ch];
+      float acc = 0.0f;
+      for (uint32_t i = lane; i < num_ac; i += 8) {
+        const float a = kInvColorFactor * vm[i];
+        const float b = base * vm[i] - vs[i];
+        const float v = fmaf(a, x, b), vw = fmaf(a, xw, b);
+        const float acoeffx2 = coeffx2 * a;
+        float d = acoeffx2 * (fabsf(vw) + 1.0f);
+        d = vw < 0.0f ? 0.0f - d : d;
+        acc = acc + (fabsf(v) >= kThres ? 0.0f : d);
+      }
+      red[8 + chain] = acc;
+    }
+    CoopSync<SCOPE>();
+    for (uint32_t ch = tid; ch < 2; ch += nt) {
+      if (red[2 + ch] != 0.0f) continue;
+      const float x = red[ch];
+      const float* l = red + 8 + 24 * ch;
+      const float sum0 = ((l[0] + l[4]) + (l[2] + l[6])) + ((l[1] + l[5]) + (l[3] + l[7]));
+      const float sum1 = ((l[8] + l[12]) + (l[10] + l[14])) + ((l[9] + l[13]) + (l[11] + l[15]));
+      const float sum2 = ((l[16] + l[20]) + (l[18] + l[22])) + ((l[17] + l[21]) + (l[19] + l[23]));
+      const float df = 2 * distance_mul * num_ac * x + sum0;
+      const float dfpeps = 2 * distance_mul * num_ac * (x + eps) + sum1;
+      const float dfmeps = 2 * distance_mul * num_ac * (x - eps) + sum2;
+      const float ddf = (dfpeps - dfmeps) / (2 * eps);
+      const float step = df / (ddf + 0.85f);
+      red[ch] = x - (step > kClamp ? kClamp : (step < -kClamp ? -kClamp : step));
+      if (fabsf(step) < 3e-3f) red[2 + ch] = 1.0f;
+    }
+    CoopSync<SCOPE>();
+    if (red[2] != 0.0f && red[3] != 0.0f) break;  // (uniform: both flags are read after the barrier)
+  }
+  for (uint32_t ch = tid; ch < 2; ch += nt) {
+    float x = num_ac == 0 ? 0.0f : red[ch];
+    const float towards_zero = 2.6f;
+    if (x >= towards_zero) {
+      x -= towards_zero;
+    } else if (x <= -towards_zero) {
+      x += towards_zero;
+    } else {
+      x = 0;
+    }
+    float r = roundf(x);
+    r = r < -128.0f ? -128.0f : (r > 127.0f ? 127.0f : r);
+    (ch == 0 ? ytox : ytob)[tile] = static_cast<int8_t>(static_cast<int32_t>(r));
+  }
 }
 
 JXLB_HD uint32_t DevPackSigned(int32_t v) { return (static_cast<uint32_t>(v) << 1) ^ (v < 0 ? 0xFFFFFFFFu : 0u); }
@@ -494,6 +616,8 @@ JXLB_HD int32_t DevModValue(const DevEPools& E, const DevEFrame& ef, const DevMo
                             uint32_t y0, uint32_t x, uint32_t y) {
   if (ch.kind == 0) return E.iarena[ch.plane + static_cast<size_t>(y0 + y) * ef.xblocks + x0 + x];
   if (ch.kind == 1) return ch.konst;
+  if (ch.kind == 3)  // chroma-from-luma map (int8 per tile; the DC group starts at tile (x0 / 8, y0 / 8))
+    return reinterpret_cast<const int8_t*>(E.barena + ch.plane)[static_cast<size_t>((y0 >> 3) + y) * ef.cmw + (x0 >> 3) + x];
   if (y == 1) return 15;  // raw quant - 1
   const int32_t pos = E.iarena[ef.block_of_num + static_cast<size_t>(g) * 65536 + x];
   return E.barena[ef.acs + pos] >> 1;
@@ -662,8 +786,9 @@ JXLB_HD void DevEncModularSample(const DevEPools& E, const DevEFrame& ef, uint32
     if (j < 2 * n01) {
       chan = j / n01;
       local = j - chan * n01;
-      ch.kind = 1;
+      ch.kind = 3;
       ch.konst = 0;
+      ch.plane = chan == 0 ? ef.ytox : ef.ytob;
       ch.w = L.cw;
       ch.h = L.chh;
     } else if (j < 2 * n01 + 2 * L.count) {

@@ -978,6 +978,9 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
           }
         ytox[ty * cmw + tx] = static_cast<int8_t>(FindBestMultiplier(byx.data(), bxx.data(), num_ac, 0.0f, 1e-9f));
         ytob[ty * cmw + tx] = static_cast<int8_t>(FindBestMultiplier(byb.data(), bbb.data(), num_ac, 1.0f, 1e-9f));
+        if (std::getenv("JXLO_DEBUG_CFL"))
+          std::fprintf(stderr, "O tile %zu %zu: n=%zu x=%d b=%d v0=%a %a %a %a\n", tx, ty, num_ac, ytox[ty * cmw + tx], ytob[ty * cmw + tx],
+                       byx[70], bxx[70], byb[70], bbb[70]);
       }
   }
 

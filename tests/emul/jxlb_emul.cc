@@ -332,11 +332,24 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
     for (uint32_t g = 0; g < d.num_dc_groups; g++) DevEncNumberBlocks(E, ef, g);
     for (uint32_t by = 0; by < H; by++)
       for (uint32_t bx = 0; bx < W; bx++) DevEncDcBlock(E, ef, bx, by);
-    std::vector<float> buf(4 * 4096 + 64);
-    for (uint32_t by = 0; by < H; by++)
+    std::vector<float> buf(4 * 4096 + 64), cfl_vals(4 * 4096), red(64);
+    for (uint32_t by = 0; by < H; by++)  // k_enc_coeffs<0>: forward transforms
       for (uint32_t bx = 0; bx < W; bx++) {
         const uint8_t a = barena[static_cast<size_t>(by) * W + bx];
-        if (a & 1) DevEncVarblock<0>(E, ef, bx, by, a >> 1, buf.data(), 0, 1);
+        if (a & 1) DevEncVarblock<0, 0>(E, ef, bx, by, a >> 1, buf.data(), 0, 1);
+      }
+    for (uint32_t ty = 0; ty < ef.cmh; ty++)  // k_enc_cfl
+      for (uint32_t tx = 0; tx < ef.cmw; tx++) {
+        DevEncCflTile<0>(E, ef, tx, ty, 0, 1, cfl_vals.data(), red.data());
+        if (std::getenv("JXLO_DEBUG_CFL"))
+          std::fprintf(stderr, "E tile %u %u: x=%d b=%d v0=%a %a %a %a\n", tx, ty, static_cast<int8_t>(barena[ef.ytox + ty * ef.cmw + tx]),
+                       static_cast<int8_t>(barena[ef.ytob + ty * ef.cmw + tx]), cfl_vals[70], cfl_vals[4096 + 70], cfl_vals[8192 + 70],
+                       cfl_vals[12288 + 70]);
+      }
+    for (uint32_t by = 0; by < H; by++)  // k_enc_coeffs<1>: quantisation
+      for (uint32_t bx = 0; bx < W; bx++) {
+        const uint8_t a = barena[static_cast<size_t>(by) * W + bx];
+        if (a & 1) DevEncVarblock<0, 1>(E, ef, bx, by, a >> 1, buf.data(), 0, 1);
       }
     // coefficient orders: statistics kernels, then the host's sort, then the custom orders go back to the "device"
     CustomOrders orders;

@@ -8,6 +8,8 @@ import emul_lib
 import jxlo
 import vardct_cases as vc
 
+CFL = True  # the chroma-from-luma fit (row E6) runs in both encoders
+
 CASES = [
     ("dct8", lambda: vc.crop(300, 400), dict(strategy_mode=0)),
     ("heuristic", lambda: vc.crop(300, 400, 500, 700), dict(strategy_mode=2)),
@@ -21,7 +23,7 @@ CASES = [
 def test_emulated_encoder_is_byte_exact(name):
     _, make, kw = next(c for c in CASES if c[0] == name)
     img = make()
-    want = jxlo.encode_vardct(img, dc_tree=1, **kw)
+    want = jxlo.encode_vardct(img, dc_tree=1, cfl=CFL, **kw)
     assert emul_lib.encode(img, **kw) == want
     # and the stream is a picture of the input
     out = jxlo.decode(want, 3, jxlo.UINT8)
@@ -35,7 +37,7 @@ def test_gpu_encoder_is_byte_exact_in_a_batch(pkg):
     enc = pkg.encoder_builder().quality(1.0).build()
     outs = enc.encode_batch(imgs)
     for img, o in zip(imgs, outs):
-        assert o.data == jxlo.encode_vardct(img, dc_tree=1, strategy_mode=2)
+        assert o.data == jxlo.encode_vardct(img, dc_tree=1, cfl=CFL, strategy_mode=2)
 
 
 @pytest.mark.gpu
@@ -45,7 +47,7 @@ def test_gpu_encoder_each_case(pkg, name):
     img = make()
     enc = pkg.JxlEncoder(quality=kw.get("distance", 1.0), speed=1 if kw["strategy_mode"] == 0 else 7)
     got = enc.encode(img.reshape(-1), img.shape[1], img.shape[0]).data
-    assert got == jxlo.encode_vardct(img, dc_tree=1, **kw)
+    assert got == jxlo.encode_vardct(img, dc_tree=1, cfl=CFL, **kw)
 
 
 @pytest.mark.gpu
@@ -54,7 +56,7 @@ def test_gpu_round_trip_4k(pkg):
     img = vc.frame_4k()
     enc = pkg.encoder_builder().build()
     data = enc.encode(img).data
-    assert data == jxlo.encode_vardct(img, dc_tree=1, strategy_mode=2)
+    assert data == jxlo.encode_vardct(img, dc_tree=1, cfl=CFL, strategy_mode=2)
     out = pkg.decode_batch([data], 3, np.uint8)[0]
     err = out.astype(np.float64) - img
     assert 10 * np.log10(255 ** 2 / (err ** 2).mean()) > 33
@@ -68,7 +70,7 @@ def test_event_api_container_output_round_trips(pkg):
     plain = pkg.encoder_builder().build().encode(img).data
     boxed = pkg.encoder_builder().use_container(True).init_buffer_size(64).build().encode(img).data
     assert pkg.check_valid_signature(boxed) and boxed[:12] == b"\0\0\0\x0cJXL \r\n\x87\n" and boxed.endswith(plain)
-    assert plain == jxlo.encode_vardct(img, dc_tree=1, strategy_mode=2)
+    assert plain == jxlo.encode_vardct(img, dc_tree=1, cfl=CFL, strategy_mode=2)
     meta, px = pkg.decoder_builder().build().decode(boxed)
     assert (meta.width, meta.height) == (400, 300)
     assert np.array_equal(np.asarray(px.data).reshape(300, 400, 3), jxlo.decode(plain, 3, jxlo.UINT8))
