@@ -415,12 +415,23 @@ def main():
     outs = out_sets[0]
     e2e_steps = max(nfl, min(args.steps, 6))
 
+    phase_s = {"set_input": 0.0, "run_wait": 0.0, "read_outputs": 0.0}
+    phase_lock = threading.Lock()
+
     def e2e_step(h):
         d, sx = decs[h], streams[h]
+        t0 = time.perf_counter()
         d.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8)
+        t1 = time.perf_counter()
         d.run(sx)
         d.wait(sx)
+        t2 = time.perf_counter()
         d.read_outputs(out_sets[h])
+        t3 = time.perf_counter()
+        with phase_lock:
+            phase_s["set_input"] += t1 - t0
+            phase_s["run_wait"] += t2 - t1
+            phase_s["read_outputs"] += t3 - t2
 
     def e2e_round(n):
         it = iter(range(n))
@@ -451,6 +462,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = pixels_per_step / e2e_s / 1e6
+    if rank == 0:  # where a step's wall time goes (summed over the overlapping handles, warm-up included)
+        n_e2e = e2e_steps + nfl
+        print("e2e phases per step (ms): " + ", ".join("%s %.1f" % (k, v / n_e2e * 1e3) for k, v in phase_s.items()),
+              file=sys.stderr)
 
     ok = wl.check(outs)  # checksum gate: the batch decodes to the golden pixels
     okt = torch.tensor([1 if ok else 0], device="cuda")

@@ -1,7 +1,4 @@
 set -x
-python bench.py > gpurun_out/bench_final_default.json 2> gpurun_out/bench_final.err; python tools/show_bench.py gpurun_out/bench_final_default.json; tail -3 gpurun_out/bench_final.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_final_reference.json 2> gpurun_out/bench_final.err; cut -c1-400 gpurun_out/bench_final_reference.json; tail -3 gpurun_out/bench_final.err
-python bench.py --workload modular > gpurun_out/bench_final_modular.json 2> gpurun_out/bench_final.err; python tools/show_bench.py gpurun_out/bench_final_modular.json; tail -3 gpurun_out/bench_final.err
-python bench.py --workload encode4k --batch 32 --steps 4 --warmup 1 > gpurun_out/bench_final_encode.json 2> gpurun_out/bench_final.err; python tools/show_bench.py gpurun_out/bench_final_encode.json; tail -3 gpurun_out/bench_final.err
-python -c "import __graft_entry__ as g; g.smoke()"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_modular_decode_sparse -s 1 -c 1 -f -o gpurun_out/r1_final_k_modular_decode_sparse_b256 python tools/ncu_workload.py 256 vardct_4k_natural.jxl 3 > gpurun_out/ncu_final.log 2>&1; tail -2 gpurun_out/ncu_final.log
+python -m pytest tests/test_encoder.py tests/test_gpu_vardct.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --workload encode4k --batch 32 --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/bench_enc_v7_b32.json 2> gpurun_out/bench_enc.err; python tools/show_bench.py gpurun_out/bench_enc_v7_b32.json; tail -3 gpurun_out/bench_enc.err
+ncu --metrics gpu__time_duration.sum --clock-control none -s 16 -c 16 --csv --log-file gpurun_out/launches_enc_v7.csv python bench.py --workload encode4k --batch 8 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_enc.log 2>&1; tail -1 gpurun_out/ncu_enc.log | cut -c1-100
