@@ -14,6 +14,10 @@ namespace jxlb {
 
 struct BatchPlan {
   std::vector<uint8_t> bytes;  // all codestreams, each starting on a 4-byte boundary, zero padded
+  // ... or, when the caller of PlanBatch provides the storage (pinned host memory the upload then reads directly,
+  // filled by the planning threads): the same layout at `ext_bytes`, and `bytes` stays empty
+  const uint8_t* ext_bytes = nullptr;
+  uint64_t ext_bytes_size = 0;
   std::vector<DevAlias> alias;
   std::vector<uint32_t> prefix, cfg, refs;
   std::vector<uint16_t> lut;
@@ -96,10 +100,14 @@ inline void BundleStreams(BatchPlan* b) {
   }
 }
 
-inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, BatchPlan* b) {
-  const uint64_t byte_base = b->bytes.size();
-  b->bytes.insert(b->bytes.end(), cs, cs + cs_size);
-  b->bytes.resize((b->bytes.size() + 3) & ~size_t{3}, 0);
+inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, BatchPlan* b, int64_t ext_base = -1) {
+  uint64_t byte_base = b->bytes.size();
+  if (ext_base >= 0) {  // the bytes already sit at ext_bytes + ext_base
+    byte_base = static_cast<uint64_t>(ext_base);
+  } else {
+    b->bytes.insert(b->bytes.end(), cs, cs + cs_size);
+    b->bytes.resize((b->bytes.size() + 3) & ~size_t{3}, 0);
+  }
   b->compressed_bytes += cs_size;
   const uint32_t alias0 = b->alias.size(), prefix0 = b->prefix.size(), cfg0 = b->cfg.size(), refs0 = b->refs.size();
   const uint32_t tree0 = b->tree.size(), codes0 = b->codes.size(), chans0 = b->chans.size(), lut0 = b->lut.size();
@@ -283,8 +291,11 @@ constexpr int kMaxProbeRounds = 24;  // one DC chain + at most 17 raw quantisati
 
 // Plans `n` files on `threads` host threads and merges them in input order. Files whose plan depends on where the
 // device stops reading a stream (ProbeCtx) are planned in rounds, one launch of `probe` per round for all of them.
+// `bytes_alloc(size)`: storage for the batch's codestream bytes (see BatchPlan::ext_bytes), or empty.
+using BytesAlloc = std::function<uint8_t*(size_t)>;
+
 inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n, const PixelFormat& fmt,
-                      int threads, BatchPlan* batch, const ProbeFn& probe = ProbeFn()) {
+                      int threads, BatchPlan* batch, const ProbeFn& probe = ProbeFn(), const BytesAlloc& bytes_alloc = BytesAlloc()) {
   std::vector<FramePlan> plans(n);
   std::vector<CodestreamView> views(n);
   std::vector<std::string> errors(n);
@@ -292,6 +303,28 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
   std::vector<size_t> todo(n);
   for (size_t i = 0; i < n; i++) todo[i] = i;
   threads = std::max(1, std::min<int>(threads, static_cast<int>(n)));
+  // Where every codestream goes in the byte pool is known as soon as the containers are opened: the planning threads
+  // copy their file there themselves (in parallel, into memory that is already mapped) instead of one thread
+  // appending 1 - 2 MB per file to a growing vector afterwards.
+  std::vector<uint64_t> byte_off(n, 0);
+  uint8_t* ext = nullptr;
+  if (bytes_alloc) {
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+      try {
+        views[i] = FindCodestream(files[i], sizes[i]);
+      } catch (const std::exception& e) {
+        throw Error("frame " + std::to_string(i) + ": " + e.what());
+      }
+      byte_off[i] = total;
+      total += (views[i].size + 3) & ~size_t{3};
+    }
+    ext = bytes_alloc(total + 64);
+    JXLB_CHECK(ext != nullptr, "out of memory (codestream staging)");
+    std::memset(ext + total, 0, 64);  // read-ahead padding for the device bit reader
+    batch->ext_bytes = ext;
+    batch->ext_bytes_size = total + 64;
+  }
   for (int round = 0; !todo.empty(); round++) {
     JXLB_CHECK(round < kMaxProbeRounds, "too many chained sub-streams");
     std::atomic<size_t> next{0};
@@ -301,7 +334,11 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
         if (k >= todo.size()) break;
         const size_t i = todo[k];
         try {
-          if (round == 0) views[i] = FindCodestream(files[i], sizes[i]);
+          if (round == 0 && !ext) views[i] = FindCodestream(files[i], sizes[i]);
+          if (round == 0 && ext) {
+            std::memcpy(ext + byte_off[i], views[i].data, views[i].size);
+            std::memset(ext + byte_off[i] + views[i].size, 0, ((views[i].size + 3) & ~size_t{3}) - views[i].size);
+          }
           plans[i] = FramePlan();
           ctx[i].next = 0;
           ctx[i].pending = false;
@@ -356,8 +393,36 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
       c.done.push_back(std::move(res));
     }
   }
-  for (size_t i = 0; i < n; i++) MergeFrame(plans[i], views[i].data, views[i].size, batch);
-  batch->bytes.resize(batch->bytes.size() + 64, 0);  // read-ahead padding for the device bit reader
+  {  // one allocation per pool instead of a doubling series
+    size_t alias = 0, lut = 0, cpool = 0, tree = 0, chans = 0, planes = 0, streams = 0, acs = 0, prefix = 0, cfg = 0, opool = 0;
+    for (const FramePlan& f : plans) {
+      alias += f.alias.size();
+      lut += f.lut.size();
+      cpool += f.v.cpool.size();
+      opool += f.v.opool.size();
+      tree += f.tree.size();
+      chans += f.chans.size();
+      planes += f.planes.size();
+      streams += f.streams.size();
+      acs += f.v.ac_streams.size();
+      prefix += f.prefix.size();
+      cfg += f.cfg.size();
+    }
+    batch->alias.reserve(alias);
+    batch->lut.reserve(lut);
+    batch->cpool.reserve(cpool);
+    batch->tree.reserve(tree);
+    batch->chans.reserve(chans);
+    batch->planes.reserve(planes);
+    batch->streams.reserve(streams);
+    batch->ac_streams.reserve(acs);
+    batch->prefix.reserve(prefix);
+    batch->cfg.reserve(cfg);
+    const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
+    batch->opool.reserve(opool + sh.opool.size());
+  }
+  for (size_t i = 0; i < n; i++) MergeFrame(plans[i], views[i].data, views[i].size, batch, ext ? static_cast<int64_t>(byte_off[i]) : -1);
+  if (!ext) batch->bytes.resize(batch->bytes.size() + 64, 0);  // read-ahead padding for the device bit reader
   BundleStreams(batch);
   if (!batch->vframes.empty()) {
     // pixel-plane slots for one wave of frames, after the per-frame planes of the float arena

@@ -419,6 +419,8 @@ struct JxlB200Decoder {
   DevBuf<DevProgram> d_group_programs, d_levels;
   DevBuf<DevFrameOut> d_frames;
   DevBuf<int32_t> d_arena, d_wp, d_ring;
+  uint8_t* h_bytes = nullptr;     // pinned staging for the codestream bytes of a batch (grows, kept across batches)
+  size_t h_bytes_cap = 0;
   DevBuf<uint64_t> d_end_bits;    // probe launches only
   uint32_t probe_launches = 0;    // Modular decode launches made while planning (probe rounds)
   // VarDCT
@@ -518,6 +520,7 @@ void JxlB200DecoderDestroy(JxlB200Decoder* dec) {
   cudaSetDevice(dec->device);
   FoldEvents(dec);
   for (cudaEvent_t e : dec->free_events) cudaEventDestroy(e);
+  if (dec->h_bytes) cudaFreeHost(dec->h_bytes);
   if (dec->stream) cudaStreamDestroy(dec->stream);
   delete dec;
 }
@@ -539,7 +542,12 @@ static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s
 static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat& fmt, bool want_end_bits) {
   CUDA_OK(cudaSetDevice(dec->device));
   cudaStream_t s = dec->stream;
-  CUDA_OK(dec->d_bytes.Upload(b.bytes, s));
+  if (b.ext_bytes) {  // pinned staging filled by the planning threads: one asynchronous copy
+    CUDA_OK(dec->d_bytes.Alloc(b.ext_bytes_size));
+    CUDA_OK(cudaMemcpyAsync(dec->d_bytes.p, b.ext_bytes, b.ext_bytes_size, cudaMemcpyHostToDevice, s));
+  } else {
+    CUDA_OK(dec->d_bytes.Upload(b.bytes, s));
+  }
   CUDA_OK(dec->d_alias.Upload(b.alias, s));
   CUDA_OK(dec->d_prefix.Upload(b.prefix, s));
   CUDA_OK(dec->d_cfg.Upload(b.cfg, s));
@@ -712,7 +720,18 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   std::unique_ptr<BatchPlan> plan(new BatchPlan());
   try {
     if (cudaSetDevice(dec->device) != cudaSuccess) throw Error("cudaSetDevice failed");
-    PlanBatch(files, sizes, n, fmt, num_threads, plan.get(), probe);
+    const BytesAlloc bytes_alloc = [dec](size_t size) -> uint8_t* {
+      if (size > dec->h_bytes_cap) {
+        if (dec->h_bytes) cudaFreeHost(dec->h_bytes);
+        dec->h_bytes = nullptr;
+        dec->h_bytes_cap = 0;
+        const size_t cap = size + size / 4;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&dec->h_bytes), cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        dec->h_bytes_cap = cap;
+      }
+      return dec->h_bytes;
+    };
+    PlanBatch(files, sizes, n, fmt, num_threads, plan.get(), probe, bytes_alloc);
   } catch (const std::exception& e) {
     dec->error = e.what();
     return 1;
