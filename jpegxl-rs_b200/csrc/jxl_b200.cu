@@ -163,16 +163,19 @@ __global__ void __launch_bounds__(256) k_dc_smooth(DevVPools V) {
 }
 
 // One warp per CTA, 32 AC streams in lock step.
-__global__ void __launch_bounds__(32) k_ac_decode(DevPools P, DevVPools V) {
-  __shared__ uint8_t colnz_s[96 * 32];
+// kAcWarps independent warps per CTA (32 streams each): the streams are latency-bound single warps, and one-warp CTAs
+// would use up the 32 CTA slots of an SM that the per-pixel kernels of other batches in flight need.
+constexpr uint32_t kAcWarps = 4;
+__global__ void __launch_bounds__(32 * kAcWarps) k_ac_decode(DevPools P, DevVPools V) {
+  __shared__ uint8_t colnz_s[kAcWarps][96 * 32];
   __shared__ uint16_t ctxtab_s[128];
-  const uint32_t lane = threadIdx.x;
-  for (uint32_t i = lane; i < 128; i += 32) ctxtab_s[i] = static_cast<uint16_t>(V.upool[V.ctxtab_off + i]);
-  for (uint32_t i = lane; i < 96 * 32; i += 32) colnz_s[i] = 0;
-  __syncwarp();
-  const uint32_t s = blockIdx.x * 32 + lane;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) ctxtab_s[i] = static_cast<uint16_t>(V.upool[V.ctxtab_off + i]);
+  for (uint32_t i = lane; i < 96 * 32; i += 32) colnz_s[warp][i] = 0;
+  __syncthreads();
+  const uint32_t s = (blockIdx.x * kAcWarps + warp) * 32 + lane;
   DevAcLaneMem m;
-  m.colnz = colnz_s + lane;
+  m.colnz = colnz_s[warp] + lane;
   m.stride = 32;
   m.freq_ctx = ctxtab_s;
   m.nnz_ctx = ctxtab_s + 64;
@@ -863,7 +866,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     }
     {
       ScopedTimer t(dec, s, kKAcDecode);
-      k_ac_decode<<<(b.ac_streams.size() + 31) / 32, 32, 0, s>>>(P, V);
+      k_ac_decode<<<(b.ac_streams.size() + 32 * kAcWarps - 1) / (32 * kAcWarps), 32 * kAcWarps, 0, s>>>(P, V);
       launches++;
     }
     const dim3 px_block(32, 8);
