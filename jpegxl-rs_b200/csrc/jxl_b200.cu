@@ -163,9 +163,8 @@ __global__ void __launch_bounds__(256) k_dc_smooth(DevVPools V) {
 }
 
 // One warp per CTA, 32 AC streams in lock step.
-// kAcWarps independent warps per CTA (32 streams each): the streams are latency-bound single warps, and one-warp CTAs
-// would use up the 32 CTA slots of an SM that the per-pixel kernels of other batches in flight need.
-constexpr uint32_t kAcWarps = 4;
+// kAcWarps independent warps per CTA (32 streams each); the streams are latency-bound single warps.
+constexpr uint32_t kAcWarps = 1;  // (measured: 4 warps per CTA is no faster with several batches in flight and 13 % slower alone)
 __global__ void __launch_bounds__(32 * kAcWarps) k_ac_decode(DevPools P, DevVPools V) {
   __shared__ uint8_t colnz_s[kAcWarps][96 * 32];
   __shared__ uint16_t ctxtab_s[128];
@@ -1431,6 +1430,19 @@ struct JxlB200Encoder {
   std::string error;
   std::vector<std::vector<uint8_t>> outputs;
   double phase_ms[3] = {0, 0, 0};  // kernels before the histogram sync, host table building, emit kernels
+  // device buffers, kept across batches (a batch of 32 4K frames uses ~20 GB: allocating and freeing that per call
+  // costs more than the kernels)
+  DevBuf<uint8_t> d_in, d_barena, d_cluster, d_sample;
+  DevBuf<float> d_farena, d_fpool, d_lut;
+  DevBuf<int32_t> d_iarena;
+  DevBuf<uint2> d_tokens;
+  DevBuf<uint16_t> d_opool, d_custom, d_rev;
+  DevBuf<uint32_t> d_upool, d_words, d_fs;
+  DevBuf<uint64_t> d_off, d_bits;
+  DevBuf<DevEncTreeNode> d_trees;
+  DevBuf<DevEFrame> d_efs;
+  uint32_t* h_words = nullptr;  // pinned: the emitted sections of a batch
+  size_t h_words_cap = 0;
 };
 
 #undef CUDA_OK
@@ -1464,6 +1476,7 @@ JxlB200Encoder* JxlB200EncoderCreate(int device) {
 void JxlB200EncoderDestroy(JxlB200Encoder* enc) {
   if (!enc) return;
   cudaSetDevice(enc->device);
+  if (enc->h_words) cudaFreeHost(enc->h_words);
   if (enc->stream) cudaStreamDestroy(enc->stream);
   delete enc;
 }
@@ -1549,13 +1562,13 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       tbase += f.L.tsize;
       inbase += (static_cast<uint64_t>(xsizes[i]) * ysizes[i] * 3 + 15) & ~uint64_t{15};
     }
-    DevBuf<uint8_t> d_in, d_barena, d_cluster;
-    DevBuf<float> d_farena, d_fpool, d_lut;
-    DevBuf<int32_t> d_iarena;
-    DevBuf<uint2> d_tokens;
-    DevBuf<uint16_t> d_opool;
-    DevBuf<uint32_t> d_upool;
-    DevBuf<DevEncTreeNode> d_trees;
+    DevBuf<uint8_t>&d_in = enc->d_in, &d_barena = enc->d_barena, &d_cluster = enc->d_cluster;
+    DevBuf<float>&d_farena = enc->d_farena, &d_fpool = enc->d_fpool, &d_lut = enc->d_lut;
+    DevBuf<int32_t>& d_iarena = enc->d_iarena;
+    DevBuf<uint2>& d_tokens = enc->d_tokens;
+    DevBuf<uint16_t>& d_opool = enc->d_opool;
+    DevBuf<uint32_t>& d_upool = enc->d_upool;
+    DevBuf<DevEncTreeNode>& d_trees = enc->d_trees;
     CUDA_OK(d_in.Alloc(inbase + 16));
     CUDA_OK(d_farena.Alloc(fbase + 16));
     CUDA_OK(d_iarena.Alloc(ibase + 16));
@@ -1604,7 +1617,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       max_groups = std::max<uint32_t>(max_groups, d.num_groups);
       max_dcg = std::max<uint32_t>(max_dcg, d.num_dc_groups);
     }
-    DevBuf<DevEFrame> d_efs;
+    DevBuf<DevEFrame>& d_efs = enc->d_efs;
     CUDA_OK(d_efs.Upload(efs, s));
     E.tree = d_trees.p;
     const uint32_t nf = static_cast<uint32_t>(n);
@@ -1618,8 +1631,8 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     k_enc_coeffs<1><<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
     // ---- coefficient orders: zero counts on the device, sort + permutation coding on the host, orders back
     std::vector<CustomOrders> orders(n);
-    DevBuf<uint16_t> d_custom;
-    DevBuf<uint8_t> d_sample;
+    DevBuf<uint16_t>& d_custom = enc->d_custom;
+    DevBuf<uint8_t>& d_sample = enc->d_sample;
     std::vector<uint16_t> custom_pool;
     std::vector<uint8_t> sample_bits;
     if (p.coeff_orders) {
@@ -1740,9 +1753,9 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       code_off[i] = CodeOff{push_fs(f.G.mod_code.Fs()), push_rev(f.G.mod_code.reverse), push_fs(f.G.ac_code.Fs()),
                             push_rev(f.G.ac_code.reverse)};
     }
-    DevBuf<uint16_t> d_rev;
-    DevBuf<uint32_t> d_words, d_fs;
-    DevBuf<uint64_t> d_off, d_bits;
+    DevBuf<uint16_t>& d_rev = enc->d_rev;
+    DevBuf<uint32_t>&d_words = enc->d_words, &d_fs = enc->d_fs;
+    DevBuf<uint64_t>&d_off = enc->d_off, &d_bits = enc->d_bits;
     std::vector<uint64_t> h_off;
     for (size_t i = 0; i < n; i++) {
       h_off.insert(h_off.end(), fr[i].dc_off.begin(), fr[i].dc_off.end());
@@ -1769,9 +1782,17 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
                                                                             dc_blocks);
     CUDA_OK(cudaEventRecord(ev[3], s));
     std::vector<uint64_t> h_bits(nsec);
-    std::vector<uint32_t> h_words(words_total + 16);
+    if (words_total + 16 > enc->h_words_cap) {  // pinned, kept across batches
+      if (enc->h_words) cudaFreeHost(enc->h_words);
+      enc->h_words = nullptr;
+      enc->h_words_cap = 0;
+      const size_t cap = words_total + 16 + words_total / 4;
+      CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&enc->h_words), cap * sizeof(uint32_t), cudaHostAllocDefault));
+      enc->h_words_cap = cap;
+    }
+    uint32_t* const h_words = enc->h_words;
     CUDA_OK(cudaMemcpyAsync(h_bits.data(), d_bits.p, nsec * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(h_words.data(), d_words.p, (words_total + 16) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(h_words, d_words.p, (words_total + 16) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
     CUDA_OK(cudaGetLastError());
     float ms = 0;
@@ -1795,11 +1816,11 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
           std::vector<EncSection> dcg, acg;  // h_bits[sec] = first bit of the section, its end = end of its region
           for (uint32_t g = 0; g < d.num_dc_groups; g++) {
             const uint64_t sec = f.bits_off + g, end = h_off[sec + 1] * 32;
-            dcg.push_back({h_words.data(), h_bits[sec], end - h_bits[sec]});
+            dcg.push_back({h_words, h_bits[sec], end - h_bits[sec]});
           }
           for (uint32_t g = 0; g < d.num_groups; g++) {
             const uint64_t sec = f.bits_off + d.num_dc_groups + g, end = h_off[sec + 1] * 32;
-            acg.push_back({h_words.data(), h_bits[sec], end - h_bits[sec]});
+            acg.push_back({h_words, h_bits[sec], end - h_bits[sec]});
           }
           enc->outputs[i] = AssembleCodestream(p, f.L, f.G, dcg, acg);
         }

@@ -720,6 +720,7 @@ struct DevBackWriter {
 JXLB_HD void DevRansPush(const uint2* tok, uint32_t n, const DevEncCode& code, DevBackWriter& w) {
   uint32_t state = 0x13u << 16;
   uint2 t = n ? tok[n - 1] : make_uint2(0, 0);
+  uint2 raw_ahead = n > 1 ? tok[n - 2] : make_uint2(0, 0);  // the token after next: its load has a whole iteration to land
   uint32_t token = 0, nbits = 0, bits = 0, fs = 0;
   if (n) {
     DevHybrid420(t.y, &token, &nbits, &bits);
@@ -727,13 +728,9 @@ JXLB_HD void DevRansPush(const uint2* tok, uint32_t n, const DevEncCode& code, D
   }
   for (uint32_t i = n; i-- > 0;) {
     const uint32_t cluster = t.x, cur_nbits = nbits, cur_bits = bits, cur_fs = fs;
-#if defined(__CUDA_ARCH__)
-    // the tokens stream in from HBM backwards, 16 per 128-byte line: ask for the line four lines ahead (measured: the
-    // wait for a token load was the largest stall of the kernel)
-    if ((i & 15) == 0 && i >= 80) asm volatile("prefetch.global.L1 [%0];" ::"l"(tok + i - 80));
-#endif
     if (i > 0) {
-      t = tok[i - 1];
+      t = raw_ahead;
+      if (i > 1) raw_ahead = tok[i - 2];
       DevHybrid420(t.y, &token, &nbits, &bits);
       fs = JXLB_LDG(code.fs + t.x * 256 + token);
     }
