@@ -59,7 +59,7 @@ class Workload:
             self.sha = [g[n]["reencoded_sha256"] for n in names]
             self.decoded_sha = [g[n]["sha256_rgb8"] for n in names]
             self.desc = ("encode %d RGB8 4K frames per GPU (3840x2160; the two decoded 4K fixtures alternating) to lossy "
-                         "VarDCT at distance 1.0, variance-heuristic block sizes 8x8 ... 64x64" % self.batch)
+                         "VarDCT at distance 1.0 (libjxl adaptive quant field, variance-heuristic block sizes 8x8 ... 64x64)" % self.batch)
             self.data = "synthetic (the decoded 4K fixtures)"
         else:
             names = ["bench.jxl"]

@@ -455,6 +455,9 @@ struct EncParams {
   uint32_t x_qm_scale = 3, b_qm_scale = 2;
   bool coeff_orders = true;  // coefficient orders from zero counts (lib/jxl/enc_coeff_order.cc); false: natural orders
   bool cfl = true;           // chroma-from-luma factors per tile (lib/jxl/enc_chroma_from_luma.cc); false: zero
+  // libjxl's effort-7 quantiser: InitialQuantField (lib/jxl/enc_adaptive_quantization.cc), global scale and DC quantiser
+  // from ComputeGlobalScaleAndQuant (lib/jxl/quantizer.cc:39-69), AdjustQuantField; false: raw quant 16 everywhere
+  bool adaptive_quant = true;
 };
 
 inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize) {
@@ -505,12 +508,66 @@ inline void WriteToc(BitWriter& w, const std::vector<size_t>& sizes) {
   w.ZeroPadToByte();
 }
 
-// Quantiser parameters of a frame (same derivation as the oracle's stream generator: quant ~ 0.79 / distance).
+// InitialQuantDC, lib/jxl/enc_adaptive_quantization.cc:1255-1267
+inline float InitialQuantDC(float butteraugli_target) {
+  const float kDcMul = 0.3f, kDcQuantPow = 0.83f, kDcQuant = 1.095924047623553f;
+  const float butteraugli_target_dc = std::max<float>(
+      0.5f * butteraugli_target, std::min<float>(butteraugli_target, kDcMul * std::pow((1.0f / kDcMul) * butteraugli_target, kDcQuantPow)));
+  return std::min(kDcQuant / butteraugli_target_dc, 50.f);
+}
+
+// Quantiser parameters of a frame. Adaptive: libjxl's effort-7 choice, lib/jxl/enc_heuristics.cc:1055, :1104-1117
+// (ComputeGlobalScaleAndQuant(InitialQuantDC(d), 0.39 / d, 0), lib/jxl/quantizer.cc:39-69); else the derivation of the
+// oracle's plain stream generator (quant ~ 0.79 / distance around a raw quant of 16).
 inline void FillQuantizer(const EncParams& p, DevEFrame* ef, uint32_t* global_scale_out, uint32_t* quant_dc_out) {
   const float quant_ac = 0.79f / std::max(0.1f, p.distance);
   const int base_raw = 16;
-  const int global_scale = std::max(1, std::min(65535 + 8192, static_cast<int>(quant_ac * 65536 / base_raw + 0.5f)));
-  const int quant_dc = std::max(1, std::min(65536, static_cast<int>(0.9f / std::max(0.1f, p.distance) * 65536 / global_scale + 0.5f)));
+  int global_scale = std::max(1, std::min(65535 + 8192, static_cast<int>(quant_ac * 65536 / base_raw + 0.5f)));
+  int quant_dc = std::max(1, std::min(65536, static_cast<int>(0.9f / std::max(0.1f, p.distance) * 65536 / global_scale + 0.5f)));
+  ef->adaptive = p.adaptive_quant ? 1 : 0;
+  if (p.adaptive_quant) {
+    const float quant_dc_f = InitialQuantDC(p.distance);
+    const float q = 0.39 / p.distance;
+    float scale = 65536 * (q - 0.0f) / 5.0f;
+    if (scale < 1) scale = 1;
+    if (scale > (1 << 15)) scale = 1 << 15;
+    int new_global_scale = static_cast<int>(scale);
+    const int scaled_quant_dc = static_cast<int>(quant_dc_f * 4096 * 1.6);
+    if (new_global_scale > scaled_quant_dc) {
+      new_global_scale = scaled_quant_dc;
+      if (new_global_scale <= 0) new_global_scale = 1;
+    }
+    global_scale = new_global_scale;
+    const float inv_gs = static_cast<float>(1.0 * 65536 / new_global_scale);
+    float fval = quant_dc_f * inv_gs + 0.5f;
+    fval = std::min<float>(1 << 16, fval);
+    quant_dc = static_cast<int>(fval);
+    // InitialQuantField / PerBlockModulations / FuzzyErosion constants (lib/jxl/enc_adaptive_quantization.cc:306-321,
+    // :380-410, :1269-1276), AdjustQuantField's mixer (:1211-1223)
+    const float target = p.gab ? p.distance : p.distance * 0.62f;
+    ef->aq_target = target;
+    const float aq_scale = 0.725f / target * 1.0f;
+    const float base_level = 0.48f * aq_scale;
+    float dampen = 1.0f;
+    if (target >= 2.0f) {
+      dampen = 1.0f - ((target - 2.0f) / (14.0f - 2.0f));
+      if (dampen < 0) dampen = 0;
+    }
+    ef->aq_mul = aq_scale * dampen;
+    ef->aq_add = (1.0f - dampen) * base_level;
+    float fmul = 0.0f;
+    if (target < 2.0f) fmul = (2.0f - target) * (1.0f / 2.0f);
+    float k0 = 0.125f + fmul * 0.0f, k1 = 0.10f + fmul * -0.10f, k2 = 0.09f + fmul * -0.09f, k3 = 0.06f + fmul * -0.06f;
+    const float kTotal = 0.29959705784054957f;
+    const float norm = kTotal / (k0 + k1 + k2 + k3);
+    ef->aq_erosion[0] = k0 * norm;
+    ef->aq_erosion[1] = k1 * norm;
+    ef->aq_erosion[2] = k2 * norm;
+    ef->aq_erosion[3] = k3 * norm;
+    float mixer = 1.0f;
+    if (p.distance > 1.54138f) mixer = std::max(0.0f, mixer - (p.distance - 1.54138f) * 0.56391f);
+    ef->aq_mixer = mixer;
+  }
   const float inv_global_scale = 1.0 * 65536 / global_scale;
   const float dc_quant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256};
   for (int c = 0; c < 3; c++) ef->mul_dc[c] = (inv_global_scale / quant_dc) * dc_quant[c];
@@ -522,7 +579,7 @@ inline void FillQuantizer(const EncParams& p, DevEFrame* ef, uint32_t* global_sc
   for (int i = 0; i < 4; i++) ef->biases[i] = kDefaultQuantBias[i];
   // chroma-from-luma fit: Quantizer::Scale() * kStrangeMultiplier * raw quant (lib/jxl/enc_chroma_from_luma.cc:311-316)
   ef->cfl = p.cfl ? 1 : 0;
-  ef->cfl_q = (global_scale * (1.0f / 65536)) * 128.0f * static_cast<float>(base_raw);
+  ef->cfl_scale128 = (global_scale * (1.0f / 65536)) * 128.0f;
   // inverse Gaborish weights (lib/jxl/enc_gaborish.cc:21-48 with mul = 1, as lib/jxl/enc_heuristics.cc:1121-1131 passes)
   ef->gab = p.gab ? 1 : 0;
   {
@@ -572,6 +629,8 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
     ef->xyb_raw[c] = f;
     f += px;
   }
+  ef->quant_field = f;
+  f += (nb + 15) & ~uint64_t{15};
   for (int c = 0; c < 3; c++) {
     ef->coef[c] = i;
     i += px;
@@ -606,7 +665,8 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
   ef->cmh = static_cast<uint32_t>((H + 7) / 8);
   ef->ytox = (nb + 15) & ~uint64_t{15};
   ef->ytob = ef->ytox + ((static_cast<uint64_t>(ef->cmw) * ef->cmh + 15) & ~uint64_t{15});
-  L.bsize = ef->ytob + ((static_cast<uint64_t>(ef->cmw) * ef->cmh + 15) & ~uint64_t{15});
+  ef->raw_quant = ef->ytob + ((static_cast<uint64_t>(ef->cmw) * ef->cmh + 15) & ~uint64_t{15});
+  L.bsize = ef->raw_quant + ((nb + 15) & ~uint64_t{15});
   L.tsize = ef->mod_tokens + ef->mod_tokens_stride * d.num_dc_groups;
   L.num_ac_clusters = num_ac_clusters;
   L.num_leaves = num_leaves;

@@ -1273,6 +1273,15 @@ __global__ void __launch_bounds__(256) k_enc_gaborish_inv(DevEPools E, const Dev
   }
 }
 
+// blockIdx.x = tile (64x64 pixels), blockIdx.y = frame: libjxl's initial quantisation field (E3).
+__global__ void __launch_bounds__(256) k_enc_aq(DevEPools E, const DevEFrame* frames) {
+  __shared__ float aq_sm[kAqSmemFloats];
+  const DevEFrame& ef = frames[blockIdx.y];
+  const uint32_t tiles_x = (ef.xblocks + 7) / 8, tiles_y = (ef.yblocks + 7) / 8;
+  if (!ef.adaptive || blockIdx.x >= tiles_x * tiles_y) return;
+  DevEncAqTile<2>(E, ef, blockIdx.x % tiles_x, blockIdx.x / tiles_x, threadIdx.x, blockDim.x, aq_sm);
+}
+
 // one thread per 256x256 group (the greedy choice is serial inside a group)
 __global__ void __launch_bounds__(32) k_enc_strategy(DevEPools E, const DevEFrame* frames) {
   const DevEFrame& ef = frames[blockIdx.y];
@@ -1538,6 +1547,8 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
         e.blk_ntok[c] += ibase;
         e.blk_bucket[c] += ibase;
       }
+      e.quant_field += fbase;
+      e.raw_quant += bbase;
       e.first_index += ibase;
       e.block_of_num += ibase;
       e.order_mask += ibase;
@@ -1623,6 +1634,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     const uint32_t nf = static_cast<uint32_t>(n);
     k_enc_xyb<<<dim3((maxW * 8 + 31) / 32, maxH, nf), dim3(32, 8), 0, s>>>(E, d_efs.p);
     if (p.gab) k_enc_gaborish_inv<<<dim3((maxW * 8 + 31) / 32, maxH, nf * 3), dim3(32, 8), 0, s>>>(E, d_efs.p);
+    if (p.adaptive_quant) k_enc_aq<<<dim3(((maxW + 7) / 8) * ((maxH + 7) / 8), nf), 256, 0, s>>>(E, d_efs.p);
     k_enc_strategy<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_number<<<dim3((max_dcg + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_dc<<<dim3((maxW * maxH + 255) / 256, nf), 256, 0, s>>>(E, d_efs.p);

@@ -60,8 +60,16 @@ struct DevEFrame {
   // varblock's coefficients in layout order inside its pixel footprint), the fit reads them, the quantisation reads both
   uint32_t cfl;         // 1: fit the factors per 64x64 tile (lib/jxl/enc_chroma_from_luma.cc), 0: all zero
   uint32_t cmw, cmh;    // tiles
-  float cfl_q;          // quantizer scale * 128 * raw quant (the reference's weighting of the coefficients)
   uint64_t ytox, ytob;  // byte arena: int8 per tile
+  // adaptive quantisation (lib/jxl/enc_adaptive_quantization.cc; constants derived on the host, FillQuantizer)
+  uint32_t adaptive;      // 1: quant field from k_enc_aq, raw quant per varblock; 0: raw quant 16 everywhere
+  float aq_target;        // butteraugli target InitialQuantField is called with
+  float aq_mul, aq_add;   // PerBlockModulations: scale * dampen, (1 - dampen) * base_level
+  float aq_erosion[4];    // FuzzyErosion weights of the 4 smallest values
+  float aq_mixer;         // AdjustQuantField: mean_max_mixer
+  float cfl_scale128;     // Quantizer::Scale() * 128 (times the raw quant: the weighting of the CfL fit)
+  uint64_t quant_field;   // float arena: xblocks * yblocks
+  uint64_t raw_quant;     // byte arena: raw quant - 1 at the first block of every varblock
   // int arena
   uint64_t coef[3];    // quantised coefficients, stored in each varblock's pixel footprint (row-major)
   uint64_t dcq[3];     // quantised DC: [0] = Y, [1] = X, [2] = B, xblocks * yblocks

@@ -118,6 +118,204 @@ JXLB_HD void DevEncGaborishInvPixel(const DevEPools& E, const DevEFrame& ef, uin
   E.farena[ef.xyb[c] + static_cast<size_t>(y) * PW + x] = sum0 + sum1;
 }
 
+// ---- adaptive quantisation: InitialQuantField / AdaptiveQuantizationMap, lib/jxl/enc_adaptive_quantization.cc:78-716,
+// one 64x64 tile (ComputeTile, :468-630) per call, `nt` cooperating threads. The planes are those before inverse
+// Gaborish. `sm`: kAqSmemFloats floats. Which pixels of a tile row take the SIMD form of the Laplacian and which the
+// scalar form (different association of the four neighbours) follows from the tile's own x range with 8 lanes
+// (AVX2), as in the oracle. The masking images of the AcStrategy search (mask, mask1x1) are not produced.
+constexpr uint32_t kAqSmemFloats = 72 * 72 + 18 * 18 + 16 * 16 + 64 * 24;
+constexpr float kAqSGmul = 226.77216153508914f;
+constexpr float kAqSGmul2 = 1.0f / 73.377132366608819f;
+constexpr float kAqLog2 = 0.693147181f;
+constexpr float kAqSGRetMul = kAqSGmul2 * 18.6580932135f * kAqLog2;
+constexpr float kAqSGVOffset = 7.7825991679894591f;
+
+template <bool INVERT>
+JXLB_HD float DevAqRatioOfDerivatives(float v) {  // :117-136
+  const float kEpsilon = 1e-2;
+  v = v < 0.0f ? 0.0f : v;
+  const float kNumMul = kAqSGRetMul * 3 * kAqSGmul;
+  const float kVOffset = kAqSGVOffset * kAqLog2 + kEpsilon;
+  const float kDenMul = kAqLog2 * kAqSGmul;
+  const float v2 = v * v;
+  const float num = fmaf(kNumMul, v2, kEpsilon);
+  const float den = fmaf(kDenMul * v, v2, kVOffset);
+  return INVERT ? num / den : den / num;
+}
+
+JXLB_HD float DevFastLog2f(float v) {  // lib/jxl/base/fast_math-inl.h:46-66
+  const float lp[3] = {-1.8503833400518310E-06f, 1.4287160470083755E+00f, 7.4245873327820566E-01f};
+  const float lq[3] = {9.9032814277590719E-01f, 1.0096718572241148E+00f, 1.7409343003366853E-01f};
+  const int32_t x_bits = DevFloatToBits(v);
+  const int32_t exp_bits = x_bits - 0x3f2aaaab;
+  const int32_t exp_shifted = exp_bits >> 23;
+  const float mantissa = DevBitsToFloat(x_bits - static_cast<int32_t>(static_cast<uint32_t>(exp_shifted) << 23));
+  return DevRational2(mantissa - 1.0f, lp, lq) + static_cast<float>(exp_shifted);
+}
+
+JXLB_HD float DevFastPow2f(float x) {  // lib/jxl/base/fast_math-inl.h:69-84
+  const float floorx = floorf(x);
+  const float exp = DevBitsToFloat(static_cast<int32_t>(static_cast<uint32_t>(static_cast<int32_t>(floorx) + 127) << 23));
+  const float frac = x - floorx;
+  float num = frac + 1.01749063e+01f;
+  num = fmaf(num, frac, 4.88687798e+01f);
+  num = fmaf(num, frac, 9.85506591e+01f);
+  num = num * exp;
+  float den = fmaf(frac, 2.10242958e-01f, -2.22328856e-02f);
+  den = fmaf(den, frac, -1.94414990e+01f);
+  den = fmaf(den, frac, 9.85506633e+01f);
+  return num / den;
+}
+
+JXLB_HD void DevAqStoreMin4(float v, float& min0, float& min1, float& min2, float& min3) {  // :356-375
+  if (v < min3) {
+    if (v < min0) {
+      min3 = min2, min2 = min1, min1 = min0, min0 = v;
+    } else if (v < min1) {
+      min3 = min2, min2 = min1, min1 = v;
+    } else if (v < min2) {
+      min3 = min2, min2 = v;
+    } else {
+      min3 = v;
+    }
+  }
+}
+
+JXLB_HD void DevAqSwapIfGreater(float& a, float& b) {
+  if (a > b) {
+    const float t = a;
+    a = b;
+    b = t;
+  }
+}
+
+template <int SCOPE>
+JXLB_HD void DevEncAqTile(const DevEPools& E, const DevEFrame& ef, uint32_t tx, uint32_t ty, uint32_t tid, uint32_t nt, float* sm) {
+  const uint32_t W = ef.xblocks, H = ef.yblocks, xsize = W * 8, ysize = H * 8;
+  const uint32_t bx0 = tx * 8, by0 = ty * 8, bx1 = bx0 + 8 < W ? bx0 + 8 : W, by1 = by0 + 8 < H ? by0 + 8 : H;
+  uint32_t x_start = bx0 * 8, x_end = bx1 * 8, y_start = by0 * 8, y_end = by1 * 8;
+  if (x_start != 0) x_start -= 4;
+  if (x_end != xsize) x_end += 4;
+  if (y_start != 0) y_start -= 4;
+  if (y_end != ysize) y_end += 4;
+  const uint32_t dw = x_end - x_start, dh = y_end - y_start, pw = dw / 4, ph = dh / 4;
+  float* diff = sm;                 // [dh][72]
+  float* pre = sm + 72 * 72;        // [ph][18]
+  float* fz = pre + 18 * 18;        // [16][16]
+  float* lanes = fz + 16 * 16;      // [64 blocks][3 modulations][8 lanes]
+  const float* P[3] = {E.farena + (ef.gab ? ef.xyb_raw[0] : ef.xyb[0]), E.farena + (ef.gab ? ef.xyb_raw[1] : ef.xyb[1]),
+                       E.farena + (ef.gab ? ef.xyb_raw[2] : ef.xyb[2])};
+  // pixels [simd_begin, simd_end) of a row go through the 8-lane loop (`for (; x + 1 + Lanes < x_end; x += Lanes)`)
+  const uint32_t simd_begin = x_start == 0 ? 1 : x_start;
+  const uint32_t simd_iters = x_end > simd_begin + 9 ? (x_end - simd_begin - 9 + 7) / 8 : 0;
+  const uint32_t simd_end = simd_begin + 8 * simd_iters;
+  const float kMaskMul = sqrtf(static_cast<float>(211.66567973503678f * 1e8));
+  for (uint32_t i = tid; i < dw * dh; i += nt) {
+    const uint32_t x = x_start + i % dw, y = y_start + i / dw;
+    const uint32_t y2 = y + 1 < ysize ? y + 1 : y, y1 = y > 0 ? y - 1 : y;
+    const float* row_in = P[1] + static_cast<size_t>(y) * xsize;
+    const float* row_in1 = P[1] + static_cast<size_t>(y1) * xsize;
+    const float* row_in2 = P[1] + static_cast<size_t>(y2) * xsize;
+    float base;
+    if (x >= simd_begin && x < simd_end) {
+      base = 0.25f * ((row_in[x + 1] + row_in[x - 1]) + (row_in2[x] + row_in1[x]));
+    } else {
+      const uint32_t x2 = x + 1 < xsize ? x + 1 : x, x1 = x > 0 ? x - 1 : x;
+      base = 0.25f * (((row_in2[x] + row_in1[x]) + row_in[x1]) + row_in[x2]);
+    }
+    const float gammac = DevAqRatioOfDerivatives<false>(row_in[x] + 0.019f);
+    float d = gammac * (row_in[x] - base);
+    d = d * d;
+    if (d >= 0.2f) d = 0.2f;
+    diff[(i / dw) * 72 + i % dw] = 0.25f * sqrtf(fmaf(d, kMaskMul, 27.505837037000106f));  // MaskingSqrt, :341-348
+  }
+  CoopSync<SCOPE>();
+  for (uint32_t i = tid; i < pw * ph; i += nt) {  // 4x4 sums: rows accumulate first, then the four columns
+    const uint32_t cx = i % pw, cy = i / pw;
+    float col[4];
+    for (uint32_t k = 0; k < 4; k++) {
+      const float* d0 = diff + (cy * 4) * 72 + cx * 4 + k;
+      col[k] = ((d0[0] + d0[72]) + d0[144]) + d0[216];
+    }
+    pre[cy * 18 + cx] = (((col[0] + col[1]) + col[2]) + col[3]) * 0.25f;
+  }
+  CoopSync<SCOPE>();
+  // FuzzyErosion (:380-451)
+  const uint32_t fx0 = x_start % 8 == 0 ? 0 : 1, fy0 = y_start % 8 == 0 ? 0 : 1;
+  const uint32_t fw = (bx1 - bx0) * 2, fh = (by1 - by0) * 2;
+  for (uint32_t i = tid; i < fw * fh; i += nt) {
+    const uint32_t x = i % fw + fx0, y = i / fw + fy0;
+    const uint32_t xm1 = x >= 1 ? x - 1 : x, xp1 = x + 1 < pw ? x + 1 : x;
+    const uint32_t ym1 = y >= 1 ? y - 1 : y, yp1 = y + 1 < ph ? y + 1 : y;
+    const float *rowt = pre + ym1 * 18, *row = pre + y * 18, *rowb = pre + yp1 * 18;
+    float min0 = row[x], min1 = row[xm1], min2 = row[xp1], min3 = rowt[xm1];
+    DevAqSwapIfGreater(min0, min1);
+    DevAqSwapIfGreater(min0, min2);
+    DevAqSwapIfGreater(min0, min3);
+    DevAqSwapIfGreater(min1, min2);
+    DevAqSwapIfGreater(min1, min3);
+    DevAqSwapIfGreater(min2, min3);
+    DevAqStoreMin4(rowt[x], min0, min1, min2, min3);
+    DevAqStoreMin4(rowt[xp1], min0, min1, min2, min3);
+    DevAqStoreMin4(rowb[xm1], min0, min1, min2, min3);
+    DevAqStoreMin4(rowb[x], min0, min1, min2, min3);
+    DevAqStoreMin4(rowb[xp1], min0, min1, min2, min3);
+    fz[(i / fw) * 16 + i % fw] =
+        ((ef.aq_erosion[0] * min0 + ef.aq_erosion[1] * min1) + ef.aq_erosion[2] * min2) + ef.aq_erosion[3] * min3;
+  }
+  // per-block modulations (:169-304): lane `l` of block `b` sums its column of the 8x8 block, row after row
+  const uint32_t nbx = bx1 - bx0, nby = by1 - by0;
+  for (uint32_t i = tid; i < nbx * nby * 8; i += nt) {
+    const uint32_t l = i % 8, b = i / 8;
+    const uint32_t px = (bx0 + b % nbx) * 8 + l, py = (by0 + b / nbx) * 8;
+    float hf = 0.0f, gamma = 0.0f, blue = 0.0f;
+    for (uint32_t dy = 0; dy < 8; dy++) {
+      const size_t at = static_cast<size_t>(py + dy) * xsize + px;
+      const float vy = P[1][at], vx = P[0][at], vb = P[2][at];
+      const float right = l == 7 ? 0.0f : fminf(0.0206f, fabsf(vy - P[1][at + 1]));
+      const float down = dy == 7 ? 0.0f : fminf(0.0206f, fabsf(vy - P[1][at + xsize]));
+      hf = hf + right;
+      hf = hf + down;
+      const float iny = vy + 0.16f;
+      gamma = gamma + DevAqRatioOfDerivatives<true>(iny - vx);
+      gamma = gamma + DevAqRatioOfDerivatives<true>(iny + vx);
+      const float p_y_effective = (vy + 0.084381641171960495f) + fabsf(vx);
+      blue = blue + (vb > p_y_effective ? fminf(vb - p_y_effective, 0.027121074570634722f) : 0.0f);
+    }
+    lanes[b * 24 + l] = hf;
+    lanes[b * 24 + 8 + l] = gamma;
+    lanes[b * 24 + 16 + l] = blue;
+  }
+  CoopSync<SCOPE>();
+  for (uint32_t b = tid; b < nbx * nby; b += nt) {
+    const uint32_t ix = b % nbx, iy = b / nbx;
+    const float* f = fz + (iy * 2) * 16 + ix * 2;
+    const float eroded = ((f[0] + f[1]) + f[16]) + f[17];
+    // ComputeMask (:84-108)
+    const float kOffset3 = 3.7179635626140772f, kOffset4 = 0.25f * kOffset3;
+    const float v1 = fmaxf(eroded * 0.80061762862741759f, 1e-3f);
+    const float v2 = 1.0f / (v1 + 302.59587815579727f);
+    const float v3 = 1.0f / fmaf(v1, v1, kOffset3);
+    const float v4 = 1.0f / fmaf(v1, v1, kOffset4);
+    float out_val = -0.7647f + fmaf(9.4708735624378946f, v4, fmaf(17.35036561631863f, v2, 6.7943250517376494f * v3));
+    const float* l = lanes + b * 24;
+    float s = ((l[0] + l[4]) + (l[2] + l[6])) + ((l[1] + l[5]) + (l[3] + l[7]));  // HfModulation
+    s = s * -0.38f;
+    s = s + 0.42f;
+    out_val = s + out_val;
+    const float overall = (((l[8] + l[12]) + (l[10] + l[14])) + ((l[9] + l[13]) + (l[11] + l[15]))) * (0.5f / 64);  // GammaModulation
+    out_val = fmaf(0.1005613337192697f, DevFastLog2f(overall), out_val);
+    const float kLimit = 0.027121074570634722f, kMaxLimit = 15.398788439047934f;  // BlueModulation
+    s = ((l[16] + l[20]) + (l[18] + l[22])) + ((l[17] + l[21]) + (l[19] + l[23]));
+    if (s >= 32 * kLimit) s = 64 * kLimit - s;
+    if (s >= kMaxLimit * kLimit) s = kMaxLimit * kLimit;
+    s = s * 0.14207000358439159f;
+    out_val = s + out_val;
+    E.farena[ef.quant_field + static_cast<size_t>(by0 + iy) * W + bx0 + ix] = DevFastPow2f(out_val * 1.442695041f) * ef.aq_mul + ef.aq_add;
+  }
+  CoopSync<SCOPE>();
+}
+
 // AcStrategy of one 256x256 group: greedy raster scan, large smooth blocks first (serial: a choice depends on
 // which blocks are still free). acs must be 0xFF on entry.
 JXLB_HD void DevEncStrategyGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g) {
@@ -169,6 +367,27 @@ JXLB_HD void DevEncStrategyGroup(const DevEPools& E, const DevEFrame& ef, uint32
       for (uint32_t y = 0; y < scy; y++)
         for (uint32_t x = 0; x < scx; x++)
           acs[pos + static_cast<size_t>(y) * W + x] = static_cast<uint8_t>((s << 1) | ((x | y) == 0 ? 1 : 0));
+      int32_t rq = 16;
+      if (ef.adaptive) {
+        // AdjustQuantField (lib/jxl/enc_adaptive_quantization.cc:1203-1253) + Quantizer::SetQuantFieldRect
+        // (lib/jxl/quantizer.cc:71-82) for this varblock
+        const float* qf = E.farena + ef.quant_field + pos;
+        float max = qf[0], mean = 0.0f;
+        for (uint32_t y = 0; y < scy; y++)
+          for (uint32_t x = 0; x < scx; x++) {
+            const float v = qf[static_cast<size_t>(y) * W + x];
+            mean = mean + v;
+            max = v > max ? v : max;
+          }
+        mean = mean / static_cast<float>(scy * scx);
+        if (scy * scx >= 4) {
+          max = max * ef.aq_mixer;
+          max = max + (1.0f - ef.aq_mixer) * mean;
+        }
+        const float val = fmaxf(1.0f, fminf(max * ef.inv_global_scale + 0.5f, 256.0f));
+        rq = static_cast<int32_t>(val);
+      }
+      E.barena[ef.raw_quant + pos] = static_cast<uint8_t>(rq - 1);
     }
   }
 }
@@ -251,7 +470,7 @@ JXLB_HD void DevEncVarblock(const DevEPools& E, const DevEFrame& ef, uint32_t bx
   CoopSync<SCOPE>();
   return;
   }
-  const float sd_base = ef.inv_global_scale / 16.0f;  // raw quant field value 16 everywhere
+  const float sd_base = ef.inv_global_scale / static_cast<float>(E.barena[ef.raw_quant + static_cast<size_t>(by) * W + bx] + 1);
   const float sd0 = sd_base * ef.x_dm, sd1 = sd_base, sd2 = sd_base * ef.b_dm;
   const size_t tile = static_cast<size_t>(by / 8) * ef.cmw + bx / 8;
   const float x_cc = 0.0f + static_cast<float>(reinterpret_cast<const int8_t*>(E.barena + ef.ytox)[tile]) * (1.0f / 84);
@@ -307,13 +526,14 @@ JXLB_HD void DevEncCflTile(const DevEPools& E, const DevEFrame& ef, uint32_t tx,
       const uint32_t lcx = si.cx > si.cy ? si.cx : si.cy, lcy = si.cx > si.cy ? si.cy : si.cx;
       const float* dm = E.fpool + E.table_off[si.table];
       const size_t origin = static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+      const float cfl_q = ef.cfl_scale128 * static_cast<float>(E.barena[ef.raw_quant + static_cast<size_t>(by) * W + bx] + 1);
       for (uint32_t k = tid; k < N; k += nt) {
         const size_t at = origin + static_cast<size_t>(k / C) * PW + k % C;
         const bool llf = k / (lcx * 8) < lcy && k % (lcx * 8) < lcx;
         const float cy = llf ? 0.0f : E.farena[ef.xyb_raw[1] + at];
         const float cxv = llf ? 0.0f : E.farena[ef.xyb_raw[0] + at];
         const float cb = llf ? 0.0f : E.farena[ef.xyb_raw[2] + at];
-        const float qqm_x = ef.cfl_q * (1.0f / dm[k]), qqm_b = ef.cfl_q * (1.0f / dm[2 * N + k]);
+        const float qqm_x = cfl_q * (1.0f / dm[k]), qqm_b = cfl_q * (1.0f / dm[2 * N + k]);
         v_m[0][num_ac + k] = cy * qqm_x;
         v_s[0][num_ac + k] = cxv * qqm_x;
         v_m[1][num_ac + k] = cy * qqm_b;
@@ -618,8 +838,8 @@ JXLB_HD int32_t DevModValue(const DevEPools& E, const DevEFrame& ef, const DevMo
   if (ch.kind == 1) return ch.konst;
   if (ch.kind == 3)  // chroma-from-luma map (int8 per tile; the DC group starts at tile (x0 / 8, y0 / 8))
     return reinterpret_cast<const int8_t*>(E.barena + ch.plane)[static_cast<size_t>((y0 >> 3) + y) * ef.cmw + (x0 >> 3) + x];
-  if (y == 1) return 15;  // raw quant - 1
   const int32_t pos = E.iarena[ef.block_of_num + static_cast<size_t>(g) * 65536 + x];
+  if (y == 1) return E.barena[ef.raw_quant + pos];  // raw quant - 1
   return E.barena[ef.acs + pos] >> 1;
 }
 

@@ -108,6 +108,7 @@ size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, fl
     p.gab_inverse = (gab & 2) == 0;
     p.coeff_orders = (gab & 4) == 0;
     p.cfl = (gab & 8) == 0;          // bit 3: no chroma-from-luma fit
+    p.adaptive_quant = (gab & 16) == 0;  // bit 4: constant quant field instead of libjxl's adaptive one
     p.epf_iters = epf_iters;
     p.dc_smoothing = dc_smoothing != 0;
     p.random_side_info = random_side_info != 0;

@@ -620,6 +620,10 @@ struct EncodeParams {
   bool gab_inverse = true;    // inverse Gaborish before the transforms when the frame signals Gaborish (E4)
   bool coeff_orders = true;   // coefficient orders from zero counts (E9); false: natural orders
   bool cfl = true;            // chroma-from-luma factors per 64x64 tile fitted to the AC coefficients (E6); false: 0
+  // libjxl's effort-7 quantiser (E3, E7): InitialQuantField on the XYB planes before inverse Gaborish, global scale and
+  // DC quantiser from ComputeGlobalScaleAndQuant(InitialQuantDC(d), 0.39 / d, 0), AdjustQuantField over each varblock,
+  // SetQuantFieldRect. false (and with random_side_info): one constant raw quant value under this file's own scale.
+  bool adaptive_quant = true;
 };
 
 struct EncoderStats {
@@ -809,6 +813,265 @@ inline void GaborishInverse(Plane xyb[3]) {
   }
 }
 
+// ---------------------------------------------------------------- adaptive quantisation (E3)
+// AdaptiveQuantizationMap / InitialQuantField, lib/jxl/enc_adaptive_quantization.cc:78-716, :1255-1276, as libjxl's
+// effort 7 runs it on the XYB planes *before* inverse Gaborish (lib/jxl/enc_heuristics.cc:1104-1117). Restated per
+// 64x64 tile like the reference (ComputeTile, :468-630), because which pixels of a tile row take the SIMD form of the
+// Laplacian (`0.25 * ((r + l) + (t + b))`) and which the scalar form (`0.25 * (((t + b) + l) + r)`) follows from the
+// tile's own x range (8 lanes: the x86 AVX2 target, as for the chroma-from-luma sums). Plain C++ expressions of the
+// reference are evaluated without contraction, MulAdd is fmaf. The two masking images that only the entropy-estimate
+// AcStrategy search reads (mask, mask1x1) are not produced.
+namespace aq {
+constexpr float kSGmul = 226.77216153508914f;
+constexpr float kSGmul2 = 1.0f / 73.377132366608819f;
+constexpr float kLog2 = 0.693147181f;
+constexpr float kSGRetMul = kSGmul2 * 18.6580932135f * kLog2;
+constexpr float kSGVOffset = 7.7825991679894591f;
+
+template <bool invert>
+inline float RatioOfDerivatives(float v) {  // :117-136
+  const float kEpsilon = 1e-2;
+  v = v < 0.0f ? 0.0f : v;
+  const float kNumMul = kSGRetMul * 3 * kSGmul;
+  const float kVOffset = kSGVOffset * kLog2 + kEpsilon;
+  const float kDenMul = kLog2 * kSGmul;
+  const float v2 = v * v;
+  const float num = std::fmaf(kNumMul, v2, kEpsilon);
+  const float den = std::fmaf(kDenMul * v, v2, kVOffset);
+  return invert ? num / den : den / num;
+}
+
+inline float MaskingSqrt(float v) {  // :341-348
+  const float kLogOffset = 27.505837037000106f;
+  const float kMul = 211.66567973503678f;
+  const float mul_v = static_cast<float>(kMul * 1e8);
+  return 0.25f * std::sqrt(std::fmaf(v, std::sqrt(mul_v), kLogOffset));
+}
+
+inline float ComputeMask(float out_val) {  // :84-108
+  const float kBase = -0.7647f, kMul4 = 9.4708735624378946f, kMul2 = 17.35036561631863f;
+  const float kOffset2 = 302.59587815579727f, kMul3 = 6.7943250517376494f, kOffset3 = 3.7179635626140772f;
+  const float kOffset4 = 0.25f * kOffset3, kMul0 = 0.80061762862741759f;
+  const float v1 = std::max(out_val * kMul0, 1e-3f);
+  const float v2 = 1.0f / (v1 + kOffset2);
+  const float v3 = 1.0f / std::fmaf(v1, v1, kOffset3);
+  const float v4 = 1.0f / std::fmaf(v1, v1, kOffset4);
+  return kBase + std::fmaf(kMul4, v4, std::fmaf(kMul2, v2, kMul3 * v3));
+}
+
+inline float SumOfLanes8(const float l[8]) { return ((l[0] + l[4]) + (l[2] + l[6])) + ((l[1] + l[5]) + (l[3] + l[7])); }
+
+inline float HfModulation(const Plane& py, size_t x, size_t y, float out_val) {  // :250-304
+  const float valmin_y = 0.0206f;
+  float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t dy = 0; dy < 8; dy++) {
+    const float* row = py.Row(y + dy) + x;
+    const float* next = dy == 7 ? row : py.Row(y + dy + 1) + x;
+    for (size_t i = 0; i < 8; i++) {
+      const float right = i == 7 ? 0.0f : std::min(valmin_y, std::fabs(row[i] - row[i + 1]));
+      sum[i] = sum[i] + right;
+      sum[i] = sum[i] + std::min(valmin_y, std::fabs(row[i] - next[i]));
+    }
+  }
+  const float kMul_y = -0.38f;
+  float s = SumOfLanes8(sum);
+  s *= kMul_y;
+  const float kOffset = 0.42f;
+  s += kOffset;
+  return s + out_val;
+}
+
+inline float GammaModulation(const Plane& px, const Plane& py, size_t x, size_t y, float out_val) {  // :169-200
+  const float kBias = 0.16f;
+  float ratio[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t dy = 0; dy < 8; dy++) {
+    const float* rx = px.Row(y + dy) + x;
+    const float* ry = py.Row(y + dy) + x;
+    for (size_t i = 0; i < 8; i++) {
+      const float iny = ry[i] + kBias, inx = rx[i];
+      ratio[i] = ratio[i] + RatioOfDerivatives<true>(iny - inx);
+      ratio[i] = ratio[i] + RatioOfDerivatives<true>(iny + inx);
+    }
+  }
+  const float overall = SumOfLanes8(ratio) * (0.5f / 64);
+  const float kGamma = 0.1005613337192697f;
+  return std::fmaf(kGamma, FastLog2f(overall), out_val);
+}
+
+inline float BlueModulation(const Plane& px, const Plane& py, const Plane& pb, size_t x, size_t y, float out_val) {  // :211-247
+  const float kLimit = 0.027121074570634722f, kOffset = 0.084381641171960495f;
+  float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t dy = 0; dy < 8; dy++) {
+    const float* rx = px.Row(y + dy) + x;
+    const float* ry = py.Row(y + dy) + x;
+    const float* rb = pb.Row(y + dy) + x;
+    for (size_t i = 0; i < 8; i++) {
+      const float p_y_effective = (ry[i] + kOffset) + std::fabs(rx[i]);
+      sum[i] = sum[i] + (rb[i] > p_y_effective ? std::min(rb[i] - p_y_effective, kLimit) : 0.0f);
+    }
+  }
+  const float kMul = 0.14207000358439159f;
+  float s = SumOfLanes8(sum);
+  if (s >= 32 * kLimit) s = 64 * kLimit - s;
+  const float kMaxLimit = 15.398788439047934f;
+  if (s >= kMaxLimit * kLimit) s = kMaxLimit * kLimit;
+  s *= kMul;
+  return s + out_val;
+}
+
+inline void StoreMin4(float v, float& min0, float& min1, float& min2, float& min3) {  // :356-375
+  if (v < min3) {
+    if (v < min0) {
+      min3 = min2, min2 = min1, min1 = min0, min0 = v;
+    } else if (v < min1) {
+      min3 = min2, min2 = min1, min1 = v;
+    } else if (v < min2) {
+      min3 = min2, min2 = v;
+    } else {
+      min3 = v;
+    }
+  }
+}
+
+// The initial quantisation field of one frame: xsize_blocks x ysize_blocks floats, row major.
+inline std::vector<float> InitialQuantField(const Plane xyb[3], float butteraugli_target, float rescale) {
+  const size_t xsize = xyb[1].w, ysize = xyb[1].h;  // whole blocks
+  const size_t W = xsize / 8, H = ysize / 8;
+  const float kAcQuant = 0.725f;
+  const float scale = kAcQuant / butteraugli_target * rescale;  // :1273-1275
+  std::vector<float> aq_map(W * H, 0.0f);
+  const float match_gamma_offset = 0.019f, limit = 0.2f;
+  // FuzzyErosion weights (:380-410)
+  float fmul = 0.0f;
+  if (butteraugli_target < 2.0f) fmul = (2.0f - butteraugli_target) * (1.0f / 2.0f);
+  float kMul0 = 0.125f + fmul * 0.0f, kMul1 = 0.10f + fmul * -0.10f, kMul2 = 0.09f + fmul * -0.09f, kMul3 = 0.06f + fmul * -0.06f;
+  const float kTotal = 0.29959705784054957f;
+  const float norm = kTotal / (kMul0 + kMul1 + kMul2 + kMul3);
+  kMul0 *= norm, kMul1 *= norm, kMul2 *= norm, kMul3 *= norm;
+  // PerBlockModulations (:306-339)
+  const float base_level = 0.48f * scale;
+  float dampen = 1.0f;
+  if (butteraugli_target >= 2.0f) {
+    dampen = 1.0f - ((butteraugli_target - 2.0f) / (14.0f - 2.0f));
+    if (dampen < 0) dampen = 0;
+  }
+  const float mul = scale * dampen, add = (1.0f - dampen) * base_level;
+
+  std::vector<float> diff_row(64 + 8), pre(18 * 18);
+  for (size_t ty = 0; ty < DivCeil(H, size_t{8}); ty++)
+    for (size_t tx = 0; tx < DivCeil(W, size_t{8}); tx++) {
+      const size_t bx0 = tx * 8, by0 = ty * 8, bx1 = std::min(W, bx0 + 8), by1 = std::min(H, by0 + 8);
+      size_t x_start = bx0 * 8, x_end = bx1 * 8, y_start = by0 * 8, y_end = by1 * 8;
+      if (x_start != 0) x_start -= 4;
+      if (x_end != xsize) x_end += 4;
+      if (y_start != 0) y_start -= 4;
+      if (y_end != ysize) y_end += 4;
+      const size_t pw = (x_end - x_start) / 4, ph = (y_end - y_start) / 4;
+      const Plane& Y = xyb[1];
+      for (size_t y = y_start; y < y_end; y++) {
+        const size_t y2 = y + 1 < ysize ? y + 1 : y, y1 = y > 0 ? y - 1 : y;
+        const float *row_in = Y.Row(y), *row_in1 = Y.Row(y1), *row_in2 = Y.Row(y2);
+        auto finish = [&](size_t x, float base) {
+          const float gammac = RatioOfDerivatives<false>(row_in[x] + match_gamma_offset);
+          float diff = gammac * (row_in[x] - base);
+          diff *= diff;
+          if (diff >= limit) diff = limit;
+          diff = MaskingSqrt(diff);
+          if ((y % 4) != 0) {
+            diff_row[x - x_start] += diff;
+          } else {
+            diff_row[x - x_start] = diff;
+          }
+        };
+        auto scalar_pixel = [&](size_t x) {
+          const size_t x2 = x + 1 < xsize ? x + 1 : x, x1 = x > 0 ? x - 1 : x;
+          finish(x, 0.25f * (row_in2[x] + row_in1[x] + row_in[x1] + row_in[x2]));
+        };
+        size_t x = x_start;
+        if (x_start == 0) {
+          scalar_pixel(x_start);
+          ++x;
+        }
+        for (; x + 1 + 8 < x_end; x += 8)
+          for (size_t i = x; i < x + 8; i++)
+            finish(i, 0.25f * ((row_in[i + 1] + row_in[i - 1]) + (row_in2[i] + row_in1[i])));
+        for (; x < x_end; ++x) scalar_pixel(x);
+        if (y % 4 == 3) {
+          float* out = pre.data() + ((y - y_start) / 4) * pw;
+          for (size_t i = 0; i < pw; i++)
+            out[i] = (diff_row[i * 4] + diff_row[i * 4 + 1] + diff_row[i * 4 + 2] + diff_row[i * 4 + 3]) * 0.25f;
+        }
+      }
+      // FuzzyErosion (:380-451): the 4 smallest of each 3x3 neighbourhood, 2x2 cells summed per block
+      const size_t fx0 = x_start % 8 == 0 ? 0 : 1, fy0 = y_start % 8 == 0 ? 0 : 1;
+      const size_t fw = (bx1 - bx0) * 2, fh = (by1 - by0) * 2;
+      for (size_t fy = 0; fy < fh; fy++) {
+        const size_t y = fy + fy0;
+        const size_t ym1 = y >= 1 ? y - 1 : y, yp1 = y + 1 < ph ? y + 1 : y;
+        const float *rowt = pre.data() + ym1 * pw, *row = pre.data() + y * pw, *rowb = pre.data() + yp1 * pw;
+        float* row_out = aq_map.data() + (by0 + fy / 2) * W + bx0;
+        for (size_t fx = 0; fx < fw; fx++) {
+          const size_t x = fx + fx0;
+          const size_t xm1 = x >= 1 ? x - 1 : x, xp1 = x + 1 < pw ? x + 1 : x;
+          float min0 = row[x], min1 = row[xm1], min2 = row[xp1], min3 = rowt[xm1];
+          if (min0 > min1) std::swap(min0, min1);
+          if (min0 > min2) std::swap(min0, min2);
+          if (min0 > min3) std::swap(min0, min3);
+          if (min1 > min2) std::swap(min1, min2);
+          if (min1 > min3) std::swap(min1, min3);
+          if (min2 > min3) std::swap(min2, min3);
+          StoreMin4(rowt[x], min0, min1, min2, min3);
+          StoreMin4(rowt[xp1], min0, min1, min2, min3);
+          StoreMin4(rowb[xm1], min0, min1, min2, min3);
+          StoreMin4(rowb[x], min0, min1, min2, min3);
+          StoreMin4(rowb[xp1], min0, min1, min2, min3);
+          const float v = kMul0 * min0 + kMul1 * min1 + kMul2 * min2 + kMul3 * min3;
+          if (fx % 2 == 0 && fy % 2 == 0) {
+            row_out[fx / 2] = v;
+          } else {
+            row_out[fx / 2] += v;
+          }
+        }
+      }
+      for (size_t by = by0; by < by1; by++)
+        for (size_t bx = bx0; bx < bx1; bx++) {
+          float out_val = ComputeMask(aq_map[by * W + bx]);
+          out_val = HfModulation(xyb[1], bx * 8, by * 8, out_val);
+          out_val = GammaModulation(xyb[0], xyb[1], bx * 8, by * 8, out_val);
+          out_val = BlueModulation(xyb[0], xyb[1], xyb[2], bx * 8, by * 8, out_val);
+          aq_map[by * W + bx] = FastPow2f(out_val * 1.442695041f) * mul + add;
+        }
+    }
+  return aq_map;
+}
+
+inline float InitialQuantDC(float butteraugli_target) {  // :1255-1267
+  const float kDcMul = 0.3f, kDcQuantPow = 0.83f, kDcQuant = 1.095924047623553f;
+  const float butteraugli_target_dc = std::max<float>(
+      0.5f * butteraugli_target, std::min<float>(butteraugli_target, kDcMul * std::pow((1.0f / kDcMul) * butteraugli_target, kDcQuantPow)));
+  return std::min(kDcQuant / butteraugli_target_dc, 50.f);
+}
+
+// Quantizer::ComputeGlobalScaleAndQuant, lib/jxl/quantizer.cc:39-69
+inline void ComputeGlobalScaleAndQuant(float quant_dc, float quant_median, float quant_median_absd, int* global_scale,
+                                       int* quant_dc_out) {
+  float scale = 65536 * (quant_median - quant_median_absd) / 5.0f;
+  if (scale < 1) scale = 1;
+  if (scale > (1 << 15)) scale = 1 << 15;
+  int new_global_scale = static_cast<int>(scale);
+  const int scaled_quant_dc = static_cast<int>(quant_dc * 4096 * 1.6);
+  if (new_global_scale > scaled_quant_dc) {
+    new_global_scale = scaled_quant_dc;
+    if (new_global_scale <= 0) new_global_scale = 1;
+  }
+  *global_scale = new_global_scale;
+  const float inv_global_scale = static_cast<float>(1.0 * 65536 / new_global_scale);
+  float fval = quant_dc * inv_global_scale + 0.5f;
+  fval = std::min<float>(1 << 16, fval);
+  *quant_dc_out = static_cast<int>(fval);
+}
+}  // namespace aq
+
 inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, const EncodeParams& p,
                                          EncoderStats* stats = nullptr) {
   JXLO_CHECK(xsize > 0 && ysize > 0, "empty image");
@@ -845,6 +1108,17 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
     }
   }
 
+  // ---- initial quantisation field (E3), from the planes before inverse Gaborish (lib/jxl/enc_heuristics.cc:1104-1117)
+  const bool adaptive = p.adaptive_quant && !p.random_side_info;
+  std::vector<float> quant_field;
+  if (adaptive) quant_field = aq::InitialQuantField(xyb, p.gab ? p.distance : p.distance * 0.62f, 1.0f);
+  if (adaptive && std::getenv("JXLO_DEBUG_AQ")) {
+    std::vector<float> v = quant_field;
+    std::sort(v.begin(), v.end());
+    std::fprintf(stderr, "O aq: min %g p10 %g median %g p90 %g max %g first %a %a %a\n", v.front(), v[v.size() / 10], v[v.size() / 2],
+                 v[v.size() * 9 / 10], v.back(), quant_field[0], quant_field[1], quant_field[W]);
+  }
+
   // ---- inverse Gaborish: the 5x5 sharpening that the decoder's Gaborish smoothing undoes
   if (p.gab && p.gab_inverse) GaborishInverse(xyb);
 
@@ -852,8 +1126,12 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   // quant value ~ 0.79 / distance as in libjxl's InitialQuantField target
   const float quant_ac = 0.79f / std::max(0.1f, p.distance);
   const int base_raw = 16;  // typical raw quant field value
-  const int global_scale = std::max(1, std::min(65535 + 8192, static_cast<int>(quant_ac * 65536 / base_raw + 0.5f)));
-  const int quant_dc = std::max(1, std::min(65536, static_cast<int>(0.9f / std::max(0.1f, p.distance) * 65536 / global_scale + 0.5f)));
+  int global_scale = std::max(1, std::min(65535 + 8192, static_cast<int>(quant_ac * 65536 / base_raw + 0.5f)));
+  int quant_dc = std::max(1, std::min(65536, static_cast<int>(0.9f / std::max(0.1f, p.distance) * 65536 / global_scale + 0.5f)));
+  if (adaptive) {  // lib/jxl/enc_heuristics.cc:1055, :1115-1116
+    const float q = 0.39 / p.distance;
+    aq::ComputeGlobalScaleAndQuant(aq::InitialQuantDC(p.distance), q, 0, &global_scale, &quant_dc);
+  }
   const float inv_global_scale = 1.0 * 65536 / global_scale;
   const float dc_quant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256};
   float mul_dc[3];
@@ -934,6 +1212,25 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
           acs[(by + y) * W + bx + x] = static_cast<uint8_t>((s << 1) | ((x | y) == 0 ? 1 : 0));
       int rq = base_raw;
       if (p.random_side_info) rq = 8 + rng() % 24;
+      if (adaptive) {
+        // AdjustQuantField (lib/jxl/enc_adaptive_quantization.cc:1203-1253) and Quantizer::SetQuantFieldRect
+        // (lib/jxl/quantizer.cc:71-82) for this varblock
+        const size_t cx = kCoveredX[s], cy = kCoveredY[s];
+        float mean_max_mixer = 1.0f;
+        if (p.distance > 1.54138f) mean_max_mixer = std::max(0.0f, mean_max_mixer - (p.distance - 1.54138f) * 0.56391f);
+        float max = quant_field[by * W + bx], mean = 0.0f;
+        for (size_t iy = 0; iy < cy; iy++)
+          for (size_t ix = 0; ix < cx; ix++) {
+            mean += quant_field[(by + iy) * W + bx + ix];
+            max = std::max(quant_field[(by + iy) * W + bx + ix], max);
+          }
+        mean /= cy * cx;
+        if (cy * cx >= 4) {
+          max *= mean_max_mixer;
+          max += (1.0f - mean_max_mixer) * mean;
+        }
+        rq = static_cast<int32_t>(std::max(1.0f, std::min<float>(max * inv_global_scale + 0.5f, 256.0f)));
+      }
       raw_quant[by * W + bx] = rq;
       num_varblocks++;
       if (stats) stats->strategy_count[s]++;

@@ -328,6 +328,13 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
             else DevEncGaborishInvPixel<false>(E, ef, c, x, y);
           }
     }
+    if (ef.adaptive) {  // k_enc_aq
+      std::vector<float> aq_sm(kAqSmemFloats);
+      for (uint32_t ty = 0; ty < (H + 7) / 8; ty++)
+        for (uint32_t tx = 0; tx < (W + 7) / 8; tx++) DevEncAqTile<0>(E, ef, tx, ty, 0, 1, aq_sm.data());
+      if (std::getenv("JXLO_DEBUG_AQ"))
+        std::fprintf(stderr, "E aq: first %a %a %a\n", farena[ef.quant_field], farena[ef.quant_field + 1], farena[ef.quant_field + W]);
+    }
     for (uint32_t g = 0; g < d.num_groups; g++) DevEncStrategyGroup(E, ef, g);
     for (uint32_t g = 0; g < d.num_dc_groups; g++) DevEncNumberBlocks(E, ef, g);
     for (uint32_t by = 0; by < H; by++)

@@ -22,8 +22,8 @@ def main():
     frames = {"vardct_4k_natural.jxl": (vc.frame_4k(), dict(distance=1.0, strategy_mode=2)),
               "vardct_4k_synthetic.jxl": (vc.synthetic(2160, 3840, 0xB200), dict(distance=1.0, strategy_mode=2))}
     for name, (img, kw) in frames.items():
-        # (the decode fixtures were written before the encoder learned inverse Gaborish / coefficient orders: both off)
-        data = jxlo.encode_vardct(img, inverse_gaborish=False, coeff_orders=False, cfl=False, **kw)
+        # (the decode fixtures were written before the encoder learned inverse Gaborish / coefficient orders: all off; nor adaptive quantisation)
+        data = jxlo.encode_vardct(img, inverse_gaborish=False, coeff_orders=False, cfl=False, adaptive_quant=False, **kw)
         open(os.path.join(HERE, name), "wb").write(data)
         px = jxlo.decode(data, 3, jxlo.UINT8)
         err = px.astype(float) - img

@@ -16,6 +16,11 @@ CASES = [
     ("single_group", lambda: vc.crop(200, 200, 100, 100), dict(strategy_mode=2)),
     ("d2_5_no_filters", lambda: vc.crop(520, 700, 300, 0), dict(strategy_mode=2, distance=2.5)),
     ("synthetic", lambda: vc.synthetic(333, 517, 4), dict(strategy_mode=2, distance=0.7)),
+    # adaptive quantisation (row E3): no Gaborish (InitialQuantField sees 0.62 * distance and the transform planes
+    # themselves), an image smaller than one 64x64 tile, a distance past the mean / max mixer ramp
+    ("no_gab", lambda: vc.crop(150, 210, 640, 900), dict(strategy_mode=2, gab=False, epf_iters=0)),
+    ("tiny", lambda: vc.crop(37, 50, 700, 1000), dict(strategy_mode=2)),
+    ("d4", lambda: vc.crop(200, 330, 900, 1200), dict(strategy_mode=2, distance=4.0)),
 ]
 
 
