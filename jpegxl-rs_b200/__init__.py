@@ -696,7 +696,9 @@ class JxlEncoder:
     def _batch_options(self) -> JxlB200EncodeOptions:
         return JxlB200EncodeOptions(float(self.quality), 0 if self.speed <= 2 else 2, 1, 2, 1)
 
-    def encode_batch(self, images: Sequence[np.ndarray]) -> List[EncoderResult]:
+    def encode_batch(self, images: Sequence[np.ndarray], gaborish: bool = True, epf_iters: int = 2) -> List[EncoderResult]:
+        """One JxlB200EncoderEncodeBatch call over independent RGB8 images. `gaborish` / `epf_iters`: the loop-filter
+        fields of the frame header (libjxl's encoder derives them from the distance; the defaults are its d = 1 values)."""
         if self.lossless:
             raise EncodeError("NotSupported: lossless encoding is not part of the GPU path")
         if self.has_alpha:
@@ -716,6 +718,8 @@ class JxlEncoder:
         xs = (ctypes.c_uint32 * n)(*[a.shape[1] for a in imgs])
         ys = (ctypes.c_uint32 * n)(*[a.shape[0] for a in imgs])
         opt = self._batch_options()
+        opt.gaborish = 1 if gaborish else 0
+        opt.epf_iters = int(epf_iters)
         if self._lib.JxlB200EncoderEncodeBatch(self._enc, ptrs, xs, ys, n, ctypes.byref(opt)) != 0:
             raise EncodeError(self._lib.JxlB200EncoderGetError(self._enc).decode())
         out = []

@@ -283,10 +283,11 @@ __global__ void __launch_bounds__(256) k_idct_big(DevVPools V, uint32_t frame0, 
 }
 
 // Render stages: blockDim (32, 8), grid (x tiles, y tiles, frames of the wave).
-__global__ void __launch_bounds__(256) k_gaborish(DevVPools V, uint32_t frame0, uint32_t in_set, uint32_t out_set) {
+// `skip_fused`: frames that k_render_fused handles (DevRenderFused) are left alone.
+__global__ void __launch_bounds__(256) k_gaborish(DevVPools V, uint32_t frame0, uint32_t in_set, uint32_t out_set, uint32_t skip_fused) {
   const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
   const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if (!vf.gab || x >= vf.xsize || y >= vf.ysize) return;
+  if (!vf.gab || x >= vf.xsize || y >= vf.ysize || (skip_fused && DevRenderFused(vf))) return;
   const bool interior = x >= 1 && y >= 1 && x + 1 < vf.xsize && y + 1 < vf.ysize;
   for (uint32_t c = 0; c < 3; c++) {
     if (interior) {
@@ -308,9 +309,10 @@ __device__ __forceinline__ uint32_t SetBeforeStage(const DevVFrame& vf, uint32_t
   return set;
 }
 
-__global__ void __launch_bounds__(256) k_epf(DevVPools V, uint32_t frame0, uint32_t stage) {
+__global__ void __launch_bounds__(256) k_epf(DevVPools V, uint32_t frame0, uint32_t stage, uint32_t skip_fused) {
   const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
-  const bool runs = vf.epf_iters > 0 && !(stage == 0 && vf.epf_iters < 3) && !(stage == 2 && vf.epf_iters < 2);
+  const bool runs = vf.epf_iters > 0 && !(stage == 0 && vf.epf_iters < 3) && !(stage == 2 && vf.epf_iters < 2) &&
+                    !(skip_fused && DevRenderFused(vf));
   const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if (!runs || x >= vf.xsize || y >= vf.ysize) return;
   const uint32_t set = SetBeforeStage(vf, stage);
@@ -318,6 +320,22 @@ __global__ void __launch_bounds__(256) k_epf(DevVPools V, uint32_t frame0, uint3
     DevEpfPixel<true>(V, vf, stage, set, set ^ 1, static_cast<int>(x), static_cast<int>(y));
   } else {
     DevEpfPixel<false>(V, vf, stage, set, set ^ 1, static_cast<int>(x), static_cast<int>(y));
+  }
+}
+
+// Gaborish + EPF + colour + output write of one 64x32 tile with the intermediate planes in shared memory
+// (DevRenderTile): grid (x tiles, y tiles, frames of the wave), 6 * cap floats of dynamic shared memory.
+__global__ void __launch_bounds__(256) k_render_fused(DevVPools V, uint32_t frame0, uint32_t cap) {
+  extern __shared__ float rt_sm[];
+  const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
+  const int tx0 = blockIdx.x * kRtW, ty0 = blockIdx.y * kRtH;
+  const int xsize = static_cast<int>(vf.xsize), ysize = static_cast<int>(vf.ysize);
+  if (!DevRenderFused(vf) || tx0 >= xsize || ty0 >= ysize) return;
+  const int H = static_cast<int>(DevRenderHalo(vf.gab, vf.epf_iters));
+  if (tx0 - H >= 0 && ty0 - H >= 0 && tx0 + kRtW + H <= xsize && ty0 + kRtH + H <= ysize) {
+    DevRenderTile<2, true>(V, vf, tx0, ty0, threadIdx.x, blockDim.x, rt_sm, cap);
+  } else {
+    DevRenderTile<2, false>(V, vf, tx0, ty0, threadIdx.x, blockDim.x, rt_sm, cap);
   }
 }
 
@@ -339,10 +357,10 @@ __global__ void __launch_bounds__(256) k_patches(DevVPools V, uint32_t frame0) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_color_write(DevVPools V, uint32_t frame0) {
+__global__ void __launch_bounds__(256) k_color_write(DevVPools V, uint32_t frame0, uint32_t skip_fused) {
   const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
   const uint32_t y = blockIdx.y * 8 + threadIdx.y;
-  if (y >= vf.ysize) return;
+  if (y >= vf.ysize || (skip_fused && DevRenderFused(vf))) return;
   const uint32_t set = SetBeforeStage(vf, 3);
   if (vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0) {
     // RGB8: each thread converts 4 consecutive pixels and writes 12 bytes as three words
@@ -441,6 +459,7 @@ struct JxlB200Decoder {
   uint32_t max_groups = 0, max_xsize = 0, max_ysize = 0, max_blocks = 0;
   bool any_gab = false;
   uint32_t max_epf = 0;
+  bool fused_render = std::getenv("JXLB200_UNFUSED_RENDER") == nullptr;
   std::vector<size_t> level_off;  // offset of each level inside d_levels
   std::vector<uint32_t> h_status;
   bool uniform_rgba8 = false;
@@ -512,6 +531,8 @@ JxlB200Decoder* JxlB200DecoderCreate(int device) {
   cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, kIdctSmemFloats * sizeof(float));
   cudaFuncSetAttribute(k_idct_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kMidSmemFloats * sizeof(float));
   cudaFuncSetAttribute(k_dc_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       6 * DevRenderTileFloats(kRtMaxHalo) * sizeof(float));
   cudaFuncSetAttribute(k_modular_decode_sparse<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_modular_decode_sparse<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   return dec;
@@ -880,28 +901,40 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
         launches += 3;
       }
       const dim3 px_grid((dec->max_xsize + 31) / 32, (dec->max_ysize + 7) / 8, nf);
-      {
+      // Frames without patches: one fused kernel (tiles in shared memory). The per-pixel kernels follow only when
+      // the batch has patches (or the fused path is switched off: JXLB200_UNFUSED_RENDER=1, for comparison).
+      const uint32_t skip_fused = dec->fused_render ? 1 : 0;
+      if (dec->fused_render) {
         ScopedTimer t(dec, s, kKFilters);
-        if (dec->any_gab) {
-          k_gaborish<<<px_grid, px_block, 0, s>>>(V, f0, 0, 1);
-          launches++;
-        }
-        for (uint32_t stage = 0; stage < 3; stage++) {
-          if (dec->max_epf == 0 || (stage == 0 && dec->max_epf < 3) || (stage == 2 && dec->max_epf < 2)) continue;
-          k_epf<<<px_grid, px_block, 0, s>>>(V, f0, stage);
-          launches++;
-        }
-      }
-      if (!b.patches.empty()) {
-        ScopedTimer t(dec, s, kKFilters);
-        k_patches<<<nf, 256, 0, s>>>(V, f0);
+        const uint32_t cap = DevRenderTileFloats(DevRenderHalo(dec->any_gab ? 1 : 0, dec->max_epf));
+        const dim3 rt_grid((dec->max_xsize + kRtW - 1) / kRtW, (dec->max_ysize + kRtH - 1) / kRtH, nf);
+        k_render_fused<<<rt_grid, 256, 6 * cap * sizeof(float), s>>>(V, f0, cap);
         launches++;
       }
-      {
-        ScopedTimer t(dec, s, kKColorWrite);
-        const dim3 cw_grid((dec->max_xsize + 127) / 128, (dec->max_ysize + 7) / 8, nf);
-        k_color_write<<<cw_grid, px_block, 0, s>>>(V, f0);
-        launches++;
+      if (!dec->fused_render || !b.patches.empty()) {
+        {
+          ScopedTimer t(dec, s, kKFilters);
+          if (dec->any_gab) {
+            k_gaborish<<<px_grid, px_block, 0, s>>>(V, f0, 0, 1, skip_fused);
+            launches++;
+          }
+          for (uint32_t stage = 0; stage < 3; stage++) {
+            if (dec->max_epf == 0 || (stage == 0 && dec->max_epf < 3) || (stage == 2 && dec->max_epf < 2)) continue;
+            k_epf<<<px_grid, px_block, 0, s>>>(V, f0, stage, skip_fused);
+            launches++;
+          }
+        }
+        if (!b.patches.empty()) {
+          ScopedTimer t(dec, s, kKFilters);
+          k_patches<<<nf, 256, 0, s>>>(V, f0);
+          launches++;
+        }
+        {
+          ScopedTimer t(dec, s, kKColorWrite);
+          const dim3 cw_grid((dec->max_xsize + 127) / 128, (dec->max_ysize + 7) / 8, nf);
+          k_color_write<<<cw_grid, px_block, 0, s>>>(V, f0, skip_fused);
+          launches++;
+        }
       }
     }
   }

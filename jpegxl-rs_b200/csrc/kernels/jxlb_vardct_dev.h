@@ -1216,29 +1216,35 @@ JXLB_HD DevPlaneView<INTERIOR> DevView(const DevVPools& V, const DevVFrame& vf, 
   return v;
 }
 
-// Gaborish, one sample of channel c (lib/jxl/render_pipeline/stage_gaborish.cc:22-100).
+// Gaborish, one sample of channel c (lib/jxl/render_pipeline/stage_gaborish.cc:22-100). VIEW: anything with At(x, y)
+// in frame coordinates (a plane in HBM, or a tile of it in shared memory).
+template <class VIEW>
+JXLB_HD float DevGaborishValue(const VIEW& m, const float* w, int x, int y) {
+  const float sum0 = m.At(x, y);
+  const float sum1 = (m.At(x - 1, y) + m.At(x + 1, y)) + (m.At(x, y - 1) + m.At(x, y + 1));
+  const float sum2 = (m.At(x - 1, y - 1) + m.At(x + 1, y - 1)) + (m.At(x - 1, y + 1) + m.At(x + 1, y + 1));
+  return fmaf(sum2, w[2], fmaf(sum1, w[1], sum0 * w[0]));
+}
+
 template <bool INTERIOR>
 JXLB_HD void DevGaborishPixel(const DevVPools& V, const DevVFrame& vf, uint32_t in_set, uint32_t out_set, uint32_t c, int x,
                               int y) {
   const DevPlaneView<INTERIOR> m = DevView<INTERIOR>(V, vf, in_set, c);
-  const float sum0 = m.At(x, y);
-  const float sum1 = (m.At(x - 1, y) + m.At(x + 1, y)) + (m.At(x, y - 1) + m.At(x, y + 1));
-  const float sum2 = (m.At(x - 1, y - 1) + m.At(x + 1, y - 1)) + (m.At(x - 1, y + 1) + m.At(x + 1, y + 1));
-  V.farena[vf.pix[out_set][c] + static_cast<size_t>(y) * m.stride + x] =
-      fmaf(sum2, vf.gab_w[c][2], fmaf(sum1, vf.gab_w[c][1], sum0 * vf.gab_w[c][0]));
+  V.farena[vf.pix[out_set][c] + static_cast<size_t>(y) * m.stride + x] = DevGaborishValue(m, vf.gab_w[c], x, y);
 }
 
 // One pixel of EPF stage 0 / 1 / 2 (lib/jxl/render_pipeline/stage_epf.cc:43-500).
-template <bool INTERIOR>
-JXLB_HD void DevEpfPixel(const DevVPools& V, const DevVFrame& vf, uint32_t stage, uint32_t in_set, uint32_t out_set, int x,
-                         int y) {
-  const DevPlaneView<INTERIOR> m[3] = {DevView<INTERIOR>(V, vf, in_set, 0), DevView<INTERIOR>(V, vf, in_set, 1),
-                                       DevView<INTERIOR>(V, vf, in_set, 2)};
-  const size_t at = static_cast<size_t>(y) * m[0].stride + x;
-  float X = m[0].p[at], Y = m[1].p[at], B = m[2].p[at];
+JXLB_HD float DevEpfSigma(const DevVPools& V, const DevVFrame& vf, int x, int y) {
   const uint32_t sbx = static_cast<uint32_t>(x) / 8 < vf.xblocks - 1 ? static_cast<uint32_t>(x) / 8 : vf.xblocks - 1;
   const uint32_t sby = static_cast<uint32_t>(y) / 8 < vf.yblocks - 1 ? static_cast<uint32_t>(y) / 8 : vf.yblocks - 1;
-  const float row_sigma = V.farena[vf.inv_sigma + static_cast<size_t>(sby) * vf.xblocks + sbx];
+  return V.farena[vf.inv_sigma + static_cast<size_t>(sby) * vf.xblocks + sbx];
+}
+
+// The three channels of pixel (x, y) after EPF stage `stage`; m[c].At reads the stage's input in frame coordinates.
+template <class VIEW>
+JXLB_HD void DevEpfValue(const VIEW* m, const DevVFrame& vf, uint32_t stage, float row_sigma, int x, int y, float* out_x,
+                         float* out_y, float* out_b) {
+  float X = m[0].At(x, y), Y = m[1].At(x, y), B = m[2].At(x, y);
   const float kMinSigma = -3.90524291751269967465540850526868f;
   if (!(row_sigma < kMinSigma)) {
     const float sm = vf.epf_sigma_scale[stage];
@@ -1342,6 +1348,19 @@ JXLB_HD void DevEpfPixel(const DevVPools& V, const DevVFrame& vf, uint32_t stage
     Y = Y * inv_w;
     B = B * inv_w;
   }
+  *out_x = X;
+  *out_y = Y;
+  *out_b = B;
+}
+
+template <bool INTERIOR>
+JXLB_HD void DevEpfPixel(const DevVPools& V, const DevVFrame& vf, uint32_t stage, uint32_t in_set, uint32_t out_set, int x,
+                         int y) {
+  const DevPlaneView<INTERIOR> m[3] = {DevView<INTERIOR>(V, vf, in_set, 0), DevView<INTERIOR>(V, vf, in_set, 1),
+                                       DevView<INTERIOR>(V, vf, in_set, 2)};
+  const size_t at = static_cast<size_t>(y) * m[0].stride + x;
+  float X, Y, B;
+  DevEpfValue(m, vf, stage, DevEpfSigma(V, vf, x, y), x, y, &X, &Y, &B);
   V.farena[vf.pix[out_set][0] + at] = X;
   V.farena[vf.pix[out_set][1] + at] = Y;
   V.farena[vf.pix[out_set][2] + at] = B;
@@ -1536,10 +1555,10 @@ JXLB_HD void DevPatchPixel(const DevVPools& V, const DevVFrame& vf, const DevPat
   }
 }
 
-JXLB_HD void DevColorPixel(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t x, uint32_t y) {
-  const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
+// One output pixel from its three filtered samples: colour transform + sample conversion + interleaved store.
+JXLB_HD void DevColorStore(const DevVPools& V, const DevVFrame& vf, float p0, float p1, float p2, uint32_t x, uint32_t y) {
   float r, g, b;
-  DevColorTransform(vf, V.farena[vf.pix[set][0] + at], V.farena[vf.pix[set][1] + at], V.farena[vf.pix[set][2] + at], &r, &g, &b);
+  DevColorTransform(vf, p0, p1, p2, &r, &g, &b);
   uint8_t* row = V.out + vf.out_off + vf.out_stride * y;
   const uint32_t nc = vf.out_channels;
   if (nc == 4 && vf.out_type == 2) {  // RGBA8: one aligned 32-bit store
@@ -1554,7 +1573,29 @@ JXLB_HD void DevColorPixel(const DevVPools& V, const DevVFrame& vf, uint32_t set
   }
 }
 
+JXLB_HD void DevColorPixel(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t x, uint32_t y) {
+  const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
+  DevColorStore(V, vf, V.farena[vf.pix[set][0] + at], V.farena[vf.pix[set][1] + at], V.farena[vf.pix[set][2] + at], x, y);
+}
+
 // Four consecutive RGB8 pixels (x multiple of 4, row 4-byte aligned): 12 bytes as three 32-bit stores.
+JXLB_HD void DevColorStoreRgb8x4(const DevVPools& V, const DevVFrame& vf, const float* p0, const float* p1, const float* p2,
+                                 uint32_t x, uint32_t y) {
+  uint32_t b[12];
+JXLB_UNROLL
+  for (uint32_t i = 0; i < 4; i++) {
+    float r, g, bl;
+    DevColorTransform(vf, p0[i], p1[i], p2[i], &r, &g, &bl);
+    b[3 * i] = DevToU8(r, x + i, y);
+    b[3 * i + 1] = DevToU8(g, x + i, y);
+    b[3 * i + 2] = DevToU8(bl, x + i, y);
+  }
+  uint32_t* o = reinterpret_cast<uint32_t*>(V.out + vf.out_off + vf.out_stride * y + 3 * static_cast<size_t>(x));
+  o[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+  o[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+  o[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+}
+
 JXLB_HD void DevColorPixelsRgb8x4(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t x, uint32_t y) {
   const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
   float p0[4], p1[4], p2[4];
@@ -1574,19 +1615,110 @@ JXLB_HD void DevColorPixelsRgb8x4(const DevVPools& V, const DevVFrame& vf, uint3
     p2[i] = V.farena[vf.pix[set][2] + at + i];
   }
 #endif
-  uint32_t b[12];
-JXLB_UNROLL
-  for (uint32_t i = 0; i < 4; i++) {
-    float r, g, bl;
-    DevColorTransform(vf, p0[i], p1[i], p2[i], &r, &g, &bl);
-    b[3 * i] = DevToU8(r, x + i, y);
-    b[3 * i + 1] = DevToU8(g, x + i, y);
-    b[3 * i + 2] = DevToU8(bl, x + i, y);
+  DevColorStoreRgb8x4(V, vf, p0, p1, p2, x, y);
+}
+
+// ---------------------------------------------------------------- fused render tile
+// Gaborish -> EPF 0 / 1 / 2 -> colour transform -> output samples for one kRtW x kRtH tile of a frame, with the
+// intermediate planes in shared memory instead of HBM: the IDCT output of the tile plus a halo of 1 (Gaborish) + 3 + 2 + 1
+// (the EPF stages that run) pixels is read once, every stage shrinks the valid region by its own radius, and the only
+// store is the interleaved output. Stages are the same functions as the per-pixel kernels (DevGaborishValue,
+// DevEpfValue, DevColorStore) on a view of the tile, so the samples are bit-identical. Mirroring happens when a stage
+// reads (frame coordinates -> mirrored frame coordinates -> tile), as in the reference, so only in-frame pixels are
+// ever computed. Frames with patches keep the per-pixel kernels (patches go between EPF and the colour transform).
+constexpr int kRtW = 64, kRtH = 32, kRtMaxHalo = 7;
+
+JXLB_HD uint32_t DevRenderHalo(uint32_t gab, uint32_t epf_iters) {
+  return (gab ? 1u : 0u) + (epf_iters >= 3 ? 3u : 0u) + (epf_iters >= 1 ? 2u : 0u) + (epf_iters >= 2 ? 1u : 0u);
+}
+JXLB_HD bool DevRenderFused(const DevVFrame& vf) { return vf.patch_count == 0; }
+// floats of one channel of one tile buffer for a batch whose largest halo is `halo`
+JXLB_HD uint32_t DevRenderTileFloats(uint32_t halo) { return (kRtW + 2 * halo) * (kRtH + 2 * halo); }
+
+template <bool INTERIOR>
+struct DevTileView {
+  const float* p;  // tile sample (x0, y0) of the frame
+  int stride, x0, y0, xsize, ysize;
+  JXLB_HD float At(int x, int y) const {
+    if (!INTERIOR) {
+      x = DevMirror(x, xsize);
+      y = DevMirror(y, ysize);
+    }
+    return p[(y - y0) * stride + (x - x0)];
   }
-  uint32_t* o = reinterpret_cast<uint32_t*>(V.out + vf.out_off + vf.out_stride * y + 3 * static_cast<size_t>(x));
-  o[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-  o[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-  o[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+};
+
+// `sm`: 6 * cap floats (two sets of three channel tiles). (tx0, ty0): frame coordinates of the tile's first pixel.
+template <int SCOPE, bool INTERIOR>
+JXLB_HD void DevRenderTile(const DevVPools& V, const DevVFrame& vf, int tx0, int ty0, uint32_t tid, uint32_t nt, float* sm,
+                           uint32_t cap) {
+  const int H = static_cast<int>(DevRenderHalo(vf.gab, vf.epf_iters));
+  const int SW = kRtW + 2 * H, SH = kRtH + 2 * H, ox = tx0 - H, oy = ty0 - H;
+  const int xsize = static_cast<int>(vf.xsize), ysize = static_cast<int>(vf.ysize);
+  const uint32_t PW = vf.xblocks * 8;
+  float* cur = sm;
+  float* nxt = sm + 3 * static_cast<size_t>(cap);
+  for (uint32_t i = tid; i < static_cast<uint32_t>(SW * SH); i += nt) {
+    const int fx = ox + static_cast<int>(i % SW), fy = oy + static_cast<int>(i / SW);
+    if (INTERIOR || (fx >= 0 && fx < xsize && fy >= 0 && fy < ysize)) {
+      const size_t at = static_cast<size_t>(fy) * PW + fx;
+      cur[i] = V.farena[vf.pix[0][0] + at];
+      cur[cap + i] = V.farena[vf.pix[0][1] + at];
+      cur[2 * cap + i] = V.farena[vf.pix[0][2] + at];
+    }
+  }
+  CoopSync<SCOPE>();
+  int r = H;
+  for (uint32_t step = 0; step < 4; step++) {  // step 0: Gaborish, 1..3: EPF stage step - 1
+    const bool runs = step == 0 ? vf.gab != 0
+                                : (vf.epf_iters > 0 && !(step == 1 && vf.epf_iters < 3) && !(step == 3 && vf.epf_iters < 2));
+    if (!runs) continue;
+    r -= step == 0 ? 1 : (step == 1 ? 3 : (step == 2 ? 2 : 1));
+    const int rw = kRtW + 2 * r, rh = kRtH + 2 * r;
+    DevTileView<INTERIOR> m[3];
+    for (int c = 0; c < 3; c++) {
+      m[c].p = cur + c * static_cast<size_t>(cap);
+      m[c].stride = SW;
+      m[c].x0 = ox;
+      m[c].y0 = oy;
+      m[c].xsize = xsize;
+      m[c].ysize = ysize;
+    }
+    for (uint32_t i = tid; i < static_cast<uint32_t>(rw * rh); i += nt) {
+      const int fx = tx0 - r + static_cast<int>(i % rw), fy = ty0 - r + static_cast<int>(i / rw);
+      if (!INTERIOR && !(fx >= 0 && fx < xsize && fy >= 0 && fy < ysize)) continue;
+      const uint32_t at = static_cast<uint32_t>((fy - oy) * SW + (fx - ox));
+      if (step == 0) {
+        nxt[at] = DevGaborishValue(m[0], vf.gab_w[0], fx, fy);
+        nxt[cap + at] = DevGaborishValue(m[1], vf.gab_w[1], fx, fy);
+        nxt[2 * cap + at] = DevGaborishValue(m[2], vf.gab_w[2], fx, fy);
+      } else {
+        float X, Y, B;
+        DevEpfValue(m, vf, step - 1, DevEpfSigma(V, vf, fx, fy), fx, fy, &X, &Y, &B);
+        nxt[at] = X;
+        nxt[cap + at] = Y;
+        nxt[2 * cap + at] = B;
+      }
+    }
+    CoopSync<SCOPE>();
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  // colour transform + output samples of the kRtW x kRtH tile
+  const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0;
+  for (uint32_t i = tid; i < static_cast<uint32_t>(kRtW / 4 * kRtH); i += nt) {
+    const int lx = static_cast<int>(i % (kRtW / 4)) * 4, ly = static_cast<int>(i / (kRtW / 4));
+    const int fx = tx0 + lx, fy = ty0 + ly;
+    if (fy >= ysize || fx >= xsize) continue;
+    const float* p = cur + (ly + H) * SW + lx + H;
+    if (x4 && fx + 4 <= xsize) {
+      DevColorStoreRgb8x4(V, vf, p, p + cap, p + 2 * static_cast<size_t>(cap), static_cast<uint32_t>(fx), static_cast<uint32_t>(fy));
+    } else {
+      for (int k = 0; k < 4 && fx + k < xsize; k++)
+        DevColorStore(V, vf, p[k], p[cap + k], p[2 * static_cast<size_t>(cap) + k], static_cast<uint32_t>(fx + k), static_cast<uint32_t>(fy));
+    }
+  }
 }
 
 }  // namespace jxlb

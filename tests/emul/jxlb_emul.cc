@@ -217,6 +217,22 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
               DevVarblock<0>(V, vf, bx, by, a >> 1, buf.data(), 0, 1);
             }
           }
+        if (DevRenderFused(vf) && std::getenv("JXLB_EMUL_UNFUSED") == nullptr) {  // k_render_fused, tile by tile
+          const uint32_t cap = DevRenderTileFloats(DevRenderHalo(vf.gab, vf.epf_iters));
+          std::vector<float> sm(6 * static_cast<size_t>(cap));
+          const int H = static_cast<int>(DevRenderHalo(vf.gab, vf.epf_iters));
+          const int xsize = static_cast<int>(vf.xsize), ysize = static_cast<int>(vf.ysize);
+          for (int ty0 = 0; ty0 < ysize; ty0 += kRtH)
+            for (int tx0 = 0; tx0 < xsize; tx0 += kRtW) {
+              std::fill(sm.begin(), sm.end(), std::numeric_limits<float>::quiet_NaN());  // a read of an unset cell shows
+              if (tx0 - H >= 0 && ty0 - H >= 0 && tx0 + kRtW + H <= xsize && ty0 + kRtH + H <= ysize) {
+                DevRenderTile<0, true>(V, vf, tx0, ty0, 0, 1, sm.data(), cap);
+              } else {
+                DevRenderTile<0, false>(V, vf, tx0, ty0, 0, 1, sm.data(), cap);
+              }
+            }
+          continue;
+        }
         uint32_t set = 0;
         if (vf.gab) {
           for (uint32_t c = 0; c < 3; c++)

@@ -51,7 +51,10 @@ def test_gpu_encoder_each_case(pkg, name):
     _, make, kw = next(c for c in CASES if c[0] == name)
     img = make()
     enc = pkg.JxlEncoder(quality=kw.get("distance", 1.0), speed=1 if kw["strategy_mode"] == 0 else 7)
-    got = enc.encode(img.reshape(-1), img.shape[1], img.shape[0]).data
+    if "gab" in kw or "epf_iters" in kw:  # loop-filter header fields: only the batch call exposes them
+        got = enc.encode_batch([img], gaborish=kw.get("gab", True), epf_iters=kw.get("epf_iters", 2))[0].data
+    else:
+        got = enc.encode(img.reshape(-1), img.shape[1], img.shape[0]).data
     assert got == jxlo.encode_vardct(img, dc_tree=1, cfl=CFL, **kw)
 
 

@@ -33,6 +33,28 @@ def test_mixed_batch_and_formats():
         assert np.array_equal(g, jxlo.decode(d, 4, jxlo.UINT16))
 
 
+@pytest.mark.parametrize("name", ["heuristic", "odd_size"])
+def test_per_pixel_render_kernels_still_match(name, monkeypatch):
+    # frames without patches take the fused render tile (DevRenderTile) by default; the per-pixel kernels they
+    # replaced stay in use for frames with patches and must give the same samples
+    monkeypatch.setenv("JXLB_EMUL_UNFUSED", "1")
+    data, shape = vc.encoded(name)
+    got = emul_lib.decode([data], 3, jxlo.UINT8, [shape])[0]
+    assert np.array_equal(got, jxlo.decode(data, 3, jxlo.UINT8))
+
+
+@pytest.mark.parametrize("h,w,epf,gab", [(33, 70, 3, True), (5, 3, 3, True), (64, 128, 2, False), (100, 65, 1, True),
+                                         (96, 192, 0, True), (71, 64, 3, False)])
+def test_fused_render_tile_borders(h, w, epf, gab):
+    # tile edges against frame edges: frames narrower than the halo (mirroring bounces twice), frames that end exactly
+    # on a tile edge, one row / column past it, every combination of stages
+    img = vc.crop(h, w, 640, 960)
+    data = jxlo.encode_vardct(img, strategy_mode=2, gab=gab, epf_iters=epf, random_side_info=True, seed=h + w)
+    for nc, dt in [(3, jxlo.UINT8), (4, jxlo.UINT16), (3, jxlo.FLOAT)]:
+        got = emul_lib.decode([data], nc, dt, [(h, w)])[0]
+        assert np.array_equal(got.view(np.uint8), jxlo.decode(data, nc, dt).view(np.uint8))
+
+
 SINGLE_SECTION = [(80, 100, 1, 3), (256, 256, 2, 4), (17, 9, 1, 5), (200, 256, 0, 6)]
 
 
