@@ -189,28 +189,27 @@ constexpr uint32_t kMidThreads = 256;
 constexpr uint32_t kMidSmemFloats = kFastBufFloats64;                   // 49 KB: three padded 64x64 channels
 
 // blockIdx.x = group, blockIdx.y = frame - frame0. Varblocks of up to 32x32 pixels: one warp each, handed out
-// dynamically. Plain DCTs take the register-IDCT fast path, the 8x8 special transforms the generic one.
+// dynamically from a list of the group's varblocks that the CTA compacts first (cell | strategy << 10). A warp asks
+// for its next varblock and requests that block's token ranges and raw quant (seven words, one per lane) before it
+// starts on the current one, so the chain list -> metadata -> tokens -> tables of a varblock is not waited for link by
+// link. Plain DCTs take the register-IDCT fast path, the 8x8 special transforms the generic one.
 __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint32_t frame0, uint32_t* has_mid) {
   extern __shared__ float idct_smem[];
-  __shared__ uint32_t next_s;
+  __shared__ uint32_t next_s, count_s;
+  __shared__ uint16_t list_s[1024];
   const DevVFrame& vf = V.frames[frame0 + blockIdx.y];
   const uint32_t g = blockIdx.x;
   if (g >= vf.xgroups * vf.ygroups) return;
   const uint32_t x0 = (g % vf.xgroups) * 32, y0 = (g / vf.xgroups) * 32;
   const uint32_t xs = min(32u, vf.xblocks - x0), ys = min(32u, vf.yblocks - y0);
   const uint8_t* acs = V.barena + vf.acs;
-  if (threadIdx.x == 0) next_s = 0;
+  if (threadIdx.x == 0) next_s = count_s = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* wbuf = idct_smem + warp * kFastBufFloats;
-  const uint32_t total = xs * ys;
   bool mid = false;
-  for (;;) {
-    uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(&next_s, 1u);
-    i = __shfl_sync(0xFFFFFFFFu, i, 0);
-    if (i >= total) break;
-    const uint32_t bx = i % xs, by = i / xs;
+  for (uint32_t cell = threadIdx.x; cell < 1024; cell += kIdctThreads) {
+    const uint32_t bx = cell & 31, by = cell >> 5;
+    if (bx >= xs || by >= ys) continue;
     const uint8_t a = acs[static_cast<size_t>(y0 + by) * vf.xblocks + x0 + bx];
     if (!(a & 1) || a == 0xFF) continue;
     const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
@@ -218,13 +217,60 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
       mid = true;
       continue;
     }
-    if (si.plain_dct) {
-      DevVarblockFast<1, 32>(V, vf, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
-    } else {
-      DevVarblock<1>(V, vf, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
-    }
+    list_s[atomicAdd(&count_s, 1u)] = static_cast<uint16_t>(cell | (static_cast<uint32_t>(a >> 1) << 10));
   }
-  if (mid && lane == 0) *has_mid = 1;  // some frame of the batch needs k_idct_mid / k_idct_big
+  if (mid) *has_mid = 1;  // some frame of the batch needs k_idct_mid / k_idct_big
+  __syncthreads();
+  const uint32_t total = count_s;
+  float* wbuf = idct_smem + warp * kFastBufFloats;
+  const size_t nb = static_cast<size_t>(vf.xblocks) * vf.yblocks;
+  const bool single_pass = vf.num_passes == 1;
+  // lane l < 6 holds tok_start / tok_count of channel l % 3 (l < 3: start), lane 6 the raw quant of the varblock
+  auto fetch = [&](uint32_t* entry) -> uint32_t {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&next_s, 1u);
+    i = __shfl_sync(0xFFFFFFFFu, i, 0);
+    if (i >= total) {
+      *entry = 0xFFFFFFFFu;
+      return 0;
+    }
+    const uint32_t e = list_s[i];
+    *entry = e;
+    const uint32_t cell = e & 1023;
+    const size_t pos = static_cast<size_t>(y0 + (cell >> 5)) * vf.xblocks + x0 + (cell & 31);
+    uint32_t word = 0;
+    if (single_pass) {
+      if (lane < 3) word = V.uarena[vf.tok_start + lane * nb + pos];
+      else if (lane < 6) word = V.uarena[vf.tok_count + (lane - 3) * nb + pos];
+      else if (lane == 6) word = reinterpret_cast<const uint16_t*>(V.barena + vf.rawq)[pos];
+    }
+    return word;
+  };
+  uint32_t entry, word = fetch(&entry);
+  while (entry != 0xFFFFFFFFu) {
+    uint32_t next_entry;
+    const uint32_t next_word = fetch(&next_entry);
+    const uint32_t cell = entry & 1023, strategy = entry >> 10;
+    const uint32_t bx = x0 + (cell & 31), by = y0 + (cell >> 5);
+    const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + strategy]);
+    if (si.plain_dct) {
+      if (single_pass) {
+        DevBlockMeta meta;
+        for (uint32_t c = 0; c < 3; c++) {
+          meta.start[c] = __shfl_sync(0xFFFFFFFFu, word, c);
+          meta.count[c] = __shfl_sync(0xFFFFFFFFu, word, 3 + c);
+        }
+        meta.rawq = __shfl_sync(0xFFFFFFFFu, word, 6);
+        DevVarblockFast<1, 32>(V, vf, bx, by, strategy, wbuf, lane, 32, &meta);
+      } else {
+        DevVarblockFast<1, 32>(V, vf, bx, by, strategy, wbuf, lane, 32);
+      }
+    } else {
+      DevVarblock<1>(V, vf, bx, by, strategy, wbuf, lane, 32);
+    }
+    entry = next_entry;
+    word = next_word;
+  }
 }
 
 // 64x32, 32x64 and 64x64 varblocks: the whole CTA per varblock, one 64-point register IDCT per thread and line.
@@ -325,17 +371,24 @@ __global__ void __launch_bounds__(256) k_epf(DevVPools V, uint32_t frame0, uint3
 
 // Gaborish + EPF + colour + output write of one 64x32 tile with the intermediate planes in shared memory
 // (DevRenderTile): grid (x tiles, y tiles, frames of the wave), 6 * cap floats of dynamic shared memory.
-__global__ void __launch_bounds__(256) k_render_fused(DevVPools V, uint32_t frame0, uint32_t cap) {
+__global__ void __launch_bounds__(256) k_render_fused(DevVPools V, uint32_t frame0, uint32_t cap, uint32_t stride) {
   extern __shared__ float rt_sm[];
   const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
   const int tx0 = blockIdx.x * kRtW, ty0 = blockIdx.y * kRtH;
   const int xsize = static_cast<int>(vf.xsize), ysize = static_cast<int>(vf.ysize);
   if (!DevRenderFused(vf) || tx0 >= xsize || ty0 >= ysize) return;
   const int H = static_cast<int>(DevRenderHalo(vf.gab, vf.epf_iters));
-  if (tx0 - H >= 0 && ty0 - H >= 0 && tx0 + kRtW + H <= xsize && ty0 + kRtH + H <= ysize) {
-    DevRenderTile<2, true>(V, vf, tx0, ty0, threadIdx.x, blockDim.x, rt_sm, cap);
+  const bool interior = tx0 - H >= 0 && ty0 - H >= 0 && tx0 + kRtW + H <= xsize && ty0 + kRtH + H <= ysize;
+  if (stride == kRtStrideSmall) {  // (the stride of the batch: its largest halo decides)
+    if (interior) {
+      DevRenderTile<2, true, kRtStrideSmall>(V, vf, tx0, ty0, threadIdx.x, blockDim.x, rt_sm, cap);
+    } else {
+      DevRenderTile<2, false, kRtStrideSmall>(V, vf, tx0, ty0, threadIdx.x, blockDim.x, rt_sm, cap);
+    }
+  } else if (interior) {
+    DevRenderTile<2, true, kRtStrideLarge>(V, vf, tx0, ty0, threadIdx.x, blockDim.x, rt_sm, cap);
   } else {
-    DevRenderTile<2, false>(V, vf, tx0, ty0, threadIdx.x, blockDim.x, rt_sm, cap);
+    DevRenderTile<2, false, kRtStrideLarge>(V, vf, tx0, ty0, threadIdx.x, blockDim.x, rt_sm, cap);
   }
 }
 
@@ -815,7 +868,10 @@ static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s
   const DevPools& P = dec->pools;
   const uint32_t block = 32;
   const size_t sparse_smem = static_cast<size_t>(7 * b.wp_width + 10) * kSparseLanes * sizeof(int32_t);
-  if (b.streams.size() <= 2 * 148 * kSparseLanes && sparse_smem <= 160 * 1024) {
+  // (JXLB200_MODULAR_DENSE=1: always the dense-lane kernel -- 32 streams per warp, rows in HBM, 6 KB of shared memory
+  // per CTA instead of 58 KB: slower alone, but it leaves the SMs' shared memory to the kernels of other batches)
+  static const bool force_dense = std::getenv("JXLB200_MODULAR_DENSE") != nullptr;
+  if (!force_dense && b.streams.size() <= 2 * 148 * kSparseLanes && sparse_smem <= 160 * 1024) {
     const uint32_t grid = (b.streams.size() + kSparseLanes - 1) / kSparseLanes;
     if (b.narrow) {
       k_modular_decode_sparse<int32_t><<<grid, block, sparse_smem, s>>>(P);
@@ -906,9 +962,10 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
       const uint32_t skip_fused = dec->fused_render ? 1 : 0;
       if (dec->fused_render) {
         ScopedTimer t(dec, s, kKFilters);
-        const uint32_t cap = DevRenderTileFloats(DevRenderHalo(dec->any_gab ? 1 : 0, dec->max_epf));
+        const uint32_t halo = DevRenderHalo(dec->any_gab ? 1 : 0, dec->max_epf);
+        const uint32_t cap = DevRenderTileFloats(halo);
         const dim3 rt_grid((dec->max_xsize + kRtW - 1) / kRtW, (dec->max_ysize + kRtH - 1) / kRtH, nf);
-        k_render_fused<<<rt_grid, 256, 6 * cap * sizeof(float), s>>>(V, f0, cap);
+        k_render_fused<<<rt_grid, 256, 6 * cap * sizeof(float), s>>>(V, f0, cap, DevRenderStride(halo));
         launches++;
       }
       if (!dec->fused_render || !b.patches.empty()) {

@@ -1041,9 +1041,27 @@ constexpr uint32_t kFastBufFloats64 = 3 * 64 * 65 + 128;  // the same for blocks
 
 // Varblock with a plain DCT of at most MAXN x MAXN pixels (MAXN = 32: strategies 0, 4..11; MAXN = 64: also
 // 18..20). `buf`: kFastBufFloats (kFastBufFloats64) floats shared by the cooperating threads.
+// Where the tokens of a varblock are (single-pass frames) and its raw quant value: what a kernel can fetch one
+// varblock ahead of the one it is working on.
+struct DevBlockMeta {
+  uint32_t start[3], count[3];  // per channel X, Y, B: first token, token count
+  uint32_t rawq;
+};
+
+JXLB_HD DevBlockMeta DevLoadBlockMeta(const DevVPools& V, const DevVFrame& vf, size_t pos) {
+  const size_t nb = static_cast<size_t>(vf.xblocks) * vf.yblocks;
+  DevBlockMeta m;
+  for (uint32_t c = 0; c < 3; c++) {
+    m.start[c] = V.uarena[vf.tok_start + c * nb + pos];
+    m.count[c] = V.uarena[vf.tok_count + c * nb + pos];
+  }
+  m.rawq = reinterpret_cast<const uint16_t*>(V.barena + vf.rawq)[pos];
+  return m;
+}
+
 template <int SCOPE, int MAXN>
 JXLB_HD void DevVarblockFast(const DevVPools& V, const DevVFrame& vf, uint32_t bx, uint32_t by, uint32_t s, float* buf,
-                             uint32_t tid, uint32_t nt) {
+                             uint32_t tid, uint32_t nt, const DevBlockMeta* prefetched = nullptr) {
   const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + s]);
   const uint32_t Rb = si.cy, Cb = si.cx, covered = Rb * Cb;
   const uint32_t R = 8 * Rb, C = 8 * Cb, N = R * C;
@@ -1058,8 +1076,21 @@ JXLB_HD void DevVarblockFast(const DevVPools& V, const DevVFrame& vf, uint32_t b
   float* scratch = buf + 3 * P;
   const float* wc = V.fpool + V.wc_off;
   // dequantisation constants (DequantBlock)
-  const uint16_t* rawq = reinterpret_cast<const uint16_t*>(V.barena + vf.rawq);
-  const float scaled = vf.inv_global_scale / static_cast<float>(rawq[pos]);
+  DevBlockMeta meta;
+  if (prefetched) {
+    meta = *prefetched;
+  } else if (vf.num_passes == 1) {
+    meta = DevLoadBlockMeta(V, vf, pos);
+  } else {
+    meta.rawq = reinterpret_cast<const uint16_t*>(V.barena + vf.rawq)[pos];
+  }
+  // single pass: the first `nt` tokens of all three channels are requested before anything waits on them
+  uint32_t first_tok[3] = {0, 0, 0};
+  if (vf.num_passes == 1) {
+    for (uint32_t c = 0; c < 3; c++)
+      if (tid < meta.count[c]) first_tok[c] = JXLB_LDG(V.tokens + meta.start[c] + tid);
+  }
+  const float scaled = vf.inv_global_scale / static_cast<float>(meta.rawq);
   const float sd[3] = {scaled * vf.x_dm, scaled, scaled * vf.b_dm};
   const size_t tile = static_cast<size_t>(by / 8) * vf.cmw + bx / 8;
   const float x_cc = vf.base_x + static_cast<float>(reinterpret_cast<const int8_t*>(V.barena + vf.ytox)[tile]) * vf.color_scale;
@@ -1070,10 +1101,10 @@ JXLB_HD void DevVarblockFast(const DevVPools& V, const DevVFrame& vf, uint32_t b
   if (vf.num_passes == 1) {
     // Y tokens: Y = dq_y; X = x_cc * dq_y (+ 0), B = b_cc * dq_y (+ 0)
     {
-      const uint32_t start = V.uarena[vf.tok_start + 1 * nb + pos], count = V.uarena[vf.tok_count + 1 * nb + pos];
-      const uint32_t* tok = V.tokens + start;
+      const uint32_t count = meta.count[1];
+      const uint32_t* tok = V.tokens + meta.start[1];
       for (uint32_t i = tid; i < count; i += nt) {
-        const uint32_t t = JXLB_LDG(tok + i);
+        const uint32_t t = i == tid ? first_tok[1] : JXLB_LDG(tok + i);
         const uint32_t k = t & 0xFFFF;
         if (k >= N) continue;
         const int32_t q = static_cast<int16_t>(t >> 16);
@@ -1086,11 +1117,11 @@ JXLB_HD void DevVarblockFast(const DevVPools& V, const DevVFrame& vf, uint32_t b
     }
     CoopSync<SCOPE>();
     for (uint32_t c = 0; c < 3; c += 2) {
-      const uint32_t start = V.uarena[vf.tok_start + c * nb + pos], count = V.uarena[vf.tok_count + c * nb + pos];
-      const uint32_t* tok = V.tokens + start;
+      const uint32_t count = meta.count[c];
+      const uint32_t* tok = V.tokens + meta.start[c];
       const float cc = c == 0 ? x_cc : b_cc;
       for (uint32_t i = tid; i < count; i += nt) {
-        const uint32_t t = JXLB_LDG(tok + i);
+        const uint32_t t = i == tid ? first_tok[c] : JXLB_LDG(tok + i);
         const uint32_t k = t & 0xFFFF;
         if (k >= N) continue;
         const int32_t q = static_cast<int16_t>(t >> 16);
@@ -1249,7 +1280,7 @@ JXLB_HD void DevEpfValue(const VIEW* m, const DevVFrame& vf, uint32_t stage, flo
   if (!(row_sigma < kMinSigma)) {
     const float sm = vf.epf_sigma_scale[stage];
     const float bsm = sm * vf.epf_border_sad_mul;
-    const int iy = y % 8, ix = x % 8;
+    const int iy = y & 7, ix = x & 7;  // (x, y are in-frame: non-negative)
     const float sad_mul = (iy == 0 || iy == 7 || ix == 0 || ix == 7) ? bsm : sm;
     const float inv_sigma = row_sigma * sad_mul;
     float w = 1.0f;
@@ -1627,29 +1658,42 @@ JXLB_HD void DevColorPixelsRgb8x4(const DevVPools& V, const DevVFrame& vf, uint3
 // reads (frame coordinates -> mirrored frame coordinates -> tile), as in the reference, so only in-frame pixels are
 // ever computed. Frames with patches keep the per-pixel kernels (patches go between EPF and the colour transform).
 constexpr int kRtW = 64, kRtH = 32, kRtMaxHalo = 7;
+// Row stride of a tile in shared memory, a compile-time constant so that a stage's taps are the centre address plus
+// immediates: 72 floats when the halo is at most 4 (Gaborish + two EPF stages), 80 otherwise.
+constexpr int kRtStrideSmall = kRtW + 2 * 4, kRtStrideLarge = 80;
 
 JXLB_HD uint32_t DevRenderHalo(uint32_t gab, uint32_t epf_iters) {
   return (gab ? 1u : 0u) + (epf_iters >= 3 ? 3u : 0u) + (epf_iters >= 1 ? 2u : 0u) + (epf_iters >= 2 ? 1u : 0u);
 }
 JXLB_HD bool DevRenderFused(const DevVFrame& vf) { return vf.patch_count == 0; }
+JXLB_HD uint32_t DevRenderStride(uint32_t halo) { return halo <= 4 ? kRtStrideSmall : kRtStrideLarge; }
 // floats of one channel of one tile buffer for a batch whose largest halo is `halo`
-JXLB_HD uint32_t DevRenderTileFloats(uint32_t halo) { return (kRtW + 2 * halo) * (kRtH + 2 * halo); }
+JXLB_HD uint32_t DevRenderTileFloats(uint32_t halo) { return DevRenderStride(halo) * (kRtH + 2 * halo); }
 
-template <bool INTERIOR>
+template <bool INTERIOR, int STRIDE>
 struct DevTileView {
   const float* p;  // tile sample (x0, y0) of the frame
-  int stride, x0, y0, xsize, ysize;
+  int x0, y0, xsize, ysize;
   JXLB_HD float At(int x, int y) const {
     if (!INTERIOR) {
       x = DevMirror(x, xsize);
       y = DevMirror(y, ysize);
     }
-    return p[(y - y0) * stride + (x - x0)];
+    return p[(y - y0) * STRIDE + (x - x0)];
   }
 };
 
-// `sm`: 6 * cap floats (two sets of three channel tiles). (tx0, ty0): frame coordinates of the tile's first pixel.
-template <int SCOPE, bool INTERIOR>
+// i / d and i % d for i * ceil(2^20 / d) < 2^32 and i < 2^20 / d * ... (i < 4096, 64 <= d <= 80 here): exact, because the
+// error of the rounded-up reciprocal, i / 2^20 < 1 / 256, stays below 1 / d.
+struct DevSmallDiv {
+  uint32_t d, m;
+  JXLB_HD explicit DevSmallDiv(uint32_t div) : d(div), m(((1u << 20) + div - 1) / div) {}
+  JXLB_HD uint32_t Div(uint32_t i) const { return (i * m) >> 20; }
+};
+
+// `sm`: 6 * cap floats (two sets of three channel tiles), rows STRIDE floats apart. (tx0, ty0): frame coordinates of
+// the tile's first pixel.
+template <int SCOPE, bool INTERIOR, int STRIDE>
 JXLB_HD void DevRenderTile(const DevVPools& V, const DevVFrame& vf, int tx0, int ty0, uint32_t tid, uint32_t nt, float* sm,
                            uint32_t cap) {
   const int H = static_cast<int>(DevRenderHalo(vf.gab, vf.epf_iters));
@@ -1658,13 +1702,18 @@ JXLB_HD void DevRenderTile(const DevVPools& V, const DevVFrame& vf, int tx0, int
   const uint32_t PW = vf.xblocks * 8;
   float* cur = sm;
   float* nxt = sm + 3 * static_cast<size_t>(cap);
-  for (uint32_t i = tid; i < static_cast<uint32_t>(SW * SH); i += nt) {
-    const int fx = ox + static_cast<int>(i % SW), fy = oy + static_cast<int>(i / SW);
-    if (INTERIOR || (fx >= 0 && fx < xsize && fy >= 0 && fy < ysize)) {
-      const size_t at = static_cast<size_t>(fy) * PW + fx;
-      cur[i] = V.farena[vf.pix[0][0] + at];
-      cur[cap + i] = V.farena[vf.pix[0][1] + at];
-      cur[2 * cap + i] = V.farena[vf.pix[0][2] + at];
+  {
+    const DevSmallDiv dv(static_cast<uint32_t>(SW));
+    for (uint32_t i = tid; i < static_cast<uint32_t>(SW * SH); i += nt) {
+      const uint32_t sy = dv.Div(i), sx = i - sy * dv.d;
+      const int fx = ox + static_cast<int>(sx), fy = oy + static_cast<int>(sy);
+      if (INTERIOR || (fx >= 0 && fx < xsize && fy >= 0 && fy < ysize)) {
+        const size_t from = static_cast<size_t>(fy) * PW + fx;
+        const uint32_t at = sy * STRIDE + sx;
+        cur[at] = V.farena[vf.pix[0][0] + from];
+        cur[cap + at] = V.farena[vf.pix[0][1] + from];
+        cur[2 * cap + at] = V.farena[vf.pix[0][2] + from];
+      }
     }
   }
   CoopSync<SCOPE>();
@@ -1675,19 +1724,20 @@ JXLB_HD void DevRenderTile(const DevVPools& V, const DevVFrame& vf, int tx0, int
     if (!runs) continue;
     r -= step == 0 ? 1 : (step == 1 ? 3 : (step == 2 ? 2 : 1));
     const int rw = kRtW + 2 * r, rh = kRtH + 2 * r;
-    DevTileView<INTERIOR> m[3];
+    DevTileView<INTERIOR, STRIDE> m[3];
     for (int c = 0; c < 3; c++) {
       m[c].p = cur + c * static_cast<size_t>(cap);
-      m[c].stride = SW;
       m[c].x0 = ox;
       m[c].y0 = oy;
       m[c].xsize = xsize;
       m[c].ysize = ysize;
     }
+    const DevSmallDiv dv(static_cast<uint32_t>(rw));
     for (uint32_t i = tid; i < static_cast<uint32_t>(rw * rh); i += nt) {
-      const int fx = tx0 - r + static_cast<int>(i % rw), fy = ty0 - r + static_cast<int>(i / rw);
+      const uint32_t ry = dv.Div(i), rx = i - ry * dv.d;
+      const int fx = tx0 - r + static_cast<int>(rx), fy = ty0 - r + static_cast<int>(ry);
       if (!INTERIOR && !(fx >= 0 && fx < xsize && fy >= 0 && fy < ysize)) continue;
-      const uint32_t at = static_cast<uint32_t>((fy - oy) * SW + (fx - ox));
+      const uint32_t at = static_cast<uint32_t>((fy - oy) * STRIDE + (fx - ox));
       if (step == 0) {
         nxt[at] = DevGaborishValue(m[0], vf.gab_w[0], fx, fy);
         nxt[cap + at] = DevGaborishValue(m[1], vf.gab_w[1], fx, fy);
@@ -1711,7 +1761,7 @@ JXLB_HD void DevRenderTile(const DevVPools& V, const DevVFrame& vf, int tx0, int
     const int lx = static_cast<int>(i % (kRtW / 4)) * 4, ly = static_cast<int>(i / (kRtW / 4));
     const int fx = tx0 + lx, fy = ty0 + ly;
     if (fy >= ysize || fx >= xsize) continue;
-    const float* p = cur + (ly + H) * SW + lx + H;
+    const float* p = cur + (ly + H) * STRIDE + lx + H;
     if (x4 && fx + 4 <= xsize) {
       DevColorStoreRgb8x4(V, vf, p, p + cap, p + 2 * static_cast<size_t>(cap), static_cast<uint32_t>(fx), static_cast<uint32_t>(fy));
     } else {

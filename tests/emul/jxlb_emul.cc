@@ -218,17 +218,23 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
             }
           }
         if (DevRenderFused(vf) && std::getenv("JXLB_EMUL_UNFUSED") == nullptr) {  // k_render_fused, tile by tile
-          const uint32_t cap = DevRenderTileFloats(DevRenderHalo(vf.gab, vf.epf_iters));
+          // (the kernel takes the stride of the batch's largest halo; here the frame's own, or the large one on request)
+          const uint32_t halo = DevRenderHalo(vf.gab, vf.epf_iters);
+          const bool large = halo > 4 || std::getenv("JXLB_EMUL_LARGE_STRIDE") != nullptr;
+          const uint32_t cap = (large ? kRtStrideLarge : kRtStrideSmall) * (kRtH + 2 * (large ? kRtMaxHalo : halo));
           std::vector<float> sm(6 * static_cast<size_t>(cap));
-          const int H = static_cast<int>(DevRenderHalo(vf.gab, vf.epf_iters));
+          const int H = static_cast<int>(halo);
           const int xsize = static_cast<int>(vf.xsize), ysize = static_cast<int>(vf.ysize);
           for (int ty0 = 0; ty0 < ysize; ty0 += kRtH)
             for (int tx0 = 0; tx0 < xsize; tx0 += kRtW) {
               std::fill(sm.begin(), sm.end(), std::numeric_limits<float>::quiet_NaN());  // a read of an unset cell shows
-              if (tx0 - H >= 0 && ty0 - H >= 0 && tx0 + kRtW + H <= xsize && ty0 + kRtH + H <= ysize) {
-                DevRenderTile<0, true>(V, vf, tx0, ty0, 0, 1, sm.data(), cap);
+              const bool interior = tx0 - H >= 0 && ty0 - H >= 0 && tx0 + kRtW + H <= xsize && ty0 + kRtH + H <= ysize;
+              if (large) {
+                if (interior) DevRenderTile<0, true, kRtStrideLarge>(V, vf, tx0, ty0, 0, 1, sm.data(), cap);
+                else DevRenderTile<0, false, kRtStrideLarge>(V, vf, tx0, ty0, 0, 1, sm.data(), cap);
               } else {
-                DevRenderTile<0, false>(V, vf, tx0, ty0, 0, 1, sm.data(), cap);
+                if (interior) DevRenderTile<0, true, kRtStrideSmall>(V, vf, tx0, ty0, 0, 1, sm.data(), cap);
+                else DevRenderTile<0, false, kRtStrideSmall>(V, vf, tx0, ty0, 0, 1, sm.data(), cap);
               }
             }
           continue;
