@@ -410,10 +410,23 @@ def main():
     # Every step: host parse + H2D of that step's bitstreams and tables, the kernels, D2H of the pixels into pinned
     # host memory. Steps run on `inflight` handles from as many host threads (ctypes drops the GIL), so the host
     # parse and the copies of one step overlap the kernels of another -- the same pipelining as above.
+    # (pinned host memory: one output set per handle in flight, bounded by this rank's share of the free host memory)
+    set_bytes = sum(dec.out_size(i) for i in range(wl.batch))
+    try:
+        import psutil
+        share = psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    except Exception:
+        share = 64e9
+    nfl_e2e = max(1, min(nfl, int(0.4 * share // max(set_bytes, 1))))
+    if nfl_e2e < nfl and rank == 0:
+        print("e2e: %d of %d handles in flight (pinned output sets of %.1f GB each, %.0f GB of host memory per rank)"
+              % (nfl_e2e, nfl, set_bytes / 1e9, share / 1e9), file=sys.stderr)
     out_sets = [[torch.empty(dec.out_size(i), dtype=torch.uint8).pin_memory().numpy() for i in range(wl.batch)]
-                for _ in range(nfl)]
+                for _ in range(nfl_e2e)]
     outs = out_sets[0]
-    e2e_steps = max(nfl, min(args.steps, 6))
+    # enough steps for the handles to fall out of lock step (parse / kernels / read-back of different steps overlap);
+    # the ramp-up and the drain stay inside the timed region
+    e2e_steps = max(3 * nfl_e2e, min(args.steps, 16))
 
     phase_s = {"set_input": 0.0, "run_wait": 0.0, "read_outputs": 0.0}
     phase_lock = threading.Lock()
@@ -445,13 +458,13 @@ def main():
                     return
                 e2e_step(h)
 
-        ts = [threading.Thread(target=worker, args=(h,)) for h in range(nfl)]
+        ts = [threading.Thread(target=worker, args=(h,)) for h in range(nfl_e2e)]
         for t in ts:
             t.start()
         for t in ts:
             t.join()
 
-    e2e_round(nfl)  # warm-up
+    e2e_round(nfl_e2e)  # warm-up
     barrier()
     t0 = time.perf_counter()
     e2e_round(e2e_steps)
@@ -463,7 +476,7 @@ def main():
     e2e_s = float(t.item())
     e2e_value = pixels_per_step / e2e_s / 1e6
     if rank == 0:  # where a step's wall time goes (summed over the overlapping handles, warm-up included)
-        n_e2e = e2e_steps + nfl
+        n_e2e = e2e_steps + nfl_e2e
         print("e2e phases per step (ms): " + ", ".join("%s %.1f" % (k, v / n_e2e * 1e3) for k, v in phase_s.items()),
               file=sys.stderr)
 
@@ -501,7 +514,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(st.compressed_bytes), "d2h_bytes_per_step": int(st.output_bytes),
                     "includes": "host parse (threads) + H2D bitstreams/tables + kernels + D2H to pinned host, "
-                                "%d steps in flight" % nfl},
+                                "%d steps in flight" % nfl_e2e},
             "gpu_launches": int(st.kernel_launches) * args.steps,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -193,7 +193,8 @@ constexpr uint32_t kMidSmemFloats = kFastBufFloats64;                   // 49 KB
 // for its next varblock and requests that block's token ranges and raw quant (seven words, one per lane) before it
 // starts on the current one, so the chain list -> metadata -> tokens -> tables of a varblock is not waited for link by
 // link. Plain DCTs take the register-IDCT fast path, the 8x8 special transforms the generic one.
-__global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint32_t frame0, uint32_t* has_mid) {
+__global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint32_t frame0, uint32_t* has_mid, uint32_t* mid_count,
+                                                                uint2* mid_list) {
   extern __shared__ float idct_smem[];
   __shared__ uint32_t next_s, count_s;
   __shared__ uint16_t list_s[1024];
@@ -215,6 +216,9 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
     const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
     if (static_cast<uint32_t>(si.cx) * si.cy > 16) {
       mid = true;
+      // 64x32 / 32x64 / 64x64: onto the wave's list for k_idct_mid (frame, block position)
+      if (static_cast<uint32_t>(si.cx) * si.cy <= 64)
+        mid_list[atomicAdd(mid_count, 1u)] = make_uint2(frame0 + blockIdx.y, (y0 + by) * vf.xblocks + x0 + bx);
       continue;
     }
     list_s[atomicAdd(&count_s, 1u)] = static_cast<uint16_t>(cell | (static_cast<uint32_t>(a >> 1) << 10));
@@ -274,23 +278,16 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
 }
 
 // 64x32, 32x64 and 64x64 varblocks: the whole CTA per varblock, one 64-point register IDCT per thread and line.
-__global__ void __launch_bounds__(kMidThreads) k_idct_mid(DevVPools V, uint32_t frame0, const uint32_t* has_mid) {
+// The CTAs stride over the list of such varblocks that k_dequant_idct made for the wave, so that a smooth group with
+// many of them does not become one CTA's serial tail.
+__global__ void __launch_bounds__(kMidThreads) k_idct_mid(DevVPools V, const uint32_t* mid_count, const uint2* mid_list) {
   extern __shared__ float idct_smem[];
-  if (*has_mid == 0) return;
-  const DevVFrame& vf = V.frames[frame0 + blockIdx.y];
-  const uint32_t g = blockIdx.x;
-  if (g >= vf.xgroups * vf.ygroups) return;
-  const uint32_t x0 = (g % vf.xgroups) * 32, y0 = (g / vf.xgroups) * 32;
-  const uint32_t xs = min(32u, vf.xblocks - x0), ys = min(32u, vf.yblocks - y0);
-  const uint8_t* acs = V.barena + vf.acs;
-  for (uint32_t i = 0; i < xs * ys; i++) {
-    const uint32_t bx = i % xs, by = i / xs;
-    const uint8_t a = acs[static_cast<size_t>(y0 + by) * vf.xblocks + x0 + bx];
-    if (!(a & 1) || a == 0xFF) continue;
-    const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
-    const uint32_t covered = static_cast<uint32_t>(si.cx) * si.cy;
-    if (covered <= 16 || covered > 64) continue;
-    DevVarblockFast<2, 64>(V, vf, x0 + bx, y0 + by, a >> 1, idct_smem, threadIdx.x, kMidThreads);
+  const uint32_t n = *mid_count;
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint2 e = mid_list[i];
+    const DevVFrame& vf = V.frames[e.x];
+    const uint8_t a = V.barena[vf.acs + e.y];
+    DevVarblockFast<2, 64>(V, vf, e.y % vf.xblocks, e.y / vf.xblocks, a >> 1, idct_smem, threadIdx.x, kMidThreads);
   }
 }
 
@@ -503,6 +500,7 @@ struct JxlB200Decoder {
   DevBuf<uint16_t> d_opool, d_lut;
   DevBuf<uint8_t> d_cpool, d_barena;
   DevBuf<uint32_t> d_upool, d_uarena, d_tokens, d_ac_status, d_ac_used, d_dc_status;
+  DevBuf<uint2> d_mid_list;  // varblocks of 64x32 ... 64x64 pixels of the wave in flight (k_dequant_idct -> k_idct_mid)
   DevBuf<uint2> d_dcg_list;
   DevBuf<DevPatch> d_patches;
   DevBuf<DevRefFrame> d_ref_frames;
@@ -715,8 +713,10 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     CUDA_OK(dec->d_uarena.Alloc(b.uarena_size + 16));
     CUDA_OK(dec->d_ac_status.Alloc(b.ac_streams.size() + 1));
     CUDA_OK(dec->d_ac_used.Alloc(b.ac_streams.size() + 1));
-    CUDA_OK(dec->d_dc_status.Alloc(dec->dcg_list.size() + 1));
+    CUDA_OK(dec->d_dc_status.Alloc(dec->dcg_list.size() + 2));
     CUDA_OK(dec->d_big_scratch.Alloc(static_cast<size_t>(JxlB200Decoder::kBigCtas) * 4 * 65536));
+    // (a 32x32-block group holds at most 32 varblocks of 64x32 pixels)
+    CUDA_OK(dec->d_mid_list.Alloc(static_cast<size_t>(std::max<uint32_t>(1, b.wave_frames)) * dec->max_groups * 32 + 1));
     DevVPools& V = dec->vpools;
     V = DevVPools{};
     V.frames = dec->d_vframes.p;
@@ -934,7 +934,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     }
     {
       ScopedTimer t(dec, s, kKDcFinish);
-      CUDA_OK(cudaMemsetAsync(dec->d_dc_status.p, 0, (dec->dcg_list.size() + 1) * 4, s));
+      CUDA_OK(cudaMemsetAsync(dec->d_dc_status.p, 0, (dec->dcg_list.size() + 2) * 4, s));
       k_dc_finish<<<dec->dcg_list.size(), 256, 65536, s>>>(P, V, dec->d_dcg_list.p);
       dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(256, (dec->max_blocks + 255) / 256)), nvf);
       k_dc_smooth<<<grid, 256, 0, s>>>(V);
@@ -950,9 +950,12 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
       const uint32_t nf = std::min<uint32_t>(b.wave_frames, nvf - f0);
       {
         ScopedTimer t(dec, s, kKDequantIdct);
-        uint32_t* has_mid = dec->d_dc_status.p + dec->dcg_list.size();  // spare word after the DC status words
-        k_dequant_idct<<<dim3(dec->max_groups, nf), kIdctThreads, kIdctSmemFloats * sizeof(float), s>>>(V, f0, has_mid);
-        k_idct_mid<<<dim3(dec->max_groups, nf), kMidThreads, kMidSmemFloats * sizeof(float), s>>>(V, f0, has_mid);
+        uint32_t* has_mid = dec->d_dc_status.p + dec->dcg_list.size();  // spare words after the DC status words
+        uint32_t* mid_count = has_mid + 1;
+        if (f0 != 0) CUDA_OK(cudaMemsetAsync(mid_count, 0, 4, s));  // (the first wave's was cleared with the DC status)
+        k_dequant_idct<<<dim3(dec->max_groups, nf), kIdctThreads, kIdctSmemFloats * sizeof(float), s>>>(V, f0, has_mid, mid_count,
+                                                                                                       dec->d_mid_list.p);
+        k_idct_mid<<<4 * 148, kMidThreads, kMidSmemFloats * sizeof(float), s>>>(V, mid_count, dec->d_mid_list.p);
         k_idct_big<<<JxlB200Decoder::kBigCtas, 256, 0, s>>>(V, f0, nf, dec->d_big_scratch.p, has_mid);
         launches += 3;
       }
