@@ -196,17 +196,18 @@ constexpr uint32_t kMidSmemFloats = kFastBufFloats64;                   // 49 KB
 __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint32_t frame0, uint32_t* has_mid, uint32_t* mid_count,
                                                                 uint2* mid_list) {
   extern __shared__ float idct_smem[];
-  __shared__ uint32_t next_s, count_s;
-  __shared__ uint16_t list_s[1024];
+  __shared__ uint32_t next_s, count_s, next8_s, count8_s, left8_s;
+  __shared__ uint16_t list_s[1024], list8_s[1024];  // varblocks of the group; 8x8 DCTs of single-pass frames apart
   const DevVFrame& vf = V.frames[frame0 + blockIdx.y];
   const uint32_t g = blockIdx.x;
   if (g >= vf.xgroups * vf.ygroups) return;
   const uint32_t x0 = (g % vf.xgroups) * 32, y0 = (g / vf.xgroups) * 32;
   const uint32_t xs = min(32u, vf.xblocks - x0), ys = min(32u, vf.yblocks - y0);
   const uint8_t* acs = V.barena + vf.acs;
-  if (threadIdx.x == 0) next_s = count_s = 0;
+  if (threadIdx.x == 0) next_s = count_s = next8_s = count8_s = left8_s = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool single_pass = vf.num_passes == 1;
   bool mid = false;
   for (uint32_t cell = threadIdx.x; cell < 1024; cell += kIdctThreads) {
     const uint32_t bx = cell & 31, by = cell >> 5;
@@ -221,14 +222,65 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
         mid_list[atomicAdd(mid_count, 1u)] = make_uint2(frame0 + blockIdx.y, (y0 + by) * vf.xblocks + x0 + bx);
       continue;
     }
-    list_s[atomicAdd(&count_s, 1u)] = static_cast<uint16_t>(cell | (static_cast<uint32_t>(a >> 1) << 10));
+    if ((a >> 1) == 0 && single_pass) {
+      list8_s[atomicAdd(&count8_s, 1u)] = static_cast<uint16_t>(cell);
+    } else {
+      list_s[atomicAdd(&count_s, 1u)] = static_cast<uint16_t>(cell | (static_cast<uint32_t>(a >> 1) << 10));
+    }
   }
   if (mid) *has_mid = 1;  // some frame of the batch needs k_idct_mid / k_idct_big
   __syncthreads();
   const uint32_t total = count_s;
   float* wbuf = idct_smem + warp * kFastBufFloats;
   const size_t nb = static_cast<size_t>(vf.xblocks) * vf.yblocks;
-  const bool single_pass = vf.num_passes == 1;
+  // 8x8 DCT blocks, four per warp at a time: the eight lanes of a quarter warp run the varblock function on their own
+  // block (tid = lane & 7 of 8 threads, own slice of the warp's buffer). All four follow the same control flow up to
+  // loop trip counts, so the function's warp-wide synchronisation points are reached by every lane. Lane 8q + l
+  // (l < 7) fetches word l of block q's metadata one quad ahead. What does not fill a quad goes one block at a time.
+  {
+    const uint32_t total8 = count8_s, quads = total8 / 4, sub = lane >> 3, t8 = lane & 7;
+    float* qbuf = wbuf + sub * 296;  // 3 * 8 * 9 floats of coefficients (+ the LLF scratch the 8x8 DCT never touches)
+    auto fetch8 = [&](uint32_t* cell_out) -> uint32_t {
+      uint32_t q = 0;
+      if (lane == 0) q = atomicAdd(&next8_s, 1u);
+      q = __shfl_sync(0xFFFFFFFFu, q, 0);
+      if (q >= quads) {
+        *cell_out = 0xFFFFFFFFu;
+        return 0;
+      }
+      const uint32_t cell = list8_s[q * 4 + sub];
+      *cell_out = cell;
+      const size_t pos = static_cast<size_t>(y0 + (cell >> 5)) * vf.xblocks + x0 + (cell & 31);
+      uint32_t word = 0;
+      if (t8 < 3) word = V.uarena[vf.tok_start + t8 * nb + pos];
+      else if (t8 < 6) word = V.uarena[vf.tok_count + (t8 - 3) * nb + pos];
+      else if (t8 == 6) word = reinterpret_cast<const uint16_t*>(V.barena + vf.rawq)[pos];
+      return word;
+    };
+    uint32_t cell, word = fetch8(&cell);
+    while (cell != 0xFFFFFFFFu) {
+      uint32_t next_cell;
+      const uint32_t next_word = fetch8(&next_cell);
+      DevBlockMeta meta;
+      for (uint32_t c = 0; c < 3; c++) {
+        meta.start[c] = __shfl_sync(0xFFFFFFFFu, word, (lane & 24) + c);
+        meta.count[c] = __shfl_sync(0xFFFFFFFFu, word, (lane & 24) + 3 + c);
+      }
+      meta.rawq = __shfl_sync(0xFFFFFFFFu, word, (lane & 24) + 6);
+      DevVarblockFast<1, 32>(V, vf, x0 + (cell & 31), y0 + (cell >> 5), 0, qbuf, t8, 8, &meta);
+      cell = next_cell;
+      word = next_word;
+    }
+    // the up to three blocks that do not fill a quad, one warp each
+    for (;;) {
+      uint32_t k = 0;
+      if (lane == 0) k = atomicAdd(&left8_s, 1u);
+      k = __shfl_sync(0xFFFFFFFFu, k, 0);
+      if (quads * 4 + k >= total8) break;
+      const uint32_t c8 = list8_s[quads * 4 + k];
+      DevVarblockFast<1, 32>(V, vf, x0 + (c8 & 31), y0 + (c8 >> 5), 0, wbuf, lane, 32);
+    }
+  }
   // lane l < 6 holds tok_start / tok_count of channel l % 3 (l < 3: start), lane 6 the raw quant of the varblock
   auto fetch = [&](uint32_t* entry) -> uint32_t {
     uint32_t i = 0;
