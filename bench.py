@@ -303,11 +303,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="vardct4k", choices=["vardct4k", "modular", "encode4k"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 256 vardct4k, 256 modular, 8 encode4k)")
-    ap.add_argument("--inflight", type=int, default=4,
+    ap.add_argument("--inflight", type=int, default=8,
                     help="decoder handles in flight, each with its own buffers and CUDA stream: the latency-bound "
                          "entropy kernels of one batch overlap the per-pixel kernels of the previous one")
     ap.add_argument("--impl", default="b200")
@@ -338,7 +338,9 @@ def main():
 
     wl = Workload(args.workload, args.batch)
     files = wl.files
-    nfl = max(1, args.inflight)
+    # handles in flight: at most --inflight, and a divisor of --steps so that every handle runs the same number of steps
+    # (no tail in which only a few handles are left)
+    nfl = max(d for d in range(1, max(1, min(args.inflight, args.steps)) + 1) if args.steps % d == 0)
     decs = [pkg.BatchDecoder(local_rank) for _ in range(nfl)]
     for d in decs:
         d.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8)
