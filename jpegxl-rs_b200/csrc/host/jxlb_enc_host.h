@@ -574,6 +574,8 @@ inline void FillQuantizer(const EncParams& p, DevEFrame* ef, uint32_t* global_sc
   ef->inv_global_scale = inv_global_scale;
   ef->x_dm = std::pow(1 / (1.25f), p.x_qm_scale - 2.0f);
   ef->b_dm = std::pow(1 / (1.25f), p.b_qm_scale - 2.0f);
+  ef->x_qm_mul = std::pow(1.25f, p.x_qm_scale - 2.0f);
+  ef->b_qm_mul = std::pow(1.25f, p.b_qm_scale - 2.0f);
   ef->distance = p.distance;
   ef->strategy_mode = p.strategy_mode;
   for (int i = 0; i < 4; i++) ef->biases[i] = kDefaultQuantBias[i];

@@ -48,6 +48,7 @@ struct DevEFrame {
   uint32_t strategy_mode;
   float distance;
   float inv_global_scale, mul_dc[3], x_dm, b_dm;
+  float x_qm_mul, b_qm_mul;  // encoder-side multipliers: pow(1.25, qm_scale - 2) (lib/jxl/enc_cache.cc:66-67)
   float biases[4];
   // input
   uint64_t rgb;        // byte arena: interleaved RGB8

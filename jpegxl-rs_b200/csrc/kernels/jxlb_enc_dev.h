@@ -432,6 +432,132 @@ JXLB_HD void DevEncDcBlock(const DevEPools& E, const DevEFrame& ef, uint32_t bx,
   E.iarena[ef.dcq[2] + pos] = qb;
 }
 
+// AdjustQuantBlockAC (lib/jxl/enc_group.cc:92-316) for channel c of one varblock: a serial pass over the coefficients
+// in layout order (the running sums are float additions in that order), then the quant / dead-zone decisions. `coef`:
+// the channel's float coefficients in the varblock's footprint (row stride PW, C coefficients per footprint row).
+// xsize >= ysize: covered blocks in coefficient-layout order. The inverse matrix is 1 / dm (as for the CfL fit).
+JXLB_HD void DevEncAdjustQuantBlockAC(float scale, uint32_t c, float qm_multiplier, uint32_t quant_kind, uint32_t xsize, uint32_t ysize,
+                                      float* thresholds, const float* coef, uint32_t PW, uint32_t C, const float* dm, int32_t* quant) {
+  const uint32_t kPartialBlockKinds = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 12) | (1u << 13) | (1u << 14) | (1u << 15) |
+                                      (1u << 16) | (1u << 17);
+  if ((1u << quant_kind) & kPartialBlockKinds) return;
+  const float qac = scale * static_cast<float>(*quant);
+  if (xsize > 1 || ysize > 1) {
+    for (int i = 0; i < 4; ++i) {
+      thresholds[i] = thresholds[i] - fminf(fmaxf(0.003f * static_cast<float>(xsize) * static_cast<float>(ysize), 0.f), 0.08f);
+      if (static_cast<double>(thresholds[i]) < 0.54) thresholds[i] = static_cast<float>(0.54);
+    }
+  }
+  float sum_of_highest_freq_row_and_column = 0, sum_of_error = 0, sum_of_vals = 0;
+  float hfNonZeros[4] = {0, 0, 0, 0}, hfMaxError[4] = {0, 0, 0, 0};
+  for (uint32_t y = 0; y < ysize * 8; y++) {
+    for (uint32_t x = 0; x < xsize * 8; x++) {
+      const uint32_t pos = y * 8 * xsize + x;
+      if (x < xsize && y < ysize) continue;
+      const uint32_t hfix = (y >= ysize * 8 / 2 ? 2u : 0u) + (x >= xsize * 8 / 2 ? 1u : 0u);
+      const float in = coef[static_cast<size_t>(pos / C) * PW + pos % C];
+      const float val = in * (((1.0f / dm[pos]) * qac) * qm_multiplier);
+      const float v = (fabsf(val) < thresholds[hfix]) ? 0.0f : rintf(val);
+      const float error = fabsf(val - v);
+      sum_of_error = sum_of_error + error;
+      sum_of_vals = sum_of_vals + fabsf(v);
+      if (c == 1 && v == 0) {
+        if (hfMaxError[hfix] < error) hfMaxError[hfix] = error;
+      }
+      if (v != 0.0f) {
+        hfNonZeros[hfix] = hfNonZeros[hfix] + fabsf(v);
+        const bool in_corner = y >= 7 * ysize && x >= 7 * xsize;
+        const bool on_border = y == ysize * 8 - 1 || x == xsize * 8 - 1;
+        const bool in_larger_corner = x >= 4 * xsize && y >= 4 * ysize;
+        if (in_corner || (on_border && in_larger_corner))
+          sum_of_highest_freq_row_and_column = sum_of_highest_freq_row_and_column + fabsf(val);
+      }
+    }
+  }
+  if (c == 1 && sum_of_vals * 8 < static_cast<float>(xsize * ysize)) {
+    const double kLimit = 0.46, kMul = 0.9999;
+    const int32_t orig_quant = *quant;
+    int32_t new_quant = *quant;
+    for (int i = 1; i < 4; ++i) {
+      if (hfNonZeros[i] == 0.0f && static_cast<double>(hfMaxError[i]) > kLimit) {
+        new_quant = orig_quant + 1;
+        break;
+      }
+    }
+    *quant = new_quant;
+    if (hfNonZeros[3] == 0.0f && static_cast<double>(hfMaxError[3]) > kLimit) {
+      thresholds[3] = static_cast<float>(kMul * static_cast<double>(hfMaxError[3]) * new_quant / orig_quant);
+    } else if ((hfNonZeros[1] == 0.0f && static_cast<double>(hfMaxError[1]) > kLimit) ||
+               (hfNonZeros[2] == 0.0f && static_cast<double>(hfMaxError[2]) > kLimit)) {
+      thresholds[1] = static_cast<float>(kMul * static_cast<double>(fmaxf(hfMaxError[1], hfMaxError[2])) * new_quant / orig_quant);
+      thresholds[2] = thresholds[1];
+    } else if (hfNonZeros[0] == 0.0f && static_cast<double>(hfMaxError[0]) > kLimit) {
+      thresholds[0] = static_cast<float>(kMul * static_cast<double>(hfMaxError[0]) * new_quant / orig_quant);
+    }
+  }
+  {
+    const float all = hfNonZeros[0] + hfNonZeros[1] + hfNonZeros[2] + hfNonZeros[3] + 1;
+    const float mul = c == 0 ? 70.0f : (c == 1 ? 30.0f : 60.0f);
+    if (mul * sum_of_highest_freq_row_and_column >= all) {
+      *quant = static_cast<int32_t>(static_cast<float>(*quant) + mul * sum_of_highest_freq_row_and_column / all);
+      if (*quant >= 256) *quant = 256 - 1;
+    }
+  }
+  if (quant_kind == 0) {
+    if (hfNonZeros[0] + hfNonZeros[1] + hfNonZeros[2] + hfNonZeros[3] < 11) {
+      *quant += 1;
+      if (*quant >= 256) *quant = 256 - 1;
+    }
+  }
+  {
+    const double kMul1[4][3] = {{0.22080615753848404, 0.45797479824262011, 0.29859235095977965},
+                                {0.70109486510286834, 0.16185281305512639, 0.14387691730035473},
+                                {0.114985964456218638, 0.44656840441027695, 0.10587658215149048},
+                                {0.46849665264409396, 0.41239077937781954, 0.088667407767185444}};
+    const double kMul2[4][3] = {{0.27450281941822197, 1.1255766549984996, 0.98950459134128388},
+                                {0.4652168675598285, 0.40945807983455818, 0.36581899811751367},
+                                {0.28034972424715715, 0.9182653201929738, 1.5581531543057416},
+                                {0.26873118114033728, 0.68863712390392484, 1.2082185408666786}};
+    const double kQuantNormalizer = 2.2942708343284721;
+    sum_of_error = static_cast<float>(static_cast<double>(sum_of_error) * kQuantNormalizer);
+    sum_of_vals = static_cast<float>(static_cast<double>(sum_of_vals) * kQuantNormalizer);
+    if (quant_kind >= 4) {
+      int ix = 3;
+      if (quant_kind == 10 || quant_kind == 11) {
+        ix = 1;
+      } else if (quant_kind == 4) {
+        ix = 0;
+      } else if (quant_kind == 5) {
+        ix = 2;
+      }
+      const double limit = kMul1[ix][c] * xsize * ysize * 8 * 8 + kMul2[ix][c] * static_cast<double>(sum_of_vals);
+      int step = static_cast<int>(static_cast<double>(sum_of_error) / limit);
+      if (step >= 2) step = 2;
+      if (step < 0) step = 0;
+      if (static_cast<double>(sum_of_error) > limit) {
+        *quant += step;
+        if (*quant >= 256) *quant = 256 - 1;
+      }
+    }
+  }
+  {
+    const int32_t div = static_cast<int32_t>(xsize * ysize);
+    int32_t activity = (static_cast<int32_t>(hfNonZeros[0]) + div / 2) / div;
+    const int32_t orig_qp_limit = 4 > *quant / 2 ? 4 : *quant / 2;
+    for (int i = 1; i < 4; ++i) {
+      const int32_t a = (static_cast<int32_t>(hfNonZeros[i]) + div / 2) / div;
+      activity = activity < a ? activity : a;
+    }
+    if (activity >= 15) activity = 15;
+    int32_t qp = *quant - activity;
+    if (c == 1) {
+      for (int i = 1; i < 4; ++i) thresholds[i] = static_cast<float>(static_cast<double>(thresholds[i]) + 0.01 * activity);
+    }
+    if (qp < orig_qp_limit) qp = orig_qp_limit;
+    *quant = qp;
+  }
+}
+
 // One varblock (plain DCT strategies), in two steps around the chroma-from-luma fit. MODE 0: forward transform, the
 // float coefficients go to the xyb_raw planes (layout order inside the varblock's footprint); `buf`: 4 * 64 * covered
 // floats. MODE 1: quantisation of those coefficients (Y round trip, chroma relative to decoded Y with the tile's factors).
@@ -470,14 +596,69 @@ JXLB_HD void DevEncVarblock(const DevEPools& E, const DevEFrame& ef, uint32_t bx
   CoopSync<SCOPE>();
   return;
   }
-  const float sd_base = ef.inv_global_scale / static_cast<float>(E.barena[ef.raw_quant + static_cast<size_t>(by) * W + bx] + 1);
-  const float sd0 = sd_base * ef.x_dm, sd1 = sd_base, sd2 = sd_base * ef.b_dm;
   const size_t tile = static_cast<size_t>(by / 8) * ef.cmw + bx / 8;
   const float x_cc = 0.0f + static_cast<float>(reinterpret_cast<const int8_t*>(E.barena + ef.ytox)[tile]) * (1.0f / 84);
   const float b_cc = 1.0f + static_cast<float>(reinterpret_cast<const int8_t*>(E.barena + ef.ytob)[tile]) * (1.0f / 84);
   const float* dm = E.fpool + E.table_off[si.table];
   const uint32_t lcx = Cb > Rb ? Cb : Rb, lcy = Cb > Rb ? Rb : Cb;
   int32_t* out[3] = {E.iarena + ef.coef[0] + origin, E.iarena + ef.coef[1] + origin, E.iarena + ef.coef[2] + origin};
+  uint8_t* raw_quant = E.barena + ef.raw_quant + static_cast<size_t>(by) * W + bx;
+  if (ef.adaptive) {
+    // libjxl's effort-7 quantisation (QuantizeRoundtripYBlockAC + ComputeCoefficients, lib/jxl/enc_group.cc:319-368,
+    // :455-491): per channel a serial statistics pass (threads 0..2; the sums are ordered), then every coefficient on
+    // its own: Y with its dead-zone thresholds, the round trip, chroma relative to decoded Y.
+    const float scale = ef.cfl_scale128 * (1.0f / 128.0f);  // Quantizer::Scale() (exact: a power-of-two factor)
+    const int32_t quant_orig = static_cast<int32_t>(*raw_quant) + 1;
+    float* shared = buf;  // [0..3]: Y thresholds, [4..6]: quant per channel
+    CoopSync<SCOPE>();
+    for (uint32_t c = tid; c < 3; c += nt) {
+      float thres[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+      int32_t quant = quant_orig;
+      const float qm_mul = c == 0 ? ef.x_qm_mul : (c == 1 ? 1.0f : ef.b_qm_mul);
+      DevEncAdjustQuantBlockAC(scale, c, qm_mul, s, lcx, lcy, thres, dct[c], PW, C, dm + c * N, &quant);
+      if (c == 1)
+        for (int k = 0; k < 4; k++) shared[k] = thres[k];
+      shared[4 + c] = static_cast<float>(quant);
+    }
+    CoopSync<SCOPE>();
+    float thres_y[4] = {shared[0], shared[1], shared[2], shared[3]};
+    const float qmax = fmaxf(shared[4], fmaxf(shared[5], shared[6]));
+    const int32_t quant = static_cast<int32_t>(qmax);
+    CoopSync<SCOPE>();
+    float thres_c[4] = {0.58f, 0.62f, 0.62f, 0.62f};
+    if (lcx * lcy >= 4) {
+      for (int i = 0; i < 4; ++i) {
+        thres_c[i] = thres_c[i] - 0.00744f * static_cast<float>(lcx) * static_cast<float>(lcy);
+        if (static_cast<double>(thres_c[i]) < 0.5) thres_c[i] = 0.5f;
+      }
+    }
+    const float qac = scale * static_cast<float>(quant);
+    const float inv_qac = ef.inv_global_scale / static_cast<float>(quant);
+    const float quantv[3] = {qac * ef.x_qm_mul, qac * 1.0f, qac * ef.b_qm_mul};
+    for (uint32_t k = tid; k < N; k += nt) {
+      const size_t at = static_cast<size_t>(k / C) * PW + k % C;
+      const uint32_t ly = k / (lcx * 8), lx = k % (lcx * 8);
+      const uint32_t hfix = (ly >= lcy * 8 / 2 ? 2u : 0u) + (lx >= lcx * 8 / 2 ? 1u : 0u);
+      const float val_y = ((1.0f / dm[N + k]) * quantv[1]) * dct[1][at];
+      int32_t qy = fabsf(val_y) >= thres_y[hfix] ? static_cast<int32_t>(rintf(val_y)) : 0;
+      const float dq_y = (DevAdjustQuantBias(1, qy, ef.biases) * dm[N + k]) * inv_qac;
+      const float in_x = fmaf(-x_cc, dq_y, dct[0][at]);
+      const float in_b = fmaf(-b_cc, dq_y, dct[2][at]);
+      const float val_x = ((1.0f / dm[k]) * quantv[0]) * in_x;
+      const float val_b = ((1.0f / dm[2 * N + k]) * quantv[2]) * in_b;
+      int32_t qx = fabsf(val_x) >= thres_c[hfix] ? static_cast<int32_t>(rintf(val_x)) : 0;
+      int32_t qb = fabsf(val_b) >= thres_c[hfix] ? static_cast<int32_t>(rintf(val_b)) : 0;
+      if (ly < lcy && lx < lcx) qx = qy = qb = 0;  // the lowest frequencies come from the DC image
+      out[0][at] = qx;
+      out[1][at] = qy;
+      out[2][at] = qb;
+    }
+    if (tid == 0) *raw_quant = static_cast<uint8_t>(quant - 1);
+    CoopSync<SCOPE>();
+    return;
+  }
+  const float sd_base = ef.inv_global_scale / static_cast<float>(*raw_quant + 1);
+  const float sd0 = sd_base * ef.x_dm, sd1 = sd_base, sd2 = sd_base * ef.b_dm;
   for (uint32_t k = tid; k < N; k += nt) {
     const size_t from = static_cast<size_t>(k / C) * PW + k % C;
     const float y_mul = dm[N + k] * sd1;

@@ -1072,6 +1072,151 @@ inline void ComputeGlobalScaleAndQuant(float quant_dc, float quant_median, float
 }
 }  // namespace aq
 
+// ---------------------------------------------------------------- quantisation of a varblock as libjxl's effort 7 does it (E8)
+// AdjustQuantBlockAC / QuantizeBlockAC / QuantizeRoundtripYBlockAC, lib/jxl/enc_group.cc:46-368, driven as in
+// ComputeCoefficients (:455-493). `xsize` >= `ysize` are the covered blocks in coefficient-layout order. The inverse
+// dequantisation matrix is taken as 1 / matrix (as for the chroma-from-luma fit). Plain C++ of the reference
+// (float / double mixes included) is evaluated as written, without contraction.
+namespace e8 {
+inline void AdjustQuantBlockAC(float scale, size_t c, float qm_multiplier, int quant_kind, size_t xsize, size_t ysize,
+                               float* thresholds, const float* block_in, const float* dm, int32_t* quant) {
+  const uint32_t kPartialBlockKinds = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 12) | (1u << 13) | (1u << 14) | (1u << 15) |
+                                      (1u << 16) | (1u << 17);  // IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, AFV0..3
+  if ((1u << quant_kind) & kPartialBlockKinds) return;
+  const float qac = scale * (*quant);
+  if (xsize > 1 || ysize > 1) {
+    for (int i = 0; i < 4; ++i) {
+      thresholds[i] -= std::min(std::max(0.003f * xsize * ysize, 0.f), 0.08f);
+      if (thresholds[i] < 0.54) thresholds[i] = 0.54;
+    }
+  }
+  float sum_of_highest_freq_row_and_column = 0, sum_of_error = 0, sum_of_vals = 0;
+  float hfNonZeros[4] = {}, hfMaxError[4] = {};
+  for (size_t y = 0; y < ysize * 8; y++) {
+    for (size_t x = 0; x < xsize * 8; x++) {
+      const size_t pos = y * 8 * xsize + x;
+      if (x < xsize && y < ysize) continue;
+      const size_t hfix = (static_cast<size_t>(y >= ysize * 8 / 2) * 2 + static_cast<size_t>(x >= xsize * 8 / 2));
+      const float val = block_in[pos] * ((1.0f / dm[pos]) * qac * qm_multiplier);
+      const float v = (std::abs(val) < thresholds[hfix]) ? 0 : rintf(val);
+      const float error = std::abs(val - v);
+      sum_of_error += error;
+      sum_of_vals += std::abs(v);
+      if (c == 1 && v == 0) {
+        if (hfMaxError[hfix] < error) hfMaxError[hfix] = error;
+      }
+      if (v != 0.0f) {
+        hfNonZeros[hfix] += std::abs(v);
+        const bool in_corner = y >= 7 * ysize && x >= 7 * xsize;
+        const bool on_border = y == ysize * 8 - 1 || x == xsize * 8 - 1;
+        const bool in_larger_corner = x >= 4 * xsize && y >= 4 * ysize;
+        if (in_corner || (on_border && in_larger_corner)) sum_of_highest_freq_row_and_column += std::abs(val);
+      }
+    }
+  }
+  if (c == 1 && sum_of_vals * 8 < xsize * ysize) {
+    const double kLimit = 0.46, kMul = 0.9999;
+    const int32_t orig_quant = *quant;
+    int32_t new_quant = *quant;
+    for (int i = 1; i < 4; ++i) {
+      if (hfNonZeros[i] == 0.0 && hfMaxError[i] > kLimit) {
+        new_quant = orig_quant + 1;
+        break;
+      }
+    }
+    *quant = new_quant;
+    if (hfNonZeros[3] == 0.0 && hfMaxError[3] > kLimit) {
+      thresholds[3] = kMul * hfMaxError[3] * new_quant / orig_quant;
+    } else if ((hfNonZeros[1] == 0.0 && hfMaxError[1] > kLimit) || (hfNonZeros[2] == 0.0 && hfMaxError[2] > kLimit)) {
+      thresholds[1] = kMul * std::max(hfMaxError[1], hfMaxError[2]) * new_quant / orig_quant;
+      thresholds[2] = thresholds[1];
+    } else if (hfNonZeros[0] == 0.0 && hfMaxError[0] > kLimit) {
+      thresholds[0] = kMul * hfMaxError[0] * new_quant / orig_quant;
+    }
+  }
+  {
+    const float all = hfNonZeros[0] + hfNonZeros[1] + hfNonZeros[2] + hfNonZeros[3] + 1;
+    const float mul[3] = {70, 30, 60};
+    if (mul[c] * sum_of_highest_freq_row_and_column >= all) {
+      *quant += mul[c] * sum_of_highest_freq_row_and_column / all;
+      if (*quant >= 256) *quant = 256 - 1;
+    }
+  }
+  if (quant_kind == 0) {
+    if (hfNonZeros[0] + hfNonZeros[1] + hfNonZeros[2] + hfNonZeros[3] < 11) {
+      *quant += 1;
+      if (*quant >= 256) *quant = 256 - 1;
+    }
+  }
+  {
+    static const double kMul1[4][3] = {{0.22080615753848404, 0.45797479824262011, 0.29859235095977965},
+                                       {0.70109486510286834, 0.16185281305512639, 0.14387691730035473},
+                                       {0.114985964456218638, 0.44656840441027695, 0.10587658215149048},
+                                       {0.46849665264409396, 0.41239077937781954, 0.088667407767185444}};
+    static const double kMul2[4][3] = {{0.27450281941822197, 1.1255766549984996, 0.98950459134128388},
+                                       {0.4652168675598285, 0.40945807983455818, 0.36581899811751367},
+                                       {0.28034972424715715, 0.9182653201929738, 1.5581531543057416},
+                                       {0.26873118114033728, 0.68863712390392484, 1.2082185408666786}};
+    const double kQuantNormalizer = 2.2942708343284721;
+    sum_of_error *= kQuantNormalizer;
+    sum_of_vals *= kQuantNormalizer;
+    if (quant_kind >= 4) {  // >= DCT16X16
+      int ix = 3;
+      if (quant_kind == 10 || quant_kind == 11) {
+        ix = 1;
+      } else if (quant_kind == 4) {
+        ix = 0;
+      } else if (quant_kind == 5) {
+        ix = 2;
+      }
+      const double limit = kMul1[ix][c] * xsize * ysize * 8 * 8 + kMul2[ix][c] * sum_of_vals;
+      int step = sum_of_error / limit;
+      if (step >= 2) step = 2;
+      if (step < 0) step = 0;
+      if (sum_of_error > limit) {
+        *quant += step;
+        if (*quant >= 256) *quant = 256 - 1;
+      }
+    }
+  }
+  {
+    const int32_t div = (xsize * ysize);
+    int32_t activity = (static_cast<int32_t>(hfNonZeros[0]) + div / 2) / div;
+    const int32_t orig_qp_limit = std::max(4, *quant / 2);
+    for (int i = 1; i < 4; ++i) activity = std::min(activity, (static_cast<int32_t>(hfNonZeros[i]) + div / 2) / div);
+    if (activity >= 15) activity = 15;
+    int32_t qp = *quant - activity;
+    if (c == 1) {
+      for (int i = 1; i < 4; ++i) thresholds[i] += 0.01 * activity;
+    }
+    if (qp < orig_qp_limit) qp = orig_qp_limit;
+    *quant = qp;
+  }
+}
+
+inline void QuantizeBlockAC(float scale, size_t c, float qm_multiplier, size_t xsize, size_t ysize, float* thresholds,
+                            const float* block_in, const float* dm, int32_t quant, int32_t* block_out) {
+  const float qac = scale * quant;
+  if (c != 1 && xsize * ysize >= 4) {
+    for (int i = 0; i < 4; ++i) {
+      thresholds[i] -= 0.00744f * xsize * ysize;
+      if (thresholds[i] < 0.5) thresholds[i] = 0.5;
+    }
+  }
+  const float quantv = qac * qm_multiplier;
+  for (size_t y = 0; y < ysize * 8; y++) {
+    const size_t yfix = static_cast<size_t>(y >= ysize * 8 / 2) * 2;
+    for (size_t x = 0; x < xsize * 8; x++) {
+      const size_t off = y * 8 * xsize + x;
+      const float threshold = thresholds[yfix + static_cast<size_t>(x >= xsize * 8 / 2)];
+      const float q = (1.0f / dm[off]) * quantv;
+      const float val = q * block_in[off];
+      block_out[off] = std::abs(val) >= threshold ? static_cast<int32_t>(rintf(val)) : 0;
+    }
+  }
+}
+}  // namespace e8
+
 inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, const EncodeParams& p,
                                          EncoderStats* stats = nullptr) {
   JXLO_CHECK(xsize > 0 && ysize > 0, "empty image");
@@ -1348,8 +1493,39 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
         const float x_cc = 0.0f + ytox[tile] * (1.0f / 84), b_cc = 1.0f + ytob[tile] * (1.0f / 84);
         for (int c = 0; c < 3; c++)
           TransformFromPixels(s, xyb[c].Row((r.y0 + by) * 8) + (r.x0 + bx) * 8, PW, coeff.data() + c * size, scratch.data());
+        if (adaptive) {
+          // QuantizeRoundtripYBlockAC + the X / B quantisation of ComputeCoefficients (lib/jxl/enc_group.cc:319-368, :455-491)
+          const float scale = global_scale * (1.0f / 65536);
+          const size_t lx = std::max(cx, cy), ly = std::min(cx, cy);
+          const float qm_mul[3] = {std::pow(1.25f, p.x_qm_scale - 2.0f), 1.0f, std::pow(1.25f, p.b_qm_scale - 2.0f)};
+          const int32_t quant_orig = raw_quant[pos];
+          int32_t max_quant = 0;
+          float thres_y[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+          for (int c : {1, 0, 2}) {
+            float thres[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+            int32_t quant = quant_orig;
+            e8::AdjustQuantBlockAC(scale, c, qm_mul[c], s, lx, ly, thres, coeff.data() + c * size, dm.data() + c * size, &quant);
+            if (c == 1)
+              for (int k = 0; k < 4; k++) thres_y[k] = thres[k];
+            max_quant = std::max(quant, max_quant);
+          }
+          const int32_t quant = max_quant;
+          e8::QuantizeBlockAC(scale, 1, 1.0f, lx, ly, thres_y, coeff.data() + size, dm.data() + size, quant, quantized + size);
+          const float inv_qac = inv_global_scale / quant;
+          for (size_t k = 0; k < size; k++) {
+            const float dq_y = (AdjustQuantBias(1, quantized[size + k], biases) * dm[size + k]) * inv_qac;
+            coeff[k] = std::fmaf(-x_cc, dq_y, coeff[k]);
+            coeff[2 * size + k] = std::fmaf(-b_cc, dq_y, coeff[2 * size + k]);
+          }
+          for (int c : {0, 2}) {
+            float thres[4] = {0.58f, 0.62f, 0.62f, 0.62f};
+            e8::QuantizeBlockAC(scale, c, qm_mul[c], lx, ly, thres, coeff.data() + c * size, dm.data() + c * size, quant,
+                                quantized + c * size);
+          }
+          raw_quant[pos] = quant;
+        }
         // Y first (the decoder adds ratio * dequantised Y to X and B)
-        for (size_t k = 0; k < size; k++) {
+        for (size_t k = 0; k < size && !adaptive; k++) {
           const int32_t q = static_cast<int32_t>(std::lrintf(coeff[size + k] / (dm[size + k] * sd[1])));
           quantized[size + k] = q;
           const float dq_y = AdjustQuantBias(1, q, biases) * (dm[size + k] * sd[1]);
