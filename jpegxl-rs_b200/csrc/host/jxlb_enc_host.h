@@ -633,6 +633,8 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
   }
   ef->quant_field = f;
   f += (nb + 15) & ~uint64_t{15};
+  ef->adj_thres = f;
+  f += 4 * ((nb + 15) & ~uint64_t{15});
   for (int c = 0; c < 3; c++) {
     ef->coef[c] = i;
     i += px;
@@ -642,6 +644,7 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
     i += nb;
   }
   ef->first_index = i; i += nb;
+  ef->adj_quant = i; i += nb;
   ef->block_of_num = i; i += d.num_dc_groups * 65536;
   for (int c = 0; c < 3; c++) {
     ef->blk_nz[c] = i; i += nb;

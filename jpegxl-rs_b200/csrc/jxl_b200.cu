@@ -1504,6 +1504,13 @@ __global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, const D
   }
 }
 
+// AdjustQuantBlockAC: thread per (block, channel); blockIdx.y = channel, blockIdx.z = frame.
+__global__ void __launch_bounds__(128) k_enc_adjust(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.z];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ef.xblocks * ef.yblocks) DevEncAdjustVarblockChannel(E, ef, i % ef.xblocks, i / ef.xblocks, blockIdx.y);
+}
+
 // Coefficient-order statistics: thread per group, then CTA per group (see DevEncOrderStatsGroup).
 __global__ void __launch_bounds__(32) k_enc_group_orders(DevEPools E, const DevEFrame* frames) {
   const DevEFrame& ef = frames[blockIdx.y];
@@ -1693,6 +1700,8 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
         e.blk_bucket[c] += ibase;
       }
       e.quant_field += fbase;
+      e.adj_thres += fbase;
+      e.adj_quant += ibase;
       e.raw_quant += bbase;
       e.first_index += ibase;
       e.block_of_num += ibase;
@@ -1785,6 +1794,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     k_enc_dc<<<dim3((maxW * maxH + 255) / 256, nf), 256, 0, s>>>(E, d_efs.p);
     k_enc_coeffs<0><<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
     k_enc_cfl<<<dim3(((maxW + 7) / 8) * ((maxH + 7) / 8), nf), 128, 4 * 4096 * sizeof(float), s>>>(E, d_efs.p);
+    if (p.adaptive_quant) k_enc_adjust<<<dim3((maxW * maxH + 127) / 128, 3, nf), 128, 0, s>>>(E, d_efs.p);
     k_enc_coeffs<1><<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
     // ---- coefficient orders: zero counts on the device, sort + permutation coding on the host, orders back
     std::vector<CustomOrders> orders(n);

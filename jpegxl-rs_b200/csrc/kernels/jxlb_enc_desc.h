@@ -71,6 +71,8 @@ struct DevEFrame {
   float cfl_scale128;     // Quantizer::Scale() * 128 (times the raw quant: the weighting of the CfL fit)
   uint64_t quant_field;   // float arena: xblocks * yblocks
   uint64_t raw_quant;     // byte arena: raw quant - 1 at the first block of every varblock
+  uint64_t adj_thres;     // float arena: 4 planes of xblocks * yblocks: the Y dead-zone thresholds of the varblock (k_enc_adjust)
+  uint64_t adj_quant;     // int arena (zeroed): the varblock's adjusted quant, max over the channels
   // int arena
   uint64_t coef[3];    // quantised coefficients, stored in each varblock's pixel footprint (row-major)
   uint64_t dcq[3];     // quantised DC: [0] = Y, [1] = X, [2] = B, xblocks * yblocks

@@ -558,6 +558,36 @@ JXLB_HD void DevEncAdjustQuantBlockAC(float scale, uint32_t c, float qm_multipli
   }
 }
 
+// Channel c of the varblock at (bx, by): AdjustQuantBlockAC on the float coefficients k_enc_coeffs<0> left in the xyb_raw
+// planes. One thread per (varblock, channel): the statistics pass is serial per channel, the varblocks are not. Results:
+// the Y thresholds (c == 1) and the maximum of the three channels' adjusted quants (the int arena is zeroed per batch).
+JXLB_HD void DevEncAdjustVarblockChannel(const DevEPools& E, const DevEFrame& ef, uint32_t bx, uint32_t by, uint32_t c) {
+  const uint32_t W = ef.xblocks, PW = W * 8;
+  const size_t pos = static_cast<size_t>(by) * W + bx;
+  const uint8_t a = E.barena[ef.acs + pos];
+  if (!ef.adaptive || !(a & 1) || a == 0xFF) return;
+  const uint32_t s = a >> 1;
+  const StrategyInfo si = UnpackStrategyInfo(E.upool[E.sinfo_off + s]);
+  const uint32_t Rb = si.cy, Cb = si.cx, C = 8 * Cb, N = 64 * Rb * Cb;
+  const uint32_t lcx = Cb > Rb ? Cb : Rb, lcy = Cb > Rb ? Rb : Cb;
+  const size_t origin = static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+  const float* dm = E.fpool + E.table_off[si.table];
+  const float scale = ef.cfl_scale128 * (1.0f / 128.0f);  // Quantizer::Scale() (exact: a power-of-two factor)
+  float thres[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+  int32_t quant = static_cast<int32_t>(E.barena[ef.raw_quant + pos]) + 1;
+  const float qm_mul = c == 0 ? ef.x_qm_mul : (c == 1 ? 1.0f : ef.b_qm_mul);
+  DevEncAdjustQuantBlockAC(scale, c, qm_mul, s, lcx, lcy, thres, E.farena + ef.xyb_raw[c] + origin, PW, C, dm + c * N, &quant);
+  if (c == 1) {
+    const size_t stride = (static_cast<size_t>(W) * ef.yblocks + 15) & ~size_t{15};
+    for (uint32_t k = 0; k < 4; k++) E.farena[ef.adj_thres + k * stride + pos] = thres[k];
+  }
+#if defined(__CUDA_ARCH__)
+  atomicMax(E.iarena + ef.adj_quant + pos, quant);
+#else
+  if (E.iarena[ef.adj_quant + pos] < quant) E.iarena[ef.adj_quant + pos] = quant;
+#endif
+}
+
 // One varblock (plain DCT strategies), in two steps around the chroma-from-luma fit. MODE 0: forward transform, the
 // float coefficients go to the xyb_raw planes (layout order inside the varblock's footprint); `buf`: 4 * 64 * covered
 // floats. MODE 1: quantisation of those coefficients (Y round trip, chroma relative to decoded Y with the tile's factors).
@@ -605,26 +635,14 @@ JXLB_HD void DevEncVarblock(const DevEPools& E, const DevEFrame& ef, uint32_t bx
   uint8_t* raw_quant = E.barena + ef.raw_quant + static_cast<size_t>(by) * W + bx;
   if (ef.adaptive) {
     // libjxl's effort-7 quantisation (QuantizeRoundtripYBlockAC + ComputeCoefficients, lib/jxl/enc_group.cc:319-368,
-    // :455-491): per channel a serial statistics pass (threads 0..2; the sums are ordered), then every coefficient on
-    // its own: Y with its dead-zone thresholds, the round trip, chroma relative to decoded Y.
+    // :455-491): the per-channel statistics pass ran in k_enc_adjust (DevEncAdjustVarblockChannel); here every
+    // coefficient on its own: Y with its dead-zone thresholds, the round trip, chroma relative to decoded Y.
     const float scale = ef.cfl_scale128 * (1.0f / 128.0f);  // Quantizer::Scale() (exact: a power-of-two factor)
-    const int32_t quant_orig = static_cast<int32_t>(*raw_quant) + 1;
-    float* shared = buf;  // [0..3]: Y thresholds, [4..6]: quant per channel
-    CoopSync<SCOPE>();
-    for (uint32_t c = tid; c < 3; c += nt) {
-      float thres[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-      int32_t quant = quant_orig;
-      const float qm_mul = c == 0 ? ef.x_qm_mul : (c == 1 ? 1.0f : ef.b_qm_mul);
-      DevEncAdjustQuantBlockAC(scale, c, qm_mul, s, lcx, lcy, thres, dct[c], PW, C, dm + c * N, &quant);
-      if (c == 1)
-        for (int k = 0; k < 4; k++) shared[k] = thres[k];
-      shared[4 + c] = static_cast<float>(quant);
-    }
-    CoopSync<SCOPE>();
-    float thres_y[4] = {shared[0], shared[1], shared[2], shared[3]};
-    const float qmax = fmaxf(shared[4], fmaxf(shared[5], shared[6]));
-    const int32_t quant = static_cast<int32_t>(qmax);
-    CoopSync<SCOPE>();
+    const size_t bpos = static_cast<size_t>(by) * W + bx;
+    const size_t tstride = (static_cast<size_t>(W) * ef.yblocks + 15) & ~size_t{15};
+    const float thres_y[4] = {E.farena[ef.adj_thres + bpos], E.farena[ef.adj_thres + tstride + bpos],
+                              E.farena[ef.adj_thres + 2 * tstride + bpos], E.farena[ef.adj_thres + 3 * tstride + bpos]};
+    const int32_t quant = E.iarena[ef.adj_quant + bpos];  // (k_enc_adjust: max over the three channels)
     float thres_c[4] = {0.58f, 0.62f, 0.62f, 0.62f};
     if (lcx * lcy >= 4) {
       for (int i = 0; i < 4; ++i) {

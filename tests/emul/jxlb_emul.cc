@@ -375,6 +375,9 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
                        static_cast<int8_t>(barena[ef.ytob + ty * ef.cmw + tx]), cfl_vals[70], cfl_vals[4096 + 70], cfl_vals[8192 + 70],
                        cfl_vals[12288 + 70]);
       }
+    for (uint32_t c = 0; c < 3; c++)  // k_enc_adjust
+      for (uint32_t by = 0; by < H; by++)
+        for (uint32_t bx = 0; bx < W; bx++) DevEncAdjustVarblockChannel(E, ef, bx, by, c);
     for (uint32_t by = 0; by < H; by++)  // k_enc_coeffs<1>: quantisation
       for (uint32_t bx = 0; bx < W; bx++) {
         const uint8_t a = barena[static_cast<size_t>(by) * W + bx];
