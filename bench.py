@@ -340,9 +340,24 @@ def main():
     files = wl.files
     # handles in flight: at most --inflight, and a divisor of --steps so that every handle runs the same number of steps
     # (no tail in which only a few handles are left)
-    nfl = max(d for d in range(1, max(1, min(args.inflight, args.steps)) + 1) if args.steps % d == 0)
-    decs = [pkg.BatchDecoder(local_rank) for _ in range(nfl)]
-    for d in decs:
+    # ... and no more than fit into HBM: the first handle's footprint (arenas + output + bitstreams) is measured, the
+    # others may take 85 % of what is free after it
+    free0, _ = torch.cuda.mem_get_info()
+    decs = [pkg.BatchDecoder(local_rank)]
+    decs[0].set_input(files, wl.channels, pkg.JXL_TYPE_UINT8)
+    decs[0].run()
+    decs[0].wait()  # (the first wait may regrow the token arena)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    per_handle = max(free0 - free1, 1)
+    fit = 1 + int(0.85 * free1 // per_handle)
+    cap = max(1, min(args.inflight, args.steps, fit))
+    nfl = max(d for d in range(1, cap + 1) if args.steps % d == 0)
+    if rank == 0 and nfl < args.inflight:
+        print("handles in flight: %d (asked for %d; %d steps; %.1f GB of HBM per handle, %.1f GB free)"
+              % (nfl, args.inflight, args.steps, per_handle / 1e9, free1 / 1e9), file=sys.stderr)
+    decs += [pkg.BatchDecoder(local_rank) for _ in range(nfl - 1)]
+    for d in decs[1:]:
         d.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8)
     dec = decs[0]
     tstreams = [torch.cuda.Stream() for _ in range(nfl)]

@@ -55,6 +55,16 @@ def test_fused_render_tile_borders(h, w, epf, gab):
         assert np.array_equal(got.view(np.uint8), jxlo.decode(data, nc, dt).view(np.uint8))
 
 
+def test_small_div_is_exact_over_its_domain():
+    # DevSmallDiv (jxlb_vardct_dev.h): i / d as (i * ceil(2^20 / d)) >> 20 for the tile index splits of k_render_fused
+    # (i < 80 * 46 cells, 64 <= d <= 80 columns)
+    for d in range(64, 81):
+        m = ((1 << 20) + d - 1) // d
+        i = np.arange(0, 4096, dtype=np.uint64)
+        assert np.array_equal((i * m) >> 20, i // d)
+        assert int(i.max()) * m < 2 ** 32
+
+
 SINGLE_SECTION = [(80, 100, 1, 3), (256, 256, 2, 4), (17, 9, 1, 5), (200, 256, 0, 6)]
 
 
