@@ -147,11 +147,11 @@ __global__ void __launch_bounds__(256) k_write_output_rgba8(DevPools P, const De
 // ------------------------------------------------------------------ VarDCT kernels
 // blockIdx.x indexes a flat list of (frame, DC group) pairs.
 __global__ void __launch_bounds__(256) k_dc_finish(DevPools P, DevVPools V, const uint2* dcg_list) {
-  extern __shared__ uint8_t acs_smem[];  // 64 KiB: the strategy map of one DC group (256 x 256 blocks)
+  __shared__ uint32_t occ_s[kDcOccWords];  // one bit per block of the DC group (256 x 256 blocks): covered or not
   __shared__ uint16_t stage_s[kDcStageEntries];
   __shared__ uint32_t sinfo_s[kNumStrategies];
   const uint2 e = dcg_list[blockIdx.x];
-  DevDcGroupFinish<2>(P, V, e.x, e.y, threadIdx.x, blockDim.x, blockIdx.x, acs_smem, stage_s, sinfo_s);
+  DevDcGroupFinish<2>(P, V, e.x, e.y, threadIdx.x, blockDim.x, blockIdx.x, occ_s, stage_s, sinfo_s);
 }
 
 __global__ void __launch_bounds__(256) k_dc_smooth(DevVPools V) {
@@ -633,7 +633,6 @@ JxlB200Decoder* JxlB200DecoderCreate(int device) {
   }
   cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, kIdctSmemFloats * sizeof(float));
   cudaFuncSetAttribute(k_idct_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kMidSmemFloats * sizeof(float));
-  cudaFuncSetAttribute(k_dc_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
   cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        6 * DevRenderTileFloats(kRtMaxHalo) * sizeof(float));
   cudaFuncSetAttribute(k_modular_decode_sparse<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -987,7 +986,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     {
       ScopedTimer t(dec, s, kKDcFinish);
       CUDA_OK(cudaMemsetAsync(dec->d_dc_status.p, 0, (dec->dcg_list.size() + 2) * 4, s));
-      k_dc_finish<<<dec->dcg_list.size(), 256, 65536, s>>>(P, V, dec->d_dcg_list.p);
+      k_dc_finish<<<dec->dcg_list.size(), 256, 0, s>>>(P, V, dec->d_dcg_list.p);
       dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(256, (dec->max_blocks + 255) / 256)), nvf);
       k_dc_smooth<<<grid, 256, 0, s>>>(V);
       launches += 2;

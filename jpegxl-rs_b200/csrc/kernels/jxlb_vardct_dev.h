@@ -78,14 +78,24 @@ JXLB_HD void CoopSync() {
 constexpr float kDevSqrt2 = 1.41421356237f;
 
 // ---------------------------------------------------------------- DC groups
-// `acs_local`: xs * ys bytes of scratch for the group's strategy map (shared memory on the device: the serial scan
-// below then runs on shared-memory latency), or nullptr to work in the frame's map directly.
+// `occ`: kDcOccWords words of scratch (shared memory on the device): one bit per block of the group, set when a varblock
+// covers it. The serial scan below finds the next free block with a find-first-set per 32 blocks and marks / tests a
+// varblock with one word per block row (a varblock never crosses a 32-block boundary); the strategy bytes go straight
+// to the frame's map.
+constexpr uint32_t kDcOccWords = 256 * 8;
+JXLB_HD uint32_t DevFfs(uint32_t v) {  // 1-based index of the lowest set bit (v != 0)
+#if defined(__CUDA_ARCH__)
+  return static_cast<uint32_t>(__ffs(static_cast<int>(v)));
+#else
+  return static_cast<uint32_t>(__builtin_ffs(static_cast<int>(v)));
+#endif
+}
 constexpr uint32_t kDcStageEntries = 2048;  // list entries staged per chunk (uint16 each) by DevDcGroupFinish
 
 // `stage` / `sinfo_stage`: kDcStageEntries uint16 + kNumStrategies uint32 of shared memory for the serial scan, or nullptr.
 template <int SCOPE>
 JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t frame, uint32_t g, uint32_t tid, uint32_t nt,
-                              uint32_t status_index, uint8_t* acs_local, uint16_t* stage = nullptr,
+                              uint32_t status_index, uint32_t* occ, uint16_t* stage = nullptr,
                               uint32_t* sinfo_stage = nullptr) {
   const DevVFrame& vf = V.frames[frame];
   const uint32_t W = vf.xblocks, H = vf.yblocks;
@@ -109,8 +119,8 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
   float* dcb = V.farena + vf.dc[2];
   uint8_t* acs_frame = V.barena + vf.acs;
   // the map the scan works on: element (x, y) of the group at acs[y * astride + x]
-  uint8_t* acs = acs_local ? acs_local : acs_frame + static_cast<size_t>(y0) * W + x0;
-  const uint32_t astride = acs_local ? xs : W;
+  uint8_t* acs = acs_frame + static_cast<size_t>(y0) * W + x0;
+  const uint32_t astride = W;
   uint8_t* qdc = V.barena + vf.qdc;
   uint8_t* sharp = V.barena + vf.sharp;
   uint16_t* rawq = reinterpret_cast<uint16_t*>(V.barena + vf.rawq);
@@ -141,6 +151,10 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
     if (sh < 0 || sh >= 8) status |= kVBadStream;
     sharp[pos] = static_cast<uint8_t>(sh & 7);
     acs[static_cast<size_t>(y) * astride + x] = 0xFF;
+  }
+  for (uint32_t i = tid; i < ys * 8; i += nt) {  // blocks past the group's width count as covered
+    const uint32_t first = (i & 7) * 32;
+    occ[i] = first >= xs ? 0xFFFFFFFFu : (xs - first >= 32 ? 0u : 0xFFFFFFFFu << (xs - first));
   }
   // colour correlation maps (one entry per 64x64 tile)
   const uint32_t cw = (xs + 7) >> 3, chh = (ys + 7) >> 3, cx0 = x0 >> 3, cy0 = y0 >> 3;
@@ -182,11 +196,19 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
         for (; iy < ys && !(status & kVBadStream); iy++, ix = 0) {
           const uint32_t y = y0 + iy;
           bool paused = false;
-          for (; ix < xs; ix++) {
+          uint32_t* orow = occ + iy * 8;
+          for (;;) {
+            // the next block of this row that no varblock covers yet
+            uint32_t wi = ix >> 5, free_bits = 0;
+            for (; wi < 8; wi++, ix = wi << 5) {
+              free_bits = ~orow[wi] & (0xFFFFFFFFu << (ix & 31));
+              if (free_bits) break;
+            }
+            if (!free_bits) break;
+            ix = (wi << 5) + DevFfs(free_bits) - 1;
             const uint32_t x = x0 + ix;
             const size_t pos = static_cast<size_t>(y) * W + x;
             uint8_t* cell = acs + static_cast<size_t>(iy) * astride + ix;
-            if (*cell != 0xFF) continue;
             if (num >= chunk_end) {
               if (last_chunk) status |= kVBadStream;  // more varblocks than list entries
               paused = true;
@@ -212,13 +234,15 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
               status |= kVBadStream;
               break;
             }
-            bool overlap = false;
-            for (uint32_t jy = 0; jy < si.cy; jy++)
-              for (uint32_t jx = 0; jx < si.cx; jx++) {
-                uint8_t& e = cell[static_cast<size_t>(jy) * astride + jx];
-                overlap |= e != 0xFF;
-                e = static_cast<uint8_t>((raw << 1) | ((jy | jx) == 0 ? 1 : 0));
-              }
+            const uint32_t mask = (si.cx >= 32 ? 0xFFFFFFFFu : ((1u << si.cx) - 1u)) << (ix & 31);
+            uint32_t overlap = 0;
+            for (uint32_t jy = 0; jy < si.cy; jy++) {
+              uint32_t& w = orow[jy * 8 + wi];
+              overlap |= w & mask;
+              w |= mask;
+              for (uint32_t jx = 0; jx < si.cx; jx++)
+                cell[static_cast<size_t>(jy) * astride + jx] = static_cast<uint8_t>((raw << 1) | ((jy | jx) == 0 ? 1 : 0));
+            }
             if (overlap) {
               status |= kVBadStream;
               break;
@@ -235,10 +259,6 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
     }
   }
   CoopSync<SCOPE>();
-  if (acs_local) {
-    for (uint32_t i = tid; i < xs * ys; i += nt)
-      acs_frame[static_cast<size_t>(y0 + i / xs) * W + x0 + i % xs] = acs_local[i];
-  }
   // (c) EPF sigma per block (ComputeSigma): every varblock fills the blocks it covers
   if (vf.epf_iters > 0) {
     float* inv_sigma = V.farena + vf.inv_sigma;

@@ -148,13 +148,13 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       for (const DevRefFrame& rf : b.ref_frames)  // k_ref_frames
         for (uint32_t i = 0; i < rf.w * rf.h; i++) DevRefFrameSample(P, V, rf, i);
       uint32_t dcg = 0;
-      std::vector<uint8_t> acs_local(65536);  // stands in for the kernel's shared memory
+      std::vector<uint32_t> occ(kDcOccWords);  // stands in for the kernel's shared memory
       for (uint32_t f = 0; f < b.vframes.size(); f++) {
         const DevVFrame& vf = b.vframes[f];
         std::vector<uint16_t> stage(kDcStageEntries);
         uint32_t sinfo_stage[kNumStrategies];
         for (uint32_t g = 0; g < vf.xdcgroups * vf.ydcgroups; g++, dcg++)
-          DevDcGroupFinish<0>(P, V, f, g, 0, 1, dcg, acs_local.data(), stage.data(), sinfo_stage);
+          DevDcGroupFinish<0>(P, V, f, g, 0, 1, dcg, occ.data(), stage.data(), sinfo_stage);
         if (!vf.skip_dc_smoothing)
           for (uint32_t y = 0; y < vf.yblocks; y++)
             for (uint32_t x = 0; x < vf.xblocks; x++) DevDcSmoothBlock(V, vf, x, y);
