@@ -1,3 +1,3 @@
 set -x
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py > gpurun_out/r1_bench_final_default.json 2> gpurun_out/bench_final.err; python tools/show_bench.py gpurun_out/r1_bench_final_default.json | head -4; tail -1 gpurun_out/bench_final.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r1_launches_bench_default_b256_final.csv python bench.py --steps 1 --warmup 1 --inflight 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+tail -1 gpurun_out/ncu_bench.log | cut -c1-200
