@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <functional>
 #include <thread>
 #include <tuple>
@@ -426,7 +427,12 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
   BundleStreams(batch);
   if (!batch->vframes.empty()) {
     // pixel-plane slots for one wave of frames, after the per-frame planes of the float arena
-    const uint64_t per_frame = 6 * batch->pix_plane_max;
+    // Two sets of three planes (ping-pong of the per-pixel filter kernels) only when those kernels run: frames
+    // without patches go through the fused render tile, which reads set 0 and writes output samples, so a wave holds
+    // twice as many frames in the same memory (half as many launches and kernel tails per batch).
+    const bool two_sets = !batch->patches.empty() || std::getenv("JXLB200_UNFUSED_RENDER") != nullptr ||
+                          std::getenv("JXLB_EMUL_UNFUSED") != nullptr;
+    const uint64_t per_frame = (two_sets ? 6 : 3) * batch->pix_plane_max;
     batch->wave_frames = static_cast<uint32_t>(
         std::max<uint64_t>(1, std::min<uint64_t>(batch->vframes.size(), kWavePixelBytes / (per_frame * 4))));
     const uint64_t pix_base = batch->farena_size;
@@ -434,7 +440,8 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
     for (size_t i = 0; i < batch->vframes.size(); i++) {
       const uint64_t slot = pix_base + (i % batch->wave_frames) * per_frame;
       for (int set = 0; set < 2; set++)
-        for (int c = 0; c < 3; c++) batch->vframes[i].pix[set][c] = slot + (set * 3 + c) * batch->pix_plane_max;
+        for (int c = 0; c < 3; c++)
+          batch->vframes[i].pix[set][c] = slot + ((two_sets ? set * 3 : 0) + c) * batch->pix_plane_max;
     }
     JXLB_CHECK(batch->tok_size < (uint64_t{1} << 32), "batch too large: token arena exceeds 2^32 entries");
     // Lanes of a warp run until their longest stream ends: put streams of similar length together, longest first

@@ -1,3 +1,3 @@
 set -x
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r1_launches_bench_default_b256_final.csv python bench.py --steps 1 --warmup 1 --inflight 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-tail -1 gpurun_out/ncu_bench.log | cut -c1-200
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py --no-cpu-baseline > gpurun_out/bench_v29_wave.json 2> gpurun_out/bench_v29.err; python tools/show_bench.py gpurun_out/bench_v29_wave.json | head -2; tail -1 gpurun_out/bench_v29.err
