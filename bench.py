@@ -438,8 +438,17 @@ def main():
     if nfl_e2e < nfl and rank == 0:
         print("e2e: %d of %d handles in flight (pinned output sets of %.1f GB each, %.0f GB of host memory per rank)"
               % (nfl_e2e, nfl, set_bytes / 1e9, share / 1e9), file=sys.stderr)
-    out_sets = [[torch.empty(dec.out_size(i), dtype=torch.uint8).pin_memory().numpy() for i in range(wl.batch)]
-                for _ in range(nfl_e2e)]
+    out_sets = []
+    for _ in range(nfl_e2e):
+        try:
+            out_sets.append([torch.empty(dec.out_size(i), dtype=torch.uint8).pin_memory().numpy() for i in range(wl.batch)])
+        except RuntimeError as e:  # the host refuses to pin more: go on with the sets there are
+            if rank == 0:
+                print("e2e: pinning stopped after %d output sets (%s)" % (len(out_sets), str(e).splitlines()[0]), file=sys.stderr)
+            break
+    if not out_sets:  # (pageable buffers as the last resort: the copies then go through the driver's staging)
+        out_sets.append([np.empty(dec.out_size(i), dtype=np.uint8) for i in range(wl.batch)])
+    nfl_e2e = len(out_sets)
     outs = out_sets[0]
     # enough steps for the handles to fall out of lock step (parse / kernels / read-back of different steps overlap);
     # the ramp-up and the drain stay inside the timed region
