@@ -279,6 +279,7 @@ def run_reference(args):
         raise SystemExit("--impl reference covers the decode workloads; the CPU encoder is timed as cpu_baseline")
     # bounded: the whole --steps K --warmup W run stays within a few minutes
     per_step = max(6.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    per_step = min(per_step, max(0.5, args.cpu_seconds))  # (--cpu-seconds below 6: quick contract checks)
     vals, ms = [], []
     cb = None
     for i in range(args.warmup + args.steps):
