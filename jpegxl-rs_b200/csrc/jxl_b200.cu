@@ -863,6 +863,11 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
     dec->error = e.what();
     return 1;
   }
+  // The upload reallocates / overwrites the device pools of the previous batch: the handle has no plan until it
+  // succeeded (a failed upload must not leave Run / ReadOutput with the old grid sizes over freed pools).
+  dec->plan.reset();
+  dec->pools = DevPools{};
+  dec->vpools = DevVPools{};
   if (UploadPlan(dec, *plan, fmt, false) != 0) return 1;
   dec->plan = std::move(plan);
   return 0;

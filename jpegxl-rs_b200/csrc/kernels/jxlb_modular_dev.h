@@ -59,20 +59,26 @@ enum DevStatus : uint32_t { kStatusOk = 0, kStatusOverread = 1, kStatusBadFinalS
 struct DevBits {
   const uint32_t* words;
   uint64_t next_word;
+  uint64_t limit_word;  // first word that lies entirely behind the section: reads as zero from there on
   uint64_t buf;
   uint32_t n;
 
-  JXLB_HD void Init(const uint32_t* w, uint64_t bit_pos) {
+  // Words at or behind `bit_end` are never loaded (lib/jxl/dec_bit_reader.h:84-103, 213-225: libjxl's reader also
+  // returns zeros past the end and reports the over-read at the end): a corrupt stream cannot walk out of the
+  // byte pool, the callers' Pos() > bit_end test then flags it.
+  JXLB_HD uint32_t Load(uint64_t w) const { return w < limit_word ? JXLB_LDG(words + w) : 0u; }
+  JXLB_HD void Init(const uint32_t* w, uint64_t bit_pos, uint64_t bit_end) {
     words = w;
     next_word = bit_pos >> 5;
+    limit_word = (bit_end + 31) >> 5;
     uint32_t sh = static_cast<uint32_t>(bit_pos & 31);
-    buf = static_cast<uint64_t>(JXLB_LDG(words + next_word)) >> sh;
+    buf = static_cast<uint64_t>(Load(next_word)) >> sh;
     next_word++;
     n = 32 - sh;
   }
   JXLB_HD void Fill() {
     if (n < 32) {
-      buf |= static_cast<uint64_t>(JXLB_LDG(words + next_word)) << n;
+      buf |= static_cast<uint64_t>(Load(next_word)) << n;
       next_word++;
       n += 32;
     }
@@ -719,7 +725,7 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
   if (lane_valid) {
     st = P.streams[s];
     code = P.codes[st.code];
-    br.Init(P.words, st.bit_pos);
+    br.Init(P.words, st.bit_pos, st.bit_end);
     uint32_t* window = (st.lz77_slot != 0xFFFFFFFFu) ? P.lz77 + (static_cast<size_t>(st.lz77_slot) << 20) : nullptr;
     reader.Init(P, code, br, st.dist_multiplier, window);
     my_chans = st.chan_end - st.chan_begin;

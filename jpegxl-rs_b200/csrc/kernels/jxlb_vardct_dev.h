@@ -348,7 +348,7 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
     y0 = gy * 32;
     xs = W - x0 < 32 ? W - x0 : 32;
     ys = vf->yblocks - y0 < 32 ? vf->yblocks - y0 : 32;
-    br.Init(P.words, st.bit_pos);
+    br.Init(P.words, st.bit_pos, st.bit_end);
     num_ctxs = vf->num_ctxs;
     uint32_t selector_bits = 0;
     while ((1u << selector_bits) < vf->num_histograms) selector_bits++;
