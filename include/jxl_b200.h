@@ -119,6 +119,10 @@ int JxlB200DecoderGetStats(const JxlB200Decoder* dec, JxlB200Stats* stats);
  * launching stream (the timed region of a benchmark). ms4 = accumulated milliseconds of
  * {entropy decode, group transforms, global transforms, output write}; runs = number of Runs. */
 int JxlB200DecoderSetProfiling(JxlB200Decoder* dec, int enabled);
+/* Profiling hook: restricts the following Run calls to the kernel classes whose bit is set (bit k = class k of
+ * JxlB200DecoderGetKernelTimesEx); the others keep the results of the last full Run. 0xFFFFFFFF (default) = all.
+ * Used by tools/interference.py to time one class next to another; never by the decode path proper. */
+int JxlB200DecoderSetPhaseMask(JxlB200Decoder* dec, uint32_t mask);
 int JxlB200DecoderGetKernelTimes(JxlB200Decoder* dec, double* ms4, uint32_t* runs);
 /* All kernel classes: ms[0..n) = {Modular entropy decode, group transforms, global transforms,
  * Modular output write, VarDCT DC finish, AC entropy decode, dequant + inverse transforms,

@@ -146,6 +146,7 @@ def load_library() -> ctypes.CDLL:
     lib.JxlB200DecoderReadOutputs.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), sz]
     lib.JxlB200DecoderGetStats.argtypes = [vp, ctypes.POINTER(JxlB200Stats)]
     lib.JxlB200DecoderSetProfiling.argtypes = [vp, ctypes.c_int]
+    lib.JxlB200DecoderSetPhaseMask.argtypes = [vp, ctypes.c_uint32]
     lib.JxlB200DecoderGetKernelTimes.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
     lib.JxlB200DecoderGetKernelTimesEx.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_uint32,
                                                    ctypes.POINTER(ctypes.c_uint32)]
@@ -227,7 +228,7 @@ EXPORTED_SYMBOLS = [
     "JxlB200DecoderCreate", "JxlB200DecoderDestroy", "JxlB200DecoderGetError", "JxlB200DecoderSetInputBatch",
     "JxlB200DecoderNumFrames", "JxlB200DecoderGetBasicInfo", "JxlB200DecoderImageOutBufferSize", "JxlB200DecoderRun",
     "JxlB200DecoderWait", "JxlB200DecoderDeviceOutput", "JxlB200DecoderReadOutput", "JxlB200DecoderReadOutputs",
-    "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderGetKernelTimes",
+    "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderSetPhaseMask", "JxlB200DecoderGetKernelTimes",
     "JxlB200DecoderGetKernelTimesEx", "JxlB200EncoderCreate", "JxlB200EncoderDestroy", "JxlB200EncoderGetError",
     "JxlB200EncoderEncodeBatch", "JxlB200EncoderOutputSize", "JxlB200EncoderReadOutput", "JxlB200EncoderGetPhaseTimes",
     "JxlDecoderVersion", "JxlSignatureCheck", "JxlDecoderCreate", "JxlDecoderReset",
@@ -500,6 +501,11 @@ class BatchDecoder:
         sizes = (ctypes.c_size_t * n)(*[o.nbytes for o in outs])
         if self._lib.JxlB200DecoderReadOutputs(self._dec, ptrs, sizes, n) != 0:
             raise GenericError(self._err())
+
+    def set_phase_mask(self, classes=None) -> None:
+        """Profiling hook: run() launches only the named kernel classes (None = all)."""
+        mask = 0xFFFFFFFF if classes is None else sum(1 << self.KERNEL_CLASSES.index(c) for c in classes)
+        self._lib.JxlB200DecoderSetPhaseMask(self._dec, mask)
 
     def set_profiling(self, enabled: bool) -> None:
         self._lib.JxlB200DecoderSetProfiling(self._dec, int(enabled))

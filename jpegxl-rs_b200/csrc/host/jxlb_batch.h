@@ -433,8 +433,10 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
     const bool two_sets = !batch->patches.empty() || std::getenv("JXLB200_UNFUSED_RENDER") != nullptr ||
                           std::getenv("JXLB_EMUL_UNFUSED") != nullptr;
     const uint64_t per_frame = (two_sets ? 6 : 3) * batch->pix_plane_max;
+    uint64_t wave_bytes = kWavePixelBytes;
+    if (const char* e = std::getenv("JXLB200_WAVE_MB")) wave_bytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;  // tuning knob
     batch->wave_frames = static_cast<uint32_t>(
-        std::max<uint64_t>(1, std::min<uint64_t>(batch->vframes.size(), kWavePixelBytes / (per_frame * 4))));
+        std::max<uint64_t>(1, std::min<uint64_t>(batch->vframes.size(), wave_bytes / (per_frame * 4))));
     const uint64_t pix_base = batch->farena_size;
     batch->farena_size += per_frame * batch->wave_frames;
     for (size_t i = 0; i < batch->vframes.size(); i++) {

@@ -5,6 +5,7 @@
 
 #include "jxlo_decode.h"
 #include "jxlo_encode.h"
+#include "jxlo_enc_modular.h"
 
 using namespace jxlo;
 
@@ -109,12 +110,39 @@ size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, fl
     p.coeff_orders = (gab & 4) == 0;
     p.cfl = (gab & 8) == 0;          // bit 3: no chroma-from-luma fit
     p.adaptive_quant = (gab & 16) == 0;  // bit 4: constant quant field instead of libjxl's adaptive one
+    p.prefix_codes = (gab & 32) != 0;    // bit 5: prefix codes instead of ANS in every stream
     p.epf_iters = epf_iters;
     p.dc_smoothing = dc_smoothing != 0;
     p.random_side_info = random_side_info != 0;
     p.num_passes = num_passes;
     p.dc_tree = dc_tree;
     g_encoded = EncodeVarDCT(rgb, xsize, ysize, p);
+    return g_encoded.size();
+  } catch (const std::exception& e) {
+    SetErr(err, errlen, e.what());
+    return 0;
+  }
+}
+// Lossless Modular stream generator (oracle/jxlo_enc_modular.h). `params`: 16 uint32 (see tests/jxlo.py encode_modular).
+size_t jxlo_encode_modular(const uint16_t* samples, uint32_t xsize, uint32_t ysize, const uint32_t* params, char* err,
+                           size_t errlen) {
+  try {
+    ModularEncodeParams p;
+    p.bits = params[0];
+    p.num_color = params[1];
+    p.alpha = params[2] != 0;
+    p.group_size_shift = params[3];
+    p.tree = static_cast<int>(params[4]);
+    p.predictor = params[5];
+    p.seed = params[6];
+    p.rct = static_cast<int>(params[7]) - 1;
+    p.palette_colors = params[8];
+    p.palette_deltas = params[9];
+    p.palette_predictor = params[10];
+    p.squeeze = params[11] != 0;
+    p.entropy = static_cast<int>(params[12]);
+    p.lz77_min_symbol = params[13] ? params[13] : 224;
+    g_encoded = EncodeModular(samples, xsize, ysize, p);
     return g_encoded.size();
   } catch (const std::exception& e) {
     SetErr(err, errlen, e.what());

@@ -17,6 +17,7 @@
 #define JXLO_ENCODE_H_
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <random>
 
@@ -219,32 +220,249 @@ inline void WriteAnsHistogram(BitWriter& w, const std::vector<int32_t>& counts) 
   }
 }
 
-// A complete entropy-coded stream over `num_ctx` contexts: header (no LZ77, context map,
-// ANS histograms) + symbols. `cluster_of[ctx]` must use ids 0..n-1 without gaps.
+// ---- prefix codes, writer side (lib/jxl/enc_huffman.cc:17-214, lib/jxl/enc_huffman_tree.cc): code lengths by a
+// length-limited Huffman construction, serialised the way ReadPrefixCode (jxlo_entropy.h) reads them -- "simple" codes
+// for up to four symbols, otherwise the code-length code + run-length symbols 16 / 17.
+inline std::vector<uint8_t> HuffmanLengths(const std::vector<uint64_t>& counts, int limit) {
+  const size_t n = counts.size();
+  std::vector<uint8_t> len(n, 0);
+  std::vector<uint64_t> c(counts);
+  for (;;) {
+    struct Node { uint64_t w; int l, r; };
+    std::vector<Node> nodes;
+    std::vector<int> live;
+    for (size_t s = 0; s < n; s++)
+      if (c[s]) {
+        nodes.push_back({c[s], -1, static_cast<int>(s)});
+        live.push_back(static_cast<int>(nodes.size()) - 1);
+      }
+    if (live.size() < 2) {
+      for (size_t s = 0; s < n; s++) len[s] = c[s] ? 1 : 0;
+      return len;
+    }
+    while (live.size() > 1) {  // (ties: lower node index first, so the result is deterministic)
+      std::stable_sort(live.begin(), live.end(), [&](int a, int b) { return nodes[a].w < nodes[b].w; });
+      const int a = live[0], b = live[1];
+      nodes.push_back({nodes[a].w + nodes[b].w, a, b});
+      live.erase(live.begin(), live.begin() + 2);
+      live.push_back(static_cast<int>(nodes.size()) - 1);
+    }
+    int max_len = 0;
+    std::vector<std::pair<int, int>> stack = {{live[0], 0}};
+    while (!stack.empty()) {
+      const auto [id, depth] = stack.back();
+      stack.pop_back();
+      if (nodes[id].l < 0) {
+        len[nodes[id].r] = static_cast<uint8_t>(depth);
+        max_len = std::max(max_len, depth);
+      } else {
+        stack.push_back({nodes[id].l, depth + 1});
+        stack.push_back({nodes[id].r, depth + 1});
+      }
+    }
+    if (max_len <= limit) return len;
+    for (auto& v : c)
+      if (v) v = std::max<uint64_t>(1, v >> 1);  // flatten and try again
+  }
+}
+
+// Canonical code words (bit-reversed: the stream is read LSB first), as BuildPrefixTable assigns them.
+inline std::vector<uint32_t> CanonicalCodes(const std::vector<uint8_t>& len) {
+  uint32_t count[kPrefixMaxBits + 2] = {0}, next[kPrefixMaxBits + 2] = {0};
+  for (uint8_t l : len) count[l]++;
+  count[0] = 0;
+  uint32_t code = 0;
+  for (int l = 1; l <= kPrefixMaxBits; l++) {
+    code = (code + count[l - 1]) << 1;
+    next[l] = code;
+  }
+  std::vector<uint32_t> out(len.size(), 0);
+  for (size_t s = 0; s < len.size(); s++)
+    if (len[s]) out[s] = ReverseBits(next[len[s]]++, len[s]);
+  return out;
+}
+
+// Writes the prefix code of one cluster; `len` receives the code lengths the decoder will derive (0 bits per symbol for
+// an alphabet of one). `counts.size()` is the alphabet size announced in the stream.
+inline void WritePrefixCode(BitWriter& w, const std::vector<uint64_t>& counts, std::vector<uint8_t>* len) {
+  const size_t alphabet = counts.size();
+  len->assign(alphabet, 0);
+  if (alphabet <= 1) return;
+  std::vector<uint32_t> used;
+  for (size_t s = 0; s < alphabet; s++)
+    if (counts[s]) used.push_back(static_cast<uint32_t>(s));
+  if (used.empty()) used.push_back(0);
+  const uint32_t max_bits = FloorLog2(static_cast<uint32_t>(alphabet - 1)) + 1;
+  if (used.size() <= 4) {  // simple code
+    w.Write(2, 1);
+    w.Write(2, used.size() - 1);
+    // lengths by rank: 2 symbols 1,1; 3 symbols 1,2,2; 4 symbols 2,2,2,2 or 1,2,3,3 -- most frequent first
+    std::vector<uint32_t> order(used);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return counts[a] > counts[b]; });
+    bool tree_select = false;
+    if (order.size() == 4) tree_select = counts[order[0]] > counts[order[2]] + counts[order[3]];
+    if (order.size() == 4 && !tree_select) std::sort(order.begin(), order.end());
+    if (order.size() == 3) std::sort(order.begin() + 1, order.end());
+    if (order.size() == 4 && tree_select) std::sort(order.begin() + 2, order.end());
+    if (order.size() == 2) std::sort(order.begin(), order.end());
+    for (uint32_t sym : order) w.Write(max_bits, sym);
+    if (order.size() == 4) w.Write(1, tree_select ? 1 : 0);
+    static const uint8_t kLens[5][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {1, 1, 0, 0}, {1, 2, 2, 0}, {2, 2, 2, 2}};
+    static const uint8_t kLens4[4] = {1, 2, 3, 3};
+    for (size_t i = 0; i < order.size(); i++) (*len)[order[i]] = order.size() == 4 && tree_select ? kLens4[i] : kLens[order.size()][i];
+    return;
+  }
+  *len = HuffmanLengths(counts, kPrefixMaxBits);
+  // trailing zero lengths are implied once the code is complete
+  size_t last = alphabet;
+  while (last > 0 && (*len)[last - 1] == 0) last--;
+  // run-length symbols: 16 = repeat the previous non-zero length 3..6 times, 17 = 3..10 zeros (one symbol per run;
+  // consecutive 16s / 17s would extend the run multiplicatively, a literal in between keeps them independent)
+  struct Rle { uint8_t sym, extra; };
+  std::vector<Rle> seq;
+  uint8_t prev = 8;
+  for (size_t i = 0; i < last;) {
+    const uint8_t v = (*len)[i];
+    size_t run = 1;
+    while (i + run < last && (*len)[i + run] == v) run++;
+    const bool last_was_rle = !seq.empty() && seq.back().sym >= 16;
+    if (v == 0 && run >= 3 && !(last_was_rle && seq.back().sym == 17)) {
+      const size_t r = std::min<size_t>(run, 10);
+      seq.push_back({17, static_cast<uint8_t>(r - 3)});
+      i += r;
+    } else if (v != 0 && v == prev && run >= 3 && !(last_was_rle && seq.back().sym == 16)) {
+      const size_t r = std::min<size_t>(run, 6);
+      seq.push_back({16, static_cast<uint8_t>(r - 3)});
+      i += r;
+    } else {
+      seq.push_back({v, 0});
+      if (v) prev = v;
+      i++;
+    }
+  }
+  std::vector<uint64_t> cl_counts(18, 0);
+  for (const Rle& r : seq) cl_counts[r.sym]++;
+  std::vector<uint8_t> cl = HuffmanLengths(cl_counts, 5);
+  size_t cl_used = 0;
+  for (uint8_t l : cl) cl_used += l != 0;
+  static const uint8_t kOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+  static const uint8_t kClBits[6] = {0, 7, 3, 2, 1, 15}, kClLen[6] = {2, 4, 3, 2, 2, 4};
+  w.Write(2, 0);  // hskip
+  int space = 32;
+  for (int i = 0; i < 18 && space > 0; i++) {
+    const uint8_t v = cl[kOrder[i]];
+    w.Write(kClLen[v], kClBits[v]);
+    if (v) space -= 32 >> v;
+  }
+  JXLO_CHECK(cl_used == 1 || space == 0, "internal: code-length code is not complete");
+  const std::vector<uint32_t> cl_code = CanonicalCodes(cl);
+  for (const Rle& r : seq) {
+    if (cl_used > 1) w.Write(cl[r.sym], cl_code[r.sym]);
+    if (r.sym == 16) w.Write(2, r.extra);
+    if (r.sym == 17) w.Write(3, r.extra);
+  }
+}
+
+struct EntropyOptions {
+  bool use_prefix = false;   // prefix codes instead of ANS
+  bool lz77 = false;         // LZ77 length / distance tokens (lib/jxl/enc_ans.cc:1040-1490, a greedy matcher here)
+  uint32_t lz77_min_symbol = 224, lz77_min_length = 3;
+};
+
+// The 120 special distances of lib/jxl/dec_ans.h:121-143 (also in SymbolReader::SpecialDistance).
+inline int LZ77SpecialDistance(uint32_t i, uint32_t dist_mult) {
+  static const int8_t k[120][2] = {
+      {0, 1},  {1, 0},  {1, 1},  {-1, 1}, {0, 2},  {2, 0},  {1, 2},  {-1, 2}, {2, 1},  {-2, 1}, {2, 2},  {-2, 2}, {0, 3},  {3, 0},  {1, 3},
+      {-1, 3}, {3, 1},  {-3, 1}, {2, 3},  {-2, 3}, {3, 2},  {-3, 2}, {0, 4},  {4, 0},  {1, 4},  {-1, 4}, {4, 1},  {-4, 1}, {3, 3},  {-3, 3},
+      {2, 4},  {-2, 4}, {4, 2},  {-4, 2}, {0, 5},  {3, 4},  {-3, 4}, {4, 3},  {-4, 3}, {5, 0},  {1, 5},  {-1, 5}, {5, 1},  {-5, 1}, {2, 5},
+      {-2, 5}, {5, 2},  {-5, 2}, {4, 4},  {-4, 4}, {3, 5},  {-3, 5}, {5, 3},  {-5, 3}, {0, 6},  {6, 0},  {1, 6},  {-1, 6}, {6, 1},  {-6, 1},
+      {2, 6},  {-2, 6}, {6, 2},  {-6, 2}, {4, 5},  {-4, 5}, {5, 4},  {-5, 4}, {3, 6},  {-3, 6}, {6, 3},  {-6, 3}, {0, 7},  {7, 0},  {1, 7},
+      {-1, 7}, {5, 5},  {-5, 5}, {7, 1},  {-7, 1}, {4, 6},  {-4, 6}, {6, 4},  {-6, 4}, {2, 7},  {-2, 7}, {7, 2},  {-7, 2}, {3, 7},  {-3, 7},
+      {7, 3},  {-7, 3}, {5, 6},  {-5, 6}, {6, 5},  {-6, 5}, {8, 0},  {4, 7},  {-4, 7}, {7, 4},  {-7, 4}, {8, 1},  {8, 2},  {6, 6},  {-6, 6},
+      {8, 3},  {5, 7},  {-5, 7}, {7, 5},  {-7, 5}, {8, 4},  {6, 7},  {-6, 7}, {7, 6},  {-7, 6}, {8, 5},  {7, 7},  {-7, 7}, {8, 6},  {8, 7}};
+  const int d = k[i][0] + static_cast<int>(dist_mult) * k[i][1];
+  return d > 1 ? d : 1;
+}
+
+// A complete entropy-coded stream over `num_ctx` contexts: header (LZ77 parameters, context map, ANS histograms or
+// prefix codes) + symbols. `cluster_of[ctx]` must use ids 0..n-1 without gaps. With LZ77 the distance context gets a
+// cluster of its own.
 class EntropyEncoder {
  public:
-  EntropyEncoder(size_t num_ctx, std::vector<uint8_t> cluster_of) : num_ctx_(num_ctx), cluster_of_(std::move(cluster_of)) {
+  EntropyEncoder(size_t num_ctx, std::vector<uint8_t> cluster_of, EntropyOptions opt = EntropyOptions())
+      : num_ctx_(num_ctx), cluster_of_(std::move(cluster_of)), opt_(opt) {
     JXLO_CHECK(cluster_of_.size() == num_ctx_, "bad cluster map");
     num_clusters_ = 1;
     for (uint8_t c : cluster_of_) num_clusters_ = std::max<uint32_t>(num_clusters_, c + 1);
+    if (opt_.lz77) {
+      dist_cluster_ = num_clusters_++;
+      cluster_of_.push_back(static_cast<uint8_t>(dist_cluster_));
+    }
     cfg_ = HybridUintConfig(4, 2, 0);
+    length_cfg_ = HybridUintConfig(0, 0, 0);
   }
 
   // Pass 1: statistics over every token that will be written with this code.
-  void Count(const std::vector<Token>& tokens) {
+  // `dist_mult`: what the decoder will pass to its symbol reader for this stream (widest channel of a Modular stream,
+  // else 0); only the LZ77 matcher looks at it.
+  void Count(const std::vector<Token>& tokens, uint32_t dist_mult = 0) {
     if (hist_.empty()) hist_.assign(num_clusters_, std::vector<uint64_t>());
-    for (const Token& t : tokens) {
-      const EncodedUint e = EncodeHybrid(cfg_, t.value);
-      std::vector<uint64_t>& h = hist_[cluster_of_[t.ctx]];
-      if (h.size() <= e.token) h.resize(e.token + 1, 0);
-      h[e.token]++;
+    auto add = [&](uint32_t cluster, uint32_t symbol) {
+      std::vector<uint64_t>& h = hist_[cluster];
+      if (h.size() <= symbol) h.resize(symbol + 1, 0);
+      h[symbol]++;
+    };
+    if (!opt_.lz77) {
+      for (const Token& t : tokens) add(cluster_of_[t.ctx], EncodeHybrid(cfg_, t.value).token);
+      return;
+    }
+    for (const Item& it : Lz77(tokens, dist_mult)) {
+      if (it.len == 0) {
+        const uint32_t tok = EncodeHybrid(cfg_, it.value).token;
+        JXLO_CHECK(tok < opt_.lz77_min_symbol, "literal token collides with the LZ77 length symbols");
+        add(cluster_of_[it.ctx], tok);
+      } else {
+        add(cluster_of_[it.ctx], opt_.lz77_min_symbol + EncodeHybrid(length_cfg_, it.len - opt_.lz77_min_length).token);
+        add(dist_cluster_, EncodeHybrid(cfg_, it.value).token);
+      }
     }
   }
 
   void WriteHeader(BitWriter& w) {
     if (hist_.empty()) hist_.assign(num_clusters_, std::vector<uint64_t>());
-    w.Write(1, 0);  // no LZ77
-    if (num_ctx_ > 1) WriteContextMap(w);
+    if (opt_.lz77) {
+      w.Write(1, 1);
+      WriteU32(w, opt_.lz77_min_symbol, Val(224), Val(512), Val(4096), BitsOffset(15, 8));
+      WriteU32(w, opt_.lz77_min_length, Val(3), Val(4), BitsOffset(2, 5), BitsOffset(8, 9));
+      WriteUintConfig(w, length_cfg_, 8);
+    } else {
+      w.Write(1, 0);  // no LZ77
+    }
+    if (cluster_of_.size() > 1) WriteContextMap(w);
+    if (opt_.use_prefix) {
+      w.Write(1, 1);
+      for (uint32_t c = 0; c < num_clusters_; c++) WriteUintConfig(w, cfg_, kPrefixMaxBits);
+      for (uint32_t c = 0; c < num_clusters_; c++) {  // alphabet sizes (VarLenUint16 of size - 1)
+        const uint32_t v = static_cast<uint32_t>(std::max<size_t>(1, hist_[c].size())) - 1;
+        if (v == 0) {
+          w.Write(1, 0);
+        } else {
+          w.Write(1, 1);
+          const unsigned n = FloorLog2(v);
+          w.Write(4, n);
+          w.Write(n, v - (1u << n));
+        }
+      }
+      plen_.assign(num_clusters_, std::vector<uint8_t>());
+      pcode_.assign(num_clusters_, std::vector<uint32_t>());
+      for (uint32_t c = 0; c < num_clusters_; c++) {
+        std::vector<uint64_t> counts = hist_[c];
+        if (counts.empty()) counts.assign(1, 0);
+        WritePrefixCode(w, counts, &plen_[c]);
+        pcode_[c] = CanonicalCodes(plen_[c]);
+      }
+      return;
+    }
     w.Write(1, 0);  // ANS, not prefix codes
     size_t max_alphabet = 1;
     for (auto& h : hist_) max_alphabet = std::max(max_alphabet, h.size());
@@ -252,11 +470,7 @@ class EntropyEncoder {
     while ((size_t{1} << log_alpha_) < max_alphabet) log_alpha_++;
     JXLO_CHECK(log_alpha_ <= 8, "alphabet too large");
     w.Write(2, log_alpha_ - 5);
-    for (uint32_t c = 0; c < num_clusters_; c++) {  // uint configs
-      w.Write(CeilLog2(log_alpha_ + 1), cfg_.split_exponent);
-      w.Write(CeilLog2(cfg_.split_exponent + 1), cfg_.msb_in_token);
-      w.Write(CeilLog2(cfg_.split_exponent - cfg_.msb_in_token + 1), cfg_.lsb_in_token);
-    }
+    for (uint32_t c = 0; c < num_clusters_; c++) WriteUintConfig(w, cfg_, log_alpha_);
     const uint32_t ts = 1u << log_alpha_;
     alias_.assign(static_cast<size_t>(num_clusters_) * ts, AliasEntry{});
     freq_.assign(num_clusters_, std::vector<int32_t>());
@@ -281,37 +495,122 @@ class EntropyEncoder {
     }
   }
 
-  // Pass 2: one ANS stream (32-bit state + interleaved refills and raw bits).
-  void WriteTokens(BitWriter& w, const std::vector<Token>& tokens) const {
+  // Pass 2: one stream. ANS: 32-bit state + interleaved refills and raw bits, built back to front; prefix codes: the
+  // symbols in order.
+  void WriteTokens(BitWriter& w, const std::vector<Token>& tokens, uint32_t dist_mult = 0) const {
+    // the symbols of the stream in decoding order: (cluster, symbol, raw bits)
+    struct Sym { uint32_t cluster, symbol, nbits, bits; };
+    std::vector<Sym> syms;
+    syms.reserve(tokens.size());
+    if (!opt_.lz77) {
+      for (const Token& t : tokens) {
+        const EncodedUint e = EncodeHybrid(cfg_, t.value);
+        syms.push_back({cluster_of_[t.ctx], e.token, e.nbits, e.bits});
+      }
+    } else {
+      for (const Item& it : Lz77(tokens, dist_mult)) {
+        if (it.len == 0) {
+          const EncodedUint e = EncodeHybrid(cfg_, it.value);
+          syms.push_back({cluster_of_[it.ctx], e.token, e.nbits, e.bits});
+        } else {
+          const EncodedUint l = EncodeHybrid(length_cfg_, it.len - opt_.lz77_min_length);
+          syms.push_back({cluster_of_[it.ctx], opt_.lz77_min_symbol + l.token, l.nbits, l.bits});
+          const EncodedUint d = EncodeHybrid(cfg_, it.value);
+          syms.push_back({dist_cluster_, d.token, d.nbits, d.bits});
+        }
+      }
+    }
+    if (opt_.use_prefix) {
+      for (const Sym& s : syms) {
+        JXLO_CHECK(s.symbol < plen_[s.cluster].size(), "token outside the prefix code");
+        w.Write(plen_[s.cluster][s.symbol], pcode_[s.cluster][s.symbol]);
+        w.Write(s.nbits, s.bits);
+      }
+      return;
+    }
     struct Out { uint32_t nbits, bits; };
     std::vector<Out> out;
-    out.reserve(tokens.size() * 2);
+    out.reserve(syms.size() * 2);
     uint32_t state = kAnsSignature << 16;
-    for (size_t i = tokens.size(); i-- > 0;) {
-      const Token& t = tokens[i];
-      const uint32_t c = cluster_of_[t.ctx];
-      const EncodedUint e = EncodeHybrid(cfg_, t.value);
-      if (e.nbits) out.push_back({e.nbits, e.bits});
-      JXLO_CHECK(e.token < freq_[c].size() && freq_[c][e.token] > 0, "token outside the histogram");
-      const uint32_t f = freq_[c][e.token];
+    for (size_t i = syms.size(); i-- > 0;) {
+      const Sym& s = syms[i];
+      const uint32_t c = s.cluster;
+      if (s.nbits) out.push_back({s.nbits, s.bits});
+      JXLO_CHECK(s.symbol < freq_[c].size() && freq_[c][s.symbol] > 0, "token outside the histogram");
+      const uint32_t f = freq_[c][s.symbol];
       if ((state >> (32 - kAnsLogTabSize)) >= f) {
         out.push_back({16, state & 0xFFFF});
         state >>= 16;
       }
-      state = ((state / f) << kAnsLogTabSize) | reverse_[c][e.token][state % f];
+      state = ((state / f) << kAnsLogTabSize) | reverse_[c][s.symbol][state % f];
     }
     w.Write(32, state);
     for (size_t i = out.size(); i-- > 0;) w.Write(out[i].nbits, out[i].bits);
   }
 
  private:
+  // One literal (len == 0: ctx, value) or one copy (len >= min_length values, `value` = the distance symbol's value).
+  struct Item { uint32_t ctx, value, len; };
+
+  // Greedy matcher over the value sequence: at every position the longest match among a few candidate distances
+  // (runs, the row above and its neighbours when the stream has a distance multiplier).
+  std::vector<Item> Lz77(const std::vector<Token>& tokens, uint32_t mult) const {
+    std::vector<Item> items;
+    const size_t n = tokens.size();
+    std::vector<uint32_t> cand = {1, 2, 3, 4, 7, 16};
+    if (mult) {
+      for (int dx = -2; dx <= 2; dx++) cand.push_back(mult + dx);
+      cand.push_back(2 * mult);
+    }
+    for (size_t i = 0; i < n;) {
+      size_t best_len = 0;
+      uint32_t best_d = 0;
+      for (uint32_t d : cand) {
+        if (d == 0 || d > i || d > kLZ77Window) continue;
+        size_t l = 0;
+        while (i + l < n && l < 65535 && tokens[i + l].value == tokens[i + l - d].value) l++;
+        if (l > best_len) {
+          best_len = l;
+          best_d = d;
+        }
+      }
+      if (best_len >= std::max<uint32_t>(opt_.lz77_min_length, 3)) {
+        uint32_t dsym;
+        if (mult == 0) {
+          dsym = best_d - 1;
+        } else {
+          dsym = best_d - 1 + kNumSpecialDistances;
+          for (uint32_t k = 0; k < kNumSpecialDistances; k++)
+            if (LZ77SpecialDistance(k, mult) == static_cast<int>(best_d)) {
+              dsym = k;
+              break;
+            }
+        }
+        items.push_back({tokens[i].ctx, dsym, static_cast<uint32_t>(best_len)});
+        i += best_len;
+      } else {
+        items.push_back({tokens[i].ctx, tokens[i].value, 0});
+        i++;
+      }
+    }
+    return items;
+  }
+
+  static void WriteUintConfig(BitWriter& w, const HybridUintConfig& c, uint32_t log_alpha) {
+    w.Write(CeilLog2(log_alpha + 1), c.split_exponent);
+    if (c.split_exponent == log_alpha) return;
+    w.Write(CeilLog2(c.split_exponent + 1), c.msb_in_token);
+    w.Write(CeilLog2(c.split_exponent - c.msb_in_token + 1), c.lsb_in_token);
+  }
+
   void WriteContextMap(BitWriter& w) {
+    const size_t n = cluster_of_.size();
     if (num_clusters_ == 1) {
       w.Write(1, 1);  // simple
       w.Write(2, 0);  // zero bits per entry
       return;
     }
-    if (num_clusters_ <= 8 && num_ctx_ < 64) {
+    if (num_clusters_ <= 8 && n < 64) {
       const unsigned bits = CeilLog2(num_clusters_);
       w.Write(1, 1);
       w.Write(2, bits);
@@ -321,7 +620,7 @@ class EntropyEncoder {
     w.Write(1, 0);  // not simple
     w.Write(1, 0);  // no move-to-front
     std::vector<Token> toks;
-    toks.reserve(num_ctx_);
+    toks.reserve(n);
     for (uint8_t c : cluster_of_) toks.push_back({0, c});
     EntropyEncoder nested(1, std::vector<uint8_t>(1, 0));
     nested.Count(toks);
@@ -331,13 +630,16 @@ class EntropyEncoder {
 
   size_t num_ctx_;
   std::vector<uint8_t> cluster_of_;
-  uint32_t num_clusters_ = 1;
-  HybridUintConfig cfg_;
+  EntropyOptions opt_;
+  uint32_t num_clusters_ = 1, dist_cluster_ = 0;
+  HybridUintConfig cfg_, length_cfg_;
   uint32_t log_alpha_ = 5;
   std::vector<std::vector<uint64_t>> hist_;
   std::vector<AliasEntry> alias_;
   std::vector<std::vector<int32_t>> freq_;
   std::vector<std::vector<std::vector<uint16_t>>> reverse_;
+  std::vector<std::vector<uint8_t>> plen_;
+  std::vector<std::vector<uint32_t>> pcode_;
 };
 
 // ---------------------------------------------------------------- Modular sub-streams (global tree)
@@ -624,6 +926,7 @@ struct EncodeParams {
   // DC quantiser from ComputeGlobalScaleAndQuant(InitialQuantDC(d), 0.39 / d, 0), AdjustQuantField over each varblock,
   // SetQuantFieldRect. false (and with random_side_info): one constant raw quant value under this file's own scale.
   bool adaptive_quant = true;
+  bool prefix_codes = false;  // every entropy-coded stream of the frame uses prefix codes instead of ANS (decoder coverage)
 };
 
 struct EncoderStats {
@@ -1725,11 +2028,13 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
     meta_chans[g] = std::move(meta);
     meta_count[g] = count;
   }
-  EntropyEncoder tree_code(6, {0, 1, 2, 3, 4, 5});
+  EntropyOptions eopt;
+  eopt.use_prefix = p.prefix_codes;
+  EntropyEncoder tree_code(6, {0, 1, 2, 3, 4, 5}, eopt);
   tree_code.Count(gtree.tokens);
   std::vector<uint8_t> leaf_clusters(gtree.num_leaves);
   for (size_t i = 0; i < gtree.num_leaves; i++) leaf_clusters[i] = static_cast<uint8_t>(i);
-  EntropyEncoder modular_code(gtree.num_leaves, leaf_clusters);
+  EntropyEncoder modular_code(gtree.num_leaves, leaf_clusters, eopt);
   for (size_t g = 0; g < dim.num_dc_groups; g++) {
     modular_code.Count(dc_toks[g]);
     modular_code.Count(meta_toks[g]);
@@ -1795,12 +2100,12 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
             }
           }
         }
-        EntropyEncoder perm_code(8, {0, 1, 2, 3, 4, 5, 6, 7});
+        EntropyEncoder perm_code(8, {0, 1, 2, 3, 4, 5, 6, 7}, eopt);
         perm_code.Count(ptoks);
         perm_code.WriteHeader(ac_global);
         perm_code.WriteTokens(ac_global, ptoks);
       }
-      pass_codes.emplace_back(bctx.NumACContexts(), clusters);
+      pass_codes.emplace_back(bctx.NumACContexts(), clusters, eopt);
       for (size_t g = 0; g < num_groups; g++) pass_codes.back().Count(group_tokens[pass * num_groups + g]);
       pass_codes.back().WriteHeader(ac_global);
     }

@@ -11,6 +11,7 @@
 #define JXLO_MODULAR_H_
 
 #include <array>
+#include <climits>
 #include <cstdlib>
 #include <vector>
 
@@ -97,6 +98,28 @@ inline void ReadTree(BitReader& br, Tree* tree, size_t size_limit) {
     to_decode += 2;
   }
   JXLO_CHECK(reader.FinalStateOk(), "tree: bad ANS final state");
+  // ValidateTree, lib/jxl/modular/encoding/dec_ma.cc:23-67: the range of every property must stay non-empty on the
+  // way down (a split value outside the range its ancestors leave is an error), height at most 2048.
+  int num_props = 0;
+  for (const TreeNode& n : *tree) num_props = std::max(num_props, n.property + 1);
+  std::vector<std::pair<int32_t, int32_t>> ranges(static_cast<size_t>(num_props) * tree->size(), {INT32_MIN, INT32_MAX});
+  std::vector<int> height(tree->size(), 0);
+  for (size_t i = 0; i < tree->size(); i++) {
+    const TreeNode& n = (*tree)[i];
+    JXLO_CHECK(height[i] <= 2048, "tree too tall");
+    if (n.property == -1) continue;
+    height[n.lchild] = height[n.rchild] = height[i] + 1;
+    for (int q = 0; q < num_props; q++) {
+      const auto cur = ranges[i * num_props + q];
+      if (q == n.property) {
+        JXLO_CHECK(!(cur.first > n.splitval || cur.second <= n.splitval), "invalid tree");
+        ranges[n.lchild * num_props + q] = {n.splitval + 1, cur.second};
+        ranges[n.rchild * num_props + q] = {cur.first, n.splitval};
+      } else {
+        ranges[n.lchild * num_props + q] = ranges[n.rchild * num_props + q] = cur;
+      }
+    }
+  }
 }
 
 struct Channel {

@@ -48,6 +48,9 @@ SMALL_CASES = [
     ("synthetic_d3", lambda: synthetic(280, 264, 5), dict(strategy_mode=2, distance=3.0)),
     ("synthetic_d05", lambda: synthetic(264, 300, 9), dict(strategy_mode=2, distance=0.5, gab=False, epf_iters=1)),
     ("odd_size", lambda: crop(257, 263, 700, 100), dict(strategy_mode=1, seed=11)),
+    # prefix codes instead of ANS in every stream of the frame (tree, DC / metadata, coefficient orders, AC passes)
+    ("prefix_codes", lambda: crop(300, 400, 100, 200), dict(strategy_mode=1, random_side_info=True, seed=3, epf_iters=1, prefix_codes=True)),
+    ("prefix_codes_two_passes", lambda: crop(280, 330, 500, 300), dict(strategy_mode=2, num_passes=2, prefix_codes=True)),
 ]
 STRATEGY_CASES = [("strategy_%d" % s, lambda: crop(264, 520, 400, 300),
                    dict(strategy_mode=100 + s, gab=False, epf_iters=0, dc_smoothing=False)) for s in range(27)]
