@@ -96,6 +96,9 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream);
 int JxlB200DecoderWait(JxlB200Decoder* dec, void* cuda_stream);
 /* Device pointer (HBM) of frame i's pixels after Run. */
 void* JxlB200DecoderDeviceOutput(const JxlB200Decoder* dec, size_t i);
+/* Size in bytes of the batch's whole output buffer in HBM: frames back to back from JxlB200DecoderDeviceOutput(dec, 0),
+ * each 256-byte aligned (what a caller hands to a collective, e.g. ncclGather, without a host round trip). */
+size_t JxlB200DecoderDeviceOutputBytes(const JxlB200Decoder* dec);
 /* Device -> host copy of frame i into `dst` (JxlDecoderSetImageOutBuffer semantics:
  * rows of align_up(xsize * channels * bytes, align) bytes). Synchronous. */
 int JxlB200DecoderReadOutput(JxlB200Decoder* dec, size_t i, void* dst, size_t size);

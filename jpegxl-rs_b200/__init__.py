@@ -147,6 +147,8 @@ def load_library() -> ctypes.CDLL:
     lib.JxlB200DecoderGetStats.argtypes = [vp, ctypes.POINTER(JxlB200Stats)]
     lib.JxlB200DecoderSetProfiling.argtypes = [vp, ctypes.c_int]
     lib.JxlB200DecoderSetPhaseMask.argtypes = [vp, ctypes.c_uint32]
+    lib.JxlB200DecoderDeviceOutputBytes.restype = ctypes.c_size_t
+    lib.JxlB200DecoderDeviceOutputBytes.argtypes = [vp]
     lib.JxlB200DecoderGetKernelTimes.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
     lib.JxlB200DecoderGetKernelTimesEx.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_uint32,
                                                    ctypes.POINTER(ctypes.c_uint32)]
@@ -228,7 +230,7 @@ EXPORTED_SYMBOLS = [
     "JxlB200DecoderCreate", "JxlB200DecoderDestroy", "JxlB200DecoderGetError", "JxlB200DecoderSetInputBatch",
     "JxlB200DecoderNumFrames", "JxlB200DecoderGetBasicInfo", "JxlB200DecoderImageOutBufferSize", "JxlB200DecoderRun",
     "JxlB200DecoderWait", "JxlB200DecoderDeviceOutput", "JxlB200DecoderReadOutput", "JxlB200DecoderReadOutputs",
-    "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderSetPhaseMask", "JxlB200DecoderGetKernelTimes",
+    "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderSetPhaseMask", "JxlB200DecoderDeviceOutputBytes", "JxlB200DecoderGetKernelTimes",
     "JxlB200DecoderGetKernelTimesEx", "JxlB200EncoderCreate", "JxlB200EncoderDestroy", "JxlB200EncoderGetError",
     "JxlB200EncoderEncodeBatch", "JxlB200EncoderOutputSize", "JxlB200EncoderReadOutput", "JxlB200EncoderGetPhaseTimes",
     "JxlDecoderVersion", "JxlSignatureCheck", "JxlDecoderCreate", "JxlDecoderReset",
@@ -486,6 +488,19 @@ class BatchDecoder:
 
     def device_output(self, i: int) -> int:
         return self._lib.JxlB200DecoderDeviceOutput(self._dec, i)
+
+    def device_output_tensor(self):
+        """The batch's whole output buffer in HBM as a torch uint8 CUDA tensor (no copy): frames back to back, each
+        256-byte aligned. What the multi-GPU gather sends."""
+        import torch
+
+        class _Buf:
+            pass
+
+        n = self._lib.JxlB200DecoderDeviceOutputBytes(self._dec)
+        b = _Buf()
+        b.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (self.device_output(0), False), "version": 2}
+        return torch.as_tensor(b, device="cuda")
 
     def read_output(self, i: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         n = self.out_size(i)

@@ -148,10 +148,9 @@ __global__ void __launch_bounds__(256) k_write_output_rgba8(DevPools P, const De
 // blockIdx.x indexes a flat list of (frame, DC group) pairs.
 __global__ void __launch_bounds__(256) k_dc_finish(DevPools P, DevVPools V, const uint2* dcg_list) {
   __shared__ uint32_t occ_s[kDcOccWords];  // one bit per block of the DC group (256 x 256 blocks): covered or not
-  __shared__ uint16_t stage_s[kDcStageEntries];
-  __shared__ uint32_t sinfo_s[kNumStrategies];
+  __shared__ uint32_t stage_s[kDcStageEntries];
   const uint2 e = dcg_list[blockIdx.x];
-  DevDcGroupFinish<2>(P, V, e.x, e.y, threadIdx.x, blockDim.x, blockIdx.x, occ_s, stage_s, sinfo_s);
+  DevDcGroupFinish<2>(P, V, e.x, e.y, threadIdx.x, blockDim.x, blockIdx.x, occ_s, stage_s);
 }
 
 __global__ void __launch_bounds__(256) k_dc_smooth(DevVPools V) {
@@ -994,7 +993,9 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     if (pm & (1u << kKDcFinish)) {
       ScopedTimer t(dec, s, kKDcFinish);
       CUDA_OK(cudaMemsetAsync(dec->d_dc_status.p, 0, (dec->dcg_list.size() + 2) * 4, s));
-      static const uint32_t dcf_threads = std::getenv("JXLB200_DCF_THREADS") ? std::atoi(std::getenv("JXLB200_DCF_THREADS")) : 256;
+      // (64 threads: the serial scan of a DC group is one thread's work; a wider CTA only parks warps on the SMs that
+      // the per-pixel kernels of other batches need -- tools/interference.py)
+      static const uint32_t dcf_threads = std::getenv("JXLB200_DCF_THREADS") ? std::atoi(std::getenv("JXLB200_DCF_THREADS")) : 64;
       k_dc_finish<<<dec->dcg_list.size(), dcf_threads, 0, s>>>(P, V, dec->d_dcg_list.p);
       dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(256, (dec->max_blocks + 255) / 256)), nvf);
       k_dc_smooth<<<grid, 256, 0, s>>>(V);
@@ -1168,6 +1169,8 @@ int JxlB200DecoderWait(JxlB200Decoder* dec, void* cuda_stream) {
   }
   return 0;
 }
+
+size_t JxlB200DecoderDeviceOutputBytes(const JxlB200Decoder* dec) { return dec && dec->plan ? dec->plan->out_size : 0; }
 
 void* JxlB200DecoderDeviceOutput(const JxlB200Decoder* dec, size_t i) {
   if (!dec || !dec->plan || i >= dec->plan->frames.size()) return nullptr;

@@ -92,11 +92,10 @@ JXLB_HD uint32_t DevFfs(uint32_t v) {  // 1-based index of the lowest set bit (v
 }
 constexpr uint32_t kDcStageEntries = 2048;  // list entries staged per chunk (uint16 each) by DevDcGroupFinish
 
-// `stage` / `sinfo_stage`: kDcStageEntries uint16 + kNumStrategies uint32 of shared memory for the serial scan, or nullptr.
+// `stage`: kDcStageEntries words of scratch (shared memory on the device) for the serial scan.
 template <int SCOPE>
 JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t frame, uint32_t g, uint32_t tid, uint32_t nt,
-                              uint32_t status_index, uint32_t* occ, uint16_t* stage = nullptr,
-                              uint32_t* sinfo_stage = nullptr) {
+                              uint32_t status_index, uint32_t* occ, uint32_t* stage) {
   const DevVFrame& vf = V.frames[frame];
   const uint32_t W = vf.xblocks, H = vf.yblocks;
   const uint32_t gx = g % vf.xdcgroups, gy = g / vf.xdcgroups;
@@ -171,111 +170,102 @@ JXLB_HD void DevDcGroupFinish(const DevPools& P, const DevVPools& V, uint32_t fr
   CoopSync<SCOPE>();
   // (b) the strategy / quant rows list one entry per varblock in raster order of their top-left
   // blocks; where the next varblock starts depends on the extents of all earlier ones: serial. The list is
-  // staged chunk by chunk (all threads load, thread 0 consumes), so that the serial scan only ever waits for
-  // shared memory (`stage` != nullptr) instead of for a dependent global load per varblock.
+  // staged chunk by chunk by all threads as packed words -- strategy | quant << 8 | cx << 16 | cy << 24 -- so that
+  // the scanning thread waits for one shared-memory word per varblock, requested one varblock ahead; it keeps the
+  // occupancy word it is filling in a register, marks the rows below in shared memory and stores only the varblock's
+  // first cell (strategy byte, raw quant). The cells a varblock covers are filled in parallel in (c).
   {
     const uint32_t cap = pl_rows.w;
     const uint32_t count = static_cast<uint32_t>(m_rows[static_cast<size_t>(cap) * 2]);
     const int32_t* row_strategy = m_rows;
     const int32_t* row_quant = m_rows + cap;
-    uint32_t num = 0, iy = 0, ix = 0;  // (thread 0's scan position, kept across chunks)
+    uint32_t num = 0, iy = 0, wi = 0;  // (thread 0's scan position, kept across chunks)
     for (uint32_t chunk = 0; chunk == 0 || chunk < count; chunk += kDcStageEntries) {
       const uint32_t chunk_end = chunk + kDcStageEntries < count ? chunk + kDcStageEntries : count;
-      if (stage) {
-        for (uint32_t i = chunk + tid; i < chunk_end; i += nt) {
-          const int32_t raw = row_strategy[i];
-          int32_t q = row_quant[i];
-          q = q < 0 ? 0 : (q > 255 ? 255 : q);
-          stage[i - chunk] = static_cast<uint16_t>((static_cast<uint32_t>(raw) < kNumStrategies ? raw : 0xFF) | (q << 8));
+      for (uint32_t i = chunk + tid; i < chunk_end; i += nt) {
+        const int32_t raw = row_strategy[i];
+        int32_t q = row_quant[i];
+        q = q < 0 ? 0 : (q > 255 ? 255 : q);
+        uint32_t e = 0xFFu;  // invalid strategy
+        if (static_cast<uint32_t>(raw) < kNumStrategies) {
+          const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + raw]);
+          e = static_cast<uint32_t>(raw) | (static_cast<uint32_t>(q) << 8) | (static_cast<uint32_t>(si.cx) << 16) |
+              (static_cast<uint32_t>(si.cy) << 24);
         }
-        for (uint32_t i = tid; chunk == 0 && i < kNumStrategies; i += nt) sinfo_stage[i] = V.upool[V.sinfo_off + i];
-        CoopSync<SCOPE>();
+        stage[i - chunk] = e;
       }
-      if (tid == 0) {
+      CoopSync<SCOPE>();
+      if (tid == 0 && !(status & kVBadStream)) {
         const bool last_chunk = chunk_end == count;
-        for (; iy < ys && !(status & kVBadStream); iy++, ix = 0) {
-          const uint32_t y = y0 + iy;
-          bool paused = false;
+        bool paused = false;
+        uint32_t e_next = num < chunk_end ? stage[num - chunk] : 0xFFu;
+        for (; iy < ys && !paused && !(status & kVBadStream); iy++, wi = 0) {
           uint32_t* orow = occ + iy * 8;
-          for (;;) {
-            // the next block of this row that no varblock covers yet
-            uint32_t wi = ix >> 5, free_bits = 0;
-            for (; wi < 8; wi++, ix = wi << 5) {
-              free_bits = ~orow[wi] & (0xFFFFFFFFu << (ix & 31));
-              if (free_bits) break;
-            }
-            if (!free_bits) break;
-            ix = (wi << 5) + DevFfs(free_bits) - 1;
-            const uint32_t x = x0 + ix;
-            const size_t pos = static_cast<size_t>(y) * W + x;
-            uint8_t* cell = acs + static_cast<size_t>(iy) * astride + ix;
-            if (num >= chunk_end) {
-              if (last_chunk) status |= kVBadStream;  // more varblocks than list entries
-              paused = true;
-              break;
-            }
-            int32_t raw, cur_q;
-            if (stage) {
-              const uint32_t e = stage[num - chunk];
-              raw = (e & 0xFF) == 0xFF ? -1 : static_cast<int32_t>(e & 0xFF);
-              cur_q = static_cast<int32_t>(e >> 8);
-            } else {
-              raw = row_strategy[num];
-              cur_q = row_quant[num];
-            }
-            if (raw < 0 || raw >= static_cast<int32_t>(kNumStrategies)) {
-              status |= kVBadStream;
-              break;
-            }
-            const StrategyInfo si = UnpackStrategyInfo(stage ? sinfo_stage[raw] : V.upool[V.sinfo_off + raw]);
-            const uint32_t next_x = (x / 32 + 1) * 32, next_y = (y / 32 + 1) * 32;  // varblocks stay inside their 256x256 group
-            const uint32_t xlim = x0 + xs, ylim = y0 + ys;
-            if (x + si.cx > next_x || x + si.cx > xlim || y + si.cy > next_y || y + si.cy > ylim) {
-              status |= kVBadStream;
-              break;
-            }
-            const uint32_t mask = (si.cx >= 32 ? 0xFFFFFFFFu : ((1u << si.cx) - 1u)) << (ix & 31);
-            uint32_t overlap = 0;
-            for (uint32_t jy = 0; jy < si.cy; jy++) {
-              uint32_t& w = orow[jy * 8 + wi];
-              overlap |= w & mask;
+          const uint32_t rows_left_in_group = 32 - (iy & 31), rows_left = ys - iy;
+          for (; wi < 8; wi++) {
+            uint32_t w = orow[wi];
+            while (~w != 0) {
+              if (num >= chunk_end) {
+                if (last_chunk) status |= kVBadStream;  // more varblocks than list entries
+                paused = true;
+                break;
+              }
+              const uint32_t e = e_next;
+              e_next = num + 1 < chunk_end ? stage[num + 1 - chunk] : 0xFFu;  // (requested one varblock ahead)
+              const uint32_t b = DevFfs(~w) - 1, ix = (wi << 5) + b;
+              const uint32_t raw = e & 0xFF, cx = (e >> 16) & 0xFF, cy = e >> 24;
+              // a varblock stays inside its 256x256 group (32 blocks) and inside the DC group
+              if (raw == 0xFF || b + cx > 32 || ix + cx > xs || cy > rows_left_in_group || cy > rows_left) {
+                status |= kVBadStream;
+                break;
+              }
+              const uint32_t mask = (cx >= 32 ? 0xFFFFFFFFu : ((1u << cx) - 1u)) << b;
+              uint32_t overlap = w & mask;
               w |= mask;
-              for (uint32_t jx = 0; jx < si.cx; jx++)
-                cell[static_cast<size_t>(jy) * astride + jx] = static_cast<uint8_t>((raw << 1) | ((jy | jx) == 0 ? 1 : 0));
+              for (uint32_t jy = 1; jy < cy; jy++) {
+                uint32_t& o = orow[jy * 8 + wi];
+                overlap |= o & mask;
+                o |= mask;
+              }
+              if (overlap) {
+                status |= kVBadStream;
+                break;
+              }
+              acs[static_cast<size_t>(iy) * astride + ix] = static_cast<uint8_t>((raw << 1) | 1);
+              rawq[static_cast<size_t>(y0 + iy) * W + x0 + ix] = static_cast<uint16_t>(1 + ((e >> 8) & 0xFF));
+              num++;
             }
-            if (overlap) {
-              status |= kVBadStream;
-              break;
-            }
-            int32_t q = cur_q;
-            q = q < 0 ? 0 : (q > 255 ? 255 : q);
-            rawq[pos] = static_cast<uint16_t>(1 + q);
-            num++;
+            orow[wi] = w;
+            if (paused || (status & kVBadStream)) break;  // (before wi moves on: the scan resumes inside this word)
           }
-          if (paused || (status & kVBadStream)) break;
+          if (paused || (status & kVBadStream)) break;  // (resume at the same row and word with the next chunk)
         }
       }
-      if (stage) CoopSync<SCOPE>();
+      CoopSync<SCOPE>();
     }
   }
-  CoopSync<SCOPE>();
-  // (c) EPF sigma per block (ComputeSigma): every varblock fills the blocks it covers
-  if (vf.epf_iters > 0) {
+  // (c) every varblock fills the cells it covers: strategy bytes (first-block flag clear) and, with EPF, the inverse
+  // sigma per block (ComputeSigma)
+  {
     float* inv_sigma = V.farena + vf.inv_sigma;
     const float kInvSigmaNum = -1.1715728752538099024f;
+    const bool epf = vf.epf_iters > 0;
     for (uint32_t i = tid; i < xs * ys; i += nt) {
       const uint32_t x = i % xs, y = i / xs;
       const size_t pos = static_cast<size_t>(y0 + y) * W + x0 + x;
       const uint8_t a = acs[static_cast<size_t>(y) * astride + x];
-      if (a == 0xFF || !(a & 1)) continue;
+      if (a == 0xFF || !(a & 1)) continue;  // (cells of other varblocks: 0xFF until their owner gets here, or filled)
       const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + (a >> 1)]);
-      const float sigma_quant = vf.epf_quant_mul / (vf.global_scale_f * static_cast<float>(rawq[pos]) * kInvSigmaNum);
-      for (uint32_t iy = 0; iy < si.cy; iy++)
-        for (uint32_t ix = 0; ix < si.cx; ix++) {
-          const size_t q = pos + static_cast<size_t>(iy) * W + ix;
-          float sigma = sigma_quant * vf.epf_sharp_lut[sharp[q]];
-          sigma = sigma < -1e-4f ? sigma : -1e-4f;
-          inv_sigma[q] = 1.0f / sigma;
+      const float sigma_quant = epf ? vf.epf_quant_mul / (vf.global_scale_f * static_cast<float>(rawq[pos]) * kInvSigmaNum) : 0.0f;
+      for (uint32_t jy = 0; jy < si.cy; jy++)
+        for (uint32_t jx = 0; jx < si.cx; jx++) {
+          if (jy | jx) acs[static_cast<size_t>(y + jy) * astride + x + jx] = static_cast<uint8_t>(a & 0xFE);
+          if (epf) {
+            const size_t q = pos + static_cast<size_t>(jy) * W + jx;
+            float sigma = sigma_quant * vf.epf_sharp_lut[sharp[q]];
+            sigma = sigma < -1e-4f ? sigma : -1e-4f;
+            inv_sigma[q] = 1.0f / sigma;
+          }
         }
     }
   }

@@ -84,6 +84,16 @@ void jxlo_transform_to_pixels(int strategy, const float* coeffs, float* pixels) 
   std::vector<float> c(coeffs, coeffs + n), scratch(3 * n + 64);
   TransformToPixels(strategy, c.data(), pixels, 8 * kCoveredX[strategy], scratch.data());
 }
+// TransformFromPixels for any AcStrategy up to 64x64; pixels is (8 * covered_y) x (8 * covered_x), dense.
+void jxlo_transform_from_pixels(int strategy, const float* pixels, float* coeffs) {
+  const size_t n = 64u * kCoveredX[strategy] * kCoveredY[strategy];
+  std::vector<float> scratch(5 * n + 1024);
+  TransformFromPixelsRef(strategy, pixels, 8 * kCoveredX[strategy], coeffs, scratch.data());
+}
+// DCFromLowestFrequencies: coefficients of one varblock -> covered_y x covered_x DC values (dense).
+void jxlo_dc_from_llf(int strategy, const float* coeffs, float* dc) {
+  DCFromLowestFrequencies(strategy, coeffs, dc, kCoveredX[strategy]);
+}
 void jxlo_llf_from_dc(int strategy, const float* dc, size_t dc_stride, float* llf) {
   LowestFrequenciesFromDC(strategy, dc, dc_stride, llf);
 }

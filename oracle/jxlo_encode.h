@@ -23,6 +23,7 @@
 
 #include "jxlo_render.h"
 #include "jxlo_vardct.h"
+#include "jxlo_enc_acs.h"
 
 namespace jxlo {
 
@@ -802,61 +803,10 @@ inline void WriteModularStream(BitWriter& w, const EntropyEncoder& code, const s
 }
 
 // ---------------------------------------------------------------- forward transforms
-// The 8x8 special transforms (IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, AFV0-3) are
-// inverted numerically from the decoder's basis: pixels = A * coeffs, coeffs = A^-1 * pixels.
-inline const std::vector<double>& SpecialForwardMatrix(int strategy) {
-  static std::map<int, std::vector<double>> cache;
-  auto it = cache.find(strategy);
-  if (it != cache.end()) return it->second;
-  std::vector<double> a(64 * 64), inv(64 * 64, 0.0);
-  float scratch[256];
-  for (int k = 0; k < 64; k++) {
-    float coeffs[64] = {0}, px[64];
-    coeffs[k] = 1.0f;
-    TransformToPixels(strategy, coeffs, px, 8, scratch);
-    for (int p = 0; p < 64; p++) a[p * 64 + k] = px[p];
-  }
-  for (int i = 0; i < 64; i++) inv[i * 64 + i] = 1.0;
-  for (int col = 0; col < 64; col++) {  // Gauss-Jordan with partial pivoting
-    int piv = col;
-    for (int r = col + 1; r < 64; r++)
-      if (std::fabs(a[r * 64 + col]) > std::fabs(a[piv * 64 + col])) piv = r;
-    JXLO_CHECK(std::fabs(a[piv * 64 + col]) > 1e-12, "singular transform basis");
-    if (piv != col)
-      for (int k = 0; k < 64; k++) {
-        std::swap(a[piv * 64 + k], a[col * 64 + k]);
-        std::swap(inv[piv * 64 + k], inv[col * 64 + k]);
-      }
-    const double d = 1.0 / a[col * 64 + col];
-    for (int k = 0; k < 64; k++) {
-      a[col * 64 + k] *= d;
-      inv[col * 64 + k] *= d;
-    }
-    for (int r = 0; r < 64; r++) {
-      if (r == col) continue;
-      const double f = a[r * 64 + col];
-      if (f == 0.0) continue;
-      for (int k = 0; k < 64; k++) {
-        a[r * 64 + k] -= f * a[col * 64 + k];
-        inv[r * 64 + k] -= f * inv[col * 64 + k];
-      }
-    }
-  }
-  return cache[strategy] = inv;
-}
-
-// TransformFromPixels: pixels (stride) -> coefficients in the decoder's layout.
+// TransformFromPixels: pixels (stride) -> coefficients in the decoder's layout: libjxl's forward transforms
+// (jxlo_enc_acs.h, lib/jxl/enc_transforms-inl.h:462-660).
 inline void TransformFromPixels(int strategy, const float* pixels, size_t stride, float* coeffs, float* scratch) {
-  if (IsPlainDCT(strategy)) {
-    ScaledDCT(kCoveredY[strategy] * 8, kCoveredX[strategy] * 8, pixels, stride, coeffs, scratch);
-    return;
-  }
-  const std::vector<double>& m = SpecialForwardMatrix(strategy);
-  for (int k = 0; k < 64; k++) {
-    double s = 0;
-    for (int p = 0; p < 64; p++) s += m[k * 64 + p] * pixels[(p / 8) * stride + (p % 8)];
-    coeffs[k] = static_cast<float>(s);
-  }
+  TransformFromPixelsRef(strategy, pixels, stride, coeffs, scratch);
 }
 
 // ---------------------------------------------------------------- colour
@@ -905,7 +855,9 @@ inline void LinearRgbToXyb(float r, float g, float b, float* x, float* y, float*
 struct EncodeParams {
   float distance = 1.0f;
   // 0: DCT8 only; 1: seeded random mix of all 27 strategies (decoder coverage);
-  // 2: variance heuristic over {8x8, 16x16, 32x32, 16x8, 8x16, 64x64}; 100 + s: strategy s wherever it fits
+  // 2: variance heuristic over {8x8, 16x16, 32x32, 16x8, 8x16, 64x64}; 100 + s: strategy s wherever it fits;
+  // 3: libjxl's effort-7 entropy-estimate search (jxlo_enc_acs.h: AcStrategyHeuristics::ProcessRect per 64x64 tile
+  //    after the DCT8 chroma-from-luma pre-pass, lib/jxl/enc_heuristics.cc:1150-1166); needs adaptive_quant
   int strategy_mode = 2;
   uint32_t seed = 1;
   bool gab = true;
@@ -1560,6 +1512,10 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   const bool adaptive = p.adaptive_quant && !p.random_side_info;
   std::vector<float> quant_field;
   if (adaptive) quant_field = aq::InitialQuantField(xyb, p.gab ? p.distance : p.distance * 0.62f, 1.0f);
+  const bool acs_search = p.strategy_mode == 3;
+  JXLO_CHECK(!acs_search || adaptive, "the AcStrategy search needs the adaptive quantisation field");
+  std::vector<float> mask1x1;  // the per-pixel masking image of the search, also from the planes before inverse Gaborish
+  if (acs_search) mask1x1 = acs::Mask1x1(xyb[1].d.data(), PW, PH, [](float v) { return aq::RatioOfDerivatives<false>(v); });
   if (adaptive && std::getenv("JXLO_DEBUG_AQ")) {
     std::vector<float> v = quant_field;
     std::sort(v.begin(), v.end());
@@ -1622,11 +1578,66 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
         if (acs[y * W + x] != 0xFF) return false;
     return true;
   };
+  if (acs_search) {
+    // per 64x64 tile: chroma-from-luma factors under 8x8 DCTs without quantisation weighting (CfLHeuristics::ComputeTile
+    // with ac_strategy == nullptr, lib/jxl/enc_chroma_from_luma.cc:196-342), then the search with those factors
+    acs::Config config;
+    acs::InitConfig(&config, p.distance);
+    std::vector<float> mats[kNumStrategies], inv_mats[kNumStrategies];
+    for (int st = 0; st <= kDCT32X64; st++) {  // all transforms up to 64x64 (AcStrategyHeuristics::Init)
+      const int t = kStrategyToQuantTable[st];
+      mats[st] = ComputeQuantTable(LibraryEncoding(t), t);
+      inv_mats[st] = ComputeQuantWeights(LibraryEncoding(t), t);
+      size_t lx = kCoveredX[st], ly = kCoveredY[st];
+      if (ly > lx) std::swap(lx, ly);
+      const size_t size = 64u * lx * ly;
+      for (int c = 0; c < 3; c++)
+        for (size_t y = 0; y < ly; y++)
+          for (size_t x = 0; x < lx; x++) inv_mats[st][c * size + y * 8 * lx + x] = 0;  // (LLF corner, quant_weights.cc:337-349)
+      config.matrix[st] = &mats[st];
+      config.inv_matrix[st] = &inv_mats[st];
+    }
+    config.quant_field = quant_field.data();
+    config.quant_stride = W;
+    config.mask1x1 = mask1x1.data();
+    config.mask_stride = PW;
+    config.mask1x1_xsize = PW;
+    for (int c = 0; c < 3; c++) config.src[c] = xyb[c].d.data();
+    config.src_stride = PW;
+    acs::AcsImage image{acs.data(), W, H};
+    std::vector<float> byx(4096), bxx(4096), byb(4096), bbb(4096), blk(3 * 4096), scr(5 * 4096 + 1024);
+    for (size_t ty = 0; ty < cmh; ty++)
+      for (size_t tx = 0; tx < cmw; tx++) {
+        const size_t x0 = tx * 8, y0 = ty * 8, x1 = std::min(W, x0 + 8), y1 = std::min(H, y0 + 8);
+        size_t num_ac = 0;
+        for (size_t by = y0; by < y1; by++)
+          for (size_t bx = x0; bx < x1; bx++) {
+            for (int c = 0; c < 3; c++) TransformFromPixelsRef(kDCT, xyb[c].Row(by * 8) + bx * 8, PW, blk.data() + c * 64, scr.data());
+            for (int c = 0; c < 3; c++) blk[c * 64] = 0;
+            for (size_t i = 0; i < 64; i++) {
+              const float qqm_x = 1.0f * inv_mats[kDCT][i], qqm_b = 1.0f * inv_mats[kDCT][128 + i];
+              byx[num_ac] = blk[64 + i] * qqm_x;
+              bxx[num_ac] = blk[i] * qqm_x;
+              byb[num_ac] = blk[64 + i] * qqm_b;
+              bbb[num_ac] = blk[128 + i] * qqm_b;
+              num_ac++;
+            }
+          }
+        const int32_t pre_x = FindBestMultiplier(byx.data(), bxx.data(), num_ac, 0.0f, 1e-9f);
+        const int32_t pre_b = FindBestMultiplier(byb.data(), bbb.data(), num_ac, 1.0f, 1e-9f);
+        const float cmap_factors[3] = {0.0f + static_cast<int8_t>(pre_x) * (1.0f / 84), 0.0f, 1.0f + static_cast<int8_t>(pre_b) * (1.0f / 84)};
+        acs::ProcessRectACS(p.distance, config, x0, y0, x1 - x0, y1 - y0, cmap_factors, blk.data(), scr.data(), &image);
+      }
+  }
   size_t num_varblocks = 0;
   for (size_t by = 0; by < H; by++) {
     for (size_t bx = 0; bx < W; bx++) {
-      if (acs[by * W + bx] != 0xFF) continue;
-      int s = kDCT;
+      if (acs_search) {
+        if (!(acs[by * W + bx] & 1)) continue;  // (the search has filled the map)
+      } else if (acs[by * W + bx] != 0xFF) {
+        continue;
+      }
+      int s = acs_search ? acs[by * W + bx] >> 1 : kDCT;
       if (p.strategy_mode == 1) {
         // all 27 strategies; the larger ones only where they are aligned to their own size
         for (int attempt = 0; attempt < 4; attempt++) {
@@ -1655,7 +1666,7 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
           }
         }
       }
-      for (size_t y = 0; y < kCoveredY[s]; y++)
+      for (size_t y = 0; y < kCoveredY[s] && !acs_search; y++)
         for (size_t x = 0; x < kCoveredX[s]; x++)
           acs[(by + y) * W + bx + x] = static_cast<uint8_t>((s << 1) | ((x | y) == 0 ? 1 : 0));
       int rq = base_raw;
@@ -1685,6 +1696,15 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
     }
   }
 
+  if (std::getenv("JXLO_DEBUG_ACS")) {
+    size_t count[kNumStrategies] = {0};
+    for (size_t i = 0; i < W * H; i++)
+      if (acs[i] & 1) count[acs[i] >> 1]++;
+    std::fprintf(stderr, "O acs:");
+    for (int st = 0; st < kNumStrategies; st++)
+      if (count[st]) std::fprintf(stderr, " %d:%zu", st, count[st]);
+    std::fprintf(stderr, "\n");
+  }
   // ---- chroma-from-luma map (E6): CfLHeuristics::ComputeTile, lib/jxl/enc_chroma_from_luma.cc:196-342, as libjxl runs it
   // after the block sizes are known (lib/jxl/enc_heuristics.cc:1176-1182): per 64x64 tile the AC coefficients of the
   // varblocks that lie inside the tile, weighted by the quantisation step, and one robust fit per chroma channel.

@@ -163,7 +163,9 @@ inline void GetQuantWeights(size_t rows, size_t cols, const DctParams& p, float*
 
 // ComputeQuantTable, quant_weights.cc:162-355. Returns the dequantisation
 // multipliers (1 / weight), 3 * num values, channel-major.
-inline std::vector<float> ComputeQuantTable(const QuantEncoding& enc, int table) {
+// The encoder-side weights of a quantisation table (what libjxl keeps as InvMatrix before it zeroes the LLF corner,
+// lib/jxl/quant_weights.cc:322-349); the dequantisation table is 1 / weights (ComputeQuantTable below).
+inline std::vector<float> ComputeQuantWeights(const QuantEncoding& enc, int table) {
   const size_t wrows = 8 * kRequiredSizeX[table], wcols = 8 * kRequiredSizeY[table];
   const size_t num = wrows * wcols;
   std::vector<float> weights(3 * num, 0.0f);
@@ -286,11 +288,14 @@ inline std::vector<float> ComputeQuantTable(const QuantEncoding& enc, int table)
     default:
       throw Error("jxlo: unresolved quant table mode");
   }
-  std::vector<float> out_table(3 * num);
-  for (size_t i = 0; i < 3 * num; i++) {
+  for (size_t i = 0; i < 3 * num; i++)
     JXLO_CHECK(!(weights[i] >= 1.0f / kAlmostZero) && !(weights[i] < kAlmostZero), "invalid quantization table");
-    out_table[i] = 1.0f / weights[i];
-  }
+  return weights;
+}
+
+inline std::vector<float> ComputeQuantTable(const QuantEncoding& enc, int table) {
+  std::vector<float> out_table = ComputeQuantWeights(enc, table);
+  for (float& v : out_table) v = 1.0f / v;
   return out_table;
 }
 

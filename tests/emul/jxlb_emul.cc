@@ -151,10 +151,9 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       std::vector<uint32_t> occ(kDcOccWords);  // stands in for the kernel's shared memory
       for (uint32_t f = 0; f < b.vframes.size(); f++) {
         const DevVFrame& vf = b.vframes[f];
-        std::vector<uint16_t> stage(kDcStageEntries);
-        uint32_t sinfo_stage[kNumStrategies];
+        std::vector<uint32_t> stage(kDcStageEntries);
         for (uint32_t g = 0; g < vf.xdcgroups * vf.ydcgroups; g++, dcg++)
-          DevDcGroupFinish<0>(P, V, f, g, 0, 1, dcg, occ.data(), stage.data(), sinfo_stage);
+          DevDcGroupFinish<0>(P, V, f, g, 0, 1, dcg, occ.data(), stage.data());
         if (!vf.skip_dc_smoothing)
           for (uint32_t y = 0; y < vf.yblocks; y++)
             for (uint32_t x = 0; x < vf.xblocks; x++) DevDcSmoothBlock(V, vf, x, y);

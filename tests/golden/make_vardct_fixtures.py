@@ -19,11 +19,15 @@ import vardct_cases as vc  # noqa: E402
 def main():
     gpath = os.path.join(HERE, "golden.json")
     g = json.load(open(gpath))
-    frames = {"vardct_4k_natural.jxl": (vc.frame_4k(), dict(distance=1.0, strategy_mode=2)),
-              "vardct_4k_synthetic.jxl": (vc.synthetic(2160, 3840, 0xB200), dict(distance=1.0, strategy_mode=2))}
+    # What a libjxl effort-7 stream at distance 1.0 exercises: block sizes and the 8x8 special transforms chosen by
+    # libjxl's entropy-estimate search (strategy_mode 3, oracle/jxlo_enc_acs.h), adaptive quantisation field, fitted
+    # chroma-from-luma maps, custom coefficient orders, inverse Gaborish, Gaborish + one EPF iteration in the loop
+    # filter (lib/jxl/enc_frame.cc:254-287: epf_iters = 1 for 0.7 <= distance < 1.5), the fixed weighted-predictor DC tree.
+    kw_e7 = dict(distance=1.0, strategy_mode=3, epf_iters=1)
+    frames = {"vardct_4k_natural.jxl": (vc.frame_4k(), kw_e7),
+              "vardct_4k_synthetic.jxl": (vc.synthetic(2160, 3840, 0xB200), kw_e7)}
     for name, (img, kw) in frames.items():
-        # (the decode fixtures were written before the encoder learned inverse Gaborish / coefficient orders: all off; nor adaptive quantisation)
-        data = jxlo.encode_vardct(img, inverse_gaborish=False, coeff_orders=False, cfl=False, adaptive_quant=False, **kw)
+        data = jxlo.encode_vardct(img, **kw)
         open(os.path.join(HERE, name), "wb").write(data)
         px = jxlo.decode(data, 3, jxlo.UINT8)
         err = px.astype(float) - img

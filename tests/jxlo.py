@@ -15,12 +15,21 @@ class Info(ctypes.Structure):
 
 
 _lib = None
+_fast = False
+
+
+def use_fast_build(on=True):
+    """Timing arms of bench.py only: load oracle/libjxlo_fast.so (-O3 -march=x86-64-v3, bit-identical output) instead of
+    the -O2 checker build. Must be called before the first use."""
+    global _fast, _lib
+    _fast = bool(on)
+    _lib = None
 
 
 def lib():
     global _lib
     if _lib is None:
-        path = os.path.join(ROOT, "oracle", "libjxlo.so")
+        path = os.path.join(ROOT, "oracle", "libjxlo_fast.so" if _fast else "libjxlo.so")
         if not os.path.exists(path):
             import subprocess
             subprocess.check_call(["make", "-s"], cwd=os.path.join(ROOT, "oracle"))
