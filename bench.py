@@ -142,6 +142,7 @@ def cpu_baseline(wl, seconds=15.0, threads=None):
     `seconds` (every thread finishes the frame it started)."""
     import jxlo
     threads = threads or (os.cpu_count() or 1)
+    jxlo.use_fast_build()  # oracle/libjxlo_fast.so: -O3 -march=x86-64-v3, bit-identical (tests/test_oracle_fast_build.py)
     jxlo.lib()
     d = jxlo.Decoded(wl.blobs[0])
     w, h = d.info.xsize, d.info.ysize
@@ -165,13 +166,17 @@ def cpu_baseline(wl, seconds=15.0, threads=None):
     dt = time.time() - t0
     frames = sum(count)
     return {"value": frames * w * h / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{frames} {wl.name} frames ({w}x{h}) in {dt:.1f} s on {threads} threads, oracle-CPU (not libjxl)"}, dt
+            "sample": f"{frames} {wl.name} frames ({w}x{h}) in {dt:.1f} s on {threads} threads, oracle-CPU (not libjxl): "
+                      "the scalar restatement built -O3 -march=x86-64-v3, one frame per thread. libjxl itself (Highway SIMD) "
+                      "cannot be built here; its own design figure is ~400 Mpx/s multithreaded decode "
+                      "(jpegxl-src/libjxl/doc/xl_overview.md:7-9), so ratios against this arm are upper bounds"}, dt
 
 
 def cpu_encode_baseline(wl, images, seconds=15.0, threads=None):
     """The oracle's plain encoder on the host cores, one frame at a time per thread."""
     import jxlo
     threads = threads or (os.cpu_count() or 1)
+    jxlo.use_fast_build()
     jxlo.lib()
     count = [0] * threads
     stop = time.time() + seconds
@@ -262,7 +267,9 @@ def run_encode(args, wl):
                 "roofline": {"bound": "hbm", "kernel": top, "achieved": alg / (phases[top] * 1e-3) / 1e9, "peak": peak,
                              "peak_kind": peak_kind, "unit": "GB/s", "frac": alg / (phases[top] * 1e-3) / 1e9 / peak,
                              "traffic": None, "algorithmic_bytes_per_launch": int(alg), "kernel_ms": phases[top],
-                             "kernel_share_of_step": phases[top] / ms_dev, "all_kernels_ms": phases}}
+                             "kernel_share_of_step": phases[top] / ms_dev,
+                             "step_achieved": alg / (ms_dev * 1e-3) / 1e9, "step_frac": alg / (ms_dev * 1e-3) / 1e9 / peak,
+                             "all_kernels_ms": phases}}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _ = cpu_encode_baseline(wl, base, seconds=args.cpu_seconds)
         print(json.dumps(line))
@@ -314,6 +321,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short encode / lossless side runs folded into `also`")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -331,41 +339,21 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (jxl_b200 has no CPU fallback)")
+    # Host side of a rank: the CPUs of its GPU's NUMA node, split between the ranks that share the node -- before any
+    # thread or pinned buffer exists, so that the planning threads, the CUDA driver's threads and the first touch of the
+    # pinned output buffers all land next to the GPU (8 ranks otherwise run 8 x 32 planning threads on 32 cores and copy
+    # across sockets).
+    host = bind_rank_to_numa(torch, local_rank, local_world)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = Workload(args.workload, args.batch)
     files = wl.files
-    # handles in flight: at most --inflight, and a divisor of --steps so that every handle runs the same number of steps
-    # (no tail in which only a few handles are left)
-    # ... and no more than fit into HBM: the first handle's footprint (arenas + output + bitstreams) is measured, the
-    # others may take 85 % of what is free after it
-    free0, _ = torch.cuda.mem_get_info()
-    decs = [pkg.BatchDecoder(local_rank)]
-    decs[0].set_input(files, wl.channels, pkg.JXL_TYPE_UINT8)
-    decs[0].run()
-    decs[0].wait()  # (the first wait may regrow the token arena)
-    torch.cuda.synchronize()
-    free1, _ = torch.cuda.mem_get_info()
-    per_handle = max(free0 - free1, 1)
-    fit = 1 + int(0.85 * free1 // per_handle)
-    cap = max(1, min(args.inflight, args.steps, fit))
-    nfl = max(d for d in range(1, cap + 1) if args.steps % d == 0)
-    if rank == 0 and nfl < args.inflight:
-        print("handles in flight: %d (asked for %d; %d steps; %.1f GB of HBM per handle, %.1f GB free)"
-              % (nfl, args.inflight, args.steps, per_handle / 1e9, free1 / 1e9), file=sys.stderr)
-    decs += [pkg.BatchDecoder(local_rank) for _ in range(nfl - 1)]
-    for d in decs[1:]:
-        d.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8)
-    dec = decs[0]
-    tstreams = [torch.cuda.Stream() for _ in range(nfl)]
-    torch.cuda.set_stream(tstreams[0])
-    streams = [t.cuda_stream for t in tstreams]
-    stream = streams[0]
-    assert all(x != 0 for x in streams)
+    plan_threads = max(1, min(host["cpus"], 32))
 
     def barrier():
         torch.cuda.synchronize()
@@ -373,11 +361,68 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # handles in flight: at most --inflight and no more than fit into HBM: the first handle's footprint (arenas + output +
+    # bitstreams) is measured, the others may take 85 % of what is free after it (and after rank 0's gather buffers);
+    # every rank uses the same number
+    free0, _ = torch.cuda.mem_get_info()
+    decs = [pkg.BatchDecoder(local_rank)]
+    decs[0].set_input(files, wl.channels, pkg.JXL_TYPE_UINT8, threads=plan_threads)
+    decs[0].run()
+    decs[0].wait()  # (the first wait may regrow the token arena)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    per_handle = max(free0 - free1, 1)
+    # ---- the one collective of the path: every step's decoded frames are gathered on rank 0, device to
+    # device over NVLink (NCCL gather of the handles' output buffers wrapped as CUDA tensors, no host round trip), on
+    # NCCL's own stream so that it overlaps the kernels of the next steps
+    out_bytes = decs[0].device_output_bytes()
+    gather_bufs = None
+    if world > 1 and rank == 0:
+        gather_bufs = [torch.empty(out_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        free1, _ = torch.cuda.mem_get_info()
+    fit = 1 + int(0.85 * free1 // per_handle)
+    cap = max(1, min(args.inflight, args.steps, fit))
+    if world > 1:
+        t = torch.tensor([cap], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        cap = int(t.item())
+    nfl = cap
+    if rank == 0 and nfl < args.inflight:
+        print("handles in flight: %d (asked for %d; %d steps; %.1f GB of HBM per handle, %.1f GB free)"
+              % (nfl, args.inflight, args.steps, per_handle / 1e9, free1 / 1e9), file=sys.stderr)
+    decs += [pkg.BatchDecoder(local_rank) for _ in range(nfl - 1)]
+    for d in decs[1:]:
+        d.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8, threads=plan_threads)
+    dec = decs[0]
+    tstreams = [torch.cuda.Stream() for _ in range(nfl)]
+    torch.cuda.set_stream(tstreams[0])
+    streams = [t.cuda_stream for t in tstreams]
+    assert all(x != 0 for x in streams)
+    out_tensors = [d.device_output_tensor() for d in decs] if world > 1 else None
+    gather_work = [None] * nfl
+
+    def gather_step(h):
+        """Enqueues the gather of handle h's output after its kernels; the handle's next run waits for it."""
+        with torch.cuda.stream(tstreams[h]):
+            gather_work[h] = dist.gather(out_tensors[h], gather_bufs, dst=0, async_op=True)
+
+    def run_step(i):
+        h = i % nfl
+        if gather_work[h] is not None:
+            with torch.cuda.stream(tstreams[h]):
+                gather_work[h].wait()  # (stream-side wait: the previous gather has read this handle's output)
+            gather_work[h] = None
+        decs[h].run(streams[h])
+        if world > 1:
+            gather_step(h)
+
     # ---- device-resident throughput: bitstreams and tables already in HBM ----
     for _ in range(max(args.warmup, 1)):
-        for d, sx in zip(decs, streams):
+        for h, (d, sx) in enumerate(zip(decs, streams)):
             d.run(sx)
             d.wait(sx)  # (the first wait may regrow the token arena and decode again)
+            if world > 1:
+                gather_step(h)
     st = dec.stats()
     for d in decs:
         d.set_profiling(True)
@@ -389,7 +434,12 @@ def main():
     for t in tstreams[1:]:
         t.wait_event(e0)
     for i in range(args.steps):  # step i runs on handle i mod inflight; same-handle steps are ordered by its stream
-        decs[i % nfl].run(streams[i % nfl])
+        run_step(i)
+    for h in range(nfl):
+        if gather_work[h] is not None:
+            with torch.cuda.stream(tstreams[h]):
+                gather_work[h].wait()
+            gather_work[h] = None
     for t in tstreams[1:]:
         tstreams[0].wait_event(t.record_event())
     e1.record(tstreams[0])
@@ -408,6 +458,7 @@ def main():
     # One more profiled pass with a single handle and nothing else on the GPU: per-kernel times without the overlap of
     # the other handles (in the timed region a kernel's event-to-event time includes waiting for SMs that another
     # handle's kernels hold, so the classes add up to more than the step).
+    barrier()
     alone_ms = {}
     decs[0].set_profiling(True)
     for _ in range(2):
@@ -424,6 +475,33 @@ def main():
     pixels_per_step = st.pixels * world
     value = pixels_per_step / (ms_per_step * 1e-3) / 1e6
 
+    # the gather alone (nothing else on the GPUs): bytes into rank 0 per second, and the check that what arrived is what
+    # every rank decoded
+    gather_info = None
+    if world > 1:
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        g0.record(tstreams[0])
+        for _ in range(reps):
+            with torch.cuda.stream(tstreams[0]):
+                dist.gather(out_tensors[0], gather_bufs, dst=0)
+        g1.record(tstreams[0])
+        barrier()
+        t = torch.tensor([g0.elapsed_time(g1) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gms = float(t.item())
+        okg = True
+        if rank == 0:
+            n0 = dec.out_size(0)
+            for r_ in range(world):  # frame 0 of every rank's share, read from rank 0's gather buffer
+                okg = okg and hashlib.sha256(gather_bufs[r_][:n0].cpu().numpy().tobytes()).hexdigest() == wl.sha[0]
+        gather_info = {"collective": "ncclGather of the decoded frames to rank 0 (device to device, every step, inside the "
+                                     "timed region, overlapping the next steps' kernels)",
+                       "bytes_per_step_into_rank0": int(out_bytes) * (world - 1), "alone_ms": gms,
+                       "alone_gbs_into_rank0": out_bytes * (world - 1) / (gms * 1e-3) / 1e9,
+                       "nvlink5_gbs_per_direction": 900.0, "gathered_checksum_ok": bool(okg)}
+
     # ---- end to end through the public API with host buffers ----
     # Every step: host parse + H2D of that step's bitstreams and tables, the kernels, D2H of the pixels into pinned
     # host memory. Steps run on `inflight` handles from as many host threads (ctypes drops the GIL), so the host
@@ -432,7 +510,7 @@ def main():
     set_bytes = sum(dec.out_size(i) for i in range(wl.batch))
     try:
         import psutil
-        share = psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        share = psutil.virtual_memory().available / max(1, local_world)
     except Exception:
         share = 64e9
     nfl_e2e = max(1, min(nfl, int(0.4 * share // max(set_bytes, 1))))
@@ -451,6 +529,22 @@ def main():
         out_sets.append([np.empty(dec.out_size(i), dtype=np.uint8) for i in range(wl.batch)])
     nfl_e2e = len(out_sets)
     outs = out_sets[0]
+
+    # The ceiling of the read-back: every rank copies its output buffer from HBM into the pinned set at the same time,
+    # nothing else running -- PCIe and host-DRAM write bandwidth shared by the ranks of the node. e2e cannot beat
+    # d2h_bytes / this.
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        dec.read_outputs(out_sets[0])
+    torch.cuda.synchronize()
+    d2h_s = (time.perf_counter() - t0) / 2
+    t = torch.tensor([d2h_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    d2h_s = float(t.item())
+    barrier()
+
     # enough steps for the handles to fall out of lock step (parse / kernels / read-back of different steps overlap);
     # the ramp-up and the drain stay inside the timed region
     e2e_steps = max(3 * nfl_e2e, min(args.steps, 16))
@@ -461,7 +555,7 @@ def main():
     def e2e_step(h):
         d, sx = decs[h], streams[h]
         t0 = time.perf_counter()
-        d.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8)
+        d.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8, threads=plan_threads)
         t1 = time.perf_counter()
         d.run(sx)
         d.wait(sx)
@@ -513,27 +607,33 @@ def main():
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
     ok = bool(okt.item())
 
+    # free the HBM and the pinned sets before the side workloads
+    del out_sets, outs, decs, dec, out_tensors, gather_bufs
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
         per_run = {k: v / max(runs, 1) for k, v in kernel_ms.items()}
         top = max(alone_ms, key=alone_ms.get) if alone_ms else max(per_run, key=per_run.get)
         # algorithmic bytes per launch: one read of the bitstream + one write of the output pixels
         alg_bytes = st.compressed_bytes + st.output_bytes
-        top_ms = per_run[top]
+        top_ms = alone_ms.get(top, per_run[top])  # the dominant kernel's launch alone on the GPU (CUDA events)
         achieved = alg_bytes / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            e = tj.get(wl.name, {})
-            if e.get("batch") == wl.batch and e.get("kernel") == top:
-                traffic = e.get("dram_bytes_per_launch")
+            e = json.load(open(tpath)).get(wl.name, {})
+            if e.get("batch") == wl.batch:
+                traffic = e.get("dram_bytes_per_step_all_kernels")
         line = {
             "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": wl.dtype, "data": wl.data,
             "config": {"workload": wl.desc, "batch_per_gpu": wl.batch, "entropy_streams": int(st.num_streams),
                        "wave_frames": int(st.wave_frames), "handles_in_flight": nfl,
+                       "host": host,
                        "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)"
                        % ((st.arena_bytes + st.output_bytes + st.compressed_bytes) / 1e9),
                        "golden_checksum_ok": ok},
@@ -541,22 +641,105 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(st.compressed_bytes), "d2h_bytes_per_step": int(st.output_bytes),
                     "includes": "host parse (threads) + H2D bitstreams/tables + kernels + D2H to pinned host, "
-                                "%d steps in flight" % nfl_e2e},
+                                "%d steps in flight" % nfl_e2e,
+                    "d2h_alone_ms_per_step": d2h_s * 1e3,
+                    "d2h_ceiling_gbs_per_gpu": st.output_bytes / d2h_s / 1e9,
+                    "d2h_ceiling_value": pixels_per_step / d2h_s / 1e6,
+                    "frac_of_d2h_ceiling": d2h_s / e2e_s,
+                    "note": "d2h_*: the read-back of one step's pixels alone, all ranks at the same time (PCIe + host DRAM "
+                            "shared by the node): the end-to-end figure cannot exceed d2h_ceiling_value"},
             "gpu_launches": int(st.kernel_launches) * args.steps,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": top_ms,
-                         "kernel_share_of_step": top_ms / ms_per_step if ms_per_step else None,
-                         "all_kernels_ms": per_run, "all_kernels_ms_one_handle_alone": alone_ms,
-                         "note": "kernel = the class with the longest launch when one handle runs alone; kernel_ms = "
-                                 "its mean event-to-event time in the timed region (%d handles overlapping)" % nfl},
+                         "kernel_share_of_step": min(1.0, top_ms / ms_per_step) if ms_per_step else None,
+                         "step_achieved": alg_bytes / (ms_per_step * 1e-3) / 1e9,
+                         "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "all_kernels_ms_overlapped": per_run, "all_kernels_ms_one_handle_alone": alone_ms,
+                         "note": "kernel = the class with the longest launch; kernel_ms = that launch alone on the GPU "
+                                 "(one handle, CUDA events on its stream); achieved = algorithmic bytes of the launch's batch "
+                                 "/ kernel_ms; step_* = the same bytes / ms_per_step (%d handles overlapping, which is why "
+                                 "the step is shorter than the sum of the classes); traffic = DRAM bytes of all kernels of "
+                                 "one step (ncu, profiles/traffic.json)" % nfl},
         }
+        if gather_info:
+            line["gather"] = gather_info
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(wl, seconds=args.cpu_seconds)
             line["cpu_baseline"] = cb
+        if world == 1 and not args.no_also and wl.name == "vardct4k":
+            line["also"] = side_workloads(args)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bind_rank_to_numa(torch, local_rank, local_world):
+    """Pins this process to its share of the CPUs next to GPU `local_rank` (sysfs local_cpulist of the GPU's PCI device;
+    an even split of the allowed CPUs when sysfs has no answer). Returns what it did for the JSON line."""
+    allowed = sorted(os.sched_getaffinity(0))
+    info = {"cpus_total": len(allowed), "ranks_on_node": local_world}
+
+    def node_cpus(i):
+        try:
+            p = torch.cuda.get_device_properties(i)
+            bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+            cpus = []
+            for part in txt.split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus += list(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.append(int(part))
+            return tuple(c for c in cpus if c in allowed)
+        except Exception:
+            return tuple()
+
+    mine = tuple(allowed)
+    if local_world > 1:
+        n = min(local_world, torch.cuda.device_count())
+        nodes = [node_cpus(i) for i in range(n)]
+        me = nodes[local_rank] if local_rank < n else tuple()
+        if me and len(me) < len(allowed):
+            sharers = [i for i in range(n) if nodes[i] == me]
+            k, m = sharers.index(local_rank), len(sharers)
+            per = max(1, len(me) // m)
+            mine = me[k * per:(k + 1) * per] if k < m - 1 else me[k * per:]
+            info["numa"] = "GPU-local CPUs split between %d ranks" % m
+        else:
+            per = max(1, len(allowed) // local_world)
+            mine = tuple(allowed[local_rank * per:(local_rank + 1) * per]) or tuple(allowed)
+            info["numa"] = "even split (one NUMA node or no sysfs answer)"
+        try:
+            os.sched_setaffinity(0, mine)
+        except OSError:
+            mine = tuple(allowed)
+    info["cpus"] = len(mine)
+    return info
+
+
+def side_workloads(args):
+    """The other two workloads of the path, short runs in their own processes after the main measurement (same JSON line
+    shape, folded into `also`): the encoder (BASELINE.json configs[2]) and the lossless Modular decode of bench.jxl-shaped
+    frames (configs[4]; the input of the reference's own criterion bench)."""
+    out = {}
+    for name, extra in (("encode4k", ["--batch", "16", "--steps", "3", "--warmup", "1"]),
+                        ("modular", ["--batch", "128", "--steps", "6", "--warmup", "3", "--inflight", "3"])):
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--no-cpu-baseline", "--no-also"] + extra
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode != 0 or not lines:
+                out[name] = {"error": (r.stderr or "no output").strip().splitlines()[-1][:300]}
+                continue
+            j = json.loads(lines[-1])
+            out[name] = {k: j.get(k) for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "dtype", "e2e", "config")}
+            rf = j.get("roofline") or {}
+            out[name]["roofline"] = {k: rf.get(k) for k in ("kernel", "achieved", "frac", "step_frac", "kernel_ms")}
+        except Exception as e:  # a side workload never takes the main line down
+            out[name] = {"error": str(e)[:300]}
+    return out
 
 
 if __name__ == "__main__":

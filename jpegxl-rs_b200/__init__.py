@@ -489,6 +489,9 @@ class BatchDecoder:
     def device_output(self, i: int) -> int:
         return self._lib.JxlB200DecoderDeviceOutput(self._dec, i)
 
+    def device_output_bytes(self) -> int:
+        return self._lib.JxlB200DecoderDeviceOutputBytes(self._dec)
+
     def device_output_tensor(self):
         """The batch's whole output buffer in HBM as a torch uint8 CUDA tensor (no copy): frames back to back, each
         256-byte aligned. What the multi-GPU gather sends."""

@@ -4,6 +4,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <thread>
@@ -297,6 +299,12 @@ using BytesAlloc = std::function<uint8_t*(size_t)>;
 
 inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n, const PixelFormat& fmt,
                       int threads, BatchPlan* batch, const ProbeFn& probe = ProbeFn(), const BytesAlloc& bytes_alloc = BytesAlloc()) {
+  const bool timing = std::getenv("JXLB200_PLAN_TIMING") != nullptr;  // stderr: where the host time of a batch goes
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+  };
+  double t_frames = 0;
   std::vector<FramePlan> plans(n);
   std::vector<CodestreamView> views(n);
   std::vector<std::string> errors(n);
@@ -351,6 +359,7 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
         }
       }
     };
+    const auto t_round = std::chrono::steady_clock::now();
     if (threads == 1 || todo.size() == 1) {
       work();
     } else {
@@ -358,6 +367,7 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
       for (int t = 0; t < std::min<int>(threads, todo.size()); t++) pool.emplace_back(work);
       for (auto& t : pool) t.join();
     }
+    t_frames += since(t_round);
     for (size_t i = 0; i < n; i++) {
       if (!errors[i].empty()) throw Error("frame " + std::to_string(i) + ": " + errors[i]);
     }
@@ -394,6 +404,7 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
       c.done.push_back(std::move(res));
     }
   }
+  const auto t_merge = std::chrono::steady_clock::now();
   {  // one allocation per pool instead of a doubling series
     size_t alias = 0, lut = 0, cpool = 0, tree = 0, chans = 0, planes = 0, streams = 0, acs = 0, prefix = 0, cfg = 0, opool = 0;
     for (const FramePlan& f : plans) {
@@ -452,6 +463,9 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
       return x.bit_end - x.bit_pos > y.bit_end - y.bit_pos;
     });
   }
+  if (timing)
+    std::fprintf(stderr, "PlanBatch: %zu files, %d threads: %.1f ms (per-file planning %.1f ms, merge %.1f ms)\n", n, threads,
+                 since(t_begin), t_frames, since(t_merge));
 }
 
 }  // namespace jxlb

@@ -11,6 +11,8 @@
 #ifndef JXLB_PLAN_H_
 #define JXLB_PLAN_H_
 
+#include <algorithm>
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <vector>
@@ -349,6 +351,9 @@ class FramePlanner {
     return off;
   }
 
+  // (JXLB200_NO_NW_LUT=1: the generic tree walk for every channel -- comparison runs and the emulation tests)
+  static bool NoNwLut() { return std::getenv("JXLB200_NO_NW_LUT") != nullptr; }
+
   // If the pruned tree at `tree_off` only tests property 15 (weighted predictor max error) and all its leaves are
   // (Weighted, offset 0, multiplier 1), builds the property -> cluster table and marks the channel.
   void TryWpLut(DevChannel* dc, bool has_refs) {
@@ -381,6 +386,58 @@ class FramePlanner {
       while (t[pos].prop >= 0) pos = v > t[pos].a ? t[pos].b : t[pos].c;
       p_->lut.push_back(static_cast<uint16_t>(static_cast<uint32_t>(t[pos].a) & 0xFFFF));
     }
+  }
+
+  // If the pruned tree at `tree_off` only tests y (property 2), N (6) and W (7) with at most kNwMaxY / kNwThresholds
+  // distinct split values each, and every leaf is (predictor other than Weighted, offset 0, multiplier 1, cluster < 256),
+  // writes the (y, N, W) bucket table (layout: kernels/jxlb_modular_dev.h, kNwOff*) and marks the channel.
+  void TryNwLut(DevChannel* dc) {
+    const DevTreeNode* t = p_->tree.data() + dc->tree_off;
+    const size_t n = p_->tree.size() - dc->tree_off;
+    std::vector<int32_t> thr[3];  // y, N, W
+    for (size_t i = 0; i < n; i++) {
+      if (t[i].prop >= 0) {
+        const int k = t[i].prop == 2 ? 0 : (t[i].prop == 6 ? 1 : (t[i].prop == 7 ? 2 : -1));
+        if (k < 0) return;
+        thr[k].push_back(t[i].a);
+      } else {
+        const uint32_t cluster = static_cast<uint32_t>(t[i].a) & 0xFFFF, predictor = static_cast<uint32_t>(t[i].a) >> 16;
+        if (predictor == 6 || predictor > 13 || cluster > 0xFF || t[i].b != 0 || t[i].c != 1) return;
+      }
+    }
+    for (auto& v : thr) {
+      std::sort(v.begin(), v.end());
+      v.erase(std::unique(v.begin(), v.end()), v.end());
+    }
+    if (thr[0].size() > kNwMaxY || thr[1].size() > kNwThresholds || thr[2].size() > kNwThresholds) return;
+    dc->nw_lut = 1;
+    dc->lut_off = p_->lut.size();
+    auto put32 = [&](int32_t v) {
+      p_->lut.push_back(static_cast<uint16_t>(static_cast<uint32_t>(v) & 0xFFFF));
+      p_->lut.push_back(static_cast<uint16_t>(static_cast<uint32_t>(v) >> 16));
+    };
+    p_->lut.push_back(static_cast<uint16_t>(thr[0].size()));
+    p_->lut.push_back(0);
+    const uint32_t cap[3] = {kNwMaxY, kNwThresholds, kNwThresholds};
+    for (int k = 0; k < 3; k++)
+      for (uint32_t i = 0; i < cap[k]; i++) put32(i < thr[k].size() ? thr[k][i] : INT32_MAX);
+    // a value with b thresholds below it: anything in (thr[b - 1], thr[b]]
+    auto rep = [&](int k, uint32_t b) -> int64_t {
+      return b == 0 ? (thr[k].empty() ? 0 : static_cast<int64_t>(thr[k][0])) : static_cast<int64_t>(thr[k][b - 1]) + 1;
+    };
+    for (uint32_t by = 0; by <= thr[0].size(); by++)
+      for (uint32_t bn = 0; bn <= kNwThresholds; bn++)
+        for (uint32_t bw = 0; bw <= kNwThresholds; bw++) {
+          // (buckets above the number of real thresholds cannot occur: the padding is INT32_MAX)
+          const int64_t v[3] = {rep(0, by), rep(1, std::min<uint32_t>(bn, thr[1].size())), rep(2, std::min<uint32_t>(bw, thr[2].size()))};
+          size_t pos = 0;
+          while (t[pos].prop >= 0) {
+            const int k = t[pos].prop == 2 ? 0 : (t[pos].prop == 6 ? 1 : 2);
+            pos = v[k] > t[pos].a ? t[pos].b : t[pos].c;
+          }
+          const uint32_t a = static_cast<uint32_t>(t[pos].a);
+          p_->lut.push_back(static_cast<uint16_t>((a & 0xFF) | ((a >> 16) << 8)));
+        }
   }
 
   // lib/jxl/modular/encoding/dec_ma.cc:23-67: property ranges must stay non-empty
@@ -721,6 +778,7 @@ class FramePlanner {
       dc.uses_wp = ch_wp;
       if (ch_wp) st.uses_wp = 1;
       if (ch_wp) TryWpLut(&dc, dc.ref_count != 0);
+      if (!ch_wp && !NoNwLut()) TryNwLut(&dc);
       p_->chans.push_back(dc);
       max_w = std::max<uint32_t>(max_w, c.w);
     }

@@ -196,15 +196,20 @@ constexpr uint32_t kMidSmemFloats = kFastBufFloats64;                   // 49 KB
 __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint32_t frame0, uint32_t* has_mid, uint32_t* mid_count,
                                                                 uint2* mid_list) {
   extern __shared__ float idct_smem[];
-  __shared__ uint32_t next_s, count_s, next8_s, count8_s, left8_s;
-  __shared__ uint16_t list_s[1024], list8_s[1024];  // varblocks of the group; 8x8 DCTs of single-pass frames apart
+  __shared__ uint32_t next_s, count_s, next8_s, count8_s, left8_s, nextS_s, countS_s;
+  __shared__ uint32_t bucket_s[2 * kSpecialBuckets];  // special 8x8 transforms per strategy: count, then fill position
+  // Varblocks of the group. list_s: everything else from the front, the special 8x8 transforms of single-pass frames
+  // (unsorted) from the back. list8_s: 8x8 DCTs of single-pass frames from the front, the special ones sorted by
+  // strategy from the back (every first block is in exactly one list: 1024 entries hold them all).
+  __shared__ uint16_t list_s[1024], list8_s[1024];
   const DevVFrame& vf = V.frames[frame0 + blockIdx.y];
   const uint32_t g = blockIdx.x;
   if (g >= vf.xgroups * vf.ygroups) return;
   const uint32_t x0 = (g % vf.xgroups) * 32, y0 = (g / vf.xgroups) * 32;
   const uint32_t xs = min(32u, vf.xblocks - x0), ys = min(32u, vf.yblocks - y0);
   const uint8_t* acs = V.barena + vf.acs;
-  if (threadIdx.x == 0) next_s = count_s = next8_s = count8_s = left8_s = 0;
+  if (threadIdx.x == 0) next_s = count_s = next8_s = count8_s = left8_s = nextS_s = countS_s = 0;
+  if (threadIdx.x < 2 * kSpecialBuckets) bucket_s[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool single_pass = vf.num_passes == 1;
@@ -224,12 +229,31 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
     }
     if ((a >> 1) == 0 && single_pass) {
       list8_s[atomicAdd(&count8_s, 1u)] = static_cast<uint16_t>(cell);
+    } else if (single_pass && !si.plain_dct && static_cast<uint32_t>(si.cx) * si.cy == 1) {
+      list_s[1023 - atomicAdd(&countS_s, 1u)] = static_cast<uint16_t>(cell | (static_cast<uint32_t>(a >> 1) << 10));
+      atomicAdd(&bucket_s[DevSpecialBucket(a >> 1)], 1u);
     } else {
       list_s[atomicAdd(&count_s, 1u)] = static_cast<uint16_t>(cell | (static_cast<uint32_t>(a >> 1) << 10));
     }
   }
   if (mid) *has_mid = 1;  // some frame of the batch needs k_idct_mid / k_idct_big
   __syncthreads();
+  const uint32_t totalS = countS_s;
+  if (totalS) {  // counting sort by strategy: the eight varblocks a warp takes at a time then mostly run the same code
+    if (threadIdx.x == 0) {
+      uint32_t off = 0;
+      for (uint32_t b = 0; b < kSpecialBuckets; b++) {
+        bucket_s[kSpecialBuckets + b] = off;
+        off += bucket_s[b];
+      }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < totalS; i += kIdctThreads) {
+      const uint16_t e = list_s[1023 - i];
+      list8_s[1023 - atomicAdd(&bucket_s[kSpecialBuckets + DevSpecialBucket(e >> 10)], 1u)] = e;
+    }
+    __syncthreads();
+  }
   const uint32_t total = count_s;
   float* wbuf = idct_smem + warp * kFastBufFloats;
   const size_t nb = static_cast<size_t>(vf.xblocks) * vf.yblocks;
@@ -279,6 +303,24 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
       if (quads * 4 + k >= total8) break;
       const uint32_t c8 = list8_s[quads * 4 + k];
       DevVarblockFast<1, 32>(V, vf, x0 + (c8 & 31), y0 + (c8 >> 5), 0, wbuf, lane, 32);
+    }
+  }
+  // special 8x8 transforms, eight per warp at a time: a group of four lanes per varblock (dequantisation from the
+  // tokens by all four, then one lane per channel runs the transform)
+  if (totalS) {
+    const uint32_t sub = lane >> 2, t4 = lane & 3;
+    float* sbuf = wbuf + sub * 3 * kSpecialChStride;
+    for (;;) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&nextS_s, 8u);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (base >= totalS) break;
+      const bool active = base + sub < totalS;
+      const uint32_t e = active ? list8_s[1023 - (base + sub)] : 0;
+      const uint32_t cell = e & 1023;
+      DevBlockMeta meta{};
+      if (active) meta = DevLoadBlockMeta(V, vf, static_cast<size_t>(y0 + (cell >> 5)) * vf.xblocks + x0 + (cell & 31));
+      DevVarblockSpecial<1>(V, vf, x0 + (cell & 31), y0 + (cell >> 5), active ? e >> 10 : 1, sbuf, t4, 4, meta, active);
     }
   }
   // lane l < 6 holds tok_start / tok_count of channel l % 3 (l < 3: start), lane 6 the raw quant of the varblock
@@ -638,6 +680,26 @@ JxlB200Decoder* JxlB200DecoderCreate(int device) {
                        6 * DevRenderTileFloats(kRtMaxHalo) * sizeof(float));
   cudaFuncSetAttribute(k_modular_decode_sparse<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_modular_decode_sparse<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  // Every kernel asks for the largest shared-memory carve-out of the L1 / shared-memory array. The split is a per-SM
+  // state that only changes when the SM is idle: a long-running entropy CTA with a few KB of shared memory otherwise
+  // pins its SM in a small-carve-out state, and the render / IDCT CTAs of the other handles in flight (52 - 86 KB
+  // each) cannot become resident next to it (tools/interference.py: AC decode in the background slowed them 4.4 x).
+  if (!std::getenv("JXLB200_NO_CARVEOUT")) {
+    const int co = cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(k_modular_decode<int32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_modular_decode<int64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_modular_decode_sparse<int32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_modular_decode_sparse<int64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_dc_finish, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_dc_smooth, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_ac_decode<1>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_ac_decode<4>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_ac_decode<8>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_idct_mid, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_idct_big, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_render_fused, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+  }
   return dec;
 }
 

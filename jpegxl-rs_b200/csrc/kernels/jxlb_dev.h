@@ -90,7 +90,19 @@ struct DevChannel {
   uint32_t lut_off;   // index into the lut pool (uint16)
   int32_t lut_lo;
   uint32_t lut_size;
+  // Second fast path (libjxl's fixed AC-metadata tree, lib/jxl/modular/encoding/enc_encoding.cc:218-264): the pruned
+  // tree only tests y, N and W with few thresholds, its leaves have offset 0 and multiplier 1 and no weighted
+  // predictor: lut_off then points at a (y, N, W) bucket table (layout: jxlb_modular_dev.h, kNwOff*).
+  uint32_t nw_lut;
+  uint32_t pad_[3];
 };
+
+// Layout of a (y, N, W) bucket table in the lut pool (uint16 units, DevChannel::lut_off): number of y thresholds;
+// the thresholds (int32 as two uint16, ascending, padded with INT32_MAX) of y, N and W; then
+// (ny + 1) x (kNwThresholds + 1) x (kNwThresholds + 1) leaves as cluster | predictor << 8.
+constexpr uint32_t kNwThresholds = 4, kNwMaxY = 7;
+constexpr uint32_t kNwOffY = 2, kNwOffN = kNwOffY + 2 * kNwMaxY, kNwOffW = kNwOffN + 2 * kNwThresholds,
+                   kNwOffTable = kNwOffW + 2 * kNwThresholds;
 
 // One Modular entropy-coded stream = one thread of the decode kernel.
 struct DevStream {

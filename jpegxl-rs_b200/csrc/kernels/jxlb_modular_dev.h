@@ -477,6 +477,10 @@ JXLB_HD WT DevPredictW(uint32_t p, WT left, WT top, WT topleft, WT topright, WT 
   }
 }
 
+JXLB_HD int32_t DevNwThreshold(const uint16_t* base, uint32_t i) {
+  return static_cast<int32_t>(static_cast<uint32_t>(JXLB_LDG(base + 2 * i)) | (static_cast<uint32_t>(JXLB_LDG(base + 2 * i + 1)) << 16));
+}
+
 struct DevWpParams {
   int32_t p1C, p2C, p3Ca, p3Cb, p3Cc, p3Cd, p3Ce;
   uint32_t w[4];
@@ -491,7 +495,13 @@ struct DevWpParams {
 // tl / t / tr / trr, loaded three positions ahead of the write), B receives the previous row's sample just before A
 // loses it and so holds the row above the previous one when the next row reads it. The weighted predictor's five
 // error rows are updated in place the same way (entries x - 1 .. x + 1 of the previous row are in registers).
-template <typename WT, bool kFast, uint32_t kLS, bool kPlainAns>
+//
+// kNw: every lane that has this slot decodes it through the (y, N, W) bucket table (DevChannel::nw_lut): the pruned
+// tree only tests the row, the sample above and the sample to the left -- libjxl's fixed AC-metadata tree
+// (lib/jxl/modular/encoding/enc_encoding.cc:218-264) -- so the leaf is table[bucket(y)][bucket(N)][bucket(W)], a bucket
+// being the number of the property's thresholds below the value: a handful of independent compares and one load
+// instead of the property stores and the dependent node loads of the tree walk; no weighted predictor, no references.
+template <typename WT, bool kFast, uint32_t kLS, bool kPlainAns, bool kNw = false>
 JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const DevChannel& ch, const DevWpParams& wpp,
                                   const int w, const int h, const int max_w, const int max_h, const uint32_t stride,
                                   int32_t* out, const bool lane_direct, const bool lane_uses_wp, const DevTreeNode* tree,
@@ -501,11 +511,11 @@ JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const 
   const uint32_t PS = m.props_stride, LS = kLS ? kLS : m.lane_stride, RW = m.ring_w, WL = m.ring_w + 2;
   int32_t* props = m.props;
   const uint32_t* divlut = m.divlut;
-  const bool uses_wp = kFast ? true : lane_uses_wp;
+  const bool uses_wp = kFast ? true : (kNw ? false : lane_uses_wp);
   // The first two levels of the tree are walked for every sample: keep them in registers.
   DevTreeNode root{}, root_l{}, root_r{};
   root.prop = -1;
-  if (!kFast && h > 0) {
+  if (!kFast && !kNw && h > 0) {
     root = DevLoadNode(tree);
     if (root.prop >= 0) {
       root_l = DevLoadNode(tree + root.b);
@@ -515,6 +525,17 @@ JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const 
   const uint32_t RS = direct ? 1 : LS;
   const uint16_t* lut = P.lut + ch.lut_off;
   const int32_t lut_lo = ch.lut_lo, lut_hi = ch.lut_lo + static_cast<int32_t>(ch.lut_size) - 1;
+  // kNw: thresholds of N and W in registers (padded with INT32_MAX: never exceeded), the row's table slice per row
+  int32_t nw_tn[kNwThresholds] = {}, nw_tw[kNwThresholds] = {};
+  uint32_t nw_ny = 0;
+  if (kNw && h > 0) {
+    nw_ny = JXLB_LDG(lut);
+    for (uint32_t i = 0; i < kNwThresholds; i++) {
+      nw_tn[i] = DevNwThreshold(lut + kNwOffN, i);
+      nw_tw[i] = DevNwThreshold(lut + kNwOffW, i);
+    }
+  }
+  const uint16_t* nw_row = lut;
   int32_t* pe[4];
   for (uint32_t i = 0; i < 4; i++) pe[i] = m.wp + static_cast<uint32_t>(i * WL) * LS;
   int32_t* er = m.wp + static_cast<uint32_t>(4 * WL) * LS;
@@ -530,7 +551,12 @@ JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const 
     int32_t* row = direct ? out_row : rowA;
     const int32_t* prev = direct ? out_row - stride : rowA;
     const int32_t* prevprev = direct ? out_row - 2 * static_cast<size_t>(stride) : rowB;
-    if (!kFast) props[2 * PS] = y;
+    if (!kFast && !kNw) props[2 * PS] = y;
+    if (kNw && row_on) {
+      uint32_t by = 0;
+      for (uint32_t i = 0; i < nw_ny; i++) by += y > DevNwThreshold(lut + kNwOffY, i) ? 1u : 0u;
+      nw_row = lut + kNwOffTable + by * ((kNwThresholds + 1) * (kNwThresholds + 1));
+    }
     int32_t prev_grad = 0;  // property 9 of the previous pixel
     // sliding neighbourhood (valid when y > 0): t = prev[x], tl = prev[x-1], tr = prev[x+1], trr = prev[x+2]
     int32_t left = 0, leftleft = 0, t = 0, tl = 0, tr = 0, trr = 0;
@@ -563,7 +589,7 @@ JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const 
         const WT n_leftleft = x > 1 ? leftleft : n_left;
         const WT n_toptop = y > 1 ? prevprev[static_cast<uint32_t>(x) * RS] : n_top;
         const WT n_toprightright = (x + 2 < w && y) ? trr : n_topright;
-        if (!kFast) {
+        if (!kFast && !kNw) {
           props[3 * PS] = x;
           props[4 * PS] = static_cast<int32_t>(n_top > 0 ? n_top : -n_top);
           props[5 * PS] = static_cast<int32_t>(n_left > 0 ? n_left : -n_left);
@@ -626,7 +652,7 @@ JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const 
           }
           wp_pred = (wp_raw + 3) >> 3;
         }
-        for (uint32_t r = 0; !kFast && r < ch.ref_count; r++) {
+        for (uint32_t r = 0; !kFast && !kNw && r < ch.ref_count; r++) {
           const DevPlane rp = P.planes[P.refs[ch.ref_off + r]];
           const int32_t* rrow = P.arena + rp.off + static_cast<size_t>(y) * w;
           const int32_t* rprev = y ? rrow - w : rrow;
@@ -647,6 +673,17 @@ JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const 
           const uint32_t cluster = JXLB_LDG(lut + (pv - lut_lo));
           const uint32_t u = kPlainAns ? reader.ReadUintPlainAns(cluster, br) : reader.ReadUint(cluster, br);
           val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) + static_cast<uint32_t>(wp_pred));
+        } else if (kNw) {
+          uint32_t bn = 0, bw = 0;
+          for (uint32_t i = 0; i < kNwThresholds; i++) {
+            bn += n_top > static_cast<WT>(nw_tn[i]) ? 1u : 0u;
+            bw += n_left > static_cast<WT>(nw_tw[i]) ? 1u : 0u;
+          }
+          const uint32_t e = JXLB_LDG(nw_row + bn * (kNwThresholds + 1) + bw);  // cluster | predictor << 8
+          const uint32_t u = kPlainAns ? reader.ReadUintPlainAns(e & 0xFF, br) : reader.ReadUint(e & 0xFF, br);
+          const WT guess = DevPredictW<WT>(e >> 8, n_left, n_top, n_topleft, n_topright, n_leftleft, n_toptop,
+                                           n_toprightright, 0);
+          val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) + static_cast<uint32_t>(guess));
         } else {
           DevTreeNode node = root;
           if (node.prop >= 0) node = props[node.prop * PS] > node.a ? root_l : root_r;
@@ -791,9 +828,14 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
     const bool uses_wp = ch.uses_wp != 0 && !direct;
     // every lane of the warp that has this channel slot qualifies for the weighted-predictor LUT path
     const bool fast = JXLB_WARP_ALL_M(k >= my_chans || (ch.wp_lut != 0 && uses_wp && ch.ref_count == 0));
+    const bool nw = JXLB_WARP_ALL_M(k >= my_chans || ch.nw_lut != 0);
     props[0] = static_cast<int32_t>(ch.prop0);
     props[15 * PS] = 0;
-    if (fast && plain_ans) {
+    if (nw && plain_ans) {
+      DevDecodeChannelRows<WT, false, kLS, true, true>(P, m, ch, wpp, w, h, max_w, max_h, stride, out, direct, uses_wp, tree, reader, br);
+    } else if (nw) {
+      DevDecodeChannelRows<WT, false, kLS, false, true>(P, m, ch, wpp, w, h, max_w, max_h, stride, out, direct, uses_wp, tree, reader, br);
+    } else if (fast && plain_ans) {
       DevDecodeChannelRows<WT, true, kLS, true>(P, m, ch, wpp, w, h, max_w, max_h, stride, out, direct, uses_wp, tree, reader, br);
     } else if (fast) {
       DevDecodeChannelRows<WT, true, kLS, false>(P, m, ch, wpp, w, h, max_w, max_h, stride, out, direct, uses_wp, tree, reader, br);

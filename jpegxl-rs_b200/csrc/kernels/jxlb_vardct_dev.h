@@ -1229,6 +1229,76 @@ JXLB_HD void DevVarblockFast(const DevVPools& V, const DevVFrame& vf, uint32_t b
   CoopSync<SCOPE>();
 }
 
+// One 8x8 varblock with a special transform (IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, AFV0-3) of a single-pass frame by
+// `nt` cooperating threads (a group of four lanes in k_dequant_idct, eight such varblocks per warp at a time; SCOPE 1:
+// every lane of the warp calls this in lock step, `active` = the lane's group has a varblock). Same arithmetic as
+// DevVarblock: dequantisation straight from the tokens as in DevVarblockFast, DC into coefficient 0, then one thread per
+// channel runs libjxl's statements (DevSpecialToPixels). `buf`: 3 channels of kSpecialChStride floats.
+constexpr uint32_t kSpecialBuckets = 9;
+JXLB_HD uint32_t DevSpecialBucket(uint32_t strategy) {  // strategies 1, 2, 3, 12 ... 17 -> 0 ... 8
+  return strategy <= 3 ? strategy - 1 : strategy - 9;
+}
+constexpr uint32_t kSpecialChStride = 65;  // (odd: the channel slots of the warp's 24 transform lanes start in different banks)
+template <int SCOPE>
+JXLB_HD void DevVarblockSpecial(const DevVPools& V, const DevVFrame& vf, uint32_t bx, uint32_t by, uint32_t s, float* buf,
+                                uint32_t tid, uint32_t nt, const DevBlockMeta& meta, bool active) {
+  const uint32_t W = vf.xblocks;
+  const size_t pos = static_cast<size_t>(by) * W + bx;
+  float* ch[3] = {buf, buf + kSpecialChStride, buf + 2 * kSpecialChStride};
+  const StrategyInfo si = UnpackStrategyInfo(V.upool[V.sinfo_off + s]);
+  const float* dm = V.fpool + vf.table_off[si.table];
+  float sd[3] = {0.0f, 0.0f, 0.0f}, x_cc = 0.0f, b_cc = 0.0f;
+  if (active) {
+    const float scaled = vf.inv_global_scale / static_cast<float>(meta.rawq);
+    sd[0] = scaled * vf.x_dm;
+    sd[1] = scaled;
+    sd[2] = scaled * vf.b_dm;
+    const size_t tile = static_cast<size_t>(by / 8) * vf.cmw + bx / 8;
+    x_cc = vf.base_x + static_cast<float>(reinterpret_cast<const int8_t*>(V.barena + vf.ytox)[tile]) * vf.color_scale;
+    b_cc = vf.base_b + static_cast<float>(reinterpret_cast<const int8_t*>(V.barena + vf.ytob)[tile]) * vf.color_scale;
+    for (uint32_t i = tid; i < 3 * kSpecialChStride; i += nt) buf[i] = 0.0f;
+  }
+  CoopSync<SCOPE>();
+  if (active) {
+    const uint32_t* tok = V.tokens + meta.start[1];
+    for (uint32_t i = tid; i < meta.count[1]; i += nt) {
+      const uint32_t t = JXLB_LDG(tok + i);
+      const uint32_t k = t & 0xFFFF;
+      if (k >= 64) continue;
+      const int32_t q = static_cast<int16_t>(t >> 16);
+      const float dq_y = DevAdjustQuantBias(1, q, vf.biases) * (JXLB_LDG(dm + 64 + k) * sd[1]);
+      ch[1][k] = dq_y;
+      ch[0][k] = fmaf(x_cc, dq_y, 0.0f);
+      ch[2][k] = fmaf(b_cc, dq_y, 0.0f);
+    }
+  }
+  CoopSync<SCOPE>();
+  if (active) {
+    for (uint32_t c = 0; c < 3; c += 2) {
+      const uint32_t* tok = V.tokens + meta.start[c];
+      const float cc = c == 0 ? x_cc : b_cc;
+      for (uint32_t i = tid; i < meta.count[c]; i += nt) {
+        const uint32_t t = JXLB_LDG(tok + i);
+        const uint32_t k = t & 0xFFFF;
+        if (k >= 64) continue;
+        const int32_t q = static_cast<int16_t>(t >> 16);
+        const float dq = DevAdjustQuantBias(static_cast<int>(c), q, vf.biases) * (JXLB_LDG(dm + c * 64 + k) * sd[c]);
+        ch[c][k] = fmaf(cc, ch[1][k], dq);
+      }
+    }
+  }
+  CoopSync<SCOPE>();
+  if (active) {
+    const uint32_t PW = W * 8;
+    for (uint32_t c = tid; c < 3; c += nt) {
+      ch[c][0] = V.farena[vf.dc_final[c] + pos];
+      float* out = V.farena + vf.pix[0][c] + static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+      DevSpecialToPixels(s, ch[c], out, static_cast<int>(PW), V.fpool + V.wc_off, V.fpool + V.afv_off);
+    }
+  }
+  CoopSync<SCOPE>();
+}
+
 // ---------------------------------------------------------------- render stages (per pixel)
 JXLB_HD int DevMirror(int x, int size) {  // lib/jxl/image_ops.h:184-195
   while (x < 0 || x >= size) x = x < 0 ? -x - 1 : 2 * size - 1 - x;

@@ -13,7 +13,14 @@
 
 using namespace jxlb;
 
+static uint64_t g_last_plan_stats[3];  // channels, of which weighted-predictor LUT, of which (y, N, W) table
+
 extern "C" {
+
+// Channel counts of the last jxlb_emul_decode plan: total, weighted-predictor LUT path, (y, N, W) table path.
+void jxlb_emul_last_plan_stats(uint64_t* out3) {
+  for (int i = 0; i < 3; i++) out3[i] = g_last_plan_stats[i];
+}
 
 // Decodes n files; returns 0 or a negative error. out must hold out_size bytes
 // laid out like the batch output buffer (frames 256-byte aligned).
@@ -91,6 +98,12 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     };
     BatchPlan b;
     PlanBatch(files, sizes, n, fmt, 2, &b, probe);
+    g_last_plan_stats[0] = b.chans.size();
+    g_last_plan_stats[1] = g_last_plan_stats[2] = 0;
+    for (const DevChannel& c : b.chans) {
+      g_last_plan_stats[1] += c.wp_lut ? 1 : 0;
+      g_last_plan_stats[2] += c.nw_lut ? 1 : 0;
+    }
     if (b.out_size > out_cap) throw Error("output buffer too small");
     std::vector<int32_t> arena(b.arena_size + 16, 0);
     DevPools P{};
@@ -212,6 +225,10 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
               DevVarblockFast<0, 32>(V, vf, bx, by, a >> 1, buf.data(), 0, 1);  // what k_dequant_idct runs for these
             } else if (si.plain_dct && si.cx * si.cy <= 64 && !generic_only) {
               DevVarblockFast<0, 64>(V, vf, bx, by, a >> 1, buf.data(), 0, 1);  // k_idct_mid
+            } else if (!si.plain_dct && si.cx * si.cy == 1 && vf.num_passes == 1 && !generic_only) {
+              // the special 8x8 transforms of single-pass frames (k_dequant_idct: four lanes per varblock)
+              const DevBlockMeta meta = DevLoadBlockMeta(V, vf, static_cast<size_t>(by) * vf.xblocks + bx);
+              DevVarblockSpecial<0>(V, vf, bx, by, a >> 1, buf.data(), 0, 1, meta, true);
             } else {
               DevVarblock<0>(V, vf, bx, by, a >> 1, buf.data(), 0, 1);
             }

@@ -46,6 +46,13 @@ def decode(files, num_channels, data_type, shapes, endianness=0, align=0):
     return res
 
 
+def last_plan_stats():
+    """(channels, channels on the weighted-predictor LUT path, channels on the (y, N, W) table path) of the last decode."""
+    v = (ctypes.c_uint64 * 3)()
+    lib().jxlb_emul_last_plan_stats(v)
+    return tuple(int(x) for x in v)
+
+
 def encode(rgb, distance=1.0, strategy_mode=2, gab=True, epf_iters=2, dc_smoothing=True) -> bytes:
     """RGB8 (H, W, 3) -> codestream, the encoder kernels' device functions run on the CPU."""
     rgb = np.ascontiguousarray(rgb, np.uint8)

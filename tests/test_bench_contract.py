@@ -20,8 +20,16 @@ def test_reference_arm_prints_one_json_line():
     assert "workload" in j["config"] and j["steps"] == 1 and j["warmup"] == 0
 
 
-def test_handles_in_flight_divide_the_steps():
-    # (the expression bench.py uses for the number of decoder handles in flight)
-    for steps, inflight, want in [(16, 8, 8), (10, 8, 5), (20, 8, 5), (7, 8, 7), (1, 8, 1), (12, 4, 4), (9, 4, 3)]:
-        cap = max(1, min(inflight, steps))
-        assert max(d for d in range(1, cap + 1) if steps % d == 0) == want
+def test_numa_binding_helper_without_sysfs():
+    # (one rank: nothing is bound, the helper reports the CPUs the process may use)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class _T:
+        class cuda:
+            @staticmethod
+            def device_count():
+                return 0
+
+    info = bench.bind_rank_to_numa(_T, 0, 1)
+    assert info["cpus"] == info["cpus_total"] == len(os.sched_getaffinity(0)) and info["ranks_on_node"] == 1

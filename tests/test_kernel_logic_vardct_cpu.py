@@ -103,3 +103,22 @@ def test_g4_sample_grey_jxl_matches_oracle():
     got = emul_lib.decode([a, grey, read_golden("sample_jpg.jxl")], 3, jxlo.UINT8, [sa, (50, 40), (50, 40)])
     assert np.array_equal(got[1], jxlo.decode(grey, 3, jxlo.UINT8))
     assert np.array_equal(got[0], jxlo.decode(a, 3, jxlo.UINT8))
+
+
+def test_ac_metadata_channels_take_the_ynw_table_path(monkeypatch):
+    # libjxl's fixed AC-metadata tree (tests y, N, W only) is decoded through the (y, N, W) bucket table
+    # (DevChannel::nw_lut); with JXLB200_NO_NW_LUT=1 the same channels take the generic tree walk. Same samples.
+    img = vc.crop(200, 300, 100, 200)
+    cases = [jxlo.encode_vardct(img, strategy_mode=3, distance=1.0, epf_iters=1),
+             jxlo.encode_vardct(img, strategy_mode=1, random_side_info=True, seed=11, epf_iters=3)]
+    for data in cases:
+        want = jxlo.decode(data, 3, jxlo.UINT8)
+        got = emul_lib.decode([data], 3, jxlo.UINT8, [(200, 300)])[0]
+        chans, wp, nw = emul_lib.last_plan_stats()
+        assert np.array_equal(got, want)
+        assert chans == 7 and wp + nw >= 4 and nw >= 1, (chans, wp, nw)
+        monkeypatch.setenv("JXLB200_NO_NW_LUT", "1")
+        got2 = emul_lib.decode([data], 3, jxlo.UINT8, [(200, 300)])[0]
+        assert emul_lib.last_plan_stats()[2] == 0
+        assert np.array_equal(got2, want)
+        monkeypatch.delenv("JXLB200_NO_NW_LUT")
