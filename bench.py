@@ -73,8 +73,38 @@ class Workload:
             self.data = "synthetic (replicas of the reference's bench.jxl)"
         self.blobs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names]
         self.files = [self.blobs[i % len(self.blobs)] for i in range(self.batch)]
+        self.distinct = False
+
+    def make_distinct(self, pkg, device):
+        """vardct4k: the batch the GPU arm decodes is `batch` DIFFERENT frames (the two base frames
+        x integer translations (13 i mod 256, 7 i mod 256) with wrap-around), written at start-up by this repo's GPU
+        encoder at distance 1.0 -- a batch of byte-identical replicas lets the lanes of the lock-step entropy kernels
+        (32 streams per warp) run perfectly converged, which no real batch does (tools/exp_distinct.py: AC decode 2.9 x
+        faster on replicas). The fixtures themselves (all transform classes, libjxl's AcStrategy search by the oracle
+        encoder) are decoded in `also.fixture_replicas`."""
+        base = pkg.decode_batch(self.blobs, 3, np.uint8, device=device)
+        self.fixture_ok = all(hashlib.sha256(b.tobytes()).hexdigest() == s for b, s in zip(base, self.sha))
+        enc = pkg.JxlEncoder(quality=1.0, device=device)
+        files = []
+        for i0 in range(0, self.batch, 16):
+            imgs = [np.ascontiguousarray(np.roll(base[i % 2], ((13 * (i // 2)) % 256, (7 * (i // 2)) % 256), axis=(0, 1)))
+                    for i in range(i0, min(self.batch, i0 + 16))]
+            files += [r.data for r in enc.encode_batch(imgs, epf_iters=1)]
+        del enc
+        self.files = files
+        self.blobs = files[:8]  # what the CPU arm cycles through
+        self.distinct = True
+        bpp = 8.0 * sum(len(f) for f in files) / (self.batch * base[0].shape[0] * base[0].shape[1])
+        self.desc = ("decode %d DIFFERENT lossy VarDCT 4K frames per GPU (3840x2160, d=1.0, 135 groups/frame, %.2f bpp: the "
+                     "two base images x integer translations, encoded at start-up by this repo's GPU encoder -- libjxl "
+                     "effort-7 heuristics except the AcStrategy search: DCT 8x8 ... 64x64, adaptive quantisation, "
+                     "chroma from luma, custom orders, Gaborish + EPF) to RGB8" % (self.batch, bpp))
+        self.data = "synthetic (GPU-encoded translations of two 4K images; no two frames share a bitstream)"
 
     def check(self, outs):
+        if self.distinct:  # no offline hashes for frames encoded at start-up: the CPU arm's oracle decode is the check
+            self.out_sha = [hashlib.sha256(outs[i].tobytes()).hexdigest() for i in range(min(8, self.batch))]
+            return self.fixture_ok
         idx = sorted({0, 1 % self.batch, self.batch // 2, self.batch - 1})
         return all(hashlib.sha256(outs[i].tobytes()).hexdigest() == self.sha[i % len(self.sha)] for i in idx)
 
@@ -149,11 +179,14 @@ def cpu_baseline(wl, seconds=15.0, threads=None):
     del d
     count = [0] * threads
     stop = time.time() + seconds
+    oracle_sha = {}
 
     def work(i):
         k = i
         while time.time() < stop:
-            jxlo.Decoded(wl.blobs[k % len(wl.blobs)]).pixels(wl.channels, jxlo.UINT8, raw=True)
+            px = jxlo.Decoded(wl.blobs[k % len(wl.blobs)]).pixels(wl.channels, jxlo.UINT8, raw=True)
+            if k < len(wl.blobs) and k not in oracle_sha:
+                oracle_sha[k] = hashlib.sha256(np.asarray(px).tobytes()).hexdigest()
             count[i] += 1
             k += 1
 
@@ -165,6 +198,7 @@ def cpu_baseline(wl, seconds=15.0, threads=None):
         t.join()
     dt = time.time() - t0
     frames = sum(count)
+    wl.oracle_sha = oracle_sha
     return {"value": frames * w * h / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{frames} {wl.name} frames ({w}x{h}) in {dt:.1f} s on {threads} threads, oracle-CPU (not libjxl): "
                       "the scalar restatement built -O3 -march=x86-64-v3, one frame per thread. libjxl itself (Highway SIMD) "
@@ -284,6 +318,16 @@ def run_reference(args):
     wl = Workload(args.workload, args.batch)
     if wl.name == "encode4k":
         raise SystemExit("--impl reference covers the decode workloads; the CPU encoder is timed as cpu_baseline")
+    if wl.name == "vardct4k" and not args.replicas:
+        # the same frames as the GPU arm decodes: they are written by the GPU encoder at start-up, so this arm needs the
+        # device for its set-up too (nothing of the timed work runs there); without one it decodes the fixtures
+        try:
+            import torch
+            if torch.cuda.is_available():
+                import __graft_entry__ as ge
+                wl.make_distinct(ge.load_package(), int(os.environ.get("LOCAL_RANK", "0")))
+        except Exception as e:
+            print("reference arm: set-up on the GPU failed (%s); decoding the fixtures" % e, file=sys.stderr)
     # bounded: the whole --steps K --warmup W run stays within a few minutes
     per_step = max(6.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
     per_step = min(per_step, max(0.5, args.cpu_seconds))  # (--cpu-seconds below 6: quick contract checks)
@@ -299,8 +343,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": wl.metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": wl.dtype, "data": wl.data,
-            "config": {"workload": wl.desc + " -- CPU arm: each step decodes as many of these frames as the host cores "
-                                             "finish in %.0f s" % per_step,
+            "config": {"workload": wl.desc,
+                       "cpu_arm": "each step decodes as many of these frames as the host cores finish in %.0f s" % per_step,
                        "note": "libjxl cannot be built in this image (Highway / brotli submodules are empty, no Rust "
                                "toolchain); the CPU arm is the scalar oracle restating libjxl 0.11.2, all host threads"},
             "cpu_baseline": cb,
@@ -321,6 +365,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true",
+                    help="vardct4k: decode replicas of the two committed fixtures instead of frames that all differ")
     ap.add_argument("--no-also", action="store_true", help="skip the short encode / lossless side runs folded into `also`")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -352,6 +398,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = Workload(args.workload, args.batch)
+    if wl.name == "vardct4k" and not args.replicas:
+        wl.make_distinct(pkg, local_rank)
     files = wl.files
     plan_threads = max(1, min(host["cpus"], 32))
 
@@ -494,8 +542,9 @@ def main():
         okg = True
         if rank == 0:
             n0 = dec.out_size(0)
+            first_sha = hashlib.sha256(dec.read_output(0).tobytes()).hexdigest()  # (every rank decodes the same batch)
             for r_ in range(world):  # frame 0 of every rank's share, read from rank 0's gather buffer
-                okg = okg and hashlib.sha256(gather_bufs[r_][:n0].cpu().numpy().tobytes()).hexdigest() == wl.sha[0]
+                okg = okg and hashlib.sha256(gather_bufs[r_][:n0].cpu().numpy().tobytes()).hexdigest() == first_sha
         gather_info = {"collective": "ncclGather of the decoded frames to rank 0 (device to device, every step, inside the "
                                      "timed region, overlapping the next steps' kernels)",
                        "bytes_per_step_into_rank0": int(out_bytes) * (world - 1), "alone_ms": gms,
@@ -667,6 +716,13 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(wl, seconds=args.cpu_seconds)
             line["cpu_baseline"] = cb
+            if wl.distinct:  # the oracle decoded the same frames: its pixels are the check of the GPU's
+                common = [k for k in getattr(wl, "oracle_sha", {}) if k < len(wl.out_sha)]
+                line["config"]["frames_checked_against_oracle"] = len(common)
+                line["config"]["golden_checksum_ok"] = bool(ok and common and all(wl.oracle_sha[k] == wl.out_sha[k] for k in common))
+        elif wl.distinct:
+            line["config"]["golden_checksum_ok"] = None  # (no oracle run in this invocation; fixtures decoded ok: see fixture_ok)
+            line["config"]["fixture_ok"] = bool(ok)
         if world == 1 and not args.no_also and wl.name == "vardct4k":
             line["also"] = side_workloads(args)
         print(json.dumps(line))
@@ -724,9 +780,10 @@ def side_workloads(args):
     shape, folded into `also`): the encoder (BASELINE.json configs[2]) and the lossless Modular decode of bench.jxl-shaped
     frames (configs[4]; the input of the reference's own criterion bench)."""
     out = {}
-    for name, extra in (("encode4k", ["--batch", "16", "--steps", "3", "--warmup", "1"]),
-                        ("modular", ["--batch", "128", "--steps", "6", "--warmup", "3", "--inflight", "3"])):
-        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--no-cpu-baseline", "--no-also"] + extra
+    for name, extra in (("fixture_replicas", ["--workload", "vardct4k", "--replicas", "--steps", "8", "--warmup", "3"]),
+                        ("encode4k", ["--workload", "encode4k", "--batch", "16", "--steps", "3", "--warmup", "1"]),
+                        ("modular", ["--workload", "modular", "--batch", "128", "--steps", "6", "--warmup", "3", "--inflight", "3"])):
+        cmd = [sys.executable, os.path.abspath(__file__), "--no-cpu-baseline", "--no-also"] + extra
         try:
             r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
             lines = [l for l in r.stdout.splitlines() if l.startswith("{")]

@@ -45,6 +45,9 @@ struct BatchPlan {
   // VarDCT frames
   std::vector<DevVFrame> vframes;
   std::vector<DevAcStream> ac_streams;
+  // per (frame, pass): the ids of its streams in ac_streams, longest first (k_ac_decode_frame)
+  std::vector<DevAcUnit> ac_units;
+  std::vector<uint32_t> ac_unit_streams;
   std::vector<float> fpool;
   std::vector<uint16_t> opool;
   std::vector<uint8_t> cpool;
@@ -197,6 +200,8 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
     vf.ytob += b->barena_size;
     vf.tok_start += b->uarena_size;
     vf.tok_count += b->uarena_size;
+    vf.blist += b->uarena_size;
+    vf.blist_count += b->uarena_size;
     vf.bctx_off += upool0;
     vf.order_index += upool0;
     vf.dcg_index += upool0;
@@ -462,6 +467,27 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
     std::stable_sort(batch->ac_streams.begin(), batch->ac_streams.end(), [](const DevAcStream& x, const DevAcStream& y) {
       return x.bit_end - x.bit_pos > y.bit_end - y.bit_pos;
     });
+    // the same streams grouped by (frame, pass), each group still longest first
+    std::vector<uint32_t> unit_of(batch->vframes.size() * kMaxPasses, 0xFFFFFFFFu);
+    for (const DevAcStream& s : batch->ac_streams) {
+      uint32_t& u = unit_of[s.frame * kMaxPasses + s.pass];
+      if (u == 0xFFFFFFFFu) {
+        u = batch->ac_units.size();
+        batch->ac_units.push_back(DevAcUnit{0, 0, s.frame, s.pass});
+      }
+      batch->ac_units[u].count++;
+    }
+    uint32_t first = 0;
+    for (DevAcUnit& u : batch->ac_units) {
+      u.first = first;
+      first += u.count;
+      u.count = 0;
+    }
+    batch->ac_unit_streams.resize(batch->ac_streams.size());
+    for (uint32_t i = 0; i < batch->ac_streams.size(); i++) {
+      DevAcUnit& u = batch->ac_units[unit_of[batch->ac_streams[i].frame * kMaxPasses + batch->ac_streams[i].pass]];
+      batch->ac_unit_streams[u.first + u.count++] = i;
+    }
   }
   if (timing)
     std::fprintf(stderr, "PlanBatch: %zu files, %d threads: %.1f ms (per-file planning %.1f ms, merge %.1f ms)\n", n, threads,

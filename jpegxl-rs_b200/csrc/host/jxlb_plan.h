@@ -391,7 +391,39 @@ class FramePlanner {
   // If the pruned tree at `tree_off` only tests y (property 2), N (6) and W (7) with at most kNwMaxY / kNwThresholds
   // distinct split values each, and every leaf is (predictor other than Weighted, offset 0, multiplier 1, cluster < 256),
   // writes the (y, N, W) bucket table (layout: kernels/jxlb_modular_dev.h, kNwOff*) and marks the channel.
+  // The gradient-property variant (nw_lut = 2): every inner node tests property 9, leaves as for TryNwLut.
+  bool TryGradLut(DevChannel* dc) {
+    const DevTreeNode* t = p_->tree.data() + dc->tree_off;
+    const size_t n = p_->tree.size() - dc->tree_off;
+    int64_t lo = INT32_MAX, hi = INT32_MIN;
+    bool inner = false;
+    for (size_t i = 0; i < n; i++) {
+      if (t[i].prop >= 0) {
+        if (t[i].prop != 9) return false;
+        inner = true;
+        lo = std::min<int64_t>(lo, t[i].a);
+        hi = std::max<int64_t>(hi, t[i].a);
+      } else {
+        const uint32_t cluster = static_cast<uint32_t>(t[i].a) & 0xFFFF, predictor = static_cast<uint32_t>(t[i].a) >> 16;
+        if (predictor == 6 || predictor > 13 || cluster > 0xFF || t[i].b != 0 || t[i].c != 1) return false;
+      }
+    }
+    if (!inner || hi - lo + 2 > 8192) return false;
+    dc->nw_lut = 2;
+    dc->lut_off = p_->lut.size();
+    dc->lut_lo = static_cast<int32_t>(lo);
+    dc->lut_size = static_cast<uint32_t>(hi - lo + 2);
+    for (int64_t v = lo; v <= hi + 1; v++) {
+      size_t pos = 0;
+      while (t[pos].prop >= 0) pos = v > t[pos].a ? t[pos].b : t[pos].c;
+      const uint32_t a = static_cast<uint32_t>(t[pos].a);
+      p_->lut.push_back(static_cast<uint16_t>((a & 0xFF) | ((a >> 16) << 8)));
+    }
+    return true;
+  }
+
   void TryNwLut(DevChannel* dc) {
+    if (TryGradLut(dc)) return;
     const DevTreeNode* t = p_->tree.data() + dc->tree_off;
     const size_t n = p_->tree.size() - dc->tree_off;
     std::vector<int32_t> thr[3];  // y, N, W

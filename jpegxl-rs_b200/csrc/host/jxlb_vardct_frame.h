@@ -376,7 +376,9 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   v.barena_size = (b + 15) & ~uint64_t{15};
   vf.tok_start = 0;
   vf.tok_count = num_passes * 3 * nb;
-  v.uarena_size = 2 * num_passes * 3 * nb;
+  vf.blist = 2 * num_passes * 3 * nb;
+  vf.blist_count = vf.blist + 2 * nb;
+  v.uarena_size = vf.blist_count + dim.num_groups;
   // quantiser
   vf.x_dm = std::pow(1 / (1.25f), fh.x_qm_scale - 2.0f);  // lib/jxl/dec_cache.h:161-162
   vf.b_dm = std::pow(1 / (1.25f), fh.b_qm_scale - 2.0f);

@@ -14,11 +14,14 @@
 //   k_idct_mid        64x32 / 32x64 / 64x64 varblocks, one CTA per varblock, staged transforms in shared memory
 //   k_idct_big        varblocks of 128x128 and larger, scratch in global memory
 //   k_gaborish / k_epf / k_color_write   render stages, one thread per pixel
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -161,6 +164,15 @@ __global__ void __launch_bounds__(256) k_dc_smooth(DevVPools V) {
     DevDcSmoothBlock(V, vf, i % vf.xblocks, i / vf.xblocks);
 }
 
+// One thread per (frame, group): the group's varblock list for the AC streams (DevBuildBlockList).
+__global__ void __launch_bounds__(128) k_block_lists(DevVPools V, uint32_t max_groups, uint32_t num_frames) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= max_groups * num_frames) return;
+  const DevVFrame& vf = V.frames[i / max_groups];
+  const uint32_t g = i % max_groups;
+  if (g < vf.xgroups * vf.ygroups) DevBuildBlockList(V, vf, g);
+}
+
 // kAcWarps independent warps per CTA, 32 AC streams in lock step each; the streams are latency-bound single warps.
 // One warp per CTA is fastest alone, but 1080 one-warp CTAs per 256 frames take the SMs' CTA slots (32 per SM) away
 // from the per-pixel kernels of other batches (tools/interference.py): several warps per CTA by default.
@@ -183,6 +195,99 @@ __global__ void __launch_bounds__(32 * kAcWarps) k_ac_decode(DevPools P, DevVPoo
   if (valid) V.ac_status[s] = status;
 }
 
+// ---- AC decode, one CTA per (frame, pass): the pass's alias tables (cp.async.bulk into shared memory, completion on
+// an mbarrier), uint configs and context map are staged once per CTA and every symbol's context -> cluster -> alias
+// entry chain then runs on shared-memory loads (the one-warp kernel above takes them from L1 / L2: with 32 lanes from
+// 32 different frames its hit rate is 78 %, ncu long_scoreboard 5 cycles per issue). Lane = one group's stream, the
+// unit's streams longest first so that the lanes of a warp end together. Plain ANS codes only.
+__device__ __forceinline__ uint32_t SmemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+struct AcFrameSmemLayout {
+  uint32_t alias_bytes, cfg_off, ctx_off, colnz_off, tab_off, bar_off, total;
+};
+__host__ __device__ inline AcFrameSmemLayout AcFrameLayout(uint32_t alias_entries, uint32_t clusters, uint32_t ctx_bytes, uint32_t warps) {
+  AcFrameSmemLayout L;
+  L.alias_bytes = alias_entries * 8;
+  L.cfg_off = L.alias_bytes;
+  L.ctx_off = L.cfg_off + ((clusters * 4 + 15) & ~15u);
+  L.colnz_off = L.ctx_off + ((ctx_bytes + 15) & ~15u);
+  L.tab_off = L.colnz_off + warps * 96 * 32;
+  L.bar_off = L.tab_off + 256;
+  L.total = L.bar_off + 16;
+  return L;
+}
+
+__global__ void __launch_bounds__(256) k_ac_decode_frame(DevPools P, DevVPools V, const DevAcUnit* units, const uint32_t* unit_streams) {
+  extern __shared__ __align__(128) uint8_t ac_smem[];
+  const DevAcUnit u = units[blockIdx.x];
+  const DevVFrame& vf = V.frames[u.frame];
+  const DevCode code = P.codes[vf.ac_code[u.pass]];
+  const uint32_t warps = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ctx_bytes = vf.num_histograms * vf.num_ctxs * 495;
+  const AcFrameSmemLayout L = AcFrameLayout(code.num_clusters << code.log_alpha_size, code.num_clusters, ctx_bytes, warps);
+  DevAlias* alias_s = reinterpret_cast<DevAlias*>(ac_smem);
+  uint32_t* cfg_s = reinterpret_cast<uint32_t*>(ac_smem + L.cfg_off);
+  uint8_t* ctx_s = ac_smem + L.ctx_off;
+  uint8_t* colnz_s = ac_smem + L.colnz_off;
+  uint16_t* tab_s = reinterpret_cast<uint16_t*>(ac_smem + L.tab_off);
+  const uint32_t bar = SmemAddr(ac_smem + L.bar_off);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the alias tables of this code: code.alias_off is a multiple of 32 entries (every code's table is
+    // clusters << log_alpha entries, log_alpha >= 5), so source, destination and size are 16-byte multiples
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(L.alias_bytes) : "memory");
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(P.alias + code.alias_off);
+    for (uint32_t off = 0; off < L.alias_bytes; off += 32768) {
+      const uint32_t n = min(32768u, L.alias_bytes - off);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       SmemAddr(ac_smem + off)),
+                   "l"(src + off), "r"(n), "r"(bar)
+                   : "memory");
+    }
+  }
+  // meanwhile: uint configs, context map, the two context tables, the non-zero columns
+  for (uint32_t i = threadIdx.x; i < code.num_clusters; i += blockDim.x) cfg_s[i] = P.cfg[code.cfg_off + i];
+  const uint8_t* ctx_g = V.cpool + vf.ctx_map_off[u.pass];
+  for (uint32_t i = threadIdx.x; i < ctx_bytes; i += blockDim.x) ctx_s[i] = ctx_g[i];
+  for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) tab_s[i] = static_cast<uint16_t>(V.upool[V.ctxtab_off + i]);
+  for (uint32_t i = threadIdx.x; i < warps * 96 * 32; i += blockDim.x) colnz_s[i] = 0;
+  {  // wait for the bulk copies (phase 0)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+  }
+  __syncthreads();
+  DevAcLaneMem m;
+  m.colnz = colnz_s + warp * 96 * 32 + lane;
+  m.stride = 32;
+  m.freq_ctx = tab_s;
+  m.nnz_ctx = tab_s + 64;
+  m.alias_s = alias_s;
+  m.cfg_s = cfg_s;
+  m.ctx_map_s = ctx_s;
+  // (a unit with more streams than threads: every warp takes another 32 after it finished -- 8K x 8K frames and beyond)
+  for (uint32_t base = warp * 32; base < u.count; base += warps * 32) {
+    const bool valid = base + lane < u.count;
+    const uint32_t s = valid ? unit_streams[u.first + base + lane] : 0;
+    const uint32_t status = DevDecodeAcStream<true, true>(P, V, s, m, valid);
+    if (valid) V.ac_status[s] = status;
+    __syncwarp();
+    if (base + warps * 32 < u.count)
+      for (uint32_t i = lane; i < 96 * 32; i += 32) colnz_s[warp * 96 * 32 + i] = 0;
+    __syncwarp();
+  }
+}
+
+constexpr uint32_t kSortKeys = 64;  // k_dequant_idct's list order: special 8x8 transforms by strategy (keys 0 .. 31), then the rest (32 .. 63)
 constexpr uint32_t kIdctThreads = 128;                                  // 4 warps, one small varblock each at a time
 constexpr uint32_t kIdctSmemFloats = (kIdctThreads / 32) * kFastBufFloats;  // 51.7 KB: four CTAs per SM
 constexpr uint32_t kMidThreads = 256;
@@ -197,10 +302,13 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
                                                                 uint2* mid_list) {
   extern __shared__ float idct_smem[];
   __shared__ uint32_t next_s, count_s, next8_s, count8_s, left8_s, nextS_s, countS_s;
-  __shared__ uint32_t bucket_s[2 * kSpecialBuckets];  // special 8x8 transforms per strategy: count, then fill position
-  // Varblocks of the group. list_s: everything else from the front, the special 8x8 transforms of single-pass frames
-  // (unsorted) from the back. list8_s: 8x8 DCTs of single-pass frames from the front, the special ones sorted by
-  // strategy from the back (every first block is in exactly one list: 1024 entries hold them all).
+  __shared__ uint32_t bucket_s[2 * kSortKeys];  // entries per sort key, then the key's fill position
+  // Varblocks of the group. list8_s, from the front: 8x8 DCTs of single-pass frames (four per warp at a time). list_s:
+  // everything else as it is found -- special 8x8 transforms of single-pass frames from the back, the rest from the
+  // front -- then both sorted by strategy into the free tail of list8_s (every first block is in exactly one list:
+  // 1024 entries hold them all): [.. | the rest | special], read backwards from 1023. Sorted, the warps of a CTA run
+  // the same transform code at the same time (the kernel was waiting for instruction fetches: ncu no_instruction
+  // stall 13.9 cycles per issue with the lists in cell order, profiles/r2_ncu_k_dequant_idct_before_sort.txt).
   __shared__ uint16_t list_s[1024], list8_s[1024];
   const DevVFrame& vf = V.frames[frame0 + blockIdx.y];
   const uint32_t g = blockIdx.x;
@@ -209,7 +317,7 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
   const uint32_t xs = min(32u, vf.xblocks - x0), ys = min(32u, vf.yblocks - y0);
   const uint8_t* acs = V.barena + vf.acs;
   if (threadIdx.x == 0) next_s = count_s = next8_s = count8_s = left8_s = nextS_s = countS_s = 0;
-  if (threadIdx.x < 2 * kSpecialBuckets) bucket_s[threadIdx.x] = 0;
+  if (threadIdx.x < 2 * kSortKeys) bucket_s[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool single_pass = vf.num_passes == 1;
@@ -231,30 +339,31 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
       list8_s[atomicAdd(&count8_s, 1u)] = static_cast<uint16_t>(cell);
     } else if (single_pass && !si.plain_dct && static_cast<uint32_t>(si.cx) * si.cy == 1) {
       list_s[1023 - atomicAdd(&countS_s, 1u)] = static_cast<uint16_t>(cell | (static_cast<uint32_t>(a >> 1) << 10));
-      atomicAdd(&bucket_s[DevSpecialBucket(a >> 1)], 1u);
+      atomicAdd(&bucket_s[(a >> 1)], 1u);
     } else {
       list_s[atomicAdd(&count_s, 1u)] = static_cast<uint16_t>(cell | (static_cast<uint32_t>(a >> 1) << 10));
+      atomicAdd(&bucket_s[32 + (a >> 1)], 1u);
     }
   }
   if (mid) *has_mid = 1;  // some frame of the batch needs k_idct_mid / k_idct_big
   __syncthreads();
-  const uint32_t totalS = countS_s;
-  if (totalS) {  // counting sort by strategy: the eight varblocks a warp takes at a time then mostly run the same code
+  const uint32_t totalS = countS_s, total = count_s;
+  if (totalS + total) {  // counting sort by (special first, strategy): position p of the order lives at list8_s[1023 - p]
     if (threadIdx.x == 0) {
       uint32_t off = 0;
-      for (uint32_t b = 0; b < kSpecialBuckets; b++) {
-        bucket_s[kSpecialBuckets + b] = off;
+      for (uint32_t b = 0; b < kSortKeys; b++) {
+        bucket_s[kSortKeys + b] = off;
         off += bucket_s[b];
       }
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < totalS; i += kIdctThreads) {
-      const uint16_t e = list_s[1023 - i];
-      list8_s[1023 - atomicAdd(&bucket_s[kSpecialBuckets + DevSpecialBucket(e >> 10)], 1u)] = e;
+    for (uint32_t i = threadIdx.x; i < totalS + total; i += kIdctThreads) {
+      const bool special = i < totalS;
+      const uint16_t e = special ? list_s[1023 - i] : list_s[i - totalS];
+      list8_s[1023 - atomicAdd(&bucket_s[kSortKeys + (special ? 0 : 32) + (e >> 10)], 1u)] = e;
     }
     __syncthreads();
   }
-  const uint32_t total = count_s;
   float* wbuf = idct_smem + warp * kFastBufFloats;
   const size_t nb = static_cast<size_t>(vf.xblocks) * vf.yblocks;
   // 8x8 DCT blocks, four per warp at a time: the eight lanes of a quarter warp run the varblock function on their own
@@ -332,7 +441,7 @@ __global__ void __launch_bounds__(kIdctThreads) k_dequant_idct(DevVPools V, uint
       *entry = 0xFFFFFFFFu;
       return 0;
     }
-    const uint32_t e = list_s[i];
+    const uint32_t e = list8_s[1023 - (totalS + i)];
     *entry = e;
     const uint32_t cell = e & 1023;
     const size_t pos = static_cast<size_t>(y0 + (cell >> 5)) * vf.xblocks + x0 + (cell & 31);
@@ -566,9 +675,69 @@ enum KernelClass {
   kKColorWrite, kNumKernelClasses
 };
 
+// ------------------------------------------------------------------ SM partition (CUDA green contexts)
+// The entropy kernels (Modular chains, DC finish, AC decode) are latency-bound single warps that sit on their SMs for
+// 50 - 150 ms and park registers / shared memory there; the per-pixel kernels of the other handles in flight then find
+// less room on every SM (tools/interference.py). With JXLB200_ENTROPY_SMS=n the SMs are split once per device into an
+// entropy partition of n SMs and a pixel partition of the rest (cuDevSmResourceSplitByCount -> cuGreenCtxCreate), and
+// every handle launches its entropy kernels into a stream of the first and its per-pixel kernels into a stream of the
+// second. The driver entry points are fetched at run time (cudaGetDriverEntryPoint): the library does not link libcuda.
+struct SmPartition {
+  bool ok = false;
+  CUgreenCtx ctx[2] = {nullptr, nullptr};  // 0: entropy, 1: pixel
+  uint32_t sms[2] = {0, 0};
+  CUresult (*stream_create)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+};
+
+static SmPartition* GetSmPartition(int device) {
+  static std::mutex mu;
+  static std::map<int, SmPartition> parts;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = parts.find(device);
+  if (it != parts.end()) return it->second.ok ? &it->second : nullptr;
+  SmPartition& p = parts[device];
+  const char* e = std::getenv("JXLB200_ENTROPY_SMS");
+  const unsigned want = e ? std::atoi(e) : 0;
+  if (want == 0) return nullptr;
+  auto entry = [](const char* name) -> void* {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) return nullptr;
+    return fn;
+  };
+  auto dev_get = reinterpret_cast<CUresult (*)(CUdevice*, int)>(entry("cuDeviceGet"));
+  auto get_res = reinterpret_cast<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>(entry("cuDeviceGetDevResource"));
+  auto split = reinterpret_cast<CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int,
+                                             unsigned int)>(entry("cuDevSmResourceSplitByCount"));
+  auto gen_desc = reinterpret_cast<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>(entry("cuDevResourceGenerateDesc"));
+  auto ctx_create = reinterpret_cast<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>(entry("cuGreenCtxCreate"));
+  p.stream_create = reinterpret_cast<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>(entry("cuGreenCtxStreamCreate"));
+  if (!dev_get || !get_res || !split || !gen_desc || !ctx_create || !p.stream_create) return nullptr;
+  cudaFree(nullptr);  // the primary context exists
+  CUdevice dev;
+  CUdevResource all, part[2];
+  unsigned int groups = 1;
+  if (dev_get(&dev, device) != CUDA_SUCCESS || get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return nullptr;
+  if (split(&part[0], &groups, &all, &part[1], 0, want) != CUDA_SUCCESS || groups != 1 || part[1].sm.smCount == 0) return nullptr;
+  for (int i = 0; i < 2; i++) {
+    CUdevResourceDesc desc;
+    if (gen_desc(&desc, &part[i], 1) != CUDA_SUCCESS) return nullptr;
+    if (ctx_create(&p.ctx[i], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return nullptr;
+    p.sms[i] = part[i].sm.smCount;
+  }
+  std::fprintf(stderr, "jxl_b200: SM partition on device %d: %u SMs entropy kernels, %u SMs per-pixel kernels\n", device, p.sms[0],
+               p.sms[1]);
+  p.ok = true;
+  return &p;
+}
+
 struct JxlB200Decoder {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // SM partition (JXLB200_ENTROPY_SMS): this handle's streams in the entropy / pixel green contexts and the events that
+  // order caller stream -> entropy kernels -> per-pixel kernels -> caller stream
+  cudaStream_t part_stream[2] = {nullptr, nullptr};
+  cudaEvent_t part_ev[3] = {nullptr, nullptr, nullptr};
   std::string error;
   std::unique_ptr<BatchPlan> plan;
   DevBuf<uint8_t> d_bytes, d_out;
@@ -590,6 +759,9 @@ struct JxlB200Decoder {
   // VarDCT
   DevBuf<DevVFrame> d_vframes;
   DevBuf<DevAcStream> d_ac_streams;
+  DevBuf<DevAcUnit> d_ac_units;
+  DevBuf<uint32_t> d_ac_unit_streams;
+  uint32_t ac_frame_smem = 0, ac_frame_threads = 0;  // k_ac_decode_frame's launch shape; 0: the one-warp kernel
   DevBuf<float> d_fpool, d_farena, d_big_scratch;
   DevBuf<uint16_t> d_opool, d_lut;
   DevBuf<uint8_t> d_cpool, d_barena;
@@ -674,32 +846,27 @@ JxlB200Decoder* JxlB200DecoderCreate(int device) {
     delete dec;
     return nullptr;
   }
+  if (SmPartition* sp = GetSmPartition(device)) {
+    bool ok = true;
+    for (int i = 0; i < 2; i++) {
+      CUstream st = nullptr;
+      ok = ok && sp->stream_create(&st, sp->ctx[i], CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+      dec->part_stream[i] = reinterpret_cast<cudaStream_t>(st);
+    }
+    for (int i = 0; i < 3; i++) ok = ok && cudaEventCreateWithFlags(&dec->part_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) dec->part_stream[0] = dec->part_stream[1] = nullptr;  // (falls back to one stream)
+  }
   cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, kIdctSmemFloats * sizeof(float));
   cudaFuncSetAttribute(k_idct_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kMidSmemFloats * sizeof(float));
   cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        6 * DevRenderTileFloats(kRtMaxHalo) * sizeof(float));
   cudaFuncSetAttribute(k_modular_decode_sparse<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_modular_decode_sparse<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  // Every kernel asks for the largest shared-memory carve-out of the L1 / shared-memory array. The split is a per-SM
-  // state that only changes when the SM is idle: a long-running entropy CTA with a few KB of shared memory otherwise
-  // pins its SM in a small-carve-out state, and the render / IDCT CTAs of the other handles in flight (52 - 86 KB
-  // each) cannot become resident next to it (tools/interference.py: AC decode in the background slowed them 4.4 x).
-  if (!std::getenv("JXLB200_NO_CARVEOUT")) {
-    const int co = cudaSharedmemCarveoutMaxShared;
-    cudaFuncSetAttribute(k_modular_decode<int32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_modular_decode<int64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_modular_decode_sparse<int32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_modular_decode_sparse<int64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_dc_finish, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_dc_smooth, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_ac_decode<1>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_ac_decode<4>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_ac_decode<8>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_idct_mid, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_idct_big, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-    cudaFuncSetAttribute(k_render_fused, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-  }
+  cudaFuncSetAttribute(k_ac_decode_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  // (Measured and not kept, profiles/r2_ab_carveout.txt: cudaFuncAttributePreferredSharedMemoryCarveout = max shared on
+  // every kernel, on the theory that a long-running entropy CTA pins its SM's L1 / shared-memory split and keeps render
+  // CTAs out. The slowdown of the per-pixel kernels next to AC decode stayed 4 x, and the entropy kernels lost 8 - 20 %
+  // to the smaller L1: the interference is issue slots, not the carve-out.)
   return dec;
 }
 
@@ -710,6 +877,10 @@ void JxlB200DecoderDestroy(JxlB200Decoder* dec) {
   for (cudaEvent_t e : dec->free_events) cudaEventDestroy(e);
   if (dec->h_bytes) cudaFreeHost(dec->h_bytes);
   if (dec->stream) cudaStreamDestroy(dec->stream);
+  for (cudaStream_t st : dec->part_stream)
+    if (st) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : dec->part_ev)
+    if (ev) cudaEventDestroy(ev);
   delete dec;
 }
 
@@ -862,6 +1033,29 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     CUDA_OK(dec->d_tokens.Alloc(b.tok_size + 16));
     V.streams = dec->d_ac_streams.p;
     V.tokens = dec->d_tokens.p;
+    // The CTA-per-(frame, pass) AC kernel (tables TMA-staged in shared memory) is opt-in, JXLB200_AC_FRAME=1; it needs
+    // plain ANS codes and tables that fit the shared memory of an SM next to a second CTA. Measured on the bench batch
+    // (profiles/r2_ab_ac_frame_kernel.txt): 74.6 ms alone against 52.9 ms for the one-warp kernel, whose warps hold 32
+    // streams of equal length from 32 frames and therefore run in lock step, while a frame's own 135 streams differ in
+    // length and diverge; its 93 KB of shared memory per CTA also starve the render CTAs of the other handles.
+    dec->ac_frame_smem = dec->ac_frame_threads = 0;
+    if (V.ac_plain_ans && !b.ac_units.empty() && std::getenv("JXLB200_AC_FRAME")) {
+      uint32_t max_count = 0, max_smem = 0;
+      for (const DevAcUnit& u : b.ac_units) max_count = std::max(max_count, u.count);
+      const uint32_t warps = std::min<uint32_t>(8, (max_count + 31) / 32);
+      for (const DevAcUnit& u : b.ac_units) {
+        const DevVFrame& vf = b.vframes[u.frame];
+        const DevCode& c = b.codes[vf.ac_code[u.pass]];
+        max_smem = std::max(max_smem, AcFrameLayout(c.num_clusters << c.log_alpha_size, c.num_clusters,
+                                                    vf.num_histograms * vf.num_ctxs * 495, warps).total);
+      }
+      if (max_smem <= 110 * 1024) {
+        dec->ac_frame_smem = max_smem;
+        dec->ac_frame_threads = warps * 32;
+        CUDA_OK(dec->d_ac_units.Upload(b.ac_units, s));
+        CUDA_OK(dec->d_ac_unit_streams.Upload(b.ac_unit_streams, s));
+      }
+    }
   }
   CUDA_OK(cudaStreamSynchronize(s));
   return 0;
@@ -1009,7 +1203,17 @@ static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s
 int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   if (!dec || !dec->plan) return 1;
   CUDA_OK(cudaSetDevice(dec->device));
-  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : dec->stream;
+  cudaStream_t caller = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : dec->stream;
+  // Without an SM partition everything runs on the caller's stream. With one: entropy kernels on the handle's stream in
+  // the entropy partition (`s`), per-pixel kernels on its stream in the pixel partition (`sp`), ordered by events.
+  const bool parted = dec->part_stream[0] != nullptr && !dec->plan->vframes.empty();
+  cudaStream_t s = parted ? dec->part_stream[0] : caller;
+  cudaStream_t sp = parted ? dec->part_stream[1] : caller;
+  if (parted) {
+    CUDA_OK(cudaEventRecord(dec->part_ev[0], caller));
+    CUDA_OK(cudaStreamWaitEvent(s, dec->part_ev[0], 0));
+    CUDA_OK(cudaStreamWaitEvent(sp, dec->part_ev[0], 0));  // (the previous run's read-back of the output is over)
+  }
   const BatchPlan& b = *dec->plan;
   const DevPools& P = dec->pools;
   uint32_t launches = 0;
@@ -1065,9 +1269,14 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     }
     if (pm & (1u << kKAcDecode)) {
       ScopedTimer t(dec, s, kKAcDecode);
+      k_block_lists<<<(dec->max_groups * nvf + 127) / 128, 128, 0, s>>>(V, dec->max_groups, nvf);
+      launches++;
       static const uint32_t ac_warps = std::getenv("JXLB200_AC_WARPS") ? std::atoi(std::getenv("JXLB200_AC_WARPS")) : 1;
       const uint32_t nst = b.ac_streams.size();
-      if (ac_warps >= 8) {
+      if (dec->ac_frame_smem != 0) {
+        k_ac_decode_frame<<<b.ac_units.size(), dec->ac_frame_threads, dec->ac_frame_smem, s>>>(P, V, dec->d_ac_units.p,
+                                                                                                dec->d_ac_unit_streams.p);
+      } else if (ac_warps >= 8) {
         k_ac_decode<8><<<(nst + 255) / 256, 256, 0, s>>>(P, V);
       } else if (ac_warps >= 4) {
         k_ac_decode<4><<<(nst + 127) / 128, 128, 0, s>>>(P, V);
@@ -1076,18 +1285,22 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
       }
       launches++;
     }
+    if (parted) {  // the per-pixel waves start when this batch's entropy kernels are through
+      CUDA_OK(cudaEventRecord(dec->part_ev[1], s));
+      CUDA_OK(cudaStreamWaitEvent(sp, dec->part_ev[1], 0));
+    }
     const dim3 px_block(32, 8);
     for (uint32_t f0 = 0; f0 < nvf; f0 += b.wave_frames) {
       const uint32_t nf = std::min<uint32_t>(b.wave_frames, nvf - f0);
       if (pm & (1u << kKDequantIdct)) {
-        ScopedTimer t(dec, s, kKDequantIdct);
+        ScopedTimer t(dec, sp, kKDequantIdct);
         uint32_t* has_mid = dec->d_dc_status.p + dec->dcg_list.size();  // spare words after the DC status words
         uint32_t* mid_count = has_mid + 1;
-        if (f0 != 0 || !(pm & (1u << kKDcFinish))) CUDA_OK(cudaMemsetAsync(mid_count, 0, 4, s));  // (the first wave's was cleared with the DC status)
-        k_dequant_idct<<<dim3(dec->max_groups, nf), kIdctThreads, kIdctSmemFloats * sizeof(float), s>>>(V, f0, has_mid, mid_count,
+        if (f0 != 0 || !(pm & (1u << kKDcFinish))) CUDA_OK(cudaMemsetAsync(mid_count, 0, 4, sp));  // (the first wave's was cleared with the DC status)
+        k_dequant_idct<<<dim3(dec->max_groups, nf), kIdctThreads, kIdctSmemFloats * sizeof(float), sp>>>(V, f0, has_mid, mid_count,
                                                                                                        dec->d_mid_list.p);
-        k_idct_mid<<<4 * 148, kMidThreads, kMidSmemFloats * sizeof(float), s>>>(V, mid_count, dec->d_mid_list.p);
-        k_idct_big<<<JxlB200Decoder::kBigCtas, 256, 0, s>>>(V, f0, nf, dec->d_big_scratch.p, has_mid);
+        k_idct_mid<<<4 * 148, kMidThreads, kMidSmemFloats * sizeof(float), sp>>>(V, mid_count, dec->d_mid_list.p);
+        k_idct_big<<<JxlB200Decoder::kBigCtas, 256, 0, sp>>>(V, f0, nf, dec->d_big_scratch.p, has_mid);
         launches += 3;
       }
       const dim3 px_grid((dec->max_xsize + 31) / 32, (dec->max_ysize + 7) / 8, nf);
@@ -1095,39 +1308,45 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
       // the batch has patches (or the fused path is switched off: JXLB200_UNFUSED_RENDER=1, for comparison).
       const uint32_t skip_fused = dec->fused_render ? 1 : 0;
       if (dec->fused_render && (pm & (1u << kKFilters))) {
-        ScopedTimer t(dec, s, kKFilters);
+        ScopedTimer t(dec, sp, kKFilters);
         const uint32_t halo = DevRenderHalo(dec->any_gab ? 1 : 0, dec->max_epf);
         const uint32_t cap = DevRenderTileFloats(halo);
         const dim3 rt_grid((dec->max_xsize + kRtW - 1) / kRtW, (dec->max_ysize + kRtH - 1) / kRtH, nf);
-        k_render_fused<<<rt_grid, 256, 6 * cap * sizeof(float), s>>>(V, f0, cap, DevRenderStride(halo));
+        k_render_fused<<<rt_grid, 256, 6 * cap * sizeof(float), sp>>>(V, f0, cap, DevRenderStride(halo));
         launches++;
       }
       if (!dec->fused_render || !b.patches.empty()) {
         {
-          ScopedTimer t(dec, s, kKFilters);
+          ScopedTimer t(dec, sp, kKFilters);
           if (dec->any_gab) {
-            k_gaborish<<<px_grid, px_block, 0, s>>>(V, f0, 0, 1, skip_fused);
+            k_gaborish<<<px_grid, px_block, 0, sp>>>(V, f0, 0, 1, skip_fused);
             launches++;
           }
           for (uint32_t stage = 0; stage < 3; stage++) {
             if (dec->max_epf == 0 || (stage == 0 && dec->max_epf < 3) || (stage == 2 && dec->max_epf < 2)) continue;
-            k_epf<<<px_grid, px_block, 0, s>>>(V, f0, stage, skip_fused);
+            k_epf<<<px_grid, px_block, 0, sp>>>(V, f0, stage, skip_fused);
             launches++;
           }
         }
         if (!b.patches.empty()) {
-          ScopedTimer t(dec, s, kKFilters);
-          k_patches<<<nf, 256, 0, s>>>(V, f0);
+          ScopedTimer t(dec, sp, kKFilters);
+          k_patches<<<nf, 256, 0, sp>>>(V, f0);
           launches++;
         }
         {
-          ScopedTimer t(dec, s, kKColorWrite);
+          ScopedTimer t(dec, sp, kKColorWrite);
           const dim3 cw_grid((dec->max_xsize + 127) / 128, (dec->max_ysize + 7) / 8, nf);
-          k_color_write<<<cw_grid, px_block, 0, s>>>(V, f0, skip_fused);
+          k_color_write<<<cw_grid, px_block, 0, sp>>>(V, f0, skip_fused);
           launches++;
         }
       }
     }
+  }
+  if (parted) {
+    CUDA_OK(cudaEventRecord(dec->part_ev[2], sp));
+    CUDA_OK(cudaStreamWaitEvent(caller, dec->part_ev[2], 0));
+    CUDA_OK(cudaEventRecord(dec->part_ev[2], s));  // (entropy-side kernels of Modular frames, if any, end here)
+    CUDA_OK(cudaStreamWaitEvent(caller, dec->part_ev[2], 0));
   }
   if (dec->profiling) dec->profiled_runs++;
   dec->launches = launches;

@@ -93,6 +93,8 @@ struct DevChannel {
   // Second fast path (libjxl's fixed AC-metadata tree, lib/jxl/modular/encoding/enc_encoding.cc:218-264): the pruned
   // tree only tests y, N and W with few thresholds, its leaves have offset 0 and multiplier 1 and no weighted
   // predictor: lut_off then points at a (y, N, W) bucket table (layout: jxlb_modular_dev.h, kNwOff*).
+  // nw_lut == 2 (libjxl's fixed gradient DC tree, enc_encoding.cc:274-282): only property 9 (W + N - NW) is tested,
+  // lut[clamp(property, lut_lo, lut_lo + lut_size - 1) - lut_lo] = cluster | predictor << 8.
   uint32_t nw_lut;
   uint32_t pad_[3];
 };

@@ -209,14 +209,17 @@ struct DevSymbolReader {
   }
 
   // The code is ANS without LZ77 (checked for the whole warp by the caller): no mode tests per symbol.
+  // kShared: `alias` and `cfg` point into shared memory (k_ac_decode_frame stages the tables there).
+  template <bool kShared = false>
   JXLB_HD uint32_t ReadUintPlainAns(uint32_t cluster, DevBits& br) {
     const uint32_t log_entry = 12 - log_alpha;
     const uint32_t res = state & 0xFFF;
     const uint32_t i = res >> log_entry;
     const uint32_t pos = res & ((1u << log_entry) - 1);
-    const uint32_t cfg_word = JXLB_LDG(cfg + cluster);
+    const uint32_t cfg_word = kShared ? cfg[cluster] : JXLB_LDG(cfg + cluster);
 #if defined(__CUDA_ARCH__)
-    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(alias + (cluster << log_alpha) + i));
+    const uint2 raw = kShared ? *reinterpret_cast<const uint2*>(alias + (cluster << log_alpha) + i)
+                              : __ldg(reinterpret_cast<const uint2*>(alias + (cluster << log_alpha) + i));
     const uint32_t cutoff = raw.x & 0xFF, right_value = (raw.x >> 8) & 0xFF, freq0 = raw.x >> 16;
     const uint32_t offsets1 = raw.y & 0xFFFF, fx = raw.y >> 16;
 #else
@@ -528,7 +531,9 @@ JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const 
   // kNw: thresholds of N and W in registers (padded with INT32_MAX: never exceeded), the row's table slice per row
   int32_t nw_tn[kNwThresholds] = {}, nw_tw[kNwThresholds] = {};
   uint32_t nw_ny = 0;
-  if (kNw && h > 0) {
+  // nw_lut == 2: the tree only tests property 9 (W + N - NW, libjxl's fixed gradient DC tree): lut[clamp(p9) - lut_lo]
+  const bool grad_lut = kNw && ch.nw_lut == 2;
+  if (kNw && h > 0 && !grad_lut) {
     nw_ny = JXLB_LDG(lut);
     for (uint32_t i = 0; i < kNwThresholds; i++) {
       nw_tn[i] = DevNwThreshold(lut + kNwOffN, i);
@@ -552,7 +557,7 @@ JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const 
     const int32_t* prev = direct ? out_row - stride : rowA;
     const int32_t* prevprev = direct ? out_row - 2 * static_cast<size_t>(stride) : rowB;
     if (!kFast && !kNw) props[2 * PS] = y;
-    if (kNw && row_on) {
+    if (kNw && row_on && !grad_lut) {
       uint32_t by = 0;
       for (uint32_t i = 0; i < nw_ny; i++) by += y > DevNwThreshold(lut + kNwOffY, i) ? 1u : 0u;
       nw_row = lut + kNwOffTable + by * ((kNwThresholds + 1) * (kNwThresholds + 1));
@@ -674,12 +679,19 @@ JXLB_HD void DevDecodeChannelRows(const DevPools& P, const DevLaneMem& m, const 
           const uint32_t u = kPlainAns ? reader.ReadUintPlainAns(cluster, br) : reader.ReadUint(cluster, br);
           val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) + static_cast<uint32_t>(wp_pred));
         } else if (kNw) {
-          uint32_t bn = 0, bw = 0;
-          for (uint32_t i = 0; i < kNwThresholds; i++) {
-            bn += n_top > static_cast<WT>(nw_tn[i]) ? 1u : 0u;
-            bw += n_left > static_cast<WT>(nw_tw[i]) ? 1u : 0u;
+          uint32_t e;  // cluster | predictor << 8
+          if (grad_lut) {
+            const WT p9 = n_left + n_top - n_topleft;
+            const WT pv = p9 < static_cast<WT>(lut_lo) ? static_cast<WT>(lut_lo) : (p9 > static_cast<WT>(lut_hi) ? static_cast<WT>(lut_hi) : p9);
+            e = JXLB_LDG(lut + static_cast<uint32_t>(static_cast<int32_t>(pv) - lut_lo));
+          } else {
+            uint32_t bn = 0, bw = 0;
+            for (uint32_t i = 0; i < kNwThresholds; i++) {
+              bn += n_top > static_cast<WT>(nw_tn[i]) ? 1u : 0u;
+              bw += n_left > static_cast<WT>(nw_tw[i]) ? 1u : 0u;
+            }
+            e = JXLB_LDG(nw_row + bn * (kNwThresholds + 1) + bw);
           }
-          const uint32_t e = JXLB_LDG(nw_row + bn * (kNwThresholds + 1) + bw);  // cluster | predictor << 8
           const uint32_t u = kPlainAns ? reader.ReadUintPlainAns(e & 0xFF, br) : reader.ReadUint(e & 0xFF, br);
           const WT guess = DevPredictW<WT>(e >> 8, n_left, n_top, n_topleft, n_topright, n_leftleft, n_toptop,
                                            n_toprightright, 0);

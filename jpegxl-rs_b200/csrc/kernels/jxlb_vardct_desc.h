@@ -37,6 +37,10 @@ struct DevVFrame {
   uint64_t acs, qdc, sharp, rawq /* uint16, 2-aligned */, ytox, ytob;
   // uarena (uint32 index): [pass][channel][block] first token / token count
   uint64_t tok_start, tok_count;
+  // uarena: per 256x256 group the list of its varblocks in decode order, two words each (DevBuildBlockList); the
+  // list of the group with first block (x0, y0) and ys block rows starts at blist + 2 * (y0 * xblocks + x0 * ys).
+  // blist_count: entries per group (0xFFFFFFFF: the strategy map of the group has a hole).
+  uint64_t blist, blist_count;
   // quantiser + colour correlation
   float mul_dc[3], inv_mul_dc[3];
   float cfl_dc_x, cfl_dc_b;
@@ -107,6 +111,13 @@ struct DevAcStream {
   uint32_t pass;
   uint32_t tok_cap;           // capacity in tokens
   uint64_t tok_off;           // first token (tokens index)
+};
+
+// The AC streams of one (frame, pass): what one CTA of k_ac_decode_frame decodes with the pass's alias tables, uint
+// configs and context map staged in shared memory. `first` indexes the batch's list of stream ids (longest first).
+struct DevAcUnit {
+  uint32_t first, count;
+  uint32_t frame, pass;
 };
 
 // AcStrategy geometry (lib/jxl/ac_strategy.h:32-80, :148-174), kStrategyOrder and

@@ -301,16 +301,73 @@ JXLB_HD void DevDcSmoothBlock(const DevVPools& V, const DevVFrame& vf, uint32_t 
 }
 
 // ---------------------------------------------------------------- AC coefficient streams
+// The varblocks of group `g` in decode order (raster order of their first blocks, lib/jxl/dec_group.cc:168-442) with
+// everything the AC stream needs to start one: word 0 = cell (by * 32 + bx inside the group) | cx << 10 |
+// log2(covered blocks) << 16 | coefficient-order id << 20 | strategy << 24; word 1 = the block context
+// (lib/jxl/ac_context.h:99-109) of channel c in byte c. One thread per group: a serial pass over <= 1024 strategy
+// bytes, run once per batch between the DC kernels and AC decode, so that the lock-step AC lanes -- which diverge on
+// every varblock start -- fetch one prefetchable record instead of walking the strategy map, the raw quant field,
+// the quant-DC buckets and the block-context thresholds link by link.
+JXLB_HD void DevBuildBlockList(const DevVPools& V, const DevVFrame& vf, uint32_t g) {
+  const uint32_t W = vf.xblocks;
+  const uint32_t x0 = (g % vf.xgroups) * 32, y0 = (g / vf.xgroups) * 32;
+  const uint32_t xs = W - x0 < 32 ? W - x0 : 32, ys = vf.yblocks - y0 < 32 ? vf.yblocks - y0 : 32;
+  const uint8_t* acs = V.barena + vf.acs;
+  const uint8_t* qdc = V.barena + vf.qdc;
+  const uint16_t* rawq = reinterpret_cast<const uint16_t*>(V.barena + vf.rawq);
+  const uint32_t* bthr = V.upool + vf.bctx_off;
+  const uint32_t nqf = vf.num_qf_thr;
+  const uint32_t bmap_off = vf.num_dc_thr[0] + vf.num_dc_thr[1] + vf.num_dc_thr[2] + nqf;
+  uint32_t* list = V.uarena + vf.blist + 2 * (static_cast<size_t>(y0) * W + static_cast<size_t>(x0) * ys);
+  uint32_t n = 0;
+  bool hole = false;
+  for (uint32_t by = 0; by < ys && !hole; by++) {
+    for (uint32_t bx = 0; bx < xs;) {
+      const size_t pos = static_cast<size_t>(y0 + by) * W + x0 + bx;
+      const uint8_t a = acs[pos];
+      if (a == 0xFF) {
+        hole = true;
+        break;
+      }
+      const StrategyInfo si = UnpackStrategyInfo(JXLB_LDG(V.upool + V.sinfo_off + (a >> 1)));
+      if (a & 1) {
+        const uint32_t qf = rawq[pos];
+        uint32_t qf_idx = 0;
+        for (uint32_t t = 0; t < nqf; t++) qf_idx += qf > bthr[bmap_off - nqf + t];
+        uint32_t ctxs = 0;
+        for (uint32_t c = 0; c < 3; c++) {
+          uint32_t idx = (c < 2 ? c ^ 1 : 2) * kNumOrders + si.order;
+          idx = idx * (nqf + 1) + qf_idx;
+          idx = idx * vf.num_dc_ctxs + qdc[pos];
+          ctxs |= ((bthr[bmap_off + (idx >> 2)] >> (8 * (idx & 3))) & 0xFF) << (8 * c);
+        }
+        list[2 * n] = (by * 32 + bx) | (static_cast<uint32_t>(si.cx) << 10) | (static_cast<uint32_t>(si.log2_covered) << 16) |
+                      (static_cast<uint32_t>(si.order) << 20) | (static_cast<uint32_t>(a >> 1) << 24);
+        list[2 * n + 1] = ctxs;
+        n++;
+      }
+      bx += si.cx;
+    }
+  }
+  V.uarena[vf.blist_count + g] = hole ? 0xFFFFFFFFu : n;
+}
+
 struct DevAcLaneMem {
   uint8_t* colnz;          // [3 * 32] entries, element stride `stride`: last non-zero bucket per column
   uint32_t stride;
   const uint16_t* freq_ctx;  // kCoeffFreqContext[64]
   const uint16_t* nnz_ctx;   // kCoeffNumNonzeroContext[64]
+  // kShared instances: the pass's tables in shared memory
+  const DevAlias* alias_s = nullptr;
+  const uint32_t* cfg_s = nullptr;
+  const uint8_t* ctx_map_s = nullptr;
 };
 
 // kPlainAns: every AC code of the batch is ANS without LZ77 (the host checked): no mode tests per symbol.
-template <bool kPlainAns = false>
+// kShared (implies kPlainAns): alias tables, uint configs and the context map are read from m.alias_s / cfg_s / ctx_map_s.
+template <bool kPlainAns = false, bool kShared = false>
 JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32_t s, const DevAcLaneMem& m, bool valid) {
+#define JXLB_AC_CTX(p) (kShared ? *(p) : JXLB_LDG(p))
   enum { kNeedBlock = 0, kReadNz = 1, kCoeff = 2, kDone = 3 };
   uint32_t mode = kDone, status = 0;
   DevAcStream st{};
@@ -321,9 +378,6 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
   uint32_t W = 0, x0 = 0, y0 = 0, xs = 0, ys = 0, shift_unused = 0;
   uint32_t ctx_offset = 0, num_ctxs = 0;
   const uint8_t* ctx_map = nullptr;
-  const uint8_t* acs = nullptr;
-  const uint8_t* qdc = nullptr;
-  const uint16_t* rawq = nullptr;
   uint32_t* tok = nullptr;
   uint32_t* ts = nullptr;
   uint32_t* tc = nullptr;
@@ -348,24 +402,37 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
     code = P.codes[vf->ac_code[st.pass]];
     reader.Init(P, code, br, 0, nullptr);
     ctx_map = V.cpool + vf->ctx_map_off[st.pass];
-    acs = V.barena + vf->acs;
-    qdc = V.barena + vf->qdc;
-    rawq = reinterpret_cast<const uint16_t*>(V.barena + vf->rawq);
+    if (kShared) {
+      reader.alias = m.alias_s;
+      reader.cfg = m.cfg_s;
+      ctx_map = m.ctx_map_s;
+    }
     tok = V.tokens + st.tok_off;
     ts = V.uarena + vf->tok_start + static_cast<size_t>(st.pass) * 3 * nb;
     tc = V.uarena + vf->tok_count + static_cast<size_t>(st.pass) * 3 * nb;
     mode = (status == 0) ? kNeedBlock : kDone;
   }
   (void)shift_unused;
-  const uint32_t* bthr = vf ? V.upool + vf->bctx_off : nullptr;
-  uint32_t nqf = 0, bmap_off = 0;
-  if (vf) {
-    nqf = vf->num_qf_thr;
-    bmap_off = vf->num_dc_thr[0] + vf->num_dc_thr[1] + vf->num_dc_thr[2] + nqf;
+  // the group's varblock list (DevBuildBlockList): `rec` is the record of the varblock being decoded, `next` the one
+  // after it, requested when `rec` is taken
+  const uint32_t* blist = nullptr;
+  uint32_t nblocks = 0, bi = 0;
+  uint32_t next_x = 0, next_y = 0;
+  if (valid && mode != kDone) {
+    blist = V.uarena + vf->blist + 2 * (static_cast<size_t>(y0) * W + static_cast<size_t>(x0) * ys);
+    nblocks = V.uarena[vf->blist_count + st.group];
+    if (nblocks == 0xFFFFFFFFu) {
+      status |= kVBadStream;
+      mode = kDone;
+      nblocks = 0;
+    } else if (nblocks > 0) {
+      next_x = blist[0];
+      next_y = blist[1];
+    }
   }
   const uint32_t LS = m.stride;
   uint32_t bx = 0, by = 0, ci = 3;                 // position inside the group, channel step (Y, X, B)
-  uint32_t cx = 1, log2c = 0, covered = 1, size = 64, ord = 0;
+  uint32_t cx = 1, log2c = 0, covered = 1, size = 64, ord = 0, bctxs = 0;
   uint32_t c = 0, k = 0, nz = 0, prev = 0, histo_offset = 0, ctx = 0, ntok = 0, chan_start = 0;
   uint32_t pre_zero = 0, pre_nonzero = 0;
   bool pre_valid = false;
@@ -374,44 +441,30 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
   for (;;) {
     if (mode == kNeedBlock) {
       if (ci >= 3) {  // next varblock in raster order of the top-left blocks
-        for (;;) {
-          if (bx >= xs) {
-            bx = 0;
-            by++;
+        if (bi >= nblocks) {
+          mode = kDone;
+        } else {
+          const uint32_t rec = next_x;
+          bctxs = next_y;
+          bi++;
+          if (bi < nblocks) {
+            next_x = blist[2 * bi];
+            next_y = blist[2 * bi + 1];
           }
-          if (by >= ys) break;
+          bx = rec & 31;
+          by = (rec >> 5) & 31;
+          cx = (rec >> 10) & 63;
+          log2c = (rec >> 16) & 15;
+          ord = (rec >> 20) & 15;
+          covered = 1u << log2c;
+          size = covered * 64;
           pos = static_cast<size_t>(y0 + by) * W + x0 + bx;
-          const uint8_t a = acs[pos];
-          if (a == 0xFF) {
-            status |= kVBadStream;
-            by = ys;
-            break;
-          }
-          const StrategyInfo si = UnpackStrategyInfo(JXLB_LDG(V.upool + V.sinfo_off + (a >> 1)));
-          cx = si.cx;
-          if (a & 1) {
-            log2c = si.log2_covered;
-            covered = 1u << log2c;
-            size = covered * 64;
-            ord = si.order;
-            break;
-          }
-          bx += cx;
+          ci = 0;
         }
-        ci = 0;
       }
-      if (by >= ys) {
-        mode = kDone;
-      } else {
+      if (mode != kDone) {
         c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);
-        // block context (lib/jxl/ac_context.h:99-109)
-        const uint32_t qf = rawq[pos];
-        uint32_t qf_idx = 0;
-        for (uint32_t t = 0; t < nqf; t++) qf_idx += qf > bthr[bmap_off - nqf + t];
-        uint32_t idx = (c < 2 ? c ^ 1 : 2) * kNumOrders + ord;
-        idx = idx * (nqf + 1) + qf_idx;
-        idx = idx * vf->num_dc_ctxs + qdc[pos];
-        const uint32_t block_ctx = (bthr[bmap_off + (idx >> 2)] >> (8 * (idx & 3))) & 0xFF;
+        const uint32_t block_ctx = (bctxs >> (8 * c)) & 0xFF;
         // predicted number of non-zeros from the top and left neighbours
         uint32_t predicted;
         const uint8_t* col = m.colnz + static_cast<size_t>(c * 32 + bx) * LS;
@@ -440,18 +493,19 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
         const uint32_t nzl = (nz + covered - 1) >> log2c;
         ctx = histo_offset + (m.nnz_ctx[nzl] + m.freq_ctx[k >> log2c]) * 2 + prev;
       }
-      cluster = JXLB_LDG(ctx_map + ctx);
+      cluster = JXLB_AC_CTX(ctx_map + ctx);
     }
     pre_valid = false;
     if (mode == kCoeff && k + 1 < size) {
       // The context of the next coefficient depends on this one only through (is it zero?): fetch the cluster
       // of both outcomes now, off the critical path of the serial rANS chain.
       const uint32_t f = m.freq_ctx[(k + 1) >> log2c];
-      pre_zero = JXLB_LDG(ctx_map + histo_offset + (m.nnz_ctx[(nz + covered - 1) >> log2c] + f) * 2);
-      pre_nonzero = nz > 1 ? JXLB_LDG(ctx_map + histo_offset + (m.nnz_ctx[(nz - 1 + covered - 1) >> log2c] + f) * 2 + 1) : 0;
+      pre_zero = JXLB_AC_CTX(ctx_map + histo_offset + (m.nnz_ctx[(nz + covered - 1) >> log2c] + f) * 2);
+      pre_nonzero = nz > 1 ? JXLB_AC_CTX(ctx_map + histo_offset + (m.nnz_ctx[(nz - 1 + covered - 1) >> log2c] + f) * 2 + 1) : 0;
       pre_valid = true;
     }
-    const uint32_t u = kPlainAns ? reader.ReadUintPlainAns(cluster, br) : reader.ReadUint(cluster, br);
+    const uint32_t u = kShared ? reader.template ReadUintPlainAns<true>(cluster, br)
+                               : (kPlainAns ? reader.ReadUintPlainAns(cluster, br) : reader.ReadUint(cluster, br));
     bool chan_done = false;
     if (mode == kReadNz) {
       nz = u;
@@ -496,7 +550,6 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
       pre_valid = false;
       tc[c * nb + pos] = (ntok < st.tok_cap ? ntok : st.tok_cap) - (chan_start < st.tok_cap ? chan_start : st.tok_cap);
       ci++;
-      if (ci >= 3) bx += cx;
       mode = kNeedBlock;
     }
   }
@@ -507,6 +560,7 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
     V.ac_used[s] = ntok;
   }
   return status;
+#undef JXLB_AC_CTX
 }
 
 // ---------------------------------------------------------------- 1-D transforms, staged
@@ -1234,10 +1288,6 @@ JXLB_HD void DevVarblockFast(const DevVPools& V, const DevVFrame& vf, uint32_t b
 // every lane of the warp calls this in lock step, `active` = the lane's group has a varblock). Same arithmetic as
 // DevVarblock: dequantisation straight from the tokens as in DevVarblockFast, DC into coefficient 0, then one thread per
 // channel runs libjxl's statements (DevSpecialToPixels). `buf`: 3 channels of kSpecialChStride floats.
-constexpr uint32_t kSpecialBuckets = 9;
-JXLB_HD uint32_t DevSpecialBucket(uint32_t strategy) {  // strategies 1, 2, 3, 12 ... 17 -> 0 ... 8
-  return strategy <= 3 ? strategy - 1 : strategy - 9;
-}
 constexpr uint32_t kSpecialChStride = 65;  // (odd: the channel slots of the warp's 24 transform lanes start in different banks)
 template <int SCOPE>
 JXLB_HD void DevVarblockSpecial(const DevVPools& V, const DevVFrame& vf, uint32_t bx, uint32_t by, uint32_t s, float* buf,

@@ -179,6 +179,8 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       for (const DevVFrame& vf : b.vframes)
         for (uint32_t p = 0; p < vf.num_passes; p++)
           if (b.codes[vf.ac_code[p]].use_prefix || b.codes[vf.ac_code[p]].lz77_enabled) ac_plain = false;
+      for (const DevVFrame& vf : b.vframes)  // k_block_lists
+        for (uint32_t g = 0; g < vf.xgroups * vf.ygroups; g++) DevBuildBlockList(V, vf, g);
       for (int attempt = 0; attempt < 2; attempt++) {
         bool overflow = false;
         V.streams = b.ac_streams.data();

@@ -109,8 +109,10 @@ def test_ac_metadata_channels_take_the_ynw_table_path(monkeypatch):
     # libjxl's fixed AC-metadata tree (tests y, N, W only) is decoded through the (y, N, W) bucket table
     # (DevChannel::nw_lut); with JXLB200_NO_NW_LUT=1 the same channels take the generic tree walk. Same samples.
     img = vc.crop(200, 300, 100, 200)
+    # (dc_tree=1: libjxl's fixed gradient DC tree, one property -> the 1-D table variant of the same path)
     cases = [jxlo.encode_vardct(img, strategy_mode=3, distance=1.0, epf_iters=1),
-             jxlo.encode_vardct(img, strategy_mode=1, random_side_info=True, seed=11, epf_iters=3)]
+             jxlo.encode_vardct(img, strategy_mode=1, random_side_info=True, seed=11, epf_iters=3),
+             jxlo.encode_vardct(img, strategy_mode=2, dc_tree=1)]
     for data in cases:
         want = jxlo.decode(data, 3, jxlo.UINT8)
         got = emul_lib.decode([data], 3, jxlo.UINT8, [(200, 300)])[0]
