@@ -146,7 +146,9 @@ typedef enum { JXL_SIG_NOT_ENOUGH_BYTES = 0, JXL_SIG_INVALID = 1, JXL_SIG_CODEST
 
 uint32_t JxlDecoderVersion(void);
 JxlSignature JxlSignatureCheck(const uint8_t* buf, size_t len);
-/* memory_manager must be NULL (custom allocators are not routed to the GPU path). */
+/* memory_manager: accepted, its callbacks are never invoked (jpegxl-rs may pass one, jpegxl-rs/src/memory.rs:24-40; the
+ * GPU path owns device memory and pinned staging). Events: BASIC_INFO, then COLOR_ENCODING when subscribed (the ICC
+ * calls fail: ICC synthesis is not built), NEED_IMAGE_OUT_BUFFER, FULL_IMAGE, SUCCESS. */
 JxlDecoder* JxlDecoderCreate(const void* memory_manager);
 void JxlDecoderReset(JxlDecoder* dec);
 void JxlDecoderDestroy(JxlDecoder* dec);

@@ -46,6 +46,7 @@ struct BatchPlan {
   std::vector<DevVFrame> vframes;
   std::vector<DevAcStream> ac_streams;
   // per (frame, pass): the ids of its streams in ac_streams, longest first (k_ac_decode_frame)
+  bool any_upsampling = false;  // some lossy frame is upsampled: the per-pixel render kernels run for it
   std::vector<DevAcUnit> ac_units;
   std::vector<uint32_t> ac_unit_streams;
   std::vector<float> fpool;
@@ -218,6 +219,11 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
       vf.ctx_map_off[p] += cpool0;
     }
     vf.out_off = b->out_size;
+    if (vf.upsampling > 1) {
+      for (int c = 0; c < 3; c++) vf.up_pix[c] += b->farena_size;
+      vf.up_kernel += fpool0;
+      b->any_upsampling = true;
+    }
     vf.patch_begin = b->patches.size();
     for (DevPatch p : v.patches) {
       for (int c = 0; c < 3; c++) p.src[c] += b->farena_size;
@@ -446,7 +452,7 @@ inline void PlanBatch(const uint8_t* const* files, const size_t* sizes, size_t n
     // Two sets of three planes (ping-pong of the per-pixel filter kernels) only when those kernels run: frames
     // without patches go through the fused render tile, which reads set 0 and writes output samples, so a wave holds
     // twice as many frames in the same memory (half as many launches and kernel tails per batch).
-    const bool two_sets = !batch->patches.empty() || std::getenv("JXLB200_UNFUSED_RENDER") != nullptr ||
+    const bool two_sets = !batch->patches.empty() || batch->any_upsampling || std::getenv("JXLB200_UNFUSED_RENDER") != nullptr ||
                           std::getenv("JXLB_EMUL_UNFUSED") != nullptr;
     const uint64_t per_frame = (two_sets ? 6 : 3) * batch->pix_plane_max;
     uint64_t wave_bytes = kWavePixelBytes;

@@ -122,7 +122,7 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
                "unsupported: patches / splines / noise / DC frame on a Modular frame");
     JXLB_CHECK(fh.blending.mode == kReplace, "unsupported: blending");
   }
-  JXLB_CHECK(fh.upsampling == 1, "unsupported: upsampling");
+  JXLB_CHECK(fh.upsampling == 1 || (!fh.is_modular && !is_ref), "unsupported: upsampling of a Modular or reference-only frame");
   for (uint32_t u : fh.ec_upsampling) JXLB_CHECK(u == 1, "unsupported: extra-channel upsampling");
   JXLB_CHECK(!fh.is_modular || (!fh.lf.gab && fh.lf.epf_iters == 0), "unsupported: loop filter on a Modular frame");
   FrameDimensions dim = ToFrameDimensions(fh);

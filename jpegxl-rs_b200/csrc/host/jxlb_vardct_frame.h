@@ -363,7 +363,32 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   }
   vf.inv_sigma = f;
   f += nb;
-  v.farena_size = (f + 3) & ~uint64_t{3};
+  f = (f + 3) & ~uint64_t{3};
+  vf.upsampling = fh.upsampling;
+  vf.up_xsize = dim.xsize_upsampled;
+  vf.up_ysize = dim.ysize_upsampled;
+  if (fh.upsampling > 1) {
+    // the upsampled planes of this frame (per frame, not per wave slot: such frames are rare) and the 5 x 5 kernels
+    // expanded from the upper triangle of weights (stage_upsampling.cc:33-47)
+    vf.up_stride = static_cast<uint32_t>((dim.xsize * fh.upsampling + 3) & ~size_t{3});
+    for (int c = 0; c < 3; c++) {
+      vf.up_pix[c] = f;
+      f += static_cast<uint64_t>(vf.up_stride) * dim.ysize * fh.upsampling;
+    }
+    const uint32_t U = fh.upsampling, half = U / 2;
+    const float* weights = U == 2 ? ((meta.custom_weights_mask & 1) ? meta.up2.data() : kDefaultUpsampling2)
+                                  : (U == 4 ? ((meta.custom_weights_mask & 2) ? meta.up4.data() : kDefaultUpsampling4)
+                                            : ((meta.custom_weights_mask & 4) ? meta.up8.data() : kDefaultUpsampling8));
+    vf.up_kernel = v.fpool.size();
+    v.fpool.resize(v.fpool.size() + 400, 0.0f);
+    float* kernel = v.fpool.data() + vf.up_kernel;
+    for (uint32_t i = 0; i < 5 * half; i++)
+      for (uint32_t j = 0; j < 5 * half; j++) {
+        const uint32_t y = std::min(i, j), x = std::max(i, j);
+        kernel[(((j / 5) * 4 + i / 5) * 5 + j % 5) * 5 + i % 5] = weights[5 * half * y - y * (y - 1) / 2 + x - y];
+      }
+  }
+  v.farena_size = f;
   v.pix_plane = static_cast<uint64_t>(W * 8) * (H * 8);
   uint64_t b = 0;
   vf.acs = b; b += nb;
@@ -421,7 +446,7 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   vf.out_channels = fmt.num_channels;
   vf.out_type = fmt.data_type;
   vf.out_big_endian = fmt.endianness == 2;
-  vf.out_stride = OutputStride(dim.xsize, fmt);
+  vf.out_stride = OutputStride(dim.xsize_upsampled, fmt);
   if (fmt.num_channels < 3) JXLB_CHECK(meta.color.IsGray(), "grey output requested for a colour image");
 }
 

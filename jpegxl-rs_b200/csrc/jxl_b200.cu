@@ -610,10 +610,27 @@ __global__ void __launch_bounds__(256) k_patches(DevVPools V, uint32_t frame0) {
   }
 }
 
+// Upsampled frames: one thread per output pixel of the upsampled planes (DevUpsamplePixel).
+__global__ void __launch_bounds__(256) k_upsample(DevVPools V, uint32_t frame0) {
+  const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
+  const uint32_t x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (vf.upsampling <= 1 || x >= vf.xsize * vf.upsampling || y >= vf.ysize * vf.upsampling) return;
+  DevUpsamplePixel(V, vf, SetBeforeStage(vf, 3), x, y);
+}
+
 __global__ void __launch_bounds__(256) k_color_write(DevVPools V, uint32_t frame0, uint32_t skip_fused) {
   const DevVFrame& vf = V.frames[frame0 + blockIdx.z];
   const uint32_t y = blockIdx.y * 8 + threadIdx.y;
-  if (y >= vf.ysize || (skip_fused && DevRenderFused(vf))) return;
+  if (skip_fused && DevRenderFused(vf)) return;
+  if (vf.upsampling > 1) {  // the image's own size, from the upsampled planes
+    if (y >= vf.up_ysize) return;
+    for (uint32_t k = 0; k < 4; k++) {
+      const uint32_t x = (blockIdx.x * 4 + k) * 32 + threadIdx.x;
+      if (x < vf.up_xsize) DevColorPixel(V, vf, 0, x, y);
+    }
+    return;
+  }
+  if (y >= vf.ysize) return;
   const uint32_t set = SetBeforeStage(vf, 3);
   if (vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0) {
     // RGB8: each thread converts 4 consecutive pixels and writes 12 bytes as three words
@@ -774,6 +791,7 @@ struct JxlB200Decoder {
   std::vector<uint32_t> h_ac_status, h_ac_used, h_dc_status;
   DevVPools vpools{};
   uint32_t max_groups = 0, max_xsize = 0, max_ysize = 0, max_blocks = 0;
+  uint32_t max_up_xsize = 0, max_up_ysize = 0;  // largest frame after upsampling
   bool any_gab = false;
   uint32_t max_epf = 0;
   bool fused_render = std::getenv("JXLB200_UNFUSED_RENDER") == nullptr;
@@ -972,6 +990,7 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
   // ---- VarDCT
   dec->dcg_list.clear();
   dec->max_groups = dec->max_xsize = dec->max_ysize = dec->max_blocks = dec->max_epf = 0;
+  dec->max_up_xsize = dec->max_up_ysize = 0;
   dec->any_gab = false;
   if (!b.vframes.empty()) {
     const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
@@ -981,6 +1000,8 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
       dec->max_groups = std::max(dec->max_groups, vf.xgroups * vf.ygroups);
       dec->max_xsize = std::max(dec->max_xsize, vf.xsize);
       dec->max_ysize = std::max(dec->max_ysize, vf.ysize);
+      dec->max_up_xsize = std::max(dec->max_up_xsize, vf.upsampling > 1 ? vf.xsize * vf.upsampling : vf.xsize);
+      dec->max_up_ysize = std::max(dec->max_up_ysize, vf.upsampling > 1 ? vf.ysize * vf.upsampling : vf.ysize);
       dec->max_blocks = std::max(dec->max_blocks, vf.xblocks * vf.yblocks);
       dec->max_epf = std::max(dec->max_epf, vf.epf_iters);
       dec->any_gab |= vf.gab != 0;
@@ -1315,7 +1336,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
         k_render_fused<<<rt_grid, 256, 6 * cap * sizeof(float), sp>>>(V, f0, cap, DevRenderStride(halo));
         launches++;
       }
-      if (!dec->fused_render || !b.patches.empty()) {
+      if (!dec->fused_render || !b.patches.empty() || b.any_upsampling) {
         {
           ScopedTimer t(dec, sp, kKFilters);
           if (dec->any_gab) {
@@ -1333,9 +1354,14 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
           k_patches<<<nf, 256, 0, sp>>>(V, f0);
           launches++;
         }
+        if (b.any_upsampling) {
+          ScopedTimer t(dec, sp, kKFilters);
+          k_upsample<<<dim3((dec->max_up_xsize + 31) / 32, (dec->max_up_ysize + 7) / 8, nf), px_block, 0, sp>>>(V, f0);
+          launches++;
+        }
         {
           ScopedTimer t(dec, sp, kKColorWrite);
-          const dim3 cw_grid((dec->max_xsize + 127) / 128, (dec->max_ysize + 7) / 8, nf);
+          const dim3 cw_grid((dec->max_up_xsize + 127) / 128, (dec->max_up_ysize + 7) / 8, nf);
           k_color_write<<<cw_grid, px_block, 0, sp>>>(V, f0, skip_fused);
           launches++;
         }
@@ -1535,7 +1561,10 @@ JxlSignature JxlSignatureCheck(const uint8_t* buf, size_t len) {  // lib/jxl/dec
 }
 
 JxlDecoder* JxlDecoderCreate(const void* memory_manager) {
-  if (memory_manager != nullptr) return nullptr;
+  // libjxl copies the JxlMemoryManager struct and allocates through it (lib/jxl/decode.cc:772-787); jpegxl-rs may pass
+  // one (jpegxl-rs/src/memory.rs:24-40). The GPU path owns device memory and pinned staging, which a host allocator
+  // callback cannot provide: the manager is accepted and its callbacks are never invoked.
+  (void)memory_manager;
   JxlDecoder* d = new JxlDecoderStruct();
   return d;
 }
@@ -1606,8 +1635,15 @@ JxlDecoderStatus JxlDecoderProcessInput(JxlDecoder* dec) {
     }
   }
   if (dec->stage == 0) {
-    dec->stage = 1;
+    dec->stage = 5;
     if (dec->events_wanted & JXL_DEC_BASIC_INFO) return JXL_DEC_BASIC_INFO;
+  }
+  if (dec->stage == 5) {
+    // libjxl emits COLOR_ENCODING after the headers and before the first frame (lib/jxl/decode.cc:1149-1500); jpegxl-rs
+    // subscribes to it when `icc_profile` is set and then asks for the ICC profile (jpegxl-rs/src/decode.rs:334-347):
+    // the ICC calls below fail loudly (ICC synthesis is SURVEY.md 8f N2, not built) instead of an empty profile.
+    dec->stage = 1;
+    if (dec->events_wanted & JXL_DEC_COLOR_ENCODING) return JXL_DEC_COLOR_ENCODING;
   }
   if (dec->stage == 1) {
     if (!(dec->events_wanted & JXL_DEC_FULL_IMAGE)) {

@@ -79,6 +79,12 @@ struct DevVFrame {
   uint64_t out_off, out_stride;
   // patches (lib/jxl/dec_patch_dictionary.cc): DevPatch range, applied in order after the loop filters
   uint32_t patch_begin, patch_count;
+  // frame upsampling (lib/jxl/render_pipeline/stage_upsampling.cc): 1, 2, 4 or 8; the filtered planes are upsampled
+  // into `up_pix` (row stride up_stride) before the colour transform, which then runs at up_xsize x up_ysize
+  uint32_t upsampling, up_xsize, up_ysize, up_stride;
+  uint32_t up_kernel;  // fpool index of kernel[4][4][5][5]
+  uint32_t up_pad_;
+  uint64_t up_pix[3];  // farena index
 };
 
 // A reference-only frame (lib/jxl/frame_header.h kReferenceOnly, saved before the colour transform): its Modular

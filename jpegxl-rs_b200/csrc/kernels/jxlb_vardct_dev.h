@@ -1735,8 +1735,48 @@ JXLB_HD void DevColorStore(const DevVPools& V, const DevVFrame& vf, float p0, fl
 }
 
 JXLB_HD void DevColorPixel(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t x, uint32_t y) {
+  if (vf.upsampling > 1) {  // the colour transform runs on the upsampled planes
+    const size_t at = static_cast<size_t>(y) * vf.up_stride + x;
+    DevColorStore(V, vf, V.farena[vf.up_pix[0] + at], V.farena[vf.up_pix[1] + at], V.farena[vf.up_pix[2] + at], x, y);
+    return;
+  }
   const size_t at = static_cast<size_t>(y) * (vf.xblocks * 8) + x;
   DevColorStore(V, vf, V.farena[vf.pix[set][0] + at], V.farena[vf.pix[set][1] + at], V.farena[vf.pix[set][2] + at], x, y);
+}
+
+// Upsampling (lib/jxl/render_pipeline/stage_upsampling.cc:28-170): output pixel (ox, oy) of the three channels from
+// the 5 x 5 neighbourhood (mirrored at the frame edges) of input pixel (ox / N, oy / N) in plane set `set`: MulAdd in
+// the order iy = -2 .. 2, ix = -2 .. 2, clamped to the neighbourhood's minimum and maximum; kernel selection as
+// Kernel<N> (:93-112).
+JXLB_HD void DevUpsamplePixel(const DevVPools& V, const DevVFrame& vf, uint32_t set, uint32_t ox, uint32_t oy) {
+  const uint32_t N = vf.upsampling;
+  const int x = static_cast<int>(ox / N), y = static_cast<int>(oy / N);
+  const uint32_t kx = ox % N, ky = oy % N, half = N / 2;
+  // kernel[a][b][c][d]: a, c from y; b, d from x
+  const bool fy = ky >= half && N > 1, fx = kx >= half && N > 1;  // second half of the period: mirrored kernel
+  const uint32_t a = N == 2 ? 0 : (fy ? half - 1 - (ky % half) : ky % half);
+  const uint32_t b = N == 2 ? 0 : (fx ? half - 1 - (kx % half) : kx % half);
+  const float* kernel = V.fpool + vf.up_kernel + (a * 4 + b) * 25;
+  const uint32_t PW = vf.xblocks * 8;
+  const int xsize = static_cast<int>(vf.xsize), ysize = static_cast<int>(vf.ysize);
+  for (uint32_t c = 0; c < 3; c++) {
+    const float* p = V.farena + vf.pix[set][c];
+    const float centre = p[static_cast<size_t>(y) * PW + x];
+    float result = 0.0f, mn = centre, mx = centre;
+    for (int iy = -2; iy <= 2; iy++) {
+      const size_t row = static_cast<size_t>(DevMirror(y + iy, ysize)) * PW;
+      const uint32_t kr = static_cast<uint32_t>(fy ? 2 - iy : iy + 2);
+      for (int ix = -2; ix <= 2; ix++) {
+        const float v = p[row + DevMirror(x + ix, xsize)];
+        const uint32_t kc = static_cast<uint32_t>(fx ? 2 - ix : ix + 2);
+        result = fmaf(kernel[kr * 5 + kc], v, result);
+        mn = mn < v ? mn : v;
+        mx = v < mx ? mx : v;
+      }
+    }
+    const float lo = result < mn ? mn : result;
+    V.farena[vf.up_pix[c] + static_cast<size_t>(oy) * vf.up_stride + ox] = mx < lo ? mx : lo;
+  }
 }
 
 // Four consecutive RGB8 pixels (x multiple of 4, row 4-byte aligned): 12 bytes as three 32-bit stores.
@@ -1795,7 +1835,7 @@ constexpr int kRtStrideSmall = kRtW + 2 * 4, kRtStrideLarge = 80;
 JXLB_HD uint32_t DevRenderHalo(uint32_t gab, uint32_t epf_iters) {
   return (gab ? 1u : 0u) + (epf_iters >= 3 ? 3u : 0u) + (epf_iters >= 1 ? 2u : 0u) + (epf_iters >= 2 ? 1u : 0u);
 }
-JXLB_HD bool DevRenderFused(const DevVFrame& vf) { return vf.patch_count == 0; }
+JXLB_HD bool DevRenderFused(const DevVFrame& vf) { return vf.patch_count == 0 && vf.upsampling <= 1; }
 JXLB_HD uint32_t DevRenderStride(uint32_t halo) { return halo <= 4 ? kRtStrideSmall : kRtStrideLarge; }
 // floats of one channel of one tile buffer for a batch whose largest halo is `halo`
 JXLB_HD uint32_t DevRenderTileFloats(uint32_t halo) { return DevRenderStride(halo) * (kRtH + 2 * halo); }

@@ -121,6 +121,7 @@ size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, fl
     p.cfl = (gab & 8) == 0;          // bit 3: no chroma-from-luma fit
     p.adaptive_quant = (gab & 16) == 0;  // bit 4: constant quant field instead of libjxl's adaptive one
     p.prefix_codes = (gab & 32) != 0;    // bit 5: prefix codes instead of ANS in every stream
+    p.upsampling = 1u << ((gab >> 6) & 3);  // bits 6-7: log2 of the frame upsampling
     p.epf_iters = epf_iters;
     p.dc_smoothing = dc_smoothing != 0;
     p.random_side_info = random_side_info != 0;

@@ -879,6 +879,9 @@ struct EncodeParams {
   // SetQuantFieldRect. false (and with random_side_info): one constant raw quant value under this file's own scale.
   bool adaptive_quant = true;
   bool prefix_codes = false;  // every entropy-coded stream of the frame uses prefix codes instead of ANS (decoder coverage)
+  // Frame upsampling (decoder coverage of lib/jxl/render_pipeline/stage_upsampling.cc): the pixels handed to the encoder
+  // are the low-resolution frame, the image header declares `upsampling` times their size.
+  uint32_t upsampling = 1;
 };
 
 struct EncoderStats {
@@ -903,7 +906,7 @@ inline void WriteFrameHeader(BitWriter& w, const EncodeParams& p) {
   w.Write(2, kRegularFrame);
   w.Write(1, 0);  // VarDCT
   WriteU64(w, p.dc_smoothing ? uint64_t{0} : uint64_t{kFlagSkipAdaptiveDCSmoothing});
-  WriteU32(w, 1, Val(1), Val(2), Val(4), Val(8));  // upsampling
+  WriteU32(w, p.upsampling, Val(1), Val(2), Val(4), Val(8));  // upsampling
   w.Write(3, p.x_qm_scale);
   w.Write(3, p.b_qm_scale);
   WriteU32(w, p.num_passes, Val(1), Val(2), Val(3), BitsOffset(3, 4));
@@ -2154,7 +2157,7 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   }
 
   BitWriter out;
-  WriteImageHeaders(out, xsize, ysize);
+  WriteImageHeaders(out, xsize * p.upsampling, ysize * p.upsampling);
   WriteFrameHeader(out, p);
   WriteToc(out, sections);
   for (const auto& s : sections) out.Append(s);

@@ -390,6 +390,52 @@ inline float FromLinear(const OutputColor& o, float v) {  // stage_from_linear.c
   throw Error("jxlo: transfer function not supported by the oracle (PQ / HLG / 709)");
 }
 
+// ---------------------------------------------------------------- upsampling
+// lib/jxl/render_pipeline/stage_upsampling.cc:28-170: every input pixel becomes N x N outputs, each a 5 x 5 weighted sum
+// of the (mirrored) neighbourhood -- MulAdd in the order iy = -2 .. 2, ix = -2 .. 2 -- clamped to the neighbourhood's
+// minimum and maximum. The N / 2 x N / 2 distinct kernels come from the upper triangle `weights` by symmetry
+// (constructor, :33-47; Kernel<N>, :93-112).
+inline Plane Upsample(const Plane& in, int N, const float* weights) {
+  const int half = N / 2;
+  std::vector<float> kernel(static_cast<size_t>(4) * 4 * 5 * 5, 0.0f);
+  auto K = [&](int a, int b, int c, int d) -> float& { return kernel[((a * 4 + b) * 5 + c) * 5 + d]; };
+  for (int i = 0; i < 5 * half; i++)
+    for (int j = 0; j < 5 * half; j++) {
+      const int y = std::min(i, j), x = std::max(i, j);
+      K(j / 5, i / 5, j % 5, i % 5) = weights[5 * half * y - y * (y - 1) / 2 + x - y];
+    }
+  auto kernel_at = [&](int x, int y, int ix, int iy) {
+    ix += 2;
+    iy += 2;
+    if (N == 2) return K(0, 0, y % 2 ? 4 - iy : iy, x % 2 ? 4 - ix : ix);
+    if (N == 4) return K(y % 4 < 2 ? y % 2 : 1 - y % 2, x % 4 < 2 ? x % 2 : 1 - x % 2, y % 4 < 2 ? iy : 4 - iy, x % 4 < 2 ? ix : 4 - ix);
+    return K(y % 8 < 4 ? y % 4 : 3 - y % 4, x % 8 < 4 ? x % 4 : 3 - x % 4, y % 8 < 4 ? iy : 4 - iy, x % 8 < 4 ? ix : 4 - ix);
+  };
+  Plane out(in.w * N, in.h * N);
+  const MirroredPlane m{in};
+  for (int y = 0; y < in.h; y++)
+    for (int x = 0; x < in.w; x++)
+      for (int oy = 0; oy < N; oy++)
+        for (int ox = 0; ox < N; ox++) {
+          float result = 0.0f, mn = in.Row(y)[x], mx = mn;
+          for (int iy = -2; iy <= 2; iy++)
+            for (int ix = -2; ix <= 2; ix++) {
+              const float v = m.At(x + ix, y + iy);
+              result = std::fmaf(kernel_at(ox, oy, ix, iy), v, result);
+              mn = std::min(v, mn);
+              mx = std::max(v, mx);
+            }
+          out.Row(y * N + oy)[x * N + ox] = std::min(std::max(result, mn), mx);  // hwy Clamp(v, lo, hi) = Min(Max(lo, v), hi)
+        }
+  return out;
+}
+
+inline const float* UpsamplingWeights(const ImageMetadata& meta, uint32_t factor) {
+  if (factor == 2) return (meta.custom_weights_mask & 1) ? meta.up2.data() : kDefaultUpsampling2;
+  if (factor == 4) return (meta.custom_weights_mask & 2) ? meta.up4.data() : kDefaultUpsampling4;
+  return (meta.custom_weights_mask & 4) ? meta.up8.data() : kDefaultUpsampling8;
+}
+
 // ---------------------------------------------------------------- the frame
 inline void VarDCTToPixels(VarDCTState* vs, std::vector<Plane>* planes) {
   const FrameHeader& fh = vs->fh;
@@ -405,8 +451,8 @@ inline void VarDCTToPixels(VarDCTState* vs, std::vector<Plane>* planes) {
 // transform) or non-linear output samples.
 inline void RenderFrame(const FrameHeader& fh, const FrameDimensions& dim, const CodestreamState& cs, VarDCTState* vs,
                         const FeatureState& feat, std::vector<Plane>* planes, bool* is_xyb) {
-  JXLO_CHECK(fh.upsampling == 1, "upsampling is not supported by the oracle");
-  for (uint32_t u : fh.ec_upsampling) JXLO_CHECK(u == 1, "extra-channel upsampling is not supported by the oracle");
+  for (uint32_t u : fh.ec_upsampling) JXLO_CHECK(u == fh.upsampling, "extra channels upsampled differently from the colour channels are not supported by the oracle");
+  JXLO_CHECK(fh.upsampling == 1 || fh.frame_type != kReferenceOnly, "upsampled reference-only frames are not supported by the oracle");
   const LoopFilter& lf = fh.lf;
   if (lf.gab) Gaborish(lf, planes->data());
   if (lf.epf_iters > 0) {
@@ -416,6 +462,9 @@ inline void RenderFrame(const FrameHeader& fh, const FrameDimensions& dim, const
     if (lf.epf_iters >= 2) EPFStage(2, lf, sigma, planes->data());
   }
   if (fh.flags & kFlagPatches) ApplyPatches(feat, cs, planes);
+  if (fh.upsampling > 1) {  // (dec_cache.cc:103-347: after patches / splines, before noise and the colour transform)
+    for (Plane& p : *planes) p = Upsample(p, static_cast<int>(fh.upsampling), UpsamplingWeights(cs.meta, fh.upsampling));
+  }
   *is_xyb = false;
   const bool can_reference = fh.CanBeReferenced() || fh.frame_type == kReferenceOnly;
   if (can_reference && fh.save_before_color_transform) {

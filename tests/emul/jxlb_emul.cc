@@ -283,6 +283,13 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
           for (uint32_t iy = 0; iy < pt.ysize; iy++)
             for (uint32_t ix = 0; ix < pt.xsize; ix++) DevPatchPixel(V, vf, pt, set, ix, iy);
         }
+        if (vf.upsampling > 1) {  // k_upsample, then k_color_write at the image's size
+          for (uint32_t y = 0; y < vf.ysize * vf.upsampling; y++)
+            for (uint32_t x = 0; x < vf.xsize * vf.upsampling; x++) DevUpsamplePixel(V, vf, set, x, y);
+          for (uint32_t y = 0; y < vf.up_ysize; y++)
+            for (uint32_t x = 0; x < vf.up_xsize; x++) DevColorPixel(V, vf, 0, x, y);
+          continue;
+        }
         const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0;
         for (uint32_t y = 0; y < vf.ysize; y++)
           for (uint32_t x = 0; x < vf.xsize; x++) {

@@ -141,3 +141,28 @@ def test_thread_runner_symbols_behave(pkg):
         destroy(r)
     assert lib.JxlThreadParallelRunnerDefaultNumWorkerThreads() >= 1
     assert lib.JxlResizableParallelRunnerSuggestThreads(256, 256) == 1
+
+
+def test_color_encoding_event_and_memory_manager(pkg):
+    # jpegxl-rs with `icc_profile` subscribes to COLOR_ENCODING and then asks for the ICC profile
+    # (jpegxl-rs/src/decode.rs:334-347): the event arrives after BASIC_INFO, the ICC calls fail loudly. Header parsing
+    # only: runs without a GPU. A memory manager is accepted (jpegxl-rs/src/memory.rs:24-40).
+    import ctypes
+    lib = pkg.load_library()
+    data = open(os.path.join(ROOT, "tests", "golden", "sample.jxl"), "rb").read()
+    lib.JxlDecoderCreate.restype = ctypes.c_void_p
+    lib.JxlDecoderCreate.argtypes = [ctypes.c_void_p]
+    mm = (ctypes.c_void_p * 3)()
+    dec = ctypes.c_void_p(lib.JxlDecoderCreate(ctypes.addressof(mm)))
+    assert dec.value
+    try:
+        assert lib.JxlDecoderSubscribeEvents(dec, pkg.JXL_DEC_BASIC_INFO | 0x100 | pkg.JXL_DEC_FULL_IMAGE) == 0
+        assert lib.JxlDecoderSetInput(dec, data, len(data)) == 0
+        lib.JxlDecoderCloseInput(dec)
+        assert lib.JxlDecoderProcessInput(dec) == pkg.JXL_DEC_BASIC_INFO
+        assert lib.JxlDecoderProcessInput(dec) == 0x100  # JXL_DEC_COLOR_ENCODING
+        size = ctypes.c_size_t(7)
+        assert lib.JxlDecoderGetICCProfileSize(dec, 1, ctypes.byref(size)) == pkg.JXL_DEC_ERROR and size.value == 0
+        assert lib.JxlDecoderProcessInput(dec) == pkg.JXL_DEC_NEED_IMAGE_OUT_BUFFER
+    finally:
+        lib.JxlDecoderDestroy(dec)

@@ -51,6 +51,11 @@ SMALL_CASES = [
     # prefix codes instead of ANS in every stream of the frame (tree, DC / metadata, coefficient orders, AC passes)
     ("prefix_codes", lambda: crop(300, 400, 100, 200), dict(strategy_mode=1, random_side_info=True, seed=3, epf_iters=1, prefix_codes=True)),
     ("prefix_codes_two_passes", lambda: crop(280, 330, 500, 300), dict(strategy_mode=2, num_passes=2, prefix_codes=True)),
+    # frame upsampling 2x / 4x / 8x (stage_upsampling.cc): the encoder is handed the low-resolution frame, the image is
+    # `upsampling` times its size; sizes that are not multiples of 8 (mirrored edges, kernels at the last column)
+    ("upsampling_2", lambda: crop(150, 203, 100, 200), dict(strategy_mode=2, upsampling=2)),
+    ("upsampling_4", lambda: crop(67, 90, 300, 800), dict(strategy_mode=1, random_side_info=True, seed=4, epf_iters=1, upsampling=4)),
+    ("upsampling_8", lambda: crop(33, 41, 640, 960), dict(strategy_mode=2, gab=False, epf_iters=0, upsampling=8)),
 ]
 STRATEGY_CASES = [("strategy_%d" % s, lambda: crop(264, 520, 400, 300),
                    dict(strategy_mode=100 + s, gab=False, epf_iters=0, dc_smoothing=False)) for s in range(27)]
@@ -61,5 +66,6 @@ def encoded(name):
     for n, make, kw in SMALL_CASES + STRATEGY_CASES:
         if n == name:
             img = make()
-            return jxlo.encode_vardct(img, **kw), img.shape[:2]
+            u = kw.get("upsampling", 1)
+            return jxlo.encode_vardct(img, **kw), (img.shape[0] * u, img.shape[1] * u)
     raise KeyError(name)
