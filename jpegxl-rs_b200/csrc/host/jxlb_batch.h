@@ -41,6 +41,7 @@ struct BatchPlan {
   uint64_t compressed_bytes = 0;
   std::vector<BasicInfo> info;
   std::vector<uint32_t> warp_chans, warp_dims_off, warp_dims;
+  uint32_t num_coop = 0;  // streams [0, num_coop) go one per warp (k_modular_decode_coop), the rest in lock-step bundles
   bool narrow = true;  // every frame promises that 16-bit buffers suffice -> 32-bit predictor math
   // VarDCT frames
   std::vector<DevVFrame> vframes;
@@ -68,7 +69,35 @@ constexpr uint64_t kWavePixelBytes = uint64_t{4} << 30;
 
 // Orders the streams so that the 32 lanes of a warp decode planes of the same shape
 // (they run one loop nest in lock step) and derives the warp-uniform loop bounds.
+// A stream the warp-cooperative kernel can decode (kernels/jxlb_modular_coop_dev.h): plain ANS without LZ77, every
+// channel on one of the table paths (FramePlanner::BuildCoopLut).
+inline bool CoopEligible(const BatchPlan& b, const DevStream& s) {
+  const DevCode& c = b.codes[s.code];
+  if (c.use_prefix || c.lz77_enabled || s.chan_end == s.chan_begin) return false;
+  for (uint32_t k = s.chan_begin; k < s.chan_end; k++) {
+    const DevChannel& ch = b.chans[k];
+    if (!ch.coop) return false;
+    if (ch.nw_lut != 0) continue;
+    if (ch.wp_lut != 0 && ch.uses_wp != 0 && ch.ref_count == 0 && !ch.dyn) continue;
+    return false;
+  }
+  return true;
+}
+
 inline void BundleStreams(BatchPlan* b) {
+  // One warp per stream pays while the batch leaves the chip empty -- the kernel then takes as long as its longest chain
+  // and a chain is 1.7 x (1024 chains) to 2.6 x (64 chains) faster that way -- but it holds 32 lanes' registers per
+  // stream for that time; a big batch of lossy frames is bound by the register file shared with the per-pixel kernels
+  // of the other handles, where the lock-step kernel (8 streams per warp) is the cheaper one. Hence a cap
+  // of one warp per scheduler. (JXLB200_NO_COOP=1: never; JXLB200_COOP_MAX=n: another cap -- comparison runs, tests.)
+  uint32_t coop_max = 4 * 148;
+  if (const char* e = std::getenv("JXLB200_COOP_MAX")) coop_max = static_cast<uint32_t>(std::strtoul(e, nullptr, 10));
+  bool coop_on = std::getenv("JXLB200_NO_COOP") == nullptr;
+  if (coop_on) {
+    uint32_t eligible = 0;
+    for (const DevStream& s : b->streams) eligible += CoopEligible(*b, s) ? 1u : 0u;
+    coop_on = eligible <= coop_max;
+  }
   auto key = [&](const DevStream& s) {
     const uint32_t n = s.chan_end - s.chan_begin;
     uint32_t w = 0, h = 0;
@@ -77,17 +106,20 @@ inline void BundleStreams(BatchPlan* b) {
       w = p.w;
       h = p.h;
     }
-    return std::make_tuple(n, w, h);
+    return std::make_tuple(coop_on && CoopEligible(*b, s) ? 1u : 0u, n, w, h);
   };
   std::stable_sort(b->streams.begin(), b->streams.end(),
                    [&](const DevStream& x, const DevStream& y) { return key(x) > key(y); });
-  const size_t num_warps = (b->streams.size() + 31) / 32;
+  b->num_coop = 0;
+  while (b->num_coop < b->streams.size() && std::get<0>(key(b->streams[b->num_coop])) != 0) b->num_coop++;
+  const size_t c0 = b->num_coop;
+  const size_t num_warps = (b->streams.size() - c0 + 31) / 32;
   b->warp_chans.assign(num_warps, 0);
   b->warp_dims_off.assign(num_warps, 0);
   b->warp_dims.clear();
   for (size_t wi = 0; wi < num_warps; wi++) {
     uint32_t nmax = 0;
-    const size_t s0 = wi * 32, s1 = std::min(b->streams.size(), s0 + 32);
+    const size_t s0 = c0 + wi * 32, s1 = std::min(b->streams.size(), s0 + 32);
     for (size_t s = s0; s < s1; s++) nmax = std::max(nmax, b->streams[s].chan_end - b->streams[s].chan_begin);
     b->warp_chans[wi] = nmax;
     b->warp_dims_off[wi] = b->warp_dims.size();
@@ -138,6 +170,8 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
     c.ref_off += refs0;
     c.tree_off += tree0;
     c.lut_off += lut0;
+    c.coop_lut_off += lut0;
+    c.coop_list_off += lut0;
     b->chans.push_back(c);
   }
   for (DevStream s : f.streams) {

@@ -472,6 +472,65 @@ class FramePlanner {
         }
   }
 
+  // The warp-cooperative kernel's view of a channel that TryWpLut / TryNwLut marked (DevChannel::coop*): the list of
+  // clusters its lanes speculate on and the table re-expressed in lanes.
+  void BuildCoopLut(DevChannel* dc) {
+    if (dc->wp_lut == 0 && dc->nw_lut == 0) return;
+    const bool nw = dc->nw_lut == 1;
+    const size_t head = nw ? kNwOffTable : 0;
+    const size_t count = nw ? (static_cast<size_t>(p_->lut[dc->lut_off]) + 1) * (kNwThresholds + 1) * (kNwThresholds + 1) : dc->lut_size;
+    const uint32_t cmask = dc->wp_lut ? 0xFFFFu : 0xFFu;
+    // visiting order: outwards from property value 0 (the frequent contexts of an error / gradient property), table
+    // order for the (y, N, W) buckets
+    std::vector<size_t> order;
+    if (nw) {
+      for (size_t i = 0; i < count; i++) order.push_back(i);
+    } else {
+      const int64_t i0 = std::min<int64_t>(std::max<int64_t>(-static_cast<int64_t>(dc->lut_lo), 0), static_cast<int64_t>(count) - 1);
+      for (int64_t d = 0; d < static_cast<int64_t>(count); d++) {
+        if (d == 0) {
+          order.push_back(i0);
+        } else {
+          if (i0 + d < static_cast<int64_t>(count)) order.push_back(i0 + d);
+          if (i0 - d >= 0) order.push_back(i0 - d);
+        }
+      }
+    }
+    std::vector<uint32_t> list;
+    for (size_t i : order) {
+      const uint32_t c = p_->lut[dc->lut_off + head + i] & cmask;
+      if (c > 0xFF) return;  // (a miss carries the cluster in 8 bits)
+      if (list.size() < 32 && std::find(list.begin(), list.end(), c) == list.end()) list.push_back(c);
+    }
+    bool miss = false;
+    for (size_t i = 0; i < count; i++)
+      miss = miss || std::find(list.begin(), list.end(), p_->lut[dc->lut_off + head + i] & cmask) == list.end();
+    dc->coop = miss ? 2 : 1;
+    dc->coop_list_off = p_->lut.size();
+    p_->lut.push_back(static_cast<uint16_t>(list.size()));
+    for (uint32_t c : list) p_->lut.push_back(static_cast<uint16_t>(c));
+    dc->coop_lut_off = p_->lut.size();
+    for (size_t i = 0; i < head; i++) p_->lut.push_back(p_->lut[dc->lut_off + i]);
+    for (size_t i = 0; i < count; i++) {
+      const uint32_t e = p_->lut[dc->lut_off + head + i];
+      const uint32_t c = e & cmask, pred = dc->wp_lut ? 0u : (e >> 8);
+      const auto it = std::find(list.begin(), list.end(), c);
+      const uint32_t leaf = it != list.end() ? static_cast<uint32_t>(it - list.begin()) : (0x8000u | c);
+      p_->lut.push_back(static_cast<uint16_t>(leaf | (pred << 8)));
+    }
+    // behind the table: the predictor of each row bucket of a (y, N, W) table / of the whole gradient table when all
+    // its leaves agree, else 0xFF (DevCoopChannelRows: rows with one of Zero / Left / Gradient take DevCoopFastRow)
+    if (!dc->wp_lut) {
+      const size_t per = nw ? (kNwThresholds + 1) * (kNwThresholds + 1) : count;
+      for (size_t b0 = 0; b0 < count; b0 += per) {
+        uint32_t pr = p_->lut[dc->lut_off + head + b0] >> 8;
+        for (size_t i = b0; i < b0 + per; i++)
+          if ((p_->lut[dc->lut_off + head + i] >> 8) != pr) pr = 0xFF;
+        p_->lut.push_back(static_cast<uint16_t>(pr));
+      }
+    }
+  }
+
   // lib/jxl/modular/encoding/dec_ma.cc:23-67: property ranges must stay non-empty
   // on the way down, which also bounds the device-side walk.
   template <typename N>
@@ -811,6 +870,7 @@ class FramePlanner {
       if (ch_wp) st.uses_wp = 1;
       if (ch_wp) TryWpLut(&dc, dc.ref_count != 0);
       if (!ch_wp && !NoNwLut()) TryNwLut(&dc);
+      BuildCoopLut(&dc);
       p_->chans.push_back(dc);
       max_w = std::max<uint32_t>(max_w, c.w);
     }

@@ -197,6 +197,7 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
         dc.dyn = chs[i].dyn;
         if (ch_wp && !chs[i].dyn) planner.TryWpLut(&dc, dc.ref_count != 0);
         if (!ch_wp && !FramePlanner::NoNwLut()) planner.TryNwLut(&dc);
+        planner.BuildCoopLut(&dc);
         if (i == 0 && first != 0) {
           dc.preamble = 1;
           dc.count_bits = count_bits;

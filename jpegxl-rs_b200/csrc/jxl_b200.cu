@@ -27,6 +27,7 @@
 
 #include "../../include/jxl_b200.h"
 #include "host/jxlb_batch.h"
+#include "kernels/jxlb_modular_coop_dev.h"
 #include "kernels/jxlb_finish_dev.h"
 #include "kernels/jxlb_vardct_dev.h"
 #include "kernels/jxlb_enc_dev.h"
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(32) k_modular_decode(DevPools P) {
   const uint32_t lane = threadIdx.x;
   for (uint32_t i = lane; i < 64; i += 32) div_s[i] = (1u << 24) / (i + 1);
   __syncwarp();
-  const uint32_t s = blockIdx.x * 32 + lane;
+  const uint32_t s = P.stream0 + blockIdx.x * 32 + lane;
   DevLaneMem m;
   m.props = props_s + lane;
   m.props_stride = 32;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(32) k_modular_decode_sparse(DevPools P) {
   const uint32_t lane = threadIdx.x;
   for (uint32_t i = lane; i < 64; i += 32) div_s[i] = (1u << 24) / (i + 1);
   __syncwarp();
-  const uint32_t s = blockIdx.x * kSparseLanes + lane;
+  const uint32_t s = P.stream0 + blockIdx.x * kSparseLanes + lane;
   DevLaneMem m;
   m.props = props_s + lane;
   m.props_stride = 32;
@@ -85,12 +86,32 @@ __global__ void __launch_bounds__(32) k_modular_decode_sparse(DevPools P) {
   m.ring = sparse_smem + (lane < kSparseLanes ? lane : 0);
   m.wp = sparse_smem + 2 * P.wp_width * kSparseLanes + (lane < kSparseLanes ? lane : 0);
   const bool valid = lane < kSparseLanes && s < P.num_streams;
-  const uint32_t bundle = s / 32;  // loop bounds of the 32-stream bundle this stream belongs to (a superset)
-  const uint32_t b0 = (blockIdx.x * kSparseLanes) / 32;
-  (void)bundle;
+  const uint32_t b0 = (blockIdx.x * kSparseLanes) / 32;  // loop bounds of the 32-stream bundle these streams belong to (a superset)
   uint64_t end_pos = 0;
   const uint32_t status = DevDecodeModularStream<WT, kSparseLanes>(P, s, m, P.warp_dims + P.warp_dims_off[b0], P.warp_chans[b0], valid, &end_pos);
   if (valid) {
+    P.status[s] = status;
+    if (P.end_bits) P.end_bits[s] = end_pos;
+  }
+}
+
+// One warp per stream (jxlb_modular_coop_dev.h): the chains of the lossy path -- DC + AC-metadata of a DC group under
+// libjxl's fixed trees -- whose latency per sample sets the time of the whole kernel. Shared memory: the warp's two
+// sample rows and the weighted predictor's five error rows.
+constexpr uint32_t kCoopWarps = 4;  // per CTA: few CTA slots per SM stay taken while the chains run
+template <typename WT>
+__global__ void __launch_bounds__(32 * kCoopWarps) k_modular_decode_coop(DevPools P) {
+  extern __shared__ int32_t coop_smem[];
+  __shared__ uint32_t div_s[64];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 64) div_s[threadIdx.x] = (1u << 24) / (threadIdx.x + 1);
+  __syncthreads();
+  const uint32_t s = blockIdx.x * kCoopWarps + warp;
+  if (s >= P.stream0) return;
+  int32_t* mine = coop_smem + warp * (7 * P.wp_width + 10);
+  uint64_t end_pos = 0;
+  const uint32_t status = DevDecodeModularStreamCoop<WT>(P, s, mine, mine + 2 * P.wp_width, P.wp_width, div_s, &end_pos);
+  if (lane == 0) {
     P.status[s] = status;
     if (P.end_bits) P.end_bits[s] = end_pos;
   }
@@ -755,6 +776,7 @@ struct JxlB200Decoder {
   // order caller stream -> entropy kernels -> per-pixel kernels -> caller stream
   cudaStream_t part_stream[2] = {nullptr, nullptr};
   cudaEvent_t part_ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t pix_done = nullptr;  // end of this handle's last per-pixel phase (PixelTurn)
   std::string error;
   std::unique_ptr<BatchPlan> plan;
   DevBuf<uint8_t> d_bytes, d_out;
@@ -852,6 +874,25 @@ struct ScopedTimer {
   }
 };
 
+// Per-pixel phases of the handles of one device take turns, in the order in which their runs were enqueued: each waits
+// for the end of the previously enqueued one. The entropy kernels of a run are chains of dependent instructions on a
+// few warps -- they need time, not the machine -- while the per-pixel kernels fill every SM; when several handles are
+// driven in lock step (a loop that enqueues one run after the other) their phases line up, all entropy phases overlap
+// each other and then all per-pixel phases fight for the SMs. With the turns the per-pixel phases run back to back and
+// every other handle's entropy phase runs underneath them. Measured (profiles/r2_pixel_turns.txt): the per-pixel phase then
+// takes 2.2 x its time alone, because the entropy kernels underneath hold registers that its CTAs need -- the step is
+// bound by register-file capacity either way and does not get shorter. Opt-in: JXLB200_PIXEL_TURNS=1.
+struct PixelTurn {
+  std::mutex mu;
+  cudaEvent_t last = nullptr;
+  JxlB200Decoder* owner = nullptr;
+};
+static PixelTurn g_pixel_turn[64];
+static bool PixelTurnsOn() {
+  static const bool on = std::getenv("JXLB200_PIXEL_TURNS") && std::atoi(std::getenv("JXLB200_PIXEL_TURNS")) != 0;
+  return on;
+}
+
 extern "C" {
 
 JxlB200Decoder* JxlB200DecoderCreate(int device) {
@@ -864,6 +905,7 @@ JxlB200Decoder* JxlB200DecoderCreate(int device) {
     delete dec;
     return nullptr;
   }
+  if (device < 64 && cudaEventCreateWithFlags(&dec->pix_done, cudaEventDisableTiming) != cudaSuccess) dec->pix_done = nullptr;
   if (SmPartition* sp = GetSmPartition(device)) {
     bool ok = true;
     for (int i = 0; i < 2; i++) {
@@ -878,6 +920,8 @@ JxlB200Decoder* JxlB200DecoderCreate(int device) {
   cudaFuncSetAttribute(k_idct_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kMidSmemFloats * sizeof(float));
   cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        6 * DevRenderTileFloats(kRtMaxHalo) * sizeof(float));
+  cudaFuncSetAttribute(k_modular_decode_coop<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_modular_decode_coop<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_modular_decode_sparse<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_modular_decode_sparse<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_ac_decode_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
@@ -893,6 +937,15 @@ void JxlB200DecoderDestroy(JxlB200Decoder* dec) {
   cudaSetDevice(dec->device);
   FoldEvents(dec);
   for (cudaEvent_t e : dec->free_events) cudaEventDestroy(e);
+  if (dec->pix_done) {
+    PixelTurn& turn = g_pixel_turn[dec->device];
+    std::lock_guard<std::mutex> lock(turn.mu);
+    if (turn.owner == dec) {
+      turn.owner = nullptr;
+      turn.last = nullptr;
+    }
+    cudaEventDestroy(dec->pix_done);
+  }
   if (dec->h_bytes) cudaFreeHost(dec->h_bytes);
   if (dec->stream) cudaStreamDestroy(dec->stream);
   for (cudaStream_t st : dec->part_stream)
@@ -949,7 +1002,7 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
   CUDA_OK(dec->d_warp_dims_off.Upload(b.warp_dims_off, s));
   CUDA_OK(dec->d_warp_dims.Upload(b.warp_dims, s));
   CUDA_OK(dec->d_arena.Alloc(b.arena_size + 16));
-  const size_t num_warps = (b.streams.size() + 31) / 32;
+  const size_t num_warps = (b.streams.size() - b.num_coop + 31) / 32;
   CUDA_OK(dec->d_wp.Alloc(num_warps * 10 * (b.wp_width + 2) * 32 + 16));
   CUDA_OK(dec->d_ring.Alloc(num_warps * 3 * b.wp_width * 32 + 16));
   CUDA_OK(dec->d_lz77.Alloc(static_cast<size_t>(b.lz77_slots) << 20));
@@ -976,6 +1029,7 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
   P.status = dec->d_status.p;
   P.end_bits = want_end_bits ? dec->d_end_bits.p : nullptr;
   P.num_streams = b.streams.size();
+  P.stream0 = b.num_coop;
   P.warp_chans = dec->d_warp_chans.p;
   P.warp_dims_off = dec->d_warp_dims_off.p;
   P.warp_dims = dec->d_warp_dims.p;
@@ -1201,21 +1255,34 @@ size_t JxlB200DecoderImageOutBufferSize(const JxlB200Decoder* dec, size_t i) {
 static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s) {
   const DevPools& P = dec->pools;
   const uint32_t block = 32;
+  if (b.num_coop != 0) {  // one warp per stream: the chains under libjxl's fixed trees
+    const size_t coop_smem = static_cast<size_t>(7 * b.wp_width + 10) * sizeof(int32_t) * kCoopWarps;
+    if (coop_smem > 200 * 1024) return 1;  // (channel widths are bounded by the group size: never)
+    const uint32_t coop_grid = (b.num_coop + kCoopWarps - 1) / kCoopWarps;
+    if (b.narrow) {
+      k_modular_decode_coop<int32_t><<<coop_grid, 32 * kCoopWarps, coop_smem, s>>>(P);
+    } else {
+      k_modular_decode_coop<int64_t><<<coop_grid, 32 * kCoopWarps, coop_smem, s>>>(P);
+    }
+    CUDA_OK(cudaGetLastError());
+    if (b.num_coop == b.streams.size()) return 0;
+  }
+  const size_t rest = b.streams.size() - b.num_coop;
   const size_t sparse_smem = static_cast<size_t>(7 * b.wp_width + 10) * kSparseLanes * sizeof(int32_t);
   // (JXLB200_MODULAR_DENSE=1: always the dense-lane kernel -- 32 streams per warp, rows in HBM, 6 KB of shared memory
   // per CTA instead of 58 KB: slower alone, but it leaves the SMs' shared memory to the kernels of other batches)
   static const bool force_dense = std::getenv("JXLB200_MODULAR_DENSE") != nullptr;
-  if (!force_dense && b.streams.size() <= 2 * 148 * kSparseLanes && sparse_smem <= 160 * 1024) {
-    const uint32_t grid = (b.streams.size() + kSparseLanes - 1) / kSparseLanes;
+  if (!force_dense && rest <= 2 * 148 * kSparseLanes && sparse_smem <= 160 * 1024) {
+    const uint32_t grid = (rest + kSparseLanes - 1) / kSparseLanes;
     if (b.narrow) {
       k_modular_decode_sparse<int32_t><<<grid, block, sparse_smem, s>>>(P);
     } else {
       k_modular_decode_sparse<int64_t><<<grid, block, sparse_smem, s>>>(P);
     }
   } else if (b.narrow) {
-    k_modular_decode<int32_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
+    k_modular_decode<int32_t><<<(rest + block - 1) / block, block, 0, s>>>(P);
   } else {
-    k_modular_decode<int64_t><<<(b.streams.size() + block - 1) / block, block, 0, s>>>(P);
+    k_modular_decode<int64_t><<<(rest + block - 1) / block, block, 0, s>>>(P);
   }
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -1242,7 +1309,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   if (!b.streams.empty() && (pm & (1u << kKModular))) {
     ScopedTimer t(dec, s, kKModular);
     if (LaunchModular(dec, b, s) != 0) return 1;
-    launches++;
+    launches += (b.num_coop != 0 ? 1u : 0u) + (b.num_coop != b.streams.size() ? 1u : 0u);
   }
   if (!b.group_programs.empty()) {
     ScopedTimer t(dec, s, kKGroupPrograms);
@@ -1311,6 +1378,13 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
       CUDA_OK(cudaStreamWaitEvent(sp, dec->part_ev[1], 0));
     }
     const dim3 px_block(32, 8);
+    const bool turns = dec->pix_done != nullptr && PixelTurnsOn();
+    std::unique_lock<std::mutex> turn_lock;
+    if (turns) {  // (held until this phase is enqueued: the order of the turns is the order of the enqueues)
+      PixelTurn& turn = g_pixel_turn[dec->device];
+      turn_lock = std::unique_lock<std::mutex>(turn.mu);
+      if (turn.last != nullptr && turn.owner != dec) CUDA_OK(cudaStreamWaitEvent(sp, turn.last, 0));
+    }
     for (uint32_t f0 = 0; f0 < nvf; f0 += b.wave_frames) {
       const uint32_t nf = std::min<uint32_t>(b.wave_frames, nvf - f0);
       if (pm & (1u << kKDequantIdct)) {
@@ -1366,6 +1440,12 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
           launches++;
         }
       }
+    }
+    if (turns) {
+      PixelTurn& turn = g_pixel_turn[dec->device];
+      CUDA_OK(cudaEventRecord(dec->pix_done, sp));
+      turn.last = dec->pix_done;
+      turn.owner = dec;
     }
   }
   if (parted) {

@@ -96,7 +96,12 @@ struct DevChannel {
   // nw_lut == 2 (libjxl's fixed gradient DC tree, enc_encoding.cc:274-282): only property 9 (W + N - NW) is tested,
   // lut[clamp(property, lut_lo, lut_lo + lut_size - 1) - lut_lo] = cluster | predictor << 8.
   uint32_t nw_lut;
-  uint32_t pad_[3];
+  // Warp-cooperative decode (kernels/jxlb_modular_coop_dev.h): `coop` != 0 when the channel has one of the table paths
+  // above (1: every cluster of the table is on the list, 2: some are not); coop_list_off -> lut pool: count (<= 32), then the clusters the lanes speculate on (lane l takes entry l;
+  // the ones nearest property value 0 when the channel uses more than 32); coop_lut_off -> a copy of the channel's
+  // table (same layout) whose leaves are  lane | predictor << 8  when the cluster is on the list and
+  // 0x8000 | cluster | predictor << 8  when it is not (decoded without speculation).
+  uint32_t coop, coop_lut_off, coop_list_off;
 };
 
 // Layout of a (y, N, W) bucket table in the lut pool (uint16 units, DevChannel::lut_off): number of y thresholds;

@@ -38,6 +38,9 @@ struct DevPools {
   uint32_t* status;      // per stream: 0 ok, else error bits
   uint64_t* end_bits;    // per stream: first bit after the stream (probe launches only, else null)
   uint32_t num_streams;
+  // streams [0, stream0) are decoded one per warp by k_modular_decode_coop (jxlb_modular_coop_dev.h), the lock-step
+  // kernels take [stream0, num_streams): their warp 0 starts at stream0
+  uint32_t stream0;
   // per warp of 32 consecutive streams: number of channel slots and, per slot, the
   // largest (width, height) among its lanes -- the warp-uniform loop bounds
   const uint32_t* warp_chans;

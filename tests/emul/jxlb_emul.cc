@@ -8,14 +8,22 @@
 #include <cstring>
 
 #include "../../jpegxl-rs_b200/csrc/host/jxlb_batch.h"
+#include "../../jpegxl-rs_b200/csrc/kernels/jxlb_modular_coop_dev.h"
 #include "../../jpegxl-rs_b200/csrc/kernels/jxlb_finish_dev.h"
 #include "../../jpegxl-rs_b200/csrc/kernels/jxlb_vardct_dev.h"
 
 using namespace jxlb;
 
+static uint64_t g_last_num_coop[2];  // streams of the last plan: one per warp (k_modular_decode_coop), total
 static uint64_t g_last_plan_stats[3];  // channels, of which weighted-predictor LUT, of which (y, N, W) table
 
 extern "C" {
+
+// Streams of the last jxlb_emul_decode plan: decoded one per warp, total.
+void jxlb_emul_last_coop_streams(uint64_t* out2) {
+  out2[0] = g_last_num_coop[0];
+  out2[1] = g_last_num_coop[1];
+}
 
 // Channel counts of the last jxlb_emul_decode plan: total, weighted-predictor LUT path, (y, N, W) table path.
 void jxlb_emul_last_plan_stats(uint64_t* out3) {
@@ -39,7 +47,7 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     fmt.align = align;
     // the Modular decode "kernel": every stream of `b`, one lane at a time
     auto run_modular = [&](const BatchPlan& b, std::vector<int32_t>& arena, DevPools* pools_out, std::vector<uint64_t>* end_bits) {
-      const size_t num_warps = (b.streams.size() + 31) / 32;
+      const size_t num_warps = (b.streams.size() - b.num_coop + 31) / 32 + 1;
       std::vector<int32_t> wp(num_warps * 10 * (b.wp_width + 2) * 32 + 16, 0);
       std::vector<int32_t> ring(num_warps * 3 * b.wp_width * 32 + 16, 0);
       std::vector<int32_t> props(kDevMaxProps * 32, 0);
@@ -64,13 +72,24 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       P.wp_width = b.wp_width;
       P.lz77 = lz.data();
       P.num_streams = b.streams.size();
+      P.stream0 = b.num_coop;
       P.warp_chans = b.warp_chans.data();
       P.warp_dims_off = b.warp_dims_off.data();
       P.warp_dims = b.warp_dims.data();
       if (end_bits) end_bits->assign(b.streams.size(), 0);
-      for (uint32_t s = 0; s < b.streams.size(); s++) {
-        // same addressing as the kernel: warp = s / 32, lane = s % 32
-        const uint32_t warp = s / 32, lane = s % 32;
+      // k_modular_decode_coop: one warp per stream; the host runs its single "lane" (jxlb_modular_coop_dev.h)
+      std::vector<int32_t> coop_rows(7 * b.wp_width + 10, 0);
+      for (uint32_t s = 0; s < b.num_coop; s++) {
+        uint64_t end = 0;
+        const uint32_t st = force_wide || !b.narrow
+                                ? DevDecodeModularStreamCoop<int64_t>(P, s, coop_rows.data(), coop_rows.data() + 2 * b.wp_width, b.wp_width, divlut, &end)
+                                : DevDecodeModularStreamCoop<int32_t>(P, s, coop_rows.data(), coop_rows.data() + 2 * b.wp_width, b.wp_width, divlut, &end);
+        if (st != 0) throw Error("stream " + std::to_string(s) + " (one per warp) failed with status " + std::to_string(st));
+        if (end_bits) (*end_bits)[s] = end;
+      }
+      for (uint32_t s = b.num_coop; s < b.streams.size(); s++) {
+        // same addressing as the kernel: warp = (s - stream0) / 32, lane = (s - stream0) % 32
+        const uint32_t warp = (s - b.num_coop) / 32, lane = (s - b.num_coop) % 32;
         DevLaneMem m;
         m.props = props.data() + lane;
         m.props_stride = 32;
@@ -98,6 +117,8 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     };
     BatchPlan b;
     PlanBatch(files, sizes, n, fmt, 2, &b, probe);
+    g_last_num_coop[0] = b.num_coop;
+    g_last_num_coop[1] = b.streams.size();
     g_last_plan_stats[0] = b.chans.size();
     g_last_plan_stats[1] = g_last_plan_stats[2] = 0;
     for (const DevChannel& c : b.chans) {

@@ -53,6 +53,13 @@ def last_plan_stats():
     return tuple(int(x) for x in v)
 
 
+def last_coop_streams():
+    """(streams decoded one per warp by k_modular_decode_coop, all Modular streams) of the last decode."""
+    v = (ctypes.c_uint64 * 2)()
+    lib().jxlb_emul_last_coop_streams(v)
+    return tuple(int(x) for x in v)
+
+
 def encode(rgb, distance=1.0, strategy_mode=2, gab=True, epf_iters=2, dc_smoothing=True) -> bytes:
     """RGB8 (H, W, 3) -> codestream, the encoder kernels' device functions run on the CPU."""
     rgb = np.ascontiguousarray(rgb, np.uint8)

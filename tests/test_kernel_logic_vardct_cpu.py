@@ -124,3 +124,30 @@ def test_ac_metadata_channels_take_the_ynw_table_path(monkeypatch):
         assert emul_lib.last_plan_stats()[2] == 0
         assert np.array_equal(got2, want)
         monkeypatch.delenv("JXLB200_NO_NW_LUT")
+
+
+def test_dc_chains_take_the_warp_cooperative_path(monkeypatch):
+    # DC-group chains under libjxl's fixed trees are decoded one per warp (k_modular_decode_coop, DevDecodeModularStreamCoop:
+    # bit window, branch-free hybrid integers, per-row predictor paths); JXLB200_NO_COOP=1 sends them back to the
+    # lock-step kernels. Weighted DC tree (34 clusters: two of them outside the 32 lanes -> the unspeculated decode),
+    # gradient DC tree (DevCoopFastRow), multi-group frames, odd sizes. Same samples either way.
+    imgs = [vc.crop(200, 300, 100, 200), vc.crop(257, 263, 700, 100), vc.crop(520, 700, 300, 500)]
+    cases = [(jxlo.encode_vardct(imgs[0], strategy_mode=3, distance=1.0, epf_iters=1), imgs[0].shape[:2]),
+             (jxlo.encode_vardct(imgs[1], strategy_mode=1, random_side_info=True, seed=11, epf_iters=3, dc_tree=1), imgs[1].shape[:2]),
+             (jxlo.encode_vardct(imgs[2], strategy_mode=2, dc_tree=1, distance=0.5), imgs[2].shape[:2]),
+             (jxlo.encode_vardct(imgs[2], strategy_mode=2, dc_tree=0, distance=4.0), imgs[2].shape[:2])]
+    for data, shape in cases:
+        want = jxlo.decode(data, 3, jxlo.UINT8)
+        got = emul_lib.decode([data], 3, jxlo.UINT8, [shape])[0]
+        coop, total = emul_lib.last_coop_streams()
+        assert coop == total >= 1, (coop, total)
+        assert np.array_equal(got, want)
+        monkeypatch.setenv("JXLB200_NO_COOP", "1")
+        got2 = emul_lib.decode([data], 3, jxlo.UINT8, [shape])[0]
+        assert emul_lib.last_coop_streams()[0] == 0
+        assert np.array_equal(got2, want)
+        monkeypatch.delenv("JXLB200_NO_COOP")
+    # the 64-bit predictor path of the same kernel
+    data, shape = cases[1]
+    got = emul_lib.decode([data], 3, jxlo.UINT8, [shape], endianness=0x100)[0]
+    assert np.array_equal(got, jxlo.decode(data, 3, jxlo.UINT8))
