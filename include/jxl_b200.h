@@ -83,6 +83,10 @@ const char* JxlB200DecoderGetError(const JxlB200Decoder* dec);
  * (jpegxl-rs/src/decode.rs:231-252). */
 int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files, const size_t* sizes, size_t n,
                                 const JxlPixelFormat* format, int num_threads);
+/* For the batches set afterwards: 1 = leave the images as coded (JxlDecoderSetKeepOrientation); default 0 = libjxl's
+ * default, the output is turned upright (lib/jxl/render_pipeline/stage_write.cc:271-288) and GetBasicInfo reports the
+ * upright size with orientation 1 (lib/jxl/decode.cc:2083-2090). */
+int JxlB200DecoderSetKeepOrientation(JxlB200Decoder* dec, int keep);
 size_t JxlB200DecoderNumFrames(const JxlB200Decoder* dec);
 int JxlB200DecoderGetBasicInfo(const JxlB200Decoder* dec, size_t i, JxlBasicInfo* info);
 /* Bytes of frame i in the requested pixel format (JxlDecoderImageOutBufferSize). */

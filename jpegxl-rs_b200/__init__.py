@@ -133,6 +133,7 @@ def load_library() -> ctypes.CDLL:
     lib.JxlB200DecoderGetError.argtypes = [vp]
     lib.JxlB200DecoderSetInputBatch.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), sz,
                                                 ctypes.POINTER(JxlPixelFormat), ctypes.c_int]
+    lib.JxlB200DecoderSetKeepOrientation.argtypes = [vp, ctypes.c_int]
     lib.JxlB200DecoderNumFrames.restype = sz
     lib.JxlB200DecoderNumFrames.argtypes = [vp]
     lib.JxlB200DecoderGetBasicInfo.argtypes = [vp, sz, ctypes.POINTER(JxlBasicInfo)]
@@ -228,7 +229,7 @@ def load_library() -> ctypes.CDLL:
 # Every symbol include/jxl_b200.h declares (checked by the CPU test-suite).
 EXPORTED_SYMBOLS = [
     "JxlB200DecoderCreate", "JxlB200DecoderDestroy", "JxlB200DecoderGetError", "JxlB200DecoderSetInputBatch",
-    "JxlB200DecoderNumFrames", "JxlB200DecoderGetBasicInfo", "JxlB200DecoderImageOutBufferSize", "JxlB200DecoderRun",
+    "JxlB200DecoderSetKeepOrientation", "JxlB200DecoderNumFrames", "JxlB200DecoderGetBasicInfo", "JxlB200DecoderImageOutBufferSize", "JxlB200DecoderRun",
     "JxlB200DecoderWait", "JxlB200DecoderDeviceOutput", "JxlB200DecoderReadOutput", "JxlB200DecoderReadOutputs",
     "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderSetPhaseMask", "JxlB200DecoderDeviceOutputBytes", "JxlB200DecoderGetKernelTimes",
     "JxlB200DecoderGetKernelTimesEx", "JxlB200EncoderCreate", "JxlB200EncoderDestroy", "JxlB200EncoderGetError",
@@ -455,7 +456,9 @@ class BatchDecoder:
         return self._lib.JxlB200DecoderGetError(self._dec).decode()
 
     def set_input(self, files: Sequence[bytes], num_channels: int = 4, data_type: int = JXL_TYPE_UINT8,
-                  endianness: int = JXL_NATIVE_ENDIAN, align: int = 0, threads: int = 0) -> None:
+                  endianness: int = JXL_NATIVE_ENDIAN, align: int = 0, threads: int = 0, keep_orientation: bool = False) -> None:
+        """keep_orientation: leave the images as coded (jpegxl-rs `skip_reorientation`); default: turned upright."""
+        self._lib.JxlB200DecoderSetKeepOrientation(self._dec, int(keep_orientation))
         n = len(files)
         bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
         ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
@@ -552,12 +555,13 @@ class BatchDecoder:
         return st
 
 
-def decode_batch(files: Sequence[bytes], num_channels: int = 4, dtype=np.uint8, device: int = 0) -> List[np.ndarray]:
+def decode_batch(files: Sequence[bytes], num_channels: int = 4, dtype=np.uint8, device: int = 0,
+                 keep_orientation: bool = False) -> List[np.ndarray]:
     """Decodes n files on the GPU and returns one (H, W, C) array per file."""
     dt = {np.dtype(np.uint8): JXL_TYPE_UINT8, np.dtype(np.uint16): JXL_TYPE_UINT16,
           np.dtype(np.float16): JXL_TYPE_FLOAT16, np.dtype(np.float32): JXL_TYPE_FLOAT}[np.dtype(dtype)]
     dec = BatchDecoder(device)
-    dec.set_input(files, num_channels, dt)
+    dec.set_input(files, num_channels, dt, keep_orientation=keep_orientation)
     dec.run()
     dec.wait()
     out = []

@@ -289,7 +289,7 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
   for (uint32_t c = 0; c < 4; c++)
     if (c < fo.num_channels && fo.plane[c] != kNoPlane) fo.plane[c] += planes0;
   fo.out_off = b->out_size;
-  const uint64_t osize = fo.stride * fo.ysize;
+  const uint64_t osize = fo.stride * ((fo.orient & 4) ? fo.xsize : fo.ysize);
   b->out_size += (osize + 255) & ~uint64_t{255};
   b->frame_out_size.push_back(osize);
   b->frames.push_back(fo);

@@ -97,7 +97,6 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   plan->pixels = static_cast<uint64_t>(bi.xsize) * bi.ysize;
   JXLB_CHECK(!meta.color.want_icc, "unsupported: embedded ICC profile");
   JXLB_CHECK(!meta.have_preview, "unsupported: preview frame");
-  JXLB_CHECK(meta.orientation == 1, "unsupported: orientation != 1");
   SizeHeader size;
   size.xsize = bi.xsize;
   size.ysize = bi.ysize;
@@ -140,7 +139,8 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
     fo.ysize = bi.ysize;
     fo.num_channels = fmt.num_channels;
     fo.data_type = fmt.data_type;
-    fo.stride = OutputStride(bi.xsize, fmt);
+    fo.orient = OrientBits(meta.orientation, fmt);
+    fo.stride = OutputStride((fo.orient & 4) ? bi.ysize : bi.xsize, fmt);
     fo.vardct = 1;
     for (uint32_t c = 0; c < 4; c++) fo.plane[c] = kNoPlane;
     return;
@@ -326,7 +326,8 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   fo.num_channels = fmt.num_channels;
   fo.data_type = fmt.data_type;
   fo.big_endian = fmt.endianness == 2;
-  fo.stride = OutputStride(bi.xsize, fmt);
+  fo.orient = OrientBits(meta.orientation, fmt);
+  fo.stride = OutputStride((fo.orient & 4) ? bi.ysize : bi.xsize, fmt);
   const uint32_t num_color = fmt.num_channels < 3 ? 1 : 3;
   const bool want_alpha = fmt.num_channels == 2 || fmt.num_channels == 4;
   const int alpha = meta.AlphaIndex();

@@ -12,7 +12,15 @@ struct PixelFormat {
   uint32_t data_type = 2;   // JxlDataType
   uint32_t endianness = 0;  // JxlEndianness
   size_t align = 0;
+  bool keep_orientation = false;  // JxlDecoderSetKeepOrientation: leave the image as coded
 };
+
+// The write stage's undo_orientation (lib/jxl/render_pipeline/stage_write.cc:271-288) as bits: 1 flip x, 2 flip y,
+// 4 transpose (pixel (x', y') after the flips is stored at row x', column y').
+inline uint32_t OrientBits(uint32_t orientation, const PixelFormat& f) {
+  const uint32_t o = f.keep_orientation ? 1 : orientation;
+  return ((o == 2 || o == 3 || o == 8 || o == 7) ? 1u : 0u) | ((o == 4 || o == 3 || o == 6 || o == 7) ? 2u : 0u) | (o >= 5 ? 4u : 0u);
+}
 
 inline size_t BytesPerSample(uint32_t data_type) { return data_type == 2 ? 1 : (data_type == 0 ? 4 : 2); }
 inline size_t OutputStride(uint32_t xsize, const PixelFormat& f) {
@@ -447,7 +455,8 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   vf.out_channels = fmt.num_channels;
   vf.out_type = fmt.data_type;
   vf.out_big_endian = fmt.endianness == 2;
-  vf.out_stride = OutputStride(dim.xsize_upsampled, fmt);
+  vf.orient = OrientBits(meta.orientation, fmt);
+  vf.out_stride = OutputStride((vf.orient & 4) ? dim.ysize_upsampled : dim.xsize_upsampled, fmt);
   if (fmt.num_channels < 3) JXLB_CHECK(meta.color.IsGray(), "grey output requested for a colour image");
 }
 

@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(256) k_color_write(DevVPools V, uint32_t frame
   }
   if (y >= vf.ysize) return;
   const uint32_t set = SetBeforeStage(vf, 3);
-  if (vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0) {
+  if (vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0 && vf.orient == 0) {
     // RGB8: each thread converts 4 consecutive pixels and writes 12 bytes as three words
     const uint32_t x = (blockIdx.x * 32 + threadIdx.x) * 4;
     if (x + 4 <= vf.xsize) {
@@ -777,6 +777,7 @@ struct JxlB200Decoder {
   cudaStream_t part_stream[2] = {nullptr, nullptr};
   cudaEvent_t part_ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t pix_done = nullptr;  // end of this handle's last per-pixel phase (PixelTurn)
+  bool keep_orientation = false;   // JxlB200DecoderSetKeepOrientation: for the batches that follow
   std::string error;
   std::unique_ptr<BatchPlan> plan;
   DevBuf<uint8_t> d_bytes, d_out;
@@ -1039,7 +1040,7 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     if (fo.vardct) continue;
     dec->any_modular_frame = true;
     for (int c = 0; c < 4; c++)
-      if (fo.is_float[c] || fo.stride % 4) dec->uniform_rgba8 = false;
+      if (fo.is_float[c] || fo.stride % 4 || fo.orient != 0) dec->uniform_rgba8 = false;
   }
   // ---- VarDCT
   dec->dcg_list.clear();
@@ -1145,6 +1146,7 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   fmt.data_type = format->data_type;
   fmt.endianness = format->endianness;
   fmt.align = format->align;
+  fmt.keep_orientation = dec->keep_orientation;
   if (fmt.num_channels < 1 || fmt.num_channels > 4 ||
       !(fmt.data_type == 0 || fmt.data_type == 2 || fmt.data_type == 3 || fmt.data_type == 5)) {
     dec->error = "invalid pixel format";
@@ -1205,9 +1207,17 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   return 0;
 }
 
+int JxlB200DecoderSetKeepOrientation(JxlB200Decoder* dec, int keep) {
+  if (!dec) return 1;
+  dec->keep_orientation = keep != 0;
+  return 0;
+}
+
 size_t JxlB200DecoderNumFrames(const JxlB200Decoder* dec) { return dec && dec->plan ? dec->plan->frames.size() : 0; }
 
-static void FillBasicInfo(const BasicInfo& bi, bool have_container, JxlBasicInfo* info) {
+// keep_orientation false (libjxl's default): the sizes are those of the upright image and the orientation reads
+// identity (lib/jxl/decode.cc:2083-2090).
+static void FillBasicInfo(const BasicInfo& bi, bool have_container, JxlBasicInfo* info, bool keep_orientation = true) {
   std::memset(info, 0, sizeof(*info));
   const ImageMetadata& m = bi.meta;
   info->have_container = have_container;
@@ -1223,6 +1233,10 @@ static void FillBasicInfo(const BasicInfo& bi, bool have_container, JxlBasicInfo
   info->have_preview = m.have_preview;
   info->have_animation = m.have_animation;
   info->orientation = m.orientation;
+  if (!keep_orientation) {
+    if (m.orientation >= 5) std::swap(info->xsize, info->ysize);
+    info->orientation = 1;
+  }
   info->num_color_channels = m.color.IsGray() ? 1 : 3;
   info->num_extra_channels = m.extra.size();
   int a = m.AlphaIndex();
@@ -1243,7 +1257,7 @@ static void FillBasicInfo(const BasicInfo& bi, bool have_container, JxlBasicInfo
 
 int JxlB200DecoderGetBasicInfo(const JxlB200Decoder* dec, size_t i, JxlBasicInfo* info) {
   if (!dec || !dec->plan || i >= dec->plan->info.size() || !info) return 1;
-  FillBasicInfo(dec->plan->info[i], false, info);
+  FillBasicInfo(dec->plan->info[i], false, info, dec->keep_orientation);
   return 0;
 }
 
@@ -1735,6 +1749,7 @@ JxlDecoderStatus JxlDecoderProcessInput(JxlDecoder* dec) {
     if (!dec->gpu) return JXL_DEC_ERROR;  // no CUDA device: fail, never fall back
     const uint8_t* files[1] = {dec->input};
     size_t sizes[1] = {dec->input_size};
+    JxlB200DecoderSetKeepOrientation(dec->gpu, dec->keep_orientation ? 1 : 0);
     if (JxlB200DecoderSetInputBatch(dec->gpu, files, sizes, 1, &dec->format, 1) != 0) return JXL_DEC_ERROR;
     if (JxlB200DecoderRun(dec->gpu, nullptr) != 0) return JXL_DEC_ERROR;
     if (JxlB200DecoderWait(dec->gpu, nullptr) != 0) return JXL_DEC_ERROR;
@@ -1748,7 +1763,7 @@ JxlDecoderStatus JxlDecoderProcessInput(JxlDecoder* dec) {
 
 JxlDecoderStatus JxlDecoderGetBasicInfo(const JxlDecoder* dec, JxlBasicInfo* info) {
   if (!dec || !dec->have_info) return JXL_DEC_NEED_MORE_INPUT;
-  if (info) FillBasicInfo(dec->info, dec->have_container, info);
+  if (info) FillBasicInfo(dec->info, dec->have_container, info, dec->keep_orientation);
   return JXL_DEC_SUCCESS;
 }
 
@@ -1761,7 +1776,8 @@ JxlDecoderStatus JxlDecoderImageOutBufferSize(const JxlDecoder* dec, const JxlPi
   f.data_type = format->data_type;
   f.endianness = format->endianness;
   f.align = format->align;
-  *size = OutputStride(dec->info.xsize, f) * dec->info.ysize;
+  const bool transpose = !dec->keep_orientation && dec->info.meta.orientation >= 5;
+  *size = transpose ? OutputStride(dec->info.ysize, f) * dec->info.xsize : OutputStride(dec->info.xsize, f) * dec->info.ysize;
   return JXL_DEC_SUCCESS;
 }
 

@@ -163,10 +163,20 @@ struct DevFrameOut {
   uint64_t out_off;        // byte offset of this frame in the output buffer
   uint64_t stride;         // bytes per output row
   uint32_t vardct;         // 1: the frame is written by the VarDCT colour kernel, not by k_write_output
-  uint32_t pad_;
+  uint32_t orient;         // undo_orientation of the output store: 1 flip x, 2 flip y, 4 transpose (stage_write.cc:271-288)
 };
 
 constexpr uint32_t kNoPlane = 0xFFFFFFFFu;
+
+// Where the write stage puts source pixel (x, y) of a w x h image (stage_write.cc:163-172, :345-366): flipped position
+// (fx, fy) -- which also indexes the dither pattern -- then row / column of the store.
+JXLB_HD void DevOrient(uint32_t orient, uint32_t w, uint32_t h, uint32_t x, uint32_t y, uint32_t* fx, uint32_t* fy,
+                       uint32_t* row, uint32_t* col) {
+  *fx = (orient & 1) ? w - 1 - x : x;
+  *fy = (orient & 2) ? h - 1 - y : y;
+  *row = (orient & 4) ? *fx : *fy;
+  *col = (orient & 4) ? *fy : *fx;
+}
 
 }  // namespace jxlb
 

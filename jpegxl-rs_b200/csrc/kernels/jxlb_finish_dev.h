@@ -294,18 +294,20 @@ JXLB_HD float DevSampleFloat(const DevPools& P, const DevFrameOut& fo, uint32_t 
 
 // Converts and stores one pixel (all channels).
 JXLB_HD void DevWritePixel(const DevPools& P, const DevFrameOut& fo, uint8_t* out, uint32_t x, uint32_t y) {
-  uint8_t* row = out + fo.out_off + fo.stride * y;
+  uint32_t dx = x, dy = y, orow = y, ocol = x;  // dither position, store position
+  if (fo.orient != 0) DevOrient(fo.orient, fo.xsize, fo.ysize, x, y, &dx, &dy, &orow, &ocol);
+  uint8_t* row = out + fo.out_off + fo.stride * orow;
   for (uint32_t c = 0; c < fo.num_channels; c++) {
     float v = DevSampleFloat(P, fo, c, x, y);
-    const size_t idx = static_cast<size_t>(x) * fo.num_channels + c;
+    const size_t idx = static_cast<size_t>(ocol) * fo.num_channels + c;
     if (fo.data_type == 2 || fo.data_type == 3) {
       const float mul = fo.data_type == 2 ? 255.0f : 65535.0f;
 #if defined(__CUDA_ARCH__)
       v = __fmul_rn(v, mul);
-      if (fo.data_type == 2) v = __fadd_rn(v, DevDither(x, y));
+      if (fo.data_type == 2) v = __fadd_rn(v, DevDither(dx, dy));
 #else
       v = v * mul;
-      if (fo.data_type == 2) v = v + DevDither(x, y);
+      if (fo.data_type == 2) v = v + DevDither(dx, dy);
 #endif
       if (!(v >= 0.0f)) v = 0.0f;
       if (v > mul) v = mul;

@@ -83,7 +83,7 @@ struct DevVFrame {
   // into `up_pix` (row stride up_stride) before the colour transform, which then runs at up_xsize x up_ysize
   uint32_t upsampling, up_xsize, up_ysize, up_stride;
   uint32_t up_kernel;  // fpool index of kernel[4][4][5][5]
-  uint32_t up_pad_;
+  uint32_t orient;     // undo_orientation of the output store: 1 flip x, 2 flip y, 4 transpose (stage_write.cc:271-288)
   uint64_t up_pix[3];  // farena index
 };
 

@@ -1720,6 +1720,16 @@ JXLB_HD void DevPatchPixel(const DevVPools& V, const DevVFrame& vf, const DevPat
 JXLB_HD void DevColorStore(const DevVPools& V, const DevVFrame& vf, float p0, float p1, float p2, uint32_t x, uint32_t y) {
   float r, g, b;
   DevColorTransform(vf, p0, p1, p2, &r, &g, &b);
+  if (vf.orient != 0) {  // (rare) the store position and the dither position follow the orientation
+    uint32_t fx, fy, orow, ocol;
+    DevOrient(vf.orient, vf.up_xsize, vf.up_ysize, x, y, &fx, &fy, &orow, &ocol);
+    uint8_t* row = V.out + vf.out_off + vf.out_stride * orow;
+    const uint32_t nc = vf.out_channels, num_color = nc < 3 ? 1 : 3;
+    const float col[3] = {r, g, b};
+    for (uint32_t c = 0; c < nc; c++)
+      DevStoreSample(row, static_cast<size_t>(ocol) * nc + c, c < num_color ? col[c] : 1.0f, vf.out_type, vf.out_big_endian, fx, fy);
+    return;
+  }
   uint8_t* row = V.out + vf.out_off + vf.out_stride * y;
   const uint32_t nc = vf.out_channels;
   if (nc == 4 && vf.out_type == 2) {  // RGBA8: one aligned 32-bit store
@@ -1926,7 +1936,7 @@ JXLB_HD void DevRenderTile(const DevVPools& V, const DevVFrame& vf, int tx0, int
     nxt = t;
   }
   // colour transform + output samples of the kRtW x kRtH tile
-  const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0;
+  const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0 && vf.orient == 0;
   for (uint32_t i = tid; i < static_cast<uint32_t>(kRtW / 4 * kRtH); i += nt) {
     const int lx = static_cast<int>(i % (kRtW / 4)) * 4, ly = static_cast<int>(i / (kRtW / 4));
     const int fx = tx0 + lx, fy = ty0 + ly;

@@ -57,11 +57,18 @@ size_t jxlo_output_size(void* h, uint32_t num_channels, uint32_t data_type, size
   return OutputStride(img->xsize, num_channels, data_type, align) * img->ysize;
 }
 
+// endianness: JxlEndianness, | 0x400 = undo the image's orientation (libjxl's default; rows are then `ysize` samples
+// wide for the transposing orientations 5 - 8).
 int jxlo_write_pixels(void* h, uint32_t num_channels, uint32_t data_type, uint32_t endianness, size_t align,
                       uint8_t* out, size_t out_size) {
   const DecodedImage* img = static_cast<const DecodedImage*>(h);
-  if (out_size < jxlo_output_size(h, num_channels, data_type, align)) return 1;
-  WritePixels(*img, num_channels, data_type, endianness, align, out);
+  const bool undo = (endianness & 0x400) != 0;
+  endianness &= 0xFF;
+  const bool transpose = undo && img->meta.orientation >= 5;
+  const size_t need = transpose ? OutputStride(img->ysize, num_channels, data_type, align) * img->xsize
+                                : jxlo_output_size(h, num_channels, data_type, align);
+  if (out_size < need) return 1;
+  WritePixels(*img, num_channels, data_type, endianness, align, out, undo);
   return 0;
 }
 
@@ -122,6 +129,7 @@ size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, fl
     p.adaptive_quant = (gab & 16) == 0;  // bit 4: constant quant field instead of libjxl's adaptive one
     p.prefix_codes = (gab & 32) != 0;    // bit 5: prefix codes instead of ANS in every stream
     p.upsampling = 1u << ((gab >> 6) & 3);  // bits 6-7: log2 of the frame upsampling
+    p.orientation = 1 + ((gab >> 8) & 7);   // bits 8-10: the image's orientation - 1
     p.epf_iters = epf_iters;
     p.dc_smoothing = dc_smoothing != 0;
     p.random_side_info = random_side_info != 0;
@@ -153,6 +161,7 @@ size_t jxlo_encode_modular(const uint16_t* samples, uint32_t xsize, uint32_t ysi
     p.squeeze = params[11] != 0;
     p.entropy = static_cast<int>(params[12]);
     p.lz77_min_symbol = params[13] ? params[13] : 224;
+    p.orientation = params[14] ? params[14] : 1;
     g_encoded = EncodeModular(samples, xsize, ysize, p);
     return g_encoded.size();
   } catch (const std::exception& e) {

@@ -268,28 +268,35 @@ inline size_t OutputStride(uint32_t xsize, uint32_t num_channels, uint32_t data_
 
 // WriteToOutputStage with the scalar dither semantics (pattern indexed by the
 // absolute pixel position). num_channels: 1 grey, 2 grey+alpha, 3 RGB, 4 RGBA.
+// undo_orientation (stage_write.cc:131-135, :163-172, :345-366, :271-288; libjxl's default, JxlDecoderSetKeepOrientation
+// false): the row is flipped in y, the pixels of a row in x -- the dither pattern is indexed by the flipped position --
+// and a transposing orientation writes pixel (x', y') at row x', column y'.
 inline void WritePixels(const DecodedImage& img, uint32_t num_channels, uint32_t data_type, uint32_t endianness,
-                        size_t align, uint8_t* out) {
+                        size_t align, uint8_t* out, bool undo_orientation = false) {
   const uint32_t num_color = num_channels < 3 ? 1 : 3;
   const bool want_alpha = num_channels == 2 || num_channels == 4;
   const int alpha_idx = img.meta.AlphaIndex();
-  const size_t stride = OutputStride(img.xsize, num_channels, data_type, align);
+  const uint32_t o = undo_orientation ? img.meta.orientation : 1;
+  const bool flip_x = o == 2 || o == 3 || o == 8 || o == 7, flip_y = o == 4 || o == 3 || o == 6 || o == 7;
+  const bool transpose = o >= 5;
+  const size_t stride = OutputStride(transpose ? img.ysize : img.xsize, num_channels, data_type, align);
   const bool swap = (endianness == kBigEndian);  // host is little-endian
   const uint32_t bits = data_type == kTypeUint8 ? 8 : 16;
   const float mul = static_cast<float>((1u << bits) - 1);
-  for (uint32_t y = 0; y < img.ysize; y++) {
-    uint8_t* row = out + stride * y;
-    for (uint32_t x = 0; x < img.xsize; x++) {
+  for (uint32_t sy = 0; sy < img.ysize; sy++) {
+    for (uint32_t sx = 0; sx < img.xsize; sx++) {
+      const uint32_t x = flip_x ? img.xsize - 1 - sx : sx, y = flip_y ? img.ysize - 1 - sy : sy;
+      uint8_t* row = out + stride * (transpose ? x : y);
       for (uint32_t c = 0; c < num_channels; c++) {
         float v;
         if (c < num_color) {
-          v = img.planes[c].Row(y)[x];
+          v = img.planes[c].Row(sy)[sx];
         } else if (want_alpha && alpha_idx >= 0) {
-          v = img.planes[3 + alpha_idx].Row(y)[x];
+          v = img.planes[3 + alpha_idx].Row(sy)[sx];
         } else {
           v = 1.0f;
         }
-        size_t idx = static_cast<size_t>(x) * num_channels + c;
+        size_t idx = static_cast<size_t>(transpose ? y : x) * num_channels + c;
         if (data_type == kTypeUint8 || data_type == kTypeUint16) {
           v = v * mul;
           if (data_type == kTypeUint8) v += kDither8x8[(y % 8) * 8 + (x % 8)];

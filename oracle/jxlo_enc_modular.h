@@ -22,6 +22,7 @@
 namespace jxlo {
 
 struct ModularEncodeParams {
+  uint32_t orientation = 1;  // ImageMetadata::orientation
   uint32_t bits = 8;              // integer bits per sample, 1 .. 16
   uint32_t num_color = 3;         // 1 (grey) or 3
   bool alpha = false;             // one alpha extra channel of the same depth
@@ -400,7 +401,13 @@ inline void WriteModularImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysiz
   WriteU32(w, xsize, BitsOffset(9, 1), BitsOffset(13, 1), BitsOffset(18, 1), BitsOffset(30, 1));
   // ImageMetadata
   w.Write(1, 0);  // not all_default
-  w.Write(1, 0);  // no extra fields
+  if (p.orientation == 1) {
+    w.Write(1, 0);  // no extra fields
+  } else {
+    w.Write(1, 1);  // extra_fields: the orientation; no intrinsic size, preview, animation
+    w.Write(3, p.orientation - 1);
+    w.Write(3, 0);
+  }
   auto bit_depth = [&]() {
     w.Write(1, 0);  // integer samples
     WriteU32(w, p.bits, Val(8), Val(10), Val(12), BitsOffset(6, 1));
@@ -432,6 +439,7 @@ inline void WriteModularImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysiz
     WriteU32(w, kTFSRGB, Val(0), Val(1), BitsOffset(4, 2), BitsOffset(6, 18));
     WriteU32(w, 1, Val(0), Val(1), BitsOffset(4, 2), BitsOffset(6, 18));  // rendering intent: relative
   }
+  if (p.orientation != 1) w.Write(1, 1);  // ToneMapping all_default (extra_fields)
   WriteU64(w, 0);  // extensions
   w.Write(1, 1);   // CustomTransformData all_default
   w.ZeroPadToByte();

@@ -882,6 +882,7 @@ struct EncodeParams {
   // Frame upsampling (decoder coverage of lib/jxl/render_pipeline/stage_upsampling.cc): the pixels handed to the encoder
   // are the low-resolution frame, the image header declares `upsampling` times their size.
   uint32_t upsampling = 1;
+  uint32_t orientation = 1;  // ImageMetadata::orientation (decoder coverage of the write stage's undo_orientation)
 };
 
 struct EncoderStats {
@@ -889,14 +890,31 @@ struct EncoderStats {
   size_t strategy_count[27] = {0};
 };
 
-inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize) {
+inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize, uint32_t orientation = 1) {
   w.Write(16, 0x0AFF);
   // SizeHeader
   w.Write(1, 0);  // not "small"
   WriteU32(w, ysize, BitsOffset(9, 1), BitsOffset(13, 1), BitsOffset(18, 1), BitsOffset(30, 1));
   w.Write(3, 0);  // no fixed aspect ratio
   WriteU32(w, xsize, BitsOffset(9, 1), BitsOffset(13, 1), BitsOffset(18, 1), BitsOffset(30, 1));
-  w.Write(1, 1);  // ImageMetadata all_default: 8-bit sRGB, XYB encoded, no extra channels
+  if (orientation == 1) {
+    w.Write(1, 1);  // ImageMetadata all_default: 8-bit sRGB, XYB encoded, no extra channels
+  } else {          // the same image with extra_fields for the orientation (lib/jxl/image_metadata.cc:258-330)
+    w.Write(1, 0);  // not all_default
+    w.Write(1, 1);  // extra_fields
+    w.Write(3, orientation - 1);
+    w.Write(1, 0);  // no intrinsic size
+    w.Write(1, 0);  // no preview
+    w.Write(1, 0);  // no animation
+    w.Write(1, 0);  // integer samples
+    WriteU32(w, 8, Val(8), Val(10), Val(12), BitsOffset(6, 1));
+    w.Write(1, 1);  // modular_16_bit_buffer_sufficient
+    WriteU32(w, 0, Val(0), Val(1), BitsOffset(4, 2), BitsOffset(12, 1));  // no extra channels
+    w.Write(1, 1);  // xyb_encoded
+    w.Write(1, 1);  // ColorEncoding all_default (sRGB)
+    w.Write(1, 1);  // ToneMapping all_default
+    WriteU64(w, 0);  // extensions
+  }
   w.Write(1, 1);  // CustomTransformData all_default
   w.ZeroPadToByte();
 }
@@ -2157,7 +2175,7 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   }
 
   BitWriter out;
-  WriteImageHeaders(out, xsize * p.upsampling, ysize * p.upsampling);
+  WriteImageHeaders(out, xsize * p.upsampling, ysize * p.upsampling, p.orientation);
   WriteFrameHeader(out, p);
   WriteToc(out, sections);
   for (const auto& s : sections) out.Append(s);

@@ -38,6 +38,7 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
   try {
     const bool force_wide = (endianness & 0x100) != 0;  // test hook: run the 64-bit predictor path
     const bool generic_only = (endianness & 0x200) != 0;  // test hook: generic varblock path for every block
+    const bool undo_orientation = (endianness & 0x400) != 0;  // libjxl's default output; the tests' default keeps the coded image
     endianness &= 0xFF;
     (void)generic_only;
     PixelFormat fmt;
@@ -45,6 +46,7 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     fmt.data_type = data_type;
     fmt.endianness = endianness;
     fmt.align = align;
+    fmt.keep_orientation = !undo_orientation;
     // the Modular decode "kernel": every stream of `b`, one lane at a time
     auto run_modular = [&](const BatchPlan& b, std::vector<int32_t>& arena, DevPools* pools_out, std::vector<uint64_t>* end_bits) {
       const size_t num_warps = (b.streams.size() - b.num_coop + 31) / 32 + 1;
@@ -311,7 +313,7 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
             for (uint32_t x = 0; x < vf.up_xsize; x++) DevColorPixel(V, vf, 0, x, y);
           continue;
         }
-        const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0;
+        const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0 && vf.orient == 0;
         for (uint32_t y = 0; y < vf.ysize; y++)
           for (uint32_t x = 0; x < vf.xsize; x++) {
             if (x4 && x % 4 == 0 && x + 4 <= vf.xsize) {  // the kernel's vector path

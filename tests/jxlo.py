@@ -73,15 +73,21 @@ class Decoded:
     def frame_info(self):
         return [lib().jxlo_frame_info(self.h, i).decode() for i in range(self.info.num_frames)]
 
-    def pixels(self, num_channels, data_type, endianness=0, align=0, raw=False):
+    def pixels(self, num_channels, data_type, endianness=0, align=0, raw=False, undo_orientation=False):
+        """undo_orientation: libjxl's default output (JxlDecoderSetKeepOrientation false): the image turned upright."""
         L = lib()
         n = L.jxlo_output_size(self.h, num_channels, data_type, align)
+        h, w = self.info.ysize, self.info.xsize
+        if undo_orientation and self.info.orientation >= 5:
+            assert align <= 1
+            h, w = w, h
         buf = np.zeros(n, np.uint8)
-        rc = L.jxlo_write_pixels(self.h, num_channels, data_type, endianness, align, buf.ctypes.data, n)
+        rc = L.jxlo_write_pixels(self.h, num_channels, data_type, endianness | (0x400 if undo_orientation else 0), align,
+                                 buf.ctypes.data, n)
         assert rc == 0
         if raw or align > 1:
             return buf
-        return buf.view(_NP[data_type]).reshape(self.info.ysize, self.info.xsize, num_channels)
+        return buf.view(_NP[data_type]).reshape(h, w, num_channels)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -89,20 +95,20 @@ class Decoded:
             self.h = None
 
 
-def decode(data: bytes, num_channels: int, data_type: int, endianness: int = 0) -> np.ndarray:
-    return Decoded(data).pixels(num_channels, data_type, endianness)
+def decode(data: bytes, num_channels: int, data_type: int, endianness: int = 0, undo_orientation: bool = False) -> np.ndarray:
+    return Decoded(data).pixels(num_channels, data_type, endianness, undo_orientation=undo_orientation)
 
 
 def encode_vardct(rgb: np.ndarray, distance=1.0, strategy_mode=2, seed=1, gab=True, epf_iters=2, dc_smoothing=True,
                   random_side_info=False, num_passes=1, dc_tree=0, inverse_gaborish=True, coeff_orders=True, cfl=True,
-                  adaptive_quant=True, prefix_codes=False, upsampling=1) -> bytes:
+                  adaptive_quant=True, prefix_codes=False, upsampling=1, orientation=1) -> bytes:
     """RGB8 (H, W, 3) -> a VarDCT codestream written by the oracle's plain encoder (stream generator)."""
     L = lib()
     rgb = np.ascontiguousarray(rgb, np.uint8)
     h, w, c = rgb.shape
     assert c == 3
     err = ctypes.create_string_buffer(512)
-    gab_arg = int(bool(gab)) | (0 if inverse_gaborish else 2) | (0 if coeff_orders else 4) | (0 if cfl else 8) | (0 if adaptive_quant else 16) | (32 if prefix_codes else 0) | ({1: 0, 2: 1, 4: 2, 8: 3}[upsampling] << 6)
+    gab_arg = int(bool(gab)) | (0 if inverse_gaborish else 2) | (0 if coeff_orders else 4) | (0 if cfl else 8) | (0 if adaptive_quant else 16) | (32 if prefix_codes else 0) | ({1: 0, 2: 1, 4: 2, 8: 3}[upsampling] << 6) | ((orientation - 1) << 8)
     n = L.jxlo_encode_vardct(rgb.ctypes.data, w, h, distance, strategy_mode, seed, gab_arg, epf_iters,
                              int(dc_smoothing), int(random_side_info), num_passes, dc_tree, err, 512)
     if n == 0:
@@ -114,7 +120,7 @@ def encode_vardct(rgb: np.ndarray, distance=1.0, strategy_mode=2, seed=1, gab=Tr
 
 def encode_modular(img: np.ndarray, bits=8, alpha=False, group_size_shift=1, tree=0, predictor=5, seed=1, rct=-1,
                    palette_colors=0, palette_deltas=0, palette_predictor=0, squeeze=False, prefix=False, lz77=False,
-                   lz77_min_symbol=224) -> bytes:
+                   lz77_min_symbol=224, orientation=1) -> bytes:
     """(H, W, C) integer samples -> a lossless Modular codestream written by the oracle's plain encoder
     (oracle/jxlo_enc_modular.h). C = 1 / 3 colour channels (+ 1 when alpha)."""
     L = lib()
@@ -123,7 +129,7 @@ def encode_modular(img: np.ndarray, bits=8, alpha=False, group_size_shift=1, tre
     num_color = c - (1 if alpha else 0)
     assert num_color in (1, 3)
     params = np.array([bits, num_color, int(alpha), group_size_shift, tree, predictor, seed, rct + 1, palette_colors,
-                       palette_deltas, palette_predictor, int(squeeze), int(prefix) | (int(lz77) << 1), lz77_min_symbol, 0, 0],
+                       palette_deltas, palette_predictor, int(squeeze), int(prefix) | (int(lz77) << 1), lz77_min_symbol, orientation, 0],
                       np.uint32)
     err = ctypes.create_string_buffer(512)
     n = L.jxlo_encode_modular(img.ctypes.data, w, h, params.ctypes.data, err, 512)

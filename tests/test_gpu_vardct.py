@@ -109,3 +109,27 @@ def test_g4_sample_grey_jxl(pkg):
     outs = pkg.decode_batch([a, grey, read_golden("sample_jpg.jxl"), grey], 3, np.uint8)
     assert np.array_equal(outs[1], jxlo.decode(grey, 3, jxlo.UINT8)) and np.array_equal(outs[3], outs[1])
     assert np.array_equal(outs[0], jxlo.decode(a, 3, jxlo.UINT8))
+
+
+def test_orientation(pkg):
+    # the write stage's undo_orientation on the GPU (all eight orientations, lossy RGB8 / RGBA16 and lossless RGBA8 in
+    # one batch), the coded image with keep_orientation, and the event API's upright size (lib/jxl/decode.cc:2083-2090)
+    img = vc.crop(70, 100, 100, 200)
+    rgba = np.random.default_rng(3).integers(0, 256, (37, 53, 4)).astype(np.uint16)
+    files = [jxlo.encode_vardct(img, strategy_mode=2, orientation=o) for o in range(1, 9)]
+    files += [jxlo.encode_vardct(img[:35, :50], strategy_mode=2, upsampling=2, orientation=o) for o in (3, 6)]
+    files += [jxlo.encode_modular(rgba, bits=8, alpha=True, orientation=o) for o in (2, 5, 7, 8)]
+    for nc, npdt, dt in [(3, np.uint8, jxlo.UINT8), (4, np.uint16, jxlo.UINT16), (4, np.uint8, jxlo.UINT8)]:
+        outs = pkg.decode_batch(files, nc, npdt)
+        kept = pkg.decode_batch(files, nc, npdt, keep_orientation=True)
+        for f, o, k in zip(files, outs, kept):
+            assert np.array_equal(o, jxlo.decode(f, nc, dt, undo_orientation=True))
+            assert np.array_equal(k, jxlo.decode(f, nc, dt))
+    dec = pkg.decoder_builder().build()
+    meta, px = dec.decode(files[5])  # orientation 6: rotated, the upright image is 100 x 70 -> 70 wide, 100 high
+    assert (meta.width, meta.height) == (70, 100) and meta.orientation == 1
+    assert np.array_equal(np.asarray(px.data).reshape(100, 70, 3), jxlo.decode(files[5], 3, jxlo.UINT8, undo_orientation=True))
+    dec = pkg.decoder_builder().skip_reorientation(True).build()
+    meta, px = dec.decode(files[5])
+    assert (meta.width, meta.height) == (100, 70) and meta.orientation == 6
+    assert np.array_equal(np.asarray(px.data).reshape(70, 100, 3), jxlo.decode(files[5], 3, jxlo.UINT8))

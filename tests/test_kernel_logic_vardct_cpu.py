@@ -151,3 +151,34 @@ def test_dc_chains_take_the_warp_cooperative_path(monkeypatch):
     data, shape = cases[1]
     got = emul_lib.decode([data], 3, jxlo.UINT8, [shape], endianness=0x100)[0]
     assert np.array_equal(got, jxlo.decode(data, 3, jxlo.UINT8))
+
+
+@pytest.mark.parametrize("o", range(1, 9))
+def test_orientation_is_undone_like_the_write_stage(o):
+    # libjxl's default output turns the image upright (stage_write.cc:131-135, :163-172, :345-366: flips, dither pattern at
+    # the flipped position, transposed store). The kernels' store (DevOrient) against the oracle's restatement and, for
+    # 16-bit samples (no dither), against the plain numpy flips of the coded image. Lossy (fused tile and, upsampled, the
+    # per-pixel colour kernel) and lossless Modular (RGBA).
+    import modular_cases as mc
+    img = vc.crop(70, 100, 100, 200)
+    flip_x, flip_y, transpose = o in (2, 3, 8, 7), o in (4, 3, 6, 7), o >= 5
+    def upright(a):
+        a = a[:, ::-1] if flip_x else a
+        a = a[::-1] if flip_y else a
+        return a.transpose(1, 0, 2) if transpose else a
+    rng = np.random.default_rng(o)
+    rgba = rng.integers(0, 256, (37, 53, 4)).astype(np.uint16)
+    files = [jxlo.encode_vardct(img, strategy_mode=2, orientation=o),
+             jxlo.encode_vardct(img[:35, :50], strategy_mode=2, upsampling=2, orientation=o),
+             jxlo.encode_modular(rgba, bits=8, alpha=True, orientation=o)]
+    shapes = [(70, 100), (70, 100), (37, 53)]
+    out_shapes = [(w, h) if transpose else (h, w) for h, w in shapes]
+    for nc, dt in [(3, jxlo.UINT8), (4, jxlo.UINT16), (4, jxlo.UINT8)]:
+        got = emul_lib.decode(files, nc, dt, out_shapes, endianness=0x400)
+        kept = emul_lib.decode(files, nc, dt, shapes)
+        for g, k, f in zip(got, kept, files):
+            want = jxlo.decode(f, nc, dt, undo_orientation=True)
+            assert np.array_equal(g, want)
+            assert np.array_equal(k, jxlo.decode(f, nc, dt))
+            if dt == jxlo.UINT16:
+                assert np.array_equal(g, upright(k))
