@@ -194,6 +194,12 @@ const char* JxlB200EncoderGetError(const JxlB200Encoder* enc);
 /* rgb[i]: xsizes[i] * ysizes[i] interleaved RGB8 samples (sRGB). Synchronous. */
 int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, const uint32_t* xsizes, const uint32_t* ysizes,
                               size_t n, const JxlB200EncodeOptions* options);
+/* Lossless (Modular) batch -- jpegxl-rs `lossless(true)` (jpegxl-rs/src/encode.rs:143, :230-234; libjxl:
+ * JxlEncoderSetFrameLossless, lib/jxl/enc_modular.cc): pixels[i] = xsizes[i] * ysizes[i] interleaved samples of
+ * num_channels each (1 grey, 2 grey + alpha, 3 RGB, 4 RGBA; sRGB), bits_per_sample 8 (uint8) or 16 (uint16, native
+ * endian). YCoCg-R + libjxl's fixed gradient tree, groups of 256 x 256; the decoded image equals the input bit for bit. */
+int JxlB200EncoderEncodeLosslessBatch(JxlB200Encoder* enc, const void* const* pixels, const uint32_t* xsizes, const uint32_t* ysizes,
+                                      size_t n, uint32_t num_channels, uint32_t bits_per_sample);
 size_t JxlB200EncoderOutputSize(const JxlB200Encoder* enc, size_t i);
 int JxlB200EncoderReadOutput(const JxlB200Encoder* enc, size_t i, uint8_t* dst, size_t size);
 /* Device time of the last EncodeBatch: {pixels -> tokens + histograms, host tables (incl. D2H), rANS emission} in ms. */

@@ -160,6 +160,8 @@ def load_library() -> ctypes.CDLL:
     lib.JxlB200EncoderGetError.argtypes = [vp]
     lib.JxlB200EncoderEncodeBatch.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32),
                                               ctypes.POINTER(ctypes.c_uint32), sz, ctypes.POINTER(JxlB200EncodeOptions)]
+    lib.JxlB200EncoderEncodeLosslessBatch.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32),
+                                                      ctypes.POINTER(ctypes.c_uint32), sz, ctypes.c_uint32, ctypes.c_uint32]
     lib.JxlB200EncoderOutputSize.restype = sz
     lib.JxlB200EncoderOutputSize.argtypes = [vp, sz]
     lib.JxlB200EncoderReadOutput.argtypes = [vp, sz, vp, sz]
@@ -233,7 +235,7 @@ EXPORTED_SYMBOLS = [
     "JxlB200DecoderWait", "JxlB200DecoderDeviceOutput", "JxlB200DecoderReadOutput", "JxlB200DecoderReadOutputs",
     "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderSetPhaseMask", "JxlB200DecoderDeviceOutputBytes", "JxlB200DecoderGetKernelTimes",
     "JxlB200DecoderGetKernelTimesEx", "JxlB200EncoderCreate", "JxlB200EncoderDestroy", "JxlB200EncoderGetError",
-    "JxlB200EncoderEncodeBatch", "JxlB200EncoderOutputSize", "JxlB200EncoderReadOutput", "JxlB200EncoderGetPhaseTimes",
+    "JxlB200EncoderEncodeBatch", "JxlB200EncoderEncodeLosslessBatch", "JxlB200EncoderOutputSize", "JxlB200EncoderReadOutput", "JxlB200EncoderGetPhaseTimes",
     "JxlDecoderVersion", "JxlSignatureCheck", "JxlDecoderCreate", "JxlDecoderReset",
     "JxlDecoderDestroy", "JxlDecoderSetParallelRunner", "JxlDecoderSubscribeEvents", "JxlDecoderSetKeepOrientation",
     "JxlDecoderSetUnpremultiplyAlpha", "JxlDecoderSetRenderSpotcolors", "JxlDecoderSetCoalescing",
@@ -728,9 +730,9 @@ class JxlEncoder:
         """One JxlB200EncoderEncodeBatch call over independent RGB8 images. `gaborish` / `epf_iters`: the loop-filter
         fields of the frame header (libjxl's encoder derives them from the distance; the defaults are its d = 1 values)."""
         if self.lossless:
-            raise EncodeError("NotSupported: lossless encoding is not part of the GPU path")
+            return self.encode_lossless_batch(images)
         if self.has_alpha:
-            raise EncodeError("NotSupported: alpha")
+            raise EncodeError("NotSupported: alpha (lossy)")
         if self.use_container:
             raise EncodeError("NotSupported: container output in batch mode")
         if self._enc is None:
@@ -749,6 +751,33 @@ class JxlEncoder:
         opt.gaborish = 1 if gaborish else 0
         opt.epf_iters = int(epf_iters)
         if self._lib.JxlB200EncoderEncodeBatch(self._enc, ptrs, xs, ys, n, ctypes.byref(opt)) != 0:
+            raise EncodeError(self._lib.JxlB200EncoderGetError(self._enc).decode())
+        out = []
+        for i in range(n):
+            size = self._lib.JxlB200EncoderOutputSize(self._enc, i)
+            buf = np.empty(size, np.uint8)
+            if self._lib.JxlB200EncoderReadOutput(self._enc, i, buf.ctypes.data, size) != 0:
+                raise EncodeError("internal: output read failed")
+            out.append(EncoderResult(buf.tobytes()))
+        return out
+
+    def encode_lossless_batch(self, images: Sequence[np.ndarray]) -> List[EncoderResult]:
+        """One JxlB200EncoderEncodeLosslessBatch call: (H, W, C) uint8 or uint16 arrays of one dtype and channel count
+        (C = 1 grey, 2 grey + alpha, 3 RGB, 4 RGBA). The decoded images equal the inputs bit for bit."""
+        if self._enc is None:
+            self._enc = self._lib.JxlB200EncoderCreate(self.device)
+            if not self._enc:
+                raise EncodeError("CannotCreateEncoder: no usable CUDA device (jxl_b200 has no CPU fallback)")
+        imgs = [np.ascontiguousarray(a) for a in images]
+        dt, nch = imgs[0].dtype, imgs[0].shape[2] if imgs[0].ndim == 3 else 0
+        for a in imgs:
+            if a.ndim != 3 or a.dtype != dt or a.shape[2] != nch or dt not in (np.uint8, np.uint16) or not 1 <= nch <= 4:
+                raise EncodeError("ApiUsage: expected (height, width, channels) uint8 / uint16 arrays of one kind")
+        n = len(imgs)
+        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in imgs])
+        xs = (ctypes.c_uint32 * n)(*[a.shape[1] for a in imgs])
+        ys = (ctypes.c_uint32 * n)(*[a.shape[0] for a in imgs])
+        if self._lib.JxlB200EncoderEncodeLosslessBatch(self._enc, ptrs, xs, ys, n, nch, 8 * dt.itemsize) != 0:
             raise EncodeError(self._lib.JxlB200EncoderGetError(self._enc).decode())
         out = []
         for i in range(n):

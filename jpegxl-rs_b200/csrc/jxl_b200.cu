@@ -31,7 +31,9 @@
 #include "kernels/jxlb_finish_dev.h"
 #include "kernels/jxlb_vardct_dev.h"
 #include "kernels/jxlb_enc_dev.h"
+#include "kernels/jxlb_encl_dev.h"
 #include "host/jxlb_enc_host.h"
+#include "host/jxlb_encl_host.h"
 
 namespace jxlb {
 
@@ -2021,6 +2023,31 @@ __global__ void __launch_bounds__(32) k_enc_emit(DevEPools E, const DevEFrame* f
   first[sec] = DevEncEmitAcGroup(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words, off[sec + 1] * 32);
 }
 
+// ---- lossless (Modular) encoder: kernels/jxlb_encl_dev.h
+__global__ void __launch_bounds__(256) k_encl_planes(DevLPools L, const DevLFrame* frames) {
+  const DevLFrame& f = frames[blockIdx.y];
+  const uint64_t n = static_cast<uint64_t>(f.xsize) * f.ysize;
+  for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) DevEnclPlanes(L, f, i);
+}
+
+__global__ void __launch_bounds__(256) k_encl_tokens(DevLPools L, const DevLFrame* frames) {
+  const DevLFrame& f = frames[blockIdx.y];
+  const uint64_t n = static_cast<uint64_t>(f.xsize) * f.ysize * f.nch;
+  for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) DevEnclToken(L, f, i);
+}
+
+// One thread per group section (a serial rANS chain each); `off[sec]` .. `off[sec + 1]` is the section's region in words.
+__global__ void __launch_bounds__(32) k_encl_emit(DevLPools L, const DevLFrame* frames, const uint32_t* fs_tables,
+                                                  const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first) {
+  const DevLFrame& f = frames[blockIdx.y];
+  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
+  if (g >= f.xgroups * f.ygroups) return;
+  const DevEncCode code{fs_tables + f.code_off[0], rev_tables + f.code_off[1]};
+  const uint32_t sec = f.sec_base + g;
+  const bool global_only = f.xsize <= kEnclGroupDim && f.ysize <= kEnclGroupDim;  // the tokens follow the host's global header
+  first[sec] = DevEnclEmitGroup(L, f, g, code, words, off[sec + 1] * 32, !global_only);
+}
+
 }  // namespace jxlb
 
 struct JxlB200Encoder {
@@ -2040,6 +2067,8 @@ struct JxlB200Encoder {
   DevBuf<uint64_t> d_off, d_bits;
   DevBuf<DevEncTreeNode> d_trees;
   DevBuf<DevEFrame> d_efs;
+  DevBuf<DevLFrame> d_lfs;      // lossless encoder
+  DevBuf<int32_t> d_lconst;     // its cutoffs and leaf table
   uint32_t* h_words = nullptr;  // pinned: the emitted sections of a batch
   size_t h_words_cap = 0;
 };
@@ -2434,6 +2463,154 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       std::vector<std::thread> pool;
       for (size_t t = 0; t < nthreads; t++) pool.emplace_back(work);
       for (auto& t : pool) t.join();
+    }
+  } catch (const std::exception& e) {
+    enc->error = e.what();
+    return 1;
+  }
+  return 0;
+}
+
+// Lossless batch: pixels[i] = xsizes[i] * ysizes[i] interleaved samples, num_channels each (1 grey, 2 grey + alpha, 3 RGB,
+// 4 RGBA), bits_per_sample 8 (uint8) or 16 (uint16, native endian). kernels/jxlb_encl_dev.h describes the stream.
+int JxlB200EncoderEncodeLosslessBatch(JxlB200Encoder* enc, const void* const* pixels, const uint32_t* xsizes, const uint32_t* ysizes,
+                                      size_t n, uint32_t num_channels, uint32_t bits_per_sample) {
+  if (!enc || !pixels || !xsizes || !ysizes || n == 0) return 1;
+  enc->error.clear();
+  enc->outputs.clear();
+  if (num_channels < 1 || num_channels > 4 || !(bits_per_sample == 8 || bits_per_sample == 16)) {
+    enc->error = "invalid lossless encode options";
+    return 1;
+  }
+  CUDA_OK(cudaSetDevice(enc->device));
+  cudaStream_t s = enc->stream;
+  try {
+    const EnclTree tree = BuildEnclTree();
+    std::vector<EnclParams> ps(n);
+    std::vector<DevLFrame> lf(n);
+    std::vector<uint64_t> h_off;  // word offset of every group section, then the end
+    uint64_t in_bytes = 0, planes = 0, toks = 0, words_total = 0;
+    uint32_t max_groups = 0;
+    uint64_t max_samples = 0;
+    const uint32_t bytes = bits_per_sample / 8;
+    for (size_t i = 0; i < n; i++) {
+      JXLB_CHECK(xsizes[i] > 0 && ysizes[i] > 0 && xsizes[i] <= (1u << 16) && ysizes[i] <= (1u << 16) && pixels[i], "bad image");
+      EnclParams& p = ps[i];
+      p.xsize = xsizes[i];
+      p.ysize = ysizes[i];
+      p.nch = num_channels;
+      p.bits = bits_per_sample;
+      DevLFrame& f = lf[i];
+      f = DevLFrame{};
+      f.xsize = p.xsize;
+      f.ysize = p.ysize;
+      f.xgroups = p.XGroups();
+      f.ygroups = p.YGroups();
+      f.nch = p.nch;
+      f.bytes = bytes;
+      const uint64_t px = static_cast<uint64_t>(p.xsize) * p.ysize;
+      f.in_off = in_bytes;
+      in_bytes += (px * p.nch * bytes + 15) & ~uint64_t{15};
+      f.plane_off = planes;
+      planes += px * p.nch;
+      f.tok_off = toks;
+      const uint32_t groups = f.xgroups * f.ygroups;
+      toks += static_cast<uint64_t>(groups) * p.nch * 65536;
+      f.hist_off = i * 34 * 256;
+      f.sec_base = static_cast<uint32_t>(h_off.size());
+      for (uint32_t g = 0; g < groups; g++) {
+        const uint32_t gx = g % f.xgroups, gy = g / f.xgroups;
+        const uint64_t gw = std::min<uint32_t>(256, p.xsize - gx * 256), gh = std::min<uint32_t>(256, p.ysize - gy * 256);
+        h_off.push_back(words_total);
+        words_total += EnclSectionWords(gw * gh * p.nch);
+      }
+      max_groups = std::max(max_groups, groups);
+      max_samples = std::max(max_samples, px * p.nch);
+    }
+    h_off.push_back(words_total);
+    const size_t nsec = h_off.size() - 1;
+    JXLB_CHECK(nsec < (size_t{1} << 31), "too many sections");
+    CUDA_OK(enc->d_in.Alloc(in_bytes + 16));
+    CUDA_OK(enc->d_iarena.Alloc(planes + n * 34 * 256 + 16));
+    CUDA_OK(enc->d_tokens.Alloc(toks + 16));
+    std::vector<int32_t> consts(kEnclCutoffValues, kEnclCutoffValues + 33);
+    for (int k = 0; k < 34; k++) consts.push_back(static_cast<int32_t>(tree.leaf_of[k]));
+    CUDA_OK(enc->d_lconst.Upload(consts, s));
+    for (size_t i = 0; i < n; i++)
+      CUDA_OK(cudaMemcpyAsync(enc->d_in.p + lf[i].in_off, pixels[i], static_cast<size_t>(xsizes[i]) * ysizes[i] * num_channels * bytes,
+                              cudaMemcpyHostToDevice, s));
+    uint32_t* d_hist = reinterpret_cast<uint32_t*>(enc->d_iarena.p + planes);
+    CUDA_OK(cudaMemsetAsync(d_hist, 0, n * 34 * 256 * sizeof(uint32_t), s));
+    CUDA_OK(enc->d_lfs.Upload(lf, s));
+    DevLPools L{};
+    L.in = enc->d_in.p;
+    L.planes = enc->d_iarena.p;
+    L.tokens = enc->d_tokens.p;
+    L.hist = d_hist;
+    L.cutoffs = enc->d_lconst.p;
+    L.leaf_of = reinterpret_cast<const uint32_t*>(enc->d_lconst.p + 33);
+    cudaEvent_t ev[4];
+    for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+    CUDA_OK(cudaEventRecord(ev[0], s));
+    const uint32_t nf = static_cast<uint32_t>(n);
+    const uint32_t px_blocks = static_cast<uint32_t>(std::min<uint64_t>(148 * 16, (max_samples + 255) / 256));
+    k_encl_planes<<<dim3(px_blocks, nf), 256, 0, s>>>(L, enc->d_lfs.p);
+    k_encl_tokens<<<dim3(px_blocks, nf), 256, 0, s>>>(L, enc->d_lfs.p);
+    CUDA_OK(cudaEventRecord(ev[1], s));
+    std::vector<uint32_t> hist(n * 34 * 256);
+    CUDA_OK(cudaMemcpyAsync(hist.data(), d_hist, hist.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    // ---- host: the global section of every frame and the encoder tables of its code
+    std::vector<BitWriter> globals(n);
+    std::vector<uint32_t> all_fs;
+    std::vector<uint16_t> all_rev;
+    for (size_t i = 0; i < n; i++) {
+      EncCode code;
+      WriteEnclGlobal(globals[i], ps[i], tree, hist.data() + i * 34 * 256, &code);
+      lf[i].code_off[0] = all_fs.size();
+      lf[i].code_off[1] = all_rev.size();
+      const std::vector<uint32_t> fsv = code.Fs();
+      all_fs.insert(all_fs.end(), fsv.begin(), fsv.end());
+      all_rev.insert(all_rev.end(), code.reverse.begin(), code.reverse.end());
+    }
+    CUDA_OK(enc->d_fs.Upload(all_fs, s));
+    CUDA_OK(enc->d_rev.Upload(all_rev, s));
+    CUDA_OK(enc->d_lfs.Upload(lf, s));
+    CUDA_OK(enc->d_off.Upload(h_off, s));
+    CUDA_OK(enc->d_bits.Alloc(nsec + 1));
+    CUDA_OK(enc->d_words.Alloc(words_total + 16));
+    CUDA_OK(cudaMemsetAsync(enc->d_words.p, 0, (words_total + 16) * sizeof(uint32_t), s));
+    CUDA_OK(cudaEventRecord(ev[2], s));
+    k_encl_emit<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(L, enc->d_lfs.p, enc->d_fs.p, enc->d_rev.p, enc->d_words.p,
+                                                                enc->d_off.p, enc->d_bits.p);
+    CUDA_OK(cudaEventRecord(ev[3], s));
+    std::vector<uint64_t> h_bits(nsec);
+    if (words_total + 16 > enc->h_words_cap) {
+      if (enc->h_words) cudaFreeHost(enc->h_words);
+      enc->h_words = nullptr;
+      enc->h_words_cap = 0;
+      const size_t cap = words_total + 16 + words_total / 4;
+      CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&enc->h_words), cap * sizeof(uint32_t), cudaHostAllocDefault));
+      enc->h_words_cap = cap;
+    }
+    CUDA_OK(cudaMemcpyAsync(h_bits.data(), enc->d_bits.p, nsec * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(enc->h_words, enc->d_words.p, (words_total + 16) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaGetLastError());
+    float ms = 0;
+    for (int k = 0; k < 3; k++) {
+      cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+      enc->phase_ms[k] = ms;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    enc->outputs.assign(n, std::vector<uint8_t>());
+    for (size_t i = 0; i < n; i++) {
+      std::vector<EncSection> groups;
+      for (uint32_t g = 0; g < lf[i].xgroups * lf[i].ygroups; g++) {
+        const uint64_t sec = lf[i].sec_base + g, end = h_off[sec + 1] * 32;
+        groups.push_back({enc->h_words, h_bits[sec], end - h_bits[sec]});
+      }
+      enc->outputs[i] = AssembleEncl(ps[i], globals[i], groups);
     }
   } catch (const std::exception& e) {
     enc->error = e.what();

@@ -336,6 +336,8 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
 // ---------------------------------------------------------------- encoder
 #include "../../jpegxl-rs_b200/csrc/host/jxlb_enc_host.h"
 #include "../../jpegxl-rs_b200/csrc/kernels/jxlb_enc_dev.h"
+#include "../../jpegxl-rs_b200/csrc/host/jxlb_encl_host.h"
+#include "../../jpegxl-rs_b200/csrc/kernels/jxlb_encl_dev.h"
 
 extern "C" {
 
@@ -491,6 +493,66 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
       acg.push_back({ac_words[g].data(), first, end - first});
     }
     const std::vector<uint8_t> cs = AssembleCodestream(p, L, G, dcg, acg);
+    if (cs.size() > out_cap) throw Error("output buffer too small");
+    std::memcpy(out, cs.data(), cs.size());
+    return static_cast<long>(cs.size());
+  } catch (const std::exception& e) {
+    std::snprintf(err, errlen, "%s", e.what());
+    return -1;
+  }
+}
+
+// Lossless (Modular) encode of one image with the device functions of kernels/jxlb_encl_dev.h run on the CPU and the
+// host code of host/jxlb_encl_host.h, in the order of JxlB200EncoderEncodeLosslessBatch; returns the size or -1.
+long jxlb_emul_encode_lossless(const void* pixels, uint32_t xsize, uint32_t ysize, uint32_t num_channels, uint32_t bits,
+                               uint8_t* out, size_t out_cap, char* err, size_t errlen) {
+  try {
+    JXLB_CHECK(num_channels >= 1 && num_channels <= 4 && (bits == 8 || bits == 16) && xsize > 0 && ysize > 0, "bad arguments");
+    const EnclTree tree = BuildEnclTree();
+    EnclParams p;
+    p.xsize = xsize;
+    p.ysize = ysize;
+    p.nch = num_channels;
+    p.bits = bits;
+    DevLFrame f{};
+    f.xsize = xsize;
+    f.ysize = ysize;
+    f.xgroups = p.XGroups();
+    f.ygroups = p.YGroups();
+    f.nch = num_channels;
+    f.bytes = bits / 8;
+    const uint64_t px = static_cast<uint64_t>(xsize) * ysize;
+    const uint32_t groups = f.xgroups * f.ygroups;
+    std::vector<int32_t> planes(px * num_channels);
+    std::vector<uint2> tokens(static_cast<size_t>(groups) * num_channels * 65536);
+    std::vector<uint32_t> hist(34 * 256, 0);
+    std::vector<int32_t> cutoffs(kEnclCutoffValues, kEnclCutoffValues + 33);
+    DevLPools L{};
+    L.in = static_cast<const uint8_t*>(pixels);
+    L.planes = planes.data();
+    L.tokens = tokens.data();
+    L.hist = hist.data();
+    L.cutoffs = cutoffs.data();
+    L.leaf_of = tree.leaf_of;
+    for (uint64_t i = 0; i < px; i++) DevEnclPlanes(L, f, i);
+    for (uint64_t i = 0; i < px * num_channels; i++) DevEnclToken(L, f, i);
+    BitWriter global;
+    EncCode code;
+    WriteEnclGlobal(global, p, tree, hist.data(), &code);
+    const std::vector<uint32_t> fs = code.Fs();
+    const DevEncCode dcode{fs.data(), code.reverse.data()};
+    std::vector<std::vector<uint32_t>> words(groups);
+    std::vector<EncSection> secs;
+    for (uint32_t g = 0; g < groups; g++) {
+      const uint32_t gx = g % f.xgroups, gy = g / f.xgroups;
+      const uint64_t gw = std::min<uint32_t>(256, xsize - gx * 256), gh = std::min<uint32_t>(256, ysize - gy * 256);
+      const size_t cap = EnclSectionWords(gw * gh * num_channels);
+      words[g].assign(cap + 1, 0);
+      const uint64_t end = cap * 32;
+      const uint64_t first = DevEnclEmitGroup(L, f, g, dcode, words[g].data(), end, !p.GlobalOnly());
+      secs.push_back({words[g].data(), first, end - first});
+    }
+    const std::vector<uint8_t> cs = AssembleEncl(p, global, secs);
     if (cs.size() > out_cap) throw Error("output buffer too small");
     std::memcpy(out, cs.data(), cs.size());
     return static_cast<long>(cs.size());

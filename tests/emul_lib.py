@@ -76,3 +76,22 @@ def encode(rgb, distance=1.0, strategy_mode=2, gab=True, epf_iters=2, dc_smoothi
     if n < 0:
         raise EmulError(err.value.decode())
     return out[:n].tobytes()
+
+
+def encode_lossless(img) -> bytes:
+    """(H, W, C) uint8 / uint16 samples (C = 1 grey, 2 grey + alpha, 3 RGB, 4 RGBA) -> lossless codestream, the lossless
+    encoder's device functions run on the CPU."""
+    img = np.ascontiguousarray(img)
+    assert img.dtype in (np.uint8, np.uint16) and img.ndim == 3
+    h, w, c = img.shape
+    cap = img.nbytes * 2 + (1 << 20)
+    out = np.zeros(cap, np.uint8)
+    err = ctypes.create_string_buffer(512)
+    L = lib()
+    L.jxlb_emul_encode_lossless.restype = ctypes.c_long
+    n = L.jxlb_emul_encode_lossless(img.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(w), ctypes.c_uint32(h), ctypes.c_uint32(c),
+                                    ctypes.c_uint32(8 * img.dtype.itemsize), out.ctypes.data_as(ctypes.c_void_p),
+                                    ctypes.c_size_t(cap), err, ctypes.c_size_t(512))
+    if n < 0:
+        raise EmulError(err.value.decode())
+    return out[:n].tobytes()

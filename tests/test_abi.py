@@ -107,8 +107,8 @@ def test_encoder_mirror_reports_the_reference_error_variants(pkg):
     img = np.zeros((8, 8, 3), np.uint8)
     with pytest.raises(pkg.EncodeError, match="ApiUsage"):  # lossless needs uses_original_profile (encode.cc:1476-1484)
         pkg.encoder_builder().lossless(True).build().encode(img)
-    with pytest.raises(pkg.EncodeError, match="NotSupported"):
-        pkg.encoder_builder().lossless(True).uses_original_profile(True).build().encode(img)
+    with pytest.raises(pkg.EncodeError, match="NotSupported"):  # lossless takes integer samples
+        pkg.encoder_builder().lossless(True).uses_original_profile(True).build().encode(np.zeros((8, 8, 3), np.float32))
     with pytest.raises(pkg.EncodeError, match="NotSupported"):
         pkg.encoder_builder().build().encode(np.zeros((8, 8, 3), np.uint16))
     with pytest.raises(pkg.EncodeError, match="NotSupported"):
@@ -119,6 +119,8 @@ def test_encoder_mirror_reports_the_reference_error_variants(pkg):
     if not torch.cuda.is_available():
         with pytest.raises(pkg.EncodeError, match="GenericError.*no usable CUDA device"):
             pkg.encoder_builder().build().encode(img)
+        with pytest.raises(pkg.EncodeError, match="GenericError.*no usable CUDA device"):  # the lossless path: no CPU fallback either
+            pkg.encoder_builder().lossless(True).uses_original_profile(True).build().encode(img)
 
 
 def test_thread_runner_symbols_behave(pkg):
