@@ -42,6 +42,14 @@ struct BatchPlan {
   std::vector<BasicInfo> info;
   std::vector<uint32_t> warp_chans, warp_dims_off, warp_dims;
   uint32_t num_coop = 0;  // streams [0, num_coop) go one per warp (k_modular_decode_coop), the rest in lock-step bundles
+  // Streams [num_early, size) are chained behind AC coefficient streams (DevStream::chain_slot): they are decoded by a
+  // second Modular launch after the AC decode kernel, one per warp or in lock-step bundles like the early ones
+  // (late_coop of them one per warp); the group programs and frame levels of VarDCT frames (the extra channels' copies
+  // and inverse transforms) run after that launch.
+  uint32_t num_early = 0, late_coop = 0, chain_slots = 0;
+  uint32_t early_warps = 0;  // lock-step bundles of the early streams (warp_chans / warp_dims index of the first late bundle)
+  std::vector<DevProgram> late_group_programs;
+  std::vector<std::vector<DevProgram>> late_levels;
   bool narrow = true;  // every frame promises that 16-bit buffers suffice -> 32-bit predictor math
   // VarDCT frames
   std::vector<DevVFrame> vframes;
@@ -106,37 +114,50 @@ inline void BundleStreams(BatchPlan* b) {
       w = p.w;
       h = p.h;
     }
-    return std::make_tuple(coop_on && CoopEligible(*b, s) ? 1u : 0u, n, w, h);
+    // early streams first, then the ones chained behind AC coefficient streams; in each part the one-per-warp streams first
+    return std::make_tuple(s.chain_slot == 0 ? 1u : 0u, coop_on && CoopEligible(*b, s) ? 1u : 0u, n, w, h);
   };
   std::stable_sort(b->streams.begin(), b->streams.end(),
                    [&](const DevStream& x, const DevStream& y) { return key(x) > key(y); });
-  b->num_coop = 0;
-  while (b->num_coop < b->streams.size() && std::get<0>(key(b->streams[b->num_coop])) != 0) b->num_coop++;
-  const size_t c0 = b->num_coop;
-  const size_t num_warps = (b->streams.size() - c0 + 31) / 32;
-  b->warp_chans.assign(num_warps, 0);
-  b->warp_dims_off.assign(num_warps, 0);
-  b->warp_dims.clear();
-  for (size_t wi = 0; wi < num_warps; wi++) {
-    uint32_t nmax = 0;
-    const size_t s0 = c0 + wi * 32, s1 = std::min(b->streams.size(), s0 + 32);
-    for (size_t s = s0; s < s1; s++) nmax = std::max(nmax, b->streams[s].chan_end - b->streams[s].chan_begin);
-    b->warp_chans[wi] = nmax;
-    b->warp_dims_off[wi] = b->warp_dims.size();
-    for (uint32_t k = 0; k < nmax; k++) {
-      uint32_t mw = 0, mh = 0;
-      for (size_t s = s0; s < s1; s++) {
-        const DevStream& st = b->streams[s];
-        if (k >= st.chan_end - st.chan_begin) continue;
-        const DevPlane& p = b->planes[b->chans[st.chan_begin + k].plane];
-        if (p.w == 0 || p.h == 0) continue;
-        mw = std::max(mw, p.w);
-        mh = std::max(mh, p.h);
-      }
-      b->warp_dims.push_back(mw);
-      b->warp_dims.push_back(mh);
+  b->num_coop = b->num_early = b->late_coop = 0;
+  for (const DevStream& s : b->streams) {
+    const auto k = key(s);
+    if (std::get<0>(k) != 0) {
+      b->num_early++;
+      if (std::get<1>(k) != 0) b->num_coop++;
+    } else if (std::get<1>(k) != 0) {
+      b->late_coop++;
     }
   }
+  b->warp_chans.clear();
+  b->warp_dims_off.clear();
+  b->warp_dims.clear();
+  // lock-step bundles of 32 streams: [num_coop, num_early), then [num_early + late_coop, size)
+  auto bundle = [&](size_t first, size_t last) {
+    for (size_t s0 = first; s0 < last; s0 += 32) {
+      const size_t s1 = std::min(last, s0 + 32);
+      uint32_t nmax = 0;
+      for (size_t s = s0; s < s1; s++) nmax = std::max(nmax, b->streams[s].chan_end - b->streams[s].chan_begin);
+      b->warp_chans.push_back(nmax);
+      b->warp_dims_off.push_back(b->warp_dims.size());
+      for (uint32_t k = 0; k < nmax; k++) {
+        uint32_t mw = 0, mh = 0;
+        for (size_t s = s0; s < s1; s++) {
+          const DevStream& st = b->streams[s];
+          if (k >= st.chan_end - st.chan_begin) continue;
+          const DevPlane& p = b->planes[b->chans[st.chan_begin + k].plane];
+          if (p.w == 0 || p.h == 0) continue;
+          mw = std::max(mw, p.w);
+          mh = std::max(mh, p.h);
+        }
+        b->warp_dims.push_back(mw);
+        b->warp_dims.push_back(mh);
+      }
+    }
+  };
+  bundle(b->num_coop, b->num_early);
+  b->early_warps = b->warp_chans.size();
+  bundle(b->num_early + b->late_coop, b->streams.size());
 }
 
 inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, BatchPlan* b, int64_t ext_base = -1) {
@@ -175,7 +196,8 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
     b->chans.push_back(c);
   }
   for (DevStream s : f.streams) {
-    s.bit_pos += byte_base * 8;
+    if (s.chain_slot == 0) s.bit_pos += byte_base * 8;
+    if (s.chain_slot != 0) s.chain_slot += b->chain_slots;
     s.bit_end += byte_base * 8;
     s.code += codes0;
     s.chan_begin += chans0;
@@ -194,17 +216,26 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
     if (o.kind == kOpPalette) o.pad += planes0;
     b->ops.push_back(o);
   }
-  for (DevProgram p : f.group_programs) {
+  for (size_t k = 0; k < f.group_programs.size(); k++) {
+    DevProgram p = f.group_programs[k];
     p.op_begin += ops0;
     p.op_end += ops0;
-    b->group_programs.push_back(p);
+    (k >= f.late_programs0 ? b->late_group_programs : b->group_programs).push_back(p);
   }
-  if (b->levels.size() < f.frame_levels.size()) b->levels.resize(f.frame_levels.size());
-  for (size_t k = 0; k < f.frame_levels.size(); k++) {
-    DevProgram p = f.frame_levels[k];
-    p.op_begin += ops0;
-    p.op_end += ops0;
-    b->levels[k].push_back(p);
+  {
+    const size_t early = std::min(f.frame_levels.size(), f.late_levels0);
+    if (b->levels.size() < early) b->levels.resize(early);
+    if (b->late_levels.size() < f.frame_levels.size() - early) b->late_levels.resize(f.frame_levels.size() - early);
+    for (size_t k = 0; k < f.frame_levels.size(); k++) {
+      DevProgram p = f.frame_levels[k];
+      p.op_begin += ops0;
+      p.op_end += ops0;
+      if (k < early) {
+        b->levels[k].push_back(p);
+      } else {
+        b->late_levels[k - early].push_back(p);
+      }
+    }
   }
   if (f.is_vardct) {
     const VarDCTPlan& v = f.v;
@@ -253,6 +284,7 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
       vf.ctx_map_off[p] += cpool0;
     }
     vf.out_off = b->out_size;
+    if (vf.alpha_plane != kNoPlane) vf.alpha_plane += planes0;
     if (vf.upsampling > 1) {
       for (int c = 0; c < 3; c++) vf.up_pix[c] += b->farena_size;
       vf.up_kernel += fpool0;
@@ -272,6 +304,7 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
       b->ref_frames.push_back(r);
     }
     for (DevAcStream s : v.ac_streams) {
+      if (s.chain_slot != 0) s.chain_slot += b->chain_slots;
       s.bit_pos += byte_base * 8;
       s.bit_end += byte_base * 8;
       s.frame = b->vframes.size();
@@ -297,6 +330,7 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
   b->wp_slots += f.wp_slots;
   b->wp_width = std::max(b->wp_width, f.wp_width);
   b->lz77_slots += f.lz77_slots;
+  b->chain_slots += f.chain_slots;
   b->max_frame_pixels = std::max<uint32_t>(b->max_frame_pixels, f.pixels);
   b->total_pixels += f.pixels;
   if (!(f.meta.modular_16_bit_buffer_sufficient && f.meta.bit_depth.bits <= 16 && !f.meta.bit_depth.floating_point))

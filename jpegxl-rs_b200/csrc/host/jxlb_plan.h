@@ -165,6 +165,10 @@ struct FramePlan {
   std::vector<DevOp> ops;
   std::vector<DevProgram> group_programs;
   std::vector<DevProgram> frame_levels;  // global transforms: one op per level, run after the group programs
+  uint32_t chain_slots = 0;              // positions the AC decode kernel hands to chained Modular streams
+  // group programs / frame levels from these indices on belong to the extra channels of the VarDCT frame: they run
+  // after the second Modular launch (BatchPlan::late_*)
+  size_t late_programs0 = static_cast<size_t>(-1), late_levels0 = static_cast<size_t>(-1);
   DevFrameOut out;
   uint64_t arena_size = 0;  // int32 elements
   uint32_t wp_slots = 0, wp_width = 0, lz77_slots = 0;
@@ -880,6 +884,61 @@ class FramePlanner {
     if (tree.lz77) st.lz77_slot = p_->lz77_slots++;
     p_->streams.push_back(st);
     return header;
+  }
+
+  // A stream whose position only the device knows (DevStream::chain_slot): the extra channels of one AC group of a
+  // VarDCT frame, which follow the group's coefficients bit by bit (lib/jxl/dec_frame.cc:478-560). The device parses the
+  // GroupHeader itself (the first channel's `preamble`) and refuses the stream unless it selects the global tree without
+  // transforms -- what libjxl's encoder writes for such groups.
+  void PlanChainedStream(const HImage& image, uint32_t stream_id, const HostTree& global, uint64_t bit_end, uint32_t chain_slot) {
+    JXLB_CHECK(global.valid, "no global tree available");
+    JXLB_CHECK(!global.lz77, "unsupported: LZ77 in the extra-channel streams of a VarDCT frame");
+    DevStream st{};
+    st.bit_pos = 0;
+    st.bit_end = bit_end;
+    st.chain_slot = chain_slot;
+    st.code = global.code;
+    st.stream_id = stream_id;
+    st.chan_begin = p_->chans.size();
+    WPHeader().Pack(st.wp_params);
+    st.num_props = global.num_props;
+    st.lz77_slot = 0xFFFFFFFFu;
+    uint32_t max_w = 0;
+    bool first = true;
+    for (size_t i = 0; i < image.ch.size(); i++) {
+      const HChan& c = image.ch[i];
+      if (!c.w || !c.h) continue;
+      DevChannel dc{};
+      dc.plane = c.plane;
+      dc.prop0 = i;
+      dc.ref_off = p_->refs.size();
+      const int want = (static_cast<int>(global.num_props) - 16) / 4;
+      for (int j = static_cast<int>(i) - 1; j >= 0 && static_cast<int>(dc.ref_count) < want; j--) {
+        const HChan& r = image.ch[j];
+        if (r.w != c.w || r.h != c.h || r.hshift != c.hshift || r.vshift != c.vshift) continue;
+        p_->refs.push_back(r.plane);
+        dc.ref_count++;
+      }
+      bool ch_wp = false;
+      dc.tree_off = PruneTree(*global.nodes, static_cast<int32_t>(i), static_cast<int32_t>(stream_id), &ch_wp);
+      dc.uses_wp = ch_wp;
+      if (ch_wp) st.uses_wp = 1;
+      if (ch_wp) TryWpLut(&dc, dc.ref_count != 0);
+      if (!ch_wp && !NoNwLut()) TryNwLut(&dc);
+      BuildCoopLut(&dc);
+      if (first) {
+        dc.preamble = 1;  // (count_bits = 0: no channel of variable width)
+        first = false;
+      }
+      p_->chans.push_back(dc);
+      max_w = std::max<uint32_t>(max_w, c.w);
+      st.dist_multiplier = std::max<uint32_t>(st.dist_multiplier, c.w);
+    }
+    st.chan_end = p_->chans.size();
+    JXLB_CHECK(st.chan_end > st.chan_begin, "internal: chained stream without channels");
+    st.max_w = max_w;
+    p_->wp_width = std::max(p_->wp_width, max_w);
+    p_->streams.push_back(st);
   }
 
  private:

@@ -35,9 +35,21 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
                             const ImageMetadata& meta, const Toc& toc, size_t base, const PixelFormat& fmt, FramePlan* plan,
                             ProbeCtx* pc = nullptr, const RefSlot* refs = nullptr) {
   JXLB_CHECK(fh.Is444(), "unsupported: chroma-subsampled VarDCT frame");
-  JXLB_CHECK(meta.extra.empty(), "unsupported: VarDCT frame with extra channels");
   JXLB_CHECK(fh.passes.num_passes <= kMaxPasses, "too many passes");
   const size_t num_passes = fh.passes.num_passes;
+  // Extra channels (alpha) of a VarDCT frame are a Modular image of their own inside the frame's sections
+  // (lib/jxl/dec_frame.cc:266-365, :478-560; lib/jxl/dec_modular.cc:188-395): the global stream in DC global, then one
+  // stream per AC group behind the group's coefficients for the channels larger than a group.
+  const size_t nb_extra = meta.extra.size();
+  if (nb_extra != 0) {
+    plan->late_programs0 = plan->group_programs.size();
+    plan->late_levels0 = plan->frame_levels.size();
+    JXLB_CHECK(num_passes == 1, "unsupported: multi-pass VarDCT frame with extra channels");
+    JXLB_CHECK(fh.upsampling == 1, "unsupported: upsampled VarDCT frame with extra channels");
+    JXLB_CHECK(!(fh.flags & kFlagPatches), "unsupported: patches in a VarDCT frame with extra channels");
+    for (const auto& bl : fh.ec_blending) JXLB_CHECK(bl.mode == kReplace, "unsupported: blending");
+    for (const auto& e : meta.extra) JXLB_CHECK(e.dim_shift == 0, "unsupported: subsampled extra channel");
+  }
   // A frame with one group and one pass has a single section in which DC global, the DC group, AC global and the AC
   // group follow each other bit by bit (lib/jxl/dec_frame.cc:597-677): `whole` walks it, and the positions that only
   // the device can know (the end of the DC / AC-metadata chain) come from the probe rounds.
@@ -62,6 +74,8 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   float dc_quant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256};
   HostBlockCtx bctx;
   HostTree global_tree;
+  HImage full;  // the extra channels
+  GroupHeader global_header;
   {
     BitReader r = section(0, &bb);
     if (fh.flags & kFlagPatches) {
@@ -153,8 +167,25 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
     vf.cfl_dc_x = vf.base_x + ytox_dc * vf.color_scale;
     vf.cfl_dc_b = vf.base_b + ytob_dc * vf.color_scale;
     if (r.ReadBool()) {
-      const size_t limit = std::min<size_t>(size_t{1} << 22, 1024 + dim.xsize * dim.ysize * 3 / 16);
+      const size_t limit = std::min<size_t>(size_t{1} << 22, 1024 + dim.xsize * dim.ysize * std::max<size_t>(3, nb_extra) / 16);
       global_tree = planner.ReadTreeAndCode(r, limit);
+    }
+    if (nb_extra != 0) {  // the global Modular stream of the extra channels (ModularFrameDecoder::DecodeGlobalInfo)
+      full.bitdepth = meta.bit_depth.bits;
+      for (size_t c = 0; c < nb_extra; c++) {
+        HChan ch;
+        ch.w = dim.xsize;
+        ch.h = dim.ysize;
+        ch.plane = planner.NewPlane(ch.w, ch.h);
+        full.ch.push_back(ch);
+      }
+      const size_t before = plan->streams.size();
+      global_header = planner.PlanStream(r, bb, full, 0, dim.group_dim, global_tree);
+      if (single && plan->streams.size() > before) {  // the DC group starts where the device stops reading this stream
+        const ProbeResult& res = planner.DeviceResult(pc, plan->streams.size() - 1, {});
+        JXLB_CHECK(res.end_bit >= bb && res.end_bit <= bb + r.Size() * 8, "global Modular stream: read past end of section");
+        r.SeekTo(res.end_bit - bb);
+      }
     }
     r.CheckInBounds();
     whole = r;
@@ -339,7 +370,79 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
       s.tok_cap = std::min<uint64_t>(3 * 65536 * 2, 2 * static_cast<uint64_t>(toc.logical_size[idx]) + 512);
       s.tok_off = v.tok_size;
       v.tok_size += s.tok_cap;
+      // the extra channels of this group (ModularStreamId::ModularAC): channels larger than a group, shift 0 .. 2
+      if (nb_extra != 0) {
+        HImage gi;
+        gi.bitdepth = full.bitdepth;
+        size_t c = full.nb_meta;
+        for (; c < full.ch.size(); c++)
+          if (static_cast<size_t>(full.ch[c].w) > dim.group_dim || static_cast<size_t>(full.ch[c].h) > dim.group_dim) break;
+        struct Dest { size_t c; int x, y; };
+        std::vector<Dest> dests;
+        const size_t gx = g % dim.xsize_groups, gy = g / dim.xsize_groups;
+        const size_t x0 = gx * dim.group_dim, y0 = gy * dim.group_dim;
+        for (; c < full.ch.size(); c++) {
+          const HChan& fc = full.ch[c];
+          const int shift = std::min(fc.hshift, fc.vshift);
+          JXLB_CHECK(shift < 3, "unsupported: DC-group Modular stream in a VarDCT frame (squeezed extra channel)");
+          const int rx = static_cast<int>(x0 >> fc.hshift), ry = static_cast<int>(y0 >> fc.vshift);
+          int rw = static_cast<int>(dim.group_dim >> fc.hshift), rh = static_cast<int>(dim.group_dim >> fc.vshift);
+          if (rx >= fc.w || ry >= fc.h) continue;
+          rw = std::min(rw, fc.w - rx);
+          rh = std::min(rh, fc.h - ry);
+          if (rw <= 0 || rh <= 0) continue;
+          HChan gc;
+          gc.w = rw;
+          gc.h = rh;
+          gc.hshift = fc.hshift;
+          gc.vshift = fc.vshift;
+          gc.plane = planner.NewPlane(rw, rh);
+          gi.ch.push_back(gc);
+          dests.push_back(Dest{c, rx, ry});
+        }
+        if (!gi.ch.empty()) {
+          s.chain_slot = ++plan->chain_slots;
+          planner.PlanChainedStream(gi, 1 + 3 * dim.num_dc_groups + kNumQuantKinds + dim.num_groups * p + g, global_tree,
+                                    s.bit_end, s.chain_slot);
+          DevProgram prog;  // (no transforms in such a stream: the program is the copy into the frame's planes)
+          prog.op_begin = plan->ops.size();
+          for (size_t i = 0; i < dests.size(); i++) {
+            DevOp cp{};
+            cp.kind = kOpCopy;
+            cp.a = gi.ch[i].plane;
+            cp.b = full.ch[dests[i].c].plane;
+            cp.p0 = dests[i].x;
+            cp.p1 = dests[i].y;
+            plan->ops.push_back(cp);
+          }
+          prog.op_end = plan->ops.size();
+          plan->group_programs.push_back(prog);
+        }
+      }
       v.ac_streams.push_back(s);
+    }
+  }
+  vf.alpha_plane = kNoPlane;
+  if (nb_extra != 0) {
+    // global inverse transforms of the extra channels, then the alpha plane for the output
+    std::vector<DevOp> global_ops;
+    planner.EmitInverse(full, global_header.wp, &global_ops);
+    for (const DevOp& op : global_ops) {
+      DevProgram lvl;
+      lvl.op_begin = plan->ops.size();
+      plan->ops.push_back(op);
+      lvl.op_end = plan->ops.size();
+      plan->frame_levels.push_back(lvl);
+    }
+    JXLB_CHECK(full.ch.size() == nb_extra, "modular: unexpected channel count after transforms");
+    const int alpha = meta.AlphaIndex();
+    if (alpha >= 0) {
+      const HChan& ch = full.ch[alpha];
+      const BitDepth& bd = meta.extra[alpha].bit_depth;
+      JXLB_CHECK(ch.w == static_cast<int>(dim.xsize) && ch.h == static_cast<int>(dim.ysize), "unsupported: subsampled channel");
+      JXLB_CHECK(!bd.floating_point && bd.bits < 23, "unsupported: float or wide alpha in a VarDCT frame");
+      vf.alpha_plane = ch.plane;
+      vf.alpha_factor = static_cast<float>(1.0 / ((1u << bd.bits) - 1));
     }
   }
 

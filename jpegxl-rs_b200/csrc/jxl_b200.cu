@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps) k_modular_decode_coop(DevPool
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < 64) div_s[threadIdx.x] = (1u << 24) / (threadIdx.x + 1);
   __syncthreads();
-  const uint32_t s = blockIdx.x * kCoopWarps + warp;
+  const uint32_t s = P.coop0 + blockIdx.x * kCoopWarps + warp;
   if (s >= P.stream0) return;
   int32_t* mine = coop_smem + warp * (7 * P.wp_width + 10);
   uint64_t end_pos = 0;
@@ -791,7 +791,9 @@ struct JxlB200Decoder {
   DevBuf<DevStream> d_streams;
   DevBuf<DevPlane> d_planes;
   DevBuf<DevOp> d_ops;
-  DevBuf<DevProgram> d_group_programs, d_levels;
+  DevBuf<DevProgram> d_group_programs, d_levels, d_late_group_programs, d_late_levels;
+  DevBuf<uint64_t> d_chain_pos;   // DevStream::chain_slot / DevAcStream::chain_slot
+  std::vector<size_t> late_level_off;
   DevBuf<DevFrameOut> d_frames;
   DevBuf<int32_t> d_arena, d_wp, d_ring;
   uint8_t* h_bytes = nullptr;     // pinned staging for the codestream bytes of a batch (grows, kept across batches)
@@ -969,7 +971,7 @@ static int UploadTokensLayout(JxlB200Decoder* dec) {
   return 0;
 }
 
-static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s);
+static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s, int phase, uint32_t* launches);
 
 // Uploads the pools of `b` and allocates the arenas; `dec->pools` / `dec->vpools` describe them afterwards.
 static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat& fmt, bool want_end_bits) {
@@ -1000,12 +1002,21 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     all_levels.insert(all_levels.end(), lvl.begin(), lvl.end());
   }
   CUDA_OK(dec->d_levels.Upload(all_levels, s));
+  CUDA_OK(dec->d_late_group_programs.Upload(b.late_group_programs, s));
+  std::vector<DevProgram> all_late_levels;
+  dec->late_level_off.clear();
+  for (const auto& lvl : b.late_levels) {
+    dec->late_level_off.push_back(all_late_levels.size());
+    all_late_levels.insert(all_late_levels.end(), lvl.begin(), lvl.end());
+  }
+  CUDA_OK(dec->d_late_levels.Upload(all_late_levels, s));
+  CUDA_OK(dec->d_chain_pos.Alloc(b.chain_slots + 1));
   CUDA_OK(dec->d_frames.Upload(b.frames, s));
   CUDA_OK(dec->d_warp_chans.Upload(b.warp_chans, s));
   CUDA_OK(dec->d_warp_dims_off.Upload(b.warp_dims_off, s));
   CUDA_OK(dec->d_warp_dims.Upload(b.warp_dims, s));
   CUDA_OK(dec->d_arena.Alloc(b.arena_size + 16));
-  const size_t num_warps = (b.streams.size() - b.num_coop + 31) / 32;
+  const size_t num_warps = b.warp_chans.size() + 1;  // (lock-step bundles of both launches)
   CUDA_OK(dec->d_wp.Alloc(num_warps * 10 * (b.wp_width + 2) * 32 + 16));
   CUDA_OK(dec->d_ring.Alloc(num_warps * 3 * b.wp_width * 32 + 16));
   CUDA_OK(dec->d_lz77.Alloc(static_cast<size_t>(b.lz77_slots) << 20));
@@ -1033,6 +1044,8 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
   P.end_bits = want_end_bits ? dec->d_end_bits.p : nullptr;
   P.num_streams = b.streams.size();
   P.stream0 = b.num_coop;
+  P.coop0 = 0;
+  P.chain_pos = dec->d_chain_pos.p;
   P.warp_chans = dec->d_warp_chans.p;
   P.warp_dims_off = dec->d_warp_dims_off.p;
   P.warp_dims = dec->d_warp_dims.p;
@@ -1103,6 +1116,9 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     V.ref_frames = dec->d_ref_frames.p;
     V.num_ref_frames = b.ref_frames.size();
     V.patches = dec->d_patches.p;
+    V.chain_pos = dec->d_chain_pos.p;
+    V.arena = dec->d_arena.p;
+    V.planes = dec->d_planes.p;
     V.ac_plain_ans = 1;
     for (const DevVFrame& vf : b.vframes)
       for (uint32_t p = 0; p < vf.num_passes; p++)
@@ -1169,7 +1185,8 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
     };
     if (UploadPlan(&tmp, pb, pf, true) != 0) throw Error("probe launch: " + tmp.error);
     ok(cudaMemsetAsync(tmp.d_arena.p, 0, pb.arena_size * sizeof(int32_t), tmp.stream));
-    if (LaunchModular(&tmp, pb, tmp.stream) != 0) throw Error("probe launch: " + tmp.error);
+    uint32_t probe_launches = 0;
+    if (LaunchModular(&tmp, pb, tmp.stream, 0, &probe_launches) != 0) throw Error("probe launch: " + tmp.error);
     ok(cudaGetLastError());
     ok(cudaMemcpyAsync(status.data(), tmp.d_status.p, status.size() * 4, cudaMemcpyDeviceToHost, tmp.stream));
     ok(cudaMemcpyAsync(end_bits->data(), tmp.d_end_bits.p, end_bits->size() * 8, cudaMemcpyDeviceToHost, tmp.stream));
@@ -1268,22 +1285,35 @@ size_t JxlB200DecoderImageOutBufferSize(const JxlB200Decoder* dec, size_t i) {
   return dec->plan->frame_out_size[i];
 }
 
-static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s) {
-  const DevPools& P = dec->pools;
+// phase 0: the streams whose position the host knows; phase 1 (after the AC decode kernel): the ones chained behind AC
+// coefficient streams (BatchPlan::num_early). Each phase: its one-per-warp streams, then its lock-step bundles.
+static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s, int phase, uint32_t* launches) {
+  DevPools P = dec->pools;
   const uint32_t block = 32;
-  if (b.num_coop != 0) {  // one warp per stream: the chains under libjxl's fixed trees
+  const uint32_t first = phase == 0 ? 0 : b.num_early, last = phase == 0 ? b.num_early : static_cast<uint32_t>(b.streams.size());
+  const uint32_t ncoop = phase == 0 ? b.num_coop : b.late_coop;
+  if (first == last) return 0;
+  P.coop0 = first;
+  P.stream0 = first + ncoop;
+  P.num_streams = last;
+  if (phase == 1) {  // the bundles of the late streams follow the early ones in the warp tables
+    P.warp_chans += b.early_warps;
+    P.warp_dims_off += b.early_warps;
+  }
+  if (ncoop != 0) {  // one warp per stream: the chains under libjxl's fixed trees
     const size_t coop_smem = static_cast<size_t>(7 * b.wp_width + 10) * sizeof(int32_t) * kCoopWarps;
     if (coop_smem > 200 * 1024) return 1;  // (channel widths are bounded by the group size: never)
-    const uint32_t coop_grid = (b.num_coop + kCoopWarps - 1) / kCoopWarps;
+    const uint32_t coop_grid = (ncoop + kCoopWarps - 1) / kCoopWarps;
     if (b.narrow) {
       k_modular_decode_coop<int32_t><<<coop_grid, 32 * kCoopWarps, coop_smem, s>>>(P);
     } else {
       k_modular_decode_coop<int64_t><<<coop_grid, 32 * kCoopWarps, coop_smem, s>>>(P);
     }
     CUDA_OK(cudaGetLastError());
-    if (b.num_coop == b.streams.size()) return 0;
+    (*launches)++;
   }
-  const size_t rest = b.streams.size() - b.num_coop;
+  const size_t rest = last - first - ncoop;
+  if (rest == 0) return 0;
   const size_t sparse_smem = static_cast<size_t>(7 * b.wp_width + 10) * kSparseLanes * sizeof(int32_t);
   // (JXLB200_MODULAR_DENSE=1: always the dense-lane kernel -- 32 streams per warp, rows in HBM, 6 KB of shared memory
   // per CTA instead of 58 KB: slower alone, but it leaves the SMs' shared memory to the kernels of other batches)
@@ -1301,6 +1331,7 @@ static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s
     k_modular_decode<int64_t><<<(rest + block - 1) / block, block, 0, s>>>(P);
   }
   CUDA_OK(cudaGetLastError());
+  (*launches)++;
   return 0;
 }
 
@@ -1324,8 +1355,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   const uint32_t pm = dec->phase_mask;
   if (!b.streams.empty() && (pm & (1u << kKModular))) {
     ScopedTimer t(dec, s, kKModular);
-    if (LaunchModular(dec, b, s) != 0) return 1;
-    launches += (b.num_coop != 0 ? 1u : 0u) + (b.num_coop != b.streams.size() ? 1u : 0u);
+    if (LaunchModular(dec, b, s, 0, &launches) != 0) return 1;
   }
   if (!b.group_programs.empty()) {
     ScopedTimer t(dec, s, kKGroupPrograms);
@@ -1388,6 +1418,26 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
         k_ac_decode<1><<<(nst + 31) / 32, 32, 0, s>>>(P, V);
       }
       launches++;
+    }
+    if (b.num_early != b.streams.size() || !b.late_group_programs.empty() || !b.late_levels.empty()) {
+      // the extra channels of VarDCT frames: the streams chained behind the AC coefficients, then their copies into the
+      // frame's planes and the global inverse transforms
+      {
+        ScopedTimer t(dec, s, kKModular);
+        if (LaunchModular(dec, b, s, 1, &launches) != 0) return 1;
+      }
+      if (!b.late_group_programs.empty()) {
+        ScopedTimer t(dec, s, kKGroupPrograms);
+        k_group_programs<<<b.late_group_programs.size(), 256, 0, s>>>(P, dec->d_ops.p, dec->d_late_group_programs.p);
+        launches++;
+      }
+      ScopedTimer t(dec, s, kKFrameLevels);
+      for (size_t k = 0; k < b.late_levels.size(); k++) {
+        const uint32_t tiles = std::max<uint32_t>(1, std::min<uint32_t>(1024, (b.max_frame_pixels + 1023) / 1024));
+        dim3 grid(tiles, b.late_levels[k].size());
+        k_frame_level<<<grid, 256, 0, s>>>(P, dec->d_ops.p, dec->d_late_levels.p + dec->late_level_off[k]);
+        launches++;
+      }
     }
     if (parted) {  // the per-pixel waves start when this batch's entropy kernels are through
       CUDA_OK(cudaEventRecord(dec->part_ev[1], s));

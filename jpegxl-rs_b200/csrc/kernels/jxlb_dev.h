@@ -126,6 +126,12 @@ struct DevStream {
   uint32_t max_w;                 // widest channel (sizes the WP scratch)
   uint32_t scratch_slot;          // WP scratch slot
   uint32_t lz77_slot;             // LZ77 window slot or 0xFFFFFFFF
+  // Streams that begin where an AC coefficient stream ends (the extra channels of a VarDCT frame: the Modular stream of
+  // an AC group follows the group's coefficients bit by bit, lib/jxl/dec_frame.cc:478-560): chain_slot - 1 indexes the
+  // positions the AC decode kernel leaves behind; the stream then starts with its GroupHeader (the first channel carries
+  // `preamble`) and is decoded in the second Modular launch. 0: bit_pos is final.
+  uint32_t chain_slot;
+  uint32_t pad_;
 };
 
 enum DevOpKind : uint32_t {

@@ -492,11 +492,14 @@ JXLB_HD uint32_t DevDecodeModularStreamCoop(const DevPools& P, uint32_t s, int32
                                             const uint32_t* divlut, uint64_t* end_pos) {
   const DevStream st = P.streams[s];
   const DevCode code = P.codes[st.code];
+  const bool chained = st.chain_slot != 0;  // starts (with its GroupHeader) where an AC coefficient stream ended
   DevCoopBits br;
-  br.Init(P.words, st.bit_pos, st.bit_end);
+  br.Init(P.words, chained ? P.chain_pos[st.chain_slot - 1] : st.bit_pos, st.bit_end);
   DevCoopReader reader;
   reader.Init(P, code);
-  {  // the initial ANS state (32 bits)
+  if (chained) {
+    reader.state = 0x13u << 16;  // (what the preamble of the first channel expects of a finished stream)
+  } else {  // the initial ANS state (32 bits)
     reader.state = DevFunnelR(br.w0, br.w1, br.o);
     br.Advance(32);
   }

@@ -37,10 +37,12 @@ struct DevPools {
   uint32_t* lz77;        // per slot: 1 << 20 entries
   uint32_t* status;      // per stream: 0 ok, else error bits
   uint64_t* end_bits;    // per stream: first bit after the stream (probe launches only, else null)
+  const uint64_t* chain_pos;  // DevStream::chain_slot: where the AC decode kernel stopped reading (null without such streams)
   uint32_t num_streams;
   // streams [0, stream0) are decoded one per warp by k_modular_decode_coop (jxlb_modular_coop_dev.h), the lock-step
   // kernels take [stream0, num_streams): their warp 0 starts at stream0
   uint32_t stream0;
+  uint32_t coop0;  // first stream of this launch's one-per-warp part: [coop0, stream0)
   // per warp of 32 consecutive streams: number of channel slots and, per slot, the
   // largest (width, height) among its lanes -- the warp-uniform loop bounds
   const uint32_t* warp_chans;
@@ -134,13 +136,14 @@ struct DevSymbolReader {
   uint64_t copy_pos, num_decoded;
   uint32_t* window;
 
-  JXLB_HD void Init(const DevPools& P, const DevCode& c, DevBits& br, uint32_t dist_multiplier, uint32_t* win) {
+  // read_state = false: the stream begins with a GroupHeader (a chained stream's preamble reads the state afterwards)
+  JXLB_HD void Init(const DevPools& P, const DevCode& c, DevBits& br, uint32_t dist_multiplier, uint32_t* win, bool read_state = true) {
     alias = P.alias + c.alias_off;
     cfg = P.cfg + c.cfg_off;
     prefix = P.prefix + c.prefix_off;
     log_alpha = c.log_alpha_size;
     use_prefix = c.use_prefix;
-    state = use_prefix ? (0x13u << 16) : br.Read(32);
+    state = (use_prefix || !read_state) ? (0x13u << 16) : br.Read(32);
     lz77_enabled = c.lz77_enabled;
     lz77_min_symbol = c.lz77_min_symbol;
     lz77_min_length = c.lz77_min_length;
@@ -777,9 +780,10 @@ JXLB_HD uint32_t DevDecodeModularStream(const DevPools& P, uint32_t s, const Dev
   if (lane_valid) {
     st = P.streams[s];
     code = P.codes[st.code];
-    br.Init(P.words, st.bit_pos, st.bit_end);
+    const bool chained = st.chain_slot != 0;  // starts (with its GroupHeader) where an AC coefficient stream ended
+    br.Init(P.words, chained ? P.chain_pos[st.chain_slot - 1] : st.bit_pos, st.bit_end);
     uint32_t* window = (st.lz77_slot != 0xFFFFFFFFu) ? P.lz77 + (static_cast<size_t>(st.lz77_slot) << 20) : nullptr;
-    reader.Init(P, code, br, st.dist_multiplier, window);
+    reader.Init(P, code, br, st.dist_multiplier, window, /*read_state=*/!chained);
     my_chans = st.chan_end - st.chan_begin;
   }
   // every lane of the warp reads plain ANS (no prefix codes, no LZ77): the per-symbol mode tests are compiled out

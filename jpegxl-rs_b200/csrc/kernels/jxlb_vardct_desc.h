@@ -84,6 +84,10 @@ struct DevVFrame {
   uint32_t upsampling, up_xsize, up_ysize, up_stride;
   uint32_t up_kernel;  // fpool index of kernel[4][4][5][5]
   uint32_t orient;     // undo_orientation of the output store: 1 flip x, 2 flip y, 4 transpose (stage_write.cc:271-288)
+  // alpha of a VarDCT frame with extra channels: the Modular plane (DevPlane index, kNoPlane: opaque) and its
+  // int -> float factor (lib/jxl/dec_modular.cc:534-708)
+  uint32_t alpha_plane;
+  float alpha_factor;
   uint64_t up_pix[3];  // farena index
 };
 
@@ -117,6 +121,8 @@ struct DevAcStream {
   uint32_t pass;
   uint32_t tok_cap;           // capacity in tokens
   uint64_t tok_off;           // first token (tokens index)
+  uint32_t chain_slot;        // != 0: the position behind the last coefficient goes to chain_pos[chain_slot - 1] (DevStream::chain_slot)
+  uint32_t pad_;
 };
 
 // The AC streams of one (frame, pass): what one CTA of k_ac_decode_frame decodes with the pass's alias tables, uint

@@ -53,6 +53,9 @@ struct DevVPools {
   uint32_t num_ref_frames;
   const DevPatch* patches;
   uint32_t ac_plain_ans;  // every AC coefficient code of the batch is ANS without LZ77
+  uint64_t* chain_pos;    // DevAcStream::chain_slot: the bit position behind the stream's last coefficient
+  const int32_t* arena;   // the Modular sample arena and plane table (alpha of VarDCT frames with extra channels)
+  const DevPlane* planes;
 };
 
 #if defined(__CUDACC__)
@@ -558,6 +561,7 @@ JXLB_HD uint32_t DevDecodeAcStream(const DevPools& P, const DevVPools& V, uint32
     if (br.Pos() > st.bit_end) status |= kVOverread;
     if (ntok > st.tok_cap) status |= kVTokenOverflow;
     V.ac_used[s] = ntok;
+    if (st.chain_slot != 0) V.chain_pos[st.chain_slot - 1] = br.Pos();
   }
   return status;
 #undef JXLB_AC_CTX
@@ -1720,6 +1724,12 @@ JXLB_HD void DevPatchPixel(const DevVPools& V, const DevVFrame& vf, const DevPat
 JXLB_HD void DevColorStore(const DevVPools& V, const DevVFrame& vf, float p0, float p1, float p2, uint32_t x, uint32_t y) {
   float r, g, b;
   DevColorTransform(vf, p0, p1, p2, &r, &g, &b);
+  // alpha: the frame's Modular extra channel (int -> float like DevSampleFloat), else opaque
+  float alpha = 1.0f;
+  if (vf.alpha_plane != kNoPlane && (vf.out_channels == 2 || vf.out_channels == 4)) {
+    const DevPlane pl = V.planes[vf.alpha_plane];
+    alpha = static_cast<float>(V.arena[pl.off + static_cast<size_t>(y) * pl.w + x]) * vf.alpha_factor;
+  }
   if (vf.orient != 0) {  // (rare) the store position and the dither position follow the orientation
     uint32_t fx, fy, orow, ocol;
     DevOrient(vf.orient, vf.up_xsize, vf.up_ysize, x, y, &fx, &fy, &orow, &ocol);
@@ -1727,19 +1737,20 @@ JXLB_HD void DevColorStore(const DevVPools& V, const DevVFrame& vf, float p0, fl
     const uint32_t nc = vf.out_channels, num_color = nc < 3 ? 1 : 3;
     const float col[3] = {r, g, b};
     for (uint32_t c = 0; c < nc; c++)
-      DevStoreSample(row, static_cast<size_t>(ocol) * nc + c, c < num_color ? col[c] : 1.0f, vf.out_type, vf.out_big_endian, fx, fy);
+      DevStoreSample(row, static_cast<size_t>(ocol) * nc + c, c < num_color ? col[c] : alpha, vf.out_type, vf.out_big_endian, fx, fy);
     return;
   }
   uint8_t* row = V.out + vf.out_off + vf.out_stride * y;
   const uint32_t nc = vf.out_channels;
   if (nc == 4 && vf.out_type == 2) {  // RGBA8: one aligned 32-bit store
-    reinterpret_cast<uint32_t*>(row)[x] = DevToU8(r, x, y) | (DevToU8(g, x, y) << 8) | (DevToU8(b, x, y) << 16) | 0xFF000000u;
+    const uint32_t a8 = vf.alpha_plane != kNoPlane ? DevToU8(alpha, x, y) : 255u;
+    reinterpret_cast<uint32_t*>(row)[x] = DevToU8(r, x, y) | (DevToU8(g, x, y) << 8) | (DevToU8(b, x, y) << 16) | (a8 << 24);
     return;
   }
   const uint32_t num_color = nc < 3 ? 1 : 3;
   const float col[3] = {r, g, b};
   for (uint32_t c = 0; c < nc; c++) {
-    const float v = c < num_color ? col[c] : 1.0f;
+    const float v = c < num_color ? col[c] : alpha;
     DevStoreSample(row, static_cast<size_t>(x) * nc + c, v, vf.out_type, vf.out_big_endian, x, y);
   }
 }

@@ -114,6 +114,10 @@ size_t jxlo_library_quant_table(int table, float* out, size_t cap) {
 // VarDCT stream generator (oracle/jxlo_encode.h). Returns the codestream size, or 0 on error;
 // call with out == NULL to get the size... the stream is kept until the next call on this thread.
 static thread_local std::vector<uint8_t> g_encoded;
+// The alpha plane (xsize * ysize uint8) of the NEXT jxlo_encode_vardct call on this thread (EncodeParams::alpha).
+static thread_local const uint8_t* g_next_alpha = nullptr;
+void jxlo_set_next_alpha(const uint8_t* alpha) { g_next_alpha = alpha; }
+
 size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float distance, int strategy_mode,
                           uint32_t seed, int gab, uint32_t epf_iters, int dc_smoothing, int random_side_info,
                           uint32_t num_passes, int dc_tree, char* err, size_t errlen) {
@@ -130,6 +134,8 @@ size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, fl
     p.prefix_codes = (gab & 32) != 0;    // bit 5: prefix codes instead of ANS in every stream
     p.upsampling = 1u << ((gab >> 6) & 3);  // bits 6-7: log2 of the frame upsampling
     p.orientation = 1 + ((gab >> 8) & 7);   // bits 8-10: the image's orientation - 1
+    p.alpha = g_next_alpha;
+    g_next_alpha = nullptr;
     p.epf_iters = epf_iters;
     p.dc_smoothing = dc_smoothing != 0;
     p.random_side_info = random_side_info != 0;

@@ -883,6 +883,10 @@ struct EncodeParams {
   // are the low-resolution frame, the image header declares `upsampling` times their size.
   uint32_t upsampling = 1;
   uint32_t orientation = 1;  // ImageMetadata::orientation (decoder coverage of the write stage's undo_orientation)
+  // One 8-bit alpha extra channel (xsize * ysize samples), coded losslessly in the frame's Modular sub-streams under the
+  // global tree the way libjxl places them (lib/jxl/enc_modular.cc:1258-1500, lib/jxl/dec_frame.cc:315-365, :478-560):
+  // the global stream when the channel fits one group, else one stream per AC group behind that group's coefficients.
+  const uint8_t* alpha = nullptr;
 };
 
 struct EncoderStats {
@@ -890,29 +894,33 @@ struct EncoderStats {
   size_t strategy_count[27] = {0};
 };
 
-inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize, uint32_t orientation = 1) {
+inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize, uint32_t orientation = 1, bool alpha = false) {
   w.Write(16, 0x0AFF);
   // SizeHeader
   w.Write(1, 0);  // not "small"
   WriteU32(w, ysize, BitsOffset(9, 1), BitsOffset(13, 1), BitsOffset(18, 1), BitsOffset(30, 1));
   w.Write(3, 0);  // no fixed aspect ratio
   WriteU32(w, xsize, BitsOffset(9, 1), BitsOffset(13, 1), BitsOffset(18, 1), BitsOffset(30, 1));
-  if (orientation == 1) {
+  if (orientation == 1 && !alpha) {
     w.Write(1, 1);  // ImageMetadata all_default: 8-bit sRGB, XYB encoded, no extra channels
-  } else {          // the same image with extra_fields for the orientation (lib/jxl/image_metadata.cc:258-330)
+  } else {          // the same image with an orientation (extra_fields) and / or an alpha channel (lib/jxl/image_metadata.cc:258-330)
     w.Write(1, 0);  // not all_default
-    w.Write(1, 1);  // extra_fields
-    w.Write(3, orientation - 1);
-    w.Write(1, 0);  // no intrinsic size
-    w.Write(1, 0);  // no preview
-    w.Write(1, 0);  // no animation
+    const bool extra_fields = orientation != 1;
+    w.Write(1, extra_fields ? 1 : 0);
+    if (extra_fields) {
+      w.Write(3, orientation - 1);
+      w.Write(1, 0);  // no intrinsic size
+      w.Write(1, 0);  // no preview
+      w.Write(1, 0);  // no animation
+    }
     w.Write(1, 0);  // integer samples
     WriteU32(w, 8, Val(8), Val(10), Val(12), BitsOffset(6, 1));
     w.Write(1, 1);  // modular_16_bit_buffer_sufficient
-    WriteU32(w, 0, Val(0), Val(1), BitsOffset(4, 2), BitsOffset(12, 1));  // no extra channels
+    WriteU32(w, alpha ? 1 : 0, Val(0), Val(1), BitsOffset(4, 2), BitsOffset(12, 1));
+    if (alpha) w.Write(1, 1);  // ExtraChannelInfo all_default: 8-bit alpha
     w.Write(1, 1);  // xyb_encoded
     w.Write(1, 1);  // ColorEncoding all_default (sRGB)
-    w.Write(1, 1);  // ToneMapping all_default
+    if (extra_fields) w.Write(1, 1);  // ToneMapping all_default
     WriteU64(w, 0);  // extensions
   }
   w.Write(1, 1);  // CustomTransformData all_default
@@ -925,6 +933,7 @@ inline void WriteFrameHeader(BitWriter& w, const EncodeParams& p) {
   w.Write(1, 0);  // VarDCT
   WriteU64(w, p.dc_smoothing ? uint64_t{0} : uint64_t{kFlagSkipAdaptiveDCSmoothing});
   WriteU32(w, p.upsampling, Val(1), Val(2), Val(4), Val(8));  // upsampling
+  if (p.alpha) WriteU32(w, p.upsampling, Val(1), Val(2), Val(4), Val(8));  // of the extra channel
   w.Write(3, p.x_qm_scale);
   w.Write(3, p.b_qm_scale);
   WriteU32(w, p.num_passes, Val(1), Val(2), Val(3), BitsOffset(3, 4));
@@ -934,6 +943,7 @@ inline void WriteFrameHeader(BitWriter& w, const EncodeParams& p) {
   }
   w.Write(1, 0);  // no custom size or origin
   WriteU32(w, 0, Val(0), Val(1), Val(2), BitsOffset(2, 3));  // blend mode kReplace
+  if (p.alpha) WriteU32(w, 0, Val(0), Val(1), Val(2), BitsOffset(2, 3));  // of the extra channel
   w.Write(1, 1);  // is_last
   WriteU32(w, 0, Val(0), Bits(4), BitsOffset(5, 16), BitsOffset(10, 48));  // name
   // LoopFilter
@@ -2069,6 +2079,34 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
     meta_chans[g] = std::move(meta);
     meta_count[g] = count;
   }
+  // The alpha channel: one Modular channel of the frame's size. It travels in the global stream when it fits one group,
+  // else in the per-group streams that follow the coefficients of each AC group (single pass: shift bracket 0 .. 2).
+  std::vector<Channel> alpha_global;                // what the global stream's header is followed by
+  std::vector<std::vector<Channel>> alpha_group(num_groups);
+  std::vector<Token> alpha_global_toks;
+  std::vector<std::vector<Token>> alpha_group_toks(num_groups);
+  if (p.alpha) {
+    JXLO_CHECK(num_passes == 1 && p.upsampling == 1, "alpha: single-pass frames without upsampling only");
+    if (xsize <= dim.group_dim && ysize <= dim.group_dim) {
+      Channel a(xsize, ysize);
+      for (uint32_t y = 0; y < ysize; y++)
+        for (uint32_t x = 0; x < xsize; x++) a.Row(y)[x] = p.alpha[static_cast<size_t>(y) * xsize + x];
+      alpha_global.push_back(std::move(a));
+      TokenizeModularStream(gtree.tree, 0, alpha_global, &alpha_global_toks);
+    } else {
+      alpha_global.push_back(Channel(0, 0));  // the header is written, no channel is small enough for the global stream
+      for (size_t g = 0; g < num_groups; g++) {
+        const size_t gx = g % dim.xsize_groups, gy = g / dim.xsize_groups;
+        const size_t x0 = gx * dim.group_dim, y0 = gy * dim.group_dim;
+        const size_t w = std::min<size_t>(dim.group_dim, xsize - x0), h = std::min<size_t>(dim.group_dim, ysize - y0);
+        Channel a(w, h);
+        for (size_t y = 0; y < h; y++)
+          for (size_t x = 0; x < w; x++) a.Row(y)[x] = p.alpha[(y0 + y) * xsize + x0 + x];
+        alpha_group[g].push_back(std::move(a));
+        TokenizeModularStream(gtree.tree, StreamModularAC(dim, g, 0), alpha_group[g], &alpha_group_toks[g]);
+      }
+    }
+  }
   EntropyOptions eopt;
   eopt.use_prefix = p.prefix_codes;
   EntropyEncoder tree_code(6, {0, 1, 2, 3, 4, 5}, eopt);
@@ -2080,6 +2118,8 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
     modular_code.Count(dc_toks[g]);
     modular_code.Count(meta_toks[g]);
   }
+  modular_code.Count(alpha_global_toks);
+  for (size_t g = 0; g < num_groups; g++) modular_code.Count(alpha_group_toks[g]);
   BitWriter dc_global;
   {
     dc_global.Write(1, 1);  // default DC quantisation
@@ -2091,6 +2131,7 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
     tree_code.WriteHeader(dc_global);
     tree_code.WriteTokens(dc_global, gtree.tokens);
     modular_code.WriteHeader(dc_global);
+    WriteModularStream(dc_global, modular_code, alpha_global, alpha_global_toks);  // (nothing without extra channels)
   }
   std::vector<BitWriter> dc_groups(dim.num_dc_groups);
   for (size_t g = 0; g < dim.num_dc_groups; g++) {
@@ -2153,8 +2194,10 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   }
   std::vector<BitWriter> ac_groups(num_groups * num_passes);
   for (size_t pass = 0; pass < num_passes; pass++)
-    for (size_t g = 0; g < num_groups; g++)
+    for (size_t g = 0; g < num_groups; g++) {
       pass_codes[pass].WriteTokens(ac_groups[pass * num_groups + g], group_tokens[pass * num_groups + g]);
+      if (pass == 0) WriteModularStream(ac_groups[g], modular_code, alpha_group[g], alpha_group_toks[g]);
+    }
 
   if (num_groups == 1 && num_passes == 1) {
     BitWriter all = dc_global;
@@ -2175,7 +2218,7 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   }
 
   BitWriter out;
-  WriteImageHeaders(out, xsize * p.upsampling, ysize * p.upsampling, p.orientation);
+  WriteImageHeaders(out, xsize * p.upsampling, ysize * p.upsampling, p.orientation, p.alpha != nullptr);
   WriteFrameHeader(out, p);
   WriteToc(out, sections);
   for (const auto& s : sections) out.Append(s);

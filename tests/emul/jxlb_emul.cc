@@ -48,8 +48,10 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
     fmt.align = align;
     fmt.keep_orientation = !undo_orientation;
     // the Modular decode "kernel": every stream of `b`, one lane at a time
-    auto run_modular = [&](const BatchPlan& b, std::vector<int32_t>& arena, DevPools* pools_out, std::vector<uint64_t>* end_bits) {
-      const size_t num_warps = (b.streams.size() - b.num_coop + 31) / 32 + 1;
+    // phase 0: the streams whose position the host knows; phase 1: the ones chained behind AC coefficient streams
+    auto run_modular = [&](const BatchPlan& b, std::vector<int32_t>& arena, DevPools* pools_out, std::vector<uint64_t>* end_bits,
+                           int phase = 0, const uint64_t* chain_pos = nullptr) {
+      const size_t num_warps = b.warp_chans.size() + 1;
       std::vector<int32_t> wp(num_warps * 10 * (b.wp_width + 2) * 32 + 16, 0);
       std::vector<int32_t> ring(num_warps * 3 * b.wp_width * 32 + 16, 0);
       std::vector<int32_t> props(kDevMaxProps * 32, 0);
@@ -74,14 +76,18 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       P.wp_width = b.wp_width;
       P.lz77 = lz.data();
       P.num_streams = b.streams.size();
-      P.stream0 = b.num_coop;
+      const uint32_t first = phase == 0 ? 0 : b.num_early, last = phase == 0 ? b.num_early : static_cast<uint32_t>(b.streams.size());
+      const uint32_t ncoop = phase == 0 ? b.num_coop : b.late_coop, warp0 = phase == 0 ? 0 : b.early_warps;
+      P.coop0 = first;
+      P.stream0 = first + ncoop;
+      P.chain_pos = chain_pos;
       P.warp_chans = b.warp_chans.data();
       P.warp_dims_off = b.warp_dims_off.data();
       P.warp_dims = b.warp_dims.data();
-      if (end_bits) end_bits->assign(b.streams.size(), 0);
+      if (end_bits && phase == 0) end_bits->assign(b.streams.size(), 0);
       // k_modular_decode_coop: one warp per stream; the host runs its single "lane" (jxlb_modular_coop_dev.h)
       std::vector<int32_t> coop_rows(7 * b.wp_width + 10, 0);
-      for (uint32_t s = 0; s < b.num_coop; s++) {
+      for (uint32_t s = first; s < first + ncoop; s++) {
         uint64_t end = 0;
         const uint32_t st = force_wide || !b.narrow
                                 ? DevDecodeModularStreamCoop<int64_t>(P, s, coop_rows.data(), coop_rows.data() + 2 * b.wp_width, b.wp_width, divlut, &end)
@@ -89,9 +95,9 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
         if (st != 0) throw Error("stream " + std::to_string(s) + " (one per warp) failed with status " + std::to_string(st));
         if (end_bits) (*end_bits)[s] = end;
       }
-      for (uint32_t s = b.num_coop; s < b.streams.size(); s++) {
-        // same addressing as the kernel: warp = (s - stream0) / 32, lane = (s - stream0) % 32
-        const uint32_t warp = (s - b.num_coop) / 32, lane = (s - b.num_coop) % 32;
+      for (uint32_t s = first + ncoop; s < last; s++) {
+        // same addressing as the kernel: warp = (s - stream0) / 32 (+ the early bundles in the late launch), lane = (s - stream0) % 32
+        const uint32_t warp = warp0 + (s - first - ncoop) / 32, lane = (s - first - ncoop) % 32;
         DevLaneMem m;
         m.props = props.data() + lane;
         m.props_stride = 32;
@@ -181,6 +187,10 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       V.ref_frames = b.ref_frames.data();
       V.num_ref_frames = b.ref_frames.size();
       V.patches = b.patches.data();
+      std::vector<uint64_t> chain_pos(b.chain_slots + 1, 0);
+      V.chain_pos = chain_pos.data();
+      V.arena = arena.data();
+      V.planes = b.planes.data();
       for (const DevRefFrame& rf : b.ref_frames)  // k_ref_frames
         for (uint32_t i = 0; i < rf.w * rf.h; i++) DevRefFrameSample(P, V, rf, i);
       uint32_t dcg = 0;
@@ -227,6 +237,16 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
         tokens.assign(b.tok_size + 16, 0);
         V.tokens = tokens.data();
       }
+      // the extra channels of VarDCT frames: the Modular streams chained behind the AC coefficients (second launch),
+      // their copies into the frame's planes, the global inverse transforms
+      if (b.num_early != b.streams.size()) run_modular(b, arena, nullptr, nullptr, 1, chain_pos.data());
+      for (const DevProgram& pr : b.late_group_programs)
+        for (uint32_t o = pr.op_begin; o < pr.op_end; o++)
+          for (uint32_t t = 0; t < nt; t++) DevRunOp(P, b.ops[o], t, nt);
+      for (const auto& lvl : b.late_levels)
+        for (const DevProgram& pr : lvl)
+          for (uint32_t o = pr.op_begin; o < pr.op_end; o++)
+            for (uint32_t t = 0; t < nt; t++) DevRunOp(P, b.ops[o], t, nt);
       for (uint32_t s = 0; s < 0 * b.ac_streams.size(); s++) {
         uint8_t colnz[96] = {0};
         DevAcLaneMem m;

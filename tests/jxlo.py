@@ -102,10 +102,17 @@ def decode(data: bytes, num_channels: int, data_type: int, endianness: int = 0, 
 def encode_vardct(rgb: np.ndarray, distance=1.0, strategy_mode=2, seed=1, gab=True, epf_iters=2, dc_smoothing=True,
                   random_side_info=False, num_passes=1, dc_tree=0, inverse_gaborish=True, coeff_orders=True, cfl=True,
                   adaptive_quant=True, prefix_codes=False, upsampling=1, orientation=1) -> bytes:
-    """RGB8 (H, W, 3) -> a VarDCT codestream written by the oracle's plain encoder (stream generator)."""
+    """RGB8 (H, W, 3) -> a VarDCT codestream written by the oracle's plain encoder (stream generator). (H, W, 4): the
+    fourth channel travels as a lossless 8-bit alpha extra channel in the frame's Modular sub-streams."""
     L = lib()
     rgb = np.ascontiguousarray(rgb, np.uint8)
     h, w, c = rgb.shape
+    alpha = None
+    if c == 4:
+        alpha = np.ascontiguousarray(rgb[:, :, 3])
+        rgb = np.ascontiguousarray(rgb[:, :, :3])
+        c = 3
+        L.jxlo_set_next_alpha(alpha.ctypes.data_as(ctypes.c_void_p))
     assert c == 3
     err = ctypes.create_string_buffer(512)
     gab_arg = int(bool(gab)) | (0 if inverse_gaborish else 2) | (0 if coeff_orders else 4) | (0 if cfl else 8) | (0 if adaptive_quant else 16) | (32 if prefix_codes else 0) | ({1: 0, 2: 1, 4: 2, 8: 3}[upsampling] << 6) | ((orientation - 1) << 8)

@@ -133,3 +133,28 @@ def test_orientation(pkg):
     meta, px = dec.decode(files[5])
     assert (meta.width, meta.height) == (100, 70) and meta.orientation == 6
     assert np.array_equal(np.asarray(px.data).reshape(70, 100, 3), jxlo.decode(files[5], 3, jxlo.UINT8))
+
+
+def test_alpha_channel_in_lossy_frames(pkg):
+    # VarDCT frames with an alpha extra channel on the GPU: the Modular streams chained behind the AC coefficients
+    # (second Modular launch), the global stream of a single-section frame (probe round); batch and event API
+    def rgba(h, w, y0=100, x0=200):
+        img = vc.crop(h, w, y0, x0)
+        a = (img[:, :, 0].astype(np.int32) + np.arange(w)[None, :] * 3) % 256
+        a[h // 3:h // 2, w // 4:w // 2] = 255
+        return np.dstack([img, a.astype(np.uint8)])
+    cases = [rgba(300, 520), rgba(200, 256), rgba(40, 50), rgba(257, 263, 700, 100), rgba(1000, 1500, 0, 0)]
+    files = [jxlo.encode_vardct(c, strategy_mode=2) for c in cases]
+    files.append(jxlo.encode_vardct(cases[0], strategy_mode=1, random_side_info=True, seed=3, epf_iters=1, dc_tree=1))
+    files.append(vc.encoded("odd_size")[0])
+    for nc, npdt, dt in [(4, np.uint8, jxlo.UINT8), (4, np.uint16, jxlo.UINT16), (3, np.uint8, jxlo.UINT8), (4, np.float32, jxlo.FLOAT)]:
+        outs = pkg.decode_batch(files, nc, npdt)
+        for f, o in zip(files, outs):
+            assert np.array_equal(o.view(np.uint8), jxlo.decode(f, nc, dt).view(np.uint8))
+    outs = pkg.decode_batch(files[:5], 4, np.uint8)
+    for o, c in zip(outs, cases):
+        assert np.array_equal(o[:, :, 3], c[:, :, 3])
+    dec = pkg.decoder_builder().build()
+    meta, px = dec.decode(files[0])
+    assert meta.has_alpha_channel and px.variant == "Uint8"
+    assert np.array_equal(np.asarray(px.data).reshape(300, 520, 4), jxlo.decode(files[0], 4, jxlo.UINT8))

@@ -182,3 +182,42 @@ def test_orientation_is_undone_like_the_write_stage(o):
             assert np.array_equal(k, jxlo.decode(f, nc, dt))
             if dt == jxlo.UINT16:
                 assert np.array_equal(g, upright(k))
+
+
+def _rgba(h, w, y0=100, x0=200):
+    img = vc.crop(h, w, y0, x0)
+    a = (img[:, :, 0].astype(np.int32) + np.arange(w)[None, :] * 3) % 256
+    a[h // 3:h // 2, w // 4:w // 2] = 255
+    return np.dstack([img, a.astype(np.uint8)])
+
+
+def test_vardct_frames_with_an_alpha_channel(monkeypatch):
+    # Lossy frames with an alpha extra channel (lib/jxl/dec_frame.cc:266-365, :478-560): the alpha samples travel in the
+    # frame's Modular sub-streams -- the global stream when the image fits one group (its end is where the DC group
+    # starts in a single-section frame: a probe round), else one stream per AC group that starts where the group's
+    # coefficients end (DevStream::chain_slot: position from the AC decode, GroupHeader parsed by the device, second
+    # Modular launch). One per warp and, with JXLB200_NO_COOP=1, in lock-step bundles; every output type; alpha dropped
+    # for RGB output; in a batch with files without alpha; with an orientation.
+    cases = [_rgba(300, 520), _rgba(200, 256), _rgba(40, 50), _rgba(257, 263, 700, 100)]
+    files = [jxlo.encode_vardct(c, strategy_mode=2) for c in cases]
+    files.append(jxlo.encode_vardct(cases[0], strategy_mode=1, random_side_info=True, seed=3, epf_iters=1, dc_tree=1))
+    files.append(jxlo.encode_vardct(cases[3], strategy_mode=2, orientation=6))
+    shapes = [c.shape[:2] for c in cases] + [cases[0].shape[:2], cases[3].shape[:2]]
+    for env in (None, "JXLB200_NO_COOP"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        for nc, dt in [(4, jxlo.UINT8), (4, jxlo.UINT16), (3, jxlo.UINT8), (4, jxlo.FLOAT)]:
+            got = emul_lib.decode(files, nc, dt, shapes)
+            for g, f in zip(got, files):
+                assert np.array_equal(g.view(np.uint8), jxlo.decode(f, nc, dt).view(np.uint8))
+        if env:
+            monkeypatch.delenv(env)
+    got = emul_lib.decode(files[:4], 4, jxlo.UINT8, shapes[:4])
+    for g, c in zip(got, cases):
+        assert np.array_equal(g[:, :, 3], c[:, :, 3])  # alpha is lossless
+    plain, sp = vc.encoded("odd_size")
+    mixed = emul_lib.decode([files[0], plain, read_golden("sample.jxl"), files[1]], 4, jxlo.UINT8, [shapes[0], sp, (50, 40), shapes[1]])
+    for g, f in zip(mixed, [files[0], plain, read_golden("sample.jxl"), files[1]]):
+        assert np.array_equal(g, jxlo.decode(f, 4, jxlo.UINT8))
+    got = emul_lib.decode([files[5]], 4, jxlo.UINT8, [(263, 257)], endianness=0x400)[0]
+    assert np.array_equal(got, jxlo.decode(files[5], 4, jxlo.UINT8, undo_orientation=True))
