@@ -187,11 +187,12 @@ typedef struct {
   int gaborish;        /* loop-filter flags written to the frame header (decoder side filters) */
   uint32_t epf_iters;
   int dc_smoothing;
+  int has_alpha;       /* 1: the input is interleaved RGBA8; alpha becomes an 8-bit extra channel, coded losslessly */
 } JxlB200EncodeOptions;
 JxlB200Encoder* JxlB200EncoderCreate(int device);
 void JxlB200EncoderDestroy(JxlB200Encoder* enc);
 const char* JxlB200EncoderGetError(const JxlB200Encoder* enc);
-/* rgb[i]: xsizes[i] * ysizes[i] interleaved RGB8 samples (sRGB). Synchronous. */
+/* rgb[i]: xsizes[i] * ysizes[i] interleaved RGB8 (options->has_alpha: RGBA8) samples (sRGB). Synchronous. */
 int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, const uint32_t* xsizes, const uint32_t* ysizes,
                               size_t n, const JxlB200EncodeOptions* options);
 /* Lossless (Modular) batch -- jpegxl-rs `lossless(true)` (jpegxl-rs/src/encode.rs:143, :230-234; libjxl:

@@ -69,7 +69,7 @@ class JxlB200Stats(ctypes.Structure):
 
 class JxlB200EncodeOptions(ctypes.Structure):
     _fields_ = [("distance", ctypes.c_float), ("strategy_mode", ctypes.c_int), ("gaborish", ctypes.c_int),
-                ("epf_iters", ctypes.c_uint32), ("dc_smoothing", ctypes.c_int)]
+                ("epf_iters", ctypes.c_uint32), ("dc_smoothing", ctypes.c_int), ("has_alpha", ctypes.c_int)]
 
 
 class JxlColorEncoding(ctypes.Structure):
@@ -731,8 +731,6 @@ class JxlEncoder:
         fields of the frame header (libjxl's encoder derives them from the distance; the defaults are its d = 1 values)."""
         if self.lossless:
             return self.encode_lossless_batch(images)
-        if self.has_alpha:
-            raise EncodeError("NotSupported: alpha (lossy)")
         if self.use_container:
             raise EncodeError("NotSupported: container output in batch mode")
         if self._enc is None:
@@ -740,9 +738,10 @@ class JxlEncoder:
             if not self._enc:
                 raise EncodeError("CannotCreateEncoder: no usable CUDA device (jxl_b200 has no CPU fallback)")
         imgs = [np.ascontiguousarray(a, np.uint8) for a in images]
+        nch = 4 if self.has_alpha else 3
         for a in imgs:
-            if a.ndim != 3 or a.shape[2] != 3:
-                raise EncodeError("ApiUsage: expected (height, width, 3) uint8 arrays")
+            if a.ndim != 3 or a.shape[2] != nch:
+                raise EncodeError("ApiUsage: expected (height, width, %d) uint8 arrays" % nch)
         n = len(imgs)
         ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in imgs])
         xs = (ctypes.c_uint32 * n)(*[a.shape[1] for a in imgs])
@@ -750,6 +749,7 @@ class JxlEncoder:
         opt = self._batch_options()
         opt.gaborish = 1 if gaborish else 0
         opt.epf_iters = int(epf_iters)
+        opt.has_alpha = 1 if self.has_alpha else 0
         if self._lib.JxlB200EncoderEncodeBatch(self._enc, ptrs, xs, ys, n, ctypes.byref(opt)) != 0:
             raise EncodeError(self._lib.JxlB200EncoderGetError(self._enc).decode())
         out = []

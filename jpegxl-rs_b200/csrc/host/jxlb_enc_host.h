@@ -458,15 +458,30 @@ struct EncParams {
   // libjxl's effort-7 quantiser: InitialQuantField (lib/jxl/enc_adaptive_quantization.cc), global scale and DC quantiser
   // from ComputeGlobalScaleAndQuant (lib/jxl/quantizer.cc:39-69), AdjustQuantField; false: raw quant 16 everywhere
   bool adaptive_quant = true;
+  // the input has a fourth, alpha channel: an 8-bit extra channel coded losslessly next to the lossy colour
+  bool alpha = false;
 };
 
-inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize) {
+inline void WriteImageHeaders(BitWriter& w, uint32_t xsize, uint32_t ysize, bool alpha = false) {
   w.Write(16, 0x0AFF);
   w.Write(1, 0);  // not "small"
   WriteU32(w, ysize, BitsOffset(9, 1), BitsOffset(13, 1), BitsOffset(18, 1), BitsOffset(30, 1));
   w.Write(3, 0);  // no fixed aspect ratio
   WriteU32(w, xsize, BitsOffset(9, 1), BitsOffset(13, 1), BitsOffset(18, 1), BitsOffset(30, 1));
-  w.Write(1, 1);  // ImageMetadata all_default: 8-bit sRGB, XYB encoded
+  if (!alpha) {
+    w.Write(1, 1);  // ImageMetadata all_default: 8-bit sRGB, XYB encoded
+  } else {          // the same with one extra channel (lib/jxl/image_metadata.cc:258-330)
+    w.Write(1, 0);  // not all_default
+    w.Write(1, 0);  // no extra_fields
+    w.Write(1, 0);  // integer samples
+    WriteU32(w, 8, Val(8), Val(10), Val(12), BitsOffset(6, 1));
+    w.Write(1, 1);  // modular_16_bit_buffer_sufficient
+    WriteU32(w, 1, Val(0), Val(1), BitsOffset(4, 2), BitsOffset(12, 1));
+    w.Write(1, 1);  // ExtraChannelInfo all_default: 8-bit alpha
+    w.Write(1, 1);  // xyb_encoded
+    w.Write(1, 1);  // ColorEncoding all_default (sRGB)
+    WriteU64(w, 0);  // extensions
+  }
   w.Write(1, 1);  // CustomTransformData all_default
   w.ZeroPadToByte();
 }
@@ -477,11 +492,13 @@ inline void WriteFrameHeader(BitWriter& w, const EncParams& p) {
   w.Write(1, 0);  // VarDCT
   WriteU64(w, p.dc_smoothing ? uint64_t{0} : uint64_t{kFlagSkipAdaptiveDCSmoothing});
   WriteU32(w, 1, Val(1), Val(2), Val(4), Val(8));  // upsampling
+  if (p.alpha) WriteU32(w, 1, Val(1), Val(2), Val(4), Val(8));  // of the extra channel
   w.Write(3, p.x_qm_scale);
   w.Write(3, p.b_qm_scale);
   WriteU32(w, 1, Val(1), Val(2), Val(3), BitsOffset(3, 4));  // one pass
   w.Write(1, 0);  // no custom size or origin
   WriteU32(w, 0, Val(0), Val(1), Val(2), BitsOffset(2, 3));  // blend mode kReplace
+  if (p.alpha) WriteU32(w, 0, Val(0), Val(1), Val(2), BitsOffset(2, 3));  // of the extra channel
   w.Write(1, 1);  // is_last
   WriteU32(w, 0, Val(0), Bits(4), BitsOffset(5, 16), BitsOffset(10, 48));  // name
   if (p.gab && p.epf_iters == 2) {
@@ -606,7 +623,8 @@ struct EncLayout {
   uint64_t fsize = 0, isize = 0, bsize = 0, tsize = 0;  // floats, int32s, bytes, tokens
 };
 
-inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_clusters, uint32_t num_leaves, DevEFrame* ef) {
+inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_clusters, uint32_t num_leaves, DevEFrame* ef,
+                                bool alpha = false) {
   EncLayout L;
   FrameHeader fh;
   fh.xsize = xsize;
@@ -673,6 +691,9 @@ inline EncLayout LayoutEncFrame(uint32_t xsize, uint32_t ysize, uint32_t num_ac_
   ef->raw_quant = ef->ytob + ((static_cast<uint64_t>(ef->cmw) * ef->cmh + 15) & ~uint64_t{15});
   L.bsize = ef->raw_quant + ((nb + 15) & ~uint64_t{15});
   L.tsize = ef->mod_tokens + ef->mod_tokens_stride * d.num_dc_groups;
+  ef->has_alpha = alpha ? 1 : 0;
+  ef->alpha_tokens = L.tsize;
+  if (alpha) L.tsize += static_cast<uint64_t>(d.num_groups) * 65536;
   L.num_ac_clusters = num_ac_clusters;
   L.num_leaves = num_leaves;
   return L;
@@ -792,8 +813,8 @@ struct EncGlobals {
 
 inline void BuildEncGlobals(const EncParams& p, const EncLayout& L, const EncTree& tree, const std::vector<uint8_t>& ac_cluster_of,
                             uint32_t global_scale, uint32_t quant_dc, const uint32_t* mod_hist, const uint32_t* ac_hist,
-                            const CustomOrders& orders, EncGlobals* g) {
-  (void)p;
+                            const CustomOrders& orders, EncGlobals* g,
+                            const std::vector<std::pair<uint32_t, uint32_t>>* global_alpha = nullptr) {
   BitWriter& d = g->dc_global;
   d.Write(1, 1);  // default DC quantisation
   WriteU32(d, global_scale, BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193));
@@ -806,6 +827,12 @@ inline void BuildEncGlobals(const EncParams& p, const EncLayout& L, const EncTre
   std::vector<uint8_t> leaves(tree.num_leaves);
   for (uint32_t i = 0; i < tree.num_leaves; i++) leaves[i] = static_cast<uint8_t>(i);
   WriteCodeHeader(d, leaves, tree.num_leaves, mod_hist, &g->mod_code);
+  if (p.alpha) {
+    // the global Modular stream of the extra channel: GroupHeader (global tree, default weighted-predictor header, no
+    // transforms); the alpha samples follow when the image fits one group (`global_alpha`), else they travel per AC group
+    d.Write(4, 0x3);
+    if (global_alpha != nullptr) WriteHostTokens(d, g->mod_code, leaves, *global_alpha);
+  }
   BitWriter& a = g->ac_global;
   a.Write(1, 1);  // default quantisation matrices
   a.Write(CeilLog2(L.dim.num_groups), 0);  // one set of histograms
@@ -843,7 +870,7 @@ inline std::vector<uint8_t> AssembleCodestream(const EncParams& p, const EncLayo
     for (const auto& s : acg) sections.push_back(bytes_of(s));
   }
   BitWriter out;
-  WriteImageHeaders(out, L.dim.xsize, L.dim.ysize);
+  WriteImageHeaders(out, L.dim.xsize, L.dim.ysize, p.alpha);
   WriteFrameHeader(out, p);
   std::vector<size_t> sizes;
   for (const auto& s : sections) sizes.push_back(s.size());

@@ -2050,6 +2050,15 @@ __global__ void __launch_bounds__(256) k_enc_modular(DevEPools E, const DevEFram
     DevEncModularSample(El, ef, g, L, i);
 }
 
+// Alpha extra channel: one thread per pixel (DevEncAlphaSample); blockIdx.y = frame.
+__global__ void __launch_bounds__(256) k_enc_alpha(DevEPools E, const DevEFrame* frames) {
+  const DevEFrame& ef = frames[blockIdx.y];
+  if (!ef.has_alpha) return;
+  const DevEPools El = FramePools(E, ef);
+  const uint64_t n = static_cast<uint64_t>(ef.xsize) * ef.ysize;
+  for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) DevEncAlphaSample(El, ef, i);
+}
+
 // rANS emission: one thread per section, written back to front so that it ends at the end of its region
 // (`off[sec]` .. `off[sec + 1]`, in words); `first[sec]` receives the bit position of its first bit. blockIdx.x
 // below `dc_blocks` handles DC-group sections (the long ones, scheduled first), the rest AC-group sections.
@@ -2070,6 +2079,14 @@ __global__ void __launch_bounds__(32) k_enc_emit(DevEPools E, const DevEFrame* f
   const DevEncCode code{fs_tables + ef.code_off[2], rev_tables + ef.code_off[3]};
   const uint32_t n = static_cast<uint32_t>(E.iarena[ef.group_tokens + g]);
   const uint32_t sec = ef.sec_base + ef.xdcgroups * ef.ydcgroups + g;
+  if (ef.has_alpha && !(ef.xsize <= 256 && ef.ysize <= 256)) {  // the group's alpha stream follows its coefficients
+    const DevEncCode mod{fs_tables + ef.code_off[0], rev_tables + ef.code_off[1]};
+    const uint32_t gx = g % ef.xgroups, gy = g / ef.xgroups;
+    const uint32_t gw = ef.xsize - (gx << 8) < 256 ? ef.xsize - (gx << 8) : 256, gh = ef.ysize - (gy << 8) < 256 ? ef.ysize - (gy << 8) : 256;
+    first[sec] = DevEncEmitAcGroup(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words, off[sec + 1] * 32,
+                                   E.tokens + ef.alpha_tokens + static_cast<size_t>(g) * 65536, gw * gh, &mod);
+    return;
+  }
   first[sec] = DevEncEmitAcGroup(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words, off[sec + 1] * 32);
 }
 
@@ -2172,6 +2189,8 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
   p.gab = opt->gaborish != 0;
   p.epf_iters = opt->epf_iters;
   p.dc_smoothing = opt->dc_smoothing != 0;
+  p.alpha = opt->has_alpha != 0;
+  const size_t in_ch = p.alpha ? 4 : 3;
   if (!(p.strategy_mode == 0 || p.strategy_mode == 2) || p.epf_iters > 3 || !(p.distance > 0.0f)) {
     enc->error = "invalid encode options";
     return 1;
@@ -2205,7 +2224,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       fh0.xsize = xsizes[i];
       fh0.ysize = ysizes[i];
       f.tree = BuildEncTree(ToFrameDimensions(fh0).num_dc_groups);
-      f.L = LayoutEncFrame(xsizes[i], ysizes[i], num_ac_clusters, f.tree.num_leaves, &f.ef);
+      f.L = LayoutEncFrame(xsizes[i], ysizes[i], num_ac_clusters, f.tree.num_leaves, &f.ef, p.alpha);
       DevEFrame& e = f.ef;
       for (int c = 0; c < 3; c++) {
         e.xyb[c] += fbase;
@@ -2234,6 +2253,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       e.ytob += bbase;
       e.ac_tokens += tbase;
       e.mod_tokens += tbase;
+      e.alpha_tokens += tbase;
       e.rgb = inbase;
       f.tree_off = treebase;
       all_trees.insert(all_trees.end(), f.tree.nodes.begin(), f.tree.nodes.end());
@@ -2242,7 +2262,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       ibase += f.L.isize;
       bbase += f.L.bsize;
       tbase += f.L.tsize;
-      inbase += (static_cast<uint64_t>(xsizes[i]) * ysizes[i] * 3 + 15) & ~uint64_t{15};
+      inbase += (static_cast<uint64_t>(xsizes[i]) * ysizes[i] * in_ch + 15) & ~uint64_t{15};
     }
     DevBuf<uint8_t>&d_in = enc->d_in, &d_barena = enc->d_barena, &d_cluster = enc->d_cluster;
     DevBuf<float>&d_farena = enc->d_farena, &d_fpool = enc->d_fpool, &d_lut = enc->d_lut;
@@ -2265,7 +2285,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     for (int i = 0; i < 256; i++) lut[i] = SrgbToLinearHost(i / 255.0f);
     CUDA_OK(d_lut.Upload(lut, s));
     for (size_t i = 0; i < n; i++)
-      CUDA_OK(cudaMemcpyAsync(d_in.p + fr[i].ef.rgb, rgb[i], static_cast<size_t>(xsizes[i]) * ysizes[i] * 3, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaMemcpyAsync(d_in.p + fr[i].ef.rgb, rgb[i], static_cast<size_t>(xsizes[i]) * ysizes[i] * in_ch, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemsetAsync(d_iarena.p, 0, (ibase + 16) * sizeof(int32_t), s));
     CUDA_OK(cudaMemsetAsync(d_barena.p, 0xFF, bbase + 16, s));
     DevEPools E{};
@@ -2365,6 +2385,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     k_enc_token_offsets<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_block_tokens<<<dim3((maxW * maxH + 127) / 128, 3, nf), 128, 0, s>>>(E, d_efs.p);
     k_enc_modular<<<dim3(256, max_dcg, nf), 256, 0, s>>>(E, d_efs.p);
+    if (p.alpha) k_enc_alpha<<<dim3(148 * 8, nf), 256, 0, s>>>(E, d_efs.p);
     CUDA_OK(cudaEventRecord(ev[1], s));
     // ---- host: histograms -> codes, global sections, section layout
     uint64_t words_total = 0, nsec = 0;
@@ -2379,6 +2400,14 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       h_small[i].resize(count);
       CUDA_OK(cudaMemcpyAsync(h_small[i].data(), d_iarena.p + first, count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
+    // an image that fits one group carries its alpha samples in the global section, which the host writes: their tokens
+    std::vector<std::vector<uint2>> h_alpha(n);
+    for (size_t i = 0; i < n && p.alpha; i++) {
+      if (xsizes[i] > 256 || ysizes[i] > 256) continue;
+      h_alpha[i].resize(static_cast<size_t>(xsizes[i]) * ysizes[i]);
+      CUDA_OK(cudaMemcpyAsync(h_alpha[i].data(), d_tokens.p + fr[i].ef.alpha_tokens, h_alpha[i].size() * sizeof(uint2),
+                              cudaMemcpyDeviceToHost, s));
+    }
     CUDA_OK(cudaStreamSynchronize(s));
     {  // histogram normalisation, header coding and table building per frame, on host threads
       std::atomic<size_t> next{0};
@@ -2392,7 +2421,10 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
             const uint64_t first = f.ef.dcg_count;
             const uint32_t* ac_hist = reinterpret_cast<const uint32_t*>(h_small[i].data() + (f.ef.ac_hist - first));
             const uint32_t* mod_hist = reinterpret_cast<const uint32_t*>(h_small[i].data() + (f.ef.mod_hist - first));
-            BuildEncGlobals(p, f.L, f.tree, ac_cluster_of, f.global_scale, f.quant_dc, mod_hist, ac_hist, orders[i], &f.G);
+            std::vector<std::pair<uint32_t, uint32_t>> global_alpha;
+            for (const uint2& t : h_alpha[i]) global_alpha.push_back({t.x, t.y});
+            BuildEncGlobals(p, f.L, f.tree, ac_cluster_of, f.global_scale, f.quant_dc, mod_hist, ac_hist, orders[i], &f.G,
+                            h_alpha[i].empty() ? nullptr : &global_alpha);
           } catch (const std::exception& e) {
             errors[i] = e.what();
           }
@@ -2422,6 +2454,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       for (uint32_t g = 0; g < d.num_groups; g++) {
         f.ac_off.push_back(words_total);
         words_total += (static_cast<uint64_t>(group_tokens[g]) * 6 + 64) / 4 + 4;
+        if (p.alpha) words_total += (65536 * 6 + 64) / 4 + 4;  // the group's alpha stream
       }
       nsec += d.num_dc_groups + d.num_groups;
       auto push_rev = [&](const std::vector<uint16_t>& v) {

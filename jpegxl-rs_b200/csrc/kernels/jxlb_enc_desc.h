@@ -98,6 +98,11 @@ struct DevEFrame {
   uint32_t tree_off;   // first node of this frame's tree in the tree pool
   uint32_t sec_base;   // index of this frame's first section (DC groups, then AC groups) in the offset / length arrays
   uint64_t code_off[6];  // uint16 table pool: Modular code freq, start, reverse; AC code freq, start, reverse
+  // An 8-bit alpha extra channel (input: interleaved RGBA8), coded losslessly in the frame's Modular sub-streams under the
+  // global tree (lib/jxl/enc_modular.cc:1258-1500): group g's tokens at alpha_tokens + g * 65536, in the global stream
+  // (group 0, stream id 0) when the image fits one group, else behind the coefficients of each AC group.
+  uint32_t has_alpha, pad_;
+  uint64_t alpha_tokens;
 };
 
 }  // namespace jxlb

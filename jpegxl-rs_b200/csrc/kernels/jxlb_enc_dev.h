@@ -66,7 +66,7 @@ JXLB_HD float DevCubeRootAndAdd(float x, float add) {  // lib/jxl/base/fast_math
 JXLB_HD void DevEncXybPixel(const DevEPools& E, const DevEFrame& ef, uint32_t x, uint32_t y) {
   const uint32_t PW = ef.xblocks * 8;
   const uint32_t sx = x < ef.xsize ? x : ef.xsize - 1, sy = y < ef.ysize ? y : ef.ysize - 1;
-  const uint8_t* px = E.bytes_in + ef.rgb + (static_cast<size_t>(sy) * ef.xsize + sx) * 3;
+  const uint8_t* px = E.bytes_in + ef.rgb + (static_cast<size_t>(sy) * ef.xsize + sx) * (ef.has_alpha ? 4 : 3);
   const float r = E.srgb_lut[px[0]], g = E.srgb_lut[px[1]], b = E.srgb_lut[px[2]];
   const float bias = 0.0037930732552754493f;
   const float kNegBiasCbrt = -0.15595420054924863f;
@@ -1035,6 +1035,8 @@ JXLB_HD int32_t DevModValue(const DevEPools& E, const DevEFrame& ef, const DevMo
                             uint32_t y0, uint32_t x, uint32_t y) {
   if (ch.kind == 0) return E.iarena[ch.plane + static_cast<size_t>(y0 + y) * ef.xblocks + x0 + x];
   if (ch.kind == 1) return ch.konst;
+  if (ch.kind == 4)  // alpha of the input pixel (x0 + x, y0 + y), x0 / y0 in pixels
+    return E.bytes_in[ef.rgb + (static_cast<size_t>(y0 + y) * ef.xsize + x0 + x) * 4 + 3];
   if (ch.kind == 3)  // chroma-from-luma map (int8 per tile; the DC group starts at tile (x0 / 8, y0 / 8))
     return reinterpret_cast<const int8_t*>(E.barena + ch.plane)[static_cast<size_t>((y0 >> 3) + y) * ef.cmw + (x0 >> 3) + x];
   const int32_t pos = E.iarena[ef.block_of_num + static_cast<size_t>(g) * 65536 + x];
@@ -1073,6 +1075,28 @@ JXLB_HD uint2 DevEncModularToken(const DevEPools& E, const DevEFrame& ef, const 
   else if (n.a == 2) guess = top;
   else if (n.a == 5) guess = DevClampedGradient(left, top, topleft);
   return make_uint2(n.l, DevPackSigned(v - guess));
+}
+
+// Alpha sample of pixel `i` of the frame -> its token in its group's alpha stream (DevEFrame::alpha_tokens), counted in
+// the Modular histograms. The stream is the global one (id 0) when the image fits one group, else ModularAC(g, pass 0);
+// neighbours inside the group's crop, the fixed global tree decides context and predictor like for every other stream.
+JXLB_HD void DevEncAlphaSample(const DevEPools& E, const DevEFrame& ef, uint64_t i) {
+  const uint32_t y = static_cast<uint32_t>(i / ef.xsize), x = static_cast<uint32_t>(i - static_cast<uint64_t>(y) * ef.xsize);
+  const bool global_only = ef.xsize <= 256 && ef.ysize <= 256;
+  const uint32_t gx = x >> 8, gy = y >> 8, lx = x & 255, ly = y & 255, g = gy * ef.xgroups + gx;
+  const uint32_t gw = ef.xsize - (gx << 8) < 256 ? ef.xsize - (gx << 8) : 256;
+  const uint32_t gh = ef.ysize - (gy << 8) < 256 ? ef.ysize - (gy << 8) : 256;
+  DevModChan ch;
+  ch.kind = 4;
+  ch.w = gw;
+  ch.h = gh;
+  ch.konst = 0;
+  ch.plane = 0;
+  const uint32_t ndc = ef.xdcgroups * ef.ydcgroups;
+  const uint32_t stream_id = global_only ? 0 : 1 + 3 * ndc + 17 + g;  // ModularStreamId::ModularAC(g, pass 0)
+  const uint2 t = DevEncModularToken(E, ef, ch, 0, stream_id, g, gx << 8, gy << 8, lx, ly);
+  E.tokens[ef.alpha_tokens + static_cast<uint64_t>(g) * 65536 + ly * gw + lx] = t;
+  DevCountToken(reinterpret_cast<uint32_t*>(E.iarena + ef.mod_hist), t.x, t.y);
 }
 
 // ---- rANS writer. Tables of one code: fs[cluster][256] = freq | first reverse slot << 16, reverse[cluster][4096].
@@ -1254,10 +1278,17 @@ JXLB_HD uint64_t DevEncEmitDcGroup(const DevEPools& E, const DevEFrame& ef, uint
   return w.cursor;
 }
 
-// An AC group section ending at bit `end_pos`; returns the position of its first bit.
-JXLB_HD uint64_t DevEncEmitAcGroup(const uint2* tok, uint32_t n, const DevEncCode& code, uint32_t* words, uint64_t end_pos) {
+// An AC group section ending at bit `end_pos`; returns the position of its first bit. `alpha_tok` (else null): the
+// `alpha_n` tokens of the group's extra-channel stream, which follows the coefficients: GroupHeader (global tree, default
+// weighted-predictor header, no transforms), then its symbols under the Modular code.
+JXLB_HD uint64_t DevEncEmitAcGroup(const uint2* tok, uint32_t n, const DevEncCode& code, uint32_t* words, uint64_t end_pos,
+                                   const uint2* alpha_tok = nullptr, uint32_t alpha_n = 0, const DevEncCode* mod_code = nullptr) {
   DevBackWriter w;
   w.Init(words, end_pos);
+  if (alpha_tok != nullptr) {
+    DevRansPush(alpha_tok, alpha_n, *mod_code, w);
+    w.Put(4, 0x3);
+  }
   DevRansPush(tok, n, code, w);
   w.Finish();
   return w.cursor;

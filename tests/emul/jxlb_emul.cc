@@ -370,7 +370,8 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
     p.strategy_mode = strategy_mode;
     p.gab = gab != 0;
     p.epf_iters = epf_iters;
-    p.dc_smoothing = dc_smoothing != 0;
+    p.dc_smoothing = (dc_smoothing & 1) != 0;
+    p.alpha = (dc_smoothing & 2) != 0;  // test hook: `rgb` holds interleaved RGBA8
     JXLB_CHECK(strategy_mode == 0 || strategy_mode == 2, "unsupported strategy mode");
     const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
     uint32_t num_ac_clusters = 0;
@@ -382,7 +383,7 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
     fh0.xsize = xsize;
     fh0.ysize = ysize;
     const EncTree tree = BuildEncTree(ToFrameDimensions(fh0).num_dc_groups);
-    const EncLayout L = LayoutEncFrame(xsize, ysize, num_ac_clusters, tree.num_leaves, &ef);
+    const EncLayout L = LayoutEncFrame(xsize, ysize, num_ac_clusters, tree.num_leaves, &ef, p.alpha);
     std::vector<float> farena(L.fsize + 16, 0.0f);
     std::vector<int32_t> iarena(L.isize + 16, 0);
     std::vector<uint8_t> barena(L.bsize + 16, 0xFF);
@@ -484,10 +485,18 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
       const DevDcGroupLayout gl = DevDcGroupGeometry(E, ef, g);
       for (uint32_t i = 0; i < gl.dc_tokens + gl.meta_tokens; i++) DevEncModularSample(E, ef, g, gl, i);
     }
+    const bool alpha_global = p.alpha && xsize <= 256 && ysize <= 256;
+    std::vector<std::pair<uint32_t, uint32_t>> global_alpha;
+    if (p.alpha) {  // k_enc_alpha
+      for (uint64_t i = 0; i < static_cast<uint64_t>(xsize) * ysize; i++) DevEncAlphaSample(E, ef, i);
+      if (alpha_global)
+        for (uint64_t i = 0; i < static_cast<uint64_t>(xsize) * ysize; i++)
+          global_alpha.push_back({tokens[ef.alpha_tokens + i].x, tokens[ef.alpha_tokens + i].y});
+    }
     EncGlobals G;
     const auto t_globals = std::chrono::steady_clock::now();
     BuildEncGlobals(p, L, tree, ac_cluster_of, global_scale, quant_dc, reinterpret_cast<uint32_t*>(iarena.data() + ef.mod_hist),
-                    reinterpret_cast<uint32_t*>(iarena.data() + ef.ac_hist), orders, &G);
+                    reinterpret_cast<uint32_t*>(iarena.data() + ef.ac_hist), orders, &G, alpha_global ? &global_alpha : nullptr);
     if (std::getenv("JXLB_EMUL_TIMING"))
       std::fprintf(stderr, "BuildEncGlobals: %.2f ms\n",
                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_globals).count());
@@ -506,10 +515,18 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
     }
     for (uint32_t g = 0; g < d.num_groups; g++) {
       const uint32_t n = static_cast<uint32_t>(iarena[ef.group_tokens + g]);
-      const size_t cap = (static_cast<size_t>(n) * 6 + 64) / 4 + 4;
+      const size_t cap = (static_cast<size_t>(n) * 6 + 64) / 4 + 4 + (p.alpha ? (65536 * 6 + 64) / 4 + 4 : 0);
       ac_words[g].assign(cap, 0);
       const uint64_t end = cap * 32;
-      const uint64_t first = DevEncEmitAcGroup(tokens.data() + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, ac, ac_words[g].data(), end);
+      uint64_t first;
+      if (p.alpha && !alpha_global) {  // as k_enc_emit
+        const uint32_t gx = g % ef.xgroups, gy = g / ef.xgroups;
+        const uint32_t gw = std::min<uint32_t>(256, xsize - (gx << 8)), gh = std::min<uint32_t>(256, ysize - (gy << 8));
+        first = DevEncEmitAcGroup(tokens.data() + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, ac, ac_words[g].data(), end,
+                                  tokens.data() + ef.alpha_tokens + static_cast<size_t>(g) * 65536, gw * gh, &mod);
+      } else {
+        first = DevEncEmitAcGroup(tokens.data() + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, ac, ac_words[g].data(), end);
+      }
       acg.push_back({ac_words[g].data(), first, end - first});
     }
     const std::vector<uint8_t> cs = AssembleCodestream(p, L, G, dcg, acg);

@@ -61,9 +61,11 @@ def last_coop_streams():
 
 
 def encode(rgb, distance=1.0, strategy_mode=2, gab=True, epf_iters=2, dc_smoothing=True) -> bytes:
-    """RGB8 (H, W, 3) -> codestream, the encoder kernels' device functions run on the CPU."""
+    """RGB8 (H, W, 3) or RGBA8 (H, W, 4: alpha as a lossless extra channel) -> codestream, the encoder kernels' device
+    functions run on the CPU."""
     rgb = np.ascontiguousarray(rgb, np.uint8)
-    h, w, _ = rgb.shape
+    h, w, nch = rgb.shape
+    dc_smoothing = int(bool(dc_smoothing)) | (2 if nch == 4 else 0)
     cap = h * w * 6 + (1 << 20)
     out = np.zeros(cap, np.uint8)
     err = ctypes.create_string_buffer(512)

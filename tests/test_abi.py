@@ -111,8 +111,8 @@ def test_encoder_mirror_reports_the_reference_error_variants(pkg):
         pkg.encoder_builder().lossless(True).uses_original_profile(True).build().encode(np.zeros((8, 8, 3), np.float32))
     with pytest.raises(pkg.EncodeError, match="NotSupported"):
         pkg.encoder_builder().build().encode(np.zeros((8, 8, 3), np.uint16))
-    with pytest.raises(pkg.EncodeError, match="NotSupported"):
-        pkg.encoder_builder().has_alpha(True).build().encode(np.zeros((8, 8, 4), np.uint8))
+    with pytest.raises(pkg.EncodeError, match="NotSupported"):  # lossy alpha is 8-bit
+        pkg.encoder_builder().has_alpha(True).build().encode(np.zeros((8, 8, 4), np.uint16))
     with pytest.raises(pkg.EncodeError, match="NotSupported"):
         pkg.encoder_builder().build().encode_jpeg(b"\xff\xd8\xff\xd9")
     import torch
