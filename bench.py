@@ -6,15 +6,20 @@
 
 A "step" = one pass of the hot path over one batch of synthetic input. Workloads:
 
-  vardct4k (default)  BATCH (256) lossy 3840x2160 VarDCT frames per GPU (BASELINE.json configs[1]; configs[3]'s 512
-                      frames are two GPUs' worth), alternating two committed fixtures
-                      (tests/golden/vardct_4k_{natural,synthetic}.jxl, written by tests/golden/make_vardct_fixtures.py),
-                      decoded to RGB8.
+  vardct4k (default)  BATCH (256) DIFFERENT lossy 3840x2160 VarDCT frames per GPU (BASELINE.json configs[1]; configs[3]'s
+                      512 frames are two GPUs' worth) decoded to RGB8: integer translations of the two committed 4K
+                      images, encoded at start-up by this repo's GPU encoder (Workload.make_distinct: replicas of one
+                      file flatter the lock-step entropy kernels). --replicas: the two committed fixtures themselves
+                      (tests/golden/vardct_4k_{natural,synthetic}.jxl, written by the oracle's restatement of libjxl's
+                      AcStrategy search: every transform class), alternating; run as a checked side run (`also`).
   encode4k            BATCH (8) RGB8 3840x2160 frames per GPU encoded to lossy VarDCT at distance 1.0 (configs[2]).
   modular             BATCH bench.jxl-shaped frames (2122x1433 lossless Modular RGBA8, 54 groups each): the input of
                       the reference's own criterion bench (jpegxl-rs/benches/decode.rs:10-40).
 
-Every rank works on its own batch (weak scaling, no data-path collective: frames are independent).
+Every rank works on its own batch (weak scaling: frames are independent); under torchrun the decoded frames of every
+step are gathered on rank 0 with NCCL inside the timed region (the one collective of the path).
+The default run folds short side runs of the other workloads into `also`: the fixtures, encode4k, modular and the
+lossless encoder (tools/bench_lossless_enc.py).
 """
 import argparse
 import hashlib
@@ -796,6 +801,14 @@ def side_workloads(args):
             out[name]["roofline"] = {k: rf.get(k) for k in ("kernel", "achieved", "frac", "step_frac", "kernel_ms")}
         except Exception as e:  # a side workload never takes the main line down
             out[name] = {"error": str(e)[:300]}
+    try:  # the lossless (Modular) encoder: 8 4K RGB8 frames per call, host buffers in, codestreams out
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_lossless_enc.py"), "8", "2"], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=240)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        out["lossless_encode4k"] = json.loads(lines[-1]) if r.returncode == 0 and lines else {
+            "error": (r.stderr or "no output").strip().splitlines()[-1][:300]}
+    except Exception as e:
+        out["lossless_encode4k"] = {"error": str(e)[:300]}
     return out
 
 

@@ -250,6 +250,7 @@ JXLB_HD void DevCoopFastRow(const uint16_t* tab, const int32_t lut_lo, const int
                                               : static_cast<WT>(DevClampedGradient(static_cast<int32_t>(n_left), static_cast<int32_t>(n_top),
                                                                                    static_cast<int32_t>(n_topleft))));
     const int32_t val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) + static_cast<uint32_t>(guess));
+    JXLB_SYNCWARP();  // the other lanes read this entry (as the previous row's) three samples ago: order that before the write
     if (lane0) {
       row[x] = val;
       if (!kDirect) out_row[x] = val;
@@ -258,7 +259,7 @@ JXLB_HD void DevCoopFastRow(const uint16_t* tab, const int32_t lut_lo, const int
     tl = t;
     t = q1;
     q1 = q2;
-    if (!first_row) {
+    if (!first_row && x < last) {  // (at the last sample the entry has just been overwritten and nothing reads q2 again)
       const int ahead = x + 3 < last ? x + 3 : last;
       q2 = prev[ahead];
     }
@@ -449,6 +450,7 @@ JXLB_HD void DevCoopChannelRows(const DevPools& P, const DevChannel& ch, const D
         const uint32_t u = reader.ReadUint(e & 0x80FF, br);
         val = static_cast<int32_t>(static_cast<uint32_t>(DevUnpackSigned(u)) + static_cast<uint32_t>(guess));
       }
+      JXLB_SYNCWARP();  // the other lanes' reads of these entries (previous row, up to three samples ago) before lane 0's writes
       if (lane0) {
         if (!direct) rowB[x] = t;  // the sample A loses below: next row's N-N
         row[x] = val;
