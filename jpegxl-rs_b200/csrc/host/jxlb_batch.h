@@ -48,6 +48,8 @@ struct BatchPlan {
   // and inverse transforms) run after that launch.
   uint32_t num_early = 0, late_coop = 0, chain_slots = 0;
   uint32_t early_warps = 0;  // lock-step bundles of the early streams (warp_chans / warp_dims index of the first late bundle)
+  std::vector<float> spl_seg;
+  std::vector<uint32_t> spl_idx;
   std::vector<DevProgram> late_group_programs;
   std::vector<std::vector<DevProgram>> late_levels;
   bool narrow = true;  // every frame promises that 16-bit buffers suffice -> 32-bit predictor math
@@ -322,6 +324,13 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
   for (uint32_t c = 0; c < 4; c++)
     if (c < fo.num_channels && fo.plane[c] != kNoPlane) fo.plane[c] += planes0;
   fo.out_off = b->out_size;
+  if (fo.has_splines) {
+    fo.spl_seg += b->spl_seg.size();
+    fo.spl_rows += b->spl_idx.size();
+    fo.spl_idx += b->spl_idx.size();
+    b->spl_seg.insert(b->spl_seg.end(), f.spl_seg.begin(), f.spl_seg.end());
+    b->spl_idx.insert(b->spl_idx.end(), f.spl_idx.begin(), f.spl_idx.end());
+  }
   const uint64_t osize = fo.stride * ((fo.orient & 4) ? fo.xsize : fo.ysize);
   b->out_size += (osize + 255) & ~uint64_t{255};
   b->frame_out_size.push_back(osize);

@@ -6,6 +6,7 @@
 #define JXLB_FRAME_PLAN_H_
 
 #include "jxlb_plan.h"
+#include "jxlb_splines.h"
 #include "jxlb_vardct_frame.h"
 
 namespace jxlb {
@@ -117,8 +118,10 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
     JXLB_CHECK(fh.frame_type == kRegularFrame && fh.is_last, "unsupported: multi-frame codestream (animation / layers)");
     JXLB_CHECK(!fh.is_modular || fh.color_transform == kCTNone, "unsupported: XYB / YCbCr Modular frame");
     JXLB_CHECK(!fh.custom_size_or_origin, "unsupported: cropped frame");
-    JXLB_CHECK(!fh.is_modular || !(fh.flags & (kFlagPatches | kFlagSplines | kFlagNoise | kFlagUseDcFrame)),
-               "unsupported: patches / splines / noise / DC frame on a Modular frame");
+    JXLB_CHECK(!fh.is_modular || !(fh.flags & (kFlagPatches | kFlagNoise | kFlagUseDcFrame)),
+               "unsupported: patches / noise / DC frame on a Modular frame");
+    JXLB_CHECK(!(fh.is_modular && (fh.flags & kFlagSplines)) || (!meta.color.IsGray() && fmt.num_channels >= 3),
+               "unsupported: splines on a grey image");
     JXLB_CHECK(fh.blending.mode == kReplace, "unsupported: blending");
   }
   JXLB_CHECK(fh.upsampling == 1 || (!fh.is_modular && !is_ref), "unsupported: upsampling of a Modular or reference-only frame");
@@ -161,7 +164,12 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   GroupHeader global_header;
 
   float dc_quant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256};
+  SplineState splines;
   auto dc_global = [&](BitReader& r, uint64_t bit_base) {
+    if (fh.flags & kFlagSplines) {  // (lib/jxl/dec_frame.cc:286-305; the base colour correlation of a Modular frame is the default)
+      ReadSplines(r, dim.xsize * dim.ysize, &splines);
+      InitSplineDrawCache(dim.xsize_upsampled, dim.ysize_upsampled, 0.0f, 1.0f, &splines);
+    }
     if (!r.ReadBool()) {  // DequantMatrices::DecodeDC (lib/jxl/quant_weights.cc:507-520): the XYB scale of Modular frames
       for (int c = 0; c < 3; c++) {
         dc_quant[c] = ReadF16(r) * (1.0f / 128.0f);
@@ -328,6 +336,28 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   fo.big_endian = fmt.endianness == 2;
   fo.orient = OrientBits(meta.orientation, fmt);
   fo.stride = OutputStride((fo.orient & 4) ? bi.ysize : bi.xsize, fmt);
+  if (!splines.segments.empty()) {  // the draw cache for DevSplinePixel
+    fo.has_splines = 1;
+    fo.spl_seg = plan->spl_seg.size();
+    for (const SplineSegment& sg : splines.segments) {
+      auto bits = [](int64_t v) {
+        const int32_t c = static_cast<int32_t>(std::min<int64_t>(std::max<int64_t>(v, INT32_MIN), INT32_MAX));
+        float f;
+        std::memcpy(&f, &c, 4);
+        return f;
+      };
+      const float w[kSplineSegmentWords] = {sg.center_x, sg.center_y, sg.inv_sigma, sg.sigma_over_4_times_intensity,
+                                            sg.color[0], sg.color[1], sg.color[2],
+                                            bits(std::llround(sg.center_x - sg.maximum_distance)),
+                                            bits(std::llround(sg.center_x + sg.maximum_distance) + 1), 0.0f};
+      plan->spl_seg.insert(plan->spl_seg.end(), w, w + kSplineSegmentWords);
+    }
+    fo.spl_rows = plan->spl_idx.size();
+    JXLB_CHECK(splines.segment_y_start.size() == bi.ysize + 1, "internal: spline row table");
+    plan->spl_idx.insert(plan->spl_idx.end(), splines.segment_y_start.begin(), splines.segment_y_start.end());
+    fo.spl_idx = plan->spl_idx.size();
+    plan->spl_idx.insert(plan->spl_idx.end(), splines.segment_indices.begin(), splines.segment_indices.end());
+  }
   const uint32_t num_color = fmt.num_channels < 3 ? 1 : 3;
   const bool want_alpha = fmt.num_channels == 2 || fmt.num_channels == 4;
   const int alpha = meta.AlphaIndex();

@@ -166,6 +166,8 @@ struct FramePlan {
   std::vector<DevProgram> group_programs;
   std::vector<DevProgram> frame_levels;  // global transforms: one op per level, run after the group programs
   uint32_t chain_slots = 0;              // positions the AC decode kernel hands to chained Modular streams
+  std::vector<float> spl_seg;            // splines of the frame (DevFrameOut::spl_*): segments ...
+  std::vector<uint32_t> spl_idx;         // ... row offsets and index lists
   // group programs / frame levels from these indices on belong to the extra channels of the VarDCT frame: they run
   // after the second Modular launch (BatchPlan::late_*)
   size_t late_programs0 = static_cast<size_t>(-1), late_levels0 = static_cast<size_t>(-1);

@@ -793,6 +793,8 @@ struct JxlB200Decoder {
   DevBuf<DevOp> d_ops;
   DevBuf<DevProgram> d_group_programs, d_levels, d_late_group_programs, d_late_levels;
   DevBuf<uint64_t> d_chain_pos;   // DevStream::chain_slot / DevAcStream::chain_slot
+  DevBuf<float> d_spl_seg;        // splines of Modular frames
+  DevBuf<uint32_t> d_spl_idx;
   std::vector<size_t> late_level_off;
   DevBuf<DevFrameOut> d_frames;
   DevBuf<int32_t> d_arena, d_wp, d_ring;
@@ -1011,6 +1013,8 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
   }
   CUDA_OK(dec->d_late_levels.Upload(all_late_levels, s));
   CUDA_OK(dec->d_chain_pos.Alloc(b.chain_slots + 1));
+  CUDA_OK(dec->d_spl_seg.Upload(b.spl_seg, s));
+  CUDA_OK(dec->d_spl_idx.Upload(b.spl_idx, s));
   CUDA_OK(dec->d_frames.Upload(b.frames, s));
   CUDA_OK(dec->d_warp_chans.Upload(b.warp_chans, s));
   CUDA_OK(dec->d_warp_dims_off.Upload(b.warp_dims_off, s));
@@ -1046,6 +1050,8 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
   P.stream0 = b.num_coop;
   P.coop0 = 0;
   P.chain_pos = dec->d_chain_pos.p;
+  P.spl_seg = dec->d_spl_seg.p;
+  P.spl_idx = dec->d_spl_idx.p;
   P.warp_chans = dec->d_warp_chans.p;
   P.warp_dims_off = dec->d_warp_dims_off.p;
   P.warp_dims = dec->d_warp_dims.p;
@@ -1055,7 +1061,7 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     if (fo.vardct) continue;
     dec->any_modular_frame = true;
     for (int c = 0; c < 4; c++)
-      if (fo.is_float[c] || fo.stride % 4 || fo.orient != 0) dec->uniform_rgba8 = false;
+      if (fo.is_float[c] || fo.stride % 4 || fo.orient != 0 || fo.has_splines) dec->uniform_rgba8 = false;
   }
   // ---- VarDCT
   dec->dcg_list.clear();

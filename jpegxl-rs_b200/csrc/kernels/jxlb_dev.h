@@ -170,7 +170,16 @@ struct DevFrameOut {
   uint64_t stride;         // bytes per output row
   uint32_t vardct;         // 1: the frame is written by the VarDCT colour kernel, not by k_write_output
   uint32_t orient;         // undo_orientation of the output store: 1 flip x, 2 flip y, 4 transpose (stage_write.cc:271-288)
+  // Splines (lib/jxl/splines.cc, render_pipeline/stage_splines.cc) of a Modular frame: added to the three colour samples
+  // before the conversion. spl_rows -> uint32 pool: ysize + 1 offsets into the frame's index list, spl_idx -> the list
+  // (segment numbers, per row in draw order), spl_seg -> float pool: kSplineSegmentWords words per segment.
+  uint32_t has_splines, spl_pad_;
+  uint64_t spl_rows, spl_idx, spl_seg;
 };
+
+// One spline segment in the float pool: centre, inverse sigma, sigma / 4 * intensity, the three colour multipliers, and
+// (as int32 bits) the first and one-past-last column it touches (llround(centre -/+ maximum distance), splines.cc:99-103).
+constexpr uint32_t kSplineSegmentWords = 10;
 
 constexpr uint32_t kNoPlane = 0xFFFFFFFFu;
 

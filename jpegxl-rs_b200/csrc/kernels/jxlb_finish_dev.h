@@ -292,13 +292,56 @@ JXLB_HD float DevSampleFloat(const DevPools& P, const DevFrameOut& fo, uint32_t 
 #endif
 }
 
+// FastErff, lib/jxl/base/fast_math-inl.h:126-146.
+JXLB_HD float DevFastErff(float x) {
+  const bool xle0 = x <= 0.0f;
+  const float absx = fabsf(x);
+  const float d1 = fmaf(absx, 7.77394369e-02f, 2.05260015e-04f);
+  const float d2 = fmaf(d1, absx, 2.32120216e-01f);
+  const float d3 = fmaf(d2, absx, 2.77820801e-01f);
+  const float d4 = fmaf(d3, absx, 1.0f);
+  const float d5 = d4 * d4;
+  const float inv = 1.0f / d5;
+  const float r = fmaf(-inv, inv, 1.0f);
+  return xle0 ? -r : r;
+}
+
+// The splines' contribution to pixel (x, y) of a Modular frame, added to the three colour samples v[0..2] in the draw
+// order of the row's segment list (lib/jxl/splines.cc:78-113 DrawSegment, :167-175 DrawSegments): every segment whose
+// column span holds x adds colour * sigma / 4 * intensity * (erf(...) - erf(...))^2.
+JXLB_HD void DevSplinePixel(const DevPools& P, const DevFrameOut& fo, uint32_t x, uint32_t y, float* v) {
+  const uint32_t* rows = P.spl_idx + fo.spl_rows;
+  const uint32_t* idx = P.spl_idx + fo.spl_idx;
+  const float fx = static_cast<float>(static_cast<int32_t>(x)), fy = static_cast<float>(y);
+  for (uint32_t i = rows[y]; i < rows[y + 1]; i++) {
+    const float* s = P.spl_seg + fo.spl_seg + static_cast<size_t>(idx[i]) * kSplineSegmentWords;
+    union { float f; int32_t i; } xa, xb;
+    xa.f = s[7];
+    xb.f = s[8];
+    const int32_t lo = xa.i > 0 ? xa.i : 0, hi = xb.i < static_cast<int32_t>(fo.xsize) ? xb.i : static_cast<int32_t>(fo.xsize);
+    if (static_cast<int32_t>(x) < lo || static_cast<int32_t>(x) >= hi) continue;
+    const float dx = fx - s[0], dy = fy - s[1];
+    const float distance = sqrtf(fmaf(dx, dx, dy * dy));
+    const float f = DevFastErff(fmaf(distance, 0.5f, 0.353553391f) * s[2]) - DevFastErff(fmaf(distance, 0.5f, -0.353553391f) * s[2]);
+    const float li = s[3] * (f * f);
+    v[0] = fmaf(s[4], li, v[0]);
+    v[1] = fmaf(s[5], li, v[1]);
+    v[2] = fmaf(s[6], li, v[2]);
+  }
+}
+
 // Converts and stores one pixel (all channels).
 JXLB_HD void DevWritePixel(const DevPools& P, const DevFrameOut& fo, uint8_t* out, uint32_t x, uint32_t y) {
   uint32_t dx = x, dy = y, orow = y, ocol = x;  // dither position, store position
   if (fo.orient != 0) DevOrient(fo.orient, fo.xsize, fo.ysize, x, y, &dx, &dy, &orow, &ocol);
   uint8_t* row = out + fo.out_off + fo.stride * orow;
+  float spl[3] = {0.0f, 0.0f, 0.0f};
+  if (fo.has_splines) {  // (three colour channels: checked by the planner)
+    for (uint32_t c = 0; c < 3; c++) spl[c] = DevSampleFloat(P, fo, c, x, y);
+    DevSplinePixel(P, fo, x, y, spl);
+  }
   for (uint32_t c = 0; c < fo.num_channels; c++) {
-    float v = DevSampleFloat(P, fo, c, x, y);
+    float v = (fo.has_splines && c < 3) ? spl[c] : DevSampleFloat(P, fo, c, x, y);
     const size_t idx = static_cast<size_t>(ocol) * fo.num_channels + c;
     if (fo.data_type == 2 || fo.data_type == 3) {
       const float mul = fo.data_type == 2 ? 255.0f : 65535.0f;

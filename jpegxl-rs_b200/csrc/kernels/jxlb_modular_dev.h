@@ -38,6 +38,8 @@ struct DevPools {
   uint32_t* status;      // per stream: 0 ok, else error bits
   uint64_t* end_bits;    // per stream: first bit after the stream (probe launches only, else null)
   const uint64_t* chain_pos;  // DevStream::chain_slot: where the AC decode kernel stopped reading (null without such streams)
+  const float* spl_seg;       // splines of Modular frames: segments (kSplineSegmentWords each), row offsets + index lists
+  const uint32_t* spl_idx;
   uint32_t num_streams;
   // streams [0, stream0) are decoded one per warp by k_modular_decode_coop (jxlb_modular_coop_dev.h), the lock-step
   // kernels take [stream0, num_streams): their warp 0 starts at stream0

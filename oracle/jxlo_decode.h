@@ -85,7 +85,7 @@ inline FrameHeader DecodeFrame(BitReader& br, CodestreamState* cs, bool is_previ
   auto section = [&](size_t i) { return BitReader(data + base + toc.offsets[i], toc.logical_size[i]); };
   auto dc_global = [&](BitReader& r) {
     if (fh.flags & kFlagPatches) ReadPatches(r, dim, cs->meta, *cs, &feat);
-    JXLO_CHECK(!(fh.flags & kFlagSplines), "splines are not supported by the oracle");
+    if (fh.flags & kFlagSplines) ReadSplines(r, dim.xsize * dim.ysize, &feat.splines);
     JXLO_CHECK(!(fh.flags & kFlagNoise), "noise is not supported by the oracle");
     if (!r.ReadBool()) {  // DequantMatrices::DecodeDC, lib/jxl/quant_weights.cc:507-520
       for (int c = 0; c < 3; c++) {
@@ -97,6 +97,9 @@ inline FrameHeader DecodeFrame(BitReader& br, CodestreamState* cs, bool is_previ
       for (int c = 0; c < 3; c++) vs->dc_quant[c] = dc_quant[c];
       VarDCTReadGlobalDC(r, vs.get());
     }
+    // (the draw cache uses the base colour correlation: lib/jxl/dec_frame.cc:300-305; defaults in a Modular frame)
+    if (fh.flags & kFlagSplines)
+      InitSplineDrawCache(dim.xsize_upsampled, dim.ysize_upsampled, vs ? vs->base_x : 0.0f, vs ? vs->base_b : 1.0f, &feat.splines);
     ModularDecodeGlobal(r, fh, dim, cs->meta, &ms);
   };
   auto dc_group = [&](BitReader& r, size_t g) {

@@ -16,6 +16,7 @@
 
 #include "jxlo_frame.h"
 #include "jxlo_vardct.h"
+#include "jxlo_splines.h"
 
 namespace jxlo {
 
@@ -30,6 +31,7 @@ struct FeatureState {
   std::vector<PatchPos> positions;
   std::vector<PatchBlending> blendings;  // (1 + num_extra) per position
   size_t blend_stride = 1;
+  SplineState splines;
 };
 
 inline void ReadPatches(BitReader& br, const FrameDimensions& dim, const ImageMetadata& meta, const CodestreamState& cs,
@@ -462,6 +464,18 @@ inline void RenderFrame(const FrameHeader& fh, const FrameDimensions& dim, const
     if (lf.epf_iters >= 2) EPFStage(2, lf, sigma, planes->data());
   }
   if (fh.flags & kFlagPatches) ApplyPatches(feat, cs, planes);
+  if ((fh.flags & kFlagSplines) && !feat.splines.segments.empty()) {
+    // SplineStage (stage_splines.cc:24-45): every row gets the segments of its list, in list order, over its whole width
+    const SplineState& sp = feat.splines;
+    Plane& s0 = (*planes)[0];
+    Plane& s1 = (*planes)[1];
+    Plane& s2 = (*planes)[2];
+    for (int y = 0; y < s0.h && static_cast<size_t>(y) + 1 < sp.segment_y_start.size(); y++)
+      for (uint32_t i = sp.segment_y_start[y]; i < sp.segment_y_start[y + 1]; i++) {
+        const SplineSegment& seg = sp.segments[sp.segment_indices[i]];
+        for (int x = 0; x < s0.w; x++) SplDrawPixel(seg, x, static_cast<size_t>(y), 0, s0.w, &s0.Row(y)[x], &s1.Row(y)[x], &s2.Row(y)[x]);
+      }
+  }
   if (fh.upsampling > 1) {  // (dec_cache.cc:103-347: after patches / splines, before noise and the colour transform)
     for (Plane& p : *planes) p = Upsample(p, static_cast<int>(fh.upsampling), UpsamplingWeights(cs.meta, fh.upsampling));
   }

@@ -81,6 +81,8 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       P.coop0 = first;
       P.stream0 = first + ncoop;
       P.chain_pos = chain_pos;
+      P.spl_seg = b.spl_seg.data();
+      P.spl_idx = b.spl_idx.data();
       P.warp_chans = b.warp_chans.data();
       P.warp_dims_off = b.warp_dims_off.data();
       P.warp_dims = b.warp_dims.data();

@@ -123,3 +123,16 @@ def test_modular_cases_match_oracle(pkg):
             img = mc.encoded(n)[1]
             if nc == img.shape[2]:
                 assert np.array_equal(o, img), n  # and lossless against the source samples
+
+
+def test_sample_2bit_as_the_reference_test(pkg):
+    # jpegxl-rs/src/tests/decode.rs:69-80: decoder.decode(SAMPLE_JXL_2BIT) -> Pixels::Uint8 of width * height * 3 samples;
+    # here also equal to the oracle (splines evaluated per pixel in the output kernel), in a batch with other files
+    d = read_golden("2bit.jxl")
+    dec = pkg.decoder_builder().build()
+    meta, px = dec.decode(d)
+    assert px.variant == "Uint8" and np.asarray(px.data).size == meta.width * meta.height * 3 == 800 * 600 * 3
+    assert np.array_equal(np.asarray(px.data).reshape(600, 800, 3), jxlo.decode(d, 3, jxlo.UINT8))
+    outs = pkg.decode_batch([read_golden("sample.jxl"), d, d], 4, np.uint16)
+    assert np.array_equal(outs[1], jxlo.decode(d, 4, jxlo.UINT16)) and np.array_equal(outs[2], outs[1])
+    assert np.array_equal(outs[0], jxlo.decode(read_golden("sample.jxl"), 4, jxlo.UINT16))
