@@ -802,7 +802,7 @@ def side_workloads(args):
         except Exception as e:  # a side workload never takes the main line down
             out[name] = {"error": str(e)[:300]}
     try:  # the lossless (Modular) encoder: 8 4K RGB8 frames per call, host buffers in, codestreams out
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_lossless_enc.py"), "8", "2"], stdout=subprocess.PIPE,
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_lossless_enc.py"), "16", "2"], stdout=subprocess.PIPE,
                            stderr=subprocess.PIPE, text=True, timeout=240)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         out["lossless_encode4k"] = json.loads(lines[-1]) if r.returncode == 0 and lines else {
