@@ -287,6 +287,13 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
     }
     vf.out_off = b->out_size;
     if (vf.alpha_plane != kNoPlane) vf.alpha_plane += planes0;
+    if (vf.has_splines) {
+      vf.spl_seg += b->spl_seg.size();
+      vf.spl_rows += b->spl_idx.size();
+      vf.spl_idx += b->spl_idx.size();
+      b->spl_seg.insert(b->spl_seg.end(), f.spl_seg.begin(), f.spl_seg.end());
+      b->spl_idx.insert(b->spl_idx.end(), f.spl_idx.begin(), f.spl_idx.end());
+    }
     if (vf.upsampling > 1) {
       for (int c = 0; c < 3; c++) vf.up_pix[c] += b->farena_size;
       vf.up_kernel += fpool0;

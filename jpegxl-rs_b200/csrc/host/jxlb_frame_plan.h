@@ -338,25 +338,7 @@ inline void PlanCodestream(const uint8_t* cs, size_t cs_size, const PixelFormat&
   fo.stride = OutputStride((fo.orient & 4) ? bi.ysize : bi.xsize, fmt);
   if (!splines.segments.empty()) {  // the draw cache for DevSplinePixel
     fo.has_splines = 1;
-    fo.spl_seg = plan->spl_seg.size();
-    for (const SplineSegment& sg : splines.segments) {
-      auto bits = [](int64_t v) {
-        const int32_t c = static_cast<int32_t>(std::min<int64_t>(std::max<int64_t>(v, INT32_MIN), INT32_MAX));
-        float f;
-        std::memcpy(&f, &c, 4);
-        return f;
-      };
-      const float w[kSplineSegmentWords] = {sg.center_x, sg.center_y, sg.inv_sigma, sg.sigma_over_4_times_intensity,
-                                            sg.color[0], sg.color[1], sg.color[2],
-                                            bits(std::llround(sg.center_x - sg.maximum_distance)),
-                                            bits(std::llround(sg.center_x + sg.maximum_distance) + 1), 0.0f};
-      plan->spl_seg.insert(plan->spl_seg.end(), w, w + kSplineSegmentWords);
-    }
-    fo.spl_rows = plan->spl_idx.size();
-    JXLB_CHECK(splines.segment_y_start.size() == bi.ysize + 1, "internal: spline row table");
-    plan->spl_idx.insert(plan->spl_idx.end(), splines.segment_y_start.begin(), splines.segment_y_start.end());
-    fo.spl_idx = plan->spl_idx.size();
-    plan->spl_idx.insert(plan->spl_idx.end(), splines.segment_indices.begin(), splines.segment_indices.end());
+    PackSplineDrawCache(splines, bi.ysize, plan, &fo.spl_seg, &fo.spl_rows, &fo.spl_idx);
   }
   const uint32_t num_color = fmt.num_channels < 3 ? 1 : 3;
   const bool want_alpha = fmt.num_channels == 2 || fmt.num_channels == 4;

@@ -29,6 +29,31 @@ inline size_t OutputStride(uint32_t xsize, const PixelFormat& f) {
   return row;
 }
 
+// The spline draw cache as the device reads it (DevSplineAdd): kSplineSegmentWords floats per segment (the column span
+// precomputed as two int32 in float words), ysize + 1 row offsets, the per-row index lists. Offsets into the plan's pools.
+inline void PackSplineDrawCache(const SplineState& splines, uint32_t ysize, FramePlan* plan, uint64_t* seg_off, uint64_t* rows_off,
+                                uint64_t* idx_off) {
+  *seg_off = plan->spl_seg.size();
+  for (const SplineSegment& sg : splines.segments) {
+    auto bits = [](int64_t v) {
+      const int32_t c = static_cast<int32_t>(std::min<int64_t>(std::max<int64_t>(v, INT32_MIN), INT32_MAX));
+      float f;
+      std::memcpy(&f, &c, 4);
+      return f;
+    };
+    const float w[kSplineSegmentWords] = {sg.center_x, sg.center_y, sg.inv_sigma, sg.sigma_over_4_times_intensity,
+                                          sg.color[0], sg.color[1], sg.color[2],
+                                          bits(std::llround(sg.center_x - sg.maximum_distance)),
+                                          bits(std::llround(sg.center_x + sg.maximum_distance) + 1), 0.0f};
+    plan->spl_seg.insert(plan->spl_seg.end(), w, w + kSplineSegmentWords);
+  }
+  *rows_off = plan->spl_idx.size();
+  JXLB_CHECK(splines.segment_y_start.size() == static_cast<size_t>(ysize) + 1, "internal: spline row table");
+  plan->spl_idx.insert(plan->spl_idx.end(), splines.segment_y_start.begin(), splines.segment_y_start.end());
+  *idx_off = plan->spl_idx.size();
+  plan->spl_idx.insert(plan->spl_idx.end(), splines.segment_indices.begin(), splines.segment_indices.end());
+}
+
 // Plans the sections of a VarDCT frame. `br` is positioned after the TOC, `base` is the byte
 // offset of the first section inside `cs`.
 inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader& fh, const FrameDimensions& dim,
@@ -59,7 +84,8 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   VarDCTPlan& v = plan->v;
   DevVFrame& vf = v.vf;
   vf = DevVFrame{};
-  JXLB_CHECK(!(fh.flags & (kFlagSplines | kFlagNoise | kFlagUseDcFrame)), "unsupported: splines / noise / DC frame");
+  JXLB_CHECK(!(fh.flags & (kFlagNoise | kFlagUseDcFrame)), "unsupported: noise / DC frame");
+  JXLB_CHECK(!((fh.flags & kFlagSplines) && fh.upsampling > 1), "unsupported: splines in an upsampled frame");
   FramePlanner planner(plan);
   const size_t W = dim.xsize_blocks, H = dim.ysize_blocks, nb = W * H;
 
@@ -134,6 +160,8 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
       }
       JXLB_CHECK(reader.FinalStateOk(), "patches: bad ANS final state");
     }
+    SplineState splines;
+    if (fh.flags & kFlagSplines) ReadSplines(r, dim.xsize * dim.ysize, &splines);  // (dec_frame.cc:286-292)
     if (!r.ReadBool()) {
       for (int c = 0; c < 3; c++) {
         dc_quant[c] = ReadF16(r) * (1.0f / 128.0f);
@@ -166,6 +194,13 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
     vf.color_scale = 1.0f / color_factor;
     vf.cfl_dc_x = vf.base_x + ytox_dc * vf.color_scale;
     vf.cfl_dc_b = vf.base_b + ytob_dc * vf.color_scale;
+    if (fh.flags & kFlagSplines) {  // the draw cache wants the base correlation (dec_frame.cc:299-305)
+      InitSplineDrawCache(dim.xsize_upsampled, dim.ysize_upsampled, vf.base_x, vf.base_b, &splines);
+      if (!splines.segments.empty()) {
+        vf.has_splines = 1;
+        PackSplineDrawCache(splines, dim.ysize, plan, &vf.spl_seg, &vf.spl_rows, &vf.spl_idx);
+      }
+    }
     if (r.ReadBool()) {
       const size_t limit = std::min<size_t>(size_t{1} << 22, 1024 + dim.xsize * dim.ysize * std::max<size_t>(3, nb_extra) / 16);
       global_tree = planner.ReadTreeAndCode(r, limit);

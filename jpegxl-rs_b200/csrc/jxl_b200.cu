@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(256) k_color_write(DevVPools V, uint32_t frame
   }
   if (y >= vf.ysize) return;
   const uint32_t set = SetBeforeStage(vf, 3);
-  if (vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0 && vf.orient == 0) {
+  if (vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0 && vf.orient == 0 && !vf.has_splines) {
     // RGB8: each thread converts 4 consecutive pixels and writes 12 bytes as three words
     const uint32_t x = (blockIdx.x * 32 + threadIdx.x) * 4;
     if (x + 4 <= vf.xsize) {
@@ -1125,6 +1125,8 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     V.chain_pos = dec->d_chain_pos.p;
     V.arena = dec->d_arena.p;
     V.planes = dec->d_planes.p;
+    V.spl_seg = dec->d_spl_seg.p;
+    V.spl_idx = dec->d_spl_idx.p;
     V.ac_plain_ans = 1;
     for (const DevVFrame& vf : b.vframes)
       for (uint32_t p = 0; p < vf.num_passes; p++)

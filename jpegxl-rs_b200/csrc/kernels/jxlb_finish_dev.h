@@ -309,16 +309,15 @@ JXLB_HD float DevFastErff(float x) {
 // The splines' contribution to pixel (x, y) of a Modular frame, added to the three colour samples v[0..2] in the draw
 // order of the row's segment list (lib/jxl/splines.cc:78-113 DrawSegment, :167-175 DrawSegments): every segment whose
 // column span holds x adds colour * sigma / 4 * intensity * (erf(...) - erf(...))^2.
-JXLB_HD void DevSplinePixel(const DevPools& P, const DevFrameOut& fo, uint32_t x, uint32_t y, float* v) {
-  const uint32_t* rows = P.spl_idx + fo.spl_rows;
-  const uint32_t* idx = P.spl_idx + fo.spl_idx;
+JXLB_HD void DevSplineAdd(const uint32_t* rows, const uint32_t* idx, const float* seg, uint32_t xsize, uint32_t x, uint32_t y,
+                          float* v) {
   const float fx = static_cast<float>(static_cast<int32_t>(x)), fy = static_cast<float>(y);
   for (uint32_t i = rows[y]; i < rows[y + 1]; i++) {
-    const float* s = P.spl_seg + fo.spl_seg + static_cast<size_t>(idx[i]) * kSplineSegmentWords;
+    const float* s = seg + static_cast<size_t>(idx[i]) * kSplineSegmentWords;
     union { float f; int32_t i; } xa, xb;
     xa.f = s[7];
     xb.f = s[8];
-    const int32_t lo = xa.i > 0 ? xa.i : 0, hi = xb.i < static_cast<int32_t>(fo.xsize) ? xb.i : static_cast<int32_t>(fo.xsize);
+    const int32_t lo = xa.i > 0 ? xa.i : 0, hi = xb.i < static_cast<int32_t>(xsize) ? xb.i : static_cast<int32_t>(xsize);
     if (static_cast<int32_t>(x) < lo || static_cast<int32_t>(x) >= hi) continue;
     const float dx = fx - s[0], dy = fy - s[1];
     const float distance = sqrtf(fmaf(dx, dx, dy * dy));
@@ -328,6 +327,10 @@ JXLB_HD void DevSplinePixel(const DevPools& P, const DevFrameOut& fo, uint32_t x
     v[1] = fmaf(s[5], li, v[1]);
     v[2] = fmaf(s[6], li, v[2]);
   }
+}
+
+JXLB_HD void DevSplinePixel(const DevPools& P, const DevFrameOut& fo, uint32_t x, uint32_t y, float* v) {
+  DevSplineAdd(P.spl_idx + fo.spl_rows, P.spl_idx + fo.spl_idx, P.spl_seg + fo.spl_seg, fo.xsize, x, y, v);
 }
 
 // Converts and stores one pixel (all channels).

@@ -89,6 +89,10 @@ struct DevVFrame {
   uint32_t alpha_plane;
   float alpha_factor;
   uint64_t up_pix[3];  // farena index
+  // splines (lib/jxl/splines.cc; stage_splines.cc): added to the X, Y, B samples in front of the colour transform;
+  // offsets into the batch's spline pools as DevFrameOut::spl_* (jxlb_dev.h)
+  uint32_t has_splines, spl_pad_;
+  uint64_t spl_rows, spl_idx, spl_seg;
 };
 
 // A reference-only frame (lib/jxl/frame_header.h kReferenceOnly, saved before the colour transform): its Modular

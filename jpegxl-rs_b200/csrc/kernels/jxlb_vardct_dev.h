@@ -56,6 +56,8 @@ struct DevVPools {
   uint64_t* chain_pos;    // DevAcStream::chain_slot: the bit position behind the stream's last coefficient
   const int32_t* arena;   // the Modular sample arena and plane table (alpha of VarDCT frames with extra channels)
   const DevPlane* planes;
+  const float* spl_seg;   // spline draw cache: segments, row offsets + index lists (DevSplineAdd)
+  const uint32_t* spl_idx;
 };
 
 #if defined(__CUDACC__)
@@ -1722,6 +1724,13 @@ JXLB_HD void DevPatchPixel(const DevVPools& V, const DevVFrame& vf, const DevPat
 
 // One output pixel from its three filtered samples: colour transform + sample conversion + interleaved store.
 JXLB_HD void DevColorStore(const DevVPools& V, const DevVFrame& vf, float p0, float p1, float p2, uint32_t x, uint32_t y) {
+  if (vf.has_splines) {  // (rare) SplineStage sits behind the loop filters and patches, in XYB
+    float v[3] = {p0, p1, p2};
+    DevSplineAdd(V.spl_idx + vf.spl_rows, V.spl_idx + vf.spl_idx, V.spl_seg + vf.spl_seg, vf.xsize, x, y, v);
+    p0 = v[0];
+    p1 = v[1];
+    p2 = v[2];
+  }
   float r, g, b;
   DevColorTransform(vf, p0, p1, p2, &r, &g, &b);
   // alpha: the frame's Modular extra channel (int -> float like DevSampleFloat), else opaque
@@ -1947,7 +1956,7 @@ JXLB_HD void DevRenderTile(const DevVPools& V, const DevVFrame& vf, int tx0, int
     nxt = t;
   }
   // colour transform + output samples of the kRtW x kRtH tile
-  const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0 && vf.orient == 0;
+  const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0 && vf.orient == 0 && !vf.has_splines;
   for (uint32_t i = tid; i < static_cast<uint32_t>(kRtW / 4 * kRtH); i += nt) {
     const int lx = static_cast<int>(i % (kRtW / 4)) * 4, ly = static_cast<int>(i / (kRtW / 4));
     const int fx = tx0 + lx, fy = ty0 + ly;

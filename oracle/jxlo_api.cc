@@ -136,6 +136,7 @@ size_t jxlo_encode_vardct(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, fl
     p.orientation = 1 + ((gab >> 8) & 7);   // bits 8-10: the image's orientation - 1
     p.alpha = g_next_alpha;
     g_next_alpha = nullptr;
+    p.splines = (gab >> 11) & 15;           // bits 11-14: number of random splines
     p.epf_iters = epf_iters;
     p.dc_smoothing = dc_smoothing != 0;
     p.random_side_info = random_side_info != 0;
@@ -168,6 +169,7 @@ size_t jxlo_encode_modular(const uint16_t* samples, uint32_t xsize, uint32_t ysi
     p.entropy = static_cast<int>(params[12]);
     p.lz77_min_symbol = params[13] ? params[13] : 224;
     p.orientation = params[14] ? params[14] : 1;
+    p.splines = params[15];
     g_encoded = EncodeModular(samples, xsize, ysize, p);
     return g_encoded.size();
   } catch (const std::exception& e) {

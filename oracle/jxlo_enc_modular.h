@@ -23,6 +23,7 @@ namespace jxlo {
 
 struct ModularEncodeParams {
   uint32_t orientation = 1;  // ImageMetadata::orientation
+  uint32_t splines = 0;      // > 0: this many seeded random splines (frame flag kSplines; three colour channels)
   uint32_t bits = 8;              // integer bits per sample, 1 .. 16
   uint32_t num_color = 3;         // 1 (grey) or 3
   bool alpha = false;             // one alpha extra channel of the same depth
@@ -449,7 +450,7 @@ inline void WriteModularFrameHeader(BitWriter& w, const ModularEncodeParams& p) 
   w.Write(1, 0);  // not all_default
   w.Write(2, kRegularFrame);
   w.Write(1, 1);  // Modular
-  WriteU64(w, 0);  // flags
+  WriteU64(w, p.splines ? uint64_t{kFlagSplines} : uint64_t{0});  // flags
   w.Write(1, 0);  // no YCbCr
   WriteU32(w, 1, Val(1), Val(2), Val(4), Val(8));  // upsampling
   if (p.alpha) WriteU32(w, 1, Val(1), Val(2), Val(4), Val(8));
@@ -602,6 +603,7 @@ inline std::vector<uint8_t> EncodeModular(const uint16_t* samples, uint32_t xsiz
     for (Stream& s : *list) code.Count(s.toks, s.dist_mult);
 
   BitWriter dc_global;
+  if (p.splines) WriteRandomSplines(dc_global, p.splines, xsize, ysize, p.seed, eopt);
   dc_global.Write(1, 1);  // default DC quantisation factors
   dc_global.Write(1, 1);  // global MA tree
   tree_code.WriteHeader(dc_global);

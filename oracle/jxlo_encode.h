@@ -852,6 +852,11 @@ inline void LinearRgbToXyb(float r, float g, float b, float* x, float* y, float*
 }
 
 // ---------------------------------------------------------------- the encoder
+// Seeded random splines written into DC global (decoder coverage of lib/jxl/splines.cc): `count` splines inside an
+// xsize x ysize frame, in the token order Splines::Decode reads (:607-650; QuantizedSpline::Decode :547-596).
+inline void WriteRandomSplines(BitWriter& w, uint32_t count, uint32_t xsize, uint32_t ysize, uint32_t seed,
+                               const EntropyOptions& eopt = EntropyOptions());
+
 struct EncodeParams {
   float distance = 1.0f;
   // 0: DCT8 only; 1: seeded random mix of all 27 strategies (decoder coverage);
@@ -887,7 +892,53 @@ struct EncodeParams {
   // global tree the way libjxl places them (lib/jxl/enc_modular.cc:1258-1500, lib/jxl/dec_frame.cc:315-365, :478-560):
   // the global stream when the channel fits one group, else one stream per AC group behind that group's coefficients.
   const uint8_t* alpha = nullptr;
+  uint32_t splines = 0;  // > 0: this many seeded random splines (frame flag kSplines, drawn over the decoded colour)
 };
+
+inline void WriteRandomSplines(BitWriter& w, uint32_t count, uint32_t xsize, uint32_t ysize, uint32_t seed, const EntropyOptions& eopt) {
+  std::mt19937 rng(seed * 2654435761u + 97u);
+  auto rnd = [&](int lo, int hi) { return lo + static_cast<int>(rng() % static_cast<uint32_t>(hi - lo + 1)); };
+  std::vector<Token> t;
+  t.push_back({2, count - 1});  // kNumSplinesContext
+  int last_x = 0, last_y = 0;
+  for (uint32_t i = 0; i < count; i++) {  // kStartingPositionContext
+    const int x = rnd(4, static_cast<int>(xsize) - 5), y = rnd(4, static_cast<int>(ysize) - 5);
+    if (i == 0) {
+      t.push_back({1, static_cast<uint32_t>(x)});
+      t.push_back({1, static_cast<uint32_t>(y)});
+    } else {
+      t.push_back({1, PackSigned(x - last_x)});
+      t.push_back({1, PackSigned(y - last_y)});
+    }
+    last_x = x;
+    last_y = y;
+  }
+  t.push_back({0, PackSigned(rnd(-2, 3))});  // kQuantizationAdjustmentContext
+  for (uint32_t i = 0; i < count; i++) {
+    const uint32_t n = static_cast<uint32_t>(rnd(1, 5));
+    t.push_back({3, n});  // kNumControlPointsContext
+    int dx = 0, dy = 0;
+    for (uint32_t k = 0; k < n; k++) {  // double deltas; the running delta never becomes (0, 0)
+      int ddx = rnd(-9, 9), ddy = rnd(-9, 9);
+      if (dx + ddx == 0 && dy + ddy == 0) ddx += 3;
+      dx += ddx;
+      dy += ddy;
+      t.push_back({4, PackSigned(ddx)});
+      t.push_back({4, PackSigned(ddy)});
+    }
+    for (int c = 0; c < 4; c++)  // X, Y, B, sigma: a strong DC term, a few small harmonics (kDCTContext)
+      for (int k = 0; k < 32; k++) {
+        int v = 0;
+        if (k == 0) v = c == 3 ? rnd(6, 30) : rnd(-60, 60);
+        else if (k < 4) v = rnd(-3, 3);
+        t.push_back({5, PackSigned(v)});
+      }
+  }
+  EntropyEncoder code(6, {0, 1, 2, 3, 4, 5}, eopt);
+  code.Count(t);
+  code.WriteHeader(w);
+  code.WriteTokens(w, t);
+}
 
 struct EncoderStats {
   size_t num_groups = 0, num_varblocks = 0, bytes = 0;
@@ -931,7 +982,7 @@ inline void WriteFrameHeader(BitWriter& w, const EncodeParams& p) {
   w.Write(1, 0);  // not all_default
   w.Write(2, kRegularFrame);
   w.Write(1, 0);  // VarDCT
-  WriteU64(w, p.dc_smoothing ? uint64_t{0} : uint64_t{kFlagSkipAdaptiveDCSmoothing});
+  WriteU64(w, (p.dc_smoothing ? uint64_t{0} : uint64_t{kFlagSkipAdaptiveDCSmoothing}) | (p.splines ? uint64_t{kFlagSplines} : uint64_t{0}));
   WriteU32(w, p.upsampling, Val(1), Val(2), Val(4), Val(8));  // upsampling
   if (p.alpha) WriteU32(w, p.upsampling, Val(1), Val(2), Val(4), Val(8));  // of the extra channel
   w.Write(3, p.x_qm_scale);
@@ -2122,6 +2173,7 @@ inline std::vector<uint8_t> EncodeVarDCT(const uint8_t* rgb, uint32_t xsize, uin
   for (size_t g = 0; g < num_groups; g++) modular_code.Count(alpha_group_toks[g]);
   BitWriter dc_global;
   {
+    if (p.splines) WriteRandomSplines(dc_global, p.splines, xsize, ysize, p.seed, eopt);
     dc_global.Write(1, 1);  // default DC quantisation
     WriteU32(dc_global, global_scale, BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193));
     WriteU32(dc_global, quant_dc, Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1));

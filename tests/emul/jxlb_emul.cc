@@ -193,6 +193,8 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
       V.chain_pos = chain_pos.data();
       V.arena = arena.data();
       V.planes = b.planes.data();
+      V.spl_seg = b.spl_seg.data();
+      V.spl_idx = b.spl_idx.data();
       for (const DevRefFrame& rf : b.ref_frames)  // k_ref_frames
         for (uint32_t i = 0; i < rf.w * rf.h; i++) DevRefFrameSample(P, V, rf, i);
       uint32_t dcg = 0;
@@ -335,7 +337,7 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
             for (uint32_t x = 0; x < vf.up_xsize; x++) DevColorPixel(V, vf, 0, x, y);
           continue;
         }
-        const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0 && vf.orient == 0;
+        const bool x4 = vf.out_type == 2 && vf.out_channels == 3 && vf.out_stride % 4 == 0 && vf.orient == 0 && !vf.has_splines;
         for (uint32_t y = 0; y < vf.ysize; y++)
           for (uint32_t x = 0; x < vf.xsize; x++) {
             if (x4 && x % 4 == 0 && x + 4 <= vf.xsize) {  // the kernel's vector path

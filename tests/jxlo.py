@@ -101,7 +101,7 @@ def decode(data: bytes, num_channels: int, data_type: int, endianness: int = 0, 
 
 def encode_vardct(rgb: np.ndarray, distance=1.0, strategy_mode=2, seed=1, gab=True, epf_iters=2, dc_smoothing=True,
                   random_side_info=False, num_passes=1, dc_tree=0, inverse_gaborish=True, coeff_orders=True, cfl=True,
-                  adaptive_quant=True, prefix_codes=False, upsampling=1, orientation=1) -> bytes:
+                  adaptive_quant=True, prefix_codes=False, upsampling=1, orientation=1, splines=0) -> bytes:
     """RGB8 (H, W, 3) -> a VarDCT codestream written by the oracle's plain encoder (stream generator). (H, W, 4): the
     fourth channel travels as a lossless 8-bit alpha extra channel in the frame's Modular sub-streams."""
     L = lib()
@@ -115,7 +115,7 @@ def encode_vardct(rgb: np.ndarray, distance=1.0, strategy_mode=2, seed=1, gab=Tr
         L.jxlo_set_next_alpha(alpha.ctypes.data_as(ctypes.c_void_p))
     assert c == 3
     err = ctypes.create_string_buffer(512)
-    gab_arg = int(bool(gab)) | (0 if inverse_gaborish else 2) | (0 if coeff_orders else 4) | (0 if cfl else 8) | (0 if adaptive_quant else 16) | (32 if prefix_codes else 0) | ({1: 0, 2: 1, 4: 2, 8: 3}[upsampling] << 6) | ((orientation - 1) << 8)
+    gab_arg = int(bool(gab)) | (0 if inverse_gaborish else 2) | (0 if coeff_orders else 4) | (0 if cfl else 8) | (0 if adaptive_quant else 16) | (32 if prefix_codes else 0) | ({1: 0, 2: 1, 4: 2, 8: 3}[upsampling] << 6) | ((orientation - 1) << 8) | (splines << 11)
     n = L.jxlo_encode_vardct(rgb.ctypes.data, w, h, distance, strategy_mode, seed, gab_arg, epf_iters,
                              int(dc_smoothing), int(random_side_info), num_passes, dc_tree, err, 512)
     if n == 0:
@@ -127,7 +127,7 @@ def encode_vardct(rgb: np.ndarray, distance=1.0, strategy_mode=2, seed=1, gab=Tr
 
 def encode_modular(img: np.ndarray, bits=8, alpha=False, group_size_shift=1, tree=0, predictor=5, seed=1, rct=-1,
                    palette_colors=0, palette_deltas=0, palette_predictor=0, squeeze=False, prefix=False, lz77=False,
-                   lz77_min_symbol=224, orientation=1) -> bytes:
+                   lz77_min_symbol=224, orientation=1, splines=0) -> bytes:
     """(H, W, C) integer samples -> a lossless Modular codestream written by the oracle's plain encoder
     (oracle/jxlo_enc_modular.h). C = 1 / 3 colour channels (+ 1 when alpha)."""
     L = lib()
@@ -136,7 +136,7 @@ def encode_modular(img: np.ndarray, bits=8, alpha=False, group_size_shift=1, tre
     num_color = c - (1 if alpha else 0)
     assert num_color in (1, 3)
     params = np.array([bits, num_color, int(alpha), group_size_shift, tree, predictor, seed, rct + 1, palette_colors,
-                       palette_deltas, palette_predictor, int(squeeze), int(prefix) | (int(lz77) << 1), lz77_min_symbol, orientation, 0],
+                       palette_deltas, palette_predictor, int(squeeze), int(prefix) | (int(lz77) << 1), lz77_min_symbol, orientation, splines],
                       np.uint32)
     err = ctypes.create_string_buffer(512)
     n = L.jxlo_encode_modular(img.ctypes.data, w, h, params.ctypes.data, err, 512)

@@ -158,3 +158,19 @@ def test_alpha_channel_in_lossy_frames(pkg):
     meta, px = dec.decode(files[0])
     assert meta.has_alpha_channel and px.variant == "Uint8"
     assert np.array_equal(np.asarray(px.data).reshape(300, 520, 4), jxlo.decode(files[0], 4, jxlo.UINT8))
+
+
+def test_splines_in_lossy_frames(pkg):
+    # splines drawn over VarDCT frames in front of the colour transform (DevColorStore -> DevSplineAdd), in a batch
+    # with spline-free frames and the reference's Modular spline fixture
+    img = vc.crop(300, 420, 100, 200)
+    files = [jxlo.encode_vardct(img, strategy_mode=2, splines=5), jxlo.encode_vardct(img[:60, :70], strategy_mode=2, splines=3),
+             jxlo.encode_vardct(vc.crop(520, 300, 50, 60), strategy_mode=3, splines=9, epf_iters=1, seed=4),
+             jxlo.encode_vardct(vc.crop(1000, 1500, 0, 0), strategy_mode=2, splines=15),
+             vc.encoded("odd_size")[0], read_golden("2bit.jxl")]
+    for nc, npdt, dt in [(3, np.uint8, jxlo.UINT8), (4, np.uint8, jxlo.UINT8), (3, np.uint16, jxlo.UINT16), (4, np.float32, jxlo.FLOAT)]:
+        outs = pkg.decode_batch(files, nc, npdt)
+        for f, o in zip(files, outs):
+            assert np.array_equal(o.view(np.uint8), jxlo.decode(f, nc, dt).view(np.uint8))
+    o = jxlo.encode_vardct(img[:100, :150], strategy_mode=2, splines=4, orientation=7)
+    assert np.array_equal(pkg.decode_batch([o], 3, np.uint8)[0], jxlo.decode(o, 3, jxlo.UINT8, undo_orientation=True))

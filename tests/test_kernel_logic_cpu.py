@@ -70,6 +70,7 @@ def test_corrupted_and_truncated_inputs_fail_with_an_error():
     files["alpha_small"] = (jxlo.encode_vardct(np.ascontiguousarray(rgba[:60, :70]), strategy_mode=2), (60, 70))
     files["lossless"] = (emul_lib.encode_lossless(np.ascontiguousarray(rgba[:150, :300])), (150, 300))
     files["2bit.jxl"] = (read_golden("2bit.jxl"), (600, 800))
+    files["lossy_splines"] = (jxlo.encode_vardct(img, strategy_mode=2, splines=6), (300, 520))
     rng = np.random.default_rng(7)
     errors = 0
     for name, (data, shape) in files.items():

@@ -221,3 +221,29 @@ def test_vardct_frames_with_an_alpha_channel(monkeypatch):
         assert np.array_equal(g, jxlo.decode(f, 4, jxlo.UINT8))
     got = emul_lib.decode([files[5]], 4, jxlo.UINT8, [(263, 257)], endianness=0x400)[0]
     assert np.array_equal(got, jxlo.decode(files[5], 4, jxlo.UINT8, undo_orientation=True))
+
+
+def test_splines_in_lossy_frames():
+    # Splines over a VarDCT frame (lib/jxl/dec_frame.cc:286-305, render_pipeline/stage_splines.cc): read from DC global
+    # in front of the DC quantisation, drawn in XYB with the frame's base colour correlation behind the loop filters;
+    # multi-group and single-section (probe round) frames, with alpha and an orientation, beside spline-free frames and
+    # the reference's spline fixture in one batch
+    img = vc.crop(300, 420, 100, 200)
+    files = [jxlo.encode_vardct(img, strategy_mode=2, splines=5), jxlo.encode_vardct(img[:60, :70], strategy_mode=2, splines=3),
+             jxlo.encode_vardct(vc.crop(520, 300, 50, 60), strategy_mode=3, splines=9, epf_iters=1, seed=4),
+             jxlo.encode_vardct(_rgba(257, 263, 700, 100), strategy_mode=2, splines=6),
+             vc.encoded("odd_size")[0], read_golden("2bit.jxl")]
+    shapes = [(300, 420), (60, 70), (520, 300), (257, 263), vc.encoded("odd_size")[1], (600, 800)]
+    plain = jxlo.decode(jxlo.encode_vardct(img, strategy_mode=2), 3, jxlo.UINT8)
+    assert (plain != jxlo.decode(files[0], 3, jxlo.UINT8)).any(axis=2).mean() > 0.05  # the splines are visible
+    for nc, dt in [(3, jxlo.UINT8), (4, jxlo.UINT8), (3, jxlo.UINT16), (4, jxlo.FLOAT)]:
+        got = emul_lib.decode(files, nc, dt, shapes)
+        for g, f in zip(got, files):
+            assert np.array_equal(g.view(np.uint8), jxlo.decode(f, nc, dt).view(np.uint8))
+    o = jxlo.encode_vardct(img[:100, :150], strategy_mode=2, splines=4, orientation=7)
+    got = emul_lib.decode([o], 3, jxlo.UINT8, [(150, 100)], endianness=0x400)[0]
+    assert np.array_equal(got, jxlo.decode(o, 3, jxlo.UINT8, undo_orientation=True))
+    # Modular frames with splines written by the oracle's encoder (2bit.jxl is the reference's own)
+    m = np.random.default_rng(1).integers(0, 256, (120, 200, 3)).astype(np.uint16)
+    e = jxlo.encode_modular(m, bits=8, tree=1, splines=4)
+    assert np.array_equal(emul_lib.decode([e], 3, jxlo.UINT8, [(120, 200)])[0], jxlo.decode(e, 3, jxlo.UINT8))
