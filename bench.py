@@ -22,6 +22,7 @@ The default run folds short side runs of the other workloads into `also`: the fi
 lossless encoder (tools/bench_lossless_enc.py).
 """
 import argparse
+import ctypes
 import hashlib
 import json
 import os
@@ -364,6 +365,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="vardct4k", choices=["vardct4k", "modular", "encode4k"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 256 vardct4k, 256 modular, 8 encode4k)")
+    ap.add_argument("--e2e-plan-threads", type=int, default=0,
+                    help="planning threads per handle in the streaming end-to-end loop (default: host cpus / handles in flight)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (default: 3 per handle in flight)")
+    ap.add_argument("--no-mallopt", action="store_true", help="leave glibc's malloc thresholds alone")
+    ap.add_argument("--e2e-serial", action="store_true",
+                    help="end-to-end loop without the streaming calls (parse, kernels and read-back of a handle one after the other)")
     ap.add_argument("--inflight", type=int, default=8,
                     help="decoder handles in flight, each with its own buffers and CUDA stream: the latency-bound "
                          "entropy kernels of one batch overlap the per-pixel kernels of the previous one")
@@ -402,6 +409,17 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    # The planner builds a few hundred MB of tables per batch in std::vectors; glibc would mmap and unmap them batch
+    # after batch (page faults on every first touch, mmap-lock traffic between the planning threads of the handles in
+    # flight): keep freed memory in the heap instead. An application-level setting, so it is made here, not in the library.
+    try:
+        if args.no_mallopt:
+            raise OSError
+        libc = ctypes.CDLL("libc.so.6")
+        libc.mallopt(-3, 32 << 20)        # M_MMAP_THRESHOLD: glibc's maximum
+        libc.mallopt(-1, (1 << 31) - 1)   # M_TRIM_THRESHOLD: never trim
+    except OSError:
+        pass
     wl = Workload(args.workload, args.batch)
     if wl.name == "vardct4k" and not args.replicas:
         wl.make_distinct(pkg, local_rank)
@@ -561,7 +579,16 @@ def main():
     # host memory. Steps run on `inflight` handles from as many host threads (ctypes drops the GIL), so the host
     # parse and the copies of one step overlap the kernels of another -- the same pipelining as above.
     # (pinned host memory: one output set per handle in flight, bounded by this rank's share of the free host memory)
-    set_bytes = sum(dec.out_size(i) for i in range(wl.batch))
+    # (one pinned arena per set, laid out like the device output buffer -- frames back to back, 256-byte aligned -- so
+    # that the frames of a wave leave in one copy: JxlB200DecoderRunToHost merges neighbours)
+    out_base = dec.device_output(0)
+    out_offs = [dec.device_output(i) - out_base for i in range(wl.batch)]
+    set_bytes = dec.device_output_bytes()
+
+    def pinned_set():
+        arena = torch.empty(set_bytes, dtype=torch.uint8).pin_memory().numpy()
+        return [arena[o:o + dec.out_size(i)] for i, o in enumerate(out_offs)]
+
     try:
         import psutil
         share = psutil.virtual_memory().available / max(1, local_world)
@@ -574,7 +601,7 @@ def main():
     out_sets = []
     for _ in range(nfl_e2e):
         try:
-            out_sets.append([torch.empty(dec.out_size(i), dtype=torch.uint8).pin_memory().numpy() for i in range(wl.batch)])
+            out_sets.append(pinned_set())
         except RuntimeError as e:  # the host refuses to pin more: go on with the sets there are
             if rank == 0:
                 print("e2e: pinning stopped after %d output sets (%s)" % (len(out_sets), str(e).splitlines()[0]), file=sys.stderr)
@@ -601,37 +628,65 @@ def main():
 
     # enough steps for the handles to fall out of lock step (parse / kernels / read-back of different steps overlap);
     # the ramp-up and the drain stay inside the timed region
-    e2e_steps = max(3 * nfl_e2e, min(args.steps, 16))
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(3 * nfl_e2e, min(args.steps, 16))
 
-    phase_s = {"set_input": 0.0, "run_wait": 0.0, "read_outputs": 0.0}
+    # A handle streams (include/jxl_b200.h, PlanBatch / CommitPlan / RunToHost): while its kernels decode step k the
+    # host parses step k + 1 into the pending plan, and every wave's frames leave for the pinned buffers as soon as they
+    # are rendered; after wait() the upload of the pending plan is all that keeps the handle off the GPU. Every step
+    # still does all of it: host parse, H2D of bitstreams and tables, kernels, D2H of every pixel.
+    phase_s = {"plan": 0.0, "commit_h2d": 0.0, "launch": 0.0, "wait_incl_d2h": 0.0}
     phase_lock = threading.Lock()
-
-    def e2e_step(h):
-        d, sx = decs[h], streams[h]
-        t0 = time.perf_counter()
-        d.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8, threads=plan_threads)
-        t1 = time.perf_counter()
-        d.run(sx)
-        d.wait(sx)
-        t2 = time.perf_counter()
-        d.read_outputs(out_sets[h])
-        t3 = time.perf_counter()
-        with phase_lock:
-            phase_s["set_input"] += t1 - t0
-            phase_s["run_wait"] += t2 - t1
-            phase_s["read_outputs"] += t3 - t2
+    # Planning runs in the shadow of the handle's kernels, so it does not have to be fast, it has to leave the cores to
+    # the threads that launch and copy: the handles share the rank's cores instead of each starting one thread per core
+    # (measured: 8 handles x 16 planning threads on 16 cores made a launch call take 300 ms).
+    stream_threads = args.e2e_plan_threads if args.e2e_plan_threads > 0 else max(1, host["cpus"] // max(nfl_e2e, 1))
 
     def e2e_round(n):
         it = iter(range(n))
         lock = threading.Lock()
 
+        def take():
+            with lock:
+                return next(it, None)
+
+        def serial_worker(h):  # --e2e-serial: set_input -> run -> wait -> read_outputs, nothing ahead (the round-1 loop)
+            d, sx = decs[h], streams[h]
+            while take() is not None:
+                d.set_input(files, wl.channels, pkg.JXL_TYPE_UINT8, threads=plan_threads)
+                d.run(sx)
+                d.wait(sx)
+                d.read_outputs(out_sets[h])
+
         def worker(h):
-            while True:
-                with lock:
-                    k = next(it, None)
-                if k is None:
-                    return
-                e2e_step(h)
+            if args.e2e_serial:
+                return serial_worker(h)
+            d, sx = decs[h], streams[h]
+            acc = dict.fromkeys(phase_s, 0.0)
+            k = take()
+            if k is None:
+                return
+            t0 = time.perf_counter()
+            d.plan(files, wl.channels, pkg.JXL_TYPE_UINT8, threads=stream_threads)
+            acc["plan"] += time.perf_counter() - t0
+            while k is not None:
+                t0 = time.perf_counter()
+                d.commit()
+                t1 = time.perf_counter()
+                d.run_to_host(out_sets[h], sx)
+                t2 = time.perf_counter()
+                k = take()
+                if k is not None:
+                    d.plan(files, wl.channels, pkg.JXL_TYPE_UINT8, threads=stream_threads)
+                t3 = time.perf_counter()
+                d.wait(sx)
+                t4 = time.perf_counter()
+                acc["commit_h2d"] += t1 - t0
+                acc["launch"] += t2 - t1
+                acc["plan"] += t3 - t2
+                acc["wait_incl_d2h"] += t4 - t3
+            with phase_lock:
+                for key, v in acc.items():
+                    phase_s[key] += v
 
         ts = [threading.Thread(target=worker, args=(h,)) for h in range(nfl_e2e)]
         for t in ts:
@@ -640,6 +695,8 @@ def main():
             t.join()
 
     e2e_round(nfl_e2e)  # warm-up
+    for key in phase_s:  # (the warm-up round pays the one-time pinned allocations of the second staging buffers)
+        phase_s[key] = 0.0
     barrier()
     t0 = time.perf_counter()
     e2e_round(e2e_steps)
@@ -651,7 +708,7 @@ def main():
     e2e_s = float(t.item())
     e2e_value = pixels_per_step / e2e_s / 1e6
     if rank == 0:  # where a step's wall time goes (summed over the overlapping handles, warm-up included)
-        n_e2e = e2e_steps + nfl_e2e
+        n_e2e = e2e_steps
         print("e2e phases per step (ms): " + ", ".join("%s %.1f" % (k, v / n_e2e * 1e3) for k, v in phase_s.items()),
               file=sys.stderr)
 
@@ -694,8 +751,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(st.compressed_bytes), "d2h_bytes_per_step": int(st.output_bytes),
-                    "includes": "host parse (threads) + H2D bitstreams/tables + kernels + D2H to pinned host, "
-                                "%d steps in flight" % nfl_e2e,
+                    "includes": "host parse (threads, a step ahead of the handle's kernels) + H2D bitstreams/tables + kernels + D2H to pinned host (per wave of rendered frames), "
+                                "%d steps in flight, %d planning threads per handle" % (nfl_e2e, stream_threads) + (" [--e2e-serial: nothing ahead, read-back after the kernels]" if args.e2e_serial else ""),
                     "d2h_alone_ms_per_step": d2h_s * 1e3,
                     "d2h_ceiling_gbs_per_gpu": st.output_bytes / d2h_s / 1e9,
                     "d2h_ceiling_value": pixels_per_step / d2h_s / 1e6,

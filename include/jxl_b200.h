@@ -109,6 +109,21 @@ int JxlB200DecoderReadOutput(JxlB200Decoder* dec, size_t i, void* dst, size_t si
 /* Device -> host copy of all frames; dsts[i] receives frame i. */
 int JxlB200DecoderReadOutputs(JxlB200Decoder* dec, void* const* dsts, const size_t* sizes, size_t n);
 
+/* Streaming use of one handle (the decode loop of a server: batch k + 1 is parsed while batch k decodes, and batch k's
+ * pixels leave for the host while its later frames are still being rendered):
+ *   PlanBatch   = the host half of SetInputBatch (parse on `num_threads` threads into a pending plan; no device work
+ *                 except the probe rounds of single-section frames) -- may run while the handle's kernels are in flight;
+ *   CommitPlan  = the device half (upload of the pending plan's bitstreams and tables; call after Wait of the batch
+ *                 before). SetInputBatch is PlanBatch + CommitPlan;
+ *   RunToHost   = Run, with frame i copied into dsts[i] (pinned host memory for the copies to overlap) on a copy stream
+ *                 as soon as the kernels that write it are through; the buffers are complete when Wait returns.
+ * The same role as feeding libjxl's decoder from one thread while another consumes JXL_DEC_FULL_IMAGE
+ * (jpegxl-rs/src/decode.rs:231-327 runs them back to back on one thread). */
+int JxlB200DecoderPlanBatch(JxlB200Decoder* dec, const uint8_t* const* files, const size_t* sizes, size_t n,
+                            const JxlPixelFormat* format, int num_threads);
+int JxlB200DecoderCommitPlan(JxlB200Decoder* dec);
+int JxlB200DecoderRunToHost(JxlB200Decoder* dec, void* cuda_stream, void* const* dsts, const size_t* sizes, size_t n);
+
 /* Workload figures for benchmarks. */
 typedef struct {
   uint64_t compressed_bytes; /* bitstream bytes resident in HBM */

@@ -145,6 +145,10 @@ def load_library() -> ctypes.CDLL:
     lib.JxlB200DecoderDeviceOutput.argtypes = [vp, sz]
     lib.JxlB200DecoderReadOutput.argtypes = [vp, sz, vp, sz]
     lib.JxlB200DecoderReadOutputs.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), sz]
+    lib.JxlB200DecoderPlanBatch.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), sz,
+                                            ctypes.POINTER(JxlPixelFormat), ctypes.c_int]
+    lib.JxlB200DecoderCommitPlan.argtypes = [vp]
+    lib.JxlB200DecoderRunToHost.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), sz]
     lib.JxlB200DecoderGetStats.argtypes = [vp, ctypes.POINTER(JxlB200Stats)]
     lib.JxlB200DecoderSetProfiling.argtypes = [vp, ctypes.c_int]
     lib.JxlB200DecoderSetPhaseMask.argtypes = [vp, ctypes.c_uint32]
@@ -233,6 +237,7 @@ EXPORTED_SYMBOLS = [
     "JxlB200DecoderCreate", "JxlB200DecoderDestroy", "JxlB200DecoderGetError", "JxlB200DecoderSetInputBatch",
     "JxlB200DecoderSetKeepOrientation", "JxlB200DecoderNumFrames", "JxlB200DecoderGetBasicInfo", "JxlB200DecoderImageOutBufferSize", "JxlB200DecoderRun",
     "JxlB200DecoderWait", "JxlB200DecoderDeviceOutput", "JxlB200DecoderReadOutput", "JxlB200DecoderReadOutputs",
+    "JxlB200DecoderPlanBatch", "JxlB200DecoderCommitPlan", "JxlB200DecoderRunToHost",
     "JxlB200DecoderGetStats", "JxlB200DecoderSetProfiling", "JxlB200DecoderSetPhaseMask", "JxlB200DecoderDeviceOutputBytes", "JxlB200DecoderGetKernelTimes",
     "JxlB200DecoderGetKernelTimesEx", "JxlB200EncoderCreate", "JxlB200EncoderDestroy", "JxlB200EncoderGetError",
     "JxlB200EncoderEncodeBatch", "JxlB200EncoderEncodeLosslessBatch", "JxlB200EncoderOutputSize", "JxlB200EncoderReadOutput", "JxlB200EncoderGetPhaseTimes",
@@ -474,8 +479,42 @@ class BatchDecoder:
         self.format = fmt
         self.num_frames = n
 
+    def plan(self, files: Sequence[bytes], num_channels: int = 4, data_type: int = JXL_TYPE_UINT8,
+             endianness: int = JXL_NATIVE_ENDIAN, align: int = 0, threads: int = 0, keep_orientation: bool = False) -> None:
+        """The host half of set_input (parse into a pending plan): may run while this handle's kernels are in flight.
+        commit() uploads it (after wait() of the batch before)."""
+        self._lib.JxlB200DecoderSetKeepOrientation(self._dec, int(keep_orientation))
+        n = len(files)
+        bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
+        ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (ctypes.c_size_t * n)(*[b.size for b in bufs])
+        fmt = JxlPixelFormat(num_channels, data_type, endianness, align)
+        if threads <= 0:
+            threads = min(os.cpu_count() or 1, 32)
+        if self._lib.JxlB200DecoderPlanBatch(self._dec, ptrs, sizes, n, ctypes.byref(fmt), threads) != 0:
+            raise GenericError(self._err())
+        self._pending = (fmt, n)
+
+    def commit(self) -> None:
+        if self._lib.JxlB200DecoderCommitPlan(self._dec) != 0:
+            raise GenericError(self._err())
+        self.format, self.num_frames = self._pending
+
     def run(self, cuda_stream: int = 0) -> None:
         if self._lib.JxlB200DecoderRun(self._dec, ctypes.c_void_p(cuda_stream)) != 0:
+            raise GenericError(self._err())
+
+    def run_to_host(self, outs: Sequence[np.ndarray], cuda_stream: int = 0) -> None:
+        """run(), with frame i copied into outs[i] (pinned memory for the copies to overlap the kernels) as soon as it
+        is rendered; complete when wait() returns. The arrays must stay alive until then."""
+        n = len(outs)
+        key = (id(outs), n)
+        if getattr(self, "_outs_key", None) != key:  # (the same list step after step: the pointer arrays are kept)
+            self._outs_ptrs = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+            self._outs_sizes = (ctypes.c_size_t * n)(*[o.nbytes for o in outs])
+            self._outs_key, self._outs_ref = key, outs
+        ptrs, sizes = self._outs_ptrs, self._outs_sizes
+        if self._lib.JxlB200DecoderRunToHost(self._dec, ctypes.c_void_p(cuda_stream), ptrs, sizes, n) != 0:
             raise GenericError(self._err())
 
     def wait(self, cuda_stream: int = 0) -> None:

@@ -55,6 +55,7 @@ struct BatchPlan {
   bool narrow = true;  // every frame promises that 16-bit buffers suffice -> 32-bit predictor math
   // VarDCT frames
   std::vector<DevVFrame> vframes;
+  std::vector<uint32_t> vframe_frame;  // vframes[k] is frame vframe_frame[k] of the batch
   std::vector<DevAcStream> ac_streams;
   // per (frame, pass): the ids of its streams in ac_streams, longest first (k_ac_decode_frame)
   bool any_upsampling = false;  // some lossy frame is upsampled: the per-pixel render kernels run for it
@@ -325,6 +326,7 @@ inline void MergeFrame(const FramePlan& f, const uint8_t* cs, size_t cs_size, Ba
     b->uarena_size += v.uarena_size;
     b->tok_size += v.tok_size;
     b->pix_plane_max = std::max(b->pix_plane_max, v.pix_plane);
+    b->vframe_frame.push_back(static_cast<uint32_t>(b->frames.size()));
     b->vframes.push_back(vf);
   }
   DevFrameOut fo = f.out;

@@ -672,6 +672,59 @@ __global__ void __launch_bounds__(256) k_color_write(DevVPools V, uint32_t frame
 }
 
 // ------------------------------------------------------------------ runtime
+// Pinned staging for the tables of a batch: a pageable source makes cudaMemcpyAsync stage and wait copy by copy (40
+// pools: 83 ms per 256-frame batch, measured); copied here first, the uploads are enqueued back to back. Blocks are
+// kept across batches; Reset() after the stream that read them was synchronised.
+struct PinnedStage {
+  struct Block { uint8_t* p; size_t cap; };
+  std::vector<Block> blocks;
+  size_t cur = 0, used = 0;
+  ~PinnedStage() {
+    for (Block& b : blocks) cudaFreeHost(b.p);
+  }
+  void Reset() { cur = 0; used = 0; }
+  uint8_t* Take(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t{255};
+    while (cur < blocks.size() && used + bytes > blocks[cur].cap) {
+      cur++;
+      used = 0;
+    }
+    if (cur == blocks.size()) {
+      Block b{nullptr, std::max<size_t>(bytes, size_t{8} << 20)};
+      if (cudaHostAlloc(reinterpret_cast<void**>(&b.p), b.cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+      blocks.push_back(b);
+      used = 0;
+    }
+    uint8_t* p = blocks[cur].p + used;
+    used += bytes;
+    return p;
+  }
+};
+
+// Pinned host words for the status read-back of a run: into pageable memory the asynchronous copy turns into a blocking
+// one that waits inside the driver for the run's kernels (other threads' launches and uploads queue up behind it).
+struct PinnedWords {
+  uint32_t* p = nullptr;
+  size_t n = 0, cap = 0;
+  ~PinnedWords() {
+    if (p) cudaFreeHost(p);
+  }
+  void resize(size_t count) {
+    if (count > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+      const size_t want = count + count / 4 + 64;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&p), want * 4, cudaHostAllocDefault) == cudaSuccess) cap = want;
+    }
+    n = cap >= count ? count : 0;
+  }
+  uint32_t* data() { return p; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  uint32_t operator[](size_t i) const { return p[i]; }
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -689,11 +742,18 @@ struct DevBuf {
     if (e == cudaSuccess) n = count;
     return e;
   }
-  cudaError_t Upload(const std::vector<T>& v, cudaStream_t s) {
+  cudaError_t Upload(const std::vector<T>& v, cudaStream_t s, PinnedStage* stage = nullptr) {
     cudaError_t e = Alloc(v.size());
     if (e != cudaSuccess) return e;
     if (v.empty()) return cudaSuccess;
-    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    const void* src = v.data();
+    if (stage && v.size() * sizeof(T) >= 16384) {  // (smaller ones travel inside the command)
+      if (uint8_t* st = stage->Take(v.size() * sizeof(T))) {
+        std::memcpy(st, v.data(), v.size() * sizeof(T));
+        src = st;
+      }
+    }
+    return cudaMemcpyAsync(p, src, v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
   }
 };
 
@@ -798,8 +858,22 @@ struct JxlB200Decoder {
   std::vector<size_t> late_level_off;
   DevBuf<DevFrameOut> d_frames;
   DevBuf<int32_t> d_arena, d_wp, d_ring;
-  uint8_t* h_bytes = nullptr;     // pinned staging for the codestream bytes of a batch (grows, kept across batches)
-  size_t h_bytes_cap = 0;
+  // pinned staging for the codestream bytes of a batch (grows, kept across batches). Two of them, used in turn: the
+  // batch planned ahead (JxlB200DecoderPlanBatch) fills one while the upload of the current batch may still read the other
+  uint8_t* h_bytes[2] = {nullptr, nullptr};
+  size_t h_bytes_cap[2] = {0, 0};
+  int h_turn = 0;
+  PinnedStage stage;                     // UploadPlan's pinned staging of the tables
+  std::unique_ptr<BatchPlan> next_plan;  // JxlB200DecoderPlanBatch -> JxlB200DecoderCommitPlan
+  PixelFormat next_fmt;
+  // JxlB200DecoderRunToHost: the frames of a wave are copied to the caller's host buffers on `copy_stream` as soon as
+  // the wave's last kernel is through (event), while the next waves compute
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_ev;
+  cudaEvent_t copy_done = nullptr;
+  cudaEvent_t sync_ev = nullptr;  // BlockingSync
+  bool copy_pending = false;
+  std::vector<void*> host_dsts;
   DevBuf<uint64_t> d_end_bits;    // probe launches only
   uint32_t probe_launches = 0;    // Modular decode launches made while planning (probe rounds)
   // VarDCT
@@ -817,7 +891,7 @@ struct JxlB200Decoder {
   DevBuf<DevPatch> d_patches;
   DevBuf<DevRefFrame> d_ref_frames;
   std::vector<uint2> dcg_list;
-  std::vector<uint32_t> h_ac_status, h_ac_used, h_dc_status;
+  PinnedWords h_ac_status, h_ac_used, h_dc_status;
   DevVPools vpools{};
   uint32_t max_groups = 0, max_xsize = 0, max_ysize = 0, max_blocks = 0;
   uint32_t max_up_xsize = 0, max_up_ysize = 0;  // largest frame after upsampling
@@ -825,7 +899,7 @@ struct JxlB200Decoder {
   uint32_t max_epf = 0;
   bool fused_render = std::getenv("JXLB200_UNFUSED_RENDER") == nullptr;
   std::vector<size_t> level_off;  // offset of each level inside d_levels
-  std::vector<uint32_t> h_status;
+  PinnedWords h_status;
   bool uniform_rgba8 = false;
   bool any_modular_frame = false;
   uint32_t launches = 0;
@@ -953,7 +1027,15 @@ void JxlB200DecoderDestroy(JxlB200Decoder* dec) {
     }
     cudaEventDestroy(dec->pix_done);
   }
-  if (dec->h_bytes) cudaFreeHost(dec->h_bytes);
+  for (uint8_t* hb : dec->h_bytes)
+    if (hb) cudaFreeHost(hb);
+  if (dec->copy_stream) {
+    cudaStreamSynchronize(dec->copy_stream);
+    cudaStreamDestroy(dec->copy_stream);
+  }
+  for (cudaEvent_t ev : dec->copy_ev) cudaEventDestroy(ev);
+  if (dec->copy_done) cudaEventDestroy(dec->copy_done);
+  if (dec->sync_ev) cudaEventDestroy(dec->sync_ev);
   if (dec->stream) cudaStreamDestroy(dec->stream);
   for (cudaStream_t st : dec->part_stream)
     if (st) cudaStreamDestroy(st);
@@ -975,50 +1057,71 @@ static int UploadTokensLayout(JxlB200Decoder* dec) {
 
 static int LaunchModular(JxlB200Decoder* dec, const BatchPlan& b, cudaStream_t s, int phase, uint32_t* launches);
 
+// Waits for stream `s` on an event that sleeps (cudaEventBlockingSync) instead of cudaStreamSynchronize's spinning: a
+// server keeps several handles in flight from as many threads, and eight threads spinning for a second each take half
+// of a 16-core host away from the planning threads of the next batches.
+static cudaError_t BlockingSync(JxlB200Decoder* dec, cudaStream_t s) {
+  static const bool spin = std::getenv("JXLB200_SPIN_WAIT") != nullptr;
+  if (spin) return cudaStreamSynchronize(s);
+  if (!dec->sync_ev) {
+    cudaError_t e = cudaEventCreateWithFlags(&dec->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(dec->sync_ev, s);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(dec->sync_ev);
+}
+
 // Uploads the pools of `b` and allocates the arenas; `dec->pools` / `dec->vpools` describe them afterwards.
 static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat& fmt, bool want_end_bits) {
   CUDA_OK(cudaSetDevice(dec->device));
   cudaStream_t s = dec->stream;
+  static const bool use_stage = std::getenv("JXLB200_NO_PINNED_STAGE") == nullptr;
+  PinnedStage* stage = use_stage ? &dec->stage : nullptr;
+  if (stage) stage->Reset();  // (the stream was synchronised at the end of the last upload)
   if (b.ext_bytes) {  // pinned staging filled by the planning threads: one asynchronous copy
     CUDA_OK(dec->d_bytes.Alloc(b.ext_bytes_size));
     CUDA_OK(cudaMemcpyAsync(dec->d_bytes.p, b.ext_bytes, b.ext_bytes_size, cudaMemcpyHostToDevice, s));
   } else {
-    CUDA_OK(dec->d_bytes.Upload(b.bytes, s));
+    CUDA_OK(dec->d_bytes.Upload(b.bytes, s, stage));
   }
-  CUDA_OK(dec->d_alias.Upload(b.alias, s));
-  CUDA_OK(dec->d_prefix.Upload(b.prefix, s));
-  CUDA_OK(dec->d_cfg.Upload(b.cfg, s));
-  CUDA_OK(dec->d_refs.Upload(b.refs, s));
-  CUDA_OK(dec->d_lut.Upload(b.lut, s));
-  CUDA_OK(dec->d_tree.Upload(b.tree, s));
-  CUDA_OK(dec->d_codes.Upload(b.codes, s));
-  CUDA_OK(dec->d_chans.Upload(b.chans, s));
-  CUDA_OK(dec->d_streams.Upload(b.streams, s));
-  CUDA_OK(dec->d_planes.Upload(b.planes, s));
-  CUDA_OK(dec->d_ops.Upload(b.ops, s));
-  CUDA_OK(dec->d_group_programs.Upload(b.group_programs, s));
+  static const bool up_timing = std::getenv("JXLB200_RUN_TIMING") != nullptr;
+  const auto ut0 = std::chrono::steady_clock::now();
+  auto ut_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ut0).count(); };
+  CUDA_OK(dec->d_alias.Upload(b.alias, s, stage));
+  CUDA_OK(dec->d_prefix.Upload(b.prefix, s, stage));
+  CUDA_OK(dec->d_cfg.Upload(b.cfg, s, stage));
+  CUDA_OK(dec->d_refs.Upload(b.refs, s, stage));
+  CUDA_OK(dec->d_lut.Upload(b.lut, s, stage));
+  CUDA_OK(dec->d_tree.Upload(b.tree, s, stage));
+  CUDA_OK(dec->d_codes.Upload(b.codes, s, stage));
+  CUDA_OK(dec->d_chans.Upload(b.chans, s, stage));
+  CUDA_OK(dec->d_streams.Upload(b.streams, s, stage));
+  CUDA_OK(dec->d_planes.Upload(b.planes, s, stage));
+  CUDA_OK(dec->d_ops.Upload(b.ops, s, stage));
+  CUDA_OK(dec->d_group_programs.Upload(b.group_programs, s, stage));
   std::vector<DevProgram> all_levels;
   dec->level_off.clear();
   for (const auto& lvl : b.levels) {
     dec->level_off.push_back(all_levels.size());
     all_levels.insert(all_levels.end(), lvl.begin(), lvl.end());
   }
-  CUDA_OK(dec->d_levels.Upload(all_levels, s));
-  CUDA_OK(dec->d_late_group_programs.Upload(b.late_group_programs, s));
+  CUDA_OK(dec->d_levels.Upload(all_levels, s, stage));
+  CUDA_OK(dec->d_late_group_programs.Upload(b.late_group_programs, s, stage));
   std::vector<DevProgram> all_late_levels;
   dec->late_level_off.clear();
   for (const auto& lvl : b.late_levels) {
     dec->late_level_off.push_back(all_late_levels.size());
     all_late_levels.insert(all_late_levels.end(), lvl.begin(), lvl.end());
   }
-  CUDA_OK(dec->d_late_levels.Upload(all_late_levels, s));
+  CUDA_OK(dec->d_late_levels.Upload(all_late_levels, s, stage));
   CUDA_OK(dec->d_chain_pos.Alloc(b.chain_slots + 1));
-  CUDA_OK(dec->d_spl_seg.Upload(b.spl_seg, s));
-  CUDA_OK(dec->d_spl_idx.Upload(b.spl_idx, s));
-  CUDA_OK(dec->d_frames.Upload(b.frames, s));
-  CUDA_OK(dec->d_warp_chans.Upload(b.warp_chans, s));
-  CUDA_OK(dec->d_warp_dims_off.Upload(b.warp_dims_off, s));
-  CUDA_OK(dec->d_warp_dims.Upload(b.warp_dims, s));
+  CUDA_OK(dec->d_spl_seg.Upload(b.spl_seg, s, stage));
+  CUDA_OK(dec->d_spl_idx.Upload(b.spl_idx, s, stage));
+  CUDA_OK(dec->d_frames.Upload(b.frames, s, stage));
+  CUDA_OK(dec->d_warp_chans.Upload(b.warp_chans, s, stage));
+  CUDA_OK(dec->d_warp_dims_off.Upload(b.warp_dims_off, s, stage));
+  CUDA_OK(dec->d_warp_dims.Upload(b.warp_dims, s, stage));
   CUDA_OK(dec->d_arena.Alloc(b.arena_size + 16));
   const size_t num_warps = b.warp_chans.size() + 1;  // (lock-step bundles of both launches)
   CUDA_OK(dec->d_wp.Alloc(num_warps * 10 * (b.wp_width + 2) * 32 + 16));
@@ -1082,14 +1185,14 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
       dec->max_epf = std::max(dec->max_epf, vf.epf_iters);
       dec->any_gab |= vf.gab != 0;
     }
-    CUDA_OK(dec->d_vframes.Upload(b.vframes, s));
-    CUDA_OK(dec->d_fpool.Upload(b.fpool, s));
-    CUDA_OK(dec->d_opool.Upload(b.opool, s));
-    CUDA_OK(dec->d_cpool.Upload(b.cpool, s));
-    CUDA_OK(dec->d_upool.Upload(b.upool, s));
-    CUDA_OK(dec->d_dcg_list.Upload(dec->dcg_list, s));
-    CUDA_OK(dec->d_patches.Upload(b.patches, s));
-    CUDA_OK(dec->d_ref_frames.Upload(b.ref_frames, s));
+    CUDA_OK(dec->d_vframes.Upload(b.vframes, s, stage));
+    CUDA_OK(dec->d_fpool.Upload(b.fpool, s, stage));
+    CUDA_OK(dec->d_opool.Upload(b.opool, s, stage));
+    CUDA_OK(dec->d_cpool.Upload(b.cpool, s, stage));
+    CUDA_OK(dec->d_upool.Upload(b.upool, s, stage));
+    CUDA_OK(dec->d_dcg_list.Upload(dec->dcg_list, s, stage));
+    CUDA_OK(dec->d_patches.Upload(b.patches, s, stage));
+    CUDA_OK(dec->d_ref_frames.Upload(b.ref_frames, s, stage));
     CUDA_OK(dec->d_farena.Alloc(b.farena_size + 16));
     CUDA_OK(dec->d_barena.Alloc(b.barena_size + 16));
     CUDA_OK(dec->d_uarena.Alloc(b.uarena_size + 16));
@@ -1131,7 +1234,7 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
     for (const DevVFrame& vf : b.vframes)
       for (uint32_t p = 0; p < vf.num_passes; p++)
         if (b.codes[vf.ac_code[p]].use_prefix || b.codes[vf.ac_code[p]].lz77_enabled) V.ac_plain_ans = 0;
-    CUDA_OK(dec->d_ac_streams.Upload(b.ac_streams, s));
+    CUDA_OK(dec->d_ac_streams.Upload(b.ac_streams, s, stage));
     CUDA_OK(dec->d_tokens.Alloc(b.tok_size + 16));
     V.streams = dec->d_ac_streams.p;
     V.tokens = dec->d_tokens.p;
@@ -1154,19 +1257,25 @@ static int UploadPlan(JxlB200Decoder* dec, const BatchPlan& b, const PixelFormat
       if (max_smem <= 110 * 1024) {
         dec->ac_frame_smem = max_smem;
         dec->ac_frame_threads = warps * 32;
-        CUDA_OK(dec->d_ac_units.Upload(b.ac_units, s));
-        CUDA_OK(dec->d_ac_unit_streams.Upload(b.ac_unit_streams, s));
+        CUDA_OK(dec->d_ac_units.Upload(b.ac_units, s, stage));
+        CUDA_OK(dec->d_ac_unit_streams.Upload(b.ac_unit_streams, s, stage));
       }
     }
   }
-  CUDA_OK(cudaStreamSynchronize(s));
+  const double ut_enq = ut_ms();
+  CUDA_OK(BlockingSync(dec, s));
+  if (up_timing)
+    std::fprintf(stderr, "UploadPlan: enqueue %.2f ms, + sync %.2f ms (bitstreams %.1f MB pinned, alias %.1f MB, orders %.1f MB, fpool %.1f MB, "
+                 "ac streams %.1f MB)\n", ut_enq, ut_ms(), b.ext_bytes_size / 1e6, b.alias.size() * sizeof(DevAlias) / 1e6,
+                 b.opool.size() * 2 / 1e6, b.fpool.size() * 4 / 1e6, b.ac_streams.size() * sizeof(DevAcStream) / 1e6);
   return 0;
 }
 
-int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files, const size_t* sizes, size_t n,
-                                const JxlPixelFormat* format, int num_threads) {
+int JxlB200DecoderPlanBatch(JxlB200Decoder* dec, const uint8_t* const* files, const size_t* sizes, size_t n,
+                            const JxlPixelFormat* format, int num_threads) {
   if (!dec || !files || !sizes || !format || n == 0) return 1;
   dec->error.clear();
+  dec->next_plan.reset();
   PixelFormat fmt;
   fmt.num_channels = format->num_channels;
   fmt.data_type = format->data_type;
@@ -1184,6 +1293,12 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
     JxlB200Decoder tmp;
     tmp.device = dec->device;
     tmp.stream = dec->stream;  // borrowed
+    struct EventGuard {
+      JxlB200Decoder* d;
+      ~EventGuard() {
+        if (d->sync_ev) cudaEventDestroy(d->sync_ev);
+      }
+    } guard{&tmp};
     PixelFormat pf;
     std::vector<uint32_t> status(pb.streams.size());
     end_bits->assign(pb.streams.size(), 0);
@@ -1208,30 +1323,61 @@ int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files
   std::unique_ptr<BatchPlan> plan(new BatchPlan());
   try {
     if (cudaSetDevice(dec->device) != cudaSuccess) throw Error("cudaSetDevice failed");
-    const BytesAlloc bytes_alloc = [dec](size_t size) -> uint8_t* {
-      if (size > dec->h_bytes_cap) {
-        if (dec->h_bytes) cudaFreeHost(dec->h_bytes);
-        dec->h_bytes = nullptr;
-        dec->h_bytes_cap = 0;
+    const int turn = dec->h_turn ^= 1;
+    const BytesAlloc bytes_alloc = [dec, turn](size_t size) -> uint8_t* {
+      if (size > dec->h_bytes_cap[turn]) {
+        if (dec->h_bytes[turn]) cudaFreeHost(dec->h_bytes[turn]);
+        dec->h_bytes[turn] = nullptr;
+        dec->h_bytes_cap[turn] = 0;
         const size_t cap = size + size / 4;
-        if (cudaHostAlloc(reinterpret_cast<void**>(&dec->h_bytes), cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-        dec->h_bytes_cap = cap;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&dec->h_bytes[turn]), cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        dec->h_bytes_cap[turn] = cap;
       }
-      return dec->h_bytes;
+      return dec->h_bytes[turn];
     };
     PlanBatch(files, sizes, n, fmt, num_threads, plan.get(), probe, bytes_alloc);
   } catch (const std::exception& e) {
     dec->error = e.what();
     return 1;
   }
+  dec->next_plan = std::move(plan);
+  dec->next_fmt = fmt;
+  return 0;
+}
+
+static void FinishCopies(JxlB200Decoder* dec) {
+  if (dec->copy_pending) BlockingSync(dec, dec->copy_stream);
+  dec->copy_pending = false;
+  dec->host_dsts.clear();
+}
+
+int JxlB200DecoderCommitPlan(JxlB200Decoder* dec) {
+  if (!dec) return 1;
+  if (!dec->next_plan) {
+    dec->error = "no planned batch to commit";
+    return 1;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  CUDA_OK(cudaSetDevice(dec->device));
+  FinishCopies(dec);
   // The upload reallocates / overwrites the device pools of the previous batch: the handle has no plan until it
   // succeeded (a failed upload must not leave Run / ReadOutput with the old grid sizes over freed pools).
+  std::unique_ptr<BatchPlan> plan = std::move(dec->next_plan);
   dec->plan.reset();
+  const double t_free = ms();
   dec->pools = DevPools{};
   dec->vpools = DevVPools{};
-  if (UploadPlan(dec, *plan, fmt, false) != 0) return 1;
+  if (UploadPlan(dec, *plan, dec->next_fmt, false) != 0) return 1;
   dec->plan = std::move(plan);
+  if (std::getenv("JXLB200_RUN_TIMING")) std::fprintf(stderr, "CommitPlan: old plan freed after %.2f ms, uploaded after %.2f ms\n", t_free, ms());
   return 0;
+}
+
+int JxlB200DecoderSetInputBatch(JxlB200Decoder* dec, const uint8_t* const* files, const size_t* sizes, size_t n,
+                                const JxlPixelFormat* format, int num_threads) {
+  if (JxlB200DecoderPlanBatch(dec, files, sizes, n, format, num_threads) != 0) return 1;
+  return JxlB200DecoderCommitPlan(dec);
 }
 
 int JxlB200DecoderSetKeepOrientation(JxlB200Decoder* dec, int keep) {
@@ -1352,6 +1498,55 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
   const bool parted = dec->part_stream[0] != nullptr && !dec->plan->vframes.empty();
   cudaStream_t s = parted ? dec->part_stream[0] : caller;
   cudaStream_t sp = parted ? dec->part_stream[1] : caller;
+  const bool to_host = !dec->host_dsts.empty();
+  std::vector<uint8_t> copied;
+  uint32_t waves_done = 0;
+  if (dec->copy_pending) CUDA_OK(cudaStreamWaitEvent(caller, dec->copy_done, 0));  // (a read-back of the old output)
+  if (to_host) {
+    if (!dec->copy_stream) {
+      CUDA_OK(cudaStreamCreateWithFlags(&dec->copy_stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&dec->copy_done, cudaEventDisableTiming));
+    }
+    copied.assign(dec->plan->frames.size(), 0);
+  }
+  // frames [..] of the list -> the caller's buffers, on the copy stream, once `after` has reached this point
+  auto copy_out = [&](cudaStream_t after, const uint32_t* frames, size_t count) -> cudaError_t {
+    if (count == 0) return cudaSuccess;
+    if (waves_done >= dec->copy_ev.size()) {
+      cudaEvent_t ev = nullptr;
+      cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+      dec->copy_ev.push_back(ev);
+    }
+    cudaEvent_t ev = dec->copy_ev[waves_done++];
+    cudaError_t e = cudaEventRecord(ev, after);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(dec->copy_stream, ev, 0);
+    // frames that follow each other in the caller's memory as they do in the output buffer (one pinned arena laid out
+    // like JxlB200DecoderDeviceOutput) leave in one copy
+    static const bool coalesce = std::getenv("JXLB200_NO_COALESCE") == nullptr;
+    for (size_t k = 0; k < count && e == cudaSuccess;) {
+      const uint32_t f0 = frames[k];
+      const uint64_t off0 = dec->plan->frames[f0].out_off;
+      uint8_t* const dst0 = static_cast<uint8_t*>(dec->host_dsts[f0]);
+      uint64_t len = dec->plan->frame_out_size[f0];
+      copied[f0] = 1;
+      size_t j = k + 1;
+      for (; coalesce && j < count; j++) {
+        const uint32_t fj = frames[j];
+        const uint64_t offj = dec->plan->frames[fj].out_off;
+        if (offj < off0 + len || static_cast<uint8_t*>(dec->host_dsts[fj]) != dst0 + (offj - off0)) break;
+        len = offj - off0 + dec->plan->frame_out_size[fj];
+        copied[fj] = 1;
+      }
+      e = cudaMemcpyAsync(dst0, dec->d_out.p + off0, len, cudaMemcpyDeviceToHost, dec->copy_stream);
+      k = j;
+    }
+    return e;
+  };
+  static const bool run_timing = std::getenv("JXLB200_RUN_TIMING") != nullptr;  // stderr: host time of the enqueue
+  const auto rt0 = std::chrono::steady_clock::now();
+  auto rt_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - rt0).count(); };
+  double rt_entropy = 0, rt_waves = 0;
   if (parted) {
     CUDA_OK(cudaEventRecord(dec->part_ev[0], caller));
     CUDA_OK(cudaStreamWaitEvent(s, dec->part_ev[0], 0));
@@ -1447,6 +1642,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
         launches++;
       }
     }
+    rt_entropy = rt_ms();
     if (parted) {  // the per-pixel waves start when this batch's entropy kernels are through
       CUDA_OK(cudaEventRecord(dec->part_ev[1], s));
       CUDA_OK(cudaStreamWaitEvent(sp, dec->part_ev[1], 0));
@@ -1514,6 +1710,7 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
           launches++;
         }
       }
+      if (to_host) CUDA_OK(copy_out(sp, b.vframe_frame.data() + f0, nf));  // this wave's frames leave while the next computes
     }
     if (turns) {
       PixelTurn& turn = g_pixel_turn[dec->device];
@@ -1528,10 +1725,42 @@ int JxlB200DecoderRun(JxlB200Decoder* dec, void* cuda_stream) {
     CUDA_OK(cudaEventRecord(dec->part_ev[2], s));  // (entropy-side kernels of Modular frames, if any, end here)
     CUDA_OK(cudaStreamWaitEvent(caller, dec->part_ev[2], 0));
   }
+  rt_waves = rt_ms();
+  if (to_host) {  // the Modular frames (written by the output kernel above)
+    std::vector<uint32_t> rest;
+    for (uint32_t i = 0; i < copied.size(); i++)
+      if (!copied[i]) rest.push_back(i);
+    CUDA_OK(copy_out(caller, rest.data(), rest.size()));
+    CUDA_OK(cudaEventRecord(dec->copy_done, dec->copy_stream));
+    dec->copy_pending = true;
+  }
   if (dec->profiling) dec->profiled_runs++;
   dec->launches = launches;
   CUDA_OK(cudaGetLastError());
+  if (run_timing)
+    std::fprintf(stderr, "Run enqueue: entropy kernels %.2f ms, + waves %.2f ms, + tail %.2f ms (%u launches, to_host %d)\n", rt_entropy,
+                 rt_waves, rt_ms(), launches, to_host ? 1 : 0);
   return 0;
+}
+
+int JxlB200DecoderRunToHost(JxlB200Decoder* dec, void* cuda_stream, void* const* dsts, const size_t* sizes, size_t n) {
+  if (!dec || !dec->plan || n != dec->plan->frames.size() || !dsts || !sizes) return 1;
+  for (size_t i = 0; i < n; i++) {
+    if (!dsts[i] || sizes[i] < dec->plan->frame_out_size[i]) {
+      dec->error = "output buffer too small";
+      return 1;
+    }
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  CUDA_OK(cudaSetDevice(dec->device));
+  FinishCopies(dec);
+  dec->host_dsts.assign(dsts, dsts + n);
+  const int rc = JxlB200DecoderRun(dec, cuda_stream);
+  if (rc != 0) FinishCopies(dec);
+  if (std::getenv("JXLB200_RUN_TIMING"))
+    std::fprintf(stderr, "RunToHost: %.2f ms in the call\n",
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  return rc;
 }
 
 int JxlB200DecoderSetPhaseMask(JxlB200Decoder* dec, uint32_t mask) {
@@ -1569,17 +1798,26 @@ static int CheckOnce(JxlB200Decoder* dec, cudaStream_t s, bool* overflow) {
   BatchPlan& b = *dec->plan;
   *overflow = false;
   dec->h_status.resize(b.streams.size());
+  if (dec->h_status.size() != b.streams.size()) {
+    dec->error = "out of memory (pinned status words)";
+    return 1;
+  }
   if (!dec->h_status.empty())
     CUDA_OK(cudaMemcpyAsync(dec->h_status.data(), dec->d_status.p, dec->h_status.size() * 4, cudaMemcpyDeviceToHost, s));
   if (!b.vframes.empty()) {
     dec->h_ac_status.resize(b.ac_streams.size());
     dec->h_ac_used.resize(b.ac_streams.size());
     dec->h_dc_status.resize(dec->dcg_list.size());
+    if (dec->h_ac_status.size() != b.ac_streams.size() || dec->h_ac_used.size() != b.ac_streams.size() ||
+        dec->h_dc_status.size() != dec->dcg_list.size()) {
+      dec->error = "out of memory (pinned status words)";
+      return 1;
+    }
     CUDA_OK(cudaMemcpyAsync(dec->h_ac_status.data(), dec->d_ac_status.p, dec->h_ac_status.size() * 4, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaMemcpyAsync(dec->h_ac_used.data(), dec->d_ac_used.p, dec->h_ac_used.size() * 4, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaMemcpyAsync(dec->h_dc_status.data(), dec->d_dc_status.p, dec->h_dc_status.size() * 4, cudaMemcpyDeviceToHost, s));
   }
-  CUDA_OK(cudaStreamSynchronize(s));
+  CUDA_OK(BlockingSync(dec, s));
   for (size_t i = 0; i < dec->h_status.size(); i++) {
     if (dec->h_status[i] != 0) {
       dec->error = "entropy-coded stream " + std::to_string(i) + " failed (status " + std::to_string(dec->h_status[i]) +
@@ -1608,8 +1846,16 @@ static int CheckOnce(JxlB200Decoder* dec, cudaStream_t s, bool* overflow) {
   return 0;
 }
 
+static int WaitForRun(JxlB200Decoder* dec, void* cuda_stream);
+
 int JxlB200DecoderWait(JxlB200Decoder* dec, void* cuda_stream) {
   if (!dec || !dec->plan) return 1;
+  const int rc = WaitForRun(dec, cuda_stream);
+  FinishCopies(dec);  // (JxlB200DecoderRunToHost: the frames are in the caller's buffers when Wait returns)
+  return rc;
+}
+
+static int WaitForRun(JxlB200Decoder* dec, void* cuda_stream) {
   CUDA_OK(cudaSetDevice(dec->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : dec->stream;
   bool overflow = false;
@@ -1662,7 +1908,7 @@ int JxlB200DecoderReadOutputs(JxlB200Decoder* dec, void* const* dsts, const size
     CUDA_OK(cudaMemcpyAsync(dsts[i], dec->d_out.p + dec->plan->frames[i].out_off, dec->plan->frame_out_size[i],
                             cudaMemcpyDeviceToHost, dec->stream));
   }
-  CUDA_OK(cudaStreamSynchronize(dec->stream));
+  CUDA_OK(BlockingSync(dec, dec->stream));
   return 0;
 }
 

@@ -136,3 +136,38 @@ def test_sample_2bit_as_the_reference_test(pkg):
     outs = pkg.decode_batch([read_golden("sample.jxl"), d, d], 4, np.uint16)
     assert np.array_equal(outs[1], jxlo.decode(d, 4, jxlo.UINT16)) and np.array_equal(outs[2], outs[1])
     assert np.array_equal(outs[0], jxlo.decode(read_golden("sample.jxl"), 4, jxlo.UINT16))
+
+
+def test_streaming_calls_plan_ahead_and_run_to_host(pkg):
+    # PlanBatch / CommitPlan / RunToHost (include/jxl_b200.h): the next batch is parsed while the current one decodes,
+    # and the frames land in the caller's buffers wave by wave -- two different batches alternating on one handle
+    # (lossy multi-group, lossy with alpha, single-section probe round, Modular, splines), pinned and pageable buffers
+    import torch
+    import vardct_cases as vc
+    img = vc.crop(300, 520, 100, 200)
+    rgba = np.dstack([img, img[:, :, 0] ^ img[:, :, 2]])
+    a = [vc.encoded("heuristic")[0], read_golden("sample.jxl"), jxlo.encode_vardct(rgba, strategy_mode=2), read_golden("2bit.jxl")]
+    b = [read_golden("bench.jxl"), jxlo.encode_vardct(img[:60, :70], strategy_mode=2, splines=3), vc.encoded("three_passes")[0]]
+    want = {0: [jxlo.decode(f, 4, jxlo.UINT8) for f in a], 1: [jxlo.decode(f, 4, jxlo.UINT8) for f in b]}
+    d = pkg.BatchDecoder(0)
+    stream = torch.cuda.Stream()
+    d.plan(a, 4, pkg.JXL_TYPE_UINT8)
+    for step in range(5):
+        cur = step % 2
+        d.commit()
+        sizes = [d.out_size(i) for i in range(len(want[cur]))]
+        if step < 3:
+            outs = [torch.empty(n, dtype=torch.uint8).pin_memory().numpy() for n in sizes]
+        else:
+            outs = [np.empty(n, dtype=np.uint8) for n in sizes]
+        d.run_to_host(outs, stream.cuda_stream)
+        d.plan(b if cur == 0 else a, 4, pkg.JXL_TYPE_UINT8)  # while the kernels run
+        d.wait(stream.cuda_stream)
+        for o, w in zip(outs, want[cur]):
+            assert np.array_equal(o.reshape(w.shape), w)
+        assert np.array_equal(d.read_output(0).reshape(want[cur][0].shape), want[cur][0])  # the device copy is still there
+    with pytest.raises(pkg.GenericError):
+        d.run_to_host([np.empty(4, dtype=np.uint8)] * len(want[0]), stream.cuda_stream)  # buffers too small
+    d2 = pkg.BatchDecoder(0)
+    with pytest.raises(pkg.GenericError):
+        d2.commit()  # nothing planned
