@@ -2313,22 +2313,25 @@ __global__ void __launch_bounds__(256) k_enc_alpha(DevEPools E, const DevEFrame*
   for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) DevEncAlphaSample(El, ef, i);
 }
 
-// rANS emission: one thread per section, written back to front so that it ends at the end of its region
-// (`off[sec]` .. `off[sec + 1]`, in words); `first[sec]` receives the bit position of its first bit. blockIdx.x
-// below `dc_blocks` handles DC-group sections (the long ones, scheduled first), the rest AC-group sections.
+// rANS emission: one warp per section (DevRansPushWarp: the lanes fetch and split the tokens, lane 0 codes), written
+// back to front so that it ends at the end of its region (`off[sec]` .. `off[sec + 1]`, in words); `first[sec]`
+// receives the bit position of its first bit. blockIdx.x below `dc_blocks` handles DC-group sections (the long ones,
+// scheduled first), the rest AC-group sections.
 __global__ void __launch_bounds__(32) k_enc_emit(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
                                                  const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first,
                                                  uint32_t dc_blocks) {
   const DevEFrame& ef = frames[blockIdx.y];
+  const uint32_t lane = threadIdx.x;
   if (blockIdx.x < dc_blocks) {
-    const uint32_t g = blockIdx.x * 32 + threadIdx.x;
+    const uint32_t g = blockIdx.x;
     if (g >= ef.xdcgroups * ef.ydcgroups) return;
     const DevEncCode code{fs_tables + ef.code_off[0], rev_tables + ef.code_off[1]};
     const uint32_t sec = ef.sec_base + g;
-    first[sec] = DevEncEmitDcGroup(E, ef, g, code, words, off[sec + 1] * 32);
+    const uint64_t pos = DevEncEmitDcGroupWarp(E, ef, g, code, words, off[sec + 1] * 32, lane);
+    if (lane == 0) first[sec] = pos;
     return;
   }
-  const uint32_t g = (blockIdx.x - dc_blocks) * 32 + threadIdx.x;
+  const uint32_t g = blockIdx.x - dc_blocks;
   if (g >= ef.xgroups * ef.ygroups) return;
   const DevEncCode code{fs_tables + ef.code_off[2], rev_tables + ef.code_off[3]};
   const uint32_t n = static_cast<uint32_t>(E.iarena[ef.group_tokens + g]);
@@ -2337,11 +2340,15 @@ __global__ void __launch_bounds__(32) k_enc_emit(DevEPools E, const DevEFrame* f
     const DevEncCode mod{fs_tables + ef.code_off[0], rev_tables + ef.code_off[1]};
     const uint32_t gx = g % ef.xgroups, gy = g / ef.xgroups;
     const uint32_t gw = ef.xsize - (gx << 8) < 256 ? ef.xsize - (gx << 8) : 256, gh = ef.ysize - (gy << 8) < 256 ? ef.ysize - (gy << 8) : 256;
-    first[sec] = DevEncEmitAcGroup(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words, off[sec + 1] * 32,
-                                   E.tokens + ef.alpha_tokens + static_cast<size_t>(g) * 65536, gw * gh, &mod);
+    const uint64_t pos = DevEncEmitAcGroupWarp(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words,
+                                               off[sec + 1] * 32, lane, E.tokens + ef.alpha_tokens + static_cast<size_t>(g) * 65536,
+                                               gw * gh, &mod);
+    if (lane == 0) first[sec] = pos;
     return;
   }
-  first[sec] = DevEncEmitAcGroup(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words, off[sec + 1] * 32);
+  const uint64_t pos = DevEncEmitAcGroupWarp(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words,
+                                             off[sec + 1] * 32, lane);
+  if (lane == 0) first[sec] = pos;
 }
 
 // ---- lossless (Modular) encoder: kernels/jxlb_encl_dev.h
@@ -2357,16 +2364,17 @@ __global__ void __launch_bounds__(256) k_encl_tokens(DevLPools L, const DevLFram
   for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) DevEnclToken(L, f, i);
 }
 
-// One thread per group section (a serial rANS chain each); `off[sec]` .. `off[sec + 1]` is the section's region in words.
+// One warp per group section (a serial rANS chain each, DevRansPushWarp); `off[sec]` .. `off[sec + 1]` is the section's region in words.
 __global__ void __launch_bounds__(32) k_encl_emit(DevLPools L, const DevLFrame* frames, const uint32_t* fs_tables,
                                                   const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first) {
   const DevLFrame& f = frames[blockIdx.y];
-  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
+  const uint32_t g = blockIdx.x;
   if (g >= f.xgroups * f.ygroups) return;
   const DevEncCode code{fs_tables + f.code_off[0], rev_tables + f.code_off[1]};
   const uint32_t sec = f.sec_base + g;
   const bool global_only = f.xsize <= kEnclGroupDim && f.ysize <= kEnclGroupDim;  // the tokens follow the host's global header
-  first[sec] = DevEnclEmitGroup(L, f, g, code, words, off[sec + 1] * 32, !global_only);
+  const uint64_t pos = DevEnclEmitGroupWarp(L, f, g, code, words, off[sec + 1] * 32, !global_only, threadIdx.x);
+  if (threadIdx.x == 0) first[sec] = pos;
 }
 
 }  // namespace jxlb
@@ -2748,8 +2756,8 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       efs[i].sec_base = static_cast<uint32_t>(fr[i].bits_off);
     }
     CUDA_OK(d_efs.Upload(efs, s));
-    const uint32_t dc_blocks = (max_dcg + 31) / 32;
-    k_enc_emit<<<dim3(dc_blocks + (max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p,
+    const uint32_t dc_blocks = max_dcg;
+    k_enc_emit<<<dim3(dc_blocks + max_groups, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p,
                                                                             dc_blocks);
     CUDA_OK(cudaEventRecord(ev[3], s));
     std::vector<uint64_t> h_bits(nsec);
@@ -2918,7 +2926,7 @@ int JxlB200EncoderEncodeLosslessBatch(JxlB200Encoder* enc, const void* const* pi
     CUDA_OK(enc->d_words.Alloc(words_total + 16));
     CUDA_OK(cudaMemsetAsync(enc->d_words.p, 0, (words_total + 16) * sizeof(uint32_t), s));
     CUDA_OK(cudaEventRecord(ev[2], s));
-    k_encl_emit<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(L, enc->d_lfs.p, enc->d_fs.p, enc->d_rev.p, enc->d_words.p,
+    k_encl_emit<<<dim3(max_groups, nf), 32, 0, s>>>(L, enc->d_lfs.p, enc->d_fs.p, enc->d_rev.p, enc->d_words.p,
                                                                 enc->d_off.p, enc->d_bits.p);
     CUDA_OK(cudaEventRecord(ev[3], s));
     std::vector<uint64_t> h_bits(nsec);

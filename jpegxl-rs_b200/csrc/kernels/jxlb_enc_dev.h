@@ -1189,6 +1189,103 @@ JXLB_HD void DevRansPush(const uint2* tok, uint32_t n, const DevEncCode& code, D
   w.Put(32, state);
 }
 
+#if defined(__CUDACC__)
+// Bits into a zero-initialised region shared with other writers of the warp: nbits <= 32, value < 2^nbits.
+__device__ __forceinline__ void DevOrBits(uint32_t* words, uint64_t pos, uint32_t nbits, uint32_t value) {
+  if (nbits == 0) return;
+  const uint32_t sh = static_cast<uint32_t>(pos & 31);
+  atomicOr(words + (pos >> 5), value << sh);
+  if (sh + nbits > 32) atomicOr(words + (pos >> 5) + 1, value >> (32 - sh));
+}
+
+// The same stream written by a warp, back to front from bit `*cursor` (uniform over the lanes, updated). The 32 lanes
+// fetch 32 tokens at a time (one coalesced load, from the end), split them, fetch their frequency entries and the
+// reciprocal of the frequency in parallel, one chunk ahead of the coder; lane 0 owns the coder state and takes the
+// tokens of a chunk from the lanes by shuffle. On its serial chain stay only the renormalisation test, the division
+// (multiply by the reciprocal + one correction) and the reverse-table load that depend on the state: the renormalised
+// 16 bits leave as fire-and-forget atomics, and every lane writes the extra bits of its own token after the chunk,
+// at the position that follows from a prefix sum of the bit counts and the chunk's renormalisation mask.
+// (One thread per section left 31 lanes of a warp to other sections with other branch histories: the warp ran them
+// one after the other, every token load was a dependent miss of its own, and the bit writer sat on the chain.)
+__device__ __forceinline__ void DevRansPushWarp(const uint2* tok, uint32_t n, const DevEncCode& code, uint32_t* words, uint64_t* cursor,
+                                                uint32_t lane) {
+  uint32_t state = 0x13u << 16;
+  uint64_t pos = *cursor;
+  auto fetch = [&](uint32_t done, uint32_t* cn, uint32_t* bt, uint32_t* fs, uint32_t* rcp) {
+    *cn = 0;
+    *bt = 0;
+    *fs = 1;
+    *rcp = 0;
+    if (done + lane < n) {
+      const uint2 t = tok[n - 1 - done - lane];
+      uint32_t token, nbits;
+      DevHybrid420(t.y, &token, &nbits, bt);
+      *cn = t.x | (nbits << 16);
+      *fs = JXLB_LDG(code.fs + t.x * 256 + token);
+      *rcp = 0xFFFFFFFFu / (*fs & 0xFFFF);  // >= 2^32 / f - 1: the quotient estimate is at most one short
+    }
+  };
+  uint32_t cn, bt, fs, rcp;
+  fetch(0, &cn, &bt, &fs, &rcp);
+  for (uint32_t done = 0; done < n; done += 32) {
+    uint32_t ncn, nbt, nfs, nrcp;
+    fetch(done + 32, &ncn, &nbt, &nfs, &nrcp);  // in flight while this chunk is coded
+    const uint32_t cnt = n - done < 32 ? n - done : 32;
+    // bits of the tokens before mine in the chunk (exclusive prefix sum of the extra-bit counts)
+    const uint32_t my_nbits = cn >> 16;
+    uint32_t incl = my_nbits;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    uint32_t mask = 0;  // lane 0: tokens of the chunk after which the state was renormalised
+    uint64_t p = pos;   // lane 0: write position
+    uint32_t c_cn = __shfl_sync(0xFFFFFFFFu, cn, 0), c_fs = __shfl_sync(0xFFFFFFFFu, fs, 0), c_rcp = __shfl_sync(0xFFFFFFFFu, rcp, 0);
+    for (uint32_t k = 0; k < cnt; k++) {
+      const uint32_t k_cn = c_cn, k_fs = c_fs, k_rcp = c_rcp;
+      const uint32_t kn = k + 1 < 32 ? k + 1 : 31;  // the next token's words do not depend on the state: ahead of the chain
+      c_cn = __shfl_sync(0xFFFFFFFFu, cn, kn);
+      c_fs = __shfl_sync(0xFFFFFFFFu, fs, kn);
+      c_rcp = __shfl_sync(0xFFFFFFFFu, rcp, kn);
+      if (lane == 0) {
+        p -= k_cn >> 16;
+        const uint32_t f = k_fs & 0xFFFF;
+        if ((state >> 20) >= f) {
+          p -= 16;
+          DevOrBits(words, p, 16, state & 0xFFFF);
+          state >>= 16;
+          mask |= 1u << k;
+        }
+        uint32_t q = __umulhi(state, k_rcp), r = state - q * f;
+        if (r >= f) {
+          q++;
+          r -= f;
+        }
+        state = (q << 12) | JXLB_LDG(code.reverse + (k_cn & 0xFFFF) * 4096 + (k_fs >> 16) + r);
+      }
+    }
+    mask = __shfl_sync(0xFFFFFFFFu, mask, 0);
+    if (lane < cnt && my_nbits != 0)
+      DevOrBits(words, pos - incl - 16ull * __popc(mask & ((1u << lane) - 1)), my_nbits, bt);
+    pos -= __shfl_sync(0xFFFFFFFFu, incl, 31) + 16ull * __popc(mask);
+    cn = ncn;
+    bt = nbt;
+    fs = nfs;
+    rcp = nrcp;
+  }
+  pos -= 32;
+  if (lane == 0) DevOrBits(words, pos, 32, state);
+  *cursor = pos;
+}
+
+// Header bits between the streams of a section, written by lane 0 (the cursor stays uniform).
+__device__ __forceinline__ void DevWarpPut(uint32_t* words, uint64_t* cursor, uint32_t nbits, uint32_t value, uint32_t lane) {
+  *cursor -= nbits;
+  if (lane == 0) DevOrBits(words, *cursor, nbits, value);
+}
+#endif
+
 // Token slots of DC group g's Modular streams: [DC Y | DC X | DC B | ytox | ytob | strategy row, quant row | sharpness].
 struct DevDcGroupLayout {
   uint32_t x0, y0, xs, ys, cw, chh, count;
@@ -1293,6 +1390,37 @@ JXLB_HD uint64_t DevEncEmitAcGroup(const uint2* tok, uint32_t n, const DevEncCod
   w.Finish();
   return w.cursor;
 }
+
+#if defined(__CUDACC__)
+// The two section writers above, a warp per section (DevRansPushWarp); returns the position of the first bit.
+__device__ __forceinline__ uint64_t DevEncEmitDcGroupWarp(const DevEPools& E, const DevEFrame& ef, uint32_t g, const DevEncCode& code,
+                                                          uint32_t* words, uint64_t end_pos, uint32_t lane) {
+  const DevDcGroupLayout L = DevDcGroupGeometry(E, ef, g);
+  const uint2* tok = E.tokens + ef.mod_tokens + ef.mod_tokens_stride * g;
+  uint64_t cursor = end_pos;
+  DevRansPushWarp(tok + L.dc_tokens, L.meta_tokens, code, words, &cursor, lane);
+  DevWarpPut(words, &cursor, 4, 0x3, lane);  // use_global_tree = 1, default WP header = 1, no transforms
+  uint32_t count_bits = 0;
+  while ((1u << count_bits) < L.xs * L.ys) count_bits++;
+  if (count_bits) DevWarpPut(words, &cursor, count_bits, L.count - 1, lane);
+  DevRansPushWarp(tok, L.dc_tokens, code, words, &cursor, lane);
+  DevWarpPut(words, &cursor, 4, 0x3, lane);
+  DevWarpPut(words, &cursor, 2, 0, lane);  // extra_precision
+  return cursor;
+}
+
+__device__ __forceinline__ uint64_t DevEncEmitAcGroupWarp(const uint2* tok, uint32_t n, const DevEncCode& code, uint32_t* words,
+                                                          uint64_t end_pos, uint32_t lane, const uint2* alpha_tok = nullptr,
+                                                          uint32_t alpha_n = 0, const DevEncCode* mod_code = nullptr) {
+  uint64_t cursor = end_pos;
+  if (alpha_tok != nullptr) {
+    DevRansPushWarp(alpha_tok, alpha_n, *mod_code, words, &cursor, lane);
+    DevWarpPut(words, &cursor, 4, 0x3, lane);
+  }
+  DevRansPushWarp(tok, n, code, words, &cursor, lane);
+  return cursor;
+}
+#endif
 
 }  // namespace jxlb
 
