@@ -844,6 +844,7 @@ inline void BuildEncGlobals(const EncParams& p, const EncLayout& L, const EncTre
 struct EncSection {
   const uint32_t* words;
   uint64_t first, nbits;
+  uint64_t first2 = 0, nbits2 = 0;  // a second piece that follows the first bit-wise (the halves of a DC-group section)
 };
 
 // Final codestream from the sections.
@@ -853,6 +854,7 @@ inline std::vector<uint8_t> AssembleCodestream(const EncParams& p, const EncLayo
   auto bytes_of = [](const EncSection& s) {
     BitWriter w;
     w.AppendWordBits(s.words, s.first, s.nbits);
+    if (s.nbits2) w.AppendWordBits(s.words, s.first2, s.nbits2);
     w.ZeroPadToByte();
     return w.Bytes();
   };
@@ -860,6 +862,7 @@ inline std::vector<uint8_t> AssembleCodestream(const EncParams& p, const EncLayo
     BitWriter all;
     all.AppendBits(g.dc_global.Bytes().data(), g.dc_global.BitsWritten());
     all.AppendWordBits(dcg[0].words, dcg[0].first, dcg[0].nbits);
+    if (dcg[0].nbits2) all.AppendWordBits(dcg[0].words, dcg[0].first2, dcg[0].nbits2);
     all.AppendBits(g.ac_global.Bytes().data(), g.ac_global.BitsWritten());
     all.AppendWordBits(acg[0].words, acg[0].first, acg[0].nbits);
     sections.push_back(all.Bytes());

@@ -2171,11 +2171,12 @@ __global__ void __launch_bounds__(256) k_enc_aq(DevEPools E, const DevEFrame* fr
   DevEncAqTile<2>(E, ef, blockIdx.x % tiles_x, blockIdx.x / tiles_x, threadIdx.x, blockDim.x, aq_sm);
 }
 
-// one thread per 256x256 group (the greedy choice is serial inside a group)
-__global__ void __launch_bounds__(32) k_enc_strategy(DevEPools E, const DevEFrame* frames) {
+// one thread per 64x64-pixel tile (the greedy choice is serial inside a tile; tiles are independent: DevEncStrategyTile)
+__global__ void __launch_bounds__(64) k_enc_strategy(DevEPools E, const DevEFrame* frames) {
   const DevEFrame& ef = frames[blockIdx.y];
-  const uint32_t g = blockIdx.x * 32 + threadIdx.x;
-  if (g < ef.xgroups * ef.ygroups) DevEncStrategyGroup(E, ef, g);
+  const uint32_t tiles_x = (ef.xblocks + 7) / 8, tiles_y = (ef.yblocks + 7) / 8;
+  const uint32_t t = blockIdx.x * 64 + threadIdx.x;
+  if (t < tiles_x * tiles_y) DevEncStrategyTile(E, ef, (t % tiles_x) * 8, (t / tiles_x) * 8);
 }
 
 __global__ void __launch_bounds__(32) k_enc_number(DevEPools E, const DevEFrame* frames) {
@@ -2315,23 +2316,25 @@ __global__ void __launch_bounds__(256) k_enc_alpha(DevEPools E, const DevEFrame*
 
 // rANS emission: one warp per section (DevRansPushWarp: the lanes fetch and split the tokens, lane 0 codes), written
 // back to front so that it ends at the end of its region (`off[sec]` .. `off[sec + 1]`, in words); `first[sec]`
-// receives the bit position of its first bit. blockIdx.x below `dc_blocks` handles DC-group sections (the long ones,
-// scheduled first), the rest AC-group sections.
+// receives the bit position of its first bit. blockIdx.x below 2 * `dc_blocks` handles the halves of the DC-group
+// sections (the long ones, scheduled first; sections [0, ndc) = DC halves, [ndc + ngroups, 2 ndc + ngroups) = metadata
+// halves), the rest AC-group sections.
 __global__ void __launch_bounds__(32) k_enc_emit(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
                                                  const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first,
                                                  uint32_t dc_blocks) {
   const DevEFrame& ef = frames[blockIdx.y];
   const uint32_t lane = threadIdx.x;
-  if (blockIdx.x < dc_blocks) {
-    const uint32_t g = blockIdx.x;
-    if (g >= ef.xdcgroups * ef.ydcgroups) return;
+  if (blockIdx.x < 2 * dc_blocks) {
+    const uint32_t half = blockIdx.x >= dc_blocks ? 1 : 0, g = blockIdx.x - half * dc_blocks;
+    const uint32_t ndc = ef.xdcgroups * ef.ydcgroups;
+    if (g >= ndc) return;
     const DevEncCode code{fs_tables + ef.code_off[0], rev_tables + ef.code_off[1]};
-    const uint32_t sec = ef.sec_base + g;
-    const uint64_t pos = DevEncEmitDcGroupWarp(E, ef, g, code, words, off[sec + 1] * 32, lane);
+    const uint32_t sec = ef.sec_base + g + half * (ndc + ef.xgroups * ef.ygroups);
+    const uint64_t pos = DevEncEmitDcGroupWarp(E, ef, g, code, words, off[sec + 1] * 32, lane, half);
     if (lane == 0) first[sec] = pos;
     return;
   }
-  const uint32_t g = blockIdx.x - dc_blocks;
+  const uint32_t g = blockIdx.x - 2 * dc_blocks;
   if (g >= ef.xgroups * ef.ygroups) return;
   const DevEncCode code{fs_tables + ef.code_off[2], rev_tables + ef.code_off[3]};
   const uint32_t n = static_cast<uint32_t>(E.iarena[ef.group_tokens + g]);
@@ -2471,7 +2474,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       uint32_t global_scale, quant_dc;
       uint64_t tree_off;
       EncGlobals G;
-      std::vector<uint64_t> ac_off, dc_off;  // word offsets of the sections
+      std::vector<uint64_t> ac_off, dc_off, meta_off;  // word offsets of the sections (DC halves, AC groups, metadata halves)
       uint64_t bits_off;                     // index of this frame's first entry in d_bits
     };
     std::vector<Frame> fr(n);
@@ -2588,7 +2591,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     k_enc_xyb<<<dim3((maxW * 8 + 31) / 32, maxH, nf), dim3(32, 8), 0, s>>>(E, d_efs.p);
     if (p.gab) k_enc_gaborish_inv<<<dim3((maxW * 8 + 31) / 32, maxH, nf * 3), dim3(32, 8), 0, s>>>(E, d_efs.p);
     if (p.adaptive_quant) k_enc_aq<<<dim3(((maxW + 7) / 8) * ((maxH + 7) / 8), nf), 256, 0, s>>>(E, d_efs.p);
-    k_enc_strategy<<<dim3((max_groups + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
+    k_enc_strategy<<<dim3((((maxW + 7) / 8) * ((maxH + 7) / 8) + 63) / 64, nf), 64, 0, s>>>(E, d_efs.p);
     k_enc_number<<<dim3((max_dcg + 31) / 32, nf), 32, 0, s>>>(E, d_efs.p);
     k_enc_dc<<<dim3((maxW * maxH + 255) / 256, nf), 256, 0, s>>>(E, d_efs.p);
     k_enc_coeffs<0><<<dim3(max_groups, nf), kEncThreads, kEncSmemFloats * sizeof(float), s>>>(E, d_efs.p);
@@ -2709,16 +2712,22 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       for (uint32_t g = 0; g < d.num_dc_groups; g++) {
         const uint32_t gx = g % d.xsize_dc_groups, gy = g / d.xsize_dc_groups;
         const uint64_t xs = std::min<uint64_t>(256, d.xsize_blocks - gx * 256), ys = std::min<uint64_t>(256, d.ysize_blocks - gy * 256);
-        const uint64_t toks = 3 * xs * ys + 2 * ((xs + 7) / 8) * ((ys + 7) / 8) + 2 * static_cast<uint64_t>(dcg_count[g]) + xs * ys;
-        f.dc_off.push_back(words_total);
-        words_total += (toks * 6 + 64) / 4 + 4;
+        f.dc_off.push_back(words_total);  // the DC half of the section (the metadata half: below)
+        words_total += (3 * xs * ys * 6 + 64) / 4 + 4;
       }
       for (uint32_t g = 0; g < d.num_groups; g++) {
         f.ac_off.push_back(words_total);
         words_total += (static_cast<uint64_t>(group_tokens[g]) * 6 + 64) / 4 + 4;
         if (p.alpha) words_total += (65536 * 6 + 64) / 4 + 4;  // the group's alpha stream
       }
-      nsec += d.num_dc_groups + d.num_groups;
+      for (uint32_t g = 0; g < d.num_dc_groups; g++) {
+        const uint32_t gx = g % d.xsize_dc_groups, gy = g / d.xsize_dc_groups;
+        const uint64_t xs = std::min<uint64_t>(256, d.xsize_blocks - gx * 256), ys = std::min<uint64_t>(256, d.ysize_blocks - gy * 256);
+        const uint64_t toks = 2 * ((xs + 7) / 8) * ((ys + 7) / 8) + 2 * static_cast<uint64_t>(dcg_count[g]) + xs * ys;
+        f.meta_off.push_back(words_total);
+        words_total += (toks * 6 + 64 + 32) / 4 + 4;
+      }
+      nsec += 2 * d.num_dc_groups + d.num_groups;
       auto push_rev = [&](const std::vector<uint16_t>& v) {
         const uint64_t off = h_rev.size();
         h_rev.insert(h_rev.end(), v.begin(), v.end());
@@ -2739,6 +2748,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     for (size_t i = 0; i < n; i++) {
       h_off.insert(h_off.end(), fr[i].dc_off.begin(), fr[i].dc_off.end());
       h_off.insert(h_off.end(), fr[i].ac_off.begin(), fr[i].ac_off.end());
+      h_off.insert(h_off.end(), fr[i].meta_off.begin(), fr[i].meta_off.end());
     }
     h_off.push_back(words_total);  // region of section k: words [h_off[k], h_off[k + 1])
     CUDA_OK(d_rev.Upload(h_rev, s));
@@ -2757,7 +2767,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     }
     CUDA_OK(d_efs.Upload(efs, s));
     const uint32_t dc_blocks = max_dcg;
-    k_enc_emit<<<dim3(dc_blocks + max_groups, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p,
+    k_enc_emit<<<dim3(2 * dc_blocks + max_groups, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p,
                                                                             dc_blocks);
     CUDA_OK(cudaEventRecord(ev[3], s));
     std::vector<uint64_t> h_bits(nsec);
@@ -2795,7 +2805,8 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
           std::vector<EncSection> dcg, acg;  // h_bits[sec] = first bit of the section, its end = end of its region
           for (uint32_t g = 0; g < d.num_dc_groups; g++) {
             const uint64_t sec = f.bits_off + g, end = h_off[sec + 1] * 32;
-            dcg.push_back({h_words, h_bits[sec], end - h_bits[sec]});
+            const uint64_t sec2 = sec + d.num_dc_groups + d.num_groups, end2 = h_off[sec2 + 1] * 32;  // the metadata half
+            dcg.push_back({h_words, h_bits[sec], end - h_bits[sec], h_bits[sec2], end2 - h_bits[sec2]});
           }
           for (uint32_t g = 0; g < d.num_groups; g++) {
             const uint64_t sec = f.bits_off + d.num_dc_groups + g, end = h_off[sec + 1] * 32;

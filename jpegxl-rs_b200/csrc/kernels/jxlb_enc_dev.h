@@ -316,12 +316,13 @@ JXLB_HD void DevEncAqTile(const DevEPools& E, const DevEFrame& ef, uint32_t tx, 
   CoopSync<SCOPE>();
 }
 
-// AcStrategy of one 256x256 group: greedy raster scan, large smooth blocks first (serial: a choice depends on
-// which blocks are still free). acs must be 0xFF on entry.
-JXLB_HD void DevEncStrategyGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g) {
+// AcStrategy of one 64x64-pixel tile (8x8 blocks at block (x0, y0)): greedy raster scan, large smooth blocks first
+// (serial: a choice depends on which blocks are still free). Every candidate is aligned to its own size and at most
+// 64x64, so it lies inside one tile: the tiles of a frame are independent (one thread each) and the result is that of
+// a raster scan over the whole group. acs must be 0xFF on entry.
+JXLB_HD void DevEncStrategyTile(const DevEPools& E, const DevEFrame& ef, uint32_t x0, uint32_t y0) {
   const uint32_t W = ef.xblocks, H = ef.yblocks, PW = W * 8;
-  const uint32_t x0 = (g % ef.xgroups) * 32, y0 = (g / ef.xgroups) * 32;
-  const uint32_t xs = W - x0 < 32 ? W - x0 : 32, ys = H - y0 < 32 ? H - y0 : 32;
+  const uint32_t xs = W - x0 < 8 ? W - x0 : 8, ys = H - y0 < 8 ? H - y0 : 8;
   uint8_t* acs = E.barena + ef.acs;
   const float* yplane = E.farena + ef.xyb[1];
   const int kCands[5] = {18, 5, 4, 6, 7};  // 64x64, 32x32, 16x16, 16x8, 8x16
@@ -390,6 +391,14 @@ JXLB_HD void DevEncStrategyGroup(const DevEPools& E, const DevEFrame& ef, uint32
       E.barena[ef.raw_quant + pos] = static_cast<uint8_t>(rq - 1);
     }
   }
+}
+
+// The tiles of one 256x256 group (host emulation of the kernel's grid).
+JXLB_HD void DevEncStrategyGroup(const DevEPools& E, const DevEFrame& ef, uint32_t g) {
+  const uint32_t x0 = (g % ef.xgroups) * 32, y0 = (g / ef.xgroups) * 32;
+  for (uint32_t ty = 0; ty < 4; ty++)
+    for (uint32_t tx = 0; tx < 4; tx++)
+      if (x0 + tx * 8 < ef.xblocks && y0 + ty * 8 < ef.yblocks) DevEncStrategyTile(E, ef, x0 + tx * 8, y0 + ty * 8);
 }
 
 // Numbers the varblocks of DC group g in raster order of their top-left blocks.
@@ -1393,16 +1402,22 @@ JXLB_HD uint64_t DevEncEmitAcGroup(const uint2* tok, uint32_t n, const DevEncCod
 
 #if defined(__CUDACC__)
 // The two section writers above, a warp per section (DevRansPushWarp); returns the position of the first bit.
+// A DC-group section is two chained streams -- [extra_precision, GroupHeader, DC samples] then [varblock count,
+// GroupHeader, AC metadata] -- of up to 196 K and 200 K tokens: by far the longest serial chains of a frame. The two
+// halves are written by two warps into regions of their own (`half` 0 / 1) and joined bit-wise by the host assembly.
 __device__ __forceinline__ uint64_t DevEncEmitDcGroupWarp(const DevEPools& E, const DevEFrame& ef, uint32_t g, const DevEncCode& code,
-                                                          uint32_t* words, uint64_t end_pos, uint32_t lane) {
+                                                          uint32_t* words, uint64_t end_pos, uint32_t lane, uint32_t half) {
   const DevDcGroupLayout L = DevDcGroupGeometry(E, ef, g);
   const uint2* tok = E.tokens + ef.mod_tokens + ef.mod_tokens_stride * g;
   uint64_t cursor = end_pos;
-  DevRansPushWarp(tok + L.dc_tokens, L.meta_tokens, code, words, &cursor, lane);
-  DevWarpPut(words, &cursor, 4, 0x3, lane);  // use_global_tree = 1, default WP header = 1, no transforms
-  uint32_t count_bits = 0;
-  while ((1u << count_bits) < L.xs * L.ys) count_bits++;
-  if (count_bits) DevWarpPut(words, &cursor, count_bits, L.count - 1, lane);
+  if (half == 1) {
+    DevRansPushWarp(tok + L.dc_tokens, L.meta_tokens, code, words, &cursor, lane);
+    DevWarpPut(words, &cursor, 4, 0x3, lane);  // use_global_tree = 1, default WP header = 1, no transforms
+    uint32_t count_bits = 0;
+    while ((1u << count_bits) < L.xs * L.ys) count_bits++;
+    if (count_bits) DevWarpPut(words, &cursor, count_bits, L.count - 1, lane);
+    return cursor;
+  }
   DevRansPushWarp(tok, L.dc_tokens, code, words, &cursor, lane);
   DevWarpPut(words, &cursor, 4, 0x3, lane);
   DevWarpPut(words, &cursor, 2, 0, lane);  // extra_precision
