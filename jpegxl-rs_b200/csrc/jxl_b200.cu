@@ -2408,6 +2408,8 @@ struct JxlB200Encoder {
   DevBuf<DevEFrame> d_efs;
   DevBuf<DevLFrame> d_lfs;      // lossless encoder
   DevBuf<int32_t> d_lconst;     // its cutoffs and leaf table
+  uint8_t* h_in = nullptr;      // pinned staging of the input frames (UploadFrames); read by the transfers of the
+  size_t h_in_cap = 0;          // current call only: every call ends with a stream synchronisation
   uint32_t* h_words = nullptr;  // pinned: the emitted sections of a batch
   size_t h_words_cap = 0;
 };
@@ -2444,11 +2446,56 @@ void JxlB200EncoderDestroy(JxlB200Encoder* enc) {
   if (!enc) return;
   cudaSetDevice(enc->device);
   if (enc->h_words) cudaFreeHost(enc->h_words);
+  if (enc->h_in) cudaFreeHost(enc->h_in);
   if (enc->stream) cudaStreamDestroy(enc->stream);
   delete enc;
 }
 
 const char* JxlB200EncoderGetError(const JxlB200Encoder* enc) { return enc ? enc->error.c_str() : "null encoder"; }
+
+// The caller's frames (pageable memory as a rule: a direct cudaMemcpyAsync stages them on one thread at a few GB/s) ->
+// device: host threads copy them into pinned staging, each enqueuing its frame's transfer as soon as its copy is done.
+static int UploadFrames(JxlB200Encoder* enc, cudaStream_t s, const void* const* src, const std::vector<uint64_t>& dev_off,
+                        const std::vector<size_t>& sizes) {
+  JxlB200Encoder* dec = enc;  // (CUDA_OK reports through ->error)
+  const size_t n = sizes.size();
+  std::vector<size_t> host_off(n);
+  size_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    host_off[i] = total;
+    total += (sizes[i] + 255) & ~size_t{255};
+  }
+  if (total > enc->h_in_cap) {
+    if (enc->h_in) cudaFreeHost(enc->h_in);
+    enc->h_in = nullptr;
+    enc->h_in_cap = 0;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&enc->h_in), total, cudaHostAllocDefault) == cudaSuccess) enc->h_in_cap = total;
+  }
+  if (enc->h_in_cap < total) {  // no pinned memory to be had: the plain way
+    for (size_t i = 0; i < n; i++) CUDA_OK(cudaMemcpyAsync(enc->d_in.p + dev_off[i], src[i], sizes[i], cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed{0};
+  auto work = [&]() {
+    cudaSetDevice(enc->device);
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= n) break;
+      std::memcpy(enc->h_in + host_off[i], src[i], sizes[i]);
+      if (cudaMemcpyAsync(enc->d_in.p + dev_off[i], enc->h_in + host_off[i], sizes[i], cudaMemcpyHostToDevice, s) != cudaSuccess) failed = 1;
+    }
+  };
+  const size_t nthreads = std::max<size_t>(1, std::min<size_t>(n, std::min<unsigned>(16, std::thread::hardware_concurrency())));
+  std::vector<std::thread> pool;
+  for (size_t t = 0; t < nthreads; t++) pool.emplace_back(work);
+  for (auto& t : pool) t.join();
+  if (failed) {
+    enc->error = "upload of the input frames failed";
+    return 1;
+  }
+  return 0;
+}
 
 // The sections were written back to front into regions sized for the worst case (6 bytes per token): what a section
 // really uses is the tail of its region. Reads where every section starts, packs the used words of all sections into
@@ -2600,8 +2647,15 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
     std::vector<float> lut(256);
     for (int i = 0; i < 256; i++) lut[i] = SrgbToLinearHost(i / 255.0f);
     CUDA_OK(d_lut.Upload(lut, s));
-    for (size_t i = 0; i < n; i++)
-      CUDA_OK(cudaMemcpyAsync(d_in.p + fr[i].ef.rgb, rgb[i], static_cast<size_t>(xsizes[i]) * ysizes[i] * in_ch, cudaMemcpyHostToDevice, s));
+    {
+      std::vector<uint64_t> dev_off(n);
+      std::vector<size_t> in_sizes(n);
+      for (size_t i = 0; i < n; i++) {
+        dev_off[i] = fr[i].ef.rgb;
+        in_sizes[i] = static_cast<size_t>(xsizes[i]) * ysizes[i] * in_ch;
+      }
+      if (UploadFrames(enc, s, reinterpret_cast<const void* const*>(rgb), dev_off, in_sizes) != 0) return 1;
+    }
     CUDA_OK(cudaMemsetAsync(d_iarena.p, 0, (ibase + 16) * sizeof(int32_t), s));
     CUDA_OK(cudaMemsetAsync(d_barena.p, 0xFF, bbase + 16, s));
     DevEPools E{};
@@ -2932,9 +2986,15 @@ int JxlB200EncoderEncodeLosslessBatch(JxlB200Encoder* enc, const void* const* pi
     std::vector<int32_t> consts(kEnclCutoffValues, kEnclCutoffValues + 33);
     for (int k = 0; k < 34; k++) consts.push_back(static_cast<int32_t>(tree.leaf_of[k]));
     CUDA_OK(enc->d_lconst.Upload(consts, s));
-    for (size_t i = 0; i < n; i++)
-      CUDA_OK(cudaMemcpyAsync(enc->d_in.p + lf[i].in_off, pixels[i], static_cast<size_t>(xsizes[i]) * ysizes[i] * num_channels * bytes,
-                              cudaMemcpyHostToDevice, s));
+    {
+      std::vector<uint64_t> dev_off(n);
+      std::vector<size_t> in_sizes(n);
+      for (size_t i = 0; i < n; i++) {
+        dev_off[i] = lf[i].in_off;
+        in_sizes[i] = static_cast<size_t>(xsizes[i]) * ysizes[i] * num_channels * bytes;
+      }
+      if (UploadFrames(enc, s, pixels, dev_off, in_sizes) != 0) return 1;
+    }
     uint32_t* d_hist = reinterpret_cast<uint32_t*>(enc->d_iarena.p + planes);
     CUDA_OK(cudaMemsetAsync(d_hist, 0, n * 34 * 256 * sizeof(uint32_t), s));
     CUDA_OK(enc->d_lfs.Upload(lf, s));
