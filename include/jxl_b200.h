@@ -213,7 +213,7 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
 /* Lossless (Modular) batch -- jpegxl-rs `lossless(true)` (jpegxl-rs/src/encode.rs:143, :230-234; libjxl:
  * JxlEncoderSetFrameLossless, lib/jxl/enc_modular.cc): pixels[i] = xsizes[i] * ysizes[i] interleaved samples of
  * num_channels each (1 grey, 2 grey + alpha, 3 RGB, 4 RGBA; sRGB), bits_per_sample 8 (uint8) or 16 (uint16, native
- * endian). YCoCg-R + libjxl's fixed gradient tree, groups of 256 x 256; the decoded image equals the input bit for bit. */
+ * endian). YCoCg-R + libjxl's fixed gradient tree, groups of 128 x 128 (group_size_shift 0); the decoded image equals the input bit for bit. */
 int JxlB200EncoderEncodeLosslessBatch(JxlB200Encoder* enc, const void* const* pixels, const uint32_t* xsizes, const uint32_t* ysizes,
                                       size_t n, uint32_t num_channels, uint32_t bits_per_sample);
 size_t JxlB200EncoderOutputSize(const JxlB200Encoder* enc, size_t i);

@@ -9,6 +9,7 @@
 
 #include <functional>
 
+#include "../kernels/jxlb_encl_const.h"
 #include "jxlb_enc_host.h"
 
 namespace jxlb {
@@ -77,9 +78,9 @@ struct EnclParams {
   bool Alpha() const { return nch == 2 || nch == 4; }
   uint32_t NumColor() const { return nch < 3 ? 1 : 3; }
   // every channel fits one group: the whole image travels in the global stream, there are no group streams
-  bool GlobalOnly() const { return xsize <= 256 && ysize <= 256; }
-  uint32_t XGroups() const { return (xsize + 255) / 256; }
-  uint32_t YGroups() const { return (ysize + 255) / 256; }
+  bool GlobalOnly() const { return xsize <= kEnclGroupDim && ysize <= kEnclGroupDim; }
+  uint32_t XGroups() const { return (xsize + kEnclGroupDim - 1) / kEnclGroupDim; }
+  uint32_t YGroups() const { return (ysize + kEnclGroupDim - 1) / kEnclGroupDim; }
 };
 
 inline void WriteEnclImageHeaders(BitWriter& w, const EnclParams& p) {
@@ -135,7 +136,7 @@ inline void WriteEnclFrameHeader(BitWriter& w, const EnclParams& p) {
   w.Write(1, 0);   // no YCbCr
   WriteU32(w, 1, Val(1), Val(2), Val(4), Val(8));  // upsampling
   if (p.Alpha()) WriteU32(w, 1, Val(1), Val(2), Val(4), Val(8));
-  w.Write(2, 1);  // group_size_shift: 256 x 256
+  w.Write(2, kEnclGroupShift);  // group_size_shift (kernels/jxlb_encl_const.h)
   WriteU32(w, 1, Val(1), Val(2), Val(3), BitsOffset(3, 4));  // one pass
   w.Write(1, 0);                                             // no custom size or origin
   WriteU32(w, 0, Val(0), Val(1), Val(2), BitsOffset(2, 3));  // blend mode kReplace
@@ -185,7 +186,7 @@ inline std::vector<uint8_t> AssembleEncl(const EnclParams& p, const BitWriter& g
     g.ZeroPadToByte();
     sections.push_back(g.Bytes());
     const uint32_t num_groups = p.XGroups() * p.YGroups();
-    const uint32_t num_dc_groups = ((p.xsize + 2047) / 2048) * ((p.ysize + 2047) / 2048);
+    const uint32_t num_dc_groups = ((p.xsize + 8 * kEnclGroupDim - 1) / (8 * kEnclGroupDim)) * ((p.ysize + 8 * kEnclGroupDim - 1) / (8 * kEnclGroupDim));
     for (uint32_t i = 0; i < num_dc_groups; i++) sections.push_back({});  // no channel is shifted by 3 or more
     sections.push_back({});                                               // AC global: empty for Modular frames
     for (uint32_t i = 0; i < num_groups; i++) {

@@ -2965,12 +2965,13 @@ int JxlB200EncoderEncodeLosslessBatch(JxlB200Encoder* enc, const void* const* pi
       planes += px * p.nch;
       f.tok_off = toks;
       const uint32_t groups = f.xgroups * f.ygroups;
-      toks += static_cast<uint64_t>(groups) * p.nch * 65536;
+      toks += static_cast<uint64_t>(groups) * p.nch * kEnclGroupSamples;
       f.hist_off = i * 34 * 256;
       f.sec_base = static_cast<uint32_t>(h_off.size());
       for (uint32_t g = 0; g < groups; g++) {
         const uint32_t gx = g % f.xgroups, gy = g / f.xgroups;
-        const uint64_t gw = std::min<uint32_t>(256, p.xsize - gx * 256), gh = std::min<uint32_t>(256, p.ysize - gy * 256);
+        const uint64_t gw = std::min<uint32_t>(kEnclGroupDim, p.xsize - gx * kEnclGroupDim);
+        const uint64_t gh = std::min<uint32_t>(kEnclGroupDim, p.ysize - gy * kEnclGroupDim);
         h_off.push_back(words_total);
         words_total += EnclSectionWords(gw * gh * p.nch);
       }

@@ -4,7 +4,7 @@
 // What libjxl's Modular encoder does per sample (lib/jxl/modular/encoding/enc_encoding.cc:296-520: properties, MA-tree
 // leaf, predictor, residual token) under a FIXED tree: libjxl's own fixed gradient tree (enc_encoding.cc:274-282 -- the
 // 33 cutoffs on property 9 = W + N - NW, Gradient predictor in every leaf) after the YCoCg-R reversible colour transform
-// (lib/jxl/modular/transform/enc_rct.cc:17-68, rct_type 6), groups of 256 x 256 (lib/jxl/enc_modular.cc:1258-1500).
+// (lib/jxl/modular/transform/enc_rct.cc:17-68, rct_type 6), groups of kEnclGroupDim x kEnclGroupDim (lib/jxl/enc_modular.cc:1258-1500).
 // With a fixed tree the context and the prediction of a sample only need its TRUE neighbours, which the encoder has:
 // every token of the image is produced independently at its final slot (thread per sample); only the rANS emission of
 // a group is a serial chain (thread per group, DevRansPush). No tree learning, palette or squeeze (libjxl's effort-7
@@ -14,10 +14,11 @@
 #define JXLB_ENCL_DEV_H_
 
 #include "jxlb_enc_dev.h"
+#include "jxlb_encl_const.h"
 
 namespace jxlb {
 
-constexpr uint32_t kEnclCutoffs = 33, kEnclGroupDim = 256;
+constexpr uint32_t kEnclCutoffs = 33;
 
 struct DevLFrame {
   uint32_t xsize, ysize, xgroups, ygroups;
@@ -25,7 +26,7 @@ struct DevLFrame {
   uint32_t bytes;       // per input sample: 1 or 2 (native endian)
   uint64_t in_off;      // byte offset of the interleaved input samples
   uint64_t plane_off;   // int32 index of channel 0's plane; channel c at plane_off + c * xsize * ysize
-  uint64_t tok_off;     // uint2 index of the first token of group 0; group g at tok_off + g * nch * 65536
+  uint64_t tok_off;     // uint2 index of the first token of group 0; group g at tok_off + g * nch * kEnclGroupSamples
   uint64_t hist_off;    // uint32 index: [34][256] token counts of the frame
   uint32_t sec_base;    // index of group 0's section in the offset / first-bit arrays
   uint32_t pad_;
@@ -87,7 +88,7 @@ JXLB_HD void DevEnclToken(const DevLPools& L, const DevLFrame& f, uint64_t i) {
   const int32_t r = v - guess;
   const uint32_t packed = (static_cast<uint32_t>(r) << 1) ^ (r < 0 ? 0xFFFFFFFFu : 0u);
   const uint32_t g = gy * f.xgroups + gx;
-  L.tokens[f.tok_off + static_cast<uint64_t>(g) * f.nch * 65536 + static_cast<uint64_t>(c) * gw * gh + ly * gw + lx] =
+  L.tokens[f.tok_off + static_cast<uint64_t>(g) * f.nch * kEnclGroupSamples + static_cast<uint64_t>(c) * gw * gh + ly * gw + lx] =
       make_uint2(cluster, packed);
   DevCountToken(L.hist + f.hist_off, cluster, packed);
 }
@@ -101,7 +102,7 @@ JXLB_HD uint64_t DevEnclEmitGroup(const DevLPools& L, const DevLFrame& f, uint32
   const uint32_t gh = f.ysize - gy * kEnclGroupDim < kEnclGroupDim ? f.ysize - gy * kEnclGroupDim : kEnclGroupDim;
   DevBackWriter w;
   w.Init(words, end_pos);
-  DevRansPush(L.tokens + f.tok_off + static_cast<uint64_t>(g) * f.nch * 65536, f.nch * gw * gh, code, w);
+  DevRansPush(L.tokens + f.tok_off + static_cast<uint64_t>(g) * f.nch * kEnclGroupSamples, f.nch * gw * gh, code, w);
   if (group_header) w.Put(4, 0x3);
   w.Finish();
   return w.cursor;
@@ -115,7 +116,7 @@ __device__ __forceinline__ uint64_t DevEnclEmitGroupWarp(const DevLPools& L, con
   const uint32_t gw = f.xsize - gx * kEnclGroupDim < kEnclGroupDim ? f.xsize - gx * kEnclGroupDim : kEnclGroupDim;
   const uint32_t gh = f.ysize - gy * kEnclGroupDim < kEnclGroupDim ? f.ysize - gy * kEnclGroupDim : kEnclGroupDim;
   uint64_t cursor = end_pos;
-  DevRansPushWarp(L.tokens + f.tok_off + static_cast<uint64_t>(g) * f.nch * 65536, f.nch * gw * gh, code, words, &cursor, lane);
+  DevRansPushWarp(L.tokens + f.tok_off + static_cast<uint64_t>(g) * f.nch * kEnclGroupSamples, f.nch * gw * gh, code, words, &cursor, lane);
   if (group_header) DevWarpPut(words, &cursor, 4, 0x3, lane);
   return cursor;
 }

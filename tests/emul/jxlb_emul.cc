@@ -565,7 +565,7 @@ long jxlb_emul_encode_lossless(const void* pixels, uint32_t xsize, uint32_t ysiz
     const uint64_t px = static_cast<uint64_t>(xsize) * ysize;
     const uint32_t groups = f.xgroups * f.ygroups;
     std::vector<int32_t> planes(px * num_channels);
-    std::vector<uint2> tokens(static_cast<size_t>(groups) * num_channels * 65536);
+    std::vector<uint2> tokens(static_cast<size_t>(groups) * num_channels * kEnclGroupSamples);
     std::vector<uint32_t> hist(34 * 256, 0);
     std::vector<int32_t> cutoffs(kEnclCutoffValues, kEnclCutoffValues + 33);
     DevLPools L{};
@@ -586,7 +586,7 @@ long jxlb_emul_encode_lossless(const void* pixels, uint32_t xsize, uint32_t ysiz
     std::vector<EncSection> secs;
     for (uint32_t g = 0; g < groups; g++) {
       const uint32_t gx = g % f.xgroups, gy = g / f.xgroups;
-      const uint64_t gw = std::min<uint32_t>(256, xsize - gx * 256), gh = std::min<uint32_t>(256, ysize - gy * 256);
+      const uint64_t gw = std::min<uint32_t>(kEnclGroupDim, xsize - gx * kEnclGroupDim), gh = std::min<uint32_t>(kEnclGroupDim, ysize - gy * kEnclGroupDim);
       const size_t cap = EnclSectionWords(gw * gh * num_channels);
       words[g].assign(cap + 1, 0);
       const uint64_t end = cap * 32;

@@ -88,7 +88,8 @@ def _lossless_cases():
     img = vc.crop(300, 520, 100, 200)
     rng = np.random.default_rng(5)
     return [("rgb8", img, dict(bits=8, alpha=False, rct=6)),
-            ("one_group", np.ascontiguousarray(img[:200, :256]), dict(bits=8, alpha=False, rct=6)),
+            ("one_group", np.ascontiguousarray(img[:100, :128]), dict(bits=8, alpha=False, rct=6)),
+            ("four_groups", np.ascontiguousarray(img[:200, :256]), dict(bits=8, alpha=False, rct=6)),
             ("rgba8", np.dstack([img, img[:, :, 0] ^ img[:, :, 1]]), dict(bits=8, alpha=True, rct=6)),
             ("grey8", np.ascontiguousarray(img[:, :, 1:2]), dict(bits=8, alpha=False, rct=-1)),
             ("grey_alpha8", np.ascontiguousarray(img[:257, :263, :2]), dict(bits=8, alpha=True, rct=-1)),
@@ -96,14 +97,14 @@ def _lossless_cases():
             ("noise16", rng.integers(0, 65536, (70, 300, 4)).astype(np.uint16), dict(bits=16, alpha=True, rct=6))]
 
 
-@pytest.mark.parametrize("case", range(7))
+@pytest.mark.parametrize("case", range(8))
 def test_lossless_encoder_logic_matches_the_oracle(case):
     # the lossless (Modular) encoder's device functions on the CPU: the stream equals the oracle's EncodeModular under the
-    # same fixed choices (YCoCg-R, libjxl's fixed gradient tree, 256 x 256 groups) byte for byte, and decodes -- by the
+    # same fixed choices (YCoCg-R, libjxl's fixed gradient tree, 128 x 128 groups) byte for byte, and decodes -- by the
     # oracle's decoder and by the decode kernels' logic -- to the input
     name, a, kw = _lossless_cases()[case]
     got = emul_lib.encode_lossless(a)
-    assert got == jxlo.encode_modular(a.astype(np.uint16), tree=1, predictor=5, group_size_shift=1, **kw), name
+    assert got == jxlo.encode_modular(a.astype(np.uint16), tree=1, predictor=5, group_size_shift=0, **kw), name
     dt = jxlo.UINT8 if a.dtype == np.uint8 else jxlo.UINT16
     assert np.array_equal(jxlo.decode(got, a.shape[2], dt), a)
     assert np.array_equal(emul_lib.decode([got], a.shape[2], dt, [a.shape[:2]])[0], a)
@@ -123,14 +124,14 @@ def test_gpu_lossless_encoder(pkg):
             enc = pkg.JxlEncoder(lossless=True, uses_original_profile=True, has_alpha=nch in (2, 4))
             outs = enc.encode_batch([a for _, a, _ in batch])
             for (n, a, kw), o in zip(batch, outs):
-                assert o.data == jxlo.encode_modular(a.astype(np.uint16), tree=1, predictor=5, group_size_shift=1, **kw), n
+                assert o.data == jxlo.encode_modular(a.astype(np.uint16), tree=1, predictor=5, group_size_shift=0, **kw), n
             dec = pkg.decode_batch([o.data for o in outs], nch, kind)
             for (n, a, kw), d in zip(batch, dec):
                 assert np.array_equal(d, a), n
-    name, a, kw = cases[2]  # RGBA8 through the event-style API
+    name, a, kw = cases[3]  # RGBA8 through the event-style API
     enc = pkg.JxlEncoder(lossless=True, uses_original_profile=True, has_alpha=True)
     res = enc.encode(a)
-    assert res.data == jxlo.encode_modular(a.astype(np.uint16), tree=1, predictor=5, group_size_shift=1, **kw)
+    assert res.data == jxlo.encode_modular(a.astype(np.uint16), tree=1, predictor=5, group_size_shift=0, **kw)
     big = vc.frame_4k()
     out = pkg.JxlEncoder(lossless=True, uses_original_profile=True).encode_batch([big])[0].data
     assert np.array_equal(pkg.decode_batch([out], 3, np.uint8)[0], big)
