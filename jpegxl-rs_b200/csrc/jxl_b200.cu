@@ -2235,6 +2235,10 @@ __global__ void __launch_bounds__(kEncThreads) k_enc_coeffs(DevEPools E, const D
       if (lane == 0) has_big_s = 1;
       continue;
     }
+    if (MODE == 0 && (a >> 1) == 0) {  // DCT8X8, most of a photograph: in registers
+      DevEncDct8Warp(E, ef, x0 + bx, y0 + by, wbuf, lane);
+      continue;
+    }
     DevEncVarblock<1, MODE>(E, ef, x0 + bx, y0 + by, a >> 1, wbuf, lane, 32);
   }
   __syncthreads();

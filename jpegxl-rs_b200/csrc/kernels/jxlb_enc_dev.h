@@ -1199,6 +1199,57 @@ JXLB_HD void DevRansPush(const uint2* tok, uint32_t n, const DevEncCode& code, D
 }
 
 #if defined(__CUDACC__)
+// Forward 8-point DCT of one line in registers: the statements of CoopDCT (jxlb_vardct_dev.h) for n = 8, element by
+// element in the same order (AddReverse / SubReverse + Multiply at 8 and 4, the 2-point butterflies, B + InverseEvenOdd
+// at 4 and 8, the 1 / 8 scale), so the coefficients are bit-identical to the generic path.
+__device__ __forceinline__ void DevFwdDct8(float* v, const float* wc) {
+  const float w0 = wc[0], w1 = wc[1], w2 = wc[2], w3 = wc[3], w4 = wc[4], w5 = wc[5];
+  const float a0 = v[0] + v[7], a1 = v[1] + v[6], a2 = v[2] + v[5], a3 = v[3] + v[4];
+  const float a4 = (v[0] - v[7]) * w2, a5 = (v[1] - v[6]) * w3, a6 = (v[2] - v[5]) * w4, a7 = (v[3] - v[4]) * w5;
+  const float b0 = a0 + a3, b1 = a1 + a2, b2 = (a0 - a3) * w0, b3 = (a1 - a2) * w1;
+  const float b4 = a4 + a7, b5 = a5 + a6, b6 = (a4 - a7) * w0, b7 = (a5 - a6) * w1;
+  const float c0 = b0 + b1, c1 = b0 - b1, c2 = b2 + b3, c3 = b2 - b3;
+  const float c4 = b4 + b5, c5 = b4 - b5, c6 = b6 + b7, c7 = b6 - b7;
+  const float d1 = fmaf(c2, kDevSqrt2, c3), d5 = fmaf(c6, kDevSqrt2, c7);  // d0 = c0, d2 = c1, d3 = c3, d4 = c4, d6 = c5, d7 = c7
+  v[0] = 0.125f * c0;
+  v[2] = 0.125f * d1;
+  v[4] = 0.125f * c1;
+  v[6] = 0.125f * c3;
+  v[1] = 0.125f * fmaf(c4, kDevSqrt2, d5);
+  v[3] = 0.125f * (d5 + c5);
+  v[5] = 0.125f * (c5 + c7);
+  v[7] = 0.125f * c7;
+}
+
+// MODE 0 of DevEncVarblock for a DCT8X8 varblock, by one warp: lane = channel * 8 + line (24 lanes). Columns, then rows
+// through 3 x 72 floats of `buf`; coefficient (yfreq, xfreq) goes to row xfreq, column yfreq of the block's footprint
+// (the layout DevEncVarblock writes for R == C).
+__device__ __forceinline__ void DevEncDct8Warp(const DevEPools& E, const DevEFrame& ef, uint32_t bx, uint32_t by, float* buf, uint32_t lane) {
+  const uint32_t PW = ef.xblocks * 8;
+  const size_t origin = static_cast<size_t>(by) * 8 * PW + static_cast<size_t>(bx) * 8;
+  const float* wc = E.fpool + E.wc_off;
+  const uint32_t c = lane >> 3, t = lane & 7;
+  float v[8];
+  if (lane < 24) {
+    const float* px = E.farena + ef.xyb[c] + origin + t;
+#pragma unroll
+    for (uint32_t y = 0; y < 8; y++) v[y] = px[static_cast<size_t>(y) * PW];
+    DevFwdDct8(v, wc);
+#pragma unroll
+    for (uint32_t y = 0; y < 8; y++) buf[c * 72 + y * 9 + t] = v[y];
+  }
+  __syncwarp();
+  if (lane < 24) {
+#pragma unroll
+    for (uint32_t x = 0; x < 8; x++) v[x] = buf[c * 72 + t * 9 + x];
+    DevFwdDct8(v, wc);
+    float* out = E.farena + ef.xyb_raw[c] + origin + t;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) out[static_cast<size_t>(k) * PW] = v[k];
+  }
+  __syncwarp();
+}
+
 // Bits into a zero-initialised region shared with other writers of the warp: nbits <= 32, value < 2^nbits.
 __device__ __forceinline__ void DevOrBits(uint32_t* words, uint64_t pos, uint32_t nbits, uint32_t value) {
   if (nbits == 0) return;
