@@ -367,7 +367,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 256 vardct4k, 256 modular, 8 encode4k)")
     ap.add_argument("--e2e-plan-threads", type=int, default=0,
                     help="planning threads per handle in the streaming end-to-end loop (default: host cpus / handles in flight)")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (default: 3 per handle in flight)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (default: 6 per handle in flight)")
     ap.add_argument("--no-mallopt", action="store_true", help="leave glibc's malloc thresholds alone")
     ap.add_argument("--e2e-serial", action="store_true",
                     help="end-to-end loop without the streaming calls (parse, kernels and read-back of a handle one after the other)")
@@ -628,7 +628,9 @@ def main():
 
     # enough steps for the handles to fall out of lock step (parse / kernels / read-back of different steps overlap);
     # the ramp-up and the drain stay inside the timed region
-    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(3 * nfl_e2e, min(args.steps, 16))
+    # (six per handle: with three, the drain at the end -- the last handles finishing with the GPU half empty -- was a
+    # tenth of the timed region and the figure moved by +- 10 % from run to run; profiles/r2_e2e_streaming.txt)
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(6 * nfl_e2e, min(args.steps, 16))
 
     # A handle streams (include/jxl_b200.h, PlanBatch / CommitPlan / RunToHost): while its kernels decode step k the
     # host parses step k + 1 into the pending plan, and every wave's frames leave for the pinned buffers as soon as they
