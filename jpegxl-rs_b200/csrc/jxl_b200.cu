@@ -2318,27 +2318,51 @@ __global__ void __launch_bounds__(256) k_enc_alpha(DevEPools E, const DevEFrame*
   for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) DevEncAlphaSample(El, ef, i);
 }
 
-// rANS emission: one warp per section (DevRansPushWarp: the lanes fetch and split the tokens, lane 0 codes), written
-// back to front so that it ends at the end of its region (`off[sec]` .. `off[sec + 1]`, in words); `first[sec]`
-// receives the bit position of its first bit. blockIdx.x below 2 * `dc_blocks` handles the halves of the DC-group
-// sections (the long ones, scheduled first; sections [0, ndc) = DC halves, [ndc + ngroups, 2 ndc + ngroups) = metadata
-// halves), the rest AC-group sections.
-__global__ void __launch_bounds__(32) k_enc_emit(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
-                                                 const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first,
-                                                 uint32_t dc_blocks) {
+// The halves of the DC-group sections: the longest chains of a frame (up to 196 K tokens), one CTA of one warp per
+// SM, the reverse tables of the half's most used contexts staged in shared memory (`slots`: per (frame, half) 64 bytes,
+// cluster -> slot or 0xFF; kEmitDcSlots tables of 8 KB): the load on the coder's serial chain is a shared-memory load
+// instead of an L2 hit. blockIdx.x = half * dc_blocks + DC group.
+constexpr uint32_t kEmitDcSlots = 27;
+__global__ void __launch_bounds__(32) k_enc_emit_dc(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
+                                                    const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first,
+                                                    uint32_t dc_blocks, const uint8_t* slots) {
+  extern __shared__ uint4 emit_smem[];
+  __shared__ uint8_t sslot[64];
+  __shared__ uint4 stage[32];
   const DevEFrame& ef = frames[blockIdx.y];
   const uint32_t lane = threadIdx.x;
-  if (blockIdx.x < 2 * dc_blocks) {
-    const uint32_t half = blockIdx.x >= dc_blocks ? 1 : 0, g = blockIdx.x - half * dc_blocks;
-    const uint32_t ndc = ef.xdcgroups * ef.ydcgroups;
-    if (g >= ndc) return;
-    const DevEncCode code{fs_tables + ef.code_off[0], rev_tables + ef.code_off[1]};
-    const uint32_t sec = ef.sec_base + g + half * (ndc + ef.xgroups * ef.ygroups);
-    const uint64_t pos = DevEncEmitDcGroupWarp(E, ef, g, code, words, off[sec + 1] * 32, lane, half);
-    if (lane == 0) first[sec] = pos;
-    return;
+  const uint32_t half = blockIdx.x >= dc_blocks ? 1 : 0, g = blockIdx.x - half * dc_blocks;
+  const uint32_t ndc = ef.xdcgroups * ef.ydcgroups;
+  if (g >= ndc) return;
+  const DevEncCode code{fs_tables + ef.code_off[0], rev_tables + ef.code_off[1]};
+  const uint8_t* my_slots = slots + (static_cast<size_t>(blockIdx.y) * 2 + half) * 64;
+  sslot[lane] = my_slots[lane];
+  sslot[lane + 32] = my_slots[lane + 32];
+  __syncwarp();
+  for (uint32_t c = 0; c < 64; c++) {  // (8 KB per staged cluster, 16 bytes per lane and step)
+    const uint32_t slot = sslot[c];
+    if (slot == 0xFF) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(code.reverse + c * 4096);
+    for (uint32_t i = lane; i < 512; i += 32) emit_smem[slot * 512 + i] = src[i];
   }
-  const uint32_t g = blockIdx.x - 2 * dc_blocks;
+  __syncwarp();
+  const uint32_t sec = ef.sec_base + g + half * (ndc + ef.xgroups * ef.ygroups);
+  const uint64_t pos = DevEncEmitDcGroupWarp(E, ef, g, code, words, off[sec + 1] * 32, lane, half, stage,
+                                             reinterpret_cast<const uint16_t*>(emit_smem), sslot);
+  if (lane == 0) first[sec] = pos;
+}
+
+// rANS emission: one warp per section (DevRansPushWarp: the lanes fetch and split the tokens, lane 0 codes), written
+// back to front so that it ends at the end of its region (`off[sec]` .. `off[sec + 1]`, in words); `first[sec]`
+// receives the bit position of its first bit. This kernel: the AC-group sections (sections [ndc, ndc + ngroups) of a
+// frame; [0, ndc) = DC halves, [ndc + ngroups, 2 ndc + ngroups) = metadata halves of the DC-group sections:
+// k_enc_emit_dc, on a second stream at the same time).
+__global__ void __launch_bounds__(32) k_enc_emit(DevEPools E, const DevEFrame* frames, const uint32_t* fs_tables,
+                                                 const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first) {
+  __shared__ uint4 stage[32];
+  const DevEFrame& ef = frames[blockIdx.y];
+  const uint32_t lane = threadIdx.x;
+  const uint32_t g = blockIdx.x;
   if (g >= ef.xgroups * ef.ygroups) return;
   const DevEncCode code{fs_tables + ef.code_off[2], rev_tables + ef.code_off[3]};
   const uint32_t n = static_cast<uint32_t>(E.iarena[ef.group_tokens + g]);
@@ -2348,13 +2372,13 @@ __global__ void __launch_bounds__(32) k_enc_emit(DevEPools E, const DevEFrame* f
     const uint32_t gx = g % ef.xgroups, gy = g / ef.xgroups;
     const uint32_t gw = ef.xsize - (gx << 8) < 256 ? ef.xsize - (gx << 8) : 256, gh = ef.ysize - (gy << 8) < 256 ? ef.ysize - (gy << 8) : 256;
     const uint64_t pos = DevEncEmitAcGroupWarp(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words,
-                                               off[sec + 1] * 32, lane, E.tokens + ef.alpha_tokens + static_cast<size_t>(g) * 65536,
+                                               off[sec + 1] * 32, lane, stage, E.tokens + ef.alpha_tokens + static_cast<size_t>(g) * 65536,
                                                gw * gh, &mod);
     if (lane == 0) first[sec] = pos;
     return;
   }
   const uint64_t pos = DevEncEmitAcGroupWarp(E.tokens + ef.ac_tokens + static_cast<size_t>(g) * 3 * 65536, n, code, words,
-                                             off[sec + 1] * 32, lane);
+                                             off[sec + 1] * 32, lane, stage);
   if (lane == 0) first[sec] = pos;
 }
 
@@ -2380,13 +2404,14 @@ __global__ void __launch_bounds__(256) k_encl_tokens(DevLPools L, const DevLFram
 // One warp per group section (a serial rANS chain each, DevRansPushWarp); `off[sec]` .. `off[sec + 1]` is the section's region in words.
 __global__ void __launch_bounds__(32) k_encl_emit(DevLPools L, const DevLFrame* frames, const uint32_t* fs_tables,
                                                   const uint16_t* rev_tables, uint32_t* words, const uint64_t* off, uint64_t* first) {
+  __shared__ uint4 stage[32];
   const DevLFrame& f = frames[blockIdx.y];
   const uint32_t g = blockIdx.x;
   if (g >= f.xgroups * f.ygroups) return;
   const DevEncCode code{fs_tables + f.code_off[0], rev_tables + f.code_off[1]};
   const uint32_t sec = f.sec_base + g;
   const bool global_only = f.xsize <= kEnclGroupDim && f.ysize <= kEnclGroupDim;  // the tokens follow the host's global header
-  const uint64_t pos = DevEnclEmitGroupWarp(L, f, g, code, words, off[sec + 1] * 32, !global_only, threadIdx.x);
+  const uint64_t pos = DevEnclEmitGroupWarp(L, f, g, code, words, off[sec + 1] * 32, !global_only, threadIdx.x, stage);
   if (threadIdx.x == 0) first[sec] = pos;
 }
 
@@ -2406,6 +2431,8 @@ struct JxlB200Encoder {
   DevBuf<uint2> d_tokens;
   DevBuf<uint16_t> d_opool, d_custom, d_rev;
   DevBuf<uint32_t> d_upool, d_words, d_fs;
+  DevBuf<uint8_t> d_slots;        // k_enc_emit_dc: cluster -> shared-memory slot per (frame, half)
+  cudaStream_t stream2 = nullptr;  // the DC halves are emitted next to the AC groups
   DevBuf<uint64_t> d_off, d_bits, d_ranges;
   DevBuf<uint32_t> d_compact;  // FetchSections
   DevBuf<DevEncTreeNode> d_trees;
@@ -2443,6 +2470,7 @@ JxlB200Encoder* JxlB200EncoderCreate(int device) {
   cudaFuncSetAttribute(k_enc_coeffs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemFloats * sizeof(float));
   cudaFuncSetAttribute(k_enc_coeffs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemFloats * sizeof(float));
   cudaFuncSetAttribute(k_enc_cfl, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * sizeof(float));
+  cudaFuncSetAttribute(k_enc_emit_dc, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitDcSlots * 8192);
   return enc;
 }
 
@@ -2451,6 +2479,7 @@ void JxlB200EncoderDestroy(JxlB200Encoder* enc) {
   cudaSetDevice(enc->device);
   if (enc->h_words) cudaFreeHost(enc->h_words);
   if (enc->h_in) cudaFreeHost(enc->h_in);
+  if (enc->stream2) cudaStreamDestroy(enc->stream2);
   if (enc->stream) cudaStreamDestroy(enc->stream);
   delete enc;
 }
@@ -2875,10 +2904,50 @@ int JxlB200EncoderEncodeBatch(JxlB200Encoder* enc, const uint8_t* const* rgb, co
       efs[i].sec_base = static_cast<uint32_t>(fr[i].bits_off);
     }
     CUDA_OK(d_efs.Upload(efs, s));
+    // which reverse tables the DC halves keep in shared memory: per frame and half the contexts of that half's subtree
+    // (the root of the global tree splits on the stream id: left = AC metadata, right = DC), most used first
+    std::vector<uint8_t> h_slots(n * 2 * 64, 0xFF);
+    for (size_t i = 0; i < n; i++) {
+      const Frame& f = fr[i];
+      const std::vector<DevEncTreeNode>& nodes = f.tree.nodes;
+      if (nodes.empty() || nodes[0].prop != 1) continue;
+      const uint32_t* mod_hist = reinterpret_cast<const uint32_t*>(h_small[i].data() + (f.ef.mod_hist - f.ef.dcg_count));
+      for (uint32_t half = 0; half < 2; half++) {
+        std::vector<std::pair<uint64_t, uint32_t>> leaves;  // (tokens, leaf)
+        std::vector<uint32_t> stack = {half == 0 ? nodes[0].r : nodes[0].l};
+        while (!stack.empty()) {
+          const uint32_t k = stack.back();
+          stack.pop_back();
+          if (k >= nodes.size()) continue;
+          if (nodes[k].prop < 0) {
+            uint64_t count = 0;
+            for (uint32_t t = 0; t < 256; t++) count += mod_hist[static_cast<size_t>(nodes[k].l) * 256 + t];
+            if (count != 0 && nodes[k].l < 64) leaves.push_back({count, nodes[k].l});
+          } else {
+            stack.push_back(nodes[k].l);
+            stack.push_back(nodes[k].r);
+          }
+        }
+        std::sort(leaves.begin(), leaves.end(), [](const auto& a, const auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+        for (uint32_t k = 0; k < leaves.size() && k < kEmitDcSlots; k++) h_slots[(i * 2 + half) * 64 + leaves[k].second] = static_cast<uint8_t>(k);
+      }
+    }
+    CUDA_OK(enc->d_slots.Upload(h_slots, s));
     const uint32_t dc_blocks = max_dcg;
-    k_enc_emit<<<dim3(2 * dc_blocks + max_groups, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p,
-                                                                            dc_blocks);
+    if (!enc->stream2) CUDA_OK(cudaStreamCreateWithFlags(&enc->stream2, cudaStreamNonBlocking));
+    cudaEvent_t fork = nullptr, join = nullptr;
+    CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(fork, s));
+    CUDA_OK(cudaStreamWaitEvent(enc->stream2, fork, 0));
+    k_enc_emit_dc<<<dim3(2 * dc_blocks, nf), 32, kEmitDcSlots * 8192, enc->stream2>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p,
+                                                                                     d_bits.p, dc_blocks, enc->d_slots.p);
+    CUDA_OK(cudaEventRecord(join, enc->stream2));
+    k_enc_emit<<<dim3(max_groups, nf), 32, 0, s>>>(E, d_efs.p, d_fs.p, d_rev.p, d_words.p, d_off.p, d_bits.p);
+    CUDA_OK(cudaStreamWaitEvent(s, join, 0));
     CUDA_OK(cudaEventRecord(ev[3], s));
+    CUDA_OK(cudaEventDestroy(fork));
+    CUDA_OK(cudaEventDestroy(join));
     std::vector<uint64_t> h_bits, h_nbits;
     if (FetchSections(enc, s, h_off, nsec, &h_bits, &h_nbits) != 0) return 1;
     uint32_t* const h_words = enc->h_words;

@@ -1267,8 +1267,15 @@ __device__ __forceinline__ void DevOrBits(uint32_t* words, uint64_t pos, uint32_
 // at the position that follows from a prefix sum of the bit counts and the chunk's renormalisation mask.
 // (One thread per section left 31 lanes of a warp to other sections with other branch histories: the warp ran them
 // one after the other, every token load was a dependent miss of its own, and the bit writer sat on the chain.)
+// kSmem: `srev` holds the reverse tables of some clusters in shared memory (4096 entries each), `sslot[cluster]` says
+// which (0xFF: not staged, read from global memory): the load on the chain then is a shared-memory load.
+// `stage`: 32 uint4 of shared memory of this warp. The chain itself runs on ALL lanes (the same state everywhere, the
+// chunk's tokens read from `stage` by broadcast): no divergent region per token, one shared-memory load instead of
+// three shuffles -- a lone warp issues an instruction every ~ 5 cycles, so the chain's length is its instruction count.
+template <bool kSmem = false>
 __device__ __forceinline__ void DevRansPushWarp(const uint2* tok, uint32_t n, const DevEncCode& code, uint32_t* words, uint64_t* cursor,
-                                                uint32_t lane) {
+                                                uint32_t lane, uint4* stage, const uint16_t* srev = nullptr,
+                                                const uint8_t* sslot = nullptr) {
   uint32_t state = 0x13u << 16;
   uint64_t pos = *cursor;
   auto fetch = [&](uint32_t done, uint32_t* cn, uint32_t* bt, uint32_t* fs, uint32_t* rcp) {
@@ -1281,6 +1288,7 @@ __device__ __forceinline__ void DevRansPushWarp(const uint2* tok, uint32_t n, co
       uint32_t token, nbits;
       DevHybrid420(t.y, &token, &nbits, bt);
       *cn = t.x | (nbits << 16);
+      if (kSmem) *cn |= static_cast<uint32_t>(sslot[t.x]) << 8;  // (clusters are below 256)
       *fs = JXLB_LDG(code.fs + t.x * 256 + token);
       *rcp = 0xFFFFFFFFu / (*fs & 0xFFFF);  // >= 2^32 / f - 1: the quotient estimate is at most one short
     }
@@ -1291,7 +1299,7 @@ __device__ __forceinline__ void DevRansPushWarp(const uint2* tok, uint32_t n, co
     uint32_t ncn, nbt, nfs, nrcp;
     fetch(done + 32, &ncn, &nbt, &nfs, &nrcp);  // in flight while this chunk is coded
     const uint32_t cnt = n - done < 32 ? n - done : 32;
-    // bits of the tokens before mine in the chunk (exclusive prefix sum of the extra-bit counts)
+    // bits of the tokens before mine in the chunk (inclusive prefix sum of the extra-bit counts)
     const uint32_t my_nbits = cn >> 16;
     uint32_t incl = my_nbits;
 #pragma unroll
@@ -1299,33 +1307,35 @@ __device__ __forceinline__ void DevRansPushWarp(const uint2* tok, uint32_t n, co
       const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
       if (lane >= d) incl += v;
     }
-    uint32_t mask = 0;  // lane 0: tokens of the chunk after which the state was renormalised
-    uint64_t p = pos;   // lane 0: write position
-    uint32_t c_cn = __shfl_sync(0xFFFFFFFFu, cn, 0), c_fs = __shfl_sync(0xFFFFFFFFu, fs, 0), c_rcp = __shfl_sync(0xFFFFFFFFu, rcp, 0);
+    stage[lane] = make_uint4(cn, fs, rcp, 0);
+    __syncwarp();
+    uint32_t mask = 0;  // tokens of the chunk after which the state was renormalised
+    uint64_t p = pos;   // write position
     for (uint32_t k = 0; k < cnt; k++) {
-      const uint32_t k_cn = c_cn, k_fs = c_fs, k_rcp = c_rcp;
-      const uint32_t kn = k + 1 < 32 ? k + 1 : 31;  // the next token's words do not depend on the state: ahead of the chain
-      c_cn = __shfl_sync(0xFFFFFFFFu, cn, kn);
-      c_fs = __shfl_sync(0xFFFFFFFFu, fs, kn);
-      c_rcp = __shfl_sync(0xFFFFFFFFu, rcp, kn);
-      if (lane == 0) {
-        p -= k_cn >> 16;
-        const uint32_t f = k_fs & 0xFFFF;
-        if ((state >> 20) >= f) {
-          p -= 16;
-          DevOrBits(words, p, 16, state & 0xFFFF);
-          state >>= 16;
-          mask |= 1u << k;
-        }
-        uint32_t q = __umulhi(state, k_rcp), r = state - q * f;
-        if (r >= f) {
-          q++;
-          r -= f;
-        }
-        state = (q << 12) | JXLB_LDG(code.reverse + (k_cn & 0xFFFF) * 4096 + (k_fs >> 16) + r);
+      const uint4 t = stage[k];
+      p -= t.x >> 16;
+      const uint32_t f = t.y & 0xFFFF;
+      if ((state >> 20) >= f) {  // (uniform)
+        p -= 16;
+        if (lane == 0) DevOrBits(words, p, 16, state & 0xFFFF);
+        state >>= 16;
+        mask |= 1u << k;
       }
+      uint32_t q = __umulhi(state, t.z), r = state - q * f;
+      if (r >= f) {
+        q++;
+        r -= f;
+      }
+      const uint32_t at = (t.y >> 16) + r, slot = (t.x >> 8) & 0xFF;
+      uint32_t rev;
+      if (kSmem && slot != 0xFF) {
+        rev = srev[slot * 4096 + at];
+      } else {
+        rev = JXLB_LDG(code.reverse + (t.x & 0xFF) * 4096 + at);
+      }
+      state = (q << 12) | rev;
     }
-    mask = __shfl_sync(0xFFFFFFFFu, mask, 0);
+    __syncwarp();  // (the next chunk overwrites `stage`)
     if (lane < cnt && my_nbits != 0)
       DevOrBits(words, pos - incl - 16ull * __popc(mask & ((1u << lane) - 1)), my_nbits, bt);
     pos -= __shfl_sync(0xFFFFFFFFu, incl, 31) + 16ull * __popc(mask);
@@ -1457,33 +1467,34 @@ JXLB_HD uint64_t DevEncEmitAcGroup(const uint2* tok, uint32_t n, const DevEncCod
 // GroupHeader, AC metadata] -- of up to 196 K and 200 K tokens: by far the longest serial chains of a frame. The two
 // halves are written by two warps into regions of their own (`half` 0 / 1) and joined bit-wise by the host assembly.
 __device__ __forceinline__ uint64_t DevEncEmitDcGroupWarp(const DevEPools& E, const DevEFrame& ef, uint32_t g, const DevEncCode& code,
-                                                          uint32_t* words, uint64_t end_pos, uint32_t lane, uint32_t half) {
+                                                          uint32_t* words, uint64_t end_pos, uint32_t lane, uint32_t half,
+                                                          uint4* stage, const uint16_t* srev, const uint8_t* sslot) {
   const DevDcGroupLayout L = DevDcGroupGeometry(E, ef, g);
   const uint2* tok = E.tokens + ef.mod_tokens + ef.mod_tokens_stride * g;
   uint64_t cursor = end_pos;
   if (half == 1) {
-    DevRansPushWarp(tok + L.dc_tokens, L.meta_tokens, code, words, &cursor, lane);
+    DevRansPushWarp<true>(tok + L.dc_tokens, L.meta_tokens, code, words, &cursor, lane, stage, srev, sslot);
     DevWarpPut(words, &cursor, 4, 0x3, lane);  // use_global_tree = 1, default WP header = 1, no transforms
     uint32_t count_bits = 0;
     while ((1u << count_bits) < L.xs * L.ys) count_bits++;
     if (count_bits) DevWarpPut(words, &cursor, count_bits, L.count - 1, lane);
     return cursor;
   }
-  DevRansPushWarp(tok, L.dc_tokens, code, words, &cursor, lane);
+  DevRansPushWarp<true>(tok, L.dc_tokens, code, words, &cursor, lane, stage, srev, sslot);
   DevWarpPut(words, &cursor, 4, 0x3, lane);
   DevWarpPut(words, &cursor, 2, 0, lane);  // extra_precision
   return cursor;
 }
 
 __device__ __forceinline__ uint64_t DevEncEmitAcGroupWarp(const uint2* tok, uint32_t n, const DevEncCode& code, uint32_t* words,
-                                                          uint64_t end_pos, uint32_t lane, const uint2* alpha_tok = nullptr,
+                                                          uint64_t end_pos, uint32_t lane, uint4* stage, const uint2* alpha_tok = nullptr,
                                                           uint32_t alpha_n = 0, const DevEncCode* mod_code = nullptr) {
   uint64_t cursor = end_pos;
   if (alpha_tok != nullptr) {
-    DevRansPushWarp(alpha_tok, alpha_n, *mod_code, words, &cursor, lane);
+    DevRansPushWarp(alpha_tok, alpha_n, *mod_code, words, &cursor, lane, stage);
     DevWarpPut(words, &cursor, 4, 0x3, lane);
   }
-  DevRansPushWarp(tok, n, code, words, &cursor, lane);
+  DevRansPushWarp(tok, n, code, words, &cursor, lane, stage);
   return cursor;
 }
 #endif

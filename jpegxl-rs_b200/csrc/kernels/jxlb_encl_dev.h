@@ -111,12 +111,12 @@ JXLB_HD uint64_t DevEnclEmitGroup(const DevLPools& L, const DevLFrame& f, uint32
 #if defined(__CUDACC__)
 // The same section written by a warp (DevRansPushWarp, jxlb_enc_dev.h); returns the position of the first bit.
 __device__ __forceinline__ uint64_t DevEnclEmitGroupWarp(const DevLPools& L, const DevLFrame& f, uint32_t g, const DevEncCode& code,
-                                                         uint32_t* words, uint64_t end_pos, bool group_header, uint32_t lane) {
+                                                         uint32_t* words, uint64_t end_pos, bool group_header, uint32_t lane, uint4* stage) {
   const uint32_t gx = g % f.xgroups, gy = g / f.xgroups;
   const uint32_t gw = f.xsize - gx * kEnclGroupDim < kEnclGroupDim ? f.xsize - gx * kEnclGroupDim : kEnclGroupDim;
   const uint32_t gh = f.ysize - gy * kEnclGroupDim < kEnclGroupDim ? f.ysize - gy * kEnclGroupDim : kEnclGroupDim;
   uint64_t cursor = end_pos;
-  DevRansPushWarp(L.tokens + f.tok_off + static_cast<uint64_t>(g) * f.nch * kEnclGroupSamples, f.nch * gw * gh, code, words, &cursor, lane);
+  DevRansPushWarp(L.tokens + f.tok_off + static_cast<uint64_t>(g) * f.nch * kEnclGroupSamples, f.nch * gw * gh, code, words, &cursor, lane, stage);
   if (group_header) DevWarpPut(words, &cursor, 4, 0x3, lane);
   return cursor;
 }
