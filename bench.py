@@ -18,7 +18,9 @@ A "step" = one pass of the hot path over one batch of synthetic input. Workloads
 
 Every rank works on its own batch (weak scaling: frames are independent); under torchrun the decoded frames of every
 step are gathered on rank 0 with NCCL inside the timed region (the one collective of the path).
-The default run folds short side runs of the other workloads into `also`: the fixtures, encode4k, modular and the
+`e2e` streams on every handle in flight (JxlB200DecoderPlanBatch / CommitPlan / RunToHost: the next step's files are
+parsed while the current step's kernels run, the frames leave for pinned host memory wave by wave); --e2e-serial is the
+loop without that. The default run folds short side runs of the other workloads into `also`: the fixtures, encode4k, modular and the
 lossless encoder (tools/bench_lossless_enc.py).
 """
 import argparse
