@@ -1198,11 +1198,10 @@ JXLB_HD void DevRansPush(const uint2* tok, uint32_t n, const DevEncCode& code, D
   w.Put(32, state);
 }
 
-#if defined(__CUDACC__)
 // Forward 8-point DCT of one line in registers: the statements of CoopDCT (jxlb_vardct_dev.h) for n = 8, element by
 // element in the same order (AddReverse / SubReverse + Multiply at 8 and 4, the 2-point butterflies, B + InverseEvenOdd
 // at 4 and 8, the 1 / 8 scale), so the coefficients are bit-identical to the generic path.
-__device__ __forceinline__ void DevFwdDct8(float* v, const float* wc) {
+JXLB_HD void DevFwdDct8(float* v, const float* wc) {
   const float w0 = wc[0], w1 = wc[1], w2 = wc[2], w3 = wc[3], w4 = wc[4], w5 = wc[5];
   const float a0 = v[0] + v[7], a1 = v[1] + v[6], a2 = v[2] + v[5], a3 = v[3] + v[4];
   const float a4 = (v[0] - v[7]) * w2, a5 = (v[1] - v[6]) * w3, a6 = (v[2] - v[5]) * w4, a7 = (v[3] - v[4]) * w5;
@@ -1221,6 +1220,7 @@ __device__ __forceinline__ void DevFwdDct8(float* v, const float* wc) {
   v[7] = 0.125f * c7;
 }
 
+#if defined(__CUDACC__)
 // MODE 0 of DevEncVarblock for a DCT8X8 varblock, by one warp: lane = channel * 8 + line (24 lanes). Columns, then rows
 // through 3 x 72 floats of `buf`; coefficient (yfreq, xfreq) goes to row xfreq, column yfreq of the block's footprint
 // (the layout DevEncVarblock writes for R == C).

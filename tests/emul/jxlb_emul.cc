@@ -360,6 +360,8 @@ int jxlb_emul_decode(const uint8_t* const* files, const size_t* sizes, size_t n,
 // ---------------------------------------------------------------- encoder
 #include "../../jpegxl-rs_b200/csrc/host/jxlb_enc_host.h"
 #include "../../jpegxl-rs_b200/csrc/kernels/jxlb_enc_dev.h"
+#include <cmath>
+#include <random>
 #include "../../jpegxl-rs_b200/csrc/host/jxlb_encl_host.h"
 #include "../../jpegxl-rs_b200/csrc/kernels/jxlb_encl_dev.h"
 
@@ -545,6 +547,25 @@ long jxlb_emul_encode(const uint8_t* rgb, uint32_t xsize, uint32_t ysize, float 
 
 // Lossless (Modular) encode of one image with the device functions of kernels/jxlb_encl_dev.h run on the CPU and the
 // host code of host/jxlb_encl_host.h, in the order of JxlB200EncoderEncodeLosslessBatch; returns the size or -1.
+// DevFwdDct8 (the register transform of the DCT8X8 fast path, kernels/jxlb_enc_dev.h) against the generic staged
+// forward DCT (CoopDCT, n = 8) on `trials` seeded random lines, including large and tiny magnitudes: the number of
+// lines whose eight coefficients are not bit-identical.
+long jxlb_emul_fwd_dct8_mismatches(uint32_t seed, uint32_t trials) {
+  const SharedVarDCTTables& sh = SharedVarDCTTables::Get();
+  const float* wc = sh.fpool.data() + sh.wc_off;
+  std::mt19937 rng(seed);
+  long bad = 0;
+  for (uint32_t t = 0; t < trials; t++) {
+    float v[8], a[8], b[8];
+    const float scale = std::ldexp(1.0f, static_cast<int>(rng() % 40) - 30);
+    for (int i = 0; i < 8; i++) v[i] = a[i] = (static_cast<float>(rng() % 2000001) - 1000000.0f) * 1e-6f * scale;
+    DevFwdDct8(v, wc);
+    const float* r = CoopDCT<0>(8, 1, 8, 1, a, b, wc, 0, 1);
+    if (std::memcmp(v, r, sizeof(v)) != 0) bad++;
+  }
+  return bad;
+}
+
 long jxlb_emul_encode_lossless(const void* pixels, uint32_t xsize, uint32_t ysize, uint32_t num_channels, uint32_t bits,
                                uint8_t* out, size_t out_cap, char* err, size_t errlen) {
   try {

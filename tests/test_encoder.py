@@ -174,3 +174,12 @@ def test_gpu_lossy_encoder_with_alpha(pkg):
         assert np.array_equal(d, jxlo.decode(o.data, 4, jxlo.UINT8))
     res = pkg.JxlEncoder(has_alpha=True).encode(ims[0])  # the libjxl-compatible calls, as jpegxl-rs drives them
     assert res.data == outs[0].data
+
+
+def test_register_dct8_is_bit_identical_to_the_staged_forward_dct():
+    # the DCT8X8 fast path of k_enc_coeffs (DevFwdDct8: a line in registers) states the generic staged forward DCT
+    # (CoopDCT, n = 8) operation by operation: bit-identical coefficients on random lines of every magnitude
+    import ctypes
+    L = emul_lib.lib()
+    L.jxlb_emul_fwd_dct8_mismatches.restype = ctypes.c_long
+    assert L.jxlb_emul_fwd_dct8_mismatches(ctypes.c_uint32(7), ctypes.c_uint32(200000)) == 0
