@@ -183,3 +183,18 @@ def test_register_dct8_is_bit_identical_to_the_staged_forward_dct():
     L = emul_lib.lib()
     L.jxlb_emul_fwd_dct8_mismatches.restype = ctypes.c_long
     assert L.jxlb_emul_fwd_dct8_mismatches(ctypes.c_uint32(7), ctypes.c_uint32(200000)) == 0
+
+
+def test_reciprocal_division_of_the_rans_writer_is_exact():
+    # DevRansPushWarp divides the coder state by a symbol frequency as umulhi(state, 0xFFFFFFFF // f) plus one
+    # correction step: exact for every frequency of a 12-bit ANS table and every 32-bit state (the estimate is never more
+    # than one short: 0xFFFFFFFF // f >= 2^32 / f - 1)
+    rng = np.random.default_rng(11)
+    for f in range(1, 4097):
+        edge = np.array([0, 1, f - 1, f, f + 1, 2**32 - 1, 2**32 - f, (2**32 // f) * f - 1, ((2**32 - 1) // f) * f], dtype=np.uint64)
+        st = np.concatenate([rng.integers(0, 2**32, 64, dtype=np.uint64), edge[edge < 2**32]])
+        q = (st * np.uint64(0xFFFFFFFF // f)) >> np.uint64(32)
+        r = st - q * np.uint64(f)
+        fix = r >= f
+        q, r = q + fix, r - fix * np.uint64(f)
+        assert np.array_equal(q, st // np.uint64(f)) and np.all(r < f), f
