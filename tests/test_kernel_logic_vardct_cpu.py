@@ -247,3 +247,14 @@ def test_splines_in_lossy_frames():
     m = np.random.default_rng(1).integers(0, 256, (120, 200, 3)).astype(np.uint16)
     e = jxlo.encode_modular(m, bits=8, tree=1, splines=4)
     assert np.array_equal(emul_lib.decode([e], 3, jxlo.UINT8, [(120, 200)])[0], jxlo.decode(e, 3, jxlo.UINT8))
+
+
+def test_splines_in_an_upsampled_frame_are_refused_by_name():
+    # libjxl draws splines on the coded planes in front of the upsampling stage (lib/jxl/dec_cache.cc:178-196); the GPU
+    # path draws them in the colour store behind it and therefore refuses the combination instead of decoding it wrongly
+    # (the oracle decodes it)
+    img = vc.crop(64, 96, 100, 200)
+    d = jxlo.encode_vardct(img, strategy_mode=2, upsampling=2, splines=3)
+    assert jxlo.decode(d, 3, jxlo.UINT8).shape == (128, 192, 3)
+    with pytest.raises(emul_lib.EmulError, match="splines in an upsampled frame"):
+        emul_lib.decode([d], 3, jxlo.UINT8, [(128, 192)])
