@@ -85,7 +85,6 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
   DevVFrame& vf = v.vf;
   vf = DevVFrame{};
   JXLB_CHECK(!(fh.flags & (kFlagNoise | kFlagUseDcFrame)), "unsupported: noise / DC frame");
-  JXLB_CHECK(!((fh.flags & kFlagSplines) && fh.upsampling > 1), "unsupported: splines in an upsampled frame");
   FramePlanner planner(plan);
   const size_t W = dim.xsize_blocks, H = dim.ysize_blocks, nb = W * H;
 
@@ -198,7 +197,7 @@ inline void PlanVarDCTFrame(const uint8_t* cs, size_t cs_size, const FrameHeader
       InitSplineDrawCache(dim.xsize_upsampled, dim.ysize_upsampled, vf.base_x, vf.base_b, &splines);
       if (!splines.segments.empty()) {
         vf.has_splines = 1;
-        PackSplineDrawCache(splines, dim.ysize, plan, &vf.spl_seg, &vf.spl_rows, &vf.spl_idx);
+        PackSplineDrawCache(splines, dim.ysize_upsampled, plan, &vf.spl_seg, &vf.spl_rows, &vf.spl_idx);
       }
     }
     if (r.ReadBool()) {

@@ -1724,7 +1724,8 @@ JXLB_HD void DevPatchPixel(const DevVPools& V, const DevVFrame& vf, const DevPat
 
 // One output pixel from its three filtered samples: colour transform + sample conversion + interleaved store.
 JXLB_HD void DevColorStore(const DevVPools& V, const DevVFrame& vf, float p0, float p1, float p2, uint32_t x, uint32_t y) {
-  if (vf.has_splines) {  // (rare) SplineStage sits behind the loop filters and patches, in XYB
+  if (vf.has_splines && vf.upsampling == 1) {  // (rare) SplineStage sits behind the loop filters and patches, in XYB
+    // (in an upsampled frame it sits in front of the upsampling: DevUpsamplePixel)
     float v[3] = {p0, p1, p2};
     DevSplineAdd(V.spl_idx + vf.spl_rows, V.spl_idx + vf.spl_idx, V.spl_seg + vf.spl_seg, vf.xsize, x, y, v);
     p0 = v[0];
@@ -1789,6 +1790,35 @@ JXLB_HD void DevUpsamplePixel(const DevVPools& V, const DevVFrame& vf, uint32_t 
   const float* kernel = V.fpool + vf.up_kernel + (a * 4 + b) * 25;
   const uint32_t PW = vf.xblocks * 8;
   const int xsize = static_cast<int>(vf.xsize), ysize = static_cast<int>(vf.ysize);
+  if (vf.has_splines) {
+    // (rare) libjxl draws the splines on the coded planes in front of the upsampling (lib/jxl/dec_cache.cc:178-196):
+    // every tap is the plane sample with the splines of its own position added; taps and channels in the order of the
+    // loop below, so that each channel's sum is the same sequence of operations
+    float result[3] = {0.0f, 0.0f, 0.0f}, mn[3], mx[3];
+    for (int iy = -2; iy <= 2; iy++) {
+      const uint32_t sy = DevMirror(y + iy, ysize);
+      const uint32_t kr = static_cast<uint32_t>(fy ? 2 - iy : iy + 2);
+      for (int ix = -2; ix <= 2; ix++) {
+        const uint32_t sx = DevMirror(x + ix, xsize);
+        const size_t at = static_cast<size_t>(sy) * PW + sx;
+        float v[3] = {V.farena[vf.pix[set][0] + at], V.farena[vf.pix[set][1] + at], V.farena[vf.pix[set][2] + at]};
+        DevSplineAdd(V.spl_idx + vf.spl_rows, V.spl_idx + vf.spl_idx, V.spl_seg + vf.spl_seg, vf.xsize, sx, sy, v);
+        const uint32_t kc = static_cast<uint32_t>(fx ? 2 - ix : ix + 2);
+        const float w = kernel[kr * 5 + kc];
+        for (uint32_t c = 0; c < 3; c++) {
+          if (iy == -2 && ix == -2) mn[c] = mx[c] = v[c];
+          result[c] = fmaf(w, v[c], result[c]);
+          mn[c] = mn[c] < v[c] ? mn[c] : v[c];
+          mx[c] = v[c] < mx[c] ? mx[c] : v[c];
+        }
+      }
+    }
+    for (uint32_t c = 0; c < 3; c++) {
+      const float lo = result[c] < mn[c] ? mn[c] : result[c];
+      V.farena[vf.up_pix[c] + static_cast<size_t>(oy) * vf.up_stride + ox] = mx[c] < lo ? mx[c] : lo;
+    }
+    return;
+  }
   for (uint32_t c = 0; c < 3; c++) {
     const float* p = V.farena + vf.pix[set][c];
     const float centre = p[static_cast<size_t>(y) * PW + x];

@@ -167,7 +167,8 @@ def test_splines_in_lossy_frames(pkg):
     files = [jxlo.encode_vardct(img, strategy_mode=2, splines=5), jxlo.encode_vardct(img[:60, :70], strategy_mode=2, splines=3),
              jxlo.encode_vardct(vc.crop(520, 300, 50, 60), strategy_mode=3, splines=9, epf_iters=1, seed=4),
              jxlo.encode_vardct(vc.crop(1000, 1500, 0, 0), strategy_mode=2, splines=15),
-             vc.encoded("odd_size")[0], read_golden("2bit.jxl")]
+             vc.encoded("odd_size")[0], read_golden("2bit.jxl"),
+             jxlo.encode_vardct(vc.crop(64, 96, 100, 200), strategy_mode=2, upsampling=2, splines=4)]  # (in front of the upsampling)
     for nc, npdt, dt in [(3, np.uint8, jxlo.UINT8), (4, np.uint8, jxlo.UINT8), (3, np.uint16, jxlo.UINT16), (4, np.float32, jxlo.FLOAT)]:
         outs = pkg.decode_batch(files, nc, npdt)
         for f, o in zip(files, outs):

@@ -249,12 +249,14 @@ def test_splines_in_lossy_frames():
     assert np.array_equal(emul_lib.decode([e], 3, jxlo.UINT8, [(120, 200)])[0], jxlo.decode(e, 3, jxlo.UINT8))
 
 
-def test_splines_in_an_upsampled_frame_are_refused_by_name():
-    # libjxl draws splines on the coded planes in front of the upsampling stage (lib/jxl/dec_cache.cc:178-196); the GPU
-    # path draws them in the colour store behind it and therefore refuses the combination instead of decoding it wrongly
-    # (the oracle decodes it)
+def test_splines_in_an_upsampled_frame():
+    # libjxl draws splines on the coded planes in front of the upsampling stage (lib/jxl/dec_cache.cc:178-196): the
+    # upsampling kernel adds them to every tap (DevUpsamplePixel); 2x and 4x, every output type, with an orientation
     img = vc.crop(64, 96, 100, 200)
-    d = jxlo.encode_vardct(img, strategy_mode=2, upsampling=2, splines=3)
-    assert jxlo.decode(d, 3, jxlo.UINT8).shape == (128, 192, 3)
-    with pytest.raises(emul_lib.EmulError, match="splines in an upsampled frame"):
-        emul_lib.decode([d], 3, jxlo.UINT8, [(128, 192)])
+    for up, kw in [(2, {}), (4, {}), (2, dict(orientation=6))]:
+        d = jxlo.encode_vardct(img, strategy_mode=2, upsampling=up, splines=4, **kw)
+        plain = jxlo.encode_vardct(img, strategy_mode=2, upsampling=up, **kw)
+        assert (jxlo.decode(d, 3, jxlo.UINT8) != jxlo.decode(plain, 3, jxlo.UINT8)).any()
+        for nc, dt in [(3, jxlo.UINT8), (4, jxlo.UINT16), (3, jxlo.FLOAT)]:
+            got = emul_lib.decode([d], nc, dt, [(64 * up, 96 * up)])[0]
+            assert np.array_equal(got.view(np.uint8), jxlo.decode(d, nc, dt).view(np.uint8)), (up, kw, nc, dt)
